@@ -1,0 +1,302 @@
+"""ctypes binding of the C-ABI declared in include/genrich_cuda.h.
+
+The binding is generic over (shared library, symbol prefix) so that the parity
+tests can drive the CPU oracle (prefix ``orc_``, built from oracle/) through the
+very same Python surface as the CUDA library (prefix ``gr_``).  Nothing in this
+package ever loads the oracle: :func:`load_cuda` is the only loader the product
+uses, and it raises if ``libgenrich_cuda.so`` is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB = os.path.join(HERE, "csrc", "libgenrich_cuda.so")
+
+GR_SKIP = -1.0
+
+
+class GrChrom(C.Structure):
+    _fields_ = [("len", C.c_uint32), ("skip", C.c_uint8), ("owned", C.c_uint8),
+                ("reserved", C.c_uint16)]
+
+
+class GrParams(C.Structure):
+    _fields_ = [("min_pqval", C.c_float), ("qval_opt", C.c_int32),
+                ("min_auc", C.c_float), ("min_len", C.c_int32),
+                ("max_gap", C.c_int32), ("keep_pileups", C.c_int32),
+                ("genome_len", C.c_uint64)]
+
+
+class GrSampleStats(C.Structure):
+    _fields_ = [("frag_len", C.c_double), ("ctrl_frag", C.c_double),
+                ("lambda_", C.c_float), ("factor", C.c_float),
+                ("genome_len", C.c_uint64), ("n_expt", C.c_uint64),
+                ("n_ctrl", C.c_uint64), ("n_pval", C.c_uint64),
+                ("n_clamped", C.c_uint64)]
+
+
+class GrPeak(C.Structure):
+    _fields_ = [("chrom", C.c_int32), ("summit", C.c_uint32),
+                ("start", C.c_int64), ("end", C.c_int64), ("auc", C.c_float),
+                ("pval", C.c_float), ("qval", C.c_float), ("reserved", C.c_float)]
+
+
+class GrRunStats(C.Structure):
+    _fields_ = [("genome_len", C.c_uint64), ("n_peaks", C.c_uint64),
+                ("peak_bp", C.c_uint64), ("n_intervals", C.c_uint64),
+                ("n_distinct_p", C.c_uint64), ("all_q_one", C.c_int32),
+                ("n_replicates", C.c_int32)]
+
+
+class GrStageTime(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("ms", C.c_double),
+                ("launches", C.c_uint64), ("bytes", C.c_uint64)]
+
+
+PEAK_DTYPE = np.dtype([("chrom", "<i4"), ("summit", "<u4"), ("start", "<i8"),
+                       ("end", "<i8"), ("auc", "<f4"), ("pval", "<f4"),
+                       ("qval", "<f4"), ("reserved", "<f4")])
+
+# every symbol include/genrich_cuda.h declares (checked by tests/test_abi.py)
+ABI_SYMBOLS = [
+    "gr_create", "gr_destroy", "gr_set_params", "gr_strerror",
+    "gr_last_error_detail", "gr_sample_begin", "gr_push_intervals",
+    "gr_push_intervals_device", "gr_sample_pileup", "gr_replicate_finish",
+    "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
+    "gr_bh_set_global", "gr_call_peaks", "gr_fetch_intervals",
+    "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
+    "gr_kernel_launches", "gr_synchronize",
+]
+
+STATUS_TEXT = {
+    0: "ok", 1: "bad argument or call order", 2: "CUDA failure",
+    3: "Cannot allocate memory", 4: ": read aligned beyond reference end",
+    5: "Experimental sample has no analyzable fragments",
+    6: "No analyzable genome (length=0)", 7: "Invalid pileup value (< 0)",
+    8: "Disallowed number of alignments", 9: "interval on unknown/unowned chromosome",
+    10: "Invalid df in pchisq()", 11: "Genome length does not match p-value length",
+    12: "no CUDA device",
+}
+
+
+class GenrichError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        msg = STATUS_TEXT.get(status, "unknown")
+        super().__init__(f"{where}: status {status} ({msg}) {detail}".strip())
+
+
+@dataclass
+class Intervals:
+    """One RLE array of the reference's ``Pileup`` type (Genrich.h:173-176)."""
+    end: np.ndarray
+    val: np.ndarray
+    expt: np.ndarray | None = None
+    ctrl: np.ndarray | None = None
+
+
+class Api:
+    """Thin functional wrapper of one shared library exporting <prefix>* symbols."""
+
+    def __init__(self, path: str, prefix: str):
+        if not os.path.exists(path):
+            raise FileNotFoundError(
+                f"{path} not found - build it first (python -c 'import __graft_entry__ as g; g.build()')")
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self.has_device = prefix == "gr_"
+        L, p = self.lib, prefix
+        vp, i32, u64, dbl = C.c_void_p, C.c_int32, C.c_uint64, C.c_double
+
+        def fn(name, res, args):
+            f = getattr(L, p + name)
+            f.restype = res
+            f.argtypes = args
+            return f
+
+        if self.has_device:
+            self.create = fn("create", C.c_int, [C.POINTER(vp), C.POINTER(GrChrom), i32, C.POINTER(GrParams), i32])
+            self.set_params = fn("set_params", C.c_int, [vp, C.POINTER(GrParams)])
+            self.strerror = fn("strerror", C.c_char_p, [C.c_int])
+            self.last_error_detail = fn("last_error_detail", C.c_char_p, [vp])
+            self.push_intervals_device = fn("push_intervals_device", C.c_int, [vp, vp, u64])
+            self.timing_enable = fn("timing_enable", C.c_int, [vp, i32])
+            self.timing_get = fn("timing_get", C.c_int, [vp, C.POINTER(GrStageTime), i32, C.POINTER(i32)])
+            self.timing_reset = fn("timing_reset", C.c_int, [vp])
+            self.kernel_launches = fn("kernel_launches", u64, [vp])
+            self.synchronize = fn("synchronize", C.c_int, [vp])
+        else:
+            self.create = fn("create", C.c_int, [C.POINTER(vp), C.POINTER(GrChrom), i32, C.POINTER(GrParams)])
+        self.destroy = fn("destroy", None, [vp])
+        self.sample_begin = fn("sample_begin", C.c_int, [vp, i32, vp])
+        self.push_intervals = fn("push_intervals", C.c_int, [vp, vp, u64])
+        self.sample_pileup = fn("sample_pileup", C.c_int, [vp, C.POINTER(dbl)])
+        self.replicate_finish = fn("replicate_finish", C.c_int, [vp, dbl, dbl, i32, u64, C.POINTER(GrSampleStats)])
+        self.replicate_end = fn("replicate_end", C.c_int, [vp, C.POINTER(GrSampleStats)])
+        self.pvalues_finalize = fn("pvalues_finalize", C.c_int, [vp])
+        self.bh_local_hist = fn("bh_local_hist", C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)])
+        self.bh_set_global = fn("bh_set_global", C.c_int, [vp, vp, vp, u64, u64])
+        self.call_peaks = fn("call_peaks", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64), C.POINTER(GrRunStats)])
+        self.fetch_intervals = fn("fetch_intervals", C.c_int,
+                                  [vp, i32, i32, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)])
+
+
+_libm = C.CDLL("libm.so.6")
+_libm_log10f = _libm.log10f
+_libm_log10f.restype = C.c_float
+_libm_log10f.argtypes = [C.c_float]
+
+_cuda_api: Api | None = None
+
+
+def load_cuda() -> Api:
+    """Load libgenrich_cuda.so.  There is no fallback: a missing library is fatal."""
+    global _cuda_api
+    if _cuda_api is None:
+        _cuda_api = Api(CUDA_LIB, "gr_")
+    return _cuda_api
+
+
+def _as_ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _np_from(ptr, n, dtype):
+    if not ptr or n == 0:
+        return np.empty(0, dtype=dtype)
+    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+
+
+class Context:
+    """One engine context (= the reference's Chrom[] plus peak parameters)."""
+
+    def __init__(self, api: Api, chrom_len, params: GrParams, device: int = 0,
+                 skip=None, owned=None):
+        self.api = api
+        n = len(chrom_len)
+        arr = (GrChrom * n)()
+        for i in range(n):
+            arr[i].len = int(chrom_len[i])
+            arr[i].skip = int(skip[i]) if skip is not None else 0
+            arr[i].owned = int(owned[i]) if owned is not None else 1
+        self.nchrom = n
+        self.chrom_len = np.asarray(chrom_len, dtype=np.uint32)
+        self._h = C.c_void_p()
+        if api.has_device:
+            rc = api.create(C.byref(self._h), arr, n, C.byref(params), device)
+        else:
+            rc = api.create(C.byref(self._h), arr, n, C.byref(params))
+        self._check(rc, "create")
+
+    def _check(self, rc, where):
+        if rc != 0:
+            detail = ""
+            if self.api.has_device and self._h:
+                d = self.api.last_error_detail(self._h)
+                detail = d.decode() if d else ""
+            raise GenrichError(rc, where, detail)
+
+    def close(self):
+        if self._h:
+            self.api.destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- seam IN ---------------------------------------------------------------
+    def sample_begin(self, is_ctrl: bool, save=None):
+        sv = None
+        if save is not None:
+            sv = np.ascontiguousarray(save, dtype=np.uint8)
+        self._check(self.api.sample_begin(self._h, int(is_ctrl), _as_ptr(sv) if sv is not None else None),
+                    "sample_begin")
+
+    def push_intervals(self, recs: np.ndarray):
+        recs = np.ascontiguousarray(recs, dtype=np.int32).reshape(-1, 4)
+        self._check(self.api.push_intervals(self._h, _as_ptr(recs), recs.shape[0]), "push_intervals")
+
+    def push_intervals_device(self, dptr: int, n: int):
+        self._check(self.api.push_intervals_device(self._h, C.c_void_p(dptr), n), "push_intervals_device")
+
+    def sample_pileup(self) -> np.ndarray:
+        sums = np.zeros(self.nchrom, dtype=np.float64)
+        self._check(self.api.sample_pileup(self._h, sums.ctypes.data_as(C.POINTER(C.c_double))), "sample_pileup")
+        return sums
+
+    def replicate_finish(self, frag_len, ctrl_frag, has_ctrl, genome_len=0) -> GrSampleStats:
+        st = GrSampleStats()
+        self._check(self.api.replicate_finish(self._h, frag_len, ctrl_frag, int(has_ctrl),
+                                              int(genome_len), C.byref(st)), "replicate_finish")
+        return st
+
+    def replicate_end(self) -> GrSampleStats:
+        st = GrSampleStats()
+        self._check(self.api.replicate_end(self._h, C.byref(st)), "replicate_end")
+        return st
+
+    # -- peaks -----------------------------------------------------------------
+    def pvalues_finalize(self):
+        self._check(self.api.pvalues_finalize(self._h), "pvalues_finalize")
+
+    def bh_local_hist_ptrs(self):
+        k, l, n = C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self.api.bh_local_hist(self._h, C.byref(k), C.byref(l), C.byref(n)), "bh_local_hist")
+        return k.value, l.value, n.value
+
+    def bh_set_global_ptrs(self, keys_ptr, lens_ptr, n, genome_len):
+        self._check(self.api.bh_set_global(self._h, C.c_void_p(keys_ptr), C.c_void_p(lens_ptr), n, genome_len),
+                    "bh_set_global")
+
+    def call_peaks(self):
+        p, n, st = C.c_void_p(), C.c_uint64(), GrRunStats()
+        self._check(self.api.call_peaks(self._h, C.byref(p), C.byref(n), C.byref(st)), "call_peaks")
+        return _np_from(p.value, n.value, PEAK_DTYPE), st
+
+    def fetch(self, which: int, replicate: int, chrom: int) -> Intervals | None:
+        e, v, x, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()
+        self._check(self.api.fetch_intervals(self._h, which, replicate, chrom, C.byref(e), C.byref(v),
+                                             C.byref(x), C.byref(c), C.byref(n)), "fetch_intervals")
+        if not e.value:
+            return None
+        return Intervals(_np_from(e.value, n.value, np.uint32), _np_from(v.value, n.value, np.float32),
+                         _np_from(x.value, n.value, np.float32) if x.value else None,
+                         _np_from(c.value, n.value, np.float32) if c.value else None)
+
+    # -- device-only helpers -----------------------------------------------------
+    def timing(self, on=True):
+        self._check(self.api.timing_enable(self._h, int(on)), "timing_enable")
+
+    def timing_get(self):
+        arr = (GrStageTime * 64)()
+        n = C.c_int32()
+        self._check(self.api.timing_get(self._h, arr, 64, C.byref(n)), "timing_get")
+        return {arr[i].name.decode(): (arr[i].ms, arr[i].launches, arr[i].bytes) for i in range(n.value)}
+
+    def timing_reset(self):
+        self._check(self.api.timing_reset(self._h), "timing_reset")
+
+    def kernel_launches(self) -> int:
+        return int(self.api.kernel_launches(self._h))
+
+    def synchronize(self):
+        self._check(self.api.synchronize(self._h), "synchronize")
+
+
+def make_params(p=None, q=None, min_auc=200.0, min_len=0, max_gap=100,
+                keep_pileups=False, genome_len=0) -> GrParams:
+    """Thresholds as getArgs() converts them (Genrich.c:5815-5817): -log10f in float."""
+    qopt = q is not None
+    thr = C.c_float(q if qopt else (0.01 if p is None else p))
+    pq = -_libm_log10f(thr)      # glibc log10f on a float, like the reference
+    return GrParams(float(pq), int(qopt), float(min_auc), int(min_len), int(max_gap),
+                    int(keep_pileups), int(genome_len))

@@ -1,0 +1,191 @@
+/* genrich_cuda.h -- C-ABI of libgenrich_cuda.so (sm_100a).
+ *
+ * The reference (jsh58/Genrich v0.6.2, one C translation unit) has no plugin or
+ * FFI surface; its only stable contract is the process boundary.  This header
+ * therefore cuts the program at the two seams where its hot path begins and
+ * ends, and exports exactly what crosses them:
+ *
+ *   seam IN   saveInterval(chrom,start,end,qname,count,...)   Genrich.c:2516
+ *             -> gr_sample_begin / gr_push_intervals
+ *   hot path  savePileupExpt 2168, calcLambda 1817, calcFactor 1980,
+ *             savePileupCtrl 2052, savePileupNoCtrl 1883, savePval 1720,
+ *             combinePval 612, computeQval 352, callPeaks 977
+ *             -> gr_sample_pileup / gr_replicate_finish / gr_call_peaks
+ *   seam OUT  printPeak(out,...,name,start,end,count,signal,pval,qval,pos)
+ *             Genrich.c:885; printInterval 770 / printPile 1697 for -f/-k
+ *             -> gr_peak records / gr_fetch_intervals
+ *
+ * Plain pointers and sizes only.  Every entry returns 0 on success or a
+ * gr_status (gr_strerror() gives the reference's own message text where the
+ * failure corresponds to one of its errCode cases, Genrich.h:97-154).
+ * One submitting host thread per context; the library never calls back.
+ *
+ * Multi-GPU: one context per device, each owning a subset of chromosomes
+ * (gr_chrom.owned).  Chromosomes are independent except for three scalars and
+ * one table, which the HOST exchanges between contexts/ranks:
+ *   - per-chromosome sum(len*val) of the experimental pileup  -> lambda
+ *   - per-chromosome sum(len*val) of the control pileup       -> scale factor
+ *   - the genome-wide histogram of distinct -log10(p) (gr_bh_local_hist /
+ *     gr_bh_set_global), which the caller all-gathers (NCCL) between the two.
+ */
+#ifndef GENRICH_CUDA_H
+#define GENRICH_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GR_SKIP (-1.0f)   /* SKIP, Genrich.h:27 */
+
+typedef enum gr_status {
+  GR_OK = 0,
+  GR_ERR_ARG = 1,        /* bad argument / call order */
+  GR_ERR_CUDA = 2,       /* CUDA runtime failure (gr_last_error_detail) */
+  GR_ERR_MEM = 3,        /* ERRMEM      Genrich.h:111 */
+  GR_ERR_POS = 4,        /* ERRPOS      Genrich.c:2531-2535: start >= chrom len */
+  GR_ERR_EXPT = 5,       /* ERREXPT     Genrich.c:2292: no analyzable fragments */
+  GR_ERR_GENOME = 6,     /* ERRGEN      Genrich.c:1828: genome length 0 */
+  GR_ERR_PILE = 7,       /* ERRPILE     Genrich.c:1921,1969: pileup < 0 */
+  GR_ERR_COUNT = 8,      /* ERRALNS     Genrich.c:2400: count not in {1,2,3,4,5,6,8,10} */
+  GR_ERR_CHROM = 9,      /* interval on an unknown / unowned chromosome */
+  GR_ERR_DF = 10,        /* ERRDF       Genrich.c:556: > 200 replicates */
+  GR_ERR_GENLEN = 11,    /* Genrich.c:377-382: histogram length != genome length */
+  GR_ERR_NODEVICE = 12   /* no CUDA device / library built without one */
+} gr_status;
+
+/* One reference sequence (Chrom, Genrich.h:183-201, the fields the path reads). */
+typedef struct gr_chrom {
+  uint32_t len;      /* Chrom.len, < 2^31 (getInt on LN:, Genrich.c:4299) */
+  uint8_t  skip;     /* Chrom.skip (-e list) : ignored everywhere */
+  uint8_t  owned;    /* 1 if this context computes this chromosome */
+  uint16_t reserved;
+} gr_chrom;
+
+/* Peak-calling parameters, as runProgram() passes them (Genrich.c:5386-5395). */
+typedef struct gr_params {
+  float    min_pqval;   /* -log10 threshold, already converted (Genrich.c:5817) */
+  int32_t  qval_opt;    /* 1: threshold applies to q (-q), 0: to p (-p) */
+  float    min_auc;     /* -a */
+  int32_t  min_len;     /* -l */
+  int32_t  max_gap;     /* -g */
+  int32_t  keep_pileups;/* 1: retain expt/ctrl columns for -f/-k output */
+  uint64_t genome_len;  /* -L; 0 = compute (calcLambda 1819-1830, findPeaks 1091-1101) */
+} gr_params;
+
+/* Per-replicate scalars (what -v prints: Genrich.c:1888, 2058, 2063). */
+typedef struct gr_sample_stats {
+  double   frag_len;     /* sum over expt pileup of len*val (savePileupExpt) */
+  double   ctrl_frag;    /* same over the control pileup (calcFactor), 0 if none */
+  float    lambda;       /* calcLambda */
+  float    factor;       /* calcFactor; 1.0f when no control */
+  uint64_t genome_len;   /* denominator used for lambda */
+  uint64_t n_expt;       /* RLE intervals, experimental (owned chroms) */
+  uint64_t n_ctrl;       /* RLE intervals, control after max(ctrl,lambda) merge */
+  uint64_t n_pval;       /* p-value intervals */
+  uint64_t n_clamped;    /* intervals clamped to [0,len] (saveInterval 2522-2544) */
+} gr_sample_stats;
+
+/* One called peak = the argument list of printPeak (Genrich.c:885). */
+typedef struct gr_peak {
+  int32_t  chrom;      /* index into the gr_chrom table */
+  uint32_t summit;     /* offset of summit from start */
+  int64_t  start;
+  int64_t  end;
+  float    auc;        /* signalValue */
+  float    pval;       /* -log10(p) at summit */
+  float    qval;       /* -log10(q) at summit, GR_SKIP if !qval_opt */
+  float    reserved;
+} gr_peak;
+
+typedef struct gr_run_stats {
+  uint64_t genome_len;   /* findPeaks 1091-1101 */
+  uint64_t n_peaks;
+  uint64_t peak_bp;      /* Genrich.c:924 */
+  uint64_t n_intervals;  /* final p/q interval count (owned chroms) */
+  uint64_t n_distinct_p; /* size of the BH table (0 if !qval_opt) */
+  int32_t  all_q_one;    /* "Warning! All q-values are 1" Genrich.c:245 */
+  int32_t  n_replicates;
+} gr_run_stats;
+
+typedef struct gr_ctx gr_ctx;
+
+/* ---- context ------------------------------------------------------------ */
+/* saveChrom 4220 builds Chrom[]; here the table arrives complete. */
+int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
+              const gr_params* params, int32_t device);
+void gr_destroy(gr_ctx* ctx);
+int gr_set_params(gr_ctx* ctx, const gr_params* params);
+const char* gr_strerror(int status);
+const char* gr_last_error_detail(const gr_ctx* ctx);
+
+/* ---- seam IN: intervals --------------------------------------------------
+ * gr_sample_begin zeroes the delta arrays (runProgram 5503-5510).  `save` is the
+ * per-chromosome Chrom.save flag for this replicate (Genrich.c:5463, 4231);
+ * NULL = all saved.  A control sample inherits the flags of its experimental
+ * sample.  Records are int32 x 4 = chrom, start, end, count with
+ * count in {1,2,3,4,5,6,8,10} (weight 1/count).  start < 0 and end > len are
+ * clamped as saveInterval does (2522-2544); start >= len is GR_ERR_POS,
+ * reported by gr_sample_pileup. */
+int gr_sample_begin(gr_ctx* ctx, int32_t is_ctrl, const uint8_t* save);
+int gr_push_intervals(gr_ctx* ctx, const int32_t* recs, uint64_t n);        /* host memory (pinned or not) */
+int gr_push_intervals_device(gr_ctx* ctx, const int32_t* d_recs, uint64_t n);/* device memory */
+
+/* Integrate the current sample (savePileupExpt 2168 / the RLE pass of
+ * calcFactor 1980).  chrom_sums[nchrom] receives, per owned chromosome, the
+ * double sum of (float)(end-start)*val (0 elsewhere); the caller adds them in
+ * chromosome order across contexts to get fragLen / ctrlFrag. */
+int gr_sample_pileup(gr_ctx* ctx, double* chrom_sums);
+
+/* Close the replicate: lambda, scale factor, max(ctrl*factor, lambda) sweep
+ * (savePileupCtrl 2052 / savePileupNoCtrl 1883), breakpoint merge and
+ * -log10(p) (savePval 1720).  has_ctrl = 0: no control was pushed.
+ * genome_len = 0: use the sum of saved owned chromosome lengths (single
+ * context) -- multi-context callers pass the global value. */
+int gr_replicate_finish(gr_ctx* ctx, double frag_len, double ctrl_frag,
+                        int32_t has_ctrl, uint64_t genome_len,
+                        gr_sample_stats* stats);
+
+/* Convenience for a single context: gr_sample_pileup for the pending
+ * sample(s) + gr_replicate_finish with local sums. */
+int gr_replicate_end(gr_ctx* ctx, gr_sample_stats* stats);
+
+/* ---- peaks ---------------------------------------------------------------
+ * gr_pvalues_finalize: Fisher combine when > 1 replicate (combinePval 612).
+ * gr_bh_local_hist / gr_bh_set_global: the exchange step of computeQval 352;
+ * pointers are DEVICE pointers (keys = float bits of -log10 p, lens = bp).
+ * gr_call_peaks runs whatever of these has not been run (single context),
+ * then callPeaks 977.  Returned arrays are owned by the context. */
+int gr_pvalues_finalize(gr_ctx* ctx);
+int gr_bh_local_hist(gr_ctx* ctx, const uint32_t** d_keys,
+                     const uint64_t** d_lens, uint64_t* n);
+int gr_bh_set_global(gr_ctx* ctx, const uint32_t* d_keys,
+                     const uint64_t* d_lens, uint64_t n, uint64_t genome_len);
+int gr_call_peaks(gr_ctx* ctx, const gr_peak** peaks, uint64_t* n,
+                  gr_run_stats* stats);
+
+/* ---- seam OUT for -f / -k (printInterval 770, printPile 1697) -------------
+ * which: 0 = experimental pileup, 1 = control pileup (last replicate),
+ *        2 = p-value intervals of `replicate` (replicate == n_replicates:
+ *            the Fisher-combined array), 3 = q-value intervals.
+ * For which 2/3 with keep_pileups, expt/ctrl receive the pileup columns.
+ * Host arrays owned by the context, valid until the next fetch. */
+int gr_fetch_intervals(gr_ctx* ctx, int32_t which, int32_t replicate,
+                       int32_t chrom, const uint32_t** end, const float** val,
+                       const float** expt, const float** ctrl, uint64_t* n);
+
+/* Device time (ms, CUDA events on the library's stream) of named stages since
+ * the last gr_timing_reset: fills up to `cap` entries. */
+typedef struct gr_stage_time { const char* name; double ms; uint64_t launches; uint64_t bytes; } gr_stage_time;
+int gr_timing_enable(gr_ctx* ctx, int32_t on);
+int gr_timing_get(gr_ctx* ctx, gr_stage_time* out, int32_t cap, int32_t* n);
+int gr_timing_reset(gr_ctx* ctx);
+uint64_t gr_kernel_launches(const gr_ctx* ctx);
+int gr_synchronize(gr_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

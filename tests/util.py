@@ -1,0 +1,95 @@
+"""Shared test plumbing: build a case's interval view, run an engine, load goldens."""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import subprocess
+
+import numpy as np
+
+from cases import Case
+from genrich_b200 import capi, host
+from genrich_b200.synth import Workload
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+ORACLE_LIB = os.path.join(ORACLE_DIR, "libgenrich_oracle.so")
+REF_FUNCS = os.path.join(ORACLE_DIR, "_ref", "libref_funcs.so")
+
+_oracle = None
+
+
+def oracle_api() -> capi.Api:
+    """The CPU oracle (test infrastructure), built on demand with gcc."""
+    global _oracle
+    if _oracle is None:
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "libgenrich_oracle.so"])
+        _oracle = capi.Api(ORACLE_LIB, "orc_")
+    return _oracle
+
+
+def names_of(case: Case):
+    return ["chr%d" % (i + 1) for i in range(len(case.chrom_len))]
+
+
+def sample_intervals(case: Case, s) -> np.ndarray:
+    w = Workload(case.chrom_len, s.nfrag, s.seed, enrich=s.enrich, spacing=s.spacing, sigma=s.sigma,
+                 multimap=s.multimap, mmax=s.mmax)
+    fr = w.fragments()
+    if s.drop_chroms:
+        fr = fr[~np.isin(fr[:, 0], list(s.drop_chroms))]
+    return host.fragments_to_intervals(fr, atac=case.atac, atac_len=case.atac_len)
+
+
+def case_inputs(case: Case):
+    reps = []
+    for e, c in case.reps:
+        save = None
+        if e.drop_chroms:
+            save = np.ones(len(case.chrom_len), dtype=np.uint8)
+            save[list(e.drop_chroms)] = 0
+        reps.append((sample_intervals(case, e), None if c is None else sample_intervals(case, c), save))
+    return reps
+
+
+def case_params(case: Case, keep=True):
+    return capi.make_params(p=case.p, q=case.q, min_auc=case.min_auc, min_len=case.min_len,
+                            max_gap=case.max_gap, keep_pileups=keep)
+
+
+def run_case(api: capi.Api, case: Case, keep=True, device=0, inputs=None):
+    par = case_params(case, keep)
+    ctx = capi.Context(api, case.chrom_len, par, device=device)
+    res = host.run_replicates(ctx, inputs if inputs is not None else case_inputs(case))
+    return ctx, res, par
+
+
+def log_lines(ctx, case: Case, par):
+    n = len(case.reps)
+    if n == 1:
+        return host.format_log(ctx, names_of(case), case.q is not None, thr=par.min_pqval)
+    return host.format_log_multi(ctx, names_of(case), n, case.q is not None, thr=par.min_pqval)
+
+
+def pile_lines(ctx, case: Case):
+    out = []
+    for r in range(len(case.reps)):
+        out += host.format_pile(ctx, names_of(case), r)
+    return out
+
+
+def sha_lines(lines) -> str:
+    h = hashlib.sha256()
+    for l in lines:
+        h.update(l.encode() + b"\n")
+    return h.hexdigest()
+
+
+def golden(case: Case):
+    with open(os.path.join(GOLDEN, case.name + ".json")) as f:
+        meta = json.load(f)
+    with open(os.path.join(GOLDEN, case.name + ".narrowPeak")) as f:
+        np_lines = f.read().split("\n")[:-1]
+    return meta, np_lines
