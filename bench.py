@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- Gbp p-value-scanned per second of the pileup -> p -> q -> peak path.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+One "step" = one whole pass of the hot path over one synthetic batch: zero the
+dense delta arrays, scatter the treatment intervals, integrate, same for the
+control, lambda / scale factor, control sweep, breakpoint union, -log10 p, (BH),
+peak scan, peaks back on the host.  At N = 1 the workload is BASELINE.json
+configs[1]: hg38-sized genome (25 chromosomes, 3.09 Gbp), 50 M treatment + 50 M
+control paired-end fragments, default peak calling (-p 0.01).  For N > 1 the same
+genome is sharded by chromosome over the ranks (strong scaling; torchrun, NCCL).
+
+`value`  = genome bp / device time per step, interval records already in HBM.
+`e2e`    = same through gr_push_intervals() from PINNED HOST buffers (H2D copies
+           inside the timed region) and peak records read back to the host.
+`roofline` is for the dominant kernel, the per-base dense scan (k_dense_scan):
+           4 B per delta cell per launch / mean launch time (CUDA events on the
+           library's stream) against the measured HBM copy bandwidth.
+`cpu_baseline` / --impl reference: the UNMODIFIED reference binary
+           (oracle/_ref/Genrich, built by `make -C oracle ref` where the sources
+           are) on the SAM view of a bounded sample of the same workload, 1 host
+           core (the reference is single-threaded, README.md:535).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
+        138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
+        83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415, 16569]
+
+WORKLOADS = {
+    # BASELINE.json configs[1]
+    "hg38_chip_50M_50M": dict(chrom_len=HG38, nt=50_000_000, nc=50_000_000, q=None, p=0.01, atac=False,
+                              spacing=60000, sigma=150.0, enrich=0.25),
+    # configs[2]: ATAC mode, 100 M fragments, -q 0.05
+    "hg38_atac_100M_q": dict(chrom_len=HG38, nt=100_000_000, nc=0, q=0.05, p=None, atac=True,
+                             spacing=60000, sigma=60.0, enrich=0.3),
+    # quick functional run
+    "mini": dict(chrom_len=[60_000_000, 40_000_000, 20_000_000], nt=2_000_000, nc=2_000_000, q=None, p=0.01,
+                 atac=False, spacing=40000, sigma=100.0, enrich=0.3),
+}
+SAMPLE = dict(chrom_len=[25_000_000] * 4, nt=1_000_000, nc=1_000_000)   # bounded CPU sample (same generator)
+
+
+def gen_fragments(chrom_len, n, seed, enrich, spacing, sigma, threads=8):
+    from genrich_b200.synth import Workload
+    w = Workload(chrom_len, n, seed, enrich=enrich, spacing=spacing, sigma=sigma)
+    out = np.empty((n, 4), dtype=np.int32)
+    step = (n + threads - 1) // threads
+    ths = []
+    for i in range(threads):
+        a, b = i * step, min(n, (i + 1) * step)
+        if a >= b:
+            break
+        t = threading.Thread(target=w.fragments, args=(a, b - a, out[a:b]))
+        t.start()
+        ths.append(t)
+    for t in ths:
+        t.join()
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = sorted(sm)[len(sm) // 2:]            # samples under load = upper half
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------
+def reference_sample_run(steps, warmup):
+    """Time the unmodified reference on the SAM view of the bounded sample."""
+    from genrich_b200.synth import Workload
+    ref = os.path.join(ROOT, "oracle", "_ref", "Genrich")
+    wl = WORKLOADS["hg38_chip_50M_50M"]
+    L = SAMPLE["chrom_len"]
+    td_ = tempfile.mkdtemp(prefix="grbench_")
+    tp, cp, op = (os.path.join(td_, x) for x in ("t.sam", "c.sam", "o.np"))
+    Workload(L, SAMPLE["nt"], 3001, enrich=wl["enrich"], spacing=wl["spacing"], sigma=wl["sigma"]).write_sam(tp)
+    Workload(L, SAMPLE["nc"], 3002, enrich=0.0).write_sam(cp)
+    G = sum(L)
+    kind = "reference"
+    cmd = [ref, "-t", tp, "-c", cp, "-o", op, "-p", "0.01"]
+    if not os.path.exists(ref):
+        raise SystemExit("oracle/_ref/Genrich missing: run `make -C oracle ref` where /root/reference exists")
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        subprocess.check_call(cmd, stderr=subprocess.DEVNULL)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    npk = sum(1 for _ in open(op))
+    for f in (tp, cp, op):
+        os.unlink(f)
+    os.rmdir(td_)
+    sec = sum(times) / len(times)
+    return {"value": G / 1e9 / sec, "unit": "Gbp/s", "cores": 1, "kind": kind,
+            "sample": "%d chrom x %d bp, %d + %d fragments (same generator), whole program incl. SAM parse, %.2f s/run, %d peaks"
+                      % (len(L), L[0], SAMPLE["nt"], SAMPLE["nc"], sec, npk),
+            "host_cores_available": os.cpu_count()}, sec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="hg38_chip_50M_50M")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = WORKLOADS[a.workload]
+    L = wl["chrom_len"]
+    G = sum(L)
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        cb, sec = reference_sample_run(a.steps, 1)
+        line = {"impl": "reference", "metric": "Gbp p-value-scanned/sec", "value": cb["value"], "unit": "Gbp/s",
+                "n_gpus": a.gpus, "steps": a.steps, "warmup": 1, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f32/f64",
+                "data": "synthetic", "config": {"workload": a.workload, "sample": cb["sample"]},
+                "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as td
+    from genrich_b200 import capi, host
+    from genrich_b200.dist import ShardedEngine
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    api = capi.load_cuda()
+    par = capi.make_params(p=wl["p"], q=wl["q"])
+    eng = ShardedEngine(api, L, par, dev)
+    ctx = eng.ctx
+
+    # synthetic interval records of this rank's chromosomes, on the host (pinned) and in HBM
+    def make(n, seed, enrich):
+        if n == 0:
+            return None, None
+        fr = gen_fragments(L, n, seed, enrich, wl["spacing"], wl["sigma"])
+        iv = eng.route(host.fragments_to_intervals(fr, atac=wl["atac"]))
+        pinned = torch.from_numpy(iv).pin_memory()
+        return pinned, pinned.to(dev)
+    t_host, t_dev = make(wl["nt"], 2001, wl["enrich"])
+    c_host, c_dev = make(wl["nc"], 2002, 0.0)
+    n_t = t_host.shape[0]
+    n_c = c_host.shape[0] if c_host is not None else 0
+    torch.cuda.synchronize()
+
+    def step(from_host):
+        ctx.reset()
+        eng.saved_any[:] = False
+        eng.sample_stats.clear()
+        if from_host:
+            pe = lambda c: c.api.push_intervals(c._h, t_host.data_ptr(), n_t)
+            pc = (lambda c: c.api.push_intervals(c._h, c_host.data_ptr(), n_c)) if n_c else None
+        else:
+            pe = lambda c: c.push_intervals_device(t_dev.data_ptr(), n_t)
+            pc = (lambda c: c.push_intervals_device(c_dev.data_ptr(), n_c)) if n_c else None
+        eng.replicate(pe, pc)
+        return eng.call_peaks()
+
+    def timed(from_host, steps, warmup, with_stages=False):
+        for _ in range(warmup):
+            step(from_host)
+        if with_stages:
+            ctx.timing(True)
+            ctx.timing_reset()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        l0 = ctx.kernel_launches()
+        dev_ms = []
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            ctx.timer_start()
+            peaks, rs = step(from_host)
+            dev_ms.append(ctx.timer_stop())
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        wall = (time.perf_counter() - w0) * 1e3 / steps
+        ms = sum(dev_ms) / len(dev_ms)
+        t = torch.tensor([ms, wall], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(t, op=td.ReduceOp.MAX)
+        stages = ctx.timing_get() if with_stages else None
+        if with_stages:
+            ctx.timing(False)
+        return float(t[0]), float(t[1]), ctx.kernel_launches() - l0, peaks, rs, stages
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, wall_dev, launches, peaks, rs, stages = timed(False, a.steps, a.warmup, with_stages=True)
+    ms_e2e, wall_e2e, _, peaks2, _, _ = timed(True, a.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+    n_samples = 2 if n_c else 1
+    peak_gbs, peak_src = measured_peak_gbs()
+    scan_ms, scan_launches, _ = stages.get("dense_scan", (0.0, 0, 0))
+    per_launch_ms = scan_ms / max(scan_launches, 1)
+    cells = ctx_cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
+    achieved = 4.0 * cells / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
+    stage_ms = {k: round(v[0] / a.steps, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])}
+    line = {
+        "metric": "Gbp p-value-scanned/sec", "value": G / 1e9 / (ms_dev * 1e-3), "unit": "Gbp/s",
+        "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32 deltas, f32 pileups, f64 -> f32 -log10 p", "data": "synthetic",
+        "config": {"workload": a.workload, "genome_bp": G, "chromosomes": len(L), "treatment_fragments": wl["nt"],
+                   "control_fragments": wl["nc"], "threshold": "-q %g" % wl["q"] if wl["q"] else "-p %g" % wl["p"],
+                   "atac": wl["atac"], "sharding": "chromosomes over %d rank(s), LPT" % world,
+                   "l2": "inputs (%.1f GB dense delta array per sample) far exceed the 126 MB L2" % (4e-9 * cells),
+                   "peaks": int(len(peaks)), "intervals_rank0": int(rs.n_intervals)},
+        "e2e": {"value": G / 1e9 / (ms_e2e * 1e-3), "unit": "Gbp/s", "ms_per_step": ms_e2e,
+                "h2d_bytes_per_step": int(16 * (n_t + n_c)), "d2h_bytes_per_step": int(peaks2.nbytes + 512),
+                "wall_ms_per_step": wall_e2e},
+        "gpu_launches": int(launches),
+        "wall_ms_per_step": wall_dev,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_dense_scan", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs if peak_gbs else None, "traffic": None, "peak_source": peak_src,
+                     "bytes_per_launch": 4 * cells, "ms_per_launch": per_launch_ms,
+                     "launches_per_step": scan_launches / a.steps, "samples_scanned_per_step": n_samples},
+        "stage_ms_per_step": stage_ms,
+    }
+    if not a.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Genrich")):
+        cb, _ = reference_sample_run(1, 0)
+        line["cpu_baseline"] = cb
+    else:
+        line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": 1, "kind": "reference",
+                                "sample": "skipped (--no-cpu-baseline or oracle/_ref missing)"}
+    print(json.dumps(line))
+    if world > 1:
+        td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

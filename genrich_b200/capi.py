@@ -64,13 +64,13 @@ PEAK_DTYPE = np.dtype([("chrom", "<i4"), ("summit", "<u4"), ("start", "<i8"),
 
 # every symbol include/genrich_cuda.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "gr_create", "gr_destroy", "gr_set_params", "gr_strerror",
+    "gr_create", "gr_destroy", "gr_set_params", "gr_reset", "gr_strerror",
     "gr_last_error_detail", "gr_sample_begin", "gr_push_intervals",
     "gr_push_intervals_device", "gr_sample_pileup", "gr_replicate_finish",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
     "gr_bh_set_global", "gr_call_peaks", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
-    "gr_kernel_launches", "gr_synchronize",
+    "gr_kernel_launches", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
 ]
 
 STATUS_TEXT = {
@@ -122,6 +122,7 @@ class Api:
         if self.has_device:
             self.create = fn("create", C.c_int, [C.POINTER(vp), C.POINTER(GrChrom), i32, C.POINTER(GrParams), i32])
             self.set_params = fn("set_params", C.c_int, [vp, C.POINTER(GrParams)])
+            self.reset = fn("reset", C.c_int, [vp])
             self.strerror = fn("strerror", C.c_char_p, [C.c_int])
             self.last_error_detail = fn("last_error_detail", C.c_char_p, [vp])
             self.push_intervals_device = fn("push_intervals_device", C.c_int, [vp, vp, u64])
@@ -130,6 +131,8 @@ class Api:
             self.timing_reset = fn("timing_reset", C.c_int, [vp])
             self.kernel_launches = fn("kernel_launches", u64, [vp])
             self.synchronize = fn("synchronize", C.c_int, [vp])
+            self.timer_start = fn("timer_start", C.c_int, [vp])
+            self.timer_stop = fn("timer_stop", C.c_int, [vp, C.POINTER(dbl)])
         else:
             self.create = fn("create", C.c_int, [C.POINTER(vp), C.POINTER(GrChrom), i32, C.POINTER(GrParams)])
         self.destroy = fn("destroy", None, [vp])
@@ -213,6 +216,9 @@ class Context:
         except Exception:
             pass
 
+    def reset(self):
+        self._check(self.api.reset(self._h), "reset")
+
     # -- seam IN ---------------------------------------------------------------
     def sample_begin(self, is_ctrl: bool, save=None):
         sv = None
@@ -290,6 +296,14 @@ class Context:
 
     def synchronize(self):
         self._check(self.api.synchronize(self._h), "synchronize")
+
+    def timer_start(self):
+        self._check(self.api.timer_start(self._h), "timer_start")
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        self._check(self.api.timer_stop(self._h, C.byref(ms)), "timer_stop")
+        return ms.value
 
 
 def make_params(p=None, q=None, min_auc=200.0, min_len=0, max_gap=100,

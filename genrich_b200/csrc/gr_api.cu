@@ -1,0 +1,1018 @@
+// gr_api.cu -- the C-ABI of include/genrich_cuda.h: context, device memory,
+// stage orchestration (the multi-stage pipeline that replaces runProgram's
+// per-chromosome loop, Genrich.c:5460-5607), timing.  Host code only; every stage
+// is a CUDA kernel from gr_dense.cu / gr_interval.cu / gr_bh.cu / gr_peaks.cu.
+// There is no CPU path: without a device gr_create fails with GR_ERR_NODEVICE.
+#include "../../include/genrich_cuda.h"
+#include "gr_common.cuh"
+#include "gr_internal.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+unsigned long long g_gr_launches = 0;
+
+// ---------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {              // retry with the exact size
+      cudaGetLastError();
+      want = bytes;
+      e = cudaMalloc(&p, want);
+    }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+  template <class T> T* as() const { return (T*)p; }
+};
+
+struct Replicate {
+  DevBuf bmU, rankU, pEnd, pVal, pExpt, pCtrl, chrom_start, present;
+  u64 n = 0;
+  std::vector<u64> chrom_start_h;
+  std::vector<uint8_t> present_h;
+  bool has_cols = false;
+  void release() {
+    bmU.release(); rankU.release(); pEnd.release(); pVal.release(); pExpt.release();
+    pCtrl.release(); chrom_start.release(); present.release();
+  }
+};
+
+struct StageRec { const char* name; cudaEvent_t a, b; u64 bytes; };
+
+enum Filling { FILL_NONE = -1, FILL_EXPT = 0, FILL_CTRL = 1 };
+
+struct gr_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr, copy = nullptr;
+  gr_params par;
+  std::string detail;
+
+  // chromosome table / layout
+  int nchrom = 0;
+  std::vector<u32> len;
+  std::vector<uint8_t> skip, owned, save, flags;
+  std::vector<u64> off;
+  std::vector<int> blk2chrom;
+  u64 T = 0, nblocks = 0;
+  DevBuf d_off, d_len, d_flags, d_blk2chrom;
+  DevLayout L;
+
+  // dense working set
+  DevBuf delta, bmE, bmC, rankE, rankC, rankTmp;
+  DevBuf lb0, lb1, lb2, ticket;
+  DevBuf small;                  // err(int) | pad | clamped(u64) | totals[3] | misc counters
+  int* d_err = nullptr; u64* d_clamped = nullptr; u64* d_totals = nullptr; u64* d_cnt = nullptr;
+  void* h_small = nullptr;       // pinned mirror
+  DevBuf accI, accF;             // [2][nchrom]
+  void* h_acc = nullptr;         // pinned, 2*nchrom u64
+
+  // RLE arrays of the current replicate
+  DevBuf exptEnd, exptVal, exptCS, exptTot;
+  DevBuf rawEnd, rawVal, rawCS, rawTot;
+  DevBuf ctrlEnd, ctrlVal, ctrlCS, ctrlTot;
+  u64 n_expt = 0, n_raw = 0, n_ctrl = 0;
+  std::vector<u64> exptCS_h, ctrlCS_h;
+
+  // interval staging
+  DevBuf stage[2];
+  cudaEvent_t stage_free[2] = { nullptr, nullptr }, stage_ready[2] = { nullptr, nullptr };
+  void* h_stage[2] = { nullptr, nullptr };
+  int stage_next = 0;
+  static const u64 STAGE_RECS = 1ull << 22;     // 4M records = 64 MB
+
+  // sample state
+  int filling = FILL_NONE;
+  bool have_expt = false, have_ctrl = false;
+  u64 n_pushed = 0, n_clamped = 0;
+  std::vector<double> expt_sums, ctrl_sums;
+
+  // replicates and final arrays
+  std::vector<Replicate*> reps;
+  bool finalized = false;
+  Replicate* comb = nullptr;       // Fisher-combined (nrep > 1)
+  Replicate* fin = nullptr;        // points at reps[0] or comb
+  DevBuf qVal;
+  bool have_q = false;
+
+  // tables / BH / peaks
+  DevBuf tKeys, tLens, tPval, tQval, tCount, slot;
+  DevBuf hk, hl, hcount;           // local histogram list
+  u64 hn = 0;
+  u32 hist_cap = 0;
+  DevBuf bk0, bk1, bl0, bl1, bhist, bksum, bx, bdk, bdq, bdl, bdcount;
+  u64 n_distinct = 0;
+  int all_q_one = 0;
+  DevBuf fsum, fdf, repviews;
+  DevBuf evIdx, evCount, headIdx, headCount, cand, candOk, peakOut, peakCount, peakBp;
+  std::vector<gr_peak> peaks_h;
+
+  // fetch caches
+  std::vector<u32> f_end; std::vector<float> f_val, f_expt, f_ctrl;
+
+  // timing
+  bool timing = false;
+  std::vector<StageRec> stages;
+  std::vector<cudaEvent_t> ev_pool;
+  u64 launches0 = 0;
+  cudaEvent_t tm_a = nullptr, tm_b = nullptr;
+};
+
+static const char* kStatusText[] = {
+  "ok", "bad argument or call order", "CUDA failure", "Cannot allocate memory",
+  ": read aligned beyond reference end", "Experimental sample has no analyzable fragments",
+  "No analyzable genome (length=0)", "Invalid pileup value (< 0)",
+  "Disallowed number of alignments", "interval on an unknown or unowned chromosome",
+  "Invalid df in pchisq()", "Genome length does not match p-value length",
+  "no CUDA device available"
+};
+
+extern "C" const char* gr_strerror(int status) {
+  if (status < 0 || status > GR_ERR_NODEVICE) return "Unknown error";
+  return kStatusText[status];
+}
+extern "C" const char* gr_last_error_detail(const gr_ctx* ctx) { return ctx ? ctx->detail.c_str() : ""; }
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e__ = (call);                                                           \
+    if (e__ != cudaSuccess) {                                                           \
+      char b__[512];                                                                    \
+      snprintf(b__, sizeof b__, "%s:%d %s -> %s", __FILE__, __LINE__, #call,           \
+               cudaGetErrorString(e__));                                                \
+      x->detail = b__;                                                                  \
+      cudaGetLastError();                                                               \
+      return e__ == cudaErrorMemoryAllocation ? GR_ERR_MEM : GR_ERR_CUDA;               \
+    }                                                                                   \
+  } while (0)
+
+#define CKL() CK(cudaGetLastError())
+
+// ---- timing ------------------------------------------------------------------
+static void stage_begin(gr_ctx* x, const char* name, u64 bytes = 0) {
+  if (!x->timing) return;
+  StageRec r;
+  r.name = name; r.bytes = bytes;
+  cudaEventCreate(&r.a);
+  cudaEventCreate(&r.b);
+  cudaEventRecord(r.a, x->stream);
+  x->stages.push_back(r);
+}
+static void stage_end(gr_ctx* x) {
+  if (!x->timing || x->stages.empty()) return;
+  cudaEventRecord(x->stages.back().b, x->stream);
+}
+
+// ---- layout ------------------------------------------------------------------
+static bool chrom_active(const gr_ctx* x, int c) { return x->owned[c] && !x->skip[c] && x->save[c]; }
+
+static int upload_flags(gr_ctx* x) {
+  for (int c = 0; c < x->nchrom; c++)
+    x->flags[c] = (uint8_t)(((x->owned[c] && !x->skip[c]) ? GR_CF_OWNED : 0) | (x->save[c] ? GR_CF_SAVE : 0));
+  CK(cudaMemcpyAsync(x->d_flags.p, x->flags.data(), x->nchrom, cudaMemcpyHostToDevice, x->stream));
+  return GR_OK;
+}
+
+static DevRle rle_view(DevBuf& e, DevBuf& v, DevBuf& cs, DevBuf& tot) {
+  DevRle r;
+  r.end = e.as<u32>(); r.val = v.as<float>(); r.chrom_start = cs.as<u64>(); r.total = tot.as<u64>();
+  return r;
+}
+
+extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
+                         const gr_params* params, int32_t device) {
+  if (!out || !chroms || nchrom <= 0 || !params) return GR_ERR_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return GR_ERR_NODEVICE; }
+  if (device < 0 || device >= ndev) return GR_ERR_ARG;
+  gr_ctx* x = new gr_ctx();
+  x->device = device;
+  x->par = *params;
+  x->nchrom = nchrom;
+  int rc = [&]() -> int {
+    CK(cudaSetDevice(device));
+    CK(cudaStreamCreateWithFlags(&x->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&x->copy, cudaStreamNonBlocking));
+    x->len.resize(nchrom); x->skip.resize(nchrom); x->owned.resize(nchrom);
+    x->save.assign(nchrom, 1); x->flags.resize(nchrom); x->off.assign(nchrom, ~0ull);
+    u64 T = 0;
+    for (int c = 0; c < nchrom; c++) {
+      x->len[c] = chroms[c].len;
+      x->skip[c] = chroms[c].skip;
+      x->owned[c] = chroms[c].owned;
+      if (chroms[c].len >= 0x80000000u) return GR_ERR_ARG;
+      if (x->owned[c] && !x->skip[c]) {
+        x->off[c] = T;
+        const u64 cells = (u64)x->len[c] + 1;
+        const u64 blocks = (cells + GR_BLOCK_SLOTS - 1) / GR_BLOCK_SLOTS;
+        for (u64 b = 0; b < blocks; b++) x->blk2chrom.push_back(c);
+        T += blocks * GR_BLOCK_SLOTS;
+      }
+    }
+    if (!T) return GR_ERR_GENOME;
+    x->T = T;
+    x->nblocks = T / GR_BLOCK_SLOTS;
+    if (T / GR_SCAN_TILE >= 0xffffffffull) return GR_ERR_ARG;
+    CK(x->d_off.ensure(nchrom * sizeof(u64)));
+    CK(x->d_len.ensure(nchrom * sizeof(u32)));
+    CK(x->d_flags.ensure(nchrom));
+    CK(x->d_blk2chrom.ensure(x->nblocks * sizeof(int)));
+    CK(cudaMemcpy(x->d_off.p, x->off.data(), nchrom * sizeof(u64), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(x->d_len.p, x->len.data(), nchrom * sizeof(u32), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(x->d_blk2chrom.p, x->blk2chrom.data(), x->nblocks * sizeof(int), cudaMemcpyHostToDevice));
+    x->L.nchrom = nchrom; x->L.T = T; x->L.nblocks = x->nblocks;
+    x->L.off = x->d_off.as<u64>(); x->L.len = x->d_len.as<u32>();
+    x->L.flags = x->d_flags.as<uint8_t>(); x->L.blk2chrom = x->d_blk2chrom.as<int>();
+    int r = upload_flags(x);
+    if (r) return r;
+
+    CK(x->delta.ensure(T * sizeof(int32_t)));
+    CK(x->bmE.ensure(T / 8));
+    CK(x->bmC.ensure(T / 8));
+    CK(x->rankE.ensure(x->nblocks * sizeof(u64)));
+    CK(x->rankC.ensure(x->nblocks * sizeof(u64)));
+    CK(x->rankTmp.ensure(x->nblocks * sizeof(u64)));
+    const u64 ntile = T / GR_SCAN_TILE;
+    CK(x->lb0.ensure(ntile * sizeof(u64)));
+    CK(x->lb1.ensure(ntile * sizeof(u64)));
+    CK(x->lb2.ensure(ntile * sizeof(u64)));
+    CK(x->ticket.ensure(64));
+    CK(x->small.ensure(256));
+    CK(cudaMemset(x->small.p, 0, 256));
+    x->d_err = x->small.as<int>();
+    x->d_clamped = (u64*)((char*)x->small.p + 8);
+    x->d_totals = (u64*)((char*)x->small.p + 16);       // 3 entries
+    x->d_cnt = (u64*)((char*)x->small.p + 64);          // 8 scratch counters
+    CK(cudaMallocHost(&x->h_small, 256));
+    CK(x->accI.ensure(2 * nchrom * sizeof(u64)));
+    CK(x->accF.ensure(2 * nchrom * sizeof(u64)));
+    CK(cudaMallocHost(&x->h_acc, 4 * nchrom * sizeof(u64)));
+    const size_t cs = (nchrom + 1) * sizeof(u64);
+    CK(x->exptCS.ensure(cs)); CK(x->rawCS.ensure(cs)); CK(x->ctrlCS.ensure(cs));
+    CK(x->exptTot.ensure(8)); CK(x->rawTot.ensure(8)); CK(x->ctrlTot.ensure(8));
+    for (int i = 0; i < 2; i++) {
+      CK(cudaEventCreateWithFlags(&x->stage_free[i], cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&x->stage_ready[i], cudaEventDisableTiming));
+    }
+    x->expt_sums.assign(nchrom, 0.0);
+    x->ctrl_sums.assign(nchrom, 0.0);
+    CK(cudaStreamSynchronize(x->stream));
+    return GR_OK;
+  }();
+  if (rc != GR_OK) {
+    // keep the detail reachable: hand the context back only on success
+    fprintf(stderr, "gr_create: %s %s\n", gr_strerror(rc), x->detail.c_str());
+    gr_destroy(x);
+    return rc;
+  }
+  *out = x;
+  return GR_OK;
+}
+
+static void free_reps(gr_ctx* x) {
+  for (auto* r : x->reps) { r->release(); delete r; }
+  x->reps.clear();
+  if (x->comb) { x->comb->release(); delete x->comb; x->comb = nullptr; }
+  x->fin = nullptr;
+}
+
+extern "C" void gr_destroy(gr_ctx* x) {
+  if (!x) return;
+  cudaSetDevice(x->device);
+  if (x->stream) cudaStreamSynchronize(x->stream);
+  free_reps(x);
+  DevBuf* all[] = { &x->d_off, &x->d_len, &x->d_flags, &x->d_blk2chrom, &x->delta, &x->bmE, &x->bmC,
+    &x->rankE, &x->rankC, &x->rankTmp, &x->lb0, &x->lb1, &x->lb2, &x->ticket, &x->small, &x->accI,
+    &x->accF, &x->exptEnd, &x->exptVal, &x->exptCS, &x->exptTot, &x->rawEnd, &x->rawVal, &x->rawCS,
+    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->stage[0], &x->stage[1],
+    &x->qVal, &x->tKeys, &x->tLens, &x->tPval, &x->tQval, &x->tCount, &x->slot, &x->hk, &x->hl,
+    &x->hcount, &x->bk0, &x->bk1, &x->bl0, &x->bl1, &x->bhist, &x->bksum, &x->bx, &x->bdk, &x->bdq,
+    &x->bdl, &x->bdcount, &x->fsum, &x->fdf, &x->repviews, &x->evIdx, &x->evCount, &x->headIdx,
+    &x->headCount, &x->cand, &x->candOk, &x->peakOut, &x->peakCount, &x->peakBp };
+  for (DevBuf* b : all) b->release();
+  if (x->h_small) cudaFreeHost(x->h_small);
+  if (x->h_acc) cudaFreeHost(x->h_acc);
+  for (int i = 0; i < 2; i++) {
+    if (x->h_stage[i]) cudaFreeHost(x->h_stage[i]);
+    if (x->stage_free[i]) cudaEventDestroy(x->stage_free[i]);
+    if (x->stage_ready[i]) cudaEventDestroy(x->stage_ready[i]);
+  }
+  for (auto& s : x->stages) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  if (x->tm_a) { cudaEventDestroy(x->tm_a); cudaEventDestroy(x->tm_b); }
+  if (x->stream) cudaStreamDestroy(x->stream);
+  if (x->copy) cudaStreamDestroy(x->copy);
+  delete x;
+}
+
+extern "C" int gr_set_params(gr_ctx* x, const gr_params* p) {
+  if (!x || !p) return GR_ERR_ARG;
+  x->par = *p;
+  x->have_q = false;
+  return GR_OK;
+}
+
+extern "C" int gr_reset(gr_ctx* x) {
+  if (!x) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  CK(cudaStreamSynchronize(x->stream));
+  free_reps(x);
+  x->finalized = false; x->have_q = false; x->have_expt = x->have_ctrl = false;
+  x->filling = FILL_NONE; x->hist_cap = 0; x->peaks_h.clear();
+  return GR_OK;
+}
+
+static int map_dev_err(int e) {
+  if (e & GR_DE_CHROM) return GR_ERR_CHROM;
+  if (e & GR_DE_COUNT) return GR_ERR_COUNT;
+  if (e & GR_DE_POS) return GR_ERR_POS;
+  if (e & (GR_DE_PILE | GR_DE_TAIL)) return GR_ERR_PILE;
+  return GR_OK;
+}
+
+// ---- seam IN -------------------------------------------------------------------
+extern "C" int gr_sample_begin(gr_ctx* x, int32_t is_ctrl, const uint8_t* save) {
+  if (!x) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  if (is_ctrl && !x->have_expt) return GR_ERR_ARG;
+  if (!is_ctrl) {
+    for (int c = 0; c < x->nchrom; c++) x->save[c] = save ? (save[c] != 0) : 1;
+    int r = upload_flags(x);
+    if (r) return r;
+    x->have_expt = false;
+    x->n_clamped = 0;
+    CK(cudaMemsetAsync(x->d_clamped, 0, sizeof(u64), x->stream));
+  }
+  x->have_ctrl = false;
+  CK(cudaMemsetAsync(x->d_err, 0, sizeof(int), x->stream));
+  stage_begin(x, "memset_delta", x->T * 4);
+  CK(cudaMemsetAsync(x->delta.p, 0, x->T * sizeof(int32_t), x->stream));   // runProgram 5503-5510
+  stage_end(x);
+  x->filling = is_ctrl ? FILL_CTRL : FILL_EXPT;
+  x->n_pushed = 0;
+  return GR_OK;
+}
+
+extern "C" int gr_push_intervals_device(gr_ctx* x, const int32_t* d_recs, uint64_t n) {
+  if (!x || x->filling == FILL_NONE || (!d_recs && n)) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  stage_begin(x, "scatter", n * 16);
+  launch_scatter(x->stream, x->L, d_recs, n, x->delta.as<int32_t>(), x->d_err, x->d_clamped);
+  CKL();
+  stage_end(x);
+  x->n_pushed += n;
+  return GR_OK;
+}
+
+extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
+  if (!x || x->filling == FILL_NONE || (!recs && n)) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  cudaPointerAttributes at;
+  bool pinned = false;
+  if (cudaPointerGetAttributes(&at, recs) == cudaSuccess) {
+    if (at.type == cudaMemoryTypeDevice) return gr_push_intervals_device(x, recs, n);
+    pinned = at.type == cudaMemoryTypeHost;
+  } else
+    cudaGetLastError();
+  const u64 CH = gr_ctx::STAGE_RECS;
+  for (u64 done = 0; done < n; done += CH) {
+    const u64 m = n - done < CH ? n - done : CH;
+    const int b = x->stage_next;
+    x->stage_next ^= 1;
+    if (!x->stage[b].p) {
+      CK(x->stage[b].ensure(CH * 16));
+      CK(cudaEventRecord(x->stage_free[b], x->stream));
+    }
+    const int32_t* src = recs + 4 * done;
+    // the copy stream may reuse slot b once the scatter that read it has finished
+    CK(cudaStreamWaitEvent(x->copy, x->stage_free[b], 0));
+    if (!pinned) {
+      if (!x->h_stage[b]) CK(cudaMallocHost(&x->h_stage[b], CH * 16));
+      CK(cudaEventSynchronize(x->stage_ready[b]));     // previous H2D out of this pinned slot is done
+      memcpy(x->h_stage[b], src, m * 16);
+      src = (const int32_t*)x->h_stage[b];
+    }
+    CK(cudaMemcpyAsync(x->stage[b].p, src, m * 16, cudaMemcpyHostToDevice, x->copy));
+    CK(cudaEventRecord(x->stage_ready[b], x->copy));
+    CK(cudaStreamWaitEvent(x->stream, x->stage_ready[b], 0));
+    stage_begin(x, "scatter", m * 16);
+    launch_scatter(x->stream, x->L, x->stage[b].as<int32_t>(), m, x->delta.as<int32_t>(), x->d_err, x->d_clamped);
+    CKL();
+    stage_end(x);
+    CK(cudaEventRecord(x->stage_free[b], x->stream));
+  }
+  if (pinned) {
+    // the caller may reuse its pinned buffer when we return
+    CK(cudaStreamSynchronize(x->copy));
+  }
+  x->n_pushed += n;
+  return GR_OK;
+}
+
+// ---- pileup integration ----------------------------------------------------------
+extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
+  if (!x || x->filling == FILL_NONE) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  const bool ctrl = x->filling == FILL_CTRL;
+  int nact = 0;
+  for (int c = 0; c < x->nchrom; c++) nact += chrom_active(x, c);
+  const u64 cap = 2 * x->n_pushed + (u64)nact + 1;
+  DevBuf& E = ctrl ? x->rawEnd : x->exptEnd;
+  DevBuf& V = ctrl ? x->rawVal : x->exptVal;
+  DevBuf& CS = ctrl ? x->rawCS : x->exptCS;
+  DevBuf& TT = ctrl ? x->rawTot : x->exptTot;
+  CK(E.ensure(cap * sizeof(u32)));
+  CK(V.ensure(cap * sizeof(float)));
+  DevRle out = rle_view(E, V, CS, TT);
+  ScanScratch sc;
+  sc.st_sum = x->lb0.as<u64>(); sc.st_cnt = x->lb1.as<u64>(); sc.ticket = x->ticket.as<u32>();
+  stage_begin(x, "dense_scan", x->T * 4);
+  launch_dense_scan(x->stream, x->L, x->delta.as<int32_t>(), sc, out,
+                    (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err);
+  CKL();
+  stage_end(x);
+  u64* aI = x->accI.as<u64>() + (ctrl ? x->nchrom : 0);
+  u64* aF = x->accF.as<u64>() + (ctrl ? x->nchrom : 0);
+  CK(cudaMemsetAsync(aI, 0, x->nchrom * sizeof(u64), x->stream));
+  CK(cudaMemsetAsync(aF, 0, x->nchrom * sizeof(u64), x->stream));
+  stage_begin(x, "rle_moment", 0);
+  launch_rle_moment(x->stream, out, cap, x->nchrom, aI, aF);
+  CKL();
+  stage_end(x);
+  u64* hI = (u64*)x->h_acc;
+  u64* hF = hI + x->nchrom;
+  CK(cudaMemcpyAsync(hI, aI, x->nchrom * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaMemcpyAsync(hF, aF, x->nchrom * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaMemcpyAsync(x->h_small, x->small.p, 64, cudaMemcpyDeviceToHost, x->stream));
+  u64* hTot = (u64*)((char*)x->h_small + 128);
+  CK(cudaMemcpyAsync(hTot, TT.p, 8, cudaMemcpyDeviceToHost, x->stream));
+  std::vector<u64>& csh = ctrl ? x->ctrlCS_h : x->exptCS_h;
+  csh.resize(x->nchrom + 1);
+  CK(cudaMemcpyAsync(csh.data(), CS.p, (x->nchrom + 1) * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaStreamSynchronize(x->stream));
+  const int derr = *(int*)x->h_small;
+  x->n_clamped = *(u64*)((char*)x->h_small + 8);
+  if (derr) { x->filling = FILL_NONE; return map_dev_err(derr); }
+  std::vector<double>& sums = ctrl ? x->ctrl_sums : x->expt_sums;
+  for (int c = 0; c < x->nchrom; c++)
+    sums[c] = (double)hI[c] + (double)hF[c] * (1.0 / 1099511627776.0);
+  if (chrom_sums) memcpy(chrom_sums, sums.data(), x->nchrom * sizeof(double));
+  if (ctrl) { x->n_raw = *hTot; x->have_ctrl = true; }
+  else { x->n_expt = *hTot; x->have_expt = true; }
+  x->filling = FILL_NONE;
+  return GR_OK;
+}
+
+// ---- p-values through the pair table ------------------------------------------------
+static int table_alloc(gr_ctx* x, u32 cap) {
+  CK(x->tKeys.ensure((size_t)cap * 8));
+  CK(x->tLens.ensure((size_t)cap * 8));
+  CK(x->tPval.ensure((size_t)cap * 4));
+  CK(x->tQval.ensure((size_t)cap * 4));
+  CK(x->tCount.ensure(8));
+  CK(cudaMemsetAsync(x->tKeys.p, 0xff, (size_t)cap * 8, x->stream));
+  CK(cudaMemsetAsync(x->tLens.p, 0, (size_t)cap * 8, x->stream));
+  CK(cudaMemsetAsync(x->tCount.p, 0, 8, x->stream));
+  return GR_OK;
+}
+static PairTable table_view(gr_ctx* x, u32 cap) {
+  PairTable t;
+  t.keys = x->tKeys.as<u64>(); t.lens = x->tLens.as<u64>(); t.pval = x->tPval.as<float>();
+  t.qval = x->tQval.as<float>(); t.cap = cap; t.count = x->tCount.as<u32>();
+  return t;
+}
+
+// run an insert kernel, growing the table until it stays under half full
+template <class F>
+static int table_build(gr_ctx* x, u64 n, u32& cap_io, F insert) {
+  u32 cap = cap_io;
+  for (;;) {
+    int r = table_alloc(x, cap);
+    if (r) return r;
+    CK(cudaMemsetAsync(x->d_err, 0, sizeof(int), x->stream));
+    insert(table_view(x, cap));
+    CKL();
+    CK(cudaMemcpyAsync(x->h_small, x->d_err, sizeof(int), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    if (!(*(int*)x->h_small & GR_DE_TABLE)) break;
+    if (cap >= (1u << 30)) { x->detail = "distinct-value table overflow"; return GR_ERR_MEM; }
+    cap <<= 2;
+  }
+  (void)n;
+  cap_io = cap;
+  return GR_OK;
+}
+
+extern "C" int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag, int32_t has_ctrl,
+                                   uint64_t genome_len, gr_sample_stats* st) {
+  if (!x || !x->have_expt) return GR_ERR_ARG;
+  if (has_ctrl && !x->have_ctrl) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  if (frag_len == 0.0) return GR_ERR_EXPT;                     // Genrich.c:2292
+  u64 G = x->par.genome_len ? x->par.genome_len : genome_len;
+  if (!G)
+    for (int c = 0; c < x->nchrom; c++)
+      if (chrom_active(x, c)) G += x->len[c];                  // calcLambda 1819-1827
+  if (!G) return GR_ERR_GENOME;
+  const float lambda = (float)(frag_len / (double)G);          // 1831
+  float factor = 1.0f;
+  if (has_ctrl && ctrl_frag != 0.0) factor = (float)(frag_len / ctrl_frag);   // 2043-2045
+
+  const int nc = x->nchrom;
+  if (has_ctrl) {
+    CK(x->ctrlEnd.ensure((x->n_raw + 1) * sizeof(u32)));
+    CK(x->ctrlVal.ensure((x->n_raw + 1) * sizeof(float)));
+    DevRle raw = rle_view(x->rawEnd, x->rawVal, x->rawCS, x->rawTot);
+    DevRle out = rle_view(x->ctrlEnd, x->ctrlVal, x->ctrlCS, x->ctrlTot);
+    CompactScratch cs;
+    cs.st = x->lb0.as<u64>(); cs.ticket = x->ticket.as<u32>();
+    if ((x->n_raw + 1023) / 1024 > x->lb0.cap / 8) CK(x->lb0.ensure(((x->n_raw + 1023) / 1024) * 8));
+    cs.st = x->lb0.as<u64>();
+    stage_begin(x, "ctrl_clamp", x->n_raw * 8);
+    launch_ctrl_clamp(x->stream, x->L, raw, x->n_raw, factor, lambda, cs, out, x->bmC.as<u32>());
+    CKL();
+    stage_end(x);
+  } else {
+    // saveLambda 1838-1843: one interval (len, lambda) per saved chromosome
+    std::vector<u32> e; std::vector<float> v; std::vector<u64> cs(nc + 1);
+    for (int c = 0; c < nc; c++) {
+      cs[c] = e.size();
+      if (chrom_active(x, c)) { e.push_back(x->len[c]); v.push_back(lambda); }
+    }
+    cs[nc] = e.size();
+    x->n_ctrl = e.size();
+    CK(x->ctrlEnd.ensure((e.size() + 1) * sizeof(u32)));
+    CK(x->ctrlVal.ensure((e.size() + 1) * sizeof(float)));
+    CK(cudaMemcpyAsync(x->ctrlEnd.p, e.data(), e.size() * sizeof(u32), cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(x->ctrlVal.p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(x->ctrlCS.p, cs.data(), (nc + 1) * sizeof(u64), cudaMemcpyHostToDevice, x->stream));
+    u64 tot = e.size();
+    CK(cudaMemcpyAsync(x->ctrlTot.p, &tot, 8, cudaMemcpyHostToDevice, x->stream));
+    stage_begin(x, "ctrl_const", x->T / 8);
+    DevRle out = rle_view(x->ctrlEnd, x->ctrlVal, x->ctrlCS, x->ctrlTot);
+    launch_ctrl_const(x->stream, x->L, lambda, out, x->bmC.as<u32>());
+    CKL();
+    stage_end(x);
+    CK(cudaStreamSynchronize(x->stream));      // host vectors go out of scope
+  }
+
+  // K4: union ranks
+  RankScratch rs;
+  rs.st[0] = x->lb0.as<u64>(); rs.st[1] = x->lb1.as<u64>(); rs.st[2] = x->lb2.as<u64>();
+  rs.ticket = x->ticket.as<u32>();
+  Replicate* rep = new Replicate();
+  x->reps.push_back(rep);
+  CK(rep->bmU.ensure(x->T / 8));
+  CK(rep->rankU.ensure(x->nblocks * sizeof(u64)));
+  CK(rep->chrom_start.ensure((nc + 1) * sizeof(u64)));
+  CK(rep->present.ensure(nc));
+  stage_begin(x, "union_rank", x->T / 4);
+  launch_union_rank(x->stream, x->L, x->bmE.as<u32>(), x->bmC.as<u32>(), rs, x->rankE.as<u64>(),
+                    x->rankC.as<u64>(), rep->rankU.as<u64>(), x->d_totals);
+  CKL();
+  stage_end(x);
+  CK(cudaMemcpyAsync(x->h_small, x->small.p, 64, cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaMemcpyAsync((char*)x->h_small + 128, x->ctrlTot.p, 8, cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaStreamSynchronize(x->stream));
+  const u64* tot = (const u64*)((char*)x->h_small + 16);
+  const u64 np = tot[2];
+  x->n_ctrl = *(u64*)((char*)x->h_small + 128);
+  if (np >= 0xfffffff0ull) { x->detail = "more than 2^32 intervals on one device"; return GR_ERR_MEM; }
+  rep->n = np;
+  CK(rep->pEnd.ensure((np + 1) * sizeof(u32)));
+  CK(rep->pVal.ensure((np + 1) * sizeof(float)));
+  CK(rep->pExpt.ensure((np + 1) * sizeof(float)));
+  CK(rep->pCtrl.ensure((np + 1) * sizeof(float)));
+  stage_begin(x, "union_emit", x->T / 4 + np * 12);
+  launch_union_emit(x->stream, x->L, x->bmE.as<u32>(), x->bmC.as<u32>(), x->rankE.as<u64>(),
+                    x->rankC.as<u64>(), rep->rankU.as<u64>(), x->exptVal.as<float>(),
+                    x->ctrlVal.as<float>(), rep->pEnd.as<u32>(), rep->pExpt.as<float>(),
+                    rep->pCtrl.as<float>(), rep->bmU.as<u32>(), rep->chrom_start.as<u64>(),
+                    x->d_totals + 2);
+  CKL();
+  stage_end(x);
+
+  // K5: -log10 p through the table of distinct (expt, ctrl) pairs
+  CK(x->slot.ensure((np + 1) * sizeof(u32)));
+  u32 cap = 1u << 20;
+  stage_begin(x, "pval", np * 16);
+  int r = table_build(x, np, cap, [&](const PairTable& t) {
+    launch_pair_insert(x->stream, rep->pEnd.as<u32>(), rep->pExpt.as<float>(), rep->pCtrl.as<float>(),
+                       np, t, x->slot.as<u32>(), 0, x->d_err);
+  });
+  if (r) return r;
+  PairTable t = table_view(x, cap);
+  launch_pair_eval(x->stream, t);
+  launch_gather_f32(x->stream, t.pval, x->slot.as<u32>(), np, rep->pVal.as<float>());
+  CKL();
+  stage_end(x);
+
+  rep->present_h.resize(nc);
+  for (int c = 0; c < nc; c++) rep->present_h[c] = chrom_active(x, c);
+  CK(cudaMemcpyAsync(rep->present.p, rep->present_h.data(), nc, cudaMemcpyHostToDevice, x->stream));
+  rep->chrom_start_h.resize(nc + 1);
+  CK(cudaMemcpyAsync(rep->chrom_start_h.data(), rep->chrom_start.p, (nc + 1) * sizeof(u64),
+                     cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaStreamSynchronize(x->stream));
+  rep->has_cols = x->par.keep_pileups != 0;
+  if (!rep->has_cols) { rep->pExpt.release(); rep->pCtrl.release(); }
+
+  x->have_expt = x->have_ctrl = false;
+  x->finalized = false;
+  x->have_q = false;
+  if (st) {
+    memset(st, 0, sizeof *st);
+    st->frag_len = frag_len;
+    st->ctrl_frag = has_ctrl ? ctrl_frag : 0.0;
+    st->lambda = lambda;
+    st->factor = factor;
+    st->genome_len = G;
+    st->n_expt = x->n_expt;
+    st->n_ctrl = x->n_ctrl;
+    st->n_pval = np;
+    st->n_clamped = x->n_clamped;
+  }
+  return GR_OK;
+}
+
+extern "C" int gr_replicate_end(gr_ctx* x, gr_sample_stats* st) {
+  if (!x) return GR_ERR_ARG;
+  const bool pending_ctrl = x->filling == FILL_CTRL;
+  if (x->filling != FILL_NONE) {
+    int r = gr_sample_pileup(x, nullptr);
+    if (r) return r;
+  }
+  const bool has_ctrl = pending_ctrl || x->have_ctrl;
+  double f = 0.0, g = 0.0;
+  for (int c = 0; c < x->nchrom; c++) { f += x->expt_sums[c]; if (has_ctrl) g += x->ctrl_sums[c]; }
+  return gr_replicate_finish(x, f, g, has_ctrl, 0, st);
+}
+
+// ---- Fisher combine ---------------------------------------------------------------
+extern "C" int gr_pvalues_finalize(gr_ctx* x) {
+  if (!x || x->reps.empty()) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  const int nrep = (int)x->reps.size();
+  if (nrep > 200) return GR_ERR_DF;                            // pchisq 556
+  if (x->comb) { x->comb->release(); delete x->comb; x->comb = nullptr; }
+  x->have_q = false;
+  if (nrep == 1) {
+    x->fin = x->reps[0];
+    x->finalized = true;
+    return GR_OK;
+  }
+  const int nc = x->nchrom;
+  Replicate* cb = new Replicate();
+  x->comb = cb;
+  CK(cb->bmU.ensure(x->T / 8));
+  CK(cb->rankU.ensure(x->nblocks * sizeof(u64)));
+  CK(cb->chrom_start.ensure((nc + 1) * sizeof(u64)));
+  CK(cb->present.ensure(nc));
+  const u64 nwords = x->T / 32;
+  stage_begin(x, "fisher_union", (u64)nrep * x->T / 8);
+  launch_or_bitmaps(x->stream, x->reps[0]->bmU.as<u32>(), x->reps[1]->bmU.as<u32>(), cb->bmU.as<u32>(), nwords);
+  for (int r = 2; r < nrep; r++)
+    launch_or_bitmaps(x->stream, cb->bmU.as<u32>(), x->reps[r]->bmU.as<u32>(), cb->bmU.as<u32>(), nwords);
+  CK(x->lb0.ensure(3 * x->nblocks * sizeof(u64) > x->lb0.cap ? 3 * x->nblocks * sizeof(u64) : x->lb0.cap));
+  CompactScratch cs;
+  cs.st = x->lb0.as<u64>(); cs.ticket = x->ticket.as<u32>();
+  launch_block_rank(x->stream, x->L, cb->bmU.as<u32>(), cs, cb->rankU.as<u64>(), x->d_totals);
+  CKL();
+  stage_end(x);
+  CK(cudaMemcpyAsync(x->h_small, x->small.p, 64, cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaStreamSynchronize(x->stream));
+  const u64 np = ((const u64*)((char*)x->h_small + 16))[2];
+  cb->n = np;
+  CK(cb->pEnd.ensure((np + 1) * sizeof(u32)));
+  CK(cb->pVal.ensure((np + 1) * sizeof(float)));
+  CK(x->fsum.ensure((np + 1) * sizeof(double)));
+  CK(x->fdf.ensure((np + 1) * sizeof(int)));
+  std::vector<RepView> views(nrep);
+  for (int r = 0; r < nrep; r++) {
+    views[r].bmU = x->reps[r]->bmU.as<u32>();
+    views[r].rankU = x->reps[r]->rankU.as<u64>();
+    views[r].pval = x->reps[r]->pVal.as<float>();
+    views[r].present = x->reps[r]->present.as<uint8_t>();
+  }
+  CK(x->repviews.ensure(nrep * sizeof(RepView)));
+  CK(cudaMemcpyAsync(x->repviews.p, views.data(), nrep * sizeof(RepView), cudaMemcpyHostToDevice, x->stream));
+  stage_begin(x, "fisher_emit", np * 16 * nrep);
+  launch_fisher_emit(x->stream, x->L, cb->bmU.as<u32>(), cb->rankU.as<u64>(), x->repviews.as<RepView>(),
+                     nrep, cb->pEnd.as<u32>(), x->fsum.as<double>(), x->fdf.as<int>(),
+                     cb->chrom_start.as<u64>(), x->d_totals + 2);
+  launch_fisher_eval(x->stream, x->fsum.as<double>(), x->fdf.as<int>(), np, cb->pVal.as<float>());
+  CKL();
+  stage_end(x);
+  cb->chrom_start_h.resize(nc + 1);
+  CK(cudaMemcpyAsync(cb->chrom_start_h.data(), cb->chrom_start.p, (nc + 1) * sizeof(u64),
+                     cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaStreamSynchronize(x->stream));      // also keeps `views` alive until the copy is done
+  cb->present_h.resize(nc);
+  for (int c = 0; c < nc; c++) cb->present_h[c] = cb->chrom_start_h[c + 1] > cb->chrom_start_h[c];
+  x->fin = cb;
+  x->finalized = true;
+  return GR_OK;
+}
+
+// ---- BH ------------------------------------------------------------------------------
+static u64 final_genome_len(const gr_ctx* x) {        // findPeaks 1091-1101
+  if (x->par.genome_len) return x->par.genome_len;
+  u64 G = 0;
+  const Replicate* f = x->fin;
+  for (int c = 0; c < x->nchrom; c++)
+    if (!x->skip[c] && f->chrom_start_h[c + 1] > f->chrom_start_h[c]) G += x->len[c];
+  return G;
+}
+
+extern "C" int gr_bh_local_hist(gr_ctx* x, const uint32_t** d_keys, const uint64_t** d_lens, uint64_t* n) {
+  if (!x) return GR_ERR_ARG;
+  if (!x->finalized) { int r = gr_pvalues_finalize(x); if (r) return r; }
+  CK(cudaSetDevice(x->device));
+  Replicate* f = x->fin;
+  const u64 np = f->n;
+  CK(x->slot.ensure((np + 1) * sizeof(u32)));
+  u32 cap = 1u << 20;
+  stage_begin(x, "bh_hist", np * 12);
+  int r = table_build(x, np, cap, [&](const PairTable& t) {
+    launch_key_insert(x->stream, f->pEnd.as<u32>(), f->pVal.as<float>(), np, f->chrom_start.as<u64>(),
+                      x->nchrom, t, x->slot.as<u32>(), x->d_err);
+  });
+  if (r) return r;
+  PairTable t = table_view(x, cap);
+  // occupied count -> list
+  CK(cudaMemcpyAsync(x->h_small, x->tCount.p, 4, cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaStreamSynchronize(x->stream));
+  const u64 occ = *(u32*)x->h_small;
+  CK(x->hk.ensure((occ + 1) * sizeof(u32)));
+  CK(x->hl.ensure((occ + 1) * sizeof(u64)));
+  CK(x->hcount.ensure(8));
+  const u64 ntile = (cap + 255) / 256;
+  CK(x->lb0.ensure(ntile * sizeof(u64) > x->lb0.cap ? ntile * sizeof(u64) : x->lb0.cap));
+  CompactScratch cs;
+  cs.st = x->lb0.as<u64>(); cs.ticket = x->ticket.as<u32>();
+  launch_table_compact(x->stream, t, cs, x->hk.as<u32>(), x->hl.as<u64>(), x->hcount.as<u64>());
+  CKL();
+  stage_end(x);
+  x->hn = occ;
+  // remember the table capacity for the q lookup
+  x->n_distinct = 0;
+  x->hist_cap = cap;
+  if (d_keys) *d_keys = x->hk.as<u32>();
+  if (d_lens) *d_lens = (const uint64_t*)x->hl.as<u64>();
+  if (n) *n = occ;
+  return GR_OK;
+}
+
+extern "C" int gr_bh_set_global(gr_ctx* x, const uint32_t* d_keys, const uint64_t* d_lens,
+                                uint64_t n, uint64_t genome_len) {
+  if (!x || !x->finalized || !genome_len) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  const u32 cap = x->hist_cap;
+  if (!cap) return GR_ERR_ARG;
+  Replicate* f = x->fin;
+  const u64 m = n ? n : 1;
+  CK(x->bk0.ensure(m * 4)); CK(x->bk1.ensure(m * 4));
+  CK(x->bl0.ensure(m * 8)); CK(x->bl1.ensure(m * 8));
+  const u64 nblk = (m + 4095) / 4096;
+  CK(x->bhist.ensure(256 * nblk * 4));
+  CK(x->bdk.ensure(m * 4)); CK(x->bdq.ensure(m * 4)); CK(x->bdl.ensure(m * 8));
+  CK(x->bdcount.ensure(8));
+  const u64 ntile = (m + 255) / 256;
+  CK(x->lb1.ensure(ntile * sizeof(u64) > x->lb1.cap ? ntile * sizeof(u64) : x->lb1.cap));
+  BhWork w;
+  w.k0 = x->bk0.as<u32>(); w.k1 = x->bk1.as<u32>(); w.l0 = x->bl0.as<u64>(); w.l1 = x->bl1.as<u64>();
+  w.hist = x->bhist.as<u32>(); w.ksum = nullptr; w.x = nullptr;
+  w.dk = x->bdk.as<u32>(); w.dq = x->bdq.as<float>(); w.dl = x->bdl.as<u64>();
+  w.dcount = x->bdcount.as<u64>();
+  w.sc.st = x->lb1.as<u64>(); w.sc.ticket = x->ticket.as<u32>();
+  w.cap = m;
+  const float logN = -log10f((float)genome_len);               // saveQval 221
+  stage_begin(x, "bh", n * 12 * 8);
+  launch_bh(x->stream, d_keys, (const u64*)d_lens, n, logN, w);
+  PairTable t = table_view(x, cap);
+  launch_table_q(x->stream, t, w.dk, w.dq, w.dcount);
+  CK(x->qVal.ensure((f->n + 1) * sizeof(float)));
+  launch_gather_f32(x->stream, t.qval, x->slot.as<u32>(), f->n, x->qVal.as<float>());
+  CKL();
+  stage_end(x);
+  CK(cudaMemcpyAsync(x->h_small, x->bdcount.p, 8, cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaStreamSynchronize(x->stream));
+  x->n_distinct = *(u64*)x->h_small;
+  x->all_q_one = 0;
+  if (x->n_distinct) {
+    float top;
+    CK(cudaMemcpy(&top, x->bdq.as<float>() + (x->n_distinct - 1), 4, cudaMemcpyDeviceToHost));
+    x->all_q_one = top == 0.0f;                                // Genrich.c:245
+  }
+  x->have_q = true;
+  return GR_OK;
+}
+
+// ---- peaks ---------------------------------------------------------------------------
+extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_run_stats* st) {
+  if (!x || x->reps.empty()) return GR_ERR_ARG;
+  if (!x->finalized) { int r = gr_pvalues_finalize(x); if (r) return r; }
+  CK(cudaSetDevice(x->device));
+  Replicate* f = x->fin;
+  const u64 G = final_genome_len(x);
+  const int qopt = x->par.qval_opt != 0;
+  if (qopt && !x->have_q) {
+    const uint32_t* k; const uint64_t* l; uint64_t hn;
+    int r = gr_bh_local_hist(x, &k, &l, &hn);
+    if (r) return r;
+    if (!G) return GR_ERR_GENOME;
+    r = gr_bh_set_global(x, k, l, hn, G);
+    if (r) return r;
+  }
+  const u64 np = f->n;
+  x->peaks_h.clear();
+  u64 peak_bp = 0;
+  if (np) {
+    CK(x->evIdx.ensure((np + 1) * sizeof(u32)));
+    CK(x->evCount.ensure(8)); CK(x->headCount.ensure(8)); CK(x->peakCount.ensure(8)); CK(x->peakBp.ensure(8));
+    const u64 nt = (np + 1023) / 1024;
+    CK(x->lb0.ensure(nt * sizeof(u64) > x->lb0.cap ? nt * sizeof(u64) : x->lb0.cap));
+    PeakWork w;
+    w.ev_idx = x->evIdx.as<u32>(); w.ev_count = x->evCount.as<u64>();
+    w.head_count = x->headCount.as<u64>(); w.out_count = x->peakCount.as<u64>(); w.peak_bp = x->peakBp.as<u64>();
+    w.sc.st = x->lb0.as<u64>(); w.sc.ticket = x->ticket.as<u32>();
+    const float* v = qopt ? x->qVal.as<float>() : f->pVal.as<float>();
+    stage_begin(x, "peak_events", np * 4);
+    launch_peak_events(x->stream, v, np, x->par.min_pqval, w);
+    CKL();
+    stage_end(x);
+    CK(cudaMemcpyAsync(x->h_small, x->evCount.p, 8, cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaStreamSynchronize(x->stream));
+    const u64 nev = *(u64*)x->h_small;
+    if (nev) {
+      CK(x->headIdx.ensure(nev * sizeof(u32)));
+      CK(x->cand.ensure(nev * sizeof(PeakRec)));
+      CK(x->candOk.ensure(nev));
+      CK(x->peakOut.ensure(nev * sizeof(PeakRec)));
+      w.head_idx = x->headIdx.as<u32>(); w.cand = x->cand.as<PeakRec>(); w.cand_ok = x->candOk.as<uint8_t>();
+      w.out = x->peakOut.as<PeakRec>();
+      stage_begin(x, "peak_scan", nev * 16);
+      launch_peak_chain(x->stream, f->pEnd.as<u32>(), f->pVal.as<float>(), x->qVal.as<float>(),
+                        f->chrom_start.as<u64>(), x->nchrom, x->par.min_pqval, qopt, x->par.max_gap,
+                        x->par.min_auc, x->par.min_len, w, nev);
+      CKL();
+      stage_end(x);
+      CK(cudaMemcpyAsync(x->h_small, x->peakCount.p, 8, cudaMemcpyDeviceToHost, x->stream));
+      CK(cudaMemcpyAsync((char*)x->h_small + 8, x->peakBp.p, 8, cudaMemcpyDeviceToHost, x->stream));
+      CK(cudaStreamSynchronize(x->stream));
+      const u64 npk = *(u64*)x->h_small;
+      peak_bp = *(u64*)((char*)x->h_small + 8);
+      x->peaks_h.resize(npk);
+      static_assert(sizeof(PeakRec) == sizeof(gr_peak), "peak record layout");
+      if (npk) CK(cudaMemcpy(x->peaks_h.data(), x->peakOut.p, npk * sizeof(gr_peak), cudaMemcpyDeviceToHost));
+    }
+  }
+  if (peaks) *peaks = x->peaks_h.data();
+  if (n) *n = x->peaks_h.size();
+  if (st) {
+    memset(st, 0, sizeof *st);
+    st->genome_len = G;
+    st->n_peaks = x->peaks_h.size();
+    st->peak_bp = peak_bp;
+    st->n_intervals = np;
+    st->n_distinct_p = qopt ? x->n_distinct : 0;
+    st->all_q_one = qopt ? x->all_q_one : 0;
+    st->n_replicates = (int)x->reps.size();
+  }
+  return GR_OK;
+}
+
+// ---- seam OUT for -f / -k --------------------------------------------------------------
+extern "C" int gr_fetch_intervals(gr_ctx* x, int32_t which, int32_t replicate, int32_t chrom,
+                                  const uint32_t** end, const float** val, const float** expt,
+                                  const float** ctrl, uint64_t* n) {
+  if (!x || chrom < 0 || chrom >= x->nchrom) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  CK(cudaStreamSynchronize(x->stream));
+  const u32* dE = nullptr; const float* dV = nullptr; const float* dX = nullptr; const float* dC = nullptr;
+  u64 a = 0, b = 0;
+  if (which == 0 || which == 1) {
+    const std::vector<u64>& cs = which ? x->ctrlCS_h : x->exptCS_h;
+    std::vector<u64> tmp;
+    const std::vector<u64>* use = &cs;
+    if (which == 1) {            // control start table lives on the device after the sweep
+      tmp.resize(x->nchrom + 1);
+      CK(cudaMemcpy(tmp.data(), x->ctrlCS.p, (x->nchrom + 1) * sizeof(u64), cudaMemcpyDeviceToHost));
+      use = &tmp;
+    }
+    if (use->size() != (size_t)x->nchrom + 1) return GR_ERR_ARG;
+    a = (*use)[chrom]; b = (*use)[chrom + 1];
+    dE = which ? x->ctrlEnd.as<u32>() : x->exptEnd.as<u32>();
+    dV = which ? x->ctrlVal.as<float>() : x->exptVal.as<float>();
+  } else if (which == 2 || which == 3) {
+    const int nrep = (int)x->reps.size();
+    Replicate* r = nullptr;
+    if (which == 3) {
+      if (!x->have_q) return GR_ERR_ARG;
+      r = x->fin;
+    } else if (replicate == nrep) {
+      if (!x->finalized) return GR_ERR_ARG;
+      r = x->fin;
+    } else if (replicate >= 0 && replicate < nrep)
+      r = x->reps[replicate];
+    else
+      return GR_ERR_ARG;
+    a = r->chrom_start_h[chrom]; b = r->chrom_start_h[chrom + 1];
+    dE = r->pEnd.as<u32>();
+    dV = which == 3 ? x->qVal.as<float>() : r->pVal.as<float>();
+    if (which == 2 && r->has_cols) { dX = r->pExpt.as<float>(); dC = r->pCtrl.as<float>(); }
+  } else
+    return GR_ERR_ARG;
+  const u64 m = b - a;
+  if (end) *end = nullptr;
+  if (val) *val = nullptr;
+  if (expt) *expt = nullptr;
+  if (ctrl) *ctrl = nullptr;
+  if (n) *n = 0;
+  if (!m) return GR_OK;
+  x->f_end.resize(m); x->f_val.resize(m);
+  CK(cudaMemcpy(x->f_end.data(), dE + a, m * sizeof(u32), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(x->f_val.data(), dV + a, m * sizeof(float), cudaMemcpyDeviceToHost));
+  if (dX) {
+    x->f_expt.resize(m); x->f_ctrl.resize(m);
+    CK(cudaMemcpy(x->f_expt.data(), dX + a, m * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(x->f_ctrl.data(), dC + a, m * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  if (end) *end = x->f_end.data();
+  if (val) *val = x->f_val.data();
+  if (expt && dX) *expt = x->f_expt.data();
+  if (ctrl && dX) *ctrl = x->f_ctrl.data();
+  if (n) *n = m;
+  return GR_OK;
+}
+
+// ---- timing / misc ------------------------------------------------------------------------
+extern "C" int gr_timing_enable(gr_ctx* x, int32_t on) {
+  if (!x) return GR_ERR_ARG;
+  x->timing = on != 0;
+  return GR_OK;
+}
+extern "C" int gr_timing_reset(gr_ctx* x) {
+  if (!x) return GR_ERR_ARG;
+  cudaSetDevice(x->device);
+  cudaStreamSynchronize(x->stream);
+  for (auto& s : x->stages) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  x->stages.clear();
+  return GR_OK;
+}
+extern "C" int gr_timing_get(gr_ctx* x, gr_stage_time* out, int32_t cap, int32_t* n) {
+  if (!x || !out || !n) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  CK(cudaStreamSynchronize(x->stream));
+  int m = 0;
+  for (auto& s : x->stages) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    int k = 0;
+    for (; k < m; k++) if (!strcmp(out[k].name, s.name)) break;
+    if (k == m) {
+      if (m == cap) continue;
+      out[m].name = s.name; out[m].ms = 0; out[m].launches = 0; out[m].bytes = 0;
+      m++;
+    }
+    out[k].ms += ms; out[k].launches += 1; out[k].bytes += s.bytes;
+  }
+  *n = m;
+  return GR_OK;
+}
+extern "C" uint64_t gr_kernel_launches(const gr_ctx* x) { (void)x; return g_gr_launches; }
+extern "C" int gr_synchronize(gr_ctx* x) {
+  if (!x) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  CK(cudaStreamSynchronize(x->copy));
+  CK(cudaStreamSynchronize(x->stream));
+  return GR_OK;
+}
+
+extern "C" int gr_timer_start(gr_ctx* x) {
+  if (!x) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  if (!x->tm_a) { CK(cudaEventCreate(&x->tm_a)); CK(cudaEventCreate(&x->tm_b)); }
+  CK(cudaEventRecord(x->tm_a, x->stream));
+  return GR_OK;
+}
+extern "C" int gr_timer_stop(gr_ctx* x, double* ms) {
+  if (!x || !ms || !x->tm_a) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  CK(cudaEventRecord(x->tm_b, x->stream));
+  CK(cudaEventSynchronize(x->tm_b));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, x->tm_a, x->tm_b));
+  *ms = f;
+  return GR_OK;
+}

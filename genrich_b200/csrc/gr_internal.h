@@ -1,0 +1,142 @@
+// gr_internal.h -- host-visible launchers of the CUDA kernels (one per stage of
+// the reference's hot path) and the argument blocks they take.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+
+// Device-resident description of the chromosome table / slot layout.
+struct DevLayout {
+  int nchrom;
+  u64 T;                    // total slots (multiple of GR_BLOCK_SLOTS)
+  u64 nblocks;              // T / GR_BLOCK_SLOTS
+  const u64* off;           // [nchrom] first slot of each chromosome (UINT64_MAX: no slots)
+  const u32* len;           // [nchrom]
+  const uint8_t* flags;     // [nchrom] GR_CF_*
+  const int* blk2chrom;     // [nblocks]
+};
+
+// One RLE array of the reference's Pileup type (Genrich.h:173-176), device side.
+struct DevRle {
+  u32* end;                 // chromosome-relative exclusive end
+  float* val;
+  u64* chrom_start;         // [nchrom+1] first interval of each chromosome
+  u64* total;               // [1] device copy of the interval count
+};
+
+// ---- K1: delta scatter (saveInterval 2516-2591) ------------------------------
+void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64 n,
+                    int32_t* delta, int* err, u64* clamped);
+
+// ---- K2: dense prefix sum + break compaction + bitmap (savePileupExpt 2168) ----
+struct ScanScratch {
+  u64* st_sum; u64* st_cnt; u32* ticket;   // look-back state, zeroed per launch
+};
+void launch_dense_scan(cudaStream_t s, const DevLayout& L, const int32_t* delta,
+                       const ScanScratch& sc, DevRle out, u32* bitmap, int* err);
+
+// ---- K2b: per-chromosome sum of (float)(end-start)*val, exact fixed point ------
+// acc_int / acc_frac: [nchrom] u64, zeroed by the caller.  sum = int + frac*2^-40.
+void launch_rle_moment(cudaStream_t s, const DevRle& r, u64 n_upper, int nchrom,
+                       u64* acc_int, u64* acc_frac);
+
+// ---- K3: control sweep max(factor*val, lambda) + RLE re-merge (savePileupCtrl) --
+struct CompactScratch { u64* st; u32* ticket; };
+void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u64 n_raw,
+                       float factor, float lambda, const CompactScratch& sc,
+                       DevRle out, u32* bitmap /* raw breaks in, surviving breaks out */);
+// no-control variant: one interval (len, lambda) per active chromosome (saveLambda 1838)
+void launch_ctrl_const(cudaStream_t s, const DevLayout& L, float lambda, DevRle out, u32* bitmap);
+
+// ---- K4: breakpoint union of expt and ctrl (savePval 1768-1791) -----------------
+struct RankScratch { u64* st[3]; u32* ticket; };
+// pass A: per-block exclusive ranks of E, C and E|C; totals[3]
+void launch_union_rank(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
+                       const RankScratch& sc, u64* rankE, u64* rankC, u64* rankU, u64* totals);
+// pass B: emit merged intervals (end, expt value, ctrl value) + union bitmap
+void launch_union_emit(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
+                       const u64* rankE, const u64* rankC, const u64* rankU,
+                       const float* exptVal, const float* ctrlVal,
+                       u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
+                       const u64* total);
+
+// ---- K5: -log10 p per interval through a table of distinct (expt, ctrl) pairs ---
+struct PairTable {
+  u64* keys;      // (expt bits << 32) | ctrl bits ; EMPTY = ~0
+  u64* lens;      // total bp per pair (BH histogram, hashPval 300)
+  float* pval;    // filled by launch_pair_eval
+  float* qval;    // filled after BH
+  u32 cap;        // power of two
+  u32* count;     // [1] occupied slots
+};
+void launch_pair_insert(cudaStream_t s, const u32* pEnd, const float* pExpt, const float* pCtrl,
+                        u64 n, const PairTable& t, u32* slot, int accumulate_len, int* err);
+void launch_pair_eval(cudaStream_t s, const PairTable& t);
+void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n, float* out);
+
+// ---- K6: Fisher combine over replicates (combinePval 612, multPval 567) ----------
+struct RepView {            // one replicate's p arrays
+  const u32* bmU; const u64* rankU; const float* pval; const uint8_t* present; /* [nchrom] */
+};
+void launch_or_bitmaps(cudaStream_t s, const u32* a, const u32* b, u32* out, u64 nwords);
+void launch_block_rank(cudaStream_t s, const DevLayout& L, const u32* bm, const CompactScratch& sc,
+                       u64* rank, u64* total);
+// for each combined break: sum of replicate p (double) and df -> sum_out/df_out; end_out
+void launch_fisher_emit(cudaStream_t s, const DevLayout& L, const u32* bmAll, const u64* rankAll,
+                        const RepView* reps_dev, int nrep, u32* end_out, double* sum_out,
+                        int* df_out, u64* chrom_start, const u64* total);
+void launch_fisher_eval(cudaStream_t s, const double* sum, const int* df, u64 n, float* pcomb);
+
+// ---- K7: Benjamini-Hochberg over the histogram of distinct p (computeQval 352) ----
+// generic single-key table used when the final p array is the Fisher-combined one
+void launch_key_insert(cudaStream_t s, const u32* pEnd, const float* pval, u64 n,
+                       const u64* chrom_start, int nchrom, const PairTable& t, u32* slot, int* err);
+void launch_table_compact(cudaStream_t s, const PairTable& t, const CompactScratch& sc,
+                          u32* keys_out, u64* lens_out, u64* count_out);
+// sort (keys,lens) ascending by key, merge equal keys, compute q per distinct key.
+// Work arrays must hold n entries each.  Results: dk (distinct keys), dq (their q),
+// *dcount.  logN = -log10f(genomeLen) is evaluated by the caller (host libm), like
+// every other scalar of the reference's CLI layer.
+struct BhWork {
+  u32* k0; u32* k1; u64* l0; u64* l1;   // ping-pong
+  u32* hist;                            // radix histograms
+  u64* ksum;                            // suffix sums
+  float* x;                             // per-key statistic
+  u32* dk; float* dq; u64* dl; u64* dcount;
+  CompactScratch sc;
+  u64 cap;
+};
+void launch_bh(cudaStream_t s, const u32* keys, const u64* lens, u64 n, float logN, const BhWork& w);
+void launch_table_q(cudaStream_t s, const PairTable& t, const u32* dk, const float* dq, const u64* dcount);
+
+// ---- K8: peak scan (callPeaks 977) ---------------------------------------------
+struct PeakRec {           // mirrors gr_peak
+  int32_t chrom; u32 summit; i64 start; i64 end; float auc, pval, qval, reserved;
+};
+struct PeakWork {
+  u32* ev_idx;             // significant / SKIP interval indices, in order
+  u64* ev_count;
+  u32* head_idx;           // indices into ev_idx where a candidate peak starts
+  u64* head_count;
+  PeakRec* cand;           // one per head
+  uint8_t* cand_ok;
+  PeakRec* out; u64* out_count; u64* peak_bp;
+  CompactScratch sc;
+};
+void launch_peak_events(cudaStream_t s, const float* v, u64 n, float thr, const PeakWork& w);
+// heads -> per-candidate walk -> compaction of valid peaks; nev = *w.ev_count (read back by the host)
+void launch_peak_chain(cudaStream_t s, const u32* pEnd, const float* pval, const float* qval,
+                       const u64* chrom_start, int nchrom, float thr, int qopt, int max_gap,
+                       float min_auc, int min_len, const PeakWork& w, u64 nev);
+
+// ---- small utilities -------------------------------------------------------------
+void launch_fill_chrom_start(cudaStream_t s, const DevLayout& L, u64* chrom_start, const u64* total);
+void launch_fill_u64(cudaStream_t s, u64* p, u64 v, u64 n);
+u64 lookback_tiles_for(u64 n_items, u32 tile);
+
+// number of kernel launches issued by this library (all contexts)
+extern unsigned long long g_gr_launches;
+#define GR_NOTE_LAUNCH() (++g_gr_launches)

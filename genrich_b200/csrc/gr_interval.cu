@@ -1,0 +1,496 @@
+// gr_interval.cu -- interval-domain kernels between the dense scan and the peak
+// scan: K3 control sweep, K4 breakpoint union, K5 -log10 p through a table of
+// distinct (expt, ctrl) pairs, K6 Fisher combine.
+#include "gr_tile.cuh"
+#include "gr_math.cuh"
+#include "gr_internal.h"
+
+// ============================================================================
+// K3: control sweep (savePileupCtrl 2103-2141).  Per raw control interval:
+// net = MAX(factor * val, lambda) in float; an interval boundary survives iff the
+// clamped value changes across it (2122) or it is the chromosome end.  Surviving
+// intervals are compacted (single pass, look-back ranks); the bits of the dropped
+// boundaries are cleared in the control break bitmap.
+#define CL_ITEMS 4
+#define CL_TILE 1024
+
+__device__ __forceinline__ float clamp_net(float factor, float v, float lambda) {
+  const float s = __fmul_rn(factor, v);
+  return s > lambda ? s : lambda;                 // MAX(val, lambda), Genrich.h:12
+}
+
+__global__ void __launch_bounds__(256)
+k_ctrl_clamp(DevLayout L, DevRle raw, u64 n, float factor, float lambda, Lookback<1> lb,
+             DevRle out, u32* __restrict__ bitmap) {
+  const u32 tile = take_ticket(lb.ticket);
+  const u64 t0 = (u64)tile * CL_TILE;
+  const u64 tl = min(t0 + CL_TILE, n) - 1;
+  const TileChrom tc = tile_chrom_range(raw.chrom_start, L.nchrom, t0, tl);
+  const u64 i0 = t0 + (u64)threadIdx.x * CL_ITEMS;
+
+  u32 e[CL_ITEMS];
+  float net[CL_ITEMS + 1];
+  bool keep[CL_ITEMS], last[CL_ITEMS];
+  int ch[CL_ITEMS];
+  u32 cnt = 0;
+#pragma unroll
+  for (int k = 0; k <= CL_ITEMS; k++) {
+    const u64 i = i0 + k;
+    net[k] = i < n ? clamp_net(factor, raw.val[i], lambda) : 0.0f;
+  }
+#pragma unroll
+  for (int k = 0; k < CL_ITEMS; k++) {
+    const u64 i = i0 + k;
+    keep[k] = false; last[k] = false; ch[k] = tc.c0; e[k] = 0;
+    if (i < n) {
+      e[k] = raw.end[i];
+      const int c = tc.c0 == tc.c1 ? tc.c0 : chrom_of_index(raw.chrom_start, L.nchrom, i);
+      ch[k] = c;
+      last[k] = (i + 1 == raw.chrom_start[c + 1]);
+      keep[k] = last[k] || net[k] != net[k + 1];
+      cnt += keep[k];
+    }
+  }
+  u32 tot;
+  u64 rank = tile_exclusive_rank(lb, tile, cnt, tot);
+  if (tile == 0 && threadIdx.x == 0) out.chrom_start[0] = 0;
+#pragma unroll
+  for (int k = 0; k < CL_ITEMS; k++) {
+    const u64 i = i0 + k;
+    if (i >= n) break;
+    if (keep[k]) {
+      out.end[rank] = e[k];
+      out.val[rank] = net[k];
+      rank++;
+      if (last[k]) out.chrom_start[ch[k] + 1] = rank;
+      if (i == n - 1) *out.total = rank;
+    } else {
+      const u64 g = L.off[ch[k]] + e[k];
+      atomicAnd(bitmap + (g >> 5), ~(1u << (g & 31)));
+    }
+  }
+}
+
+// chromosomes without intervals take the running count (forward fill)
+__global__ void k_fill_forward(int nchrom, const u64* raw_start, u64* out_start) {
+  if (threadIdx.x || blockIdx.x) return;
+  for (int c = 0; c < nchrom; c++)
+    if (raw_start[c + 1] == raw_start[c]) out_start[c + 1] = out_start[c];
+}
+
+void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u64 n_raw,
+                       float factor, float lambda, const CompactScratch& sc,
+                       DevRle out, u32* bitmap) {
+  if (!n_raw) return;
+  const u64 ntiles = (n_raw + CL_TILE - 1) / CL_TILE;
+  cudaMemsetAsync(sc.st, 0, ntiles * sizeof(u64), s);
+  cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
+  Lookback<1> lb;
+  lb.st[0] = sc.st; lb.ticket = sc.ticket;
+  k_ctrl_clamp<<<(unsigned)ntiles, 256, 0, s>>>(L, raw, n_raw, factor, lambda, lb, out, bitmap); GR_NOTE_LAUNCH();
+  k_fill_forward<<<1, 32, 0, s>>>(L.nchrom, raw.chrom_start, out.chrom_start); GR_NOTE_LAUNCH();
+}
+
+// no control: one interval (len, lambda) per active chromosome (saveLambda 1838-1843);
+// the RLE arrays themselves are tiny and written by the host, this sets the bits.
+__global__ void k_ctrl_const_bits(DevLayout L, u32* bitmap) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= L.nchrom) return;
+  const u64 off = L.off[c];
+  if (off == ~0ull) return;
+  if ((L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) != (GR_CF_OWNED | GR_CF_SAVE)) return;
+  const u64 g = off + L.len[c];
+  atomicOr(bitmap + (g >> 5), 1u << (g & 31));
+}
+void launch_ctrl_const(cudaStream_t s, const DevLayout& L, float lambda, DevRle out, u32* bitmap) {
+  (void)lambda; (void)out;
+  cudaMemsetAsync(bitmap, 0, (L.T / 32) * sizeof(u32), s);
+  k_ctrl_const_bits<<<(L.nchrom + 127) / 128, 128, 0, s>>>(L, bitmap); GR_NOTE_LAUNCH();
+}
+
+// ============================================================================
+// K4: union of experimental and control breakpoints (savePval 1768-1791,
+// countIntervals 1661) on the break bitmaps.  Pass A ranks the set bits of E, C and
+// E|C per 8192-cell block (look-back over three counters); pass B walks the set
+// bits of E|C and gathers the pileup values: the interval ending at a break lies
+// in the experimental interval number (#E breaks before it), same for control.
+__global__ void __launch_bounds__(256)
+k_union_rank(const u32* __restrict__ bmE, const u32* __restrict__ bmC, Lookback<3> lb,
+             u64* __restrict__ rankE, u64* __restrict__ rankC, u64* __restrict__ rankU,
+             u64* __restrict__ totals, u32 nblocks) {
+  __shared__ u32 sm[3][8];
+  const u32 blk = take_ticket(lb.ticket);
+  const u64 widx = (u64)blk * 256 + threadIdx.x;
+  const u32 E = bmE[widx], C = bmC ? bmC[widx] : 0u;
+  u32 a = __reduce_add_sync(GR_FULL, __popc(E));
+  u32 b = __reduce_add_sync(GR_FULL, __popc(C));
+  u32 u = __reduce_add_sync(GR_FULL, __popc(E | C));
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { sm[0][w] = a; sm[1][w] = b; sm[2][w] = u; }
+  __syncthreads();
+  if (w == 0) {
+    i64 agg[3] = { 0, 0, 0 }, ex[3];
+    for (int k = 0; k < 8; k++) { agg[0] += sm[0][k]; agg[1] += sm[1][k]; agg[2] += sm[2][k]; }
+    lookback_exclusive<3>(lb, blk, agg, ex);
+    if (lane == 0) {
+      rankE[blk] = (u64)ex[0];
+      if (rankC) rankC[blk] = (u64)ex[1];
+      rankU[blk] = (u64)ex[2];
+      if (blk == nblocks - 1) {
+        totals[0] = (u64)(ex[0] + agg[0]);
+        totals[1] = (u64)(ex[1] + agg[1]);
+        totals[2] = (u64)(ex[2] + agg[2]);
+      }
+    }
+  }
+}
+
+void launch_union_rank(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
+                       const RankScratch& sc, u64* rankE, u64* rankC, u64* rankU, u64* totals) {
+  for (int k = 0; k < 3; k++) cudaMemsetAsync(sc.st[k], 0, L.nblocks * sizeof(u64), s);
+  cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
+  Lookback<3> lb;
+  for (int k = 0; k < 3; k++) lb.st[k] = sc.st[k];
+  lb.ticket = sc.ticket;
+  k_union_rank<<<(unsigned)L.nblocks, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks); GR_NOTE_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256)
+k_union_emit(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ bmC,
+             const u64* __restrict__ rankE, const u64* __restrict__ rankC,
+             const u64* __restrict__ rankU, const float* __restrict__ exptVal,
+             const float* __restrict__ ctrlVal, u32* __restrict__ pEnd,
+             float* __restrict__ pExpt, float* __restrict__ pCtrl, u32* __restrict__ bmU,
+             u64* __restrict__ chrom_start) {
+  __shared__ u32 sm_a[8], sm_u[8];
+  const u32 blk = blockIdx.x;
+  const u64 widx = (u64)blk * 256 + threadIdx.x;
+  const u32 E = bmE[widx], C = bmC[widx];
+  u32 U = E | C;
+  bmU[widx] = U;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 pa = __popc(E) | (__popc(C) << 16);
+  const u32 pu = __popc(U);
+  const u32 ia = warp_incl_scan_u32(pa, lane), iu = warp_incl_scan_u32(pu, lane);
+  if (lane == 31) { sm_a[w] = ia; sm_u[w] = iu; }
+  __syncthreads();
+  u32 xa = ia - pa, xu = iu - pu;
+  for (int k = 0; k < w; k++) { xa += sm_a[k]; xu += sm_u[k]; }
+  const int c = L.blk2chrom[blk];
+  const u64 off = L.off[c];
+  if (threadIdx.x == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = rankU[blk];
+  if (!U) return;
+  u64 u = rankU[blk] + xu;
+  const u64 re = rankE[blk] + (xa & 0xffff), rc = rankC[blk] + (xa >> 16);
+  const u32 jw = (u32)((u64)blk * GR_BLOCK_SLOTS + (u64)threadIdx.x * 32 - off);
+  while (U) {
+    const int b = __ffs(U) - 1;
+    const u32 low = (1u << b) - 1;
+    pEnd[u] = jw + b;
+    pExpt[u] = exptVal[re + __popc(E & low)];
+    pCtrl[u] = ctrlVal[rc + __popc(C & low)];
+    u++;
+    U &= U - 1;
+  }
+}
+
+void launch_union_emit(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
+                       const u64* rankE, const u64* rankC, const u64* rankU,
+                       const float* exptVal, const float* ctrlVal,
+                       u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
+                       const u64* total) {
+  k_union_emit<<<(unsigned)L.nblocks, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
+                                                   pEnd, pExpt, pCtrl, bmU, chrom_start); GR_NOTE_LAUNCH();
+  launch_fill_chrom_start(s, L, chrom_start, total);
+}
+
+// ============================================================================
+// K5: -log10 p per merged interval (calcPval 1628).  p is a pure function of the
+// (expt, ctrl) float pair and the pairs take few distinct values, so the FP64
+// evaluation runs once per distinct pair: open-addressing table keyed by the 64
+// bits of the pair, then a gather.  The same table code, keyed by the 32 bits of
+// -log10 p and accumulating interval lengths, is the genome-wide histogram of
+// hashPval 300 / recordPval 277 (exact float equality == equal bit patterns here:
+// all keys are >= +0).
+#define TBL_EMPTY (~0ull)
+
+__device__ __forceinline__ u32 mix64(u64 k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdULL;
+  k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ULL;
+  k ^= k >> 33;
+  return (u32)k;
+}
+
+// find-or-insert; returns slot, or ~0u when the probe sequence is exhausted
+__device__ __forceinline__ u32 table_upsert(const PairTable& t, u64 key, bool& fresh) {
+  const u32 mask = t.cap - 1;
+  u32 h = mix64(key) & mask;
+  fresh = false;
+  for (u32 probe = 0; probe < 512; probe++) {
+    u64 k = t.keys[h];
+    if (k == key) return h;
+    if (k == TBL_EMPTY) {
+      k = atomicCAS(t.keys + h, TBL_EMPTY, key);
+      if (k == TBL_EMPTY) { fresh = true; return h; }
+      if (k == key) return h;
+    }
+    h = (h + 1) & mask;
+  }
+  return ~0u;
+}
+
+__global__ void __launch_bounds__(256)
+k_pair_insert(const float* __restrict__ pExpt, const float* __restrict__ pCtrl, u64 n,
+              PairTable t, u32* __restrict__ slot, int* __restrict__ err) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  bool fresh = false;
+  bool bad = false;
+  if (i < n) {
+    const u64 key = ((u64)__float_as_uint(pExpt[i]) << 32) | __float_as_uint(pCtrl[i]);
+    const u32 h = table_upsert(t, key, fresh);
+    bad = h == ~0u;
+    slot[i] = bad ? 0u : h;
+  }
+  const u32 nf = __popc(__ballot_sync(GR_FULL, fresh));
+  if ((threadIdx.x & 31) == 0 && nf) {
+    const u32 tot = atomicAdd(t.count, nf) + nf;
+    if (tot > (t.cap >> 1)) bad = true;
+  }
+  if (bad) atomicOr(err, GR_DE_TABLE);
+}
+
+void launch_pair_insert(cudaStream_t s, const u32* pEnd, const float* pExpt, const float* pCtrl,
+                        u64 n, const PairTable& t, u32* slot, int accumulate_len, int* err) {
+  (void)pEnd; (void)accumulate_len;
+  if (!n) return;
+  k_pair_insert<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pExpt, pCtrl, n, t, slot, err); GR_NOTE_LAUNCH();
+}
+
+__global__ void __launch_bounds__(128)
+k_pair_eval(PairTable t) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.cap) return;
+  const u64 k = t.keys[i];
+  if (k == TBL_EMPTY) return;
+  t.pval[i] = gm_calc_pval(__uint_as_float((u32)(k >> 32)), __uint_as_float((u32)k));
+}
+void launch_pair_eval(cudaStream_t s, const PairTable& t) {
+  k_pair_eval<<<(t.cap + 127) / 128, 128, 0, s>>>(t); GR_NOTE_LAUNCH();
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_f32(const float* __restrict__ table, const u32* __restrict__ slot, u64 n,
+             float* __restrict__ out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const u32 s = slot[i];
+    out[i] = s == ~0u ? -1.0f : table[s];      // ~0: SKIP interval, never entered in the table
+  }
+}
+void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n, float* out) {
+  if (n) { k_gather_f32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(table, slot, n, out); GR_NOTE_LAUNCH(); }
+}
+
+// histogram insert keyed by the bits of -log10 p; lengths are added with one
+// atomic per distinct key per warp (hot keys such as p == 0 would otherwise
+// serialise in L2).  SKIP (-1) is not recorded (hashPval 319).
+__global__ void __launch_bounds__(256)
+k_key_insert(const u32* __restrict__ pEnd, const float* __restrict__ pval, u64 n,
+             const u64* __restrict__ chrom_start, int nchrom, PairTable t,
+             u32* __restrict__ slot, int* __restrict__ err) {
+  const u64 t0 = (u64)blockIdx.x * blockDim.x;
+  const u64 tl = min(t0 + blockDim.x, n) - 1;
+  const TileChrom tc = tile_chrom_range(chrom_start, nchrom, t0, tl);
+  const u64 i = t0 + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool fresh = false, bad = false;
+  u32 h = 0xfffffffeu;                 // lanes without a key never match a real slot
+  u32 len = 0;
+  if (i < n) {
+    const float p = pval[i];
+    if (p != -1.0f) {
+      const int c = tc.c0 == tc.c1 ? tc.c0 : chrom_of_index(chrom_start, nchrom, i);
+      const u32 e = pEnd[i];
+      len = e - (i == chrom_start[c] ? 0u : pEnd[i - 1]);
+      h = table_upsert(t, (u64)__float_as_uint(p), fresh);
+      bad = h == ~0u;
+      if (bad) h = 0xfffffffeu;
+      slot[i] = bad ? 0u : h;
+    } else
+      slot[i] = ~0u;
+  }
+  // warp-aggregate equal slots
+  const u32 peers = __match_any_sync(GR_FULL, h);
+  u64 tot = 0;
+  if (peers == (1u << lane)) tot = len;
+  else {
+    for (u32 rem = peers; rem; rem &= rem - 1) {
+      // every lane of the group walks the same member list
+      const int src = __ffs(rem) - 1;
+      tot += __shfl_sync(peers, len, src);
+    }
+  }
+  if (h < 0xfffffffeu && lane == __ffs(peers) - 1 && tot) atomicAdd(t.lens + h, tot);
+  const u32 nf = __popc(__ballot_sync(GR_FULL, fresh));
+  if (lane == 0 && nf) {
+    const u32 c2 = atomicAdd(t.count, nf) + nf;
+    if (c2 > (t.cap >> 1)) bad = true;
+  }
+  if (bad) atomicOr(err, GR_DE_TABLE);
+}
+
+void launch_key_insert(cudaStream_t s, const u32* pEnd, const float* pval, u64 n,
+                       const u64* chrom_start, int nchrom, const PairTable& t, u32* slot, int* err) {
+  if (!n) return;
+  k_key_insert<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pEnd, pval, n, chrom_start, nchrom, t, slot, err); GR_NOTE_LAUNCH();
+}
+
+// table -> dense (key, len) list
+__global__ void __launch_bounds__(256)
+k_table_compact(PairTable t, Lookback<1> lb, u32* __restrict__ keys_out,
+                u64* __restrict__ lens_out, u64* __restrict__ count_out, u32 ntiles) {
+  const u32 tile = take_ticket(lb.ticket);
+  const u32 i = tile * 256 + threadIdx.x;
+  const u64 k = i < t.cap ? t.keys[i] : TBL_EMPTY;
+  const u32 f = k != TBL_EMPTY;
+  u32 tot;
+  const u64 r = tile_exclusive_rank(lb, tile, f, tot);
+  if (f) { keys_out[r] = (u32)k; lens_out[r] = t.lens[i]; }
+  if (tile == ntiles - 1 && threadIdx.x == 255) *count_out = r + f;
+}
+
+void launch_table_compact(cudaStream_t s, const PairTable& t, const CompactScratch& sc,
+                          u32* keys_out, u64* lens_out, u64* count_out) {
+  const u32 ntiles = (t.cap + 255) / 256;
+  cudaMemsetAsync(sc.st, 0, (size_t)ntiles * sizeof(u64), s);
+  cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
+  Lookback<1> lb;
+  lb.st[0] = sc.st; lb.ticket = sc.ticket;
+  k_table_compact<<<ntiles, 256, 0, s>>>(t, lb, keys_out, lens_out, count_out, ntiles); GR_NOTE_LAUNCH();
+}
+
+// q of every occupied slot: binary search of its key among the distinct keys
+__global__ void __launch_bounds__(256)
+k_table_q(PairTable t, const u32* __restrict__ dk, const float* __restrict__ dq,
+          const u64* __restrict__ dcount) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= t.cap) return;
+  const u64 k = t.keys[i];
+  if (k == TBL_EMPTY) return;
+  const u32 key = (u32)k;
+  u64 lo = 0, hi = *dcount;
+  while (lo < hi) {
+    const u64 mid = (lo + hi) >> 1;
+    if (dk[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  t.qval[i] = dq[lo];
+}
+void launch_table_q(cudaStream_t s, const PairTable& t, const u32* dk, const float* dq, const u64* dcount) {
+  k_table_q<<<(t.cap + 255) / 256, 256, 0, s>>>(t, dk, dq, dcount); GR_NOTE_LAUNCH();
+}
+
+// ============================================================================
+// K6: Fisher's method over replicates (combinePval 612-667, multPval 567-583).
+// The union of the replicates' breakpoints is the OR of their union bitmaps; at
+// each combined break the replicate's interval number is its own bit rank.
+__global__ void __launch_bounds__(256)
+k_or_bitmaps(const u32* __restrict__ a, const u32* __restrict__ b, u32* __restrict__ out, u64 n) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] | b[i];
+}
+void launch_or_bitmaps(cudaStream_t s, const u32* a, const u32* b, u32* out, u64 nwords) {
+  if (nwords) { k_or_bitmaps<<<(unsigned)((nwords + 255) / 256), 256, 0, s>>>(a, b, out, nwords); GR_NOTE_LAUNCH(); }
+}
+
+void launch_block_rank(cudaStream_t s, const DevLayout& L, const u32* bm, const CompactScratch& sc,
+                       u64* rank, u64* total) {
+  // reuse the three-counter kernel with C absent: totals[] needs 3 entries
+  RankScratch rs;
+  rs.st[0] = sc.st; rs.st[1] = sc.st + L.nblocks; rs.st[2] = sc.st + 2 * L.nblocks;
+  rs.ticket = sc.ticket;
+  launch_union_rank(s, L, bm, nullptr, rs, rank, nullptr, rank, total);
+}
+
+__global__ void __launch_bounds__(256)
+k_fisher_emit(DevLayout L, const u32* __restrict__ bmAll, const u64* __restrict__ rankAll,
+              const RepView* __restrict__ reps, int nrep, u32* __restrict__ end_out,
+              double* __restrict__ sum_out, int* __restrict__ df_out, u64* __restrict__ chrom_start) {
+  __shared__ u32 sm_w[8];
+  const u32 blk = blockIdx.x;
+  const u64 widx = (u64)blk * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 A = bmAll[widx];
+  const int c = L.blk2chrom[blk];
+  const u64 off = L.off[c];
+  // rank of this word's first bit in the combined array
+  const u32 pa = __popc(A);
+  const u32 ia = warp_incl_scan_u32(pa, lane);
+  if (lane == 31) sm_w[w] = ia;
+  __syncthreads();
+  u32 xa = ia - pa;
+  for (int k = 0; k < w; k++) xa += sm_w[k];
+  const u64 u0 = rankAll[blk] + xa;
+  if (threadIdx.x == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = rankAll[blk];
+  const u32 jw = (u32)((u64)blk * GR_BLOCK_SLOTS + (u64)threadIdx.x * 32 - off);
+  {
+    u64 u = u0;
+    for (u32 m = A; m; m &= m - 1) {
+      end_out[u] = jw + (__ffs(m) - 1);
+      sum_out[u] = 0.0;
+      df_out[u] = 0;
+      u++;
+    }
+  }
+  for (int r = 0; r < nrep; r++) {                 // replicate order = summation order (570-574)
+    const RepView rv = reps[r];
+    __syncthreads();
+    if (!rv.present[c]) continue;                  // pval[j] == NULL (571)
+    const u32 R = rv.bmU[widx];
+    const u32 pr = __popc(R);
+    const u32 ir = warp_incl_scan_u32(pr, lane);
+    if (lane == 31) sm_w[w] = ir;
+    __syncthreads();
+    u32 xr = ir - pr;
+    for (int k = 0; k < w; k++) xr += sm_w[k];
+    const u64 r0 = rv.rankU[blk] + xr;
+    u64 u = u0;
+    for (u32 m = A; m; m &= m - 1) {
+      const int b = __ffs(m) - 1;
+      const float p = rv.pval[r0 + __popc(R & ((1u << b) - 1))];
+      if (p != -1.0f) {
+        sum_out[u] += (double)p;
+        df_out[u] += 2;
+      }
+      u++;
+    }
+  }
+}
+
+void launch_fisher_emit(cudaStream_t s, const DevLayout& L, const u32* bmAll, const u64* rankAll,
+                        const RepView* reps_dev, int nrep, u32* end_out, double* sum_out,
+                        int* df_out, u64* chrom_start, const u64* total) {
+  k_fisher_emit<<<(unsigned)L.nblocks, 256, 0, s>>>(L, bmAll, rankAll, reps_dev, nrep, end_out,
+                                                    sum_out, df_out, chrom_start); GR_NOTE_LAUNCH();
+  launch_fill_chrom_start(s, L, chrom_start, total);
+}
+
+__global__ void __launch_bounds__(128)
+k_fisher_eval(const double* __restrict__ sum, const int* __restrict__ df, u64 n,
+              float* __restrict__ out) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int d = df[i];
+  const double s = sum[i];
+  float r;
+  if (d == 0) r = -1.0f;
+  else if (d == 2 || s == 0.0) r = (float)s;
+  else {
+    const double p = gm_pchisq(2.0 * s / GR_LOG10E, d);
+    r = p > (double)FLT_MAX ? FLT_MAX : (float)p;
+  }
+  out[i] = r;
+}
+void launch_fisher_eval(cudaStream_t s, const double* sum, const int* df, u64 n, float* pcomb) {
+  if (n) { k_fisher_eval<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(sum, df, n, pcomb); GR_NOTE_LAUNCH(); }
+}
+

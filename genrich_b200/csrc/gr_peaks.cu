@@ -1,0 +1,181 @@
+// gr_peaks.cu -- K8: the peak scan (callPeaks 977-1069, updatePeak 943,
+// checkPeak 916, resetVars 932) restated for parallel execution.
+//
+// The reference walks the intervals of a chromosome once, carrying one open peak.
+// Equivalent formulation: the significant intervals (v > threshold) are linked
+// into candidate peaks; two consecutive significant intervals of a chromosome
+// stay in the same candidate unless a SKIP interval lies between them or the
+// non-significant stretch between them is longer than maxGap (the test at 1032
+// fires on the last such interval, whose end is the next significant start).
+// Each candidate is then walked sequentially by one thread, in interval order,
+// so the float AUC (950) and the summit rules (956-969) see the reference's
+// exact operation order.  Candidates are independent, so peaks run in parallel.
+#include "gr_tile.cuh"
+#include "gr_internal.h"
+
+#define PK_SKIP (-1.0f)
+
+// ---- events: indices of significant or SKIP intervals, in order -----------------
+__global__ void __launch_bounds__(256)
+k_peak_events(const float* __restrict__ v, u64 n, float thr, Lookback<1> lb,
+              u32* __restrict__ ev_idx, u64* __restrict__ ev_count, u32 ntiles) {
+  const u32 tile = take_ticket(lb.ticket);
+  const u64 i0 = ((u64)tile * 256 + threadIdx.x) * 4;
+  u32 m = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (i0 + k < n) {
+      const float x = v[i0 + k];
+      if (x > thr || x == PK_SKIP) m |= 1u << k;
+    }
+  u32 tot;
+  u64 r = tile_exclusive_rank(lb, tile, __popc(m), tot);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (m & (1u << k)) ev_idx[r++] = (u32)(i0 + k);
+  if (tile == ntiles - 1 && threadIdx.x == 255) *ev_count = r;
+}
+
+void launch_peak_events(cudaStream_t s, const float* v, u64 n, float thr, const PeakWork& w) {
+  cudaMemsetAsync(w.ev_count, 0, sizeof(u64), s);
+  if (!n) return;
+  const u32 ntiles = (u32)((n + 1023) / 1024);
+  cudaMemsetAsync(w.sc.st, 0, (size_t)ntiles * sizeof(u64), s);
+  cudaMemsetAsync(w.sc.ticket, 0, sizeof(u32), s);
+  Lookback<1> lb;
+  lb.st[0] = w.sc.st; lb.ticket = w.sc.ticket;
+  k_peak_events<<<ntiles, 256, 0, s>>>(v, n, thr, lb, w.ev_idx, w.ev_count, ntiles); GR_NOTE_LAUNCH();
+}
+
+// ---- heads: events that open a candidate ------------------------------------------
+__global__ void __launch_bounds__(256)
+k_peak_heads(const u32* __restrict__ pEnd, const float* __restrict__ v,
+             const u64* __restrict__ chrom_start, int nchrom, int max_gap,
+             const u32* __restrict__ ev_idx, const u64* __restrict__ ev_count, Lookback<1> lb,
+             u32* __restrict__ head_idx, u64* __restrict__ head_count) {
+  const u64 nev = *ev_count;
+  const u32 tile = take_ticket(lb.ticket);
+  const u64 t = (u64)tile * 256 + threadIdx.x;
+  u32 head = 0;
+  if (t < nev) {
+    const u32 idx = ev_idx[t];
+    if (v[idx] != PK_SKIP) {
+      head = 1;
+      if (t > 0) {
+        const u32 prev = ev_idx[t - 1];
+        if (v[prev] != PK_SKIP) {
+          const int c = chrom_of_index(chrom_start, nchrom, idx);
+          if ((u64)prev >= chrom_start[c]) {                 // same chromosome
+            if (prev + 1 == idx) head = 0;                   // adjacent: no interval in between
+            else {
+              const i64 gap = (i64)pEnd[idx - 1] - (i64)pEnd[prev];   // start[idx] - peakEnd
+              if (!(gap > (i64)max_gap)) head = 0;           // 1032
+            }
+          }
+        }
+      }
+    }
+  }
+  u32 tot;
+  const u64 r = tile_exclusive_rank(lb, tile, head, tot);
+  if (head) head_idx[r] = (u32)t;
+  // every tile up to the capacity runs; the one holding the last event reports
+  if (t + 1 == nev) *head_count = r + head;
+}
+
+// ---- walk: one thread per candidate ------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_peak_walk(const u32* __restrict__ pEnd, const float* __restrict__ pval,
+            const float* __restrict__ qval, const u64* __restrict__ chrom_start, int nchrom,
+            float thr, int qopt, float min_auc, int min_len,
+            const u32* __restrict__ ev_idx, const u64* __restrict__ ev_count,
+            const u32* __restrict__ head_idx, const u64* __restrict__ head_count,
+            PeakRec* __restrict__ cand, uint8_t* __restrict__ cand_ok) {
+  const u64 h = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  const u64 nh = *head_count;
+  if (h >= nh) return;
+  const u64 nev = *ev_count;
+  const u64 t0 = head_idx[h];
+  const u64 t1 = h + 1 < nh ? head_idx[h + 1] : nev;
+  const float* __restrict__ v = qopt ? qval : pval;
+  const u32 first = ev_idx[t0];
+  const int c = chrom_of_index(chrom_start, nchrom, first);
+  const u64 cs = chrom_start[c];
+
+  float auc = 0.0f, sVal = -1.0f, sP = -1.0f, sQ = -1.0f;     // 1001-1006
+  i64 pStart = -1, pEndv = -1;
+  u32 sPos = 0, sLen = 0;
+  for (u64 t = t0; t < t1; t++) {
+    const u32 idx = ev_idx[t];
+    const float x = v[idx];
+    if (x == PK_SKIP) break;                                    // 1031: SKIP closes the candidate
+    const u32 end = pEnd[idx];
+    const u32 start = (u64)idx == cs ? 0u : pEnd[idx - 1];
+    const u32 len = end - start;
+    auc = __fadd_rn(auc, __fmul_rn(__uint2float_rn(len), __fsub_rn(x, thr)));   // 950, no FMA
+    if (pStart == -1) pStart = start;
+    pEndv = end;
+    if (x > sVal) {                                             // 956-961
+      sVal = x;
+      sP = pval[idx];
+      sQ = qopt ? qval[idx] : PK_SKIP;
+      sPos = (u32)((end + start) / 2 - (u32)pStart);            // uint32 arithmetic, 960
+      sLen = len;
+    } else if (x == sVal && len > sLen) {                       // 962-968
+      sPos = (u32)((end + start) / 2 - (u32)pStart);
+      sLen = len;
+    }
+  }
+  PeakRec r;
+  r.chrom = c; r.summit = sPos; r.start = pStart; r.end = pEndv;
+  r.auc = auc; r.pval = sP; r.qval = sQ; r.reserved = 0.0f;
+  cand[h] = r;
+  cand_ok[h] = (pStart != -1 && auc >= min_auc && pEndv - pStart >= (i64)min_len) ? 1 : 0;   // 920
+}
+
+__global__ void __launch_bounds__(256)
+k_peak_compact(const PeakRec* __restrict__ cand, const uint8_t* __restrict__ ok,
+               const u64* __restrict__ head_count, Lookback<1> lb, PeakRec* __restrict__ out,
+               u64* __restrict__ out_count, u64* __restrict__ peak_bp) {
+  const u64 nh = *head_count;
+  const u32 tile = take_ticket(lb.ticket);
+  const u64 h = (u64)tile * 256 + threadIdx.x;
+  const u32 f = h < nh && ok[h];
+  u32 tot;
+  const u64 r = tile_exclusive_rank(lb, tile, f, tot);
+  u64 bp = 0;
+  if (f) {
+    const PeakRec p = cand[h];
+    out[r] = p;
+    bp = (u64)(p.end - p.start);                               // 924
+  }
+  bp = warp_sum_u64(bp);
+  if ((threadIdx.x & 31) == 0 && bp) atomicAdd(peak_bp, bp);
+  if (h + 1 == nh) *out_count = r + f;
+}
+
+// The three follow-up kernels are sized by the event / head counts, which the
+// host reads back once (two u64) after the events kernel.
+void launch_peak_chain(cudaStream_t s, const u32* pEnd, const float* pval, const float* qval,
+                       const u64* chrom_start, int nchrom, float thr, int qopt, int max_gap,
+                       float min_auc, int min_len, const PeakWork& w, u64 nev) {
+  cudaMemsetAsync(w.head_count, 0, sizeof(u64), s);
+  cudaMemsetAsync(w.out_count, 0, sizeof(u64), s);
+  cudaMemsetAsync(w.peak_bp, 0, sizeof(u64), s);
+  if (!nev) return;
+  const float* v = qopt ? qval : pval;
+  const u32 nt = (u32)((nev + 255) / 256);
+  Lookback<1> lb;
+  lb.st[0] = w.sc.st; lb.ticket = w.sc.ticket;
+  cudaMemsetAsync(w.sc.st, 0, (size_t)nt * sizeof(u64), s);
+  cudaMemsetAsync(w.sc.ticket, 0, sizeof(u32), s);
+  k_peak_heads<<<nt, 256, 0, s>>>(pEnd, v, chrom_start, nchrom, max_gap, w.ev_idx, w.ev_count, lb,
+                                  w.head_idx, w.head_count); GR_NOTE_LAUNCH();
+  // heads <= events: size the walk and the compaction by nev
+  k_peak_walk<<<(unsigned)((nev + 127) / 128), 128, 0, s>>>(pEnd, pval, qval, chrom_start, nchrom, thr,
+                                                            qopt, min_auc, min_len, w.ev_idx, w.ev_count,
+                                                            w.head_idx, w.head_count, w.cand, w.cand_ok); GR_NOTE_LAUNCH();
+  cudaMemsetAsync(w.sc.st, 0, (size_t)nt * sizeof(u64), s);
+  cudaMemsetAsync(w.sc.ticket, 0, sizeof(u32), s);
+  k_peak_compact<<<nt, 256, 0, s>>>(w.cand, w.cand_ok, w.head_count, lb, w.out, w.out_count, w.peak_bp); GR_NOTE_LAUNCH();
+}

@@ -1,0 +1,146 @@
+"""Multi-GPU dispatcher: chromosomes sharded over ranks, one process per GPU.
+
+This is what runProgram's per-chromosome loop (Genrich.c:5460-5607) becomes.  Every
+rank owns a subset of the chromosomes (greedy LPT by length) and runs the whole
+hot path on them; only three things cross ranks, all through torch.distributed:
+
+  * per-chromosome sum(len*val) of the experimental pileup  -> lambda   (all_reduce, nchrom doubles)
+  * per-chromosome sum(len*val) of the control pileup       -> factor   (all_reduce, nchrom doubles)
+  * the histogram of distinct -log10 p that Benjamini-Hochberg needs    (all_gather, -q only)
+
+Each chromosome has exactly one non-zero contributor, so the all_reduce is exact,
+and the totals are then added in chromosome order on every rank: lambda and the
+scale factor are bit-identical to the single-GPU run.  Peaks come back to rank 0
+in chromosome order (callPeaks numbers them globally, Genrich.c:986).
+
+The engine is whatever :class:`~genrich_b200.capi.Api` the caller passes -- the CUDA
+library in production (NCCL backend), and in the CPU test-suite the oracle twin
+(gloo backend), which exercises exactly this host logic.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+import torch.distributed as td
+
+from .capi import Api, Context, GrParams, PEAK_DTYPE
+from .host import lpt_shard
+
+
+class _CudaView:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def _tensor_from_ptr(ptr: int, n: int, np_dtype, device: torch.device) -> torch.Tensor:
+    if n == 0:
+        return torch.empty(0, dtype=torch.from_numpy(np.empty(0, np_dtype)).dtype, device=device)
+    if device.type == "cuda":
+        return torch.as_tensor(_CudaView(ptr, n, np.dtype(np_dtype).str), device=device)
+    buf = (C.c_char * (n * np.dtype(np_dtype).itemsize)).from_address(ptr)
+    return torch.from_numpy(np.frombuffer(buf, dtype=np_dtype, count=n).copy())
+
+
+class ShardedEngine:
+    def __init__(self, api: Api, chrom_len, params: GrParams, device: torch.device, skip=None):
+        self.world = td.get_world_size() if td.is_initialized() else 1
+        self.rank = td.get_rank() if td.is_initialized() else 0
+        self.device = device
+        self.chrom_len = np.asarray(chrom_len, dtype=np.uint32)
+        self.nchrom = len(chrom_len)
+        self.skip = np.zeros(self.nchrom, np.uint8) if skip is None else np.asarray(skip, np.uint8)
+        self.owner = lpt_shard(np.where(self.skip != 0, 0, self.chrom_len), self.world)
+        self.owned = (self.owner == self.rank).astype(np.uint8)
+        dev_index = device.index if device.type == "cuda" and device.index is not None else 0
+        self.ctx = Context(api, chrom_len, params, device=dev_index, skip=self.skip, owned=self.owned)
+        self.params = params
+        self.saved_any = np.zeros(self.nchrom, dtype=bool)
+        self.sample_stats = []
+
+    # records of chromosomes this rank does not own are dropped here (host routing)
+    def route(self, recs: np.ndarray) -> np.ndarray:
+        recs = np.ascontiguousarray(recs, dtype=np.int32).reshape(-1, 4)
+        if self.world == 1:
+            return recs
+        return recs[self.owned[recs[:, 0]] != 0]
+
+    def _reduce_sums(self, sums: np.ndarray) -> float:
+        if self.world > 1:
+            t = torch.from_numpy(sums).to(self.device)
+            td.all_reduce(t, op=td.ReduceOp.SUM)
+            sums = t.cpu().numpy()
+        tot = 0.0
+        for v in sums:                       # chromosome order, like the reference's running sum
+            tot += float(v)
+        return tot
+
+    def replicate(self, push_expt, push_ctrl=None, save=None):
+        """push_*: callables that feed this rank's records into self.ctx."""
+        sv = np.ones(self.nchrom, np.uint8) if save is None else np.asarray(save, np.uint8)
+        self.saved_any |= (sv != 0) & (self.skip == 0)
+        self.ctx.sample_begin(False, sv)
+        push_expt(self.ctx)
+        frag = self._reduce_sums(self.ctx.sample_pileup())
+        ctrl = 0.0
+        if push_ctrl is not None:
+            self.ctx.sample_begin(True)
+            push_ctrl(self.ctx)
+            ctrl = self._reduce_sums(self.ctx.sample_pileup())
+        glen = int(self.chrom_len[(sv != 0) & (self.skip == 0)].astype(np.int64).sum())   # calcLambda 1819-1827
+        st = self.ctx.replicate_finish(frag, ctrl, push_ctrl is not None, glen)
+        self.sample_stats.append(st)
+        return st
+
+    def _exchange_histogram(self):
+        kp, lp, n = self.ctx.bh_local_hist_ptrs()
+        keys = _tensor_from_ptr(kp, n, np.uint32, self.device).view(torch.int32)
+        lens = _tensor_from_ptr(lp, n, np.uint64, self.device).view(torch.int64)
+        if self.world > 1:
+            cnt = torch.tensor([n], dtype=torch.int64, device=self.device)
+            cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+            td.all_gather(cnts, cnt)
+            sizes = [int(c.item()) for c in cnts]
+            m = max(max(sizes), 1)
+            kpad = torch.zeros(m, dtype=torch.int32, device=self.device)
+            lpad = torch.zeros(m, dtype=torch.int64, device=self.device)
+            kpad[:n] = keys
+            lpad[:n] = lens
+            kall = [torch.empty_like(kpad) for _ in range(self.world)]
+            lall = [torch.empty_like(lpad) for _ in range(self.world)]
+            td.all_gather(kall, kpad)        # the one data-path collective (NCCL over NVLink)
+            td.all_gather(lall, lpad)
+            keys = torch.cat([k[:s] for k, s in zip(kall, sizes)]).contiguous()
+            lens = torch.cat([l[:s] for l, s in zip(lall, sizes)]).contiguous()
+        return keys, lens
+
+    def call_peaks(self):
+        """Returns (peaks, run_stats) -- peaks of ALL chromosomes on rank 0, own peaks elsewhere."""
+        self.ctx.pvalues_finalize()
+        if self.params.qval_opt:
+            G = int(self.params.genome_len) or int(self.chrom_len[self.saved_any].astype(np.int64).sum())
+            keys, lens = self._exchange_histogram()
+            if self.device.type == "cuda":
+                torch.cuda.current_stream(self.device).synchronize()
+            self._keep = (keys, lens)
+            self.ctx.bh_set_global_ptrs(keys.data_ptr(), lens.data_ptr(), keys.numel(), G)
+        peaks, rs = self.ctx.call_peaks()
+        if self.world > 1:
+            buf = torch.from_numpy(peaks.view(np.uint8).copy()).to(self.device)
+            cnt = torch.tensor([buf.numel()], dtype=torch.int64, device=self.device)
+            cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+            td.all_gather(cnts, cnt)
+            sizes = [int(c.item()) for c in cnts]
+            m = max(max(sizes), 1)
+            pad = torch.zeros(m, dtype=torch.uint8, device=self.device)
+            pad[:buf.numel()] = buf
+            allb = [torch.empty_like(pad) for _ in range(self.world)]
+            td.all_gather(allb, pad)
+            parts = [np.frombuffer(b[:s].cpu().numpy().tobytes(), dtype=PEAK_DTYPE) for b, s in zip(allb, sizes)]
+            allp = np.concatenate(parts) if parts else peaks
+            order = np.lexsort((allp["start"], allp["chrom"]))
+            peaks = allp[order]
+        return peaks, rs

@@ -118,6 +118,8 @@ int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
               const gr_params* params, int32_t device);
 void gr_destroy(gr_ctx* ctx);
 int gr_set_params(gr_ctx* ctx, const gr_params* params);
+/* Forget all replicates and results (a new runProgram on the same chromosome table). */
+int gr_reset(gr_ctx* ctx);
 const char* gr_strerror(int status);
 const char* gr_last_error_detail(const gr_ctx* ctx);
 
@@ -183,6 +185,9 @@ int gr_timing_enable(gr_ctx* ctx, int32_t on);
 int gr_timing_get(gr_ctx* ctx, gr_stage_time* out, int32_t cap, int32_t* n);
 int gr_timing_reset(gr_ctx* ctx);
 uint64_t gr_kernel_launches(const gr_ctx* ctx);
+/* CUDA events on the library's own stream: ms between start and stop as the device saw it */
+int gr_timer_start(gr_ctx* ctx);
+int gr_timer_stop(gr_ctx* ctx, double* ms);
 int gr_synchronize(gr_ctx* ctx);
 
 #ifdef __cplusplus

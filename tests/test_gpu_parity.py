@@ -1,0 +1,216 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the pinned CPU oracle on the
+same seeded inputs, against the reference's own narrowPeak files (tests/golden), and
+-- at sizes the oracle cannot reach in seconds -- through size-independent
+properties.  Bars: bit-exact for coordinates, interval partitions, pileup floats,
+lambda, scale factor; <= 1e-4 absolute on -log10 p / -log10 q (BASELINE.json)."""
+import numpy as np
+import pytest
+
+import util
+from cases import CASES, BY_NAME, Case, Sample
+from genrich_b200 import capi, host
+from genrich_b200.synth import Workload
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+def _bits(a):
+    return np.asarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _cmp_intervals(g, o, exact_val, what):
+    assert (g is None) == (o is None), what
+    if g is None:
+        return 0.0
+    assert np.array_equal(g.end, o.end), what + ": interval ends differ"
+    if exact_val:
+        assert np.array_equal(_bits(g.val), _bits(o.val)), what + ": values differ"
+        return 0.0
+    fin = np.isfinite(o.val) & (o.val < 3e38)
+    assert np.array_equal(_bits(g.val[~fin]), _bits(o.val[~fin])), what
+    d = np.max(np.abs(g.val[fin].astype(np.float64) - o.val[fin])) if fin.any() else 0.0
+    assert d <= TOL, (what, d)
+    return d
+
+
+def _parse_np(lines):
+    rows = []
+    for l in lines:
+        f = l.split("\t")
+        rows.append((f[0], int(f[1]), int(f[2]), int(f[4]), float(f[6]), float(f[7]), float(f[8]), int(f[9])))
+    return rows
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_case_matches_oracle_and_reference(case):
+    inputs = util.case_inputs(case)
+    ctx_o, res_o, par = util.run_case(util.oracle_api(), case, inputs=inputs)
+    ctx_g, res_g, _ = util.run_case(capi.load_cuda(), case, inputs=inputs)
+    nrep = len(case.reps)
+
+    # scalars of every replicate: bit-exact
+    for so, sg in zip(res_o.sample_stats, res_g.sample_stats):
+        assert _bits(sg.lambda_) == _bits(so.lambda_)
+        assert _bits(sg.factor) == _bits(so.factor)
+        assert sg.frag_len == so.frag_len and sg.ctrl_frag == so.ctrl_frag
+        assert (sg.n_expt, sg.n_ctrl, sg.n_pval, sg.n_clamped, sg.genome_len) == \
+               (so.n_expt, so.n_ctrl, so.n_pval, so.n_clamped, so.genome_len)
+
+    # pileups of the last replicate, p arrays of every replicate, combined p, q
+    worst = 0.0
+    for ci in range(len(case.chrom_len)):
+        _cmp_intervals(ctx_g.fetch(0, 0, ci), ctx_o.fetch(0, 0, ci), True, "expt pileup chr%d" % ci)
+        _cmp_intervals(ctx_g.fetch(1, 0, ci), ctx_o.fetch(1, 0, ci), True, "ctrl pileup chr%d" % ci)
+        for r in range(nrep + (1 if nrep > 1 else 0)):
+            g, o = ctx_g.fetch(2, r, ci), ctx_o.fetch(2, r, ci)
+            worst = max(worst, _cmp_intervals(g, o, False, "p rep%d chr%d" % (r, ci)))
+            if g is not None and r < nrep:
+                assert np.array_equal(_bits(g.expt), _bits(o.expt))
+                assert np.array_equal(_bits(g.ctrl), _bits(o.ctrl))
+        if case.q is not None:
+            worst = max(worst, _cmp_intervals(ctx_g.fetch(3, 0, ci), ctx_o.fetch(3, 0, ci), False, "q chr%d" % ci))
+
+    # peaks vs the oracle
+    a, b = res_g.peaks, res_o.peaks
+    assert len(a) == len(b)
+    for f in ("chrom", "start", "end", "summit"):
+        assert np.array_equal(a[f], b[f]), f
+    if len(a):
+        assert np.max(np.abs(a["pval"] - b["pval"])) <= TOL
+        assert np.max(np.abs(a["qval"] - b["qval"])) <= TOL
+        assert np.allclose(a["auc"], b["auc"], rtol=1e-4, atol=1e-3)
+    rg, ro = res_g.run_stats, res_o.run_stats
+    assert (rg.genome_len, rg.n_peaks, rg.peak_bp, rg.n_intervals, rg.all_q_one, rg.n_replicates) == \
+           (ro.genome_len, ro.n_peaks, ro.peak_bp, ro.n_intervals, ro.all_q_one, ro.n_replicates)
+    if case.q is not None:
+        assert rg.n_distinct_p == ro.n_distinct_p
+
+    # peaks vs the reference's own narrowPeak file: coordinates and counts bit-exact
+    meta, gold = util.golden(case)
+    got = _parse_np(host.format_narrowpeak(a, util.names_of(case)))
+    ref = _parse_np(gold)
+    assert len(got) == len(ref) == meta["peaks"]
+    for x, y in zip(got, ref):
+        assert x[:3] == y[:3] and x[7] == y[7], (x, y)         # chrom, start, end, summit
+        assert abs(x[5] - y[5]) <= TOL + 1e-6 and abs(x[6] - y[6]) <= TOL + 1e-6
+        assert abs(x[4] - y[4]) <= 1e-4 * max(1.0, abs(y[4]))
+        assert abs(x[3] - y[3]) <= 1
+    print("%s: worst |d(-log10 p/q)| = %.3g" % (case.name, worst))
+
+
+def test_repeatable_and_chunking_invariant():
+    """Same input pushed in different chunkings / twice gives identical bits
+    (integer atomics and the fixed-point length sums are order-free)."""
+    case = BY_NAME["c5_multimap_ctrl_p"]
+    inputs = util.case_inputs(case)
+    api = capi.load_cuda()
+    outs = []
+    for chunk in (1 << 22, 7001, 1 << 22):
+        ctx = capi.Context(api, case.chrom_len, util.case_params(case))
+        res = host.run_replicates(ctx, inputs, chunk=chunk)
+        p = [ctx.fetch(2, 0, c) for c in range(len(case.chrom_len))]
+        outs.append((res, p))
+    for res, p in outs[1:]:
+        assert res.peaks.tobytes() == outs[0][0].peaks.tobytes()
+        assert res.sample_stats[0].frag_len == outs[0][0].sample_stats[0].frag_len
+        for x, y in zip(p, outs[0][1]):
+            assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
+
+
+def test_edge_inputs():
+    api = capi.load_cuda()
+    orc = util.oracle_api()
+    L = [5000, 8192, 8191, 1, 20000]
+    recs = np.array([
+        [0, 0, 5000, 1],         # whole chromosome
+        [0, -50, 10, 2],         # clamped at 0
+        [0, 4990, 6000, 3],      # clamped at len
+        [1, 0, 1, 1], [1, 8191, 8192, 1],   # first and last base of a block-sized chromosome
+        [2, 8190, 8191, 10], [2, 0, 8191, 8],
+        [3, 0, 1, 1],            # one-base chromosome
+        [4, 100, 100, 5],        # empty interval: +w and -w on the same cell
+        [4, 300, 900, 6], [4, 300, 900, 6], [4, 300, 900, 6], [4, 300, 900, 6], [4, 300, 900, 6], [4, 300, 900, 6],
+        [4, 19999, 25000, 4],
+    ], dtype=np.int32)
+    for q in (None, 0.5):
+        par = capi.make_params(p=0.2 if q is None else None, q=q, min_auc=0.5, keep_pileups=True)
+        res = []
+        for a in (orc, api):
+            ctx = capi.Context(a, L, par)
+            r = host.run_replicates(ctx, [(recs, None)])
+            res.append((ctx, r))
+        (co, ro), (cg, rg) = res
+        assert ro.sample_stats[0].n_clamped == rg.sample_stats[0].n_clamped == 3
+        assert _bits(ro.sample_stats[0].lambda_) == _bits(rg.sample_stats[0].lambda_)
+        for ci in range(len(L)):
+            _cmp_intervals(cg.fetch(0, 0, ci), co.fetch(0, 0, ci), True, "edge expt %d" % ci)
+            _cmp_intervals(cg.fetch(2, 0, ci), co.fetch(2, 0, ci), False, "edge p %d" % ci)
+        assert np.array_equal(rg.peaks["start"], ro.peaks["start"]) and np.array_equal(rg.peaks["end"], ro.peaks["end"])
+
+
+def test_error_codes():
+    api = capi.load_cuda()
+    par = capi.make_params(p=0.01)
+    # start beyond the reference end -> ERRPOS (Genrich.c:2531)
+    ctx = capi.Context(api, [1000], par)
+    ctx.sample_begin(False)
+    ctx.push_intervals(np.array([[0, 1000, 1100, 1]], dtype=np.int32))
+    with pytest.raises(capi.GenrichError) as e:
+        ctx.sample_pileup()
+    assert e.value.status == 4
+    # disallowed count -> ERRALNS (2400)
+    ctx = capi.Context(api, [1000], par)
+    ctx.sample_begin(False)
+    ctx.push_intervals(np.array([[0, 10, 20, 7]], dtype=np.int32))
+    with pytest.raises(capi.GenrichError) as e:
+        ctx.sample_pileup()
+    assert e.value.status == 8
+    # no fragments at all -> ERREXPT (2292)
+    ctx = capi.Context(api, [1000], par)
+    ctx.sample_begin(False)
+    with pytest.raises(capi.GenrichError) as e:
+        ctx.replicate_end()
+    assert e.value.status == 5
+
+
+def test_large_properties():
+    """200 Mbp / 4 M + 4 M fragments: properties that need no oracle.
+    sum(interval lengths) == genome; every chromosome's last end == its length;
+    ends strictly increase; sum(len*val) of the experimental pileup == total
+    fragment bp (exact for integer weights); peaks lie inside chromosomes, are
+    ordered, and every summit is inside its peak; a second run is bit-identical."""
+    L = [60_000_000, 50_000_000, 40_000_000, 30_000_000, 20_000_000]
+    t = Workload(L, 4_000_000, 101, enrich=0.3, spacing=40000, sigma=100.0).fragments()
+    c = Workload(L, 4_000_000, 102, enrich=0.0).fragments()
+    api = capi.load_cuda()
+    par = capi.make_params(q=0.05)
+    runs = []
+    for _ in range(2):
+        ctx = capi.Context(api, L, par)
+        res = host.run_replicates(ctx, [(t, c)])
+        runs.append((ctx, res))
+    ctx, res = runs[0]
+    st = res.sample_stats[0]
+    assert st.frag_len == float(np.sum((t[:, 2] - t[:, 1]).astype(np.int64)))
+    assert st.ctrl_frag == float(np.sum((c[:, 2] - c[:, 1]).astype(np.int64)))
+    tot = 0
+    for ci, ln in enumerate(L):
+        for which in (0, 1, 2, 3):
+            iv = ctx.fetch(which, 0, ci)
+            assert iv.end[-1] == ln
+            assert np.all(np.diff(iv.end.astype(np.int64)) > 0)
+        iv = ctx.fetch(2, 0, ci)
+        tot += int(iv.end[-1])
+        q = ctx.fetch(3, 0, ci)
+        assert np.all(q.val >= 0) and np.all(q.val <= iv.val + 1e-3)     # q <= p on the -log10 scale
+    assert tot == sum(L) == res.run_stats.genome_len
+    pk = res.peaks
+    assert len(pk) > 100
+    assert np.all(pk["start"] < pk["end"]) and np.all(pk["end"] <= np.asarray(L)[pk["chrom"]])
+    assert np.all(pk["summit"] < pk["end"] - pk["start"])
+    key = pk["chrom"].astype(np.int64) * (1 << 32) + pk["start"]
+    assert np.all(np.diff(key) > 0)
+    assert np.all(pk["qval"] > par.min_pqval)
+    assert runs[1][1].peaks.tobytes() == pk.tobytes()
