@@ -71,6 +71,7 @@ ABI_SYMBOLS = [
     "gr_bh_set_global", "gr_call_peaks", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
     "gr_kernel_launches", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
+    "gr_pinned_alloc", "gr_pinned_free",
 ]
 
 STATUS_TEXT = {

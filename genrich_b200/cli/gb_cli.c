@@ -1,0 +1,424 @@
+/* gb_cli.c -- genrich-b200: the Genrich command line over libgenrich_cuda.so.
+ *
+ * Same options, inputs, outputs, messages and exit status as the reference
+ * (getArgs 5718-5827, runProgram 5386-5695, usage 34-71); the per-chromosome
+ * loops of runProgram/findPeaks are replaced by calls into the C-ABI of
+ * include/genrich_cuda.h.  Not implemented on this path (fatal if requested):
+ *   -r/-R PCR duplicate removal, -E BED exclusions, -P peaks from a log file.
+ */
+#include "gb_host.h"
+#include <float.h>
+#include <getopt.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+void* gr_pinned_alloc(size_t bytes);     /* exported by libgenrich_cuda.so */
+void gr_pinned_free(void* p);
+
+#define GB_OPTIONS "ht:c:o:f:k:b:zyw:xjd:De:E:m:s:p:q:a:l:g:rR:XPSL:vVG:"
+
+static struct option gb_long[] = {
+  {"help", no_argument, NULL, 'h'}, {"verbose", no_argument, NULL, 'v'},
+  {"version", no_argument, NULL, 'V'}, {"gpu", required_argument, NULL, 'G'}, {0, 0, 0, 0}
+};
+
+static void usage(void) {
+  fprintf(stderr, "Usage: ./genrich-b200  -t <file>  -o <file>  [optional arguments]\n");
+  fprintf(stderr, "Required arguments:\n");
+  fprintf(stderr, "  -t  <file>       Input SAM/BAM file(s) for experimental sample(s)\n");
+  fprintf(stderr, "  -o  <file>       Output peak file (in ENCODE narrowPeak format)\n");
+  fprintf(stderr, "Optional I/O arguments:\n");
+  fprintf(stderr, "  -c  <file>       Input SAM/BAM file(s) for control sample(s)\n");
+  fprintf(stderr, "  -f  <file>       Output bedgraph-ish file for p/q values\n");
+  fprintf(stderr, "  -k  <file>       Output bedgraph-ish file for pileups and p-values\n");
+  fprintf(stderr, "  -b  <file>       Output BED file for reads/fragments/intervals\n");
+  fprintf(stderr, "Filtering options:\n");
+  fprintf(stderr, "  -e  <arg>        Comma-separated list of chromosomes to exclude\n");
+  fprintf(stderr, "  -m  <int>        Minimum MAPQ to keep an alignment (def. 0)\n");
+  fprintf(stderr, "  -s  <float>      Keep sec alns with AS >= bestAS - <float> (def. 0)\n");
+  fprintf(stderr, "  -y               Keep unpaired alignments (def. false)\n");
+  fprintf(stderr, "  -w  <int>        Keep unpaired alns, lengths changed to <int>\n");
+  fprintf(stderr, "  -x               Keep unpaired alns, lengths changed to paired avg\n");
+  fprintf(stderr, "Options for ATAC-seq:\n");
+  fprintf(stderr, "  -j               Use ATAC-seq mode (def. false)\n");
+  fprintf(stderr, "  -d  <int>        Expand cut sites to <int> bp (def. 100)\n");
+  fprintf(stderr, "  -D               Skip Tn5 adjustments of cut sites (def. false)\n");
+  fprintf(stderr, "Options for peak-calling:\n");
+  fprintf(stderr, "  -p  <float>      Maximum p-value (def. 0.01)\n");
+  fprintf(stderr, "  -q  <float>      Maximum q-value (FDR-adjusted p-value; def. 1)\n");
+  fprintf(stderr, "  -a  <float>      Minimum AUC for a peak (def. 200.0)\n");
+  fprintf(stderr, "  -l  <int>        Minimum length of a peak (def. 0)\n");
+  fprintf(stderr, "  -g  <int>        Maximum distance between signif. sites (def. 100)\n");
+  fprintf(stderr, "Other options:\n");
+  fprintf(stderr, "  -X               Skip peak-calling\n");
+  fprintf(stderr, "  -z               Option to gzip-compress output(s)\n");
+  fprintf(stderr, "  -v               Option to print status updates/counts to stderr\n");
+  fprintf(stderr, "  --gpu <int>      CUDA device to use (def. 0)\n");
+  exit(EXIT_FAILURE);
+}
+
+/* logCounts 5295-5374 (without the duplicate-removal block) */
+static void log_counts(const HDecode* d, bool bam) {
+  const HCounts* c = &d->cnt;
+  const HOpts* o = d->opt;
+  if (c->err_count > GB_MAX_ALNS)
+    fprintf(stderr, "(another %ld warning messages suppressed)\n", (long)(c->err_count - GB_MAX_ALNS));
+  const double avg = c->paired_pr ? c->total_len / c->paired_pr : 0.0;
+  fprintf(stderr, "  %s records analyzed: %11ld\n", bam ? "BAM" : "SAM", (long)c->count);
+  if (c->unmapped) fprintf(stderr, "    Unmapped:           %11ld\n", (long)c->unmapped);
+  if (c->supp) fprintf(stderr, "    Supp./dups/lowQual: %11ld\n", (long)c->supp);
+  if (c->skipped) {
+    fprintf(stderr, "    To skipped refs:    %11ld\n", (long)c->skipped);
+    fprintf(stderr, "      (");
+    bool first = true;
+    for (int i = 0; i < d->tab->n; i++)
+      if (d->tab->c[i].skip || !d->tab->c[i].save) {
+        fprintf(stderr, "%s%s", first ? "" : ",", d->tab->c[i].name);
+        first = false;
+      }
+    fprintf(stderr, ")\n");
+  }
+  if (c->low_mapq) fprintf(stderr, "    MAPQ < %-2d:          %11ld\n", o->min_mapq, (long)c->low_mapq);
+  fprintf(stderr, "    Paired alignments:  %11ld\n", (long)c->paired);
+  if (c->sec_pair) fprintf(stderr, "      secondary alns:   %11ld\n", (long)c->sec_pair);
+  if (c->orphan) fprintf(stderr, "      \"orphan\" alns:    %11ld\t** Warning! **\n", (long)c->orphan);
+  fprintf(stderr, "    Unpaired alignments:%11ld\n", (long)c->single);
+  if (c->sec_single) fprintf(stderr, "      secondary alns:   %11ld\n", (long)c->sec_single);
+  fprintf(stderr, "  Fragments analyzed:   %11ld\n", (long)(c->single_pr + c->paired_pr));
+  fprintf(stderr, "    Full fragments:     %11ld\n", (long)c->paired_pr);
+  if (c->paired_pr && !o->atac_opt) fprintf(stderr, "      (avg. length: %.1fbp)\n", avg);
+  if (o->single_opt) {
+    fprintf(stderr, "    Half fragments:     %11ld\n", (long)c->single_pr);
+    if (c->single_pr) {
+      fprintf(stderr, "      (from unpaired alns");
+      if (o->extend_opt) fprintf(stderr, ", extended to %dbp", o->extend);
+      else if (o->avg_ext_opt && c->paired_pr) fprintf(stderr, ", extended to %dbp", (int)(avg + 0.5));
+      fprintf(stderr, ")\n");
+    }
+  }
+  if (o->atac_opt) {
+    fprintf(stderr, "    ATAC-seq cut sites: %11ld\n", (long)(2 * c->paired_pr + c->single_pr));
+    fprintf(stderr, "      (expanded to length %dbp)\n", o->atac_len5 + o->atac_len3);
+  }
+}
+
+static void chk(gr_ctx* ctx, int rc, const char* what) {
+  if (!rc) return;
+  /* statuses that correspond to one of the reference's errCode cases print its text */
+  if (rc == GR_ERR_EXPT || rc == GR_ERR_GENOME || rc == GR_ERR_MEM) gb_die("", gr_strerror(rc));
+  char msg[1024];
+  snprintf(msg, sizeof msg, "%s: %s %s", what, gr_strerror(rc), ctx ? gr_last_error_detail(ctx) : "");
+  gb_die(msg, rc == GR_ERR_PILE || rc == GR_ERR_COUNT || rc == GR_ERR_DF
+         ? "\n  (internal error: please open an Issue on https://github.com/jsh58/Genrich)" : "");
+}
+
+/* split a list on ", " like strtok_r(.., COM, ..) at Genrich.c:5457 */
+static int split_list(char* s, char*** out) {
+  int n = 0;
+  *out = NULL;
+  if (!s) return 0;
+  char* save;
+  for (char* t = strtok_r(s, ", ", &save); t; t = strtok_r(NULL, ", ", &save)) {
+    *out = (char**)gb_realloc(*out, (n + 1) * sizeof(char*));
+    (*out)[n++] = t;
+  }
+  return n;
+}
+
+/* -k: printPileHeader 1680 + printPile 1697 for one replicate */
+static void write_pile(gr_ctx* ctx, HOut* out, const HChromTab* tab, int rep, const char* ename, const char* cname) {
+  gb_out_printf(out, "# experimental file: %s; control file: %s\n", ename,
+                cname && strcmp(cname, "null") ? cname : "NA");
+  gb_out_printf(out, "chr\tstart\tend\texperimental\tcontrol\t-log(p)\n");
+  for (int c = 0; c < tab->n; c++) {
+    const uint32_t* end; const float *val, *ex, *ct; uint64_t n;
+    chk(ctx, gr_fetch_intervals(ctx, 2, rep, c, &end, &val, &ex, &ct, &n), "fetch");
+    uint32_t start = 0;
+    for (uint64_t m = 0; m < n; m++) {
+      if (ct[m] == GR_SKIP)
+        gb_out_printf(out, "%s\t%d\t%d\t%f\t%f\t%s\n", tab->c[c].name, start, end[m], ex[m], 0.0f, "NA");
+      else
+        gb_out_printf(out, "%s\t%d\t%d\t%f\t%f\t%f\n", tab->c[c].name, start, end[m], ex[m], ct[m], val[m]);
+      start = end[m];
+    }
+  }
+}
+
+typedef struct { uint32_t* end; float *val, *ex, *ct; uint64_t n; } Arr;
+static Arr fetch_copy(gr_ctx* ctx, int which, int rep, int c, bool cols) {
+  const uint32_t* end; const float *val, *ex, *ct; uint64_t n;
+  chk(ctx, gr_fetch_intervals(ctx, which, rep, c, &end, &val, &ex, &ct, &n), "fetch");
+  Arr a = { NULL, NULL, NULL, NULL, n };
+  if (!n || !end) { a.n = 0; return a; }
+  a.end = (uint32_t*)gb_alloc(n * 4); memcpy(a.end, end, n * 4);
+  a.val = (float*)gb_alloc(n * 4); memcpy(a.val, val, n * 4);
+  if (cols && ex) {
+    a.ex = (float*)gb_alloc(n * 4); memcpy(a.ex, ex, n * 4);
+    a.ct = (float*)gb_alloc(n * 4); memcpy(a.ct, ct, n * 4);
+  }
+  return a;
+}
+static void arr_free(Arr* a) { free(a->end); free(a->val); free(a->ex); free(a->ct); }
+
+/* -f: printLogHeader 674 + printInterval 770 / printIntervalN 724 as callPeaks / logIntervals emit them */
+static void write_log(gr_ctx* ctx, HOut* out, const HChromTab* tab, int nrep, const HOpts* o, float thr) {
+  const bool sig_col = o->peaks_opt, q = o->qval_opt;
+  if (nrep > 1) {
+    gb_out_printf(out, "chr\tstart\tend");
+    for (int i = 0; i < nrep; i++) gb_out_printf(out, "\t-log(p)_%d", i);
+    gb_out_printf(out, "\t-log(p)_comb");
+  } else
+    gb_out_printf(out, "chr\tstart\tend\texperimental\tcontrol\t-log(p)");
+  if (q) gb_out_printf(out, "\t-log(q)");
+  if (sig_col) gb_out_printf(out, "\tsignif");
+  gb_out_printf(out, "\n");
+  for (int c = 0; c < tab->n; c++) {
+    Arr fin = fetch_copy(ctx, 2, nrep > 1 ? nrep : 0, c, nrep == 1);
+    if (!fin.n) continue;
+    Arr qv = { 0 };
+    if (q) qv = fetch_copy(ctx, 3, 0, c, false);
+    Arr* reps = NULL;
+    uint64_t* idx = NULL;
+    if (nrep > 1) {
+      reps = (Arr*)gb_alloc(nrep * sizeof(Arr));
+      idx = (uint64_t*)calloc(nrep, sizeof(uint64_t));
+      for (int r = 0; r < nrep; r++) reps[r] = fetch_copy(ctx, 2, r, c, false);
+    }
+    uint32_t start = 0;
+    for (uint64_t m = 0; m < fin.n; m++) {
+      const float pv = fin.val[m], qq = q ? qv.val[m] : GR_SKIP;
+      const bool sig = sig_col && (q ? qq : pv) > thr;
+      if (nrep == 1) {
+        if (fin.ct[m] == GR_SKIP) {
+          gb_out_printf(out, "%s\t%d\t%d\t%f\t%f\t%s", tab->c[c].name, start, fin.end[m], fin.ex[m], 0.0f, "NA");
+          if (q) gb_out_printf(out, "\t%s", "NA");
+          gb_out_printf(out, "\n");
+        } else {
+          gb_out_printf(out, "%s\t%d\t%d\t%f\t%f\t%f", tab->c[c].name, start, fin.end[m], fin.ex[m], fin.ct[m], pv);
+          if (q) gb_out_printf(out, "\t%f", qq);
+          gb_out_printf(out, "%s\n", sig ? "\t*" : "");
+        }
+      } else {
+        gb_out_printf(out, "%s\t%d\t%d", tab->c[c].name, start, fin.end[m]);
+        for (int r = 0; r < nrep; r++) {
+          if (!reps[r].n || reps[r].val[idx[r]] == GR_SKIP) gb_out_printf(out, "\t%s", "NA");
+          else gb_out_printf(out, "\t%f", reps[r].val[idx[r]]);
+        }
+        if (pv == GR_SKIP) {
+          gb_out_printf(out, "\t%s", "NA");
+          if (q) gb_out_printf(out, "\t%s", "NA");
+        } else {
+          gb_out_printf(out, "\t%f", pv);
+          if (q) gb_out_printf(out, "\t%f", qq);
+        }
+        gb_out_printf(out, "%s\n", sig ? "\t*" : "");
+        for (int r = 0; r < nrep; r++)
+          if (reps[r].n && reps[r].end[idx[r]] == fin.end[m]) idx[r]++;
+      }
+      start = fin.end[m];
+    }
+    arr_free(&fin);
+    if (q) arr_free(&qv);
+    if (reps) { for (int r = 0; r < nrep; r++) arr_free(&reps[r]); free(reps); free(idx); }
+  }
+}
+
+int main(int argc, char** argv) {
+  HOpts o;
+  memset(&o, 0, sizeof o);
+  o.min_len = 0; o.max_gap = 100; o.atac_len5 = 100; o.pqvalue = 0.01f; o.min_auc = 200.0f;
+  o.atac_adj = true; o.peaks_opt = true; o.sort_opt = true;
+  bool dups = false, peaks_only = false;
+  char* xfile = NULL;
+  int c;
+  while ((c = getopt_long(argc, argv, GB_OPTIONS, gb_long, NULL)) != -1)
+    switch (c) {
+      case 't': o.in_files = optarg; break;
+      case 'c': o.ctrl_files = optarg; break;
+      case 'o': o.out_file = optarg; break;
+      case 'f': o.log_file = optarg; break;
+      case 'k': o.pile_file = optarg; break;
+      case 'b': o.bed_file = optarg; break;
+      case 'z': o.gz_out = true; break;
+      case 'y': o.single_opt = true; break;
+      case 'w': o.extend = gb_parse_int(optarg); o.extend_opt = true; break;
+      case 'x': o.avg_ext_opt = true; break;
+      case 'j': o.atac_opt = true; break;
+      case 'd': o.atac_len5 = gb_parse_int(optarg); break;
+      case 'D': o.atac_adj = false; break;
+      case 'e': o.xchrom = optarg; break;
+      case 'E': xfile = optarg; break;
+      case 'm': o.min_mapq = gb_parse_int(optarg); break;
+      case 's': o.as_diff = gb_parse_float(optarg); break;
+      case 'p': o.pqvalue = gb_parse_float(optarg); break;
+      case 'q': o.pqvalue = gb_parse_float(optarg); o.qval_opt = true; break;
+      case 'a': o.min_auc = gb_parse_float(optarg); break;
+      case 'l': o.min_len = gb_parse_int(optarg); break;
+      case 'g': o.max_gap = gb_parse_int(optarg); break;
+      case 'r': dups = true; break;
+      case 'R': dups = true; break;
+      case 'X': o.peaks_opt = false; break;
+      case 'P': peaks_only = true; break;
+      case 'S': o.sort_opt = false; break;
+      case 'L': { char* e; o.genome_len = (uint64_t)strtol(optarg, &e, 10); if (*e) gb_die(optarg, ": cannot convert to int"); break; }
+      case 'v': o.verbose = true; break;
+      case 'V': fprintf(stderr, "genrich-b200, version %s\n", GB_VERSION); exit(EXIT_FAILURE);
+      case 'G': o.device = gb_parse_int(optarg); break;
+      case 'h': usage(); break;
+      default: exit(EXIT_FAILURE);
+    }
+  if (optind < argc) gb_die(argv[optind], ": unknown command-line argument");
+  if ((o.peaks_opt && !o.out_file) || !o.in_files) {
+    fprintf(stderr, "Error! Need input/output files\n");
+    usage();
+  }
+  if (dups) gb_die("-r/-R", ": PCR duplicate removal is not available in genrich-b200");
+  if (xfile) gb_die("-E", ": BED exclusion lists are not available in genrich-b200");
+  if (peaks_only) gb_die("-P", ": peak-calling from a log file is not available in genrich-b200");
+  if (o.avg_ext_opt) { o.single_opt = true; o.extend_opt = false; }
+  if (o.extend_opt) { o.single_opt = true; if (o.extend <= 0) gb_die("", "Extension length must be > 0"); }
+  if (o.atac_opt) {
+    o.avg_ext_opt = o.extend_opt = false;
+    if (o.atac_len5 <= 0) gb_die("", "ATAC-seq interval length must be > 0");
+    o.atac_len3 = (int)(o.atac_len5 / 2.0f + 0.5f);
+    o.atac_len5 /= 2;
+  }
+  if (o.min_len < 0) gb_die("", "Minimum peak length must be >= 0");
+  if (o.min_auc < 0.0f) gb_die("", "Minimum AUC must be >= 0.0");
+  if (o.as_diff < 0.0f) gb_die("", "Secondary alignment score threshold must be >= 0.0");
+  if (o.pqvalue <= 0.0f || o.pqvalue > 1.0f) gb_die("", "p-/q-value must be in (0,1]");
+  const float thr = -log10f(o.pqvalue);                       /* 5817 */
+
+  /* file lists */
+  char **tf, **cf;
+  const int nt = split_list(o.in_files, &tf);
+  const int ncf = split_list(o.ctrl_files, &cf);
+  if (!nt) { fprintf(stderr, "Error! Need input/output files\n"); usage(); }
+
+  /* the engine needs the whole chromosome table first: header-only pass, in the
+   * order the reference meets the files (t0, c0, t1, c1, ...) */
+  HChromTab tab = { NULL, 0 };
+  for (int r = 0; r < nt; r++) {
+    gb_scan_header(tf[r], &tab, false, &o);
+    if (r < ncf && strcmp(cf[r], "null")) gb_scan_header(cf[r], &tab, true, &o);
+  }
+  if (!tab.n) gb_die("", "No analyzable genome (length=0)");
+  gr_chrom* gc = (gr_chrom*)gb_alloc(tab.n * sizeof(gr_chrom));
+  for (int i = 0; i < tab.n; i++) {
+    gc[i].len = tab.c[i].len;
+    gc[i].skip = tab.c[i].skip || !tab.c[i].ever_saved;     /* control-only references are never used (4244) */
+    gc[i].owned = 1;
+    gc[i].reserved = 0;
+  }
+  gr_params par;
+  par.min_pqval = thr; par.qval_opt = o.qval_opt; par.min_auc = o.min_auc; par.min_len = o.min_len;
+  par.max_gap = o.max_gap; par.keep_pileups = (o.log_file || o.pile_file) ? 1 : 0; par.genome_len = o.genome_len;
+  gr_ctx* ctx = NULL;
+  chk(NULL, gr_create(&ctx, gc, tab.n, &par, o.device), "gr_create");
+
+  HOut bed = { NULL, NULL }, pile = { NULL, NULL };
+  if (o.bed_file) gb_out_open(&bed, o.bed_file, o.gz_out);
+  if (o.pile_file) gb_out_open(&pile, o.pile_file, o.gz_out);
+  HIvBuf buf;
+  buf.cap = 1u << 20;
+  buf.n = 0;
+  buf.recs = (int32_t*)gr_pinned_alloc(buf.cap * 16);
+  if (!buf.recs) gb_die("", "Cannot allocate memory");
+  uint8_t* save = (uint8_t*)gb_alloc(tab.n);
+
+  HDecode d;
+  memset(&d, 0, sizeof d);
+  d.opt = &o; d.tab = &tab; d.ctx = ctx; d.buf = &buf; d.bed = o.bed_file ? &bed : NULL;
+
+  for (int r = 0; r < nt; r++) {
+    const char* cname = r < ncf ? cf[r] : NULL;
+    const bool has_ctrl = cname && strcmp(cname, "null");
+    for (int i = 0; i < tab.n; i++) tab.c[i].save = false;          /* 5463-5464 */
+    gb_scan_header(tf[r], &tab, false, &o);
+    for (int i = 0; i < tab.n; i++) save[i] = tab.c[i].save;
+    for (int s = 0; s < 2; s++) {
+      const char* fname = s ? cname : tf[r];
+      if (s && !has_ctrl) {
+        if (o.verbose) fprintf(stderr, "- control file #%d not provided -\n", r);
+        break;
+      }
+      HIn probe;
+      gb_in_open(&probe, fname);
+      const bool bam = probe.is_bam;
+      gb_in_close(&probe, fname);
+      if (o.verbose)
+        fprintf(stderr, "Processing %s file #%d: %s\n", s ? "control" : "experimental", r, fname);
+      chk(ctx, gr_sample_begin(ctx, s, s ? NULL : save), "gr_sample_begin");
+      memset(&d.cnt, 0, sizeof d.cnt);
+      d.ctrl = s; d.sample = r;
+      gb_decode_file(&d, fname);
+      if (o.verbose) log_counts(&d, bam);
+      if (!s && has_ctrl) chk(ctx, gr_sample_pileup(ctx, NULL), "gr_sample_pileup");
+    }
+    gr_sample_stats st;
+    chk(ctx, gr_replicate_end(ctx, &st), "gr_replicate_end");
+    if (o.verbose) {
+      fprintf(stderr, "  Background pileup value: %f\n", st.lambda);                 /* 1888, 2058 */
+      if (has_ctrl) {
+        fprintf(stderr, "  Scaling factor for control pileup: %f\n", st.factor);     /* 2063 */
+        if (st.factor > 5.0f) fprintf(stderr, "  ** Warning! Large scaling may mask true signal **\n");
+      }
+    }
+    if (o.pile_file) write_pile(ctx, &pile, &tab, r, tf[r], cname);
+  }
+
+  const gr_peak* peaks = NULL;
+  uint64_t npk = 0;
+  gr_run_stats rs;
+  memset(&rs, 0, sizeof rs);
+  if (o.peaks_opt || o.log_file) {
+    if (!o.peaks_opt) {
+      /* -X: p (and q) only; a threshold no value can pass keeps the peak list empty */
+      gr_params p2 = par;
+      p2.min_pqval = FLT_MAX;
+      gr_set_params(ctx, &p2);
+    }
+    chk(ctx, gr_call_peaks(ctx, &peaks, &npk, &rs), "gr_call_peaks");
+  }
+  if (o.verbose) {                                                    /* findPeaks 1103-1117 */
+    if (o.peaks_opt) {
+      fprintf(stderr, "Peak-calling parameters:\n");
+      fprintf(stderr, "  Genome length: %ldbp\n", (long)rs.genome_len);
+      fprintf(stderr, "  Significance threshold: -log(%c) > %.3f\n", o.qval_opt ? 'q' : 'p', thr);
+      fprintf(stderr, "  Min. AUC: %.3f\n", o.min_auc);
+      if (o.min_len) fprintf(stderr, "  Min. peak length: %dbp\n", o.min_len);
+      fprintf(stderr, "  Max. gap between sites: %dbp\n", o.max_gap);
+    } else {
+      fprintf(stderr, "- peak-calling skipped -\n");
+      fprintf(stderr, "  Genome length: %ldbp\n", (long)rs.genome_len);
+    }
+    if (o.qval_opt && rs.all_q_one) fprintf(stderr, "Warning! All q-values are 1\n");
+  }
+  if (o.peaks_opt) {
+    HOut out;
+    gb_out_open(&out, o.out_file, o.gz_out);
+    for (uint64_t i = 0; i < npk; i++) {                              /* printPeak 885-909 */
+      const gr_peak* p = &peaks[i];
+      unsigned score = (unsigned)(1000.0f * p->auc / (p->end - p->start) + 0.5f);
+      if (score > 1000) score = 1000;
+      gb_out_printf(&out, "%s\t%ld\t%ld\tpeak_%d\t%d\t.\t%f\t%f", tab.c[p->chrom].name, (long)p->start,
+                    (long)p->end, (int)i, score, p->auc, p->pval);
+      if (p->qval == GR_SKIP) gb_out_printf(&out, "\t-1\t%d\n", p->summit);
+      else gb_out_printf(&out, "\t%f\t%d\n", p->qval, p->summit);
+    }
+    gb_out_close(&out, o.out_file);
+    if (o.verbose) fprintf(stderr, "Peaks identified: %d (%ldbp)\n", (int)npk, (long)rs.peak_bp);
+  }
+  if (o.log_file) {
+    HOut lg;
+    gb_out_open(&lg, o.log_file, o.gz_out);
+    write_log(ctx, &lg, &tab, nt, &o, thr);
+    gb_out_close(&lg, o.log_file);
+  }
+  if (o.pile_file) gb_out_close(&pile, o.pile_file);
+  if (o.bed_file) gb_out_close(&bed, o.bed_file);
+  gr_pinned_free(buf.recs);
+  gr_destroy(ctx);
+  return EXIT_SUCCESS;
+}

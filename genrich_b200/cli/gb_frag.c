@@ -1,0 +1,257 @@
+/* gb_frag.c -- mate pairing, multimap weighting and interval transforms on the
+ * host cores; the output is the stream of (chrom, start, end, count) records the
+ * device consumes.  Behaviour follows parseAlign (Genrich.c:4141-4212),
+ * processAlns (3187-3265), processPair (3122-3176), processSingle (3019-3083),
+ * subsamplePair/Single (3089, 2985), saveFragment (2754), saveFragAtac (2728),
+ * saveUnpair (2689), processAvgExt (2614) and the clamping half of saveInterval
+ * (2522-2544); -r duplicate removal is not implemented. */
+#include "gb_host.h"
+#include <stdlib.h>
+#include <string.h>
+
+#define ATAC_ADJ_F 5      /* ATACADJF, Genrich.h:35 */
+#define ATAC_ADJ_R (-5)   /* ATACADJR, Genrich.h:36 */
+
+void gb_flush_intervals(HDecode* d) {
+  if (!d->buf->n) return;
+  int rc = gr_push_intervals(d->ctx, d->buf->recs, d->buf->n);
+  if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
+  d->buf->n = 0;
+}
+
+/* saveInterval 2516-2591, host half: clamp, messages, BED line, enqueue */
+void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const char* qname, uint8_t count) {
+  const HChrom* c = &d->tab->c[chrom];
+  if (start < 0) {
+    if (d->opt->verbose) {
+      if (d->cnt.err_count < GB_MAX_ALNS)
+        fprintf(stderr, "Warning! Read %s prevented from extending below 0 on %s\n", qname, c->name);
+      d->cnt.err_count++;
+    }
+    start = 0;
+  }
+  if (start >= (int64_t)c->len) {
+    char msg[2 * GB_MAX_ALNS + 32];
+    snprintf(msg, sizeof msg, "Read %s, ref. %s", qname, c->name);
+    gb_die(msg, ": read aligned beyond reference end");
+  }
+  if (end > (int64_t)c->len) {
+    if (d->opt->verbose) {
+      if (d->cnt.err_count < GB_MAX_ALNS)
+        fprintf(stderr, "Warning! Read %s prevented from extending past %d on %s\n", qname, c->len, c->name);
+      d->cnt.err_count++;
+    }
+    end = c->len;
+  }
+  if (d->bed)
+    gb_out_printf(d->bed, "%s\t%ld\t%ld\t%s_%d_%c_%d\n", c->name, (long)start, (long)end, qname, count,
+                  d->ctrl ? 'C' : 'E', d->sample);
+  HIvBuf* b = d->buf;
+  if (b->n == b->cap) gb_flush_intervals(d);
+  int32_t* r = b->recs + 4 * b->n++;
+  r[0] = chrom; r[1] = (int32_t)start; r[2] = (int32_t)end; r[3] = count;
+}
+
+static bool usable(const HDecode* d, const HAln* a) {
+  const HChrom* c = &d->tab->c[a->chrom];
+  return c->save && !c->skip;
+}
+
+/* parseAlign 4141-4212 (without the -r quality sums) */
+bool gb_parse_align(HDecode* d, uint16_t flag, int chrom, uint32_t pos, int length, uint32_t pnext, float score) {
+  if (flag & 0x1) {
+    if ((flag & 0xC0) == 0xC0) gb_die("", "Linear template with >2 reads -- not allowed");
+    if (!(flag & 0xC0)) gb_die("", "Unknown index of paired alignment");
+  }
+  const HChrom* c = &d->tab->c[chrom];
+  const bool ignored = c->skip || !c->save;
+  const bool rev = flag & 0x10, r1 = flag & 0x40, secondary = flag & 0x100;
+  const uint32_t end5 = rev ? pos + length : pos;      /* 5' end of this read */
+  if ((flag & 0x3) == 0x3) {
+    if (ignored) d->cnt.skipped++;
+    else { d->cnt.paired++; if (secondary) d->cnt.sec_pair++; }
+    for (int i = 0; i < d->naln; i++) {                  /* look for the waiting mate, 4180-4190 */
+      HAln* a = &d->aln[i];
+      if (a->paired && !a->full && a->chrom == chrom
+          && (r1 ? (!a->first && a->pos[0] == pos) : (a->first && a->pos[1] == pos))
+          && (secondary ? !a->primary : a->primary)) {
+        if (r1) a->pos[0] = end5; else a->pos[1] = end5;   /* updatePairedAln 4049-4060 */
+        if (score == GB_NOSCORE) a->score = GB_NOSCORE;
+        else if (a->score != GB_NOSCORE) a->score += score;
+        a->full = true;
+        return true;
+      }
+    }
+    if (d->naln == GB_MAX_ALNS) return false;            /* savePairedAln 4066-4096 */
+    HAln* a = &d->aln[d->naln++];
+    a->chrom = chrom; a->score = score; a->primary = !secondary; a->full = false; a->paired = true;
+    a->strand = false;
+    if (r1) { a->pos[0] = end5; a->pos[1] = pnext; a->first = true; }
+    else { a->pos[0] = pnext; a->pos[1] = end5; a->first = false; }
+    return true;
+  }
+  if (ignored) d->cnt.skipped++;
+  else { d->cnt.single++; if (secondary) d->cnt.sec_single++; }
+  if (!d->opt->single_opt) return true;
+  if (d->naln == GB_MAX_ALNS) return false;              /* saveSingleAln 4102-4122 */
+  HAln* a = &d->aln[d->naln++];
+  a->chrom = chrom; a->score = score; a->primary = !secondary; a->paired = false; a->full = false;
+  a->strand = !rev; a->first = r1;
+  a->pos[0] = pos; a->pos[1] = pos + length;
+  return true;
+}
+
+/* counts 7, 9 and > 10 are cut back to 6, 8, 10 by raising the score floor to the
+ * (new count)-th best score (subsamplePair 3089-3115 / subsampleSingle 2985-3012) */
+static void tighten(float* scores, int k, uint8_t* count, float* floor_) {
+  for (int i = 1; i < k; i++) {             /* insertion sort, descending */
+    float v = scores[i];
+    int j = i - 1;
+    while (j >= 0 && scores[j] < v) { scores[j + 1] = scores[j]; j--; }
+    scores[j + 1] = v;
+  }
+  *count = *count > 10 ? 10 : (uint8_t)(*count - 1);
+  *floor_ = scores[*count - 1];
+}
+
+static void emit_fragment(HDecode* d, const char* qname, const HAln* a, uint8_t count, uint64_t* frag_len) {
+  const HOpts* o = d->opt;
+  uint32_t s = a->pos[0], e = a->pos[1];
+  if (s > e) { uint32_t t = s; s = e; e = t; }          /* saveFragment 2759-2766 */
+  if (!o->atac_opt) {
+    gb_emit_interval(d, a->chrom, s, e, qname, count);
+    *frag_len += (e > (uint32_t)d->tab->c[a->chrom].len ? d->tab->c[a->chrom].len : e) - s;
+    return;
+  }
+  if (o->atac_adj) { s += ATAC_ADJ_F; e += ATAC_ADJ_R; }   /* saveFragAtac 2733-2748, uint32 arithmetic */
+  if (s + o->atac_len3 >= (uint32_t)(int)(e - o->atac_len3))
+    gb_emit_interval(d, a->chrom, (int)(s - o->atac_len5), (int64_t)e + o->atac_len5, qname, count);
+  else {
+    gb_emit_interval(d, a->chrom, (int)(s - o->atac_len5), (int64_t)s + o->atac_len3, qname, count);
+    gb_emit_interval(d, a->chrom, (int)(e - o->atac_len3), (int64_t)e + o->atac_len5, qname, count);
+  }
+}
+
+static void emit_unpaired(HDecode* d, const char* qname, HAln* a, uint8_t count) {   /* saveUnpair 2689-2721 */
+  const HOpts* o = d->opt;
+  if (o->extend_opt) {
+    if (a->strand) gb_emit_interval(d, a->chrom, a->pos[0], (int64_t)a->pos[0] + o->extend, qname, count);
+    else gb_emit_interval(d, a->chrom, (int)(a->pos[1] - o->extend), a->pos[1], qname, count);
+  } else if (o->atac_opt) {
+    if (a->strand) {
+      if (o->atac_adj) a->pos[0] += ATAC_ADJ_F;
+      gb_emit_interval(d, a->chrom, (int)(a->pos[0] - o->atac_len5), (int64_t)a->pos[0] + o->atac_len3, qname, count);
+    } else {
+      if (o->atac_adj) a->pos[1] += ATAC_ADJ_R;
+      gb_emit_interval(d, a->chrom, (int)(a->pos[1] - o->atac_len3), (int64_t)a->pos[1] + o->atac_len5, qname, count);
+    }
+  } else
+    gb_emit_interval(d, a->chrom, a->pos[0], a->pos[1], qname, count);
+}
+
+static void defer_unpaired(HDecode* d, const char* qname, const HAln* a, uint8_t count) {   /* saveAvgExt 2654 */
+  if (d->n_unp == d->cap_unp) {
+    d->cap_unp = d->cap_unp ? 2 * d->cap_unp : 65536;
+    d->unp = (HUnpaired*)gb_realloc(d->unp, d->cap_unp * sizeof(HUnpaired));
+  }
+  HUnpaired* u = &d->unp[d->n_unp++];
+  u->chrom = a->chrom; u->pos[0] = a->pos[0]; u->pos[1] = a->pos[1]; u->strand = a->strand; u->count = count;
+  u->name = (char*)gb_alloc(strlen(qname) + 1);
+  strcpy(u->name, qname);
+}
+
+/* processPair 3122-3176 */
+static int do_pairs(HDecode* d, const char* qname, float best) {
+  float floor_ = best;
+  if (floor_ != GB_NOSCORE) floor_ -= d->opt->as_diff;
+  float sc[GB_MAX_ALNS];
+  int k = 0;
+  for (int i = 0; i < d->naln; i++) {
+    const HAln* a = &d->aln[i];
+    if (a->paired && a->full && a->score >= floor_ && usable(d, a)) sc[k++] = a->score;
+  }
+  if (!k) return 0;
+  uint8_t count = (uint8_t)k;
+  if (k > 10 || k == 7 || k == 9) tighten(sc, k, &count, &floor_);
+  uint64_t frag_len = 0;
+  uint8_t saved = 0;
+  for (int i = 0; i < d->naln && saved < count; i++) {
+    const HAln* a = &d->aln[i];
+    if (a->paired && a->full && a->score >= floor_ && usable(d, a)) {
+      emit_fragment(d, qname, a, count, &frag_len);
+      saved++;
+    }
+  }
+  d->cnt.total_len += (double)frag_len / count;
+  return 1;
+}
+
+/* processSingle 3019-3083 */
+static int do_singles(HDecode* d, const char* qname, float best, bool first) {
+  float floor_ = best;
+  if (floor_ != GB_NOSCORE) floor_ -= d->opt->as_diff;
+  float sc[GB_MAX_ALNS];
+  int k = 0;
+  for (int i = 0; i < d->naln; i++) {
+    const HAln* a = &d->aln[i];
+    if (!a->paired && a->first == first && a->score >= floor_ && usable(d, a)) sc[k++] = a->score;
+  }
+  if (!k) return 0;
+  uint8_t count = (uint8_t)k;
+  if (k > 10 || k == 7 || k == 9) tighten(sc, k, &count, &floor_);
+  uint8_t saved = 0;
+  for (int i = 0; i < d->naln && saved < count; i++) {
+    HAln* a = &d->aln[i];
+    if (!a->paired && a->first == first && a->score >= floor_ && usable(d, a)) {
+      if (d->opt->avg_ext_opt) defer_unpaired(d, qname, a, count);
+      else emit_unpaired(d, qname, a, count);
+      saved++;
+    }
+  }
+  return 1;
+}
+
+/* processAlns 3187-3265 */
+void gb_process_alns(HDecode* d, const char* qname) {
+  float best_pr = GB_NOSCORE, best_r1 = GB_NOSCORE, best_r2 = GB_NOSCORE;
+  bool pair = false, s1 = false, s2 = false;
+  for (int i = 0; i < d->naln; i++) {
+    const HAln* a = &d->aln[i];
+    if (a->paired) {
+      if (a->full) {
+        if (!pair || best_pr < a->score) best_pr = a->score;
+        pair = true;
+      } else
+        d->cnt.orphan++;
+    } else if (d->opt->single_opt && !pair) {
+      if (a->first && best_r1 <= a->score) { best_r1 = a->score; s1 = true; }
+      else if (!a->first && best_r2 <= a->score) { best_r2 = a->score; s2 = true; }
+    }
+  }
+  if (pair)
+    d->cnt.paired_pr += do_pairs(d, qname, best_pr);
+  else if (d->opt->single_opt) {
+    if (s1) d->cnt.single_pr += do_singles(d, qname, best_r1, true);
+    if (s2) d->cnt.single_pr += do_singles(d, qname, best_r2, false);
+  }
+}
+
+/* processAvgExt 2614-2647 (calcAvgLen 2597) */
+void gb_process_avg_ext(HDecode* d) {
+  int avg = 0;
+  if (!d->cnt.paired_pr) {
+    if (d->opt->verbose) {
+      fprintf(stderr, "Warning! No paired alignments to calculate avg frag ");
+      fprintf(stderr, "length --\n  Printing unpaired alignments \"as is\"\n");
+    }
+  } else
+    avg = (int)(d->cnt.total_len / d->cnt.paired_pr + 0.5);
+  for (size_t i = 0; i < d->n_unp; i++) {
+    HUnpaired* u = &d->unp[i];
+    if (!avg) gb_emit_interval(d, u->chrom, u->pos[0], u->pos[1], u->name, u->count);
+    else if (u->strand) gb_emit_interval(d, u->chrom, u->pos[0], (int64_t)u->pos[0] + avg, u->name, u->count);
+    else gb_emit_interval(d, u->chrom, (int)(u->pos[1] - avg), u->pos[1], u->name, u->count);
+    free(u->name);
+  }
+  d->n_unp = 0;
+}

@@ -1,0 +1,132 @@
+/* gb_host.h -- host side (plain C) of the genrich-b200 command-line program.
+ *
+ * Everything the reference does on the host stays on the host: option parsing
+ * (getArgs, Genrich.c:5718), SAM/BAM decode (readSAM 4468, readBAM 4983), mate
+ * pairing and fragment inference (parseAlign 4141, processAlns 3187), interval
+ * transforms (saveFragment 2754, saveFragAtac 2728, saveUnpair 2689) and the text
+ * writers (printPeak 885, printInterval 770, printPile 1697, printBED 2497).
+ * The hot path between them is libgenrich_cuda.so (include/genrich_cuda.h).
+ */
+#ifndef GB_HOST_H
+#define GB_HOST_H
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <zlib.h>
+#include "../../include/genrich_cuda.h"
+
+#define GB_VERSION   "0.6.2-b200"
+#define GB_MAX_LINE  65520     /* MAX_SIZE, Genrich.h:16 */
+#define GB_MAX_ALNS  128       /* MAX_ALNS, Genrich.h:17 */
+#define GB_NOSCORE   (-3.402823466e+38F)   /* NOSCORE = -FLT_MAX, Genrich.h:43 */
+
+typedef struct {
+  char* name;
+  uint32_t len;
+  bool skip;        /* -e */
+  bool save;        /* present in the current replicate's experimental header */
+  bool ever_saved;
+} HChrom;
+
+typedef struct {
+  HChrom* c;
+  int n;
+} HChromTab;
+
+/* one alignment of the current read name (Aln, Genrich.h:203-214) */
+typedef struct {
+  int chrom;
+  uint32_t pos[2];
+  float score;
+  bool primary, paired, full, first, strand;
+} HAln;
+
+typedef struct {        /* unpaired alignment deferred for -x */
+  int chrom;
+  uint32_t pos[2];
+  bool strand;
+  uint8_t count;
+  char* name;
+} HUnpaired;
+
+typedef struct {
+  /* files */
+  char *in_files, *ctrl_files, *out_file, *log_file, *pile_file, *bed_file, *xchrom;
+  /* options (same meaning and defaults as getArgs 5720-5733) */
+  bool gz_out, single_opt, extend_opt, avg_ext_opt, atac_opt, atac_adj, qval_opt;
+  bool peaks_opt, sort_opt, verbose;
+  int extend, min_mapq, min_len, max_gap, atac_len5, atac_len3;
+  float as_diff, pqvalue, min_auc;
+  uint64_t genome_len;
+  int device;
+} HOpts;
+
+typedef struct {        /* per-file counters (logCounts 5295) */
+  uint64_t count, unmapped, supp, skipped, low_mapq, paired, sec_pair, orphan;
+  uint64_t single, sec_single, single_pr, paired_pr, err_count;
+  double total_len;
+} HCounts;
+
+/* growable pinned buffer of int32 x 4 interval records */
+typedef struct {
+  int32_t* recs;
+  size_t n, cap;
+} HIvBuf;
+
+/* text sink: plain FILE or gzip */
+typedef struct {
+  FILE* f;
+  gzFile gz;
+} HOut;
+
+/* input stream: plain FILE or gzip/BGZF */
+typedef struct {
+  FILE* f;
+  gzFile gz;
+  bool is_gz, is_bam;
+} HIn;
+
+/* state of one input file being decoded */
+typedef struct {
+  const HOpts* opt;
+  HChromTab* tab;
+  gr_ctx* ctx;
+  HIvBuf* buf;
+  HOut* bed;            /* -b, may be NULL */
+  bool ctrl;
+  int sample;
+  HCounts cnt;
+  HAln aln[GB_MAX_ALNS];
+  int naln;
+  char read_name[GB_MAX_ALNS + 1];
+  HUnpaired* unp;       /* -x */
+  size_t n_unp, cap_unp;
+} HDecode;
+
+/* gb_util.c */
+void gb_die(const char* msg, const char* suffix);          /* "Error! <msg><suffix>" + exit(1), like error() 78 */
+void* gb_alloc(size_t n);
+void* gb_realloc(void* p, size_t n);
+int gb_parse_int(const char* s);
+float gb_parse_float(const char* s);
+void gb_out_open(HOut* o, const char* path, bool gz);      /* openWrite 5076 */
+void gb_out_close(HOut* o, const char* path);
+void gb_out_printf(HOut* o, const char* fmt, ...);
+bool gb_in_open(HIn* in, const char* path);                /* openRead 5132 + checkBAM 5107 */
+void gb_in_close(HIn* in, const char* path);
+char* gb_in_gets(HIn* in, char* line, int size);
+
+/* gb_decode.c */
+int gb_chrom_add(HChromTab* t, const char* name, uint32_t len, bool ctrl, const HOpts* opt);  /* saveChrom 4220 */
+int gb_chrom_find(const HChromTab* t, const char* name);
+void gb_scan_header(const char* path, HChromTab* tab, bool ctrl, const HOpts* opt);  /* header-only pass */
+void gb_decode_file(HDecode* d, const char* path);          /* readSAM 4468 / readBAM 4983 */
+void gb_flush_intervals(HDecode* d);
+
+/* gb_frag.c */
+bool gb_parse_align(HDecode* d, uint16_t flag, int chrom, uint32_t pos, int length, uint32_t pnext, float score);
+void gb_process_alns(HDecode* d, const char* qname);
+void gb_process_avg_ext(HDecode* d);
+void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const char* qname, uint8_t count);
+
+#endif

@@ -100,6 +100,7 @@ struct gr_ctx {
 
   // replicates and final arrays
   std::vector<Replicate*> reps;
+  std::vector<Replicate*> pool;     // released replicates, buffers kept for reuse
   bool finalized = false;
   Replicate* comb = nullptr;       // Fisher-combined (nrep > 1)
   Replicate* fin = nullptr;        // points at reps[0] or comb
@@ -280,11 +281,31 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
   return GR_OK;
 }
 
-static void free_reps(gr_ctx* x) {
-  for (auto* r : x->reps) { r->release(); delete r; }
+static void free_reps(gr_ctx* x, bool keep_buffers = false) {
+  for (auto* r : x->reps) {
+    if (keep_buffers) x->pool.push_back(r);
+    else { r->release(); delete r; }
+  }
   x->reps.clear();
-  if (x->comb) { x->comb->release(); delete x->comb; x->comb = nullptr; }
+  if (x->comb) {
+    if (keep_buffers) x->pool.push_back(x->comb);
+    else { x->comb->release(); delete x->comb; }
+    x->comb = nullptr;
+  }
+  if (!keep_buffers) {
+    for (auto* r : x->pool) { r->release(); delete r; }
+    x->pool.clear();
+  }
   x->fin = nullptr;
+}
+static Replicate* new_replicate(gr_ctx* x) {
+  if (!x->pool.empty()) {
+    Replicate* r = x->pool.back();
+    x->pool.pop_back();
+    r->n = 0; r->has_cols = false;
+    return r;
+  }
+  return new Replicate();
 }
 
 extern "C" void gr_destroy(gr_ctx* x) {
@@ -326,7 +347,7 @@ extern "C" int gr_reset(gr_ctx* x) {
   if (!x) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
   CK(cudaStreamSynchronize(x->stream));
-  free_reps(x);
+  free_reps(x, true);
   x->finalized = false; x->have_q = false; x->have_expt = x->have_ctrl = false;
   x->filling = FILL_NONE; x->hist_cap = 0; x->peaks_h.clear();
   return GR_OK;
@@ -570,7 +591,7 @@ extern "C" int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag,
   RankScratch rs;
   rs.st[0] = x->lb0.as<u64>(); rs.st[1] = x->lb1.as<u64>(); rs.st[2] = x->lb2.as<u64>();
   rs.ticket = x->ticket.as<u32>();
-  Replicate* rep = new Replicate();
+  Replicate* rep = new_replicate(x);
   x->reps.push_back(rep);
   CK(rep->bmU.ensure(x->T / 8));
   CK(rep->rankU.ensure(x->nblocks * sizeof(u64)));
@@ -625,7 +646,6 @@ extern "C" int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag,
                      cudaMemcpyDeviceToHost, x->stream));
   CK(cudaStreamSynchronize(x->stream));
   rep->has_cols = x->par.keep_pileups != 0;
-  if (!rep->has_cols) { rep->pExpt.release(); rep->pCtrl.release(); }
 
   x->have_expt = x->have_ctrl = false;
   x->finalized = false;
@@ -664,7 +684,7 @@ extern "C" int gr_pvalues_finalize(gr_ctx* x) {
   CK(cudaSetDevice(x->device));
   const int nrep = (int)x->reps.size();
   if (nrep > 200) return GR_ERR_DF;                            // pchisq 556
-  if (x->comb) { x->comb->release(); delete x->comb; x->comb = nullptr; }
+  if (x->comb) { x->pool.push_back(x->comb); x->comb = nullptr; }
   x->have_q = false;
   if (nrep == 1) {
     x->fin = x->reps[0];
@@ -672,7 +692,7 @@ extern "C" int gr_pvalues_finalize(gr_ctx* x) {
     return GR_OK;
   }
   const int nc = x->nchrom;
-  Replicate* cb = new Replicate();
+  Replicate* cb = new_replicate(x);
   x->comb = cb;
   CK(cb->bmU.ensure(x->T / 8));
   CK(cb->rankU.ensure(x->nblocks * sizeof(u64)));
@@ -1016,3 +1036,10 @@ extern "C" int gr_timer_stop(gr_ctx* x, double* ms) {
   *ms = f;
   return GR_OK;
 }
+
+extern "C" void* gr_pinned_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void gr_pinned_free(void* p) { if (p) cudaFreeHost(p); }

@@ -189,6 +189,9 @@ uint64_t gr_kernel_launches(const gr_ctx* ctx);
 int gr_timer_start(gr_ctx* ctx);
 int gr_timer_stop(gr_ctx* ctx, double* ms);
 int gr_synchronize(gr_ctx* ctx);
+/* page-locked host memory for the caller-owned interval staging buffers */
+void* gr_pinned_alloc(size_t bytes);
+void gr_pinned_free(void* p);
 
 #ifdef __cplusplus
 }

@@ -25,28 +25,10 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from cases import CASES  # noqa: E402
+import util  # noqa: E402
 from genrich_b200.synth import Workload  # noqa: E402
 
 REF = os.path.join(ROOT, "oracle", "_ref", "Genrich")
-
-
-def write_sam(sample, chrom_len, path):
-    w = Workload(chrom_len, sample.nfrag, sample.seed, enrich=sample.enrich, spacing=sample.spacing,
-                 sigma=sample.sigma, multimap=sample.multimap, mmax=sample.mmax)
-    w.write_sam(path)
-    if sample.drop_chroms:
-        drop = {"chr%d" % (c + 1) for c in sample.drop_chroms}
-        keep = []
-        with open(path) as f:
-            for line in f:
-                if line.startswith("@SQ"):
-                    if line.split("\t")[1][3:] in drop:
-                        continue
-                elif not line.startswith("@") and line.split("\t")[2] in drop:
-                    continue
-                keep.append(line)
-        with open(path, "w") as f:
-            f.writelines(keep)
 
 
 def sha(path):
@@ -65,17 +47,7 @@ def main():
         if only and case.name not in only:
             continue
         with tempfile.TemporaryDirectory() as td:
-            tfiles, cfiles = [], []
-            for r, (e, c) in enumerate(case.reps):
-                tp = os.path.join(td, "t%d.sam" % r)
-                write_sam(e, case.chrom_len, tp)
-                tfiles.append(tp)
-                if c is None:
-                    cfiles.append("null")
-                else:
-                    cp = os.path.join(td, "c%d.sam" % r)
-                    write_sam(c, case.chrom_len, cp)
-                    cfiles.append(cp)
+            tfiles, cfiles = util.write_case_sams(case, td)
             out = os.path.join(HERE, case.name + ".narrowPeak")
             logf = os.path.join(td, "log.f")
             pile = os.path.join(td, "pile.k")

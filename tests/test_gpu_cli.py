@@ -1,0 +1,185 @@
+"""The drop-in program: genrich-b200 (host C: SAM/BAM decode, pairing, fragment
+inference, text writers) over the CUDA library, run as a process on the SAM view of
+each case and compared with (a) the narrowPeak file the unmodified reference wrote
+(tests/golden) and (b) the -f / -k / -b text the pinned oracle produces."""
+import gzip
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+import util
+from cases import CASES, BY_NAME
+from genrich_b200 import host
+
+pytestmark = pytest.mark.gpu
+
+CLI = os.path.join(util.ROOT, "genrich_b200", "bin", "genrich-b200")
+
+
+def _close_lines(got, want, float_cols, tol=1e-4):
+    assert len(got) == len(want), (len(got), len(want))
+    for g, w in zip(got, want):
+        if g == w:
+            continue
+        gf, wf = g.split("\t"), w.split("\t")
+        assert len(gf) == len(wf), (g, w)
+        for i, (a, b) in enumerate(zip(gf, wf)):
+            if a == b:
+                continue
+            assert i in float_cols, (g, w)
+            fa, fb = float(a), float(b)
+            assert abs(fa - fb) <= tol + 2e-6 * abs(fb) + 1.1e-6, (g, w)
+
+
+def _run_cli(case, td, extra=()):
+    tfiles, cfiles = util.write_case_sams(case, td)
+    out, logf, pile, bed = (os.path.join(td, x) for x in ("o.np", "o.f", "o.k", "o.b"))
+    cmd = [CLI, "-t", ",".join(tfiles), "-o", out, "-f", logf, "-k", pile, "-b", bed, "-v"] + case.ref_args() + list(extra)
+    if any(c != "null" for c in cfiles):
+        cmd += ["-c", ",".join(cfiles)]
+    r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    rd = lambda p: open(p).read().split("\n")[:-1]
+    return rd(out), rd(logf), rd(pile), rd(bed), r.stderr
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: c.name)
+def test_cli_matches_reference_and_oracle(case, tmp_path):
+    np_lines, log, pile, bed, err = _run_cli(case, str(tmp_path))
+    meta, gold = util.golden(case)
+    # narrowPeak vs the reference's own file
+    assert len(np_lines) == len(gold) == meta["peaks"]
+    for g, w in zip(np_lines, gold):
+        gf, wf = g.split("\t"), w.split("\t")
+        assert gf[:4] == wf[:4] and gf[5] == wf[5] and gf[9] == wf[9], (g, w)   # chrom start end name . summit
+        assert abs(int(gf[4]) - int(wf[4])) <= 1
+        assert abs(float(gf[6]) - float(wf[6])) <= 1e-4 * max(1.0, float(wf[6]))
+        assert abs(float(gf[7]) - float(wf[7])) <= 1e-4 + 1e-6
+        assert abs(float(gf[8]) - float(wf[8])) <= 1e-4 + 1e-6
+    # -v scalars exactly as the reference printed them
+    import re
+    lam = [float(x) for x in re.findall(r"Background pileup value: ([0-9.]+)", err)]
+    fac = [float(x) for x in re.findall(r"Scaling factor for control pileup: ([0-9.]+)", err)]
+    assert lam == meta["lambda"] and fac == meta["factor"]
+    assert int(re.search(r"Genome length: (\d+)bp", err).group(1)) == meta["genome_len"]
+    assert int(re.search(r"Peaks identified: (\d+)", err).group(1)) == meta["peaks"]
+    assert int(re.search(r"Peaks identified: \d+ \((\d+)bp\)", err).group(1)) == meta["peak_bp"]
+    assert ("All q-values are 1" in err) == meta["all_q_one"]
+    assert len(re.findall(r"prevented from extending", err)) == meta["clamp_warnings"]
+    # -f / -k vs the oracle's text (itself byte-identical to the reference's, test_oracle_pin)
+    ctx, res, par = util.run_case(util.oracle_api(), case)
+    nrep = len(case.reps)
+    want_log = util.log_lines(ctx, case, par)
+    ncol = len(want_log[0].split("\t"))
+    _close_lines(log, want_log, set(range(3, ncol)))
+    want_pile = util.pile_lines(ctx, case)
+    got_pile = [l for l in pile if not l.startswith("#")]
+    _close_lines(got_pile, want_pile, {5})
+    assert len(log) == meta["log_lines"] and len(got_pile) == meta["pile_lines"]
+    # -b: every interval the host emitted, clamped, in order
+    want = []
+    for r, (e, c, _) in enumerate(util.case_inputs(case)):
+        for arr, tag in ((e, "E"), (c, "C")):
+            if arr is None:
+                continue
+            L = np.asarray(case.chrom_len, dtype=np.int64)[arr[:, 0]]
+            s = np.maximum(arr[:, 1].astype(np.int64), 0)
+            t = np.minimum(arr[:, 2].astype(np.int64), L)
+            want += ["chr%d\t%d\t%d\t%d_%s_%d" % (a + 1, b, c2, k, tag, r) for a, b, c2, k in zip(arr[:, 0], s, t, arr[:, 3])]
+    got = []
+    for l in bed:
+        f = l.split("\t")
+        nm = f[3].split("_")
+        got.append("%s\t%s\t%s\t%s_%s_%s" % (f[0], f[1], f[2], nm[-3], nm[-2], nm[-1]))
+    assert got == want
+
+
+def _sam_to_bam(sam_path, bam_path):
+    """Minimal uncompressed-field BAM writer (BGZF blocks via zlib) for the test."""
+    refs, recs, text = [], [], []
+    for line in open(sam_path):
+        if line.startswith("@"):
+            text.append(line)
+            if line.startswith("@SQ"):
+                f = dict(x.split(":", 1) for x in line.rstrip("\n").split("\t")[1:])
+                refs.append((f["SN"], int(f["LN"])))
+            continue
+        recs.append(line.rstrip("\n").split("\t"))
+    rid = {n: i for i, (n, _) in enumerate(refs)}
+    txt = "".join(text).encode()
+    out = bytearray(b"BAM\x01" + struct.pack("<i", len(txt)) + txt + struct.pack("<i", len(refs)))
+    for n, l in refs:
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+    ops = "MIDNSHP=X"
+    for f in recs:
+        qn = f[0].encode() + b"\0"
+        cig = []
+        num = ""
+        for ch in f[5]:
+            if ch.isdigit():
+                num += ch
+            else:
+                cig.append((int(num) << 4) | ops.index(ch))
+                num = ""
+        seq_len = sum(c >> 4 for c in cig if (c & 15) in (0, 1, 4, 7, 8))
+        aux = b""
+        for t in f[11:]:
+            tag, ty, val = t.split(":", 2)
+            if ty == "i":
+                aux += tag.encode() + b"c" + struct.pack("<b", int(val))
+        body = struct.pack("<iiIIiiii", rid[f[2]], int(f[3]) - 1, (4680 << 16) | (int(f[4]) << 8) | len(qn),
+                           (int(f[1]) << 16) | len(cig), seq_len, rid[f[2]], int(f[7]) - 1, int(f[8]))
+        body += qn + b"".join(struct.pack("<I", c) for c in cig) + b"\0" * ((seq_len + 1) // 2) + b"\xff" * seq_len + aux
+        out += struct.pack("<i", len(body)) + body
+    with open(bam_path, "wb") as g:
+        for i in range(0, len(out), 60000):                 # BGZF members
+            chunk = bytes(out[i:i + 60000])
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            g.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp +
+                    struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+        g.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def test_cli_bam_and_gz_inputs(tmp_path):
+    """BAM (BGZF) and gzip-compressed SAM inputs give the same peaks as plain SAM."""
+    case = BY_NAME["c5_multimap_ctrl_p"]
+    td = str(tmp_path)
+    tfiles, cfiles = util.write_case_sams(case, td)
+    base = os.path.join(td, "plain.np")
+    args = case.ref_args()
+    subprocess.check_call([CLI, "-t", tfiles[0], "-c", cfiles[0], "-o", base] + args)
+    bam_t, bam_c = os.path.join(td, "t.bam"), os.path.join(td, "c.bam")
+    _sam_to_bam(tfiles[0], bam_t)
+    _sam_to_bam(cfiles[0], bam_c)
+    o2 = os.path.join(td, "bam.np")
+    subprocess.check_call([CLI, "-t", bam_t, "-c", bam_c, "-o", o2] + args)
+    assert open(o2).read() == open(base).read()
+    gz_t = os.path.join(td, "t.sam.gz")
+    with open(tfiles[0], "rb") as f, gzip.open(gz_t, "wb") as g:
+        g.write(f.read())
+    o3 = os.path.join(td, "gz.np")
+    subprocess.check_call([CLI, "-t", gz_t, "-c", cfiles[0], "-o", o3] + args)
+    assert open(o3).read() == open(base).read()
+    meta, gold = util.golden(case)
+    assert [l.split("\t")[:3] for l in open(base).read().split("\n")[:-1]] == [l.split("\t")[:3] for l in gold]
+
+
+def test_cli_errors(tmp_path):
+    td = str(tmp_path)
+    r = subprocess.run([CLI, "-o", os.path.join(td, "x")], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Error! Need input/output files" in r.stderr
+    bad = os.path.join(td, "bad.sam")
+    open(bad, "w").write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chr1\tLN:1000\n")
+    r = subprocess.run([CLI, "-t", bad, "-o", os.path.join(td, "x")], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "not sorted by queryname" in r.stderr
+    emp = os.path.join(td, "empty.sam")
+    open(emp, "w").write("@HD\tVN:1.6\tSO:queryname\n@SQ\tSN:chr1\tLN:1000\n")
+    r = subprocess.run([CLI, "-t", emp, "-o", os.path.join(td, "x")], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Experimental sample has no analyzable fragments" in r.stderr
+    r = subprocess.run([CLI, "-t", emp, "-o", os.path.join(td, "x"), "-p", "1.5"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "p-/q-value must be in (0,1]" in r.stderr

@@ -93,3 +93,38 @@ def golden(case: Case):
     with open(os.path.join(GOLDEN, case.name + ".narrowPeak")) as f:
         np_lines = f.read().split("\n")[:-1]
     return meta, np_lines
+
+
+def write_sample_sam(case: Case, s, path: str) -> None:
+    """SAM view of one sample (what the reference binary / the CLI read)."""
+    w = Workload(case.chrom_len, s.nfrag, s.seed, enrich=s.enrich, spacing=s.spacing, sigma=s.sigma,
+                 multimap=s.multimap, mmax=s.mmax)
+    w.write_sam(path)
+    if s.drop_chroms:
+        drop = {"chr%d" % (c + 1) for c in s.drop_chroms}
+        keep = []
+        with open(path) as f:
+            for line in f:
+                if line.startswith("@SQ"):
+                    if line.split("\t")[1][3:] in drop:
+                        continue
+                elif not line.startswith("@") and line.split("\t")[2] in drop:
+                    continue
+                keep.append(line)
+        with open(path, "w") as f:
+            f.writelines(keep)
+
+
+def write_case_sams(case: Case, td: str):
+    tfiles, cfiles = [], []
+    for r, (e, c) in enumerate(case.reps):
+        tp = os.path.join(td, "t%d.sam" % r)
+        write_sample_sam(case, e, tp)
+        tfiles.append(tp)
+        if c is None:
+            cfiles.append("null")
+        else:
+            cp = os.path.join(td, "c%d.sam" % r)
+            write_sample_sam(case, c, cp)
+            cfiles.append(cp)
+    return tfiles, cfiles
