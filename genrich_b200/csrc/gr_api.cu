@@ -245,7 +245,7 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     CK(x->rankC.ensure(x->nblocks * sizeof(u64)));
     CK(x->rankTmp.ensure(x->nblocks * sizeof(u64)));
     const u64 ntile = T / GR_SCAN_TILE;
-    CK(x->lb0.ensure(ntile * sizeof(u64)));
+    CK(x->lb0.ensure((2 * ntile + 4096) * sizeof(u64) * 2));   // dense-scan status words (agg + group + round)
     CK(x->lb1.ensure(ntile * sizeof(u64)));
     CK(x->lb2.ensure(ntile * sizeof(u64)));
     CK(x->ticket.ensure(64));

@@ -11,8 +11,7 @@
 // clamped value changes across it (2122) or it is the chromosome end.  Surviving
 // intervals are compacted (single pass, look-back ranks); the bits of the dropped
 // boundaries are cleared in the control break bitmap.
-#define CL_ITEMS 4
-#define CL_TILE 1024
+#define CL_TILE 8192          // raw intervals per look-back tile (8 warps x 32 rounds x 32 lanes)
 
 __device__ __forceinline__ float clamp_net(float factor, float v, float lambda) {
   const float s = __fmul_rn(factor, v);
@@ -26,48 +25,54 @@ k_ctrl_clamp(DevLayout L, DevRle raw, u64 n, float factor, float lambda, Lookbac
   const u64 t0 = (u64)tile * CL_TILE;
   const u64 tl = min(t0 + CL_TILE, n) - 1;
   const TileChrom tc = tile_chrom_range(raw.chrom_start, L.nchrom, t0, tl);
-  const u64 i0 = t0 + (u64)threadIdx.x * CL_ITEMS;
+  const bool uni = tc.c0 == tc.c1;
+  const u64 uni_end = uni ? raw.chrom_start[tc.c0 + 1] : 0;      // one past the chromosome's last interval
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u64 wbase = t0 + (u64)w * 1024;
 
-  u32 e[CL_ITEMS];
-  float net[CL_ITEMS + 1];
-  bool keep[CL_ITEMS], last[CL_ITEMS];
-  int ch[CL_ITEMS];
-  u32 cnt = 0;
-#pragma unroll
-  for (int k = 0; k <= CL_ITEMS; k++) {
-    const u64 i = i0 + k;
-    net[k] = i < n ? clamp_net(factor, raw.val[i], lambda) : 0.0f;
-  }
-#pragma unroll
-  for (int k = 0; k < CL_ITEMS; k++) {
-    const u64 i = i0 + k;
-    keep[k] = false; last[k] = false; ch[k] = tc.c0; e[k] = 0;
+  // pass 1: which boundaries survive; dropped ones leave the break bitmap right away
+  u32 mine = 0, cnt = 0;
+#pragma unroll 4
+  for (int k = 0; k < 32; k++) {
+    const u64 i = wbase + k * 32 + lane;
+    bool keep = false;
     if (i < n) {
-      e[k] = raw.end[i];
-      const int c = tc.c0 == tc.c1 ? tc.c0 : chrom_of_index(raw.chrom_start, L.nchrom, i);
-      ch[k] = c;
-      last[k] = (i + 1 == raw.chrom_start[c + 1]);
-      keep[k] = last[k] || net[k] != net[k + 1];
-      cnt += keep[k];
+      const float net = clamp_net(factor, raw.val[i], lambda);
+      int c = tc.c0;
+      bool last;
+      if (uni) last = i + 1 == uni_end;
+      else { c = chrom_of_index(raw.chrom_start, L.nchrom, i); last = i + 1 == raw.chrom_start[c + 1]; }
+      keep = last || net != clamp_net(factor, raw.val[i + 1], lambda);
+      if (!keep) {
+        const u64 g = L.off[c] + raw.end[i];
+        atomicAnd(bitmap + (g >> 5), ~(1u << (g & 31)));
+      }
     }
+    const u32 bal = __ballot_sync(GR_FULL, keep);
+    if (lane == k) mine = bal;
+    cnt += __popc(bal);
   }
   u32 tot;
-  u64 rank = tile_exclusive_rank(lb, tile, cnt, tot);
+  u64 r = tile_exclusive_rank(lb, tile, lane == 31 ? cnt : 0u, tot);
+  r = __shfl_sync(GR_FULL, r, 31);
   if (tile == 0 && threadIdx.x == 0) out.chrom_start[0] = 0;
-#pragma unroll
-  for (int k = 0; k < CL_ITEMS; k++) {
-    const u64 i = i0 + k;
-    if (i >= n) break;
-    if (keep[k]) {
-      out.end[rank] = e[k];
-      out.val[rank] = net[k];
-      rank++;
-      if (last[k]) out.chrom_start[ch[k] + 1] = rank;
-      if (i == n - 1) *out.total = rank;
-    } else {
-      const u64 g = L.off[ch[k]] + e[k];
-      atomicAnd(bitmap + (g >> 5), ~(1u << (g & 31)));
+
+  // pass 2: write the survivors at their rank (values re-read: still in L1/L2)
+  for (int k = 0; k < 32; k++) {
+    const u32 bal = __shfl_sync(GR_FULL, mine, k);
+    if (bal & (1u << lane)) {
+      const u64 i = wbase + k * 32 + lane;
+      const u64 rank = r + __popc(bal & ((1u << lane) - 1));
+      out.end[rank] = raw.end[i];
+      out.val[rank] = clamp_net(factor, raw.val[i], lambda);
+      int c = tc.c0;
+      bool last;
+      if (uni) last = i + 1 == uni_end;
+      else { c = chrom_of_index(raw.chrom_start, L.nchrom, i); last = i + 1 == raw.chrom_start[c + 1]; }
+      if (last) out.chrom_start[c + 1] = rank + 1;
+      if (i == n - 1) *out.total = rank + 1;
     }
+    r += __popc(bal);
   }
 }
 
@@ -114,45 +119,72 @@ void launch_ctrl_const(cudaStream_t s, const DevLayout& L, float lambda, DevRle 
 // E|C per 8192-cell block (look-back over three counters); pass B walks the set
 // bits of E|C and gathers the pileup values: the interval ending at a break lies
 // in the experimental interval number (#E breaks before it), same for control.
+#define UR_BLOCKS 16        // bitmap blocks (of 256 words) per look-back tile
 __global__ void __launch_bounds__(256)
 k_union_rank(const u32* __restrict__ bmE, const u32* __restrict__ bmC, Lookback<3> lb,
              u64* __restrict__ rankE, u64* __restrict__ rankC, u64* __restrict__ rankU,
-             u64* __restrict__ totals, u32 nblocks) {
-  __shared__ u32 sm[3][8];
-  const u32 blk = take_ticket(lb.ticket);
-  const u64 widx = (u64)blk * 256 + threadIdx.x;
-  const u32 E = bmE[widx], C = bmC ? bmC[widx] : 0u;
-  u32 a = __reduce_add_sync(GR_FULL, __popc(E));
-  u32 b = __reduce_add_sync(GR_FULL, __popc(C));
-  u32 u = __reduce_add_sync(GR_FULL, __popc(E | C));
+             u64* __restrict__ totals, u32 nblocks, u32 ntiles) {
+  __shared__ u32 sm[UR_BLOCKS][3][8];
+  __shared__ u32 sm_blk[UR_BLOCKS][3];
+  __shared__ i64 sm_ex[3];
+  const u32 tile = take_ticket(lb.ticket);
+  const u32 b0 = tile * UR_BLOCKS;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) { sm[0][w] = a; sm[1][w] = b; sm[2][w] = u; }
+  u32 E[UR_BLOCKS], C[UR_BLOCKS];
+#pragma unroll
+  for (int b = 0; b < UR_BLOCKS; b++) {
+    const u64 widx = (u64)(b0 + b) * 256 + threadIdx.x;
+    const bool on = b0 + b < nblocks;
+    E[b] = on ? bmE[widx] : 0u;
+    C[b] = (on && bmC) ? bmC[widx] : 0u;
+  }
+#pragma unroll
+  for (int b = 0; b < UR_BLOCKS; b++) {
+    const u32 a = __reduce_add_sync(GR_FULL, __popc(E[b]));
+    const u32 c = __reduce_add_sync(GR_FULL, __popc(C[b]));
+    const u32 u = __reduce_add_sync(GR_FULL, __popc(E[b] | C[b]));
+    if (lane == 0) { sm[b][0][w] = a; sm[b][1][w] = c; sm[b][2][w] = u; }
+  }
+  __syncthreads();
+  if (threadIdx.x < UR_BLOCKS * 3) {
+    const int b = threadIdx.x / 3, k = threadIdx.x % 3;
+    u32 t = 0;
+    for (int q = 0; q < 8; q++) t += sm[b][k][q];
+    sm_blk[b][k] = t;
+  }
   __syncthreads();
   if (w == 0) {
     i64 agg[3] = { 0, 0, 0 }, ex[3];
-    for (int k = 0; k < 8; k++) { agg[0] += sm[0][k]; agg[1] += sm[1][k]; agg[2] += sm[2][k]; }
-    lookback_exclusive<3>(lb, blk, agg, ex);
+    for (int b = 0; b < UR_BLOCKS; b++) { agg[0] += sm_blk[b][0]; agg[1] += sm_blk[b][1]; agg[2] += sm_blk[b][2]; }
+    lookback_exclusive<3, 2>(lb, tile, agg, ex);
     if (lane == 0) {
-      rankE[blk] = (u64)ex[0];
-      if (rankC) rankC[blk] = (u64)ex[1];
-      rankU[blk] = (u64)ex[2];
-      if (blk == nblocks - 1) {
+      sm_ex[0] = ex[0]; sm_ex[1] = ex[1]; sm_ex[2] = ex[2];
+      if (tile == ntiles - 1) {
         totals[0] = (u64)(ex[0] + agg[0]);
         totals[1] = (u64)(ex[1] + agg[1]);
         totals[2] = (u64)(ex[2] + agg[2]);
       }
     }
   }
+  __syncthreads();
+  if (threadIdx.x < UR_BLOCKS && b0 + threadIdx.x < nblocks) {
+    u64 e = (u64)sm_ex[0], c = (u64)sm_ex[1], u = (u64)sm_ex[2];
+    for (u32 b = 0; b < threadIdx.x; b++) { e += sm_blk[b][0]; c += sm_blk[b][1]; u += sm_blk[b][2]; }
+    rankE[b0 + threadIdx.x] = e;
+    if (rankC) rankC[b0 + threadIdx.x] = c;
+    rankU[b0 + threadIdx.x] = u;
+  }
 }
 
 void launch_union_rank(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
                        const RankScratch& sc, u64* rankE, u64* rankC, u64* rankU, u64* totals) {
-  for (int k = 0; k < 3; k++) cudaMemsetAsync(sc.st[k], 0, L.nblocks * sizeof(u64), s);
+  const u32 ntiles = (u32)((L.nblocks + UR_BLOCKS - 1) / UR_BLOCKS);
+  for (int k = 0; k < 3; k++) cudaMemsetAsync(sc.st[k], 0, (size_t)ntiles * sizeof(u64), s);
   cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
   Lookback<3> lb;
   for (int k = 0; k < 3; k++) lb.st[k] = sc.st[k];
   lb.ticket = sc.ticket;
-  k_union_rank<<<(unsigned)L.nblocks, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks); GR_NOTE_LAUNCH();
+  k_union_rank<<<ntiles, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks, ntiles); GR_NOTE_LAUNCH();
 }
 
 __global__ void __launch_bounds__(256)

@@ -16,30 +16,45 @@
 #define PK_SKIP (-1.0f)
 
 // ---- events: indices of significant or SKIP intervals, in order -----------------
+// 8192 intervals per look-back tile: each warp takes 1024 consecutive values in 32
+// coalesced rounds, ranks them with one ballot per round (order preserved) and
+// keeps the 32 ballots in one register per lane for the write pass.
+#define PE_TILE 8192
 __global__ void __launch_bounds__(256)
 k_peak_events(const float* __restrict__ v, u64 n, float thr, Lookback<1> lb,
               u32* __restrict__ ev_idx, u64* __restrict__ ev_count, u32 ntiles) {
   const u32 tile = take_ticket(lb.ticket);
-  const u64 i0 = ((u64)tile * 256 + threadIdx.x) * 4;
-  u32 m = 0;
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (i0 + k < n) {
-      const float x = v[i0 + k];
-      if (x > thr || x == PK_SKIP) m |= 1u << k;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u64 wbase = (u64)tile * PE_TILE + (u64)w * 1024;
+  u32 mine = 0, cnt = 0;
+#pragma unroll 8
+  for (int k = 0; k < 32; k++) {
+    const u64 i = wbase + k * 32 + lane;
+    bool f = false;
+    if (i < n) {
+      const float x = v[i];
+      f = x > thr || x == PK_SKIP;
     }
+    const u32 bal = __ballot_sync(GR_FULL, f);
+    if (lane == k) mine = bal;
+    cnt += __popc(bal);                        // warp-uniform
+  }
+  // rank of the warp's first event: block scan over the 8 warp counts + look-back
   u32 tot;
-  u64 r = tile_exclusive_rank(lb, tile, __popc(m), tot);
-#pragma unroll
-  for (int k = 0; k < 4; k++)
-    if (m & (1u << k)) ev_idx[r++] = (u32)(i0 + k);
+  u64 r = tile_exclusive_rank(lb, tile, lane == 31 ? cnt : 0u, tot);   // lane 31 carries the warp's count
+  r = __shfl_sync(GR_FULL, r, 31);             // exclusive rank of lane 31 == rank of the warp's first event
+  for (int k = 0; k < 32; k++) {
+    const u32 bal = __shfl_sync(GR_FULL, mine, k);
+    if (bal & (1u << lane)) ev_idx[r + __popc(bal & ((1u << lane) - 1))] = (u32)(wbase + k * 32 + lane);
+    r += __popc(bal);
+  }
   if (tile == ntiles - 1 && threadIdx.x == 255) *ev_count = r;
 }
 
 void launch_peak_events(cudaStream_t s, const float* v, u64 n, float thr, const PeakWork& w) {
   cudaMemsetAsync(w.ev_count, 0, sizeof(u64), s);
   if (!n) return;
-  const u32 ntiles = (u32)((n + 1023) / 1024);
+  const u32 ntiles = (u32)((n + PE_TILE - 1) / PE_TILE);
   cudaMemsetAsync(w.sc.st, 0, (size_t)ntiles * sizeof(u64), s);
   cudaMemsetAsync(w.sc.ticket, 0, sizeof(u32), s);
   Lookback<1> lb;
