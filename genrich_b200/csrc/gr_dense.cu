@@ -60,25 +60,30 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64
 //   grid = co-resident CTAs only (2 per SM, cooperative launch); tiles of 8192
 //   cells are dealt round-robin: in round k CTA b works on tile kG+b.
 //   Per CTA: 16 compute warps + 1 exchange warp.
-//   * loads: cp.async (LDGSTS, 16 B/thread/op, coalesced) into a 3-stage XOR-swizzled
-//     shared-memory ring; 1-2 tiles (32-64 KB) per CTA are always in flight to HBM.
+//   * loads: cp.async (LDGSTS, 16 B/thread/op, coalesced) into a 2-stage XOR-swizzled
+//     shared-memory ring; the stage of tile k is refilled with tile k+2 as soon as
+//     its cells are in registers, so 1-2 tiles (32-64 KB) per CTA are always in
+//     flight to HBM.
 //   * A(k)  compute warps: 16 consecutive cells per thread (conflict-free LDS.128),
 //           thread/warp/block scan of (sum, #breaks), break bitmap written, tile
-//           aggregate handed to the exchange warp.
-//   * X(k)  exchange warp, concurrently with A(k+1): publishes the aggregate and
-//           gathers the exclusive prefix of the tile with ONE L2 round trip:
+//           aggregate handed to the exchange warp; the tile's breaks (~6 % of the
+//           cells) are parked as (position, tile-local height) in a small side buffer.
+//   * X(k)  exchange warp, concurrently with A(k+1), A(k+2): publishes the aggregate
+//           and gathers the tile's exclusive prefix with two L2 round trips:
 //             agg[tile]      the tile's own (sum, #breaks)
 //             grp[k*NG + g]  total of the 32 tiles of CTA-group g in round k
 //           exclusive(kG+b) = (totals of all rounds < k, kept in registers)
 //                           + sum_{g' < g} grp[k,g'] + sum_{b' in group, b' < b} agg.
-//           Every dependency is on aggregates of the same or the previous round;
-//           nothing waits for another tile's *prefix*, so there is no serial chain.
-//   * B(k)  compute warps, after A(k+1): re-read tile k from its stage, add the
-//           prefix, write each break as (end, value) at its global rank.
+//           Every dependency is on AGGREGATES of the same or the previous round;
+//           nothing waits for another tile's prefix, so there is no serial chain.
+//   * B(k)  compute warps, two rounds later: all 512 threads convert the parked
+//           breaks densely -- add the prefix, rebuild the reference float, store
+//           (end, value) at consecutive global ranks (fully coalesced).
 //   History (profiles/README.md): 32-wide decoupled look-back 0.92 TB/s; ticketed
-//   persistent tiles 0.16 TB/s; 320-wide look-back 0.77 TB/s; two-level exchange
-//   without the A/B split 1.03 TB/s (60 % of warp samples parked on the barrier
-//   behind the exchange round trip).
+//   persistent tiles 0.16 TB/s; 320-wide look-back 0.77 TB/s; two-level exchange,
+//   prefix awaited in place 1.03 TB/s; + exchange warp, emission one round late
+//   1.84 TB/s; + dense conversion of the breaks 2.1 TB/s (33 % of warp samples still
+//   parked behind the exchange: CTAs drift by more than one round).
 //
 // A break closes an interval at chromosome position j iff 1 <= j < len and
 // delta[j] != 0, or j == len (Genrich.c:2241, 2268); its value is the running sum
@@ -89,10 +94,13 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64
 #define SC_THREADS 544            // + one exchange warp
 #define SC_ITEMS 16
 #define SC_STAGE_INT4 2048        // 32 KB per stage
-#define SC_NSTAGE 3
+#define SC_NSTAGE 2
+#define SC_LAG 2                  // rounds between A(k) and B(k)
+#define SC_NSLOT 3                // side buffers / hand-over slots (SC_LAG + 1)
+#define SC_SIDE_CAP 1536          // parked breaks per tile (8 B each); denser tiles take the in-place path
 #define BAR_COMPUTE 1
-#define BAR_AGG 2                 // +parity
-#define BAR_PREFIX 4              // +parity
+#define BAR_AGG 2                 // + slot
+#define BAR_PREFIX 5              // + slot
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -151,14 +159,15 @@ __device__ __forceinline__ void sc_load_items(const int4* stage, int tid, int (&
 __global__ void __launch_bounds__(SC_THREADS, 2)
 k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
              u32* __restrict__ bitmap, int* __restrict__ err, u32 ntiles) {
-  extern __shared__ int4 sm_x[];                       // SC_NSTAGE * SC_STAGE_INT4
+  extern __shared__ int4 sm_x[];                       // SC_NSTAGE stages, then SC_NSLOT side buffers
   __shared__ u32 sm_wsum[SC_WARPS], sm_wcnt[SC_WARPS];
-  __shared__ u32 sm_agg_sum[2], sm_agg_cnt[2];
-  __shared__ u32 sm_ex_sum[2];
-  __shared__ u64 sm_ex_cnt[2];
+  __shared__ u32 sm_agg_sum[SC_NSLOT], sm_agg_cnt[SC_NSLOT];
+  __shared__ u32 sm_ex_sum[SC_NSLOT];
+  __shared__ u64 sm_ex_cnt[SC_NSLOT];
 
   const int tid = threadIdx.x, lane = tid & 31;
   const u32 G = gridDim.x, b = blockIdx.x;
+  int2* side = reinterpret_cast<int2*>(sm_x + SC_NSTAGE * SC_STAGE_INT4);
 
   // ------------------------------------------------------------ exchange warp
   if (tid >= SC_CT) {
@@ -167,8 +176,9 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
     u64 rnd_c = 0;
     u32 k = 0;
     for (u32 tile = b; tile < ntiles; tile += G, k++) {
-      named_sync(BAR_AGG + (k & 1), 64);               // aggregate of tile k is in shared memory
-      const u32 agg_s = sm_agg_sum[k & 1], agg_c = sm_agg_cnt[k & 1];
+      const int slot = k % SC_NSLOT;
+      named_sync(BAR_AGG + slot, 64);                  // aggregate of tile k is in shared memory
+      const u32 agg_s = sm_agg_sum[slot], agg_c = sm_agg_cnt[slot];
       if (lane == 0) st_status(S.agg + tile, 1, agg_s, agg_c);
       const u32 last_b = min(G - 1, ntiles - 1 - k * G);
       const bool need_a = (u32)lane < j, need_g = (u32)lane < g, need_p = k > 0 && (u32)lane < ng;
@@ -177,7 +187,7 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
       const ulonglong2* pp = S.grp + (u64)(k - 1) * ng + lane;   // only dereferenced when k > 0
       // (1) the group's own aggregates: as soon as they are in, the group's last tile
       //     publishes the group total -- it must NOT wait for the totals of earlier
-      //     groups, or the ten groups of a round serialise (measured: 35 polls/tile)
+      //     groups, or the groups of a round serialise (measured: 35 polls per tile)
       ulonglong2 va;
       for (;;) {
         va.x = va.y = 0;
@@ -215,113 +225,74 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
       }
       rnd_s += s_p; rnd_c += c_p;
       if (lane == 0) {
-        sm_ex_sum[k & 1] = rnd_s + s_g + s_in;
-        sm_ex_cnt[k & 1] = rnd_c + c_g + c_in;
+        sm_ex_sum[slot] = rnd_s + s_g + s_in;
+        sm_ex_cnt[slot] = rnd_c + c_g + c_in;
       }
       __syncwarp();
-      named_arrive(BAR_PREFIX + (k & 1), SC_THREADS);  // prefix of tile k is in shared memory
+      named_arrive(BAR_PREFIX + slot, SC_THREADS);     // prefix of tile k is in shared memory
     }
     return;
   }
 
   // ------------------------------------------------------------ compute warps
   const int w = tid >> 5;
-  auto issue = [&](u32 tile, int stage) {              // chunk g (16 B) -> swizzled slot
-    if (tile < ntiles) {
-      const int4* src = reinterpret_cast<const int4*>(delta + (u64)tile * GR_BLOCK_SLOTS);
-      int4* dst = sm_x + stage * SC_STAGE_INT4;
+  const int swt = sc_swz(tid);                         // swizzled chunk of this thread inside a 512-chunk quarter
+  const int4* src = reinterpret_cast<const int4*>(delta) + (u64)b * (GR_BLOCK_SLOTS / 4) + tid;
+  const u64 src_step = (u64)G * (GR_BLOCK_SLOTS / 4);
+  auto issue = [&](bool on, int stage, const int4* from) {   // chunk q*512+tid (16 B) -> swizzled slot
+    if (on) {
+      int4* dst = sm_x + stage * SC_STAGE_INT4 + swt;
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int gch = q * SC_CT + tid;
-        cp_async16(dst + sc_swz(gch), src + gch);
-      }
+      for (int q = 0; q < 4; q++) cp_async16(dst + q * SC_CT, from + q * SC_CT);
     }
     cp_async_commit();
   };
-
-  issue(b, 0);
-  issue(b + G, 1);
+  issue(b < ntiles, 0, src);
+  issue(b + G < ntiles, 1, src + src_step);
   TileMeta meta = tile_meta(L, b, ntiles);
 
-  // state of the tile whose breaks are still to be written (B phase)
-  u32 p_tile = 0, p_jb = 0, p_pre_sum = 0, p_wx_cnt = 0, p_lane_cnt_incl = 0, p_m = 0, p_tcnt = 0;
-  int p_c = 0;
-  bool p_first = false, have_prev = false;
+  // per-slot state of tiles whose breaks are parked: written by thread 0 in A(k), read by
+  // everyone in B(k) two rounds (and several barriers) later
+  __shared__ u32 sm_q[SC_NSLOT][6];                    // cnt, jb, tile, chrom, first, live
+  if (tid < SC_NSLOT) sm_q[tid][5] = 0;
 
-  auto emit_prev = [&](u32 k_prev) {
-    named_sync(BAR_PREFIX + (k_prev & 1), SC_THREADS);
-    const u32 ex_sum = sm_ex_sum[k_prev & 1];
-    const u64 ex_cnt = sm_ex_cnt[k_prev & 1];
+  // B: convert and store the parked breaks of the tile in `slot`
+  auto finish = [&](int slot, u32 cnt_, u32 jb_, u32 tile_, u32 tcnt_, int c_, bool first_) {
+    named_sync(BAR_PREFIX + slot, SC_THREADS);
+    const u32 ex_sum = sm_ex_sum[slot];
+    const u64 ex_cnt = sm_ex_cnt[slot];
     if (tid == 0) {
-      if (p_first) {
-        out.chrom_start[p_c] = ex_cnt;
+      if (first_) {
+        out.chrom_start[c_] = ex_cnt;
         if (ex_sum != 0) atomicOr(err, GR_DE_TAIL);    // previous chromosome did not return to 0 (2283-2289)
       }
-      if (p_tile == ntiles - 1) {
-        *out.total = ex_cnt + p_tcnt;
-        out.chrom_start[L.nchrom] = ex_cnt + p_tcnt;
+      if (tile_ == ntiles - 1) {
+        *out.total = ex_cnt + tcnt_;
+        out.chrom_start[L.nchrom] = ex_cnt + tcnt_;
       }
     }
-    // Breaks are ~6 % of the cells: walking 16 predicated per-item blocks with one or
-    // two live lanes each made the kernel instruction-bound (ncu r1d: 42 thread
-    // instructions per cell, 19 of 32 lanes active).  Instead every lane drops its
-    // (position, height) pairs into the warp's own 2 KB slice of the stage it has
-    // just read (cheap, sparse), and the warp then converts and stores them densely:
-    // lane n handles the n-th break, so the global stores are fully coalesced.
-    const u32 wcnt = __shfl_sync(GR_FULL, p_lane_cnt_incl, 31);          // breaks of this warp
-    if (wcnt) {                                                          // warp-uniform
-      int4* stage4 = sm_x + (k_prev % SC_NSTAGE) * SC_STAGE_INT4;
-      int d[SC_ITEMS];
-      sc_load_items(stage4, tid, d);
-      __syncwarp();                                                      // every lane has its cells
-      const u64 wrank = ex_cnt + p_wx_cnt;                               // rank of the warp's first break
-      const u32 wpos0 = p_jb + (u32)w * (32 * SC_ITEMS);                 // chromosome position of the warp's first cell
-      u32 run = ex_sum + p_pre_sum;                                      // exclusive prefix before d[0]
-      if (wcnt <= 256) {
-        int2* st = reinterpret_cast<int2*>(stage4 + w * 128);            // 256 entries of 8 B
-        u32 r = p_lane_cnt_incl - __popc(p_m);
-#pragma unroll
-        for (int i = 0; i < SC_ITEMS; i++) {
-          if (p_m & (1u << i)) st[r++] = make_int2(lane * SC_ITEMS + i, (int)run);
-          run += (u32)d[i];
-        }
-        __syncwarp();
-        bool neg = false;
-        for (u32 n = lane; n < wcnt; n += 32) {
-          const int2 e = st[n];
-          neg |= e.y < 0;
-          out.end[wrank + n] = wpos0 + (u32)e.x;
-          out.val[wrank + n] = units_to_val(e.y < 0 ? 0 : e.y);
-        }
-        if (neg) atomicOr(err, GR_DE_PILE);                              // ERRPILE 1921, 1969
-      } else if (p_m) {                                                  // > 256 breaks in 512 cells: direct path
-        u64 rank = wrank + (p_lane_cnt_incl - __popc(p_m));
-        bool neg = false;
-#pragma unroll
-        for (int i = 0; i < SC_ITEMS; i++) {
-          if (p_m & (1u << i)) {
-            const int N = (int)run;
-            neg |= N < 0;
-            out.end[rank] = wpos0 + lane * SC_ITEMS + i;
-            out.val[rank] = units_to_val(N < 0 ? 0 : N);
-            rank++;
-          }
-          run += (u32)d[i];
-        }
-        if (neg) atomicOr(err, GR_DE_PILE);
-      }
+    const int2* sb = side + slot * SC_SIDE_CAP;
+    bool neg = false;
+    for (u32 n = tid; n < cnt_; n += SC_CT) {          // lane n <-> n-th break: coalesced stores
+      const int2 e = sb[n];
+      const int N = (int)(ex_sum + (u32)e.y);
+      neg |= N < 0;
+      out.end[ex_cnt + n] = jb_ + (u32)e.x;
+      out.val[ex_cnt + n] = units_to_val(N < 0 ? 0 : N);
     }
+    if (neg) atomicOr(err, GR_DE_PILE);                // ERRPILE 1921, 1969
   };
 
   u32 k = 0;
   for (u32 tile = b; tile < ntiles; tile += G, k++) {
-    // ---- A(k): scan tile k, publish its aggregate
+    const int slot = k % SC_NSLOT;
     // chromosome of the tile after this one: first hop now, second hop after the scan
     const int c_next = tile + G < ntiles ? L.blk2chrom[tile + G] : 0;
+    // ---- A(k): scan tile k
     cp_async_wait<1>();
     named_sync(BAR_COMPUTE, SC_CT);                    // tile k is in shared memory (all threads' copies)
     int d[SC_ITEMS];
-    sc_load_items(sm_x + (k % SC_NSTAGE) * SC_STAGE_INT4, tid, d);
+    sc_load_items(sm_x + (k & 1) * SC_STAGE_INT4, tid, d);
     const u64 tbase = (u64)tile * GR_BLOCK_SLOTS;
     const u32 jb = (u32)(tbase - meta.off);            // chromosome position of the tile's first cell
     const u32 len = meta.len;
@@ -352,36 +323,92 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
       const u32 hi = __shfl_down_sync(GR_FULL, m, 1);
       if (!(lane & 1)) bitmap[(tbase >> 5) + (tid >> 1)] = m | (hi << 16);
     }
-    named_sync(BAR_COMPUTE, SC_CT);
-    u32 wx_sum = 0, wx_cnt = 0, t_sum = 0, t_cnt = 0;
-#pragma unroll
-    for (int q = 0; q < SC_WARPS; q++) {
-      const u32 a = sm_wsum[q], c2 = sm_wcnt[q];
-      if (q < w) { wx_sum += a; wx_cnt += c2; }
-      t_sum += a; t_cnt += c2;
-    }
+    named_sync(BAR_COMPUTE, SC_CT);                    // cells are in registers: the stage is free
+    src += src_step;
+    issue(tile + 2 * G < ntiles, k & 1, src + src_step);   // tile k+2 -> the stage just read
+    // exclusive prefix over the 16 warp totals: lanes 0..15 scan them, everyone picks its warp's
+    u32 vs = lane < SC_WARPS ? sm_wsum[lane] : 0u, vc = lane < SC_WARPS ? sm_wcnt[lane] : 0u;
+    const u32 is_ = warp_incl_scan_u32(vs, lane), ic_ = warp_incl_scan_u32(vc, lane);
+    const u32 t_sum = __shfl_sync(GR_FULL, is_, SC_WARPS - 1), t_cnt = __shfl_sync(GR_FULL, ic_, SC_WARPS - 1);
+    const u32 wx_sum = __shfl_sync(GR_FULL, is_ - vs, w), wx_cnt = __shfl_sync(GR_FULL, ic_ - vc, w);
     if (w == 0) {
-      if (lane == 0) { sm_agg_sum[k & 1] = t_sum; sm_agg_cnt[k & 1] = t_cnt; }
+      if (lane == 0) { sm_agg_sum[slot] = t_sum; sm_agg_cnt[slot] = t_cnt; }
       __syncwarp();
-      named_arrive(BAR_AGG + (k & 1), 64);             // hand over to the exchange warp
+      named_arrive(BAR_AGG + slot, 64);                // hand over to the exchange warp
     }
-    const u32 n_pre_sum = wx_sum + (wi_sum - run);
+    const u32 pre_sum = wx_sum + (wi_sum - run);       // tile-local exclusive prefix before d[0]
+    const u32 pre_cnt = wx_cnt + (wi_cnt - cnt);
+    const bool first = tbase == meta.off;
+    if (t_cnt <= SC_SIDE_CAP) {
+      // park the breaks: (position in tile, tile-local height)
+      if (m) {
+        int2* sb = side + slot * SC_SIDE_CAP + pre_cnt;
+        u32 rr = pre_sum;
+        const int p0 = tid * SC_ITEMS;
+#pragma unroll
+        for (int i = 0; i < SC_ITEMS; i++) {
+          if (m & (1u << i)) *sb++ = make_int2(p0 + i, (int)rr);
+          rr += (u32)d[i];
+        }
+      }
+      if (tid == 0) {
+        sm_q[slot][0] = t_cnt; sm_q[slot][1] = jb; sm_q[slot][2] = tile; sm_q[slot][3] = (u32)meta.c;
+        sm_q[slot][4] = first; sm_q[slot][5] = 1;
+      }
+    } else {
+      // more than SC_SIDE_CAP breaks in 8192 cells: wait for this tile's prefix and write from registers
+      named_sync(BAR_PREFIX + slot, SC_THREADS);
+      const u32 ex_sum = sm_ex_sum[slot];
+      const u64 ex_cnt = sm_ex_cnt[slot];
+      if (tid == 0) {
+        if (first) {
+          out.chrom_start[meta.c] = ex_cnt;
+          if (ex_sum != 0) atomicOr(err, GR_DE_TAIL);
+        }
+        if (tile == ntiles - 1) {
+          *out.total = ex_cnt + t_cnt;
+          out.chrom_start[L.nchrom] = ex_cnt + t_cnt;
+        }
+      }
+      if (m) {
+        u32 rr = ex_sum + pre_sum;
+        u64 rank = ex_cnt + pre_cnt;
+        const u32 j0 = jb + tid * SC_ITEMS;
+        bool neg = false;
+#pragma unroll
+        for (int i = 0; i < SC_ITEMS; i++) {
+          if (m & (1u << i)) {
+            const int N = (int)rr;
+            neg |= N < 0;
+            out.end[rank] = j0 + i;
+            out.val[rank] = units_to_val(N < 0 ? 0 : N);
+            rank++;
+          }
+          rr += (u32)d[i];
+        }
+        if (neg) atomicOr(err, GR_DE_PILE);
+      }
+      if (tid == 0) sm_q[slot][5] = 0;
+    }
     TileMeta meta_next;
     meta_next.c = c_next;
     meta_next.off = L.off[c_next];
     meta_next.len = L.len[c_next];
     meta_next.act = (L.flags[c_next] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
 
-    // ---- B(k-1): write the breaks of the previous tile (its prefix arrived meanwhile)
-    if (have_prev) emit_prev(k - 1);
-    named_sync(BAR_COMPUTE, SC_CT);                    // stage (k+2)%3 == (k-1)%3 is free; sm_w* reusable
-    issue(tile + 2 * G, (k + 2) % SC_NSTAGE);
-
-    p_tile = tile; p_jb = jb; p_pre_sum = n_pre_sum; p_wx_cnt = wx_cnt; p_lane_cnt_incl = wi_cnt; p_m = m; p_tcnt = t_cnt;
-    p_c = meta.c; p_first = tbase == meta.off; have_prev = true;
+    // ---- B(k-LAG): the prefix of that tile has had two rounds to arrive
+    if (k >= SC_LAG) {
+      const int ps = (k - SC_LAG) % SC_NSLOT;
+      if (sm_q[ps][5]) finish(ps, sm_q[ps][0], sm_q[ps][1], sm_q[ps][2], sm_q[ps][0], (int)sm_q[ps][3], sm_q[ps][4] != 0);
+    }
     meta = meta_next;
   }
-  if (have_prev) emit_prev(k - 1);
+  // drain
+  named_sync(BAR_COMPUTE, SC_CT);
+  for (u32 kk = (k >= SC_LAG ? k - SC_LAG : 0); kk < k; kk++) {
+    const int ps = kk % SC_NSLOT;
+    if (sm_q[ps][5]) finish(ps, sm_q[ps][0], sm_q[ps][1], sm_q[ps][2], sm_q[ps][0], (int)sm_q[ps][3], sm_q[ps][4] != 0);
+  }
   cp_async_wait<0>();
 }
 
@@ -403,7 +430,7 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, const int32_t* delta,
                        const ScanScratch& sc, DevRle out, u32* bitmap, int* err) {
   const u64 ntiles = L.nblocks;                        // one tile per 8192-cell block
   static int grid = 0;
-  const size_t smem = (size_t)SC_NSTAGE * SC_STAGE_INT4 * sizeof(int4);
+  const size_t smem = (size_t)SC_NSTAGE * SC_STAGE_INT4 * sizeof(int4) + (size_t)SC_NSLOT * SC_SIDE_CAP * sizeof(int2);
   if (!grid) {
     int dev = 0, sms = 0, per = 0;
     cudaGetDevice(&dev);

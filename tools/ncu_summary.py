@@ -38,15 +38,21 @@ def main():
             if k in hdr:
                 i = hdr.index(k)
                 print("  %-82s %s %s" % (k, r[i], units[i]))
-    src = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
-    if len(src) > 2:
+    allsrc = list(csv.reader(io.StringIO(run([rep, "--page", "source", "--csv"]))))
+    starts = [i for i, r in enumerate(allsrc) if r and r[0] == "Kernel Name"] + [len(allsrc)]
+    for si in range(len(starts) - 1):
+        src = allsrc[starts[si]:starts[si + 1]]
+        if len(src) <= 2:
+            continue
+        print("source page of:", src[0][1][:60])
         h = src[1]
-        data = src[2:]
-        iS, iSrc = h.index("# Samples"), h.index("Source")
+        data = [r for r in src[2:] if len(r) == len(h)]
+        iS, iSrc, iEx = h.index("# Samples"), h.index("Source"), h.index("Instructions Executed")
         i0, i1 = h.index("stall_barrier"), h.index("stall_wait")
         names = h[i0:i1 + 1]
         tot = sum(int(r[iS]) for r in data)
-        print("warp-state samples: %d; top instructions (SASS, samples, dominant stall):" % tot)
+        print("warp-state samples: %d; warp instructions executed: %d; top instructions (SASS, samples, dominant stall):"
+              % (tot, sum(int(r[iEx]) for r in data)))
         for i in sorted(sorted(range(len(data)), key=lambda i: -int(data[i][iS]))[:14]):
             r = data[i]
             st = sorted(((int(r[i0 + k]), names[k]) for k in range(len(names))), reverse=True)
