@@ -97,7 +97,7 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64
 #define SC_NSTAGE 2
 #define SC_LAG 2                  // rounds between A(k) and B(k)
 #define SC_NSLOT 3                // side buffers / hand-over slots (SC_LAG + 1)
-#define SC_SIDE_CAP 1536          // parked breaks per tile (8 B each); denser tiles take the in-place path
+#define SC_SIDE_CAP 1536          // parked breaks per tile (8 B each); denser tiles take the dense path
 #define BAR_COMPUTE 1
 #define BAR_AGG 2                 // + slot
 #define BAR_PREFIX 5              // + slot
@@ -142,14 +142,11 @@ __device__ __forceinline__ TileMeta tile_meta(const DevLayout& L, u32 tile, u32 
   return m;
 }
 
-// 16-byte chunk g of a tile lives at chunk g ^ ((g >> 3) & 3) of its stage: the
-// striped cp.async writes stay contiguous and the blocked reads (thread t reads
-// chunks 4t..4t+3) hit 8 distinct 16-byte bank groups per quarter warp.
-__device__ __forceinline__ int sc_swz(int g) { return g ^ ((g >> 3) & 3); }
-
+// blocked read of a thread's 16 cells from an (unswizzled) stage: used only by the
+// rare dense path, so the 4-way bank conflict does not matter
 __device__ __forceinline__ void sc_load_items(const int4* stage, int tid, int (&d)[SC_ITEMS]) {
-  const int4 x0 = stage[sc_swz(4 * tid + 0)], x1 = stage[sc_swz(4 * tid + 1)];
-  const int4 x2 = stage[sc_swz(4 * tid + 2)], x3 = stage[sc_swz(4 * tid + 3)];
+  const int4 x0 = stage[4 * tid + 0], x1 = stage[4 * tid + 1];
+  const int4 x2 = stage[4 * tid + 2], x3 = stage[4 * tid + 3];
   d[0] = x0.x; d[1] = x0.y; d[2] = x0.z; d[3] = x0.w;
   d[4] = x1.x; d[5] = x1.y; d[6] = x1.z; d[7] = x1.w;
   d[8] = x2.x; d[9] = x2.y; d[10] = x2.z; d[11] = x2.w;
@@ -164,6 +161,9 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
   __shared__ u32 sm_agg_sum[SC_NSLOT], sm_agg_cnt[SC_NSLOT];
   __shared__ u32 sm_ex_sum[SC_NSLOT];
   __shared__ u64 sm_ex_cnt[SC_NSLOT];
+  __shared__ u32 sm_q[SC_NSLOT][5];                    // jb, tile, chrom, first|live<<1, #breaks
+  __shared__ u32 sm_bm[SC_CT / 2];                     // the tile's break bitmap (16 words per warp)
+  __shared__ unsigned char sm_list[SC_WARPS * 128];    // per warp: its non-zero chunks
 
   const int tid = threadIdx.x, lane = tid & 31;
   const u32 G = gridDim.x, b = blockIdx.x;
@@ -194,6 +194,7 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
         if (need_a) va = ld_status(pa);
         const bool ok = !need_a || ((va.x >> 62) == 1 && (va.y >> 62) == 1);
         if (__all_sync(GR_FULL, ok)) break;
+        __nanosleep(64);
       }
       u32 s_in = need_a ? (u32)va.x : 0u;
       u64 c_in = need_a ? (va.y & GR_LB_PAYLOAD) : 0ull;
@@ -213,6 +214,7 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
         const bool ok = (!need_g || ((vg.x >> 62) == 1 && (vg.y >> 62) == 1)) &&
                         (!need_p || ((vp.x >> 62) == 1 && (vp.y >> 62) == 1));
         if (__all_sync(GR_FULL, ok)) break;
+        __nanosleep(64);
       }
       u32 s_g = need_g ? (u32)vg.x : 0u, s_p = need_p ? (u32)vp.x : 0u;
       u64 c_g = need_g ? (vg.y & GR_LB_PAYLOAD) : 0ull, c_p = need_p ? (vp.y & GR_LB_PAYLOAD) : 0ull;
@@ -236,12 +238,11 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
 
   // ------------------------------------------------------------ compute warps
   const int w = tid >> 5;
-  const int swt = sc_swz(tid);                         // swizzled chunk of this thread inside a 512-chunk quarter
   const int4* src = reinterpret_cast<const int4*>(delta) + (u64)b * (GR_BLOCK_SLOTS / 4) + tid;
   const u64 src_step = (u64)G * (GR_BLOCK_SLOTS / 4);
-  auto issue = [&](bool on, int stage, const int4* from) {   // chunk q*512+tid (16 B) -> swizzled slot
+  auto issue = [&](bool on, int stage, const int4* from) {   // chunk q*512+tid (16 B), same place in the stage
     if (on) {
-      int4* dst = sm_x + stage * SC_STAGE_INT4 + swt;
+      int4* dst = sm_x + stage * SC_STAGE_INT4 + tid;
 #pragma unroll
       for (int q = 0; q < 4; q++) cp_async16(dst + q * SC_CT, from + q * SC_CT);
     }
@@ -250,31 +251,29 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
   issue(b < ntiles, 0, src);
   issue(b + G < ntiles, 1, src + src_step);
   TileMeta meta = tile_meta(L, b, ntiles);
+  if (tid < SC_NSLOT) sm_q[tid][3] = 0;
 
-  // per-slot state of tiles whose breaks are parked: written by thread 0 in A(k), read by
-  // everyone in B(k) two rounds (and several barriers) later
-  __shared__ u32 sm_q[SC_NSLOT][6];                    // cnt, jb, tile, chrom, first, live
-  if (tid < SC_NSLOT) sm_q[tid][5] = 0;
-
-  // B: convert and store the parked breaks of the tile in `slot`
-  auto finish = [&](int slot, u32 cnt_, u32 jb_, u32 tile_, u32 tcnt_, int c_, bool first_) {
+  // B: convert and store the parked breaks of the tile in `slot` (all 512 threads, dense)
+  auto finish = [&](int slot) {
+    const u32 jb_ = sm_q[slot][0], tile_ = sm_q[slot][1], fl = sm_q[slot][3];
+    const int c_ = (int)sm_q[slot][2];
+    const u32 cnt_ = sm_q[slot][4];
     named_sync(BAR_PREFIX + slot, SC_THREADS);
     const u32 ex_sum = sm_ex_sum[slot];
     const u64 ex_cnt = sm_ex_cnt[slot];
     if (tid == 0) {
-      if (first_) {
+      if (fl & 1) {
         out.chrom_start[c_] = ex_cnt;
         if (ex_sum != 0) atomicOr(err, GR_DE_TAIL);    // previous chromosome did not return to 0 (2283-2289)
       }
       if (tile_ == ntiles - 1) {
-        *out.total = ex_cnt + tcnt_;
-        out.chrom_start[L.nchrom] = ex_cnt + tcnt_;
+        *out.total = ex_cnt + cnt_;
+        out.chrom_start[L.nchrom] = ex_cnt + cnt_;
       }
     }
-    const int2* sb = side + slot * SC_SIDE_CAP;
     bool neg = false;
-    for (u32 n = tid; n < cnt_; n += SC_CT) {          // lane n <-> n-th break: coalesced stores
-      const int2 e = sb[n];
+    for (u32 n = tid; n < cnt_; n += SC_CT) {          // thread n <-> n-th break of the tile: coalesced stores
+      const int2 e = side[slot * SC_SIDE_CAP + n];
       const int N = (int)(ex_sum + (u32)e.y);
       neg |= N < 0;
       out.end[ex_cnt + n] = jb_ + (u32)e.x;
@@ -288,23 +287,21 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
     const int slot = k % SC_NSLOT;
     // chromosome of the tile after this one: first hop now, second hop after the scan
     const int c_next = tile + G < ntiles ? L.blk2chrom[tile + G] : 0;
-    // ---- A(k): scan tile k
     cp_async_wait<1>();
     named_sync(BAR_COMPUTE, SC_CT);                    // tile k is in shared memory (all threads' copies)
-    int d[SC_ITEMS];
-    sc_load_items(sm_x + (k & 1) * SC_STAGE_INT4, tid, d);
+    const int4* stage = sm_x + (k & 1) * SC_STAGE_INT4;
     const u64 tbase = (u64)tile * GR_BLOCK_SLOTS;
     const u32 jb = (u32)(tbase - meta.off);            // chromosome position of the tile's first cell
     const u32 len = meta.len;
     const bool interior = jb >= 1 && (u64)jb + GR_BLOCK_SLOTS <= (u64)len;
-    u32 run = 0, m = 0;
-    if (interior) {
-#pragma unroll
-      for (int i = 0; i < SC_ITEMS; i++) {
-        run += (u32)d[i];
-        m |= (d[i] != 0 ? 1u : 0u) << i;
-      }
-    } else {
+    bool fast = interior;
+
+    // dense scan of the thread's 16 cells (chromosome ends, over-full tiles)
+    int d[SC_ITEMS];
+    u32 run = 0, m = 0, cnt = 0, wi_sum = 0, wi_cnt = 0;
+    auto dense_part1 = [&]() {
+      sc_load_items(stage, tid, d);
+      run = 0; m = 0;
       const u32 j0 = jb + tid * SC_ITEMS;
 #pragma unroll
       for (int i = 0; i < SC_ITEMS; i++) {
@@ -313,50 +310,111 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
         const bool brk = (jj == len) || (d[i] != 0 && jj >= 1 && jj < len);
         m |= (brk ? 1u : 0u) << i;
       }
-    }
-    if (!meta.act) m = 0;
-    const u32 cnt = __popc(m);
-    const u32 wi_sum = warp_incl_scan_u32(run, lane);
-    const u32 wi_cnt = warp_incl_scan_u32(cnt, lane);
-    if (lane == 31) { sm_wsum[w] = wi_sum; sm_wcnt[w] = wi_cnt; }
-    {
+      if (!meta.act) m = 0;
+      cnt = __popc(m);
+      wi_sum = warp_incl_scan_u32(run, lane);
+      wi_cnt = warp_incl_scan_u32(cnt, lane);
+      if (lane == 31) { sm_wsum[w] = wi_sum; sm_wcnt[w] = wi_cnt; }
       const u32 hi = __shfl_down_sync(GR_FULL, m, 1);
       if (!(lane & 1)) bitmap[(tbase >> 5) + (tid >> 1)] = m | (hi << 16);
-    }
-    named_sync(BAR_COMPUTE, SC_CT);                    // cells are in registers: the stage is free
-    src += src_step;
-    issue(tile + 2 * G < ntiles, k & 1, src + src_step);   // tile k+2 -> the stage just read
+    };
+
+    const int4* wst = stage + w * 128;                 // this warp's 512 cells = 128 chunks of 16 B
+    unsigned char* wlist = sm_list + w * 128;          // indices of its non-zero chunks, in order
+    u32 nnz = 0;
+    if (fast) {
+      // ---- A(k), sparse-aware: ~94 % of the cells are zero; they neither move the running
+      // sum nor break an interval.  Each warp tests its 128 chunks with four coalesced
+      // LDS.128 + ballots, lists the non-zero ones, and from here on only they cost work.
+      u32 cprev = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int4 x = wst[r * 32 + lane];
+        const bool nz = (x.x | x.y | x.z | x.w) != 0;
+        const u32 M = __ballot_sync(GR_FULL, nz);
+        if (nz) wlist[cprev + __popc(M & ((1u << lane) - 1))] = (unsigned char)(r * 32 + lane);
+        cprev += __popc(M);
+      }
+      nnz = cprev;
+      if (lane < 16) sm_bm[w * 16 + lane] = 0;
+      __syncwarp();
+      // phase 1: the warp's totals (sum of deltas, number of non-zero cells)
+      u32 ts = 0, tc = 0;
+      for (u32 base = 0; base < nnz; base += 32) {
+        const u32 n = base + lane;
+        int4 x = make_int4(0, 0, 0, 0);
+        if (n < nnz) x = wst[wlist[n]];
+        const u32 c4 = (x.x != 0) + (x.y != 0) + (x.z != 0) + (x.w != 0);
+        ts += __reduce_add_sync(GR_FULL, (u32)x.x + (u32)x.y + (u32)x.z + (u32)x.w);
+        tc += __reduce_add_sync(GR_FULL, c4);
+      }
+      if (lane == 0) { sm_wsum[w] = ts; sm_wcnt[w] = tc; }
+    } else
+      dense_part1();
+    named_sync(BAR_COMPUTE, SC_CT);                    // warp totals are in shared memory
     // exclusive prefix over the 16 warp totals: lanes 0..15 scan them, everyone picks its warp's
     u32 vs = lane < SC_WARPS ? sm_wsum[lane] : 0u, vc = lane < SC_WARPS ? sm_wcnt[lane] : 0u;
-    const u32 is_ = warp_incl_scan_u32(vs, lane), ic_ = warp_incl_scan_u32(vc, lane);
-    const u32 t_sum = __shfl_sync(GR_FULL, is_, SC_WARPS - 1), t_cnt = __shfl_sync(GR_FULL, ic_, SC_WARPS - 1);
-    const u32 wx_sum = __shfl_sync(GR_FULL, is_ - vs, w), wx_cnt = __shfl_sync(GR_FULL, ic_ - vc, w);
+    u32 is_ = warp_incl_scan_u32(vs, lane), ic_ = warp_incl_scan_u32(vc, lane);
+    u32 t_sum = __shfl_sync(GR_FULL, is_, SC_WARPS - 1), t_cnt = __shfl_sync(GR_FULL, ic_, SC_WARPS - 1);
+    if (fast && t_cnt > SC_SIDE_CAP) {                 // > 18.75 % of the tile's cells are breaks: dense path
+      named_sync(BAR_COMPUTE, SC_CT);                  // everyone has read the totals
+      dense_part1();
+      named_sync(BAR_COMPUTE, SC_CT);
+      vs = lane < SC_WARPS ? sm_wsum[lane] : 0u; vc = lane < SC_WARPS ? sm_wcnt[lane] : 0u;
+      is_ = warp_incl_scan_u32(vs, lane); ic_ = warp_incl_scan_u32(vc, lane);
+      t_sum = __shfl_sync(GR_FULL, is_, SC_WARPS - 1); t_cnt = __shfl_sync(GR_FULL, ic_, SC_WARPS - 1);
+      fast = false;
+    }
+    const bool first = tbase == meta.off;
     if (w == 0) {
-      if (lane == 0) { sm_agg_sum[slot] = t_sum; sm_agg_cnt[slot] = t_cnt; }
+      if (lane == 0) {
+        sm_agg_sum[slot] = t_sum; sm_agg_cnt[slot] = t_cnt;
+        if (fast) {
+          sm_q[slot][0] = jb; sm_q[slot][1] = tile; sm_q[slot][2] = (u32)meta.c; sm_q[slot][3] = (first ? 1u : 0u) | 2u;
+          sm_q[slot][4] = t_cnt;
+        } else
+          sm_q[slot][3] = 0;
+      }
       __syncwarp();
       named_arrive(BAR_AGG + slot, 64);                // hand over to the exchange warp
     }
-    const u32 pre_sum = wx_sum + (wi_sum - run);       // tile-local exclusive prefix before d[0]
-    const u32 pre_cnt = wx_cnt + (wi_cnt - cnt);
-    const bool first = tbase == meta.off;
-    if (t_cnt <= SC_SIDE_CAP) {
-      // park the breaks: (position in tile, tile-local height)
-      if (m) {
-        int2* sb = side + slot * SC_SIDE_CAP + pre_cnt;
-        u32 rr = pre_sum;
-        const int p0 = tid * SC_ITEMS;
-#pragma unroll
-        for (int i = 0; i < SC_ITEMS; i++) {
-          if (m & (1u << i)) *sb++ = make_int2(p0 + i, (int)rr);
-          rr += (u32)d[i];
+    if (fast) {
+      // phase 2: park the breaks at their rank inside the tile: (position, tile-local height)
+      const u32 wx_sum = __shfl_sync(GR_FULL, is_ - vs, w), wx_cnt = __shfl_sync(GR_FULL, ic_ - vc, w);
+      int2* sb = side + slot * SC_SIDE_CAP;
+      u32 carry_s = wx_sum, carry_c = wx_cnt;
+      for (u32 base = 0; base < nnz; base += 32) {
+        const u32 n = base + lane;
+        const bool on = n < nnz;
+        int4 x = make_int4(0, 0, 0, 0);
+        u32 q = 0;
+        if (on) { q = wlist[n]; x = wst[q]; }
+        const u32 m4 = (x.x != 0 ? 1u : 0u) | (x.y != 0 ? 2u : 0u) | (x.z != 0 ? 4u : 0u) | (x.w != 0 ? 8u : 0u);
+        const u32 c4 = __popc(m4);
+        const u32 s1 = (u32)x.x, s2 = s1 + (u32)x.y, s3 = s2 + (u32)x.z, s4 = s3 + (u32)x.w;
+        const u32 inc_s = warp_incl_scan_u32(s4, lane), inc_c = warp_incl_scan_u32(c4, lane);
+        if (on) {
+          const u32 ex_s = carry_s + inc_s - s4;       // tile-local running sum before this chunk
+          int2* e = sb + (carry_c + inc_c - c4);
+          const int p0 = w * 512 + (int)(q * 4);
+          if (m4 & 1u) *e++ = make_int2(p0, (int)ex_s);
+          if (m4 & 2u) *e++ = make_int2(p0 + 1, (int)(ex_s + s1));
+          if (m4 & 4u) *e++ = make_int2(p0 + 2, (int)(ex_s + s2));
+          if (m4 & 8u) *e++ = make_int2(p0 + 3, (int)(ex_s + s3));
+          atomicOr(&sm_bm[w * 16 + (q >> 3)], m4 << ((q & 7) * 4));
         }
+        carry_s += __shfl_sync(GR_FULL, inc_s, 31);
+        carry_c += __shfl_sync(GR_FULL, inc_c, 31);
       }
-      if (tid == 0) {
-        sm_q[slot][0] = t_cnt; sm_q[slot][1] = jb; sm_q[slot][2] = tile; sm_q[slot][3] = (u32)meta.c;
-        sm_q[slot][4] = first; sm_q[slot][5] = 1;
-      }
-    } else {
-      // more than SC_SIDE_CAP breaks in 8192 cells: wait for this tile's prefix and write from registers
+      __syncwarp();
+      if (lane < 16) bitmap[(tbase >> 5) + w * 16 + lane] = sm_bm[w * 16 + lane];
+      named_sync(BAR_COMPUTE, SC_CT);                  // the stage has been consumed: refill it
+      src += src_step;
+      issue(tile + 2 * G < ntiles, k & 1, src + src_step);
+    }
+    if (!fast) {
+      // dense path: wait for this tile's prefix and write its breaks from registers
+      const u32 wx_sum = __shfl_sync(GR_FULL, is_ - vs, w), wx_cnt = __shfl_sync(GR_FULL, ic_ - vc, w);
       named_sync(BAR_PREFIX + slot, SC_THREADS);
       const u32 ex_sum = sm_ex_sum[slot];
       const u64 ex_cnt = sm_ex_cnt[slot];
@@ -371,8 +429,8 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
         }
       }
       if (m) {
-        u32 rr = ex_sum + pre_sum;
-        u64 rank = ex_cnt + pre_cnt;
+        u32 rr = ex_sum + wx_sum + (wi_sum - run);
+        u64 rank = ex_cnt + wx_cnt + (wi_cnt - cnt);
         const u32 j0 = jb + tid * SC_ITEMS;
         bool neg = false;
 #pragma unroll
@@ -388,7 +446,9 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
         }
         if (neg) atomicOr(err, GR_DE_PILE);
       }
-      if (tid == 0) sm_q[slot][5] = 0;
+      named_sync(BAR_COMPUTE, SC_CT);                  // everyone is done with the stage
+      src += src_step;
+      issue(tile + 2 * G < ntiles, k & 1, src + src_step);
     }
     TileMeta meta_next;
     meta_next.c = c_next;
@@ -399,15 +459,14 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
     // ---- B(k-LAG): the prefix of that tile has had two rounds to arrive
     if (k >= SC_LAG) {
       const int ps = (k - SC_LAG) % SC_NSLOT;
-      if (sm_q[ps][5]) finish(ps, sm_q[ps][0], sm_q[ps][1], sm_q[ps][2], sm_q[ps][0], (int)sm_q[ps][3], sm_q[ps][4] != 0);
+      if (sm_q[ps][3] & 2u) finish(ps);
     }
     meta = meta_next;
   }
-  // drain
   named_sync(BAR_COMPUTE, SC_CT);
   for (u32 kk = (k >= SC_LAG ? k - SC_LAG : 0); kk < k; kk++) {
     const int ps = kk % SC_NSLOT;
-    if (sm_q[ps][5]) finish(ps, sm_q[ps][0], sm_q[ps][1], sm_q[ps][2], sm_q[ps][0], (int)sm_q[ps][3], sm_q[ps][4] != 0);
+    if (sm_q[ps][3] & 2u) finish(ps);
   }
   cp_async_wait<0>();
 }
