@@ -10,6 +10,7 @@
 #include <float.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -95,6 +96,8 @@ struct gr_ctx {
   // sample state
   int filling = FILL_NONE;
   bool have_expt = false, have_ctrl = false;
+  bool delta_clean = false;         // the delta array is known to be all zero
+  int zero_after = 1;               // dense scan clears behind itself (GR_SCAN_ZERO=0: memset per sample)
   u64 n_pushed = 0, n_clamped = 0;
   std::vector<double> expt_sums, ctrl_sums;
 
@@ -268,6 +271,7 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     }
     x->expt_sums.assign(nchrom, 0.0);
     x->ctrl_sums.assign(nchrom, 0.0);
+    { const char* e = getenv("GR_SCAN_ZERO"); if (e) x->zero_after = atoi(e) != 0; }
     CK(cudaStreamSynchronize(x->stream));
     return GR_OK;
   }();
@@ -376,9 +380,12 @@ extern "C" int gr_sample_begin(gr_ctx* x, int32_t is_ctrl, const uint8_t* save) 
   }
   x->have_ctrl = false;
   CK(cudaMemsetAsync(x->d_err, 0, sizeof(int), x->stream));
-  stage_begin(x, "memset_delta", x->T * 4);
-  CK(cudaMemsetAsync(x->delta.p, 0, x->T * sizeof(int32_t), x->stream));   // runProgram 5503-5510
-  stage_end(x);
+  if (!x->delta_clean) {
+    stage_begin(x, "memset_delta", x->T * 4);
+    CK(cudaMemsetAsync(x->delta.p, 0, x->T * sizeof(int32_t), x->stream));   // runProgram 5503-5510
+    stage_end(x);
+  }
+  x->delta_clean = false;
   x->filling = is_ctrl ? FILL_CTRL : FILL_EXPT;
   x->n_pushed = 0;
   return GR_OK;
@@ -459,7 +466,7 @@ extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
   sc.st_sum = x->lb0.as<u64>(); sc.st_cnt = x->lb1.as<u64>(); sc.ticket = x->ticket.as<u32>();
   stage_begin(x, "dense_scan", x->T * 4);
   launch_dense_scan(x->stream, x->L, x->delta.as<int32_t>(), sc, out,
-                    (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err);
+                    (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, x->zero_after);
   CKL();
   stage_end(x);
   u64* aI = x->accI.as<u64>() + (ctrl ? x->nchrom : 0);
@@ -484,6 +491,7 @@ extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
   const int derr = *(int*)x->h_small;
   x->n_clamped = *(u64*)((char*)x->h_small + 8);
   if (derr) { x->filling = FILL_NONE; return map_dev_err(derr); }
+  x->delta_clean = x->zero_after != 0;       // the scan left the array all zero
   std::vector<double>& sums = ctrl ? x->ctrl_sums : x->expt_sums;
   for (int c = 0; c < x->nchrom; c++)
     sums[c] = (double)hI[c] + (double)hF[c] * (1.0 / 1099511627776.0);

@@ -6,6 +6,7 @@
 // (2013-2038).  HBM-bound int32 work: no tensor cores.
 #include "gr_common.cuh"
 #include "gr_internal.h"
+#include <stdlib.h>
 
 // ============================================================================
 // K1: two int32 reductions (RED.ADD) per interval record into the dense delta
@@ -95,12 +96,9 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64
 #define SC_ITEMS 16
 #define SC_STAGE_INT4 2048        // 32 KB per stage
 #define SC_NSTAGE 2
-#define SC_LAG 2                  // rounds between A(k) and B(k)
-#define SC_NSLOT 3                // side buffers / hand-over slots (SC_LAG + 1)
-#define SC_SIDE_CAP 1536          // parked breaks per tile (8 B each); denser tiles take the dense path
 #define BAR_COMPUTE 1
 #define BAR_AGG 2                 // + slot
-#define BAR_PREFIX 5              // + slot
+#define BAR_PREFIX 8              // + slot
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -153,9 +151,13 @@ __device__ __forceinline__ void sc_load_items(const int4* stage, int tid, int (&
   d[12] = x3.x; d[13] = x3.y; d[14] = x3.z; d[15] = x3.w;
 }
 
+// SC_LAG: rounds between A(k) and B(k); SC_NSLOT = SC_LAG + 1 side buffers / hand-over slots;
+// SC_SIDE_CAP: parked breaks per tile (8 B each) -- denser tiles take the dense path.
+template <int SC_LAG, int SC_SIDE_CAP>
 __global__ void __launch_bounds__(SC_THREADS, 2)
-k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
-             u32* __restrict__ bitmap, int* __restrict__ err, u32 ntiles) {
+k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
+             u32* __restrict__ bitmap, int* __restrict__ err, u32 ntiles, int zero_after) {
+  constexpr int SC_NSLOT = SC_LAG + 1;
   extern __shared__ int4 sm_x[];                       // SC_NSTAGE stages, then SC_NSLOT side buffers
   __shared__ u32 sm_wsum[SC_WARPS], sm_wcnt[SC_WARPS];
   __shared__ u32 sm_agg_sum[SC_NSLOT], sm_agg_cnt[SC_NSLOT];
@@ -185,36 +187,49 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
       const ulonglong2* pa = S.agg + (tile - j) + lane;
       const ulonglong2* pg = S.grp + (u64)k * ng + lane;
       const ulonglong2* pp = S.grp + (u64)(k - 1) * ng + lane;   // only dereferenced when k > 0
-      // (1) the group's own aggregates: as soon as they are in, the group's last tile
-      //     publishes the group total -- it must NOT wait for the totals of earlier
-      //     groups, or the groups of a round serialise (measured: 35 polls per tile)
-      ulonglong2 va;
+      // One polling loop, all loads of a round issued together (one L2 round trip when
+      // everything is there).  The group's last tile publishes the group total as soon
+      // as the group's own aggregates are in -- it must NOT wait for the totals of
+      // earlier groups, or the groups of a round serialise (measured: 35 polls per tile).
+      const bool is_last = b == min(32u * g + 31u, last_b);
+      ulonglong2 va, vg, vp;
+      va.x = va.y = vg.x = vg.y = vp.x = vp.y = 0;
+      bool ok_a = !need_a, ok_o = !(need_g || need_p), published = !is_last;
+      u32 s_in = 0;
+      u64 c_in = 0;
       for (;;) {
-        va.x = va.y = 0;
-        if (need_a) va = ld_status(pa);
-        const bool ok = !need_a || ((va.x >> 62) == 1 && (va.y >> 62) == 1);
-        if (__all_sync(GR_FULL, ok)) break;
-        __nanosleep(64);
-      }
-      u32 s_in = need_a ? (u32)va.x : 0u;
-      u64 c_in = need_a ? (va.y & GR_LB_PAYLOAD) : 0ull;
+        if (!ok_a) {
+          va = ld_status(pa);
+          ok_a = (va.x >> 62) == 1 && (va.y >> 62) == 1;
+        }
+        if (!ok_o) {
+          bool okg = true, okp = true;
+          if (need_g) { vg = ld_status(pg); okg = (vg.x >> 62) == 1 && (vg.y >> 62) == 1; }
+          if (need_p) { vp = ld_status(pp); okp = (vp.x >> 62) == 1 && (vp.y >> 62) == 1; }
+          ok_o = okg && okp;
+        }
+        const bool all_a = __all_sync(GR_FULL, ok_a);
+        if (all_a && !published) {
+          s_in = need_a ? (u32)va.x : 0u;
+          c_in = need_a ? (va.y & GR_LB_PAYLOAD) : 0ull;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        s_in += __shfl_xor_sync(GR_FULL, s_in, o);
-        c_in += __shfl_xor_sync(GR_FULL, c_in, o);
+          for (int o = 16; o > 0; o >>= 1) {
+            s_in += __shfl_xor_sync(GR_FULL, s_in, o);
+            c_in += __shfl_xor_sync(GR_FULL, c_in, o);
+          }
+          if (lane == 0) st_status(S.grp + (u64)k * ng + g, 1, s_in + agg_s, c_in + agg_c);
+          published = true;
+        }
+        if (all_a && __all_sync(GR_FULL, ok_o)) break;
       }
-      if (lane == 0 && b == min(32u * g + 31u, last_b))
-        st_status(S.grp + (u64)k * ng + g, 1, s_in + agg_s, c_in + agg_c);
-      // (2) totals of the earlier groups of this round and of all groups of the previous round
-      ulonglong2 vg, vp;
-      for (;;) {
-        vg.x = vg.y = vp.x = vp.y = 0;
-        if (need_g) vg = ld_status(pg);
-        if (need_p) vp = ld_status(pp);
-        const bool ok = (!need_g || ((vg.x >> 62) == 1 && (vg.y >> 62) == 1)) &&
-                        (!need_p || ((vp.x >> 62) == 1 && (vp.y >> 62) == 1));
-        if (__all_sync(GR_FULL, ok)) break;
-        __nanosleep(64);
+      if (!is_last) {
+        s_in = need_a ? (u32)va.x : 0u;
+        c_in = need_a ? (va.y & GR_LB_PAYLOAD) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s_in += __shfl_xor_sync(GR_FULL, s_in, o);
+          c_in += __shfl_xor_sync(GR_FULL, c_in, o);
+        }
       }
       u32 s_g = need_g ? (u32)vg.x : 0u, s_p = need_p ? (u32)vp.x : 0u;
       u64 c_g = need_g ? (vg.y & GR_LB_PAYLOAD) : 0ull, c_p = need_p ? (vp.y & GR_LB_PAYLOAD) : 0ull;
@@ -238,7 +253,7 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
 
   // ------------------------------------------------------------ compute warps
   const int w = tid >> 5;
-  const int4* src = reinterpret_cast<const int4*>(delta) + (u64)b * (GR_BLOCK_SLOTS / 4) + tid;
+  const int4* src = reinterpret_cast<const int4*>(delta) + (u64)b * (GR_BLOCK_SLOTS / 4) + tid;   // read side
   const u64 src_step = (u64)G * (GR_BLOCK_SLOTS / 4);
   auto issue = [&](bool on, int stage, const int4* from) {   // chunk q*512+tid (16 B), same place in the stage
     if (on) {
@@ -278,6 +293,9 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
       neg |= N < 0;
       out.end[ex_cnt + n] = jb_ + (u32)e.x;
       out.val[ex_cnt + n] = units_to_val(N < 0 ? 0 : N);
+      // every break of an interior tile is a non-zero cell and vice versa: clearing them
+      // leaves the whole delta array zero for the next sample (no 4 B/bp memset)
+      if (zero_after) delta[(u64)tile_ * GR_BLOCK_SLOTS + (u32)e.x] = 0;
     }
     if (neg) atomicOr(err, GR_DE_PILE);                // ERRPILE 1921, 1969
   };
@@ -446,6 +464,11 @@ k_dense_scan(const int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRl
         }
         if (neg) atomicOr(err, GR_DE_PILE);
       }
+      if (zero_after) {
+#pragma unroll
+        for (int i = 0; i < SC_ITEMS; i++)
+          if (d[i] != 0) delta[tbase + tid * SC_ITEMS + i] = 0;
+      }
       named_sync(BAR_COMPUTE, SC_CT);                  // everyone is done with the stage
       src += src_step;
       issue(tile + 2 * G < ntiles, k & 1, src + src_step);
@@ -485,17 +508,19 @@ void launch_fill_chrom_start(cudaStream_t s, const DevLayout& L, u64* chrom_star
   k_fill_chrom_start<<<1, 32, 0, s>>>(L, chrom_start, total); GR_NOTE_LAUNCH();
 }
 
-void launch_dense_scan(cudaStream_t s, const DevLayout& L, const int32_t* delta,
-                       const ScanScratch& sc, DevRle out, u32* bitmap, int* err) {
+template <int LAG, int CAP>
+static void launch_dense_scan_t(cudaStream_t s, const DevLayout& L, int32_t* delta,
+                                const ScanScratch& sc, DevRle out, u32* bitmap, int* err, int zero_after) {
   const u64 ntiles = L.nblocks;                        // one tile per 8192-cell block
   static int grid = 0;
-  const size_t smem = (size_t)SC_NSTAGE * SC_STAGE_INT4 * sizeof(int4) + (size_t)SC_NSLOT * SC_SIDE_CAP * sizeof(int2);
+  const size_t smem = (size_t)SC_NSTAGE * SC_STAGE_INT4 * sizeof(int4) + (size_t)(LAG + 1) * CAP * sizeof(int2);
+  auto kern = k_dense_scan<LAG, CAP>;
   if (!grid) {
     int dev = 0, sms = 0, per = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(k_dense_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_dense_scan, SC_THREADS, smem);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, SC_THREADS, smem);
     if (per < 1) per = 1;
     if (per > 2) per = 2;
     grid = sms * per;                                  // persistent: co-resident CTAs only
@@ -511,11 +536,24 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, const int32_t* delta,
   cudaMemsetAsync(sc.st_sum, 0, (ntiles + nrounds * st.ngroups) * sizeof(ulonglong2), s);
   u32 nt = (u32)ntiles;
   DevLayout Lc = L;
-  void* args[] = { (void*)&delta, (void*)&Lc, (void*)&st, (void*)&out, (void*)&bitmap, (void*)&err, (void*)&nt };
+  void* args[] = { (void*)&delta, (void*)&Lc, (void*)&st, (void*)&out, (void*)&bitmap, (void*)&err, (void*)&nt, (void*)&zero_after };
   // cooperative launch: fails instead of deadlocking if the CTAs cannot all be resident
-  cudaLaunchCooperativeKernel((const void*)k_dense_scan, dim3(g), dim3(SC_THREADS), args, smem, s);
+  cudaLaunchCooperativeKernel((const void*)kern, dim3(g), dim3(SC_THREADS), args, smem, s);
   GR_NOTE_LAUNCH();
   launch_fill_chrom_start(s, L, out.chrom_start, out.total);
+}
+
+void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
+                       const ScanScratch& sc, DevRle out, u32* bitmap, int* err, int zero_after) {
+  static int lag = -1;
+  if (lag < 0) {
+    const char* e = getenv("GR_SCAN_LAG");             // tuning knob; default chosen from measurements
+    lag = e ? atoi(e) : 2;
+  }
+  if (lag == 3) launch_dense_scan_t<3, 1280>(s, L, delta, sc, out, bitmap, err, zero_after);
+  else if (lag == 4) launch_dense_scan_t<4, 1024>(s, L, delta, sc, out, bitmap, err, zero_after);
+  else if (lag == 1) launch_dense_scan_t<1, 1536>(s, L, delta, sc, out, bitmap, err, zero_after);
+  else launch_dense_scan_t<2, 1536>(s, L, delta, sc, out, bitmap, err, zero_after);
 }
 
 // ============================================================================

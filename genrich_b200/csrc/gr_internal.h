@@ -35,8 +35,10 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64
 struct ScanScratch {
   u64* st_sum; u64* st_cnt; u32* ticket;   // look-back state, zeroed per launch
 };
-void launch_dense_scan(cudaStream_t s, const DevLayout& L, const int32_t* delta,
-                       const ScanScratch& sc, DevRle out, u32* bitmap, int* err);
+// zero_after: the scan clears every non-zero delta cell behind itself, so the array is all
+// zero again when the kernel ends (the next sample then needs no 4 B/bp memset)
+void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
+                       const ScanScratch& sc, DevRle out, u32* bitmap, int* err, int zero_after);
 
 // ---- K2b: per-chromosome sum of (float)(end-start)*val, exact fixed point ------
 // acc_int / acc_frac: [nchrom] u64, zeroed by the caller.  sum = int + frac*2^-40.
