@@ -66,9 +66,9 @@ PEAK_DTYPE = np.dtype([("chrom", "<i4"), ("summit", "<u4"), ("start", "<i8"),
 ABI_SYMBOLS = [
     "gr_create", "gr_destroy", "gr_set_params", "gr_reset", "gr_strerror",
     "gr_last_error_detail", "gr_sample_begin", "gr_push_intervals",
-    "gr_push_intervals_device", "gr_sample_pileup", "gr_replicate_finish",
+    "gr_push_intervals_device", "gr_prefetch_intervals", "gr_sample_pileup", "gr_replicate_finish",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
-    "gr_bh_set_global", "gr_call_peaks", "gr_fetch_intervals",
+    "gr_bh_set_global", "gr_call_peaks", "gr_peaks_device", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
     "gr_kernel_launches", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
     "gr_pinned_alloc", "gr_pinned_free",
@@ -127,6 +127,8 @@ class Api:
             self.strerror = fn("strerror", C.c_char_p, [C.c_int])
             self.last_error_detail = fn("last_error_detail", C.c_char_p, [vp])
             self.push_intervals_device = fn("push_intervals_device", C.c_int, [vp, vp, u64])
+            self.prefetch_intervals = fn("prefetch_intervals", C.c_int, [vp, vp, u64])
+            self.peaks_device = fn("peaks_device", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)])
             self.timing_enable = fn("timing_enable", C.c_int, [vp, i32])
             self.timing_get = fn("timing_get", C.c_int, [vp, C.POINTER(GrStageTime), i32, C.POINTER(i32)])
             self.timing_reset = fn("timing_reset", C.c_int, [vp])
@@ -235,6 +237,12 @@ class Context:
     def push_intervals_device(self, dptr: int, n: int):
         self._check(self.api.push_intervals_device(self._h, C.c_void_p(dptr), n), "push_intervals_device")
 
+    def prefetch_ptr(self, host_ptr: int, n: int):
+        self._check(self.api.prefetch_intervals(self._h, C.c_void_p(host_ptr), n), "prefetch_intervals")
+
+    def push_ptr(self, host_ptr: int, n: int):
+        self._check(self.api.push_intervals(self._h, C.c_void_p(host_ptr), n), "push_intervals")
+
     def sample_pileup(self) -> np.ndarray:
         sums = np.zeros(self.nchrom, dtype=np.float64)
         self._check(self.api.sample_pileup(self._h, sums.ctypes.data_as(C.POINTER(C.c_double))), "sample_pileup")
@@ -268,6 +276,11 @@ class Context:
         p, n, st = C.c_void_p(), C.c_uint64(), GrRunStats()
         self._check(self.api.call_peaks(self._h, C.byref(p), C.byref(n), C.byref(st)), "call_peaks")
         return _np_from(p.value, n.value, PEAK_DTYPE), st
+
+    def peaks_device_ptr(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(self.api.peaks_device(self._h, C.byref(p), C.byref(n)), "peaks_device")
+        return p.value or 0, n.value
 
     def fetch(self, which: int, replicate: int, chrom: int) -> Intervals | None:
         e, v, x, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_uint64()

@@ -88,10 +88,16 @@ struct gr_ctx {
 
   // interval staging
   DevBuf stage[2];
+  DevBuf binRecs, binCnt, binCursor;   // locality pass in front of the scatter
+  u64 bin_min = 1ull << 21;            // pushes smaller than this go straight to the scatter (GR_SCATTER_BIN=0: never bin)
   cudaEvent_t stage_free[2] = { nullptr, nullptr }, stage_ready[2] = { nullptr, nullptr };
   void* h_stage[2] = { nullptr, nullptr };
   int stage_next = 0;
   static const u64 STAGE_RECS = 1ull << 22;     // 4M records = 64 MB
+
+  // prefetched host buffers (gr_prefetch_intervals)
+  struct Prefetch { DevBuf buf; const int32_t* host = nullptr; u64 n = 0; cudaEvent_t ready = nullptr, freed = nullptr; bool live = false; };
+  Prefetch pf[2];
 
   // sample state
   int filling = FILL_NONE;
@@ -272,6 +278,7 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     x->expt_sums.assign(nchrom, 0.0);
     x->ctrl_sums.assign(nchrom, 0.0);
     { const char* e = getenv("GR_SCAN_ZERO"); if (e) x->zero_after = atoi(e) != 0; }
+    { const char* e = getenv("GR_SCATTER_BIN"); if (e && !atoi(e)) x->bin_min = 0; }
     CK(cudaStreamSynchronize(x->stream));
     return GR_OK;
   }();
@@ -320,7 +327,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   DevBuf* all[] = { &x->d_off, &x->d_len, &x->d_flags, &x->d_blk2chrom, &x->delta, &x->bmE, &x->bmC,
     &x->rankE, &x->rankC, &x->rankTmp, &x->lb0, &x->lb1, &x->lb2, &x->ticket, &x->small, &x->accI,
     &x->accF, &x->exptEnd, &x->exptVal, &x->exptCS, &x->exptTot, &x->rawEnd, &x->rawVal, &x->rawCS,
-    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->stage[0], &x->stage[1],
+    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->stage[0], &x->stage[1], &x->binRecs, &x->binCnt, &x->binCursor,
     &x->qVal, &x->tKeys, &x->tLens, &x->tPval, &x->tQval, &x->tCount, &x->slot, &x->hk, &x->hl,
     &x->hcount, &x->bk0, &x->bk1, &x->bl0, &x->bl1, &x->bhist, &x->bksum, &x->bx, &x->bdk, &x->bdq,
     &x->bdl, &x->bdcount, &x->fsum, &x->fdf, &x->repviews, &x->evIdx, &x->evCount, &x->headIdx,
@@ -335,6 +342,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   }
   for (auto& s : x->stages) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   if (x->tm_a) { cudaEventDestroy(x->tm_a); cudaEventDestroy(x->tm_b); }
+  for (auto& p : x->pf) { p.buf.release(); if (p.ready) { cudaEventDestroy(p.ready); cudaEventDestroy(p.freed); } }
   if (x->stream) cudaStreamDestroy(x->stream);
   if (x->copy) cudaStreamDestroy(x->copy);
   delete x;
@@ -391,20 +399,68 @@ extern "C" int gr_sample_begin(gr_ctx* x, int32_t is_ctrl, const uint8_t* save) 
   return GR_OK;
 }
 
+static int scatter_records(gr_ctx* x, const int32_t* d_recs, u64 n) {
+  if (x->bin_min && n >= x->bin_min) {
+    CK(x->binRecs.ensure(n * 16));
+    CK(x->binCnt.ensure(8192 * sizeof(u32)));
+    CK(x->binCursor.ensure(8192 * sizeof(u64)));
+    launch_scatter_binned(x->stream, x->L, d_recs, n, x->delta.as<int32_t>(), x->d_err, x->d_clamped,
+                          x->binRecs.as<int32_t>(), x->binCnt.as<u32>(), x->binCursor.as<u64>());
+  } else
+    launch_scatter(x->stream, x->L, d_recs, n, x->delta.as<int32_t>(), x->d_err, x->d_clamped);
+  return GR_OK;
+}
+
 extern "C" int gr_push_intervals_device(gr_ctx* x, const int32_t* d_recs, uint64_t n) {
   if (!x || x->filling == FILL_NONE || (!d_recs && n)) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
   stage_begin(x, "scatter", n * 16);
-  launch_scatter(x->stream, x->L, d_recs, n, x->delta.as<int32_t>(), x->d_err, x->d_clamped);
+  { int r = scatter_records(x, d_recs, n); if (r) return r; }
   CKL();
   stage_end(x);
   x->n_pushed += n;
   return GR_OK;
 }
 
+extern "C" int gr_prefetch_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
+  if (!x || !recs || !n) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, recs) != cudaSuccess || at.type != cudaMemoryTypeHost) {
+    cudaGetLastError();
+    return GR_OK;                              // not pinned: nothing to gain, the push will stage it
+  }
+  for (auto& p : x->pf) {
+    if (p.live) continue;
+    if (!p.ready) {
+      CK(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
+      CK(cudaEventCreateWithFlags(&p.freed, cudaEventDisableTiming));
+    } else
+      CK(cudaStreamWaitEvent(x->copy, p.freed, 0));     // the scatter that last read this buffer is done
+    CK(p.buf.ensure(n * 16));
+    CK(cudaMemcpyAsync(p.buf.p, recs, n * 16, cudaMemcpyHostToDevice, x->copy));
+    CK(cudaEventRecord(p.ready, x->copy));
+    p.host = recs; p.n = n; p.live = true;
+    return GR_OK;
+  }
+  return GR_OK;                                // both slots busy: ignored
+}
+
 extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
   if (!x || x->filling == FILL_NONE || (!recs && n)) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
+  for (auto& p : x->pf)
+    if (p.live && p.host == recs && p.n == n) {          // already on its way (gr_prefetch_intervals)
+      CK(cudaStreamWaitEvent(x->stream, p.ready, 0));
+      stage_begin(x, "scatter", n * 16);
+      { int r = scatter_records(x, p.buf.as<int32_t>(), n); if (r) return r; }
+      CKL();
+      stage_end(x);
+      CK(cudaEventRecord(p.freed, x->stream));
+      p.live = false;
+      x->n_pushed += n;
+      return GR_OK;
+    }
   cudaPointerAttributes at;
   bool pinned = false;
   if (cudaPointerGetAttributes(&at, recs) == cudaSuccess) {
@@ -434,7 +490,7 @@ extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
     CK(cudaEventRecord(x->stage_ready[b], x->copy));
     CK(cudaStreamWaitEvent(x->stream, x->stage_ready[b], 0));
     stage_begin(x, "scatter", m * 16);
-    launch_scatter(x->stream, x->L, x->stage[b].as<int32_t>(), m, x->delta.as<int32_t>(), x->d_err, x->d_clamped);
+    { int r = scatter_records(x, x->stage[b].as<int32_t>(), m); if (r) return r; }
     CKL();
     stage_end(x);
     CK(cudaEventRecord(x->stage_free[b], x->stream));
@@ -1051,3 +1107,10 @@ extern "C" void* gr_pinned_alloc(size_t bytes) {
   return p;
 }
 extern "C" void gr_pinned_free(void* p) { if (p) cudaFreeHost(p); }
+
+extern "C" int gr_peaks_device(gr_ctx* x, const gr_peak** d_peaks, uint64_t* n) {
+  if (!x || !d_peaks || !n) return GR_ERR_ARG;
+  *d_peaks = x->peaks_h.empty() ? nullptr : (const gr_peak*)x->peakOut.p;
+  *n = x->peaks_h.size();
+  return GR_OK;
+}

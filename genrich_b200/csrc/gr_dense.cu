@@ -54,6 +54,126 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64
   k_scatter<<<(unsigned)blocks, 256, 0, s>>>((const int4*)recs, n, L, delta, err, clamped); GR_NOTE_LAUNCH();
 }
 
+// ----------------------------------------------------------------------------
+// Locality pass in front of K1.  Read names arrive in queryname order, i.e. the
+// records hit the 12 GB delta array at random: every RED.ADD costs a DRAM read of a
+// line it shares with nobody and a write-back (ncu r01_f: 8.5 GB read + 3.2 GB
+// written for 100 M atomics, 30 % of DRAM peak).  Records are therefore first moved
+// into ~3000 buckets of 2^20 cells by the cell of their start (a fragment ends a
+// few hundred cells further, i.e. in the same bucket); the scatter then sweeps the
+// array bucket by bucket with the whole grid inside an L2-sized window, so each
+// touched line is fetched and written back once, in address order.  The order of
+// records inside a bucket is arbitrary -- integer atomics make the result the same.
+#define BIN_CHUNK 8192            // records per CTA in the move pass
+
+__device__ __forceinline__ u32 bin_of(const int4 r, const DevLayout& L, int shift) {
+  const int c = r.x;
+  if (c < 0 || c >= L.nchrom) return 0;
+  const u64 off = L.off[c];
+  if (off == ~0ull) return 0;
+  i64 s = r.y;
+  if (s < 0) s = 0;
+  return (u32)((off + (u64)s) >> shift);
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_count(const int4* __restrict__ recs, u64 n, DevLayout L, int shift, u32 nb, u32* __restrict__ cnt) {
+  extern __shared__ u32 sh[];
+  for (u32 i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u32 bkt = bin_of(ld_stream_v4(recs + i), L, shift);
+    if (bkt >= nb) bkt = nb - 1;
+    atomicAdd(&sh[bkt], 1u);
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < nb; i += blockDim.x)
+    if (sh[i]) atomicAdd(cnt + i, sh[i]);
+}
+
+// exclusive scan of the bucket counts into the running cursors (one block)
+__global__ void __launch_bounds__(1024)
+k_bin_scan(const u32* __restrict__ cnt, u32 nb, u64* __restrict__ cursor) {
+  __shared__ u64 sm_w[32];
+  __shared__ u64 sm_carry;
+  if (threadIdx.x == 0) sm_carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (u32 base = 0; base < nb; base += 1024) {
+    const u32 i = base + threadIdx.x;
+    const u64 v = i < nb ? cnt[i] : 0;
+    u64 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 t = __shfl_up_sync(GR_FULL, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) sm_w[w] = inc;
+    __syncthreads();
+    u64 wx = 0, tot = 0;
+    for (int k = 0; k < 32; k++) { const u64 a = sm_w[k]; if (k < w) wx += a; tot += a; }
+    const u64 carry = sm_carry;
+    if (i < nb) cursor[i] = carry + wx + inc - v;
+    __syncthreads();
+    if (threadIdx.x == 0) sm_carry = carry + tot;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_bin_move(const int4* __restrict__ recs, u64 n, DevLayout L, int shift, u32 nb,
+           u64* __restrict__ cursor, int4* __restrict__ out) {
+  extern __shared__ u32 sh[];                 // [nb] counts, then fill positions; [nb] reserved bases (low 32 bits) ...
+  u32* cnt = sh;
+  u64* base = reinterpret_cast<u64*>(sh + ((nb + 1) & ~1u));
+  for (u32 i = threadIdx.x; i < nb; i += blockDim.x) cnt[i] = 0;
+  __syncthreads();
+  const u64 lo = (u64)blockIdx.x * BIN_CHUNK;
+  const u64 hi = min(lo + BIN_CHUNK, n);
+  for (u64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    u32 bkt = bin_of(recs[i], L, shift);
+    if (bkt >= nb) bkt = nb - 1;
+    atomicAdd(&cnt[bkt], 1u);
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < nb; i += blockDim.x) {
+    const u32 c = cnt[i];
+    if (c) base[i] = atomicAdd(cursor + i, (u64)c);     // this CTA's slice of bucket i
+    cnt[i] = 0;
+  }
+  __syncthreads();
+  for (u64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+    const int4 r = recs[i];                             // second read of the chunk: L1/L2
+    u32 bkt = bin_of(r, L, shift);
+    if (bkt >= nb) bkt = nb - 1;
+    out[base[bkt] + atomicAdd(&cnt[bkt], 1u)] = r;
+  }
+}
+
+void launch_scatter_binned(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64 n,
+                           int32_t* delta, int* err, u64* clamped, int32_t* scratch_recs,
+                           u32* bin_cnt, u64* bin_cursor) {
+  if (!n) return;
+  int shift = 20;
+  while ((L.T >> shift) + 1 > 6144) shift++;
+  const u32 nb = (u32)(L.T >> shift) + 1;
+  cudaMemsetAsync(bin_cnt, 0, nb * sizeof(u32), s);
+  u64 blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_bin_count<<<(unsigned)blocks, 256, nb * sizeof(u32), s>>>((const int4*)recs, n, L, shift, nb, bin_cnt); GR_NOTE_LAUNCH();
+  k_bin_scan<<<1, 1024, 0, s>>>(bin_cnt, nb, bin_cursor); GR_NOTE_LAUNCH();
+  const size_t smem = (((size_t)nb + 1) & ~(size_t)1) * sizeof(u32) + (size_t)nb * sizeof(u64);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_bin_move, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    attr_set = true;
+  }
+  k_bin_move<<<(unsigned)((n + BIN_CHUNK - 1) / BIN_CHUNK), 256, smem, s>>>((const int4*)recs, n, L, shift, nb, bin_cursor,
+                                                                            (int4*)scratch_recs); GR_NOTE_LAUNCH();
+  launch_scatter(s, L, scratch_recs, n, delta, err, clamped);
+}
+
 // ============================================================================
 // K2: one pass over the dense int32 delta cells -- persistent, software-pipelined,
 // warp-specialised.
@@ -90,11 +210,7 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64
 // delta[j] != 0, or j == len (Genrich.c:2241, 2268); its value is the running sum
 // BEFORE delta[j] is added (2245), rebuilt as the reference float.
 // Running sums are kept modulo 2^32: every true prefix fits in int32.
-#define SC_CT 512                 // compute threads
-#define SC_WARPS 16
-#define SC_THREADS 544            // + one exchange warp
 #define SC_ITEMS 16
-#define SC_STAGE_INT4 2048        // 32 KB per stage
 #define SC_NSTAGE 2
 #define BAR_COMPUTE 1
 #define BAR_AGG 2                 // + slot
@@ -128,11 +244,11 @@ __device__ __forceinline__ void st_status(ulonglong2* p, u64 flag, u32 sum, u64 
 struct ScanStatus { ulonglong2* agg; ulonglong2* grp; u32 ngroups; };
 
 struct TileMeta { u64 off; u32 len; int c; bool act; };
-__device__ __forceinline__ TileMeta tile_meta(const DevLayout& L, u32 tile, u32 ntiles) {
+__device__ __forceinline__ TileMeta tile_meta(const DevLayout& L, u32 tile, u32 ntiles, u32 tile_cells) {
   TileMeta m;
   m.c = 0; m.off = 0; m.len = 0; m.act = false;
   if (tile < ntiles) {
-    m.c = L.blk2chrom[tile];
+    m.c = L.blk2chrom[((u64)tile * tile_cells) >> GR_BLOCK_SHIFT];
     m.off = L.off[m.c];
     m.len = L.len[m.c];
     m.act = (L.flags[m.c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
@@ -153,11 +269,14 @@ __device__ __forceinline__ void sc_load_items(const int4* stage, int tid, int (&
 
 // SC_LAG: rounds between A(k) and B(k); SC_NSLOT = SC_LAG + 1 side buffers / hand-over slots;
 // SC_SIDE_CAP: parked breaks per tile (8 B each) -- denser tiles take the dense path.
-template <int SC_LAG, int SC_SIDE_CAP>
-__global__ void __launch_bounds__(SC_THREADS, 2)
+// SC_CT: compute threads per CTA (16 cells each -> SC_CT*16 cells per tile), + one exchange warp.
+template <int SC_CT, int SC_LAG, int SC_SIDE_CAP>
+__global__ void __launch_bounds__(SC_CT + 32, SC_CT == 512 ? 2 : 4)
 k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
              u32* __restrict__ bitmap, int* __restrict__ err, u32 ntiles, int zero_after) {
   constexpr int SC_NSLOT = SC_LAG + 1;
+  constexpr int SC_WARPS = SC_CT / 32, SC_THREADS = SC_CT + 32, SC_STAGE_INT4 = SC_CT * 4;
+  constexpr u32 TILE = SC_CT * 16;                     // cells per tile (a divisor of GR_BLOCK_SLOTS)
   extern __shared__ int4 sm_x[];                       // SC_NSTAGE stages, then SC_NSLOT side buffers
   __shared__ u32 sm_wsum[SC_WARPS], sm_wcnt[SC_WARPS];
   __shared__ u32 sm_agg_sum[SC_NSLOT], sm_agg_cnt[SC_NSLOT];
@@ -253,8 +372,8 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
 
   // ------------------------------------------------------------ compute warps
   const int w = tid >> 5;
-  const int4* src = reinterpret_cast<const int4*>(delta) + (u64)b * (GR_BLOCK_SLOTS / 4) + tid;   // read side
-  const u64 src_step = (u64)G * (GR_BLOCK_SLOTS / 4);
+  const int4* src = reinterpret_cast<const int4*>(delta) + (u64)b * (TILE / 4) + tid;   // read side
+  const u64 src_step = (u64)G * (TILE / 4);
   auto issue = [&](bool on, int stage, const int4* from) {   // chunk q*512+tid (16 B), same place in the stage
     if (on) {
       int4* dst = sm_x + stage * SC_STAGE_INT4 + tid;
@@ -265,7 +384,7 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
   };
   issue(b < ntiles, 0, src);
   issue(b + G < ntiles, 1, src + src_step);
-  TileMeta meta = tile_meta(L, b, ntiles);
+  TileMeta meta = tile_meta(L, b, ntiles, TILE);
   if (tid < SC_NSLOT) sm_q[tid][3] = 0;
 
   // B: convert and store the parked breaks of the tile in `slot` (all 512 threads, dense)
@@ -295,7 +414,7 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
       out.val[ex_cnt + n] = units_to_val(N < 0 ? 0 : N);
       // every break of an interior tile is a non-zero cell and vice versa: clearing them
       // leaves the whole delta array zero for the next sample (no 4 B/bp memset)
-      if (zero_after) delta[(u64)tile_ * GR_BLOCK_SLOTS + (u32)e.x] = 0;
+      if (zero_after) delta[(u64)tile_ * TILE + (u32)e.x] = 0;
     }
     if (neg) atomicOr(err, GR_DE_PILE);                // ERRPILE 1921, 1969
   };
@@ -304,14 +423,14 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
   for (u32 tile = b; tile < ntiles; tile += G, k++) {
     const int slot = k % SC_NSLOT;
     // chromosome of the tile after this one: first hop now, second hop after the scan
-    const int c_next = tile + G < ntiles ? L.blk2chrom[tile + G] : 0;
+    const int c_next = tile + G < ntiles ? L.blk2chrom[((u64)(tile + G) * TILE) >> GR_BLOCK_SHIFT] : 0;
     cp_async_wait<1>();
     named_sync(BAR_COMPUTE, SC_CT);                    // tile k is in shared memory (all threads' copies)
     const int4* stage = sm_x + (k & 1) * SC_STAGE_INT4;
-    const u64 tbase = (u64)tile * GR_BLOCK_SLOTS;
+    const u64 tbase = (u64)tile * TILE;
     const u32 jb = (u32)(tbase - meta.off);            // chromosome position of the tile's first cell
     const u32 len = meta.len;
-    const bool interior = jb >= 1 && (u64)jb + GR_BLOCK_SLOTS <= (u64)len;
+    const bool interior = jb >= 1 && (u64)jb + TILE <= (u64)len;
     bool fast = interior;
 
     // dense scan of the thread's 16 cells (chromosome ends, over-full tiles)
@@ -508,13 +627,14 @@ void launch_fill_chrom_start(cudaStream_t s, const DevLayout& L, u64* chrom_star
   k_fill_chrom_start<<<1, 32, 0, s>>>(L, chrom_start, total); GR_NOTE_LAUNCH();
 }
 
-template <int LAG, int CAP>
+template <int CT, int LAG, int CAP>
 static void launch_dense_scan_t(cudaStream_t s, const DevLayout& L, int32_t* delta,
                                 const ScanScratch& sc, DevRle out, u32* bitmap, int* err, int zero_after) {
-  const u64 ntiles = L.nblocks;                        // one tile per 8192-cell block
+  const u64 ntiles = L.T / (CT * 16);
   static int grid = 0;
-  const size_t smem = (size_t)SC_NSTAGE * SC_STAGE_INT4 * sizeof(int4) + (size_t)(LAG + 1) * CAP * sizeof(int2);
-  auto kern = k_dense_scan<LAG, CAP>;
+  const size_t smem = (size_t)SC_NSTAGE * (CT * 4) * sizeof(int4) + (size_t)(LAG + 1) * CAP * sizeof(int2);
+  auto kern = k_dense_scan<CT, LAG, CAP>;
+  constexpr int SC_THREADS = CT + 32;
   if (!grid) {
     int dev = 0, sms = 0, per = 0;
     cudaGetDevice(&dev);
@@ -522,7 +642,7 @@ static void launch_dense_scan_t(cudaStream_t s, const DevLayout& L, int32_t* del
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, SC_THREADS, smem);
     if (per < 1) per = 1;
-    if (per > 2) per = 2;
+    if (per > (CT == 512 ? 2 : 4)) per = CT == 512 ? 2 : 4;
     grid = sms * per;                                  // persistent: co-resident CTAs only
     if (grid > 1024) grid = 1024;                      // one lane per CTA group in the exchange
   }
@@ -550,10 +670,17 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
     const char* e = getenv("GR_SCAN_LAG");             // tuning knob; default chosen from measurements
     lag = e ? atoi(e) : 2;
   }
-  if (lag == 3) launch_dense_scan_t<3, 1280>(s, L, delta, sc, out, bitmap, err, zero_after);
-  else if (lag == 4) launch_dense_scan_t<4, 1024>(s, L, delta, sc, out, bitmap, err, zero_after);
-  else if (lag == 1) launch_dense_scan_t<1, 1536>(s, L, delta, sc, out, bitmap, err, zero_after);
-  else launch_dense_scan_t<2, 1536>(s, L, delta, sc, out, bitmap, err, zero_after);
+  static int ct = -1;
+  if (ct < 0) {
+    const char* e = getenv("GR_SCAN_CT");
+    ct = e ? atoi(e) : 512;
+  }
+  if (ct == 256) {
+    if (lag == 3) launch_dense_scan_t<256, 3, 768>(s, L, delta, sc, out, bitmap, err, zero_after);
+    else launch_dense_scan_t<256, 2, 768>(s, L, delta, sc, out, bitmap, err, zero_after);
+  } else if (lag == 3) launch_dense_scan_t<512, 3, 1280>(s, L, delta, sc, out, bitmap, err, zero_after);
+  else if (lag == 1) launch_dense_scan_t<512, 1, 1536>(s, L, delta, sc, out, bitmap, err, zero_after);
+  else launch_dense_scan_t<512, 2, 1536>(s, L, delta, sc, out, bitmap, err, zero_after);
 }
 
 // ============================================================================
@@ -570,7 +697,7 @@ k_rle_moment(DevRle r, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ 
   // each CTA owns one contiguous slice of the interval array, so its running
   // chromosome changes at most a handful of times: sums stay in registers and
   // reach the per-chromosome counters with O(#CTAs) atomics instead of O(n/256)
-  const u64 per = ((n + gridDim.x - 1) / gridDim.x + 255) / 256 * 256;
+  const u64 per = ((n + gridDim.x - 1) / gridDim.x + 1023) / 1024 * 1024;
   const u64 lo = (u64)blockIdx.x * per;
   const u64 hi = min(lo + per, n);
   u64 pi = 0, pf = 0;
@@ -592,8 +719,8 @@ k_rle_moment(DevRle r, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ 
     }
     pi = 0; pf = 0;
   };
-  for (u64 base = lo; base < hi; base += 256) {
-    const u64 last = min(base + 256, hi) - 1;
+  for (u64 base = lo; base < hi; base += 1024) {       // 4 intervals per thread per round
+    const u64 last = min(base + 1024, hi) - 1;
     __syncthreads();
     if (threadIdx.x == 0) {
       sm_c0 = chrom_of_index(r.chrom_start, nchrom, base);
@@ -601,31 +728,38 @@ k_rle_moment(DevRle r, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ 
     }
     __syncthreads();
     const int c0 = sm_c0, c1 = sm_c1;
-    const u64 i = base + threadIdx.x;
     if (c0 == c1) {
       if (c0 != cur) { flush(); cur = c0; }
-      if (i < hi) {
-        const u32 e = r.end[i];
-        const u32 st = (i == r.chrom_start[c0]) ? 0u : r.end[i - 1];
-        const float p = __fmul_rn(__uint2float_rn(e - st), r.val[i]);
-        const u64 ip = (u64)p;                         // p >= 0
-        pi += ip;
-        pf += (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);   // exact: fraction * 2^40
-        if (pf >> 62) { pi += pf >> 40; pf &= (1ull << 40) - 1; }
+      const u64 cs = r.chrom_start[c0];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const u64 i = base + j * 256 + threadIdx.x;
+        if (i < hi) {
+          const u32 e = r.end[i];
+          const u32 st = (i == cs) ? 0u : r.end[i - 1];
+          const float p = __fmul_rn(__uint2float_rn(e - st), r.val[i]);
+          const u64 ip = (u64)p;                       // p >= 0
+          pi += ip;
+          pf += (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);   // exact: fraction * 2^40
+        }
       }
+      if (pf >> 62) { pi += pf >> 40; pf &= (1ull << 40) - 1; }
     } else {
-      // a chromosome boundary inside the tile (rare): per-interval atomics
+      // a chromosome boundary inside the round (rare): per-interval atomics
       flush();
       cur = -1;
-      if (i < hi) {
-        const int c = chrom_of_index(r.chrom_start, nchrom, i);
-        const u32 e = r.end[i];
-        const u32 st = (i == r.chrom_start[c]) ? 0u : r.end[i - 1];
-        const float p = __fmul_rn(__uint2float_rn(e - st), r.val[i]);
-        const u64 ip = (u64)p;
-        const u64 fp = (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);
-        if (ip) atomicAdd(acc_int + c, ip);
-        if (fp) atomicAdd(acc_frac + c, fp);
+      for (int j = 0; j < 4; j++) {
+        const u64 i = base + j * 256 + threadIdx.x;
+        if (i < hi) {
+          const int c = chrom_of_index(r.chrom_start, nchrom, i);
+          const u32 e = r.end[i];
+          const u32 st = (i == r.chrom_start[c]) ? 0u : r.end[i - 1];
+          const float p = __fmul_rn(__uint2float_rn(e - st), r.val[i]);
+          const u64 ip = (u64)p;
+          const u64 fp = (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);
+          if (ip) atomicAdd(acc_int + c, ip);
+          if (fp) atomicAdd(acc_frac + c, fp);
+        }
       }
     }
   }

@@ -31,6 +31,12 @@ struct DevRle {
 void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64 n,
                     int32_t* delta, int* err, u64* clamped);
 
+// same, behind a locality pass that first moves the records into ~3000 position buckets
+// (scratch_recs: n records; bin_cnt / bin_cursor: 8192 entries each)
+void launch_scatter_binned(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64 n,
+                           int32_t* delta, int* err, u64* clamped, int32_t* scratch_recs,
+                           u32* bin_cnt, u64* bin_cursor);
+
 // ---- K2: dense prefix sum + break compaction + bitmap (savePileupExpt 2168) ----
 struct ScanScratch {
   u64* st_sum; u64* st_cnt; u32* ticket;   // look-back state, zeroed per launch

@@ -20,6 +20,8 @@ library in production (NCCL backend), and in the CPU test-suite the oracle twin
 from __future__ import annotations
 
 import ctypes as C
+import os
+import time
 
 import numpy as np
 import torch
@@ -46,10 +48,17 @@ def _tensor_from_ptr(ptr: int, n: int, np_dtype, device: torch.device) -> torch.
 
 
 class ShardedEngine:
-    def __init__(self, api: Api, chrom_len, params: GrParams, device: torch.device, skip=None):
+    def __init__(self, api: Api, chrom_len, params: GrParams, device: torch.device, skip=None, host_group=None):
+        """host_group: process group for the small HOST-side exchanges (two per-chromosome
+        double vectors per replicate, the peak records).  With NCCL as the default backend
+        pass a gloo group (``td.new_group(backend="gloo")``): these values live on the host,
+        and a loopback exchange costs ~0.1 ms where an NCCL call costs a device round trip
+        plus two stream syncs.  The BH histogram -- the one device-resident exchange --
+        always goes through the default (NCCL) group."""
         self.world = td.get_world_size() if td.is_initialized() else 1
         self.rank = td.get_rank() if td.is_initialized() else 0
         self.device = device
+        self.host_group = host_group
         self.chrom_len = np.asarray(chrom_len, dtype=np.uint32)
         self.nchrom = len(chrom_len)
         self.skip = np.zeros(self.nchrom, np.uint8) if skip is None else np.asarray(skip, np.uint8)
@@ -60,6 +69,12 @@ class ShardedEngine:
         self.params = params
         self.saved_any = np.zeros(self.nchrom, dtype=bool)
         self.sample_stats = []
+        self.debug = bool(os.environ.get("GR_DIST_DEBUG"))
+        self.t_acc = {}
+
+    def _tick(self, name, t0):
+        if self.debug:
+            self.t_acc[name] = self.t_acc.get(name, 0.0) + (time.perf_counter() - t0)
 
     # records of chromosomes this rank does not own are dropped here (host routing)
     def route(self, recs: np.ndarray) -> np.ndarray:
@@ -69,29 +84,44 @@ class ShardedEngine:
         return recs[self.owned[recs[:, 0]] != 0]
 
     def _reduce_sums(self, sums: np.ndarray) -> float:
+        t0 = time.perf_counter()
         if self.world > 1:
-            t = torch.from_numpy(sums).to(self.device)
-            td.all_reduce(t, op=td.ReduceOp.SUM)
-            sums = t.cpu().numpy()
+            if self.host_group is not None or self.device.type == "cpu":
+                t = torch.from_numpy(np.ascontiguousarray(sums))
+                td.all_reduce(t, op=td.ReduceOp.SUM, group=self.host_group)
+                sums = t.numpy()
+            else:
+                t = torch.from_numpy(sums).to(self.device)
+                td.all_reduce(t, op=td.ReduceOp.SUM)
+                sums = t.cpu().numpy()
         tot = 0.0
         for v in sums:                       # chromosome order, like the reference's running sum
             tot += float(v)
+        self._tick("reduce_sums", t0)
         return tot
 
     def replicate(self, push_expt, push_ctrl=None, save=None):
         """push_*: callables that feed this rank's records into self.ctx."""
         sv = np.ones(self.nchrom, np.uint8) if save is None else np.asarray(save, np.uint8)
         self.saved_any |= (sv != 0) & (self.skip == 0)
+        t0 = time.perf_counter()
         self.ctx.sample_begin(False, sv)
         push_expt(self.ctx)
-        frag = self._reduce_sums(self.ctx.sample_pileup())
+        s0 = self.ctx.sample_pileup()
+        self._tick("expt_push_pileup", t0)
+        frag = self._reduce_sums(s0)
         ctrl = 0.0
         if push_ctrl is not None:
+            t0 = time.perf_counter()
             self.ctx.sample_begin(True)
             push_ctrl(self.ctx)
-            ctrl = self._reduce_sums(self.ctx.sample_pileup())
+            s1 = self.ctx.sample_pileup()
+            self._tick("ctrl_push_pileup", t0)
+            ctrl = self._reduce_sums(s1)
         glen = int(self.chrom_len[(sv != 0) & (self.skip == 0)].astype(np.int64).sum())   # calcLambda 1819-1827
+        t0 = time.perf_counter()
         st = self.ctx.replicate_finish(frag, ctrl, push_ctrl is not None, glen)
+        self._tick("replicate_finish", t0)
         self.sample_stats.append(st)
         return st
 
@@ -127,20 +157,37 @@ class ShardedEngine:
                 torch.cuda.current_stream(self.device).synchronize()
             self._keep = (keys, lens)
             self.ctx.bh_set_global_ptrs(keys.data_ptr(), lens.data_ptr(), keys.numel(), G)
+        t0 = time.perf_counter()
         peaks, rs = self.ctx.call_peaks()
+        self._tick("call_peaks", t0)
+        t0 = time.perf_counter()
         if self.world > 1:
-            buf = torch.from_numpy(peaks.view(np.uint8).copy()).to(self.device)
-            cnt = torch.tensor([buf.numel()], dtype=torch.int64, device=self.device)
+            if self.device.type == "cuda":
+                # the records are still in device memory: all-gather them there (NCCL), one
+                # device->host copy on rank 0; the other ranks keep their own peaks
+                dptr, n = self.ctx.peaks_device_ptr()
+                nbytes = n * PEAK_DTYPE.itemsize
+                buf = _tensor_from_ptr(dptr, nbytes, np.uint8, self.device)
+                dev, grp = self.device, None
+            else:
+                buf = torch.from_numpy(peaks.view(np.uint8).copy())
+                dev, grp = torch.device("cpu"), self.host_group
+            cnt = torch.tensor([buf.numel()], dtype=torch.int64, device=dev)
             cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
-            td.all_gather(cnts, cnt)
+            td.all_gather(cnts, cnt, group=grp)
             sizes = [int(c.item()) for c in cnts]
             m = max(max(sizes), 1)
-            pad = torch.zeros(m, dtype=torch.uint8, device=self.device)
+            pad = torch.zeros(m, dtype=torch.uint8, device=dev)
             pad[:buf.numel()] = buf
-            allb = [torch.empty_like(pad) for _ in range(self.world)]
-            td.all_gather(allb, pad)
-            parts = [np.frombuffer(b[:s].cpu().numpy().tobytes(), dtype=PEAK_DTYPE) for b, s in zip(allb, sizes)]
-            allp = np.concatenate(parts) if parts else peaks
-            order = np.lexsort((allp["start"], allp["chrom"]))
-            peaks = allp[order]
+            allb = torch.empty(self.world * m, dtype=torch.uint8, device=dev)
+            td.all_gather_into_tensor(allb, pad, group=grp) if dev.type == "cuda" else \
+                td.all_gather(list(allb.view(self.world, m).unbind(0)), pad, group=grp)
+            if self.rank == 0:
+                host = allb.cpu().numpy().reshape(self.world, m)
+                parts = [np.frombuffer(host[r, :s].tobytes(), dtype=PEAK_DTYPE) for r, s in enumerate(sizes)]
+                allp = np.concatenate(parts)
+                # every rank's list is already in (chromosome, start) order and chromosomes are
+                # disjoint across ranks: a stable sort on the chromosome index merges them
+                peaks = allp[np.argsort(allp["chrom"], kind="stable")]
+        self._tick("gather_peaks", t0)
         return peaks, rs

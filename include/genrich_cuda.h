@@ -134,6 +134,12 @@ const char* gr_last_error_detail(const gr_ctx* ctx);
 int gr_sample_begin(gr_ctx* ctx, int32_t is_ctrl, const uint8_t* save);
 int gr_push_intervals(gr_ctx* ctx, const int32_t* recs, uint64_t n);        /* host memory (pinned or not) */
 int gr_push_intervals_device(gr_ctx* ctx, const int32_t* d_recs, uint64_t n);/* device memory */
+/* Optional hint, callable at any time: start copying a PINNED host buffer that a later
+ * gr_push_intervals(ctx, recs, n) -- same pointer, same n, contents unchanged -- will
+ * consume.  The copy runs on the library's copy stream behind whatever the device is
+ * doing (e.g. the control sample travels while the treatment sample is integrated).
+ * At most two buffers can be in flight; a third request is ignored (returns 0). */
+int gr_prefetch_intervals(gr_ctx* ctx, const int32_t* recs, uint64_t n);
 
 /* Integrate the current sample (savePileupExpt 2168 / the RLE pass of
  * calcFactor 1980).  chrom_sums[nchrom] receives, per owned chromosome, the
@@ -167,6 +173,9 @@ int gr_bh_set_global(gr_ctx* ctx, const uint32_t* d_keys,
                      const uint64_t* d_lens, uint64_t n, uint64_t genome_len);
 int gr_call_peaks(gr_ctx* ctx, const gr_peak** peaks, uint64_t* n,
                   gr_run_stats* stats);
+/* The same records where gr_call_peaks left them in DEVICE memory (valid until the next
+ * call on the context): lets a multi-GPU launcher all-gather them without a host bounce. */
+int gr_peaks_device(gr_ctx* ctx, const gr_peak** d_peaks, uint64_t* n);
 
 /* ---- seam OUT for -f / -k (printInterval 770, printPile 1697) -------------
  * which: 0 = experimental pileup, 1 = control pileup (last replicate),
