@@ -72,7 +72,7 @@ struct gr_ctx {
 
   // dense working set
   DevBuf delta, bmE, bmC, rankE, rankC, rankTmp;
-  DevBuf lb0, lb1, lb2, ticket;
+  DevBuf lb0, lb1, lb2, ticket, scanWs;
   DevBuf small;                  // err(int) | pad | clamped(u64) | totals[3] | misc counters
   int* d_err = nullptr; u64* d_clamped = nullptr; u64* d_totals = nullptr; u64* d_cnt = nullptr;
   void* h_small = nullptr;       // pinned mirror
@@ -325,7 +325,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   if (x->stream) cudaStreamSynchronize(x->stream);
   free_reps(x);
   DevBuf* all[] = { &x->d_off, &x->d_len, &x->d_flags, &x->d_blk2chrom, &x->delta, &x->bmE, &x->bmC,
-    &x->rankE, &x->rankC, &x->rankTmp, &x->lb0, &x->lb1, &x->lb2, &x->ticket, &x->small, &x->accI,
+    &x->rankE, &x->rankC, &x->rankTmp, &x->lb0, &x->lb1, &x->lb2, &x->ticket, &x->scanWs, &x->small, &x->accI,
     &x->accF, &x->exptEnd, &x->exptVal, &x->exptCS, &x->exptTot, &x->rawEnd, &x->rawVal, &x->rawCS,
     &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->stage[0], &x->stage[1], &x->binRecs, &x->binCnt, &x->binCursor,
     &x->qVal, &x->tKeys, &x->tLens, &x->tPval, &x->tQval, &x->tCount, &x->slot, &x->hk, &x->hl,
@@ -518,8 +518,10 @@ extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
   CK(E.ensure(cap * sizeof(u32)));
   CK(V.ensure(cap * sizeof(float)));
   DevRle out = rle_view(E, V, CS, TT);
+  CK(x->scanWs.ensure(dense_scan_ws_bytes(cap, x->nchrom)));
   ScanScratch sc;
   sc.st_sum = x->lb0.as<u64>(); sc.st_cnt = x->lb1.as<u64>(); sc.ticket = x->ticket.as<u32>();
+  sc.ws = x->scanWs.p; sc.cap = cap;
   stage_begin(x, "dense_scan", x->T * 4);
   launch_dense_scan(x->stream, x->L, x->delta.as<int32_t>(), sc, out,
                     (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, x->zero_after);

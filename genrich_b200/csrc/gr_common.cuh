@@ -200,6 +200,26 @@ __device__ __forceinline__ float units_to_val(int N) {
   return v;
 }
 
+// Table form for kernels that convert many heights: entry r = N mod 120 holds the three
+// fractional terms (already divided, correctly rounded) and the borrow of the integer part.
+__device__ __forceinline__ void units_lut_fill(float4* lut, int tid, int nthreads) {
+  for (int r = tid; r < 120; r += nthreads) {
+    const int s = (2 * (r % 3)) % 3;
+    const int t = (3 * (r % 5)) % 5;
+    const int e = (4 * s + 4 * t - r) & 7;
+    const int borrow = (15 * e + 20 * s + 12 * t - r) / 120;       // 0 or 1
+    lut[r] = make_float4(__fdiv_rn((float)e, 8.0f), __fdiv_rn((float)s, 6.0f), __fdiv_rn((float)t, 10.0f),
+                         __int_as_float(borrow));
+  }
+}
+__device__ __forceinline__ float units_to_val_lut(const float4* lut, int N) {
+  const int q = N / 120;
+  const float4 f = lut[N - q * 120];
+  float v = __fadd_rn((float)(q - __float_as_int(f.w)), f.x);
+  v = __fadd_rn(v, f.y);
+  return __fadd_rn(v, f.z);
+}
+
 // index of the chromosome whose interval range [start[c], start[c+1]) holds i
 // (start has n+1 monotone entries)
 __device__ __forceinline__ int chrom_of_index(const u64* __restrict__ start, int n, u64 i) {

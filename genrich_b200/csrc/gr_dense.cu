@@ -7,6 +7,7 @@
 #include "gr_common.cuh"
 #include "gr_internal.h"
 #include <stdlib.h>
+#include <stdio.h>
 
 // ============================================================================
 // K1: two int32 reductions (RED.ADD) per interval record into the dense delta
@@ -285,6 +286,7 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
   __shared__ u32 sm_q[SC_NSLOT][5];                    // jb, tile, chrom, first|live<<1, #breaks
   __shared__ u32 sm_bm[SC_CT / 2];                     // the tile's break bitmap (16 words per warp)
   __shared__ unsigned char sm_list[SC_WARPS * 128];    // per warp: its non-zero chunks
+  __shared__ float4 sm_lut[120];                       // height mod 120 -> fractional float terms
 
   const int tid = threadIdx.x, lane = tid & 31;
   const u32 G = gridDim.x, b = blockIdx.x;
@@ -386,6 +388,7 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
   issue(b + G < ntiles, 1, src + src_step);
   TileMeta meta = tile_meta(L, b, ntiles, TILE);
   if (tid < SC_NSLOT) sm_q[tid][3] = 0;
+  units_lut_fill(sm_lut, tid, SC_CT);                  // visible after the first BAR_COMPUTE sync
 
   // B: convert and store the parked breaks of the tile in `slot` (all 512 threads, dense)
   auto finish = [&](int slot) {
@@ -411,7 +414,7 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
       const int N = (int)(ex_sum + (u32)e.y);
       neg |= N < 0;
       out.end[ex_cnt + n] = jb_ + (u32)e.x;
-      out.val[ex_cnt + n] = units_to_val(N < 0 ? 0 : N);
+      out.val[ex_cnt + n] = units_to_val_lut(sm_lut, N < 0 ? 0 : N);
       // every break of an interior tile is a non-zero cell and vice versa: clearing them
       // leaves the whole delta array zero for the next sample (no 4 B/bp memset)
       if (zero_after) delta[(u64)tile_ * TILE + (u32)e.x] = 0;
@@ -576,7 +579,7 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
             const int N = (int)rr;
             neg |= N < 0;
             out.end[rank] = j0 + i;
-            out.val[rank] = units_to_val(N < 0 ? 0 : N);
+            out.val[rank] = units_to_val_lut(sm_lut, N < 0 ? 0 : N);
             rank++;
           }
           rr += (u32)d[i];
@@ -613,6 +616,627 @@ k_dense_scan(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
   cp_async_wait<0>();
 }
 
+
+// ----------------------------------------------------------------------------
+// K2, warp-autonomous form.  Same tiling, same exchange, same results as above, but
+// the 16 compute warps of a CTA never meet at a CTA barrier:
+//   * every warp streams ITS OWN 512 cells of each tile through a private 2-stage
+//     cp.async ring (4 x 512 contiguous bytes per tile, waited on with __syncwarp only);
+//   * one pass per tile: non-zero 16-byte chunks are listed (ballot), counted, the warp
+//     reserves room in the tile's side pool (one shared-memory atomic) and parks its
+//     breaks as (position, WARP-local height); its totals go to shared memory and it
+//     bar.arrive's -- it does not wait for the block prefix;
+//   * the exchange warp sums the 16 warp totals, publishes / gathers as before, and
+//     hands each warp its own exclusive prefix (sum, rank); completion is signalled
+//     through an mbarrier per slot, so a warp that converts its parked breaks LAG
+//     tiles later waits alone, and only if the prefix is not there yet.
+// Slot ring: a pool slot is rewritten at tile k+NSLOT by warps that have converted
+// tile k+NSLOT-LAG, which the exchange releases only after EVERY warp arrived for that
+// tile, i.e. after every warp converted tile k+NSLOT-2*LAG: NSLOT = 2*LAG is safe.
+#define SCW_NONE 0xffffffffu
+#ifdef GR_SCAN_PROF
+__device__ unsigned long long g_scan_prof[8];
+__device__ __forceinline__ u64 gtime() { u64 t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define PROF_T(v) const u64 v = gtime()
+#define PROF_ADD(i, x) do { if (lane == 0) atomicAdd(&g_scan_prof[i], (unsigned long long)(x)); } while (0)
+#else
+#define PROF_T(v)
+#define PROF_ADD(i, x)
+#endif
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(u64* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" :: "r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n"
+      "D_%=:\n\t}" :: "r"(a), "r"(parity) : "memory");
+}
+
+template <int LAG, int CAP, int NX>
+__global__ void __launch_bounds__(512 + 32 * NX, 2)
+k_dense_scan_w(int32_t* __restrict__ delta, DevLayout L, ScanStatus S, DevRle out,
+               u32* __restrict__ bitmap, int* __restrict__ err, u32 ntiles, int zero_after) {
+  constexpr int NSLOT = 2 * LAG, CT = 512, NW = 16;
+  constexpr u32 TILE = 8192;
+  extern __shared__ int4 sm_x[];                       // per warp 2 stages x 128 chunks, then NSLOT pools
+  __shared__ u32 sm_wsum[NSLOT][NW], sm_wcnt[NSLOT][NW], sm_woff[NSLOT][NW];
+  __shared__ u32 sm_pre_sum[NSLOT][NW];
+  __shared__ u64 sm_pre_cnt[NSLOT][NW];
+  __shared__ u32 sm_alloc[NSLOT];
+  __shared__ u32 sm_rs[4], sm_rready;                  // running totals of completed rounds (exchange warps)
+  __shared__ u64 sm_rc[4];
+  __shared__ u64 sm_bar[NSLOT];
+  __shared__ u32 sm_bm[NW * 16];
+  __shared__ unsigned char sm_list[NW * 128];
+  __shared__ float4 sm_lut[120];
+
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const u32 G = gridDim.x, b = blockIdx.x;
+  int2* pool = reinterpret_cast<int2*>(sm_x + NW * 2 * 128);
+
+  units_lut_fill(sm_lut, tid, 512 + 32 * NX);
+  if (tid < NSLOT) { sm_alloc[tid] = 0; mbar_init(&sm_bar[tid], 1); }
+  if (tid == 0) { sm_rs[0] = 0; sm_rc[0] = 0; sm_rready = 0; }
+  __syncthreads();
+
+  // ------------------------------------------------------------ exchange warp
+  // NX exchange warps take the rounds in turn (round k -> warp k % NX), so NX exchanges are
+  // in flight per CTA.  One hop: a tile's aggregate is ONE 64-bit status word
+  // (flag:2 | #breaks:30 | sum:32); the exchange of tile (k, b) reads the words of ALL
+  // tiles of round k -- those before b give the exclusive prefix inside the round, all of
+  // them the round total -- and the total of the earlier rounds is handed from round to
+  // round inside the CTA through shared memory.  (The two-level agg -> group-total scheme
+  // needed two dependent store->poll hops, ~8 us under load: three tiles of slack did not
+  // cover it and half of all warp samples sat waiting for a prefix.)
+  if (w >= NW) {
+    u64* agg64 = reinterpret_cast<u64*>(S.agg);
+    for (u32 k = (u32)(w - NW); (u64)b + (u64)k * G < ntiles; k += NX) {
+      const u32 tile = b + k * G;
+      const int slot = k % NSLOT;
+      // what lane 0 needs for the chromosome bookkeeping, fetched ahead of the barrier
+      const int c_t = L.blk2chrom[tile];
+      const u64 off_t = L.off[c_t];
+      const u32 nb = min(G, ntiles - k * G);           // tiles in this round
+      const u64* base = agg64 + (u64)k * G;
+      PROF_T(t0);
+      named_sync(BAR_AGG + slot, 544);                 // (16 compute warps + this one) all warp totals are in
+      PROF_T(t1);
+      const u32 ws = lane < NW ? sm_wsum[slot][lane] : 0u, wc = lane < NW ? sm_wcnt[slot][lane] : 0u;
+      if (lane == 0) sm_alloc[slot] = 0;
+      const u32 is_ = warp_incl_scan_u32(ws, lane), ic_ = warp_incl_scan_u32(wc, lane);
+      const u32 agg_s = __shfl_sync(GR_FULL, is_, NW - 1), agg_c = __shfl_sync(GR_FULL, ic_, NW - 1);
+      if (lane == 0) st_relaxed_u64(agg64 + tile, (1ull << 62) | ((u64)agg_c << 32) | agg_s);
+      u32 pre_s = 0, pre_c = 0, tot_s = 0, tot_c = 0;
+      for (u32 c0 = 0; c0 < nb; c0 += 256) {           // 8 status words per lane and pass
+        u64 v[8];
+        u32 pending = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (c0 + i * 32 + lane < nb) pending |= 1u << i;
+        for (;;) {
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            if (pending & (1u << i)) v[i] = ld_relaxed_u64(base + c0 + i * 32 + lane);
+#pragma unroll
+          for (int i = 0; i < 8; i++)
+            if ((pending & (1u << i)) && (v[i] >> 62) == 1) {
+              pending &= ~(1u << i);
+              const u32 vs = (u32)v[i], vc = (u32)(v[i] >> 32) & 0x3fffffffu;
+              tot_s += vs; tot_c += vc;
+              if (c0 + i * 32 + lane < b) { pre_s += vs; pre_c += vc; }
+            }
+          PROF_ADD(3, 1);
+          if (__all_sync(GR_FULL, pending == 0)) break;
+        }
+      }
+      PROF_T(t2);
+      pre_s = __reduce_add_sync(GR_FULL, pre_s); pre_c = __reduce_add_sync(GR_FULL, pre_c);
+      tot_s = __reduce_add_sync(GR_FULL, tot_s); tot_c = __reduce_add_sync(GR_FULL, tot_c);
+      // totals of the rounds before k: from the warp that exchanged round k-1
+      while (*(volatile u32*)&sm_rready < k) { }
+      __threadfence_block();
+      PROF_T(t3);
+      PROF_ADD(0, t1 - t0); PROF_ADD(1, t2 - t1); PROF_ADD(2, t3 - t2); PROF_ADD(4, 1);
+      const u32 r_s = sm_rs[k & 3];
+      const u64 r_c = sm_rc[k & 3];
+      if (lane == 0) {
+        sm_rs[(k + 1) & 3] = r_s + tot_s;
+        sm_rc[(k + 1) & 3] = r_c + tot_c;
+        __threadfence_block();
+        *(volatile u32*)&sm_rready = k + 1;
+      }
+      const u32 ex_s = r_s + pre_s;
+      const u64 ex_c = r_c + pre_c;
+      if (lane < NW) {
+        sm_pre_sum[slot][lane] = ex_s + (is_ - ws);
+        sm_pre_cnt[slot][lane] = ex_c + (u64)(ic_ - wc);
+      }
+      if (lane == 0) {
+        if ((u64)tile * TILE == off_t) {               // first tile of a chromosome
+          out.chrom_start[c_t] = ex_c;
+          if (ex_s != 0) atomicOr(err, GR_DE_TAIL);    // previous chromosome did not return to 0 (2283-2289)
+        }
+        if (tile == ntiles - 1) {
+          *out.total = ex_c + agg_c;
+          out.chrom_start[L.nchrom] = ex_c + agg_c;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm_bar[slot]);       // release: the 16 prefixes of tile k are visible
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------ compute warps
+  int4* wring = sm_x + w * 256;                        // this warp's two stages of 128 chunks
+  unsigned char* wlist = sm_list + w * 128;
+  const int4* src = reinterpret_cast<const int4*>(delta) + (u64)b * (TILE / 4) + w * 128 + lane;
+  const u64 src_step = (u64)G * (TILE / 4);
+  auto issue = [&](bool on, int stage, const int4* from) {
+    if (on) {
+      int4* dst = wring + stage * 128 + lane;
+#pragma unroll
+      for (int r = 0; r < 4; r++) cp_async16(dst + r * 32, from + r * 32);
+    }
+    cp_async_commit();
+  };
+  issue(b < ntiles, 0, src);
+  issue(b + G < ntiles, 1, src + src_step);
+  TileMeta meta = tile_meta(L, b, ntiles, TILE);
+  u32 jb_hist[LAG];                                    // chromosome position of the first cell of tiles k-1 .. k-LAG
+#pragma unroll
+  for (int i = 0; i < LAG; i++) jb_hist[i] = 0;
+  const u32 lt_mask = (1u << lane) - 1;
+
+  // B: convert this warp's parked breaks of tile kk (dense, coalesced within the warp's run)
+  auto finish = [&](u32 kk, u32 jb_) {
+    const int slot = kk % NSLOT;
+    const u32 off = sm_woff[slot][w];
+    if (off == SCW_NONE) return;
+    const u32 tc = sm_wcnt[slot][w];
+    PROF_T(tw0);
+    mbar_wait(&sm_bar[slot], (kk / NSLOT) & 1);
+    PROF_T(tw1);
+    if (w == 0) { PROF_ADD(5, tw1 - tw0); PROF_ADD(6, 1); }
+    const u32 ps = sm_pre_sum[slot][w];
+    const u64 pc = sm_pre_cnt[slot][w];
+    const u64 tb = (u64)(b + kk * G) * TILE;
+    const int2* sb = pool + slot * CAP + off;
+    bool neg = false;
+    for (u32 n = lane; n < tc; n += 32) {
+      const int2 e = sb[n];
+      const int N = (int)(ps + (u32)e.y);
+      neg |= N < 0;
+      out.end[pc + n] = jb_ + (u32)e.x;
+      out.val[pc + n] = units_to_val_lut(sm_lut, N < 0 ? 0 : N);
+      // every break of an interior tile is a non-zero cell and vice versa: clearing them
+      // leaves the whole delta array zero for the next sample (no 4 B/bp memset)
+      if (zero_after) delta[tb + (u32)e.x] = 0;
+    }
+    if (neg) atomicOr(err, GR_DE_PILE);                // ERRPILE 1921, 1969
+  };
+
+  u32 k = 0;
+  for (u32 tile = b; tile < ntiles; tile += G, k++) {
+    const int slot = k % NSLOT;
+    const int c_next = tile + G < ntiles ? L.blk2chrom[tile + G] : 0;
+    if (k >= LAG) finish(k - LAG, jb_hist[LAG - 1]);
+    cp_async_wait<1>();
+    __syncwarp();                                      // the warp's 512 cells of tile k are in its stage
+    const int4* wst = wring + (k & 1) * 128;
+    const u64 tbase = (u64)tile * TILE;
+    const u32 jb = (u32)(tbase - meta.off);
+    const u32 len = meta.len;
+    bool fast = jb >= 1 && (u64)jb + TILE <= (u64)len;
+    u32 nnz = 0, tc = 0, off = 0;
+    if (fast) {
+      // list the non-zero chunks, count the non-zero cells
+      u32 cc = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int4 x = wst[r * 32 + lane];
+        const u32 c4 = min((u32)x.x, 1u) + min((u32)x.y, 1u) + min((u32)x.z, 1u) + min((u32)x.w, 1u);
+        const u32 M = __ballot_sync(GR_FULL, c4 != 0);
+        if (c4) wlist[nnz + __popc(M & lt_mask)] = (unsigned char)(r * 32 + lane);
+        nnz += __popc(M);
+        cc += c4;
+      }
+      tc = __reduce_add_sync(GR_FULL, cc);
+      if (lane == 0) off = atomicAdd(&sm_alloc[slot], tc);
+      off = __shfl_sync(GR_FULL, off, 0);
+      if (off + tc > (u32)CAP) fast = false;           // side pool full: this warp goes the dense way
+    }
+    if (fast) {
+      if (lane < 16) sm_bm[w * 16 + lane] = 0;
+      __syncwarp();
+      int2* sb = pool + slot * CAP;
+      u32 carry_s = 0, carry_c = off;
+      for (u32 base = 0; base < nnz; base += 32) {
+        const u32 n = base + lane;
+        const bool on = n < nnz;
+        int4 x = make_int4(0, 0, 0, 0);
+        u32 q = 0;
+        if (on) { q = wlist[n]; x = wst[q]; }
+        const u32 m4 = (x.x != 0 ? 1u : 0u) | (x.y != 0 ? 2u : 0u) | (x.z != 0 ? 4u : 0u) | (x.w != 0 ? 8u : 0u);
+        const u32 c4 = __popc(m4);
+        const u32 s1 = (u32)x.x, s2 = s1 + (u32)x.y, s3 = s2 + (u32)x.z, s4 = s3 + (u32)x.w;
+        const u32 inc_s = warp_incl_scan_u32(s4, lane), inc_c = warp_incl_scan_u32(c4, lane);
+        if (on) {
+          const u32 ex_s = carry_s + inc_s - s4;       // warp-local running sum before this chunk
+          int2* e = sb + (carry_c + inc_c - c4);
+          const int p0 = w * 512 + (int)(q * 4);
+          if (m4 & 1u) *e++ = make_int2(p0, (int)ex_s);
+          if (m4 & 2u) *e++ = make_int2(p0 + 1, (int)(ex_s + s1));
+          if (m4 & 4u) *e++ = make_int2(p0 + 2, (int)(ex_s + s2));
+          if (m4 & 8u) *e++ = make_int2(p0 + 3, (int)(ex_s + s3));
+          atomicOr(&sm_bm[w * 16 + (q >> 3)], m4 << ((q & 7) * 4));
+        }
+        carry_s += __shfl_sync(GR_FULL, inc_s, 31);
+        carry_c += __shfl_sync(GR_FULL, inc_c, 31);
+      }
+      if (lane == 0) { sm_wsum[slot][w] = carry_s; sm_wcnt[slot][w] = tc; sm_woff[slot][w] = off; }
+      __syncwarp();
+      named_arrive(BAR_AGG + slot, 544);               // hand the totals to the exchange warp; do not wait
+      if (lane < 16) bitmap[(tbase >> 5) + w * 16 + lane] = sm_bm[w * 16 + lane];
+    } else {
+      // dense: chromosome ends, inactive chromosomes, over-full tiles.  16 consecutive cells per lane.
+      int d[SC_ITEMS];
+      sc_load_items(wst, lane, d);
+      u32 run = 0, m = 0;
+      const u32 j0 = jb + w * 512 + lane * SC_ITEMS;
+#pragma unroll
+      for (int i = 0; i < SC_ITEMS; i++) {
+        run += (u32)d[i];
+        const u32 jj = j0 + i;
+        const bool brk = (jj == len) || (d[i] != 0 && jj >= 1 && jj < len);
+        m |= (brk ? 1u : 0u) << i;
+      }
+      if (!meta.act) m = 0;
+      const u32 cnt = __popc(m);
+      const u32 wi_sum = warp_incl_scan_u32(run, lane), wi_cnt = warp_incl_scan_u32(cnt, lane);
+      if (lane == 31) { sm_wsum[slot][w] = wi_sum; sm_wcnt[slot][w] = wi_cnt; sm_woff[slot][w] = SCW_NONE; }
+      __syncwarp();
+      named_arrive(BAR_AGG + slot, 544);
+      const u32 hi = __shfl_down_sync(GR_FULL, m, 1);
+      if (!(lane & 1)) bitmap[(tbase >> 5) + w * 16 + (lane >> 1)] = m | (hi << 16);
+      mbar_wait(&sm_bar[slot], (k / NSLOT) & 1);       // this tile's prefix, synchronously (rare)
+      if (m) {
+        u32 rr = sm_pre_sum[slot][w] + (wi_sum - run);
+        u64 rank = sm_pre_cnt[slot][w] + (wi_cnt - cnt);
+        bool neg = false;
+#pragma unroll
+        for (int i = 0; i < SC_ITEMS; i++) {
+          if (m & (1u << i)) {
+            const int N = (int)rr;
+            neg |= N < 0;
+            out.end[rank] = j0 + i;
+            out.val[rank] = units_to_val_lut(sm_lut, N < 0 ? 0 : N);
+            rank++;
+          }
+          rr += (u32)d[i];
+        }
+        if (neg) atomicOr(err, GR_DE_PILE);
+      }
+      if (zero_after) {
+#pragma unroll
+        for (int i = 0; i < SC_ITEMS; i++)
+          if (d[i] != 0) delta[tbase + w * 512 + lane * SC_ITEMS + i] = 0;
+      }
+    }
+    __syncwarp();                                      // every lane is done with the stage: refill it
+    src += src_step;
+    issue(tile + 2 * G < ntiles, k & 1, src + src_step);
+#pragma unroll
+    for (int i = LAG - 1; i > 0; i--) jb_hist[i] = jb_hist[i - 1];
+    jb_hist[0] = jb;
+    meta.c = c_next;
+    meta.off = L.off[c_next];
+    meta.len = L.len[c_next];
+    meta.act = (L.flags[c_next] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
+  }
+  // drain: tiles k-LAG .. k-1 (jb_hist[LAG-1] is the oldest)
+#pragma unroll
+  for (int i = LAG - 1; i >= 0; i--)
+    if (k >= (u32)(i + 1)) finish(k - 1 - i, jb_hist[i]);
+  cp_async_wait<0>();
+}
+
+
+// ============================================================================
+// K2, streaming form: no cross-warp dependency at all inside the 4 B/cell pass.
+//
+// Why: in every single-pass variant above a tile's breaks need the tile's global prefix
+// (running height, rank) before they can be written, i.e. a store -> poll hop between CTAs.
+// Measured on B200 under a 2 TB/s stream: one poll of the status words takes ~1.4 us and an
+// exchange ~5 polls (everybody waits for the round's slowest CTA): 7-11 us against a tile
+// time of 4 us; two or three tiles of slack did not hide it and 30-50 % of all warp samples
+// sat on the prefix wait.
+//
+// So the pass over the cells does not wait for anything:
+//   K2a k_scan_stream  every WARP owns a contiguous run of 512-cell spans and walks it
+//        alone with its own cp.async ring, carrying (height, #breaks) in registers, both
+//        relative to the start of its run.  Breaks are appended -- as (end coordinate,
+//        run-relative height) -- to 256-entry pages taken from a global page counter; the
+//        break bitmap is written and the non-zero cells are cleared on the way.
+//   K2b k_scan_fix     one CTA: exclusive scan over the per-warp totals (<= 8192 warps),
+//        chromosome starts, tail check.
+//   K2c k_scan_place   moves every page to its final rank, adds the warp's base height and
+//        rebuilds the reference float: 8 B read + 8 B written per INTERVAL (~0.1 B/cell).
+#define SS_PAGE 256
+#define SS_PAGE_SHIFT 8
+#define SS_MAX_WARPS 8192
+struct StreamWs {
+  u32* pend; int* ph;          // provisional entries, max_pages * SS_PAGE each
+  uint2* page_meta;            // page -> (warp, sequence number inside the warp's run)
+  u32* page_ctr;               // pages handed out
+  uint2* warp_tot;             // per warp: (sum of its deltas, its #breaks)
+  ulonglong2* warp_base;       // per warp: (height, rank) at the start of its run
+  uint4* marks;                // per chromosome: (warp, height, rank) at its first cell, run-relative
+  u32 max_pages;
+};
+
+template <int NSTAGE>
+__global__ void __launch_bounds__(512, 2)
+k_scan_stream(int32_t* __restrict__ delta, DevLayout L, StreamWs W, u32* __restrict__ bitmap,
+              int* __restrict__ err, u32 nspans, u32 R, int zero_after) {
+  extern __shared__ int4 sm_x[];                       // per warp NSTAGE stages of 128 chunks
+  __shared__ u32 sm_bm[16 * 16];
+  __shared__ unsigned char sm_list[16 * 128];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 gw = blockIdx.x * 16 + w;
+  const u32 s0 = gw * R, s1 = min(s0 + R, nspans);
+  if (s0 >= s1) {
+    if (lane == 0 && gw < SS_MAX_WARPS) W.warp_tot[gw] = make_uint2(0, 0);
+    return;
+  }
+  int4* wring = sm_x + w * (NSTAGE * 128);
+  unsigned char* wlist = sm_list + w * 128;
+  const int4* src = reinterpret_cast<const int4*>(delta) + (u64)s0 * 128 + lane;
+  auto issue = [&](bool on, int stage, const int4* from) {
+    if (on) {
+      int4* dst = wring + stage * 128 + lane;
+#pragma unroll
+      for (int r = 0; r < 4; r++) cp_async16(dst + r * 32, from + r * 32);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int st = 0; st < NSTAGE; st++) issue(s0 + st < s1, st, src + (u64)st * 128);
+
+  // output pages: `cur` is being filled (sequence cur_seq), `nxt` is in hand so that a batch
+  // may run over the page end; the page after that is requested as soon as `nxt` becomes `cur`
+  u32 cur = 0, nxt = 0, cur_seq = 0, pend_reg = 0;
+  bool pending = false;
+  if (lane == 0) {
+    cur = atomicAdd(W.page_ctr, 2u);
+    if (cur + 1 < W.max_pages) { W.page_meta[cur] = make_uint2(gw, 0); W.page_meta[cur + 1] = make_uint2(gw, 1); }
+  }
+  cur = __shfl_sync(GR_FULL, cur, 0);
+  nxt = cur + 1;
+  auto resolve = [&]() {
+    if (pending) {
+      nxt = __shfl_sync(GR_FULL, pend_reg, 0);
+      if (lane == 0 && nxt < W.max_pages) W.page_meta[nxt] = make_uint2(gw, cur_seq + 1);
+      pending = false;
+    }
+  };
+  auto advance = [&]() {                                // nxt becomes cur, ask for another page
+    resolve();
+    cur = nxt; cur_seq++;
+    if (lane == 0) pend_reg = atomicAdd(W.page_ctr, 1u);
+    pending = true;
+  };
+  auto put = [&](u32 idx, u32 pos, u32 h) {            // idx: rank inside the warp's run
+    const u32 pg = (idx >> SS_PAGE_SHIFT) == cur_seq ? cur : nxt;
+    if (pg < W.max_pages) {
+      const u64 a = ((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1));
+      W.pend[a] = pos; W.ph[a] = (int)h;
+    }
+  };
+
+  const u32 lt_mask = (1u << lane) - 1;
+  u32 run_s = 0, run_c = 0;                            // height / #breaks since the start of the run
+  u32 cur_blk = 0xffffffffu, jb_blk = 0, len = 0;
+  int c = 0;
+  bool act = false;
+  u32 it = 0;
+  for (u32 sp = s0; sp < s1; sp++, it++) {
+    const u32 blk = sp >> 4;
+    if (blk != cur_blk) {                              // chromosome of this 8192-cell block (warp-uniform)
+      cur_blk = blk;
+      c = L.blk2chrom[blk];
+      jb_blk = (u32)(((u64)blk << GR_BLOCK_SHIFT) - L.off[c]);
+      len = L.len[c];
+      act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
+    }
+    const u32 jb = jb_blk + (sp & 15u) * 512u;         // chromosome position of the span's first cell
+    if (jb == 0 && lane == 0) W.marks[c] = make_uint4(gw, run_s, run_c, 1u);
+    cp_async_wait<NSTAGE - 1>();
+    __syncwarp();
+    const int4* wst = wring + (it % NSTAGE) * 128;
+    int4* gcell = reinterpret_cast<int4*>(delta) + (u64)sp * 128;
+    const bool fast = act && jb >= 1 && (u64)jb + 512 <= (u64)len;
+    if (fast) {
+      // ~94 % of the cells are zero: list the non-zero 16-byte chunks, work only on them
+      u32 nnz = 0;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        const int4 x = wst[r * 32 + lane];
+        const bool nz = (x.x | x.y | x.z | x.w) != 0;
+        const u32 M = __ballot_sync(GR_FULL, nz);
+        if (nz) wlist[nnz + __popc(M & lt_mask)] = (unsigned char)(r * 32 + lane);
+        nnz += __popc(M);
+      }
+      if (lane < 16) sm_bm[w * 16 + lane] = 0;
+      __syncwarp();
+      for (u32 base = 0; base < nnz; base += 32) {
+        resolve();
+        const u32 n = base + lane;
+        const bool on = n < nnz;
+        int4 x = make_int4(0, 0, 0, 0);
+        u32 q = 0;
+        if (on) { q = wlist[n]; x = wst[q]; }
+        const u32 m4 = (x.x != 0 ? 1u : 0u) | (x.y != 0 ? 2u : 0u) | (x.z != 0 ? 4u : 0u) | (x.w != 0 ? 8u : 0u);
+        const u32 c4 = __popc(m4);
+        const u32 s1_ = (u32)x.x, s2_ = s1_ + (u32)x.y, s3_ = s2_ + (u32)x.z, s4_ = s3_ + (u32)x.w;
+        const u32 inc_s = warp_incl_scan_u32(s4_, lane), inc_c = warp_incl_scan_u32(c4, lane);
+        if (on) {
+          const u32 h0 = run_s + inc_s - s4_;          // height before this chunk
+          u32 idx = run_c + inc_c - c4;
+          const u32 p0 = jb + q * 4;
+          if (m4 & 1u) put(idx++, p0, h0);
+          if (m4 & 2u) put(idx++, p0 + 1, h0 + s1_);
+          if (m4 & 4u) put(idx++, p0 + 2, h0 + s2_);
+          if (m4 & 8u) put(idx++, p0 + 3, h0 + s3_);
+          atomicOr(&sm_bm[w * 16 + (q >> 3)], m4 << ((q & 7) * 4));
+          // every break of an interior span is a non-zero cell and vice versa: clearing the
+          // chunk leaves the delta array all zero for the next sample (no 4 B/bp memset)
+          if (zero_after) gcell[q] = make_int4(0, 0, 0, 0);
+        }
+        run_s += __shfl_sync(GR_FULL, inc_s, 31);
+        run_c += __shfl_sync(GR_FULL, inc_c, 31);
+        if ((run_c >> SS_PAGE_SHIFT) > cur_seq) advance();
+      }
+      __syncwarp();
+      if (lane < 16) bitmap[(u64)sp * 16 + lane] = sm_bm[w * 16 + lane];
+    } else {
+      // dense: chromosome ends, inactive chromosomes.  16 consecutive cells per lane.
+      int d[SC_ITEMS];
+      sc_load_items(wst, lane, d);
+      u32 run = 0, m = 0;
+      const u32 j0 = jb + lane * SC_ITEMS;
+#pragma unroll
+      for (int i = 0; i < SC_ITEMS; i++) {
+        run += (u32)d[i];
+        const u32 jj = j0 + i;
+        const bool brk = (jj == len) || (d[i] != 0 && jj >= 1 && jj < len);
+        m |= (brk ? 1u : 0u) << i;
+      }
+      if (!act) m = 0;
+      const u32 cnt = __popc(m);
+      const u32 wi_sum = warp_incl_scan_u32(run, lane), wi_cnt = warp_incl_scan_u32(cnt, lane);
+      const u32 hi = __shfl_down_sync(GR_FULL, m, 1);
+      if (!(lane & 1)) bitmap[(u64)sp * 16 + (lane >> 1)] = m | (hi << 16);
+      const u32 tot_c = __shfl_sync(GR_FULL, wi_cnt, 31);
+      if (tot_c) {
+        // up to 512 entries: page by page
+        const u32 first_idx = run_c + (wi_cnt - cnt);
+        const u32 last_seq = (run_c + tot_c - 1) >> SS_PAGE_SHIFT;
+        for (;;) {
+          resolve();
+          u32 idx = first_idx, rr = run_s + (wi_sum - run);
+#pragma unroll
+          for (int i = 0; i < SC_ITEMS; i++) {
+            if (m & (1u << i)) {
+              if ((idx >> SS_PAGE_SHIFT) == cur_seq) put(idx, j0 + i, rr);
+              idx++;
+            }
+            rr += (u32)d[i];
+          }
+          if (cur_seq >= last_seq) break;
+          advance();
+        }
+        if (((run_c + tot_c) >> SS_PAGE_SHIFT) > cur_seq) advance();
+      }
+      run_s += __shfl_sync(GR_FULL, wi_sum, 31);
+      run_c += tot_c;
+      if (zero_after) {
+#pragma unroll
+        for (int i = 0; i < SC_ITEMS; i++)
+          if (d[i] != 0) delta[(u64)sp * 512 + lane * SC_ITEMS + i] = 0;
+      }
+    }
+    __syncwarp();                                      // every lane is done with the stage: refill it
+    issue(sp + NSTAGE < s1, it % NSTAGE, src + (u64)(it + NSTAGE) * 128);
+  }
+  resolve();                                           // a page still on order gets its (unused) label
+  if (lane == 0) W.warp_tot[gw] = make_uint2(run_s, run_c);
+  cp_async_wait<0>();
+}
+
+// K2b: one CTA.  Exclusive scan of the per-warp totals; chromosome starts; tail check.
+__global__ void __launch_bounds__(1024)
+k_scan_fix(DevLayout L, StreamWs W, DevRle out, int* __restrict__ err, u32 nwarps) {
+  __shared__ u32 sh_s[1024];
+  __shared__ u64 sh_c[1024];
+  const int t = threadIdx.x;
+  const u32 per = (nwarps + 1023) / 1024;
+  const u32 a = min(nwarps, t * per), b = min(nwarps, a + per);
+  u32 s = 0;
+  u64 c = 0;
+  for (u32 i = a; i < b; i++) { const uint2 v = W.warp_tot[i]; s += v.x; c += v.y; }
+  sh_s[t] = s; sh_c[t] = c;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    u32 vs = 0; u64 vc = 0;
+    if (t >= o) { vs = sh_s[t - o]; vc = sh_c[t - o]; }
+    __syncthreads();
+    sh_s[t] += vs; sh_c[t] += vc;
+    __syncthreads();
+  }
+  u32 bs = sh_s[t] - s;
+  u64 bc = sh_c[t] - c;
+  for (u32 i = a; i < b; i++) {
+    const uint2 v = W.warp_tot[i];
+    W.warp_base[i] = make_ulonglong2(bs, bc);
+    bs += v.x; bc += v.y;
+  }
+  const u64 total = sh_c[1023];
+  __syncthreads();
+  for (int ch = t; ch < L.nchrom; ch += 1024) {
+    if (L.off[ch] == ~0ull) continue;
+    const uint4 mk = W.marks[ch];
+    const ulonglong2 wb = W.warp_base[mk.x];
+    out.chrom_start[ch] = wb.y + mk.z;
+    if ((u32)wb.x + mk.y != 0) atomicOr(err, GR_DE_TAIL);   // previous chromosome did not return to 0 (2283-2289)
+  }
+  if (t == 0) { *out.total = total; out.chrom_start[L.nchrom] = total; }
+  __syncthreads();
+  if (t == 0) {
+    u64 next = total;
+    for (int ch = L.nchrom - 1; ch >= 0; ch--) {
+      if (L.off[ch] == ~0ull) out.chrom_start[ch] = next;
+      else next = out.chrom_start[ch];
+    }
+  }
+}
+
+// K2c: every page goes to its final rank; heights become the reference's floats.
+__global__ void __launch_bounds__(SS_PAGE)
+k_scan_place(StreamWs W, DevRle out, int* __restrict__ err) {
+  __shared__ float4 sm_lut[120];
+  units_lut_fill(sm_lut, threadIdx.x, SS_PAGE);
+  __syncthreads();
+  const u32 npages = min(*W.page_ctr, W.max_pages);
+  bool neg = false;
+  for (u32 p = blockIdx.x; p < npages; p += gridDim.x) {
+    const uint2 meta = W.page_meta[p];
+    const u32 tot = W.warp_tot[meta.x].y, first = meta.y << SS_PAGE_SHIFT;
+    if (first >= tot) continue;                        // the page a warp held in reserve
+    const u32 n = min((u32)SS_PAGE, tot - first);
+    if (threadIdx.x < n) {
+      const ulonglong2 wb = W.warp_base[meta.x];
+      const u64 a = ((u64)p << SS_PAGE_SHIFT) + threadIdx.x;
+      const int N = (int)((u32)wb.x + (u32)W.ph[a]);
+      neg |= N < 0;
+      const u64 rank = wb.y + first + threadIdx.x;
+      out.end[rank] = W.pend[a];
+      out.val[rank] = units_to_val_lut(sm_lut, N < 0 ? 0 : N);
+    }
+  }
+  if (neg) atomicOr(err, GR_DE_PILE);                  // ERRPILE 1921, 1969
+}
+
 __global__ void k_fill_chrom_start(DevLayout L, u64* chrom_start, const u64* total) {
   if (threadIdx.x || blockIdx.x) return;
   u64 next = *total;
@@ -645,6 +1269,7 @@ static void launch_dense_scan_t(cudaStream_t s, const DevLayout& L, int32_t* del
     if (per > (CT == 512 ? 2 : 4)) per = CT == 512 ? 2 : 4;
     grid = sms * per;                                  // persistent: co-resident CTAs only
     if (grid > 1024) grid = 1024;                      // one lane per CTA group in the exchange
+    if (getenv("GR_SCAN_DEBUG")) fprintf(stderr, "k_dense_scan<%d,%d,%d>: %d CTAs/SM, grid %d, smem %zu\n", CT, LAG, CAP, per, grid, smem);
   }
   unsigned g = (unsigned)(ntiles < (u64)grid ? ntiles : (u64)grid);
   const u64 nrounds = (ntiles + g - 1) / g;
@@ -663,8 +1288,119 @@ static void launch_dense_scan_t(cudaStream_t s, const DevLayout& L, int32_t* del
   launch_fill_chrom_start(s, L, out.chrom_start, out.total);
 }
 
+size_t dense_scan_ws_bytes(u64 cap, int nchrom) {
+  const u64 max_pages = (cap / SS_PAGE + 2 * SS_MAX_WARPS + 3) & ~1ull;
+  return (size_t)(max_pages * SS_PAGE * 8 + max_pages * 8 + SS_MAX_WARPS * (8 + 16) + (u64)nchrom * 16 + 256);
+}
+
+static void launch_scan_stream(cudaStream_t s, const DevLayout& L, int32_t* delta,
+                               const ScanScratch& sc, DevRle out, u32* bitmap, int* err, int zero_after) {
+  static int grid = 0, nstage = 0;
+  if (!grid) {
+    const char* e = getenv("GR_SCAN_STAGES");
+    nstage = e ? atoi(e) : 3;
+    if (nstage != 2 && nstage != 4) nstage = 3;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    grid = sms * 2;
+    if (grid * 16 > SS_MAX_WARPS) grid = SS_MAX_WARPS / 16;
+    cudaFuncSetAttribute(k_scan_stream<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 2 * 2048);
+    cudaFuncSetAttribute(k_scan_stream<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 3 * 2048);
+    cudaFuncSetAttribute(k_scan_stream<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 4 * 2048);
+  }
+  StreamWs W;
+  const u64 max_pages = (sc.cap / SS_PAGE + 2 * SS_MAX_WARPS + 3) & ~1ull;   // even: keeps the 16-byte arrays aligned
+  char* p = (char*)sc.ws;
+  W.pend = (u32*)p; p += max_pages * SS_PAGE * 4;
+  W.ph = (int*)p; p += max_pages * SS_PAGE * 4;
+  W.page_meta = (uint2*)p; p += max_pages * 8;
+  W.warp_base = (ulonglong2*)p; p += SS_MAX_WARPS * 16;
+  W.warp_tot = (uint2*)p; p += SS_MAX_WARPS * 8;
+  W.marks = (uint4*)p; p += (u64)L.nchrom * 16;
+  W.page_ctr = (u32*)p;
+  W.max_pages = (u32)max_pages;
+  cudaMemsetAsync(W.page_ctr, 0, 4, s);
+  const u32 nspans = (u32)(L.T / 512);
+  const u32 nwarps = (u32)grid * 16;
+  const u32 R = (nspans + nwarps - 1) / nwarps;
+  const size_t smem = (size_t)16 * nstage * 2048;
+  if (nstage == 2) k_scan_stream<2><<<grid, 512, smem, s>>>(delta, L, W, bitmap, err, nspans, R, zero_after);
+  else if (nstage == 4) k_scan_stream<4><<<grid, 512, smem, s>>>(delta, L, W, bitmap, err, nspans, R, zero_after);
+  else k_scan_stream<3><<<grid, 512, smem, s>>>(delta, L, W, bitmap, err, nspans, R, zero_after);
+  GR_NOTE_LAUNCH();
+  k_scan_fix<<<1, 1024, 0, s>>>(L, W, out, err, nwarps); GR_NOTE_LAUNCH();
+  k_scan_place<<<148 * 8, SS_PAGE, 0, s>>>(W, out, err); GR_NOTE_LAUNCH();
+}
+
+template <int LAG, int CAP, int NX>
+static void launch_dense_scan_w(cudaStream_t s, const DevLayout& L, int32_t* delta,
+                                const ScanScratch& sc, DevRle out, u32* bitmap, int* err, int zero_after) {
+  const u64 ntiles = L.nblocks;                        // one tile per 8192-cell block
+  static int grid = 0;
+  const size_t smem = (size_t)16 * 2 * 128 * sizeof(int4) + (size_t)(2 * LAG) * CAP * sizeof(int2);
+  auto kern = k_dense_scan_w<LAG, CAP, NX>;
+  constexpr int threads = 512 + 32 * NX;
+  if (!grid) {
+    int dev = 0, sms = 0, per = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, threads, smem);
+    if (per < 1) per = 1;
+    if (per > 2) per = 2;
+    grid = sms * per;                                  // persistent: co-resident CTAs only
+    if (grid > 1024) grid = 1024;                      // one lane per CTA group in the exchange
+    if (getenv("GR_SCAN_DEBUG")) fprintf(stderr, "k_dense_scan_w<%d,%d,%d>: %d CTAs/SM, grid %d, smem %zu\n", LAG, CAP, NX, per, grid, smem);
+  }
+  unsigned g = (unsigned)(ntiles < (u64)grid ? ntiles : (u64)grid);
+  const u64 nrounds = (ntiles + g - 1) / g;
+  ScanStatus st;
+  st.ngroups = (g + 31) / 32;
+  st.agg = (ulonglong2*)sc.st_sum;
+  st.grp = st.agg + ntiles;
+  cudaMemsetAsync(sc.st_sum, 0, (ntiles + nrounds * st.ngroups) * sizeof(ulonglong2), s);
+  u32 nt = (u32)ntiles;
+  DevLayout Lc = L;
+  void* args[] = { (void*)&delta, (void*)&Lc, (void*)&st, (void*)&out, (void*)&bitmap, (void*)&err, (void*)&nt, (void*)&zero_after };
+  cudaLaunchCooperativeKernel((const void*)kern, dim3(g), dim3(threads), args, smem, s);
+  GR_NOTE_LAUNCH();
+#ifdef GR_SCAN_PROF
+  {
+    static int nl = 0;
+    if (++nl == 12) {
+      unsigned long long h[8];
+      cudaStreamSynchronize(s);
+      cudaMemcpyFromSymbol(h, g_scan_prof, sizeof(h));
+      const double n = (double)h[4], m = (double)h[6];
+      fprintf(stderr, "scan prof (12 launches): per exchange: agg-wait %.0f ns, poll %.0f ns (%.2f polls), sibling %.0f ns; "
+              "warp0 prefix wait %.0f ns per tile (%.0f exchanges, %.0f finishes)\n",
+              h[0] / n, h[1] / n, h[3] / n, h[2] / n, h[5] / m, n, m);
+    }
+  }
+#endif
+  launch_fill_chrom_start(s, L, out.chrom_start, out.total);
+}
+
 void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
                        const ScanScratch& sc, DevRle out, u32* bitmap, int* err, int zero_after) {
+  static int ver = -1;
+  if (ver < 0) {
+    const char* e = getenv("GR_SCAN_V");
+    ver = e ? atoi(e) : 4;
+  }
+  if (ver == 4) { launch_scan_stream(s, L, delta, sc, out, bitmap, err, zero_after); return; }
+  if (ver == 3) {
+    static int wl = -1;
+    if (wl < 0) { const char* e = getenv("GR_SCAN_LAG"); wl = e ? atoi(e) : 2; }
+    static int nx = -1;
+    if (nx < 0) { const char* e = getenv("GR_SCAN_NX"); nx = e ? atoi(e) : 2; }
+    if (wl == 3) launch_dense_scan_w<3, 864, 2>(s, L, delta, sc, out, bitmap, err, zero_after);
+    else if (nx == 1) launch_dense_scan_w<2, 1216, 1>(s, L, delta, sc, out, bitmap, err, zero_after);
+    else if (nx == 3) launch_dense_scan_w<2, 1216, 3>(s, L, delta, sc, out, bitmap, err, zero_after);
+    else launch_dense_scan_w<2, 1216, 2>(s, L, delta, sc, out, bitmap, err, zero_after);
+    return;
+  }
   static int lag = -1;
   if (lag < 0) {
     const char* e = getenv("GR_SCAN_LAG");             // tuning knob; default chosen from measurements
