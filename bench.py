@@ -14,9 +14,11 @@ genome is sharded by chromosome over the ranks (strong scaling; torchrun, NCCL).
 `value`  = genome bp / device time per step, interval records already in HBM.
 `e2e`    = same through gr_push_intervals() from PINNED HOST buffers (H2D copies
            inside the timed region) and peak records read back to the host.
-`roofline` is for the dominant kernel, the per-base dense scan (k_dense_scan):
+`roofline` is for the dominant kernel, the per-base dense scan (k_scan_stream):
            4 B per delta cell per launch / mean launch time (CUDA events on the
-           library's stream) against the measured HBM copy bandwidth.
+           library's stream) against the measured HBM copy bandwidth.  Its
+           companion `scan_place` (moves the breaks to their final rank, 16 B per
+           interval) is timed as a stage of its own and quoted next to it.
 `cpu_baseline` / --impl reference: the UNMODIFIED reference binary
            (oracle/_ref/Genrich, built by `make -C oracle ref` where the sources
            are) on the SAM view of a bounded sample of the same workload, 1 host
@@ -53,6 +55,11 @@ WORKLOADS = {
                  atac=False, spacing=40000, sigma=100.0, enrich=0.3),
 }
 SAMPLE = dict(chrom_len=[25_000_000] * 4, nt=1_000_000, nc=1_000_000)   # bounded CPU sample (same generator)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_stream launch (bytes), from the
+# committed ncu capture of exactly this command; null for configurations that were not captured
+NCU_TRAFFIC = {("hg38_chip_50M_50M", 1): 12.56e9 + 3.42e9}
 
 
 def gen_fragments(chrom_len, n, seed, enrich, spacing, sigma, threads=8):
@@ -297,6 +304,7 @@ def main():
     peak_gbs, peak_src = measured_peak_gbs()
     scan_ms, scan_launches, _ = stages.get("dense_scan", (0.0, 0, 0))
     per_launch_ms = scan_ms / max(scan_launches, 1)
+    place_ms, place_launches, _ = stages.get("scan_place", (0.0, 0, 0))
     cells = ctx_cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
     achieved = 4.0 * cells / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
     stage_ms = {k: round(v[0] / a.steps, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])}
@@ -316,9 +324,12 @@ def main():
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_dev,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_dense_scan", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs if peak_gbs else None, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "k_scan_stream", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs if peak_gbs else None,
+                     # ncu --set full, hg38 workload, 1 GPU (profiles/r01_scan_stream_ncu.txt): dram read + write per launch
+                     "traffic": NCU_TRAFFIC.get((a.workload, world)), "peak_source": peak_src,
                      "bytes_per_launch": 4 * cells, "ms_per_launch": per_launch_ms,
+                     "companion_scan_place_ms_per_launch": place_ms / max(place_launches, 1),
                      "launches_per_step": scan_launches / a.steps, "samples_scanned_per_step": n_samples},
         "stage_ms_per_step": stage_ms,
     }

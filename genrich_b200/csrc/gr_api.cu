@@ -254,7 +254,7 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     CK(x->rankC.ensure(x->nblocks * sizeof(u64)));
     CK(x->rankTmp.ensure(x->nblocks * sizeof(u64)));
     const u64 ntile = T / GR_SCAN_TILE;
-    CK(x->lb0.ensure((2 * ntile + 4096) * sizeof(u64) * 2));   // dense-scan status words (agg + group + round)
+    CK(x->lb0.ensure(ntile * sizeof(u64)));
     CK(x->lb1.ensure(ntile * sizeof(u64)));
     CK(x->lb2.ensure(ntile * sizeof(u64)));
     CK(x->ticket.ensure(64));
@@ -520,11 +520,14 @@ extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
   DevRle out = rle_view(E, V, CS, TT);
   CK(x->scanWs.ensure(dense_scan_ws_bytes(cap, x->nchrom)));
   ScanScratch sc;
-  sc.st_sum = x->lb0.as<u64>(); sc.st_cnt = x->lb1.as<u64>(); sc.ticket = x->ticket.as<u32>();
   sc.ws = x->scanWs.p; sc.cap = cap;
   stage_begin(x, "dense_scan", x->T * 4);
-  launch_dense_scan(x->stream, x->L, x->delta.as<int32_t>(), sc, out,
+  launch_dense_scan(x->stream, x->L, x->delta.as<int32_t>(), sc,
                     (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, x->zero_after);
+  CKL();
+  stage_end(x);
+  stage_begin(x, "scan_place", cap * 16);
+  launch_scan_place(x->stream, x->L, sc, out, x->d_err);
   CKL();
   stage_end(x);
   u64* aI = x->accI.as<u64>() + (ctrl ? x->nchrom : 0);

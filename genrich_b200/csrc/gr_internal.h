@@ -39,14 +39,14 @@ void launch_scatter_binned(cudaStream_t s, const DevLayout& L, const int32_t* re
 
 // ---- K2: dense prefix sum + break compaction + bitmap (savePileupExpt 2168) ----
 struct ScanScratch {
-  u64* st_sum; u64* st_cnt; u32* ticket;   // look-back state, zeroed per launch
-  void* ws; u64 cap;                       // streaming scan: workspace of dense_scan_ws_bytes(cap, nchrom), cap = max #breaks
+  void* ws; u64 cap;        // workspace of dense_scan_ws_bytes(cap, nchrom); cap = upper bound of the #breaks
 };
 size_t dense_scan_ws_bytes(u64 cap, int nchrom);
 // zero_after: the scan clears every non-zero delta cell behind itself, so the array is all
 // zero again when the kernel ends (the next sample then needs no 4 B/bp memset)
 void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
-                       const ScanScratch& sc, DevRle out, u32* bitmap, int* err, int zero_after);
+                       const ScanScratch& sc, u32* bitmap, int* err, int zero_after);
+void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err);
 
 // ---- K2b: per-chromosome sum of (float)(end-start)*val, exact fixed point ------
 // acc_int / acc_frac: [nchrom] u64, zeroed by the caller.  sum = int + frac*2^-40.
