@@ -12,7 +12,7 @@ control paired-end fragments, default peak calling (-p 0.01).  For N > 1 the sam
 genome is sharded by chromosome over the ranks (strong scaling; torchrun, NCCL).
 
 `value`  = genome bp / device time per step, interval records already in HBM.
-`e2e`    = same through gr_push_intervals() from PINNED HOST buffers (H2D copies
+`e2e`    = same through gr_push_packed() from PINNED HOST buffers (H2D copies
            inside the timed region) and peak records read back to the host.
 `roofline` is for the dominant kernel, the per-base dense scan (k_scan_stream):
            4 B per delta cell per launch / mean launch time (CUDA events on the
@@ -226,7 +226,10 @@ def main():
             return None, None
         fr = gen_fragments(L, n, seed, enrich, wl["spacing"], wl["sigma"])
         iv = eng.route(host.fragments_to_intervals(fr, atac=wl["atac"]))
-        pinned = torch.from_numpy(iv).pin_memory()
+        # the producer side of the C-ABI hands over 8-byte GR_PACK records (gr_push_packed)
+        packed, rest = host.pack_records(iv)
+        assert rest.shape[0] == 0, "synthetic workload has records that do not pack"
+        pinned = torch.from_numpy(packed.view(np.int64)).pin_memory()
         return pinned, pinned.to(dev)
     t_host, t_dev = make(wl["nt"], 2001, wl["enrich"])
     c_host, c_dev = make(wl["nc"], 2002, 0.0)
@@ -243,17 +246,17 @@ def main():
             # sent while the treatment sample is being integrated, and the next step's treatment
             # sample while this step's peaks are called (gr_prefetch_intervals)
             def pe(c):
-                c.push_ptr(t_host.data_ptr(), n_t)
+                c.push_packed_ptr(t_host.data_ptr(), n_t)
                 if n_c:
-                    c.prefetch_ptr(c_host.data_ptr(), n_c)
+                    c.prefetch_packed_ptr(c_host.data_ptr(), n_c)
 
             def pc_(c):
-                c.push_ptr(c_host.data_ptr(), n_c)
-                c.prefetch_ptr(t_host.data_ptr(), n_t)
+                c.push_packed_ptr(c_host.data_ptr(), n_c)
+                c.prefetch_packed_ptr(t_host.data_ptr(), n_t)
             pc = pc_ if n_c else None
         else:
-            pe = lambda c: c.push_intervals_device(t_dev.data_ptr(), n_t)
-            pc = (lambda c: c.push_intervals_device(c_dev.data_ptr(), n_c)) if n_c else None
+            pe = lambda c: c.push_packed_ptr(t_dev.data_ptr(), n_t)
+            pc = (lambda c: c.push_packed_ptr(c_dev.data_ptr(), n_c)) if n_c else None
         eng.replicate(pe, pc)
         return eng.call_peaks()
 
@@ -319,7 +322,7 @@ def main():
                    "l2": "inputs (%.1f GB dense delta array per sample) far exceed the 126 MB L2" % (4e-9 * cells),
                    "peaks": int(len(peaks)), "intervals_rank0": int(rs.n_intervals)},
         "e2e": {"value": G / 1e9 / (ms_e2e * 1e-3), "unit": "Gbp/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(16 * (n_t + n_c)), "d2h_bytes_per_step": int(peaks2.nbytes + 512),
+                "h2d_bytes_per_step": int(8 * (n_t + n_c)), "d2h_bytes_per_step": int(peaks2.nbytes + 512),
                 "wall_ms_per_step": wall_e2e},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_dev,

@@ -66,7 +66,8 @@ PEAK_DTYPE = np.dtype([("chrom", "<i4"), ("summit", "<u4"), ("start", "<i8"),
 ABI_SYMBOLS = [
     "gr_create", "gr_destroy", "gr_set_params", "gr_reset", "gr_strerror",
     "gr_last_error_detail", "gr_sample_begin", "gr_push_intervals",
-    "gr_push_intervals_device", "gr_prefetch_intervals", "gr_sample_pileup", "gr_replicate_finish",
+    "gr_push_intervals_device", "gr_prefetch_intervals", "gr_push_packed", "gr_prefetch_packed",
+    "gr_sample_pileup", "gr_replicate_finish",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
     "gr_bh_set_global", "gr_call_peaks", "gr_peaks_device", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
@@ -128,6 +129,8 @@ class Api:
             self.last_error_detail = fn("last_error_detail", C.c_char_p, [vp])
             self.push_intervals_device = fn("push_intervals_device", C.c_int, [vp, vp, u64])
             self.prefetch_intervals = fn("prefetch_intervals", C.c_int, [vp, vp, u64])
+            self.push_packed = fn("push_packed", C.c_int, [vp, vp, u64])
+            self.prefetch_packed = fn("prefetch_packed", C.c_int, [vp, vp, u64])
             self.peaks_device = fn("peaks_device", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)])
             self.timing_enable = fn("timing_enable", C.c_int, [vp, i32])
             self.timing_get = fn("timing_get", C.c_int, [vp, C.POINTER(GrStageTime), i32, C.POINTER(i32)])
@@ -239,6 +242,18 @@ class Context:
 
     def prefetch_ptr(self, host_ptr: int, n: int):
         self._check(self.api.prefetch_intervals(self._h, C.c_void_p(host_ptr), n), "prefetch_intervals")
+
+    def push_packed(self, recs: np.ndarray):
+        """recs: uint64 GR_PACK records (host.pack_records)."""
+        recs = np.ascontiguousarray(recs, dtype=np.uint64)
+        self._check(self.api.push_packed(self._h, _as_ptr(recs), recs.shape[0]), "push_packed")
+
+    def push_packed_ptr(self, ptr: int, n: int):
+        """ptr: host (pinned or not) or device address of n GR_PACK records."""
+        self._check(self.api.push_packed(self._h, C.c_void_p(ptr), n), "push_packed")
+
+    def prefetch_packed_ptr(self, host_ptr: int, n: int):
+        self._check(self.api.prefetch_packed(self._h, C.c_void_p(host_ptr), n), "prefetch_packed")
 
     def push_ptr(self, host_ptr: int, n: int):
         self._check(self.api.push_intervals(self._h, C.c_void_p(host_ptr), n), "push_intervals")

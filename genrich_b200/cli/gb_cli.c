@@ -324,7 +324,10 @@ int main(int argc, char** argv) {
   buf.cap = 1u << 20;
   buf.n = 0;
   buf.recs = (int32_t*)gr_pinned_alloc(buf.cap * 16);
-  if (!buf.recs) gb_die("", "Cannot allocate memory");
+  buf.cap_pk = 1u << 21;
+  buf.npk = 0;
+  buf.pk = (uint64_t*)gr_pinned_alloc(buf.cap_pk * 8);
+  if (!buf.recs || !buf.pk) gb_die("", "Cannot allocate memory");
   uint8_t* save = (uint8_t*)gb_alloc(tab.n);
 
   HDecode d;
@@ -419,6 +422,7 @@ int main(int argc, char** argv) {
   if (o.pile_file) gb_out_close(&pile, o.pile_file);
   if (o.bed_file) gb_out_close(&bed, o.bed_file);
   gr_pinned_free(buf.recs);
+  gr_pinned_free(buf.pk);
   gr_destroy(ctx);
   return EXIT_SUCCESS;
 }

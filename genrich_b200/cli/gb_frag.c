@@ -13,10 +13,17 @@
 #define ATAC_ADJ_R (-5)   /* ATACADJR, Genrich.h:36 */
 
 void gb_flush_intervals(HDecode* d) {
-  if (!d->buf->n) return;
-  int rc = gr_push_intervals(d->ctx, d->buf->recs, d->buf->n);
-  if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
-  d->buf->n = 0;
+  HIvBuf* b = d->buf;
+  if (b->npk) {
+    int rc = gr_push_packed(d->ctx, b->pk, b->npk);
+    if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
+    b->npk = 0;
+  }
+  if (b->n) {
+    int rc = gr_push_intervals(d->ctx, b->recs, b->n);
+    if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
+    b->n = 0;
+  }
 }
 
 /* saveInterval 2516-2591, host half: clamp, messages, BED line, enqueue */
@@ -47,6 +54,11 @@ void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const c
     gb_out_printf(d->bed, "%s\t%ld\t%ld\t%s_%d_%c_%d\n", c->name, (long)start, (long)end, qname, count,
                   d->ctrl ? 'C' : 'E', d->sample);
   HIvBuf* b = d->buf;
+  if (end - start >= 0 && end - start < (int64_t)GR_PACK_MAX_LEN && (uint32_t)chrom < GR_PACK_MAX_CHROM) {
+    if (b->npk == b->cap_pk) gb_flush_intervals(d);
+    b->pk[b->npk++] = GR_PACK(chrom, start, end, count);
+    return;
+  }
   if (b->n == b->cap) gb_flush_intervals(d);
   int32_t* r = b->recs + 4 * b->n++;
   r[0] = chrom; r[1] = (int32_t)start; r[2] = (int32_t)end; r[3] = count;

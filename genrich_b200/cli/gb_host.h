@@ -67,10 +67,13 @@ typedef struct {        /* per-file counters (logCounts 5295) */
   double total_len;
 } HCounts;
 
-/* growable pinned buffer of int32 x 4 interval records */
+/* pinned buffers of interval records: the 8-byte GR_PACK form for whatever fits it
+ * (half the PCIe bytes), int32 x 4 for the rest */
 typedef struct {
   int32_t* recs;
   size_t n, cap;
+  uint64_t* pk;
+  size_t npk, cap_pk;
 } HIvBuf;
 
 /* text sink: plain FILE or gzip */

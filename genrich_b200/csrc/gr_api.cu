@@ -89,14 +89,14 @@ struct gr_ctx {
   // interval staging
   DevBuf stage[2];
   DevBuf binRecs, binCnt, binCursor;   // locality pass in front of the scatter
-  u64 bin_min = 1ull << 21;            // pushes smaller than this go straight to the scatter (GR_SCATTER_BIN=0: never bin)
+  u64 bin_min = 0;                     // GR_SCATTER_BIN=1: pushes of >= 2^21 records take the locality pass (measured slower)
   cudaEvent_t stage_free[2] = { nullptr, nullptr }, stage_ready[2] = { nullptr, nullptr };
   void* h_stage[2] = { nullptr, nullptr };
   int stage_next = 0;
   static const u64 STAGE_RECS = 1ull << 22;     // 4M records = 64 MB
 
   // prefetched host buffers (gr_prefetch_intervals)
-  struct Prefetch { DevBuf buf; const int32_t* host = nullptr; u64 n = 0; cudaEvent_t ready = nullptr, freed = nullptr; bool live = false; };
+  struct Prefetch { DevBuf buf; const void* host = nullptr; u64 n = 0; cudaEvent_t ready = nullptr, freed = nullptr; bool live = false; };
   Prefetch pf[2];
 
   // sample state
@@ -278,7 +278,7 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     x->expt_sums.assign(nchrom, 0.0);
     x->ctrl_sums.assign(nchrom, 0.0);
     { const char* e = getenv("GR_SCAN_ZERO"); if (e) x->zero_after = atoi(e) != 0; }
-    { const char* e = getenv("GR_SCATTER_BIN"); if (e && !atoi(e)) x->bin_min = 0; }
+    { const char* e = getenv("GR_SCATTER_BIN"); if (e && atoi(e)) x->bin_min = 1ull << 21; }
     CK(cudaStreamSynchronize(x->stream));
     return GR_OK;
   }();
@@ -399,30 +399,31 @@ extern "C" int gr_sample_begin(gr_ctx* x, int32_t is_ctrl, const uint8_t* save) 
   return GR_OK;
 }
 
-static int scatter_records(gr_ctx* x, const int32_t* d_recs, u64 n) {
-  if (x->bin_min && n >= x->bin_min) {
+// rb: bytes per record -- 16 (int32 x 4) or 8 (GR_PACK)
+static int scatter_records(gr_ctx* x, const void* d_recs, u64 n, int rb) {
+  if (rb == 16 && x->bin_min && n >= x->bin_min) {
     CK(x->binRecs.ensure(n * 16));
     CK(x->binCnt.ensure(8192 * sizeof(u32)));
     CK(x->binCursor.ensure(8192 * sizeof(u64)));
-    launch_scatter_binned(x->stream, x->L, d_recs, n, x->delta.as<int32_t>(), x->d_err, x->d_clamped,
+    launch_scatter_binned(x->stream, x->L, (const int32_t*)d_recs, n, x->delta.as<int32_t>(), x->d_err, x->d_clamped,
                           x->binRecs.as<int32_t>(), x->binCnt.as<u32>(), x->binCursor.as<u64>());
   } else
-    launch_scatter(x->stream, x->L, d_recs, n, x->delta.as<int32_t>(), x->d_err, x->d_clamped);
+    launch_scatter(x->stream, x->L, d_recs, n, rb == 8, x->delta.as<int32_t>(), x->d_err, x->d_clamped);
   return GR_OK;
 }
 
-extern "C" int gr_push_intervals_device(gr_ctx* x, const int32_t* d_recs, uint64_t n) {
+static int push_device(gr_ctx* x, const void* d_recs, u64 n, int rb) {
   if (!x || x->filling == FILL_NONE || (!d_recs && n)) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
-  stage_begin(x, "scatter", n * 16);
-  { int r = scatter_records(x, d_recs, n); if (r) return r; }
+  stage_begin(x, "scatter", n * rb);
+  { int r = scatter_records(x, d_recs, n, rb); if (r) return r; }
   CKL();
   stage_end(x);
   x->n_pushed += n;
   return GR_OK;
 }
 
-extern "C" int gr_prefetch_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
+static int prefetch_any(gr_ctx* x, const void* recs, u64 n, int rb) {
   if (!x || !recs || !n) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
   cudaPointerAttributes at;
@@ -437,8 +438,8 @@ extern "C" int gr_prefetch_intervals(gr_ctx* x, const int32_t* recs, uint64_t n)
       CK(cudaEventCreateWithFlags(&p.freed, cudaEventDisableTiming));
     } else
       CK(cudaStreamWaitEvent(x->copy, p.freed, 0));     // the scatter that last read this buffer is done
-    CK(p.buf.ensure(n * 16));
-    CK(cudaMemcpyAsync(p.buf.p, recs, n * 16, cudaMemcpyHostToDevice, x->copy));
+    CK(p.buf.ensure(n * rb));
+    CK(cudaMemcpyAsync(p.buf.p, recs, n * rb, cudaMemcpyHostToDevice, x->copy));
     CK(cudaEventRecord(p.ready, x->copy));
     p.host = recs; p.n = n; p.live = true;
     return GR_OK;
@@ -446,14 +447,14 @@ extern "C" int gr_prefetch_intervals(gr_ctx* x, const int32_t* recs, uint64_t n)
   return GR_OK;                                // both slots busy: ignored
 }
 
-extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
+static int push_any(gr_ctx* x, const void* recs, u64 n, int rb) {
   if (!x || x->filling == FILL_NONE || (!recs && n)) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
   for (auto& p : x->pf)
-    if (p.live && p.host == recs && p.n == n) {          // already on its way (gr_prefetch_intervals)
+    if (p.live && p.host == recs && p.n == n) {          // already on its way (gr_prefetch_*)
       CK(cudaStreamWaitEvent(x->stream, p.ready, 0));
-      stage_begin(x, "scatter", n * 16);
-      { int r = scatter_records(x, p.buf.as<int32_t>(), n); if (r) return r; }
+      stage_begin(x, "scatter", n * rb);
+      { int r = scatter_records(x, p.buf.p, n, rb); if (r) return r; }
       CKL();
       stage_end(x);
       CK(cudaEventRecord(p.freed, x->stream));
@@ -464,7 +465,7 @@ extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
   cudaPointerAttributes at;
   bool pinned = false;
   if (cudaPointerGetAttributes(&at, recs) == cudaSuccess) {
-    if (at.type == cudaMemoryTypeDevice) return gr_push_intervals_device(x, recs, n);
+    if (at.type == cudaMemoryTypeDevice) return push_device(x, recs, n, rb);
     pinned = at.type == cudaMemoryTypeHost;
   } else
     cudaGetLastError();
@@ -477,20 +478,20 @@ extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
       CK(x->stage[b].ensure(CH * 16));
       CK(cudaEventRecord(x->stage_free[b], x->stream));
     }
-    const int32_t* src = recs + 4 * done;
+    const char* src = (const char*)recs + done * rb;
     // the copy stream may reuse slot b once the scatter that read it has finished
     CK(cudaStreamWaitEvent(x->copy, x->stage_free[b], 0));
     if (!pinned) {
       if (!x->h_stage[b]) CK(cudaMallocHost(&x->h_stage[b], CH * 16));
       CK(cudaEventSynchronize(x->stage_ready[b]));     // previous H2D out of this pinned slot is done
-      memcpy(x->h_stage[b], src, m * 16);
-      src = (const int32_t*)x->h_stage[b];
+      memcpy(x->h_stage[b], src, m * rb);
+      src = (const char*)x->h_stage[b];
     }
-    CK(cudaMemcpyAsync(x->stage[b].p, src, m * 16, cudaMemcpyHostToDevice, x->copy));
+    CK(cudaMemcpyAsync(x->stage[b].p, src, m * rb, cudaMemcpyHostToDevice, x->copy));
     CK(cudaEventRecord(x->stage_ready[b], x->copy));
     CK(cudaStreamWaitEvent(x->stream, x->stage_ready[b], 0));
-    stage_begin(x, "scatter", m * 16);
-    { int r = scatter_records(x, x->stage[b].as<int32_t>(), m); if (r) return r; }
+    stage_begin(x, "scatter", m * rb);
+    { int r = scatter_records(x, x->stage[b].p, m, rb); if (r) return r; }
     CKL();
     stage_end(x);
     CK(cudaEventRecord(x->stage_free[b], x->stream));
@@ -502,6 +503,12 @@ extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) {
   x->n_pushed += n;
   return GR_OK;
 }
+
+extern "C" int gr_push_intervals_device(gr_ctx* x, const int32_t* d_recs, uint64_t n) { return push_device(x, d_recs, n, 16); }
+extern "C" int gr_prefetch_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) { return prefetch_any(x, recs, n, 16); }
+extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) { return push_any(x, recs, n, 16); }
+extern "C" int gr_prefetch_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) { return prefetch_any(x, recs, n, 8); }
+extern "C" int gr_push_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) { return push_any(x, recs, n, 8); }
 
 // ---- pileup integration ----------------------------------------------------------
 extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {

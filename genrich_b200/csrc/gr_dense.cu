@@ -13,15 +13,27 @@
 // K1: two int32 reductions (RED.ADD) per interval record into the dense delta
 // array, in units of 1/120 (weights 120/count, count in {1,2,3,4,5,6,8,10}:
 // addFrac 2311 / subFrac 2412).  Clamping as saveInterval 2522-2544.
+// PACKED: 8-byte records (include/genrich_cuda.h, GR_PACK), else int32 x 4.
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
-k_scatter(const int4* __restrict__ recs, u64 n, DevLayout L, int32_t* __restrict__ delta,
+k_scatter(const void* __restrict__ recs, u64 n, DevLayout L, int32_t* __restrict__ delta,
           int* __restrict__ err, u64* __restrict__ clamped) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   int e_local = 0;
   u32 c_local = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const int4 r = ld_stream_v4(recs + i);
-    const int c = r.x;
+    int c, cnt;
+    i64 s, e;
+    if (PACKED) {
+      const u64 v = __ldcs(reinterpret_cast<const u64*>(recs) + i);
+      s = (i64)(u32)v;
+      e = s + (i64)((v >> 32) & 0x3fffu);
+      c = (int)((v >> 46) & 0x3fffu);
+      cnt = (int)(v >> 60);
+    } else {
+      const int4 r = ld_stream_v4(reinterpret_cast<const int4*>(recs) + i);
+      c = r.x; s = r.y; e = r.z; cnt = r.w;
+    }
     if (c < 0 || c >= L.nchrom) { e_local |= GR_DE_CHROM; continue; }
     const uint8_t f = L.flags[c];
     const u64 off = L.off[c];
@@ -30,10 +42,8 @@ k_scatter(const int4* __restrict__ recs, u64 n, DevLayout L, int32_t* __restrict
       continue;
     }
     if (!(f & GR_CF_SAVE)) continue;         // processPair 3137-3138: not in this replicate
-    const int cnt = r.w;
     if (cnt < 1 || cnt > 10 || !((1 << cnt) & 0x57E)) { e_local |= GR_DE_COUNT; continue; }
     const i64 len = L.len[c];
-    i64 s = r.y, e = r.z;
     bool cl = false;
     if (s < 0) { s = 0; cl = true; }
     if (s >= len || e < 0) { e_local |= GR_DE_POS; continue; }
@@ -47,12 +57,14 @@ k_scatter(const int4* __restrict__ recs, u64 n, DevLayout L, int32_t* __restrict
   if (c_local) atomicAdd(clamped, (u64)c_local);
 }
 
-void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64 n,
+void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
                     int32_t* delta, int* err, u64* clamped) {
   if (!n) return;
   u64 blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  k_scatter<<<(unsigned)blocks, 256, 0, s>>>((const int4*)recs, n, L, delta, err, clamped); GR_NOTE_LAUNCH();
+  if (packed) k_scatter<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, delta, err, clamped);
+  else k_scatter<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, delta, err, clamped);
+  GR_NOTE_LAUNCH();
 }
 
 // ----------------------------------------------------------------------------
@@ -172,7 +184,7 @@ void launch_scatter_binned(cudaStream_t s, const DevLayout& L, const int32_t* re
   }
   k_bin_move<<<(unsigned)((n + BIN_CHUNK - 1) / BIN_CHUNK), 256, smem, s>>>((const int4*)recs, n, L, shift, nb, bin_cursor,
                                                                             (int4*)scratch_recs); GR_NOTE_LAUNCH();
-  launch_scatter(s, L, scratch_recs, n, delta, err, clamped);
+  launch_scatter(s, L, scratch_recs, n, 0, delta, err, clamped);
 }
 
 // ============================================================================

@@ -28,7 +28,7 @@ struct DevRle {
 };
 
 // ---- K1: delta scatter (saveInterval 2516-2591) ------------------------------
-void launch_scatter(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64 n,
+void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
                     int32_t* delta, int* err, u64* clamped);
 
 // same, behind a locality pass that first moves the records into ~3000 position buckets

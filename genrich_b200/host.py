@@ -66,20 +66,30 @@ class RunResult:
     sample_stats: list = field(default_factory=list)
 
 
-def run_replicates(ctx: Context, replicates, chunk: int = 1 << 22) -> RunResult:
-    """replicates: list of (expt_intervals, ctrl_intervals_or_None[, save_mask])."""
+def run_replicates(ctx: Context, replicates, chunk: int = 1 << 22, packed: bool = False) -> RunResult:
+    """replicates: list of (expt_intervals, ctrl_intervals_or_None[, save_mask]).
+    packed: send the records in the 8-byte GR_PACK form (what does not fit goes the 16-byte way)."""
+    def push(recs):
+        if not packed:
+            ctx.push_intervals(recs)
+            return
+        pk, rest = pack_records(recs)
+        if len(pk):
+            ctx.push_packed(pk)
+        if len(rest):
+            ctx.push_intervals(rest)
     stats = []
     for rep in replicates:
         expt, ctrl = rep[0], rep[1]
         save = rep[2] if len(rep) > 2 else None
         ctx.sample_begin(False, save)
         for i in range(0, len(expt), chunk):
-            ctx.push_intervals(expt[i:i + chunk])
+            push(expt[i:i + chunk])
         if ctrl is not None:
             ctx.sample_pileup()
             ctx.sample_begin(True)
             for i in range(0, len(ctrl), chunk):
-                ctx.push_intervals(ctrl[i:i + chunk])
+                push(ctrl[i:i + chunk])
         stats.append(ctx.replicate_end())
     peaks, rs = ctx.call_peaks()
     return RunResult(peaks, rs, stats)
@@ -135,6 +145,31 @@ def format_log(ctx: Context, names, qval: bool, thr: float | None = None) -> lis
             out.append(line)
             start = int(pv.end[m])
     return out
+
+
+PACK_MAX_LEN = 1 << 14      # include/genrich_cuda.h GR_PACK_MAX_LEN / GR_PACK_MAX_CHROM
+PACK_MAX_CHROM = 1 << 14
+
+
+def pack_records(recs: np.ndarray):
+    """(chrom, start, end, count) int32 records -> (uint64 GR_PACK records, the records that do not fit).
+
+    The 8-byte form is what travels best over PCIe; whatever it cannot express (start < 0,
+    an interval of 16384 bp or more, chromosome index >= 16384) stays in the 16-byte form and
+    is pushed through gr_push_intervals -- the two may be mixed within a sample."""
+    recs = np.ascontiguousarray(recs, dtype=np.int32).reshape(-1, 4)
+    c, s, e, k = (recs[:, i].astype(np.int64) for i in range(4))
+    ln = e - s
+    ok = (s >= 0) & (ln >= 0) & (ln < PACK_MAX_LEN) & (c >= 0) & (c < PACK_MAX_CHROM) & (k >= 0) & (k < 16)
+    if ok.all():
+        sel = slice(None)
+        rest = recs[:0]
+    else:
+        sel = ok
+        rest = recs[~ok]
+    packed = (s[sel].astype(np.uint64) | (ln[sel].astype(np.uint64) << np.uint64(32))
+              | (c[sel].astype(np.uint64) << np.uint64(46)) | (k[sel].astype(np.uint64) << np.uint64(60)))
+    return np.ascontiguousarray(packed, dtype=np.uint64), np.ascontiguousarray(rest)
 
 
 def lpt_shard(chrom_len, world: int) -> np.ndarray:

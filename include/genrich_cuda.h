@@ -141,6 +141,23 @@ int gr_push_intervals_device(gr_ctx* ctx, const int32_t* d_recs, uint64_t n);/* 
  * At most two buffers can be in flight; a third request is ignored (returns 0). */
 int gr_prefetch_intervals(gr_ctx* ctx, const int32_t* recs, uint64_t n);
 
+/* Compact wire format of the same four saveInterval arguments, 8 bytes per record:
+ *   bits  0-31  start            (0 <= start < 2^32)
+ *   bits 32-45  end - start      (< GR_PACK_MAX_LEN)
+ *   bits 46-59  chromosome index (< GR_PACK_MAX_CHROM)
+ *   bits 60-63  count            (as above)
+ * Semantics are those of gr_push_intervals on the unpacked record; a record that does not
+ * fit (start < 0, a longer interval, more chromosomes) goes through gr_push_intervals --
+ * both may be mixed freely within one sample.  The host -> device copy is what bounds the
+ * end-to-end rate of the hot path (PCIe), so producers should pack: half the bytes.
+ * gr_push_packed accepts host (pinned or not) and device pointers. */
+#define GR_PACK_MAX_LEN   (1u << 14)
+#define GR_PACK_MAX_CHROM (1u << 14)
+#define GR_PACK(chrom, start, end, count) \
+  ((uint64_t)(uint32_t)(start) | ((uint64_t)((end) - (start)) << 32) | ((uint64_t)(chrom) << 46) | ((uint64_t)(count) << 60))
+int gr_push_packed(gr_ctx* ctx, const uint64_t* recs, uint64_t n);
+int gr_prefetch_packed(gr_ctx* ctx, const uint64_t* recs, uint64_t n);
+
 /* Integrate the current sample (savePileupExpt 2168 / the RLE pass of
  * calcFactor 1980).  chrom_sums[nchrom] receives, per owned chromosome, the
  * double sum of (float)(end-start)*val (0 elsewhere); the caller adds them in

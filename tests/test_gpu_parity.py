@@ -144,6 +144,27 @@ def test_repeatable_and_chunking_invariant():
             assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
 
 
+def test_packed_records_same_bits():
+    """gr_push_packed (8-byte records) == gr_push_intervals on the same intervals, including
+    records that cannot be packed (negative start, >= 16384 bp) and travel the 16-byte way."""
+    api = capi.load_cuda()
+    for name in ("c5_multimap_ctrl_p", "c2_ctrl_q"):
+        case = BY_NAME[name]
+        inputs = [list(r) for r in util.case_inputs(case)]
+        extra = np.array([[0, -40, 180, 1], [0, 1000, 1000 + 20000, 2], [1 % len(case.chrom_len), 5, 16388, 1]], np.int32)
+        inputs[0][0] = np.concatenate([inputs[0][0], extra])
+        outs = []
+        for packed in (False, True):
+            ctx = capi.Context(api, case.chrom_len, util.case_params(case))
+            res = host.run_replicates(ctx, inputs, chunk=50001, packed=packed)
+            outs.append((res, [ctx.fetch(2, 0, c) for c in range(len(case.chrom_len))]))
+        (ra, pa), (rb, pb) = outs
+        assert ra.peaks.tobytes() == rb.peaks.tobytes() and len(ra.peaks) > 0
+        assert ra.sample_stats[0].frag_len == rb.sample_stats[0].frag_len
+        for x, y in zip(pa, pb):
+            assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
+
+
 def test_edge_inputs():
     api = capi.load_cuda()
     orc = util.oracle_api()

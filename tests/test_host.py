@@ -95,3 +95,25 @@ def test_lpt_owner_covers_everything():
     L = [100, 90, 80, 10, 5, 1]
     own = host.lpt_shard(L, 3)
     assert set(own) == {0, 1, 2} and len(own) == len(L)
+
+
+def test_pack_records_roundtrip():
+    rng = np.random.default_rng(5)
+    n = 5000
+    recs = np.stack([rng.integers(0, 30, n), rng.integers(0, 2**31 - 20000, n), np.zeros(n, np.int64),
+                     rng.choice([1, 2, 3, 4, 5, 6, 8, 10], n)], axis=1)
+    recs[:, 2] = recs[:, 1] + rng.integers(0, 3000, n)
+    recs = recs.astype(np.int32)
+    recs[7] = (3, -5, 100, 1)                 # negative start
+    recs[8] = (3, 100, 100 + host.PACK_MAX_LEN, 2)   # too long
+    recs[9] = (3, 100, 100 + host.PACK_MAX_LEN - 1, 2)   # just fits
+    packed, rest = host.pack_records(recs)
+    assert len(packed) == n - 2 and len(rest) == 2
+    assert rest.tolist() == [recs[7].tolist(), recs[8].tolist()]
+    s = (packed & np.uint64(0xffffffff)).astype(np.int64)
+    ln = ((packed >> np.uint64(32)) & np.uint64(0x3fff)).astype(np.int64)
+    c = ((packed >> np.uint64(46)) & np.uint64(0x3fff)).astype(np.int64)
+    k = (packed >> np.uint64(60)).astype(np.int64)
+    keep = np.ones(n, bool); keep[[7, 8]] = False
+    back = np.stack([c, s, s + ln, k], axis=1).astype(np.int32)
+    assert np.array_equal(back, recs[keep])
