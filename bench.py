@@ -263,6 +263,7 @@ def main():
     def timed(from_host, steps, warmup, with_stages=False):
         for _ in range(warmup):
             step(from_host)
+        eng.t_acc.clear()
         if with_stages:
             ctx.timing(True)
             ctx.timing_reset()
@@ -297,7 +298,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     if eng.debug:
-        print("rank %d host-side seconds (all steps): %s" % (rank, {k: round(v, 4) for k, v in eng.t_acc.items()}),
+        print("rank %d host-side ms per step (e2e arm): %s" % (rank, {k: round(v * 1e3 / a.steps, 3) for k, v in eng.t_acc.items()}),
               file=sys.stderr, flush=True)
     if rank != 0:
         if world > 1:

@@ -86,18 +86,24 @@ struct gr_ctx {
   u64 n_expt = 0, n_raw = 0, n_ctrl = 0;
   std::vector<u64> exptCS_h, ctrlCS_h;
 
-  // interval staging
-  DevBuf stage[2];
-  DevBuf binRecs, binCnt, binCursor;   // locality pass in front of the scatter
-  u64 bin_min = 0;                     // GR_SCATTER_BIN=1: pushes of >= 2^21 records take the locality pass (measured slower)
-  cudaEvent_t stage_free[2] = { nullptr, nullptr }, stage_ready[2] = { nullptr, nullptr };
+  // Interval records of the sample being filled.  A push only makes the records device-resident
+  // and remembers where they are; gr_sample_pileup consumes all segments at once (it has to
+  // know the per-block record counts of the whole sample before it can bucket them).
+  struct SegBuf { DevBuf buf; cudaEvent_t freed = nullptr; };          // device copies of host pushes, recycled
+  struct Prefetch { DevBuf buf; const void* host = nullptr; u64 n = 0; cudaEvent_t ready = nullptr, freed = nullptr;
+                    bool live = false, in_use = false; };
+  struct Segment { const void* d; u64 n; int rb; SegBuf* own; Prefetch* pf; };
+  std::vector<Segment> segs;
+  std::vector<SegBuf*> seg_free, seg_used;
+  Prefetch pf[2];                      // buffers on their way ahead of their push (gr_prefetch_*)
+  cudaEvent_t h_ready[2] = { nullptr, nullptr };   // pinned bounce buffers for pageable sources
   void* h_stage[2] = { nullptr, nullptr };
   int stage_next = 0;
-  static const u64 STAGE_RECS = 1ull << 22;     // 4M records = 64 MB
-
-  // prefetched host buffers (gr_prefetch_intervals)
-  struct Prefetch { DevBuf buf; const void* host = nullptr; u64 n = 0; cudaEvent_t ready = nullptr, freed = nullptr; bool live = false; };
-  Prefetch pf[2];
+  static const u64 STAGE_BYTES = 64ull << 20;
+  cudaEvent_t ev_copy = nullptr;
+  // bucketed build (large samples)
+  DevBuf sbCnt, sbStart, sbCursor, sbBucket, sbSpill, sbSpillCtr;
+  u64 sb_min = 1ull << 20;             // samples with fewer records use the plain scatter (GR_SB_MIN)
 
   // sample state
   int filling = FILL_NONE;
@@ -271,14 +277,11 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     const size_t cs = (nchrom + 1) * sizeof(u64);
     CK(x->exptCS.ensure(cs)); CK(x->rawCS.ensure(cs)); CK(x->ctrlCS.ensure(cs));
     CK(x->exptTot.ensure(8)); CK(x->rawTot.ensure(8)); CK(x->ctrlTot.ensure(8));
-    for (int i = 0; i < 2; i++) {
-      CK(cudaEventCreateWithFlags(&x->stage_free[i], cudaEventDisableTiming));
-      CK(cudaEventCreateWithFlags(&x->stage_ready[i], cudaEventDisableTiming));
-    }
     x->expt_sums.assign(nchrom, 0.0);
     x->ctrl_sums.assign(nchrom, 0.0);
     { const char* e = getenv("GR_SCAN_ZERO"); if (e) x->zero_after = atoi(e) != 0; }
-    { const char* e = getenv("GR_SCATTER_BIN"); if (e && atoi(e)) x->bin_min = 1ull << 21; }
+    { const char* e = getenv("GR_SB_MIN"); if (e) x->sb_min = strtoull(e, nullptr, 10); }
+    CK(cudaEventCreateWithFlags(&x->ev_copy, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(x->stream));
     return GR_OK;
   }();
@@ -327,7 +330,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   DevBuf* all[] = { &x->d_off, &x->d_len, &x->d_flags, &x->d_blk2chrom, &x->delta, &x->bmE, &x->bmC,
     &x->rankE, &x->rankC, &x->rankTmp, &x->lb0, &x->lb1, &x->lb2, &x->ticket, &x->scanWs, &x->small, &x->accI,
     &x->accF, &x->exptEnd, &x->exptVal, &x->exptCS, &x->exptTot, &x->rawEnd, &x->rawVal, &x->rawCS,
-    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->stage[0], &x->stage[1], &x->binRecs, &x->binCnt, &x->binCursor,
+    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->sbCnt, &x->sbStart, &x->sbCursor, &x->sbBucket, &x->sbSpill, &x->sbSpillCtr,
     &x->qVal, &x->tKeys, &x->tLens, &x->tPval, &x->tQval, &x->tCount, &x->slot, &x->hk, &x->hl,
     &x->hcount, &x->bk0, &x->bk1, &x->bl0, &x->bl1, &x->bhist, &x->bksum, &x->bx, &x->bdk, &x->bdq,
     &x->bdl, &x->bdcount, &x->fsum, &x->fdf, &x->repviews, &x->evIdx, &x->evCount, &x->headIdx,
@@ -337,9 +340,11 @@ extern "C" void gr_destroy(gr_ctx* x) {
   if (x->h_acc) cudaFreeHost(x->h_acc);
   for (int i = 0; i < 2; i++) {
     if (x->h_stage[i]) cudaFreeHost(x->h_stage[i]);
-    if (x->stage_free[i]) cudaEventDestroy(x->stage_free[i]);
-    if (x->stage_ready[i]) cudaEventDestroy(x->stage_ready[i]);
+    if (x->h_ready[i]) cudaEventDestroy(x->h_ready[i]);
   }
+  if (x->ev_copy) cudaEventDestroy(x->ev_copy);
+  for (auto* v : { &x->seg_free, &x->seg_used })
+    for (auto* sb : *v) { sb->buf.release(); if (sb->freed) cudaEventDestroy(sb->freed); delete sb; }
   for (auto& s : x->stages) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   if (x->tm_a) { cudaEventDestroy(x->tm_a); cudaEventDestroy(x->tm_b); }
   for (auto& p : x->pf) { p.buf.release(); if (p.ready) { cudaEventDestroy(p.ready); cudaEventDestroy(p.freed); } }
@@ -388,37 +393,20 @@ extern "C" int gr_sample_begin(gr_ctx* x, int32_t is_ctrl, const uint8_t* save) 
   }
   x->have_ctrl = false;
   CK(cudaMemsetAsync(x->d_err, 0, sizeof(int), x->stream));
-  if (!x->delta_clean) {
-    stage_begin(x, "memset_delta", x->T * 4);
-    CK(cudaMemsetAsync(x->delta.p, 0, x->T * sizeof(int32_t), x->stream));   // runProgram 5503-5510
-    stage_end(x);
-  }
-  x->delta_clean = false;
+  // records of an abandoned sample are dropped
+  for (auto& g : x->segs) if (g.pf) g.pf->in_use = false;
+  for (auto* b : x->seg_used) x->seg_free.push_back(b);
+  x->seg_used.clear();
+  x->segs.clear();
   x->filling = is_ctrl ? FILL_CTRL : FILL_EXPT;
   x->n_pushed = 0;
   return GR_OK;
 }
 
 // rb: bytes per record -- 16 (int32 x 4) or 8 (GR_PACK)
-static int scatter_records(gr_ctx* x, const void* d_recs, u64 n, int rb) {
-  if (rb == 16 && x->bin_min && n >= x->bin_min) {
-    CK(x->binRecs.ensure(n * 16));
-    CK(x->binCnt.ensure(8192 * sizeof(u32)));
-    CK(x->binCursor.ensure(8192 * sizeof(u64)));
-    launch_scatter_binned(x->stream, x->L, (const int32_t*)d_recs, n, x->delta.as<int32_t>(), x->d_err, x->d_clamped,
-                          x->binRecs.as<int32_t>(), x->binCnt.as<u32>(), x->binCursor.as<u64>());
-  } else
-    launch_scatter(x->stream, x->L, d_recs, n, rb == 8, x->delta.as<int32_t>(), x->d_err, x->d_clamped);
-  return GR_OK;
-}
-
 static int push_device(gr_ctx* x, const void* d_recs, u64 n, int rb) {
   if (!x || x->filling == FILL_NONE || (!d_recs && n)) return GR_ERR_ARG;
-  CK(cudaSetDevice(x->device));
-  stage_begin(x, "scatter", n * rb);
-  { int r = scatter_records(x, d_recs, n, rb); if (r) return r; }
-  CKL();
-  stage_end(x);
+  if (n) x->segs.push_back({ d_recs, n, rb, nullptr, nullptr });      // the caller keeps it unchanged until the pileup
   x->n_pushed += n;
   return GR_OK;
 }
@@ -432,12 +420,12 @@ static int prefetch_any(gr_ctx* x, const void* recs, u64 n, int rb) {
     return GR_OK;                              // not pinned: nothing to gain, the push will stage it
   }
   for (auto& p : x->pf) {
-    if (p.live) continue;
+    if (p.live || p.in_use) continue;
     if (!p.ready) {
       CK(cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
       CK(cudaEventCreateWithFlags(&p.freed, cudaEventDisableTiming));
     } else
-      CK(cudaStreamWaitEvent(x->copy, p.freed, 0));     // the scatter that last read this buffer is done
+      CK(cudaStreamWaitEvent(x->copy, p.freed, 0));     // the pileup that last read this buffer is done
     CK(p.buf.ensure(n * rb));
     CK(cudaMemcpyAsync(p.buf.p, recs, n * rb, cudaMemcpyHostToDevice, x->copy));
     CK(cudaEventRecord(p.ready, x->copy));
@@ -449,16 +437,13 @@ static int prefetch_any(gr_ctx* x, const void* recs, u64 n, int rb) {
 
 static int push_any(gr_ctx* x, const void* recs, u64 n, int rb) {
   if (!x || x->filling == FILL_NONE || (!recs && n)) return GR_ERR_ARG;
+  if (!n) return GR_OK;
   CK(cudaSetDevice(x->device));
   for (auto& p : x->pf)
     if (p.live && p.host == recs && p.n == n) {          // already on its way (gr_prefetch_*)
       CK(cudaStreamWaitEvent(x->stream, p.ready, 0));
-      stage_begin(x, "scatter", n * rb);
-      { int r = scatter_records(x, p.buf.p, n, rb); if (r) return r; }
-      CKL();
-      stage_end(x);
-      CK(cudaEventRecord(p.freed, x->stream));
-      p.live = false;
+      p.live = false; p.in_use = true;
+      x->segs.push_back({ p.buf.p, n, rb, nullptr, &p });
       x->n_pushed += n;
       return GR_OK;
     }
@@ -469,42 +454,96 @@ static int push_any(gr_ctx* x, const void* recs, u64 n, int rb) {
     pinned = at.type == cudaMemoryTypeHost;
   } else
     cudaGetLastError();
-  const u64 CH = gr_ctx::STAGE_RECS;
-  for (u64 done = 0; done < n; done += CH) {
-    const u64 m = n - done < CH ? n - done : CH;
-    const int b = x->stage_next;
-    x->stage_next ^= 1;
-    if (!x->stage[b].p) {
-      CK(x->stage[b].ensure(CH * 16));
-      CK(cudaEventRecord(x->stage_free[b], x->stream));
-    }
-    const char* src = (const char*)recs + done * rb;
-    // the copy stream may reuse slot b once the scatter that read it has finished
-    CK(cudaStreamWaitEvent(x->copy, x->stage_free[b], 0));
-    if (!pinned) {
-      if (!x->h_stage[b]) CK(cudaMallocHost(&x->h_stage[b], CH * 16));
-      CK(cudaEventSynchronize(x->stage_ready[b]));     // previous H2D out of this pinned slot is done
-      memcpy(x->h_stage[b], src, m * rb);
-      src = (const char*)x->h_stage[b];
-    }
-    CK(cudaMemcpyAsync(x->stage[b].p, src, m * rb, cudaMemcpyHostToDevice, x->copy));
-    CK(cudaEventRecord(x->stage_ready[b], x->copy));
-    CK(cudaStreamWaitEvent(x->stream, x->stage_ready[b], 0));
-    stage_begin(x, "scatter", m * rb);
-    { int r = scatter_records(x, x->stage[b].p, m, rb); if (r) return r; }
-    CKL();
-    stage_end(x);
-    CK(cudaEventRecord(x->stage_free[b], x->stream));
-  }
+  // a device copy of our own, kept until the pileup
+  gr_ctx::SegBuf* sb = nullptr;
+  if (!x->seg_free.empty()) { sb = x->seg_free.back(); x->seg_free.pop_back(); }
+  else { sb = new gr_ctx::SegBuf(); if (cudaEventCreateWithFlags(&sb->freed, cudaEventDisableTiming) != cudaSuccess) { delete sb; return GR_ERR_CUDA; } CK(cudaEventRecord(sb->freed, x->stream)); }
+  x->seg_used.push_back(sb);
+  CK(cudaStreamWaitEvent(x->copy, sb->freed, 0));        // the pileup that last read it is done
+  CK(sb->buf.ensure(n * rb));
+  const u64 bytes = n * rb;
   if (pinned) {
-    // the caller may reuse its pinned buffer when we return
-    CK(cudaStreamSynchronize(x->copy));
+    CK(cudaMemcpyAsync(sb->buf.p, recs, bytes, cudaMemcpyHostToDevice, x->copy));
+  } else {
+    for (u64 done = 0; done < bytes; done += gr_ctx::STAGE_BYTES) {
+      const u64 m = bytes - done < gr_ctx::STAGE_BYTES ? bytes - done : gr_ctx::STAGE_BYTES;
+      const int b = x->stage_next;
+      x->stage_next ^= 1;
+      if (!x->h_stage[b]) {
+        CK(cudaMallocHost(&x->h_stage[b], gr_ctx::STAGE_BYTES));
+        CK(cudaEventCreateWithFlags(&x->h_ready[b], cudaEventDisableTiming));
+      } else
+        CK(cudaEventSynchronize(x->h_ready[b]));         // previous H2D out of this pinned slot is done
+      memcpy(x->h_stage[b], (const char*)recs + done, m);
+      CK(cudaMemcpyAsync((char*)sb->buf.p + done, x->h_stage[b], m, cudaMemcpyHostToDevice, x->copy));
+      CK(cudaEventRecord(x->h_ready[b], x->copy));
+    }
   }
+  CK(cudaEventRecord(x->ev_copy, x->copy));
+  CK(cudaStreamWaitEvent(x->stream, x->ev_copy, 0));
+  if (pinned) CK(cudaStreamSynchronize(x->copy));        // the caller may reuse its pinned buffer when we return
+  x->segs.push_back({ sb->buf.p, n, rb, sb, nullptr });
   x->n_pushed += n;
   return GR_OK;
 }
 
-extern "C" int gr_push_intervals_device(gr_ctx* x, const int32_t* d_recs, uint64_t n) { return push_device(x, d_recs, n, 16); }
+// all records of the sample -> the delta array (called by gr_sample_pileup)
+static int consume_segments(gr_ctx* x, bool* built) {
+  int32_t* delta = x->delta.as<int32_t>();
+  const bool sb = x->n_pushed >= x->sb_min && x->T < (1ull << 32);
+  u64 bytes = 0;
+  for (auto& g : x->segs) bytes += g.n * g.rb;
+  if (sb) {
+    CK(x->sbCnt.ensure(x->nblocks * 4));
+    CK(x->sbStart.ensure((x->nblocks + 1) * 4));
+    CK(x->sbCursor.ensure(x->nblocks * 4));
+    CK(x->sbBucket.ensure(x->n_pushed * 8));
+    CK(x->sbSpill.ensure(x->n_pushed * 8));
+    CK(x->sbSpillCtr.ensure(4));
+    stage_begin(x, "bucket", bytes);
+    CK(cudaMemsetAsync(x->sbCnt.p, 0, x->nblocks * 4, x->stream));
+    for (auto& g : x->segs)
+      launch_sb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
+    launch_sb_scan(x->stream, x->L, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>());
+    for (auto& g : x->segs)
+      launch_sb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u64>());
+    CKL();
+    stage_end(x);
+    stage_begin(x, "build", x->T * 4);
+    launch_sb_build(x->stream, x->L, x->sbBucket.as<u64>(), x->sbStart.as<u32>(), delta,
+                    x->sbSpill.as<uint2>(), x->sbSpillCtr.as<u32>());
+    CKL();
+    stage_end(x);
+    x->delta_clean = false;
+  } else {
+    if (!x->delta_clean) {
+      stage_begin(x, "memset_delta", x->T * 4);
+      CK(cudaMemsetAsync(delta, 0, x->T * sizeof(int32_t), x->stream));   // runProgram 5503-5510
+      stage_end(x);
+    }
+    stage_begin(x, "scatter", bytes);
+    for (auto& g : x->segs)
+      launch_scatter(x->stream, x->L, g.d, g.n, g.rb == 8, delta, x->d_err, x->d_clamped);
+    CKL();
+    stage_end(x);
+    x->delta_clean = false;
+  }
+  // the buffers may be refilled once the kernels above have read them
+  for (auto& g : x->segs) {
+    if (g.own) CK(cudaEventRecord(g.own->freed, x->stream));
+    if (g.pf) { CK(cudaEventRecord(g.pf->freed, x->stream)); g.pf->in_use = false; }
+  }
+  for (auto* b : x->seg_used) x->seg_free.push_back(b);
+  x->seg_used.clear();
+  x->segs.clear();
+  *built = sb;
+  return GR_OK;
+}
+
+extern "C" int gr_push_intervals_device(gr_ctx* x, const int32_t* d_recs, uint64_t n) {
+  if (x) { CK(cudaSetDevice(x->device)); }
+  return push_device(x, d_recs, n, 16);
+}
 extern "C" int gr_prefetch_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) { return prefetch_any(x, recs, n, 16); }
 extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) { return push_any(x, recs, n, 16); }
 extern "C" int gr_prefetch_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) { return prefetch_any(x, recs, n, 8); }
@@ -526,11 +565,16 @@ extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
   CK(V.ensure(cap * sizeof(float)));
   DevRle out = rle_view(E, V, CS, TT);
   CK(x->scanWs.ensure(dense_scan_ws_bytes(cap, x->nchrom)));
+  bool built = false;
+  { int r = consume_segments(x, &built); if (r) return r; }
+  // after the plain scatter the scan clears the cells behind itself (the next small sample
+  // finds the array zero); a built array is overwritten as a whole by the next build anyway
+  const int zero_after = built ? 0 : x->zero_after;
   ScanScratch sc;
   sc.ws = x->scanWs.p; sc.cap = cap;
   stage_begin(x, "dense_scan", x->T * 4);
   launch_dense_scan(x->stream, x->L, x->delta.as<int32_t>(), sc,
-                    (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, x->zero_after);
+                    (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, zero_after);
   CKL();
   stage_end(x);
   stage_begin(x, "scan_place", cap * 16);
@@ -559,7 +603,7 @@ extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
   const int derr = *(int*)x->h_small;
   x->n_clamped = *(u64*)((char*)x->h_small + 8);
   if (derr) { x->filling = FILL_NONE; return map_dev_err(derr); }
-  x->delta_clean = x->zero_after != 0;       // the scan left the array all zero
+  x->delta_clean = zero_after != 0;          // the scan left the array all zero
   std::vector<double>& sums = ctrl ? x->ctrl_sums : x->expt_sums;
   for (int c = 0; c < x->nchrom; c++)
     sums[c] = (double)hI[c] + (double)hF[c] * (1.0 / 1099511627776.0);

@@ -13,7 +13,53 @@
 // K1: two int32 reductions (RED.ADD) per interval record into the dense delta
 // array, in units of 1/120 (weights 120/count, count in {1,2,3,4,5,6,8,10}:
 // addFrac 2311 / subFrac 2412).  Clamping as saveInterval 2522-2544.
-// PACKED: 8-byte records (include/genrich_cuda.h, GR_PACK), else int32 x 4.
+// Two forms.  Small samples: k_scatter, the two reductions straight into the (all-zero)
+// array.  Large samples: the records are first bucketed by the 8192-cell block of their
+// start (count -> scan -> cursor move; the bucket array is written once, 8 B per record),
+// then k_sb_build assembles every block of the delta array in shared memory and writes it
+// out densely -- the array is WRITTEN sequentially once instead of being hit by 2 random
+// read-modify-writes per record (ncu: 8.5 GB read + 3.2 GB written per 50 M records, 30 %
+// of DRAM peak), and needs no clearing before or after.
+
+// One record, decoded and checked as saveInterval does (2522-2544).  PACKED: 8-byte records
+// (include/genrich_cuda.h, GR_PACK), else int32 x 4.  Returns false for records that are
+// dropped (unsaved chromosome) or in error (flagged in e_local).
+template <bool PACKED>
+__device__ __forceinline__ bool decode_record(const void* __restrict__ recs, u64 i, const DevLayout& L,
+                                              u64& s_slot, u32& span, int& w, int& e_local, u32& c_local) {
+  int c, cnt;
+  i64 s, e;
+  if (PACKED) {
+    const u64 v = __ldcs(reinterpret_cast<const u64*>(recs) + i);
+    s = (i64)(u32)v;
+    e = s + (i64)((v >> 32) & 0x3fffu);
+    c = (int)((v >> 46) & 0x3fffu);
+    cnt = (int)(v >> 60);
+  } else {
+    const int4 r = ld_stream_v4(reinterpret_cast<const int4*>(recs) + i);
+    c = r.x; s = r.y; e = r.z; cnt = r.w;
+  }
+  if (c < 0 || c >= L.nchrom) { e_local |= GR_DE_CHROM; return false; }
+  const uint8_t f = L.flags[c];
+  const u64 off = L.off[c];
+  if (off == ~0ull) {                      // not owned by this context, or -e skipped
+    if (!(f & GR_CF_OWNED)) e_local |= GR_DE_CHROM;
+    return false;
+  }
+  if (!(f & GR_CF_SAVE)) return false;     // processPair 3137-3138: not in this replicate
+  if (cnt < 1 || cnt > 10 || !((1 << cnt) & 0x57E)) { e_local |= GR_DE_COUNT; return false; }
+  const i64 len = L.len[c];
+  bool cl = false;
+  if (s < 0) { s = 0; cl = true; }
+  if (s >= len || e < s) { e_local |= GR_DE_POS; return false; }
+  if (e > len) { e = len; cl = true; }
+  c_local += cl;
+  s_slot = off + (u64)s;
+  span = (u32)(e - s);
+  w = 120 / cnt;
+  return true;
+}
+
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_scatter(const void* __restrict__ recs, u64 n, DevLayout L, int32_t* __restrict__ delta,
@@ -22,36 +68,10 @@ k_scatter(const void* __restrict__ recs, u64 n, DevLayout L, int32_t* __restrict
   int e_local = 0;
   u32 c_local = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    int c, cnt;
-    i64 s, e;
-    if (PACKED) {
-      const u64 v = __ldcs(reinterpret_cast<const u64*>(recs) + i);
-      s = (i64)(u32)v;
-      e = s + (i64)((v >> 32) & 0x3fffu);
-      c = (int)((v >> 46) & 0x3fffu);
-      cnt = (int)(v >> 60);
-    } else {
-      const int4 r = ld_stream_v4(reinterpret_cast<const int4*>(recs) + i);
-      c = r.x; s = r.y; e = r.z; cnt = r.w;
-    }
-    if (c < 0 || c >= L.nchrom) { e_local |= GR_DE_CHROM; continue; }
-    const uint8_t f = L.flags[c];
-    const u64 off = L.off[c];
-    if (off == ~0ull) {                      // not owned by this context, or -e skipped
-      if (!(f & GR_CF_OWNED)) e_local |= GR_DE_CHROM;
-      continue;
-    }
-    if (!(f & GR_CF_SAVE)) continue;         // processPair 3137-3138: not in this replicate
-    if (cnt < 1 || cnt > 10 || !((1 << cnt) & 0x57E)) { e_local |= GR_DE_COUNT; continue; }
-    const i64 len = L.len[c];
-    bool cl = false;
-    if (s < 0) { s = 0; cl = true; }
-    if (s >= len || e < 0) { e_local |= GR_DE_POS; continue; }
-    if (e > len) { e = len; cl = true; }
-    c_local += cl;
-    const int w = 120 / cnt;
-    atomicAdd(delta + off + s, w);
-    atomicAdd(delta + off + e, -w);
+    u64 s_slot; u32 span; int w;
+    if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
+    atomicAdd(delta + s_slot, w);
+    atomicAdd(delta + s_slot + span, -w);
   }
   if (e_local) atomicOr(err, e_local);
   if (c_local) atomicAdd(clamped, (u64)c_local);
@@ -67,124 +87,127 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
   GR_NOTE_LAUNCH();
 }
 
-// ----------------------------------------------------------------------------
-// Locality pass in front of K1.  Read names arrive in queryname order, i.e. the
-// records hit the 12 GB delta array at random: every RED.ADD costs a DRAM read of a
-// line it shares with nobody and a write-back (ncu r01_f: 8.5 GB read + 3.2 GB
-// written for 100 M atomics, 30 % of DRAM peak).  Records are therefore first moved
-// into ~3000 buckets of 2^20 cells by the cell of their start (a fragment ends a
-// few hundred cells further, i.e. in the same bucket); the scatter then sweeps the
-// array bucket by bucket with the whole grid inside an L2-sized window, so each
-// touched line is fetched and written back once, in address order.  The order of
-// records inside a bucket is arbitrary -- integer atomics make the result the same.
-#define BIN_CHUNK 8192            // records per CTA in the move pass
-
-__device__ __forceinline__ u32 bin_of(const int4 r, const DevLayout& L, int shift) {
-  const int c = r.x;
-  if (c < 0 || c >= L.nchrom) return 0;
-  const u64 off = L.off[c];
-  if (off == ~0ull) return 0;
-  i64 s = r.y;
-  if (s < 0) s = 0;
-  return (u32)((off + (u64)s) >> shift);
-}
-
+// ---- bucketed build ------------------------------------------------------------------
+// bucket entry: bits 0-31 interval length in cells, 32-44 offset of the start inside its
+// block, 45-51 weight (120/count)
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
-k_bin_count(const int4* __restrict__ recs, u64 n, DevLayout L, int shift, u32 nb, u32* __restrict__ cnt) {
-  extern __shared__ u32 sh[];
-  for (u32 i = threadIdx.x; i < nb; i += blockDim.x) sh[i] = 0;
-  __syncthreads();
+k_sb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ blk_cnt,
+           int* __restrict__ err, u64* __restrict__ clamped) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
+  int e_local = 0;
+  u32 c_local = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    u32 bkt = bin_of(ld_stream_v4(recs + i), L, shift);
-    if (bkt >= nb) bkt = nb - 1;
-    atomicAdd(&sh[bkt], 1u);
+    u64 s_slot; u32 span; int w;
+    if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
+    atomicAdd(blk_cnt + (s_slot >> GR_BLOCK_SHIFT), 1u);
   }
-  __syncthreads();
-  for (u32 i = threadIdx.x; i < nb; i += blockDim.x)
-    if (sh[i]) atomicAdd(cnt + i, sh[i]);
+  if (e_local) atomicOr(err, e_local);       // errors and clamp counts are reported by this pass only
+  if (c_local) atomicAdd(clamped, (u64)c_local);
 }
 
-// exclusive scan of the bucket counts into the running cursors (one block)
+// exclusive scan of the per-block counts (one CTA; nblocks is ~4e5 for a human genome)
 __global__ void __launch_bounds__(1024)
-k_bin_scan(const u32* __restrict__ cnt, u32 nb, u64* __restrict__ cursor) {
-  __shared__ u64 sm_w[32];
-  __shared__ u64 sm_carry;
-  if (threadIdx.x == 0) sm_carry = 0;
+k_sb_scan(const u32* __restrict__ blk_cnt, u32* __restrict__ blk_start, u32* __restrict__ cursor, u64 nblocks) {
+  __shared__ u32 sh[1024];
+  const int t = threadIdx.x;
+  const u64 per = (nblocks + 1023) / 1024;
+  const u64 a = min(nblocks, (u64)t * per), b = min(nblocks, a + per);
+  u32 s = 0;
+  for (u64 i = a; i < b; i++) s += blk_cnt[i];
+  sh[t] = s;
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (u32 base = 0; base < nb; base += 1024) {
-    const u32 i = base + threadIdx.x;
-    const u64 v = i < nb ? cnt[i] : 0;
-    u64 inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const u64 t = __shfl_up_sync(GR_FULL, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) sm_w[w] = inc;
+  for (int o = 1; o < 1024; o <<= 1) {
+    u32 v = t >= o ? sh[t - o] : 0u;
     __syncthreads();
-    u64 wx = 0, tot = 0;
-    for (int k = 0; k < 32; k++) { const u64 a = sm_w[k]; if (k < w) wx += a; tot += a; }
-    const u64 carry = sm_carry;
-    if (i < nb) cursor[i] = carry + wx + inc - v;
-    __syncthreads();
-    if (threadIdx.x == 0) sm_carry = carry + tot;
+    sh[t] += v;
     __syncthreads();
   }
+  u32 run = sh[t] - s;
+  for (u64 i = a; i < b; i++) {
+    blk_start[i] = run; cursor[i] = run;
+    run += blk_cnt[i];
+  }
+  if (t == 1023) blk_start[nblocks] = sh[1023];
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+k_sb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u64* __restrict__ bucketed) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  int e_local = 0;
+  u32 c_local = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u64 s_slot; u32 span; int w;
+    if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
+    const u32 pos = atomicAdd(cursor + (s_slot >> GR_BLOCK_SHIFT), 1u);
+    bucketed[pos] = (u64)span | ((s_slot & (GR_BLOCK_SLOTS - 1)) << 32) | ((u64)w << 45);
+  }
+}
+
+// One CTA per 8192-cell block: assemble it in shared memory, write it out.  An interval
+// that ends in a later block leaves its end to k_sb_spill (the later block is written by
+// another CTA, at an unknown time).
+__global__ void __launch_bounds__(256)
+k_sb_build(const u64* __restrict__ bucketed, const u32* __restrict__ blk_start, int32_t* __restrict__ delta,
+           uint2* __restrict__ spill, u32* __restrict__ spill_ctr) {
+  __shared__ int4 sm4[GR_BLOCK_SLOTS / 4];
+  int* sm = reinterpret_cast<int*>(sm4);
+  const u32 blk = blockIdx.x;
+  const u32 a = blk_start[blk], b = blk_start[blk + 1];
+#pragma unroll
+  for (int i = 0; i < 8; i++) sm4[i * 256 + threadIdx.x] = make_int4(0, 0, 0, 0);
+  __syncthreads();
+  for (u32 i = a + threadIdx.x; i < b; i += 256) {
+    const u64 v = __ldcs(bucketed + i);
+    const u32 so = (u32)(v >> 32) & (GR_BLOCK_SLOTS - 1), span = (u32)v;
+    const int w = (int)(v >> 45);
+    atomicAdd(sm + so, w);
+    const u64 eo = (u64)so + span;
+    if (eo < GR_BLOCK_SLOTS) atomicAdd(sm + (u32)eo, -w);
+    else spill[atomicAdd(spill_ctr, 1u)] = make_uint2((u32)((((u64)blk << GR_BLOCK_SHIFT) + eo) & 0xffffffffu),
+                                                      (u32)(((((u64)blk << GR_BLOCK_SHIFT) + eo) >> 32) << 8) | (u32)w);
+  }
+  __syncthreads();
+  int4* out = reinterpret_cast<int4*>(delta) + (u64)blk * (GR_BLOCK_SLOTS / 4);
+#pragma unroll
+  for (int i = 0; i < 8; i++) out[i * 256 + threadIdx.x] = sm4[i * 256 + threadIdx.x];
 }
 
 __global__ void __launch_bounds__(256)
-k_bin_move(const int4* __restrict__ recs, u64 n, DevLayout L, int shift, u32 nb,
-           u64* __restrict__ cursor, int4* __restrict__ out) {
-  extern __shared__ u32 sh[];                 // [nb] counts, then fill positions; [nb] reserved bases (low 32 bits) ...
-  u32* cnt = sh;
-  u64* base = reinterpret_cast<u64*>(sh + ((nb + 1) & ~1u));
-  for (u32 i = threadIdx.x; i < nb; i += blockDim.x) cnt[i] = 0;
-  __syncthreads();
-  const u64 lo = (u64)blockIdx.x * BIN_CHUNK;
-  const u64 hi = min(lo + BIN_CHUNK, n);
-  for (u64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    u32 bkt = bin_of(recs[i], L, shift);
-    if (bkt >= nb) bkt = nb - 1;
-    atomicAdd(&cnt[bkt], 1u);
-  }
-  __syncthreads();
-  for (u32 i = threadIdx.x; i < nb; i += blockDim.x) {
-    const u32 c = cnt[i];
-    if (c) base[i] = atomicAdd(cursor + i, (u64)c);     // this CTA's slice of bucket i
-    cnt[i] = 0;
-  }
-  __syncthreads();
-  for (u64 i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-    const int4 r = recs[i];                             // second read of the chunk: L1/L2
-    u32 bkt = bin_of(r, L, shift);
-    if (bkt >= nb) bkt = nb - 1;
-    out[base[bkt] + atomicAdd(&cnt[bkt], 1u)] = r;
+k_sb_spill(const uint2* __restrict__ spill, const u32* __restrict__ spill_ctr, int32_t* __restrict__ delta) {
+  const u32 n = *spill_ctr;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint2 v = spill[i];
+    atomicAdd(delta + (((u64)(v.y >> 8) << 32) | v.x), -(int)(v.y & 0xffu));
   }
 }
 
-void launch_scatter_binned(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64 n,
-                           int32_t* delta, int* err, u64* clamped, int32_t* scratch_recs,
-                           u32* bin_cnt, u64* bin_cursor) {
+void launch_sb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
+                     u32* blk_cnt, int* err, u64* clamped) {
   if (!n) return;
-  int shift = 20;
-  while ((L.T >> shift) + 1 > 6144) shift++;
-  const u32 nb = (u32)(L.T >> shift) + 1;
-  cudaMemsetAsync(bin_cnt, 0, nb * sizeof(u32), s);
   u64 blocks = (n + 255) / 256;
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  k_bin_count<<<(unsigned)blocks, 256, nb * sizeof(u32), s>>>((const int4*)recs, n, L, shift, nb, bin_cnt); GR_NOTE_LAUNCH();
-  k_bin_scan<<<1, 1024, 0, s>>>(bin_cnt, nb, bin_cursor); GR_NOTE_LAUNCH();
-  const size_t smem = (((size_t)nb + 1) & ~(size_t)1) * sizeof(u32) + (size_t)nb * sizeof(u64);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_bin_move, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    attr_set = true;
-  }
-  k_bin_move<<<(unsigned)((n + BIN_CHUNK - 1) / BIN_CHUNK), 256, smem, s>>>((const int4*)recs, n, L, shift, nb, bin_cursor,
-                                                                            (int4*)scratch_recs); GR_NOTE_LAUNCH();
-  launch_scatter(s, L, scratch_recs, n, 0, delta, err, clamped);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (packed) k_sb_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
+  else k_sb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
+  GR_NOTE_LAUNCH();
+}
+void launch_sb_scan(cudaStream_t s, const DevLayout& L, const u32* blk_cnt, u32* blk_start, u32* cursor) {
+  k_sb_scan<<<1, 1024, 0, s>>>(blk_cnt, blk_start, cursor, L.nblocks); GR_NOTE_LAUNCH();
+}
+void launch_sb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u64* bucketed) {
+  if (!n) return;
+  u64 blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (packed) k_sb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
+  else k_sb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
+  GR_NOTE_LAUNCH();
+}
+void launch_sb_build(cudaStream_t s, const DevLayout& L, const u64* bucketed, const u32* blk_start,
+                     int32_t* delta, uint2* spill, u32* spill_ctr) {
+  cudaMemsetAsync(spill_ctr, 0, 4, s);
+  k_sb_build<<<(unsigned)L.nblocks, 256, 0, s>>>(bucketed, blk_start, delta, spill, spill_ctr); GR_NOTE_LAUNCH();
+  k_sb_spill<<<148 * 2, 256, 0, s>>>(spill, spill_ctr, delta); GR_NOTE_LAUNCH();
 }
 
 // ============================================================================

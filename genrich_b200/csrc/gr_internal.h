@@ -33,9 +33,13 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
 
 // same, behind a locality pass that first moves the records into ~3000 position buckets
 // (scratch_recs: n records; bin_cnt / bin_cursor: 8192 entries each)
-void launch_scatter_binned(cudaStream_t s, const DevLayout& L, const int32_t* recs, u64 n,
-                           int32_t* delta, int* err, u64* clamped, int32_t* scratch_recs,
-                           u32* bin_cnt, u64* bin_cursor);
+// bucketed build of the delta array (large samples): count -> scan -> move -> build (+ spills)
+void launch_sb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
+                     u32* blk_cnt, int* err, u64* clamped);
+void launch_sb_scan(cudaStream_t s, const DevLayout& L, const u32* blk_cnt, u32* blk_start, u32* cursor);
+void launch_sb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u64* bucketed);
+void launch_sb_build(cudaStream_t s, const DevLayout& L, const u64* bucketed, const u32* blk_start,
+                     int32_t* delta, uint2* spill, u32* spill_ctr);
 
 // ---- K2: dense prefix sum + break compaction + bitmap (savePileupExpt 2168) ----
 struct ScanScratch {

@@ -176,6 +176,7 @@ class ShardedEngine:
             cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
             td.all_gather(cnts, cnt, group=grp)
             sizes = [int(c.item()) for c in cnts]
+            self._tick("gather_counts", t0)
             m = max(max(sizes), 1)
             pad = torch.zeros(m, dtype=torch.uint8, device=dev)
             pad[:buf.numel()] = buf
@@ -184,10 +185,16 @@ class ShardedEngine:
                 td.all_gather(list(allb.view(self.world, m).unbind(0)), pad, group=grp)
             if self.rank == 0:
                 host = allb.cpu().numpy().reshape(self.world, m)
-                parts = [np.frombuffer(host[r, :s].tobytes(), dtype=PEAK_DTYPE) for r, s in enumerate(sizes)]
-                allp = np.concatenate(parts)
-                # every rank's list is already in (chromosome, start) order and chromosomes are
-                # disjoint across ranks: a stable sort on the chromosome index merges them
-                peaks = allp[np.argsort(allp["chrom"], kind="stable")]
+                parts = [host[r, :s].view(PEAK_DTYPE) for r, s in enumerate(sizes)]
+                # every rank's list is in (chromosome, start) order and a chromosome has one owner:
+                # the global list is the owners' per-chromosome runs in chromosome order
+                chrom_col = [np.ascontiguousarray(p["chrom"]) for p in parts]
+                runs = []
+                for c in range(self.nchrom):
+                    r = int(self.owner[c])
+                    lo, hi = np.searchsorted(chrom_col[r], [c, c + 1])
+                    if hi > lo:
+                        runs.append(parts[r][lo:hi])
+                peaks = np.concatenate(runs) if runs else np.empty(0, PEAK_DTYPE)
         self._tick("gather_peaks", t0)
         return peaks, rs

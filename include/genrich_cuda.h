@@ -129,8 +129,10 @@ const char* gr_last_error_detail(const gr_ctx* ctx);
  * NULL = all saved.  A control sample inherits the flags of its experimental
  * sample.  Records are int32 x 4 = chrom, start, end, count with
  * count in {1,2,3,4,5,6,8,10} (weight 1/count).  start < 0 and end > len are
- * clamped as saveInterval does (2522-2544); start >= len is GR_ERR_POS,
- * reported by gr_sample_pileup. */
+ * clamped as saveInterval does (2522-2544); start >= len (or end < start, which the
+ * reference's callers never produce) is GR_ERR_POS, reported by gr_sample_pileup.
+ * Records are consumed by gr_sample_pileup: host buffers are copied before the push
+ * returns, DEVICE buffers must stay unchanged until gr_sample_pileup has returned. */
 int gr_sample_begin(gr_ctx* ctx, int32_t is_ctrl, const uint8_t* save);
 int gr_push_intervals(gr_ctx* ctx, const int32_t* recs, uint64_t n);        /* host memory (pinned or not) */
 int gr_push_intervals_device(gr_ctx* ctx, const int32_t* d_recs, uint64_t n);/* device memory */

@@ -165,6 +165,30 @@ def test_packed_records_same_bits():
             assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
 
 
+def test_bucketed_build_same_bits(monkeypatch):
+    """Large samples build the delta array block by block from bucketed records, small ones use
+    atomic reductions: same array, same everything after it.  GR_SB_MIN forces either way."""
+    api = capi.load_cuda()
+    for name in ("c5_multimap_ctrl_p", "c3_atac_q", "fisher_missing_chrom"):
+        case = BY_NAME[name]
+        inputs = util.case_inputs(case)
+        outs = []
+        for sb_min, packed in (("1", False), ("1000000000", False), ("1", True)):
+            monkeypatch.setenv("GR_SB_MIN", sb_min)
+            ctx = capi.Context(api, case.chrom_len, util.case_params(case))
+            res = host.run_replicates(ctx, inputs, chunk=30011, packed=packed)
+            outs.append((res, [ctx.fetch(2, 0, c) for c in range(len(case.chrom_len))]))
+        monkeypatch.delenv("GR_SB_MIN")
+        for res, p in outs[1:]:
+            assert res.peaks.tobytes() == outs[0][0].peaks.tobytes() and len(res.peaks) > 0
+            assert res.sample_stats[0].frag_len == outs[0][0].sample_stats[0].frag_len
+            for x, y in zip(p, outs[0][1]):
+                if x is None or y is None:
+                    assert x is None and y is None
+                    continue
+                assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
+
+
 def test_edge_inputs():
     api = capi.load_cuda()
     orc = util.oracle_api()
