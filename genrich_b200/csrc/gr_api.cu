@@ -497,20 +497,23 @@ static int consume_segments(gr_ctx* x, bool* built) {
     CK(x->sbCnt.ensure(x->nblocks * 4));
     CK(x->sbStart.ensure((x->nblocks + 1) * 4));
     CK(x->sbCursor.ensure(x->nblocks * 4));
-    CK(x->sbBucket.ensure(x->n_pushed * 8));
-    CK(x->sbSpill.ensure(x->n_pushed * 8));
-    CK(x->sbSpillCtr.ensure(4));
+    CK(x->sbBucket.ensure(x->n_pushed * 4));
+    CK(x->sbSpill.ensure(x->n_pushed * 16));             // worst case: every interval is long (two entries each)
+    CK(x->sbSpillCtr.ensure(4 + (x->nblocks / 4096 + 2) * 4));      // spill counter, then the scan's chunk sums
     stage_begin(x, "bucket", bytes);
     CK(cudaMemsetAsync(x->sbCnt.p, 0, x->nblocks * 4, x->stream));
     for (auto& g : x->segs)
       launch_sb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
-    launch_sb_scan(x->stream, x->L, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>());
+    launch_sb_scan(x->stream, x->L, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
+                   x->sbSpillCtr.as<u32>() + 1);
+    CK(cudaMemsetAsync(x->sbSpillCtr.p, 0, 4, x->stream));
     for (auto& g : x->segs)
-      launch_sb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u64>());
+      launch_sb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(),
+                     x->sbSpill.as<uint2>(), x->sbSpillCtr.as<u32>());
     CKL();
     stage_end(x);
     stage_begin(x, "build", x->T * 4);
-    launch_sb_build(x->stream, x->L, x->sbBucket.as<u64>(), x->sbStart.as<u32>(), delta,
+    launch_sb_build(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), delta,
                     x->sbSpill.as<uint2>(), x->sbSpillCtr.as<u32>());
     CKL();
     stage_end(x);

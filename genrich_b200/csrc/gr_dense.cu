@@ -88,8 +88,14 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
 }
 
 // ---- bucketed build ------------------------------------------------------------------
-// bucket entry: bits 0-31 interval length in cells, 32-44 offset of the start inside its
-// block, 45-51 weight (120/count)
+// bucket entry (4 bytes): bits 0-14 interval length in cells, 15-27 offset of the start inside
+// its block, 28-31 count.  Intervals of SB_LONG cells or more (none in sequencing data, but
+// legal) bypass the buckets: both their ends go to the spill list, applied by reductions
+// after the blocks are written -- as do the ends of intervals that reach into a later block.
+#define SB_LONG (1u << 15)
+__device__ __forceinline__ uint2 sb_spill_entry(u64 slot, int w) {       // w signed, |w| <= 120
+  return make_uint2((u32)slot, ((u32)(slot >> 32) << 8) | ((u32)w & 0xffu));
+}
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_sb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ blk_cnt,
@@ -100,48 +106,89 @@ k_sb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ 
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     u64 s_slot; u32 span; int w;
     if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
-    atomicAdd(blk_cnt + (s_slot >> GR_BLOCK_SHIFT), 1u);
+    if (span < SB_LONG) atomicAdd(blk_cnt + (s_slot >> GR_BLOCK_SHIFT), 1u);
   }
   if (e_local) atomicOr(err, e_local);       // errors and clamp counts are reported by this pass only
   if (c_local) atomicAdd(clamped, (u64)c_local);
 }
 
-// exclusive scan of the per-block counts (one CTA; nblocks is ~4e5 for a human genome)
+// exclusive scan of the per-block counts (~4e5 for a human genome) in three small steps:
+// sums of 4096-counter chunks, scan of the <= 1024 chunk sums (one CTA), rescan with the base
+#define SB_CHUNK 4096
+__global__ void __launch_bounds__(256)
+k_sb_scan1(const u32* __restrict__ blk_cnt, u32* __restrict__ chunk_sum, u64 nblocks) {
+  __shared__ u32 sh[8];
+  const u64 base = (u64)blockIdx.x * SB_CHUNK;
+  u32 s = 0;
+  for (int i = threadIdx.x; i < SB_CHUNK; i += 256)
+    if (base + i < nblocks) s += blk_cnt[base + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(GR_FULL, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { u32 t = 0; for (int k = 0; k < 8; k++) t += sh[k]; chunk_sum[blockIdx.x] = t; }
+}
 __global__ void __launch_bounds__(1024)
-k_sb_scan(const u32* __restrict__ blk_cnt, u32* __restrict__ blk_start, u32* __restrict__ cursor, u64 nblocks) {
+k_sb_scan2(u32* __restrict__ chunk_sum, u32 nchunks, u32* __restrict__ blk_start, u64 nblocks) {
   __shared__ u32 sh[1024];
   const int t = threadIdx.x;
-  const u64 per = (nblocks + 1023) / 1024;
-  const u64 a = min(nblocks, (u64)t * per), b = min(nblocks, a + per);
-  u32 s = 0;
-  for (u64 i = a; i < b; i++) s += blk_cnt[i];
-  sh[t] = s;
+  u32 carry = 0;
+  for (u32 c0 = 0; c0 < nchunks; c0 += 1024) {          // one round unless the genome has > 4e6 blocks
+    const u32 v = c0 + t < nchunks ? chunk_sum[c0 + t] : 0u;
+    sh[t] = v;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+      const u32 x = t >= o ? sh[t - o] : 0u;
+      __syncthreads();
+      sh[t] += x;
+      __syncthreads();
+    }
+    if (c0 + t < nchunks) chunk_sum[c0 + t] = carry + sh[t] - v;    // exclusive
+    const u32 tot = sh[1023];
+    __syncthreads();
+    carry += tot;
+  }
+  if (t == 0) blk_start[nblocks] = carry;
+}
+__global__ void __launch_bounds__(256)
+k_sb_scan3(const u32* __restrict__ blk_cnt, const u32* __restrict__ chunk_base, u32* __restrict__ blk_start,
+           u32* __restrict__ cursor, u64 nblocks) {
+  __shared__ u32 sh[8];
+  const u64 base = (u64)blockIdx.x * SB_CHUNK + threadIdx.x * 16;     // 16 consecutive counters per thread
+  u32 v[16], s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) { v[i] = base + i < nblocks ? blk_cnt[base + i] : 0u; s += v[i]; }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u32 wi = warp_incl_scan_u32(s, lane);
+  if (lane == 31) sh[w] = wi;
   __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {
-    u32 v = t >= o ? sh[t - o] : 0u;
-    __syncthreads();
-    sh[t] += v;
-    __syncthreads();
+  u32 run = chunk_base[blockIdx.x] + wi - s;
+  for (int k = 0; k < w; k++) run += sh[k];
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    if (base + i < nblocks) { blk_start[base + i] = run; cursor[base + i] = run; }
+    run += v[i];
   }
-  u32 run = sh[t] - s;
-  for (u64 i = a; i < b; i++) {
-    blk_start[i] = run; cursor[i] = run;
-    run += blk_cnt[i];
-  }
-  if (t == 1023) blk_start[nblocks] = sh[1023];
 }
 
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
-k_sb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u64* __restrict__ bucketed) {
+k_sb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed,
+          uint2* __restrict__ spill, u32* __restrict__ spill_ctr) {
   const u64 stride = (u64)gridDim.x * blockDim.x;
   int e_local = 0;
   u32 c_local = 0;
   for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     u64 s_slot; u32 span; int w;
     if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
-    const u32 pos = atomicAdd(cursor + (s_slot >> GR_BLOCK_SHIFT), 1u);
-    bucketed[pos] = (u64)span | ((s_slot & (GR_BLOCK_SLOTS - 1)) << 32) | ((u64)w << 45);
+    if (span < SB_LONG) {
+      const u32 pos = atomicAdd(cursor + (s_slot >> GR_BLOCK_SHIFT), 1u);
+      bucketed[pos] = span | ((u32)(s_slot & (GR_BLOCK_SLOTS - 1)) << 15) | ((u32)(120 / w) << 28);
+    } else {
+      const u32 k = atomicAdd(spill_ctr, 2u);
+      spill[k] = sb_spill_entry(s_slot, w);
+      spill[k + 1] = sb_spill_entry(s_slot + span, -w);
+    }
   }
 }
 
@@ -149,7 +196,7 @@ k_sb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
 // that ends in a later block leaves its end to k_sb_spill (the later block is written by
 // another CTA, at an unknown time).
 __global__ void __launch_bounds__(256)
-k_sb_build(const u64* __restrict__ bucketed, const u32* __restrict__ blk_start, int32_t* __restrict__ delta,
+k_sb_build(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, int32_t* __restrict__ delta,
            uint2* __restrict__ spill, u32* __restrict__ spill_ctr) {
   __shared__ int4 sm4[GR_BLOCK_SLOTS / 4];
   int* sm = reinterpret_cast<int*>(sm4);
@@ -159,14 +206,13 @@ k_sb_build(const u64* __restrict__ bucketed, const u32* __restrict__ blk_start, 
   for (int i = 0; i < 8; i++) sm4[i * 256 + threadIdx.x] = make_int4(0, 0, 0, 0);
   __syncthreads();
   for (u32 i = a + threadIdx.x; i < b; i += 256) {
-    const u64 v = __ldcs(bucketed + i);
-    const u32 so = (u32)(v >> 32) & (GR_BLOCK_SLOTS - 1), span = (u32)v;
-    const int w = (int)(v >> 45);
+    const u32 v = __ldcs(bucketed + i);
+    const u32 so = (v >> 15) & (GR_BLOCK_SLOTS - 1), span = v & (SB_LONG - 1);
+    const int w = 120 / (int)(v >> 28);
     atomicAdd(sm + so, w);
-    const u64 eo = (u64)so + span;
-    if (eo < GR_BLOCK_SLOTS) atomicAdd(sm + (u32)eo, -w);
-    else spill[atomicAdd(spill_ctr, 1u)] = make_uint2((u32)((((u64)blk << GR_BLOCK_SHIFT) + eo) & 0xffffffffu),
-                                                      (u32)(((((u64)blk << GR_BLOCK_SHIFT) + eo) >> 32) << 8) | (u32)w);
+    const u32 eo = so + span;
+    if (eo < GR_BLOCK_SLOTS) atomicAdd(sm + eo, -w);
+    else spill[atomicAdd(spill_ctr, 1u)] = sb_spill_entry(((u64)blk << GR_BLOCK_SHIFT) + eo, -w);
   }
   __syncthreads();
   int4* out = reinterpret_cast<int4*>(delta) + (u64)blk * (GR_BLOCK_SLOTS / 4);
@@ -179,7 +225,7 @@ k_sb_spill(const uint2* __restrict__ spill, const u32* __restrict__ spill_ctr, i
   const u32 n = *spill_ctr;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint2 v = spill[i];
-    atomicAdd(delta + (((u64)(v.y >> 8) << 32) | v.x), -(int)(v.y & 0xffu));
+    atomicAdd(delta + (((u64)(v.y >> 8) << 32) | v.x), (int)(signed char)(v.y & 0xffu));
   }
 }
 
@@ -192,20 +238,25 @@ void launch_sb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n
   else k_sb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
   GR_NOTE_LAUNCH();
 }
-void launch_sb_scan(cudaStream_t s, const DevLayout& L, const u32* blk_cnt, u32* blk_start, u32* cursor) {
-  k_sb_scan<<<1, 1024, 0, s>>>(blk_cnt, blk_start, cursor, L.nblocks); GR_NOTE_LAUNCH();
+// chunk_sum: scratch of ceil(nblocks / 4096) words
+void launch_sb_scan(cudaStream_t s, const DevLayout& L, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum) {
+  const u32 nchunks = (u32)((L.nblocks + SB_CHUNK - 1) / SB_CHUNK);
+  k_sb_scan1<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, L.nblocks); GR_NOTE_LAUNCH();
+  k_sb_scan2<<<1, 1024, 0, s>>>(chunk_sum, nchunks, blk_start, L.nblocks); GR_NOTE_LAUNCH();
+  k_sb_scan3<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, blk_start, cursor, L.nblocks); GR_NOTE_LAUNCH();
 }
-void launch_sb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u64* bucketed) {
+// spill_ctr must be zero before the first move of a sample
+void launch_sb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
+                    uint2* spill, u32* spill_ctr) {
   if (!n) return;
   u64 blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_sb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
-  else k_sb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
+  if (packed) k_sb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, spill, spill_ctr);
+  else k_sb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, spill, spill_ctr);
   GR_NOTE_LAUNCH();
 }
-void launch_sb_build(cudaStream_t s, const DevLayout& L, const u64* bucketed, const u32* blk_start,
+void launch_sb_build(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
                      int32_t* delta, uint2* spill, u32* spill_ctr) {
-  cudaMemsetAsync(spill_ctr, 0, 4, s);
   k_sb_build<<<(unsigned)L.nblocks, 256, 0, s>>>(bucketed, blk_start, delta, spill, spill_ctr); GR_NOTE_LAUNCH();
   k_sb_spill<<<148 * 2, 256, 0, s>>>(spill, spill_ctr, delta); GR_NOTE_LAUNCH();
 }

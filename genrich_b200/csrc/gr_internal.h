@@ -36,9 +36,10 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
 // bucketed build of the delta array (large samples): count -> scan -> move -> build (+ spills)
 void launch_sb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
                      u32* blk_cnt, int* err, u64* clamped);
-void launch_sb_scan(cudaStream_t s, const DevLayout& L, const u32* blk_cnt, u32* blk_start, u32* cursor);
-void launch_sb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u64* bucketed);
-void launch_sb_build(cudaStream_t s, const DevLayout& L, const u64* bucketed, const u32* blk_start,
+void launch_sb_scan(cudaStream_t s, const DevLayout& L, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum);
+void launch_sb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
+                    uint2* spill, u32* spill_ctr);
+void launch_sb_build(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
                      int32_t* delta, uint2* spill, u32* spill_ctr);
 
 // ---- K2: dense prefix sum + break compaction + bitmap (savePileupExpt 2168) ----

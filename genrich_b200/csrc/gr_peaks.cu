@@ -63,39 +63,51 @@ void launch_peak_events(cudaStream_t s, const float* v, u64 n, float thr, const 
 }
 
 // ---- heads: events that open a candidate ------------------------------------------
+// 8 consecutive events per thread (2048 per tile): one ticket and one look-back per 2048.
+#define PK_HEAD_PER 8
 __global__ void __launch_bounds__(256)
 k_peak_heads(const u32* __restrict__ pEnd, const float* __restrict__ v,
              const u64* __restrict__ chrom_start, int nchrom, int max_gap,
              const u32* __restrict__ ev_idx, const u64* __restrict__ ev_count, Lookback<1> lb,
              u32* __restrict__ head_idx, u64* __restrict__ head_count) {
   const u64 nev = *ev_count;
+  if ((u64)blockIdx.x * (256 * PK_HEAD_PER) >= nev) return;      // launched for the capacity; tickets stay dense
   const u32 tile = take_ticket(lb.ticket);
-  const u64 t = (u64)tile * 256 + threadIdx.x;
-  u32 head = 0;
-  if (t < nev) {
+  const u64 t0 = ((u64)tile * 256 + threadIdx.x) * PK_HEAD_PER;
+  u32 mask = 0;
+  u32 prev = 0;
+  bool have_prev = false, prev_skip = false;
+  if (t0 > 0 && t0 < nev) { prev = ev_idx[t0 - 1]; have_prev = true; prev_skip = v[prev] == PK_SKIP; }
+#pragma unroll
+  for (int i = 0; i < PK_HEAD_PER; i++) {
+    const u64 t = t0 + i;
+    if (t >= nev) break;
     const u32 idx = ev_idx[t];
-    if (v[idx] != PK_SKIP) {
+    const bool skip = v[idx] == PK_SKIP;
+    u32 head = 0;
+    if (!skip) {
       head = 1;
-      if (t > 0) {
-        const u32 prev = ev_idx[t - 1];
-        if (v[prev] != PK_SKIP) {
-          const int c = chrom_of_index(chrom_start, nchrom, idx);
-          if ((u64)prev >= chrom_start[c]) {                 // same chromosome
-            if (prev + 1 == idx) head = 0;                   // adjacent: no interval in between
-            else {
-              const i64 gap = (i64)pEnd[idx - 1] - (i64)pEnd[prev];   // start[idx] - peakEnd
-              if (!(gap > (i64)max_gap)) head = 0;           // 1032
-            }
+      if (have_prev && !prev_skip) {
+        const int c = chrom_of_index(chrom_start, nchrom, idx);
+        if ((u64)prev >= chrom_start[c]) {                 // same chromosome
+          if (prev + 1 == idx) head = 0;                   // adjacent: no interval in between
+          else {
+            const i64 gap = (i64)pEnd[idx - 1] - (i64)pEnd[prev];   // start[idx] - peakEnd
+            if (!(gap > (i64)max_gap)) head = 0;           // 1032
           }
         }
       }
     }
+    mask |= head << i;
+    prev = idx; have_prev = true; prev_skip = skip;
   }
   u32 tot;
-  const u64 r = tile_exclusive_rank(lb, tile, head, tot);
-  if (head) head_idx[r] = (u32)t;
-  // every tile up to the capacity runs; the one holding the last event reports
-  if (t + 1 == nev) *head_count = r + head;
+  u64 r = tile_exclusive_rank(lb, tile, (u32)__popc(mask), tot);
+#pragma unroll
+  for (int i = 0; i < PK_HEAD_PER; i++)
+    if (mask & (1u << i)) head_idx[r++] = (u32)(t0 + i);
+  // the thread holding the last event reports
+  if (t0 < nev && t0 + PK_HEAD_PER >= nev) *head_count = r;
 }
 
 // ---- walk: one thread per candidate ------------------------------------------------
@@ -153,6 +165,7 @@ k_peak_compact(const PeakRec* __restrict__ cand, const uint8_t* __restrict__ ok,
                const u64* __restrict__ head_count, Lookback<1> lb, PeakRec* __restrict__ out,
                u64* __restrict__ out_count, u64* __restrict__ peak_bp) {
   const u64 nh = *head_count;
+  if ((u64)blockIdx.x * 256 >= nh) return;              // launched for the capacity; tickets stay dense
   const u32 tile = take_ticket(lb.ticket);
   const u64 h = (u64)tile * 256 + threadIdx.x;
   const u32 f = h < nh && ok[h];
@@ -180,11 +193,12 @@ void launch_peak_chain(cudaStream_t s, const u32* pEnd, const float* pval, const
   if (!nev) return;
   const float* v = qopt ? qval : pval;
   const u32 nt = (u32)((nev + 255) / 256);
+  const u32 nth = (u32)((nev + 256 * PK_HEAD_PER - 1) / (256 * PK_HEAD_PER));
   Lookback<1> lb;
   lb.st[0] = w.sc.st; lb.ticket = w.sc.ticket;
   cudaMemsetAsync(w.sc.st, 0, (size_t)nt * sizeof(u64), s);
   cudaMemsetAsync(w.sc.ticket, 0, sizeof(u32), s);
-  k_peak_heads<<<nt, 256, 0, s>>>(pEnd, v, chrom_start, nchrom, max_gap, w.ev_idx, w.ev_count, lb,
+  k_peak_heads<<<nth, 256, 0, s>>>(pEnd, v, chrom_start, nchrom, max_gap, w.ev_idx, w.ev_count, lb,
                                   w.head_idx, w.head_count); GR_NOTE_LAUNCH();
   // heads <= events: size the walk and the compaction by nev
   k_peak_walk<<<(unsigned)((nev + 127) / 128), 128, 0, s>>>(pEnd, pval, qval, chrom_start, nchrom, thr,

@@ -171,7 +171,10 @@ def test_bucketed_build_same_bits(monkeypatch):
     api = capi.load_cuda()
     for name in ("c5_multimap_ctrl_p", "c3_atac_q", "fisher_missing_chrom"):
         case = BY_NAME[name]
-        inputs = util.case_inputs(case)
+        inputs = [list(r) for r in util.case_inputs(case)]
+        # an interval longer than a bucket entry can hold, and one that spans three blocks
+        extra = np.array([[0, 1000, 41000, 2], [0, 8000, 3 * 8192 + 5, 1], [0, 8191, 8193, 4]], np.int32)
+        inputs[0][0] = np.concatenate([inputs[0][0], extra])
         outs = []
         for sb_min, packed in (("1", False), ("1000000000", False), ("1", True)):
             monkeypatch.setenv("GR_SB_MIN", sb_min)
