@@ -257,7 +257,7 @@ def main():
         else:
             pe = lambda c: c.push_packed_ptr(t_dev.data_ptr(), n_t)
             pc = (lambda c: c.push_packed_ptr(c_dev.data_ptr(), n_c)) if n_c else None
-        eng.replicate(pe, pc)
+        eng.replicate(pe, pc, want_stats=False)
         return eng.call_peaks()
 
     def timed(from_host, steps, warmup, with_stages=False):

@@ -67,7 +67,8 @@ ABI_SYMBOLS = [
     "gr_create", "gr_destroy", "gr_set_params", "gr_reset", "gr_strerror",
     "gr_last_error_detail", "gr_sample_begin", "gr_push_intervals",
     "gr_push_intervals_device", "gr_prefetch_intervals", "gr_push_packed", "gr_prefetch_packed",
-    "gr_sample_pileup", "gr_replicate_finish",
+    "gr_sample_pileup", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
+    "gr_sums_device", "gr_stream", "gr_replicate_stats",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
     "gr_bh_set_global", "gr_call_peaks", "gr_peaks_device", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
@@ -129,6 +130,11 @@ class Api:
             self.last_error_detail = fn("last_error_detail", C.c_char_p, [vp])
             self.push_intervals_device = fn("push_intervals_device", C.c_int, [vp, vp, u64])
             self.prefetch_intervals = fn("prefetch_intervals", C.c_int, [vp, vp, u64])
+            self.sample_sums = fn("sample_sums", C.c_int, [vp, C.POINTER(dbl), C.POINTER(dbl)])
+            self.replicate_finish_device = fn("replicate_finish_device", C.c_int, [vp, i32, u64])
+            self.sums_device = fn("sums_device", C.c_int, [vp, C.POINTER(vp), C.POINTER(vp)])
+            self.stream = fn("stream", vp, [vp])
+            self.replicate_stats = fn("replicate_stats", C.c_int, [vp, i32, C.POINTER(GrSampleStats)])
             self.push_packed = fn("push_packed", C.c_int, [vp, vp, u64])
             self.prefetch_packed = fn("prefetch_packed", C.c_int, [vp, vp, u64])
             self.peaks_device = fn("peaks_device", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)])
@@ -267,6 +273,34 @@ class Context:
         st = GrSampleStats()
         self._check(self.api.replicate_finish(self._h, frag_len, ctrl_frag, int(has_ctrl),
                                               int(genome_len), C.byref(st)), "replicate_finish")
+        return st
+
+    # -- the same without host round trips (CUDA library only) ---------------------
+    def sample_pileup_async(self):
+        self._check(self.api.sample_pileup(self._h, None), "sample_pileup")
+
+    def sample_sums(self, want_ctrl=True):
+        e = np.zeros(self.nchrom, dtype=np.float64)
+        c = np.zeros(self.nchrom, dtype=np.float64) if want_ctrl else None
+        dp = C.POINTER(C.c_double)
+        self._check(self.api.sample_sums(self._h, e.ctypes.data_as(dp), c.ctypes.data_as(dp) if want_ctrl else None),
+                    "sample_sums")
+        return e, c
+
+    def replicate_finish_device(self, has_ctrl, genome_len=0):
+        self._check(self.api.replicate_finish_device(self._h, int(has_ctrl), int(genome_len)), "replicate_finish_device")
+
+    def sums_device_ptrs(self):
+        e, c = C.c_void_p(), C.c_void_p()
+        self._check(self.api.sums_device(self._h, C.byref(e), C.byref(c)), "sums_device")
+        return e.value, c.value
+
+    def stream_handle(self) -> int:
+        return int(self.api.stream(self._h) or 0)
+
+    def replicate_stats(self, replicate: int) -> GrSampleStats:
+        st = GrSampleStats()
+        self._check(self.api.replicate_stats(self._h, replicate, C.byref(st)), "replicate_stats")
         return st
 
     def replicate_end(self) -> GrSampleStats:

@@ -40,13 +40,17 @@ struct DevBuf {
 
 struct Replicate {
   DevBuf bmU, rankU, pEnd, pVal, pExpt, pCtrl, chrom_start, present;
-  u64 n = 0;
+  DevBuf cnt;                 // device: [0] number of p intervals, [1] number of control intervals
+  u64 n = 0;                  // host mirror of cnt[0] (valid when the context is not lagging)
+  u64 n_upper = 0;            // what the arrays were sized for
+  u64 n_ctrl = 0;
+  bool has_ctrl = false;
   std::vector<u64> chrom_start_h;
   std::vector<uint8_t> present_h;
   bool has_cols = false;
   void release() {
     bmU.release(); rankU.release(); pEnd.release(); pVal.release(); pExpt.release();
-    pCtrl.release(); chrom_start.release(); present.release();
+    pCtrl.release(); chrom_start.release(); present.release(); cnt.release();
   }
 };
 
@@ -104,6 +108,24 @@ struct gr_ctx {
   // bucketed build (large samples)
   DevBuf sbCnt, sbStart, sbCursor, sbBucket, sbSpill, sbSpillCtr;
   u64 sb_min = 1ull << 20;             // samples with fewer records use the plain scatter (GR_SB_MIN)
+
+  // Host mirrors of device-side results lag behind while `lag` is set: nothing on the hot path
+  // waits for the device between gr_sample_begin and the peak records; whoever needs a mirror
+  // (sums, interval counts, per-chromosome starts, device error bits) calls materialize().
+  bool lag = false;
+  bool pend_pile[2] = { false, false };
+  std::vector<Replicate*> pend_reps;
+  int retry_flags = 0;              // GR_DE_TABLE / GR_DE_CAP seen by the last materialize()
+  u64 cap_expt = 0, cap_raw = 0;    // capacities (upper bounds of the interval counts) of the current sample arrays
+  u32 pair_cap = 1u << 20;          // pair-table capacity, grown on overflow and remembered
+  u64 head_cap = 0;                 // candidate-peak capacity of the last peak call
+  DevBuf dpar;                      // device: float factor, lambda (+ pad)
+  DevBuf dsums;                     // device: double[2][nchrom], per-chromosome sum(len*val) of expt / ctrl
+  float* h_fl = nullptr;            // pinned ring of (factor, lambda) pairs for the H2D copy
+  int h_fl_next = 0;
+  u64* h_mat = nullptr;             // pinned landing area of materialize(): 2 + 4 chromosome-start tables
+  gr_peak* h_peaks = nullptr;       // pinned: the first PEAK_SPEC records come back with the counts
+  static const u64 PEAK_SPEC = 1u << 16;
 
   // sample state
   int filling = FILL_NONE;
@@ -271,6 +293,12 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     x->d_totals = (u64*)((char*)x->small.p + 16);       // 3 entries
     x->d_cnt = (u64*)((char*)x->small.p + 64);          // 8 scratch counters
     CK(cudaMallocHost(&x->h_small, 256));
+    CK(x->dpar.ensure(64));
+    CK(x->dsums.ensure(2 * nchrom * sizeof(double)));
+    CK(cudaMemsetAsync(x->dsums.p, 0, 2 * nchrom * sizeof(double), x->stream));
+    CK(cudaMallocHost((void**)&x->h_fl, 16 * 2 * sizeof(float)));
+    CK(cudaMallocHost((void**)&x->h_peaks, gr_ctx::PEAK_SPEC * sizeof(gr_peak)));
+    CK(cudaMallocHost((void**)&x->h_mat, 6 * (size_t)(nchrom + 3) * sizeof(u64)));
     CK(x->accI.ensure(2 * nchrom * sizeof(u64)));
     CK(x->accF.ensure(2 * nchrom * sizeof(u64)));
     CK(cudaMallocHost(&x->h_acc, 4 * nchrom * sizeof(u64)));
@@ -281,6 +309,9 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     x->ctrl_sums.assign(nchrom, 0.0);
     { const char* e = getenv("GR_SCAN_ZERO"); if (e) x->zero_after = atoi(e) != 0; }
     { const char* e = getenv("GR_SB_MIN"); if (e) x->sb_min = strtoull(e, nullptr, 10); }
+    // test knobs: start the optimistic capacities small enough to exercise the retry paths
+    { const char* e = getenv("GR_PAIR_CAP"); if (e) { u32 v = (u32)strtoul(e, nullptr, 10); u32 c = 64; while (c < v) c <<= 1; x->pair_cap = c; } }
+    { const char* e = getenv("GR_HEAD_CAP"); if (e) x->head_cap = strtoull(e, nullptr, 10); }
     CK(cudaEventCreateWithFlags(&x->ev_copy, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(x->stream));
     return GR_OK;
@@ -337,6 +368,11 @@ extern "C" void gr_destroy(gr_ctx* x) {
     &x->headCount, &x->cand, &x->candOk, &x->peakOut, &x->peakCount, &x->peakBp };
   for (DevBuf* b : all) b->release();
   if (x->h_small) cudaFreeHost(x->h_small);
+  if (x->h_fl) cudaFreeHost(x->h_fl);
+  if (x->h_peaks) cudaFreeHost(x->h_peaks);
+  if (x->h_mat) cudaFreeHost(x->h_mat);
+  x->dpar.release();
+  x->dsums.release();
   if (x->h_acc) cudaFreeHost(x->h_acc);
   for (int i = 0; i < 2; i++) {
     if (x->h_stage[i]) cudaFreeHost(x->h_stage[i]);
@@ -363,8 +399,10 @@ extern "C" int gr_set_params(gr_ctx* x, const gr_params* p) {
 extern "C" int gr_reset(gr_ctx* x) {
   if (!x) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
-  CK(cudaStreamSynchronize(x->stream));
+  // no device round trip: the replicate buffers go back to the pool and are reused in stream order
   free_reps(x, true);
+  x->pend_reps.clear();
+  x->pend_pile[0] = x->pend_pile[1] = false;
   x->finalized = false; x->have_q = false; x->have_expt = x->have_ctrl = false;
   x->filling = FILL_NONE; x->hist_cap = 0; x->peaks_h.clear();
   return GR_OK;
@@ -375,6 +413,7 @@ static int map_dev_err(int e) {
   if (e & GR_DE_COUNT) return GR_ERR_COUNT;
   if (e & GR_DE_POS) return GR_ERR_POS;
   if (e & (GR_DE_PILE | GR_DE_TAIL)) return GR_ERR_PILE;
+  if (e & GR_DE_EXPT) return GR_ERR_EXPT;
   return GR_OK;
 }
 
@@ -392,7 +431,6 @@ extern "C" int gr_sample_begin(gr_ctx* x, int32_t is_ctrl, const uint8_t* save) 
     CK(cudaMemsetAsync(x->d_clamped, 0, sizeof(u64), x->stream));
   }
   x->have_ctrl = false;
-  CK(cudaMemsetAsync(x->d_err, 0, sizeof(int), x->stream));
   // records of an abandoned sample are dropped
   for (auto& g : x->segs) if (g.pf) g.pf->in_use = false;
   for (auto* b : x->seg_used) x->seg_free.push_back(b);
@@ -552,10 +590,75 @@ extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) { r
 extern "C" int gr_prefetch_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) { return prefetch_any(x, recs, n, 8); }
 extern "C" int gr_push_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) { return push_any(x, recs, n, 8); }
 
+// ---- host mirrors ------------------------------------------------------------------
+// One device round trip that brings every lagging host mirror up to date and reports the
+// device-side error bits.  GR_DE_TABLE / GR_DE_CAP (an optimistically sized table or buffer
+// was too small) are not errors: they are left in x->retry_flags for the caller that can redo
+// the stage with more room.
+static int map_dev_err(int e);
+static int materialize(gr_ctx* x) {
+  if (!x->lag) return GR_OK;
+  const int nc = x->nchrom;
+  const size_t row = (size_t)nc + 3;                           // nc+1 starts, then two counts
+  u64* hI = (u64*)x->h_acc;
+  CK(cudaMemcpyAsync(x->h_small, x->small.p, 64, cudaMemcpyDeviceToHost, x->stream));
+  for (int k = 0; k < 2; k++) {
+    if (!x->pend_pile[k]) continue;
+    CK(cudaMemcpyAsync(hI + 2 * k * nc, x->accI.as<u64>() + k * nc, nc * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(hI + (2 * k + 1) * nc, x->accF.as<u64>() + k * nc, nc * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
+    u64* m = x->h_mat + k * row;
+    CK(cudaMemcpyAsync(m, (k ? x->rawCS : x->exptCS).p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(m + nc + 1, (k ? x->rawTot : x->exptTot).p, 8, cudaMemcpyDeviceToHost, x->stream));
+  }
+  // up to four replicates land in pinned memory; more (many replicates finished without asking
+  // for statistics) take the slower pageable way
+  for (size_t i = 0; i < x->pend_reps.size(); i++) {
+    Replicate* r = x->pend_reps[i];
+    if (i < 4) {
+      u64* m = x->h_mat + (2 + i) * row;
+      CK(cudaMemcpyAsync(m, r->chrom_start.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
+      CK(cudaMemcpyAsync(m + nc + 1, r->cnt.p, 16, cudaMemcpyDeviceToHost, x->stream));
+    } else {
+      r->chrom_start_h.resize(nc + 1);
+      CK(cudaMemcpy(r->chrom_start_h.data(), r->chrom_start.p, (nc + 1) * sizeof(u64), cudaMemcpyDeviceToHost));
+      u64 c2[2];
+      CK(cudaMemcpy(c2, r->cnt.p, 16, cudaMemcpyDeviceToHost));
+      r->n = c2[0]; r->n_ctrl = c2[1];
+    }
+  }
+  CK(cudaMemsetAsync(x->d_err, 0, sizeof(int), x->stream));     // the bits are ours now
+  CK(cudaStreamSynchronize(x->stream));
+  const int derr = *(int*)x->h_small;
+  x->n_clamped = *(u64*)((char*)x->h_small + 8);
+  for (int k = 0; k < 2; k++) {
+    if (!x->pend_pile[k]) continue;
+    std::vector<double>& sums = k ? x->ctrl_sums : x->expt_sums;
+    for (int c = 0; c < nc; c++)
+      sums[c] = (double)hI[2 * k * nc + c] + (double)hI[(2 * k + 1) * nc + c] * (1.0 / 1099511627776.0);
+    const u64* m = x->h_mat + k * row;
+    std::vector<u64>& csh = k ? x->ctrlCS_h : x->exptCS_h;
+    csh.assign(m, m + nc + 1);
+    (k ? x->n_raw : x->n_expt) = m[nc + 1];
+    x->pend_pile[k] = false;
+  }
+  for (size_t i = 0; i < x->pend_reps.size() && i < 4; i++) {
+    Replicate* r = x->pend_reps[i];
+    const u64* m = x->h_mat + (2 + i) * row;
+    r->chrom_start_h.assign(m, m + nc + 1);
+    r->n = m[nc + 1];
+    r->n_ctrl = m[nc + 2];
+  }
+  x->pend_reps.clear();
+  x->lag = false;
+  x->retry_flags = derr & (GR_DE_TABLE | GR_DE_CAP);
+  const int hard = derr & ~(GR_DE_TABLE | GR_DE_CAP);
+  if (hard) { x->filling = FILL_NONE; return map_dev_err(hard); }
+  return GR_OK;
+}
+
 // ---- pileup integration ----------------------------------------------------------
-extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
-  if (!x || x->filling == FILL_NONE) return GR_ERR_ARG;
-  CK(cudaSetDevice(x->device));
+// Enqueues everything; the host learns the sums / counts at the next materialize().
+static int pileup_enqueue(gr_ctx* x) {
   const bool ctrl = x->filling == FILL_CTRL;
   int nact = 0;
   for (int c = 0; c < x->nchrom; c++) nact += chrom_active(x, c);
@@ -590,30 +693,40 @@ extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
   CK(cudaMemsetAsync(aF, 0, x->nchrom * sizeof(u64), x->stream));
   stage_begin(x, "rle_moment", 0);
   launch_rle_moment(x->stream, out, cap, x->nchrom, aI, aF);
+  launch_sums_double(x->stream, aI, aF, x->nchrom, x->dsums.as<double>() + (ctrl ? x->nchrom : 0));
   CKL();
   stage_end(x);
-  u64* hI = (u64*)x->h_acc;
-  u64* hF = hI + x->nchrom;
-  CK(cudaMemcpyAsync(hI, aI, x->nchrom * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
-  CK(cudaMemcpyAsync(hF, aF, x->nchrom * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
-  CK(cudaMemcpyAsync(x->h_small, x->small.p, 64, cudaMemcpyDeviceToHost, x->stream));
-  u64* hTot = (u64*)((char*)x->h_small + 128);
-  CK(cudaMemcpyAsync(hTot, TT.p, 8, cudaMemcpyDeviceToHost, x->stream));
-  std::vector<u64>& csh = ctrl ? x->ctrlCS_h : x->exptCS_h;
-  csh.resize(x->nchrom + 1);
-  CK(cudaMemcpyAsync(csh.data(), CS.p, (x->nchrom + 1) * sizeof(u64), cudaMemcpyDeviceToHost, x->stream));
-  CK(cudaStreamSynchronize(x->stream));
-  const int derr = *(int*)x->h_small;
-  x->n_clamped = *(u64*)((char*)x->h_small + 8);
-  if (derr) { x->filling = FILL_NONE; return map_dev_err(derr); }
   x->delta_clean = zero_after != 0;          // the scan left the array all zero
-  std::vector<double>& sums = ctrl ? x->ctrl_sums : x->expt_sums;
-  for (int c = 0; c < x->nchrom; c++)
-    sums[c] = (double)hI[c] + (double)hF[c] * (1.0 / 1099511627776.0);
-  if (chrom_sums) memcpy(chrom_sums, sums.data(), x->nchrom * sizeof(double));
-  if (ctrl) { x->n_raw = *hTot; x->have_ctrl = true; }
-  else { x->n_expt = *hTot; x->have_expt = true; }
+  (ctrl ? x->cap_raw : x->cap_expt) = cap;
+  x->pend_pile[ctrl ? 1 : 0] = true;
+  x->lag = true;
+  if (ctrl) x->have_ctrl = true; else x->have_expt = true;
   x->filling = FILL_NONE;
+  return GR_OK;
+}
+
+// chrom_sums == NULL: nothing is waited for (the sums come with gr_sample_sums, or never leave
+// the device: gr_replicate_finish_device)
+extern "C" int gr_sample_pileup(gr_ctx* x, double* chrom_sums) {
+  if (!x || x->filling == FILL_NONE) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  const bool ctrl = x->filling == FILL_CTRL;
+  { int r = pileup_enqueue(x); if (r) return r; }
+  if (!chrom_sums) return GR_OK;
+  { int r = materialize(x); if (r) return r; }
+  memcpy(chrom_sums, (ctrl ? x->ctrl_sums : x->expt_sums).data(), x->nchrom * sizeof(double));
+  return GR_OK;
+}
+
+extern "C" int gr_sample_sums(gr_ctx* x, double* expt_sums, double* ctrl_sums) {
+  if (!x || !x->have_expt) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  { int r = materialize(x); if (r) return r; }
+  if (expt_sums) memcpy(expt_sums, x->expt_sums.data(), x->nchrom * sizeof(double));
+  if (ctrl_sums) {
+    if (x->have_ctrl) memcpy(ctrl_sums, x->ctrl_sums.data(), x->nchrom * sizeof(double));
+    else memset(ctrl_sums, 0, x->nchrom * sizeof(double));
+  }
   return GR_OK;
 }
 
@@ -636,19 +749,21 @@ static PairTable table_view(gr_ctx* x, u32 cap) {
   return t;
 }
 
-// run an insert kernel, growing the table until it stays under half full
+// Host-counted builds (BH histogram): run an insert kernel, growing the table until it stays
+// under half full.
 template <class F>
 static int table_build(gr_ctx* x, u64 n, u32& cap_io, F insert) {
   u32 cap = cap_io;
+  { int r = materialize(x); if (r) return r; }
   for (;;) {
     int r = table_alloc(x, cap);
     if (r) return r;
-    CK(cudaMemsetAsync(x->d_err, 0, sizeof(int), x->stream));
     insert(table_view(x, cap));
     CKL();
-    CK(cudaMemcpyAsync(x->h_small, x->d_err, sizeof(int), cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
-    if (!(*(int*)x->h_small & GR_DE_TABLE)) break;
+    x->lag = true;
+    r = materialize(x);
+    if (r) return r;
+    if (!(x->retry_flags & GR_DE_TABLE)) break;
     if (cap >= (1u << 30)) { x->detail = "distinct-value table overflow"; return GR_ERR_MEM; }
     cap <<= 2;
   }
@@ -657,65 +772,75 @@ static int table_build(gr_ctx* x, u64 n, u32& cap_io, F insert) {
   return GR_OK;
 }
 
-extern "C" int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag, int32_t has_ctrl,
-                                   uint64_t genome_len, gr_sample_stats* st) {
-  if (!x || !x->have_expt) return GR_ERR_ARG;
-  if (has_ctrl && !x->have_ctrl) return GR_ERR_ARG;
-  CK(cudaSetDevice(x->device));
-  if (frag_len == 0.0) return GR_ERR_EXPT;                     // Genrich.c:2292
-  u64 G = x->par.genome_len ? x->par.genome_len : genome_len;
-  if (!G)
-    for (int c = 0; c < x->nchrom; c++)
-      if (chrom_active(x, c)) G += x->len[c];                  // calcLambda 1819-1827
-  if (!G) return GR_ERR_GENOME;
-  const float lambda = (float)(frag_len / (double)G);          // 1831
-  float factor = 1.0f;
-  if (has_ctrl && ctrl_frag != 0.0) factor = (float)(frag_len / ctrl_frag);   // 2043-2045
+// K5 for one replicate: -log10 p through the table of distinct (expt, ctrl) pairs.  The table
+// capacity is a remembered guess; an overflow shows up as GR_DE_TABLE at the next materialize()
+// and the stage is simply run again with a larger table (its inputs are still in place).
+static int rep_stage_pvals(gr_ctx* x, Replicate* rep) {
+  CK(x->slot.ensure((rep->n_upper + 1) * sizeof(u32)));
+  const u64* n_dev = rep->cnt.as<u64>();
+  stage_begin(x, "pval", rep->n_upper * 16);
+  { int r = table_alloc(x, x->pair_cap); if (r) return r; }
+  PairTable t = table_view(x, x->pair_cap);
+  launch_pair_insert(x->stream, rep->pExpt.as<float>(), rep->pCtrl.as<float>(), rep->n_upper, n_dev, t,
+                     x->slot.as<u32>(), x->d_err);
+  launch_pair_eval(x->stream, t);
+  launch_gather_f32(x->stream, t.pval, x->slot.as<u32>(), rep->n_upper, n_dev, rep->pVal.as<float>());
+  CKL();
+  stage_end(x);
+  x->lag = true;
+  return GR_OK;
+}
 
+// the part of a replicate that follows the two pileups; factor and lambda are already in x->dpar
+static int replicate_tail(gr_ctx* x, bool has_ctrl) {
   const int nc = x->nchrom;
+  int nact = 0;
+  for (int c = 0; c < nc; c++) nact += chrom_active(x, c);
+  Replicate* rep = new_replicate(x);
+  x->reps.push_back(rep);
+  rep->has_ctrl = has_ctrl;
+  CK(rep->cnt.ensure(16));
+  u64 n_ctrl_upper;
   if (has_ctrl) {
-    CK(x->ctrlEnd.ensure((x->n_raw + 1) * sizeof(u32)));
-    CK(x->ctrlVal.ensure((x->n_raw + 1) * sizeof(float)));
+    n_ctrl_upper = x->cap_raw;
+    CK(x->ctrlEnd.ensure((x->cap_raw + 1) * sizeof(u32)));
+    CK(x->ctrlVal.ensure((x->cap_raw + 1) * sizeof(float)));
     DevRle raw = rle_view(x->rawEnd, x->rawVal, x->rawCS, x->rawTot);
     DevRle out = rle_view(x->ctrlEnd, x->ctrlVal, x->ctrlCS, x->ctrlTot);
     CompactScratch cs;
+    CK(x->lb0.ensure(((x->cap_raw + 1023) / 1024 + 1) * 8 > x->lb0.cap ? ((x->cap_raw + 1023) / 1024 + 1) * 8 : x->lb0.cap));
     cs.st = x->lb0.as<u64>(); cs.ticket = x->ticket.as<u32>();
-    if ((x->n_raw + 1023) / 1024 > x->lb0.cap / 8) CK(x->lb0.ensure(((x->n_raw + 1023) / 1024) * 8));
-    cs.st = x->lb0.as<u64>();
-    stage_begin(x, "ctrl_clamp", x->n_raw * 8);
-    launch_ctrl_clamp(x->stream, x->L, raw, x->n_raw, factor, lambda, cs, out, x->bmC.as<u32>());
+    stage_begin(x, "ctrl_clamp", x->cap_raw * 8);
+    launch_ctrl_clamp(x->stream, x->L, raw, x->cap_raw, x->dpar.as<float>(), cs, out, x->bmC.as<u32>());
     CKL();
     stage_end(x);
   } else {
     // saveLambda 1838-1843: one interval (len, lambda) per saved chromosome
-    std::vector<u32> e; std::vector<float> v; std::vector<u64> cs(nc + 1);
+    std::vector<u32> e; std::vector<u64> cs(nc + 1);
     for (int c = 0; c < nc; c++) {
       cs[c] = e.size();
-      if (chrom_active(x, c)) { e.push_back(x->len[c]); v.push_back(lambda); }
+      if (chrom_active(x, c)) e.push_back(x->len[c]);
     }
     cs[nc] = e.size();
-    x->n_ctrl = e.size();
+    n_ctrl_upper = e.size();
     CK(x->ctrlEnd.ensure((e.size() + 1) * sizeof(u32)));
     CK(x->ctrlVal.ensure((e.size() + 1) * sizeof(float)));
+    // pageable sources: the driver stages them before the call returns
     CK(cudaMemcpyAsync(x->ctrlEnd.p, e.data(), e.size() * sizeof(u32), cudaMemcpyHostToDevice, x->stream));
-    CK(cudaMemcpyAsync(x->ctrlVal.p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, x->stream));
     CK(cudaMemcpyAsync(x->ctrlCS.p, cs.data(), (nc + 1) * sizeof(u64), cudaMemcpyHostToDevice, x->stream));
     u64 tot = e.size();
     CK(cudaMemcpyAsync(x->ctrlTot.p, &tot, 8, cudaMemcpyHostToDevice, x->stream));
     stage_begin(x, "ctrl_const", x->T / 8);
     DevRle out = rle_view(x->ctrlEnd, x->ctrlVal, x->ctrlCS, x->ctrlTot);
-    launch_ctrl_const(x->stream, x->L, lambda, out, x->bmC.as<u32>());
+    launch_ctrl_const(x->stream, x->L, x->dpar.as<float>() + 1, e.size(), out, x->bmC.as<u32>());
     CKL();
     stage_end(x);
-    CK(cudaStreamSynchronize(x->stream));      // host vectors go out of scope
   }
 
   // K4: union ranks
   RankScratch rs;
   rs.st[0] = x->lb0.as<u64>(); rs.st[1] = x->lb1.as<u64>(); rs.st[2] = x->lb2.as<u64>();
   rs.ticket = x->ticket.as<u32>();
-  Replicate* rep = new_replicate(x);
-  x->reps.push_back(rep);
   CK(rep->bmU.ensure(x->T / 8));
   CK(rep->rankU.ensure(x->nblocks * sizeof(u64)));
   CK(rep->chrom_start.ensure((nc + 1) * sizeof(u64)));
@@ -725,19 +850,17 @@ extern "C" int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag,
                     x->rankC.as<u64>(), rep->rankU.as<u64>(), x->d_totals);
   CKL();
   stage_end(x);
-  CK(cudaMemcpyAsync(x->h_small, x->small.p, 64, cudaMemcpyDeviceToHost, x->stream));
-  CK(cudaMemcpyAsync((char*)x->h_small + 128, x->ctrlTot.p, 8, cudaMemcpyDeviceToHost, x->stream));
-  CK(cudaStreamSynchronize(x->stream));
-  const u64* tot = (const u64*)((char*)x->h_small + 16);
-  const u64 np = tot[2];
-  x->n_ctrl = *(u64*)((char*)x->h_small + 128);
-  if (np >= 0xfffffff0ull) { x->detail = "more than 2^32 intervals on one device"; return GR_ERR_MEM; }
-  rep->n = np;
-  CK(rep->pEnd.ensure((np + 1) * sizeof(u32)));
-  CK(rep->pVal.ensure((np + 1) * sizeof(float)));
-  CK(rep->pExpt.ensure((np + 1) * sizeof(float)));
-  CK(rep->pCtrl.ensure((np + 1) * sizeof(float)));
-  stage_begin(x, "union_emit", x->T / 4 + np * 12);
+  // the counts of this replicate stay on the device (cnt[0] = #p intervals, cnt[1] = #control intervals)
+  CK(cudaMemcpyAsync(rep->cnt.p, x->d_totals + 2, 8, cudaMemcpyDeviceToDevice, x->stream));
+  CK(cudaMemcpyAsync((char*)rep->cnt.p + 8, x->ctrlTot.p, 8, cudaMemcpyDeviceToDevice, x->stream));
+  const u64 np_upper = x->cap_expt + n_ctrl_upper;
+  if (np_upper >= 0xfffffff0ull) { x->detail = "more than 2^32 intervals on one device"; return GR_ERR_MEM; }
+  rep->n_upper = np_upper;
+  CK(rep->pEnd.ensure((np_upper + 1) * sizeof(u32)));
+  CK(rep->pVal.ensure((np_upper + 1) * sizeof(float)));
+  CK(rep->pExpt.ensure((np_upper + 1) * sizeof(float)));
+  CK(rep->pCtrl.ensure((np_upper + 1) * sizeof(float)));
+  stage_begin(x, "union_emit", x->T / 4 + np_upper * 12);
   launch_union_emit(x->stream, x->L, x->bmE.as<u32>(), x->bmC.as<u32>(), x->rankE.as<u64>(),
                     x->rankC.as<u64>(), rep->rankU.as<u64>(), x->exptVal.as<float>(),
                     x->ctrlVal.as<float>(), rep->pEnd.as<u32>(), rep->pExpt.as<float>(),
@@ -745,46 +868,119 @@ extern "C" int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag,
                     x->d_totals + 2);
   CKL();
   stage_end(x);
-
-  // K5: -log10 p through the table of distinct (expt, ctrl) pairs
-  CK(x->slot.ensure((np + 1) * sizeof(u32)));
-  u32 cap = 1u << 20;
-  stage_begin(x, "pval", np * 16);
-  int r = table_build(x, np, cap, [&](const PairTable& t) {
-    launch_pair_insert(x->stream, rep->pEnd.as<u32>(), rep->pExpt.as<float>(), rep->pCtrl.as<float>(),
-                       np, t, x->slot.as<u32>(), 0, x->d_err);
-  });
-  if (r) return r;
-  PairTable t = table_view(x, cap);
-  launch_pair_eval(x->stream, t);
-  launch_gather_f32(x->stream, t.pval, x->slot.as<u32>(), np, rep->pVal.as<float>());
-  CKL();
-  stage_end(x);
+  { int r = rep_stage_pvals(x, rep); if (r) return r; }
 
   rep->present_h.resize(nc);
   for (int c = 0; c < nc; c++) rep->present_h[c] = chrom_active(x, c);
   CK(cudaMemcpyAsync(rep->present.p, rep->present_h.data(), nc, cudaMemcpyHostToDevice, x->stream));
-  rep->chrom_start_h.resize(nc + 1);
-  CK(cudaMemcpyAsync(rep->chrom_start_h.data(), rep->chrom_start.p, (nc + 1) * sizeof(u64),
-                     cudaMemcpyDeviceToHost, x->stream));
-  CK(cudaStreamSynchronize(x->stream));
   rep->has_cols = x->par.keep_pileups != 0;
-
+  x->pend_reps.push_back(rep);
+  x->lag = true;
   x->have_expt = x->have_ctrl = false;
   x->finalized = false;
   x->have_q = false;
-  if (st) {
-    memset(st, 0, sizeof *st);
-    st->frag_len = frag_len;
-    st->ctrl_frag = has_ctrl ? ctrl_frag : 0.0;
-    st->lambda = lambda;
-    st->factor = factor;
-    st->genome_len = G;
-    st->n_expt = x->n_expt;
-    st->n_ctrl = x->n_ctrl;
-    st->n_pval = np;
-    st->n_clamped = x->n_clamped;
+  return GR_OK;
+}
+
+// a table that overflowed is rebuilt, four times larger, for every replicate
+static int redo_pvals(gr_ctx* x) {
+  while (x->retry_flags & GR_DE_TABLE) {
+    if (x->pair_cap >= (1u << 30)) { x->detail = "distinct-value table overflow"; return GR_ERR_MEM; }
+    x->pair_cap <<= 2;
+    x->retry_flags &= ~GR_DE_TABLE;
+    for (Replicate* r : x->reps) { int rc = rep_stage_pvals(x, r); if (rc) return rc; }
+    int rc = materialize(x);
+    if (rc) return rc;
   }
+  return GR_OK;
+}
+
+static u64 replicate_genome_len(const gr_ctx* x, u64 genome_len) {
+  u64 G = x->par.genome_len ? x->par.genome_len : genome_len;
+  if (!G)
+    for (int c = 0; c < x->nchrom; c++)
+      if (chrom_active(x, c)) G += x->len[c];                  // calcLambda 1819-1827
+  return G;
+}
+
+static void fill_stats(gr_ctx* x, gr_sample_stats* st, double frag_len, double ctrl_frag, bool has_ctrl,
+                       float lambda, float factor, u64 G) {
+  const Replicate* rep = x->reps.back();
+  memset(st, 0, sizeof *st);
+  st->frag_len = frag_len;
+  st->ctrl_frag = has_ctrl ? ctrl_frag : 0.0;
+  st->lambda = lambda;
+  st->factor = factor;
+  st->genome_len = G;
+  st->n_expt = x->n_expt;
+  st->n_ctrl = rep->n_ctrl;
+  st->n_pval = rep->n;
+  st->n_clamped = x->n_clamped;
+}
+
+// st == NULL: nothing is waited for
+extern "C" int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag, int32_t has_ctrl,
+                                   uint64_t genome_len, gr_sample_stats* st) {
+  if (!x || !x->have_expt) return GR_ERR_ARG;
+  if (has_ctrl && !x->have_ctrl) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  if (frag_len == 0.0) return GR_ERR_EXPT;                     // Genrich.c:2292
+  const u64 G = replicate_genome_len(x, genome_len);
+  if (!G) return GR_ERR_GENOME;
+  const float lambda = (float)(frag_len / (double)G);          // 1831
+  float factor = 1.0f;
+  if (has_ctrl && ctrl_frag != 0.0) factor = (float)(frag_len / ctrl_frag);   // 2043-2045
+  float* fl = x->h_fl + 2 * (x->h_fl_next++ & 15);             // pinned, one slot per call in flight
+  fl[0] = factor; fl[1] = lambda;
+  CK(cudaMemcpyAsync(x->dpar.p, fl, 2 * sizeof(float), cudaMemcpyHostToDevice, x->stream));
+  { int r = replicate_tail(x, has_ctrl != 0); if (r) return r; }
+  if (st) {
+    int r = materialize(x);
+    if (r) return r;
+    r = redo_pvals(x);
+    if (r) return r;
+    fill_stats(x, st, frag_len, ctrl_frag, has_ctrl != 0, lambda, factor, G);
+  }
+  return GR_OK;
+}
+
+// Same, with the sums taken where they are: on the device (gr_sums_device), possibly after the
+// caller all-reduced them across ranks in the library's stream (gr_stream).  lambda and the
+// scale factor are computed by one thread exactly as calcLambda / calcFactor do (per-chromosome
+// doubles added in chromosome order, Genrich.c:1831, 2043-2045); the host is not involved.
+extern "C" int gr_replicate_finish_device(gr_ctx* x, int32_t has_ctrl, uint64_t genome_len) {
+  if (!x || !x->have_expt) return GR_ERR_ARG;
+  if (has_ctrl && !x->have_ctrl) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  const u64 G = replicate_genome_len(x, genome_len);
+  if (!G) return GR_ERR_GENOME;
+  launch_lambda_factor(x->stream, x->dsums.as<double>(), x->nchrom, has_ctrl != 0, G, x->dpar.as<float>(), x->d_err);
+  CKL();
+  return replicate_tail(x, has_ctrl != 0);
+}
+
+extern "C" int gr_sums_device(gr_ctx* x, double** d_expt_sums, double** d_ctrl_sums) {
+  if (!x) return GR_ERR_ARG;
+  if (d_expt_sums) *d_expt_sums = x->dsums.as<double>();
+  if (d_ctrl_sums) *d_ctrl_sums = x->dsums.as<double>() + x->nchrom;
+  return GR_OK;
+}
+
+extern "C" void* gr_stream(gr_ctx* x) { return x ? (void*)x->stream : nullptr; }
+
+extern "C" int gr_replicate_stats(gr_ctx* x, int32_t replicate, gr_sample_stats* st) {
+  if (!x || !st || replicate < 0 || replicate >= (int)x->reps.size()) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  { int r = materialize(x); if (r) return r; }
+  { int r = redo_pvals(x); if (r) return r; }
+  const Replicate* rep = x->reps[replicate];
+  float fl[2];
+  CK(cudaMemcpy(fl, x->dpar.p, sizeof fl, cudaMemcpyDeviceToHost));   // the last replicate's scalars
+  memset(st, 0, sizeof *st);
+  st->n_ctrl = rep->n_ctrl;
+  st->n_pval = rep->n;
+  st->n_clamped = x->n_clamped;
+  if (replicate == (int)x->reps.size() - 1) { st->factor = fl[0]; st->lambda = fl[1]; st->n_expt = x->n_expt; }
   return GR_OK;
 }
 
@@ -796,6 +992,7 @@ extern "C" int gr_replicate_end(gr_ctx* x, gr_sample_stats* st) {
     if (r) return r;
   }
   const bool has_ctrl = pending_ctrl || x->have_ctrl;
+  { int r = materialize(x); if (r) return r; }                 // the sums of both samples, one round trip
   double f = 0.0, g = 0.0;
   for (int c = 0; c < x->nchrom; c++) { f += x->expt_sums[c]; if (has_ctrl) g += x->ctrl_sums[c]; }
   return gr_replicate_finish(x, f, g, has_ctrl, 0, st);
@@ -814,6 +1011,8 @@ extern "C" int gr_pvalues_finalize(gr_ctx* x) {
     x->finalized = true;
     return GR_OK;
   }
+  { int r = materialize(x); if (r) return r; }
+  { int r = redo_pvals(x); if (r) return r; }
   const int nc = x->nchrom;
   Replicate* cb = new_replicate(x);
   x->comb = cb;
@@ -835,7 +1034,9 @@ extern "C" int gr_pvalues_finalize(gr_ctx* x) {
   CK(cudaMemcpyAsync(x->h_small, x->small.p, 64, cudaMemcpyDeviceToHost, x->stream));
   CK(cudaStreamSynchronize(x->stream));
   const u64 np = ((const u64*)((char*)x->h_small + 16))[2];
-  cb->n = np;
+  cb->n = np; cb->n_upper = np; cb->n_ctrl = 0; cb->has_ctrl = false;
+  CK(cb->cnt.ensure(16));
+  CK(cudaMemcpyAsync(cb->cnt.p, x->d_totals + 2, 8, cudaMemcpyDeviceToDevice, x->stream));
   CK(cb->pEnd.ensure((np + 1) * sizeof(u32)));
   CK(cb->pVal.ensure((np + 1) * sizeof(float)));
   CK(x->fsum.ensure((np + 1) * sizeof(double)));
@@ -881,9 +1082,11 @@ extern "C" int gr_bh_local_hist(gr_ctx* x, const uint32_t** d_keys, const uint64
   if (!x) return GR_ERR_ARG;
   if (!x->finalized) { int r = gr_pvalues_finalize(x); if (r) return r; }
   CK(cudaSetDevice(x->device));
+  { int r = materialize(x); if (r) return r; }
+  { int r = redo_pvals(x); if (r) return r; }
   Replicate* f = x->fin;
   const u64 np = f->n;
-  CK(x->slot.ensure((np + 1) * sizeof(u32)));
+  CK(x->slot.ensure((f->n_upper + 1) * sizeof(u32)));
   u32 cap = 1u << 20;
   stage_begin(x, "bh_hist", np * 12);
   int r = table_build(x, np, cap, [&](const PairTable& t) {
@@ -945,7 +1148,7 @@ extern "C" int gr_bh_set_global(gr_ctx* x, const uint32_t* d_keys, const uint64_
   PairTable t = table_view(x, cap);
   launch_table_q(x->stream, t, w.dk, w.dq, w.dcount);
   CK(x->qVal.ensure((f->n + 1) * sizeof(float)));
-  launch_gather_f32(x->stream, t.qval, x->slot.as<u32>(), f->n, x->qVal.as<float>());
+  launch_gather_f32(x->stream, t.qval, x->slot.as<u32>(), f->n, f->cnt.as<u64>(), x->qVal.as<float>());
   CKL();
   stage_end(x);
   CK(cudaMemcpyAsync(x->h_small, x->bdcount.p, 8, cudaMemcpyDeviceToHost, x->stream));
@@ -962,72 +1165,95 @@ extern "C" int gr_bh_set_global(gr_ctx* x, const uint32_t* d_keys, const uint64_
 }
 
 // ---- peaks ---------------------------------------------------------------------------
+// events -> heads -> walk -> compaction, all sized by upper bounds with the counts on the device
+static int peaks_enqueue(gr_ctx* x, Replicate* f, int qopt) {
+  const u64 nu = f->n_upper;
+  CK(x->evIdx.ensure((nu + 1) * sizeof(u32)));
+  CK(x->headIdx.ensure((nu + 1) * sizeof(u32)));
+  CK(x->evCount.ensure(8)); CK(x->headCount.ensure(8)); CK(x->peakCount.ensure(8)); CK(x->peakBp.ensure(8));
+  if (!x->head_cap) x->head_cap = nu / 16 > (1u << 20) ? nu / 16 : (1u << 20);
+  if (x->head_cap > nu + 1) x->head_cap = nu + 1;
+  const u64 hc = x->head_cap;
+  CK(x->cand.ensure(hc * sizeof(PeakRec)));
+  CK(x->candOk.ensure(hc));
+  CK(x->peakOut.ensure(hc * sizeof(PeakRec)));
+  const u64 nt = (nu + 2047) / 2048 + (hc + 255) / 256 + 2;     // status words of the largest tiling
+  CK(x->lb0.ensure(nt * sizeof(u64) > x->lb0.cap ? nt * sizeof(u64) : x->lb0.cap));
+  PeakWork w;
+  w.ev_idx = x->evIdx.as<u32>(); w.ev_count = x->evCount.as<u64>();
+  w.head_idx = x->headIdx.as<u32>(); w.head_count = x->headCount.as<u64>();
+  w.cand = x->cand.as<PeakRec>(); w.cand_ok = x->candOk.as<uint8_t>();
+  w.out = x->peakOut.as<PeakRec>(); w.out_count = x->peakCount.as<u64>(); w.peak_bp = x->peakBp.as<u64>();
+  w.sc.st = x->lb0.as<u64>(); w.sc.ticket = x->ticket.as<u32>();
+  const float* v = qopt ? x->qVal.as<float>() : f->pVal.as<float>();
+  stage_begin(x, "peak_events", nu * 4);
+  launch_peak_events(x->stream, v, nu, f->cnt.as<u64>(), x->par.min_pqval, w);
+  CKL();
+  stage_end(x);
+  stage_begin(x, "peak_scan", nu);
+  launch_peak_chain(x->stream, f->pEnd.as<u32>(), f->pVal.as<float>(), x->qVal.as<float>(),
+                    f->chrom_start.as<u64>(), x->nchrom, x->par.min_pqval, qopt, x->par.max_gap,
+                    x->par.min_auc, x->par.min_len, w, nu, hc, x->d_err);
+  CKL();
+  stage_end(x);
+  // the counts and the first PEAK_SPEC records come back together
+  CK(cudaMemcpyAsync((char*)x->h_small + 192, x->peakCount.p, 8, cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaMemcpyAsync((char*)x->h_small + 200, x->peakBp.p, 8, cudaMemcpyDeviceToHost, x->stream));
+  const u64 spec = hc < gr_ctx::PEAK_SPEC ? hc : gr_ctx::PEAK_SPEC;
+  CK(cudaMemcpyAsync(x->h_peaks, x->peakOut.p, spec * sizeof(gr_peak), cudaMemcpyDeviceToHost, x->stream));
+  x->lag = true;
+  return GR_OK;
+}
+
 extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_run_stats* st) {
   if (!x || x->reps.empty()) return GR_ERR_ARG;
   if (!x->finalized) { int r = gr_pvalues_finalize(x); if (r) return r; }
   CK(cudaSetDevice(x->device));
   Replicate* f = x->fin;
-  const u64 G = final_genome_len(x);
   const int qopt = x->par.qval_opt != 0;
   if (qopt && !x->have_q) {
     const uint32_t* k; const uint64_t* l; uint64_t hn;
     int r = gr_bh_local_hist(x, &k, &l, &hn);
     if (r) return r;
+    const u64 G = final_genome_len(x);
     if (!G) return GR_ERR_GENOME;
     r = gr_bh_set_global(x, k, l, hn, G);
     if (r) return r;
   }
-  const u64 np = f->n;
-  x->peaks_h.clear();
-  u64 peak_bp = 0;
-  if (np) {
-    CK(x->evIdx.ensure((np + 1) * sizeof(u32)));
-    CK(x->evCount.ensure(8)); CK(x->headCount.ensure(8)); CK(x->peakCount.ensure(8)); CK(x->peakBp.ensure(8));
-    const u64 nt = (np + 1023) / 1024;
-    CK(x->lb0.ensure(nt * sizeof(u64) > x->lb0.cap ? nt * sizeof(u64) : x->lb0.cap));
-    PeakWork w;
-    w.ev_idx = x->evIdx.as<u32>(); w.ev_count = x->evCount.as<u64>();
-    w.head_count = x->headCount.as<u64>(); w.out_count = x->peakCount.as<u64>(); w.peak_bp = x->peakBp.as<u64>();
-    w.sc.st = x->lb0.as<u64>(); w.sc.ticket = x->ticket.as<u32>();
-    const float* v = qopt ? x->qVal.as<float>() : f->pVal.as<float>();
-    stage_begin(x, "peak_events", np * 4);
-    launch_peak_events(x->stream, v, np, x->par.min_pqval, w);
-    CKL();
-    stage_end(x);
-    CK(cudaMemcpyAsync(x->h_small, x->evCount.p, 8, cudaMemcpyDeviceToHost, x->stream));
-    CK(cudaStreamSynchronize(x->stream));
-    const u64 nev = *(u64*)x->h_small;
-    if (nev) {
-      CK(x->headIdx.ensure(nev * sizeof(u32)));
-      CK(x->cand.ensure(nev * sizeof(PeakRec)));
-      CK(x->candOk.ensure(nev));
-      CK(x->peakOut.ensure(nev * sizeof(PeakRec)));
-      w.head_idx = x->headIdx.as<u32>(); w.cand = x->cand.as<PeakRec>(); w.cand_ok = x->candOk.as<uint8_t>();
-      w.out = x->peakOut.as<PeakRec>();
-      stage_begin(x, "peak_scan", nev * 16);
-      launch_peak_chain(x->stream, f->pEnd.as<u32>(), f->pVal.as<float>(), x->qVal.as<float>(),
-                        f->chrom_start.as<u64>(), x->nchrom, x->par.min_pqval, qopt, x->par.max_gap,
-                        x->par.min_auc, x->par.min_len, w, nev);
-      CKL();
-      stage_end(x);
-      CK(cudaMemcpyAsync(x->h_small, x->peakCount.p, 8, cudaMemcpyDeviceToHost, x->stream));
-      CK(cudaMemcpyAsync((char*)x->h_small + 8, x->peakBp.p, 8, cudaMemcpyDeviceToHost, x->stream));
-      CK(cudaStreamSynchronize(x->stream));
-      const u64 npk = *(u64*)x->h_small;
-      peak_bp = *(u64*)((char*)x->h_small + 8);
-      x->peaks_h.resize(npk);
-      static_assert(sizeof(PeakRec) == sizeof(gr_peak), "peak record layout");
-      if (npk) CK(cudaMemcpy(x->peaks_h.data(), x->peakOut.p, npk * sizeof(gr_peak), cudaMemcpyDeviceToHost));
+  static_assert(sizeof(PeakRec) == sizeof(gr_peak), "peak record layout");
+  u64 npk = 0, peak_bp = 0;
+  for (;;) {
+    { int r = peaks_enqueue(x, f, qopt); if (r) return r; }
+    { int r = materialize(x); if (r) return r; }               // the one round trip of a peak call
+    if (x->retry_flags & GR_DE_TABLE) {                        // -log10 p came from an overflowed table
+      int r = redo_pvals(x);
+      if (r) return r;
+      if (qopt) { x->have_q = false; return gr_call_peaks(x, peaks, n, st); }
+      continue;
     }
+    if (x->retry_flags & GR_DE_CAP) {                          // more candidate peaks than room: once more, with room
+      x->retry_flags &= ~GR_DE_CAP;
+      x->head_cap = x->head_cap * 8 < f->n_upper + 1 ? x->head_cap * 8 : f->n_upper + 1;
+      continue;
+    }
+    npk = *(u64*)((char*)x->h_small + 192);
+    peak_bp = *(u64*)((char*)x->h_small + 200);
+    break;
   }
+  x->peaks_h.resize(npk);
+  const u64 spec = npk < gr_ctx::PEAK_SPEC ? npk : gr_ctx::PEAK_SPEC;
+  if (spec) memcpy(x->peaks_h.data(), x->h_peaks, spec * sizeof(gr_peak));
+  if (npk > spec)
+    CK(cudaMemcpy(x->peaks_h.data() + spec, x->peakOut.as<gr_peak>() + spec, (npk - spec) * sizeof(gr_peak),
+                  cudaMemcpyDeviceToHost));
   if (peaks) *peaks = x->peaks_h.data();
   if (n) *n = x->peaks_h.size();
   if (st) {
     memset(st, 0, sizeof *st);
-    st->genome_len = G;
+    st->genome_len = final_genome_len(x);
     st->n_peaks = x->peaks_h.size();
     st->peak_bp = peak_bp;
-    st->n_intervals = np;
+    st->n_intervals = f->n;
     st->n_distinct_p = qopt ? x->n_distinct : 0;
     st->all_q_one = qopt ? x->all_q_one : 0;
     st->n_replicates = (int)x->reps.size();
@@ -1041,6 +1267,8 @@ extern "C" int gr_fetch_intervals(gr_ctx* x, int32_t which, int32_t replicate, i
                                   const float** ctrl, uint64_t* n) {
   if (!x || chrom < 0 || chrom >= x->nchrom) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
+  { int r = materialize(x); if (r) return r; }
+  { int r = redo_pvals(x); if (r) return r; }
   CK(cudaStreamSynchronize(x->stream));
   const u32* dE = nullptr; const float* dV = nullptr; const float* dX = nullptr; const float* dC = nullptr;
   u64 a = 0, b = 0;

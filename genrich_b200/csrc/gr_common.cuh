@@ -33,6 +33,8 @@ typedef unsigned int u32;
 #define GR_DE_PILE   8
 #define GR_DE_TAIL   16             // running sum not 0 at a chromosome start
 #define GR_DE_TABLE  32             // hash table over its load limit (host retries)
+#define GR_DE_CAP    64             // an optimistically sized buffer was too small (host retries)
+#define GR_DE_EXPT   128            // no analyzable fragments in the experimental sample (2292)
 
 // ---------------------------------------------------------------------------
 // memory helpers

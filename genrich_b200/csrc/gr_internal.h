@@ -60,11 +60,16 @@ void launch_rle_moment(cudaStream_t s, const DevRle& r, u64 n_upper, int nchrom,
 
 // ---- K3: control sweep max(factor*val, lambda) + RLE re-merge (savePileupCtrl) --
 struct CompactScratch { u64* st; u32* ticket; };
-void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u64 n_raw,
-                       float factor, float lambda, const CompactScratch& sc,
+// n_upper: capacity of the raw array (the count is read from raw.total); factor_lambda: device float[2]
+void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u64 n_upper,
+                       const float* factor_lambda, const CompactScratch& sc,
                        DevRle out, u32* bitmap /* raw breaks in, surviving breaks out */);
 // no-control variant: one interval (len, lambda) per active chromosome (saveLambda 1838)
-void launch_ctrl_const(cudaStream_t s, const DevLayout& L, float lambda, DevRle out, u32* bitmap);
+void launch_ctrl_const(cudaStream_t s, const DevLayout& L, const float* lambda_dev, u64 n, DevRle out, u32* bitmap);
+// per-chromosome fixed-point sums -> doubles; lambda and the scale factor from them, on the device
+void launch_sums_double(cudaStream_t s, const u64* acc_int, const u64* acc_frac, int nchrom, double* out);
+void launch_lambda_factor(cudaStream_t s, const double* sums, int nchrom, bool has_ctrl, u64 genome_len,
+                          float* factor_lambda, int* err);
 
 // ---- K4: breakpoint union of expt and ctrl (savePval 1768-1791) -----------------
 struct RankScratch { u64* st[3]; u32* ticket; };
@@ -87,10 +92,11 @@ struct PairTable {
   u32 cap;        // power of two
   u32* count;     // [1] occupied slots
 };
-void launch_pair_insert(cudaStream_t s, const u32* pEnd, const float* pExpt, const float* pCtrl,
-                        u64 n, const PairTable& t, u32* slot, int accumulate_len, int* err);
+// n_upper sizes the launch, the count itself is read from *n_dev
+void launch_pair_insert(cudaStream_t s, const float* pExpt, const float* pCtrl, u64 n_upper, const u64* n_dev,
+                        const PairTable& t, u32* slot, int* err);
 void launch_pair_eval(cudaStream_t s, const PairTable& t);
-void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n, float* out);
+void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n_upper, const u64* n_dev, float* out);
 
 // ---- K6: Fisher combine over replicates (combinePval 612, multPval 567) ----------
 struct RepView {            // one replicate's p arrays
@@ -141,11 +147,14 @@ struct PeakWork {
   PeakRec* out; u64* out_count; u64* peak_bp;
   CompactScratch sc;
 };
-void launch_peak_events(cudaStream_t s, const float* v, u64 n, float thr, const PeakWork& w);
-// heads -> per-candidate walk -> compaction of valid peaks; nev = *w.ev_count (read back by the host)
+// Counts stay on the device: n_upper / nev_upper size the status words and buffers, the kernels
+// are persistent and read the actual counts (*n_dev, *w.ev_count, *w.head_count) themselves.
+void launch_peak_events(cudaStream_t s, const float* v, u64 n_upper, const u64* n_dev, float thr, const PeakWork& w);
+// heads -> per-candidate walk -> compaction of valid peaks.  head_idx holds nev_upper entries;
+// cand / cand_ok / out hold hcap (more candidates than that: GR_DE_CAP in *err, the host retries)
 void launch_peak_chain(cudaStream_t s, const u32* pEnd, const float* pval, const float* qval,
                        const u64* chrom_start, int nchrom, float thr, int qopt, int max_gap,
-                       float min_auc, int min_len, const PeakWork& w, u64 nev);
+                       float min_auc, int min_len, const PeakWork& w, u64 nev_upper, u64 hcap, int* err);
 
 // ---- small utilities -------------------------------------------------------------
 void launch_fill_chrom_start(cudaStream_t s, const DevLayout& L, u64* chrom_start, const u64* total);

@@ -19,8 +19,13 @@ __device__ __forceinline__ float clamp_net(float factor, float v, float lambda) 
 }
 
 __global__ void __launch_bounds__(256)
-k_ctrl_clamp(DevLayout L, DevRle raw, u64 n, float factor, float lambda, Lookback<1> lb,
+k_ctrl_clamp(DevLayout L, DevRle raw, const float* __restrict__ fl, Lookback<1> lb,
              DevRle out, u32* __restrict__ bitmap) {
+  // launched for the capacity of the raw array; the interval count and the two scalars
+  // (scale factor, lambda) are read from device memory: no host round trip in between
+  const u64 n = *raw.total;
+  if ((u64)blockIdx.x * CL_TILE >= n) return;            // tickets stay dense
+  const float factor = fl[0], lambda = fl[1];
   const u32 tile = take_ticket(lb.ticket);
   const u64 t0 = (u64)tile * CL_TILE;
   const u64 tl = min(t0 + CL_TILE, n) - 1;
@@ -83,21 +88,22 @@ __global__ void k_fill_forward(int nchrom, const u64* raw_start, u64* out_start)
     if (raw_start[c + 1] == raw_start[c]) out_start[c + 1] = out_start[c];
 }
 
-void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u64 n_raw,
-                       float factor, float lambda, const CompactScratch& sc,
+void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u64 n_upper,
+                       const float* factor_lambda, const CompactScratch& sc,
                        DevRle out, u32* bitmap) {
-  if (!n_raw) return;
-  const u64 ntiles = (n_raw + CL_TILE - 1) / CL_TILE;
+  cudaMemsetAsync(out.total, 0, sizeof(u64), s);
+  if (!n_upper) return;
+  const u64 ntiles = (n_upper + CL_TILE - 1) / CL_TILE;
   cudaMemsetAsync(sc.st, 0, ntiles * sizeof(u64), s);
   cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
   Lookback<1> lb;
   lb.st[0] = sc.st; lb.ticket = sc.ticket;
-  k_ctrl_clamp<<<(unsigned)ntiles, 256, 0, s>>>(L, raw, n_raw, factor, lambda, lb, out, bitmap); GR_NOTE_LAUNCH();
+  k_ctrl_clamp<<<(unsigned)ntiles, 256, 0, s>>>(L, raw, factor_lambda, lb, out, bitmap); GR_NOTE_LAUNCH();
   k_fill_forward<<<1, 32, 0, s>>>(L.nchrom, raw.chrom_start, out.chrom_start); GR_NOTE_LAUNCH();
 }
 
 // no control: one interval (len, lambda) per active chromosome (saveLambda 1838-1843);
-// the RLE arrays themselves are tiny and written by the host, this sets the bits.
+// the ends are written by the host, the values (lambda lives on the device) and the bits here.
 __global__ void k_ctrl_const_bits(DevLayout L, u32* bitmap) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= L.nchrom) return;
@@ -107,10 +113,42 @@ __global__ void k_ctrl_const_bits(DevLayout L, u32* bitmap) {
   const u64 g = off + L.len[c];
   atomicOr(bitmap + (g >> 5), 1u << (g & 31));
 }
-void launch_ctrl_const(cudaStream_t s, const DevLayout& L, float lambda, DevRle out, u32* bitmap) {
-  (void)lambda; (void)out;
+__global__ void k_fill_from(float* out, const float* __restrict__ value, u64 n) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = *value;
+}
+void launch_ctrl_const(cudaStream_t s, const DevLayout& L, const float* lambda_dev, u64 n, DevRle out, u32* bitmap) {
   cudaMemsetAsync(bitmap, 0, (L.T / 32) * sizeof(u32), s);
   k_ctrl_const_bits<<<(L.nchrom + 127) / 128, 128, 0, s>>>(L, bitmap); GR_NOTE_LAUNCH();
+  if (n) { k_fill_from<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(out.val, lambda_dev, n); GR_NOTE_LAUNCH(); }
+}
+
+// fixed-point per-chromosome sums (integer part, 2^-40 fraction) -> doubles
+__global__ void k_sums_double(const u64* __restrict__ acc_int, const u64* __restrict__ acc_frac, int nchrom,
+                              double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < nchrom) out[c] = (double)acc_int[c] + (double)acc_frac[c] * (1.0 / 1099511627776.0);
+}
+void launch_sums_double(cudaStream_t s, const u64* acc_int, const u64* acc_frac, int nchrom, double* out) {
+  k_sums_double<<<(nchrom + 127) / 128, 128, 0, s>>>(acc_int, acc_frac, nchrom, out); GR_NOTE_LAUNCH();
+}
+
+// calcLambda 1817-1832 / calcFactor 2043-2045 on the device: the per-chromosome doubles are
+// added in chromosome order by one thread, like the reference's running sums
+__global__ void k_lambda_factor(const double* __restrict__ sums, int nchrom, int has_ctrl, u64 genome_len,
+                                float* __restrict__ factor_lambda, int* __restrict__ err) {
+  if (threadIdx.x || blockIdx.x) return;
+  double f = 0.0, g = 0.0;
+  for (int c = 0; c < nchrom; c++) { f += sums[c]; if (has_ctrl) g += sums[nchrom + c]; }
+  if (f == 0.0) atomicOr(err, GR_DE_EXPT);                       // Genrich.c:2292
+  float factor = 1.0f;
+  if (has_ctrl && g != 0.0) factor = (float)(f / g);
+  factor_lambda[0] = factor;
+  factor_lambda[1] = (float)(f / (double)genome_len);
+}
+void launch_lambda_factor(cudaStream_t s, const double* sums, int nchrom, bool has_ctrl, u64 genome_len,
+                          float* factor_lambda, int* err) {
+  k_lambda_factor<<<1, 32, 0, s>>>(sums, nchrom, has_ctrl ? 1 : 0, genome_len, factor_lambda, err); GR_NOTE_LAUNCH();
 }
 
 // ============================================================================
@@ -272,30 +310,37 @@ __device__ __forceinline__ u32 table_upsert(const PairTable& t, u64 key, bool& f
 }
 
 __global__ void __launch_bounds__(256)
-k_pair_insert(const float* __restrict__ pExpt, const float* __restrict__ pCtrl, u64 n,
+k_pair_insert(const float* __restrict__ pExpt, const float* __restrict__ pCtrl, const u64* __restrict__ n_dev,
               PairTable t, u32* __restrict__ slot, int* __restrict__ err) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  bool fresh = false;
+  const u64 n = *n_dev;                                  // interval count, device side
+  const u64 stride = (u64)gridDim.x * blockDim.x;
   bool bad = false;
-  if (i < n) {
-    const u64 key = ((u64)__float_as_uint(pExpt[i]) << 32) | __float_as_uint(pCtrl[i]);
-    const u32 h = table_upsert(t, key, fresh);
-    bad = h == ~0u;
-    slot[i] = bad ? 0u : h;
-  }
-  const u32 nf = __popc(__ballot_sync(GR_FULL, fresh));
-  if ((threadIdx.x & 31) == 0 && nf) {
-    const u32 tot = atomicAdd(t.count, nf) + nf;
-    if (tot > (t.cap >> 1)) bad = true;
+  for (u64 i0 = (u64)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {    // warp-uniform trip count
+    const u64 i = i0 + threadIdx.x;
+    bool fresh = false;
+    if (i < n) {
+      const u64 key = ((u64)__float_as_uint(pExpt[i]) << 32) | __float_as_uint(pCtrl[i]);
+      const u32 h = table_upsert(t, key, fresh);
+      if (h == ~0u) bad = true;
+      slot[i] = h == ~0u ? 0u : h;
+    }
+    const u32 nf = __popc(__ballot_sync(GR_FULL, fresh));
+    if ((threadIdx.x & 31) == 0 && nf) {
+      const u32 tot = atomicAdd(t.count, nf) + nf;
+      if (tot > (t.cap >> 1)) bad = true;
+    }
   }
   if (bad) atomicOr(err, GR_DE_TABLE);
 }
 
-void launch_pair_insert(cudaStream_t s, const u32* pEnd, const float* pExpt, const float* pCtrl,
-                        u64 n, const PairTable& t, u32* slot, int accumulate_len, int* err) {
-  (void)pEnd; (void)accumulate_len;
-  if (!n) return;
-  k_pair_insert<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pExpt, pCtrl, n, t, slot, err); GR_NOTE_LAUNCH();
+static unsigned capped_grid(u64 n_upper) {
+  const u64 b = (n_upper + 255) / 256;
+  return (unsigned)(b < 148 * 32 ? (b ? b : 1) : 148 * 32);
+}
+void launch_pair_insert(cudaStream_t s, const float* pExpt, const float* pCtrl, u64 n_upper, const u64* n_dev,
+                        const PairTable& t, u32* slot, int* err) {
+  if (!n_upper) return;
+  k_pair_insert<<<capped_grid(n_upper), 256, 0, s>>>(pExpt, pCtrl, n_dev, t, slot, err); GR_NOTE_LAUNCH();
 }
 
 __global__ void __launch_bounds__(128)
@@ -311,16 +356,17 @@ void launch_pair_eval(cudaStream_t s, const PairTable& t) {
 }
 
 __global__ void __launch_bounds__(256)
-k_gather_f32(const float* __restrict__ table, const u32* __restrict__ slot, u64 n,
+k_gather_f32(const float* __restrict__ table, const u32* __restrict__ slot, const u64* __restrict__ n_dev,
              float* __restrict__ out) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
+  const u64 n = *n_dev;
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const u32 s = slot[i];
     out[i] = s == ~0u ? -1.0f : table[s];      // ~0: SKIP interval, never entered in the table
   }
 }
-void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n, float* out) {
-  if (n) { k_gather_f32<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(table, slot, n, out); GR_NOTE_LAUNCH(); }
+void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n_upper, const u64* n_dev, float* out) {
+  if (n_upper) { k_gather_f32<<<capped_grid(n_upper), 256, 0, s>>>(table, slot, n_dev, out); GR_NOTE_LAUNCH(); }
 }
 
 // histogram insert keyed by the bits of -log10 p; lengths are added with one

@@ -20,94 +20,106 @@
 // coalesced rounds, ranks them with one ballot per round (order preserved) and
 // keeps the 32 ballots in one register per lane for the write pass.
 #define PE_TILE 8192
+#define PK_GRID (148 * 8)        // persistent CTAs: tiles are taken by ticket until the (device-side) count is exhausted
 __global__ void __launch_bounds__(256)
-k_peak_events(const float* __restrict__ v, u64 n, float thr, Lookback<1> lb,
-              u32* __restrict__ ev_idx, u64* __restrict__ ev_count, u32 ntiles) {
-  const u32 tile = take_ticket(lb.ticket);
+k_peak_events(const float* __restrict__ v, const u64* __restrict__ n_dev, float thr, Lookback<1> lb,
+              u32* __restrict__ ev_idx, u64* __restrict__ ev_count) {
+  const u64 n = *n_dev;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const u64 wbase = (u64)tile * PE_TILE + (u64)w * 1024;
-  u32 mine = 0, cnt = 0;
+  for (;;) {
+    const u32 tile = take_ticket(lb.ticket);
+    if ((u64)tile * PE_TILE >= n) break;
+    const u64 wbase = (u64)tile * PE_TILE + (u64)w * 1024;
+    u32 mine = 0, cnt = 0;
 #pragma unroll 8
-  for (int k = 0; k < 32; k++) {
-    const u64 i = wbase + k * 32 + lane;
-    bool f = false;
-    if (i < n) {
-      const float x = v[i];
-      f = x > thr || x == PK_SKIP;
+    for (int k = 0; k < 32; k++) {
+      const u64 i = wbase + k * 32 + lane;
+      bool f = false;
+      if (i < n) {
+        const float x = v[i];
+        f = x > thr || x == PK_SKIP;
+      }
+      const u32 bal = __ballot_sync(GR_FULL, f);
+      if (lane == k) mine = bal;
+      cnt += __popc(bal);                        // warp-uniform
     }
-    const u32 bal = __ballot_sync(GR_FULL, f);
-    if (lane == k) mine = bal;
-    cnt += __popc(bal);                        // warp-uniform
+    // rank of the warp's first event: block scan over the 8 warp counts + look-back
+    u32 tot;
+    u64 r = tile_exclusive_rank(lb, tile, lane == 31 ? cnt : 0u, tot);   // lane 31 carries the warp's count
+    r = __shfl_sync(GR_FULL, r, 31);             // exclusive rank of lane 31 == rank of the warp's first event
+    for (int k = 0; k < 32; k++) {
+      const u32 bal = __shfl_sync(GR_FULL, mine, k);
+      if (bal & (1u << lane)) ev_idx[r + __popc(bal & ((1u << lane) - 1))] = (u32)(wbase + k * 32 + lane);
+      r += __popc(bal);
+    }
+    if ((u64)(tile + 1) * PE_TILE >= n && threadIdx.x == 255) *ev_count = r;
+    __syncthreads();                             // shared scratch of the ticket / rank helpers is reused
   }
-  // rank of the warp's first event: block scan over the 8 warp counts + look-back
-  u32 tot;
-  u64 r = tile_exclusive_rank(lb, tile, lane == 31 ? cnt : 0u, tot);   // lane 31 carries the warp's count
-  r = __shfl_sync(GR_FULL, r, 31);             // exclusive rank of lane 31 == rank of the warp's first event
-  for (int k = 0; k < 32; k++) {
-    const u32 bal = __shfl_sync(GR_FULL, mine, k);
-    if (bal & (1u << lane)) ev_idx[r + __popc(bal & ((1u << lane) - 1))] = (u32)(wbase + k * 32 + lane);
-    r += __popc(bal);
-  }
-  if (tile == ntiles - 1 && threadIdx.x == 255) *ev_count = r;
 }
 
-void launch_peak_events(cudaStream_t s, const float* v, u64 n, float thr, const PeakWork& w) {
+// n_upper bounds the interval count (sizes the status words); the count is read from *n_dev
+void launch_peak_events(cudaStream_t s, const float* v, u64 n_upper, const u64* n_dev, float thr, const PeakWork& w) {
   cudaMemsetAsync(w.ev_count, 0, sizeof(u64), s);
-  if (!n) return;
-  const u32 ntiles = (u32)((n + PE_TILE - 1) / PE_TILE);
+  if (!n_upper) return;
+  const u64 ntiles = (n_upper + PE_TILE - 1) / PE_TILE;
   cudaMemsetAsync(w.sc.st, 0, (size_t)ntiles * sizeof(u64), s);
   cudaMemsetAsync(w.sc.ticket, 0, sizeof(u32), s);
   Lookback<1> lb;
   lb.st[0] = w.sc.st; lb.ticket = w.sc.ticket;
-  k_peak_events<<<ntiles, 256, 0, s>>>(v, n, thr, lb, w.ev_idx, w.ev_count, ntiles); GR_NOTE_LAUNCH();
+  k_peak_events<<<(unsigned)(ntiles < PK_GRID ? ntiles : PK_GRID), 256, 0, s>>>(v, n_dev, thr, lb, w.ev_idx, w.ev_count);
+  GR_NOTE_LAUNCH();
 }
 
 // ---- heads: events that open a candidate ------------------------------------------
 // 8 consecutive events per thread (2048 per tile): one ticket and one look-back per 2048.
 #define PK_HEAD_PER 8
+#define PK_HEAD_TILE (256 * PK_HEAD_PER)
 __global__ void __launch_bounds__(256)
 k_peak_heads(const u32* __restrict__ pEnd, const float* __restrict__ v,
              const u64* __restrict__ chrom_start, int nchrom, int max_gap,
              const u32* __restrict__ ev_idx, const u64* __restrict__ ev_count, Lookback<1> lb,
              u32* __restrict__ head_idx, u64* __restrict__ head_count) {
   const u64 nev = *ev_count;
-  if ((u64)blockIdx.x * (256 * PK_HEAD_PER) >= nev) return;      // launched for the capacity; tickets stay dense
-  const u32 tile = take_ticket(lb.ticket);
-  const u64 t0 = ((u64)tile * 256 + threadIdx.x) * PK_HEAD_PER;
-  u32 mask = 0;
-  u32 prev = 0;
-  bool have_prev = false, prev_skip = false;
-  if (t0 > 0 && t0 < nev) { prev = ev_idx[t0 - 1]; have_prev = true; prev_skip = v[prev] == PK_SKIP; }
+  for (;;) {
+    const u32 tile = take_ticket(lb.ticket);
+    if ((u64)tile * PK_HEAD_TILE >= nev) break;
+    const u64 t0 = ((u64)tile * 256 + threadIdx.x) * PK_HEAD_PER;
+    u32 mask = 0;
+    u32 prev = 0;
+    bool have_prev = false, prev_skip = false;
+    if (t0 > 0 && t0 < nev) { prev = ev_idx[t0 - 1]; have_prev = true; prev_skip = v[prev] == PK_SKIP; }
 #pragma unroll
-  for (int i = 0; i < PK_HEAD_PER; i++) {
-    const u64 t = t0 + i;
-    if (t >= nev) break;
-    const u32 idx = ev_idx[t];
-    const bool skip = v[idx] == PK_SKIP;
-    u32 head = 0;
-    if (!skip) {
-      head = 1;
-      if (have_prev && !prev_skip) {
-        const int c = chrom_of_index(chrom_start, nchrom, idx);
-        if ((u64)prev >= chrom_start[c]) {                 // same chromosome
-          if (prev + 1 == idx) head = 0;                   // adjacent: no interval in between
-          else {
-            const i64 gap = (i64)pEnd[idx - 1] - (i64)pEnd[prev];   // start[idx] - peakEnd
-            if (!(gap > (i64)max_gap)) head = 0;           // 1032
+    for (int i = 0; i < PK_HEAD_PER; i++) {
+      const u64 t = t0 + i;
+      if (t >= nev) break;
+      const u32 idx = ev_idx[t];
+      const bool skip = v[idx] == PK_SKIP;
+      u32 head = 0;
+      if (!skip) {
+        head = 1;
+        if (have_prev && !prev_skip) {
+          const int c = chrom_of_index(chrom_start, nchrom, idx);
+          if ((u64)prev >= chrom_start[c]) {                 // same chromosome
+            if (prev + 1 == idx) head = 0;                   // adjacent: no interval in between
+            else {
+              const i64 gap = (i64)pEnd[idx - 1] - (i64)pEnd[prev];   // start[idx] - peakEnd
+              if (!(gap > (i64)max_gap)) head = 0;           // 1032
+            }
           }
         }
       }
+      mask |= head << i;
+      prev = idx; have_prev = true; prev_skip = skip;
     }
-    mask |= head << i;
-    prev = idx; have_prev = true; prev_skip = skip;
-  }
-  u32 tot;
-  u64 r = tile_exclusive_rank(lb, tile, (u32)__popc(mask), tot);
+    u32 tot;
+    u64 r = tile_exclusive_rank(lb, tile, (u32)__popc(mask), tot);
 #pragma unroll
-  for (int i = 0; i < PK_HEAD_PER; i++)
-    if (mask & (1u << i)) head_idx[r++] = (u32)(t0 + i);
-  // the thread holding the last event reports
-  if (t0 < nev && t0 + PK_HEAD_PER >= nev) *head_count = r;
+    for (int i = 0; i < PK_HEAD_PER; i++)
+      if (mask & (1u << i)) head_idx[r++] = (u32)(t0 + i);
+    // the thread holding the last event reports
+    if (t0 < nev && t0 + PK_HEAD_PER >= nev) *head_count = r;
+    __syncthreads();
+  }
 }
 
 // ---- walk: one thread per candidate ------------------------------------------------
@@ -117,11 +129,14 @@ k_peak_walk(const u32* __restrict__ pEnd, const float* __restrict__ pval,
             float thr, int qopt, float min_auc, int min_len,
             const u32* __restrict__ ev_idx, const u64* __restrict__ ev_count,
             const u32* __restrict__ head_idx, const u64* __restrict__ head_count,
-            PeakRec* __restrict__ cand, uint8_t* __restrict__ cand_ok) {
-  const u64 h = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+            PeakRec* __restrict__ cand, uint8_t* __restrict__ cand_ok, u64 hcap, int* __restrict__ err) {
   const u64 nh = *head_count;
-  if (h >= nh) return;
+  if (nh > hcap) {                                       // candidate buffers were sized optimistically
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, GR_DE_CAP);
+    return;
+  }
   const u64 nev = *ev_count;
+  for (u64 h = (u64)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (u64)gridDim.x * blockDim.x) {
   const u64 t0 = head_idx[h];
   const u64 t1 = h + 1 < nh ? head_idx[h + 1] : nev;
   const float* __restrict__ v = qopt ? qval : pval;
@@ -158,53 +173,60 @@ k_peak_walk(const u32* __restrict__ pEnd, const float* __restrict__ pval,
   r.auc = auc; r.pval = sP; r.qval = sQ; r.reserved = 0.0f;
   cand[h] = r;
   cand_ok[h] = (pStart != -1 && auc >= min_auc && pEndv - pStart >= (i64)min_len) ? 1 : 0;   // 920
+  }
 }
 
 __global__ void __launch_bounds__(256)
 k_peak_compact(const PeakRec* __restrict__ cand, const uint8_t* __restrict__ ok,
                const u64* __restrict__ head_count, Lookback<1> lb, PeakRec* __restrict__ out,
-               u64* __restrict__ out_count, u64* __restrict__ peak_bp) {
+               u64* __restrict__ out_count, u64* __restrict__ peak_bp, u64 hcap) {
   const u64 nh = *head_count;
-  if ((u64)blockIdx.x * 256 >= nh) return;              // launched for the capacity; tickets stay dense
-  const u32 tile = take_ticket(lb.ticket);
-  const u64 h = (u64)tile * 256 + threadIdx.x;
-  const u32 f = h < nh && ok[h];
-  u32 tot;
-  const u64 r = tile_exclusive_rank(lb, tile, f, tot);
-  u64 bp = 0;
-  if (f) {
-    const PeakRec p = cand[h];
-    out[r] = p;
-    bp = (u64)(p.end - p.start);                               // 924
+  if (nh > hcap) return;                                 // flagged by the walk
+  for (;;) {
+    const u32 tile = take_ticket(lb.ticket);
+    if ((u64)tile * 256 >= nh) break;
+    const u64 h = (u64)tile * 256 + threadIdx.x;
+    const u32 f = h < nh && ok[h];
+    u32 tot;
+    const u64 r = tile_exclusive_rank(lb, tile, f, tot);
+    u64 bp = 0;
+    if (f) {
+      const PeakRec p = cand[h];
+      out[r] = p;
+      bp = (u64)(p.end - p.start);                               // 924
+    }
+    bp = warp_sum_u64(bp);
+    if ((threadIdx.x & 31) == 0 && bp) atomicAdd(peak_bp, bp);
+    if (h + 1 == nh) *out_count = r + f;
+    __syncthreads();
   }
-  bp = warp_sum_u64(bp);
-  if ((threadIdx.x & 31) == 0 && bp) atomicAdd(peak_bp, bp);
-  if (h + 1 == nh) *out_count = r + f;
 }
 
-// The three follow-up kernels are sized by the event / head counts, which the
-// host reads back once (two u64) after the events kernel.
+// The three follow-up kernels take their sizes (event / head counts) from device memory:
+// the host does not wait between the events kernel and the peak records.
 void launch_peak_chain(cudaStream_t s, const u32* pEnd, const float* pval, const float* qval,
                        const u64* chrom_start, int nchrom, float thr, int qopt, int max_gap,
-                       float min_auc, int min_len, const PeakWork& w, u64 nev) {
+                       float min_auc, int min_len, const PeakWork& w, u64 nev_upper, u64 hcap, int* err) {
   cudaMemsetAsync(w.head_count, 0, sizeof(u64), s);
   cudaMemsetAsync(w.out_count, 0, sizeof(u64), s);
   cudaMemsetAsync(w.peak_bp, 0, sizeof(u64), s);
-  if (!nev) return;
+  if (!nev_upper) return;
   const float* v = qopt ? qval : pval;
-  const u32 nt = (u32)((nev + 255) / 256);
-  const u32 nth = (u32)((nev + 256 * PK_HEAD_PER - 1) / (256 * PK_HEAD_PER));
+  const u64 nth = (nev_upper + PK_HEAD_TILE - 1) / PK_HEAD_TILE;
   Lookback<1> lb;
   lb.st[0] = w.sc.st; lb.ticket = w.sc.ticket;
-  cudaMemsetAsync(w.sc.st, 0, (size_t)nt * sizeof(u64), s);
+  cudaMemsetAsync(w.sc.st, 0, (size_t)nth * sizeof(u64), s);
   cudaMemsetAsync(w.sc.ticket, 0, sizeof(u32), s);
-  k_peak_heads<<<nth, 256, 0, s>>>(pEnd, v, chrom_start, nchrom, max_gap, w.ev_idx, w.ev_count, lb,
-                                  w.head_idx, w.head_count); GR_NOTE_LAUNCH();
-  // heads <= events: size the walk and the compaction by nev
-  k_peak_walk<<<(unsigned)((nev + 127) / 128), 128, 0, s>>>(pEnd, pval, qval, chrom_start, nchrom, thr,
-                                                            qopt, min_auc, min_len, w.ev_idx, w.ev_count,
-                                                            w.head_idx, w.head_count, w.cand, w.cand_ok); GR_NOTE_LAUNCH();
-  cudaMemsetAsync(w.sc.st, 0, (size_t)nt * sizeof(u64), s);
+  k_peak_heads<<<(unsigned)(nth < PK_GRID ? nth : PK_GRID), 256, 0, s>>>(pEnd, v, chrom_start, nchrom, max_gap, w.ev_idx,
+                                                                      w.ev_count, lb, w.head_idx, w.head_count);
+  GR_NOTE_LAUNCH();
+  k_peak_walk<<<PK_GRID, 128, 0, s>>>(pEnd, pval, qval, chrom_start, nchrom, thr, qopt, min_auc, min_len, w.ev_idx,
+                                      w.ev_count, w.head_idx, w.head_count, w.cand, w.cand_ok, hcap, err);
+  GR_NOTE_LAUNCH();
+  const u64 ntc = (hcap + 255) / 256;
+  cudaMemsetAsync(w.sc.st, 0, (size_t)ntc * sizeof(u64), s);
   cudaMemsetAsync(w.sc.ticket, 0, sizeof(u32), s);
-  k_peak_compact<<<nt, 256, 0, s>>>(w.cand, w.cand_ok, w.head_count, lb, w.out, w.out_count, w.peak_bp); GR_NOTE_LAUNCH();
+  k_peak_compact<<<(unsigned)(ntc < PK_GRID ? ntc : PK_GRID), 256, 0, s>>>(w.cand, w.cand_ok, w.head_count, lb, w.out,
+                                                                        w.out_count, w.peak_bp, hcap);
+  GR_NOTE_LAUNCH();
 }

@@ -69,6 +69,8 @@ class ShardedEngine:
         self.params = params
         self.saved_any = np.zeros(self.nchrom, dtype=bool)
         self.sample_stats = []
+        self._ext_stream = None
+        self._dsums = None
         self.debug = bool(os.environ.get("GR_DIST_DEBUG"))
         self.t_acc = {}
 
@@ -100,10 +102,39 @@ class ShardedEngine:
         self._tick("reduce_sums", t0)
         return tot
 
-    def replicate(self, push_expt, push_ctrl=None, save=None):
-        """push_*: callables that feed this rank's records into self.ctx."""
+    def replicate(self, push_expt, push_ctrl=None, save=None, want_stats=True):
+        """push_*: callables that feed this rank's records into self.ctx.
+
+        CUDA library with want_stats=False: nothing waits for the device -- both pileups are
+        enqueued, the per-chromosome sums are all-reduced where they are (NCCL on the library's
+        own stream) and lambda / the scale factor are computed on the device."""
         sv = np.ones(self.nchrom, np.uint8) if save is None else np.asarray(save, np.uint8)
         self.saved_any |= (sv != 0) & (self.skip == 0)
+        glen = int(self.chrom_len[(sv != 0) & (self.skip == 0)].astype(np.int64).sum())   # calcLambda 1819-1827
+        if self.ctx.api.has_device and self.device.type == "cuda" and not want_stats:
+            t0 = time.perf_counter()
+            self.ctx.sample_begin(False, sv)
+            push_expt(self.ctx)
+            self.ctx.sample_pileup_async()
+            if push_ctrl is not None:
+                self.ctx.sample_begin(True)
+                push_ctrl(self.ctx)
+                self.ctx.sample_pileup_async()
+            self._tick("push_pileup", t0)
+            t0 = time.perf_counter()
+            if self.world > 1:
+                if self._ext_stream is None:
+                    self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=self.device)
+                    ep, _ = self.ctx.sums_device_ptrs()
+                    self._dsums = _tensor_from_ptr(ep, 2 * self.nchrom, np.float64, self.device)
+                with torch.cuda.stream(self._ext_stream):
+                    td.all_reduce(self._dsums, op=td.ReduceOp.SUM)      # every chromosome has one owner: exact
+            self._tick("reduce_sums", t0)
+            t0 = time.perf_counter()
+            self.ctx.replicate_finish_device(push_ctrl is not None, glen)
+            self._tick("replicate_finish", t0)
+            self.sample_stats.append(None)
+            return None
         t0 = time.perf_counter()
         self.ctx.sample_begin(False, sv)
         push_expt(self.ctx)
@@ -118,7 +149,6 @@ class ShardedEngine:
             s1 = self.ctx.sample_pileup()
             self._tick("ctrl_push_pileup", t0)
             ctrl = self._reduce_sums(s1)
-        glen = int(self.chrom_len[(sv != 0) & (self.skip == 0)].astype(np.int64).sum())   # calcLambda 1819-1827
         t0 = time.perf_counter()
         st = self.ctx.replicate_finish(frag, ctrl, push_ctrl is not None, glen)
         self._tick("replicate_finish", t0)

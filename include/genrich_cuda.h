@@ -165,6 +165,10 @@ int gr_prefetch_packed(gr_ctx* ctx, const uint64_t* recs, uint64_t n);
  * double sum of (float)(end-start)*val (0 elsewhere); the caller adds them in
  * chromosome order across contexts to get fragLen / ctrlFrag. */
 int gr_sample_pileup(gr_ctx* ctx, double* chrom_sums);
+/* Nothing on this path makes the host wait for the device unless it asks for a result.
+ * chrom_sums == NULL above only enqueues the work; the sums of the experimental and the
+ * control sample (NULL: not wanted) are then fetched together, one device round trip: */
+int gr_sample_sums(gr_ctx* ctx, double* expt_sums, double* ctrl_sums);
 
 /* Close the replicate: lambda, scale factor, max(ctrl*factor, lambda) sweep
  * (savePileupCtrl 2052 / savePileupNoCtrl 1883), breakpoint merge and
@@ -173,7 +177,17 @@ int gr_sample_pileup(gr_ctx* ctx, double* chrom_sums);
  * context) -- multi-context callers pass the global value. */
 int gr_replicate_finish(gr_ctx* ctx, double frag_len, double ctrl_frag,
                         int32_t has_ctrl, uint64_t genome_len,
-                        gr_sample_stats* stats);
+                        gr_sample_stats* stats /* NULL: do not wait for the counts */);
+
+/* The same with the sums left where they are -- on the device: lambda and the scale factor are
+ * computed there (calcLambda 1817 / calcFactor 2043-2045, per-chromosome doubles added in
+ * chromosome order) and the host never waits.  gr_sums_device exposes the two double[nchrom]
+ * arrays so that a multi-GPU launcher can all-reduce them in place, in gr_stream's order
+ * (every chromosome has one owner: the sum is exact).  Statistics afterwards, on request. */
+int gr_replicate_finish_device(gr_ctx* ctx, int32_t has_ctrl, uint64_t genome_len);
+int gr_sums_device(gr_ctx* ctx, double** d_expt_sums, double** d_ctrl_sums);
+void* gr_stream(gr_ctx* ctx);                       /* the context's cudaStream_t */
+int gr_replicate_stats(gr_ctx* ctx, int32_t replicate, gr_sample_stats* stats);
 
 /* Convenience for a single context: gr_sample_pileup for the pending
  * sample(s) + gr_replicate_finish with local sums. */

@@ -192,6 +192,38 @@ def test_bucketed_build_same_bits(monkeypatch):
                 assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
 
 
+def test_async_path_and_retries(monkeypatch):
+    """The no-round-trip path (counts, lambda and the scale factor stay on the device; tables and
+    candidate buffers sized optimistically) gives the same bits as the synchronous one, also when
+    the optimistic sizes are wrong and the stages have to be run again."""
+    import torch
+    from genrich_b200.dist import ShardedEngine
+    api = capi.load_cuda()
+    dev = torch.device("cuda", 0)
+    for name in ("c2_ctrl_p", "c1_smoke", "c5_multimap_ctrl_p"):
+        case = BY_NAME[name]
+        inputs = util.case_inputs(case)
+        ctx0, ref, par = util.run_case(api, case)
+        for env in ({}, {"GR_PAIR_CAP": "64", "GR_HEAD_CAP": "3"}):
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            eng = ShardedEngine(api, case.chrom_len, par, dev)
+            for rep in inputs:
+                expt, ctrl = rep[0], rep[1]
+                eng.replicate(lambda c: c.push_intervals(expt),
+                              (lambda c: c.push_intervals(ctrl)) if ctrl is not None else None, want_stats=False)
+            peaks, rs = eng.call_peaks()
+            for k in env:
+                monkeypatch.delenv(k)
+            assert peaks.tobytes() == ref.peaks.tobytes() and len(peaks) > 0
+            assert rs.n_intervals == ref.run_stats.n_intervals
+            st = eng.ctx.replicate_stats(0)
+            assert st.lambda_ == ref.sample_stats[0].lambda_ and st.factor == ref.sample_stats[0].factor
+            for c in range(len(case.chrom_len)):
+                a, b = eng.ctx.fetch(2, 0, c), ctx0.fetch(2, 0, c)
+                assert np.array_equal(a.end, b.end) and np.array_equal(_bits(a.val), _bits(b.val))
+
+
 def test_edge_inputs():
     api = capi.load_cuda()
     orc = util.oracle_api()
