@@ -121,9 +121,10 @@ struct gr_ctx {
   u64 head_cap = 0;                 // candidate-peak capacity of the last peak call
   DevBuf dpar;                      // device: float factor, lambda (+ pad)
   DevBuf dsums;                     // device: double[2][nchrom], per-chromosome sum(len*val) of expt / ctrl
-  float* h_fl = nullptr;            // pinned ring of (factor, lambda) pairs for the H2D copy
-  int h_fl_next = 0;
   u64* h_mat = nullptr;             // pinned landing area of materialize(): 2 + 4 chromosome-start tables
+  char* h_up = nullptr;             // pinned ring for small host -> device uploads (a pageable source would make
+  size_t up_pos = 0;                // cudaMemcpyAsync wait for the stream)
+  static const size_t UP_BYTES = 1u << 20;
   gr_peak* h_peaks = nullptr;       // pinned: the first PEAK_SPEC records come back with the counts
   static const u64 PEAK_SPEC = 1u << 16;
 
@@ -215,11 +216,29 @@ static void stage_end(gr_ctx* x) {
 // ---- layout ------------------------------------------------------------------
 static bool chrom_active(const gr_ctx* x, int c) { return x->owned[c] && !x->skip[c] && x->save[c]; }
 
+// small host -> device copy that does not stall the host: the bytes are parked in a pinned ring
+static int upload(gr_ctx* x, void* dst, const void* src, size_t bytes) {
+  if (!bytes) return GR_OK;
+  if (bytes > gr_ctx::UP_BYTES / 4) {                    // too big for the ring: the plain (waiting) copy
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, x->stream));
+    return GR_OK;
+  }
+  const size_t need = (bytes + 63) & ~(size_t)63;
+  if (x->up_pos + need > gr_ctx::UP_BYTES) {             // wrap: everything parked so far must have left
+    CK(cudaStreamSynchronize(x->stream));
+    x->up_pos = 0;
+  }
+  char* slot = x->h_up + x->up_pos;
+  x->up_pos += need;
+  memcpy(slot, src, bytes);
+  CK(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, x->stream));
+  return GR_OK;
+}
+
 static int upload_flags(gr_ctx* x) {
   for (int c = 0; c < x->nchrom; c++)
     x->flags[c] = (uint8_t)(((x->owned[c] && !x->skip[c]) ? GR_CF_OWNED : 0) | (x->save[c] ? GR_CF_SAVE : 0));
-  CK(cudaMemcpyAsync(x->d_flags.p, x->flags.data(), x->nchrom, cudaMemcpyHostToDevice, x->stream));
-  return GR_OK;
+  return upload(x, x->d_flags.p, x->flags.data(), x->nchrom);
 }
 
 static DevRle rle_view(DevBuf& e, DevBuf& v, DevBuf& cs, DevBuf& tot) {
@@ -272,6 +291,7 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     x->L.nchrom = nchrom; x->L.T = T; x->L.nblocks = x->nblocks;
     x->L.off = x->d_off.as<u64>(); x->L.len = x->d_len.as<u32>();
     x->L.flags = x->d_flags.as<uint8_t>(); x->L.blk2chrom = x->d_blk2chrom.as<int>();
+    CK(cudaMallocHost((void**)&x->h_up, gr_ctx::UP_BYTES));
     int r = upload_flags(x);
     if (r) return r;
 
@@ -296,7 +316,6 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     CK(x->dpar.ensure(64));
     CK(x->dsums.ensure(2 * nchrom * sizeof(double)));
     CK(cudaMemsetAsync(x->dsums.p, 0, 2 * nchrom * sizeof(double), x->stream));
-    CK(cudaMallocHost((void**)&x->h_fl, 16 * 2 * sizeof(float)));
     CK(cudaMallocHost((void**)&x->h_peaks, gr_ctx::PEAK_SPEC * sizeof(gr_peak)));
     CK(cudaMallocHost((void**)&x->h_mat, 6 * (size_t)(nchrom + 3) * sizeof(u64)));
     CK(x->accI.ensure(2 * nchrom * sizeof(u64)));
@@ -368,9 +387,9 @@ extern "C" void gr_destroy(gr_ctx* x) {
     &x->headCount, &x->cand, &x->candOk, &x->peakOut, &x->peakCount, &x->peakBp };
   for (DevBuf* b : all) b->release();
   if (x->h_small) cudaFreeHost(x->h_small);
-  if (x->h_fl) cudaFreeHost(x->h_fl);
   if (x->h_peaks) cudaFreeHost(x->h_peaks);
   if (x->h_mat) cudaFreeHost(x->h_mat);
+  if (x->h_up) cudaFreeHost(x->h_up);
   x->dpar.release();
   x->dsums.release();
   if (x->h_acc) cudaFreeHost(x->h_acc);
@@ -825,11 +844,10 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
     n_ctrl_upper = e.size();
     CK(x->ctrlEnd.ensure((e.size() + 1) * sizeof(u32)));
     CK(x->ctrlVal.ensure((e.size() + 1) * sizeof(float)));
-    // pageable sources: the driver stages them before the call returns
-    CK(cudaMemcpyAsync(x->ctrlEnd.p, e.data(), e.size() * sizeof(u32), cudaMemcpyHostToDevice, x->stream));
-    CK(cudaMemcpyAsync(x->ctrlCS.p, cs.data(), (nc + 1) * sizeof(u64), cudaMemcpyHostToDevice, x->stream));
+    { int r = upload(x, x->ctrlEnd.p, e.data(), e.size() * sizeof(u32)); if (r) return r; }
+    { int r = upload(x, x->ctrlCS.p, cs.data(), (nc + 1) * sizeof(u64)); if (r) return r; }
     u64 tot = e.size();
-    CK(cudaMemcpyAsync(x->ctrlTot.p, &tot, 8, cudaMemcpyHostToDevice, x->stream));
+    { int r = upload(x, x->ctrlTot.p, &tot, 8); if (r) return r; }
     stage_begin(x, "ctrl_const", x->T / 8);
     DevRle out = rle_view(x->ctrlEnd, x->ctrlVal, x->ctrlCS, x->ctrlTot);
     launch_ctrl_const(x->stream, x->L, x->dpar.as<float>() + 1, e.size(), out, x->bmC.as<u32>());
@@ -872,7 +890,7 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
 
   rep->present_h.resize(nc);
   for (int c = 0; c < nc; c++) rep->present_h[c] = chrom_active(x, c);
-  CK(cudaMemcpyAsync(rep->present.p, rep->present_h.data(), nc, cudaMemcpyHostToDevice, x->stream));
+  { int r = upload(x, rep->present.p, rep->present_h.data(), nc); if (r) return r; }
   rep->has_cols = x->par.keep_pileups != 0;
   x->pend_reps.push_back(rep);
   x->lag = true;
@@ -930,9 +948,8 @@ extern "C" int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag,
   const float lambda = (float)(frag_len / (double)G);          // 1831
   float factor = 1.0f;
   if (has_ctrl && ctrl_frag != 0.0) factor = (float)(frag_len / ctrl_frag);   // 2043-2045
-  float* fl = x->h_fl + 2 * (x->h_fl_next++ & 15);             // pinned, one slot per call in flight
-  fl[0] = factor; fl[1] = lambda;
-  CK(cudaMemcpyAsync(x->dpar.p, fl, 2 * sizeof(float), cudaMemcpyHostToDevice, x->stream));
+  const float fl[2] = { factor, lambda };
+  { int r = upload(x, x->dpar.p, fl, sizeof fl); if (r) return r; }
   { int r = replicate_tail(x, has_ctrl != 0); if (r) return r; }
   if (st) {
     int r = materialize(x);
@@ -1049,7 +1066,7 @@ extern "C" int gr_pvalues_finalize(gr_ctx* x) {
     views[r].present = x->reps[r]->present.as<uint8_t>();
   }
   CK(x->repviews.ensure(nrep * sizeof(RepView)));
-  CK(cudaMemcpyAsync(x->repviews.p, views.data(), nrep * sizeof(RepView), cudaMemcpyHostToDevice, x->stream));
+  { int r = upload(x, x->repviews.p, views.data(), nrep * sizeof(RepView)); if (r) return r; }
   stage_begin(x, "fisher_emit", np * 16 * nrep);
   launch_fisher_emit(x->stream, x->L, cb->bmU.as<u32>(), cb->rankU.as<u64>(), x->repviews.as<RepView>(),
                      nrep, cb->pEnd.as<u32>(), x->fsum.as<double>(), x->fdf.as<int>(),
@@ -1345,6 +1362,15 @@ extern "C" int gr_timing_get(gr_ctx* x, gr_stage_time* out, int32_t cap, int32_t
   if (!x || !out || !n) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
   CK(cudaStreamSynchronize(x->stream));
+  if (getenv("GR_GAP_DEBUG")) {            // time between the end of a stage and the start of the next one
+    for (size_t i = 0; i + 1 < x->stages.size() && i < 40; i++) {
+      float d = 0.f, g = 0.f;
+      cudaEventElapsedTime(&d, x->stages[i].a, x->stages[i].b);
+      cudaEventElapsedTime(&g, x->stages[i].b, x->stages[i + 1].a);
+      fprintf(stderr, "stage %-12s %8.3f ms, then idle/untimed %8.3f ms\n", x->stages[i].name, d, g);
+    }
+    cudaGetLastError();
+  }
   int m = 0;
   for (auto& s : x->stages) {
     float ms = 0.f;

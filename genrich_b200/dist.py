@@ -71,6 +71,8 @@ class ShardedEngine:
         self.sample_stats = []
         self._ext_stream = None
         self._dsums = None
+        self._gather_cap = 1 << 16          # peak records per rank in the gather slot (grown on demand)
+        self._send = self._recv = self._host = None
         self.debug = bool(os.environ.get("GR_DIST_DEBUG"))
         self.t_acc = {}
 
@@ -192,39 +194,62 @@ class ShardedEngine:
         self._tick("call_peaks", t0)
         t0 = time.perf_counter()
         if self.world > 1:
+            isz = PEAK_DTYPE.itemsize
             if self.device.type == "cuda":
-                # the records are still in device memory: all-gather them there (NCCL), one
-                # device->host copy on rank 0; the other ranks keep their own peaks
+                # One collective: every rank contributes a fixed-size slot [count | records] straight
+                # from device memory (NCCL all-gather over NVLink); rank 0 brings the lot to pinned
+                # host memory in one copy.  A slot that turns out too small is seen by every rank in
+                # the gathered counts, and the exchange is simply repeated with a larger one.
                 dptr, n = self.ctx.peaks_device_ptr()
-                nbytes = n * PEAK_DTYPE.itemsize
-                buf = _tensor_from_ptr(dptr, nbytes, np.uint8, self.device)
-                dev, grp = self.device, None
+                while True:
+                    capb = self._gather_cap * isz
+                    if self._send is None or self._send.numel() != capb + 16:
+                        self._send = torch.zeros(capb + 16, dtype=torch.uint8, device=self.device)
+                        self._recv = torch.empty(self.world * (capb + 16), dtype=torch.uint8, device=self.device)
+                        self._host = torch.empty(self.world * (capb + 16), dtype=torch.uint8).pin_memory()
+                    self._send[:8].view(torch.int64)[0] = n
+                    m = min(n, self._gather_cap) * isz
+                    if m:
+                        self._send[16:16 + m] = _tensor_from_ptr(dptr, m, np.uint8, self.device)
+                    td.all_gather_into_tensor(self._recv, self._send)
+                    self._host.copy_(self._recv, non_blocking=True)
+                    torch.cuda.current_stream(self.device).synchronize()
+                    host = self._host.numpy().reshape(self.world, capb + 16)
+                    counts = [int(host[r, :8].view(np.int64)[0]) for r in range(self.world)]
+                    if max(counts) <= self._gather_cap:
+                        break
+                    self._gather_cap = 2 * max(counts)
+                host = host[:, 16:]
+                sizes = [c * isz for c in counts]
             else:
                 buf = torch.from_numpy(peaks.view(np.uint8).copy())
-                dev, grp = torch.device("cpu"), self.host_group
-            cnt = torch.tensor([buf.numel()], dtype=torch.int64, device=dev)
-            cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
-            td.all_gather(cnts, cnt, group=grp)
-            sizes = [int(c.item()) for c in cnts]
-            self._tick("gather_counts", t0)
-            m = max(max(sizes), 1)
-            pad = torch.zeros(m, dtype=torch.uint8, device=dev)
-            pad[:buf.numel()] = buf
-            allb = torch.empty(self.world * m, dtype=torch.uint8, device=dev)
-            td.all_gather_into_tensor(allb, pad, group=grp) if dev.type == "cuda" else \
-                td.all_gather(list(allb.view(self.world, m).unbind(0)), pad, group=grp)
+                cnt = torch.tensor([buf.numel()], dtype=torch.int64)
+                cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
+                td.all_gather(cnts, cnt, group=self.host_group)
+                sizes = [int(c.item()) for c in cnts]
+                m = max(max(sizes), 1)
+                pad = torch.zeros(m, dtype=torch.uint8)
+                pad[:buf.numel()] = buf
+                allb = torch.empty(self.world * m, dtype=torch.uint8)
+                td.all_gather(list(allb.view(self.world, m).unbind(0)), pad, group=self.host_group)
+                host = allb.numpy().reshape(self.world, m)
+            self._tick("gather_exchange", t0)
             if self.rank == 0:
-                host = allb.cpu().numpy().reshape(self.world, m)
-                parts = [host[r, :s].view(PEAK_DTYPE) for r, s in enumerate(sizes)]
                 # every rank's list is in (chromosome, start) order and a chromosome has one owner:
-                # the global list is the owners' per-chromosome runs in chromosome order
-                chrom_col = [np.ascontiguousarray(p["chrom"]) for p in parts]
-                runs = []
+                # the global list is the owners' per-chromosome runs in chromosome order.  Byte
+                # slices: numpy copies structured records one by one, plain bytes with memcpy.
+                edges = []
+                for r, sz in enumerate(sizes):
+                    col = np.ascontiguousarray(host[r, :sz].view(PEAK_DTYPE)["chrom"])
+                    edges.append(np.searchsorted(col, np.arange(self.nchrom + 1)) * isz)
+                out = np.empty(sum(sizes), np.uint8)
+                pos = 0
                 for c in range(self.nchrom):
                     r = int(self.owner[c])
-                    lo, hi = np.searchsorted(chrom_col[r], [c, c + 1])
+                    lo, hi = int(edges[r][c]), int(edges[r][c + 1])
                     if hi > lo:
-                        runs.append(parts[r][lo:hi])
-                peaks = np.concatenate(runs) if runs else np.empty(0, PEAK_DTYPE)
+                        out[pos:pos + hi - lo] = host[r, lo:hi]
+                        pos += hi - lo
+                peaks = out[:pos].view(PEAK_DTYPE)
         self._tick("gather_peaks", t0)
         return peaks, rs
