@@ -70,7 +70,7 @@ ABI_SYMBOLS = [
     "gr_sample_pileup", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
     "gr_sums_device", "gr_stream", "gr_replicate_stats",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
-    "gr_bh_set_global", "gr_call_peaks", "gr_peaks_device", "gr_fetch_intervals",
+    "gr_bh_set_global", "gr_call_peaks", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
     "gr_kernel_launches", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
     "gr_pinned_alloc", "gr_pinned_free",
@@ -138,6 +138,7 @@ class Api:
             self.push_packed = fn("push_packed", C.c_int, [vp, vp, u64])
             self.prefetch_packed = fn("prefetch_packed", C.c_int, [vp, vp, u64])
             self.peaks_device = fn("peaks_device", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)])
+            self.merge_peaks = fn("merge_peaks", C.c_int, [C.POINTER(vp), C.POINTER(u64), i32, vp])
             self.timing_enable = fn("timing_enable", C.c_int, [vp, i32])
             self.timing_get = fn("timing_get", C.c_int, [vp, C.POINTER(GrStageTime), i32, C.POINTER(i32)])
             self.timing_reset = fn("timing_reset", C.c_int, [vp])
@@ -321,9 +322,12 @@ class Context:
         self._check(self.api.bh_set_global(self._h, C.c_void_p(keys_ptr), C.c_void_p(lens_ptr), n, genome_len),
                     "bh_set_global")
 
-    def call_peaks(self):
+    def call_peaks(self, to_host=True):
+        """to_host=False (CUDA library): the records stay on the device (peaks_device_ptr)."""
         p, n, st = C.c_void_p(), C.c_uint64(), GrRunStats()
-        self._check(self.api.call_peaks(self._h, C.byref(p), C.byref(n), C.byref(st)), "call_peaks")
+        self._check(self.api.call_peaks(self._h, C.byref(p) if to_host else None, C.byref(n), C.byref(st)), "call_peaks")
+        if not to_host:
+            return np.empty(0, PEAK_DTYPE), st
         return _np_from(p.value, n.value, PEAK_DTYPE), st
 
     def peaks_device_ptr(self):

@@ -156,6 +156,7 @@ struct gr_ctx {
   DevBuf fsum, fdf, repviews;
   DevBuf evIdx, evCount, headIdx, headCount, cand, candOk, peakOut, peakCount, peakBp;
   std::vector<gr_peak> peaks_h;
+  u64 n_peaks = 0;
 
   // fetch caches
   std::vector<u32> f_end; std::vector<float> f_val, f_expt, f_ctrl;
@@ -1183,7 +1184,7 @@ extern "C" int gr_bh_set_global(gr_ctx* x, const uint32_t* d_keys, const uint64_
 
 // ---- peaks ---------------------------------------------------------------------------
 // events -> heads -> walk -> compaction, all sized by upper bounds with the counts on the device
-static int peaks_enqueue(gr_ctx* x, Replicate* f, int qopt) {
+static int peaks_enqueue(gr_ctx* x, Replicate* f, int qopt, bool want_host) {
   const u64 nu = f->n_upper;
   CK(x->evIdx.ensure((nu + 1) * sizeof(u32)));
   CK(x->headIdx.ensure((nu + 1) * sizeof(u32)));
@@ -1217,7 +1218,8 @@ static int peaks_enqueue(gr_ctx* x, Replicate* f, int qopt) {
   CK(cudaMemcpyAsync((char*)x->h_small + 192, x->peakCount.p, 8, cudaMemcpyDeviceToHost, x->stream));
   CK(cudaMemcpyAsync((char*)x->h_small + 200, x->peakBp.p, 8, cudaMemcpyDeviceToHost, x->stream));
   const u64 spec = hc < gr_ctx::PEAK_SPEC ? hc : gr_ctx::PEAK_SPEC;
-  CK(cudaMemcpyAsync(x->h_peaks, x->peakOut.p, spec * sizeof(gr_peak), cudaMemcpyDeviceToHost, x->stream));
+  if (want_host)
+    CK(cudaMemcpyAsync(x->h_peaks, x->peakOut.p, spec * sizeof(gr_peak), cudaMemcpyDeviceToHost, x->stream));
   x->lag = true;
   return GR_OK;
 }
@@ -1240,7 +1242,7 @@ extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_r
   static_assert(sizeof(PeakRec) == sizeof(gr_peak), "peak record layout");
   u64 npk = 0, peak_bp = 0;
   for (;;) {
-    { int r = peaks_enqueue(x, f, qopt); if (r) return r; }
+    { int r = peaks_enqueue(x, f, qopt, peaks != nullptr); if (r) return r; }
     { int r = materialize(x); if (r) return r; }               // the one round trip of a peak call
     if (x->retry_flags & GR_DE_TABLE) {                        // -log10 p came from an overflowed table
       int r = redo_pvals(x);
@@ -1257,18 +1259,21 @@ extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_r
     peak_bp = *(u64*)((char*)x->h_small + 200);
     break;
   }
-  x->peaks_h.resize(npk);
-  const u64 spec = npk < gr_ctx::PEAK_SPEC ? npk : gr_ctx::PEAK_SPEC;
-  if (spec) memcpy(x->peaks_h.data(), x->h_peaks, spec * sizeof(gr_peak));
-  if (npk > spec)
-    CK(cudaMemcpy(x->peaks_h.data() + spec, x->peakOut.as<gr_peak>() + spec, (npk - spec) * sizeof(gr_peak),
-                  cudaMemcpyDeviceToHost));
-  if (peaks) *peaks = x->peaks_h.data();
-  if (n) *n = x->peaks_h.size();
+  x->n_peaks = npk;
+  if (peaks) {                                                 // peaks == NULL: the records stay on the device (gr_peaks_device)
+    x->peaks_h.resize(npk);
+    const u64 spec = npk < gr_ctx::PEAK_SPEC ? npk : gr_ctx::PEAK_SPEC;
+    if (spec) memcpy(x->peaks_h.data(), x->h_peaks, spec * sizeof(gr_peak));
+    if (npk > spec)
+      CK(cudaMemcpy(x->peaks_h.data() + spec, x->peakOut.as<gr_peak>() + spec, (npk - spec) * sizeof(gr_peak),
+                    cudaMemcpyDeviceToHost));
+    *peaks = x->peaks_h.data();
+  }
+  if (n) *n = npk;
   if (st) {
     memset(st, 0, sizeof *st);
     st->genome_len = final_genome_len(x);
-    st->n_peaks = x->peaks_h.size();
+    st->n_peaks = npk;
     st->peak_bp = peak_bp;
     st->n_intervals = f->n;
     st->n_distinct_p = qopt ? x->n_distinct : 0;
@@ -1421,9 +1426,32 @@ extern "C" void* gr_pinned_alloc(size_t bytes) {
 }
 extern "C" void gr_pinned_free(void* p) { if (p) cudaFreeHost(p); }
 
+// Host utility for multi-context callers: the peak lists of the contexts (each in chromosome
+// order, every chromosome in exactly one list) -> one list in chromosome order (callPeaks
+// numbers peaks in that order, Genrich.c:986).  Runs are moved with memcpy.
+extern "C" int gr_merge_peaks(const gr_peak* const* lists, const uint64_t* counts, int32_t nlists, gr_peak* out) {
+  if (nlists < 0 || (nlists && (!lists || !counts)) || !out) return GR_ERR_ARG;
+  std::vector<u64> pos(nlists, 0);
+  u64 w = 0;
+  for (;;) {
+    int best = -1;
+    for (int i = 0; i < nlists; i++)
+      if (pos[i] < counts[i] && (best < 0 || lists[i][pos[i]].chrom < lists[best][pos[best]].chrom)) best = i;
+    if (best < 0) break;
+    const gr_peak* l = lists[best];
+    const int32_t c = l[pos[best]].chrom;
+    u64 e = pos[best];
+    while (e < counts[best] && l[e].chrom == c) e++;
+    memcpy(out + w, l + pos[best], (e - pos[best]) * sizeof(gr_peak));
+    w += e - pos[best];
+    pos[best] = e;
+  }
+  return GR_OK;
+}
+
 extern "C" int gr_peaks_device(gr_ctx* x, const gr_peak** d_peaks, uint64_t* n) {
   if (!x || !d_peaks || !n) return GR_ERR_ARG;
-  *d_peaks = x->peaks_h.empty() ? nullptr : (const gr_peak*)x->peakOut.p;
-  *n = x->peaks_h.size();
+  *d_peaks = x->n_peaks ? (const gr_peak*)x->peakOut.p : nullptr;
+  *n = x->n_peaks;
   return GR_OK;
 }

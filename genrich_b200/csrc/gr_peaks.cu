@@ -147,25 +147,40 @@ k_peak_walk(const u32* __restrict__ pEnd, const float* __restrict__ pval,
   float auc = 0.0f, sVal = -1.0f, sP = -1.0f, sQ = -1.0f;     // 1001-1006
   i64 pStart = -1, pEndv = -1;
   u32 sPos = 0, sLen = 0;
-  for (u64 t = t0; t < t1; t++) {
-    const u32 idx = ev_idx[t];
-    const float x = v[idx];
-    if (x == PK_SKIP) break;                                    // 1031: SKIP closes the candidate
-    const u32 end = pEnd[idx];
-    const u32 start = (u64)idx == cs ? 0u : pEnd[idx - 1];
-    const u32 len = end - start;
-    auc = __fadd_rn(auc, __fmul_rn(__uint2float_rn(len), __fsub_rn(x, thr)));   // 950, no FMA
-    if (pStart == -1) pStart = start;
-    pEndv = end;
-    if (x > sVal) {                                             // 956-961
-      sVal = x;
-      sP = pval[idx];
-      sQ = qopt ? qval[idx] : PK_SKIP;
-      sPos = (u32)((end + start) / 2 - (u32)pStart);            // uint32 arithmetic, 960
-      sLen = len;
-    } else if (x == sVal && len > sLen) {                       // 962-968
-      sPos = (u32)((end + start) / 2 - (u32)pStart);
-      sLen = len;
+  // The arithmetic is a chain (float AUC in interval order), the loads are not: four events
+  // are fetched at a time so that their latencies overlap (a long candidate is one thread's
+  // critical path, and on a small shard the whole kernel's).
+  bool open = true;
+  for (u64 t = t0; t < t1 && open; t += 4) {
+    u32 idx[4], end[4], start[4];
+    float xv[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) idx[k] = t + k < t1 ? ev_idx[t + k] : first;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      xv[k] = v[idx[k]];
+      end[k] = pEnd[idx[k]];
+      start[k] = (u64)idx[k] == cs ? 0u : pEnd[idx[k] - 1];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (t + k >= t1) break;
+      const float x = xv[k];
+      if (x == PK_SKIP) { open = false; break; }                 // 1031: SKIP closes the candidate
+      const u32 len = end[k] - start[k];
+      auc = __fadd_rn(auc, __fmul_rn(__uint2float_rn(len), __fsub_rn(x, thr)));   // 950, no FMA
+      if (pStart == -1) pStart = start[k];
+      pEndv = end[k];
+      if (x > sVal) {                                             // 956-961
+        sVal = x;
+        sP = pval[idx[k]];
+        sQ = qopt ? qval[idx[k]] : PK_SKIP;
+        sPos = (u32)((end[k] + start[k]) / 2 - (u32)pStart);      // uint32 arithmetic, 960
+        sLen = len;
+      } else if (x == sVal && len > sLen) {                       // 962-968
+        sPos = (u32)((end[k] + start[k]) / 2 - (u32)pStart);
+        sLen = len;
+      }
     }
   }
   PeakRec r;

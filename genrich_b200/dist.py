@@ -71,7 +71,7 @@ class ShardedEngine:
         self.sample_stats = []
         self._ext_stream = None
         self._dsums = None
-        self._gather_cap = 1 << 16          # peak records per rank in the gather slot (grown on demand)
+        self._gather_cap = 1 << 13          # peak records per rank in the gather slot (grown on demand)
         self._send = self._recv = self._host = None
         self.debug = bool(os.environ.get("GR_DIST_DEBUG"))
         self.t_acc = {}
@@ -180,7 +180,8 @@ class ShardedEngine:
         return keys, lens
 
     def call_peaks(self):
-        """Returns (peaks, run_stats) -- peaks of ALL chromosomes on rank 0, own peaks elsewhere."""
+        """Returns (peaks, run_stats) -- peaks of ALL chromosomes on rank 0; elsewhere the rank's own peaks
+        (host engines) or none (CUDA: they stay on the device)."""
         self.ctx.pvalues_finalize()
         if self.params.qval_opt:
             G = int(self.params.genome_len) or int(self.chrom_len[self.saved_any].astype(np.int64).sum())
@@ -190,37 +191,51 @@ class ShardedEngine:
             self._keep = (keys, lens)
             self.ctx.bh_set_global_ptrs(keys.data_ptr(), lens.data_ptr(), keys.numel(), G)
         t0 = time.perf_counter()
-        peaks, rs = self.ctx.call_peaks()
+        cuda_gather = self.world > 1 and self.device.type == "cuda"
+        peaks, rs = self.ctx.call_peaks(to_host=not cuda_gather) if self.ctx.api.has_device else self.ctx.call_peaks()
         self._tick("call_peaks", t0)
         t0 = time.perf_counter()
         if self.world > 1:
             isz = PEAK_DTYPE.itemsize
-            if self.device.type == "cuda":
+            if cuda_gather:
                 # One collective: every rank contributes a fixed-size slot [count | records] straight
                 # from device memory (NCCL all-gather over NVLink); rank 0 brings the lot to pinned
-                # host memory in one copy.  A slot that turns out too small is seen by every rank in
-                # the gathered counts, and the exchange is simply repeated with a larger one.
+                # host memory in one copy, the others only the counts.  A slot that turns out too
+                # small is seen by every rank in the gathered counts, and the exchange is simply
+                # repeated with a larger one.
                 dptr, n = self.ctx.peaks_device_ptr()
                 while True:
                     capb = self._gather_cap * isz
-                    if self._send is None or self._send.numel() != capb + 16:
-                        self._send = torch.zeros(capb + 16, dtype=torch.uint8, device=self.device)
-                        self._recv = torch.empty(self.world * (capb + 16), dtype=torch.uint8, device=self.device)
-                        self._host = torch.empty(self.world * (capb + 16), dtype=torch.uint8).pin_memory()
+                    slot = capb + 16
+                    if self._send is None or self._send.numel() != slot:
+                        self._send = torch.zeros(slot, dtype=torch.uint8, device=self.device)
+                        self._recv = torch.empty(self.world * slot, dtype=torch.uint8, device=self.device)
+                        self._host = torch.empty(self.world * slot, dtype=torch.uint8).pin_memory()
                     self._send[:8].view(torch.int64)[0] = n
                     m = min(n, self._gather_cap) * isz
                     if m:
                         self._send[16:16 + m] = _tensor_from_ptr(dptr, m, np.uint8, self.device)
                     td.all_gather_into_tensor(self._recv, self._send)
-                    self._host.copy_(self._recv, non_blocking=True)
+                    hv = self._host.view(self.world, slot)
+                    if self.rank == 0:
+                        self._host.copy_(self._recv, non_blocking=True)
+                    else:
+                        hv[:, :16].copy_(self._recv.view(self.world, slot)[:, :16], non_blocking=True)
                     torch.cuda.current_stream(self.device).synchronize()
-                    host = self._host.numpy().reshape(self.world, capb + 16)
+                    host = self._host.numpy().reshape(self.world, slot)
                     counts = [int(host[r, :8].view(np.int64)[0]) for r in range(self.world)]
                     if max(counts) <= self._gather_cap:
                         break
                     self._gather_cap = 2 * max(counts)
-                host = host[:, 16:]
-                sizes = [c * isz for c in counts]
+                self._tick("gather_exchange", t0)
+                if self.rank == 0:
+                    total = sum(counts)
+                    peaks = np.empty(total, PEAK_DTYPE)
+                    lists = (C.c_void_p * self.world)(*[host[r, 16:].ctypes.data for r in range(self.world)])
+                    cnts = (C.c_uint64 * self.world)(*counts)
+                    rc = self.ctx.api.merge_peaks(lists, cnts, self.world, peaks.ctypes.data_as(C.c_void_p))
+                    if rc:
+                        raise RuntimeError("gr_merge_peaks failed: %d" % rc)
             else:
                 buf = torch.from_numpy(peaks.view(np.uint8).copy())
                 cnt = torch.tensor([buf.numel()], dtype=torch.int64)
@@ -233,23 +248,21 @@ class ShardedEngine:
                 allb = torch.empty(self.world * m, dtype=torch.uint8)
                 td.all_gather(list(allb.view(self.world, m).unbind(0)), pad, group=self.host_group)
                 host = allb.numpy().reshape(self.world, m)
-            self._tick("gather_exchange", t0)
-            if self.rank == 0:
-                # every rank's list is in (chromosome, start) order and a chromosome has one owner:
-                # the global list is the owners' per-chromosome runs in chromosome order.  Byte
-                # slices: numpy copies structured records one by one, plain bytes with memcpy.
-                edges = []
-                for r, sz in enumerate(sizes):
-                    col = np.ascontiguousarray(host[r, :sz].view(PEAK_DTYPE)["chrom"])
-                    edges.append(np.searchsorted(col, np.arange(self.nchrom + 1)) * isz)
-                out = np.empty(sum(sizes), np.uint8)
-                pos = 0
-                for c in range(self.nchrom):
-                    r = int(self.owner[c])
-                    lo, hi = int(edges[r][c]), int(edges[r][c + 1])
-                    if hi > lo:
-                        out[pos:pos + hi - lo] = host[r, lo:hi]
-                        pos += hi - lo
-                peaks = out[:pos].view(PEAK_DTYPE)
+                if self.rank == 0:
+                    # every rank's list is in (chromosome, start) order and a chromosome has one owner:
+                    # the global list is the owners' per-chromosome runs in chromosome order
+                    edges = []
+                    for r, sz in enumerate(sizes):
+                        col = np.ascontiguousarray(host[r, :sz].view(PEAK_DTYPE)["chrom"])
+                        edges.append(np.searchsorted(col, np.arange(self.nchrom + 1)) * isz)
+                    out = np.empty(sum(sizes), np.uint8)
+                    pos = 0
+                    for c in range(self.nchrom):
+                        r = int(self.owner[c])
+                        lo, hi = int(edges[r][c]), int(edges[r][c + 1])
+                        if hi > lo:
+                            out[pos:pos + hi - lo] = host[r, lo:hi]
+                            pos += hi - lo
+                    peaks = out[:pos].view(PEAK_DTYPE)
         self._tick("gather_peaks", t0)
         return peaks, rs

@@ -209,6 +209,11 @@ int gr_call_peaks(gr_ctx* ctx, const gr_peak** peaks, uint64_t* n,
 /* The same records where gr_call_peaks left them in DEVICE memory (valid until the next
  * call on the context): lets a multi-GPU launcher all-gather them without a host bounce. */
 int gr_peaks_device(gr_ctx* ctx, const gr_peak** d_peaks, uint64_t* n);
+/* gr_call_peaks with peaks == NULL leaves the records on the device (n and stats are still
+ * filled).  Host utility for launchers that gathered several contexts' lists (each in chromosome
+ * order, every chromosome in exactly one of them): one list in chromosome order, the order in
+ * which callPeaks numbers the peaks (Genrich.c:986).  `out` holds the sum of the counts. */
+int gr_merge_peaks(const gr_peak* const* lists, const uint64_t* counts, int32_t nlists, gr_peak* out);
 
 /* ---- seam OUT for -f / -k (printInterval 770, printPile 1697) -------------
  * which: 0 = experimental pileup, 1 = control pileup (last replicate),
