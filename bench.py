@@ -59,7 +59,7 @@ SAMPLE = dict(chrom_len=[25_000_000] * 4, nt=1_000_000, nc=1_000_000)   # bounde
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_stream launch (bytes), from the
 # committed ncu capture of exactly this command; null for configurations that were not captured
-NCU_TRAFFIC = {("hg38_chip_50M_50M", 1): 12.56e9 + 3.42e9}
+NCU_TRAFFIC = {("hg38_chip_50M_50M", 1, "k_scan_stream"): 12.56e9 + 3.42e9}
 
 
 def gen_fragments(chrom_len, n, seed, enrich, spacing, sigma, threads=8):
@@ -306,7 +306,9 @@ def main():
         return
     n_samples = 2 if n_c else 1
     peak_gbs, peak_src = measured_peak_gbs()
-    scan_ms, scan_launches, _ = stages.get("dense_scan", (0.0, 0, 0))
+    fused = "fused_scan" in stages
+    scan_kernel = "k_fb_scan" if fused else "k_scan_stream"
+    scan_ms, scan_launches, _ = stages.get("fused_scan" if fused else "dense_scan", (0.0, 0, 0))
     per_launch_ms = scan_ms / max(scan_launches, 1)
     place_ms, place_launches, _ = stages.get("scan_place", (0.0, 0, 0))
     cells = ctx_cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
@@ -328,10 +330,10 @@ def main():
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_dev,
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "k_scan_stream", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs if peak_gbs else None,
                      # ncu --set full, hg38 workload, 1 GPU (profiles/r01_scan_stream_ncu.txt): dram read + write per launch
-                     "traffic": NCU_TRAFFIC.get((a.workload, world)), "peak_source": peak_src,
+                     "traffic": NCU_TRAFFIC.get((a.workload, world, scan_kernel)), "peak_source": peak_src,
                      "bytes_per_launch": 4 * cells, "ms_per_launch": per_launch_ms,
                      "companion_scan_place_ms_per_launch": place_ms / max(place_launches, 1),
                      "launches_per_step": scan_launches / a.steps, "samples_scanned_per_step": n_samples},

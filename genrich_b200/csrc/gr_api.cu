@@ -108,6 +108,9 @@ struct gr_ctx {
   // bucketed build (large samples)
   DevBuf sbCnt, sbStart, sbCursor, sbBucket, sbSpill, sbSpillCtr;
   u64 sb_min = 1ull << 20;             // samples with fewer records use the plain scatter (GR_SB_MIN)
+  int fused = 1;                       // buckets -> breaks in shared memory, no delta array in HBM (GR_FUSED=0: dense array)
+  u64 fused_min = 1ull << 16;          // ... for samples of at least this many records (GR_FUSED_MIN)
+  u32 scan_owners = 0;                 // run owners of the last scan (0: the warps of k_scan_stream)
 
   // Host mirrors of device-side results lag behind while `lag` is set: nothing on the hot path
   // waits for the device between gr_sample_begin and the peak records; whoever needs a mirror
@@ -329,6 +332,8 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     x->ctrl_sums.assign(nchrom, 0.0);
     { const char* e = getenv("GR_SCAN_ZERO"); if (e) x->zero_after = atoi(e) != 0; }
     { const char* e = getenv("GR_SB_MIN"); if (e) x->sb_min = strtoull(e, nullptr, 10); }
+    { const char* e = getenv("GR_FUSED"); if (e) x->fused = atoi(e) != 0; }
+    { const char* e = getenv("GR_FUSED_MIN"); if (e) x->fused_min = strtoull(e, nullptr, 10); }
     // test knobs: start the optimistic capacities small enough to exercise the retry paths
     { const char* e = getenv("GR_PAIR_CAP"); if (e) { u32 v = (u32)strtoul(e, nullptr, 10); u32 c = 64; while (c < v) c <<= 1; x->pair_cap = c; } }
     { const char* e = getenv("GR_HEAD_CAP"); if (e) x->head_cap = strtoull(e, nullptr, 10); }
@@ -546,12 +551,31 @@ static int push_any(gr_ctx* x, const void* recs, u64 n, int rb) {
 }
 
 // all records of the sample -> the delta array (called by gr_sample_pileup)
-static int consume_segments(gr_ctx* x, bool* built) {
+// *built: 0 = plain scatter, 1 = delta array built block by block, 2 = events bucketed for the
+// fused scan (the delta array is not touched)
+static int consume_segments(gr_ctx* x, int* built) {
   int32_t* delta = x->delta.as<int32_t>();
-  const bool sb = x->n_pushed >= x->sb_min && x->T < (1ull << 32);
+  const bool fb = x->fused && x->n_pushed >= x->fused_min && x->n_pushed < (1ull << 31) && x->nblocks < (1ull << 32);
+  const bool sb = !fb && x->n_pushed >= x->sb_min && x->T < (1ull << 32);
   u64 bytes = 0;
   for (auto& g : x->segs) bytes += g.n * g.rb;
-  if (sb) {
+  if (fb) {
+    CK(x->sbCnt.ensure(x->nblocks * 4));
+    CK(x->sbStart.ensure((x->nblocks + 1) * 4));
+    CK(x->sbCursor.ensure(x->nblocks * 4));
+    CK(x->sbBucket.ensure(x->n_pushed * 8));             // at most two event entries per record
+    CK(x->sbSpillCtr.ensure(4 + (x->nblocks / 4096 + 2) * 4));      // (unused word), then the scan's chunk sums
+    stage_begin(x, "bucket", bytes);
+    CK(cudaMemsetAsync(x->sbCnt.p, 0, x->nblocks * 4, x->stream));
+    for (auto& g : x->segs)
+      launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
+    launch_sb_scan(x->stream, x->L, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
+                   x->sbSpillCtr.as<u32>() + 1);
+    for (auto& g : x->segs)
+      launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>());
+    CKL();
+    stage_end(x);
+  } else if (sb) {
     CK(x->sbCnt.ensure(x->nblocks * 4));
     CK(x->sbStart.ensure((x->nblocks + 1) * 4));
     CK(x->sbCursor.ensure(x->nblocks * 4));
@@ -597,7 +621,7 @@ static int consume_segments(gr_ctx* x, bool* built) {
   for (auto* b : x->seg_used) x->seg_free.push_back(b);
   x->seg_used.clear();
   x->segs.clear();
-  *built = sb;
+  *built = fb ? 2 : sb ? 1 : 0;
   return GR_OK;
 }
 
@@ -691,20 +715,29 @@ static int pileup_enqueue(gr_ctx* x) {
   CK(V.ensure(cap * sizeof(float)));
   DevRle out = rle_view(E, V, CS, TT);
   CK(x->scanWs.ensure(dense_scan_ws_bytes(cap, x->nchrom)));
-  bool built = false;
+  int built = 0;
   { int r = consume_segments(x, &built); if (r) return r; }
   // after the plain scatter the scan clears the cells behind itself (the next small sample
   // finds the array zero); a built array is overwritten as a whole by the next build anyway
   const int zero_after = built ? 0 : x->zero_after;
   ScanScratch sc;
   sc.ws = x->scanWs.p; sc.cap = cap;
-  stage_begin(x, "dense_scan", x->T * 4);
-  launch_dense_scan(x->stream, x->L, x->delta.as<int32_t>(), sc,
-                    (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, zero_after);
-  CKL();
-  stage_end(x);
+  u32 owners = 0;
+  if (built == 2) {
+    stage_begin(x, "fused_scan", x->T * 4);
+    owners = launch_fb_scan(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), sc,
+                            (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err);
+    CKL();
+    stage_end(x);
+  } else {
+    stage_begin(x, "dense_scan", x->T * 4);
+    launch_dense_scan(x->stream, x->L, x->delta.as<int32_t>(), sc,
+                      (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, zero_after);
+    CKL();
+    stage_end(x);
+  }
   stage_begin(x, "scan_place", cap * 16);
-  launch_scan_place(x->stream, x->L, sc, out, x->d_err);
+  launch_scan_place(x->stream, x->L, sc, out, x->d_err, owners);
   CKL();
   stage_end(x);
   u64* aI = x->accI.as<u64>() + (ctrl ? x->nchrom : 0);
@@ -716,7 +749,7 @@ static int pileup_enqueue(gr_ctx* x) {
   launch_sums_double(x->stream, aI, aF, x->nchrom, x->dsums.as<double>() + (ctrl ? x->nchrom : 0));
   CKL();
   stage_end(x);
-  x->delta_clean = zero_after != 0;          // the scan left the array all zero
+  if (built != 2) x->delta_clean = zero_after != 0;          // the scan left the array all zero
   (ctrl ? x->cap_raw : x->cap_expt) = cap;
   x->pend_pile[ctrl ? 1 : 0] = true;
   x->lag = true;

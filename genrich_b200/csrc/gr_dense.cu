@@ -318,6 +318,9 @@ __device__ __forceinline__ void sc_load_items(const int4* stage, int tid, int (&
 #define SS_PAGE 256
 #define SS_PAGE_SHIFT 8
 #define SS_MAX_WARPS 8192
+// pages beyond cap / SS_PAGE: two per warp of k_scan_stream (8192 x 2), or up to 66 per CTA of
+// k_fb_scan (148 x 6 x 66 = 58608)
+#define SS_SPARE_PAGES (8 * SS_MAX_WARPS)
 struct StreamWs {
   uint2* pent;                 // provisional entries (end coordinate, run-relative height), max_pages * SS_PAGE
   uint2* page_meta;            // page -> (warp, sequence number inside the warp's run)
@@ -606,7 +609,7 @@ void launch_fill_chrom_start(cudaStream_t s, const DevLayout& L, u64* chrom_star
 }
 
 size_t dense_scan_ws_bytes(u64 cap, int nchrom) {
-  const u64 max_pages = (cap / SS_PAGE + 2 * SS_MAX_WARPS + 3) & ~1ull;
+  const u64 max_pages = (cap / SS_PAGE + SS_SPARE_PAGES + 3) & ~1ull;
   return (size_t)(max_pages * SS_PAGE * 8 + max_pages * 8 + SS_MAX_WARPS * (8 + 16) + (u64)nchrom * 16 + 256);
 }
 
@@ -624,7 +627,7 @@ static int scan_stream_warps() {                       // warps of one K2a launc
 
 static StreamWs stream_ws(const ScanScratch& sc, int nchrom) {
   StreamWs W;
-  const u64 max_pages = (sc.cap / SS_PAGE + 2 * SS_MAX_WARPS + 3) & ~1ull;   // even: keeps the 16-byte arrays aligned
+  const u64 max_pages = (sc.cap / SS_PAGE + SS_SPARE_PAGES + 3) & ~1ull;   // even: keeps the 16-byte arrays aligned
   char* p = (char*)sc.ws;
   W.pent = (uint2*)p; p += max_pages * SS_PAGE * 8;
   W.page_meta = (uint2*)p; p += max_pages * 8;
@@ -667,10 +670,288 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
 }
 
 // ... and K2b + K2c, which put the breaks where the rest of the pipeline expects them
-void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err) {
+void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners) {
   const StreamWs W = stream_ws(sc, L.nchrom);
-  k_scan_fix<<<1, 1024, 0, s>>>(L, W, out, err, (u32)scan_stream_warps()); GR_NOTE_LAUNCH();
+  k_scan_fix<<<1, 1024, 0, s>>>(L, W, out, err, owners ? owners : (u32)scan_stream_warps()); GR_NOTE_LAUNCH();
   k_scan_place<<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err); GR_NOTE_LAUNCH();
+}
+
+// ============================================================================
+// K1+K2 fused: the delta array never goes to HBM.
+//
+// The bucketed build above writes every 8192-cell block of the delta array once (4 B/cell)
+// and the streaming scan reads it once (4 B/cell): 2 x 12.35 GB per hg38 sample for an array
+// whose cells are ~97 % zero.  Here the block is assembled in shared memory and scanned where
+// it lies: HBM sees the bucket entries (4 B per record), the breaks (8 B each) and the break
+// bitmap (1 bit per cell).
+//
+// Buckets: one 4-byte EVENT entry per record in the block of its start; a record whose end
+// lies in a later block gets a second, end-only entry in that block -- so every block is
+// self-contained (no spill list, no limit on the interval length).
+//   bits 0-12 cell offset inside the block | 13-25 interval length (kind 0) | 26-29 count |
+//   30-31 kind: 0 = start and end in this block, 1 = start only, 2 = end only
+// k_fb_scan: a CTA owns a contiguous run of blocks and carries (height, #breaks) relative to
+// the start of its run, exactly like a warp of k_scan_stream does for its run of spans; the
+// breaks go to the same pages and k_scan_fix / k_scan_place finish the job (owner = CTA).
+// Per block: events -> smem cells (atomicAdd) + a 256-word occupancy bitmap (atomicOr); each
+// thread then owns one bitmap word = 32 cells and only looks at the cells whose bit is set,
+// clearing them behind itself, so the 32 KB of cells are zeroed once per kernel, not per block.
+#define FB_KIND_BOTH 0u
+#define FB_KIND_START 1u
+#define FB_KIND_END 2u
+__device__ __forceinline__ u32 fb_entry(u32 so, u32 span, int cnt, u32 kind) {
+  return so | (span << 13) | ((u32)cnt << 26) | (kind << 30);
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ blk_cnt,
+           int* __restrict__ err, u64* __restrict__ clamped) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  int e_local = 0;
+  u32 c_local = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u64 s_slot; u32 span; int w;
+    if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
+    const u64 bs = s_slot >> GR_BLOCK_SHIFT, be = (s_slot + span) >> GR_BLOCK_SHIFT;
+    atomicAdd(blk_cnt + bs, 1u);
+    if (be != bs) atomicAdd(blk_cnt + be, 1u);
+  }
+  if (e_local) atomicOr(err, e_local);       // errors and clamp counts are reported by this pass only
+  if (c_local) atomicAdd(clamped, (u64)c_local);
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed) {
+  const u64 stride = (u64)gridDim.x * blockDim.x;
+  int e_local = 0;
+  u32 c_local = 0;
+  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    u64 s_slot; u32 span; int w;
+    if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
+    const u64 e_slot = s_slot + span;
+    const u64 bs = s_slot >> GR_BLOCK_SHIFT, be = e_slot >> GR_BLOCK_SHIFT;
+    const u32 so = (u32)(s_slot & (GR_BLOCK_SLOTS - 1));
+    const int cnt = 120 / w;
+    if (be == bs) {
+      bucketed[atomicAdd(cursor + bs, 1u)] = fb_entry(so, span, cnt, FB_KIND_BOTH);
+    } else {
+      bucketed[atomicAdd(cursor + bs, 1u)] = fb_entry(so, 0, cnt, FB_KIND_START);
+      bucketed[atomicAdd(cursor + be, 1u)] = fb_entry((u32)(e_slot & (GR_BLOCK_SLOTS - 1)), 0, cnt, FB_KIND_END);
+    }
+  }
+}
+
+#define FB_THREADS 256
+#define FB_RING 128                                    // page ring: sequence numbers in flight <= 2 * 33 + 2
+template <int CPS>
+__global__ void __launch_bounds__(FB_THREADS, CPS)
+k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
+          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R) {
+  __shared__ int sm_cell[GR_BLOCK_SLOTS];
+  __shared__ u32 sm_occ[GR_BLOCK_SLOTS / 32];
+  __shared__ u32 sm_pg[FB_RING];
+  __shared__ u32 sm_ws[8], sm_wc[8];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const u32 owner = blockIdx.x;
+  const u32 b0 = owner * R, b1 = min(b0 + R, nblocks);
+  if (b0 >= b1) {
+    if (t == 0) W.warp_tot[owner] = make_uint2(0, 0);
+    return;
+  }
+  for (int i = t; i < GR_BLOCK_SLOTS; i += FB_THREADS) sm_cell[i] = 0;
+  sm_occ[t] = 0;
+
+  // bucket bounds of blocks b, b+1, b+2 (rolling; the entry for b+3 is fetched a block ahead)
+  const u32* bs_ptr = blk_start;
+  auto ld_start = [&](u32 i) { return bs_ptr[min(i, nblocks)]; };
+  u32 sA = ld_start(b0), sB = ld_start(b0 + 1), sC = ld_start(b0 + 2);
+  // upper bound of the breaks of a block: two cells per entry, plus the chromosome end
+  auto ub_of = [&](u32 a, u32 b) { return min(2u * (b - a) + 1u, (u32)GR_BLOCK_SLOTS + 1u); };
+
+  // pages (thread 0): have_seq = highest sequence number that has a page; a request for more
+  // is issued one block before it is needed and its answer is only looked at a block later
+  const u32 last_page = W.max_pages - 1;
+  int have_seq = -1;
+  u32 pend_p0 = 0;
+  int pend_k = 0;
+  auto page_take = [&]() {                               // label the pages of the answered request
+    for (int i = 0; i < pend_k; i++) {
+      u32 pg = pend_p0 + (u32)i;
+      if (pg > last_page) { atomicOr(err, GR_DE_TABLE); pg = last_page; }
+      have_seq++;
+      W.page_meta[pg] = make_uint2(owner, (u32)have_seq);
+      sm_pg[have_seq & (FB_RING - 1)] = pg;
+    }
+    pend_k = 0;
+  };
+  auto page_ask = [&](u32 upto_idx) {                    // make sure sequence upto_idx >> 8 will have a page
+    const int target = (int)(upto_idx >> SS_PAGE_SHIFT);
+    if (target > have_seq) {
+      pend_k = target - have_seq;
+      pend_p0 = atomicAdd(W.page_ctr, (u32)pend_k);
+    }
+  };
+  if (t == 0) page_ask(ub_of(sA, sB));
+
+  // the first two rounds of the block's entries are fetched while the previous block is worked on
+  u32 v0 = 0, v1 = 0;
+  if (sA + t < sB) v0 = __ldcs(bucketed + sA + t);
+  if (sA + FB_THREADS + t < sB) v1 = __ldcs(bucketed + sA + FB_THREADS + t);
+
+  auto apply = [&](u32 v) {
+    const u32 so = v & (GR_BLOCK_SLOTS - 1), kind = v >> 30;
+    const int w = 120 / (int)((v >> 26) & 15u);
+    if (kind == FB_KIND_END) {
+      atomicAdd(sm_cell + so, -w);
+      atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
+    } else {
+      atomicAdd(sm_cell + so, w);
+      atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
+      if (kind == FB_KIND_BOTH) {
+        const u32 eo = so + ((v >> 13) & (GR_BLOCK_SLOTS - 1));
+        atomicAdd(sm_cell + eo, -w);
+        atomicOr(sm_occ + (eo >> 5), 1u << (eo & 31));
+      }
+    }
+  };
+
+  u32 run_s = 0, run_c = 0;                            // height / #breaks since the start of the run
+  int c = -1, c_next = L.blk2chrom[b0];
+  u64 off = 0;
+  u32 len = 0;
+  bool act = false;
+  __syncthreads();
+  for (u32 b = b0; b < b1; b++) {
+    const int cn = c_next;
+    if (b + 1 < b1) c_next = L.blk2chrom[b + 1];
+    if (cn != c) {                                     // ~25 times per genome
+      c = cn;
+      off = L.off[c];
+      len = L.len[c];
+      act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
+    }
+    const u32 sD = ld_start(b + 3);                    // used two blocks from now
+    const u32 jb = (u32)(((u64)b << GR_BLOCK_SHIFT) - off);       // chromosome position of the block's first cell
+    if (t == 0) {
+      if (jb == 0) W.marks[c] = make_uint4(owner, run_s, run_c, 1u);
+      page_take();                                     // covers this block (asked for a block ago)
+      page_ask(run_c + ub_of(sA, sB) + (b + 1 < b1 ? ub_of(sB, sC) : 0u));
+    }
+    const bool has_end = act && len >= jb && len - jb < GR_BLOCK_SLOTS;   // cell `len` lies in this block
+    if (sA == sB && !has_end) {                        // nothing in this block
+      bitmap[(u64)b * (GR_BLOCK_SLOTS / 32) + t] = 0;
+      if (sB + t < sC) v0 = __ldcs(bucketed + sB + t);
+      if (sB + FB_THREADS + t < sC) v1 = __ldcs(bucketed + sB + FB_THREADS + t);
+      sA = sB; sB = sC; sC = sD;
+      continue;
+    }
+    // ---- events -> cells
+    if (sA + t < sB) apply(v0);
+    if (sA + FB_THREADS + t < sB) apply(v1);
+    for (u32 i = sA + 2 * FB_THREADS + t; i < sB; i += FB_THREADS) apply(__ldcs(bucketed + i));
+    if (sB + t < sC) v0 = __ldcs(bucketed + sB + t);   // next block's entries: in flight during the scan
+    if (sB + FB_THREADS + t < sC) v1 = __ldcs(bucketed + sB + FB_THREADS + t);
+    __syncthreads();
+    // ---- this thread's 32 cells: sum of the deltas, break mask
+    u32 mo = sm_occ[t];
+    sm_occ[t] = 0;
+    if (has_end && (int)((len - jb) >> 5) == t) mo |= 1u << ((len - jb) & 31);
+    const int cbase = t * 32;
+    const u32 jt = jb + (u32)cbase;
+    u32 s = 0, m = 0;
+    for (u32 mm = mo; mm; mm &= mm - 1) {
+      const int bit = __ffs(mm) - 1;
+      const int d = sm_cell[cbase + bit];
+      const u32 j = jt + (u32)bit;
+      s += (u32)d;
+      const bool brk = (j == len) || (d != 0 && j >= 1u && j < len);
+      m |= (brk ? 1u : 0u) << bit;
+    }
+    if (!act) m = 0;
+    const u32 cnt = __popc(m);
+    const u32 wi_s = warp_incl_scan_u32(s, lane), wi_c = warp_incl_scan_u32(cnt, lane);
+    if (lane == 31) { sm_ws[wid] = wi_s; sm_wc[wid] = wi_c; }
+    __syncthreads();
+    u32 h = run_s + wi_s - s, idx = run_c + wi_c - cnt, tot_s = 0, tot_c = 0;
+#pragma unroll
+    for (int k = 0; k < FB_THREADS / 32; k++) {
+      const u32 a = sm_ws[k], q = sm_wc[k];
+      if (k < wid) { h += a; idx += q; }
+      tot_s += a; tot_c += q;
+    }
+    // ---- emit, clearing the cells behind
+    for (u32 mm = mo; mm; mm &= mm - 1) {
+      const int bit = __ffs(mm) - 1;
+      const int d = sm_cell[cbase + bit];
+      sm_cell[cbase + bit] = 0;
+      if ((m >> bit) & 1u) {
+        const u32 pg = sm_pg[(idx >> SS_PAGE_SHIFT) & (FB_RING - 1)];
+        W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(jt + (u32)bit, h);
+        idx++;
+      }
+      h += (u32)d;
+    }
+    bitmap[(u64)b * (GR_BLOCK_SLOTS / 32) + t] = m;
+    run_s += tot_s;
+    run_c += tot_c;
+    sA = sB; sB = sC; sC = sD;
+    __syncthreads();                                   // cells, occupancy words and scan scratch are free again
+  }
+  if (t == 0) {
+    page_take();                                       // every page handed out carries a label
+    W.warp_tot[owner] = make_uint2(run_s, run_c);
+  }
+}
+
+void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
+                     u32* blk_cnt, int* err, u64* clamped) {
+  if (!n) return;
+  u64 blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (packed) k_fb_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
+  else k_fb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
+  GR_NOTE_LAUNCH();
+}
+void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed) {
+  if (!n) return;
+  u64 blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
+  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
+  GR_NOTE_LAUNCH();
+}
+
+static u32 fb_owners() {                               // CTAs of one k_fb_scan launch
+  static u32 n = 0;
+  if (!n) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("GR_FUSED_CPS");            // tuning knob: CTAs per SM (4 or 6)
+    const int cps = e && atoi(e) == 4 ? 4 : 6;
+    n = (u32)(sms * cps);
+    if (n > SS_MAX_WARPS) n = SS_MAX_WARPS;
+  }
+  return n;
+}
+
+// bucketed events -> breaks (pages) + break bitmap; launch_scan_place(..., owners) follows
+u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
+                   const ScanScratch& sc, u32* bitmap, int* err) {
+  const StreamWs W = stream_ws(sc, L.nchrom);
+  cudaMemsetAsync(W.page_ctr, 0, 4, s);
+  const u32 owners = fb_owners();
+  const u32 nb = (u32)L.nblocks;
+  const u32 R = (nb + owners - 1) / owners;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (owners == (u32)sms * 4) k_fb_scan<4><<<owners, FB_THREADS, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
+  else k_fb_scan<6><<<owners, FB_THREADS, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
+  GR_NOTE_LAUNCH();
+  return owners;
 }
 
 // ============================================================================

@@ -51,7 +51,16 @@ size_t dense_scan_ws_bytes(u64 cap, int nchrom);
 // zero again when the kernel ends (the next sample then needs no 4 B/bp memset)
 void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
                        const ScanScratch& sc, u32* bitmap, int* err, int zero_after);
-void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err);
+// owners: run owners of the scan that filled the pages (0: the warps of launch_dense_scan)
+void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners);
+
+// ---- K1+K2 fused: event buckets -> breaks, the delta cells live in shared memory only ----
+void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
+                     u32* blk_cnt, int* err, u64* clamped);
+void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed);
+// returns the number of run owners (CTAs), to be handed to launch_scan_place
+u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
+                   const ScanScratch& sc, u32* bitmap, int* err);
 
 // ---- K2b: per-chromosome sum of (float)(end-start)*val, exact fixed point ------
 // acc_int / acc_frac: [nchrom] u64, zeroed by the caller.  sum = int + frac*2^-40.

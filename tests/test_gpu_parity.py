@@ -192,6 +192,96 @@ def test_bucketed_build_same_bits(monkeypatch):
                 assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
 
 
+def _run_modes(monkeypatch, chrom_len, par, inputs, modes, chunk=30011, packed=False):
+    """The same replicates through several scan paths (environment read by gr_create)."""
+    api = capi.load_cuda()
+    outs = []
+    for env in modes:
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx = capi.Context(api, chrom_len, par)
+        res = host.run_replicates(ctx, inputs, chunk=chunk, packed=packed)
+        outs.append((res, [[ctx.fetch(w, 0, c) for c in range(len(chrom_len))] for w in (0, 1, 2)]))
+        for k in env:
+            monkeypatch.delenv(k)
+    return outs
+
+
+def _same_outs(a, b, what):
+    (ra, pa), (rb, pb) = a, b
+    assert ra.peaks.tobytes() == rb.peaks.tobytes(), what
+    for sa, sb in zip(ra.sample_stats, rb.sample_stats):
+        assert (sa.frag_len, sa.ctrl_frag, sa.n_expt, sa.n_ctrl, sa.n_pval, sa.n_clamped) == \
+               (sb.frag_len, sb.ctrl_frag, sb.n_expt, sb.n_ctrl, sb.n_pval, sb.n_clamped), what
+        assert _bits(sa.lambda_) == _bits(sb.lambda_) and _bits(sa.factor) == _bits(sb.factor), what
+    for wa, wb in zip(pa, pb):
+        for x, y in zip(wa, wb):
+            assert (x is None) == (y is None), what
+            if x is not None:
+                assert np.array_equal(x.end, y.end), what
+                assert np.array_equal(_bits(x.val), _bits(y.val)), what
+
+
+FUSED = {"GR_FUSED": "1", "GR_FUSED_MIN": "1"}
+PLAIN = {"GR_FUSED": "0", "GR_SB_MIN": "1000000000"}
+
+
+def test_fused_scan_same_bits(monkeypatch):
+    """The fused path (events bucketed per 8192-cell block, the block assembled and scanned in
+    shared memory, no delta array in HBM) against the plain scatter + streaming scan: every
+    seeded case, the edge inputs, intervals that span several blocks, packed records."""
+    for case in CASES:
+        inputs = [list(r) for r in util.case_inputs(case)]
+        extra = np.array([[0, 1000, 41000, 2], [0, 8000, 3 * 8192 + 5, 1], [0, 8191, 8193, 4], [0, 8192, 8192, 3],
+                          [0, 16383, 16384, 5], [0, 0, 8192, 6]], np.int32)
+        extra = extra[extra[:, 2] <= case.chrom_len[0]]
+        inputs[0][0] = np.concatenate([inputs[0][0], extra])
+        par = util.case_params(case)
+        outs = _run_modes(monkeypatch, case.chrom_len, par, inputs, (PLAIN, FUSED))
+        _same_outs(outs[0], outs[1], case.name)
+        assert len(outs[0][0].peaks) > 0 or case.name == "null_q"
+    # packed records through the fused path
+    case = BY_NAME["c2_ctrl_q"]
+    inputs = util.case_inputs(case)
+    par = util.case_params(case)
+    a = _run_modes(monkeypatch, case.chrom_len, par, inputs, (PLAIN,))[0]
+    b = _run_modes(monkeypatch, case.chrom_len, par, inputs, (FUSED,), packed=True, chunk=7001)[0]
+    _same_outs(a, b, "packed")
+    # edge inputs: chromosome ends on block boundaries, one-base chromosome, empty interval
+    L = [5000, 8192, 8191, 1, 20000, 16384, 16383]
+    recs = np.array([
+        [0, 0, 5000, 1], [0, -50, 10, 2], [0, 4990, 6000, 3],
+        [1, 0, 1, 1], [1, 8191, 8192, 1],
+        [2, 8190, 8191, 10], [2, 0, 8191, 8],
+        [3, 0, 1, 1],
+        [4, 100, 100, 5],
+        [4, 300, 900, 6], [4, 300, 900, 6], [4, 300, 900, 6], [4, 300, 900, 6], [4, 300, 900, 6], [4, 300, 900, 6],
+        [4, 19999, 25000, 4],
+        [5, 0, 16384, 1], [5, 8191, 8192, 2], [5, 8192, 8193, 2], [5, 16383, 16384, 3],
+        [6, 0, 16383, 1], [6, 8100, 16383, 2], [6, 16382, 16383, 3],
+    ], dtype=np.int32)
+    par = capi.make_params(p=0.2, min_auc=0.5, keep_pileups=True)
+    outs = _run_modes(monkeypatch, L, par, [(recs, None)], (PLAIN, FUSED))
+    _same_outs(outs[0], outs[1], "edge")
+    assert outs[1][0].sample_stats[0].n_clamped == 3
+
+
+def test_fused_scan_large(monkeypatch):
+    """200 Mbp / 4 M + 4 M fragments with hot spots (thousands of events in one block, more than
+    two rounds of bucket entries, many pages per run owner): fused == bucketed build == exact sums."""
+    L = [60_000_000, 50_000_000, 40_000_000, 30_000_000, 20_000_000]
+    t = Workload(L, 4_000_000, 101, enrich=0.5, spacing=400000, sigma=60.0).fragments()
+    c = Workload(L, 4_000_000, 102, enrich=0.0).fragments()
+    par = capi.make_params(p=0.01, min_auc=20.0)
+    outs = _run_modes(monkeypatch, L, par, [(t, c)], ({"GR_FUSED": "0"}, {"GR_FUSED": "1"}, {"GR_FUSED": "1", "GR_FUSED_CPS": "4"}),
+                      chunk=1 << 22)
+    _same_outs(outs[0], outs[1], "large")
+    _same_outs(outs[0], outs[2], "large cps4")
+    st = outs[1][0].sample_stats[0]
+    assert st.frag_len == float(np.sum((t[:, 2] - t[:, 1]).astype(np.int64)))
+    assert len(outs[1][0].peaks) > 100
+
+
 def test_async_path_and_retries(monkeypatch):
     """The no-round-trip path (counts, lambda and the scale factor stay on the device; tables and
     candidate buffers sized optimistically) gives the same bits as the synchronous one, also when
