@@ -555,24 +555,26 @@ static int push_any(gr_ctx* x, const void* recs, u64 n, int rb) {
 // fused scan (the delta array is not touched)
 static int consume_segments(gr_ctx* x, int* built) {
   int32_t* delta = x->delta.as<int32_t>();
-  const bool fb = x->fused && x->n_pushed >= x->fused_min && x->n_pushed < (1ull << 31) && x->nblocks < (1ull << 32);
+  const bool fb = x->fused && x->n_pushed >= x->fused_min && x->n_pushed < (1ull << 31) && (x->T >> 11) < (1ull << 32);
   const bool sb = !fb && x->n_pushed >= x->sb_min && x->T < (1ull << 32);
   u64 bytes = 0;
   for (auto& g : x->segs) bytes += g.n * g.rb;
   if (fb) {
-    CK(x->sbCnt.ensure(x->nblocks * 4));
-    CK(x->sbStart.ensure((x->nblocks + 1) * 4));
-    CK(x->sbCursor.ensure(x->nblocks * 4));
+    const int sh = fb_bucket_shift();
+    const u64 nbk = x->T >> sh;
+    CK(x->sbCnt.ensure(nbk * 4));
+    CK(x->sbStart.ensure((nbk + 1) * 4));
+    CK(x->sbCursor.ensure(nbk * 4));
     CK(x->sbBucket.ensure(x->n_pushed * 8));             // at most two event entries per record
-    CK(x->sbSpillCtr.ensure(4 + (x->nblocks / 4096 + 2) * 4));      // (unused word), then the scan's chunk sums
+    CK(x->sbSpillCtr.ensure(4 + (nbk / 4096 + 2) * 4));  // (unused word), then the scan's chunk sums
     stage_begin(x, "bucket", bytes);
-    CK(cudaMemsetAsync(x->sbCnt.p, 0, x->nblocks * 4, x->stream));
+    CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4, x->stream));
     for (auto& g : x->segs)
-      launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
-    launch_sb_scan(x->stream, x->L, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
+      launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped, sh);
+    launch_sb_scan(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
                    x->sbSpillCtr.as<u32>() + 1);
     for (auto& g : x->segs)
-      launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>());
+      launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
     CKL();
     stage_end(x);
   } else if (sb) {
@@ -586,7 +588,7 @@ static int consume_segments(gr_ctx* x, int* built) {
     CK(cudaMemsetAsync(x->sbCnt.p, 0, x->nblocks * 4, x->stream));
     for (auto& g : x->segs)
       launch_sb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
-    launch_sb_scan(x->stream, x->L, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
+    launch_sb_scan(x->stream, x->nblocks, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
                    x->sbSpillCtr.as<u32>() + 1);
     CK(cudaMemsetAsync(x->sbSpillCtr.p, 0, 4, x->stream));
     for (auto& g : x->segs)

@@ -24,19 +24,27 @@
 // One record, decoded and checked as saveInterval does (2522-2544).  PACKED: 8-byte records
 // (include/genrich_cuda.h, GR_PACK), else int32 x 4.  Returns false for records that are
 // dropped (unsaved chromosome) or in error (flagged in e_local).
+// raw record: the 8-byte packed word (in .x/.y) or the int32 x 4 form
 template <bool PACKED>
-__device__ __forceinline__ bool decode_record(const void* __restrict__ recs, u64 i, const DevLayout& L,
-                                              u64& s_slot, u32& span, int& w, int& e_local, u32& c_local) {
+__device__ __forceinline__ int4 load_raw(const void* __restrict__ recs, u64 i) {
+  if (PACKED) {
+    const u64 v = __ldcs(reinterpret_cast<const u64*>(recs) + i);
+    return make_int4((int)(u32)v, (int)(u32)(v >> 32), 0, 0);
+  }
+  return ld_stream_v4(reinterpret_cast<const int4*>(recs) + i);
+}
+template <bool PACKED>
+__device__ __forceinline__ bool decode_raw(const int4 r, const DevLayout& L,
+                                           u64& s_slot, u32& span, int& w, int& e_local, u32& c_local) {
   int c, cnt;
   i64 s, e;
   if (PACKED) {
-    const u64 v = __ldcs(reinterpret_cast<const u64*>(recs) + i);
-    s = (i64)(u32)v;
-    e = s + (i64)((v >> 32) & 0x3fffu);
-    c = (int)((v >> 46) & 0x3fffu);
-    cnt = (int)(v >> 60);
+    const u32 hi = (u32)r.y;
+    s = (i64)(u32)r.x;
+    e = s + (i64)(hi & 0x3fffu);
+    c = (int)((hi >> 14) & 0x3fffu);
+    cnt = (int)(hi >> 28);
   } else {
-    const int4 r = ld_stream_v4(reinterpret_cast<const int4*>(recs) + i);
     c = r.x; s = r.y; e = r.z; cnt = r.w;
   }
   if (c < 0 || c >= L.nchrom) { e_local |= GR_DE_CHROM; return false; }
@@ -58,6 +66,11 @@ __device__ __forceinline__ bool decode_record(const void* __restrict__ recs, u64
   span = (u32)(e - s);
   w = 120 / cnt;
   return true;
+}
+template <bool PACKED>
+__device__ __forceinline__ bool decode_record(const void* __restrict__ recs, u64 i, const DevLayout& L,
+                                              u64& s_slot, u32& span, int& w, int& e_local, u32& c_local) {
+  return decode_raw<PACKED>(load_raw<PACKED>(recs, i), L, s_slot, span, w, e_local, c_local);
 }
 
 template <bool PACKED>
@@ -239,11 +252,11 @@ void launch_sb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n
   GR_NOTE_LAUNCH();
 }
 // chunk_sum: scratch of ceil(nblocks / 4096) words
-void launch_sb_scan(cudaStream_t s, const DevLayout& L, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum) {
-  const u32 nchunks = (u32)((L.nblocks + SB_CHUNK - 1) / SB_CHUNK);
-  k_sb_scan1<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, L.nblocks); GR_NOTE_LAUNCH();
-  k_sb_scan2<<<1, 1024, 0, s>>>(chunk_sum, nchunks, blk_start, L.nblocks); GR_NOTE_LAUNCH();
-  k_sb_scan3<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, blk_start, cursor, L.nblocks); GR_NOTE_LAUNCH();
+void launch_sb_scan(cudaStream_t s, u64 nbuckets, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum) {
+  const u32 nchunks = (u32)((nbuckets + SB_CHUNK - 1) / SB_CHUNK);
+  k_sb_scan1<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, nbuckets); GR_NOTE_LAUNCH();
+  k_sb_scan2<<<1, 1024, 0, s>>>(chunk_sum, nchunks, blk_start, nbuckets); GR_NOTE_LAUNCH();
+  k_sb_scan3<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, blk_start, cursor, nbuckets); GR_NOTE_LAUNCH();
 }
 // spill_ctr must be zero before the first move of a sample
 void launch_sb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
@@ -320,7 +333,7 @@ __device__ __forceinline__ void sc_load_items(const int4* stage, int tid, int (&
 #define SS_MAX_WARPS 8192
 // pages beyond cap / SS_PAGE: two per warp of k_scan_stream (8192 x 2), or up to 66 per CTA of
 // k_fb_scan (148 x 6 x 66 = 58608)
-#define SS_SPARE_PAGES (8 * SS_MAX_WARPS)
+#define SS_SPARE_PAGES (16 * SS_MAX_WARPS)
 struct StreamWs {
   uint2* pent;                 // provisional entries (end coordinate, run-relative height), max_pages * SS_PAGE
   uint2* page_meta;            // page -> (warp, sequence number inside the warp's run)
@@ -703,19 +716,30 @@ __device__ __forceinline__ u32 fb_entry(u32 so, u32 span, int cnt, u32 kind) {
   return so | (span << 13) | ((u32)cnt << 26) | (kind << 30);
 }
 
+// Both passes keep FB_UNROLL records per thread in flight (one load / one cursor atomic at a
+// time left them waiting on the memory latency: ncu long-scoreboard stalls 32 and 51 per issue).
+#define FB_UNROLL 4
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ blk_cnt,
-           int* __restrict__ err, u64* __restrict__ clamped) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
+           int* __restrict__ err, u64* __restrict__ clamped, int shift) {
+  const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
   int e_local = 0;
   u32 c_local = 0;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    u64 s_slot; u32 span; int w;
-    if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
-    const u64 bs = s_slot >> GR_BLOCK_SHIFT, be = (s_slot + span) >> GR_BLOCK_SHIFT;
-    atomicAdd(blk_cnt + bs, 1u);
-    if (be != bs) atomicAdd(blk_cnt + be, 1u);
+  for (u64 i0 = (u64)blockIdx.x * (256 * FB_UNROLL) + threadIdx.x; i0 < n; i0 += stride) {
+    int4 r[FB_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++)
+      if (i0 + k * 256 < n) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++) {
+      if (i0 + k * 256 >= n) break;
+      u64 s_slot; u32 span; int w;
+      if (!decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local)) continue;
+      const u64 bs = s_slot >> shift, be = (s_slot + span) >> shift;
+      atomicAdd(blk_cnt + bs, 1u);
+      if (be != bs) atomicAdd(blk_cnt + be, 1u);
+    }
   }
   if (e_local) atomicOr(err, e_local);       // errors and clamp counts are reported by this pass only
   if (c_local) atomicAdd(clamped, (u64)c_local);
@@ -723,36 +747,58 @@ k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ 
 
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
-k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed) {
-  const u64 stride = (u64)gridDim.x * blockDim.x;
+k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed,
+          int shift) {
+  const u32 omask = (1u << shift) - 1;
+  const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
   int e_local = 0;
   u32 c_local = 0;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    u64 s_slot; u32 span; int w;
-    if (!decode_record<PACKED>(recs, i, L, s_slot, span, w, e_local, c_local)) continue;
-    const u64 e_slot = s_slot + span;
-    const u64 bs = s_slot >> GR_BLOCK_SHIFT, be = e_slot >> GR_BLOCK_SHIFT;
-    const u32 so = (u32)(s_slot & (GR_BLOCK_SLOTS - 1));
-    const int cnt = 120 / w;
-    if (be == bs) {
-      bucketed[atomicAdd(cursor + bs, 1u)] = fb_entry(so, span, cnt, FB_KIND_BOTH);
-    } else {
-      bucketed[atomicAdd(cursor + bs, 1u)] = fb_entry(so, 0, cnt, FB_KIND_START);
-      bucketed[atomicAdd(cursor + be, 1u)] = fb_entry((u32)(e_slot & (GR_BLOCK_SLOTS - 1)), 0, cnt, FB_KIND_END);
+  for (u64 i0 = (u64)blockIdx.x * (256 * FB_UNROLL) + threadIdx.x; i0 < n; i0 += stride) {
+    int4 r[FB_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++)
+      if (i0 + k * 256 < n) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
+    bool ok[FB_UNROLL], two[FB_UNROLL];
+    u32 e0[FB_UNROLL], e1[FB_UNROLL], bs[FB_UNROLL], be[FB_UNROLL], p0[FB_UNROLL], p1[FB_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++) {
+      u64 s_slot = 0; u32 span = 0; int w = 120;
+      ok[k] = i0 + k * 256 < n && decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local);
+      const u64 e_slot = s_slot + span;
+      bs[k] = (u32)(s_slot >> shift);
+      be[k] = (u32)(e_slot >> shift);
+      two[k] = ok[k] && be[k] != bs[k];
+      const u32 so = (u32)s_slot & omask;
+      const int cnt = 120 / w;
+      e0[k] = two[k] ? fb_entry(so, 0, cnt, FB_KIND_START) : fb_entry(so, span, cnt, FB_KIND_BOTH);
+      e1[k] = fb_entry((u32)e_slot & omask, 0, cnt, FB_KIND_END);
+    }
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++) {              // the cursor atomics of all records, back to back
+      p0[k] = ok[k] ? atomicAdd(cursor + bs[k], 1u) : 0u;
+      p1[k] = two[k] ? atomicAdd(cursor + be[k], 1u) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++) {
+      if (ok[k]) bucketed[p0[k]] = e0[k];
+      if (two[k]) bucketed[p1[k]] = e1[k];
     }
   }
 }
 
-#define FB_THREADS 256
+#define FB_WORDS (GR_BLOCK_SLOTS / 32)                 // occupancy / break bitmap words per block
 #define FB_RING 128                                    // page ring: sequence numbers in flight <= 2 * 33 + 2
-template <int CPS>
-__global__ void __launch_bounds__(FB_THREADS, CPS)
+// NT threads per CTA, each owning WPT = 256 / NT consecutive bitmap words (32 * WPT cells);
+// PF entry registers per thread are fetched one block ahead (PF * NT = 512 entries).
+template <int CPS, int NT>
+__global__ void __launch_bounds__(NT, CPS)
 k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
           u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R) {
+  constexpr int WPT = FB_WORDS / NT, PF = 512 / NT, NW = NT / 32;
   __shared__ int sm_cell[GR_BLOCK_SLOTS];
-  __shared__ u32 sm_occ[GR_BLOCK_SLOTS / 32];
+  __shared__ u32 sm_occ[FB_WORDS];
   __shared__ u32 sm_pg[FB_RING];
-  __shared__ u32 sm_ws[8], sm_wc[8];
+  __shared__ u32 sm_ws[NW], sm_wc[NW];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const u32 owner = blockIdx.x;
   const u32 b0 = owner * R, b1 = min(b0 + R, nblocks);
@@ -760,12 +806,11 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
     if (t == 0) W.warp_tot[owner] = make_uint2(0, 0);
     return;
   }
-  for (int i = t; i < GR_BLOCK_SLOTS; i += FB_THREADS) sm_cell[i] = 0;
-  sm_occ[t] = 0;
+  for (int i = t; i < GR_BLOCK_SLOTS; i += NT) sm_cell[i] = 0;
+  for (int i = t; i < FB_WORDS; i += NT) sm_occ[i] = 0;
 
   // bucket bounds of blocks b, b+1, b+2 (rolling; the entry for b+3 is fetched a block ahead)
-  const u32* bs_ptr = blk_start;
-  auto ld_start = [&](u32 i) { return bs_ptr[min(i, nblocks)]; };
+  auto ld_start = [&](u32 i) { return blk_start[min(i, nblocks)]; };
   u32 sA = ld_start(b0), sB = ld_start(b0 + 1), sC = ld_start(b0 + 2);
   // upper bound of the breaks of a block: two cells per entry, plus the chromosome end
   auto ub_of = [&](u32 a, u32 b) { return min(2u * (b - a) + 1u, (u32)GR_BLOCK_SLOTS + 1u); };
@@ -795,41 +840,39 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   };
   if (t == 0) page_ask(ub_of(sA, sB));
 
-  // the first two rounds of the block's entries are fetched while the previous block is worked on
-  u32 v0 = 0, v1 = 0;
-  if (sA + t < sB) v0 = __ldcs(bucketed + sA + t);
-  if (sA + FB_THREADS + t < sB) v1 = __ldcs(bucketed + sA + FB_THREADS + t);
+  // the first PF rounds of a block's entries are fetched while the previous block is worked on
+  u32 v[PF];
+#pragma unroll
+  for (int k = 0; k < PF; k++) {
+    v[k] = 0;
+    if (sA + k * NT + t < sB) v[k] = __ldcs(bucketed + sA + k * NT + t);
+  }
 
-  auto apply = [&](u32 v) {
-    const u32 so = v & (GR_BLOCK_SLOTS - 1), kind = v >> 30;
-    const int w = 120 / (int)((v >> 26) & 15u);
-    if (kind == FB_KIND_END) {
-      atomicAdd(sm_cell + so, -w);
-      atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
-    } else {
-      atomicAdd(sm_cell + so, w);
-      atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
-      if (kind == FB_KIND_BOTH) {
-        const u32 eo = so + ((v >> 13) & (GR_BLOCK_SLOTS - 1));
-        atomicAdd(sm_cell + eo, -w);
-        atomicOr(sm_occ + (eo >> 5), 1u << (eo & 31));
-      }
+  auto apply = [&](u32 e) {
+    const u32 so = e & (GR_BLOCK_SLOTS - 1), kind = e >> 30;
+    const int w = 120 / (int)((e >> 26) & 15u);
+    atomicAdd(sm_cell + so, kind == FB_KIND_END ? -w : w);
+    atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
+    if (kind == FB_KIND_BOTH) {
+      const u32 eo = so + ((e >> 13) & (GR_BLOCK_SLOTS - 1));
+      atomicAdd(sm_cell + eo, -w);
+      atomicOr(sm_occ + (eo >> 5), 1u << (eo & 31));
     }
   };
 
   u32 run_s = 0, run_c = 0;                            // height / #breaks since the start of the run
-  int c = -1, c_next = L.blk2chrom[b0];
+  int c = -1;
+  u32 c_last_blk = 0;                                  // last block of chromosome c
   u64 off = 0;
   u32 len = 0;
   bool act = false;
   __syncthreads();
   for (u32 b = b0; b < b1; b++) {
-    const int cn = c_next;
-    if (b + 1 < b1) c_next = L.blk2chrom[b + 1];
-    if (cn != c) {                                     // ~25 times per genome
-      c = cn;
+    if (c < 0 || b > c_last_blk) {                     // ~25 times per genome
+      c = L.blk2chrom[b];
       off = L.off[c];
       len = L.len[c];
+      c_last_blk = (u32)((off + len) >> GR_BLOCK_SHIFT);
       act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
     }
     const u32 sD = ld_start(b + 3);                    // used two blocks from now
@@ -839,61 +882,78 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
       page_take();                                     // covers this block (asked for a block ago)
       page_ask(run_c + ub_of(sA, sB) + (b + 1 < b1 ? ub_of(sB, sC) : 0u));
     }
-    const bool has_end = act && len >= jb && len - jb < GR_BLOCK_SLOTS;   // cell `len` lies in this block
+    const bool has_end = act && b == c_last_blk;       // cell `len` lies in this block
+    u32* const bm_out = bitmap + (u64)b * FB_WORDS + t * WPT;
     if (sA == sB && !has_end) {                        // nothing in this block
-      bitmap[(u64)b * (GR_BLOCK_SLOTS / 32) + t] = 0;
-      if (sB + t < sC) v0 = __ldcs(bucketed + sB + t);
-      if (sB + FB_THREADS + t < sC) v1 = __ldcs(bucketed + sB + FB_THREADS + t);
+      if (WPT == 1) bm_out[0] = 0;
+      else if (WPT == 2) *reinterpret_cast<uint2*>(bm_out) = make_uint2(0, 0);
+      else *reinterpret_cast<uint4*>(bm_out) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < PF; k++)
+        if (sB + k * NT + t < sC) v[k] = __ldcs(bucketed + sB + k * NT + t);
       sA = sB; sB = sC; sC = sD;
       continue;
     }
     // ---- events -> cells
-    if (sA + t < sB) apply(v0);
-    if (sA + FB_THREADS + t < sB) apply(v1);
-    for (u32 i = sA + 2 * FB_THREADS + t; i < sB; i += FB_THREADS) apply(__ldcs(bucketed + i));
-    if (sB + t < sC) v0 = __ldcs(bucketed + sB + t);   // next block's entries: in flight during the scan
-    if (sB + FB_THREADS + t < sC) v1 = __ldcs(bucketed + sB + FB_THREADS + t);
+#pragma unroll
+    for (int k = 0; k < PF; k++)
+      if (sA + k * NT + t < sB) apply(v[k]);
+    for (u32 i = sA + PF * NT + t; i < sB; i += NT) apply(__ldcs(bucketed + i));
+#pragma unroll
+    for (int k = 0; k < PF; k++)                       // next block's entries: in flight during the scan
+      if (sB + k * NT + t < sC) v[k] = __ldcs(bucketed + sB + k * NT + t);
     __syncthreads();
-    // ---- this thread's 32 cells: sum of the deltas, break mask
-    u32 mo = sm_occ[t];
-    sm_occ[t] = 0;
-    if (has_end && (int)((len - jb) >> 5) == t) mo |= 1u << ((len - jb) & 31);
-    const int cbase = t * 32;
+    // ---- this thread's 32 * WPT cells: sum of the deltas, break masks
+    const u32 end_cell = len - jb;                     // meaningful if has_end
+    u32 mo[WPT], m[WPT];
+    u32 s = 0, cnt = 0;
+    const int cbase = t * (32 * WPT);
     const u32 jt = jb + (u32)cbase;
-    u32 s = 0, m = 0;
-    for (u32 mm = mo; mm; mm &= mm - 1) {
-      const int bit = __ffs(mm) - 1;
-      const int d = sm_cell[cbase + bit];
-      const u32 j = jt + (u32)bit;
-      s += (u32)d;
-      const bool brk = (j == len) || (d != 0 && j >= 1u && j < len);
-      m |= (brk ? 1u : 0u) << bit;
+#pragma unroll
+    for (int q = 0; q < WPT; q++) {
+      mo[q] = sm_occ[t * WPT + q];
+      sm_occ[t * WPT + q] = 0;
+      if (has_end && (int)(end_cell >> 5) == t * WPT + q) mo[q] |= 1u << (end_cell & 31);
+      m[q] = 0;
+      for (u32 mm = mo[q]; mm; mm &= mm - 1) {
+        const int bit = __ffs(mm) - 1;
+        const int d = sm_cell[cbase + q * 32 + bit];
+        const u32 j = jt + (u32)(q * 32 + bit);
+        s += (u32)d;
+        const bool brk = (j == len) || (d != 0 && j >= 1u && j < len);
+        m[q] |= (brk ? 1u : 0u) << bit;
+      }
+      if (!act) m[q] = 0;
+      cnt += __popc(m[q]);
     }
-    if (!act) m = 0;
-    const u32 cnt = __popc(m);
     const u32 wi_s = warp_incl_scan_u32(s, lane), wi_c = warp_incl_scan_u32(cnt, lane);
     if (lane == 31) { sm_ws[wid] = wi_s; sm_wc[wid] = wi_c; }
     __syncthreads();
     u32 h = run_s + wi_s - s, idx = run_c + wi_c - cnt, tot_s = 0, tot_c = 0;
 #pragma unroll
-    for (int k = 0; k < FB_THREADS / 32; k++) {
+    for (int k = 0; k < NW; k++) {
       const u32 a = sm_ws[k], q = sm_wc[k];
       if (k < wid) { h += a; idx += q; }
       tot_s += a; tot_c += q;
     }
     // ---- emit, clearing the cells behind
-    for (u32 mm = mo; mm; mm &= mm - 1) {
-      const int bit = __ffs(mm) - 1;
-      const int d = sm_cell[cbase + bit];
-      sm_cell[cbase + bit] = 0;
-      if ((m >> bit) & 1u) {
-        const u32 pg = sm_pg[(idx >> SS_PAGE_SHIFT) & (FB_RING - 1)];
-        W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(jt + (u32)bit, h);
-        idx++;
+#pragma unroll
+    for (int q = 0; q < WPT; q++) {
+      for (u32 mm = mo[q]; mm; mm &= mm - 1) {
+        const int bit = __ffs(mm) - 1;
+        const int d = sm_cell[cbase + q * 32 + bit];
+        sm_cell[cbase + q * 32 + bit] = 0;
+        if ((m[q] >> bit) & 1u) {
+          const u32 pg = sm_pg[(idx >> SS_PAGE_SHIFT) & (FB_RING - 1)];
+          W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(jt + (u32)(q * 32 + bit), h);
+          idx++;
+        }
+        h += (u32)d;
       }
-      h += (u32)d;
     }
-    bitmap[(u64)b * (GR_BLOCK_SLOTS / 32) + t] = m;
+    if (WPT == 1) bm_out[0] = m[0];
+    else if (WPT == 2) *reinterpret_cast<uint2*>(bm_out) = make_uint2(m[0], m[WPT > 1 ? 1 : 0]);
+    else *reinterpret_cast<uint4*>(bm_out) = make_uint4(m[0], m[WPT > 1 ? 1 : 0], m[WPT > 2 ? 2 : 0], m[WPT > 3 ? 3 : 0]);
     run_s += tot_s;
     run_c += tot_c;
     sA = sB; sB = sC; sC = sD;
@@ -905,36 +965,197 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   }
 }
 
+// Warp-owned form: the buckets are 2^SHIFT cells (2048 or 4096), every WARP owns a contiguous
+// run of them and a private cell array -- no __syncthreads anywhere, 24 (12) independent warps
+// per SM instead of 6 CTAs that meet at three barriers per block (ncu on the CTA form: 6 barrier
+// stall cycles per issued instruction, issue slots half empty).
+#define FW_RING 64                                     // page ring per warp: <= 2 * 17 + 2 sequence numbers in flight
+template <int SHIFT>
+__global__ void __launch_bounds__(128)
+k_fw_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
+          u32* __restrict__ bitmap, int* __restrict__ err, u32 nbk, u32 R) {
+  constexpr int CELLS = 1 << SHIFT, WORDS = CELLS / 32, WPT = WORDS / 32, PF = 2;
+  extern __shared__ int sm_cell_all[];                  // 4 * CELLS
+  __shared__ u32 sm_occ_all[4 * WORDS];
+  __shared__ u32 sm_pg_all[4 * FW_RING];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int* const sm_cell = sm_cell_all + wid * CELLS;
+  u32* const sm_occ = sm_occ_all + wid * WORDS;
+  u32* const sm_pg = sm_pg_all + wid * FW_RING;
+  const u32 owner = blockIdx.x * 4 + wid;
+  const u32 b0 = owner * R, b1 = min(b0 + R, nbk);
+  if (b0 >= b1) {
+    if (lane == 0 && owner < SS_MAX_WARPS) W.warp_tot[owner] = make_uint2(0, 0);
+    return;
+  }
+  for (int i = lane; i < CELLS; i += 32) sm_cell[i] = 0;
+  for (int i = lane; i < WORDS; i += 32) sm_occ[i] = 0;
+
+  auto ld_start = [&](u32 i) { return blk_start[min(i, nbk)]; };
+  u32 sA = ld_start(b0), sB = ld_start(b0 + 1), sC = ld_start(b0 + 2);
+  auto ub_of = [&](u32 a, u32 b) { return min(2u * (b - a) + 1u, (u32)CELLS + 1u); };
+
+  const u32 last_page = W.max_pages - 1;
+  int have_seq = -1;
+  u32 pend_p0 = 0;
+  int pend_k = 0;
+  auto page_take = [&]() {
+    for (int i = 0; i < pend_k; i++) {
+      u32 pg = pend_p0 + (u32)i;
+      if (pg > last_page) { atomicOr(err, GR_DE_TABLE); pg = last_page; }
+      have_seq++;
+      W.page_meta[pg] = make_uint2(owner, (u32)have_seq);
+      sm_pg[have_seq & (FW_RING - 1)] = pg;
+    }
+    pend_k = 0;
+  };
+  auto page_ask = [&](u32 upto_idx) {
+    const int target = (int)(upto_idx >> SS_PAGE_SHIFT);
+    if (target > have_seq) {
+      pend_k = target - have_seq;
+      pend_p0 = atomicAdd(W.page_ctr, (u32)pend_k);
+    }
+  };
+  if (lane == 0) page_ask(ub_of(sA, sB));
+
+  u32 v[PF];
+#pragma unroll
+  for (int k = 0; k < PF; k++) {
+    v[k] = 0;
+    if (sA + k * 32 + lane < sB) v[k] = __ldcs(bucketed + sA + k * 32 + lane);
+  }
+  auto apply = [&](u32 e) {
+    const u32 so = e & (CELLS - 1), kind = e >> 30;
+    const int w = 120 / (int)((e >> 26) & 15u);
+    atomicAdd(sm_cell + so, kind == FB_KIND_END ? -w : w);
+    atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
+    if (kind == FB_KIND_BOTH) {
+      const u32 eo = so + ((e >> 13) & (GR_BLOCK_SLOTS - 1));
+      atomicAdd(sm_cell + eo, -w);
+      atomicOr(sm_occ + (eo >> 5), 1u << (eo & 31));
+    }
+  };
+
+  u32 run_s = 0, run_c = 0;
+  int c = -1;
+  u32 c_last_bk = 0;
+  u64 off = 0;
+  u32 len = 0;
+  bool act = false;
+  __syncwarp();
+  for (u32 b = b0; b < b1; b++) {
+    if (c < 0 || b > c_last_bk) {                      // ~25 times per genome
+      c = L.blk2chrom[b >> (GR_BLOCK_SHIFT - SHIFT)];
+      off = L.off[c];
+      len = L.len[c];
+      c_last_bk = (u32)((off + len) >> SHIFT);
+      act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
+    }
+    const u32 sD = ld_start(b + 3);
+    const u32 jb = (u32)(((u64)b << SHIFT) - off);     // chromosome position of the bucket's first cell
+    if (lane == 0) {
+      if (jb == 0) W.marks[c] = make_uint4(owner, run_s, run_c, 1u);
+      page_take();
+      page_ask(run_c + ub_of(sA, sB) + (b + 1 < b1 ? ub_of(sB, sC) : 0u));
+    }
+    const bool has_end = act && b == c_last_bk;        // cell `len` lies in this bucket
+    u32* const bm_out = bitmap + (u64)b * WORDS + lane * WPT;
+    if (sA == sB && !has_end) {                        // nothing in this bucket
+      if (WPT == 2) *reinterpret_cast<uint2*>(bm_out) = make_uint2(0, 0);
+      else *reinterpret_cast<uint4*>(bm_out) = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < PF; k++)
+        if (sB + k * 32 + lane < sC) v[k] = __ldcs(bucketed + sB + k * 32 + lane);
+      sA = sB; sB = sC; sC = sD;
+      continue;
+    }
+#pragma unroll
+    for (int k = 0; k < PF; k++)
+      if (sA + k * 32 + lane < sB) apply(v[k]);
+    for (u32 i = sA + PF * 32 + lane; i < sB; i += 32) apply(__ldcs(bucketed + i));
+#pragma unroll
+    for (int k = 0; k < PF; k++)
+      if (sB + k * 32 + lane < sC) v[k] = __ldcs(bucketed + sB + k * 32 + lane);
+    __syncwarp();
+    const u32 end_cell = len - jb;                     // meaningful if has_end
+    u32 mo[WPT], m[WPT];
+    u32 s = 0, cnt = 0;
+    const int cbase = lane * (32 * WPT);
+    const u32 jt = jb + (u32)cbase;
+#pragma unroll
+    for (int q = 0; q < WPT; q++) {
+      mo[q] = sm_occ[lane * WPT + q];
+      sm_occ[lane * WPT + q] = 0;
+      if (has_end && (int)(end_cell >> 5) == lane * WPT + q) mo[q] |= 1u << (end_cell & 31);
+      m[q] = 0;
+      for (u32 mm = mo[q]; mm; mm &= mm - 1) {
+        const int bit = __ffs(mm) - 1;
+        const int d = sm_cell[cbase + q * 32 + bit];
+        const u32 j = jt + (u32)(q * 32 + bit);
+        s += (u32)d;
+        const bool brk = (j == len) || (d != 0 && j >= 1u && j < len);
+        m[q] |= (brk ? 1u : 0u) << bit;
+      }
+      if (!act) m[q] = 0;
+      cnt += __popc(m[q]);
+    }
+    const u32 wi_s = warp_incl_scan_u32(s, lane), wi_c = warp_incl_scan_u32(cnt, lane);
+    u32 h = run_s + wi_s - s, idx = run_c + wi_c - cnt;
+#pragma unroll
+    for (int q = 0; q < WPT; q++) {
+      for (u32 mm = mo[q]; mm; mm &= mm - 1) {
+        const int bit = __ffs(mm) - 1;
+        const int d = sm_cell[cbase + q * 32 + bit];
+        sm_cell[cbase + q * 32 + bit] = 0;
+        if ((m[q] >> bit) & 1u) {
+          const u32 pg = sm_pg[(idx >> SS_PAGE_SHIFT) & (FW_RING - 1)];
+          W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(jt + (u32)(q * 32 + bit), h);
+          idx++;
+        }
+        h += (u32)d;
+      }
+    }
+    if (WPT == 2) *reinterpret_cast<uint2*>(bm_out) = make_uint2(m[0], m[1]);
+    else *reinterpret_cast<uint4*>(bm_out) = make_uint4(m[0], m[1], m[WPT > 2 ? 2 : 0], m[WPT > 3 ? 3 : 0]);
+    run_s += __shfl_sync(GR_FULL, wi_s, 31);
+    run_c += __shfl_sync(GR_FULL, wi_c, 31);
+    sA = sB; sB = sC; sC = sD;
+    __syncwarp();                                      // cells and occupancy words are free again
+  }
+  if (lane == 0) {
+    page_take();
+    W.warp_tot[owner] = make_uint2(run_s, run_c);
+  }
+}
+
 void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
-                     u32* blk_cnt, int* err, u64* clamped) {
+                     u32* blk_cnt, int* err, u64* clamped, int shift) {
   if (!n) return;
-  u64 blocks = (n + 255) / 256;
+  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_fb_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
-  else k_fb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
+  if (packed) k_fb_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped, shift);
+  else k_fb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped, shift);
   GR_NOTE_LAUNCH();
 }
-void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed) {
+void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
+                    int shift) {
   if (!n) return;
-  u64 blocks = (n + 255) / 256;
+  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
-  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
+  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, shift);
+  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, shift);
   GR_NOTE_LAUNCH();
 }
 
-static u32 fb_owners() {                               // CTAs of one k_fb_scan launch
-  static u32 n = 0;
-  if (!n) {
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char* e = getenv("GR_FUSED_CPS");            // tuning knob: CTAs per SM (4 or 6)
-    const int cps = e && atoi(e) == 4 ? 4 : 6;
-    n = (u32)(sms * cps);
-    if (n > SS_MAX_WARPS) n = SS_MAX_WARPS;
-  }
-  return n;
+static int fb_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+// GR_FUSED_SHIFT: log2 of the bucket size -- 13 (default): CTA-owned 8192-cell blocks (k_fb_scan,
+// with GR_FUSED_CPS / GR_FUSED_NT); 11 or 12: warp-owned buckets (k_fw_scan).  Measured on the
+// hg38 workload, ms per sample (bucket passes + scan): 13: 1.02 + 1.55; 12: 1.31 + 1.80;
+// 11: 1.84 + 1.25 -- the scan likes small buckets (more independent owners per SM), the move
+// pass does not (4x the open write sectors in L2).
+int fb_bucket_shift() {                                // read per call: the tests switch it inside one process
+  const int sh = fb_env("GR_FUSED_SHIFT", 13);
+  return sh < 11 || sh > 13 ? 13 : sh;
 }
 
 // bucketed events -> breaks (pages) + break bitmap; launch_scan_place(..., owners) follows
@@ -942,14 +1163,39 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
                    const ScanScratch& sc, u32* bitmap, int* err) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   cudaMemsetAsync(W.page_ctr, 0, 4, s);
-  const u32 owners = fb_owners();
-  const u32 nb = (u32)L.nblocks;
-  const u32 R = (nb + owners - 1) / owners;
-  int dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (owners == (u32)sms * 4) k_fb_scan<4><<<owners, FB_THREADS, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
-  else k_fb_scan<6><<<owners, FB_THREADS, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int cps = fb_env("GR_FUSED_CPS", 6) == 4 ? 4 : 6, nt = fb_env("GR_FUSED_NT", 128);
+  const int sh = fb_bucket_shift();
+  u32 owners;
+  if (sh == 13) {
+    owners = (u32)(sms * cps);
+    const u32 nb = (u32)L.nblocks;
+    const u32 R = (nb + owners - 1) / owners;
+#define FB_LAUNCH(C, N) k_fb_scan<C, N><<<owners, N, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R)
+    if (cps == 4) { if (nt == 256) FB_LAUNCH(4, 256); else if (nt == 64) FB_LAUNCH(4, 64); else FB_LAUNCH(4, 128); }
+    else { if (nt == 256) FB_LAUNCH(6, 256); else if (nt == 64) FB_LAUNCH(6, 64); else FB_LAUNCH(6, 128); }
+#undef FB_LAUNCH
+  } else {
+    const int ctas = sms * (sh == 11 ? 6 : 3);         // 4 warps each: 35 KB (68 KB) of shared memory per CTA
+    owners = (u32)ctas * 4;
+    if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
+    const u32 nbk = (u32)(L.T >> sh);
+    const u32 R = (nbk + owners - 1) / owners;
+    const size_t smem = (size_t)16 << sh;              // 4 warps x 2^sh cells x 4 bytes
+    static bool init = false;
+    if (!init) {
+      cudaFuncSetAttribute(k_fw_scan<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 11);
+      cudaFuncSetAttribute(k_fw_scan<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12);
+      init = true;
+    }
+    if (sh == 11) k_fw_scan<11><<<owners / 4, 128, smem, s>>>(bucketed, blk_start, L, W, bitmap, err, nbk, R);
+    else k_fw_scan<12><<<owners / 4, 128, smem, s>>>(bucketed, blk_start, L, W, bitmap, err, nbk, R);
+  }
   GR_NOTE_LAUNCH();
   return owners;
 }

@@ -36,7 +36,7 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
 // bucketed build of the delta array (large samples): count -> scan -> move -> build (+ spills)
 void launch_sb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
                      u32* blk_cnt, int* err, u64* clamped);
-void launch_sb_scan(cudaStream_t s, const DevLayout& L, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum);
+void launch_sb_scan(cudaStream_t s, u64 nbuckets, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum);
 void launch_sb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
                     uint2* spill, u32* spill_ctr);
 void launch_sb_build(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
@@ -55,9 +55,12 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
 void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners);
 
 // ---- K1+K2 fused: event buckets -> breaks, the delta cells live in shared memory only ----
+// buckets of 2^shift cells, shift = fb_bucket_shift()
+int fb_bucket_shift();
 void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
-                     u32* blk_cnt, int* err, u64* clamped);
-void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed);
+                     u32* blk_cnt, int* err, u64* clamped, int shift);
+void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
+                    int shift);
 // returns the number of run owners (CTAs), to be handed to launch_scan_place
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
                    const ScanScratch& sc, u32* bitmap, int* err);

@@ -261,8 +261,10 @@ def test_fused_scan_same_bits(monkeypatch):
         [6, 0, 16383, 1], [6, 8100, 16383, 2], [6, 16382, 16383, 3],
     ], dtype=np.int32)
     par = capi.make_params(p=0.2, min_auc=0.5, keep_pileups=True)
-    outs = _run_modes(monkeypatch, L, par, [(recs, None)], (PLAIN, FUSED))
-    _same_outs(outs[0], outs[1], "edge")
+    modes = (PLAIN, FUSED, dict(FUSED, GR_FUSED_SHIFT="12"), dict(FUSED, GR_FUSED_SHIFT="11"))
+    outs = _run_modes(monkeypatch, L, par, [(recs, None)], modes)
+    for o in outs[1:]:
+        _same_outs(outs[0], o, "edge")
     assert outs[1][0].sample_stats[0].n_clamped == 3
 
 
@@ -273,10 +275,11 @@ def test_fused_scan_large(monkeypatch):
     t = Workload(L, 4_000_000, 101, enrich=0.5, spacing=400000, sigma=60.0).fragments()
     c = Workload(L, 4_000_000, 102, enrich=0.0).fragments()
     par = capi.make_params(p=0.01, min_auc=20.0)
-    outs = _run_modes(monkeypatch, L, par, [(t, c)], ({"GR_FUSED": "0"}, {"GR_FUSED": "1"}, {"GR_FUSED": "1", "GR_FUSED_CPS": "4"}),
-                      chunk=1 << 22)
-    _same_outs(outs[0], outs[1], "large")
-    _same_outs(outs[0], outs[2], "large cps4")
+    modes = ({"GR_FUSED": "0"}, {"GR_FUSED": "1"}, {"GR_FUSED": "1", "GR_FUSED_SHIFT": "12"},
+             {"GR_FUSED": "1", "GR_FUSED_SHIFT": "11"}, {"GR_FUSED": "1", "GR_FUSED_SHIFT": "13", "GR_FUSED_NT": "256", "GR_FUSED_CPS": "4"})
+    outs = _run_modes(monkeypatch, L, par, [(t, c)], modes, chunk=1 << 22)
+    for o, md in zip(outs[1:], modes[1:]):
+        _same_outs(outs[0], o, "large %s" % md)
     st = outs[1][0].sample_stats[0]
     assert st.frag_len == float(np.sum((t[:, 2] - t[:, 1]).astype(np.int64)))
     assert len(outs[1][0].peaks) > 100
