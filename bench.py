@@ -59,7 +59,8 @@ SAMPLE = dict(chrom_len=[25_000_000] * 4, nt=1_000_000, nc=1_000_000)   # bounde
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_stream launch (bytes), from the
 # committed ncu capture of exactly this command; null for configurations that were not captured
-NCU_TRAFFIC = {("hg38_chip_50M_50M", 1, "k_scan_stream"): 12.56e9 + 3.42e9}
+NCU_TRAFFIC = {("hg38_chip_50M_50M", 1, "k_scan_stream"): 12.36e9 + 1.10e9,      # built array: nothing to clear behind
+               ("hg38_chip_50M_50M", 1, "k_fb_scan"): 0.225e9 + 1.051e9}
 
 
 def gen_fragments(chrom_len, n, seed, enrich, spacing, sigma, threads=8):
@@ -180,6 +181,7 @@ def main():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="hg38_chip_50M_50M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-formulation (GR_FUSED=0) comparison pass")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -237,7 +239,8 @@ def main():
     n_c = c_host.shape[0] if c_host is not None else 0
     torch.cuda.synchronize()
 
-    def step(from_host):
+    def step(from_host, eng=eng):
+        ctx = eng.ctx
         ctx.reset()
         eng.saved_any[:] = False
         eng.sample_stats.clear()
@@ -260,9 +263,10 @@ def main():
         eng.replicate(pe, pc, want_stats=False)
         return eng.call_peaks()
 
-    def timed(from_host, steps, warmup, with_stages=False):
+    def timed(from_host, steps, warmup, with_stages=False, eng=eng):
+        ctx = eng.ctx
         for _ in range(warmup):
-            step(from_host)
+            step(from_host, eng)
         eng.t_acc.clear()
         if with_stages:
             ctx.timing(True)
@@ -275,7 +279,7 @@ def main():
         w0 = time.perf_counter()
         for _ in range(steps):
             ctx.timer_start()
-            peaks, rs = step(from_host)
+            peaks, rs = step(from_host, eng)
             dev_ms.append(ctx.timer_stop())
         torch.cuda.synchronize()
         if world > 1:
@@ -296,6 +300,17 @@ def main():
     ms_dev, wall_dev, launches, peaks, rs, stages = timed(False, a.steps, a.warmup, with_stages=True)
     ms_e2e, wall_e2e, _, peaks2, _, _ = timed(True, a.steps, 1)
     clocks = sampler.stop() if rank == 0 else None
+    # the same per-base pass in its dense formulation (delta array in HBM: bucketed build, then
+    # k_scan_stream reads 4 B per cell): the kernel the HBM-read roofline is literally about
+    dense = None
+    if world == 1 and not a.no_dense:
+        os.environ["GR_FUSED"] = "0"
+        eng_d = ShardedEngine(api, L, par, dev, host_group=None)
+        del os.environ["GR_FUSED"]
+        ms_d, _, _, peaks_d, _, st_d = timed(False, max(2, a.steps // 2), 3, with_stages=True, eng=eng_d)
+        assert peaks_d.tobytes() == peaks.tobytes(), "dense and fused formulations disagree"
+        dense = (ms_d, st_d)
+        del eng_d
 
     if eng.debug:
         print("rank %d host-side ms per step (e2e arm): %s" % (rank, {k: round(v * 1e3 / a.steps, 3) for k, v in eng.t_acc.items()}),
@@ -313,6 +328,18 @@ def main():
     place_ms, place_launches, _ = stages.get("scan_place", (0.0, 0, 0))
     cells = ctx_cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
     achieved = 4.0 * cells / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
+    dense_obj = None
+    if dense is not None:
+        d_ms, d_n, _ = dense[1].get("dense_scan", (0.0, 0, 0))
+        b_ms, b_n, _ = dense[1].get("build", (0.0, 0, 0))
+        d_per = d_ms / max(d_n, 1)
+        d_ach = 4.0 * cells / (d_per * 1e-3) / 1e9 if d_per else 0.0
+        dense_obj = {"kernel": "k_scan_stream", "achieved": d_ach, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": d_ach / peak_gbs if peak_gbs else None, "ms_per_launch": d_per,
+                     "build_ms_per_launch": b_ms / max(b_n, 1), "ms_per_step": dense[0],
+                     "traffic": NCU_TRAFFIC.get((a.workload, world, "k_scan_stream")),
+                     "note": "GR_FUSED=0: the delta array is written to HBM by k_sb_build and read back by "
+                             "k_scan_stream (4 B per cell each way); same peaks, bit for bit"}
     stage_ms = {k: round(v[0] / a.steps, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])}
     line = {
         "metric": "Gbp p-value-scanned/sec", "value": G / 1e9 / (ms_dev * 1e-3), "unit": "Gbp/s",
@@ -336,7 +363,13 @@ def main():
                      "traffic": NCU_TRAFFIC.get((a.workload, world, scan_kernel)), "peak_source": peak_src,
                      "bytes_per_launch": 4 * cells, "ms_per_launch": per_launch_ms,
                      "companion_scan_place_ms_per_launch": place_ms / max(place_launches, 1),
-                     "launches_per_step": scan_launches / a.steps, "samples_scanned_per_step": n_samples},
+                     "launches_per_step": scan_launches / a.steps, "samples_scanned_per_step": n_samples,
+                     "note": ("the delta cells of k_fb_scan live in shared memory only: `achieved` divides the ALGORITHMIC "
+                              "bytes of the per-base pass (SURVEY 8d: 4 B per base per sample array) by the launch time, "
+                              "`traffic` is what the kernel really moves through DRAM (bucket entries in, breaks and "
+                              "bitmap out); frac > 1 = faster than any kernel that reads the array from HBM could be"
+                              if fused else "4 B per delta cell read from HBM"),
+                     "dense_formulation": dense_obj},
         "stage_ms_per_step": stage_ms,
     }
     if not a.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Genrich")):
