@@ -64,7 +64,7 @@ PEAK_DTYPE = np.dtype([("chrom", "<i4"), ("summit", "<u4"), ("start", "<i8"),
 
 # every symbol include/genrich_cuda.h declares (checked by tests/test_abi.py)
 ABI_SYMBOLS = [
-    "gr_create", "gr_destroy", "gr_set_params", "gr_reset", "gr_strerror",
+    "gr_create", "gr_destroy", "gr_set_exclusions", "gr_excluded_bp", "gr_set_params", "gr_reset", "gr_strerror",
     "gr_last_error_detail", "gr_sample_begin", "gr_push_intervals",
     "gr_push_intervals_device", "gr_prefetch_intervals", "gr_push_packed", "gr_prefetch_packed",
     "gr_sample_pileup", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
@@ -149,6 +149,8 @@ class Api:
         else:
             self.create = fn("create", C.c_int, [C.POINTER(vp), C.POINTER(GrChrom), i32, C.POINTER(GrParams)])
         self.destroy = fn("destroy", None, [vp])
+        self.set_exclusions = fn("set_exclusions", C.c_int, [vp, vp, vp, vp, u64])
+        self.excluded_bp = fn("excluded_bp", C.c_int, [vp, vp])
         self.sample_begin = fn("sample_begin", C.c_int, [vp, i32, vp])
         self.push_intervals = fn("push_intervals", C.c_int, [vp, vp, u64])
         self.sample_pileup = fn("sample_pileup", C.c_int, [vp, C.POINTER(dbl)])
@@ -231,6 +233,21 @@ class Context:
 
     def reset(self):
         self._check(self.api.reset(self._h), "reset")
+
+    def set_exclusions(self, regions):
+        """regions: iterable of (chromosome index, start, end) -- the -E BED records, unmerged.
+        Call before the first sample."""
+        r = np.asarray(list(regions), dtype=np.int64).reshape(-1, 3)
+        c = np.ascontiguousarray(r[:, 0], dtype=np.int32)
+        a = np.ascontiguousarray(r[:, 1], dtype=np.uint32)
+        b = np.ascontiguousarray(r[:, 2], dtype=np.uint32)
+        self._check(self.api.set_exclusions(self._h, _as_ptr(c), _as_ptr(a), _as_ptr(b), len(c)), "set_exclusions")
+
+    def excluded_bp(self) -> np.ndarray:
+        """Excluded bp per chromosome after merging / clamping (saveXBed 1144)."""
+        out = np.zeros(self.nchrom, dtype=np.uint64)
+        self._check(self.api.excluded_bp(self._h, _as_ptr(out)), "excluded_bp")
+        return out
 
     # -- seam IN ---------------------------------------------------------------
     def sample_begin(self, is_ctrl: bool, save=None):

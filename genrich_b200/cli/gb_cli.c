@@ -224,6 +224,61 @@ static void write_log(gr_ctx* ctx, HOut* out, const HChromTab* tab, int nrep, co
   }
 }
 
+/* -E: loadBED 5187-5240 (comma-separated BED files, plain or gzip; start < end, both >= 0) and
+ * the -v warnings of saveXBed 1151-1192.  Records of unknown references are ignored, as in the
+ * reference (saveXBed only looks for the names of the chromosomes it knows); sorting, clamping
+ * and merging happen in the library (gr_set_exclusions), exactly as saveXBed does them. */
+static void load_exclusions(gr_ctx* ctx, char* xfile, const HChromTab* tab, bool verbose) {
+  int32_t* chrom = NULL;
+  uint32_t *start = NULL, *end = NULL;
+  size_t n = 0, cap = 0;
+  static char line[65536];
+  char* save_list;
+  for (char* fname = strtok_r(xfile, ",", &save_list); fname; fname = strtok_r(NULL, ",", &save_list)) {
+    HIn in;
+    gb_in_open(&in, fname);
+    while (gb_in_gets(&in, line, sizeof line)) {
+      char copy[256];
+      snprintf(copy, sizeof copy, "%s", line);
+      char* sp;
+      char* name = strtok_r(line, "\t", &sp);
+      if (!name) gb_die(copy, ": poorly formatted BED record");
+      int pos[2];
+      for (int i = 0; i < 2; i++) {
+        char* val = strtok_r(NULL, i ? "\t\n" : "\t", &sp);
+        if (!val) gb_die(copy, ": poorly formatted BED record");
+        pos[i] = gb_parse_int(val);
+      }
+      if (pos[1] <= pos[0] || pos[0] < 0 || pos[1] < 0) {
+        char msg[512];
+        snprintf(msg, sizeof msg, "%s, %d - %d", name, pos[0], pos[1]);
+        gb_die(msg, ": poorly formatted BED record");
+      }
+      const int c = gb_chrom_find(tab, name);
+      if (c < 0) continue;
+      const uint32_t len = tab->c[c].len;
+      if (verbose && (uint32_t)pos[0] >= len) {
+        fprintf(stderr, "Warning! BED interval (%s, %d - %d) ignored\n", name, pos[0], pos[1]);
+        fprintf(stderr, "  - located off end of reference %s (length %d)\n", name, (int)len);
+      } else if (verbose && (uint32_t)pos[1] > len) {
+        fprintf(stderr, "Warning! BED interval (%s, %d - %d) extends ", name, pos[0], pos[1]);
+        fprintf(stderr, "past end of ref.\n  - edited to (%s, %d - %d)\n", name, pos[0], (int)len);
+      }
+      if (n == cap) {
+        cap = cap ? 2 * cap : 1024;
+        chrom = (int32_t*)gb_realloc(chrom, cap * sizeof *chrom);
+        start = (uint32_t*)gb_realloc(start, cap * sizeof *start);
+        end = (uint32_t*)gb_realloc(end, cap * sizeof *end);
+      }
+      chrom[n] = c; start[n] = (uint32_t)pos[0]; end[n] = (uint32_t)pos[1];
+      n++;
+    }
+    gb_in_close(&in, fname);
+  }
+  chk(ctx, gr_set_exclusions(ctx, chrom, start, end, n), "gr_set_exclusions");
+  free(chrom); free(start); free(end);
+}
+
 int main(int argc, char** argv) {
   HOpts o;
   memset(&o, 0, sizeof o);
@@ -274,7 +329,6 @@ int main(int argc, char** argv) {
     usage();
   }
   if (dups) gb_die("-r/-R", ": PCR duplicate removal is not available in genrich-b200");
-  if (xfile) gb_die("-E", ": BED exclusion lists are not available in genrich-b200");
   if (peaks_only) gb_die("-P", ": peak-calling from a log file is not available in genrich-b200");
   if (o.avg_ext_opt) { o.single_opt = true; o.extend_opt = false; }
   if (o.extend_opt) { o.single_opt = true; if (o.extend <= 0) gb_die("", "Extension length must be > 0"); }
@@ -316,6 +370,7 @@ int main(int argc, char** argv) {
   par.max_gap = o.max_gap; par.keep_pileups = (o.log_file || o.pile_file) ? 1 : 0; par.genome_len = o.genome_len;
   gr_ctx* ctx = NULL;
   chk(NULL, gr_create(&ctx, gc, tab.n, &par, o.device), "gr_create");
+  if (xfile) load_exclusions(ctx, xfile, &tab, o.verbose);
 
   HOut bed = { NULL, NULL }, pile = { NULL, NULL };
   if (o.bed_file) gb_out_open(&bed, o.bed_file, o.gz_out);

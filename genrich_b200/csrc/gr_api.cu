@@ -110,7 +110,14 @@ struct gr_ctx {
   u64 sb_min = 1ull << 20;             // samples with fewer records use the plain scatter (GR_SB_MIN)
   int fused = 1;                       // buckets -> breaks in shared memory, no delta array in HBM (GR_FUSED=0: dense array)
   u64 fused_min = 1ull << 16;          // ... for samples of at least this many records (GR_FUSED_MIN)
-  u32 scan_owners = 0;                 // run owners of the last scan (0: the warps of k_scan_stream)
+  // -E regions (saveXBed 1144): per chromosome the merged, clamped boundary list start0,end0,start1,...
+  std::vector<std::vector<u32>> bed;
+  std::vector<u64> bed_bp;             // excluded bp per chromosome
+  bool has_bed = false;
+  DevBuf bedMarks, blkBed;             // boundary cell slots (u64); per 8192-cell block: bit 0 starts inside a region, bit 1 holds boundaries
+  u32 n_marks = 0;
+  DevBuf ccSlots, ccSkip;              // no-control pileup: break slots and SKIP flags of its intervals
+  int fb_shift = 13;                   // bucket shift of the sample whose events are bucketed right now
 
   // Host mirrors of device-side results lag behind while `lag` is set: nothing on the hot path
   // waits for the device between gr_sample_begin and the peak records; whoever needs a mirror
@@ -386,7 +393,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   DevBuf* all[] = { &x->d_off, &x->d_len, &x->d_flags, &x->d_blk2chrom, &x->delta, &x->bmE, &x->bmC,
     &x->rankE, &x->rankC, &x->rankTmp, &x->lb0, &x->lb1, &x->lb2, &x->ticket, &x->scanWs, &x->small, &x->accI,
     &x->accF, &x->exptEnd, &x->exptVal, &x->exptCS, &x->exptTot, &x->rawEnd, &x->rawVal, &x->rawCS,
-    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->sbCnt, &x->sbStart, &x->sbCursor, &x->sbBucket, &x->sbSpill, &x->sbSpillCtr,
+    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->sbCnt, &x->sbStart, &x->sbCursor, &x->sbBucket, &x->sbSpill, &x->sbSpillCtr, &x->bedMarks, &x->blkBed, &x->ccSlots, &x->ccSkip,
     &x->qVal, &x->tKeys, &x->tLens, &x->tPval, &x->tQval, &x->tCount, &x->slot, &x->hk, &x->hl,
     &x->hcount, &x->bk0, &x->bk1, &x->bl0, &x->bl1, &x->bhist, &x->bksum, &x->bx, &x->bdk, &x->bdq,
     &x->bdl, &x->bdcount, &x->fsum, &x->fdf, &x->repviews, &x->evIdx, &x->evCount, &x->headIdx,
@@ -418,6 +425,76 @@ extern "C" int gr_set_params(gr_ctx* x, const gr_params* p) {
   if (!x || !p) return GR_ERR_ARG;
   x->par = *p;
   x->have_q = false;
+  return GR_OK;
+}
+
+// -E: the BED records as read (loadBED 5187 has checked start < end), any order, overlapping or
+// not.  Per chromosome exactly what saveXBed 1144-1206 does: records starting beyond the end
+// are dropped, the rest sorted by start, ends clamped to the chromosome length, overlapping or
+// touching regions merged.  Must precede the first sample.
+extern "C" int gr_set_exclusions(gr_ctx* x, const int32_t* chrom, const uint32_t* start, const uint32_t* end, uint64_t n) {
+  if (!x || (n && (!chrom || !start || !end))) return GR_ERR_ARG;
+  if (!x->reps.empty() || x->filling != FILL_NONE || x->have_expt) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  for (u64 i = 0; i < n; i++)
+    if (chrom[i] < 0 || chrom[i] >= x->nchrom || end[i] <= start[i]) return GR_ERR_ARG;
+  const int nc = x->nchrom;
+  x->bed.assign(nc, std::vector<u32>());
+  x->bed_bp.assign(nc, 0);
+  x->has_bed = false;
+  std::vector<u64> marks;
+  std::vector<uint8_t> blk(x->nblocks, 0);
+  for (int c = 0; c < nc; c++) {
+    std::vector<u32>& b = x->bed[c];
+    const u32 len = x->len[c];
+    for (u64 i = 0; i < n; i++) {
+      if (chrom[i] != c || start[i] >= len) continue;          // 1151-1160
+      size_t j = 0;
+      while (j < b.size() && start[i] > b[j]) j += 2;          // 1163-1176: before the first start >= this one
+      b.insert(b.begin() + j, { start[i], end[i] });
+    }
+    size_t i = 0;
+    while (i < b.size()) {                                     // 1181-1204
+      if (b[i + 1] > len) b[i + 1] = len;
+      if (i && b[i] <= b[i - 1]) {
+        if (b[i + 1] > b[i - 1]) b[i - 1] = b[i + 1];
+        b.erase(b.begin() + i, b.begin() + i + 2);
+      } else
+        i += 2;
+    }
+    for (size_t k = 0; k < b.size(); k += 2) x->bed_bp[c] += b[k + 1] - b[k];
+    if (b.empty()) continue;
+    x->has_bed = true;
+    if (x->off[c] == ~0ull) continue;                          // not computed here
+    // boundaries that close an interval (1 <= b < len) become marks; per block the region state at its start
+    const u64 blk0 = x->off[c] >> GR_BLOCK_SHIFT, nblk = ((u64)len + 1 + GR_BLOCK_SLOTS - 1) / GR_BLOCK_SLOTS;
+    size_t k = 0;                                              // boundaries before the block's first counted position
+    for (u64 q = 0; q < nblk; q++) {
+      const u64 first = q ? q * GR_BLOCK_SLOTS : 1;            // boundary 0 opens a region but closes no interval
+      while (k < b.size() && b[k] < first) k++;
+      uint8_t v = (uint8_t)(k & 1);
+      for (size_t m = k; m < b.size() && b[m] < (q + 1) * GR_BLOCK_SLOTS; m++)
+        if (b[m] >= 1 && b[m] < len) { v |= 2; break; }
+      blk[blk0 + q] = v;
+    }
+    for (u32 pos : b)
+      if (pos >= 1 && pos < len) marks.push_back(x->off[c] + pos);
+  }
+  x->n_marks = (u32)marks.size();
+  if (x->has_bed) {
+    CK(x->blkBed.ensure(x->nblocks));
+    CK(cudaMemcpy(x->blkBed.p, blk.data(), x->nblocks, cudaMemcpyHostToDevice));
+    if (x->n_marks) {
+      CK(x->bedMarks.ensure(marks.size() * sizeof(u64)));
+      CK(cudaMemcpy(x->bedMarks.p, marks.data(), marks.size() * sizeof(u64), cudaMemcpyHostToDevice));
+    }
+  }
+  return GR_OK;
+}
+
+extern "C" int gr_excluded_bp(gr_ctx* x, uint64_t* per_chrom) {
+  if (!x || !per_chrom) return GR_ERR_ARG;
+  for (int c = 0; c < x->nchrom; c++) per_chrom[c] = x->has_bed ? x->bed_bp[c] : 0;
   return GR_OK;
 }
 
@@ -555,26 +632,32 @@ static int push_any(gr_ctx* x, const void* recs, u64 n, int rb) {
 // fused scan (the delta array is not touched)
 static int consume_segments(gr_ctx* x, int* built) {
   int32_t* delta = x->delta.as<int32_t>();
-  const bool fb = x->fused && x->n_pushed >= x->fused_min && x->n_pushed < (1ull << 31) && (x->T >> 11) < (1ull << 32);
+  const bool fb_ok = x->n_pushed < (1ull << 31) && (x->T >> 11) < (1ull << 32);
+  // -E regions are built into the fused scan only: every sample, whatever its size, goes that way
+  if (x->has_bed && !fb_ok) { x->detail = "-E regions with more than 2^31 records in one sample"; return GR_ERR_ARG; }
+  const bool fb = fb_ok && (x->has_bed || (x->fused && x->n_pushed >= x->fused_min));
   const bool sb = !fb && x->n_pushed >= x->sb_min && x->T < (1ull << 32);
   u64 bytes = 0;
   for (auto& g : x->segs) bytes += g.n * g.rb;
   if (fb) {
-    const int sh = fb_bucket_shift();
+    const int sh = x->has_bed ? GR_BLOCK_SHIFT : fb_bucket_shift();
+    x->fb_shift = sh;
     const u64 nbk = x->T >> sh;
     CK(x->sbCnt.ensure(nbk * 4));
     CK(x->sbStart.ensure((nbk + 1) * 4));
     CK(x->sbCursor.ensure(nbk * 4));
-    CK(x->sbBucket.ensure(x->n_pushed * 8));             // at most two event entries per record
+    CK(x->sbBucket.ensure(x->n_pushed * 8 + (u64)x->n_marks * 4 + 16));   // at most two event entries per record
     CK(x->sbSpillCtr.ensure(4 + (nbk / 4096 + 2) * 4));  // (unused word), then the scan's chunk sums
     stage_begin(x, "bucket", bytes);
     CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4, x->stream));
     for (auto& g : x->segs)
       launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped, sh);
+    launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, x->sbCnt.as<u32>(), nullptr, nullptr, sh);
     launch_sb_scan(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
                    x->sbSpillCtr.as<u32>() + 1);
     for (auto& g : x->segs)
       launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
+    launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, nullptr, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
     CKL();
     stage_end(x);
   } else if (sb) {
@@ -708,7 +791,7 @@ static int pileup_enqueue(gr_ctx* x) {
   const bool ctrl = x->filling == FILL_CTRL;
   int nact = 0;
   for (int c = 0; c < x->nchrom; c++) nact += chrom_active(x, c);
-  const u64 cap = 2 * x->n_pushed + (u64)nact + 1;
+  const u64 cap = 2 * x->n_pushed + (u64)nact + 1 + x->n_marks;
   DevBuf& E = ctrl ? x->rawEnd : x->exptEnd;
   DevBuf& V = ctrl ? x->rawVal : x->exptVal;
   DevBuf& CS = ctrl ? x->rawCS : x->exptCS;
@@ -728,7 +811,8 @@ static int pileup_enqueue(gr_ctx* x) {
   if (built == 2) {
     stage_begin(x, "fused_scan", x->T * 4);
     owners = launch_fb_scan(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), sc,
-                            (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err);
+                            (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, x->fb_shift,
+                            x->has_bed ? x->blkBed.as<uint8_t>() : nullptr);
     CKL();
     stage_end(x);
   } else {
@@ -739,7 +823,7 @@ static int pileup_enqueue(gr_ctx* x) {
     stage_end(x);
   }
   stage_begin(x, "scan_place", cap * 16);
-  launch_scan_place(x->stream, x->L, sc, out, x->d_err, owners);
+  launch_scan_place(x->stream, x->L, sc, out, x->d_err, owners, ctrl ? GR_SKIP : 0.0f);
   CKL();
   stage_end(x);
   u64* aI = x->accI.as<u64>() + (ctrl ? x->nchrom : 0);
@@ -870,23 +954,37 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
     CKL();
     stage_end(x);
   } else {
-    // saveLambda 1838-1843: one interval (len, lambda) per saved chromosome
-    std::vector<u32> e; std::vector<u64> cs(nc + 1);
+    // saveLambda 1838-1877: lambda over every saved chromosome, SKIP inside its -E regions
+    std::vector<u32> e; std::vector<u64> cs(nc + 1), slots; std::vector<uint8_t> skp;
     for (int c = 0; c < nc; c++) {
       cs[c] = e.size();
-      if (chrom_active(x, c)) e.push_back(x->len[c]);
+      if (!chrom_active(x, c)) continue;
+      const u32 len = x->len[c];
+      bool save = true;
+      if (x->has_bed)
+        for (u32 b : x->bed[c]) {                              // boundary 0 opens a region and closes no interval;
+          if (b >= len) break;                                 // boundary len: the last interval is closed below
+          if (b >= 1) { e.push_back(b); slots.push_back(x->off[c] + b); skp.push_back(save ? 0 : 1); }
+          save = !save;
+        }
+      e.push_back(len); slots.push_back(x->off[c] + len); skp.push_back(save ? 0 : 1);
     }
     cs[nc] = e.size();
     n_ctrl_upper = e.size();
     CK(x->ctrlEnd.ensure((e.size() + 1) * sizeof(u32)));
     CK(x->ctrlVal.ensure((e.size() + 1) * sizeof(float)));
+    CK(x->ccSlots.ensure((e.size() + 1) * sizeof(u64)));
+    CK(x->ccSkip.ensure(e.size() + 1));
     { int r = upload(x, x->ctrlEnd.p, e.data(), e.size() * sizeof(u32)); if (r) return r; }
+    { int r = upload(x, x->ccSlots.p, slots.data(), slots.size() * sizeof(u64)); if (r) return r; }
+    { int r = upload(x, x->ccSkip.p, skp.data(), skp.size()); if (r) return r; }
     { int r = upload(x, x->ctrlCS.p, cs.data(), (nc + 1) * sizeof(u64)); if (r) return r; }
     u64 tot = e.size();
     { int r = upload(x, x->ctrlTot.p, &tot, 8); if (r) return r; }
     stage_begin(x, "ctrl_const", x->T / 8);
     DevRle out = rle_view(x->ctrlEnd, x->ctrlVal, x->ctrlCS, x->ctrlTot);
-    launch_ctrl_const(x->stream, x->L, x->dpar.as<float>() + 1, e.size(), out, x->bmC.as<u32>());
+    launch_ctrl_const(x->stream, x->L, x->dpar.as<float>() + 1, e.size(), out, x->bmC.as<u32>(),
+                      x->ccSlots.as<u64>(), x->ccSkip.as<uint8_t>());
     CKL();
     stage_end(x);
   }
@@ -953,7 +1051,7 @@ static u64 replicate_genome_len(const gr_ctx* x, u64 genome_len) {
   u64 G = x->par.genome_len ? x->par.genome_len : genome_len;
   if (!G)
     for (int c = 0; c < x->nchrom; c++)
-      if (chrom_active(x, c)) G += x->len[c];                  // calcLambda 1819-1827
+      if (chrom_active(x, c)) G += x->len[c] - (x->has_bed ? x->bed_bp[c] : 0);   // calcLambda 1819-1827
   return G;
 }
 
@@ -1127,7 +1225,7 @@ static u64 final_genome_len(const gr_ctx* x) {        // findPeaks 1091-1101
   u64 G = 0;
   const Replicate* f = x->fin;
   for (int c = 0; c < x->nchrom; c++)
-    if (!x->skip[c] && f->chrom_start_h[c + 1] > f->chrom_start_h[c]) G += x->len[c];
+    if (!x->skip[c] && f->chrom_start_h[c + 1] > f->chrom_start_h[c]) G += x->len[c] - (x->has_bed ? x->bed_bp[c] : 0);
   return G;
 }
 

@@ -584,7 +584,7 @@ k_scan_fix(DevLayout L, StreamWs W, DevRle out, int* __restrict__ err, u32 nwarp
 // K2c: every page goes to its final rank; heights become the reference's floats.
 // Two pages per CTA and step: their three-deep lookup chains (page -> warp -> base) overlap.
 __global__ void __launch_bounds__(2 * SS_PAGE)
-k_scan_place(StreamWs W, DevRle out, int* __restrict__ err) {
+k_scan_place(StreamWs W, DevRle out, int* __restrict__ err, float excl_val) {
   __shared__ float4 sm_lut[120];
   units_lut_fill(sm_lut, threadIdx.x, 2 * SS_PAGE);
   __syncthreads();
@@ -600,8 +600,9 @@ k_scan_place(StreamWs W, DevRle out, int* __restrict__ err) {
     const int N = (int)((u32)wb.x + e.y);
     neg |= N < 0;
     const u64 rank = wb.y + first + t;
-    out.end[rank] = e.x;
-    out.val[rank] = units_to_val_lut(sm_lut, N < 0 ? 0 : N);
+    out.end[rank] = e.x & 0x7fffffffu;
+    // bit 31: the interval lies in a -E region -- 0.0f in the experimental pileup (2248), SKIP in the control's (2124)
+    out.val[rank] = (e.x >> 31) ? excl_val : units_to_val_lut(sm_lut, N < 0 ? 0 : N);
   }
   if (neg) atomicOr(err, GR_DE_PILE);                  // ERRPILE 1921, 1969
 }
@@ -683,10 +684,11 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
 }
 
 // ... and K2b + K2c, which put the breaks where the rest of the pipeline expects them
-void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners) {
+void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners,
+                       float excl_val) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   k_scan_fix<<<1, 1024, 0, s>>>(L, W, out, err, owners ? owners : (u32)scan_stream_warps()); GR_NOTE_LAUNCH();
-  k_scan_place<<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err); GR_NOTE_LAUNCH();
+  k_scan_place<<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err, excl_val); GR_NOTE_LAUNCH();
 }
 
 // ============================================================================
@@ -702,7 +704,8 @@ void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc
 // lies in a later block gets a second, end-only entry in that block -- so every block is
 // self-contained (no spill list, no limit on the interval length).
 //   bits 0-12 cell offset inside the block | 13-25 interval length (kind 0) | 26-29 count |
-//   30-31 kind: 0 = start and end in this block, 1 = start only, 2 = end only
+//   30-31 kind: 0 = start and end in this block, 1 = start only, 2 = end only, 3 = -E region
+//   boundary (no weight: the cell becomes a break whatever its delta, Genrich.c:2241)
 // k_fb_scan: a CTA owns a contiguous run of blocks and carries (height, #breaks) relative to
 // the start of its run, exactly like a warp of k_scan_stream does for its run of spans; the
 // breaks go to the same pages and k_scan_fix / k_scan_place finish the job (owner = CTA).
@@ -712,6 +715,7 @@ void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc
 #define FB_KIND_BOTH 0u
 #define FB_KIND_START 1u
 #define FB_KIND_END 2u
+#define FB_KIND_MARK 3u                                // -E region boundary: forces a break, carries no weight
 __device__ __forceinline__ u32 fb_entry(u32 so, u32 span, int cnt, u32 kind) {
   return so | (span << 13) | ((u32)cnt << 26) | (kind << 30);
 }
@@ -786,17 +790,35 @@ k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
   }
 }
 
+// -E region boundaries (a few thousand at most): one pseudo entry each, so that the scan finds
+// them in the occupancy bitmap like any other event.  cursor == NULL: count pass.
+__global__ void k_fb_marks(const u64* __restrict__ marks, u32 n, u32* __restrict__ blk_cnt,
+                           u32* __restrict__ cursor, u32* __restrict__ bucketed, int shift) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u64 slot = marks[i];
+  const u32 b = (u32)(slot >> shift);
+  if (!cursor) atomicAdd(blk_cnt + b, 1u);
+  else bucketed[atomicAdd(cursor + b, 1u)] = fb_entry((u32)slot & ((1u << shift) - 1), 0, 1, FB_KIND_MARK);
+}
+void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed, int shift) {
+  if (!n) return;
+  k_fb_marks<<<(n + 127) / 128, 128, 0, s>>>(marks, n, blk_cnt, cursor, bucketed, shift); GR_NOTE_LAUNCH();
+}
+
 #define FB_WORDS (GR_BLOCK_SLOTS / 32)                 // occupancy / break bitmap words per block
 #define FB_RING 128                                    // page ring: sequence numbers in flight <= 2 * 33 + 2
 // NT threads per CTA, each owning WPT = 256 / NT consecutive bitmap words (32 * WPT cells);
 // PF entry registers per thread are fetched one block ahead (PF * NT = 512 entries).
-template <int CPS, int NT>
+template <int CPS, int NT, bool BED>
 __global__ void __launch_bounds__(NT, CPS)
 k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
-          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R) {
+          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R,
+          const uint8_t* __restrict__ blk_bed /* NULL: no -E regions */) {
   constexpr int WPT = FB_WORDS / NT, PF = 512 / NT, NW = NT / 32;
   __shared__ int sm_cell[GR_BLOCK_SLOTS];
   __shared__ u32 sm_occ[FB_WORDS];
+  __shared__ u32 sm_mark[BED ? FB_WORDS : 1];          // -E region boundaries of the block (rare)
   __shared__ u32 sm_pg[FB_RING];
   __shared__ u32 sm_ws[NW], sm_wc[NW];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -807,7 +829,7 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
     return;
   }
   for (int i = t; i < GR_BLOCK_SLOTS; i += NT) sm_cell[i] = 0;
-  for (int i = t; i < FB_WORDS; i += NT) sm_occ[i] = 0;
+  for (int i = t; i < FB_WORDS; i += NT) { sm_occ[i] = 0; if (BED) sm_mark[i] = 0; }
 
   // bucket bounds of blocks b, b+1, b+2 (rolling; the entry for b+3 is fetched a block ahead)
   auto ld_start = [&](u32 i) { return blk_start[min(i, nblocks)]; };
@@ -851,8 +873,9 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   auto apply = [&](u32 e) {
     const u32 so = e & (GR_BLOCK_SLOTS - 1), kind = e >> 30;
     const int w = 120 / (int)((e >> 26) & 15u);
-    atomicAdd(sm_cell + so, kind == FB_KIND_END ? -w : w);
     atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
+    if (BED && kind == FB_KIND_MARK) { atomicOr(sm_mark + (so >> 5), 1u << (so & 31)); return; }
+    atomicAdd(sm_cell + so, kind == FB_KIND_END ? -w : w);
     if (kind == FB_KIND_BOTH) {
       const u32 eo = so + ((e >> 13) & (GR_BLOCK_SLOTS - 1));
       atomicAdd(sm_cell + eo, -w);
@@ -905,27 +928,43 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
     __syncthreads();
     // ---- this thread's 32 * WPT cells: sum of the deltas, break masks
     const u32 end_cell = len - jb;                     // meaningful if has_end
-    u32 mo[WPT], m[WPT];
+    u32 mo[WPT], m[WPT], mk[WPT], xm[WPT];             // occupied, breaks, region boundaries, "interval ending here is excluded"
     u32 s = 0, cnt = 0;
     const int cbase = t * (32 * WPT);
     const u32 jt = jb + (u32)cbase;
+    // -E: bit 0 of the block's byte = the interval running into the block is inside a region,
+    // bit 1 = the block holds region boundaries (then, and only then, sm_mark is looked at)
+    const u32 bed = BED ? (u32)blk_bed[b] : 0u;
+    u32 excl_in = bed & 1u;                            // state of the interval ending at this thread's first cell
+    if (bed & 2u)
+      for (int i = 0; i < t * WPT; i++) excl_in ^= __popc(sm_mark[i]) & 1u;
 #pragma unroll
     for (int q = 0; q < WPT; q++) {
       mo[q] = sm_occ[t * WPT + q];
-      sm_occ[t * WPT + q] = 0;
+      mk[q] = (bed & 2u) ? sm_mark[t * WPT + q] : 0u;
       if (has_end && (int)(end_cell >> 5) == t * WPT + q) mo[q] |= 1u << (end_cell & 31);
-      m[q] = 0;
+      m[q] = 0; xm[q] = 0;
       for (u32 mm = mo[q]; mm; mm &= mm - 1) {
         const int bit = __ffs(mm) - 1;
         const int d = sm_cell[cbase + q * 32 + bit];
         const u32 j = jt + (u32)(q * 32 + bit);
         s += (u32)d;
-        const bool brk = (j == len) || (d != 0 && j >= 1u && j < len);
+        const bool mark = (mk[q] >> bit) & 1u;
+        const bool brk = (j == len) || (j >= 1u && j < len && (mark || (!excl_in && d != 0)));
         m[q] |= (brk ? 1u : 0u) << bit;
+        xm[q] |= excl_in << bit;
+        excl_in ^= mark ? 1u : 0u;                     // the region state flips AFTER the interval is closed (2256-2263)
       }
       if (!act) m[q] = 0;
       cnt += __popc(m[q]);
     }
+    if (bed & 2u) {                                    // every thread has read what it needs of sm_mark
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < WPT; q++) sm_mark[t * WPT + q] = 0;
+    }
+#pragma unroll
+    for (int q = 0; q < WPT; q++) sm_occ[t * WPT + q] = 0;
     const u32 wi_s = warp_incl_scan_u32(s, lane), wi_c = warp_incl_scan_u32(cnt, lane);
     if (lane == 31) { sm_ws[wid] = wi_s; sm_wc[wid] = wi_c; }
     __syncthreads();
@@ -936,7 +975,7 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
       if (k < wid) { h += a; idx += q; }
       tot_s += a; tot_c += q;
     }
-    // ---- emit, clearing the cells behind
+    // ---- emit, clearing the cells behind.  Bit 31 of the coordinate: the interval is excluded.
 #pragma unroll
     for (int q = 0; q < WPT; q++) {
       for (u32 mm = mo[q]; mm; mm &= mm - 1) {
@@ -945,7 +984,8 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
         sm_cell[cbase + q * 32 + bit] = 0;
         if ((m[q] >> bit) & 1u) {
           const u32 pg = sm_pg[(idx >> SS_PAGE_SHIFT) & (FB_RING - 1)];
-          W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(jt + (u32)(q * 32 + bit), h);
+          W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] =
+              make_uint2((jt + (u32)(q * 32 + bit)) | (((xm[q] >> bit) & 1u) << 31), h);
           idx++;
         }
         h += (u32)d;
@@ -1160,7 +1200,7 @@ int fb_bucket_shift() {                                // read per call: the tes
 
 // bucketed events -> breaks (pages) + break bitmap; launch_scan_place(..., owners) follows
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
-                   const ScanScratch& sc, u32* bitmap, int* err) {
+                   const ScanScratch& sc, u32* bitmap, int* err, int sh, const uint8_t* blk_bed) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   cudaMemsetAsync(W.page_ctr, 0, 4, s);
   static int sms = 0;
@@ -1170,14 +1210,15 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int cps = fb_env("GR_FUSED_CPS", 6) == 4 ? 4 : 6, nt = fb_env("GR_FUSED_NT", 128);
-  const int sh = fb_bucket_shift();
   u32 owners;
   if (sh == 13) {
     owners = (u32)(sms * cps);
     const u32 nb = (u32)L.nblocks;
     const u32 R = (nb + owners - 1) / owners;
-#define FB_LAUNCH(C, N) k_fb_scan<C, N><<<owners, N, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R)
-    if (cps == 4) { if (nt == 256) FB_LAUNCH(4, 256); else if (nt == 64) FB_LAUNCH(4, 64); else FB_LAUNCH(4, 128); }
+#define FB_LAUNCH(C, N) k_fb_scan<C, N, false><<<owners, N, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr)
+    if (blk_bed) k_fb_scan<6, 128, true><<<owners = (u32)(sms * 6), 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb,
+                                                                              (nb + sms * 6 - 1) / (sms * 6), blk_bed);
+    else if (cps == 4) { if (nt == 256) FB_LAUNCH(4, 256); else if (nt == 64) FB_LAUNCH(4, 64); else FB_LAUNCH(4, 128); }
     else { if (nt == 256) FB_LAUNCH(6, 256); else if (nt == 64) FB_LAUNCH(6, 64); else FB_LAUNCH(6, 128); }
 #undef FB_LAUNCH
   } else {
@@ -1254,7 +1295,8 @@ k_rle_moment(DevRle r, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ 
         if (i < hi) {
           const u32 e = r.end[i];
           const u32 st = (i == cs) ? 0u : r.end[i - 1];
-          const float p = __fmul_rn(__uint2float_rn(e - st), r.val[i]);
+          const float v = r.val[i];
+          const float p = v < 0.0f ? 0.0f : __fmul_rn(__uint2float_rn(e - st), v);     // SKIP (-E region): not counted (2016)
           const u64 ip = (u64)p;                       // p >= 0
           pi += ip;
           pf += (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);   // exact: fraction * 2^40
@@ -1271,7 +1313,8 @@ k_rle_moment(DevRle r, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ 
           const int c = chrom_of_index(r.chrom_start, nchrom, i);
           const u32 e = r.end[i];
           const u32 st = (i == r.chrom_start[c]) ? 0u : r.end[i - 1];
-          const float p = __fmul_rn(__uint2float_rn(e - st), r.val[i]);
+          const float v = r.val[i];
+          const float p = v < 0.0f ? 0.0f : __fmul_rn(__uint2float_rn(e - st), v);
           const u64 ip = (u64)p;
           const u64 fp = (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);
           if (ip) atomicAdd(acc_int + c, ip);

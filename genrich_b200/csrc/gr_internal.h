@@ -52,7 +52,9 @@ size_t dense_scan_ws_bytes(u64 cap, int nchrom);
 void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
                        const ScanScratch& sc, u32* bitmap, int* err, int zero_after);
 // owners: run owners of the scan that filled the pages (0: the warps of launch_dense_scan)
-void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners);
+// excl_val: value of the intervals the scan flagged as lying in a -E region (0.0f expt, SKIP ctrl)
+void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners,
+                       float excl_val);
 
 // ---- K1+K2 fused: event buckets -> breaks, the delta cells live in shared memory only ----
 // buckets of 2^shift cells, shift = fb_bucket_shift()
@@ -62,8 +64,12 @@ void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n
 void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
                     int shift);
 // returns the number of run owners (CTAs), to be handed to launch_scan_place
+// sh: bucket shift the entries were made with; blk_bed: per 8192-cell block, bit 0 = the block
+// starts inside a -E region, bit 1 = it holds region boundaries (NULL: no regions; needs sh == 13)
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
-                   const ScanScratch& sc, u32* bitmap, int* err);
+                   const ScanScratch& sc, u32* bitmap, int* err, int sh, const uint8_t* blk_bed);
+// -E region boundaries as pseudo entries (cursor == NULL: count pass)
+void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed, int shift);
 
 // ---- K2b: per-chromosome sum of (float)(end-start)*val, exact fixed point ------
 // acc_int / acc_frac: [nchrom] u64, zeroed by the caller.  sum = int + frac*2^-40.
@@ -77,7 +83,10 @@ void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u6
                        const float* factor_lambda, const CompactScratch& sc,
                        DevRle out, u32* bitmap /* raw breaks in, surviving breaks out */);
 // no-control variant: one interval (len, lambda) per active chromosome (saveLambda 1838)
-void launch_ctrl_const(cudaStream_t s, const DevLayout& L, const float* lambda_dev, u64 n, DevRle out, u32* bitmap);
+// ends, chromosome starts and the total are written by the host; here the values (lambda, or SKIP
+// where skip[i] != 0: -E regions) and the break bits at the n cell slots
+void launch_ctrl_const(cudaStream_t s, const DevLayout& L, const float* lambda_dev, u64 n, DevRle out, u32* bitmap,
+                       const u64* slots, const uint8_t* skip);
 // per-chromosome fixed-point sums -> doubles; lambda and the scale factor from them, on the device
 void launch_sums_double(cudaStream_t s, const u64* acc_int, const u64* acc_frac, int nchrom, double* out);
 void launch_lambda_factor(cudaStream_t s, const double* sums, int nchrom, bool has_ctrl, u64 genome_len,

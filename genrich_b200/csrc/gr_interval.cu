@@ -14,6 +14,7 @@
 #define CL_TILE 8192          // raw intervals per look-back tile (8 warps x 32 rounds x 32 lanes)
 
 __device__ __forceinline__ float clamp_net(float factor, float v, float lambda) {
+  if (v == -1.0f) return -1.0f;                    // SKIP: inside a -E region (2124); never equals a clamped value
   const float s = __fmul_rn(factor, v);
   return s > lambda ? s : lambda;                 // MAX(val, lambda), Genrich.h:12
 }
@@ -102,25 +103,21 @@ void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u6
   k_fill_forward<<<1, 32, 0, s>>>(L.nchrom, raw.chrom_start, out.chrom_start); GR_NOTE_LAUNCH();
 }
 
-// no control: one interval (len, lambda) per active chromosome (saveLambda 1838-1843);
-// the ends are written by the host, the values (lambda lives on the device) and the bits here.
-__global__ void k_ctrl_const_bits(DevLayout L, u32* bitmap) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= L.nchrom) return;
-  const u64 off = L.off[c];
-  if (off == ~0ull) return;
-  if ((L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) != (GR_CF_OWNED | GR_CF_SAVE)) return;
-  const u64 g = off + L.len[c];
+// no control: lambda over every active chromosome, SKIP inside its -E regions (saveLambda
+// 1838-1877).  The host knows the partition (chromosome ends and region boundaries) and writes
+// the ends; the values (lambda lives on the device) and the break bits are set here.
+__global__ void k_ctrl_const(const float* __restrict__ lambda, u64 n, float* __restrict__ val, u32* __restrict__ bitmap,
+                             const u64* __restrict__ slots, const uint8_t* __restrict__ skip) {
+  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  val[i] = skip[i] ? -1.0f : *lambda;
+  const u64 g = slots[i];
   atomicOr(bitmap + (g >> 5), 1u << (g & 31));
 }
-__global__ void k_fill_from(float* out, const float* __restrict__ value, u64 n) {
-  const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = *value;
-}
-void launch_ctrl_const(cudaStream_t s, const DevLayout& L, const float* lambda_dev, u64 n, DevRle out, u32* bitmap) {
+void launch_ctrl_const(cudaStream_t s, const DevLayout& L, const float* lambda_dev, u64 n, DevRle out, u32* bitmap,
+                       const u64* slots, const uint8_t* skip) {
   cudaMemsetAsync(bitmap, 0, (L.T / 32) * sizeof(u32), s);
-  k_ctrl_const_bits<<<(L.nchrom + 127) / 128, 128, 0, s>>>(L, bitmap); GR_NOTE_LAUNCH();
-  if (n) { k_fill_from<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(out.val, lambda_dev, n); GR_NOTE_LAUNCH(); }
+  if (n) { k_ctrl_const<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(lambda_dev, n, out.val, bitmap, slots, skip); GR_NOTE_LAUNCH(); }
 }
 
 // fixed-point per-chromosome sums (integer part, 2^-40 fraction) -> doubles

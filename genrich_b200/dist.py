@@ -48,13 +48,15 @@ def _tensor_from_ptr(ptr: int, n: int, np_dtype, device: torch.device) -> torch.
 
 
 class ShardedEngine:
-    def __init__(self, api: Api, chrom_len, params: GrParams, device: torch.device, skip=None, host_group=None):
+    def __init__(self, api: Api, chrom_len, params: GrParams, device: torch.device, skip=None, host_group=None,
+                 exclusions=None):
         """host_group: process group for the small HOST-side exchanges (two per-chromosome
         double vectors per replicate, the peak records).  With NCCL as the default backend
         pass a gloo group (``td.new_group(backend="gloo")``): these values live on the host,
         and a loopback exchange costs ~0.1 ms where an NCCL call costs a device round trip
         plus two stream syncs.  The BH histogram -- the one device-resident exchange --
-        always goes through the default (NCCL) group."""
+        always goes through the default (NCCL) group.
+        exclusions: -E regions as (chromosome index, start, end) records; every rank gets them all."""
         self.world = td.get_world_size() if td.is_initialized() else 1
         self.rank = td.get_rank() if td.is_initialized() else 0
         self.device = device
@@ -67,6 +69,10 @@ class ShardedEngine:
         dev_index = device.index if device.type == "cuda" and device.index is not None else 0
         self.ctx = Context(api, chrom_len, params, device=dev_index, skip=self.skip, owned=self.owned)
         self.params = params
+        self.excluded = np.zeros(self.nchrom, dtype=np.int64)      # bp per chromosome (saveXBed-merged)
+        if exclusions is not None and len(exclusions):
+            self.ctx.set_exclusions(exclusions)
+            self.excluded = self.ctx.excluded_bp().astype(np.int64)
         self.saved_any = np.zeros(self.nchrom, dtype=bool)
         self.sample_stats = []
         self._ext_stream = None
@@ -112,7 +118,8 @@ class ShardedEngine:
         own stream) and lambda / the scale factor are computed on the device."""
         sv = np.ones(self.nchrom, np.uint8) if save is None else np.asarray(save, np.uint8)
         self.saved_any |= (sv != 0) & (self.skip == 0)
-        glen = int(self.chrom_len[(sv != 0) & (self.skip == 0)].astype(np.int64).sum())   # calcLambda 1819-1827
+        act = (sv != 0) & (self.skip == 0)
+        glen = int((self.chrom_len[act].astype(np.int64) - self.excluded[act]).sum())      # calcLambda 1819-1827
         if self.ctx.api.has_device and self.device.type == "cuda" and not want_stats:
             t0 = time.perf_counter()
             self.ctx.sample_begin(False, sv)
@@ -184,7 +191,8 @@ class ShardedEngine:
         (host engines) or none (CUDA: they stay on the device)."""
         self.ctx.pvalues_finalize()
         if self.params.qval_opt:
-            G = int(self.params.genome_len) or int(self.chrom_len[self.saved_any].astype(np.int64).sum())
+            G = int(self.params.genome_len) or int((self.chrom_len[self.saved_any].astype(np.int64)
+                                                    - self.excluded[self.saved_any]).sum())     # findPeaks 1091-1101
             keys, lens = self._exchange_histogram()
             if self.device.type == "cuda":
                 torch.cuda.current_stream(self.device).synchronize()

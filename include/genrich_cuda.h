@@ -117,6 +117,18 @@ typedef struct gr_ctx gr_ctx;
 int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
               const gr_params* params, int32_t device);
 void gr_destroy(gr_ctx* ctx);
+/* -E: genomic regions to exclude (loadBED 5187 -> saveXBed 1144, called from saveChrom 4265).
+ * The records as the BED file lists them: any order, overlapping or not, start < end; the
+ * library sorts, clamps and merges them per chromosome exactly as saveXBed does.  Inside a
+ * region the experimental pileup is 0 (Genrich.c:2248), the control pileup -- and with it p and
+ * q -- SKIP (2124, 1632), region boundaries always close an interval (2241, 2122), the regions
+ * count neither for lambda (1824) nor for the scale factor (2016) nor for the BH genome length
+ * (1097), and no peak extends into one (1031).  Call before the first sample of the context.
+ * gr_excluded_bp: excluded bp per chromosome after merging (for callers that pass their own
+ * genome length to gr_replicate_finish* / gr_bh_set_global). */
+int gr_set_exclusions(gr_ctx* ctx, const int32_t* chrom, const uint32_t* start,
+                      const uint32_t* end, uint64_t n);
+int gr_excluded_bp(gr_ctx* ctx, uint64_t* per_chrom /* [nchrom] */);
 int gr_set_params(gr_ctx* ctx, const gr_params* params);
 /* Forget all replicates and results (a new runProgram on the same chromosome table). */
 int gr_reset(gr_ctx* ctx);

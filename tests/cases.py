@@ -8,6 +8,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 
 L3 = [300000, 200000, 100000]
+BED3 = [(0, 50000, 61000), (0, 0, 1500), (0, 60500, 70000), (0, 70000, 70500), (0, 150000, 150001), (0, 299000, 400000),
+        (1, 19900, 20100), (1, 39000, 41000), (1, 40000, 40500), (1, 250000, 260000), (2, 99999, 100000), (2, 8191, 8193)]
 
 
 @dataclass
@@ -20,6 +22,7 @@ class Sample:
     multimap: float = 0.0
     mmax: int = 12
     drop_chroms: tuple = ()      # chromosomes (0-based) removed from this file's header and reads
+    empty_chroms: tuple = ()     # chromosomes whose reads are removed, header kept (Chrom.diff stays NULL)
 
 
 @dataclass
@@ -36,6 +39,7 @@ class Case:
     atac_len: int = 100
     as_diff: float = 0.0
     extra: list = field(default_factory=list)
+    bed: list = field(default_factory=list)   # -E regions: (chromosome index, start, end), as a BED file would list them
 
     def ref_args(self):
         a = []
@@ -81,6 +85,15 @@ CASES = [
     Case("fisher_missing_chrom", L3, [(Sample(60000, 21), None), (Sample(60000, 23, drop_chroms=(2,)), None)], q=0.05),
     # all q-values are 1 (no enrichment) -> zero peaks, warning path
     Case("null_q", [200000], [(Sample(20000, 51, enrich=0.0), None)], q=0.05),
+    # -E excluded regions: overlapping / touching / unsorted records, a region at 0, one running past the
+    # chromosome end, one starting beyond it (ignored), regions cutting through peaks (spacing 20000)
+    Case("bed_ctrl_q", L3, [(Sample(60000, 21), Sample(60000, 22, enrich=0.0))], q=0.05, bed=BED3),
+    Case("bed_noctrl_p", L3, [(Sample(60000, 21), None)], p=0.01, bed=BED3),
+    Case("bed_fisher_q", L3, [(Sample(60000, 21), Sample(60000, 22, enrich=0.0)),
+                              (Sample(60000, 23, drop_chroms=(2,)), None)], q=0.05, bed=BED3),
+    # a chromosome that never receives a read, with regions on it (saveLambda 1847-1877 / saveConst 2178)
+    Case("bed_empty_chrom", [300000, 50000], [(Sample(30000, 61, empty_chroms=(1,)), Sample(30000, 62, enrich=0.0, empty_chroms=(1,)))],
+         p=0.01, bed=[(1, 0, 1000), (1, 20000, 60000), (0, 100, 200)]),
 ]
 
 BY_NAME = {c.name: c for c in CASES}

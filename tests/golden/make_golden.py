@@ -54,6 +54,10 @@ def main():
             cmd = [REF, "-t", ",".join(tfiles), "-o", out, "-f", logf, "-k", pile, "-v"] + case.ref_args()
             if any(c != "null" for c in cfiles):
                 cmd += ["-c", ",".join(cfiles)]
+            if case.bed:
+                bedf = os.path.join(td, "x.bed")
+                util.write_case_bed(case, bedf)
+                cmd += ["-E", bedf]
             r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
             if r.returncode != 0:
                 raise SystemExit("reference failed on %s:\n%s" % (case.name, r.stderr))

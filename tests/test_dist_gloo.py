@@ -33,7 +33,7 @@ def _worker(rank, world, port, case_name, out_dir):
     td.init_process_group("gloo", rank=rank, world_size=world)
     case = BY_NAME[case_name]
     api = util.oracle_api()
-    eng = ShardedEngine(api, case.chrom_len, util.case_params(case), torch.device("cpu"))
+    eng = ShardedEngine(api, case.chrom_len, util.case_params(case), torch.device("cpu"), exclusions=case.bed)
     for expt, ctrl, save in util.case_inputs(case):
         e, c = eng.route(expt), (None if ctrl is None else eng.route(ctrl))
         eng.replicate(lambda cx: cx.push_intervals(e),
@@ -48,7 +48,7 @@ def _worker(rank, world, port, case_name, out_dir):
     td.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["c2_ctrl_q", "c4_fisher_q", "fisher_missing_chrom", "c5_multimap_ctrl_p"])
+@pytest.mark.parametrize("name", ["c2_ctrl_q", "c4_fisher_q", "fisher_missing_chrom", "c5_multimap_ctrl_p", "bed_fisher_q"])
 def test_two_ranks_equal_one(name, tmp_path):
     case = BY_NAME[name]
     _, ref, _ = util.run_case(util.oracle_api(), case)

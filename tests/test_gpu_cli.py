@@ -41,6 +41,10 @@ def _run_cli(case, td, extra=()):
     cmd = [CLI, "-t", ",".join(tfiles), "-o", out, "-f", logf, "-k", pile, "-b", bed, "-v"] + case.ref_args() + list(extra)
     if any(c != "null" for c in cfiles):
         cmd += ["-c", ",".join(cfiles)]
+    if case.bed:
+        bedf = os.path.join(td, "x.bed")
+        util.write_case_bed(case, bedf)
+        cmd += ["-E", bedf]
     r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr
     rd = lambda p: open(p).read().split("\n")[:-1]

@@ -36,7 +36,8 @@ def _worker(rank, world, port, case_name, out_dir, want_stats):
     hg = td.new_group(backend="gloo")
     case = BY_NAME[case_name]
     api = capi.load_cuda()
-    eng = ShardedEngine(api, case.chrom_len, util.case_params(case), torch.device("cuda", rank), host_group=hg)
+    eng = ShardedEngine(api, case.chrom_len, util.case_params(case), torch.device("cuda", rank), host_group=hg,
+                        exclusions=case.bed)
     for expt, ctrl, save in util.case_inputs(case):
         e, c = eng.route(expt), (None if ctrl is None else eng.route(ctrl))
         eng.replicate(lambda cx: cx.push_intervals(e),
@@ -49,7 +50,7 @@ def _worker(rank, world, port, case_name, out_dir, want_stats):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 @pytest.mark.parametrize("want_stats", [True, False])
-@pytest.mark.parametrize("name", ["c2_ctrl_q", "c5_multimap_ctrl_p", "fisher_missing_chrom"])
+@pytest.mark.parametrize("name", ["c2_ctrl_q", "c5_multimap_ctrl_p", "fisher_missing_chrom", "bed_ctrl_q"])
 def test_two_gpus_equal_oracle(name, want_stats, tmp_path):
     case = BY_NAME[name]
     _, ref, _ = util.run_case(util.oracle_api(), case)

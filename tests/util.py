@@ -38,8 +38,8 @@ def sample_intervals(case: Case, s) -> np.ndarray:
     w = Workload(case.chrom_len, s.nfrag, s.seed, enrich=s.enrich, spacing=s.spacing, sigma=s.sigma,
                  multimap=s.multimap, mmax=s.mmax)
     fr = w.fragments()
-    if s.drop_chroms:
-        fr = fr[~np.isin(fr[:, 0], list(s.drop_chroms))]
+    if s.drop_chroms or s.empty_chroms:
+        fr = fr[~np.isin(fr[:, 0], list(s.drop_chroms) + list(s.empty_chroms))]
     return host.fragments_to_intervals(fr, atac=case.atac, atac_len=case.atac_len)
 
 
@@ -62,6 +62,8 @@ def case_params(case: Case, keep=True):
 def run_case(api: capi.Api, case: Case, keep=True, device=0, inputs=None):
     par = case_params(case, keep)
     ctx = capi.Context(api, case.chrom_len, par, device=device)
+    if case.bed:
+        ctx.set_exclusions(case.bed)
     res = host.run_replicates(ctx, inputs if inputs is not None else case_inputs(case))
     return ctx, res, par
 
@@ -100,19 +102,27 @@ def write_sample_sam(case: Case, s, path: str) -> None:
     w = Workload(case.chrom_len, s.nfrag, s.seed, enrich=s.enrich, spacing=s.spacing, sigma=s.sigma,
                  multimap=s.multimap, mmax=s.mmax)
     w.write_sam(path)
-    if s.drop_chroms:
+    if s.drop_chroms or s.empty_chroms:
         drop = {"chr%d" % (c + 1) for c in s.drop_chroms}
+        empty = {"chr%d" % (c + 1) for c in s.empty_chroms}
         keep = []
         with open(path) as f:
             for line in f:
                 if line.startswith("@SQ"):
                     if line.split("\t")[1][3:] in drop:
                         continue
-                elif not line.startswith("@") and line.split("\t")[2] in drop:
+                elif not line.startswith("@") and line.split("\t")[2] in drop | empty:
                     continue
                 keep.append(line)
         with open(path, "w") as f:
             f.writelines(keep)
+
+
+def write_case_bed(case: Case, path: str) -> None:
+    """The -E file of a case: its regions as BED records, in the order given (unsorted, overlapping)."""
+    with open(path, "w") as f:
+        for c, a, b in case.bed:
+            f.write("chr%d\t%d\t%d\n" % (c + 1, a, b))
 
 
 def write_case_sams(case: Case, td: str):
