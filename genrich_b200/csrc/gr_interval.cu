@@ -222,42 +222,114 @@ void launch_union_rank(cudaStream_t s, const DevLayout& L, const u32* bmE, const
   k_union_rank<<<ntiles, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks, ntiles); GR_NOTE_LAUNCH();
 }
 
+// Pass B.  A CTA takes UE_BLOCKS consecutive bitmap blocks.  Walking the set bits thread by
+// thread (first version) made every warp wait for its fullest word -- five or six dependent
+// DRAM round trips for gathers that were two cache lines wide -- and kept only two loads per
+// thread in flight (1.34 ms per hg38 replicate, 0.4 of the HBM rate).  Here the breaks are first
+// listed in shared memory in rank order (cell offset, experimental / control interval number
+// relative to the CTA's first block); the list is then streamed by all threads, UE_UNROLL
+// entries per thread at a time: gathers and stores are coalesced and every thread has
+// 2 * UE_UNROLL independent loads in flight.
+#define UE_BLOCKS 4
+#define UE_CAP 4096            // list entries per round (a CTA with more breaks takes several rounds)
+#define UE_UNROLL 4
 __global__ void __launch_bounds__(256)
 k_union_emit(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ bmC,
              const u64* __restrict__ rankE, const u64* __restrict__ rankC,
              const u64* __restrict__ rankU, const float* __restrict__ exptVal,
              const float* __restrict__ ctrlVal, u32* __restrict__ pEnd,
              float* __restrict__ pExpt, float* __restrict__ pCtrl, u32* __restrict__ bmU,
-             u64* __restrict__ chrom_start) {
-  __shared__ u32 sm_a[8], sm_u[8];
-  const u32 blk = blockIdx.x;
-  const u64 widx = (u64)blk * 256 + threadIdx.x;
-  const u32 E = bmE[widx], C = bmC[widx];
-  u32 U = E | C;
-  bmU[widx] = U;
+             u64* __restrict__ chrom_start, u32 nblocks) {
+  __shared__ u32 sm_ent[UE_CAP];                 // bits 0-14: cell offset inside the CTA's blocks, 15-31: experimental interval number
+  __shared__ unsigned short sm_ctl[UE_CAP];      // control interval number
+  __shared__ u32 sm_a[UE_BLOCKS * 8], sm_u[UE_BLOCKS * 8];
+  __shared__ u32 sm_jb[UE_BLOCKS];
+  __shared__ u32 sm_tot;
+  const u32 b0 = blockIdx.x * UE_BLOCKS;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const u32 pa = __popc(E) | (__popc(C) << 16);
-  const u32 pu = __popc(U);
-  const u32 ia = warp_incl_scan_u32(pa, lane), iu = warp_incl_scan_u32(pu, lane);
-  if (lane == 31) { sm_a[w] = ia; sm_u[w] = iu; }
+  u32 E[UE_BLOCKS], C[UE_BLOCKS];
+#pragma unroll
+  for (int k = 0; k < UE_BLOCKS; k++) {
+    const bool on = b0 + k < nblocks;
+    const u64 widx = (u64)(b0 + k) * 256 + threadIdx.x;
+    E[k] = on ? bmE[widx] : 0u;
+    C[k] = on ? bmC[widx] : 0u;
+  }
+  const u64 RE0 = rankE[b0], RC0 = rankC[b0], RU0 = rankU[b0];
+  if (threadIdx.x < UE_BLOCKS && b0 + threadIdx.x < nblocks) {
+    const u32 blk = b0 + threadIdx.x;
+    const int c = L.blk2chrom[blk];
+    const u64 off = L.off[c];
+    sm_jb[threadIdx.x] = (u32)((u64)blk * GR_BLOCK_SLOTS - off);
+    if ((u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = rankU[blk];
+  }
+  // exclusive ranks of every word inside the CTA's range, order (block, word): E and C counts
+  // travel packed (<= 32768 each), U alone
+  u32 xa[UE_BLOCKS], xu[UE_BLOCKS];
+#pragma unroll
+  for (int k = 0; k < UE_BLOCKS; k++) {
+    const u32 U = E[k] | C[k];
+    if (b0 + k < nblocks) bmU[(u64)(b0 + k) * 256 + threadIdx.x] = U;
+    const u32 pa = __popc(E[k]) | (__popc(C[k]) << 16), pu = __popc(U);
+    const u32 ia = warp_incl_scan_u32(pa, lane), iu = warp_incl_scan_u32(pu, lane);
+    if (lane == 31) { sm_a[k * 8 + w] = ia; sm_u[k * 8 + w] = iu; }
+    xa[k] = ia - pa; xu[k] = iu - pu;
+  }
   __syncthreads();
-  u32 xa = ia - pa, xu = iu - pu;
-  for (int k = 0; k < w; k++) { xa += sm_a[k]; xu += sm_u[k]; }
-  const int c = L.blk2chrom[blk];
-  const u64 off = L.off[c];
-  if (threadIdx.x == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = rankU[blk];
-  if (!U) return;
-  u64 u = rankU[blk] + xu;
-  const u64 re = rankE[blk] + (xa & 0xffff), rc = rankC[blk] + (xa >> 16);
-  const u32 jw = (u32)((u64)blk * GR_BLOCK_SLOTS + (u64)threadIdx.x * 32 - off);
-  while (U) {
-    const int b = __ffs(U) - 1;
-    const u32 low = (1u << b) - 1;
-    pEnd[u] = jw + b;
-    pExpt[u] = exptVal[re + __popc(E & low)];
-    pCtrl[u] = ctrlVal[rc + __popc(C & low)];
-    u++;
-    U &= U - 1;
+  if (w == 0) {                                  // UE_BLOCKS * 8 == 32 warp totals -> exclusive
+    const u32 va = sm_a[lane], vu = sm_u[lane];
+    const u32 ia = warp_incl_scan_u32(va, lane), iu = warp_incl_scan_u32(vu, lane);
+    sm_a[lane] = ia - va; sm_u[lane] = iu - vu;
+    if (lane == 31) sm_tot = iu;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < UE_BLOCKS; k++) { xa[k] += sm_a[k * 8 + w]; xu[k] += sm_u[k * 8 + w]; }
+  const u32 tot = sm_tot;
+  for (u32 lo = 0; lo < tot; lo += UE_CAP) {
+    if (lo) __syncthreads();                     // the previous round's list has been streamed
+#pragma unroll
+    for (int k = 0; k < UE_BLOCKS; k++) {
+      u32 U = E[k] | C[k];
+      u32 u = xu[k];
+      if (u >= lo + UE_CAP || u + __popc(U) <= lo) continue;
+      const u32 cell0 = ((u32)k << GR_BLOCK_SHIFT) | (threadIdx.x << 5);
+      while (U) {
+        const int b = __ffs(U) - 1;
+        const u32 low = (1u << b) - 1;
+        if (u >= lo && u < lo + UE_CAP) {
+          sm_ent[u - lo] = (cell0 + b) | (((xa[k] & 0xffff) + __popc(E[k] & low)) << 15);
+          sm_ctl[u - lo] = (unsigned short)((xa[k] >> 16) + __popc(C[k] & low));
+        }
+        u++;
+        U &= U - 1;
+      }
+    }
+    __syncthreads();
+    const u32 cnt = min(tot - lo, (u32)UE_CAP);
+    for (u32 i0 = threadIdx.x; i0 < cnt; i0 += 256 * UE_UNROLL) {
+      u32 en[UE_UNROLL];
+      float ve[UE_UNROLL], vc[UE_UNROLL];
+#pragma unroll
+      for (int q = 0; q < UE_UNROLL; q++) {
+        const u32 i = i0 + q * 256;
+        if (i < cnt) {
+          en[q] = sm_ent[i];
+          ve[q] = exptVal[RE0 + (en[q] >> 15)];
+          vc[q] = ctrlVal[RC0 + sm_ctl[i]];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UE_UNROLL; q++) {
+        const u32 i = i0 + q * 256;
+        if (i < cnt) {
+          const u64 u = RU0 + lo + i;
+          pEnd[u] = sm_jb[(en[q] >> GR_BLOCK_SHIFT) & (UE_BLOCKS - 1)] + (en[q] & (GR_BLOCK_SLOTS - 1));
+          pExpt[u] = ve[q];
+          pCtrl[u] = vc[q];
+        }
+      }
+    }
   }
 }
 
@@ -266,8 +338,9 @@ void launch_union_emit(cudaStream_t s, const DevLayout& L, const u32* bmE, const
                        const float* exptVal, const float* ctrlVal,
                        u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
                        const u64* total) {
-  k_union_emit<<<(unsigned)L.nblocks, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
-                                                   pEnd, pExpt, pCtrl, bmU, chrom_start); GR_NOTE_LAUNCH();
+  const unsigned grid = (unsigned)((L.nblocks + UE_BLOCKS - 1) / UE_BLOCKS);
+  k_union_emit<<<grid, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
+                                    pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks); GR_NOTE_LAUNCH();
   launch_fill_chrom_start(s, L, chrom_start, total);
 }
 
@@ -306,22 +379,41 @@ __device__ __forceinline__ u32 table_upsert(const PairTable& t, u64 key, bool& f
   return ~0u;
 }
 
+// The first probe of PI_UNROLL keys is in flight together (the table is L2-resident, a probe
+// is one L2 round trip; one key at a time left the kernel waiting on it).
+#define PI_UNROLL 4
 __global__ void __launch_bounds__(256)
 k_pair_insert(const float* __restrict__ pExpt, const float* __restrict__ pCtrl, const u64* __restrict__ n_dev,
               PairTable t, u32* __restrict__ slot, int* __restrict__ err) {
   const u64 n = *n_dev;                                  // interval count, device side
-  const u64 stride = (u64)gridDim.x * blockDim.x;
+  const u64 stride = (u64)gridDim.x * (256 * PI_UNROLL);
+  const u32 mask = t.cap - 1;
   bool bad = false;
-  for (u64 i0 = (u64)blockIdx.x * blockDim.x; i0 < n; i0 += stride) {    // warp-uniform trip count
-    const u64 i = i0 + threadIdx.x;
-    bool fresh = false;
-    if (i < n) {
-      const u64 key = ((u64)__float_as_uint(pExpt[i]) << 32) | __float_as_uint(pCtrl[i]);
-      const u32 h = table_upsert(t, key, fresh);
-      if (h == ~0u) bad = true;
-      slot[i] = h == ~0u ? 0u : h;
+  for (u64 i0 = (u64)blockIdx.x * (256 * PI_UNROLL); i0 < n; i0 += stride) {    // warp-uniform trip count
+    u64 key[PI_UNROLL], k0[PI_UNROLL];
+    u32 h[PI_UNROLL];
+#pragma unroll
+    for (int q = 0; q < PI_UNROLL; q++) {
+      const u64 i = i0 + q * 256 + threadIdx.x;
+      key[q] = i < n ? ((u64)__float_as_uint(pExpt[i]) << 32) | __float_as_uint(pCtrl[i]) : 0ull;
     }
-    const u32 nf = __popc(__ballot_sync(GR_FULL, fresh));
+#pragma unroll
+    for (int q = 0; q < PI_UNROLL; q++) {
+      h[q] = mix64(key[q]) & mask;
+      k0[q] = t.keys[h[q]];
+    }
+    u32 nf = 0;
+#pragma unroll
+    for (int q = 0; q < PI_UNROLL; q++) {
+      const u64 i = i0 + q * 256 + threadIdx.x;
+      bool fresh = false;
+      if (i < n) {
+        const u32 hs = k0[q] == key[q] ? h[q] : table_upsert(t, key[q], fresh);
+        if (hs == ~0u) bad = true;
+        slot[i] = hs == ~0u ? 0u : hs;
+      }
+      nf += __popc(__ballot_sync(GR_FULL, fresh));
+    }
     if ((threadIdx.x & 31) == 0 && nf) {
       const u32 tot = atomicAdd(t.count, nf) + nf;
       if (tot > (t.cap >> 1)) bad = true;
@@ -356,10 +448,17 @@ __global__ void __launch_bounds__(256)
 k_gather_f32(const float* __restrict__ table, const u32* __restrict__ slot, const u64* __restrict__ n_dev,
              float* __restrict__ out) {
   const u64 n = *n_dev;
-  const u64 stride = (u64)gridDim.x * blockDim.x;
-  for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const u32 s = slot[i];
-    out[i] = s == ~0u ? -1.0f : table[s];      // ~0: SKIP interval, never entered in the table
+  const u64 stride = (u64)gridDim.x * (256 * PI_UNROLL);
+  for (u64 i0 = (u64)blockIdx.x * (256 * PI_UNROLL) + threadIdx.x; i0 < n; i0 += stride) {
+    u32 sl[PI_UNROLL];
+    float v[PI_UNROLL];
+#pragma unroll
+    for (int q = 0; q < PI_UNROLL; q++) sl[q] = i0 + q * 256 < n ? slot[i0 + q * 256] : ~0u;
+#pragma unroll
+    for (int q = 0; q < PI_UNROLL; q++) v[q] = sl[q] == ~0u ? -1.0f : table[sl[q]];   // ~0: SKIP interval, never entered in the table
+#pragma unroll
+    for (int q = 0; q < PI_UNROLL; q++)
+      if (i0 + q * 256 < n) out[i0 + q * 256] = v[q];
   }
 }
 void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n_upper, const u64* n_dev, float* out) {

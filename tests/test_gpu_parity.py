@@ -358,6 +358,53 @@ def test_edge_inputs():
         assert np.array_equal(rg.peaks["start"], ro.peaks["start"]) and np.array_equal(rg.peaks["end"], ro.peaks["end"])
 
 
+def test_dense_breaks_vs_oracle(monkeypatch):
+    """Nearly every base is an interval boundary (short fragments at ~40x): the union pass lists
+    more breaks per CTA than one round of its shared-memory list holds, pages of the scan fill
+    within one block, the control sweep drops and keeps boundaries side by side.  Plain and fused
+    paths against the oracle, pileups / partitions bit for bit."""
+    rng = np.random.default_rng(77)
+    L = [70000, 9000, 8192]
+
+    def sample(n, seed, wmax):
+        r = np.random.default_rng(seed)
+        ch = r.choice(len(L), size=n, p=np.asarray(L) / sum(L)).astype(np.int32)
+        ln = r.integers(1, 40, size=n).astype(np.int32)
+        st = (r.random(n) * (np.asarray(L)[ch] - ln)).astype(np.int32)
+        w = r.choice([1, 2, 3, 4, 5, 6, 8, 10], size=n).astype(np.int32) if wmax else np.ones(n, np.int32)
+        return np.stack([ch, st, st + ln, w], axis=1).astype(np.int32)
+    t, c = sample(160000, 1, True), sample(120000, 2, False)
+    hot = sample(30000, 3, False)
+    hot = hot[hot[:, 0] == 0]
+    ln = hot[:, 2] - hot[:, 1]
+    hot[:, 1] = hot[:, 1] % 3000 + 30000                  # piled onto chr1:30000-33040
+    hot[:, 2] = hot[:, 1] + ln
+    t = np.concatenate([t, hot])
+    par = capi.make_params(p=0.05, min_auc=2.0, keep_pileups=True)
+    ctx_o = capi.Context(util.oracle_api(), L, par)
+    res_o = host.run_replicates(ctx_o, [(t, c)])
+    for env in (PLAIN, FUSED):
+        for k in ("GR_FUSED", "GR_FUSED_MIN", "GR_SB_MIN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        ctx_g = capi.Context(capi.load_cuda(), L, par)
+        res_g = host.run_replicates(ctx_g, [(t, c)])
+        assert _bits(res_g.sample_stats[0].lambda_) == _bits(res_o.sample_stats[0].lambda_)
+        assert _bits(res_g.sample_stats[0].factor) == _bits(res_o.sample_stats[0].factor)
+        for ci in range(len(L)):
+            _cmp_intervals(ctx_g.fetch(0, 0, ci), ctx_o.fetch(0, 0, ci), True, "dense expt")
+            _cmp_intervals(ctx_g.fetch(1, 0, ci), ctx_o.fetch(1, 0, ci), True, "dense ctrl")
+            _cmp_intervals(ctx_g.fetch(2, 0, ci), ctx_o.fetch(2, 0, ci), False, "dense p")
+        n_iv = sum(len(ctx_g.fetch(2, 0, ci).end) for ci in range(len(L)))
+        assert n_iv > 0.8 * sum(L)                      # the case is what it claims to be
+        a, b = res_g.peaks, res_o.peaks
+        assert len(a) == len(b) and len(a) > 0
+        for f in ("chrom", "start", "end", "summit"):
+            assert np.array_equal(a[f], b[f]), f
+    del rng
+
+
 def test_error_codes():
     api = capi.load_cuda()
     par = capi.make_params(p=0.01)
