@@ -83,7 +83,7 @@ STATUS_TEXT = {
     6: "No analyzable genome (length=0)", 7: "Invalid pileup value (< 0)",
     8: "Disallowed number of alignments", 9: "interval on unknown/unowned chromosome",
     10: "Invalid df in pchisq()", 11: "Genome length does not match p-value length",
-    12: "no CUDA device",
+    12: "no CUDA device", 13: "more than 32767 fragment starts/ends on one base (int16 saturation, Genrich.c:2558)",
 }
 
 

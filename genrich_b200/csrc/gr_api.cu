@@ -185,11 +185,12 @@ static const char* kStatusText[] = {
   "No analyzable genome (length=0)", "Invalid pileup value (< 0)",
   "Disallowed number of alignments", "interval on an unknown or unowned chromosome",
   "Invalid df in pchisq()", "Genome length does not match p-value length",
-  "no CUDA device available"
+  "no CUDA device available",
+  "More than 32767 fragments start or end at one position (the reference's counters saturate there)"
 };
 
 extern "C" const char* gr_strerror(int status) {
-  if (status < 0 || status > GR_ERR_NODEVICE) return "Unknown error";
+  if (status < 0 || status > GR_ERR_SATURATED) return "Unknown error";
   return kStatusText[status];
 }
 extern "C" const char* gr_last_error_detail(const gr_ctx* ctx) { return ctx ? ctx->detail.c_str() : ""; }
@@ -515,6 +516,7 @@ static int map_dev_err(int e) {
   if (e & GR_DE_COUNT) return GR_ERR_COUNT;
   if (e & GR_DE_POS) return GR_ERR_POS;
   if (e & (GR_DE_PILE | GR_DE_TAIL)) return GR_ERR_PILE;
+  if (e & GR_DE_SAT) return GR_ERR_SATURATED;
   if (e & GR_DE_EXPT) return GR_ERR_EXPT;
   return GR_OK;
 }

@@ -35,6 +35,13 @@ typedef unsigned int u32;
 #define GR_DE_TABLE  32             // hash table over its load limit (host retries)
 #define GR_DE_CAP    64             // an optimistically sized buffer was too small (host retries)
 #define GR_DE_EXPT   128            // no analyzable fragments in the experimental sample (2292)
+#define GR_DE_SAT    256            // a delta cell beyond the reference's int16 range (saveInterval 2558-2573)
+
+// A delta cell, in 1/120 units, that the reference's (int16 cov, uint8 frac) cell cannot hold: it
+// would have skipped intervals there (cov == INT16_MAX before a start, INT16_MIN before an end).
+#define GR_SAT_HI (32767 * 120)
+#define GR_SAT_LO (-32768 * 120)
+__device__ __forceinline__ bool cell_saturated(int d) { return d > GR_SAT_HI || d < GR_SAT_LO; }
 
 // ---------------------------------------------------------------------------
 // memory helpers

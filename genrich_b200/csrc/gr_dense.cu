@@ -409,6 +409,7 @@ k_scan_stream(int32_t* __restrict__ delta, DevLayout L, StreamWs W, u32* __restr
 
   const u32 lt_mask = (1u << lane) - 1;
   u32 run_s = 0, run_c = 0;                            // height / #breaks since the start of the run
+  bool sat = false;                                    // a cell beyond the reference's int16 range (2558-2573)
   int stg = 0;
   // chromosome of the current 8192-cell block; the next block's is fetched one block ahead
   const u32 last_blk = (s1 - 1) >> 4;
@@ -455,6 +456,7 @@ k_scan_stream(int32_t* __restrict__ delta, DevLayout L, StreamWs W, u32* __restr
           u32 q = 0;
           if (on) { q = wlist[n]; x = wst[q]; }
           const u32 m4 = (x.x != 0 ? 1u : 0u) | (x.y != 0 ? 2u : 0u) | (x.z != 0 ? 4u : 0u) | (x.w != 0 ? 8u : 0u);
+          sat |= cell_saturated(x.x) | cell_saturated(x.y) | cell_saturated(x.z) | cell_saturated(x.w);
           const u32 c4 = __popc(m4);
           const u32 s1_ = (u32)x.x, s2_ = s1_ + (u32)x.y, s3_ = s2_ + (u32)x.z, s4_ = s3_ + (u32)x.w;
           const u32 inc_s = warp_incl_scan_u32(s4_, lane), inc_c = warp_incl_scan_u32(c4, lane);
@@ -486,6 +488,7 @@ k_scan_stream(int32_t* __restrict__ delta, DevLayout L, StreamWs W, u32* __restr
 #pragma unroll
         for (int i = 0; i < SC_ITEMS; i++) {
           run += (u32)d[i];
+          sat |= cell_saturated(d[i]);
           const u32 jj = j0 + i;
           const bool brk = (jj == len) || (d[i] != 0 && jj >= 1 && jj < len);
           m |= (brk ? 1u : 0u) << i;
@@ -530,6 +533,7 @@ k_scan_stream(int32_t* __restrict__ delta, DevLayout L, StreamWs W, u32* __restr
     }
   }
   resolve();                                           // a page still on order gets its (unused) label
+  if (sat) atomicOr(err, GR_DE_SAT);
   if (lane == 0) W.warp_tot[gw] = make_uint2(run_s, run_c);
   cp_async_wait<0>();
 }
@@ -902,6 +906,7 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   };
 
   u32 run_s = 0, run_c = 0;                            // height / #breaks since the start of the run
+  bool sat = false;                                    // a cell beyond the reference's int16 range (2558-2573)
   int c = -1;
   u32 c_last_blk = 0;                                  // last block of chromosome c
   u64 off = 0;
@@ -967,6 +972,7 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
         const int d = sm_cell[cbase + q * 32 + bit];
         const u32 j = jt + (u32)(q * 32 + bit);
         s += (u32)d;
+        sat |= cell_saturated(d);
         const bool mark = (mk[q] >> bit) & 1u;
         const bool brk = (j == len) || (j >= 1u && j < len && (mark || (!excl_in && d != 0)));
         m[q] |= (brk ? 1u : 0u) << bit;
@@ -1017,6 +1023,7 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
     sA = sB; sB = sC; sC = sD;
     __syncthreads();                                   // cells, occupancy words and scan scratch are free again
   }
+  if (sat) atomicOr(err, GR_DE_SAT);
   if (t == 0) {
     page_take();                                       // every page handed out carries a label
     W.warp_tot[owner] = make_uint2(run_s, run_c);
@@ -1095,6 +1102,7 @@ k_fw_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   };
 
   u32 run_s = 0, run_c = 0;
+  bool sat = false;
   int c = -1;
   u32 c_last_bk = 0;
   u64 off = 0;
@@ -1151,6 +1159,7 @@ k_fw_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
         const int d = sm_cell[cbase + q * 32 + bit];
         const u32 j = jt + (u32)(q * 32 + bit);
         s += (u32)d;
+        sat |= cell_saturated(d);
         const bool brk = (j == len) || (d != 0 && j >= 1u && j < len);
         m[q] |= (brk ? 1u : 0u) << bit;
       }
@@ -1180,6 +1189,7 @@ k_fw_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
     sA = sB; sB = sC; sC = sD;
     __syncwarp();                                      // cells and occupancy words are free again
   }
+  if (sat) atomicOr(err, GR_DE_SAT);
   if (lane == 0) {
     page_take();
     W.warp_tot[owner] = make_uint2(run_s, run_c);

@@ -53,7 +53,12 @@ typedef enum gr_status {
   GR_ERR_CHROM = 9,      /* interval on an unknown / unowned chromosome */
   GR_ERR_DF = 10,        /* ERRDF       Genrich.c:556: > 200 replicates */
   GR_ERR_GENLEN = 11,    /* Genrich.c:377-382: histogram length != genome length */
-  GR_ERR_NODEVICE = 12   /* no CUDA device / library built without one */
+  GR_ERR_NODEVICE = 12,  /* no CUDA device / library built without one */
+  GR_ERR_SATURATED = 13  /* more than 32767 interval starts (32768 ends) on one base: the reference's int16
+                            delta counters saturate there and it silently SKIPS further intervals, in arrival
+                            order (saveInterval, Genrich.c:2558-2573).  That order-dependent rule is not
+                            reproduced; the condition is detected and reported instead of returning different
+                            pileups.  Reported by gr_sample_pileup / the next call that waits for the device. */
 } gr_status;
 
 /* One reference sequence (Chrom, Genrich.h:183-201, the fields the path reads). */

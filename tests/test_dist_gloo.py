@@ -44,7 +44,8 @@ def _worker(rank, world, port, case_name, out_dir):
         np.save(os.path.join(out_dir, "scal.npy"),
                 np.array([[s.lambda_, s.factor] for s in eng.sample_stats], dtype=np.float32))
     owned = [c for c in range(len(case.chrom_len)) if eng.owned[c]]
-    assert 0 < len(owned) < len(case.chrom_len)
+    assert len(owned) < len(case.chrom_len)
+    assert len(owned) > 0 or world > len(case.chrom_len)
     td.destroy_process_group()
 
 
@@ -59,6 +60,18 @@ def test_two_ranks_equal_one(name, tmp_path):
     assert peaks.tobytes() == ref.peaks.tobytes()
     want = np.array([[s.lambda_, s.factor] for s in ref.sample_stats], dtype=np.float32)
     assert np.array_equal(scal.view(np.uint32), want.view(np.uint32))
+
+
+def test_more_ranks_than_chromosomes(tmp_path):
+    """Four ranks, three chromosomes: one rank owns nothing and still takes part in every exchange
+    (sums, histogram all-gather with an empty list, peak gather with an empty list)."""
+    for name in ("c2_ctrl_q", "bed_fisher_q"):
+        case = BY_NAME[name]
+        _, ref, _ = util.run_case(util.oracle_api(), case)
+        port = _free_port()
+        mp.spawn(_worker, args=(4, port, name, str(tmp_path)), nprocs=4, join=True)
+        peaks = np.load(os.path.join(tmp_path, "peaks.npy"))
+        assert peaks.tobytes() == ref.peaks.tobytes() and len(peaks) > 0
 
 
 def test_lpt_shard_balances():

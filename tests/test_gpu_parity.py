@@ -405,7 +405,7 @@ def test_dense_breaks_vs_oracle(monkeypatch):
     del rng
 
 
-def test_error_codes():
+def test_error_codes(monkeypatch):
     api = capi.load_cuda()
     par = capi.make_params(p=0.01)
     # start beyond the reference end -> ERRPOS (Genrich.c:2531)
@@ -428,6 +428,26 @@ def test_error_codes():
     with pytest.raises(capi.GenrichError) as e:
         ctx.replicate_end()
     assert e.value.status == 5
+    # more starts on one base than the reference's int16 counter holds (saveInterval 2558-2573 would
+    # skip the rest, in arrival order): reported, on every scan path; one start fewer is fine
+    for env in (PLAIN, FUSED, dict(FUSED, GR_FUSED_SHIFT="11")):
+        for k in ("GR_FUSED", "GR_FUSED_MIN", "GR_SB_MIN", "GR_FUSED_SHIFT"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for n, want in ((32767, 0), (32768, 13)):
+            recs = np.tile(np.array([[0, 5000, 5100, 1]], dtype=np.int32), (n, 1))
+            recs[:, 2] += np.arange(n, dtype=np.int32) % 3000          # ends spread out: only the start cell is hot
+            for a in (util.oracle_api(), api):
+                ctx = capi.Context(a, [20000, 9000], par)
+                ctx.sample_begin(False)
+                ctx.push_intervals(recs)
+                if want:
+                    with pytest.raises(capi.GenrichError) as e:
+                        ctx.sample_pileup()
+                    assert e.value.status == want, (env, n)
+                else:
+                    ctx.sample_pileup()
 
 
 def test_large_properties():

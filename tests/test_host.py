@@ -117,3 +117,23 @@ def test_pack_records_roundtrip():
     keep = np.ones(n, bool); keep[[7, 8]] = False
     back = np.stack([c, s, s + ln, k], axis=1).astype(np.int32)
     assert np.array_equal(back, recs[keep])
+
+
+def test_oracle_reports_int16_saturation():
+    """More than 32767 starts on one base: the reference skips further intervals there in arrival
+    order (saveInterval, Genrich.c:2558-2573); neither side restates that -- both report it."""
+    import pytest
+    from genrich_b200 import capi
+    import util
+    par = capi.make_params(p=0.01)
+    for n, want in ((32767, 0), (32768, 13)):
+        recs = np.tile(np.array([[0, 500, 600, 1]], dtype=np.int32), (n, 1))
+        ctx = capi.Context(util.oracle_api(), [2000], par)
+        ctx.sample_begin(False)
+        ctx.push_intervals(recs)
+        if want:
+            with pytest.raises(capi.GenrichError) as e:
+                ctx.sample_pileup()
+            assert e.value.status == want
+        else:
+            ctx.sample_pileup()

@@ -1,10 +1,12 @@
 mkdir -p gpurun_out
-( timeout 600 python -m pytest tests/test_gpu_dist.py -q -x 2>&1 | tail -6 ) > gpurun_out/c10_pytest.log
-cat gpurun_out/c10_pytest.log
-n=2
-timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $n --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/c10_bench_${n}gpu.json 2> gpurun_out/c10_bench_$n.err
-python -c "
+( timeout 600 python -m pytest tests -m gpu -q -x 2>&1 | tail -25 ) > gpurun_out/c11_pytest.log
+cat gpurun_out/c11_pytest.log
+timeout 400 python bench.py > gpurun_out/c11_bench.json 2> gpurun_out/c11_bench.err
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/c10_bench_${n}gpu.json').read().strip().split('\n')[-1])
-print('${n}gpu: step %.2f ms  value %.1f e2e %.2f ms  peaks %d' % (d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], d['config']['peaks']), d['stage_ms_per_step'])"
-tail -3 gpurun_out/c10_bench_$n.err
+d=json.loads(open('gpurun_out/c11_bench.json').read().strip().split('\n')[-1])
+print('step %.2f ms e2e %.2f peaks %d launches %d' % (d['ms_per_step'], d['e2e']['ms_per_step'], d['config']['peaks'], d['gpu_launches']), d['stage_ms_per_step'], d['roofline']['frac'], d['cpu_baseline']['value'])
+PY
+tail -3 gpurun_out/c11_bench.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 420 --csv --log-file gpurun_out/c11_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-dense > gpurun_out/c11_ncu_bench.log 2>&1
+tail -2 gpurun_out/c11_ncu_bench.log | cut -c1-300
