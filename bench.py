@@ -82,8 +82,11 @@ def gen_fragments(chrom_len, n, seed, enrich, spacing, sigma, threads=8):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).
+
+    The poller is started well before the timed region (nvidia-smi needs ~1 s to come up) and
+    every line carries a timestamp; stop(t0, t1) keeps the samples taken inside the timed window."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -95,12 +98,13 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                       "--format=csv,noheader,nounits", "-lms", "25"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -110,26 +114,32 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.f:
             c = [x.strip() for x in line.split(",")]
-            if len(c) < 9:
+            if len(c) < 10:
                 continue
             try:
-                sm.append(float(c[1]))
-                mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except ValueError:
+                ts = float("nan")                    # unknown format: the sample still counts for the whole run
+            try:
+                rows.append((ts, float(c[2]), float(c[3]),
+                             [n for n, v in zip(names, c[6:10]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nme, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
         os.unlink(self.f.name)
-        if not sm:
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        hi = sorted(sm)[len(sm) // 2:]            # samples under load = upper half
-        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        inside = [r for r in rows if t0 is not None and t0 - 0.03 <= r[0] <= t1 + 0.03]
+        window = "timed region"
+        if len(inside) < 2:                          # clock skew / too short a run: everything since the start
+            inside, window = rows, "whole run (fewer than 2 samples fell inside the timed region)"
+        sm = [r[1] for r in inside]
+        reasons = sorted({x for r in inside for x in r[3]})
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(r[2] for r in inside), "reasons": reasons,
+                "samples": len(inside), "window": window}
 
 
 def measured_peak_gbs():
@@ -213,6 +223,9 @@ def main():
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()                                # comes up while the workload is generated
     host_group = None
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
@@ -263,6 +276,25 @@ def main():
         eng.replicate(pe, pc, want_stats=False)
         return eng.call_peaks()
 
+    trace = {}
+    if os.environ.get("GR_BENCH_TRACE"):
+        # host time of every library call of a step (debugging aid: where the host keeps the GPU waiting)
+        def wrap(obj, name, key=None):
+            f = getattr(obj, name)
+            name = key or name
+
+            def g(*a_, **k_):
+                t0 = time.perf_counter()
+                r = f(*a_, **k_)
+                trace[name] = trace.get(name, 0.0) + time.perf_counter() - t0
+                return r
+            setattr(obj, f.__name__, g)
+        for nm in ("reset", "sample_begin", "push_packed_ptr", "prefetch_packed_ptr", "sample_pileup_async",
+                   "replicate_finish_device", "pvalues_finalize", "call_peaks", "timer_start", "timer_stop"):
+            wrap(eng.ctx, nm)
+        wrap(eng, "replicate", "eng.replicate (incl. the calls above)")
+        wrap(eng, "call_peaks", "eng.call_peaks (incl. call_peaks)")
+
     def timed(from_host, steps, warmup, with_stages=False, eng=eng):
         ctx = eng.ctx
         for _ in range(warmup):
@@ -294,17 +326,20 @@ def main():
             ctx.timing(False)
         return float(t[0]), float(t[1]), ctx.kernel_launches() - l0, peaks, rs, stages
 
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_w0 = time.time()
     # headline: K steps, nothing but the step itself in the stream; the per-stage CUDA events (two
     # per stage, ~20 stages per step) are recorded in a separate short pass of the same step
     ms_dev, wall_dev, launches, peaks, rs, _ = timed(False, a.steps, a.warmup)
+    if trace:
+        print("host ms per step by call (device arm, %d steps incl. warm-up): %s" % (
+            a.steps + a.warmup, {k: round(v * 1e3 / (a.steps + a.warmup), 3) for k, v in trace.items()}),
+            file=sys.stderr, flush=True)
+        trace.clear()
     ms_e2e, wall_e2e, _, peaks2, _, _ = timed(True, a.steps, 1)
     st_steps = max(2, a.steps // 2)
     ms_staged, _, _, peaks3, _, stages = timed(False, st_steps, 1, with_stages=True)
     assert peaks3.tobytes() == peaks.tobytes()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(t_w0, time.time()) if rank == 0 else None
     # the same per-base pass in its dense formulation (delta array in HBM: bucketed build, then
     # k_scan_stream reads 4 B per cell): the kernel the HBM-read roofline is literally about
     dense = None

@@ -187,8 +187,11 @@ def _as_ptr(a: np.ndarray):
 def _np_from(ptr, n, dtype):
     if not ptr or n == 0:
         return np.empty(0, dtype=dtype)
-    buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
-    return np.frombuffer(buf, dtype=dtype, count=n).copy()
+    # one memmove into a fresh array: np.frombuffer(...).copy() of a structured dtype copies field by
+    # field (1.3 ms for 51 k peak records where the memmove takes 0.09 ms)
+    out = np.empty(n, dtype=dtype)
+    C.memmove(out.ctypes.data, ptr, n * np.dtype(dtype).itemsize)
+    return out
 
 
 class Context:

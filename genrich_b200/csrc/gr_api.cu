@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <chrono>
 #include <vector>
 
 unsigned long long g_gr_launches = 0;
@@ -209,6 +210,17 @@ extern "C" const char* gr_last_error_detail(const gr_ctx* ctx) { return ctx ? ct
   } while (0)
 
 #define CKL() CK(cudaGetLastError())
+
+// GR_GAP_DEBUG: host time between probes (where does the host keep the device waiting?)
+static bool g_gap_debug = getenv("GR_GAP_DEBUG") != nullptr;
+static std::chrono::steady_clock::time_point g_ht_last = std::chrono::steady_clock::now();
+static inline void ht_probe(const char* label) {
+  if (!g_gap_debug) return;
+  const auto t = std::chrono::steady_clock::now();
+  fprintf(stderr, "  host +%8.3f ms  %s\n", std::chrono::duration<double, std::milli>(t - g_ht_last).count(), label);
+  g_ht_last = t;
+}
+#define HT(label) ht_probe(label)
 
 // ---- timing ------------------------------------------------------------------
 static void stage_begin(gr_ctx* x, const char* name, u64 bytes = 0) {
@@ -523,6 +535,7 @@ static int map_dev_err(int e) {
 
 // ---- seam IN -------------------------------------------------------------------
 extern "C" int gr_sample_begin(gr_ctx* x, int32_t is_ctrl, const uint8_t* save) {
+  HT("sample_begin: enter");
   if (!x) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));
   if (is_ctrl && !x->have_expt) return GR_ERR_ARG;
@@ -650,16 +663,19 @@ static int consume_segments(gr_ctx* x, int* built) {
     CK(x->sbCursor.ensure(nbk * 4));
     CK(x->sbBucket.ensure(x->n_pushed * 8 + (u64)x->n_marks * 4 + 16));   // at most two event entries per record
     CK(x->sbSpillCtr.ensure(4 + (nbk / 4096 + 2) * 4));  // (unused word), then the scan's chunk sums
+    HT("consume: bucket buffers ensured");
     stage_begin(x, "bucket", bytes);
     CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4, x->stream));
     for (auto& g : x->segs)
       launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped, sh);
+    HT("consume: memset + count launched");
     launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, x->sbCnt.as<u32>(), nullptr, nullptr, sh);
     launch_sb_scan(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
                    x->sbSpillCtr.as<u32>() + 1);
     for (auto& g : x->segs)
       launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
     launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, nullptr, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
+    HT("consume: scans + move launched");
     CKL();
     stage_end(x);
   } else if (sb) {
@@ -790,6 +806,7 @@ static int materialize(gr_ctx* x) {
 // ---- pileup integration ----------------------------------------------------------
 // Enqueues everything; the host learns the sums / counts at the next materialize().
 static int pileup_enqueue(gr_ctx* x) {
+  HT("pileup_enqueue: enter");
   const bool ctrl = x->filling == FILL_CTRL;
   int nact = 0;
   for (int c = 0; c < x->nchrom; c++) nact += chrom_active(x, c);
@@ -802,8 +819,10 @@ static int pileup_enqueue(gr_ctx* x) {
   CK(V.ensure(cap * sizeof(float)));
   DevRle out = rle_view(E, V, CS, TT);
   CK(x->scanWs.ensure(dense_scan_ws_bytes(cap, x->nchrom)));
+  HT("pileup_enqueue: buffers ensured");
   int built = 0;
   { int r = consume_segments(x, &built); if (r) return r; }
+  HT("pileup_enqueue: segments consumed");
   // after the plain scatter the scan clears the cells behind itself (the next small sample
   // finds the array zero); a built array is overwritten as a whole by the next build anyway
   const int zero_after = built ? 0 : x->zero_after;
@@ -826,6 +845,7 @@ static int pileup_enqueue(gr_ctx* x) {
   }
   stage_begin(x, "scan_place", cap * 16);
   launch_scan_place(x->stream, x->L, sc, out, x->d_err, owners, ctrl ? GR_SKIP : 0.0f);
+  HT("pileup_enqueue: scan + place launched");
   CKL();
   stage_end(x);
   u64* aI = x->accI.as<u64>() + (ctrl ? x->nchrom : 0);
@@ -835,6 +855,7 @@ static int pileup_enqueue(gr_ctx* x) {
   stage_begin(x, "rle_moment", 0);
   launch_rle_moment(x->stream, out, cap, x->nchrom, aI, aF);
   launch_sums_double(x->stream, aI, aF, x->nchrom, x->dsums.as<double>() + (ctrl ? x->nchrom : 0));
+  HT("pileup_enqueue: moments launched");
   CKL();
   stage_end(x);
   if (built != 2) x->delta_clean = zero_after != 0;          // the scan left the array all zero
@@ -934,6 +955,7 @@ static int rep_stage_pvals(gr_ctx* x, Replicate* rep) {
 
 // the part of a replicate that follows the two pileups; factor and lambda are already in x->dpar
 static int replicate_tail(gr_ctx* x, bool has_ctrl) {
+  HT("replicate_tail: enter");
   const int nc = x->nchrom;
   int nact = 0;
   for (int c = 0; c < nc; c++) nact += chrom_active(x, c);
@@ -953,6 +975,7 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
     cs.st = x->lb0.as<u64>(); cs.ticket = x->ticket.as<u32>();
     stage_begin(x, "ctrl_clamp", x->cap_raw * 8);
     launch_ctrl_clamp(x->stream, x->L, raw, x->cap_raw, x->dpar.as<float>(), cs, out, x->bmC.as<u32>());
+    HT("replicate_tail: ctrl_clamp launched");
     CKL();
     stage_end(x);
   } else {
@@ -1002,6 +1025,7 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
   stage_begin(x, "union_rank", x->T / 4);
   launch_union_rank(x->stream, x->L, x->bmE.as<u32>(), x->bmC.as<u32>(), rs, x->rankE.as<u64>(),
                     x->rankC.as<u64>(), rep->rankU.as<u64>(), x->d_totals);
+  HT("replicate_tail: union_rank launched");
   CKL();
   stage_end(x);
   // the counts of this replicate stay on the device (cnt[0] = #p intervals, cnt[1] = #control intervals)
@@ -1021,12 +1045,15 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
                     rep->pCtrl.as<float>(), rep->bmU.as<u32>(), rep->chrom_start.as<u64>(),
                     x->d_totals + 2);
   CKL();
+  HT("replicate_tail: union_emit launched");
   stage_end(x);
   { int r = rep_stage_pvals(x, rep); if (r) return r; }
+  HT("replicate_tail: pvals launched");
 
   rep->present_h.resize(nc);
   for (int c = 0; c < nc; c++) rep->present_h[c] = chrom_active(x, c);
   { int r = upload(x, rep->present.p, rep->present_h.data(), nc); if (r) return r; }
+  HT("replicate_tail: present uploaded");
   rep->has_cols = x->par.keep_pileups != 0;
   x->pend_reps.push_back(rep);
   x->lag = true;
@@ -1375,10 +1402,20 @@ extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_r
     if (r) return r;
   }
   static_assert(sizeof(PeakRec) == sizeof(gr_peak), "peak record layout");
+  static const bool gap_debug = getenv("GR_GAP_DEBUG") != nullptr;
   u64 npk = 0, peak_bp = 0;
   for (;;) {
+    const auto t_a = std::chrono::steady_clock::now();
     { int r = peaks_enqueue(x, f, qopt, peaks != nullptr); if (r) return r; }
+    const auto t_b = std::chrono::steady_clock::now();
     { int r = materialize(x); if (r) return r; }               // the one round trip of a peak call
+    HT("call_peaks: device waited for");
+    if (gap_debug) {
+      const auto t_c = std::chrono::steady_clock::now();
+      fprintf(stderr, "gr_call_peaks: enqueue %.3f ms, wait for the device %.3f ms\n",
+              std::chrono::duration<double, std::milli>(t_b - t_a).count(),
+              std::chrono::duration<double, std::milli>(t_c - t_b).count());
+    }
     if (x->retry_flags & GR_DE_TABLE) {                        // -log10 p came from an overflowed table
       int r = redo_pvals(x);
       if (r) return r;
@@ -1396,15 +1433,28 @@ extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_r
   }
   x->n_peaks = npk;
   if (peaks) {                                                 // peaks == NULL: the records stay on the device (gr_peaks_device)
-    x->peaks_h.resize(npk);
     const u64 spec = npk < gr_ctx::PEAK_SPEC ? npk : gr_ctx::PEAK_SPEC;
-    if (spec) memcpy(x->peaks_h.data(), x->h_peaks, spec * sizeof(gr_peak));
-    if (npk > spec)
+    if (npk <= gr_ctx::PEAK_SPEC) {
+      // the usual case: every record came back with the counts -- hand out the pinned buffer itself
+      // (valid until the next peak call, like the reference's printPeak arguments it stands for)
+      *peaks = x->h_peaks;
+    } else {
+      x->peaks_h.resize(npk);
+      memcpy(x->peaks_h.data(), x->h_peaks, spec * sizeof(gr_peak));
       CK(cudaMemcpy(x->peaks_h.data() + spec, x->peakOut.as<gr_peak>() + spec, (npk - spec) * sizeof(gr_peak),
                     cudaMemcpyDeviceToHost));
-    *peaks = x->peaks_h.data();
+      *peaks = x->peaks_h.data();
+    }
   }
   if (n) *n = npk;
+  HT("call_peaks: peaks on the host");
+  if (gap_debug) {
+    static auto t_last = std::chrono::steady_clock::now();
+    const auto t_d = std::chrono::steady_clock::now();
+    fprintf(stderr, "gr_call_peaks: returns %.3f ms after the previous return\n",
+            std::chrono::duration<double, std::milli>(t_d - t_last).count());
+    t_last = t_d;
+  }
   if (st) {
     memset(st, 0, sizeof *st);
     st->genome_len = final_genome_len(x);

@@ -586,10 +586,10 @@ k_scan_fix(DevLayout L, StreamWs W, DevRle out, int* __restrict__ err, u32 nwarp
 }
 
 // K2c: every page goes to its final rank; heights become the reference's floats.
-// The lookup chain of a page is three loads deep (page -> owner -> base), so every half CTA
-// keeps SP_UNROLL pages in flight: with one page per step the kernel sat at the latency of
-// the chain (0.37 ms per hg38 sample for 1.5 GB of traffic).
-#define SP_UNROLL 4
+// 16 B per break (1.5 GB per hg38 sample) in 0.37 ms: 4.1 TB/s with ONE page per half CTA and
+// step; keeping four pages in flight (SP_UNROLL 4) was measured slower (0.41 ms), so the
+// three-deep lookup chain (page -> owner -> base) is not what bounds it.
+#define SP_UNROLL 1
 __global__ void __launch_bounds__(2 * SS_PAGE)
 k_scan_place(StreamWs W, DevRle out, int* __restrict__ err, float excl_val) {
   __shared__ float4 sm_lut[120];

@@ -1,6 +1,7 @@
 // gr_interval.cu -- interval-domain kernels between the dense scan and the peak
 // scan: K3 control sweep, K4 breakpoint union, K5 -log10 p through a table of
 // distinct (expt, ctrl) pairs, K6 Fisher combine.
+#include <stdlib.h>
 #include "gr_tile.cuh"
 #include "gr_math.cuh"
 #include "gr_internal.h"
@@ -230,9 +231,9 @@ void launch_union_rank(cudaStream_t s, const DevLayout& L, const u32* bmE, const
 // relative to the CTA's first block); the list is then streamed by all threads, UE_UNROLL
 // entries per thread at a time: gathers and stores are coalesced and every thread has
 // 2 * UE_UNROLL independent loads in flight.
-#define UE_BLOCKS 4
 #define UE_CAP 4096            // list entries per round (a CTA with more breaks takes several rounds)
 #define UE_UNROLL 4
+template <int UE_BLOCKS>
 __global__ void __launch_bounds__(256)
 k_union_emit(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ bmC,
              const u64* __restrict__ rankE, const u64* __restrict__ rankC,
@@ -276,10 +277,10 @@ k_union_emit(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ b
     xa[k] = ia - pa; xu[k] = iu - pu;
   }
   __syncthreads();
-  if (w == 0) {                                  // UE_BLOCKS * 8 == 32 warp totals -> exclusive
-    const u32 va = sm_a[lane], vu = sm_u[lane];
+  if (w == 0) {                                  // UE_BLOCKS * 8 <= 32 warp totals -> exclusive
+    const u32 va = lane < UE_BLOCKS * 8 ? sm_a[lane] : 0u, vu = lane < UE_BLOCKS * 8 ? sm_u[lane] : 0u;
     const u32 ia = warp_incl_scan_u32(va, lane), iu = warp_incl_scan_u32(vu, lane);
-    sm_a[lane] = ia - va; sm_u[lane] = iu - vu;
+    if (lane < UE_BLOCKS * 8) { sm_a[lane] = ia - va; sm_u[lane] = iu - vu; }
     if (lane == 31) sm_tot = iu;
   }
   __syncthreads();
@@ -338,9 +339,17 @@ void launch_union_emit(cudaStream_t s, const DevLayout& L, const u32* bmE, const
                        const float* exptVal, const float* ctrlVal,
                        u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
                        const u64* total) {
-  const unsigned grid = (unsigned)((L.nblocks + UE_BLOCKS - 1) / UE_BLOCKS);
-  k_union_emit<<<grid, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
-                                    pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks); GR_NOTE_LAUNCH();
+  // bitmap blocks per CTA: 4 (default) or 2 (GR_UE_BLOCKS=2: fewer registers, more CTAs per SM)
+  static int ub = 0;
+  if (!ub) { const char* e = getenv("GR_UE_BLOCKS"); ub = e && atoi(e) == 2 ? 2 : 4; }
+  const unsigned grid = (unsigned)((L.nblocks + ub - 1) / ub);
+  if (ub == 2)
+    k_union_emit<2><<<grid, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
+                                         pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks);
+  else
+    k_union_emit<4><<<grid, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
+                                         pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks);
+  GR_NOTE_LAUNCH();
   launch_fill_chrom_start(s, L, chrom_start, total);
 }
 

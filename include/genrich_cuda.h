@@ -215,7 +215,9 @@ int gr_replicate_end(gr_ctx* ctx, gr_sample_stats* stats);
  * gr_bh_local_hist / gr_bh_set_global: the exchange step of computeQval 352;
  * pointers are DEVICE pointers (keys = float bits of -log10 p, lens = bp).
  * gr_call_peaks runs whatever of these has not been run (single context),
- * then callPeaks 977.  Returned arrays are owned by the context. */
+ * then callPeaks 977.  The returned array is owned by the context (pinned host memory the
+ * records were copied into; no second copy) and stays valid until the next gr_call_peaks,
+ * gr_reset or gr_destroy on that context. */
 int gr_pvalues_finalize(gr_ctx* ctx);
 int gr_bh_local_hist(gr_ctx* ctx, const uint32_t** d_keys,
                      const uint64_t** d_lens, uint64_t* n);

@@ -1,0 +1,76 @@
+/* cli_twin.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * The entry points of include/genrich_cuda.h that the host program (genrich_b200/cli/)
+ * calls, implemented on the CPU oracle (genrich_oracle.c).  Linking the host program's own
+ * sources against this file instead of libgenrich_cuda.so gives `_test/genrich-b200-oracle`:
+ * the same option parsing, SAM/BAM decode, mate pairing, duplicate removal, interval
+ * transforms and text writers, with the oracle standing in for the GPU.  The CPU test-suite
+ * runs it on the SAM view of every seeded case and compares its narrowPeak / -f / -k text
+ * with the files the unmodified reference wrote (tests/golden) BYTE FOR BYTE -- the host C
+ * code is thereby checked on every round, without a GPU.  The product binary
+ * (genrich_b200/bin/genrich-b200) links libgenrich_cuda.so and nothing from oracle/.
+ */
+#include <stdlib.h>
+#include <string.h>
+#include "genrich_oracle.h"
+
+struct gr_ctx { orc_ctx* o; };
+
+int orc_set_params(orc_ctx* x, const gr_params* p);
+
+int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom, const gr_params* params, int32_t device) {
+  (void)device;
+  gr_ctx* x = (gr_ctx*)calloc(1, sizeof *x);
+  int rc = orc_create(&x->o, chroms, nchrom, params);
+  if (rc) { free(x); return rc; }
+  *out = x;
+  return GR_OK;
+}
+void gr_destroy(gr_ctx* x) { if (x) { orc_destroy(x->o); free(x); } }
+int gr_set_params(gr_ctx* x, const gr_params* p) { return orc_set_params(x->o, p); }
+int gr_set_exclusions(gr_ctx* x, const int32_t* chrom, const uint32_t* start, const uint32_t* end, uint64_t n) {
+  return orc_set_exclusions(x->o, chrom, start, end, n);
+}
+int gr_sample_begin(gr_ctx* x, int32_t is_ctrl, const uint8_t* save) { return orc_sample_begin(x->o, is_ctrl, save); }
+int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) { return orc_push_intervals(x->o, recs, n); }
+int gr_push_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) {        /* GR_PACK, include/genrich_cuda.h */
+  int32_t r[4 * 1024];
+  for (uint64_t i = 0; i < n;) {
+    uint64_t k = 0;
+    for (; k < 1024 && i < n; k++, i++) {
+      const uint64_t w = recs[i];
+      const int32_t start = (int32_t)(uint32_t)w;
+      r[4 * k] = (int32_t)((w >> 46) & 0x3fff);
+      r[4 * k + 1] = start;
+      r[4 * k + 2] = start + (int32_t)((w >> 32) & 0x3fff);
+      r[4 * k + 3] = (int32_t)(w >> 60);
+    }
+    int rc = orc_push_intervals(x->o, r, k);
+    if (rc) return rc;
+  }
+  return GR_OK;
+}
+int gr_sample_pileup(gr_ctx* x, double* sums) { return orc_sample_pileup(x->o, sums); }
+int gr_replicate_end(gr_ctx* x, gr_sample_stats* st) { return orc_replicate_end(x->o, st); }
+int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_run_stats* st) {
+  return orc_call_peaks(x->o, peaks, n, st);
+}
+int gr_fetch_intervals(gr_ctx* x, int32_t which, int32_t replicate, int32_t chrom, const uint32_t** end,
+                       const float** val, const float** expt, const float** ctrl, uint64_t* n) {
+  return orc_fetch_intervals(x->o, which, replicate, chrom, end, val, expt, ctrl, n);
+}
+void* gr_pinned_alloc(size_t bytes) { return malloc(bytes); }
+void gr_pinned_free(void* p) { free(p); }
+const char* gr_last_error_detail(const gr_ctx* x) { (void)x; return ""; }
+const char* gr_strerror(int status) {
+  static const char* text[] = {
+    "ok", "bad argument or call order", "CUDA failure", "Cannot allocate memory",
+    ": read aligned beyond reference end", "Experimental sample has no analyzable fragments",
+    "No analyzable genome (length=0)", "Invalid pileup value (< 0)",
+    "Disallowed number of alignments", "interval on an unknown or unowned chromosome",
+    "Invalid df in pchisq()", "Genome length does not match p-value length",
+    "no CUDA device available",
+    "More than 32767 fragments start or end at one position (the reference's counters saturate there)"
+  };
+  return status < 0 || status > GR_ERR_SATURATED ? "Unknown error" : text[status];
+}

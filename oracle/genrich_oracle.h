@@ -19,6 +19,7 @@ typedef struct orc_ctx orc_ctx;
 int  orc_create(orc_ctx** out, const gr_chrom* chroms, int32_t nchrom,
                 const gr_params* params);
 void orc_destroy(orc_ctx* ctx);
+int  orc_set_params(orc_ctx* ctx, const gr_params* params);
 int  orc_set_exclusions(orc_ctx* ctx, const int32_t* chrom, const uint32_t* start,
                         const uint32_t* end, uint64_t n);
 int  orc_excluded_bp(orc_ctx* ctx, uint64_t* per_chrom);
