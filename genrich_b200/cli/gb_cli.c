@@ -3,8 +3,7 @@
  * Same options, inputs, outputs, messages and exit status as the reference
  * (getArgs 5718-5827, runProgram 5386-5695, usage 34-71); the per-chromosome
  * loops of runProgram/findPeaks are replaced by calls into the C-ABI of
- * include/genrich_cuda.h.  Not implemented on this path (fatal if requested):
- *   -r/-R PCR duplicate removal, -E BED exclusions, -P peaks from a log file.
+ * include/genrich_cuda.h.  Not implemented (fatal if requested): -P, peaks from a log file.
  */
 #include "gb_host.h"
 #include <float.h>
@@ -33,8 +32,11 @@ static void usage(void) {
   fprintf(stderr, "  -f  <file>       Output bedgraph-ish file for p/q values\n");
   fprintf(stderr, "  -k  <file>       Output bedgraph-ish file for pileups and p-values\n");
   fprintf(stderr, "  -b  <file>       Output BED file for reads/fragments/intervals\n");
+  fprintf(stderr, "  -R  <file>       Output file for PCR duplicates (only with -r)\n");
   fprintf(stderr, "Filtering options:\n");
+  fprintf(stderr, "  -r               Remove PCR duplicates\n");
   fprintf(stderr, "  -e  <arg>        Comma-separated list of chromosomes to exclude\n");
+  fprintf(stderr, "  -E  <file>       Input BED file(s) of genomic regions to exclude\n");
   fprintf(stderr, "  -m  <int>        Minimum MAPQ to keep an alignment (def. 0)\n");
   fprintf(stderr, "  -s  <float>      Keep sec alns with AS >= bestAS - <float> (def. 0)\n");
   fprintf(stderr, "  -y               Keep unpaired alignments (def. false)\n");
@@ -58,7 +60,7 @@ static void usage(void) {
   exit(EXIT_FAILURE);
 }
 
-/* logCounts 5295-5374 (without the duplicate-removal block) */
+/* logCounts 5295-5374 */
 static void log_counts(const HDecode* d, bool bam) {
   const HCounts* c = &d->cnt;
   const HOpts* o = d->opt;
@@ -85,6 +87,20 @@ static void log_counts(const HDecode* d, bool bam) {
   if (c->orphan) fprintf(stderr, "      \"orphan\" alns:    %11ld\t** Warning! **\n", (long)c->orphan);
   fprintf(stderr, "    Unpaired alignments:%11ld\n", (long)c->single);
   if (c->sec_single) fprintf(stderr, "      secondary alns:   %11ld\n", (long)c->sec_single);
+  if (o->dups_opt) {
+    fprintf(stderr, "  PCR duplicates --\n");
+    fprintf(stderr, "    Paired aln sets:    %11ld\n", (long)c->count_pr);
+    fprintf(stderr, "      duplicates:       %11ld (%.1f%%)\n", (long)c->dups_pr,
+            c->count_pr ? 100.0f * c->dups_pr / c->count_pr : 0.0f);
+    if (o->single_opt) {
+      fprintf(stderr, "    Discordant aln sets:%11ld\n", (long)c->count_dc);
+      fprintf(stderr, "      duplicates:       %11ld (%.1f%%)\n", (long)c->dups_dc,
+              c->count_dc ? 100.0f * c->dups_dc / c->count_dc : 0.0f);
+      fprintf(stderr, "    Singleton aln sets: %11ld\n", (long)c->count_sn);
+      fprintf(stderr, "      duplicates:       %11ld (%.1f%%)\n", (long)c->dups_sn,
+              c->count_sn ? 100.0f * c->dups_sn / c->count_sn : 0.0f);
+    }
+  }
   fprintf(stderr, "  Fragments analyzed:   %11ld\n", (long)(c->single_pr + c->paired_pr));
   fprintf(stderr, "    Full fragments:     %11ld\n", (long)c->paired_pr);
   if (c->paired_pr && !o->atac_opt) fprintf(stderr, "      (avg. length: %.1fbp)\n", avg);
@@ -284,7 +300,7 @@ int main(int argc, char** argv) {
   memset(&o, 0, sizeof o);
   o.min_len = 0; o.max_gap = 100; o.atac_len5 = 100; o.pqvalue = 0.01f; o.min_auc = 200.0f;
   o.atac_adj = true; o.peaks_opt = true; o.sort_opt = true;
-  bool dups = false, peaks_only = false;
+  bool peaks_only = false;
   char* xfile = NULL;
   int c;
   while ((c = getopt_long(argc, argv, GB_OPTIONS, gb_long, NULL)) != -1)
@@ -311,8 +327,8 @@ int main(int argc, char** argv) {
       case 'a': o.min_auc = gb_parse_float(optarg); break;
       case 'l': o.min_len = gb_parse_int(optarg); break;
       case 'g': o.max_gap = gb_parse_int(optarg); break;
-      case 'r': dups = true; break;
-      case 'R': dups = true; break;
+      case 'r': o.dups_opt = true; break;
+      case 'R': o.dups_file = optarg; break;
       case 'X': o.peaks_opt = false; break;
       case 'P': peaks_only = true; break;
       case 'S': o.sort_opt = false; break;
@@ -328,7 +344,6 @@ int main(int argc, char** argv) {
     fprintf(stderr, "Error! Need input/output files\n");
     usage();
   }
-  if (dups) gb_die("-r/-R", ": PCR duplicate removal is not available in genrich-b200");
   if (peaks_only) gb_die("-P", ": peak-calling from a log file is not available in genrich-b200");
   if (o.avg_ext_opt) { o.single_opt = true; o.extend_opt = false; }
   if (o.extend_opt) { o.single_opt = true; if (o.extend <= 0) gb_die("", "Extension length must be > 0"); }
@@ -372,7 +387,9 @@ int main(int argc, char** argv) {
   chk(NULL, gr_create(&ctx, gc, tab.n, &par, o.device), "gr_create");
   if (xfile) load_exclusions(ctx, xfile, &tab, o.verbose);
 
-  HOut bed = { NULL, NULL }, pile = { NULL, NULL };
+  HOut bed = { NULL, NULL }, pile = { NULL, NULL }, dupf = { NULL, NULL };
+  const bool dups_verb = o.dups_opt && o.dups_file;              /* 5411-5415 */
+  if (dups_verb) gb_out_open(&dupf, o.dups_file, o.gz_out);
   if (o.bed_file) gb_out_open(&bed, o.bed_file, o.gz_out);
   if (o.pile_file) gb_out_open(&pile, o.pile_file, o.gz_out);
   HIvBuf buf;
@@ -388,6 +405,7 @@ int main(int argc, char** argv) {
   HDecode d;
   memset(&d, 0, sizeof d);
   d.opt = &o; d.tab = &tab; d.ctx = ctx; d.buf = &buf; d.bed = o.bed_file ? &bed : NULL;
+  d.dups = dups_verb ? &dupf : NULL;
 
   for (int r = 0; r < nt; r++) {
     const char* cname = r < ncf ? cf[r] : NULL;
@@ -407,6 +425,7 @@ int main(int argc, char** argv) {
       gb_in_close(&probe, fname);
       if (o.verbose)
         fprintf(stderr, "Processing %s file #%d: %s\n", s ? "control" : "experimental", r, fname);
+      if (dups_verb) gb_out_printf(&dupf, "# %s file #%d: %s\n", s ? "control" : "experimental", r, fname);   /* 5493-5499 */
       chk(ctx, gr_sample_begin(ctx, s, s ? NULL : save), "gr_sample_begin");
       memset(&d.cnt, 0, sizeof d.cnt);
       d.ctrl = s; d.sample = r;
@@ -476,6 +495,7 @@ int main(int argc, char** argv) {
   }
   if (o.pile_file) gb_out_close(&pile, o.pile_file);
   if (o.bed_file) gb_out_close(&bed, o.bed_file);
+  if (dups_verb) gb_out_close(&dupf, o.dups_file);
   gr_pinned_free(buf.recs);
   gr_pinned_free(buf.pk);
   gr_destroy(ctx);

@@ -137,6 +137,7 @@ static void new_read_name(HDecode* d, const char* qname) {
   if (d->read_name[0] == '\0' || strcmp(qname, d->read_name)) {
     if (d->read_name[0] != '\0') gb_process_alns(d, d->read_name);
     d->naln = 0;
+    d->qual_r1 = d->qual_r2 = 0;                            /* 4575 */
     strncpy(d->read_name, qname, GB_MAX_ALNS);
     d->read_name[GB_MAX_ALNS] = '\0';
   }
@@ -226,7 +227,7 @@ static void decode_sam(HDecode* d, HIn* in) {
     new_read_name(d, qname);
     const int length = sam_ref_dist(qname, f[9], f[5]);
     const float score = sam_score(extra);
-    if (!gb_parse_align(d, flag, chrom, pos, length, pnext, score) && o->verbose)
+    if (!gb_parse_align(d, flag, chrom, pos, length, pnext, score, f[10], (int)strlen(f[10]), 33) && o->verbose)
       fprintf(stderr, "Warning! Read %s has more than %d alignments\n", qname, GB_MAX_ALNS);
   }
   free(line);
@@ -315,7 +316,10 @@ static void decode_bam(HDecode* d, HIn* in) {               /* parseBAM 4826-497
       else if (op == 2) length += ol;
     }
     const float score = bam_score(extra, (int)(blk + bs - extra));
-    if (!gb_parse_align(d, flag, idx[refID], (uint32_t)pos, length, (uint32_t)next_pos, score) && o->verbose)
+    /* the raw quality bytes follow the packed sequence; they are handed over as the reference does
+     * (parseBAM 4911-4915: a char* into the block, length l_seq, offset 0) */
+    const char* qual = (const char*)(cig + 4 * (size_t)n_cigar + (size_t)(l_seq + 1) / 2);
+    if (!gb_parse_align(d, flag, idx[refID], (uint32_t)pos, length, (uint32_t)next_pos, score, qual, l_seq, 0) && o->verbose)
       fprintf(stderr, "Warning! Read %s has more than %d alignments\n", qname, GB_MAX_ALNS);
   }
   free(blk);
@@ -326,11 +330,13 @@ void gb_decode_file(HDecode* d, const char* path) {
   HIn in;
   gb_in_open(&in, path);
   d->naln = 0;
+  d->qual_r1 = d->qual_r2 = 0;
   if (in.is_bam) decode_bam(d, &in);
   else decode_sam(d, &in);
   if (d->read_name[0] != '\0') gb_process_alns(d, d->read_name);   /* last set, 4593 */
   d->naln = 0;
-  if (d->opt->avg_ext_opt) gb_process_avg_ext(d);
+  if (d->opt->dups_opt) gb_find_dups(d);                            /* 4605-4615 */
+  else if (d->opt->avg_ext_opt) gb_process_avg_ext(d);
   gb_flush_intervals(d);
   gb_in_close(&in, path);
 }

@@ -4,7 +4,7 @@
  * processAlns (3187-3265), processPair (3122-3176), processSingle (3019-3083),
  * subsamplePair/Single (3089, 2985), saveFragment (2754), saveFragAtac (2728),
  * saveUnpair (2689), processAvgExt (2614) and the clamping half of saveInterval
- * (2522-2544); -r duplicate removal is not implemented. */
+ * (2522-2544); -r duplicate removal is gb_dups.c. */
 #include "gb_host.h"
 #include <stdlib.h>
 #include <string.h>
@@ -69,11 +69,24 @@ static bool usable(const HDecode* d, const HAln* a) {
   return c->save && !c->skip;
 }
 
-/* parseAlign 4141-4212 (without the -r quality sums) */
-bool gb_parse_align(HDecode* d, uint16_t flag, int chrom, uint32_t pos, int length, uint32_t pnext, float score) {
+/* sumQual 4127-4134: the bytes are added as (signed) chars, like the reference does */
+static uint16_t sum_qual(const char* qual, int len, int offset) {
+  if ((int)qual[0] == 0xFF) return 0;         /* never true where char is signed -- kept as written (4128) */
+  int sum = 0;
+  for (int i = 0; i < len; i++) sum += qual[i] - offset;
+  return sum > UINT16_MAX ? UINT16_MAX : (uint16_t)sum;
+}
+
+/* parseAlign 4141-4212 */
+bool gb_parse_align(HDecode* d, uint16_t flag, int chrom, uint32_t pos, int length, uint32_t pnext, float score,
+                    const char* qual, int qual_len, int qual_offset) {
   if (flag & 0x1) {
     if ((flag & 0xC0) == 0xC0) gb_die("", "Linear template with >2 reads -- not allowed");
     if (!(flag & 0xC0)) gb_die("", "Unknown index of paired alignment");
+  }
+  if (d->opt->dups_opt) {                       /* 4157-4165: first record of each mate that has qualities */
+    uint16_t* q = (flag & 0x40) ? &d->qual_r1 : &d->qual_r2;
+    if (!*q && strcmp(qual, "*")) *q = sum_qual(qual, qual_len, qual_offset);
   }
   const HChrom* c = &d->tab->c[chrom];
   const bool ignored = c->skip || !c->save;
@@ -144,11 +157,11 @@ static void emit_fragment(HDecode* d, const char* qname, const HAln* a, uint8_t 
   }
 }
 
-static void emit_unpaired(HDecode* d, const char* qname, HAln* a, uint8_t count) {   /* saveUnpair 2689-2721 */
+static void emit_unpaired(HDecode* d, const char* qname, HAln* a, uint8_t count, bool extend_opt, int extend) {   /* saveUnpair 2689-2721 */
   const HOpts* o = d->opt;
-  if (o->extend_opt) {
-    if (a->strand) gb_emit_interval(d, a->chrom, a->pos[0], (int64_t)a->pos[0] + o->extend, qname, count);
-    else gb_emit_interval(d, a->chrom, (int)(a->pos[1] - o->extend), a->pos[1], qname, count);
+  if (extend_opt) {
+    if (a->strand) gb_emit_interval(d, a->chrom, a->pos[0], (int64_t)a->pos[0] + extend, qname, count);
+    else gb_emit_interval(d, a->chrom, (int)(a->pos[1] - extend), a->pos[1], qname, count);
   } else if (o->atac_opt) {
     if (a->strand) {
       if (o->atac_adj) a->pos[0] += ATAC_ADJ_F;
@@ -173,13 +186,13 @@ static void defer_unpaired(HDecode* d, const char* qname, const HAln* a, uint8_t
 }
 
 /* processPair 3122-3176 */
-static int do_pairs(HDecode* d, const char* qname, float best) {
+int gb_do_pairs(HDecode* d, const char* qname, const HAln* aln, int naln, float best) {
   float floor_ = best;
   if (floor_ != GB_NOSCORE) floor_ -= d->opt->as_diff;
   float sc[GB_MAX_ALNS];
   int k = 0;
-  for (int i = 0; i < d->naln; i++) {
-    const HAln* a = &d->aln[i];
+  for (int i = 0; i < naln; i++) {
+    const HAln* a = &aln[i];
     if (a->paired && a->full && a->score >= floor_ && usable(d, a)) sc[k++] = a->score;
   }
   if (!k) return 0;
@@ -187,8 +200,8 @@ static int do_pairs(HDecode* d, const char* qname, float best) {
   if (k > 10 || k == 7 || k == 9) tighten(sc, k, &count, &floor_);
   uint64_t frag_len = 0;
   uint8_t saved = 0;
-  for (int i = 0; i < d->naln && saved < count; i++) {
-    const HAln* a = &d->aln[i];
+  for (int i = 0; i < naln && saved < count; i++) {
+    const HAln* a = &aln[i];
     if (a->paired && a->full && a->score >= floor_ && usable(d, a)) {
       emit_fragment(d, qname, a, count, &frag_len);
       saved++;
@@ -198,25 +211,27 @@ static int do_pairs(HDecode* d, const char* qname, float best) {
   return 1;
 }
 
-/* processSingle 3019-3083 */
-static int do_singles(HDecode* d, const char* qname, float best, bool first) {
+/* processSingle 3019-3083.  extend_opt / extend: -w, or the average fragment length found after the
+ * paired sets of a -r run (findDups 4015-4019); defer: -x without -r (saveAvgExt 2654) */
+int gb_do_singles(HDecode* d, const char* qname, HAln* aln, int naln, float best, bool first,
+                  bool extend_opt, int extend, bool defer) {
   float floor_ = best;
   if (floor_ != GB_NOSCORE) floor_ -= d->opt->as_diff;
   float sc[GB_MAX_ALNS];
   int k = 0;
-  for (int i = 0; i < d->naln; i++) {
-    const HAln* a = &d->aln[i];
+  for (int i = 0; i < naln; i++) {
+    const HAln* a = &aln[i];
     if (!a->paired && a->first == first && a->score >= floor_ && usable(d, a)) sc[k++] = a->score;
   }
   if (!k) return 0;
   uint8_t count = (uint8_t)k;
   if (k > 10 || k == 7 || k == 9) tighten(sc, k, &count, &floor_);
   uint8_t saved = 0;
-  for (int i = 0; i < d->naln && saved < count; i++) {
-    HAln* a = &d->aln[i];
+  for (int i = 0; i < naln && saved < count; i++) {
+    HAln* a = &aln[i];
     if (!a->paired && a->first == first && a->score >= floor_ && usable(d, a)) {
-      if (d->opt->avg_ext_opt) defer_unpaired(d, qname, a, count);
-      else emit_unpaired(d, qname, a, count);
+      if (defer) defer_unpaired(d, qname, a, count);
+      else emit_unpaired(d, qname, a, count, extend_opt, extend);
       saved++;
     }
   }
@@ -240,11 +255,16 @@ void gb_process_alns(HDecode* d, const char* qname) {
       else if (!a->first && best_r2 <= a->score) { best_r2 = a->score; s2 = true; }
     }
   }
+  if (d->opt->dups_opt) {                       /* 3228-3235: kept for the end of the file */
+    gb_save_alns(d, qname, pair, s1, s2, best_pr, best_r1, best_r2);
+    return;
+  }
+  const HOpts* o = d->opt;
   if (pair)
-    d->cnt.paired_pr += do_pairs(d, qname, best_pr);
-  else if (d->opt->single_opt) {
-    if (s1) d->cnt.single_pr += do_singles(d, qname, best_r1, true);
-    if (s2) d->cnt.single_pr += do_singles(d, qname, best_r2, false);
+    d->cnt.paired_pr += gb_do_pairs(d, qname, d->aln, d->naln, best_pr);
+  else if (o->single_opt) {
+    if (s1) d->cnt.single_pr += gb_do_singles(d, qname, d->aln, d->naln, best_r1, true, o->extend_opt, o->extend, o->avg_ext_opt);
+    if (s2) d->cnt.single_pr += gb_do_singles(d, qname, d->aln, d->naln, best_r2, false, o->extend_opt, o->extend, o->avg_ext_opt);
   }
 }
 

@@ -49,9 +49,27 @@ typedef struct {        /* unpaired alignment deferred for -x */
   char* name;
 } HUnpaired;
 
+/* one read name's alignment set, kept until the end of the file for -r (Read, Genrich.h:216-229) */
+typedef struct {
+  char* name;
+  uint16_t qual;        /* sum of the quality scores (both mates for pairs / discordant sets) */
+  bool first;           /* singleton sets: which mate */
+  float score, score_r2;
+  HAln* aln;            /* paired: complete pairs within as_diff of the best, positions ordered;
+                           discordant: the R1 alignments; singleton: the alignments */
+  HAln* aln_r2;         /* discordant: the R2 alignments */
+  uint8_t naln, naln_r2;
+} HRead;
+
+typedef struct {
+  HRead* r;
+  size_t n, cap;
+} HReadList;
+
 typedef struct {
   /* files */
-  char *in_files, *ctrl_files, *out_file, *log_file, *pile_file, *bed_file, *xchrom;
+  char *in_files, *ctrl_files, *out_file, *log_file, *pile_file, *bed_file, *xchrom, *dups_file;
+  bool dups_opt;        /* -r */
   /* options (same meaning and defaults as getArgs 5720-5733) */
   bool gz_out, single_opt, extend_opt, avg_ext_opt, atac_opt, atac_adj, qval_opt;
   bool peaks_opt, sort_opt, verbose;
@@ -64,6 +82,7 @@ typedef struct {
 typedef struct {        /* per-file counters (logCounts 5295) */
   uint64_t count, unmapped, supp, skipped, low_mapq, paired, sec_pair, orphan;
   uint64_t single, sec_single, single_pr, paired_pr, err_count;
+  uint64_t count_pr, dups_pr, count_dc, dups_dc, count_sn, dups_sn;   /* -r */
   double total_len;
 } HCounts;
 
@@ -104,6 +123,10 @@ typedef struct {
   char read_name[GB_MAX_ALNS + 1];
   HUnpaired* unp;       /* -x */
   size_t n_unp, cap_unp;
+  /* -r: quality sums of the current read name, the alignment sets of the file, the -R sink */
+  uint16_t qual_r1, qual_r2;
+  HReadList rd_pr, rd_dc, rd_sn;
+  HOut* dups;
 } HDecode;
 
 /* gb_util.c */
@@ -127,9 +150,17 @@ void gb_decode_file(HDecode* d, const char* path);          /* readSAM 4468 / re
 void gb_flush_intervals(HDecode* d);
 
 /* gb_frag.c */
-bool gb_parse_align(HDecode* d, uint16_t flag, int chrom, uint32_t pos, int length, uint32_t pnext, float score);
+bool gb_parse_align(HDecode* d, uint16_t flag, int chrom, uint32_t pos, int length, uint32_t pnext, float score,
+                    const char* qual, int qual_len, int qual_offset);
 void gb_process_alns(HDecode* d, const char* qname);
 void gb_process_avg_ext(HDecode* d);
 void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const char* qname, uint8_t count);
+int gb_do_pairs(HDecode* d, const char* qname, const HAln* aln, int naln, float best);      /* processPair 3122 */
+int gb_do_singles(HDecode* d, const char* qname, HAln* aln, int naln, float best, bool first,
+                  bool extend_opt, int extend, bool defer);                                /* processSingle 3019 */
+
+/* gb_dups.c: -r PCR duplicate removal (saveAlns 2940, findDups 3949) */
+void gb_save_alns(HDecode* d, const char* qname, bool pair, bool s1, bool s2, float best_pr, float best_r1, float best_r2);
+void gb_find_dups(HDecode* d);
 
 #endif

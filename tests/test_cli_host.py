@@ -66,3 +66,89 @@ def test_host_program_matches_reference_files(twin, case, tmp_path):
     assert int(re.search(r"Peaks identified: \d+ \((\d+)bp\)", err).group(1)) == meta["peak_bp"]
     assert ("All q-values are 1" in err) == meta["all_q_one"]
     assert len(re.findall(r"prevented from extending", err)) == meta["clamp_warnings"]
+
+
+# ---- host-side options on SAM files with unpaired / discordant alignments, PCR duplicates,
+# ---- quality strings and low MAPQ (tests/hostcases.py): -y -w -x -m -e -X -r -R
+from hostcases import HOST_CASES, write_host_sams, host_cmd  # noqa: E402
+import json  # noqa: E402
+
+
+def host_golden(h):
+    with open(os.path.join(util.GOLDEN, h.name + ".json")) as f:
+        meta = json.load(f)
+    p = os.path.join(util.GOLDEN, h.name + ".narrowPeak")
+    peaks = open(p).read() if os.path.exists(p) else None
+    return meta, peaks
+
+
+def check_host_case(binary, h, td, exact=True):
+    tfiles, cfiles = write_host_sams(h, td)
+    cmd, out, logf, dupf = host_cmd(binary, h, td, tfiles, cfiles)
+    r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    meta, peaks = host_golden(h)
+    err = r.stderr.replace(td, "@")
+    if h.dups_log:
+        assert _sha(dupf, True) == (meta["dups_sha256"], meta["dups_lines"])      # the whole -R log
+    if exact:
+        assert err == meta["stderr"]                                   # the complete -v text
+        if peaks is not None:
+            assert open(out).read() == peaks
+        assert _sha(logf) == (meta["log_sha256"], meta["log_lines"])
+    return out, logf, err, meta, peaks
+
+
+@pytest.mark.parametrize("h", HOST_CASES, ids=lambda h: h.name)
+def test_host_options_match_reference(twin, h, tmp_path):
+    check_host_case(twin, h, str(tmp_path))
+
+
+def test_host_bam_and_gz_inputs(twin, tmp_path):
+    """BAM (BGZF, raw quality bytes) and gzip-compressed SAM give what plain SAM gives -- with -r,
+    where the order of evaluation depends on the quality sums read from either format."""
+    h = [x for x in HOST_CASES if x.name == "host_r_y"][0]
+    td = str(tmp_path)
+    tfiles, cfiles = write_host_sams(h, td)
+    bam = os.path.join(td, "t.bam")
+    util.sam_to_bam(tfiles[0], bam)
+    gz = os.path.join(td, "t.sam.gz")
+    import gzip
+    with open(tfiles[0], "rb") as f, gzip.open(gz, "wb") as g:
+        g.write(f.read())
+    meta, peaks = host_golden(h)
+    for path in (bam, gz):
+        cmd, out, logf, dupf = host_cmd(twin, h, td, [path], cfiles)
+        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr
+        assert open(out).read() == peaks
+        assert _sha(logf) == (meta["log_sha256"], meta["log_lines"])
+        assert _sha(dupf, True) == (meta["dups_sha256"], meta["dups_lines"])
+        want = meta["stderr"].replace("@/mt0.sam", path.replace(td, "@"))
+        if path == bam:
+            want = want.replace("SAM records analyzed", "BAM records analyzed")
+        assert r.stderr.replace(td, "@") == want
+
+
+def test_host_errors(twin, tmp_path):
+    td = str(tmp_path)
+    r = subprocess.run([twin, "-o", os.path.join(td, "x")], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Error! Need input/output files" in r.stderr
+    bad = os.path.join(td, "bad.sam")
+    open(bad, "w").write("@HD\tVN:1.6\tSO:coordinate\n@SQ\tSN:chr1\tLN:1000\n")
+    r = subprocess.run([twin, "-t", bad, "-o", os.path.join(td, "x")], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "not sorted by queryname" in r.stderr
+    emp = os.path.join(td, "empty.sam")
+    open(emp, "w").write("@HD\tVN:1.6\tSO:queryname\n@SQ\tSN:chr1\tLN:1000\n")
+    r = subprocess.run([twin, "-t", emp, "-o", os.path.join(td, "x")], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Experimental sample has no analyzable fragments" in r.stderr
+    sat = os.path.join(td, "sat.sam")                    # 32768 identical fragments: the int16 saturation rule
+    with open(sat, "w") as f:
+        f.write("@HD\tVN:1.6\tSO:queryname\n@SQ\tSN:chr1\tLN:5000\n")
+        for i in range(32768):
+            f.write("r%d\t99\tchr1\t1001\t42\t50M\t=\t1201\t250\t*\t*\n" % i)
+            f.write("r%d\t147\tchr1\t1201\t42\t50M\t=\t1001\t-250\t*\t*\n" % i)
+    r = subprocess.run([twin, "-t", sat, "-o", os.path.join(td, "x")], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "saturate" in r.stderr
+    r = subprocess.run([twin, "-t", sat, "-o", os.path.join(td, "x"), "-r"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr                   # ... which -r (one copy left) avoids

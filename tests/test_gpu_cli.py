@@ -102,51 +102,7 @@ def test_cli_matches_reference_and_oracle(case, tmp_path):
     assert got == want
 
 
-def _sam_to_bam(sam_path, bam_path):
-    """Minimal uncompressed-field BAM writer (BGZF blocks via zlib) for the test."""
-    refs, recs, text = [], [], []
-    for line in open(sam_path):
-        if line.startswith("@"):
-            text.append(line)
-            if line.startswith("@SQ"):
-                f = dict(x.split(":", 1) for x in line.rstrip("\n").split("\t")[1:])
-                refs.append((f["SN"], int(f["LN"])))
-            continue
-        recs.append(line.rstrip("\n").split("\t"))
-    rid = {n: i for i, (n, _) in enumerate(refs)}
-    txt = "".join(text).encode()
-    out = bytearray(b"BAM\x01" + struct.pack("<i", len(txt)) + txt + struct.pack("<i", len(refs)))
-    for n, l in refs:
-        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
-    ops = "MIDNSHP=X"
-    for f in recs:
-        qn = f[0].encode() + b"\0"
-        cig = []
-        num = ""
-        for ch in f[5]:
-            if ch.isdigit():
-                num += ch
-            else:
-                cig.append((int(num) << 4) | ops.index(ch))
-                num = ""
-        seq_len = sum(c >> 4 for c in cig if (c & 15) in (0, 1, 4, 7, 8))
-        aux = b""
-        for t in f[11:]:
-            tag, ty, val = t.split(":", 2)
-            if ty == "i":
-                aux += tag.encode() + b"c" + struct.pack("<b", int(val))
-        body = struct.pack("<iiIIiiii", rid[f[2]], int(f[3]) - 1, (4680 << 16) | (int(f[4]) << 8) | len(qn),
-                           (int(f[1]) << 16) | len(cig), seq_len, rid[f[2]], int(f[7]) - 1, int(f[8]))
-        body += qn + b"".join(struct.pack("<I", c) for c in cig) + b"\0" * ((seq_len + 1) // 2) + b"\xff" * seq_len + aux
-        out += struct.pack("<i", len(body)) + body
-    with open(bam_path, "wb") as g:
-        for i in range(0, len(out), 60000):                 # BGZF members
-            chunk = bytes(out[i:i + 60000])
-            co = zlib.compressobj(6, zlib.DEFLATED, -15)
-            comp = co.compress(chunk) + co.flush()
-            g.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp +
-                    struct.pack("<II", zlib.crc32(chunk), len(chunk)))
-        g.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+_sam_to_bam = util.sam_to_bam
 
 
 def test_cli_bam_and_gz_inputs(tmp_path):
@@ -187,3 +143,25 @@ def test_cli_errors(tmp_path):
     assert r.returncode == 1 and "Experimental sample has no analyzable fragments" in r.stderr
     r = subprocess.run([CLI, "-t", emp, "-o", os.path.join(td, "x"), "-p", "1.5"], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "p-/q-value must be in (0,1]" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["host_r_y", "host_w", "host_r_multimap", "host_m_e"])
+def test_cli_host_options(name, tmp_path):
+    """-y / -w / -m / -e / -r / -R on SAM files with unpaired and discordant alignments, PCR
+    duplicates and quality strings, against what the unmodified reference wrote for them
+    (tests/golden/host_*): coordinates, counts and the whole -v / -R text exactly, -log10 p / q
+    within 1e-4.  (All eleven host cases run byte-exact on CPU: tests/test_cli_host.py.)"""
+    from hostcases import HOST_BY_NAME
+    from test_cli_host import check_host_case
+    out, logf, err, meta, peaks = check_host_case(CLI, HOST_BY_NAME[name], str(tmp_path), exact=False)
+    assert err == meta["stderr"]
+    got, gold = open(out).read().split("\n")[:-1], peaks.split("\n")[:-1]
+    assert len(got) == len(gold) == meta["peaks"]
+    for g, w in zip(got, gold):
+        gf, wf = g.split("\t"), w.split("\t")
+        assert gf[:4] == wf[:4] and gf[5] == wf[5] and gf[9] == wf[9], (g, w)
+        assert abs(int(gf[4]) - int(wf[4])) <= 1
+        assert abs(float(gf[6]) - float(wf[6])) <= 1e-4 * max(1.0, float(wf[6]))
+        assert abs(float(gf[7]) - float(wf[7])) <= 1e-4 + 1e-6
+        assert abs(float(gf[8]) - float(wf[8])) <= 1e-4 + 1e-6
+    assert sum(1 for _ in open(logf)) == meta["log_lines"]

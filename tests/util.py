@@ -4,7 +4,9 @@ from __future__ import annotations
 import hashlib
 import json
 import os
+import struct
 import subprocess
+import zlib
 
 import numpy as np
 
@@ -138,3 +140,52 @@ def write_case_sams(case: Case, td: str):
             write_sample_sam(case, c, cp)
             cfiles.append(cp)
     return tfiles, cfiles
+
+
+def sam_to_bam(sam_path, bam_path):
+    """Minimal BAM writer (BGZF blocks via zlib) for the tests; QUAL strings are kept."""
+    refs, recs, text = [], [], []
+    for line in open(sam_path):
+        if line.startswith("@"):
+            text.append(line)
+            if line.startswith("@SQ"):
+                f = dict(x.split(":", 1) for x in line.rstrip("\n").split("\t")[1:])
+                refs.append((f["SN"], int(f["LN"])))
+            continue
+        recs.append(line.rstrip("\n").split("\t"))
+    rid = {n: i for i, (n, _) in enumerate(refs)}
+    txt = "".join(text).encode()
+    out = bytearray(b"BAM\x01" + struct.pack("<i", len(txt)) + txt + struct.pack("<i", len(refs)))
+    for n, l in refs:
+        out += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", l)
+    ops = "MIDNSHP=X"
+    for f in recs:
+        qn = f[0].encode() + b"\0"
+        cig = []
+        num = ""
+        for ch in f[5]:
+            if ch.isdigit():
+                num += ch
+            else:
+                cig.append((int(num) << 4) | ops.index(ch))
+                num = ""
+        seq_len = sum(c >> 4 for c in cig if (c & 15) in (0, 1, 4, 7, 8))
+        aux = b""
+        for t in f[11:]:
+            tag, ty, val = t.split(":", 2)
+            if ty == "i":
+                aux += tag.encode() + b"c" + struct.pack("<b", int(val))
+        body = struct.pack("<iiIIiiii", rid[f[2]], int(f[3]) - 1, (4680 << 16) | (int(f[4]) << 8) | len(qn),
+                           (int(f[1]) << 16) | len(cig), seq_len, rid[f[2]], int(f[7]) - 1, int(f[8]))
+        qual = b"\xff" * seq_len if f[10] == "*" else bytes(ord(ch) - 33 for ch in f[10])
+        assert len(qual) == seq_len
+        body += qn + b"".join(struct.pack("<I", c) for c in cig) + b"\0" * ((seq_len + 1) // 2) + qual + aux
+        out += struct.pack("<i", len(body)) + body
+    with open(bam_path, "wb") as g:
+        for i in range(0, len(out), 60000):                 # BGZF members
+            chunk = bytes(out[i:i + 60000])
+            co = zlib.compressobj(6, zlib.DEFLATED, -15)
+            comp = co.compress(chunk) + co.flush()
+            g.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp +
+                    struct.pack("<II", zlib.crc32(chunk), len(chunk)))
+        g.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
