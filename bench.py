@@ -192,6 +192,9 @@ def main():
     ap.add_argument("--workload", default="hg38_chip_50M_50M")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-dense", action="store_true", help="skip the dense-formulation (GR_FUSED=0) comparison pass")
+    ap.add_argument("--no-pack6", action="store_true", help="e2e arm with 8-byte records even where 6-byte records fit")
+    ap.add_argument("--prefetch-depth", type=int, default=2,
+                    help="e2e arm: samples sent ahead of their push (2: both samples of the next step, 1: the next sample)")
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -238,16 +241,25 @@ def main():
     # synthetic interval records of this rank's chromosomes, on the host (pinned) and in HBM
     def make(n, seed, enrich):
         if n == 0:
-            return None, None
+            return None, None, None
         fr = gen_fragments(L, n, seed, enrich, wl["spacing"], wl["sigma"])
         iv = eng.route(host.fragments_to_intervals(fr, atac=wl["atac"]))
-        # the producer side of the C-ABI hands over 8-byte GR_PACK records (gr_push_packed)
+        # the producer side of the C-ABI hands over 8-byte GR_PACK records (gr_push_packed) ...
         packed, rest = host.pack_records(iv)
         assert rest.shape[0] == 0, "synthetic workload has records that do not pack"
         pinned = torch.from_numpy(packed.view(np.int64)).pin_memory()
-        return pinned, pinned.to(dev)
-    t_host, t_dev = make(wl["nt"], 2001, wl["enrich"])
-    c_host, c_dev = make(wl["nc"], 2002, 0.0)
+        # ... or, where the context's layout fits 32 bits, 6-byte GR_PACK6 records (gr_push_packed6):
+        # the e2e arm is bound by the host -> device copy, 25 % fewer bytes
+        p6 = None
+        if layout6 is not None and not a.no_pack6:
+            r6, rest6 = host.pack6_records(iv, layout6, L)
+            if rest6.shape[0] == 0:
+                p6 = torch.from_numpy(r6.view(np.int16).reshape(-1)).pin_memory()
+        return pinned, pinned.to(dev), p6
+    layout6 = ctx.pack6_layout()
+    t_host, t_dev, t_h6 = make(wl["nt"], 2001, wl["enrich"])
+    c_host, c_dev, c_h6 = make(wl["nc"], 2002, 0.0)
+    use6 = t_h6 is not None and (c_host is None or c_h6 is not None)
     n_t = t_host.shape[0]
     n_c = c_host.shape[0] if c_host is not None else 0
     torch.cuda.synchronize()
@@ -257,7 +269,27 @@ def main():
         ctx.reset()
         eng.saved_any[:] = False
         eng.sample_stats.clear()
-        if from_host:
+        ahead = None
+        if from_host and use6:
+            # Both samples of the NEXT step are sent while this step computes (the library's two
+            # prefetch slots; a slot is refilled as soon as the pileup that read it is done), so
+            # in steady state every step's 0.6 GB of input travels under the previous step's kernels.
+            def pe(c):
+                c.push_packed6_ptr(t_h6.data_ptr(), n_t)
+                if n_c and a.prefetch_depth < 2:
+                    c.prefetch_packed6_ptr(c_h6.data_ptr(), n_c)
+
+            def pc_(c):
+                c.push_packed6_ptr(c_h6.data_ptr(), n_c)
+                if a.prefetch_depth < 2:
+                    c.prefetch_packed6_ptr(t_h6.data_ptr(), n_t)
+            pc = pc_ if n_c else None
+            if a.prefetch_depth >= 2 or not n_c:
+                def ahead(c):
+                    c.prefetch_packed6_ptr(t_h6.data_ptr(), n_t)
+                    if n_c:
+                        c.prefetch_packed6_ptr(c_h6.data_ptr(), n_c)
+        elif from_host:
             # host (pinned) -> device copies are inside the timed region; the control sample is
             # sent while the treatment sample is being integrated, and the next step's treatment
             # sample while this step's peaks are called (gr_prefetch_intervals)
@@ -274,6 +306,8 @@ def main():
             pe = lambda c: c.push_packed_ptr(t_dev.data_ptr(), n_t)
             pc = (lambda c: c.push_packed_ptr(c_dev.data_ptr(), n_c)) if n_c else None
         eng.replicate(pe, pc, want_stats=False)
+        if ahead is not None:
+            ahead(eng.ctx)
         return eng.call_peaks()
 
     trace = {}
@@ -393,7 +427,8 @@ def main():
                    "l2": "inputs (%.1f GB dense delta array per sample) far exceed the 126 MB L2" % (4e-9 * cells),
                    "peaks": int(len(peaks)), "intervals_rank0": int(rs.n_intervals)},
         "e2e": {"value": G / 1e9 / (ms_e2e * 1e-3), "unit": "Gbp/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(8 * (n_t + n_c)), "d2h_bytes_per_step": int(peaks2.nbytes + 512),
+                "h2d_bytes_per_step": int((6 if use6 else 8) * (n_t + n_c)), "d2h_bytes_per_step": int(peaks2.nbytes + 512),
+                "record_format": "GR_PACK6 (6 B per record, expanded on the device)" if use6 else "GR_PACK (8 B per record)",
                 "wall_ms_per_step": wall_e2e},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_dev,

@@ -67,6 +67,7 @@ ABI_SYMBOLS = [
     "gr_create", "gr_destroy", "gr_set_exclusions", "gr_excluded_bp", "gr_set_params", "gr_reset", "gr_strerror",
     "gr_last_error_detail", "gr_sample_begin", "gr_push_intervals",
     "gr_push_intervals_device", "gr_prefetch_intervals", "gr_push_packed", "gr_prefetch_packed",
+    "gr_pack6_layout", "gr_push_packed6", "gr_prefetch_packed6",
     "gr_sample_pileup", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
     "gr_sums_device", "gr_stream", "gr_replicate_stats",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
@@ -137,6 +138,9 @@ class Api:
             self.replicate_stats = fn("replicate_stats", C.c_int, [vp, i32, C.POINTER(GrSampleStats)])
             self.push_packed = fn("push_packed", C.c_int, [vp, vp, u64])
             self.prefetch_packed = fn("prefetch_packed", C.c_int, [vp, vp, u64])
+            self.pack6_layout = fn("pack6_layout", C.c_int, [vp, vp])
+            self.push_packed6 = fn("push_packed6", C.c_int, [vp, vp, u64])
+            self.prefetch_packed6 = fn("prefetch_packed6", C.c_int, [vp, vp, u64])
             self.peaks_device = fn("peaks_device", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)])
             self.merge_peaks = fn("merge_peaks", C.c_int, [C.POINTER(vp), C.POINTER(u64), i32, vp])
             self.timing_enable = fn("timing_enable", C.c_int, [vp, i32])
@@ -281,6 +285,24 @@ class Context:
 
     def prefetch_packed_ptr(self, host_ptr: int, n: int):
         self._check(self.api.prefetch_packed(self._h, C.c_void_p(host_ptr), n), "prefetch_packed")
+
+    def pack6_layout(self):
+        """Cell offset of every chromosome in this context's layout (uint64; all-ones = not held here),
+        or None when the layout does not fit the 6-byte record format."""
+        off = np.zeros(self.nchrom, dtype=np.uint64)
+        if self.api.pack6_layout(self._h, _as_ptr(off)) != 0:
+            return None
+        return off
+
+    def push_packed6(self, recs: np.ndarray):
+        recs = np.ascontiguousarray(recs, dtype=np.uint16).reshape(-1, 3)
+        self._check(self.api.push_packed6(self._h, _as_ptr(recs), recs.shape[0]), "push_packed6")
+
+    def push_packed6_ptr(self, ptr: int, n: int):
+        self._check(self.api.push_packed6(self._h, C.c_void_p(ptr), n), "push_packed6")
+
+    def prefetch_packed6_ptr(self, host_ptr: int, n: int):
+        self._check(self.api.prefetch_packed6(self._h, C.c_void_p(host_ptr), n), "prefetch_packed6")
 
     def push_ptr(self, host_ptr: int, n: int):
         self._check(self.api.push_intervals(self._h, C.c_void_p(host_ptr), n), "push_intervals")

@@ -99,6 +99,7 @@ struct gr_ctx {
                     bool live = false, in_use = false; };
   struct Segment { const void* d; u64 n; int rb; SegBuf* own; Prefetch* pf; };
   std::vector<Segment> segs;
+  DevBuf unpack6;                      // GR_PACK6 segments expanded to GR_PACK words (gr_sample_pileup)
   std::vector<SegBuf*> seg_free, seg_used;
   Prefetch pf[2];                      // buffers on their way ahead of their push (gr_prefetch_*)
   cudaEvent_t h_ready[2] = { nullptr, nullptr };   // pinned bounce buffers for pageable sources
@@ -418,6 +419,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   if (x->h_up) cudaFreeHost(x->h_up);
   x->dpar.release();
   x->dsums.release();
+  x->unpack6.release();
   if (x->h_acc) cudaFreeHost(x->h_acc);
   for (int i = 0; i < 2; i++) {
     if (x->h_stage[i]) cudaFreeHost(x->h_stage[i]);
@@ -647,6 +649,27 @@ static int push_any(gr_ctx* x, const void* recs, u64 n, int rb) {
 // fused scan (the delta array is not touched)
 static int consume_segments(gr_ctx* x, int* built) {
   int32_t* delta = x->delta.as<int32_t>();
+  {
+    // 6-byte records become 8-byte words first (one streaming pass); the bucket / scatter
+    // kernels below then see nothing new.  The source buffers are released with the others at
+    // the end of this function, i.e. after the expansion has read them (stream order).
+    u64 n6 = 0;
+    for (auto& g : x->segs) if (g.rb == 6) n6 += g.n;
+    if (n6) {
+      CK(x->unpack6.ensure(n6 * 8));
+      stage_begin(x, "unpack6", n6 * 14);
+      u64 at = 0;
+      for (auto& g : x->segs) {
+        if (g.rb != 6) continue;
+        u64* out = x->unpack6.as<u64>() + at;
+        launch_unpack6(x->stream, x->L, g.d, g.n, out, x->d_err);
+        g.d = out; g.rb = 8;
+        at += g.n;
+      }
+      CKL();
+      stage_end(x);
+    }
+  }
   const bool fb_ok = x->n_pushed < (1ull << 31) && (x->T >> 11) < (1ull << 32);
   // -E regions are built into the fused scan only: every sample, whatever its size, goes that way
   if (x->has_bed && !fb_ok) { x->detail = "-E regions with more than 2^31 records in one sample"; return GR_ERR_ARG; }
@@ -736,6 +759,17 @@ extern "C" int gr_prefetch_intervals(gr_ctx* x, const int32_t* recs, uint64_t n)
 extern "C" int gr_push_intervals(gr_ctx* x, const int32_t* recs, uint64_t n) { return push_any(x, recs, n, 16); }
 extern "C" int gr_prefetch_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) { return prefetch_any(x, recs, n, 8); }
 extern "C" int gr_push_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) { return push_any(x, recs, n, 8); }
+extern "C" int gr_prefetch_packed6(gr_ctx* x, const uint16_t* recs, uint64_t n) { return prefetch_any(x, recs, n, 6); }
+extern "C" int gr_push_packed6(gr_ctx* x, const uint16_t* recs, uint64_t n) {
+  if (x && (x->T > (1ull << 32) || x->nchrom > 16384)) return GR_ERR_ARG;      // gr_pack6_layout said so
+  return push_any(x, recs, n, 6);
+}
+extern "C" int gr_pack6_layout(gr_ctx* x, uint64_t* cell_offset) {
+  if (!x || !cell_offset) return GR_ERR_ARG;
+  if (x->T > (1ull << 32) || x->nchrom > 16384) return GR_ERR_ARG;             // the layout does not fit the format
+  for (int c = 0; c < x->nchrom; c++) cell_offset[c] = x->off[c];
+  return GR_OK;
+}
 
 // ---- host mirrors ------------------------------------------------------------------
 // One device round trip that brings every lagging host mirror up to date and reports the

@@ -105,6 +105,33 @@ void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
 // its block, 28-31 count.  Intervals of SB_LONG cells or more (none in sequencing data, but
 // legal) bypass the buckets: both their ends go to the spill list, applied by reductions
 // after the blocks are written -- as do the ends of intervals that reach into a later block.
+// 6-byte records (GR_PACK6: cell of the start in this context's layout, length, count) -> the
+// 8-byte GR_PACK words every other kernel reads.  One streaming pass: 6 B in, 8 B out per record.
+__global__ void __launch_bounds__(256)
+k_unpack6(const unsigned short* __restrict__ recs, u64 n, DevLayout L, u64* __restrict__ out, int* __restrict__ err) {
+  const u64 stride = (u64)gridDim.x * 256;
+  int e_local = 0;
+  for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += stride) {
+    const u32 w0 = __ldcs(recs + 3 * i), w1 = __ldcs(recs + 3 * i + 1), w2 = __ldcs(recs + 3 * i + 2);
+    const u64 cell = (u64)(w0 | (w1 << 16));
+    u64 v;
+    if (cell >= L.T) { e_local |= GR_DE_CHROM; v = 0; }      // count 0: dropped (and reported) by the next pass
+    else {
+      const int c = L.blk2chrom[cell >> GR_BLOCK_SHIFT];
+      const u64 start = cell - L.off[c];                     // >= len (padding cells): ERRPOS in the next pass
+      v = start | ((u64)(w2 & 0xfffu) << 32) | ((u64)c << 46) | ((u64)(w2 >> 12) << 60);
+    }
+    out[i] = v;
+  }
+  if (e_local) atomicOr(err, e_local);
+}
+void launch_unpack6(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, u64* out, int* err) {
+  if (!n) return;
+  u64 blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  k_unpack6<<<(unsigned)blocks, 256, 0, s>>>((const unsigned short*)recs, n, L, out, err); GR_NOTE_LAUNCH();
+}
+
 #define SB_LONG (1u << 15)
 __device__ __forceinline__ uint2 sb_spill_entry(u64 slot, int w) {       // w signed, |w| <= 120
   return make_uint2((u32)slot, ((u32)(slot >> 32) << 8) | ((u32)w & 0xffu));

@@ -28,6 +28,7 @@ struct DevRle {
 };
 
 // ---- K1: delta scatter (saveInterval 2516-2591) ------------------------------
+void launch_unpack6(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, u64* out, int* err);
 void launch_scatter(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
                     int32_t* delta, int* err, u64* clamped);
 

@@ -68,11 +68,20 @@ class RunResult:
 
 def run_replicates(ctx: Context, replicates, chunk: int = 1 << 22, packed: bool = False) -> RunResult:
     """replicates: list of (expt_intervals, ctrl_intervals_or_None[, save_mask]).
-    packed: send the records in the 8-byte GR_PACK form (what does not fit goes the 16-byte way)."""
+    packed: True -- send the records in the 8-byte GR_PACK form (what does not fit goes the 16-byte
+    way); 6 -- in the 6-byte GR_PACK6 form first, then 8, then 16."""
+    layout = ctx.pack6_layout() if packed == 6 else None
+
     def push(recs):
         if not packed:
             ctx.push_intervals(recs)
             return
+        if layout is not None:                       # packed == 6: 6-byte records first, 8-byte for what is left
+            p6, recs = pack6_records(recs, layout, ctx.chrom_len)
+            if len(p6):
+                ctx.push_packed6(p6)
+            if not len(recs):
+                return
         pk, rest = pack_records(recs)
         if len(pk):
             ctx.push_packed(pk)
@@ -170,6 +179,32 @@ def pack_records(recs: np.ndarray):
     packed = (s[sel].astype(np.uint64) | (ln[sel].astype(np.uint64) << np.uint64(32))
               | (c[sel].astype(np.uint64) << np.uint64(46)) | (k[sel].astype(np.uint64) << np.uint64(60)))
     return np.ascontiguousarray(packed, dtype=np.uint64), np.ascontiguousarray(rest)
+
+
+PACK6_MAX_LEN = 1 << 12
+
+
+def pack6_records(recs: np.ndarray, cell_offset: np.ndarray, chrom_len):
+    """(chrom, start, end, count) int32 records -> (uint16 (n, 3) GR_PACK6 records, the records that
+    do not fit).  cell_offset: Context.pack6_layout().  A record fits when it lies inside a
+    chromosome the context holds (no clamping needed) and is shorter than 4096 bp; the rest goes on
+    through pack_records / push_intervals."""
+    recs = np.ascontiguousarray(recs, dtype=np.int32).reshape(-1, 4)
+    c, s, e, k = (recs[:, i].astype(np.int64) for i in range(4))
+    nchrom = len(cell_offset)
+    cc = np.clip(c, 0, nchrom - 1)
+    off = np.asarray(cell_offset, dtype=np.uint64)[cc]
+    ln = e - s
+    ok = ((c >= 0) & (c < nchrom) & (off != np.uint64(0xFFFFFFFFFFFFFFFF)) & (s >= 0) & (ln >= 0) & (ln < PACK6_MAX_LEN)
+          & (e <= np.asarray(chrom_len, dtype=np.int64)[cc]) & (k >= 0) & (k < 16))
+    sel = slice(None) if ok.all() else ok
+    rest = recs[:0] if ok.all() else recs[~ok]
+    cell = off[sel] + s[sel].astype(np.uint64)
+    out = np.empty((cell.shape[0], 3), dtype=np.uint16)
+    out[:, 0] = (cell & np.uint64(0xFFFF)).astype(np.uint16)
+    out[:, 1] = ((cell >> np.uint64(16)) & np.uint64(0xFFFF)).astype(np.uint16)
+    out[:, 2] = (ln[sel] | (k[sel] << 12)).astype(np.uint16)
+    return out, np.ascontiguousarray(rest)
 
 
 def lpt_shard(chrom_len, world: int) -> np.ndarray:

@@ -177,6 +177,25 @@ int gr_prefetch_intervals(gr_ctx* ctx, const int32_t* recs, uint64_t n);
 int gr_push_packed(gr_ctx* ctx, const uint64_t* recs, uint64_t n);
 int gr_prefetch_packed(gr_ctx* ctx, const uint64_t* recs, uint64_t n);
 
+/* The densest wire format, 6 bytes per record (three little-endian uint16 words): the start is
+ * given as a CELL of the context's own layout, so the chromosome index needs no bits of its own.
+ *   words 0-1  cell of the start = gr_pack6_layout()[chrom] + start   (32 bits)
+ *   word  2    bits 0-11 end - start (< GR_PACK6_MAX_LEN), bits 12-15 count
+ * gr_pack6_layout fills cell_offset[nchrom] (UINT64_MAX for chromosomes this context does not hold:
+ * skipped or owned by another rank) and fails with GR_ERR_ARG when the context's layout does not
+ * fit 32 bits (genomes beyond ~4.29 G cells on one device) -- then the format is not available.
+ * A record must lie inside its chromosome (0 <= start <= end <= len): clamping, longer intervals
+ * and everything else keep going through gr_push_packed / gr_push_intervals; all three may be
+ * mixed within a sample.  The library expands the records to GR_PACK words on the device (one
+ * streaming pass, 14 B per record) -- against 25 % fewer bytes over PCIe, which is what bounds the
+ * end-to-end rate.  Host (pinned or not) and device pointers are accepted. */
+#define GR_PACK6_MAX_LEN (1u << 12)
+#define GR_PACK6(dst, cell, len, count) \
+  ((dst)[0] = (uint16_t)(cell), (dst)[1] = (uint16_t)((uint32_t)(cell) >> 16), (dst)[2] = (uint16_t)((len) | ((count) << 12)))
+int gr_pack6_layout(gr_ctx* ctx, uint64_t* cell_offset /* [nchrom] */);
+int gr_push_packed6(gr_ctx* ctx, const uint16_t* recs, uint64_t n);
+int gr_prefetch_packed6(gr_ctx* ctx, const uint16_t* recs, uint64_t n);
+
 /* Integrate the current sample (savePileupExpt 2168 / the RLE pass of
  * calcFactor 1980).  chrom_sums[nchrom] receives, per owned chromosome, the
  * double sum of (float)(end-start)*val (0 elsewhere); the caller adds them in

@@ -173,6 +173,46 @@ def test_packed_records_same_bits():
             assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
 
 
+def test_packed6_records_same_bits(monkeypatch):
+    """gr_push_packed6 (6-byte records, expanded on the device) == gr_push_intervals on the same
+    intervals: every scan path, records that do not fit the format (clamped, 4096 bp or longer)
+    mixed in through the 8- and 16-byte forms, a -E case, a skipped chromosome."""
+    api = capi.load_cuda()
+    for env in (FUSED, PLAIN):
+        for k in ("GR_FUSED", "GR_FUSED_MIN", "GR_SB_MIN"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for name in ("c5_multimap_ctrl_p", "c2_ctrl_q", "bed_ctrl_q"):
+            case = BY_NAME[name]
+            inputs = [list(r) for r in util.case_inputs(case)]
+            extra = np.array([[0, -40, 180, 1], [0, 1000, 1000 + 20000, 2], [1 % len(case.chrom_len), 5, 4200, 1],
+                              [0, case.chrom_len[0] - 30, case.chrom_len[0] + 50, 3]], np.int32)
+            inputs[0][0] = np.concatenate([inputs[0][0], extra])
+            outs = []
+            for packed in (False, 6):
+                ctx = capi.Context(api, case.chrom_len, util.case_params(case))
+                if case.bed:
+                    ctx.set_exclusions(case.bed)
+                if packed:
+                    assert ctx.pack6_layout() is not None
+                res = host.run_replicates(ctx, inputs, chunk=50001, packed=packed)
+                outs.append((res, [ctx.fetch(2, 0, c) for c in range(len(case.chrom_len))]))
+            (ra, pa), (rb, pb) = outs
+            assert ra.peaks.tobytes() == rb.peaks.tobytes() and len(ra.peaks) > 0
+            assert ra.sample_stats[0].frag_len == rb.sample_stats[0].frag_len
+            assert ra.sample_stats[0].n_clamped == rb.sample_stats[0].n_clamped
+            for x, y in zip(pa, pb):
+                assert np.array_equal(x.end, y.end) and np.array_equal(_bits(x.val), _bits(y.val))
+    # a cell beyond the layout is an error, not a crash
+    ctx = capi.Context(api, [20000, 9000], capi.make_params(p=0.01))
+    ctx.sample_begin(False)
+    ctx.push_packed6(np.array([[0xFFFF, 0xFFFF, 100 | (1 << 12)]], dtype=np.uint16))
+    with pytest.raises(capi.GenrichError) as e:
+        ctx.sample_pileup()
+    assert e.value.status == 9
+
+
 def test_bucketed_build_same_bits(monkeypatch):
     """Large samples build the delta array block by block from bucketed records, small ones use
     atomic reductions: same array, same everything after it.  GR_SB_MIN forces either way."""

@@ -137,3 +137,21 @@ def test_oracle_reports_int16_saturation():
             assert e.value.status == want
         else:
             ctx.sample_pileup()
+
+
+def test_pack6_records_roundtrip():
+    """GR_PACK6 (6-byte records: cell of the start in the context's layout, length, count) packs what
+    it can and leaves the rest; unpacking with the layout gives the records back."""
+    L = [300000, 200000, 100000]
+    off = np.array([0, 303104, np.uint64(0xFFFFFFFFFFFFFFFF)], dtype=np.uint64)      # chr3 not held by this context
+    recs = np.array([[0, 10, 260, 1], [1, 199900, 200000, 10], [0, 299000, 300100, 2],   # past the end: clamped elsewhere
+                     [0, -5, 100, 1], [1, 5, 5000, 3], [2, 10, 20, 1], [0, 0, 0, 8], [1, 0, 4095, 6]], dtype=np.int32)
+    p6, rest = host.pack6_records(recs, off, L)
+    assert p6.shape == (4, 3) and p6.dtype == np.uint16
+    assert rest.tolist() == [[0, 299000, 300100, 2], [0, -5, 100, 1], [1, 5, 5000, 3], [2, 10, 20, 1]]
+    cell = p6[:, 0].astype(np.uint64) | (p6[:, 1].astype(np.uint64) << np.uint64(16))
+    ln, cnt = p6[:, 2] & 0xFFF, p6[:, 2] >> 12
+    chrom = np.where(cell >= off[1], 1, 0)
+    start = cell - off[chrom]
+    back = np.stack([chrom, start, start + ln, cnt], axis=1).astype(np.int32)
+    assert back.tolist() == [[0, 10, 260, 1], [1, 199900, 200000, 10], [0, 0, 0, 8], [1, 0, 4095, 6]]
