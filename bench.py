@@ -21,7 +21,8 @@ genome is sharded by chromosome over the ranks (strong scaling; torchrun, NCCL).
            interval) is timed as a stage of its own and quoted next to it.
 `cpu_baseline` / --impl reference: the UNMODIFIED reference binary
            (oracle/_ref/Genrich, built by `make -C oracle ref` where the sources
-           are) on the SAM view of a bounded sample of the same workload, 1 host
+           are) on the SAM view of a bounded sample of the same workload (8 x 50 Mbp,
+           6.5 M + 6.5 M fragments: the workload's depth; ~19 s per run), 1 host
            core (the reference is single-threaded, README.md:535).
 """
 import argparse
@@ -54,7 +55,8 @@ WORKLOADS = {
     "mini": dict(chrom_len=[60_000_000, 40_000_000, 20_000_000], nt=2_000_000, nc=2_000_000, q=None, p=0.01,
                  atac=False, spacing=40000, sigma=100.0, enrich=0.3),
 }
-SAMPLE = dict(chrom_len=[25_000_000] * 4, nt=1_000_000, nc=1_000_000)   # bounded CPU sample (same generator)
+# bounded CPU sample (same generator, same depth as the workload: 50 M fragments x 400 Mbp / 3.09 Gbp): ~19 s per run
+SAMPLE = dict(chrom_len=[50_000_000] * 8, nt=6_500_000, nc=6_500_000)
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_stream launch (bytes), from the
