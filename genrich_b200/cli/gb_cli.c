@@ -8,6 +8,7 @@
 #include "gb_host.h"
 #include <float.h>
 #include <getopt.h>
+#include <unistd.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -19,7 +20,8 @@ void gr_pinned_free(void* p);
 
 static struct option gb_long[] = {
   {"help", no_argument, NULL, 'h'}, {"verbose", no_argument, NULL, 'v'},
-  {"version", no_argument, NULL, 'V'}, {"gpu", required_argument, NULL, 'G'}, {0, 0, 0, 0}
+  {"version", no_argument, NULL, 'V'}, {"gpu", required_argument, NULL, 'G'},
+  {"threads", required_argument, NULL, 'T'}, {0, 0, 0, 0}
 };
 
 static void usage(void) {
@@ -57,6 +59,7 @@ static void usage(void) {
   fprintf(stderr, "  -z               Option to gzip-compress output(s)\n");
   fprintf(stderr, "  -v               Option to print status updates/counts to stderr\n");
   fprintf(stderr, "  --gpu <int>      CUDA device to use (def. 0)\n");
+  fprintf(stderr, "  --threads <int>  Host threads decoding a plain SAM file (def. all cores, at most 16)\n");
   exit(EXIT_FAILURE);
 }
 
@@ -336,10 +339,15 @@ int main(int argc, char** argv) {
       case 'v': o.verbose = true; break;
       case 'V': fprintf(stderr, "genrich-b200, version %s\n", GB_VERSION); exit(EXIT_FAILURE);
       case 'G': o.device = gb_parse_int(optarg); break;
+      case 'T': o.threads = gb_parse_int(optarg); break;
       case 'h': usage(); break;
       default: exit(EXIT_FAILURE);
     }
   if (optind < argc) gb_die(argv[optind], ": unknown command-line argument");
+  if (o.threads <= 0) {
+    long nc = sysconf(_SC_NPROCESSORS_ONLN);
+    o.threads = nc < 1 ? 1 : nc > 16 ? 16 : (int)nc;
+  }
   if ((o.peaks_opt && !o.out_file) || !o.in_files) {
     fprintf(stderr, "Error! Need input/output files\n");
     usage();

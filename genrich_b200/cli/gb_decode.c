@@ -2,10 +2,17 @@
  * 4350, parseCigar 4408, calcDist 4451, getScore 4383, checkHeader 4307,
  * loadChrom 4275, saveChrom 4220; readBAM 4983, parseBAM 4826, loadBAMfields
  * 4665, calcDistBAM 4697, getBAMscore 4751).  The decoder hands each record to
- * gb_parse_align() and each completed read name to gb_process_alns(). */
+ * gb_parse_align() and each completed read name to gb_process_alns().  Plain SAM files are
+ * decoded by several threads (decode_sam_threads), BGZF members inflated by several threads
+ * (bgzf_*); both give the byte stream / record sequence of the sequential path. */
 #include "gb_host.h"
+#include <fcntl.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 int gb_chrom_find(const HChromTab* t, const char* name) {
   for (int i = 0; i < t->n; i++)
@@ -71,9 +78,191 @@ static void sam_header_line(char* line, HChromTab* tab, bool ctrl, const HOpts* 
   }
 }
 
-static int32_t gz_i32(gzFile g, bool must) {              /* readInt32 4633 */
+/* ---- BGZF inflate on several host threads ---------------------------------------------------
+ * A BAM file is a series of independent gzip members of at most 64 KB (BGZF); each carries its
+ * compressed size in a 'BC' extra subfield and its uncompressed size in its last four bytes, so
+ * the members can be found by hopping over the mapped file without inflating anything.  Batches
+ * of members (64 MB of uncompressed data) are inflated by all threads at once into one of two
+ * buffers, while the record parser reads the other: the single-threaded gzread of the reference's
+ * readBAM (4983) becomes a read from memory.  The byte stream, and so everything decoded from it,
+ * is the same. */
+typedef struct {
+  unsigned char* buf;
+  size_t cap, len;
+  size_t* coff;            /* per member: offset of the deflate data in the file */
+  uint32_t *csz, *usz, *crc;
+  size_t* uoff;
+  int nblk, capblk;
+} BgzfBatch;
+
+typedef struct {
+  const unsigned char* base;
+  size_t size, pos;        /* mapped file, next member to schedule */
+  int nthreads;
+  size_t batch_bytes;
+  BgzfBatch b[2];
+  int cur, filling;        /* batch being read / batch the background filler works on */
+  size_t rd;
+  pthread_t bg;
+  bool bg_running;
+} BgzfMT;
+
+typedef struct { BgzfMT* mt; BgzfBatch* b; int t; } BgzfJob;
+
+static void* bgzf_inflate_part(void* arg) {
+  BgzfJob* j = (BgzfJob*)arg;
+  BgzfBatch* b = j->b;
+  const int n = j->mt->nthreads;
+  const int lo = (int)((long)b->nblk * j->t / n), hi = (int)((long)b->nblk * (j->t + 1) / n);
+  for (int i = lo; i < hi; i++) {
+    if (!b->usz[i]) continue;                              /* the empty end-of-file member */
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) gb_die("", "Cannot parse BAM file");
+    zs.next_in = (Bytef*)(j->mt->base + b->coff[i]);
+    zs.avail_in = b->csz[i];
+    zs.next_out = b->buf + b->uoff[i];
+    zs.avail_out = b->usz[i];
+    const int rc = inflate(&zs, Z_FINISH);
+    if (rc != Z_STREAM_END || zs.avail_out != 0) gb_die("", "Cannot parse BAM file");
+    inflateEnd(&zs);
+    if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), b->buf + b->uoff[i], b->usz[i]) != b->crc[i])
+      gb_die("", "Cannot parse BAM file");
+  }
+  return NULL;
+}
+
+/* schedule the next batch of members and inflate it; false: the file is not BGZF */
+static bool bgzf_fill(BgzfMT* m, BgzfBatch* b) {
+  b->nblk = 0;
+  b->len = 0;
+  while (m->pos < m->size && b->len < m->batch_bytes) {
+    const unsigned char* h = m->base + m->pos;
+    if (m->size - m->pos < 28 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return false;
+    const unsigned xlen = h[10] | (h[11] << 8);
+    if (m->size - m->pos < 12 + (size_t)xlen + 8) return false;
+    unsigned bsize = 0;
+    for (unsigned x = 0; x + 4 <= xlen;) {
+      const unsigned char* sf = h + 12 + x;
+      const unsigned slen = sf[2] | (sf[3] << 8);
+      if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (sf[4] | (sf[5] << 8)) + 1u;
+      x += 4 + slen;
+    }
+    if (!bsize || bsize < 12 + xlen + 8 || m->size - m->pos < bsize) return false;
+    if (b->nblk == b->capblk) {
+      b->capblk = b->capblk ? 2 * b->capblk : 2048;
+      b->coff = (size_t*)gb_realloc(b->coff, (size_t)b->capblk * sizeof(size_t));
+      b->uoff = (size_t*)gb_realloc(b->uoff, (size_t)b->capblk * sizeof(size_t));
+      b->csz = (uint32_t*)gb_realloc(b->csz, (size_t)b->capblk * 4);
+      b->usz = (uint32_t*)gb_realloc(b->usz, (size_t)b->capblk * 4);
+      b->crc = (uint32_t*)gb_realloc(b->crc, (size_t)b->capblk * 4);
+    }
+    const unsigned char* tail = h + bsize - 8;
+    const int i = b->nblk++;
+    b->coff[i] = m->pos + 12 + xlen;
+    b->csz[i] = bsize - 12 - xlen - 8;
+    b->crc[i] = (uint32_t)tail[0] | ((uint32_t)tail[1] << 8) | ((uint32_t)tail[2] << 16) | ((uint32_t)tail[3] << 24);
+    b->usz[i] = (uint32_t)tail[4] | ((uint32_t)tail[5] << 8) | ((uint32_t)tail[6] << 16) | ((uint32_t)tail[7] << 24);
+    if (b->usz[i] > 65536) return false;
+    b->uoff[i] = b->len;
+    b->len += b->usz[i];
+    m->pos += bsize;
+  }
+  if (b->len > b->cap) {
+    b->cap = b->len;
+    b->buf = (unsigned char*)gb_realloc(b->buf, b->cap);
+  }
+  const int n = m->nthreads;
+  pthread_t* th = (pthread_t*)gb_alloc((size_t)n * sizeof(pthread_t));
+  BgzfJob* jobs = (BgzfJob*)gb_alloc((size_t)n * sizeof(BgzfJob));
+  for (int t = 0; t < n; t++) {
+    jobs[t].mt = m; jobs[t].b = b; jobs[t].t = t;
+    if (pthread_create(&th[t], NULL, bgzf_inflate_part, &jobs[t])) gb_die("", "Cannot start a decode thread");
+  }
+  for (int t = 0; t < n; t++) pthread_join(th[t], NULL);
+  free(th);
+  free(jobs);
+  return true;
+}
+
+static void* bgzf_bg(void* arg) {
+  BgzfMT* m = (BgzfMT*)arg;
+  if (!bgzf_fill(m, &m->b[m->filling])) gb_die("", "Cannot parse BAM file");
+  return NULL;
+}
+
+static BgzfMT* bgzf_open(const char* path, int nthreads) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return NULL;
+  struct stat st;
+  off_t min_bytes = 4 << 20;
+  { const char* e = getenv("GB_THREAD_MIN_BYTES"); if (e) min_bytes = (off_t)atoll(e); }   /* test knob */
+  if (fstat(fd, &st) || !S_ISREG(st.st_mode) || st.st_size < min_bytes) { close(fd); return NULL; }
+  void* base = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (base == MAP_FAILED) return NULL;
+  madvise(base, (size_t)st.st_size, MADV_SEQUENTIAL);
+  BgzfMT* m = (BgzfMT*)calloc(1, sizeof *m);
+  if (!m) gb_die("", "Cannot allocate memory");
+  m->base = (const unsigned char*)base;
+  m->size = (size_t)st.st_size;
+  m->nthreads = nthreads;
+  m->batch_bytes = 64u << 20;
+  { const char* e = getenv("GB_BGZF_BATCH_BYTES"); if (e && atoll(e) > 0) m->batch_bytes = (size_t)atoll(e); }  /* test knob */
+  if (!bgzf_fill(m, &m->b[0])) {                            /* not BGZF (plain gzip): the caller keeps gzread */
+    munmap(base, m->size);
+    free(m->b[0].buf); free(m->b[0].coff); free(m->b[0].uoff); free(m->b[0].csz); free(m->b[0].usz); free(m->b[0].crc);
+    free(m);
+    return NULL;
+  }
+  m->cur = 0;
+  m->filling = 1;
+  m->bg_running = pthread_create(&m->bg, NULL, bgzf_bg, m) == 0;
+  if (!m->bg_running) gb_die("", "Cannot start a decode thread");
+  return m;
+}
+
+static int bgzf_read(BgzfMT* m, void* dst, unsigned n) {
+  unsigned got = 0;
+  while (got < n) {
+    BgzfBatch* b = &m->b[m->cur];
+    if (m->rd == b->len) {                                  /* this batch is used up: take the one filled meanwhile */
+      if (!m->bg_running) break;
+      pthread_join(m->bg, NULL);
+      m->bg_running = false;
+      m->cur ^= 1;
+      m->rd = 0;
+      if (!m->b[m->cur].len) break;                         /* end of file */
+      m->filling = m->cur ^ 1;
+      m->bg_running = pthread_create(&m->bg, NULL, bgzf_bg, m) == 0;
+      if (!m->bg_running) gb_die("", "Cannot start a decode thread");
+      continue;
+    }
+    size_t k = b->len - m->rd;
+    if (k > n - got) k = n - got;
+    memcpy((char*)dst + got, b->buf + m->rd, k);
+    m->rd += k;
+    got += (unsigned)k;
+  }
+  return (int)got;
+}
+
+static void bgzf_close(BgzfMT* m) {
+  if (m->bg_running) pthread_join(m->bg, NULL);
+  for (int i = 0; i < 2; i++) {
+    free(m->b[i].buf); free(m->b[i].coff); free(m->b[i].uoff); free(m->b[i].csz); free(m->b[i].usz); free(m->b[i].crc);
+  }
+  munmap((void*)m->base, m->size);
+  free(m);
+}
+
+/* where the BAM byte stream comes from: zlib's gzread, or the threaded inflater above */
+typedef struct { gzFile gz; BgzfMT* mt; } BamSrc;
+static int bam_read(BamSrc* s, void* dst, unsigned n) { return s->mt ? bgzf_read(s->mt, dst, n) : gzread(s->gz, dst, n); }
+
+static int32_t src_i32(BamSrc* g, bool must) {            /* readInt32 4633 */
   unsigned char b[4];
-  int n = gzread(g, b, 4);
+  int n = bam_read(g, b, 4);
   if (n != 4) {
     if (must || n > 0) gb_die("", "Cannot parse BAM file");
     return -1;
@@ -83,11 +272,11 @@ static int32_t gz_i32(gzFile g, bool must) {              /* readInt32 4633 */
 
 /* BAM header: text (first line = @HD) + reference table (readBAM 5007-5055).
  * idx_out (malloc'd) maps BAM refID -> table index. */
-static int* bam_header(HIn* in, HChromTab* tab, bool ctrl, const HOpts* opt, int* n_ref_out) {
-  int32_t l_text = gz_i32(in->gz, true);
+static int* bam_header(BamSrc* in, HChromTab* tab, bool ctrl, const HOpts* opt, int* n_ref_out) {
+  int32_t l_text = src_i32(in, true);
   if (l_text < 0) gb_die("", "Cannot parse BAM file");
   char* text = (char*)gb_alloc((size_t)l_text + 1);
-  if (gzread(in->gz, text, (unsigned)l_text) != l_text) gb_die("", "Cannot parse BAM file");
+  if (bam_read(in, text, (unsigned)l_text) != l_text) gb_die("", "Cannot parse BAM file");
   text[l_text] = '\0';
   char* nl = strpbrk(text, "\n");
   if (nl) *nl = '\0';
@@ -100,15 +289,15 @@ static int* bam_header(HIn* in, HChromTab* tab, bool ctrl, const HOpts* opt, int
   if (opt->sort_opt && (!order || strcmp(order, "queryname")))
     gb_die("", "SAM/BAM file not sorted by queryname (samtools sort -n)");
   free(text);
-  int32_t n_ref = gz_i32(in->gz, true);
+  int32_t n_ref = src_i32(in, true);
   if (n_ref < 0) gb_die("", "Cannot parse BAM file");
   int* idx = (int*)gb_alloc((size_t)(n_ref ? n_ref : 1) * sizeof(int));
   char name[GB_MAX_LINE];
   for (int i = 0; i < n_ref; i++) {
-    int32_t l = gz_i32(in->gz, true);
+    int32_t l = src_i32(in, true);
     if (l < 1 || l > GB_MAX_LINE) gb_die("", "Cannot parse BAM file");
-    if (gzread(in->gz, name, (unsigned)l) != l || name[l - 1] != '\0') gb_die("", "Cannot parse BAM file");
-    idx[i] = gb_chrom_add(tab, name, (uint32_t)gz_i32(in->gz, true), ctrl, opt);
+    if (bam_read(in, name, (unsigned)l) != l || name[l - 1] != '\0') gb_die("", "Cannot parse BAM file");
+    idx[i] = gb_chrom_add(tab, name, (uint32_t)src_i32(in, true), ctrl, opt);
   }
   *n_ref_out = n_ref;
   return idx;
@@ -121,7 +310,8 @@ void gb_scan_header(const char* path, HChromTab* tab, bool ctrl, const HOpts* op
   gb_in_open(&in, path);
   if (in.is_bam) {
     int n_ref;
-    free(bam_header(&in, tab, ctrl, opt, &n_ref));
+    BamSrc src = { in.gz, NULL };
+    free(bam_header(&src, tab, ctrl, opt, &n_ref));
   } else {
     char* line = (char*)gb_alloc(GB_MAX_LINE);
     while (gb_in_gets(&in, line, GB_MAX_LINE)) {
@@ -182,55 +372,230 @@ static float sam_score(char* extra) {                     /* getScore 4383 */
   return GB_NOSCORE;
 }
 
-static void decode_sam(HDecode* d, HIn* in) {
+/* one alignment record of a SAM file (the body of readSAM's loop, 4518-4590); `line` is modified */
+static void sam_record(HDecode* d, char* line) {
   const HOpts* o = d->opt;
+  char* f[12];
+  char* p = line;
+  int nf = 0;
+  while (nf < 11) {                               /* 11 mandatory fields, loadFields 4350 */
+    f[nf++] = p;
+    char* t = strchr(p, '\t');
+    if (!t) break;
+    *t = '\0';
+    p = t + 1;
+  }
+  if (nf < 11) gb_die(f[0], ": poorly formatted SAM/BAM record");
+  char* extra = NULL;
+  {
+    char* t = strchr(f[10], '\t');
+    if (t) { *t = '\0'; extra = t + 1; }
+    else f[10][strcspn(f[10], "\n")] = '\0';
+  }
+  const char* qname = f[0];
+  const uint16_t flag = (uint16_t)gb_parse_int(f[1]);
+  const char* rname = f[2];
+  const uint32_t pos = (uint32_t)(gb_parse_int(f[3]) - 1);
+  const int mapq = (uint8_t)gb_parse_int(f[4]);
+  const uint32_t pnext = (uint32_t)(gb_parse_int(f[7]) - 1);
+  (void)gb_parse_int(f[8]);
+  d->cnt.count++;
+  if (flag & 0x4) { d->cnt.unmapped++; return; }
+  if (!strcmp(qname, "*") || !strcmp(rname, "*")) gb_die(qname, ": poorly formatted SAM/BAM record");
+  if (flag & 0xE00) { d->cnt.supp++; return; }
+  int chrom = d->last_chrom;
+  if (chrom < 0 || chrom >= d->tab->n || strcmp(d->tab->c[chrom].name, rname)) {
+    chrom = gb_chrom_find(d->tab, rname);
+    if (chrom < 0) gb_die(rname, ": cannot find reference sequence name in SAM header");
+    d->last_chrom = chrom;
+  }
+  if (mapq < o->min_mapq) { d->cnt.low_mapq++; return; }
+  new_read_name(d, qname);
+  const int length = sam_ref_dist(qname, f[9], f[5]);
+  const float score = sam_score(extra);
+  if (!gb_parse_align(d, flag, chrom, pos, length, pnext, score, f[10], (int)strlen(f[10]), 33) && o->verbose) {
+    char w[GB_MAX_ALNS + 96];
+    snprintf(w, sizeof w, "Warning! Read %s has more than %d alignments\n", qname, GB_MAX_ALNS);
+    gb_warn(d, false, w);
+  }
+}
+
+static void decode_sam(HDecode* d, HIn* in) {
   char* line = (char*)gb_alloc(GB_MAX_LINE);
   bool past_header = false;
   while (gb_in_gets(in, line, GB_MAX_LINE)) {
     if (line[0] == '@') {
       if (past_header) gb_die(line, ": misplaced SAM header line");
-      sam_header_line(line, d->tab, d->ctrl, o);   /* idempotent: the table was pre-scanned */
+      sam_header_line(line, d->tab, d->ctrl, d->opt);   /* idempotent: the table was pre-scanned */
       continue;
     }
     past_header = true;
-    char* f[12];
-    char* p = line;
-    int nf = 0;
-    while (nf < 11) {                               /* 11 mandatory fields, loadFields 4350 */
-      f[nf++] = p;
-      char* t = strchr(p, '\t');
-      if (!t) break;
-      *t = '\0';
-      p = t + 1;
-    }
-    if (nf < 11) gb_die(f[0], ": poorly formatted SAM/BAM record");
-    char* extra = NULL;
-    {
-      char* t = strchr(f[10], '\t');
-      if (t) { *t = '\0'; extra = t + 1; }
-      else f[10][strcspn(f[10], "\n")] = '\0';
-    }
-    const char* qname = f[0];
-    const uint16_t flag = (uint16_t)gb_parse_int(f[1]);
-    const char* rname = f[2];
-    const uint32_t pos = (uint32_t)(gb_parse_int(f[3]) - 1);
-    const int mapq = (uint8_t)gb_parse_int(f[4]);
-    const uint32_t pnext = (uint32_t)(gb_parse_int(f[7]) - 1);
-    (void)gb_parse_int(f[8]);
-    d->cnt.count++;
-    if (flag & 0x4) { d->cnt.unmapped++; continue; }
-    if (!strcmp(qname, "*") || !strcmp(rname, "*")) gb_die(qname, ": poorly formatted SAM/BAM record");
-    if (flag & 0xE00) { d->cnt.supp++; continue; }
-    const int chrom = gb_chrom_find(d->tab, rname);
-    if (chrom < 0) gb_die(rname, ": cannot find reference sequence name in SAM header");
-    if (mapq < o->min_mapq) { d->cnt.low_mapq++; continue; }
-    new_read_name(d, qname);
-    const int length = sam_ref_dist(qname, f[9], f[5]);
-    const float score = sam_score(extra);
-    if (!gb_parse_align(d, flag, chrom, pos, length, pnext, score, f[10], (int)strlen(f[10]), 33) && o->verbose)
-      fprintf(stderr, "Warning! Read %s has more than %d alignments\n", qname, GB_MAX_ALNS);
+    sam_record(d, line);
   }
   free(line);
+}
+
+/* ---- several host threads on one plain SAM file --------------------------------------------
+ * The file is mapped and its body cut into one piece per thread, each cut moved forward to the
+ * next line that starts a new read name (the file is grouped by name), so every alignment set is
+ * seen whole by one worker.  A worker is an ordinary decoder with its own alignment array,
+ * counters, interval buffers and lists; full interval buffers go to the engine one at a time
+ * (gb_flush_intervals).  What depends on file order is put back in file order afterwards: the
+ * -x and -r lists are concatenated piece by piece and the -v warnings replayed with the
+ * reference's cap (saveInterval 2524: the first MAX_ALNS of them).  The pileups do not depend on
+ * the order of the interval records at all (integer adds on the device), so the peaks are those
+ * of the sequential decode, bit for bit.  Not order-free in the last bits: the double sum of
+ * fragment lengths behind the printed average length (and the -x extension derived from it) is
+ * added per piece and then over the pieces. */
+typedef struct {
+  HDecode d;
+  HIvBuf buf;
+  HWarnLog wl;
+  const char* beg;
+  const char* end;
+} SamWorker;
+
+static void* sam_worker(void* arg) {
+  SamWorker* w = (SamWorker*)arg;
+  HDecode* d = &w->d;
+  char* line = (char*)gb_alloc(GB_MAX_LINE);
+  for (const char* p = w->beg; p < w->end;) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(w->end - p));
+    size_t n = nl ? (size_t)(nl - p) + 1 : (size_t)(w->end - p);
+    if (n > GB_MAX_LINE - 1) n = GB_MAX_LINE - 1;        /* what fgets would have handed over */
+    memcpy(line, p, n);
+    line[n] = '\0';
+    p += n;
+    if (line[0] == '@') gb_die(line, ": misplaced SAM header line");
+    sam_record(d, line);
+  }
+  if (d->read_name[0] != '\0') gb_process_alns(d, d->read_name);
+  d->naln = 0;
+  gb_flush_intervals(d);
+  free(line);
+  return NULL;
+}
+
+static size_t qname_len(const char* p, const char* end) {
+  const char* t = (const char*)memchr(p, '\t', (size_t)(end - p));
+  return t ? (size_t)(t - p) : (size_t)(end - p);
+}
+
+static void list_append(HReadList* dst, HReadList* src) {
+  if (!src->n) { free(src->r); return; }
+  if (dst->n + src->n > dst->cap) {
+    dst->cap = dst->n + src->n;
+    dst->r = (HRead*)gb_realloc(dst->r, dst->cap * sizeof(HRead));
+  }
+  memcpy(dst->r + dst->n, src->r, src->n * sizeof(HRead));
+  dst->n += src->n;
+  free(src->r);
+}
+
+/* returns false if the file is not worth / not fit for the threaded path */
+static bool decode_sam_threads(HDecode* d, const char* path, int nthreads) {
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return false;
+  struct stat st;
+  off_t min_bytes = 8 << 20;                             /* smaller files are not worth the threads */
+  { const char* e = getenv("GB_THREAD_MIN_BYTES"); if (e) min_bytes = (off_t)atoll(e); }   /* test knob */
+  if (fstat(fd, &st) || !S_ISREG(st.st_mode) || st.st_size < min_bytes) { close(fd); return false; }
+  const size_t size = (size_t)st.st_size;
+  const char* base = (const char*)mmap(NULL, size, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (base == MAP_FAILED) return false;
+  madvise((void*)base, size, MADV_SEQUENTIAL);
+  const char* end = base + size;
+  /* header lines (the table was pre-scanned; this repeats readSAM's checks) */
+  const char* p = base;
+  char* line = (char*)gb_alloc(GB_MAX_LINE);
+  while (p < end && *p == '@') {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    size_t n = nl ? (size_t)(nl - p) + 1 : (size_t)(end - p);
+    if (n > GB_MAX_LINE - 1) n = GB_MAX_LINE - 1;
+    memcpy(line, p, n);
+    line[n] = '\0';
+    p += n;
+    sam_header_line(line, d->tab, d->ctrl, d->opt);
+  }
+  free(line);
+  /* cuts: at a line start whose read name differs from the line before */
+  const char** cut = (const char**)gb_alloc((size_t)(nthreads + 1) * sizeof(char*));
+  cut[0] = p;
+  cut[nthreads] = end;
+  for (int k = 1; k < nthreads; k++) {
+    const char* q = p + (size_t)(end - p) / (size_t)nthreads * (size_t)k;
+    if (q < cut[k - 1]) q = cut[k - 1];
+    /* back to the start of the line that holds q, then forward while the name repeats */
+    while (q > p && q[-1] != '\n') q--;
+    while (q < end && q > p) {
+      const char* prev = q - 1;                         /* the newline that ends the previous line */
+      while (prev > p && prev[-1] != '\n') prev--;
+      const size_t a = qname_len(prev, end), b = qname_len(q, end);
+      if (a != b || memcmp(prev, q, a)) break;
+      const char* nl = (const char*)memchr(q, '\n', (size_t)(end - q));
+      q = nl ? nl + 1 : end;
+    }
+    cut[k] = q;
+  }
+  SamWorker* ws = (SamWorker*)calloc((size_t)nthreads, sizeof(SamWorker));
+  pthread_t* th = (pthread_t*)gb_alloc((size_t)nthreads * sizeof(pthread_t));
+  if (!ws) gb_die("", "Cannot allocate memory");
+  for (int k = 0; k < nthreads; k++) {
+    SamWorker* w = &ws[k];
+    w->d.opt = d->opt; w->d.tab = d->tab; w->d.ctx = d->ctx; w->d.bed = NULL; w->d.dups = NULL;
+    w->d.ctrl = d->ctrl; w->d.sample = d->sample;
+    w->d.last_chrom = -1;
+    w->d.wlog = &w->wl;
+    w->buf.cap = 1u << 16; w->buf.cap_pk = 1u << 19;
+    w->buf.recs = (int32_t*)gr_pinned_alloc(w->buf.cap * 16);
+    w->buf.pk = (uint64_t*)gr_pinned_alloc(w->buf.cap_pk * 8);
+    if (!w->buf.recs || !w->buf.pk) gb_die("", "Cannot allocate memory");
+    w->d.buf = &w->buf;
+    w->beg = cut[k]; w->end = cut[k + 1];
+    if (pthread_create(&th[k], NULL, sam_worker, w)) gb_die("", "Cannot start a decode thread");
+  }
+  for (int k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+  /* file order again */
+  for (int k = 0; k < nthreads; k++) {
+    SamWorker* w = &ws[k];
+    const HCounts* c = &w->d.cnt;
+    for (size_t i = 0; i < w->wl.n; i++) {                 /* replay with the cap on the counted kind */
+      if (!w->wl.counted[i]) fputs(w->wl.msg[i], stderr);
+      else if (d->cnt.err_count < GB_MAX_ALNS) { fputs(w->wl.msg[i], stderr); d->cnt.err_count++; }
+      else d->cnt.err_count++;
+      free(w->wl.msg[i]);
+    }
+    /* counted warnings a worker did not log (its own 129th and later) */
+    {
+      uint64_t logged = 0;
+      for (size_t i = 0; i < w->wl.n; i++) logged += w->wl.counted[i];
+      d->cnt.err_count += c->err_count - logged;
+    }
+    free(w->wl.msg); free(w->wl.counted);
+    d->cnt.count += c->count; d->cnt.unmapped += c->unmapped; d->cnt.supp += c->supp; d->cnt.skipped += c->skipped;
+    d->cnt.low_mapq += c->low_mapq; d->cnt.paired += c->paired; d->cnt.sec_pair += c->sec_pair;
+    d->cnt.orphan += c->orphan; d->cnt.single += c->single; d->cnt.sec_single += c->sec_single;
+    d->cnt.single_pr += c->single_pr; d->cnt.paired_pr += c->paired_pr; d->cnt.total_len += c->total_len;
+    if (w->d.n_unp) {
+      if (d->n_unp + w->d.n_unp > d->cap_unp) {
+        d->cap_unp = d->n_unp + w->d.n_unp;
+        d->unp = (HUnpaired*)gb_realloc(d->unp, d->cap_unp * sizeof(HUnpaired));
+      }
+      memcpy(d->unp + d->n_unp, w->d.unp, w->d.n_unp * sizeof(HUnpaired));
+      d->n_unp += w->d.n_unp;
+    }
+    free(w->d.unp);
+    list_append(&d->rd_pr, &w->d.rd_pr);
+    list_append(&d->rd_dc, &w->d.rd_dc);
+    list_append(&d->rd_sn, &w->d.rd_sn);
+    gr_pinned_free(w->buf.recs);
+    gr_pinned_free(w->buf.pk);
+  }
+  free(ws); free(th); free(cut);
+  munmap((void*)base, size);
+  d->read_name[0] = '\0';
+  return true;
 }
 
 static float bam_score(const unsigned char* x, int len) {  /* getBAMscore 4751 */
@@ -279,18 +644,18 @@ static inline int32_t le32(const unsigned char* b) {
   return (int32_t)(b[0] | (b[1] << 8) | (b[2] << 16) | ((uint32_t)b[3] << 24));
 }
 
-static void decode_bam(HDecode* d, HIn* in) {               /* parseBAM 4826-4977 */
+static void decode_bam(HDecode* d, BamSrc* in) {            /* parseBAM 4826-4977 */
   const HOpts* o = d->opt;
   int n_ref;
   int* idx = bam_header(in, d->tab, d->ctrl, o, &n_ref);
   unsigned char* blk = (unsigned char*)gb_alloc(GB_MAX_LINE * 4);
   size_t cap = GB_MAX_LINE * 4;
   for (;;) {
-    const int32_t bs = gz_i32(in->gz, false);
+    const int32_t bs = src_i32(in, false);
     if (bs < 0) break;
     if (bs < 32) gb_die("", "Cannot parse BAM file");
     if ((size_t)bs > cap) { cap = (size_t)bs; blk = (unsigned char*)gb_realloc(blk, cap); }
-    if (gzread(in->gz, blk, (unsigned)bs) != bs) gb_die("", "Cannot parse BAM file");
+    if (bam_read(in, blk, (unsigned)bs) != bs) gb_die("", "Cannot parse BAM file");
     const int32_t refID = le32(blk), pos = le32(blk + 4);
     const uint32_t bin_mq_nl = (uint32_t)le32(blk + 8), flag_nc = (uint32_t)le32(blk + 12);
     const int l_name = bin_mq_nl & 0xFF, mapq = (bin_mq_nl >> 8) & 0xFF;
@@ -321,6 +686,7 @@ static void decode_bam(HDecode* d, HIn* in) {               /* parseBAM 4826-497
     const char* qual = (const char*)(cig + 4 * (size_t)n_cigar + (size_t)(l_seq + 1) / 2);
     if (!gb_parse_align(d, flag, idx[refID], (uint32_t)pos, length, (uint32_t)next_pos, score, qual, l_seq, 0) && o->verbose)
       fprintf(stderr, "Warning! Read %s has more than %d alignments\n", qname, GB_MAX_ALNS);
+    (void)o;
   }
   free(blk);
   free(idx);
@@ -331,9 +697,25 @@ void gb_decode_file(HDecode* d, const char* path) {
   gb_in_open(&in, path);
   d->naln = 0;
   d->qual_r1 = d->qual_r2 = 0;
-  if (in.is_bam) decode_bam(d, &in);
-  else decode_sam(d, &in);
-  if (d->read_name[0] != '\0') gb_process_alns(d, d->read_name);   /* last set, 4593 */
+  d->last_chrom = -1;
+  d->read_name[0] = '\0';
+  /* plain SAM files are decoded by several threads; -b wants its lines in file order */
+  const bool threaded = !in.is_gz && !in.is_bam && !d->bed && d->opt->threads > 1 && strcmp(path, "-")
+      && decode_sam_threads(d, path, d->opt->threads);
+  if (!threaded) {
+    if (in.is_bam) {
+      /* BGZF members are inflated by all threads, two batches deep; plain gzip keeps gzread */
+      BamSrc src = { in.gz, d->opt->threads > 1 ? bgzf_open(path, d->opt->threads) : NULL };
+      if (src.mt) {
+        char magic[4];
+        if (bgzf_read(src.mt, magic, 4) != 4 || memcmp(magic, "BAM\1", 4)) gb_die("", "Cannot parse BAM file");
+      }
+      decode_bam(d, &src);
+      if (src.mt) bgzf_close(src.mt);
+    } else
+      decode_sam(d, &in);
+    if (d->read_name[0] != '\0') gb_process_alns(d, d->read_name);   /* last set, 4593 */
+  }
   d->naln = 0;
   if (d->opt->dups_opt) gb_find_dups(d);                            /* 4605-4615 */
   else if (d->opt->avg_ext_opt) gb_process_avg_ext(d);

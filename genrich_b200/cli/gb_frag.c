@@ -6,14 +6,24 @@
  * saveUnpair (2689), processAvgExt (2614) and the clamping half of saveInterval
  * (2522-2544); -r duplicate removal is gb_dups.c. */
 #include "gb_host.h"
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
+
+/* the engine takes records from one submitter at a time (include/genrich_cuda.h): decode workers
+ * hand their full buffers over one after the other */
+static pthread_mutex_t push_mu = PTHREAD_MUTEX_INITIALIZER;
 
 #define ATAC_ADJ_F 5      /* ATACADJF, Genrich.h:35 */
 #define ATAC_ADJ_R (-5)   /* ATACADJR, Genrich.h:36 */
 
 void gb_flush_intervals(HDecode* d) {
   HIvBuf* b = d->buf;
+  if (!b->npk && !b->n) return;
+  static int drop = -1;                        /* GB_DECODE_ONLY: measurement aid, the records are discarded */
+  if (drop < 0) drop = getenv("GB_DECODE_ONLY") != NULL;
+  if (drop) { b->npk = 0; b->n = 0; return; }
+  pthread_mutex_lock(&push_mu);
   if (b->npk) {
     int rc = gr_push_packed(d->ctx, b->pk, b->npk);
     if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
@@ -24,6 +34,22 @@ void gb_flush_intervals(HDecode* d) {
     if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
     b->n = 0;
   }
+  pthread_mutex_unlock(&push_mu);
+}
+
+/* "counted" warnings are the ones saveInterval stops printing after MAX_ALNS of them (2524, 2538) */
+void gb_warn(HDecode* d, bool counted, const char* msg) {
+  if (counted && d->cnt.err_count++ >= GB_MAX_ALNS) return;
+  if (!d->wlog) { fputs(msg, stderr); return; }
+  HWarnLog* w = d->wlog;
+  if (w->n == w->cap) {
+    w->cap = w->cap ? 2 * w->cap : 64;
+    w->msg = (char**)gb_realloc(w->msg, w->cap * sizeof(char*));
+    w->counted = (uint8_t*)gb_realloc(w->counted, w->cap);
+  }
+  w->msg[w->n] = (char*)gb_alloc(strlen(msg) + 1);
+  strcpy(w->msg[w->n], msg);
+  w->counted[w->n++] = counted;
 }
 
 /* saveInterval 2516-2591, host half: clamp, messages, BED line, enqueue */
@@ -31,9 +57,12 @@ void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const c
   const HChrom* c = &d->tab->c[chrom];
   if (start < 0) {
     if (d->opt->verbose) {
-      if (d->cnt.err_count < GB_MAX_ALNS)
-        fprintf(stderr, "Warning! Read %s prevented from extending below 0 on %s\n", qname, c->name);
-      d->cnt.err_count++;
+      if (d->cnt.err_count >= GB_MAX_ALNS) d->cnt.err_count++;
+      else {
+        char w[2 * GB_MAX_ALNS + 96];
+        snprintf(w, sizeof w, "Warning! Read %s prevented from extending below 0 on %s\n", qname, c->name);
+        gb_warn(d, true, w);
+      }
     }
     start = 0;
   }
@@ -44,9 +73,12 @@ void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const c
   }
   if (end > (int64_t)c->len) {
     if (d->opt->verbose) {
-      if (d->cnt.err_count < GB_MAX_ALNS)
-        fprintf(stderr, "Warning! Read %s prevented from extending past %d on %s\n", qname, c->len, c->name);
-      d->cnt.err_count++;
+      if (d->cnt.err_count >= GB_MAX_ALNS) d->cnt.err_count++;
+      else {
+        char w[2 * GB_MAX_ALNS + 96];
+        snprintf(w, sizeof w, "Warning! Read %s prevented from extending past %d on %s\n", qname, c->len, c->name);
+        gb_warn(d, true, w);
+      }
     }
     end = c->len;
   }

@@ -77,6 +77,7 @@ typedef struct {
   float as_diff, pqvalue, min_auc;
   uint64_t genome_len;
   int device;
+  int threads;          /* host threads decoding one plain SAM file (--threads; 1 = the sequential path) */
 } HOpts;
 
 typedef struct {        /* per-file counters (logCounts 5295) */
@@ -108,7 +109,14 @@ typedef struct {
   bool is_gz, is_bam;
 } HIn;
 
-/* state of one input file being decoded */
+/* -v warnings of a decode worker, replayed in file order once the workers are done */
+typedef struct {
+  char** msg;
+  uint8_t* counted;     /* 1: one of the messages the reference stops printing after MAX_ALNS of them */
+  size_t n, cap;
+} HWarnLog;
+
+/* state of one input file being decoded (or of one worker's share of it) */
 typedef struct {
   const HOpts* opt;
   HChromTab* tab;
@@ -127,6 +135,8 @@ typedef struct {
   uint16_t qual_r1, qual_r2;
   HReadList rd_pr, rd_dc, rd_sn;
   HOut* dups;
+  HWarnLog* wlog;       /* NULL: warnings go to stderr as they arise */
+  int last_chrom;       /* one-entry cache of the reference-name lookup */
 } HDecode;
 
 /* gb_util.c */
@@ -155,6 +165,7 @@ bool gb_parse_align(HDecode* d, uint16_t flag, int chrom, uint32_t pos, int leng
 void gb_process_alns(HDecode* d, const char* qname);
 void gb_process_avg_ext(HDecode* d);
 void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const char* qname, uint8_t count);
+void gb_warn(HDecode* d, bool counted, const char* msg);   /* -v warning: now, or logged for the file-order replay */
 int gb_do_pairs(HDecode* d, const char* qname, const HAln* aln, int naln, float best);      /* processPair 3122 */
 int gb_do_singles(HDecode* d, const char* qname, HAln* aln, int naln, float best, bool first,
                   bool extend_opt, int extend, bool defer);                                /* processSingle 3019 */

@@ -117,9 +117,13 @@ def test_host_bam_and_gz_inputs(twin, tmp_path):
     with open(tfiles[0], "rb") as f, gzip.open(gz, "wb") as g:
         g.write(f.read())
     meta, peaks = host_golden(h)
-    for path in (bam, gz):
+    # (file, host threads, environment): BAM through zlib's gzread, then through the threaded BGZF
+    # inflater with batches so small that records straddle many of them
+    mt = dict(os.environ, GB_THREAD_MIN_BYTES="1", GB_BGZF_BATCH_BYTES="150000")
+    for path, threads, env in ((bam, 1, None), (bam, 3, mt), (bam, 8, dict(mt, GB_BGZF_BATCH_BYTES="1")), (gz, 4, mt)):
         cmd, out, logf, dupf = host_cmd(twin, h, td, [path], cfiles)
-        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+        cmd += ["--threads", str(threads)]
+        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True, env=env)
         assert r.returncode == 0, r.stderr
         assert open(out).read() == peaks
         assert _sha(logf) == (meta["log_sha256"], meta["log_lines"])
@@ -152,3 +156,27 @@ def test_host_errors(twin, tmp_path):
     assert r.returncode == 1 and "saturate" in r.stderr
     r = subprocess.run([twin, "-t", sat, "-o", os.path.join(td, "x"), "-r"], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr                   # ... which -r (one copy left) avoids
+
+
+@pytest.mark.parametrize("threads", [2, 5])
+def test_threaded_decode_same_output(twin, threads, tmp_path, monkeypatch):
+    """--threads N: a plain SAM file cut into N pieces at read-name boundaries and decoded by N
+    threads gives the files of the sequential decode -- i.e. the reference's, byte for byte --
+    including the -r duplicate log and the -v text (warnings replayed in file order)."""
+    monkeypatch.setenv("GB_THREAD_MIN_BYTES", "1")
+    names = ["c2_ctrl_q", "c3_atac_q", "c5_multimap_ctrl_p", "c4_fisher_q", "bed_fisher_q"]
+    for name in names:
+        case = BY_NAME[name]
+        td = str(tmp_path / (name + str(threads)))
+        os.makedirs(td)
+        out, logf, pile, err = run_twin(twin, case, td, extra=["--threads", str(threads)])
+        meta, gold = util.golden(case)
+        assert open(out).read().split("\n")[:-1] == gold
+        assert _sha(logf) == (meta["log_sha256"], meta["log_lines"])
+        assert len(re.findall(r"prevented from extending", err)) == meta["clamp_warnings"]
+    for h in HOST_CASES:
+        if h.name in ("host_y", "host_x", "host_r", "host_r_y", "host_r_x", "host_r_multimap", "host_m_e"):
+            td = str(tmp_path / (h.name + str(threads)))
+            os.makedirs(td)
+            h2 = type(h)(h.name, h.case, list(h.args) + ["--threads", str(threads)], h.dups_log)
+            check_host_case(twin, h2, td)

@@ -165,3 +165,26 @@ def test_cli_host_options(name, tmp_path):
         assert abs(float(gf[7]) - float(wf[7])) <= 1e-4 + 1e-6
         assert abs(float(gf[8]) - float(wf[8])) <= 1e-4 + 1e-6
     assert sum(1 for _ in open(logf)) == meta["log_lines"]
+
+
+def test_cli_threaded_decode(tmp_path, monkeypatch):
+    """Several host threads feeding one context (plain SAM cut at read-name boundaries; BGZF members
+    inflated in parallel): the same narrowPeak file as the sequential decode, byte for byte --
+    interval order does not matter to the integer pileups."""
+    monkeypatch.setenv("GB_THREAD_MIN_BYTES", "1")
+    monkeypatch.setenv("GB_BGZF_BATCH_BYTES", "200000")
+    case = BY_NAME["c5_multimap_ctrl_p"]
+    td = str(tmp_path)
+    tfiles, cfiles = util.write_case_sams(case, td)
+    args = case.ref_args()
+    outs = []
+    for th in (1, 6):
+        o = os.path.join(td, "t%d.np" % th)
+        subprocess.check_call([CLI, "-t", tfiles[0], "-c", cfiles[0], "-o", o, "--threads", str(th)] + args)
+        outs.append(open(o).read())
+    bam_t = os.path.join(td, "t.bam")
+    _sam_to_bam(tfiles[0], bam_t)
+    o = os.path.join(td, "bam6.np")
+    subprocess.check_call([CLI, "-t", bam_t, "-c", cfiles[0], "-o", o, "--threads", "6"] + args)
+    outs.append(open(o).read())
+    assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 0
