@@ -132,6 +132,38 @@ static void chk(gr_ctx* ctx, int rc, const char* what) {
          ? "\n  (internal error: please open an Issue on https://github.com/jsh58/Genrich)" : "");
 }
 
+/* "-" as an input file name: the reference reads uncompressed SAM from stdin (openRead 5135-5165).
+ * Here every input is read twice (the engine needs the whole chromosome table before the first
+ * record), so stdin is first copied to a temporary file, which stands in for "-" from then on. */
+static char* g_spool = NULL;
+static void spool_remove(void) { if (g_spool) unlink(g_spool); }
+static const char* real_path(const char* name) {
+  if (strcmp(name, "-")) return name;
+  if (g_spool) return g_spool;
+  const char* dir = getenv("TMPDIR");
+  if (!dir || !*dir) dir = "/tmp";
+  g_spool = (char*)gb_alloc(strlen(dir) + 32);
+  sprintf(g_spool, "%s/genrich-b200.XXXXXX", dir);
+  const int fd = mkstemp(g_spool);
+  if (fd < 0) gb_die(g_spool, ": cannot open file for writing");
+  atexit(spool_remove);
+  static char buf[1 << 20];
+  size_t n, total = 0;
+  while ((n = fread(buf, 1, sizeof buf, stdin)) > 0) {
+    if (!total && n >= 2 && (unsigned char)buf[0] == 0x1F && (unsigned char)buf[1] == 0x8B)
+      gb_die("", "Cannot pipe in gzip-compressed file (use zcat instead)");
+    for (size_t off = 0; off < n;) {
+      const ssize_t w = write(fd, buf + off, n - off);
+      if (w <= 0) gb_die(g_spool, ": cannot write to file");
+      off += (size_t)w;
+    }
+    total += n;
+  }
+  close(fd);
+  if (!total) gb_die("-", ": cannot open file for reading");
+  return g_spool;
+}
+
 /* split a list on ", " like strtok_r(.., COM, ..) at Genrich.c:5457 */
 static int split_list(char* s, char*** out) {
   int n = 0;
@@ -377,8 +409,8 @@ int main(int argc, char** argv) {
    * order the reference meets the files (t0, c0, t1, c1, ...) */
   HChromTab tab = { NULL, 0 };
   for (int r = 0; r < nt; r++) {
-    gb_scan_header(tf[r], &tab, false, &o);
-    if (r < ncf && strcmp(cf[r], "null")) gb_scan_header(cf[r], &tab, true, &o);
+    gb_scan_header(real_path(tf[r]), &tab, false, &o);
+    if (r < ncf && strcmp(cf[r], "null")) gb_scan_header(real_path(cf[r]), &tab, true, &o);
   }
   if (!tab.n) gb_die("", "No analyzable genome (length=0)");
   gr_chrom* gc = (gr_chrom*)gb_alloc(tab.n * sizeof(gr_chrom));
@@ -419,7 +451,7 @@ int main(int argc, char** argv) {
     const char* cname = r < ncf ? cf[r] : NULL;
     const bool has_ctrl = cname && strcmp(cname, "null");
     for (int i = 0; i < tab.n; i++) tab.c[i].save = false;          /* 5463-5464 */
-    gb_scan_header(tf[r], &tab, false, &o);
+    gb_scan_header(real_path(tf[r]), &tab, false, &o);
     for (int i = 0; i < tab.n; i++) save[i] = tab.c[i].save;
     for (int s = 0; s < 2; s++) {
       const char* fname = s ? cname : tf[r];
@@ -428,16 +460,16 @@ int main(int argc, char** argv) {
         break;
       }
       HIn probe;
-      gb_in_open(&probe, fname);
+      gb_in_open(&probe, real_path(fname));
       const bool bam = probe.is_bam;
-      gb_in_close(&probe, fname);
+      gb_in_close(&probe, real_path(fname));
       if (o.verbose)
         fprintf(stderr, "Processing %s file #%d: %s\n", s ? "control" : "experimental", r, fname);
       if (dups_verb) gb_out_printf(&dupf, "# %s file #%d: %s\n", s ? "control" : "experimental", r, fname);   /* 5493-5499 */
       chk(ctx, gr_sample_begin(ctx, s, s ? NULL : save), "gr_sample_begin");
       memset(&d.cnt, 0, sizeof d.cnt);
       d.ctrl = s; d.sample = r;
-      gb_decode_file(&d, fname);
+      gb_decode_file(&d, real_path(fname));
       if (o.verbose) log_counts(&d, bam);
       if (!s && has_ctrl) chk(ctx, gr_sample_pileup(ctx, NULL), "gr_sample_pileup");
     }

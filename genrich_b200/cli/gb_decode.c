@@ -305,7 +305,6 @@ static int* bam_header(BamSrc* in, HChromTab* tab, bool ctrl, const HOpts* opt, 
 
 /* header-only pass: the engine needs the complete chromosome table up front */
 void gb_scan_header(const char* path, HChromTab* tab, bool ctrl, const HOpts* opt) {
-  if (!strcmp(path, "-")) gb_die(path, ": reading alignments from stdin is not supported (the chromosome table is scanned first)");
   HIn in;
   gb_in_open(&in, path);
   if (in.is_bam) {

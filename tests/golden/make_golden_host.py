@@ -4,7 +4,7 @@ mutated SAM files of tests/hostcases.py (unpaired / discordant alignments, PCR d
 strings, low MAPQ) with the host-side options of each case.  Run in the build container only.
 
   host_<case>.narrowPeak   the reference's -o file, verbatim (absent for -X)
-  host_<case>.json         sha256 + line count of its -f log and of its -R duplicates log (without
+  host_<case>.json         sha256 + line count of its -f log, its -b interval file and its -R duplicates log (without
                            the '# ... file' lines, which hold temporary paths), and the complete -v
                            text with the temporary directory replaced by '@'
 """
@@ -44,12 +44,14 @@ def main():
             continue
         with tempfile.TemporaryDirectory() as td:
             tfiles, cfiles = write_host_sams(hc, td)
-            cmd, out, logf, dupf = host_cmd(REF, hc, td, tfiles, cfiles)
+            bedf = os.path.join(td, "o.bed")
+            cmd, out, logf, dupf = host_cmd(REF, hc, td, tfiles, cfiles, bed=bedf)
             r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
             if r.returncode != 0:
                 raise SystemExit("reference failed on %s:\n%s" % (hc.name, r.stderr))
-            meta = {"args": cmd[1:][cmd[1:].index("-v"):], "stderr": r.stderr.replace(td, "@")}
+            meta = {"args": [x for x in cmd[1:][cmd[1:].index("-v"):] if x not in ("-b", bedf)], "stderr": r.stderr.replace(td, "@")}
             meta["log_sha256"], meta["log_lines"] = sha(logf)
+            meta["bed_sha256"], meta["bed_lines"] = sha(bedf)
             if hc.dups_log:
                 meta["dups_sha256"], meta["dups_lines"] = sha(dupf, True)
             if os.path.exists(out):

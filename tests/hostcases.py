@@ -127,9 +127,11 @@ def write_host_sams(h: HostCase, td: str):
     return outs_t, outs_c
 
 
-def host_cmd(binary: str, h: HostCase, td: str, tfiles, cfiles):
+def host_cmd(binary: str, h: HostCase, td: str, tfiles, cfiles, bed=None):
     out, logf, dupf = (os.path.join(td, x) for x in ("o.np", "o.f", "o.R"))
     cmd = [binary, "-t", ",".join(tfiles), "-f", logf, "-v"] + h.case.ref_args() + list(h.args)
+    if bed:
+        cmd += ["-b", bed]
     if "-X" not in h.args:
         cmd += ["-o", out]
     if any(c != "null" for c in cfiles):

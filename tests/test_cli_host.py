@@ -84,10 +84,13 @@ def host_golden(h):
 
 def check_host_case(binary, h, td, exact=True):
     tfiles, cfiles = write_host_sams(h, td)
-    cmd, out, logf, dupf = host_cmd(binary, h, td, tfiles, cfiles)
+    bedf = None if "--threads" in h.args else os.path.join(td, "o.bed")     # -b keeps the decode on one thread
+    cmd, out, logf, dupf = host_cmd(binary, h, td, tfiles, cfiles, bed=bedf)
     r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr
     meta, peaks = host_golden(h)
+    if bedf:
+        assert _sha(bedf) == (meta["bed_sha256"], meta["bed_lines"])               # the whole -b file
     err = r.stderr.replace(td, "@")
     if h.dups_log:
         assert _sha(dupf, True) == (meta["dups_sha256"], meta["dups_lines"])      # the whole -R log
@@ -180,3 +183,35 @@ def test_threaded_decode_same_output(twin, threads, tmp_path, monkeypatch):
             os.makedirs(td)
             h2 = type(h)(h.name, h.case, list(h.args) + ["--threads", str(threads)], h.dups_log)
             check_host_case(twin, h2, td)
+
+
+def test_host_stdin_gzip_out_and_bed(twin, tmp_path):
+    """-t - (SAM piped in; spooled, since every input is read twice), -z (gzip-compressed outputs)
+    and -b (the interval file) against the reference's files."""
+    import gzip
+    case = BY_NAME["c2_ctrl_p"]
+    td = str(tmp_path)
+    tfiles, cfiles = util.write_case_sams(case, td)
+    meta, gold = util.golden(case)
+    out, bed = os.path.join(td, "o.np"), os.path.join(td, "o.bed")
+    with open(tfiles[0], "rb") as f:
+        r = subprocess.run([twin, "-t", "-", "-c", cfiles[0], "-o", out, "-b", bed, "-z", "-v"] + case.ref_args(),
+                           stdin=f, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "Processing experimental file #0: -\n" in r.stderr
+    assert gzip.open(out + ".gz", "rt").read().split("\n")[:-1] == gold
+    # -b: one line per interval, in file order, "<read>_<count>_<E|C>_<sample>"
+    want = []
+    for arr, tag in zip(util.case_inputs(case)[0][:2], "EC"):
+        want += ["chr%d\t%d\t%d\t%d_%s_0" % (a + 1, b, c2, k, tag) for a, b, c2, k in arr.tolist()]
+    got = []
+    for l in gzip.open(bed + ".gz", "rt").read().split("\n")[:-1]:
+        f = l.split("\t")
+        nm = f[3].split("_")
+        got.append("%s\t%s\t%s\t%s_%s_%s" % (f[0], f[1], f[2], nm[-3], nm[-2], nm[-1]))
+    assert got == want
+    with gzip.open(os.path.join(td, "t.gz"), "wb") as g, open(tfiles[0], "rb") as f:
+        g.write(f.read())
+    with open(os.path.join(td, "t.gz"), "rb") as f:
+        r = subprocess.run([twin, "-t", "-", "-o", out], stdin=f, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Cannot pipe in gzip-compressed file" in r.stderr
