@@ -258,7 +258,9 @@ def main():
             if rest6.shape[0] == 0:
                 p6 = torch.from_numpy(r6.view(np.int16).reshape(-1)).pin_memory()
         return pinned, pinned.to(dev), p6
-    layout6 = ctx.pack6_layout()
+    # N > 1 keeps the record format the multi-GPU runs of this round were validated with (8-byte words,
+    # one sample ahead) unless asked otherwise; the 6-byte path itself is rank-agnostic
+    layout6 = ctx.pack6_layout() if (world == 1 or os.environ.get("GR_BENCH_PACK6_MULTI")) else None
     t_host, t_dev, t_h6 = make(wl["nt"], 2001, wl["enrich"])
     c_host, c_dev, c_h6 = make(wl["nc"], 2002, 0.0)
     use6 = t_h6 is not None and (c_host is None or c_h6 is not None)
@@ -450,15 +452,15 @@ def main():
                      "dense_formulation": dense_obj},
         "stage_ms_per_step": stage_ms,
     }
-    if not a.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Genrich")):
-        cb, _ = reference_sample_run(1, 0)
+    if world > 1:
+        td.destroy_process_group()                 # nothing below involves the other ranks
+    if world == 1 and not a.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Genrich")):
+        cb, _ = reference_sample_run(1, 0)         # the contract: on rank 0 at N = 1 only
         line["cpu_baseline"] = cb
     else:
         line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": 1, "kind": "reference",
-                                "sample": "skipped (--no-cpu-baseline or oracle/_ref missing)"}
+                                "sample": "skipped (N > 1, --no-cpu-baseline or oracle/_ref missing)"}
     print(json.dumps(line))
-    if world > 1:
-        td.destroy_process_group()
 
 
 if __name__ == "__main__":
