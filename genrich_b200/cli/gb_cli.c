@@ -290,7 +290,7 @@ static void load_exclusions(gr_ctx* ctx, char* xfile, const HChromTab* tab, bool
     gb_in_open(&in, fname);
     while (gb_in_gets(&in, line, sizeof line)) {
       char copy[256];
-      snprintf(copy, sizeof copy, "%s", line);
+      snprintf(copy, sizeof copy, "%.255s", line);
       char* sp;
       char* name = strtok_r(line, "\t", &sp);
       if (!name) gb_die(copy, ": poorly formatted BED record");
