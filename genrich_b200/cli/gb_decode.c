@@ -366,6 +366,13 @@ static float sam_score(char* extra) {                     /* getScore 4383 */
     if (f[0] == 'A' && f[1] == 'S' && f[2] == ':') {
       char* v = strchr(f + 3, ':');
       if (!v) return GB_NOSCORE;
+      /* "AS:i:<int>": a short decimal integer converts exactly like strtof does; the rest goes to it */
+      const char* p = v + 1;
+      const bool neg = *p == '-';
+      if (neg) p++;
+      int iv = 0, nd = 0;
+      while (*p >= '0' && *p <= '9' && nd < 8) { iv = iv * 10 + (*p - '0'); p++; nd++; }
+      if (nd > 0 && nd < 8 && *p == '\0') return neg ? -(float)iv : (float)iv;
       return gb_parse_float(v + 1);
     }
   return GB_NOSCORE;

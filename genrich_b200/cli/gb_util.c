@@ -22,6 +22,16 @@ void* gb_realloc(void* p, size_t n) {
 }
 
 int gb_parse_int(const char* s) {            /* getInt 117 */
+  /* plain decimal numbers of up to nine digits (every numeric SAM field in practice) take a short
+   * loop; anything else -- blanks, '+', overflow, garbage -- goes through strtol like the reference */
+  {
+    const char* p = s;
+    const bool neg = *p == '-';
+    if (neg) p++;
+    int v = 0, nd = 0;
+    while (*p >= '0' && *p <= '9' && nd < 10) { v = v * 10 + (*p - '0'); p++; nd++; }
+    if (nd > 0 && nd < 10 && *p == '\0') return neg ? -v : v;
+  }
   char* end;
   long v = strtol(s, &end, 10);
   if (*end != '\0') gb_die(s, ": cannot convert to int");
