@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "gr_sample_pileup", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
     "gr_sums_device", "gr_stream", "gr_replicate_stats",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
-    "gr_bh_set_global", "gr_call_peaks", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
+    "gr_bh_set_global", "gr_bh_local_hist_host", "gr_bh_set_global_host", "gr_call_peaks", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
     "gr_kernel_launches", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
     "gr_pinned_alloc", "gr_pinned_free",
@@ -142,6 +142,8 @@ class Api:
             self.push_packed6 = fn("push_packed6", C.c_int, [vp, vp, u64])
             self.prefetch_packed6 = fn("prefetch_packed6", C.c_int, [vp, vp, u64])
             self.peaks_device = fn("peaks_device", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)])
+            self.bh_local_hist_host = fn("bh_local_hist_host", C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)])
+            self.bh_set_global_host = fn("bh_set_global_host", C.c_int, [vp, vp, vp, u64, u64])
             self.merge_peaks = fn("merge_peaks", C.c_int, [C.POINTER(vp), C.POINTER(u64), i32, vp])
             self.timing_enable = fn("timing_enable", C.c_int, [vp, i32])
             self.timing_get = fn("timing_get", C.c_int, [vp, C.POINTER(GrStageTime), i32, C.POINTER(i32)])

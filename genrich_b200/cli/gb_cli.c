@@ -21,7 +21,7 @@ void gr_pinned_free(void* p);
 static struct option gb_long[] = {
   {"help", no_argument, NULL, 'h'}, {"verbose", no_argument, NULL, 'v'},
   {"version", no_argument, NULL, 'V'}, {"gpu", required_argument, NULL, 'G'},
-  {"threads", required_argument, NULL, 'T'}, {0, 0, 0, 0}
+  {"threads", required_argument, NULL, 'T'}, {"gpus", required_argument, NULL, 'N'}, {0, 0, 0, 0}
 };
 
 static void usage(void) {
@@ -59,6 +59,7 @@ static void usage(void) {
   fprintf(stderr, "  -z               Option to gzip-compress output(s)\n");
   fprintf(stderr, "  -v               Option to print status updates/counts to stderr\n");
   fprintf(stderr, "  --gpu <int>      CUDA device to use (def. 0)\n");
+  fprintf(stderr, "  --gpus <int>     Number of devices, starting at --gpu; chromosomes are sharded over them (def. 1)\n");
   fprintf(stderr, "  --threads <int>  Host threads decoding a plain SAM file (def. all cores, at most 16)\n");
   exit(EXIT_FAILURE);
 }
@@ -178,12 +179,13 @@ static int split_list(char* s, char*** out) {
 }
 
 /* -k: printPileHeader 1680 + printPile 1697 for one replicate */
-static void write_pile(gr_ctx* ctx, HOut* out, const HChromTab* tab, int rep, const char* ename, const char* cname) {
+static void write_pile(gr_ctx** ctxs, const int* owner, HOut* out, const HChromTab* tab, int rep, const char* ename, const char* cname) {
   gb_out_printf(out, "# experimental file: %s; control file: %s\n", ename,
                 cname && strcmp(cname, "null") ? cname : "NA");
   gb_out_printf(out, "chr\tstart\tend\texperimental\tcontrol\t-log(p)\n");
   for (int c = 0; c < tab->n; c++) {
     const uint32_t* end; const float *val, *ex, *ct; uint64_t n;
+    gr_ctx* ctx = ctxs[owner[c]];                              /* the device that holds this chromosome */
     chk(ctx, gr_fetch_intervals(ctx, 2, rep, c, &end, &val, &ex, &ct, &n), "fetch");
     uint32_t start = 0;
     for (uint64_t m = 0; m < n; m++) {
@@ -213,7 +215,7 @@ static Arr fetch_copy(gr_ctx* ctx, int which, int rep, int c, bool cols) {
 static void arr_free(Arr* a) { free(a->end); free(a->val); free(a->ex); free(a->ct); }
 
 /* -f: printLogHeader 674 + printInterval 770 / printIntervalN 724 as callPeaks / logIntervals emit them */
-static void write_log(gr_ctx* ctx, HOut* out, const HChromTab* tab, int nrep, const HOpts* o, float thr) {
+static void write_log(gr_ctx** ctxs, const int* owner, HOut* out, const HChromTab* tab, int nrep, const HOpts* o, float thr) {
   const bool sig_col = o->peaks_opt, q = o->qval_opt;
   if (nrep > 1) {
     gb_out_printf(out, "chr\tstart\tend");
@@ -225,6 +227,7 @@ static void write_log(gr_ctx* ctx, HOut* out, const HChromTab* tab, int nrep, co
   if (sig_col) gb_out_printf(out, "\tsignif");
   gb_out_printf(out, "\n");
   for (int c = 0; c < tab->n; c++) {
+    gr_ctx* ctx = ctxs[owner[c]];
     Arr fin = fetch_copy(ctx, 2, nrep > 1 ? nrep : 0, c, nrep == 1);
     if (!fin.n) continue;
     Arr qv = { 0 };
@@ -279,7 +282,7 @@ static void write_log(gr_ctx* ctx, HOut* out, const HChromTab* tab, int nrep, co
  * the -v warnings of saveXBed 1151-1192.  Records of unknown references are ignored, as in the
  * reference (saveXBed only looks for the names of the chromosomes it knows); sorting, clamping
  * and merging happen in the library (gr_set_exclusions), exactly as saveXBed does them. */
-static void load_exclusions(gr_ctx* ctx, char* xfile, const HChromTab* tab, bool verbose) {
+static void load_exclusions(gr_ctx** ctxs, int nctx, char* xfile, const HChromTab* tab, bool verbose) {
   int32_t* chrom = NULL;
   uint32_t *start = NULL, *end = NULL;
   size_t n = 0, cap = 0;
@@ -326,7 +329,8 @@ static void load_exclusions(gr_ctx* ctx, char* xfile, const HChromTab* tab, bool
     }
     gb_in_close(&in, fname);
   }
-  chk(ctx, gr_set_exclusions(ctx, chrom, start, end, n), "gr_set_exclusions");
+  for (int k = 0; k < nctx; k++)                               /* every device gets every region */
+    chk(ctxs[k], gr_set_exclusions(ctxs[k], chrom, start, end, n), "gr_set_exclusions");
   free(chrom); free(start); free(end);
 }
 
@@ -372,6 +376,7 @@ int main(int argc, char** argv) {
       case 'V': fprintf(stderr, "genrich-b200, version %s\n", GB_VERSION); exit(EXIT_FAILURE);
       case 'G': o.device = gb_parse_int(optarg); break;
       case 'T': o.threads = gb_parse_int(optarg); break;
+      case 'N': o.gpus = gb_parse_int(optarg); break;
       case 'h': usage(); break;
       default: exit(EXIT_FAILURE);
     }
@@ -413,38 +418,78 @@ int main(int argc, char** argv) {
     if (r < ncf && strcmp(cf[r], "null")) gb_scan_header(real_path(cf[r]), &tab, true, &o);
   }
   if (!tab.n) gb_die("", "No analyzable genome (length=0)");
-  gr_chrom* gc = (gr_chrom*)gb_alloc(tab.n * sizeof(gr_chrom));
-  for (int i = 0; i < tab.n; i++) {
-    gc[i].len = tab.c[i].len;
-    gc[i].skip = tab.c[i].skip || !tab.c[i].ever_saved;     /* control-only references are never used (4244) */
-    gc[i].owned = 1;
-    gc[i].reserved = 0;
+  /* Chromosomes are sharded over the devices (runProgram's per-chromosome loop, 5460-5607, becomes
+   * the dispatcher): greedy longest-first assignment to the least loaded device.  Every context
+   * knows the whole table and owns its share; what crosses devices goes through this host: the
+   * per-chromosome sums behind lambda and the scale factor, the p-value histogram behind BH, and
+   * the order of the peaks. */
+  int nctx = o.gpus < 1 ? 1 : o.gpus;
+  int* owner = (int*)calloc((size_t)tab.n, sizeof(int));
+  if (!owner) gb_die("", "Cannot allocate memory");
+  if (nctx > 1) {
+    int usable = 0;
+    for (int i = 0; i < tab.n; i++) usable += !(tab.c[i].skip || !tab.c[i].ever_saved);
+    if (nctx > usable) nctx = usable > 0 ? usable : 1;        /* no device without a chromosome */
+  }
+  if (nctx > 1) {
+    uint64_t* load = (uint64_t*)calloc((size_t)nctx, sizeof(uint64_t));
+    bool* done = (bool*)calloc((size_t)tab.n, sizeof(bool));
+    for (int i = 0; i < tab.n; i++) done[i] = tab.c[i].skip || !tab.c[i].ever_saved;
+    for (;;) {
+      int best = -1;
+      for (int i = 0; i < tab.n; i++)
+        if (!done[i] && (best < 0 || tab.c[i].len > tab.c[best].len)) best = i;
+      if (best < 0) break;
+      int k = 0;
+      for (int g = 1; g < nctx; g++) if (load[g] < load[k]) k = g;
+      owner[best] = k;
+      load[k] += tab.c[best].len;
+      done[best] = true;
+    }
+    free(load); free(done);
   }
   gr_params par;
   par.min_pqval = thr; par.qval_opt = o.qval_opt; par.min_auc = o.min_auc; par.min_len = o.min_len;
   par.max_gap = o.max_gap; par.keep_pileups = (o.log_file || o.pile_file) ? 1 : 0; par.genome_len = o.genome_len;
-  gr_ctx* ctx = NULL;
-  chk(NULL, gr_create(&ctx, gc, tab.n, &par, o.device), "gr_create");
-  if (xfile) load_exclusions(ctx, xfile, &tab, o.verbose);
+  gr_ctx** ctxs = (gr_ctx**)calloc((size_t)nctx, sizeof(gr_ctx*));
+  gr_chrom* gc = (gr_chrom*)gb_alloc(tab.n * sizeof(gr_chrom));
+  for (int k = 0; k < nctx; k++) {
+    for (int i = 0; i < tab.n; i++) {
+      gc[i].len = tab.c[i].len;
+      gc[i].skip = tab.c[i].skip || !tab.c[i].ever_saved;     /* control-only references are never used (4244) */
+      gc[i].owned = owner[i] == k;
+      gc[i].reserved = 0;
+    }
+    chk(NULL, gr_create(&ctxs[k], gc, tab.n, &par, o.device + k), "gr_create");
+  }
+  gr_ctx* ctx = ctxs[0];
+  if (xfile) load_exclusions(ctxs, nctx, xfile, &tab, o.verbose);
+  uint64_t* xbp = (uint64_t*)calloc((size_t)tab.n, sizeof(uint64_t));          /* excluded bp per chromosome */
+  if (xfile) chk(ctx, gr_excluded_bp(ctx, xbp), "gr_excluded_bp");
 
   HOut bed = { NULL, NULL }, pile = { NULL, NULL }, dupf = { NULL, NULL };
   const bool dups_verb = o.dups_opt && o.dups_file;              /* 5411-5415 */
   if (dups_verb) gb_out_open(&dupf, o.dups_file, o.gz_out);
   if (o.bed_file) gb_out_open(&bed, o.bed_file, o.gz_out);
   if (o.pile_file) gb_out_open(&pile, o.pile_file, o.gz_out);
-  HIvBuf buf;
-  buf.cap = 1u << 20;
-  buf.n = 0;
-  buf.recs = (int32_t*)gr_pinned_alloc(buf.cap * 16);
-  buf.cap_pk = 1u << 21;
-  buf.npk = 0;
-  buf.pk = (uint64_t*)gr_pinned_alloc(buf.cap_pk * 8);
-  if (!buf.recs || !buf.pk) gb_die("", "Cannot allocate memory");
+  HIvBuf* bufs = (HIvBuf*)calloc((size_t)nctx, sizeof(HIvBuf));
+  for (int k = 0; k < nctx; k++) {
+    bufs[k].cap = 1u << 20;
+    bufs[k].recs = (int32_t*)gr_pinned_alloc(bufs[k].cap * 16);
+    bufs[k].cap_pk = 1u << 21;
+    bufs[k].pk = (uint64_t*)gr_pinned_alloc(bufs[k].cap_pk * 8);
+    if (!bufs[k].recs || !bufs[k].pk) gb_die("", "Cannot allocate memory");
+  }
   uint8_t* save = (uint8_t*)gb_alloc(tab.n);
+  double* sums = (double*)gb_alloc((size_t)tab.n * sizeof(double));
+  double* esum = (double*)gb_alloc((size_t)tab.n * sizeof(double));
+  double* csum = (double*)gb_alloc((size_t)tab.n * sizeof(double));
+  bool* ever = (bool*)calloc((size_t)tab.n, sizeof(bool));     /* chromosomes that got a p-value array (findPeaks 1091) */
 
   HDecode d;
   memset(&d, 0, sizeof d);
-  d.opt = &o; d.tab = &tab; d.ctx = ctx; d.buf = &buf; d.bed = o.bed_file ? &bed : NULL;
+  d.opt = &o; d.tab = &tab; d.bed = o.bed_file ? &bed : NULL;
+  d.nctx = nctx; d.ctxs = ctxs; d.owner = owner; d.bufs = bufs;
   d.dups = dups_verb ? &dupf : NULL;
 
   for (int r = 0; r < nt; r++) {
@@ -452,7 +497,8 @@ int main(int argc, char** argv) {
     const bool has_ctrl = cname && strcmp(cname, "null");
     for (int i = 0; i < tab.n; i++) tab.c[i].save = false;          /* 5463-5464 */
     gb_scan_header(real_path(tf[r]), &tab, false, &o);
-    for (int i = 0; i < tab.n; i++) save[i] = tab.c[i].save;
+    for (int i = 0; i < tab.n; i++) { save[i] = tab.c[i].save; if (save[i] && !tab.c[i].skip) ever[i] = true; }
+    for (int i = 0; i < tab.n; i++) esum[i] = csum[i] = 0.0;
     for (int s = 0; s < 2; s++) {
       const char* fname = s ? cname : tf[r];
       if (s && !has_ctrl) {
@@ -466,15 +512,37 @@ int main(int argc, char** argv) {
       if (o.verbose)
         fprintf(stderr, "Processing %s file #%d: %s\n", s ? "control" : "experimental", r, fname);
       if (dups_verb) gb_out_printf(&dupf, "# %s file #%d: %s\n", s ? "control" : "experimental", r, fname);   /* 5493-5499 */
-      chk(ctx, gr_sample_begin(ctx, s, s ? NULL : save), "gr_sample_begin");
+      for (int k = 0; k < nctx; k++) chk(ctxs[k], gr_sample_begin(ctxs[k], s, s ? NULL : save), "gr_sample_begin");
       memset(&d.cnt, 0, sizeof d.cnt);
       d.ctrl = s; d.sample = r;
       gb_decode_file(&d, real_path(fname));
       if (o.verbose) log_counts(&d, bam);
-      if (!s && has_ctrl) chk(ctx, gr_sample_pileup(ctx, NULL), "gr_sample_pileup");
+      if (nctx == 1) {
+        if (!s && has_ctrl) chk(ctx, gr_sample_pileup(ctx, NULL), "gr_sample_pileup");
+      } else {
+        /* every device integrates its chromosomes (all enqueued before the first is waited for);
+         * a chromosome has one owner, so the per-chromosome sums simply add up */
+        for (int k = 0; k < nctx; k++) {
+          chk(ctxs[k], gr_sample_pileup(ctxs[k], sums), "gr_sample_pileup");
+          for (int i = 0; i < tab.n; i++) (s ? csum : esum)[i] += sums[i];
+        }
+      }
     }
     gr_sample_stats st;
-    chk(ctx, gr_replicate_end(ctx, &st), "gr_replicate_end");
+    if (nctx == 1)
+      chk(ctx, gr_replicate_end(ctx, &st), "gr_replicate_end");
+    else {
+      double frag = 0.0, ctl = 0.0;                                   /* chromosome order, like the running sums */
+      uint64_t glen = 0;                                              /* calcLambda 1819-1827 */
+      for (int i = 0; i < tab.n; i++) {
+        frag += esum[i];
+        ctl += csum[i];
+        if (save[i] && !tab.c[i].skip) glen += tab.c[i].len - xbp[i];
+      }
+      if (o.genome_len) glen = o.genome_len;
+      for (int k = 0; k < nctx; k++)
+        chk(ctxs[k], gr_replicate_finish(ctxs[k], frag, ctl, has_ctrl, glen, &st), "gr_replicate_finish");
+    }
     if (o.verbose) {
       fprintf(stderr, "  Background pileup value: %f\n", st.lambda);                 /* 1888, 2058 */
       if (has_ctrl) {
@@ -482,10 +550,11 @@ int main(int argc, char** argv) {
         if (st.factor > 5.0f) fprintf(stderr, "  ** Warning! Large scaling may mask true signal **\n");
       }
     }
-    if (o.pile_file) write_pile(ctx, &pile, &tab, r, tf[r], cname);
+    if (o.pile_file) write_pile(ctxs, owner, &pile, &tab, r, tf[r], cname);
   }
 
   const gr_peak* peaks = NULL;
+  gr_peak* merged = NULL;
   uint64_t npk = 0;
   gr_run_stats rs;
   memset(&rs, 0, sizeof rs);
@@ -494,9 +563,46 @@ int main(int argc, char** argv) {
       /* -X: p (and q) only; a threshold no value can pass keeps the peak list empty */
       gr_params p2 = par;
       p2.min_pqval = FLT_MAX;
-      gr_set_params(ctx, &p2);
+      for (int k = 0; k < nctx; k++) gr_set_params(ctxs[k], &p2);
     }
-    chk(ctx, gr_call_peaks(ctx, &peaks, &npk, &rs), "gr_call_peaks");
+    if (nctx == 1)
+      chk(ctx, gr_call_peaks(ctx, &peaks, &npk, &rs), "gr_call_peaks");
+    else {
+      uint64_t G = o.genome_len;                                       /* findPeaks 1091-1101 */
+      if (!G) for (int i = 0; i < tab.n; i++) if (ever[i]) G += tab.c[i].len - xbp[i];
+      if (o.qval_opt) {
+        /* computeQval 352 sees ONE histogram: every device gets the concatenation of all local lists */
+        uint32_t* keys = NULL; uint64_t* lens = NULL; uint64_t tot = 0;
+        for (int k = 0; k < nctx; k++) {
+          const uint32_t* hk; const uint64_t* hl; uint64_t hn;
+          chk(ctxs[k], gr_bh_local_hist_host(ctxs[k], &hk, &hl, &hn), "gr_bh_local_hist_host");
+          keys = (uint32_t*)gb_realloc(keys, (tot + hn + 1) * sizeof(uint32_t));
+          lens = (uint64_t*)gb_realloc(lens, (tot + hn + 1) * sizeof(uint64_t));
+          memcpy(keys + tot, hk, hn * sizeof(uint32_t));
+          memcpy(lens + tot, hl, hn * sizeof(uint64_t));
+          tot += hn;
+        }
+        for (int k = 0; k < nctx; k++)
+          chk(ctxs[k], gr_bh_set_global_host(ctxs[k], keys, lens, tot, G), "gr_bh_set_global_host");
+        free(keys); free(lens);
+      }
+      const gr_peak** lists = (const gr_peak**)gb_alloc((size_t)nctx * sizeof(gr_peak*));
+      uint64_t* counts = (uint64_t*)gb_alloc((size_t)nctx * sizeof(uint64_t));
+      for (int k = 0; k < nctx; k++) {
+        gr_run_stats rk;
+        memset(&rk, 0, sizeof rk);
+        chk(ctxs[k], gr_call_peaks(ctxs[k], &lists[k], &counts[k], &rk), "gr_call_peaks");
+        npk += counts[k];
+        rs.peak_bp += rk.peak_bp;
+        if (!k) rs.all_q_one = rk.all_q_one;
+      }
+      rs.genome_len = G;
+      rs.n_peaks = npk;
+      merged = (gr_peak*)gb_alloc((npk + 1) * sizeof(gr_peak));      /* peak_N follows the chromosome order (986-987) */
+      chk(ctx, gr_merge_peaks(lists, counts, nctx, merged), "gr_merge_peaks");
+      peaks = merged;
+      free(lists); free(counts);
+    }
   }
   if (o.verbose) {                                                    /* findPeaks 1103-1117 */
     if (o.peaks_opt) {
@@ -530,14 +636,17 @@ int main(int argc, char** argv) {
   if (o.log_file) {
     HOut lg;
     gb_out_open(&lg, o.log_file, o.gz_out);
-    write_log(ctx, &lg, &tab, nt, &o, thr);
+    write_log(ctxs, owner, &lg, &tab, nt, &o, thr);
     gb_out_close(&lg, o.log_file);
   }
   if (o.pile_file) gb_out_close(&pile, o.pile_file);
   if (o.bed_file) gb_out_close(&bed, o.bed_file);
   if (dups_verb) gb_out_close(&dupf, o.dups_file);
-  gr_pinned_free(buf.recs);
-  gr_pinned_free(buf.pk);
-  gr_destroy(ctx);
+  for (int k = 0; k < nctx; k++) {
+    gr_pinned_free(bufs[k].recs);
+    gr_pinned_free(bufs[k].pk);
+    gr_destroy(ctxs[k]);
+  }
+  free(merged);
   return EXIT_SUCCESS;
 }

@@ -455,7 +455,7 @@ static void decode_sam(HDecode* d, HIn* in) {
  * added per piece and then over the pieces. */
 typedef struct {
   HDecode d;
-  HIvBuf buf;
+  HIvBuf* bufs;            /* one per engine context */
   HWarnLog wl;
   const char* beg;
   const char* end;
@@ -549,15 +549,21 @@ static bool decode_sam_threads(HDecode* d, const char* path, int nthreads) {
   if (!ws) gb_die("", "Cannot allocate memory");
   for (int k = 0; k < nthreads; k++) {
     SamWorker* w = &ws[k];
-    w->d.opt = d->opt; w->d.tab = d->tab; w->d.ctx = d->ctx; w->d.bed = NULL; w->d.dups = NULL;
+    w->d.opt = d->opt; w->d.tab = d->tab; w->d.bed = NULL; w->d.dups = NULL;
+    w->d.nctx = d->nctx; w->d.ctxs = d->ctxs; w->d.owner = d->owner;
     w->d.ctrl = d->ctrl; w->d.sample = d->sample;
     w->d.last_chrom = -1;
     w->d.wlog = &w->wl;
-    w->buf.cap = 1u << 16; w->buf.cap_pk = 1u << 19;
-    w->buf.recs = (int32_t*)gr_pinned_alloc(w->buf.cap * 16);
-    w->buf.pk = (uint64_t*)gr_pinned_alloc(w->buf.cap_pk * 8);
-    if (!w->buf.recs || !w->buf.pk) gb_die("", "Cannot allocate memory");
-    w->d.buf = &w->buf;
+    w->bufs = (HIvBuf*)calloc((size_t)d->nctx, sizeof(HIvBuf));
+    if (!w->bufs) gb_die("", "Cannot allocate memory");
+    for (int g = 0; g < d->nctx; g++) {
+      HIvBuf* b = &w->bufs[g];
+      b->cap = 1u << 16; b->cap_pk = d->nctx > 1 ? 1u << 18 : 1u << 19;
+      b->recs = (int32_t*)gr_pinned_alloc(b->cap * 16);
+      b->pk = (uint64_t*)gr_pinned_alloc(b->cap_pk * 8);
+      if (!b->recs || !b->pk) gb_die("", "Cannot allocate memory");
+    }
+    w->d.bufs = w->bufs;
     w->beg = cut[k]; w->end = cut[k + 1];
     if (pthread_create(&th[k], NULL, sam_worker, w)) gb_die("", "Cannot start a decode thread");
   }
@@ -595,8 +601,8 @@ static bool decode_sam_threads(HDecode* d, const char* path, int nthreads) {
     list_append(&d->rd_pr, &w->d.rd_pr);
     list_append(&d->rd_dc, &w->d.rd_dc);
     list_append(&d->rd_sn, &w->d.rd_sn);
-    gr_pinned_free(w->buf.recs);
-    gr_pinned_free(w->buf.pk);
+    for (int g = 0; g < d->nctx; g++) { gr_pinned_free(w->bufs[g].recs); gr_pinned_free(w->bufs[g].pk); }
+    free(w->bufs);
   }
   free(ws); free(th); free(cut);
   munmap((void*)base, size);

@@ -17,24 +17,28 @@ static pthread_mutex_t push_mu = PTHREAD_MUTEX_INITIALIZER;
 #define ATAC_ADJ_F 5      /* ATACADJF, Genrich.h:35 */
 #define ATAC_ADJ_R (-5)   /* ATACADJR, Genrich.h:36 */
 
-void gb_flush_intervals(HDecode* d) {
-  HIvBuf* b = d->buf;
+static void flush_one(HDecode* d, int k) {
+  HIvBuf* b = &d->bufs[k];
   if (!b->npk && !b->n) return;
   static int drop = -1;                        /* GB_DECODE_ONLY: measurement aid, the records are discarded */
   if (drop < 0) drop = getenv("GB_DECODE_ONLY") != NULL;
   if (drop) { b->npk = 0; b->n = 0; return; }
   pthread_mutex_lock(&push_mu);
   if (b->npk) {
-    int rc = gr_push_packed(d->ctx, b->pk, b->npk);
+    int rc = gr_push_packed(d->ctxs[k], b->pk, b->npk);
     if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
     b->npk = 0;
   }
   if (b->n) {
-    int rc = gr_push_intervals(d->ctx, b->recs, b->n);
+    int rc = gr_push_intervals(d->ctxs[k], b->recs, b->n);
     if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
     b->n = 0;
   }
   pthread_mutex_unlock(&push_mu);
+}
+
+void gb_flush_intervals(HDecode* d) {
+  for (int k = 0; k < d->nctx; k++) flush_one(d, k);
 }
 
 /* "counted" warnings are the ones saveInterval stops printing after MAX_ALNS of them (2524, 2538) */
@@ -85,13 +89,14 @@ void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const c
   if (d->bed)
     gb_out_printf(d->bed, "%s\t%ld\t%ld\t%s_%d_%c_%d\n", c->name, (long)start, (long)end, qname, count,
                   d->ctrl ? 'C' : 'E', d->sample);
-  HIvBuf* b = d->buf;
+  const int k = d->nctx > 1 ? d->owner[chrom] : 0;         /* the device that holds this chromosome */
+  HIvBuf* b = &d->bufs[k];
   if (end - start >= 0 && end - start < (int64_t)GR_PACK_MAX_LEN && (uint32_t)chrom < GR_PACK_MAX_CHROM) {
-    if (b->npk == b->cap_pk) gb_flush_intervals(d);
+    if (b->npk == b->cap_pk) flush_one(d, k);
     b->pk[b->npk++] = GR_PACK(chrom, start, end, count);
     return;
   }
-  if (b->n == b->cap) gb_flush_intervals(d);
+  if (b->n == b->cap) flush_one(d, k);
   int32_t* r = b->recs + 4 * b->n++;
   r[0] = chrom; r[1] = (int32_t)start; r[2] = (int32_t)end; r[3] = count;
 }

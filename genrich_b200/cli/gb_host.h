@@ -78,6 +78,7 @@ typedef struct {
   uint64_t genome_len;
   int device;
   int threads;          /* host threads decoding one plain SAM file (--threads; 1 = the sequential path) */
+  int gpus;             /* devices device .. device + gpus - 1, chromosomes sharded over them (--gpus) */
 } HOpts;
 
 typedef struct {        /* per-file counters (logCounts 5295) */
@@ -120,8 +121,12 @@ typedef struct {
 typedef struct {
   const HOpts* opt;
   HChromTab* tab;
-  gr_ctx* ctx;
-  HIvBuf* buf;
+  /* one engine context per device; owner[chrom] says which one holds a chromosome (all 0 with one
+   * device), bufs[k] collects the records bound for context k */
+  int nctx;
+  gr_ctx** ctxs;
+  const int* owner;
+  HIvBuf* bufs;
   HOut* bed;            /* -b, may be NULL */
   bool ctrl;
   int sample;

@@ -160,6 +160,9 @@ struct gr_ctx {
   // tables / BH / peaks
   DevBuf tKeys, tLens, tPval, tQval, tCount, slot;
   DevBuf hk, hl, hcount;           // local histogram list
+  DevBuf ghk, ghl;                 // global histogram handed over from host memory (gr_bh_set_global_host)
+  std::vector<uint32_t> hk_h;      // host copies of the local list (gr_bh_local_hist_host)
+  std::vector<uint64_t> hl_h;
   u64 hn = 0;
   u32 hist_cap = 0;
   DevBuf bk0, bk1, bl0, bl1, bhist, bksum, bx, bdk, bdq, bdl, bdcount;
@@ -420,6 +423,8 @@ extern "C" void gr_destroy(gr_ctx* x) {
   x->dpar.release();
   x->dsums.release();
   x->unpack6.release();
+  x->ghk.release();
+  x->ghl.release();
   if (x->h_acc) cudaFreeHost(x->h_acc);
   for (int i = 0; i < 2; i++) {
     if (x->h_stage[i]) cudaFreeHost(x->h_stage[i]);
@@ -1376,6 +1381,36 @@ extern "C" int gr_bh_set_global(gr_ctx* x, const uint32_t* d_keys, const uint64_
   }
   x->have_q = true;
   return GR_OK;
+}
+
+// The same exchange with the lists in HOST memory: for a caller that drives several contexts from
+// one process without a device-side collective (the host program's --gpus: computeQval 352 sees
+// one histogram, so every context gets the concatenation of all local lists).
+extern "C" int gr_bh_local_hist_host(gr_ctx* x, const uint32_t** keys, const uint64_t** lens, uint64_t* n) {
+  if (!x || !keys || !lens || !n) return GR_ERR_ARG;
+  const uint32_t* dk; const uint64_t* dl; uint64_t hn = 0;
+  { int r = gr_bh_local_hist(x, &dk, &dl, &hn); if (r) return r; }
+  x->hk_h.resize(hn ? hn : 1);
+  x->hl_h.resize(hn ? hn : 1);
+  if (hn) {
+    CK(cudaMemcpyAsync(x->hk_h.data(), dk, hn * sizeof(uint32_t), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(x->hl_h.data(), dl, hn * sizeof(uint64_t), cudaMemcpyDeviceToHost, x->stream));
+  }
+  CK(cudaStreamSynchronize(x->stream));
+  *keys = x->hk_h.data(); *lens = x->hl_h.data(); *n = hn;
+  return GR_OK;
+}
+extern "C" int gr_bh_set_global_host(gr_ctx* x, const uint32_t* keys, const uint64_t* lens, uint64_t n,
+                                     uint64_t genome_len) {
+  if (!x || (n && (!keys || !lens))) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  CK(x->ghk.ensure((n ? n : 1) * sizeof(uint32_t)));
+  CK(x->ghl.ensure((n ? n : 1) * sizeof(uint64_t)));
+  if (n) {
+    CK(cudaMemcpyAsync(x->ghk.p, keys, n * sizeof(uint32_t), cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(x->ghl.p, lens, n * sizeof(uint64_t), cudaMemcpyHostToDevice, x->stream));
+  }
+  return gr_bh_set_global(x, x->ghk.as<uint32_t>(), x->ghl.as<uint64_t>(), n, genome_len);   // waits for the device itself
 }
 
 // ---- peaks ---------------------------------------------------------------------------

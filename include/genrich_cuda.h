@@ -242,6 +242,12 @@ int gr_bh_local_hist(gr_ctx* ctx, const uint32_t** d_keys,
                      const uint64_t** d_lens, uint64_t* n);
 int gr_bh_set_global(gr_ctx* ctx, const uint32_t* d_keys,
                      const uint64_t* d_lens, uint64_t n, uint64_t genome_len);
+/* The same exchange through HOST memory, for one process that drives several contexts without a
+ * device-side collective: keys / lens returned by the first call are host arrays owned by the
+ * context (valid until its next call); the second takes the concatenation of every context's list. */
+int gr_bh_local_hist_host(gr_ctx* ctx, const uint32_t** keys, const uint64_t** lens, uint64_t* n);
+int gr_bh_set_global_host(gr_ctx* ctx, const uint32_t* keys, const uint64_t* lens, uint64_t n,
+                          uint64_t genome_len);
 int gr_call_peaks(gr_ctx* ctx, const gr_peak** peaks, uint64_t* n,
                   gr_run_stats* stats);
 /* The same records where gr_call_peaks left them in DEVICE memory (valid until the next

@@ -59,6 +59,32 @@ int gr_fetch_intervals(gr_ctx* x, int32_t which, int32_t replicate, int32_t chro
                        const float** val, const float** expt, const float** ctrl, uint64_t* n) {
   return orc_fetch_intervals(x->o, which, replicate, chrom, end, val, expt, ctrl, n);
 }
+int gr_replicate_finish(gr_ctx* x, double frag_len, double ctrl_frag, int32_t has_ctrl, uint64_t genome_len,
+                        gr_sample_stats* st) {
+  return orc_replicate_finish(x->o, frag_len, ctrl_frag, has_ctrl, genome_len, st);
+}
+int gr_excluded_bp(gr_ctx* x, uint64_t* per_chrom) { return orc_excluded_bp(x->o, per_chrom); }
+int gr_pvalues_finalize(gr_ctx* x) { return orc_pvalues_finalize(x->o); }
+int gr_bh_local_hist_host(gr_ctx* x, const uint32_t** keys, const uint64_t** lens, uint64_t* n) {
+  return orc_bh_local_hist(x->o, keys, lens, n);            /* the oracle's lists are host arrays anyway */
+}
+int gr_bh_set_global_host(gr_ctx* x, const uint32_t* keys, const uint64_t* lens, uint64_t n, uint64_t genome_len) {
+  return orc_bh_set_global(x->o, keys, lens, n, genome_len);
+}
+/* every list is in (chromosome, start) order and a chromosome has one owner (callPeaks 986-987) */
+int gr_merge_peaks(const gr_peak* const* lists, const uint64_t* counts, int32_t nlists, gr_peak* out) {
+  uint64_t pos[64] = { 0 }, w = 0;
+  if (nlists < 0 || nlists > 64) return GR_ERR_ARG;
+  for (;;) {
+    int best = -1;
+    for (int i = 0; i < nlists; i++)
+      if (pos[i] < counts[i] && (best < 0 || lists[i][pos[i]].chrom < lists[best][pos[best]].chrom)) best = i;
+    if (best < 0) break;
+    const int32_t c = lists[best][pos[best]].chrom;
+    while (pos[best] < counts[best] && lists[best][pos[best]].chrom == c) out[w++] = lists[best][pos[best]++];
+  }
+  return GR_OK;
+}
 void* gr_pinned_alloc(size_t bytes) { return malloc(bytes); }
 void gr_pinned_free(void* p) { free(p); }
 const char* gr_last_error_detail(const gr_ctx* x) { (void)x; return ""; }

@@ -215,3 +215,34 @@ def test_host_stdin_gzip_out_and_bed(twin, tmp_path):
     with open(os.path.join(td, "t.gz"), "rb") as f:
         r = subprocess.run([twin, "-t", "-", "-o", out], stdin=f, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Cannot pipe in gzip-compressed file" in r.stderr
+
+
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_sharded_contexts_same_output(twin, gpus, tmp_path, monkeypatch):
+    """--gpus N: the host program's own dispatcher -- chromosomes sharded over N engine contexts, the
+    per-chromosome sums added on the host, one p-value histogram handed to every context, peaks
+    merged in chromosome order -- reproduces the reference's files for every seeded case (narrowPeak,
+    -f, -k byte for byte; lambda, scale factor, genome length, peak counts in the -v text), also
+    together with --threads.  (Here the contexts are oracle contexts; on the GPU box they are devices.)"""
+    monkeypatch.setenv("GB_THREAD_MIN_BYTES", "1")
+    for case in CASES:
+        td = str(tmp_path / (case.name + str(gpus)))
+        os.makedirs(td)
+        extra = ["--gpus", str(gpus)] + (["--threads", "3"] if case.name in ("c2_ctrl_q", "c4_fisher_q") else [])
+        out, logf, pile, err = run_twin(twin, case, td, extra=extra)
+        meta, gold = util.golden(case)
+        assert open(out).read().split("\n")[:-1] == gold, case.name
+        assert _sha(logf) == (meta["log_sha256"], meta["log_lines"]), case.name
+        assert _sha(pile, True) == (meta["pile_sha256"], meta["pile_lines"]), case.name
+        lam = [float(x) for x in re.findall(r"Background pileup value: ([0-9.]+)", err)]
+        fac = [float(x) for x in re.findall(r"Scaling factor for control pileup: ([0-9.]+)", err)]
+        assert lam == meta["lambda"] and fac == meta["factor"], case.name
+        assert int(re.search(r"Genome length: (\d+)bp", err).group(1)) == meta["genome_len"]
+        assert int(re.search(r"Peaks identified: \d+ \((\d+)bp\)", err).group(1)) == meta["peak_bp"]
+        assert ("All q-values are 1" in err) == meta["all_q_one"]
+    for h in HOST_CASES:
+        if h.name in ("host_r_y", "host_x", "host_m_e", "host_X"):
+            td = str(tmp_path / (h.name + str(gpus)))
+            os.makedirs(td)
+            h2 = type(h)(h.name, h.case, list(h.args) + ["--gpus", str(gpus)], h.dups_log)
+            check_host_case(twin, h2, td)
