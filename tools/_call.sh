@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-( timeout 300 python -m pytest tests/test_gpu_cli.py -q -x 2>&1 | tail -6 ) > gpurun_out/c19_pytest.log
-cat gpurun_out/c19_pytest.log
+( timeout 45 python -m pytest tests/test_gpu_cli.py -q -x -k "c2_ctrl_q or bed_fisher_q or threaded or host_r_y" 2>&1 | tail -4 ) > gpurun_out/c20_pytest.log
+cat gpurun_out/c20_pytest.log
