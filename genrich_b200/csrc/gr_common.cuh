@@ -6,7 +6,9 @@
 //  * warp / block scans, streaming 128-bit loads, relaxed gpu-scope status words
 //  * the 1/120-unit -> reference float reconstruction (getVal, Genrich.c:1902)
 #pragma once
+#ifndef GR_EMU                      // tests/emu: the kernels compiled for the host (lock-step emulation)
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 typedef unsigned long long u64;
@@ -45,6 +47,11 @@ __device__ __forceinline__ bool cell_saturated(int d) { return d > GR_SAT_HI || 
 
 // ---------------------------------------------------------------------------
 // memory helpers
+#ifdef GR_EMU
+__device__ __forceinline__ int4 ld_stream_v4(const int4* p) { return *p; }
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) { return *(const volatile u64*)p; }
+__device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) { *(volatile u64*)p = v; }
+#else
 __device__ __forceinline__ int4 ld_stream_v4(const int4* p) {
   int4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
@@ -59,6 +66,7 @@ __device__ __forceinline__ u64 ld_relaxed_u64(const u64* p) {
 __device__ __forceinline__ void st_relaxed_u64(u64* p, u64 v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
 }
+#endif
 
 // ---------------------------------------------------------------------------
 // warp primitives

@@ -1223,6 +1223,253 @@ k_fw_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   }
 }
 
+// Rank form (GR_FUSED_RANK=1; not the default until it has been measured): warp-owned 8192-cell
+// blocks WITHOUT a cell array.  A block of the hg38 workload holds ~265 entries = ~400 distinct
+// event cells out of 8192; k_fb_scan spends its time in three CTA barriers per block and in a
+// walk whose length is the fullest thread's (ncu: issue slots half empty), and the warp-owned
+// k_fw_scan needs small buckets (its cell array is per warp), which the move pass pays for.
+// Here a warp keeps only the block's 256-word occupancy bitmap and, per DISTINCT event cell, a
+// sum and a position:
+//   P1  entries -> occupancy bits
+//   P2  exclusive popcount prefix per word              (rank of a cell = prefix + bits below it)
+//   P3  entries again -> sum[rank] += +-w, pos[rank] = cell
+//   P4  the dense list, 32 ranks per round: height = inclusive warp scan, break test, ballot ->
+//       page entries; a cell whose deltas cancel (or that lies outside [1, len]) leaves the bitmap
+//   P5  the occupancy words ARE the break bitmap: written out, cleared
+// Every lane has work in every round, nothing is walked, no __syncthreads.  A block with more
+// than CAP distinct cells takes several rounds of P3/P4, cut at word boundaries (so that the bits
+// P4 clears never sit below a cell that still has to be ranked).  Output contract = k_fw_scan's
+// (owner = warp: pages, warp_tot, marks), so k_scan_fix / k_scan_place follow unchanged.
+// SLOT: the entries of block b lie at bucketed[b * slot_cap ...] and blk_start[b] is their count
+// (fixed-capacity buckets, filled by k_fb_move_slot without a count pass).
+#define FR_RING 128                                    // page ring per warp: <= 2 * 33 + 2 sequence numbers in flight
+#define FR_PF 8                                        // entry registers per lane (256 entries prefetched per block)
+template <int CAP, int CPS, bool SLOT>
+__global__ void __launch_bounds__(128, CPS)
+k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
+          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R, u32 slot_cap,
+          const int* __restrict__ gate) {
+  __shared__ __align__(16) u32 sm_occ_all[4 * FB_WORDS];
+  __shared__ __align__(16) u32 sm_pre_all[4 * FB_WORDS];
+  __shared__ int sm_sum_all[4 * CAP];
+  __shared__ unsigned short sm_pos_all[4 * CAP];
+  __shared__ u32 sm_pg_all[4 * FR_RING];
+  if (SLOT && gate && *gate) return;                   // a slot overflowed: the exact two-pass path runs instead
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  u32* const sm_occ = sm_occ_all + wid * FB_WORDS;
+  u32* const sm_pre = sm_pre_all + wid * FB_WORDS;
+  int* const sm_sum = sm_sum_all + wid * CAP;
+  unsigned short* const sm_pos = sm_pos_all + wid * CAP;
+  u32* const sm_pg = sm_pg_all + wid * FR_RING;
+  const u32 owner = blockIdx.x * 4 + wid;
+  const u32 b0 = owner * R, b1 = min(b0 + R, nblocks);
+  if (b0 >= b1) {
+    if (lane == 0 && owner < SS_MAX_WARPS) W.warp_tot[owner] = make_uint2(0, 0);
+    return;
+  }
+  for (int i = lane; i < FB_WORDS; i += 32) sm_occ[i] = 0;
+  for (int i = lane; i < CAP; i += 32) sm_sum[i] = 0;
+
+  // entries of block i: n_of(i) of them, starting at lo_of(i)
+  auto n_of = [&](u32 i) -> u32 {
+    if (i >= nblocks) return 0u;
+    if (SLOT) return min(blk_start[i], slot_cap);
+    return blk_start[i + 1] - blk_start[i];
+  };
+  auto lo_of = [&](u32 i) -> u64 {
+    if (SLOT) return (u64)i * slot_cap;
+    return (u64)blk_start[min(i, nblocks)];
+  };
+  auto ub_of = [&](u32 n) { return min(2u * n + 1u, (u32)GR_BLOCK_SLOTS + 1u); };   // breaks of a block, upper bound
+  u32 nA = n_of(b0), nB = n_of(b0 + 1);
+  const u32* eA = bucketed + lo_of(b0);
+
+  const u32 last_page = W.max_pages - 1;
+  int have_seq = -1;
+  u32 pend_p0 = 0;
+  int pend_k = 0;
+  auto page_take = [&]() {
+    for (int i = 0; i < pend_k; i++) {
+      u32 pg = pend_p0 + (u32)i;
+      if (pg > last_page) { atomicOr(err, GR_DE_TABLE); pg = last_page; }
+      have_seq++;
+      W.page_meta[pg] = make_uint2(owner, (u32)have_seq);
+      sm_pg[have_seq & (FR_RING - 1)] = pg;
+    }
+    pend_k = 0;
+  };
+  auto page_ask = [&](u32 upto_idx) {
+    const int target = (int)(upto_idx >> SS_PAGE_SHIFT);
+    if (target > have_seq) {
+      pend_k = target - have_seq;
+      pend_p0 = atomicAdd(W.page_ctr, (u32)pend_k);
+    }
+  };
+  if (lane == 0) page_ask(ub_of(nA));
+
+  u32 v[FR_PF];
+#pragma unroll
+  for (int k = 0; k < FR_PF; k++) {
+    v[k] = 0;
+    if ((u32)(k * 32 + lane) < nA) v[k] = __ldcs(eA + k * 32 + lane);
+  }
+
+  u32 run_s = 0, run_c = 0;                            // height / #breaks since the start of the run
+  bool sat = false;
+  int c = -1;
+  u32 c_last_blk = 0;
+  u64 off = 0;
+  u32 len = 0;
+  bool act = false;
+  __syncwarp();
+  for (u32 b = b0; b < b1; b++) {
+    if (c < 0 || b > c_last_blk) {                     // ~25 times per genome
+      c = L.blk2chrom[b];
+      off = L.off[c];
+      len = L.len[c];
+      c_last_blk = (u32)((off + len) >> GR_BLOCK_SHIFT);
+      act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
+    }
+    const u32 nC = n_of(b + 2);                        // used from the next block on
+    const u32* const eB = bucketed + lo_of(b + 1);
+    const u32 jb = (u32)(((u64)b << GR_BLOCK_SHIFT) - off);       // chromosome position of the block's first cell
+    if (lane == 0) {
+      if (jb == 0) W.marks[c] = make_uint4(owner, run_s, run_c, 1u);
+      page_take();                                     // covers this block (asked for a block ago)
+      page_ask(run_c + ub_of(nA) + (b + 1 < b1 ? ub_of(nB) : 0u));
+    }
+    const bool has_end = act && b == c_last_blk;       // cell `len` lies in this block
+    uint4* const bm_out = reinterpret_cast<uint4*>(bitmap + (u64)b * FB_WORDS + lane * 8);
+    if (nA == 0 && !has_end) {                         // nothing in this block
+      bm_out[0] = make_uint4(0, 0, 0, 0);
+      bm_out[1] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int k = 0; k < FR_PF; k++)
+        if ((u32)(k * 32 + lane) < nB) v[k] = __ldcs(eB + k * 32 + lane);
+      nA = nB; nB = nC; eA = eB;
+      continue;
+    }
+    const u32 end_cell = len - jb;                     // meaningful if has_end
+    // ---- P1: occupancy
+    auto mark = [&](u32 e) {
+      const u32 so = e & (GR_BLOCK_SLOTS - 1);
+      atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
+      if ((e >> 30) == FB_KIND_BOTH) {
+        const u32 eo = so + ((e >> 13) & (GR_BLOCK_SLOTS - 1));
+        atomicOr(sm_occ + (eo >> 5), 1u << (eo & 31));
+      }
+    };
+#pragma unroll
+    for (int k = 0; k < FR_PF; k++)
+      if ((u32)(k * 32 + lane) < nA) mark(v[k]);
+    for (u32 i = FR_PF * 32 + lane; i < nA; i += 32) mark(__ldg(eA + i));
+    if (has_end && lane == 0) atomicOr(sm_occ + (end_cell >> 5), 1u << (end_cell & 31));
+    __syncwarp();
+    // ---- P2: exclusive prefix of the word popcounts (lane: words 8 * lane .. 8 * lane + 7)
+    u32 n_pos;
+    {
+      const uint4 o0 = *reinterpret_cast<const uint4*>(sm_occ + lane * 8);
+      const uint4 o1 = *reinterpret_cast<const uint4*>(sm_occ + lane * 8 + 4);
+      const u32 c0 = __popc(o0.x), c1 = __popc(o0.y), c2 = __popc(o0.z), c3 = __popc(o0.w);
+      const u32 c4 = __popc(o1.x), c5 = __popc(o1.y), c6 = __popc(o1.z), c7 = __popc(o1.w);
+      const u32 mine = c0 + c1 + c2 + c3 + c4 + c5 + c6 + c7;
+      const u32 inc = warp_incl_scan_u32(mine, lane);
+      uint4 p0, p1;
+      p0.x = inc - mine; p0.y = p0.x + c0; p0.z = p0.y + c1; p0.w = p0.z + c2;
+      p1.x = p0.w + c3; p1.y = p1.x + c4; p1.z = p1.y + c5; p1.w = p1.z + c6;
+      *reinterpret_cast<uint4*>(sm_pre + lane * 8) = p0;
+      *reinterpret_cast<uint4*>(sm_pre + lane * 8 + 4) = p1;
+      n_pos = __shfl_sync(GR_FULL, inc, 31);
+    }
+    __syncwarp();
+    // ---- rounds of at most CAP distinct cells (one round unless the block is unusually full)
+    u32 lo = 0;
+    while (true) {
+      u32 hi = n_pos;
+      if (n_pos - lo > (u32)CAP) {                     // cut at a word boundary: words [0, w_hi) hold <= lo + CAP cells
+        u32 k = 0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          const int w = lane * 8 + q;
+          k += (sm_pre[w] + __popc(sm_occ[w]) <= lo + (u32)CAP) ? 1u : 0u;
+        }
+        const u32 w_hi = __reduce_add_sync(GR_FULL, k);
+        hi = w_hi < (u32)FB_WORDS ? sm_pre[w_hi] : n_pos;
+      }
+      const u32 span = hi - lo;
+      const bool last_round = hi >= n_pos;
+      // ---- P3: sums and positions by rank
+      auto touch = [&](u32 so, int w) {
+        const u32 wd = so >> 5;
+        const u32 r = sm_pre[wd] + __popc(sm_occ[wd] & ((1u << (so & 31)) - 1u)) - lo;
+        if (r < span) {
+          if (w) atomicAdd(sm_sum + r, w);
+          sm_pos[r] = (unsigned short)so;
+        }
+      };
+      auto add = [&](u32 e) {
+        const u32 so = e & (GR_BLOCK_SLOTS - 1), kind = e >> 30;
+        const int w = 120 / (int)((e >> 26) & 15u);
+        touch(so, kind == FB_KIND_END ? -w : w);
+        if (kind == FB_KIND_BOTH) touch(so + ((e >> 13) & (GR_BLOCK_SLOTS - 1)), -w);
+      };
+#pragma unroll
+      for (int k = 0; k < FR_PF; k++)
+        if ((u32)(k * 32 + lane) < nA) add(v[k]);
+      for (u32 i = FR_PF * 32 + lane; i < nA; i += 32) add(__ldg(eA + i));
+      if (has_end && lane == 0) touch(end_cell, 0);
+      if (last_round) {                                // next block's entries: in flight during P4 / P5
+#pragma unroll
+        for (int k = 0; k < FR_PF; k++)
+          if ((u32)(k * 32 + lane) < nB) v[k] = __ldcs(eB + k * 32 + lane);
+      }
+      __syncwarp();
+      // ---- P4: heights, breaks
+      for (u32 r0 = 0; r0 < span; r0 += 32) {
+        const u32 r = r0 + lane;
+        const bool on = r < span;
+        int d = 0;
+        u32 p = 0;
+        if (on) { d = sm_sum[r]; sm_sum[r] = 0; p = sm_pos[r]; }
+        const u32 inc = warp_incl_scan_u32((u32)d, lane);
+        const u32 j = jb + p;
+        sat |= cell_saturated(d);
+        const bool brk = on && act && ((j == len) || (d != 0 && j >= 1u && j < len));
+        const u32 bal = __ballot_sync(GR_FULL, brk);
+        if (brk) {
+          const u32 idx = run_c + __popc(bal & ((1u << lane) - 1u));
+          const u32 pg = sm_pg[(idx >> SS_PAGE_SHIFT) & (FR_RING - 1)];
+          W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(j, run_s + inc - (u32)d);
+        } else if (on && act) {
+          atomicAnd(sm_occ + (p >> 5), ~(1u << (p & 31)));        // not a break: leaves the bitmap
+        }
+        run_s += __shfl_sync(GR_FULL, inc, 31);
+        run_c += __popc(bal);
+      }
+      __syncwarp();
+      if (last_round) break;
+      lo = hi;
+    }
+    // ---- P5: what is left of the occupancy words is the break bitmap
+    {
+      uint4 o0 = *reinterpret_cast<const uint4*>(sm_occ + lane * 8);
+      uint4 o1 = *reinterpret_cast<const uint4*>(sm_occ + lane * 8 + 4);
+      *reinterpret_cast<uint4*>(sm_occ + lane * 8) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(sm_occ + lane * 8 + 4) = make_uint4(0, 0, 0, 0);
+      if (!act) { o0 = make_uint4(0, 0, 0, 0); o1 = o0; }
+      bm_out[0] = o0;
+      bm_out[1] = o1;
+    }
+    nA = nB; nB = nC; eA = eB;
+    __syncwarp();                                      // occupancy words are free again
+  }
+  if (sat) atomicOr(err, GR_DE_SAT);
+  if (lane == 0) {
+    page_take();
+    W.warp_tot[owner] = make_uint2(run_s, run_c);
+  }
+}
+
 void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
                      u32* blk_cnt, int* err, u64* clamped, int shift) {
   if (!n) return;
@@ -1266,7 +1513,19 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
   }
   const int cps = fb_env("GR_FUSED_CPS", 6) == 4 ? 4 : 6, nt = fb_env("GR_FUSED_NT", 128);
   u32 owners;
-  if (sh == 13) {
+  const int rank_form = blk_bed ? 0 : fb_env("GR_FUSED_RANK", 0);   // -E marks exist in k_fb_scan only
+  if (sh == 13 && rank_form) {
+    // warp-owned 8192-cell blocks, rank form (k_fr_scan): 9 CTAs x 4 warps per SM with 512 distinct
+    // cells per round, 6 with 1024 (GR_FR_CAP)
+    const int cap = fb_env("GR_FR_CAP", 512) == 1024 ? 1024 : 512;
+    const int ctas = sms * (cap == 1024 ? 6 : 9);
+    owners = (u32)ctas * 4;
+    if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
+    const u32 nb = (u32)L.nblocks;
+    const u32 R = (nb + owners - 1) / owners;
+    if (cap == 1024) k_fr_scan<1024, 6, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr);
+    else k_fr_scan<512, 9, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr);
+  } else if (sh == 13) {
     owners = (u32)(sms * cps);
     const u32 nb = (u32)L.nblocks;
     const u32 R = (nb + owners - 1) / owners;

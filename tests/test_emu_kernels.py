@@ -1,0 +1,25 @@
+"""CUDA kernels on the CPU: tests/emu compiles kernels of genrich_b200/csrc *as they are* (extracted
+by name from the .cu files) against a lock-step emulation of warps / CTAs (tests/emu/cuda_emu.h) and
+compares kernels that have not been on a GPU yet with the ones validated there, and both with a plain
+per-cell walk.  Test infrastructure only; the product path never runs on the CPU."""
+import os
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+def _run(target):
+    subprocess.check_call(["make", "-s", "-C", EMU, "_build/" + target])
+    p = subprocess.run([os.path.join(EMU, "_build", target)], capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
+    return p.stdout
+
+
+def test_fused_scan_rank_form_equals_validated_kernel():
+    """k_fr_scan (GR_FUSED_RANK=1: warp-owned 8192-cell blocks, rank form, 64 / 512 / 1024 distinct
+    cells per round) == k_fb_scan (the default, validated on the B200) == per-cell walk: interval
+    ends, float bits, chromosome starts, break bitmap, error flags; edge inputs, hot spots,
+    fractional weights, blocks that need several rounds, unsaved and foreign chromosomes."""
+    out = _run("emu_fused_scan")
+    assert "FAIL" not in out and out.count(" ok") >= 5, out
