@@ -110,6 +110,8 @@ struct gr_ctx {
   // bucketed build (large samples)
   DevBuf sbCnt, sbStart, sbCursor, sbBucket, sbSpill, sbSpillCtr;
   u64 sb_min = 1ull << 20;             // samples with fewer records use the plain scatter (GR_SB_MIN)
+  DevBuf sbSlotCnt, dGate;             // slot path (GR_FB_SLOTS=1): entries per fixed-capacity bucket, overflow flag
+  u32 slot_cap = 0;                    // entries per bucket of the current sample (0: exact buckets)
   int fused = 1;                       // buckets -> breaks in shared memory, no delta array in HBM (GR_FUSED=0: dense array)
   u64 fused_min = 1ull << 16;          // ... for samples of at least this many records (GR_FUSED_MIN)
   // -E regions (saveXBed 1144): per chromosome the merged, clamped boundary list start0,end0,start1,...
@@ -423,6 +425,8 @@ extern "C" void gr_destroy(gr_ctx* x) {
   x->dpar.release();
   x->dsums.release();
   x->unpack6.release();
+  x->sbSlotCnt.release();
+  x->dGate.release();
   x->ghk.release();
   x->ghl.release();
   if (x->h_acc) cudaFreeHost(x->h_acc);
@@ -692,14 +696,47 @@ static int consume_segments(gr_ctx* x, int* built) {
     CK(x->sbBucket.ensure(x->n_pushed * 8 + (u64)x->n_marks * 4 + 16));   // at most two event entries per record
     CK(x->sbSpillCtr.ensure(4 + (nbk / 4096 + 2) * 4));  // (unused word), then the scan's chunk sums
     HT("consume: bucket buffers ensured");
+    x->slot_cap = 0;
+    if (!x->has_bed && sh == GR_BLOCK_SHIFT && fb_slots()) {
+      // Fixed-capacity buckets: 4 x the mean number of entries per block, a power of two >= 256.
+      // One pass over the records; the exact chain below runs behind it, gated on the overflow flag.
+      u64 cap = 256;
+      while (cap < 4 * (x->n_pushed / (nbk ? nbk : 1) + 1)) cap <<= 1;
+      if (nbk * cap < (1ull << 32)) {
+        x->slot_cap = (u32)cap;
+        CK(x->sbBucket.ensure(nbk * cap * 4));
+        CK(x->sbSlotCnt.ensure(nbk * 4));
+        CK(x->dGate.ensure(4));
+      }
+    }
     stage_begin(x, "bucket", bytes);
+    const int* gate = nullptr;
+    if (x->slot_cap) {
+      gate = x->dGate.as<int>();
+      CK(cudaMemsetAsync(x->sbSlotCnt.p, 0, nbk * 4, x->stream));
+      CK(cudaMemsetAsync(x->dGate.p, 0, 4, x->stream));
+      for (auto& g : x->segs)
+        launch_fb_move_slot(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbSlotCnt.as<u32>(), x->sbBucket.as<u32>(),
+                            x->slot_cap, x->dGate.as<int>(), x->d_err, x->d_clamped);
+      // the slot scan has to read the slots before the (gated) exact move may overwrite them: it is
+      // launched by pileup_enqueue, i.e. behind the chain below -- which is gated and touches
+      // sbBucket only if the slot scan is going to return at once
+    }
     CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4, x->stream));
+    if (gate) {
+      for (auto& g : x->segs)
+        launch_fb_count_gated(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, gate);
+    } else
     for (auto& g : x->segs)
       launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped, sh);
     HT("consume: memset + count launched");
     launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, x->sbCnt.as<u32>(), nullptr, nullptr, sh);
     launch_sb_scan(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
                    x->sbSpillCtr.as<u32>() + 1);
+    if (gate) {
+      for (auto& g : x->segs)
+        launch_fb_move_gated(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), gate);
+    } else
     for (auto& g : x->segs)
       launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
     launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, nullptr, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
@@ -870,6 +907,11 @@ static int pileup_enqueue(gr_ctx* x) {
   u32 owners = 0;
   if (built == 2) {
     stage_begin(x, "fused_scan", x->T * 4);
+    if (x->slot_cap)
+      owners = launch_fr_scan_slot(x->stream, x->L, x->sbBucket.as<u32>(), x->sbSlotCnt.as<u32>(), x->slot_cap,
+                                   x->sbStart.as<u32>(), sc, (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err,
+                                   x->dGate.as<int>());
+    else
     owners = launch_fb_scan(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), sc,
                             (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, x->fb_shift,
                             x->has_bed ? x->blkBed.as<uint8_t>() : nullptr);

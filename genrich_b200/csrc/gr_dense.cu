@@ -775,7 +775,8 @@ __device__ __forceinline__ u32 fb_entry(u32 so, u32 span, int cnt, u32 kind) {
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ blk_cnt,
-           int* __restrict__ err, u64* __restrict__ clamped, int shift) {
+           int* __restrict__ err, u64* __restrict__ clamped, int shift, const int* __restrict__ gate = nullptr) {
+  if (gate && !*gate) return;                // fallback of the slot path: runs only if a slot overflowed
   const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
   int e_local = 0;
   u32 c_local = 0;
@@ -795,13 +796,14 @@ k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ 
     }
   }
   if (e_local) atomicOr(err, e_local);       // errors and clamp counts are reported by this pass only
-  if (c_local) atomicAdd(clamped, (u64)c_local);
+  if (c_local && clamped) atomicAdd(clamped, (u64)c_local);
 }
 
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed,
-          int shift) {
+          int shift, const int* __restrict__ gate = nullptr) {
+  if (gate && !*gate) return;
   const u32 omask = (1u << shift) - 1;
   const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
   int e_local = 0;
@@ -837,6 +839,60 @@ k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
       if (two[k]) bucketed[p1[k]] = e1[k];
     }
   }
+}
+
+// Fixed-capacity buckets (GR_FB_SLOTS=1, with the rank-form scan): block b owns the entries
+// bucketed[b * cap .. b * cap + cap) and cnt[b] counts them, so the count pass and the scan of the
+// block counts are not needed -- one pass over the records instead of two (the count pass is
+// 0.30 ms of the 1.0 ms the bucket stage takes per hg38 sample).  An entry that finds its slot
+// full raises *gate: the slot scan then returns at once and the exact count -> scan -> move
+// chain, launched behind it with the same gate, does the sample instead (decided on the device,
+// while the records are still there; nothing is lost but the time of this pass).
+// Errors and the clamp count are reported by this pass (the gated count pass reports errors
+// again -- the same bits -- and leaves the clamp count alone).
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+k_fb_move_slot(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cnt, u32* __restrict__ bucketed,
+               u32 cap, int* __restrict__ gate, int* __restrict__ err, u64* __restrict__ clamped) {
+  const u32 omask = GR_BLOCK_SLOTS - 1;
+  const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
+  int e_local = 0;
+  u32 c_local = 0;
+  bool over = false;
+  for (u64 i0 = (u64)blockIdx.x * (256 * FB_UNROLL) + threadIdx.x; i0 < n; i0 += stride) {
+    int4 r[FB_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++)
+      if (i0 + k * 256 < n) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
+    bool ok[FB_UNROLL], two[FB_UNROLL];
+    u32 e0[FB_UNROLL], e1[FB_UNROLL], bs[FB_UNROLL], be[FB_UNROLL], p0[FB_UNROLL], p1[FB_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++) {
+      u64 s_slot = 0; u32 span = 0; int w = 120;
+      ok[k] = i0 + k * 256 < n && decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local);
+      const u64 e_slot = s_slot + span;
+      bs[k] = (u32)(s_slot >> GR_BLOCK_SHIFT);
+      be[k] = (u32)(e_slot >> GR_BLOCK_SHIFT);
+      two[k] = ok[k] && be[k] != bs[k];
+      const u32 so = (u32)s_slot & omask;
+      const int c = 120 / w;
+      e0[k] = two[k] ? fb_entry(so, 0, c, FB_KIND_START) : fb_entry(so, span, c, FB_KIND_BOTH);
+      e1[k] = fb_entry((u32)e_slot & omask, 0, c, FB_KIND_END);
+    }
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++) {              // the counter atomics of all records, back to back
+      p0[k] = ok[k] ? atomicAdd(cnt + bs[k], 1u) : 0u;
+      p1[k] = two[k] ? atomicAdd(cnt + be[k], 1u) : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++) {
+      if (ok[k]) { if (p0[k] < cap) bucketed[(u64)bs[k] * cap + p0[k]] = e0[k]; else over = true; }
+      if (two[k]) { if (p1[k] < cap) bucketed[(u64)be[k] * cap + p1[k]] = e1[k]; else over = true; }
+    }
+  }
+  if (over) atomicOr(gate, 1);
+  if (e_local) atomicOr(err, e_local);
+  if (c_local) atomicAdd(clamped, (u64)c_local);
 }
 
 // -E region boundaries (a few thousand at most): one pseudo entry each, so that the scan finds
@@ -1248,13 +1304,15 @@ template <int CAP, int CPS, bool SLOT>
 __global__ void __launch_bounds__(128, CPS)
 k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
           u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R, u32 slot_cap,
-          const int* __restrict__ gate) {
+          const int* __restrict__ gate, int gate_on) {
   __shared__ __align__(16) u32 sm_occ_all[4 * FB_WORDS];
   __shared__ __align__(16) u32 sm_pre_all[4 * FB_WORDS];
   __shared__ int sm_sum_all[4 * CAP];
   __shared__ unsigned short sm_pos_all[4 * CAP];
   __shared__ u32 sm_pg_all[4 * FR_RING];
-  if (SLOT && gate && *gate) return;                   // a slot overflowed: the exact two-pass path runs instead
+  // slot path: the scan over the slots runs unless one overflowed (gate_on 0), the scan behind the
+  // exact two-pass chain only if one did (gate_on 1)
+  if (gate && (*gate != 0) != (gate_on != 0)) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u32* const sm_occ = sm_occ_all + wid * FB_WORDS;
   u32* const sm_pre = sm_pre_all + wid * FB_WORDS;
@@ -1489,6 +1547,35 @@ void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
   GR_NOTE_LAUNCH();
 }
 
+void launch_fb_move_slot(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cnt, u32* bucketed,
+                         u32 cap, int* gate, int* err, u64* clamped) {
+  if (!n) return;
+  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (packed) k_fb_move_slot<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cnt, bucketed, cap, gate, err, clamped);
+  else k_fb_move_slot<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cnt, bucketed, cap, gate, err, clamped);
+  GR_NOTE_LAUNCH();
+}
+// the exact chain behind the slot pass: runs on the device only if *gate was raised
+void launch_fb_count_gated(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
+                           u32* blk_cnt, int* err, const int* gate) {
+  if (!n) return;
+  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (packed) k_fb_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, nullptr, GR_BLOCK_SHIFT, gate);
+  else k_fb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, nullptr, GR_BLOCK_SHIFT, gate);
+  GR_NOTE_LAUNCH();
+}
+void launch_fb_move_gated(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor,
+                          u32* bucketed, const int* gate) {
+  if (!n) return;
+  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, GR_BLOCK_SHIFT, gate);
+  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, GR_BLOCK_SHIFT, gate);
+  GR_NOTE_LAUNCH();
+}
+
 static int fb_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 // GR_FUSED_SHIFT: log2 of the bucket size -- 13 (default): CTA-owned 8192-cell blocks (k_fb_scan,
 // with GR_FUSED_CPS / GR_FUSED_NT); 11 or 12: warp-owned buckets (k_fw_scan).  Measured on the
@@ -1523,8 +1610,8 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
     if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
     const u32 nb = (u32)L.nblocks;
     const u32 R = (nb + owners - 1) / owners;
-    if (cap == 1024) k_fr_scan<1024, 6, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr);
-    else k_fr_scan<512, 9, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr);
+    if (cap == 1024) k_fr_scan<1024, 6, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr, 0);
+    else k_fr_scan<512, 9, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr, 0);
   } else if (sh == 13) {
     owners = (u32)(sms * cps);
     const u32 nb = (u32)L.nblocks;
@@ -1552,6 +1639,38 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
     else k_fw_scan<12><<<owners / 4, 128, smem, s>>>(bucketed, blk_start, L, W, bitmap, err, nbk, R);
   }
   GR_NOTE_LAUNCH();
+  return owners;
+}
+
+// Slot path: the rank-form scan over the fixed-capacity buckets, and behind it the same scan over
+// the exact buckets; *gate (raised by k_fb_move_slot on overflow) decides on the device which of
+// the two does anything.  Both fill the same pages / totals, so what follows does not care.
+bool fb_rank_form() { return fb_env("GR_FUSED_RANK", 0) != 0; }
+bool fb_slots() { return fb_env("GR_FB_SLOTS", 0) != 0 && fb_rank_form() && fb_bucket_shift() == 13; }
+u32 launch_fr_scan_slot(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* slot_cnt, u32 slot_cap,
+                        const u32* blk_start, const ScanScratch& sc, u32* bitmap, int* err, const int* gate) {
+  const StreamWs W = stream_ws(sc, L.nchrom);
+  cudaMemsetAsync(W.page_ctr, 0, 4, s);
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int cap = fb_env("GR_FR_CAP", 512) == 1024 ? 1024 : 512;
+  const int ctas = sms * (cap == 1024 ? 6 : 9);
+  u32 owners = (u32)ctas * 4;
+  if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
+  const u32 nb = (u32)L.nblocks;
+  const u32 R = (nb + owners - 1) / owners;
+  if (cap == 1024) {
+    k_fr_scan<1024, 6, true><<<owners / 4, 128, 0, s>>>(bucketed, slot_cnt, L, W, bitmap, err, nb, R, slot_cap, gate, 0);
+    k_fr_scan<1024, 6, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, gate, 1);
+  } else {
+    k_fr_scan<512, 9, true><<<owners / 4, 128, 0, s>>>(bucketed, slot_cnt, L, W, bitmap, err, nb, R, slot_cap, gate, 0);
+    k_fr_scan<512, 9, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, gate, 1);
+  }
+  GR_NOTE_LAUNCH(); GR_NOTE_LAUNCH();
   return owners;
 }
 

@@ -69,6 +69,18 @@ void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
 // starts inside a -E region, bit 1 = it holds region boundaries (NULL: no regions; needs sh == 13)
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
                    const ScanScratch& sc, u32* bitmap, int* err, int sh, const uint8_t* blk_bed);
+// rank-form scan (GR_FUSED_RANK=1) over fixed-capacity buckets (GR_FB_SLOTS=1): one pass over the
+// records (launch_fb_move_slot), the exact chain behind it gated on the overflow flag
+bool fb_rank_form();
+bool fb_slots();
+void launch_fb_move_slot(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cnt, u32* bucketed,
+                         u32 cap, int* gate, int* err, u64* clamped);
+void launch_fb_count_gated(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
+                           u32* blk_cnt, int* err, const int* gate);
+void launch_fb_move_gated(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor,
+                          u32* bucketed, const int* gate);
+u32 launch_fr_scan_slot(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* slot_cnt, u32 slot_cap,
+                        const u32* blk_start, const ScanScratch& sc, u32* bitmap, int* err, const int* gate);
 // -E region boundaries as pseudo entries (cursor == NULL: count pass)
 void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed, int shift);
 

@@ -115,6 +115,11 @@ struct Cta {
 };
 static Cta* g = nullptr;
 static unsigned long long n_switches = 0;
+// EMU_ORDER=0 lanes resumed in order, 1 in reverse, 2 in an order that changes from pass to pass: code
+// that is only correct because of the order in which the emulation happens to run the lanes
+// (a missing __syncwarp / __syncthreads) has three chances to show
+static int order_mode = getenv("EMU_ORDER") ? atoi(getenv("EMU_ORDER")) : 0;
+static unsigned order_salt = 0;
 
 static void entry() {
   g->body();
@@ -194,9 +199,10 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
         // the lanes of this warp, round-robin, until every one of them is done or parked at the CTA barrier
         for (;;) {
           bool any = false;
-          for (int l = 0; l < 32; l++) {
+          for (int l0 = 0; l0 < 32; l0++) {
+            const int l = order_mode == 0 ? l0 : order_mode == 1 ? 31 - l0 : (int)((l0 * 13 + order_salt) & 31);
             const int t = (int)wi * 32 + l;
-            if (t >= (int)nt) break;
+            if (t >= (int)nt) continue;
             Fiber& f = cta.f[t];
             if (f.done) continue;
             if (f.wait == 2 && cta.b_gen == f.bgen) continue;         // parked at the CTA barrier
@@ -206,6 +212,7 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
             swapcontext(&cta.sched, &f.ctx);
             any = true; progressed = true;
           }
+          if (order_mode == 2) order_salt = order_salt * 1103515245u + 12345u;
           if (!any) break;
         }
       }

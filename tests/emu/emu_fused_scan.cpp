@@ -2,7 +2,8 @@
 // for the host through cuda_emu.h, on seeded interval records:
 //   k_fb_count -> k_sb_scan1..3 -> k_fb_move -> k_fb_scan  (the path validated on the B200) -> k_scan_fix -> k_scan_place
 //   the same buckets -> k_fr_scan<CAP> (rank form) -> k_scan_fix -> k_scan_place
-//   k_fb_move_slot -> k_fr_scan<CAP, ., SLOT> (fixed-capacity buckets, no count pass)
+//   k_fb_move_slot -> k_fr_scan<CAP, ., SLOT> (fixed-capacity buckets, no count pass), with roomy slots
+//   and with slots so small that the exact chain behind the gate has to take over
 // and a plain per-cell prefix sum written here.  All of them must give the same RLE pileup
 // (interval ends, float bits, chromosome starts) and the same break bitmap.
 #include "cuda_emu.h"
@@ -153,9 +154,44 @@ static Result run_rank(const Layout& Lh, const u32* bucketed, const u32* blk_sta
   memset(bitmap, 0x5A, L.T / 8);
   int err = err0;                                     // what the bucket passes flagged
   const u32 owners = ctas * 4, nb = (u32)L.nblocks, R = (nb + owners - 1) / owners;
-  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, false>(bucketed, blk_start, L, W, bitmap, &err, nb, R, 0u, nullptr); });
+  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, false>(bucketed, blk_start, L, W, bitmap, &err, nb, R, 0u, nullptr, 0); });
   Result r = finish(Lh, ws, owners, bitmap, &err);
   free(bitmap);
+  return r;
+}
+
+// The slot path as gr_api.cu enqueues it: one pass into fixed-capacity buckets, the exact chain
+// behind it gated on the overflow flag, then both scans (only one of them does anything).
+template <int CAP>
+static Result run_slots(const Layout& Lh, const int4* recs, u64 n, u32 slot_cap, u64 cap, u32 ctas, bool* overflowed, u64* n_clamped) {
+  const DevLayout L = Lh.dev();
+  const u64 nbk = L.nblocks;
+  u32* scnt = dalloc<u32>(nbk + 1); u32* cnt = dalloc<u32>(nbk + 1); u32* start = dalloc<u32>(nbk + 2);
+  u32* cursor = dalloc<u32>(nbk + 1); u32* chunk = dalloc<u32>(nbk / SB_CHUNK + 4);
+  u32* bucketed = dalloc<u32>(std::max<u64>(nbk * slot_cap, 2 * n + 16));
+  memset(bucketed, 0xC3, std::max<u64>(nbk * slot_cap, 2 * n + 16) * 4);
+  memset(scnt, 0, (nbk + 1) * 4);
+  memset(cnt, 0, (nbk + 1) * 4);
+  int err = 0, gate = 0; u64 clamped = 0;
+  emu::launch(4, 256, [&] { k_fb_move_slot<false>(recs, n, L, scnt, bucketed, slot_cap, &gate, &err, &clamped); });
+  const int* g = &gate;
+  emu::launch(4, 256, [&] { k_fb_count<false>(recs, n, L, cnt, &err, nullptr, GR_BLOCK_SHIFT, g); });
+  const u32 nchunks = (u32)((nbk + SB_CHUNK - 1) / SB_CHUNK);
+  emu::launch(nchunks, 256, [&] { k_sb_scan1(cnt, chunk, nbk); });
+  emu::launch(1, 1024, [&] { k_sb_scan2(chunk, nchunks, start, nbk); });
+  emu::launch(nchunks, 256, [&] { k_sb_scan3(cnt, chunk, start, cursor, nbk); });
+  emu::launch(4, 256, [&] { k_fb_move<false>(recs, n, L, cursor, bucketed, GR_BLOCK_SHIFT, g); });
+  Ws ws(cap, L.nchrom);
+  StreamWs W = ws.W;
+  u32* bitmap = dalloc<u32>(L.T / 32);
+  memset(bitmap, 0x5A, L.T / 8);
+  const u32 owners = ctas * 4, nb = (u32)nbk, R = (nb + owners - 1) / owners;
+  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, true>(bucketed, scnt, L, W, bitmap, &err, nb, R, slot_cap, g, 0); });
+  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, false>(bucketed, start, L, W, bitmap, &err, nb, R, 0u, g, 1); });
+  Result r = finish(Lh, ws, owners, bitmap, &err);
+  *overflowed = gate != 0;
+  *n_clamped = clamped;
+  free(scnt); free(cnt); free(start); free(cursor); free(chunk); free(bucketed); free(bitmap);
   return r;
 }
 
@@ -203,6 +239,22 @@ static int run_case(const char* name, const std::vector<u32>& len, const std::ve
   if (!(r64 == base)) { diff("k_fr_scan<64> vs k_fb_scan", r64, base); bad++; }
   if (!(r512 == base)) { diff("k_fr_scan<512> vs k_fb_scan", r512, base); bad++; }
   if (!(r1024 == base)) { diff("k_fr_scan<1024> vs k_fb_scan", r1024, base); bad++; }
+  // ---- slot path: roomy slots (no overflow), and slots so small that the gated exact chain takes over
+  {
+    u64 mx = 0;
+    for (u64 b = 0; b < nbk; b++) mx = std::max<u64>(mx, cnt[b]);
+    u32 roomy = 4; while (roomy < mx) roomy <<= 1;
+    bool ov = false;
+    u64 cl = 0;
+    const Result s1 = run_slots<512>(Lh, recs, n, roomy, cap, ctas, &ov, &cl);
+    if (!(s1 == base) || ov || cl != clamped) { diff("slot path (roomy) vs k_fb_scan", s1, base); bad++; }
+    const Result s2 = run_slots<64>(Lh, recs, n, roomy, cap, ctas + 2, &ov, &cl);
+    if (!(s2 == base) || ov || cl != clamped) { diff("slot path (roomy, 64 per round) vs k_fb_scan", s2, base); bad++; }
+    if (mx > 4) {
+      const Result s3 = run_slots<512>(Lh, recs, n, 4, cap, ctas, &ov, &cl);
+      if (!(s3 == base) || !ov || cl != clamped) { diff("slot path (overflow -> exact chain) vs k_fb_scan", s3, base); bad++; }
+    }
+  }
   printf("%-28s %8llu records %7llu blocks %9llu intervals  err %d  %s\n", name, (unsigned long long)n,
          (unsigned long long)nbk, (unsigned long long)base.total, base.err, bad ? "FAIL" : "ok");
   free(recs); free(cnt); free(start); free(cursor); free(chunk); free(bucketed);

@@ -5,21 +5,26 @@ per-cell walk.  Test infrastructure only; the product path never runs on the CPU
 import os
 import subprocess
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EMU = os.path.join(ROOT, "tests", "emu")
 
 
-def _run(target):
+def _run(target, order=0):
     subprocess.check_call(["make", "-s", "-C", EMU, "_build/" + target])
-    p = subprocess.run([os.path.join(EMU, "_build", target)], capture_output=True, text=True, timeout=900)
+    p = subprocess.run([os.path.join(EMU, "_build", target)], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, EMU_ORDER=str(order)))
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-3000:]
     return p.stdout
 
 
-def test_fused_scan_rank_form_equals_validated_kernel():
+@pytest.mark.parametrize("order", [0, 1, 2])
+def test_fused_scan_rank_form_equals_validated_kernel(order):
     """k_fr_scan (GR_FUSED_RANK=1: warp-owned 8192-cell blocks, rank form, 64 / 512 / 1024 distinct
     cells per round) == k_fb_scan (the default, validated on the B200) == per-cell walk: interval
     ends, float bits, chromosome starts, break bitmap, error flags; edge inputs, hot spots,
-    fractional weights, blocks that need several rounds, unsaved and foreign chromosomes."""
-    out = _run("emu_fused_scan")
+    fractional weights, blocks that need several rounds, unsaved and foreign chromosomes.  Also the
+    slot path (GR_FB_SLOTS=1: k_fb_move_slot + the gated exact chain), without and with overflow."""
+    out = _run("emu_fused_scan", order)     # lanes resumed in order / in reverse / in a changing order
     assert "FAIL" not in out and out.count(" ok") >= 5, out
