@@ -334,6 +334,103 @@ k_union_emit(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ b
   }
 }
 
+// Warp form (GR_UE_WARP=1; not the default until it has been measured): one WARP per bitmap block,
+// every lane owning 8 consecutive words (256 cells) of it.  ncu on k_union_emit: instruction bound
+// (sm throughput 67 %, DRAM 34 %) -- a thread there owns one word of each of four blocks, so
+// every block costs its warp two 5-step scans plus a cross-warp exchange, and the list loop runs as
+// long as the fullest of 32 single words.  Here the per-word counts add up inside the lane: two warp
+// scans per BLOCK (one packed E|C, one U), no __syncthreads, and the list loop runs over 8 words per
+// lane (the lanes' bit counts are far more even than single words').  Same outputs, bit for bit.
+#define UW_CAP 512             // list entries per round and warp
+__global__ void __launch_bounds__(256)
+k_union_emit_w(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ bmC,
+               const u64* __restrict__ rankE, const u64* __restrict__ rankC,
+               const u64* __restrict__ rankU, const float* __restrict__ exptVal,
+               const float* __restrict__ ctrlVal, u32* __restrict__ pEnd,
+               float* __restrict__ pExpt, float* __restrict__ pCtrl, u32* __restrict__ bmU,
+               u64* __restrict__ chrom_start, u32 nblocks) {
+  __shared__ u32 sm_ent_all[8 * UW_CAP];          // bits 0-12: cell offset inside the block, 13-31: experimental interval number
+  __shared__ unsigned short sm_ctl_all[8 * UW_CAP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  u32* const sm_ent = sm_ent_all + w * UW_CAP;
+  unsigned short* const sm_ctl = sm_ctl_all + w * UW_CAP;
+  const u32 blk = blockIdx.x * 8 + w;
+  if (blk >= nblocks) return;                    // warp-uniform
+  u32 E[8], C[8];
+  {
+    const uint4* pe = reinterpret_cast<const uint4*>(bmE + (u64)blk * 256 + lane * 8);
+    const uint4* pc = reinterpret_cast<const uint4*>(bmC + (u64)blk * 256 + lane * 8);
+    const uint4 e0 = pe[0], e1 = pe[1], c0 = pc[0], c1 = pc[1];
+    E[0] = e0.x; E[1] = e0.y; E[2] = e0.z; E[3] = e0.w; E[4] = e1.x; E[5] = e1.y; E[6] = e1.z; E[7] = e1.w;
+    C[0] = c0.x; C[1] = c0.y; C[2] = c0.z; C[3] = c0.w; C[4] = c1.x; C[5] = c1.y; C[6] = c1.z; C[7] = c1.w;
+  }
+  const u64 RE0 = rankE[blk], RC0 = rankC[blk], RU0 = rankU[blk];
+  const int c = L.blk2chrom[blk];
+  const u64 off = L.off[c];
+  const u32 jb = (u32)((u64)blk * GR_BLOCK_SLOTS - off);
+  if (lane == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = RU0;
+  {
+    uint4* pu = reinterpret_cast<uint4*>(bmU + (u64)blk * 256 + lane * 8);
+    pu[0] = make_uint4(E[0] | C[0], E[1] | C[1], E[2] | C[2], E[3] | C[3]);
+    pu[1] = make_uint4(E[4] | C[4], E[5] | C[5], E[6] | C[6], E[7] | C[7]);
+  }
+  u32 pa = 0, pu_ = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) { pa += __popc(E[q]) | (__popc(C[q]) << 16); pu_ += __popc(E[q] | C[q]); }
+  const u32 ia = warp_incl_scan_u32(pa, lane), iu = warp_incl_scan_u32(pu_, lane);
+  const u32 xa = ia - pa, xu = iu - pu_;          // E and C counts travel packed (<= 8192 each)
+  const u32 tot = __shfl_sync(GR_FULL, iu, 31);
+  for (u32 lo = 0; lo < tot; lo += UW_CAP) {
+    if (lo) __syncwarp();                        // the previous round's list has been streamed
+    u32 e = xa & 0xffffu, cc = xa >> 16, u = xu;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      u32 U = E[q] | C[q];
+      const u32 nu = __popc(U);
+      if (u < lo + UW_CAP && u + nu > lo) {
+        const u32 cell0 = (u32)(lane * 256 + q * 32);
+        u32 uu = u;
+        while (U) {
+          const int b = __ffs(U) - 1;
+          const u32 low = (1u << b) - 1;
+          if (uu >= lo && uu < lo + UW_CAP) {
+            sm_ent[uu - lo] = (cell0 + b) | ((e + __popc(E[q] & low)) << 13);
+            sm_ctl[uu - lo] = (unsigned short)(cc + __popc(C[q] & low));
+          }
+          uu++;
+          U &= U - 1;
+        }
+      }
+      u += nu; e += __popc(E[q]); cc += __popc(C[q]);
+    }
+    __syncwarp();
+    const u32 cnt = min(tot - lo, (u32)UW_CAP);
+    for (u32 i0 = lane; i0 < cnt; i0 += 32 * UE_UNROLL) {
+      u32 en[UE_UNROLL];
+      float ve[UE_UNROLL], vc[UE_UNROLL];
+#pragma unroll
+      for (int q = 0; q < UE_UNROLL; q++) {
+        const u32 i = i0 + q * 32;
+        if (i < cnt) {
+          en[q] = sm_ent[i];
+          ve[q] = exptVal[RE0 + (en[q] >> 13)];
+          vc[q] = ctrlVal[RC0 + sm_ctl[i]];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < UE_UNROLL; q++) {
+        const u32 i = i0 + q * 32;
+        if (i < cnt) {
+          const u64 uo = RU0 + lo + i;
+          pEnd[uo] = jb + (en[q] & (GR_BLOCK_SLOTS - 1));
+          pExpt[uo] = ve[q];
+          pCtrl[uo] = vc[q];
+        }
+      }
+    }
+  }
+}
+
 void launch_union_emit(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
                        const u64* rankE, const u64* rankC, const u64* rankU,
                        const float* exptVal, const float* ctrlVal,
@@ -343,7 +440,11 @@ void launch_union_emit(cudaStream_t s, const DevLayout& L, const u32* bmE, const
   static int ub = 0;
   if (!ub) { const char* e = getenv("GR_UE_BLOCKS"); ub = e && atoi(e) == 2 ? 2 : 4; }
   const unsigned grid = (unsigned)((L.nblocks + ub - 1) / ub);
-  if (ub == 2)
+  const char* uw = getenv("GR_UE_WARP");         // read per call: the tests switch it inside one process
+  if (uw && atoi(uw))
+    k_union_emit_w<<<(unsigned)((L.nblocks + 7) / 8), 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
+                                                                    pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks);
+  else if (ub == 2)
     k_union_emit<2><<<grid, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
                                          pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks);
   else

@@ -28,3 +28,12 @@ def test_fused_scan_rank_form_equals_validated_kernel(order):
     slot path (GR_FB_SLOTS=1: k_fb_move_slot + the gated exact chain), without and with overflow."""
     out = _run("emu_fused_scan", order)     # lanes resumed in order / in reverse / in a changing order
     assert "FAIL" not in out and out.count(" ok") >= 5, out
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_union_emit_warp_form_equals_validated_kernel(order):
+    """k_union_emit_w (GR_UE_WARP=1: one warp per bitmap block) == k_union_emit<4> / <2> (validated on
+    the B200) == a plain walk over the bits: interval ends, gathered pileup values, union bitmap,
+    chromosome starts; empty, sparse and dense blocks (several list rounds), partial last CTA."""
+    out = _run("emu_union", order)
+    assert "FAIL" not in out and out.count(" ok") == 4, out
