@@ -70,7 +70,9 @@ VARIANTS = {
     "rank512_slots": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1"},
     "rank1024_slots": {"GR_FUSED_RANK": "1", "GR_FR_CAP": "1024", "GR_FB_SLOTS": "1"},
     "ue_warp": {"GR_UE_WARP": "1"},
-    "all": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1", "GR_UE_WARP": "1"},
+    "ur_groups2": {"GR_UR_GROUPS": "2"},
+    "ur_groups4": {"GR_UR_GROUPS": "4"},
+    "all": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4"},
 }
 
 

@@ -212,14 +212,91 @@ k_union_rank(const u32* __restrict__ bmE, const u32* __restrict__ bmC, Lookback<
   }
 }
 
+// Grouped form (GR_UR_GROUPS=2|4; not the default until it has been measured): G x 16 blocks per
+// look-back tile.  The pass reads 0.77 GB per hg38 replicate (0.13 ms at the HBM rate) but takes
+// 0.5 ms: with ~1200 tiles resident, a tile's look-back walks ~20 windows of 64 predecessors, one L2
+// round trip each, before it meets a published inclusive prefix -- 23.5 k tiles pay that.  A tile of
+// G x 16 blocks pays it once for G times the data.
+template <int G>
+__global__ void __launch_bounds__(256)
+k_union_rank_g(const u32* __restrict__ bmE, const u32* __restrict__ bmC, Lookback<3> lb,
+               u64* __restrict__ rankE, u64* __restrict__ rankC, u64* __restrict__ rankU,
+               u64* __restrict__ totals, u32 nblocks, u32 ntiles) {
+  constexpr int NB = UR_BLOCKS * G;
+  __shared__ u32 sm[UR_BLOCKS][3][8];
+  __shared__ u32 sm_blk[NB][3];
+  __shared__ i64 sm_ex[3];
+  const u32 tile = take_ticket(lb.ticket);
+  const u32 b0 = tile * NB;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int g = 0; g < G; g++) {
+    u32 E[UR_BLOCKS], C[UR_BLOCKS];
+#pragma unroll
+    for (int b = 0; b < UR_BLOCKS; b++) {
+      const u32 blk = b0 + g * UR_BLOCKS + b;
+      const u64 widx = (u64)blk * 256 + threadIdx.x;
+      const bool on = blk < nblocks;
+      E[b] = on ? bmE[widx] : 0u;
+      C[b] = (on && bmC) ? bmC[widx] : 0u;
+    }
+#pragma unroll
+    for (int b = 0; b < UR_BLOCKS; b++) {
+      const u32 a = __reduce_add_sync(GR_FULL, __popc(E[b]));
+      const u32 c = __reduce_add_sync(GR_FULL, __popc(C[b]));
+      const u32 u = __reduce_add_sync(GR_FULL, __popc(E[b] | C[b]));
+      if (lane == 0) { sm[b][0][w] = a; sm[b][1][w] = c; sm[b][2][w] = u; }
+    }
+    __syncthreads();
+    if (threadIdx.x < UR_BLOCKS * 3) {
+      const int b = threadIdx.x / 3, k = threadIdx.x % 3;
+      u32 t = 0;
+      for (int q = 0; q < 8; q++) t += sm[b][k][q];
+      sm_blk[g * UR_BLOCKS + b][k] = t;
+    }
+    __syncthreads();                             // sm is rewritten by the next group
+  }
+  if (w == 0) {
+    i64 agg[3] = { 0, 0, 0 }, ex[3];
+    for (int b = 0; b < NB; b++) { agg[0] += sm_blk[b][0]; agg[1] += sm_blk[b][1]; agg[2] += sm_blk[b][2]; }
+    lookback_exclusive<3, 2>(lb, tile, agg, ex);
+    if (lane == 0) {
+      sm_ex[0] = ex[0]; sm_ex[1] = ex[1]; sm_ex[2] = ex[2];
+      if (tile == ntiles - 1) {
+        totals[0] = (u64)(ex[0] + agg[0]);
+        totals[1] = (u64)(ex[1] + agg[1]);
+        totals[2] = (u64)(ex[2] + agg[2]);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NB && b0 + threadIdx.x < nblocks) {
+    u64 e = (u64)sm_ex[0], c = (u64)sm_ex[1], u = (u64)sm_ex[2];
+    for (u32 b = 0; b < threadIdx.x; b++) { e += sm_blk[b][0]; c += sm_blk[b][1]; u += sm_blk[b][2]; }
+    rankE[b0 + threadIdx.x] = e;
+    if (rankC) rankC[b0 + threadIdx.x] = c;
+    rankU[b0 + threadIdx.x] = u;
+  }
+}
+
 void launch_union_rank(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
                        const RankScratch& sc, u64* rankE, u64* rankC, u64* rankU, u64* totals) {
-  const u32 ntiles = (u32)((L.nblocks + UR_BLOCKS - 1) / UR_BLOCKS);
+  const char* ge = getenv("GR_UR_GROUPS");       // read per call: the tests switch it inside one process
+  const int groups = ge ? atoi(ge) : 1;
+  const u32 per = UR_BLOCKS * (groups == 4 ? 4 : groups == 2 ? 2 : 1);
+  const u32 ntiles = (u32)((L.nblocks + per - 1) / per);
   for (int k = 0; k < 3; k++) cudaMemsetAsync(sc.st[k], 0, (size_t)ntiles * sizeof(u64), s);
   cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
   Lookback<3> lb;
   for (int k = 0; k < 3; k++) lb.st[k] = sc.st[k];
   lb.ticket = sc.ticket;
+  if (per == UR_BLOCKS * 4) {
+    k_union_rank_g<4><<<ntiles, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks, ntiles); GR_NOTE_LAUNCH();
+    return;
+  }
+  if (per == UR_BLOCKS * 2) {
+    k_union_rank_g<2><<<ntiles, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks, ntiles); GR_NOTE_LAUNCH();
+    return;
+  }
   k_union_rank<<<ntiles, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks, ntiles); GR_NOTE_LAUNCH();
 }
 

@@ -21,7 +21,8 @@ int main() {
   int bad = 0;
   for (int trial = 0; trial < 4; trial++) {
     // chromosomes of 3, 1, 7, 2 (+trial) blocks
-    std::vector<u32> nblk = {3, 1, 7, (u32)(2 + trial)};
+    std::vector<u32> nblk = {3, 1, 7, (u32)(2 + trial), (u32)(trial * 37)};
+    if (!trial) nblk.pop_back();
     std::vector<u64> off; std::vector<u32> len; std::vector<uint8_t> flags; std::vector<int> b2c;
     u64 T = 0;
     for (size_t c = 0; c < nblk.size(); c++) {
@@ -56,6 +57,22 @@ int main() {
       }
     }
     rE[nb] = e; rC[nb] = c; rU[nb] = u;
+    // K4 pass A: per-block ranks through the look-back, 16 / 32 / 64 blocks per tile
+    for (int G : {1, 2, 4}) {
+      const u32 per = UR_BLOCKS * G, ntiles = (nb + per - 1) / per;
+      std::vector<u64> st0(ntiles + 1, 0), st1(ntiles + 1, 0), st2(ntiles + 1, 0), gE(nb + 1, ~0ull), gC(nb + 1, ~0ull), gU(nb + 1, ~0ull);
+      u64 totals[3] = {~0ull, ~0ull, ~0ull};
+      u32 ticket = 0;
+      Lookback<3> lb;
+      lb.st[0] = st0.data(); lb.st[1] = st1.data(); lb.st[2] = st2.data(); lb.ticket = &ticket;
+      if (G == 1) emu::launch(ntiles, 256, [&] { k_union_rank(bmE, bmC, lb, gE.data(), gC.data(), gU.data(), totals, nb, ntiles); });
+      else if (G == 2) emu::launch(ntiles, 256, [&] { k_union_rank_g<2>(bmE, bmC, lb, gE.data(), gC.data(), gU.data(), totals, nb, ntiles); });
+      else emu::launch(ntiles, 256, [&] { k_union_rank_g<4>(bmE, bmC, lb, gE.data(), gC.data(), gU.data(), totals, nb, ntiles); });
+      bool ok = totals[0] == e && totals[1] == c && totals[2] == u;
+      for (u32 b = 0; b < nb; b++) ok = ok && gE[b] == rE[b] && gC[b] == rC[b] && gU[b] == rU[b];
+      if (!ok) { bad++; fprintf(stderr, "MISMATCH trial %d: union rank, %d blocks per tile\n", trial, UR_BLOCKS * G); }
+      printf("trial %d: union rank, %2d blocks per tile  %s\n", trial, UR_BLOCKS * G, ok ? "ok" : "FAIL");
+    }
     std::vector<float> ev(e + 2), cv(c + 2);
     for (auto& x : ev) x = (float)(rng() % 100000) / 7.0f;
     for (auto& x : cv) x = (float)(rng() % 100000) / 3.0f;

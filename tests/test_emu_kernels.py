@@ -34,6 +34,7 @@ def test_fused_scan_rank_form_equals_validated_kernel(order):
 def test_union_emit_warp_form_equals_validated_kernel(order):
     """k_union_emit_w (GR_UE_WARP=1: one warp per bitmap block) == k_union_emit<4> / <2> (validated on
     the B200) == a plain walk over the bits: interval ends, gathered pileup values, union bitmap,
-    chromosome starts; empty, sparse and dense blocks (several list rounds), partial last CTA."""
+    chromosome starts; empty, sparse and dense blocks (several list rounds), partial last CTA.
+    Also k_union_rank_g<2|4> (GR_UR_GROUPS: 32 / 64 blocks per look-back tile) == k_union_rank == host ranks."""
     out = _run("emu_union", order)
-    assert "FAIL" not in out and out.count(" ok") == 4, out
+    assert "FAIL" not in out and out.count(" ok") == 16, out
