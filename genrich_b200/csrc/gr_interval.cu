@@ -83,6 +83,102 @@ k_ctrl_clamp(DevLayout L, DevRle raw, const float* __restrict__ fl, Lookback<1> 
   }
 }
 
+// Long-tile form (GR_CL_TILES=4; not the default until it has been measured): M x 8192 raw intervals
+// per look-back tile and a 128-wide look-back window.  With ~1200 tiles resident and a 32-wide
+// window a tile's look-back walks some 30 windows (one L2 round trip each) before it meets a
+// published inclusive prefix; 12 k tiles per hg38 replicate pay that.  Same two passes, same outputs.
+template <int PER>
+__device__ __forceinline__ u64 tile_exclusive_rank_p(const Lookback<1>& lb, u32 tile, u32 cnt, u32& tile_total) {
+  __shared__ u32 sm_w[32];
+  __shared__ u64 sm_ex;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const u32 wi = warp_incl_scan_u32(cnt, lane);
+  if (lane == 31) sm_w[w] = wi;
+  __syncthreads();
+  u32 wx = 0, tot = 0;
+  for (int k = 0; k < nw; k++) {
+    const u32 a = sm_w[k];
+    if (k < w) wx += a;
+    tot += a;
+  }
+  if (w == 0) {
+    i64 agg[1] = { (i64)tot }, ex[1];
+    lookback_exclusive<1, PER>(lb, tile, agg, ex);
+    if (lane == 0) sm_ex = (u64)ex[0];
+  }
+  __syncthreads();
+  tile_total = tot;
+  return sm_ex + wx + (wi - cnt);
+}
+
+template <int M>
+__global__ void __launch_bounds__(256)
+k_ctrl_clamp_m(DevLayout L, DevRle raw, const float* __restrict__ fl, Lookback<1> lb,
+               DevRle out, u32* __restrict__ bitmap) {
+  constexpr u64 TILE = (u64)CL_TILE * M;
+  const u64 n = *raw.total;
+  if ((u64)blockIdx.x * TILE >= n) return;               // tickets stay dense
+  const float factor = fl[0], lambda = fl[1];
+  const u32 tile = take_ticket(lb.ticket);
+  const u64 t0 = (u64)tile * TILE;
+  const u64 tl = min(t0 + TILE, n) - 1;
+  const TileChrom tc = tile_chrom_range(raw.chrom_start, L.nchrom, t0, tl);
+  const bool uni = tc.c0 == tc.c1;
+  const u64 uni_end = uni ? raw.chrom_start[tc.c0 + 1] : 0;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const u64 wbase = t0 + (u64)w * (1024 * M);             // a warp owns 1024 * M consecutive intervals
+
+  u32 mine[M], cnt = 0;
+#pragma unroll
+  for (int m = 0; m < M; m++) {
+    mine[m] = 0;
+#pragma unroll 4
+    for (int k = 0; k < 32; k++) {
+      const u64 i = wbase + (u64)(m * 32 + k) * 32 + lane;
+      bool keep = false;
+      if (i < n) {
+        const float net = clamp_net(factor, raw.val[i], lambda);
+        int c = tc.c0;
+        bool last;
+        if (uni) last = i + 1 == uni_end;
+        else { c = chrom_of_index(raw.chrom_start, L.nchrom, i); last = i + 1 == raw.chrom_start[c + 1]; }
+        keep = last || net != clamp_net(factor, raw.val[i + 1], lambda);
+        if (!keep) {
+          const u64 g = L.off[c] + raw.end[i];
+          atomicAnd(bitmap + (g >> 5), ~(1u << (g & 31)));
+        }
+      }
+      const u32 bal = __ballot_sync(GR_FULL, keep);
+      if (lane == k) mine[m] = bal;
+      cnt += __popc(bal);
+    }
+  }
+  u32 tot;
+  u64 r = tile_exclusive_rank_p<4>(lb, tile, lane == 31 ? cnt : 0u, tot);
+  r = __shfl_sync(GR_FULL, r, 31);
+  if (tile == 0 && threadIdx.x == 0) out.chrom_start[0] = 0;
+
+#pragma unroll
+  for (int m = 0; m < M; m++) {
+    for (int k = 0; k < 32; k++) {
+      const u32 bal = __shfl_sync(GR_FULL, mine[m], k);
+      if (bal & (1u << lane)) {
+        const u64 i = wbase + (u64)(m * 32 + k) * 32 + lane;
+        const u64 rank = r + __popc(bal & ((1u << lane) - 1));
+        out.end[rank] = raw.end[i];
+        out.val[rank] = clamp_net(factor, raw.val[i], lambda);
+        int c = tc.c0;
+        bool last;
+        if (uni) last = i + 1 == uni_end;
+        else { c = chrom_of_index(raw.chrom_start, L.nchrom, i); last = i + 1 == raw.chrom_start[c + 1]; }
+        if (last) out.chrom_start[c + 1] = rank + 1;
+        if (i == n - 1) *out.total = rank + 1;
+      }
+      r += __popc(bal);
+    }
+  }
+}
+
 // chromosomes without intervals take the running count (forward fill)
 __global__ void k_fill_forward(int nchrom, const u64* raw_start, u64* out_start) {
   if (threadIdx.x || blockIdx.x) return;
@@ -95,11 +191,18 @@ void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u6
                        DevRle out, u32* bitmap) {
   cudaMemsetAsync(out.total, 0, sizeof(u64), s);
   if (!n_upper) return;
-  const u64 ntiles = (n_upper + CL_TILE - 1) / CL_TILE;
+  const char* te = getenv("GR_CL_TILES");        // read per call: the tests switch it inside one process
+  const int m = te && atoi(te) == 4 ? 4 : 1;
+  const u64 ntiles = (n_upper + (u64)CL_TILE * m - 1) / ((u64)CL_TILE * m);
   cudaMemsetAsync(sc.st, 0, ntiles * sizeof(u64), s);
   cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
   Lookback<1> lb;
   lb.st[0] = sc.st; lb.ticket = sc.ticket;
+  if (m == 4) {
+    k_ctrl_clamp_m<4><<<(unsigned)ntiles, 256, 0, s>>>(L, raw, factor_lambda, lb, out, bitmap); GR_NOTE_LAUNCH();
+    k_fill_forward<<<1, 32, 0, s>>>(L.nchrom, raw.chrom_start, out.chrom_start); GR_NOTE_LAUNCH();
+    return;
+  }
   k_ctrl_clamp<<<(unsigned)ntiles, 256, 0, s>>>(L, raw, factor_lambda, lb, out, bitmap); GR_NOTE_LAUNCH();
   k_fill_forward<<<1, 32, 0, s>>>(L.nchrom, raw.chrom_start, out.chrom_start); GR_NOTE_LAUNCH();
 }

@@ -38,3 +38,12 @@ def test_union_emit_warp_form_equals_validated_kernel(order):
     Also k_union_rank_g<2|4> (GR_UR_GROUPS: 32 / 64 blocks per look-back tile) == k_union_rank == host ranks."""
     out = _run("emu_union", order)
     assert "FAIL" not in out and out.count(" ok") == 16, out
+
+
+@pytest.mark.parametrize("order", [0, 2])
+def test_ctrl_clamp_long_tiles_equals_validated_kernel(order):
+    """k_ctrl_clamp_m<4> (GR_CL_TILES=4: 32768 raw intervals per look-back tile, 128-wide window) ==
+    k_ctrl_clamp (validated on the B200) == a plain loop over savePileupCtrl's rule: clamped values,
+    surviving boundaries, chromosome starts (chromosomes with one / no intervals / no slots), bitmap."""
+    out = _run("emu_ctrl", order)
+    assert "FAIL" not in out and out.count(" ok") == 6, out
