@@ -433,6 +433,8 @@ def main():
             file=sys.stderr, flush=True)
         trace.clear()
     ms_e2e, wall_e2e, _, peaks2, _, _ = timed(True, a.steps, 1)
+    # rank 0's host time by phase of the e2e arm (where the host waits for the device it is device time too)
+    host_phase = {k: round(v * 1e3 / a.steps, 4) for k, v in eng.t_acc.items()}
     st_steps = max(2, a.steps // 2)
     ms_staged, _, _, peaks3, _, stages = timed(False, st_steps, 1, with_stages=True)
     assert peaks3.tobytes() == peaks.tobytes()
@@ -515,6 +517,7 @@ def main():
                      "dense_formulation": dense_obj},
         "stage_ms_per_step": stage_ms,
         "variants": variants,
+        "host_phase_ms_per_step_e2e": host_phase,
     }
     if world > 1:
         td.destroy_process_group()                 # nothing below involves the other ranks

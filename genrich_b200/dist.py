@@ -83,8 +83,8 @@ class ShardedEngine:
         self.t_acc = {}
 
     def _tick(self, name, t0):
-        if self.debug:
-            self.t_acc[name] = self.t_acc.get(name, 0.0) + (time.perf_counter() - t0)
+        # host time by phase, always collected (two clock reads per phase); bench.py reports it
+        self.t_acc[name] = self.t_acc.get(name, 0.0) + (time.perf_counter() - t0)
 
     # records of chromosomes this rank does not own are dropped here (host routing)
     def route(self, recs: np.ndarray) -> np.ndarray:
