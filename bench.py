@@ -73,6 +73,8 @@ VARIANTS = {
     "ur_groups2": {"GR_UR_GROUPS": "2"},
     "ur_groups4": {"GR_UR_GROUPS": "4"},
     "cl_tiles4": {"GR_CL_TILES": "4"},
+    "p2": {"GR_FB_P2": "1"},
+    "all_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
     "all": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
 }
 

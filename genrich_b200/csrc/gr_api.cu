@@ -110,6 +110,7 @@ struct gr_ctx {
   // bucketed build (large samples)
   DevBuf sbCnt, sbStart, sbCursor, sbBucket, sbSpill, sbSpillCtr;
   u64 sb_min = 1ull << 20;             // samples with fewer records use the plain scatter (GR_SB_MIN)
+  DevBuf p1Cnt, p1Base, p1Cur, p1Pairs;   // two-level partition (GR_FB_P2=1)
   DevBuf sbSlotCnt, dGate;             // slot path (GR_FB_SLOTS=1): entries per fixed-capacity bucket, overflow flag
   u32 slot_cap = 0;                    // entries per bucket of the current sample (0: exact buckets)
   int fused = 1;                       // buckets -> breaks in shared memory, no delta array in HBM (GR_FUSED=0: dense array)
@@ -425,6 +426,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   x->dpar.release();
   x->dsums.release();
   x->unpack6.release();
+  x->p1Cnt.release(); x->p1Base.release(); x->p1Cur.release(); x->p1Pairs.release();
   x->sbSlotCnt.release();
   x->dGate.release();
   x->ghk.release();
@@ -709,6 +711,27 @@ static int consume_segments(gr_ctx* x, int* built) {
         CK(x->dGate.ensure(4));
       }
     }
+    int fsh = -1;
+    if (!x->has_bed && sh == GR_BLOCK_SHIFT && !x->slot_cap && fb_p2()) fsh = fb_p2_shift(nbk);
+    if (fsh >= 0) {
+      // two-level partition: coarse bins of 2^fsh blocks, then one CTA per bin (same outputs as the chain below)
+      const u32 nb1 = (u32)((nbk + (1ull << fsh) - 1) >> fsh);
+      CK(x->p1Cnt.ensure(1024 * 4));
+      CK(x->p1Base.ensure(1025 * 4));
+      CK(x->p1Cur.ensure(1024 * 4));
+      CK(x->p1Pairs.ensure(x->n_pushed * 16 + 16));
+      stage_begin(x, "bucket", bytes);
+      CK(cudaMemsetAsync(x->p1Cnt.p, 0, 1024 * 4, x->stream));
+      for (auto& g : x->segs)
+        launch_p1_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->p1Cnt.as<u32>(), fsh, x->d_err, x->d_clamped);
+      launch_p1_scan(x->stream, x->p1Cnt.as<u32>(), nb1, x->p1Base.as<u32>(), x->p1Cur.as<u32>());
+      for (auto& g : x->segs)
+        launch_p1_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->p1Cur.as<u32>(), x->p1Pairs.as<u64>(), fsh, nb1);
+      launch_p2(x->stream, x->p1Pairs.as<u64>(), x->p1Base.as<u32>(), nb1, fsh, nbk, x->sbStart.as<u32>(),
+                x->sbBucket.as<u32>());
+      CKL();
+      stage_end(x);
+    } else {
     stage_begin(x, "bucket", bytes);
     const int* gate = nullptr;
     if (x->slot_cap) {
@@ -743,6 +766,7 @@ static int consume_segments(gr_ctx* x, int* built) {
     HT("consume: scans + move launched");
     CKL();
     stage_end(x);
+    }
   } else if (sb) {
     CK(x->sbCnt.ensure(x->nblocks * 4));
     CK(x->sbStart.ensure((x->nblocks + 1) * 4));

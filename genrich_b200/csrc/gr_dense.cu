@@ -895,6 +895,179 @@ k_fb_move_slot(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restric
   if (c_local) atomicAdd(clamped, (u64)c_local);
 }
 
+// Two-level partition (GR_FB_P2=1; not the default until it has been measured).  k_fb_move is bound
+// by RETURNING L2 atomics (one per entry: 52 M ATOM in 0.69 ms, and the count pass pays the same
+// number of REDs), because consecutive records fall into unrelated buckets.  Here the entries are
+// first partitioned into <= 1024 COARSE bins of F = 2^fsh blocks each: a CTA histograms a tile of
+// 16384 records in shared memory and reserves room with one global atomic per bin and tile (~20 x
+// fewer); then one CTA per coarse bin sorts its ~70 k (block, entry) pairs -- L2 resident -- into
+// the exact per-block buckets with shared-memory counters only, and writes blk_start on the way.
+// Output = what count -> scan -> move produce (entries of a bucket in another order, which no
+// consumer depends on).
+//   k_p1_count  records -> pairs per coarse bin (shared-memory histogram; errors, clamp count)
+//   k_p1_scan   exclusive scan of the <= 1024 bin counts
+//   k_p1_move   records -> (block << 32 | entry) pairs, grouped by coarse bin
+//   k_p2        one CTA per bin: pairs -> buckets + blk_start
+#define P1_MAXB 1024
+#define P1_TILE 16384
+#define P2_MAXF 4096
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+k_p1_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cnt1, int fsh,
+           int* __restrict__ err, u64* __restrict__ clamped) {
+  __shared__ u32 sm_h[P1_MAXB];
+  for (int i = threadIdx.x; i < P1_MAXB; i += 256) sm_h[i] = 0;
+  __syncthreads();
+  const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
+  int e_local = 0;
+  u32 c_local = 0;
+  for (u64 i0 = (u64)blockIdx.x * (256 * FB_UNROLL) + threadIdx.x; i0 < n; i0 += stride) {
+    int4 r[FB_UNROLL];
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++)
+      if (i0 + k * 256 < n) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
+#pragma unroll
+    for (int k = 0; k < FB_UNROLL; k++) {
+      if (i0 + k * 256 >= n) break;
+      u64 s_slot; u32 span; int w;
+      if (!decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local)) continue;
+      const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)((s_slot + span) >> GR_BLOCK_SHIFT);
+      atomicAdd(sm_h + (bs >> fsh), 1u);
+      if (be != bs) atomicAdd(sm_h + (be >> fsh), 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < P1_MAXB; i += 256)
+    if (sm_h[i]) atomicAdd(cnt1 + i, sm_h[i]);
+  if (e_local) atomicOr(err, e_local);       // errors and clamp counts are reported by this pass only
+  if (c_local) atomicAdd(clamped, (u64)c_local);
+}
+
+__global__ void __launch_bounds__(1024)
+k_p1_scan(const u32* __restrict__ cnt1, u32 nb1, u32* __restrict__ base1, u32* __restrict__ cursor1) {
+  __shared__ u32 sh[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const u32 v = (u32)t < nb1 ? cnt1[t] : 0u;
+  const u32 wi = warp_incl_scan_u32(v, lane);
+  if (lane == 31) sh[w] = wi;
+  __syncthreads();
+  if (w == 0) {
+    const u32 x = sh[lane];
+    const u32 xi = warp_incl_scan_u32(x, lane);
+    sh[lane] = xi - x;
+  }
+  __syncthreads();
+  const u32 ex = sh[w] + wi - v;
+  if ((u32)t < nb1) { base1[t] = ex; cursor1[t] = ex; }
+  if ((u32)t == nb1 - 1) base1[nb1] = ex + v;
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(256)
+k_p1_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor1, u64* __restrict__ pairs,
+          int fsh, u32 nb1) {
+  __shared__ u32 sm_h[P1_MAXB];
+  const u32 omask = GR_BLOCK_SLOTS - 1;
+  const u64 ntiles = (n + P1_TILE - 1) / P1_TILE;
+  for (u32 i = threadIdx.x; i < nb1; i += 256) sm_h[i] = 0;
+  __syncthreads();
+  int e_local = 0;
+  u32 c_local = 0;
+  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const u64 t0 = tile * P1_TILE, t1 = min(t0 + (u64)P1_TILE, n);
+    // pass A: pairs of this tile per coarse bin
+    for (u64 i0 = t0 + threadIdx.x; i0 < t1; i0 += 256 * FB_UNROLL) {
+      int4 r[FB_UNROLL];
+#pragma unroll
+      for (int k = 0; k < FB_UNROLL; k++)
+        if (i0 + k * 256 < t1) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
+#pragma unroll
+      for (int k = 0; k < FB_UNROLL; k++) {
+        if (i0 + k * 256 >= t1) break;
+        u64 s_slot; u32 span; int w;
+        if (!decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local)) continue;
+        const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)((s_slot + span) >> GR_BLOCK_SHIFT);
+        atomicAdd(sm_h + (bs >> fsh), 1u);
+        if (be != bs) atomicAdd(sm_h + (be >> fsh), 1u);
+      }
+    }
+    __syncthreads();
+    // room for them: one global atomic per non-empty bin
+    for (u32 i = threadIdx.x; i < nb1; i += 256) {
+      const u32 h = sm_h[i];
+      sm_h[i] = h ? atomicAdd(cursor1 + i, h) : 0u;
+    }
+    __syncthreads();
+    // pass B: the records again (they are in L1 / L2), every pair to its place
+    for (u64 i0 = t0 + threadIdx.x; i0 < t1; i0 += 256 * FB_UNROLL) {
+      int4 r[FB_UNROLL];
+#pragma unroll
+      for (int k = 0; k < FB_UNROLL; k++)
+        if (i0 + k * 256 < t1) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
+#pragma unroll
+      for (int k = 0; k < FB_UNROLL; k++) {
+        if (i0 + k * 256 >= t1) break;
+        u64 s_slot; u32 span; int w;
+        if (!decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local)) continue;
+        const u64 e_slot = s_slot + span;
+        const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)(e_slot >> GR_BLOCK_SHIFT);
+        const u32 so = (u32)s_slot & omask;
+        const int cnt = 120 / w;
+        if (be != bs) {
+          pairs[atomicAdd(sm_h + (bs >> fsh), 1u)] = ((u64)bs << 32) | fb_entry(so, 0, cnt, FB_KIND_START);
+          pairs[atomicAdd(sm_h + (be >> fsh), 1u)] = ((u64)be << 32) | fb_entry((u32)e_slot & omask, 0, cnt, FB_KIND_END);
+        } else {
+          pairs[atomicAdd(sm_h + (bs >> fsh), 1u)] = ((u64)bs << 32) | fb_entry(so, span, cnt, FB_KIND_BOTH);
+        }
+      }
+    }
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < nb1; i += 256) sm_h[i] = 0;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(512)
+k_p2(const u64* __restrict__ pairs, const u32* __restrict__ base1, u32 nb1, int fsh, u32 nblocks,
+     u32* __restrict__ blk_start, u32* __restrict__ bucketed) {
+  __shared__ u32 sm_c[P2_MAXF];
+  __shared__ u32 sm_w[16];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const u32 bin = blockIdx.x, F = 1u << fsh, blk0 = bin << fsh;
+  const u32 a = base1[bin], b = base1[bin + 1];
+  for (u32 i = t; i < F; i += 512) sm_c[i] = 0;
+  __syncthreads();
+  for (u32 i = a + t; i < b; i += 512) atomicAdd(sm_c + ((u32)(pairs[i] >> 32) - blk0), 1u);
+  __syncthreads();
+  // exclusive scan of the F block counts: every thread owns K = F / 512 consecutive counters
+  const u32 K = F >> 9;
+  u32 s = 0;
+  for (u32 k = 0; k < K; k++) s += sm_c[t * K + k];
+  const u32 wi = warp_incl_scan_u32(s, lane);
+  if (lane == 31) sm_w[w] = wi;
+  __syncthreads();
+  if (w == 0) {
+    const u32 x = lane < 16 ? sm_w[lane] : 0u;
+    const u32 xi = warp_incl_scan_u32(x, lane);
+    if (lane < 16) sm_w[lane] = xi - x;
+  }
+  __syncthreads();
+  u32 run = a + sm_w[w] + wi - s;
+  for (u32 k = 0; k < K; k++) {
+    const u32 c = sm_c[t * K + k];
+    const u32 blk = blk0 + t * K + k;
+    if (blk < nblocks) blk_start[blk] = run;
+    sm_c[t * K + k] = run;                               // becomes the bucket's cursor
+    run += c;
+  }
+  if (bin == nb1 - 1 && t == 0) blk_start[nblocks] = b;
+  __syncthreads();
+  for (u32 i = a + t; i < b; i += 512) {
+    const u64 p = pairs[i];
+    bucketed[atomicAdd(sm_c + ((u32)(p >> 32) - blk0), 1u)] = (u32)p;
+  }
+}
+
 // -E region boundaries (a few thousand at most): one pseudo entry each, so that the scan finds
 // them in the occupancy bitmap like any other event.  cursor == NULL: count pass.
 __global__ void k_fb_marks(const u64* __restrict__ marks, u32 n, u32* __restrict__ blk_cnt,
@@ -1576,6 +1749,38 @@ void launch_fb_move_gated(cudaStream_t s, const DevLayout& L, const void* recs, 
   GR_NOTE_LAUNCH();
 }
 
+// fsh: log2 of the blocks per coarse bin -- at least 512 blocks, at most 1024 bins
+int fb_p2_shift(u64 nblocks) {
+  int fsh = 9;
+  while (((nblocks + (1ull << fsh) - 1) >> fsh) > P1_MAXB) fsh++;
+  return fsh <= 12 ? fsh : -1;                 // more than 4 M blocks (34 Gbp on one device): not this way
+}
+void launch_p1_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cnt1, int fsh,
+                     int* err, u64* clamped) {
+  if (!n) return;
+  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (packed) k_p1_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cnt1, fsh, err, clamped);
+  else k_p1_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cnt1, fsh, err, clamped);
+  GR_NOTE_LAUNCH();
+}
+void launch_p1_scan(cudaStream_t s, const u32* cnt1, u32 nb1, u32* base1, u32* cursor1) {
+  k_p1_scan<<<1, 1024, 0, s>>>(cnt1, nb1, base1, cursor1); GR_NOTE_LAUNCH();
+}
+void launch_p1_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor1, u64* pairs,
+                    int fsh, u32 nb1) {
+  if (!n) return;
+  u64 blocks = (n + P1_TILE - 1) / P1_TILE;
+  if (blocks > 148 * 6) blocks = 148 * 6;
+  if (packed) k_p1_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor1, pairs, fsh, nb1);
+  else k_p1_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor1, pairs, fsh, nb1);
+  GR_NOTE_LAUNCH();
+}
+void launch_p2(cudaStream_t s, const u64* pairs, const u32* base1, u32 nb1, int fsh, u64 nblocks, u32* blk_start,
+               u32* bucketed) {
+  k_p2<<<nb1, 512, 0, s>>>(pairs, base1, nb1, fsh, (u32)nblocks, blk_start, bucketed); GR_NOTE_LAUNCH();
+}
+
 static int fb_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 // GR_FUSED_SHIFT: log2 of the bucket size -- 13 (default): CTA-owned 8192-cell blocks (k_fb_scan,
 // with GR_FUSED_CPS / GR_FUSED_NT); 11 or 12: warp-owned buckets (k_fw_scan).  Measured on the
@@ -1645,6 +1850,7 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
 // Slot path: the rank-form scan over the fixed-capacity buckets, and behind it the same scan over
 // the exact buckets; *gate (raised by k_fb_move_slot on overflow) decides on the device which of
 // the two does anything.  Both fill the same pages / totals, so what follows does not care.
+bool fb_p2() { return fb_env("GR_FB_P2", 0) != 0 && fb_bucket_shift() == 13; }
 bool fb_rank_form() { return fb_env("GR_FUSED_RANK", 0) != 0; }
 bool fb_slots() { return fb_env("GR_FB_SLOTS", 0) != 0 && fb_rank_form() && fb_bucket_shift() == 13; }
 u32 launch_fr_scan_slot(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* slot_cnt, u32 slot_cap,

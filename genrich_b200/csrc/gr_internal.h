@@ -81,6 +81,16 @@ void launch_fb_move_gated(cudaStream_t s, const DevLayout& L, const void* recs, 
                           u32* bucketed, const int* gate);
 u32 launch_fr_scan_slot(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* slot_cnt, u32 slot_cap,
                         const u32* blk_start, const ScanScratch& sc, u32* bitmap, int* err, const int* gate);
+// two-level partition (GR_FB_P2=1): coarse bins of 2^fsh blocks, then one CTA per bin
+bool fb_p2();
+int fb_p2_shift(u64 nblocks);
+void launch_p1_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cnt1, int fsh,
+                     int* err, u64* clamped);
+void launch_p1_scan(cudaStream_t s, const u32* cnt1, u32 nb1, u32* base1, u32* cursor1);
+void launch_p1_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor1, u64* pairs,
+                    int fsh, u32 nb1);
+void launch_p2(cudaStream_t s, const u64* pairs, const u32* base1, u32 nb1, int fsh, u64 nblocks, u32* blk_start,
+               u32* bucketed);
 // -E region boundaries as pseudo entries (cursor == NULL: count pass)
 void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed, int shift);
 

@@ -4,6 +4,7 @@
 //   the same buckets -> k_fr_scan<CAP> (rank form) -> k_scan_fix -> k_scan_place
 //   k_fb_move_slot -> k_fr_scan<CAP, ., SLOT> (fixed-capacity buckets, no count pass), with roomy slots
 //   and with slots so small that the exact chain behind the gate has to take over
+//   k_p1_count -> k_p1_scan -> k_p1_move -> k_p2 (two-level partition): same buckets as count -> scan -> move
 // and a plain per-cell prefix sum written here.  All of them must give the same RLE pileup
 // (interval ends, float bits, chromosome starts) and the same break bitmap.
 #include "cuda_emu.h"
@@ -255,6 +256,29 @@ static int run_case(const char* name, const std::vector<u32>& len, const std::ve
       if (!(s3 == base) || !ov || cl != clamped) { diff("slot path (overflow -> exact chain) vs k_fb_scan", s3, base); bad++; }
     }
   }
+  // ---- two-level partition (GR_FB_P2=1): same blk_start, same entries per bucket (order inside a bucket is free)
+  {
+    const int fsh = 9;
+    const u32 nb1 = (u32)((nbk + (1ull << fsh) - 1) >> fsh);
+    u32* cnt1 = dalloc<u32>(1024); u32* base1 = dalloc<u32>(1025); u32* cur1 = dalloc<u32>(1024);
+    u64* pairs = dalloc<u64>(2 * n + 16);
+    u32* start2 = dalloc<u32>(nbk + 2); u32* bucket2 = dalloc<u32>(2 * n + 16);
+    memset(cnt1, 0, 1024 * 4); memset(start2, 0xEE, (nbk + 2) * 4); memset(bucket2, 0xEE, (2 * n + 16) * 4);
+    int err2 = 0; u64 cl2 = 0;
+    emu::launch(3, 256, [&] { k_p1_count<false>(recs, n, L, cnt1, fsh, &err2, &cl2); });
+    emu::launch(1, 1024, [&] { k_p1_scan(cnt1, nb1, base1, cur1); });
+    emu::launch(2, 256, [&] { k_p1_move<false>(recs, n, L, cur1, pairs, fsh, nb1); });
+    emu::launch(nb1, 512, [&] { k_p2(pairs, base1, nb1, fsh, (u32)nbk, start2, bucket2); });
+    bool ok = err2 == err && cl2 == clamped;
+    for (u64 b = 0; b <= nbk; b++) ok = ok && start2[b] == start[b];
+    for (u64 b = 0; ok && b < nbk; b++) {
+      std::vector<u32> x(bucketed + start[b], bucketed + start[b + 1]), y(bucket2 + start2[b], bucket2 + start2[b + 1]);
+      std::sort(x.begin(), x.end()); std::sort(y.begin(), y.end());
+      ok = x == y;
+    }
+    if (!ok) { fprintf(stderr, "MISMATCH two-level partition vs count/scan/move (err %d vs %d, clamped %llu vs %llu)\n", err2, err, cl2, clamped); bad++; }
+    free(cnt1); free(base1); free(cur1); free(pairs); free(start2); free(bucket2);
+  }
   printf("%-28s %8llu records %7llu blocks %9llu intervals  err %d  %s\n", name, (unsigned long long)n,
          (unsigned long long)nbk, (unsigned long long)base.total, base.err, bad ? "FAIL" : "ok");
   free(recs); free(cnt); free(start); free(cursor); free(chunk); free(bucketed);
@@ -309,6 +333,11 @@ int main() {
     fl[1] = GR_CF_OWNED;                                 // in the header, not in this replicate (Chrom.save false)
     fl[2] = 0;                                           // not owned by this context
     bad += run_case("unsaved / foreign chromosome", len, fl, gen(len, fl, 20000, 0.2, true), 5);
+  }
+  {  // more than two coarse bins of the two-level partition (512 blocks each), several tiles of 16384 records
+    std::vector<u32> len = {8192u * 700 - 5, 8192u * 610 + 77, 50000};
+    std::vector<uint8_t> fl(len.size(), A);
+    bad += run_case("1317 blocks, 3 coarse bins", len, fl, gen(len, fl, 40000, 0.1, true), 4);
   }
   printf("fiber switches: %llu\n", emu::n_switches);
   return bad ? 1 : 0;
