@@ -408,6 +408,7 @@ def main():
         _, _, _, base_peaks, _, _ = timed(False, 2, 3)
         out = {}
         for name, env in VARIANTS.items():
+            eng_v = None
             try:
                 os.environ.update(env)
                 eng_v = ShardedEngine(api, L, par, dev, host_group=None)
@@ -416,12 +417,16 @@ def main():
                              "peaks_identical": bool(peaks_v.tobytes() == base_peaks.tobytes()), "peaks": int(len(peaks_v)),
                              "stage_ms_per_step": {k: round(v[0] / a.steps, 4) for k, v in
                                                    sorted(st_v.items(), key=lambda kv: -kv[1][0])[:6]}}
-                del eng_v
             except Exception as e:                     # a variant that fails says so; the others still run
                 out[name] = {"env": env, "error": repr(e)[:300]}
             finally:
                 for k in env:
                     os.environ.pop(k, None)
+                if eng_v is not None:
+                    try:
+                        eng_v.ctx.close()              # its device buffers go back before the next variant allocates
+                    except Exception:
+                        pass
         print(json.dumps(out))
         return
 
