@@ -64,18 +64,18 @@ SAMPLE = dict(chrom_len=[50_000_000] * 8, nt=6_500_000, nc=6_500_000)
 # The default run times each of them in a CHILD process (a fault or a hang there cannot take the
 # headline with it), asserts that the peaks are the default path's byte for byte, and reports
 # ms per step under "variants" -- information for the next round, never part of `value` / `e2e`.
-VARIANTS = {
-    "rank512": {"GR_FUSED_RANK": "1"},
-    "rank1024": {"GR_FUSED_RANK": "1", "GR_FR_CAP": "1024"},
-    "rank512_slots": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1"},
-    "rank1024_slots": {"GR_FUSED_RANK": "1", "GR_FR_CAP": "1024", "GR_FB_SLOTS": "1"},
-    "ue_warp": {"GR_UE_WARP": "1"},
+VARIANTS = {           # simplest first: a faulting kernel poisons the child's context for everything after it
     "ur_groups2": {"GR_UR_GROUPS": "2"},
     "ur_groups4": {"GR_UR_GROUPS": "4"},
     "cl_tiles4": {"GR_CL_TILES": "4"},
+    "ue_warp": {"GR_UE_WARP": "1"},
+    "rank512": {"GR_FUSED_RANK": "1"},
+    "rank1024": {"GR_FUSED_RANK": "1", "GR_FR_CAP": "1024"},
     "p2": {"GR_FB_P2": "1"},
-    "all_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
+    "rank512_slots": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1"},
+    "rank512_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1"},
     "all": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
+    "all_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
 }
 
 
