@@ -1471,6 +1471,11 @@ k_fw_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
 // (owner = warp: pages, warp_tot, marks), so k_scan_fix / k_scan_place follow unchanged.
 // SLOT: the entries of block b lie at bucketed[b * slot_cap ...] and blk_start[b] is their count
 // (fixed-capacity buckets, filled by k_fb_move_slot without a count pass).
+// 120 / count without the division subroutine (one per entry otherwise): byte `count` of a 16-entry table
+__device__ __forceinline__ int fr_weight(u32 count) {
+  const u64 t = (count & 8u) ? 0x0808090A0A0C0D0Full : 0x1114181E283C7800ull;   // 120 / 8..15 | 120 / 0..7 (0 -> 0)
+  return (int)((t >> ((count & 7u) * 8u)) & 0xffu);
+}
 #define FR_RING 128                                    // page ring per warp: <= 2 * 33 + 2 sequence numbers in flight
 #define FR_PF 8                                        // entry registers per lane (256 entries prefetched per block)
 template <int CAP, int CPS, bool SLOT>
@@ -1640,7 +1645,7 @@ k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
       };
       auto add = [&](u32 e) {
         const u32 so = e & (GR_BLOCK_SLOTS - 1), kind = e >> 30;
-        const int w = 120 / (int)((e >> 26) & 15u);
+        const int w = fr_weight((e >> 26) & 15u);
         touch(so, kind == FB_KIND_END ? -w : w);
         if (kind == FB_KIND_BOTH) touch(so + ((e >> 13) & (GR_BLOCK_SLOTS - 1)), -w);
       };
