@@ -316,6 +316,11 @@ void launch_sb_build(cudaStream_t s, const DevLayout& L, const u32* bucketed, co
 // prefix hand-over between CTAs, not by HBM.
 #define SC_ITEMS 16
 
+#ifdef GR_EMU                       // tests/emu: the copy completes at once (a stronger guarantee than the ring relies on)
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) { memcpy(smem, gmem, 16); }
+__device__ __forceinline__ void cp_async_commit() {}
+template <int N> __device__ __forceinline__ void cp_async_wait() {}
+#else
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
@@ -324,6 +329,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
 }
+#endif
 
 // blocked read of a thread's 16 cells from an (unswizzled) stage: used only by the
 // rare dense path, so the 4-way bank conflict does not matter

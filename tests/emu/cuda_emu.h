@@ -71,6 +71,10 @@ static inline float __int_as_float(int u) { float f; memcpy(&f, &u, 4); return f
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
+static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline float __uint2float_rn(unsigned v) { return (float)v; }
+static inline float __ull2float_rn(unsigned long long v) { return (float)v; }
+static inline float __int2float_rn(int v) { return (float)v; }
 template <typename T> static inline T __ldcs(const T* p) { return *p; }
 template <typename T> static inline T __ldg(const T* p) { return *p; }
 template <typename T> static inline T __ldcg(const T* p) { return *p; }
@@ -89,19 +93,27 @@ template <typename T, typename C, typename V> static inline T atomicCAS(T* p, C 
 // ---- the scheduler -------------------------------------------------------------------------
 namespace emu {
 enum { STACK = 256 * 1024 };
+struct Group {                             // one rendezvous point: the lanes named by `mask`
+  unsigned mask = 0;
+  int arrived = 0, pending = 0;            // pending: participants that have not read the last result yet
+  unsigned long long gen = 0;
+  unsigned long long slot[2][32];          // operands of the collective, double-buffered by generation
+  unsigned amask[2] = {0, 0};              // lanes that delivered an operand in that generation
+};
 struct Fiber {
   ucontext_t ctx;
   char* stack = nullptr;
   bool done = false;
   int wait = 0;              // 0 runnable, 1 at a warp rendezvous, 2 at the CTA barrier
+  Group* grp = nullptr;
   unsigned long long wgen = 0, bgen = 0;   // generation the fiber waits to see completed
 };
 struct Warp {
-  int arrived = 0;
-  unsigned long long gen = 0;
-  unsigned long long slot[2][32];          // operands of the collective, double-buffered by generation
+  Group full;                              // all live lanes (the usual case)
+  Group part[33];                          // partial masks (__match_any_sync peers, ...), found by mask
   int live = 32;                           // lanes that have not returned
   int init_live = 32;
+  unsigned live_mask = 0xffffffffu;
 };
 struct Cta {
   std::vector<Fiber> f;
@@ -121,6 +133,11 @@ static unsigned long long n_switches = 0;
 static int order_mode = getenv("EMU_ORDER") ? atoi(getenv("EMU_ORDER")) : 0;
 static unsigned order_salt = 0;
 
+static inline void release_if_complete(Warp& w, Group& gr) {
+  if (gr.arrived > 0 && gr.arrived >= __builtin_popcount(gr.mask & w.live_mask)) {
+    gr.pending += gr.arrived; gr.arrived = 0; gr.gen++; gr.amask[gr.gen & 1] = 0;
+  }
+}
 static void entry() {
   g->body();
   Fiber& me = g->f[g->cur];
@@ -128,9 +145,12 @@ static void entry() {
   g->live--;
   Warp& w = g->w[g->cur >> 5];
   w.live--;
+  w.live_mask &= ~(1u << (g->cur & 31));
   if (g->live > 0 && g->b_arrived == g->live) { g->b_arrived = 0; g->b_gen++; }   // the others were waiting for this one
-  // a lane that returns while its siblings wait must not leave them hanging: the code base only
-  // returns warp-uniformly before collectives, which the counters below would flag otherwise
+  // lanes that have returned do not take part (CUDA: "all non-exited threads named in mask")
+  w.full.mask = w.live_mask;
+  release_if_complete(w, w.full);
+  for (Group& gr : w.part) release_if_complete(w, gr);
   swapcontext(&me.ctx, &g->sched);
 }
 static inline void yield_() {
@@ -138,24 +158,36 @@ static inline void yield_() {
   n_switches++;
   swapcontext(&me.ctx, &g->sched);
 }
-// warp rendezvous; returns the generation index (parity selects the operand buffer)
-static inline unsigned long long warp_arrive(unsigned long long operand, Warp*& wp) {
+// warp rendezvous of the lanes in `mask`; returns the generation (its parity selects the operand
+// buffer) and the group, which the caller reads its result from and then leaves
+static inline unsigned long long warp_arrive(unsigned long long operand, Group*& gp, unsigned mask = 0xffffffffu) {
   const int t = g->cur;
   Warp& w = g->w[t >> 5];
-  wp = &w;
-  const unsigned long long mygen = w.gen;
-  w.slot[mygen & 1][t & 31] = operand;
-  if (w.live != w.init_live) {
-    fprintf(stderr, "emu: warp collective after a divergent return (thread %d)\n", t); abort();
+  mask &= w.live_mask;
+  Group* gr = nullptr;
+  if (mask == w.live_mask) { gr = &w.full; gr->mask = mask; }
+  else {
+    for (Group& c : w.part) if (c.mask == mask && (c.arrived || c.pending)) { gr = &c; break; }
+    if (!gr) for (Group& c : w.part) if (c.mask == mask) { gr = &c; break; }
+    if (!gr) for (Group& c : w.part) if (!c.arrived && !c.pending) { gr = &c; c.mask = mask; c.gen = 0; c.amask[0] = c.amask[1] = 0; break; }
+    if (!gr) { fprintf(stderr, "emu: out of rendezvous groups\n"); abort(); }
   }
-  w.arrived++;
-  if (w.arrived == w.live) { w.arrived = 0; w.gen++; return mygen; }
+  gp = gr;
+  const unsigned long long mygen = gr->gen;
+  gr->slot[mygen & 1][t & 31] = operand;
+  gr->amask[mygen & 1] |= 1u << (t & 31);
+  gr->arrived++;
+  if (gr->arrived >= __builtin_popcount(gr->mask & w.live_mask)) {
+    gr->pending += gr->arrived; gr->arrived = 0; gr->gen++; gr->amask[gr->gen & 1] = 0;
+    return mygen;
+  }
   Fiber& me = g->f[t];
-  me.wait = 1; me.wgen = mygen;
-  while (w.gen == mygen) yield_();
+  me.wait = 1; me.grp = gr; me.wgen = mygen;
+  while (gr->gen == mygen) yield_();
   me.wait = 0;
   return mygen;
 }
+static inline void warp_leave(Group* gr) { gr->pending--; }
 static inline void cta_barrier() {
   const int t = g->cur;
   const unsigned long long mygen = g->b_gen;
@@ -189,8 +221,11 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
       makecontext(&f.ctx, (void (*)())entry, 0);
     }
     for (size_t wi = 0; wi < cta.w.size(); wi++) {
-      cta.w[wi].arrived = 0;
-      cta.w[wi].live = cta.w[wi].init_live = (int)std::min<unsigned>(32, nt - (unsigned)wi * 32);
+      Warp& w = cta.w[wi];
+      w.live = w.init_live = (int)std::min<unsigned>(32, nt - (unsigned)wi * 32);
+      w.live_mask = w.live == 32 ? 0xffffffffu : ((1u << w.live) - 1u);
+      w.full = Group(); w.full.mask = w.live_mask;
+      for (Group& gr : w.part) gr = Group();
     }
     blockIdx = uint3{b, 0, 0};
     while (cta.live > 0) {
@@ -206,7 +241,7 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
             Fiber& f = cta.f[t];
             if (f.done) continue;
             if (f.wait == 2 && cta.b_gen == f.bgen) continue;         // parked at the CTA barrier
-            if (f.wait == 1 && cta.w[wi].gen == f.wgen) continue;     // waits for its siblings
+            if (f.wait == 1 && f.grp->gen == f.wgen) continue;        // waits for its siblings
             cta.cur = t;
             threadIdx = uint3{(unsigned)t, 0, 0};
             swapcontext(&cta.sched, &f.ctx);
@@ -224,53 +259,49 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
 }
 }  // namespace emu
 
-// ---- collectives (full mask) ---------------------------------------------------------------
+// ---- collectives ------------------------------------------------------------------------------
+#define emu_lane_in(gr, l) (((gr)->amask[gen & 1] >> (l)) & 1u)      /* lane l delivered an operand to this rendezvous */
 static inline void __syncthreads() { emu::cta_barrier(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu::Warp* w; emu::warp_arrive(0, w); }
+static inline void __syncwarp(unsigned m = 0xffffffffu) { emu::Group* w; emu::warp_arrive(0, w, m); emu::warp_leave(w); }
 template <typename T> static inline T emu_bits_to(unsigned long long v) { T r; memcpy(&r, &v, sizeof(T)); return r; }
 template <typename T> static inline unsigned long long emu_to_bits(T v) { unsigned long long r = 0; memcpy(&r, &v, sizeof(T)); return r; }
-template <typename T> static inline T __shfl_sync(unsigned, T v, int src) {
-  emu::Warp* w; const unsigned long long gen = emu::warp_arrive(emu_to_bits(v), w);
-  return emu_bits_to<T>(w->slot[gen & 1][src & 31]);
-}
-template <typename T> static inline T __shfl_up_sync(unsigned, T v, unsigned d) {
-  const int lane = (int)(threadIdx.x & 31);
-  emu::Warp* w; const unsigned long long gen = emu::warp_arrive(emu_to_bits(v), w);
-  return lane >= (int)d ? emu_bits_to<T>(w->slot[gen & 1][lane - (int)d]) : v;
-}
-template <typename T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
-  const int lane = (int)(threadIdx.x & 31);
-  emu::Warp* w; const unsigned long long gen = emu::warp_arrive(emu_to_bits(v), w);
-  return lane + (int)d < 32 ? emu_bits_to<T>(w->slot[gen & 1][lane + (int)d]) : v;
-}
-template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int m) {
-  const int lane = (int)(threadIdx.x & 31);
-  emu::Warp* w; const unsigned long long gen = emu::warp_arrive(emu_to_bits(v), w);
-  return emu_bits_to<T>(w->slot[gen & 1][(lane ^ m) & 31]);
-}
-static inline unsigned __ballot_sync(unsigned, bool p) {
-  emu::Warp* w; const unsigned long long gen = emu::warp_arrive(p ? 1ull : 0ull, w);
-  unsigned r = 0;
-  for (int l = 0; l < w->live; l++) r |= (unsigned)(w->slot[gen & 1][l] & 1ull) << l;
+template <typename T> static inline T __shfl_sync(unsigned m, T v, int src) {
+  emu::Group* w; const unsigned long long gen = emu::warp_arrive(emu_to_bits(v), w, m);
+  const T r = emu_bits_to<T>(w->slot[gen & 1][src & 31]);
+  emu::warp_leave(w);
   return r;
 }
+template <typename T> static inline T __shfl_up_sync(unsigned m, T v, unsigned d) {
+  const int lane = (int)(threadIdx.x & 31);
+  emu::Group* w; const unsigned long long gen = emu::warp_arrive(emu_to_bits(v), w, m);
+  const T r = lane >= (int)d ? emu_bits_to<T>(w->slot[gen & 1][lane - (int)d]) : v;
+  emu::warp_leave(w);
+  return r;
+}
+template <typename T> static inline T __shfl_down_sync(unsigned m, T v, unsigned d) {
+  const int lane = (int)(threadIdx.x & 31);
+  emu::Group* w; const unsigned long long gen = emu::warp_arrive(emu_to_bits(v), w, m);
+  const T r = lane + (int)d < 32 ? emu_bits_to<T>(w->slot[gen & 1][lane + (int)d]) : v;
+  emu::warp_leave(w);
+  return r;
+}
+template <typename T> static inline T __shfl_xor_sync(unsigned m, T v, int x) {
+  const int lane = (int)(threadIdx.x & 31);
+  emu::Group* w; const unsigned long long gen = emu::warp_arrive(emu_to_bits(v), w, m);
+  const T r = emu_bits_to<T>(w->slot[gen & 1][(lane ^ x) & 31]);
+  emu::warp_leave(w);
+  return r;
+}
+#define EMU_REDUCE(init, expr)                                                          \
+  emu::Group* w; const unsigned long long gen = emu::warp_arrive(operand, w, m);          \
+  unsigned r = init;                                                                    \
+  for (int l = 0; l < 32; l++) if (emu_lane_in(w, l)) { const unsigned long long x = w->slot[gen & 1][l]; (void)x; expr; } \
+  emu::warp_leave(w);                                                                   \
+  return r;
+static inline unsigned __ballot_sync(unsigned m, bool p) { const unsigned long long operand = p ? 1ull : 0ull; EMU_REDUCE(0u, r |= (unsigned)(x & 1ull) << l) }
 static inline bool __any_sync(unsigned m, bool p) { return __ballot_sync(m, p) != 0; }
 static inline bool __all_sync(unsigned m, bool p) { return __ballot_sync(m, !p) == 0; }
-static inline unsigned __reduce_add_sync(unsigned, unsigned v) {
-  emu::Warp* w; const unsigned long long gen = emu::warp_arrive(v, w);
-  unsigned r = 0;
-  for (int l = 0; l < w->live; l++) r += (unsigned)w->slot[gen & 1][l];
-  return r;
-}
-static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
-  emu::Warp* w; const unsigned long long gen = emu::warp_arrive(v, w);
-  unsigned r = 0;
-  for (int l = 0; l < w->live; l++) r = std::max(r, (unsigned)w->slot[gen & 1][l]);
-  return r;
-}
-static inline unsigned __reduce_or_sync(unsigned, unsigned v) {
-  emu::Warp* w; const unsigned long long gen = emu::warp_arrive(v, w);
-  unsigned r = 0;
-  for (int l = 0; l < w->live; l++) r |= (unsigned)w->slot[gen & 1][l];
-  return r;
-}
+static inline unsigned __reduce_add_sync(unsigned m, unsigned v) { const unsigned long long operand = v; EMU_REDUCE(0u, r += (unsigned)x) }
+static inline unsigned __reduce_max_sync(unsigned m, unsigned v) { const unsigned long long operand = v; EMU_REDUCE(0u, r = std::max(r, (unsigned)x)) }
+static inline unsigned __reduce_or_sync(unsigned m, unsigned v) { const unsigned long long operand = v; EMU_REDUCE(0u, r |= (unsigned)x) }
+static inline unsigned __match_any_sync(unsigned m, unsigned long long v) { const unsigned long long operand = v; EMU_REDUCE(0u, r |= (unsigned)(x == operand) << l) }
