@@ -3,7 +3,7 @@
 // extract.py) on the host cores, so that a kernel written where no GPU is at hand can be checked
 // against the kernels already validated on the device.  Nothing in the product includes it.
 //
-// Model: one CTA at a time; every thread of the CTA is a ucontext fiber on ONE OS thread.  A
+// Model: one CTA at a time; every thread of the CTA is a fiber (own stack, hand-written switch) on ONE OS thread.  A
 // warp-level collective (__shfl*_sync, __ballot_sync, __reduce_*_sync, __syncwarp) or a CTA
 // barrier (__syncthreads) is a rendezvous: the fiber publishes its operand, yields, and is
 // resumed once every participant has arrived.  The scheduler runs the lanes of one warp
@@ -16,7 +16,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <ucontext.h>
 #include <algorithm>
 #include <functional>
 #include <vector>
@@ -101,7 +100,7 @@ struct Group {                             // one rendezvous point: the lanes na
   unsigned amask[2] = {0, 0};              // lanes that delivered an operand in that generation
 };
 struct Fiber {
-  ucontext_t ctx;
+  void* sp = nullptr;        // saved stack pointer while the fiber is not running
   char* stack = nullptr;
   bool done = false;
   int wait = 0;              // 0 runnable, 1 at a warp rendezvous, 2 at the CTA barrier
@@ -122,11 +121,21 @@ struct Cta {
   int b_arrived = 0;
   unsigned long long b_gen = 0;
   int cur = -1;
-  ucontext_t sched;
+  void* sched_sp = nullptr;
   std::function<void()> body;
 };
 static Cta* g = nullptr;
 static unsigned long long n_switches = 0;
+// Context switch between fibers (x86-64 SysV): callee-saved registers and the stack pointer; no signal
+// mask round trip (swapcontext makes two system calls per switch, which was 40 % of the run time).
+__attribute__((naked, noinline)) static void emu_switch(void** /*save_sp*/, void* /*load_sp*/) {
+  asm volatile(
+      "pushq %rbp\n\t" "pushq %rbx\n\t" "pushq %r12\n\t" "pushq %r13\n\t" "pushq %r14\n\t" "pushq %r15\n\t"
+      "movq %rsp, (%rdi)\n\t"
+      "movq %rsi, %rsp\n\t"
+      "popq %r15\n\t" "popq %r14\n\t" "popq %r13\n\t" "popq %r12\n\t" "popq %rbx\n\t" "popq %rbp\n\t"
+      "ret\n\t");
+}
 // EMU_ORDER=0 lanes resumed in order, 1 in reverse, 2 in an order that changes from pass to pass: code
 // that is only correct because of the order in which the emulation happens to run the lanes
 // (a missing __syncwarp / __syncthreads) has three chances to show
@@ -151,12 +160,13 @@ static void entry() {
   w.full.mask = w.live_mask;
   release_if_complete(w, w.full);
   for (Group& gr : w.part) release_if_complete(w, gr);
-  swapcontext(&me.ctx, &g->sched);
+  emu_switch(&me.sp, g->sched_sp);
+  abort();                                 // a finished fiber is never resumed
 }
 static inline void yield_() {
   Fiber& me = g->f[g->cur];
   n_switches++;
-  swapcontext(&me.ctx, &g->sched);
+  emu_switch(&me.sp, g->sched_sp);
 }
 // warp rendezvous of the lanes in `mask`; returns the generation (its parity selects the operand
 // buffer) and the group, which the caller reads its result from and then leaves
@@ -206,7 +216,9 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
   cta.nt = (int)nt;
   cta.f.resize(nt);
   cta.w.resize((nt + 31) / 32);
-  for (auto& f : cta.f) f.stack = (char*)malloc(STACK);
+  static std::vector<char*> stack_pool;    // stacks are kept across launches (fresh ones cost a page fault per fiber)
+  while (stack_pool.size() < nt) stack_pool.push_back((char*)malloc(STACK));
+  for (unsigned i = 0; i < nt; i++) cta.f[i].stack = stack_pool[i];
   cta.body = body;
   gridDim = dim3(grid); blockDim = dim3(nt);
   for (unsigned b = 0; b < grid; b++) {
@@ -214,11 +226,13 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
     for (unsigned i = 0; i < nt; i++) {
       Fiber& f = cta.f[i];
       f.done = false; f.wait = 0;
-      getcontext(&f.ctx);
-      f.ctx.uc_stack.ss_sp = f.stack;
-      f.ctx.uc_stack.ss_size = STACK;
-      f.ctx.uc_link = &cta.sched;
-      makecontext(&f.ctx, (void (*)())entry, 0);
+      // initial frame: six callee-saved registers, then `entry` as the return address of emu_switch;
+      // after that `ret` the stack pointer is 8 mod 16, as at any function entry
+      void** top = (void**)(((uintptr_t)f.stack + STACK) & ~(uintptr_t)15);
+      top[-1] = nullptr;
+      top[-2] = (void*)entry;
+      for (int k = 3; k <= 8; k++) top[-k] = nullptr;
+      f.sp = (void*)(top - 8);
     }
     for (size_t wi = 0; wi < cta.w.size(); wi++) {
       Warp& w = cta.w[wi];
@@ -244,7 +258,7 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
             if (f.wait == 1 && f.grp->gen == f.wgen) continue;        // waits for its siblings
             cta.cur = t;
             threadIdx = uint3{(unsigned)t, 0, 0};
-            swapcontext(&cta.sched, &f.ctx);
+            emu_switch(&cta.sched_sp, f.sp);
             any = true; progressed = true;
           }
           if (order_mode == 2) order_salt = order_salt * 1103515245u + 12345u;
@@ -254,7 +268,6 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
       if (!progressed) { fprintf(stderr, "emu: deadlock in CTA %u\n", b); abort(); }
     }
   }
-  for (auto& f : cta.f) free(f.stack);
   g = nullptr;
 }
 }  // namespace emu

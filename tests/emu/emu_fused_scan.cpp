@@ -53,7 +53,11 @@ struct Ws {
     const u64 max_pages = (cap / SS_PAGE + SS_SPARE_PAGES + 3) & ~1ull;
     const size_t bytes = (size_t)(max_pages * SS_PAGE * 8 + max_pages * 8 + SS_MAX_WARPS * (8 + 16) + (u64)nchrom * 16 + 256);
     mem = aligned_alloc(64, (bytes + 63) / 64 * 64);
-    memset(mem, 0xA5, bytes);                         // stale garbage, like a reused device buffer
+    // stale garbage, like a reused device buffer (the page area is 268 MB: only its first 16 MB, which is
+    // more than any case here fills, and everything behind it)
+    const size_t pent_bytes = (size_t)max_pages * SS_PAGE * 8;
+    memset(mem, 0xA5, std::min<size_t>(pent_bytes, 16u << 20));
+    memset((char*)mem + pent_bytes, 0xA5, bytes - pent_bytes);
     char* p = (char*)mem;
     W.pent = (uint2*)p; p += max_pages * SS_PAGE * 8;
     W.page_meta = (uint2*)p; p += max_pages * 8;
