@@ -8,3 +8,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_sessionstart(session):
+    # GR_EMU_AS_CUDA=1: the `-m gpu` tests drive the CPU-emulated build of the CUDA library
+    # (tests/emu/_build/libgenrich_emu.so, see tests/test_emu_library.py) instead of the real one.
+    # A development aid for boxes without a GPU; the driver's GPU run never sets it.
+    if os.environ.get("GR_EMU_AS_CUDA"):
+        import subprocess
+        from genrich_b200 import capi
+        emu = os.path.join(ROOT, "tests", "emu")
+        subprocess.check_call(["make", "-s", "-C", emu, "_build/libgenrich_emu.so"])
+        capi._cuda_api = capi.Api(os.path.join(emu, "_build", "libgenrich_emu.so"), "gr_")
