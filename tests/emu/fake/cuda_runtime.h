@@ -35,6 +35,22 @@ template <typename F> static void launch_k(dim3 grid, dim3 block, size_t smem, F
 }
 }  // namespace emu
 
+// EMU_DEVICES "devices" (default 1) share the one address space, but every device allocation remembers
+// the device that was current when it was made, and copies / memsets that touch it from another
+// current device abort: a missing cudaSetDevice in a multi-context caller shows up here
+static inline int emu_ndev() { const char* e = getenv("EMU_DEVICES"); return e ? atoi(e) : 1; }
+static int emu_cur_dev = 0;
+namespace emu { static std::map<char*, int> region_dev; }
+static inline void emu_check_dev(const void* p, const char* what) {
+  auto it = emu::regions.upper_bound((char*)p);
+  if (it == emu::regions.begin()) return;
+  --it;
+  if ((char*)p >= it->first + it->second.first || it->second.second != 2 /* device */) return;
+  if (emu::region_dev[it->first] != emu_cur_dev) {
+    fprintf(stderr, "emu: %s touches memory of device %d while device %d is current\n", what, emu::region_dev[it->first], emu_cur_dev);
+    abort();
+  }
+}
 static inline cudaError_t cudaMalloc(void** p, size_t n) {
   *p = aligned_alloc(256, (n + 255) / 256 * 256 + 256);
   if (!*p) return cudaErrorMemoryAllocation;
@@ -47,6 +63,7 @@ static inline cudaError_t cudaMalloc(void** p, size_t n) {
   memset(*p, zero ? 0 : getenv("EMU_FILL") ? atoi(getenv("EMU_FILL")) : 0xCD, n);
   if (getenv("EMU_ALLOC_LOG")) fprintf(stderr, "emu: cudaMalloc #%d %zu bytes\n", k, n);
   emu::regions[(char*)*p] = {n, cudaMemoryTypeDevice};
+  emu::region_dev[(char*)*p] = emu_cur_dev;
   return cudaSuccess;
 }
 template <typename T> static inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
@@ -68,10 +85,10 @@ static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, con
   }
   return cudaSuccess;
 }
-static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { memmove(d, s, n); return cudaSuccess; }
-static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { emu_check_dev(d, "cudaMemcpy"); emu_check_dev(s, "cudaMemcpy"); memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { emu_check_dev(d, "cudaMemcpyAsync"); emu_check_dev(s, "cudaMemcpyAsync"); memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset(void* d, int v, size_t n) { emu_check_dev(d, "cudaMemset"); memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { emu_check_dev(d, "cudaMemsetAsync"); memset(d, v, n); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = (cudaStream_t)malloc(8); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreate(cudaStream_t* s) { return cudaStreamCreateWithFlags(s, 0); }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { free(s); return cudaSuccess; }
@@ -91,9 +108,9 @@ static inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t a, cudaEve
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
 static inline const char* cudaGetErrorString(cudaError_t e) { return e ? "emulated CUDA error" : "no error"; }
-static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : cudaErrorInvalidValue; }
-static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= emu_ndev()) return cudaErrorInvalidValue; emu_cur_dev = d; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = emu_cur_dev; return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = emu_ndev(); return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int* v, int attr, int) {
   *v = attr == cudaDevAttrMultiProcessorCount ? emu::sm_count() : 0;
   return cudaSuccess;

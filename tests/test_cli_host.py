@@ -20,6 +20,12 @@ TWIN = os.path.join(util.ORACLE_DIR, "_test", "genrich-b200-oracle")
 
 @pytest.fixture(scope="module")
 def twin():
+    if os.environ.get("GR_EMU_AS_CUDA"):
+        # development aid: the same tests with the host program over the CPU-emulated CUDA library (tests/emu)
+        # instead of the oracle -- e.g. --gpus N over N emulated devices (set EMU_DEVICES=4)
+        emu = os.path.join(util.ROOT, "tests", "emu")
+        subprocess.check_call(["make", "-s", "-C", emu, "_build/genrich-b200-emu"])
+        return os.path.join(emu, "_build", "genrich-b200-emu")
     subprocess.check_call(["make", "-s", "-C", util.ORACLE_DIR, "cli_twin"])
     return TWIN
 

@@ -108,3 +108,37 @@ def test_variant_parity_script_under_emulation(emu_api):
                         "GR_UE_WARP=1", "GR_UR_GROUPS=4", "GR_CL_TILES=4"], capture_output=True, text=True, timeout=1200,
                        env=dict(os.environ, GR_EMU_AS_CUDA="1"))
     assert p.returncode == 0 and "identical to the default path" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
+
+
+def test_host_program_over_emulated_devices(emu_api, tmp_path):
+    """The host program linked against the emulated CUDA library, --gpus 3 over three emulated devices
+    (every device allocation remembers its device; a copy or memset issued while another device is
+    current aborts): chromosomes sharded over three contexts of the CUDA library -- per-chromosome sums
+    added on the host, one p-value histogram through gr_bh_*_host, peaks merged in chromosome order --
+    reproduce the reference's narrowPeak, -f and -k files byte for byte."""
+    import hashlib
+    subprocess.check_call(["make", "-s", "-C", EMU, "_build/genrich-b200-emu"])
+    cli = os.path.join(EMU, "_build", "genrich-b200-emu")
+    for name in ("c2_ctrl_q", "c4_fisher_q", "bed_ctrl_q"):
+        case = BY_NAME[name]
+        td = str(tmp_path / name)
+        os.makedirs(td)
+        tfiles, cfiles = util.write_case_sams(case, td)
+        out, logf, pile = (os.path.join(td, x) for x in ("o.np", "o.f", "o.k"))
+        cmd = [cli, "-t", ",".join(tfiles), "-o", out, "-f", logf, "-k", pile, "--gpus", "3"] + case.ref_args()
+        if any(c != "null" for c in cfiles):
+            cmd += ["-c", ",".join(cfiles)]
+        if case.bed:
+            bedf = os.path.join(td, "x.bed")
+            util.write_case_bed(case, bedf)
+            cmd += ["-E", bedf]
+        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True, env=dict(os.environ, EMU_DEVICES="4"))
+        assert r.returncode == 0, r.stderr
+        meta, gold = util.golden(case)
+        assert open(out).read().split("\n")[:-1] == gold, name
+        h = hashlib.sha256()
+        nl = 0
+        for line in open(logf, "rb"):
+            h.update(line)
+            nl += 1
+        assert (h.hexdigest(), nl) == (meta["log_sha256"], meta["log_lines"]), name

@@ -18,6 +18,9 @@ from genrich_b200 import host
 pytestmark = pytest.mark.gpu
 
 CLI = os.path.join(util.ROOT, "genrich_b200", "bin", "genrich-b200")
+if os.environ.get("GR_EMU_AS_CUDA"):       # development aid: the host program over the CPU-emulated library (tests/emu)
+    subprocess.check_call(["make", "-s", "-C", os.path.join(util.ROOT, "tests", "emu"), "_build/genrich-b200-emu"])
+    CLI = os.path.join(util.ROOT, "tests", "emu", "_build", "genrich-b200-emu")
 
 
 def _close_lines(got, want, float_cols, tol=1e-4):
