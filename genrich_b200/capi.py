@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "gr_sample_pileup", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
     "gr_sums_device", "gr_stream", "gr_replicate_stats",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
-    "gr_bh_set_global", "gr_bh_local_hist_host", "gr_bh_set_global_host", "gr_call_peaks", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
+    "gr_bh_set_global", "gr_bh_local_hist_host", "gr_bh_set_global_host", "gr_load_pvalues", "gr_call_peaks", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
     "gr_kernel_launches", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
     "gr_pinned_alloc", "gr_pinned_free",

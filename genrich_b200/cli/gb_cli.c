@@ -3,7 +3,7 @@
  * Same options, inputs, outputs, messages and exit status as the reference
  * (getArgs 5718-5827, runProgram 5386-5695, usage 34-71); the per-chromosome
  * loops of runProgram/findPeaks are replaced by calls into the C-ABI of
- * include/genrich_cuda.h.  Not implemented (fatal if requested): -P, peaks from a log file.
+ * include/genrich_cuda.h.  -P (peaks from a log file) lives in gb_peaksonly.c.
  */
 #include "gb_host.h"
 #include <float.h>
@@ -385,11 +385,10 @@ int main(int argc, char** argv) {
     long nc = sysconf(_SC_NPROCESSORS_ONLN);
     o.threads = nc < 1 ? 1 : nc > 16 ? 16 : (int)nc;
   }
-  if ((o.peaks_opt && !o.out_file) || !o.in_files) {
+  if ((o.peaks_opt && !o.out_file) || (peaks_only && !o.log_file) || (!peaks_only && !o.in_files)) {   /* 5776-5778 */
     fprintf(stderr, "Error! Need input/output files\n");
     usage();
   }
-  if (peaks_only) gb_die("-P", ": peak-calling from a log file is not available in genrich-b200");
   if (o.avg_ext_opt) { o.single_opt = true; o.extend_opt = false; }
   if (o.extend_opt) { o.single_opt = true; if (o.extend <= 0) gb_die("", "Extension length must be > 0"); }
   if (o.atac_opt) {
@@ -403,6 +402,7 @@ int main(int argc, char** argv) {
   if (o.as_diff < 0.0f) gb_die("", "Secondary alignment score threshold must be >= 0.0");
   if (o.pqvalue <= 0.0f || o.pqvalue > 1.0f) gb_die("", "p-/q-value must be in (0,1]");
   const float thr = -log10f(o.pqvalue);                       /* 5817 */
+  if (peaks_only) return gb_peaks_only(&o, xfile, thr);       /* -P: runProgram 5398-5403 */
 
   /* file lists */
   char **tf, **cf;

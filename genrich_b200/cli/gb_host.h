@@ -160,6 +160,7 @@ char* gb_in_gets(HIn* in, char* line, int size);
 /* gb_decode.c */
 int gb_chrom_add(HChromTab* t, const char* name, uint32_t len, bool ctrl, const HOpts* opt);  /* saveChrom 4220 */
 int gb_chrom_find(const HChromTab* t, const char* name);
+int gb_peaks_only(const HOpts* o, char* xfile, float thr);  /* -P: findPeaksOnly 5243 / callPeaksLog 1277 (gb_peaksonly.c) */
 void gb_scan_header(const char* path, HChromTab* tab, bool ctrl, const HOpts* opt);  /* header-only pass */
 void gb_decode_file(HDecode* d, const char* path);          /* readSAM 4468 / readBAM 4983 */
 void gb_flush_intervals(HDecode* d);

@@ -1479,6 +1479,51 @@ extern "C" int gr_bh_set_global_host(gr_ctx* x, const uint32_t* keys, const uint
   return gr_bh_set_global(x, x->ghk.as<uint32_t>(), x->ghl.as<uint64_t>(), n, genome_len);   // waits for the device itself
 }
 
+// -P: the final p (and q) arrays come from the caller (callPeaksLog 1277); K8 runs on them as on computed ones
+extern "C" int gr_load_pvalues(gr_ctx* x, const uint64_t* chrom_start, const uint32_t* end, const float* pval,
+                               const float* qval, uint64_t n) {
+  if (!x || !chrom_start || (n && (!end || !pval))) return GR_ERR_ARG;
+  if ((x->par.qval_opt != 0) != (qval != nullptr)) return GR_ERR_ARG;
+  if (chrom_start[0] != 0 || chrom_start[x->nchrom] != n || n >= 0xfffffff0ull || !x->reps.empty()) return GR_ERR_ARG;
+  for (int c = 0; c < x->nchrom; c++) if (chrom_start[c + 1] < chrom_start[c]) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  { int r = materialize(x); if (r) return r; }
+  const int nc = x->nchrom;
+  Replicate* rep = new_replicate(x);
+  x->reps.push_back(rep);
+  rep->has_ctrl = false;
+  rep->has_cols = false;
+  rep->n = rep->n_upper = n;
+  rep->n_ctrl = 0;
+  CK(rep->cnt.ensure(16));
+  CK(rep->pEnd.ensure((n + 1) * sizeof(u32)));
+  CK(rep->pVal.ensure((n + 1) * sizeof(float)));
+  CK(rep->chrom_start.ensure((nc + 1) * sizeof(u64)));
+  CK(rep->present.ensure(nc));
+  const u64 cnt2[2] = { n, 0 };
+  { int r = upload(x, rep->cnt.p, cnt2, 16); if (r) return r; }
+  { int r = upload(x, rep->chrom_start.p, chrom_start, (nc + 1) * sizeof(u64)); if (r) return r; }
+  if (n) {
+    CK(cudaMemcpyAsync(rep->pEnd.p, end, n * sizeof(u32), cudaMemcpyHostToDevice, x->stream));
+    CK(cudaMemcpyAsync(rep->pVal.p, pval, n * sizeof(float), cudaMemcpyHostToDevice, x->stream));
+  }
+  rep->chrom_start_h.assign(chrom_start, chrom_start + nc + 1);
+  rep->present_h.resize(nc);
+  for (int c = 0; c < nc; c++) rep->present_h[c] = chrom_start[c + 1] > chrom_start[c];
+  { int r = upload(x, rep->present.p, rep->present_h.data(), nc); if (r) return r; }
+  if (qval) {
+    CK(x->qVal.ensure((n + 1) * sizeof(float)));
+    if (n) CK(cudaMemcpyAsync(x->qVal.p, qval, n * sizeof(float), cudaMemcpyHostToDevice, x->stream));
+    x->have_q = true;
+    x->n_distinct = 0;
+    x->all_q_one = 0;
+  }
+  CK(cudaStreamSynchronize(x->stream));          // the caller's arrays may go away when we return
+  x->fin = rep;
+  x->finalized = true;
+  return GR_OK;
+}
+
 // ---- peaks ---------------------------------------------------------------------------
 // events -> heads -> walk -> compaction, all sized by upper bounds with the counts on the device
 static int peaks_enqueue(gr_ctx* x, Replicate* f, int qopt, bool want_host) {

@@ -248,6 +248,14 @@ int gr_bh_set_global(gr_ctx* ctx, const uint32_t* d_keys,
 int gr_bh_local_hist_host(gr_ctx* ctx, const uint32_t** keys, const uint64_t** lens, uint64_t* n);
 int gr_bh_set_global_host(gr_ctx* ctx, const uint32_t* keys, const uint64_t* lens, uint64_t n,
                           uint64_t genome_len);
+/* -P (callPeaksLog, Genrich.c:1277-1470: peaks from an already written -f log): the significance
+ * values come from the caller instead of from pileups.  chrom_start[nchrom+1] delimits every
+ * chromosome's run inside end / pval / qval (n = chrom_start[nchrom] intervals; an interval starts
+ * where the previous one of its chromosome ends, the first at 0; GR_SKIP = "NA" / excluded).
+ * qval must be given iff the context was created with qval_opt: the q-values are the log's, no
+ * Benjamini-Hochberg pass is run (1343-1345, 1383-1389).  gr_call_peaks follows. */
+int gr_load_pvalues(gr_ctx* ctx, const uint64_t* chrom_start, const uint32_t* end,
+                    const float* pval, const float* qval, uint64_t n);
 int gr_call_peaks(gr_ctx* ctx, const gr_peak** peaks, uint64_t* n,
                   gr_run_stats* stats);
 /* The same records where gr_call_peaks left them in DEVICE memory (valid until the next

@@ -52,6 +52,9 @@ int gr_push_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) {        /* GR_P
 }
 int gr_sample_pileup(gr_ctx* x, double* sums) { return orc_sample_pileup(x->o, sums); }
 int gr_replicate_end(gr_ctx* x, gr_sample_stats* st) { return orc_replicate_end(x->o, st); }
+int gr_load_pvalues(gr_ctx* x, const uint64_t* cs, const uint32_t* end, const float* pval, const float* qval, uint64_t n) {
+  return orc_load_pvalues(x->o, cs, end, pval, qval, n);
+}
 int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_run_stats* st) {
   return orc_call_peaks(x->o, peaks, n, st);
 }

@@ -35,6 +35,8 @@ int  orc_bh_local_hist(orc_ctx* ctx, const uint32_t** keys,
                        const uint64_t** lens, uint64_t* n);
 int  orc_bh_set_global(orc_ctx* ctx, const uint32_t* keys,
                        const uint64_t* lens, uint64_t n, uint64_t genome_len);
+int  orc_load_pvalues(orc_ctx* ctx, const uint64_t* chrom_start, const uint32_t* end,
+                      const float* pval, const float* qval, uint64_t n);   /* callPeaksLog 1277 */
 int  orc_call_peaks(orc_ctx* ctx, const gr_peak** peaks, uint64_t* n,
                     gr_run_stats* stats);
 int  orc_fetch_intervals(orc_ctx* ctx, int32_t which, int32_t replicate,

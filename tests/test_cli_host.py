@@ -252,3 +252,60 @@ def test_sharded_contexts_same_output(twin, gpus, tmp_path, monkeypatch):
             os.makedirs(td)
             h2 = type(h)(h.name, h.case, list(h.args) + ["--gpus", str(gpus)], h.dups_log)
             check_host_case(twin, h2, td)
+
+
+PONLY = sorted(f[:-5] for f in os.listdir(util.GOLDEN) if f.startswith("ponly_") and f.endswith(".json"))
+
+
+def test_peaks_only(twin, tmp_path):
+    """-P (peaks from a -f log: findPeaksOnly 5243, callPeaksLog 1277): the host program parses its own
+    -f log -- byte for byte the reference's -- and calls peaks on the log's -log(p) / -log(q) columns
+    with new thresholds, -e, and new -E regions; narrowPeak files, genome length, peak counts and
+    warnings equal what the unmodified reference produced with the same arguments
+    (tests/golden/ponly_*, make_golden_peaksonly.py).  Also gzip input and the error texts."""
+    import gzip
+    import json
+    logs = {}
+    for name in PONLY:
+        meta = json.load(open(os.path.join(util.GOLDEN, name + ".json")))
+        cname = meta["case"]
+        if cname not in logs:
+            td = str(tmp_path / cname)
+            os.makedirs(td)
+            logs[cname] = run_twin(twin, BY_NAME[cname], td)[1]
+            cm, _ = util.golden(BY_NAME[cname])
+            assert _sha(logs[cname]) == (cm["log_sha256"], cm["log_lines"])
+        out = str(tmp_path / (name + ".np"))
+        cmd = [twin, "-P", "-f", logs[cname], "-o", out, "-v"] + meta["args"]
+        if meta["bed_case"]:
+            bedf = str(tmp_path / (name + ".bed"))
+            util.write_case_bed(BY_NAME[meta["bed_case"]], bedf)
+            cmd += ["-E", bedf]
+        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, (name, r.stderr)
+        gold = open(os.path.join(util.GOLDEN, name + ".narrowPeak")).read()
+        assert open(out).read() == gold, name
+        err = r.stderr
+        assert int(re.search(r"Genome length: (\d+)bp", err).group(1)) == meta["genome_len"], name
+        assert int(re.search(r"Peaks identified: (\d+)", err).group(1)) == meta["peaks"], name
+        assert int(re.search(r"Peaks identified: \d+ \((\d+)bp\)", err).group(1)) == meta["peak_bp"], name
+        assert ("Skipping given BED regions" in err) == meta["warn_bed"], name
+        assert len(re.findall(r"Skipping chromosome", err)) == meta["warn_chr"], name
+    # gzip-compressed log in, gzip-compressed peaks out
+    lg = logs["c2_ctrl_q"]
+    gz = str(tmp_path / "log.gz")
+    with open(lg, "rb") as f, gzip.open(gz, "wb") as g:
+        g.write(f.read())
+    out = str(tmp_path / "z.np")
+    r = subprocess.run([twin, "-P", "-f", gz, "-o", out, "-q", "0.05", "-z"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert gzip.open(out + ".gz", "rt").read() == open(os.path.join(util.GOLDEN, "ponly_c2_same.narrowPeak")).read()   # openWrite 5088: ".gz" appended
+    # a -p log has no -log(q) column; a log without header fields; missing -f
+    r = subprocess.run([twin, "-P", "-f", logs["c1_smoke"], "-o", out, "-q", "0.05"], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Error! -log(q): cannot find field in header of bedgraph-ish log file" in r.stderr
+    bad = str(tmp_path / "bad.f")
+    open(bad, "w").write("chr\tstart\tend\nchr1\t0\t10\n")
+    r = subprocess.run([twin, "-P", "-f", bad, "-o", out], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Error! -log(p): cannot find field in header" in r.stderr
+    r = subprocess.run([twin, "-P", "-o", out], stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 1 and "Need input/output files" in r.stderr
