@@ -19,4 +19,6 @@ def pytest_sessionstart(session):
         from genrich_b200 import capi
         emu = os.path.join(ROOT, "tests", "emu")
         subprocess.check_call(["make", "-s", "-C", emu, "_build/libgenrich_emu.so"])
-        capi._cuda_api = capi.Api(os.path.join(emu, "_build", "libgenrich_emu.so"), "gr_")
+        # GR_EMU_LIB: another build of it, e.g. one compiled with -fsanitize=address (run python under
+        # LD_PRELOAD=libasan.so then): device buffers get red zones, kernels' out-of-bounds accesses abort
+        capi._cuda_api = capi.Api(os.environ.get("GR_EMU_LIB") or os.path.join(emu, "_build", "libgenrich_emu.so"), "gr_")

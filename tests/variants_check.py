@@ -61,7 +61,7 @@ def main():
         k, v = kv.split("=")
         variant[k] = v
     if os.environ.get("GR_EMU_AS_CUDA"):       # development aid: the CPU-emulated build of the library (tests/emu)
-        capi._cuda_api = capi.Api(os.path.join(ROOT, "tests", "emu", "_build", "libgenrich_emu.so"), "gr_")
+        capi._cuda_api = capi.Api(os.environ.get("GR_EMU_LIB") or os.path.join(ROOT, "tests", "emu", "_build", "libgenrich_emu.so"), "gr_")
     api = capi.load_cuda()
     n = 0
     for case in CASES:
