@@ -142,3 +142,28 @@ def test_host_program_over_emulated_devices(emu_api, tmp_path):
             h.update(line)
             nl += 1
         assert (h.hexdigest(), nl) == (meta["log_sha256"], meta["log_lines"]), name
+
+
+def test_peaks_only_over_emulated_library(emu_api, tmp_path):
+    """-P with the host program over the emulated CUDA library: gr_load_pvalues + the K8 kernels on the
+    -log(p) / -log(q) columns of a -f log, against the unmodified reference's -P files (tests/golden/ponly_*)."""
+    import json
+    subprocess.check_call(["make", "-s", "-C", EMU, "_build/genrich-b200-emu"])
+    cli = os.path.join(EMU, "_build", "genrich-b200-emu")
+    case = BY_NAME["c2_ctrl_q"]
+    td = str(tmp_path)
+    tfiles, cfiles = util.write_case_sams(case, td)
+    logf = os.path.join(td, "o.f")
+    subprocess.run([cli, "-t", ",".join(tfiles), "-c", ",".join(cfiles), "-o", os.path.join(td, "o.np"), "-f", logf] + case.ref_args(),
+                   check=True, stderr=subprocess.DEVNULL)
+    for name in ("ponly_c2_same", "ponly_c2_p_strict", "ponly_c2_q_skipchr", "ponly_c2_newbed", "ponly_c2_newbed_q"):
+        meta = json.load(open(os.path.join(util.GOLDEN, name + ".json")))
+        out = os.path.join(td, name + ".np")
+        cmd = [cli, "-P", "-f", logf, "-o", out] + meta["args"]
+        if meta["bed_case"]:
+            bedf = os.path.join(td, name + ".bed")
+            util.write_case_bed(BY_NAME[meta["bed_case"]], bedf)
+            cmd += ["-E", bedf]
+        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, (name, r.stderr)
+        assert open(out).read() == open(os.path.join(util.GOLDEN, name + ".narrowPeak")).read(), name
