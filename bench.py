@@ -505,7 +505,8 @@ def main():
         "e2e": {"value": G / 1e9 / (ms_e2e * 1e-3), "unit": "Gbp/s", "ms_per_step": ms_e2e,
                 "h2d_bytes_per_step": int((6 if use6 else 8) * (n_t + n_c)), "d2h_bytes_per_step": int(peaks2.nbytes + 512),
                 "record_format": "GR_PACK6 (6 B per record, expanded on the device)" if use6 else "GR_PACK (8 B per record)",
-                "wall_ms_per_step": wall_e2e},
+                "wall_ms_per_step": wall_e2e,
+                "peaks_identical_to_device_arm": bool(peaks2.tobytes() == peaks.tobytes())},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_dev,
         "clocks": clocks,

@@ -167,3 +167,59 @@ def test_peaks_only_over_emulated_library(emu_api, tmp_path):
         r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
         assert r.returncode == 0, (name, r.stderr)
         assert open(out).read() == open(os.path.join(util.GOLDEN, name + ".narrowPeak")).read(), name
+
+
+def test_bench_e2e_call_pattern(emu_api, monkeypatch):
+    """The call sequence of bench.py's e2e arm, which no other test drives: 6-byte records in PINNED host
+    buffers, both samples of the NEXT step sent ahead (gr_prefetch_packed6, two slots) while the current
+    step runs without host round trips (sample_pileup_async, replicate_finish_device), gr_reset between
+    steps -- three steps give the peaks of the plain synchronous path, and so does the 8-byte variant."""
+    import ctypes as C
+    from genrich_b200 import host
+    for k, v in FUSED.items():
+        monkeypatch.setenv(k, v)
+    case = BY_NAME["c2_ctrl_p"]
+    (t, c), = [r[:2] for r in util.case_inputs(case)]
+    par = util.case_params(case)
+    ref = host.run_replicates(capi.Context(emu_api, case.chrom_len, par), [(t, c)]).peaks
+    assert len(ref) > 0
+    ctx = capi.Context(emu_api, case.chrom_len, par)
+    lib = C.CDLL(LIB)
+    lib.gr_pinned_alloc.restype = C.c_void_p
+    lib.gr_pinned_alloc.argtypes = [C.c_size_t]
+    lib.gr_pinned_free.argtypes = [C.c_void_p]
+    layout = ctx.pack6_layout()
+    assert layout is not None
+    bufs = []
+
+    def pinned(a):
+        p = lib.gr_pinned_alloc(a.nbytes)
+        C.memmove(p, a.ctypes.data, a.nbytes)
+        bufs.append(p)
+        return p
+    t6, rest = host.pack6_records(t, layout, case.chrom_len)
+    c6, rest2 = host.pack6_records(c, layout, case.chrom_len)
+    assert not len(rest) and not len(rest2)
+    t8, _ = host.pack_records(t)
+    c8, _ = host.pack_records(c)
+    pt6, pc6, pt8, pc8 = pinned(t6), pinned(c6), pinned(t8), pinned(c8)
+    glen = int(sum(case.chrom_len))
+    for six in (True, False):
+        pt, pc = (pt6, pc6) if six else (pt8, pc8)
+        push = ctx.push_packed6_ptr if six else ctx.push_packed_ptr
+        pre = ctx.prefetch_packed6_ptr if six else ctx.prefetch_packed_ptr
+        for step in range(3):
+            ctx.reset()
+            ctx.sample_begin(False, None)
+            push(pt, len(t))
+            ctx.sample_pileup_async()
+            ctx.sample_begin(True)
+            push(pc, len(c))
+            ctx.sample_pileup_async()
+            ctx.replicate_finish_device(True, glen)
+            pre(pt, len(t))                                  # the next step's samples travel under this step's kernels
+            pre(pc, len(c))
+            peaks, _ = ctx.call_peaks()
+            assert peaks.tobytes() == ref.tobytes(), (six, step)
+    for p in bufs:
+        lib.gr_pinned_free(p)
