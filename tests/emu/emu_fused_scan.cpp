@@ -293,7 +293,7 @@ int main() {
   int bad = 0;
   const uint8_t A = GR_CF_OWNED | GR_CF_SAVE;
   {  // edge inputs: chromosome ends on block boundaries, one-base chromosome, empty interval, equal records
-    std::vector<u32> len = {5000, 8192, 8191, 1, 20000, 16384, 16383};
+    std::vector<u32> len = {5000, 8192, 8191, 1, 20000, 16384, 16383, 30000, 40000};   // 7: its end cell is alone in a block; 8: no record at all
     std::vector<int4> r = {
         {0, 0, 5000, 1}, {0, -50, 10, 2}, {0, 4990, 6000, 3}, {1, 0, 1, 1}, {1, 8191, 8192, 1},
         {2, 8190, 8191, 10}, {2, 0, 8191, 8}, {3, 0, 1, 1}, {4, 100, 100, 5},
@@ -301,7 +301,7 @@ int main() {
         {4, 19999, 25000, 4}, {5, 0, 16384, 1}, {5, 8191, 8192, 2}, {5, 8192, 8193, 2}, {5, 16383, 16384, 3},
         {6, 0, 16383, 1}, {6, 8100, 16383, 2}, {6, 16382, 16383, 3},
         {4, 1000, 1500, 2}, {4, 1500, 2000, 2},          // an end and a start of equal weight on one cell: no break
-        {4, 3000, 3100, 3}, {4, 3100, 3200, 5}};
+        {4, 3000, 3100, 3}, {4, 3100, 3200, 5}, {7, 100, 200, 1}};
     bad += run_case("edge", len, std::vector<uint8_t>(len.size(), A), r, 2);
   }
   std::mt19937_64 rng(20261017);
