@@ -71,6 +71,8 @@ VARIANTS = {           # simplest first: a faulting kernel poisons the child's c
     "ue_warp": {"GR_UE_WARP": "1"},
     "rank512": {"GR_FUSED_RANK": "1"},
     "rank1024": {"GR_FUSED_RANK": "1", "GR_FR_CAP": "1024"},
+    "rank512_cps7": {"GR_FUSED_RANK": "1", "GR_FR_CPS": "7"},
+    "rank512_pf4": {"GR_FUSED_RANK": "1", "GR_FR_PF": "4"},
     "p2": {"GR_FB_P2": "1"},
     "rank512_slots": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1"},
     "rank512_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1"},

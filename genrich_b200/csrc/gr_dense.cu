@@ -1483,8 +1483,8 @@ __device__ __forceinline__ int fr_weight(u32 count) {
   return (int)((t >> ((count & 7u) * 8u)) & 0xffu);
 }
 #define FR_RING 128                                    // page ring per warp: <= 2 * 33 + 2 sequence numbers in flight
-#define FR_PF 8                                        // entry registers per lane (256 entries prefetched per block)
-template <int CAP, int CPS, bool SLOT>
+// PF: entry registers per lane (32 * PF entries of a block are prefetched while the previous block is worked on)
+template <int CAP, int CPS, int PF, bool SLOT>
 __global__ void __launch_bounds__(128, CPS)
 k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
           u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R, u32 slot_cap,
@@ -1549,9 +1549,9 @@ k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   };
   if (lane == 0) page_ask(ub_of(nA));
 
-  u32 v[FR_PF];
+  u32 v[PF];
 #pragma unroll
-  for (int k = 0; k < FR_PF; k++) {
+  for (int k = 0; k < PF; k++) {
     v[k] = 0;
     if ((u32)(k * 32 + lane) < nA) v[k] = __ldcs(eA + k * 32 + lane);
   }
@@ -1586,7 +1586,7 @@ k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
       bm_out[0] = make_uint4(0, 0, 0, 0);
       bm_out[1] = make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int k = 0; k < FR_PF; k++)
+      for (int k = 0; k < PF; k++)
         if ((u32)(k * 32 + lane) < nB) v[k] = __ldcs(eB + k * 32 + lane);
       nA = nB; nB = nC; eA = eB;
       continue;
@@ -1602,9 +1602,9 @@ k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
       }
     };
 #pragma unroll
-    for (int k = 0; k < FR_PF; k++)
+    for (int k = 0; k < PF; k++)
       if ((u32)(k * 32 + lane) < nA) mark(v[k]);
-    for (u32 i = FR_PF * 32 + lane; i < nA; i += 32) mark(__ldg(eA + i));
+    for (u32 i = PF * 32 + lane; i < nA; i += 32) mark(__ldg(eA + i));
     if (has_end && lane == 0) atomicOr(sm_occ + (end_cell >> 5), 1u << (end_cell & 31));
     __syncwarp();
     // ---- P2: exclusive prefix of the word popcounts (lane: words 8 * lane .. 8 * lane + 7)
@@ -1656,13 +1656,13 @@ k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
         if (kind == FB_KIND_BOTH) touch(so + ((e >> 13) & (GR_BLOCK_SLOTS - 1)), -w);
       };
 #pragma unroll
-      for (int k = 0; k < FR_PF; k++)
+      for (int k = 0; k < PF; k++)
         if ((u32)(k * 32 + lane) < nA) add(v[k]);
-      for (u32 i = FR_PF * 32 + lane; i < nA; i += 32) add(__ldg(eA + i));
+      for (u32 i = PF * 32 + lane; i < nA; i += 32) add(__ldg(eA + i));
       if (has_end && lane == 0) touch(end_cell, 0);
       if (last_round) {                                // next block's entries: in flight during P4 / P5
 #pragma unroll
-        for (int k = 0; k < FR_PF; k++)
+        for (int k = 0; k < PF; k++)
           if ((u32)(k * 32 + lane) < nB) v[k] = __ldcs(eB + k * 32 + lane);
       }
       __syncwarp();
@@ -1820,14 +1820,21 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
   if (sh == 13 && rank_form) {
     // warp-owned 8192-cell blocks, rank form (k_fr_scan): 9 CTAs x 4 warps per SM with 512 distinct
     // cells per round, 6 with 1024 (GR_FR_CAP)
+    // knobs: GR_FR_CAP 512 | 1024 distinct cells per round, GR_FR_CPS 9 | 7 CTAs per SM (56 / 72 registers),
+    // GR_FR_PF 8 | 4 entry registers per lane
     const int cap = fb_env("GR_FR_CAP", 512) == 1024 ? 1024 : 512;
-    const int ctas = sms * (cap == 1024 ? 6 : 9);
+    const int cps = cap == 1024 ? 6 : (fb_env("GR_FR_CPS", 9) == 7 ? 7 : 9);
+    const int pf = fb_env("GR_FR_PF", 8) == 4 ? 4 : 8;
+    const int ctas = sms * cps;
     owners = (u32)ctas * 4;
     if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
     const u32 nb = (u32)L.nblocks;
     const u32 R = (nb + owners - 1) / owners;
-    if (cap == 1024) k_fr_scan<1024, 6, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr, 0);
-    else k_fr_scan<512, 9, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr, 0);
+#define FR_GO(C, P, F) k_fr_scan<C, P, F, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr, 0)
+    if (cap == 1024) { if (pf == 4) FR_GO(1024, 6, 4); else FR_GO(1024, 6, 8); }
+    else if (cps == 7) { if (pf == 4) FR_GO(512, 7, 4); else FR_GO(512, 7, 8); }
+    else { if (pf == 4) FR_GO(512, 9, 4); else FR_GO(512, 9, 8); }
+#undef FR_GO
   } else if (sh == 13) {
     owners = (u32)(sms * cps);
     const u32 nb = (u32)L.nblocks;
@@ -1875,18 +1882,19 @@ u32 launch_fr_scan_slot(cudaStream_t s, const DevLayout& L, const u32* bucketed,
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int cap = fb_env("GR_FR_CAP", 512) == 1024 ? 1024 : 512;
-  const int ctas = sms * (cap == 1024 ? 6 : 9);
+  const int cps = cap == 1024 ? 6 : (fb_env("GR_FR_CPS", 9) == 7 ? 7 : 9);
+  const int ctas = sms * cps;
   u32 owners = (u32)ctas * 4;
   if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
   const u32 nb = (u32)L.nblocks;
   const u32 R = (nb + owners - 1) / owners;
-  if (cap == 1024) {
-    k_fr_scan<1024, 6, true><<<owners / 4, 128, 0, s>>>(bucketed, slot_cnt, L, W, bitmap, err, nb, R, slot_cap, gate, 0);
-    k_fr_scan<1024, 6, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, gate, 1);
-  } else {
-    k_fr_scan<512, 9, true><<<owners / 4, 128, 0, s>>>(bucketed, slot_cnt, L, W, bitmap, err, nb, R, slot_cap, gate, 0);
-    k_fr_scan<512, 9, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, gate, 1);
-  }
+#define FR_GO2(C, P) do { \
+    k_fr_scan<C, P, 8, true><<<owners / 4, 128, 0, s>>>(bucketed, slot_cnt, L, W, bitmap, err, nb, R, slot_cap, gate, 0); \
+    k_fr_scan<C, P, 8, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, gate, 1); } while (0)
+  if (cap == 1024) FR_GO2(1024, 6);
+  else if (cps == 7) FR_GO2(512, 7);
+  else FR_GO2(512, 9);
+#undef FR_GO2
   GR_NOTE_LAUNCH(); GR_NOTE_LAUNCH();
   return owners;
 }

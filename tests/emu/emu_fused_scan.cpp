@@ -159,7 +159,7 @@ static Result run_rank(const Layout& Lh, const u32* bucketed, const u32* blk_sta
   memset(bitmap, 0x5A, L.T / 8);
   int err = err0;                                     // what the bucket passes flagged
   const u32 owners = ctas * 4, nb = (u32)L.nblocks, R = (nb + owners - 1) / owners;
-  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, false>(bucketed, blk_start, L, W, bitmap, &err, nb, R, 0u, nullptr, 0); });
+  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, (CAP == 512 ? 4 : 8), false>(bucketed, blk_start, L, W, bitmap, &err, nb, R, 0u, nullptr, 0); });
   Result r = finish(Lh, ws, owners, bitmap, &err);
   free(bitmap);
   return r;
@@ -191,8 +191,8 @@ static Result run_slots(const Layout& Lh, const int4* recs, u64 n, u32 slot_cap,
   u32* bitmap = dalloc<u32>(L.T / 32);
   memset(bitmap, 0x5A, L.T / 8);
   const u32 owners = ctas * 4, nb = (u32)nbk, R = (nb + owners - 1) / owners;
-  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, true>(bucketed, scnt, L, W, bitmap, &err, nb, R, slot_cap, g, 0); });
-  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, false>(bucketed, start, L, W, bitmap, &err, nb, R, 0u, g, 1); });
+  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, (CAP == 512 ? 4 : 8), true>(bucketed, scnt, L, W, bitmap, &err, nb, R, slot_cap, g, 0); });
+  emu::launch(ctas, 128, [&] { k_fr_scan<CAP, 1, (CAP == 512 ? 4 : 8), false>(bucketed, start, L, W, bitmap, &err, nb, R, 0u, g, 1); });
   Result r = finish(Lh, ws, owners, bitmap, &err);
   *overflowed = gate != 0;
   *n_clamped = clamped;
