@@ -69,6 +69,7 @@ VARIANTS = {           # simplest first: a faulting kernel poisons the child's c
     "ur_groups4": {"GR_UR_GROUPS": "4"},
     "cl_tiles4": {"GR_CL_TILES": "4"},
     "ue_warp": {"GR_UE_WARP": "1"},
+    "ue_pair": {"GR_UE_PAIR": "1"},
     "rank512": {"GR_FUSED_RANK": "1"},
     "rank1024": {"GR_FUSED_RANK": "1", "GR_FR_CAP": "1024"},
     "rank512_cps7": {"GR_FUSED_RANK": "1", "GR_FR_CPS": "7"},
@@ -78,6 +79,7 @@ VARIANTS = {           # simplest first: a faulting kernel poisons the child's c
     "rank512_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1"},
     "all": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
     "all_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
+    "all_p2_pair": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1", "GR_UE_PAIR": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
 }
 
 

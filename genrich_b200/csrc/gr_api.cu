@@ -1042,12 +1042,14 @@ static int table_build(gr_ctx* x, u64 n, u32& cap_io, F insert) {
 // K5 for one replicate: -log10 p through the table of distinct (expt, ctrl) pairs.  The table
 // capacity is a remembered guess; an overflow shows up as GR_DE_TABLE at the next materialize()
 // and the stage is simply run again with a larger table (its inputs are still in place).
-static int rep_stage_pvals(gr_ctx* x, Replicate* rep) {
+// inserted: the table was filled by the union emit (GR_UE_PAIR=1); only the evaluation and the gather are left
+static int rep_stage_pvals(gr_ctx* x, Replicate* rep, bool inserted = false) {
   CK(x->slot.ensure((rep->n_upper + 1) * sizeof(u32)));
   const u64* n_dev = rep->cnt.as<u64>();
   stage_begin(x, "pval", rep->n_upper * 16);
-  { int r = table_alloc(x, x->pair_cap); if (r) return r; }
+  if (!inserted) { int r = table_alloc(x, x->pair_cap); if (r) return r; }
   PairTable t = table_view(x, x->pair_cap);
+  if (!inserted)
   launch_pair_insert(x->stream, rep->pExpt.as<float>(), rep->pCtrl.as<float>(), rep->n_upper, n_dev, t,
                      x->slot.as<u32>(), x->d_err);
   launch_pair_eval(x->stream, t);
@@ -1143,7 +1145,20 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
   CK(rep->pVal.ensure((np_upper + 1) * sizeof(float)));
   CK(rep->pExpt.ensure((np_upper + 1) * sizeof(float)));
   CK(rep->pCtrl.ensure((np_upper + 1) * sizeof(float)));
+  const bool fuse_pair = ue_pair_fused();
+  if (fuse_pair) {                                             // the table the emit inserts into
+    CK(x->slot.ensure((np_upper + 1) * sizeof(u32)));
+    int r = table_alloc(x, x->pair_cap);
+    if (r) return r;
+  }
   stage_begin(x, "union_emit", x->T / 4 + np_upper * 12);
+  if (fuse_pair)
+    launch_union_emit_pair(x->stream, x->L, x->bmE.as<u32>(), x->bmC.as<u32>(), x->rankE.as<u64>(),
+                           x->rankC.as<u64>(), rep->rankU.as<u64>(), x->exptVal.as<float>(),
+                           x->ctrlVal.as<float>(), rep->pEnd.as<u32>(), rep->pExpt.as<float>(),
+                           rep->pCtrl.as<float>(), rep->bmU.as<u32>(), rep->chrom_start.as<u64>(),
+                           x->d_totals + 2, table_view(x, x->pair_cap), x->slot.as<u32>(), x->d_err);
+  else
   launch_union_emit(x->stream, x->L, x->bmE.as<u32>(), x->bmC.as<u32>(), x->rankE.as<u64>(),
                     x->rankC.as<u64>(), rep->rankU.as<u64>(), x->exptVal.as<float>(),
                     x->ctrlVal.as<float>(), rep->pEnd.as<u32>(), rep->pExpt.as<float>(),
@@ -1152,7 +1167,7 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
   CKL();
   HT("replicate_tail: union_emit launched");
   stage_end(x);
-  { int r = rep_stage_pvals(x, rep); if (r) return r; }
+  { int r = rep_stage_pvals(x, rep, fuse_pair); if (r) return r; }
   HT("replicate_tail: pvals launched");
 
   rep->present_h.resize(nc);

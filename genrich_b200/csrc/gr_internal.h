@@ -140,6 +140,13 @@ struct PairTable {
 void launch_pair_insert(cudaStream_t s, const float* pExpt, const float* pCtrl, u64 n_upper, const u64* n_dev,
                         const PairTable& t, u32* slot, int* err);
 void launch_pair_eval(cudaStream_t s, const PairTable& t);
+// union emit (warp form) with the pair insert folded in (GR_UE_PAIR=1)
+bool ue_pair_fused();
+void launch_union_emit_pair(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
+                            const u64* rankE, const u64* rankC, const u64* rankU,
+                            const float* exptVal, const float* ctrlVal,
+                            u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
+                            const u64* total, const PairTable& t, u32* slot, int* err);
 void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n_upper, const u64* n_dev, float* out);
 
 // ---- K6: Fisher combine over replicates (combinePval 612, multPval 567) ----------

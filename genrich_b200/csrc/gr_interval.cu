@@ -722,6 +722,134 @@ void launch_pair_insert(cudaStream_t s, const float* pExpt, const float* pCtrl, 
   k_pair_insert<<<capped_grid(n_upper), 256, 0, s>>>(pExpt, pCtrl, n_dev, t, slot, err); GR_NOTE_LAUNCH();
 }
 
+#define WP_UNROLL 2             // entries per lane in flight (4 spills registers next to the 16 bitmap words)
+// k_union_emit_w with K5's table insert folded in (GR_UE_PAIR=1; not the default until it has been measured):
+// the (expt, ctrl) pair of every union interval is in registers here, so the find-or-insert of
+// k_pair_insert happens in place and only the slot is written -- k_pair_insert's pass over pExpt / pCtrl
+// (8 B per interval read again) disappears.  pExpt / pCtrl are still written (the overflow redo and -f / -k read them).
+__global__ void __launch_bounds__(256)
+k_union_emit_wp(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ bmC,
+               const u64* __restrict__ rankE, const u64* __restrict__ rankC,
+               const u64* __restrict__ rankU, const float* __restrict__ exptVal,
+               const float* __restrict__ ctrlVal, u32* __restrict__ pEnd,
+               float* __restrict__ pExpt, float* __restrict__ pCtrl, u32* __restrict__ bmU,
+               u64* __restrict__ chrom_start, u32 nblocks, PairTable t, u32* __restrict__ slot, int* __restrict__ err) {
+  __shared__ u32 sm_ent_all[8 * UW_CAP];          // bits 0-12: cell offset inside the block, 13-31: experimental interval number
+  __shared__ unsigned short sm_ctl_all[8 * UW_CAP];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  u32* const sm_ent = sm_ent_all + w * UW_CAP;
+  unsigned short* const sm_ctl = sm_ctl_all + w * UW_CAP;
+  const u32 blk = blockIdx.x * 8 + w;
+  if (blk >= nblocks) return;                    // warp-uniform
+  u32 E[8], C[8];
+  {
+    const uint4* pe = reinterpret_cast<const uint4*>(bmE + (u64)blk * 256 + lane * 8);
+    const uint4* pc = reinterpret_cast<const uint4*>(bmC + (u64)blk * 256 + lane * 8);
+    const uint4 e0 = pe[0], e1 = pe[1], c0 = pc[0], c1 = pc[1];
+    E[0] = e0.x; E[1] = e0.y; E[2] = e0.z; E[3] = e0.w; E[4] = e1.x; E[5] = e1.y; E[6] = e1.z; E[7] = e1.w;
+    C[0] = c0.x; C[1] = c0.y; C[2] = c0.z; C[3] = c0.w; C[4] = c1.x; C[5] = c1.y; C[6] = c1.z; C[7] = c1.w;
+  }
+  const u64 RE0 = rankE[blk], RC0 = rankC[blk], RU0 = rankU[blk];
+  const int c = L.blk2chrom[blk];
+  const u64 off = L.off[c];
+  const u32 jb = (u32)((u64)blk * GR_BLOCK_SLOTS - off);
+  if (lane == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = RU0;
+  {
+    uint4* pu = reinterpret_cast<uint4*>(bmU + (u64)blk * 256 + lane * 8);
+    pu[0] = make_uint4(E[0] | C[0], E[1] | C[1], E[2] | C[2], E[3] | C[3]);
+    pu[1] = make_uint4(E[4] | C[4], E[5] | C[5], E[6] | C[6], E[7] | C[7]);
+  }
+  u32 pa = 0, pu_ = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) { pa += __popc(E[q]) | (__popc(C[q]) << 16); pu_ += __popc(E[q] | C[q]); }
+  const u32 ia = warp_incl_scan_u32(pa, lane), iu = warp_incl_scan_u32(pu_, lane);
+  const u32 xa = ia - pa, xu = iu - pu_;          // E and C counts travel packed (<= 8192 each)
+  const u32 tot = __shfl_sync(GR_FULL, iu, 31);
+  const u32 tmask = t.cap - 1;
+  bool bad = false;
+  for (u32 lo = 0; lo < tot; lo += UW_CAP) {
+    if (lo) __syncwarp();                        // the previous round's list has been streamed
+    u32 e = xa & 0xffffu, cc = xa >> 16, u = xu;
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      u32 U = E[q] | C[q];
+      const u32 nu = __popc(U);
+      if (u < lo + UW_CAP && u + nu > lo) {
+        const u32 cell0 = (u32)(lane * 256 + q * 32);
+        u32 uu = u;
+        while (U) {
+          const int b = __ffs(U) - 1;
+          const u32 low = (1u << b) - 1;
+          if (uu >= lo && uu < lo + UW_CAP) {
+            sm_ent[uu - lo] = (cell0 + b) | ((e + __popc(E[q] & low)) << 13);
+            sm_ctl[uu - lo] = (unsigned short)(cc + __popc(C[q] & low));
+          }
+          uu++;
+          U &= U - 1;
+        }
+      }
+      u += nu; e += __popc(E[q]); cc += __popc(C[q]);
+    }
+    __syncwarp();
+    const u32 cnt = min(tot - lo, (u32)UW_CAP);
+    for (u32 base = 0; base < cnt; base += 32 * WP_UNROLL) {        // warp-uniform trip count (ballots inside)
+      u32 en[WP_UNROLL], h[WP_UNROLL];
+      float ve[WP_UNROLL], vc[WP_UNROLL];
+      u64 key[WP_UNROLL], k0[WP_UNROLL];
+#pragma unroll
+      for (int q = 0; q < WP_UNROLL; q++) {
+        const u32 i = base + q * 32 + lane;
+        en[q] = 0; ve[q] = 0.0f; vc[q] = 0.0f;
+        if (i < cnt) {
+          en[q] = sm_ent[i];
+          ve[q] = exptVal[RE0 + (en[q] >> 13)];
+          vc[q] = ctrlVal[RC0 + sm_ctl[i]];
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < WP_UNROLL; q++) {                         // the first probe of every key is in flight together
+        key[q] = ((u64)__float_as_uint(ve[q]) << 32) | __float_as_uint(vc[q]);
+        h[q] = mix64(key[q]) & tmask;
+        k0[q] = t.keys[h[q]];
+      }
+      u32 nf = 0;
+#pragma unroll
+      for (int q = 0; q < WP_UNROLL; q++) {
+        const u32 i = base + q * 32 + lane;
+        bool fresh = false;
+        if (i < cnt) {
+          const u32 hs = k0[q] == key[q] ? h[q] : table_upsert(t, key[q], fresh);
+          if (hs == ~0u) bad = true;
+          const u64 uo = RU0 + lo + i;
+          pEnd[uo] = jb + (en[q] & (GR_BLOCK_SLOTS - 1));
+          pExpt[uo] = ve[q];
+          pCtrl[uo] = vc[q];
+          slot[uo] = hs == ~0u ? 0u : hs;
+        }
+        nf += __popc(__ballot_sync(GR_FULL, fresh));
+      }
+      if (lane == 0 && nf) {
+        const u32 tot2 = atomicAdd(t.count, nf) + nf;
+        if (tot2 > (t.cap >> 1)) bad = true;
+      }
+    }
+  }
+  if (bad) atomicOr(err, GR_DE_TABLE);
+}
+
+
+void launch_union_emit_pair(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
+                            const u64* rankE, const u64* rankC, const u64* rankU,
+                            const float* exptVal, const float* ctrlVal,
+                            u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
+                            const u64* total, const PairTable& t, u32* slot, int* err) {
+  k_union_emit_wp<<<(unsigned)((L.nblocks + 7) / 8), 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
+                                                                   pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks, t, slot, err);
+  GR_NOTE_LAUNCH();
+  launch_fill_chrom_start(s, L, chrom_start, total);
+}
+bool ue_pair_fused() { const char* e = getenv("GR_UE_PAIR"); return e && atoi(e) != 0; }
+
 __global__ void __launch_bounds__(128)
 k_pair_eval(PairTable t) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
