@@ -77,5 +77,6 @@ def test_cli_peaks_only_on_device(tmp_path):
         for g, w in zip(got, want):
             gf, wf = g.split("\t"), w.split("\t")
             assert gf[:4] == wf[:4] and gf[9] == wf[9], (name, g, w)          # name, start, end, peak_N, summit
-            for i in (6, 7, 8):                                               # the device's own -f text can differ in the 6th decimal
-                assert abs(float(gf[i]) - float(wf[i])) <= 1e-4 + 2e-6 * abs(float(wf[i])), (name, g, w)
+            for i in (6, 7, 8):      # the device's own -f text can differ from the reference's in the 6th decimal of p / q;
+                                     # the AUC (column 6) sums such differences over up to ~1000 bp
+                assert abs(float(gf[i]) - float(wf[i])) <= 1e-4 + (1e-5 if i == 6 else 2e-6) * abs(float(wf[i])), (name, g, w)
