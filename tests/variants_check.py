@@ -89,7 +89,7 @@ def main():
     assert b[0].sample_stats[0].n_clamped == 3
     # 200 Mbp / 4 M + 4 M fragments with hot spots: thousands of events in one block, many pages per owner
     # (under emulation: a tenth of it)
-    scale = 10 if os.environ.get("GR_EMU_AS_CUDA") else 1
+    scale = int(os.environ.get("GR_EMU_SCALE", "10")) if os.environ.get("GR_EMU_AS_CUDA") else 1
     L = [x // scale for x in (60_000_000, 50_000_000, 40_000_000, 30_000_000, 20_000_000)]
     t = Workload(L, 4_000_000 // scale, 101, enrich=0.5, spacing=400000 // scale, sigma=60.0).fragments()
     c = Workload(L, 4_000_000 // scale, 102, enrich=0.0).fragments()
