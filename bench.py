@@ -65,6 +65,7 @@ SAMPLE = dict(chrom_len=[50_000_000] * 8, nt=6_500_000, nc=6_500_000)
 # headline with it), asserts that the peaks are the default path's byte for byte, and reports
 # ms per step under "variants" -- information for the next round, never part of `value` / `e2e`.
 VARIANTS = {           # simplest first: a faulting kernel poisons the child's context for everything after it
+    "rm_per8": {"GR_RM_PER": "8"},
     "ur_groups2": {"GR_UR_GROUPS": "2"},
     "ur_groups4": {"GR_UR_GROUPS": "4"},
     "cl_tiles4": {"GR_CL_TILES": "4"},

@@ -18,6 +18,7 @@ VARIANTS = {
     "rank512_slots": ["GR_FUSED_RANK=1", "GR_FB_SLOTS=1"],
     "ue_warp": ["GR_UE_WARP=1"],
     "ue_pair": ["GR_UE_PAIR=1"],
+    "rm_per8": ["GR_RM_PER=8"],
     "ur_groups4": ["GR_UR_GROUPS=4"],
     "cl_tiles4": ["GR_CL_TILES=4"],
     "p2": ["GR_FB_P2=1"],
