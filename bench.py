@@ -86,18 +86,29 @@ VARIANTS = {           # simplest first: a faulting kernel poisons the child's c
 
 def run_variant_probe(a, timeout=300):
     cmd = [sys.executable, os.path.abspath(__file__), "--variant-probe", "--steps", "3", "--workload", a.workload]
+    def last_json(text):
+        for line in reversed((text or "").strip().split("\n")):
+            if line.startswith("{"):
+                try:
+                    return json.loads(line)
+                except ValueError:
+                    continue
+        return None
     try:
         p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
-    except subprocess.TimeoutExpired:
-        return {"error": "variant probe timed out after %d s" % timeout}
+    except subprocess.TimeoutExpired as e:
+        # the child prints the results so far after every variant: a variant that hangs costs only itself
+        out = e.stdout.decode() if isinstance(e.stdout, bytes) else e.stdout
+        got = last_json(out) or {}
+        got["error"] = "variant probe timed out after %d s (results so far kept)" % timeout
+        return got
     except Exception as e:
         return {"error": repr(e)[:300]}
-    for line in reversed(p.stdout.strip().split("\n")):
-        if line.startswith("{"):
-            try:
-                return json.loads(line)
-            except ValueError:
-                break
+    got = last_json(p.stdout)
+    if got is not None:
+        if p.returncode:
+            got["error"] = "variant probe exit %d: %s" % (p.returncode, (p.stderr or "")[-300:])
+        return got
     return {"error": "variant probe exit %d: %s" % (p.returncode, (p.stderr or p.stdout)[-300:])}
 
 
@@ -432,7 +443,7 @@ def main():
                         eng_v.ctx.close()              # its device buffers go back before the next variant allocates
                     except Exception:
                         pass
-        print(json.dumps(out))
+            print(json.dumps(out), flush=True)         # cumulative: the parent keeps the last complete line
         return
 
     t_w0 = time.time()
