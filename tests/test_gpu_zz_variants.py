@@ -12,26 +12,35 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-VARIANTS = {
-    "rank512": ["GR_FUSED_RANK=1"],
-    "rank1024": ["GR_FUSED_RANK=1", "GR_FR_CAP=1024"],
-    "rank512_slots": ["GR_FUSED_RANK=1", "GR_FB_SLOTS=1"],
-    "ue_warp": ["GR_UE_WARP=1"],
-    "ue_pair": ["GR_UE_PAIR=1"],
+VARIANTS = {           # simplest first
     "rm_per8": ["GR_RM_PER=8"],
     "ur_groups4": ["GR_UR_GROUPS=4"],
     "cl_tiles4": ["GR_CL_TILES=4"],
+    "ue_warp": ["GR_UE_WARP=1"],
+    "ue_pair": ["GR_UE_PAIR=1"],
+    "rank512": ["GR_FUSED_RANK=1"],
+    "rank1024": ["GR_FUSED_RANK=1", "GR_FR_CAP=1024"],
     "p2": ["GR_FB_P2=1"],
-    "all_p2": ["GR_FUSED_RANK=1", "GR_FB_P2=1", "GR_UE_WARP=1", "GR_UR_GROUPS=4", "GR_CL_TILES=4"],
-    "all": ["GR_FUSED_RANK=1", "GR_FB_SLOTS=1", "GR_UE_WARP=1", "GR_UR_GROUPS=4", "GR_CL_TILES=4"],
+    "rank512_slots": ["GR_FUSED_RANK=1", "GR_FB_SLOTS=1"],
+    "all": ["GR_FUSED_RANK=1", "GR_FB_SLOTS=1", "GR_UE_WARP=1", "GR_UR_GROUPS=4", "GR_CL_TILES=4", "GR_RM_PER=8"],
+    "all_p2": ["GR_FUSED_RANK=1", "GR_FB_P2=1", "GR_UE_PAIR=1", "GR_UR_GROUPS=4", "GR_CL_TILES=4", "GR_RM_PER=8"],
 }
 
 
+_HUNG = []          # a variant that ran into its time limit: the ones after it are skipped (the GPU run has a budget)
+
+
 @pytest.mark.xfail(reason="variant not yet run on a device (CPU-emulated only)", strict=False)
-@pytest.mark.parametrize("name", sorted(VARIANTS))
+@pytest.mark.parametrize("name", list(VARIANTS))          # simplest first
 def test_variant_same_bits_as_default(name):
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "variants_check.py")] + VARIANTS[name],
-                       capture_output=True, text=True, timeout=420)
+    if _HUNG:
+        pytest.skip("variant %s ran into its time limit; the remaining variants are not started" % _HUNG[0])
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "variants_check.py")] + VARIANTS[name],
+                           capture_output=True, text=True, timeout=150)
+    except subprocess.TimeoutExpired:
+        _HUNG.append(name)
+        raise
     print(p.stdout[-2000:], p.stderr[-4000:])
     assert p.returncode == 0
 
