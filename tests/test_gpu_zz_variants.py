@@ -71,7 +71,7 @@ def test_cli_peaks_only_on_device(tmp_path):
                 bedf = os.path.join(td, "x.bed")
                 util.write_case_bed(case, bedf)
                 cmd += ["-E", bedf]
-            subprocess.run(cmd, check=True, stderr=subprocess.DEVNULL)
+            subprocess.run(cmd, check=True, stderr=subprocess.DEVNULL, timeout=120)
             logs[cname] = logf
         out = str(tmp_path / (name + ".np"))
         cmd = [cli, "-P", "-f", logs[cname], "-o", out] + meta["args"]
@@ -79,7 +79,7 @@ def test_cli_peaks_only_on_device(tmp_path):
             bedf = str(tmp_path / (name + ".bed"))
             util.write_case_bed(BY_NAME[meta["bed_case"]], bedf)
             cmd += ["-E", bedf]
-        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True, timeout=120)
         assert r.returncode == 0, (name, r.stderr)
         got = open(out).read().split("\n")[:-1]
         want = open(os.path.join(golden, name + ".narrowPeak")).read().split("\n")[:-1]
