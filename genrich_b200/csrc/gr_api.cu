@@ -704,6 +704,7 @@ static int consume_segments(gr_ctx* x, int* built) {
       // One pass over the records; the exact chain below runs behind it, gated on the overflow flag.
       u64 cap = 256;
       while (cap < 4 * (x->n_pushed / (nbk ? nbk : 1) + 1)) cap <<= 1;
+      if (const char* e = getenv("GR_FB_SLOT_CAP")) cap = strtoull(e, nullptr, 10) ? strtoull(e, nullptr, 10) : cap;   // tests: force the overflow path
       if (nbk * cap < (1ull << 32)) {
         x->slot_cap = (u32)cap;
         CK(x->sbBucket.ensure(nbk * cap * 4));

@@ -31,6 +31,8 @@ MODES = {
     "rank512": dict(FUSED, GR_FUSED_RANK="1"),
     "rank1024_slots": dict(FUSED, GR_FUSED_RANK="1", GR_FR_CAP="1024", GR_FB_SLOTS="1"),
     "p2": dict(FUSED, GR_FB_P2="1"),
+    # slots of 4 entries overflow in every sample: the device-side gate hands the sample to the exact chain
+    "slots_overflow": dict(FUSED, GR_FUSED_RANK="1", GR_FB_SLOTS="1", GR_FB_SLOT_CAP="4"),
     "all": dict(FUSED, GR_FUSED_RANK="1", GR_FB_SLOTS="1", GR_UE_WARP="1", GR_UR_GROUPS="4", GR_CL_TILES="4"),
     "all_p2": dict(FUSED, GR_FUSED_RANK="1", GR_FB_P2="1", GR_UE_WARP="1", GR_UR_GROUPS="2", GR_CL_TILES="4"),
     "all_p2_pair": dict(FUSED, GR_FUSED_RANK="1", GR_FR_CPS="7", GR_FR_PF="4", GR_FB_P2="1", GR_UE_PAIR="1", GR_UR_GROUPS="4", GR_CL_TILES="4"),
