@@ -3,29 +3,38 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
 
-One "step" = one whole pass of the hot path over one synthetic batch: zero the
-dense delta arrays, scatter the treatment intervals, integrate, same for the
-control, lambda / scale factor, control sweep, breakpoint union, -log10 p, (BH),
-peak scan, peaks back on the host.  At N = 1 the workload is BASELINE.json
-configs[1]: hg38-sized genome (25 chromosomes, 3.09 Gbp), 50 M treatment + 50 M
-control paired-end fragments, default peak calling (-p 0.01).  For N > 1 the same
-genome is sharded by chromosome over the ranks (strong scaling; torchrun, NCCL).
+One "step" = one whole pass of the hot path over one synthetic batch: for every replicate the
+treatment records are bucketed and integrated, same for its control, lambda / scale factor,
+control sweep, breakpoint union, -log10 p; then (Fisher combine), (Benjamini-Hochberg incl. the
+histogram all-gather at N > 1), the peak scan, and the peaks back on the host.
+
+Workloads (BASELINE.json `configs`; --workload):
+  hg38_chip_50M_50M   configs[1]  hg38-sized (25 chromosomes, 3.09 Gbp), 50 M + 50 M fragments, -p 0.01
+                                  -- the configuration the metric is quoted on; the default at every N
+  hg38_atac_100M_q    configs[2]  ATAC (-j -d 100), 100 M fragments, -q 0.05
+  hg38_fisher3        configs[3]  3 replicates x 50 M + 1 control, Fisher's method, -p 0.01
+  g10_multimap_1B_q   configs[4]  10 Gbp (40 x 250 Mbp), 1 B fragments, 30 % multimapped (-s 20), -q 0.05
+                                  (needs >= 8 GPUs' worth of memory: run it with --gpus 8)
+  g10_shard_125M_q                one rank's share of configs[4] (5 x 250 Mbp, 125 M fragments): its 1-GPU twin
+  mini                            quick functional run
+For N > 1 the same genome is sharded by chromosome over the ranks (strong scaling; torchrun, NCCL).
 
 `value`  = genome bp / device time per step, interval records already in HBM.
-`e2e`    = same through gr_push_packed() from PINNED HOST buffers (H2D copies
-           inside the timed region) and peak records read back to the host.
-`roofline` is for the dominant kernel, the per-base dense scan (k_scan_stream):
-           4 B per delta cell per launch / mean launch time (CUDA events on the
-           library's stream) against the measured HBM copy bandwidth.  Its
-           companion `scan_place` (moves the breaks to their final rank, 16 B per
-           interval) is timed as a stage of its own and quoted next to it.
-`cpu_baseline` / --impl reference: the UNMODIFIED reference binary
-           (oracle/_ref/Genrich, built by `make -C oracle ref` where the sources
-           are) on the SAM view of a bounded sample of the same workload (8 x 50 Mbp,
-           6.5 M + 6.5 M fragments: the workload's depth; ~19 s per run), 1 host
-           core (the reference is single-threaded, README.md:535).
+`e2e`    = same through gr_push_packed6 / gr_push_packed from PINNED HOST buffers (H2D copies inside
+           the timed region) with the peak records read back to the host.
+`roofline` is for the per-base pass (k_fr_scan): ALGORITHMIC bytes (4 B per delta cell per sample
+           array) / mean launch time, next to what the kernel and the whole step really
+           move through DRAM (`traffic`, `frac_dram`, `step`), from the committed ncu pass
+           profiles/r02_dram_by_stage.json, and to the dense formulation (k_scan_stream).
+`parity` = in-run gate: bounded samples pushed through the GPU and compared with the narrowPeak
+           files the UNMODIFIED reference wrote for the same SAM view in this very run.
+`cpu_baseline` / --impl reference: oracle/_ref/Genrich (built by `make -C oracle ref` where the
+           sources are) on the SAM view of a bounded, depth-matched sample of the workload, 1 host core
+           (the reference is single-threaded, README.md:535); `hot_path` = the share of that time spent
+           in the functions of the path (gprof, -pg build), i.e. without SAM parsing.
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -43,99 +52,49 @@ sys.path.insert(0, ROOT)
 HG38 = [248956422, 242193529, 198295559, 190214555, 181538259, 170805979, 159345973, 145138636,
         138394717, 133797422, 135086622, 133275309, 114364328, 107043718, 101991189, 90338345,
         83257441, 80373285, 58617616, 64444167, 46709983, 50818468, 156040895, 57227415, 16569]
+G10 = [250_000_000] * 40
 
+# reps: per replicate (treatment fragments, control fragments or 0).  sample: the bounded CPU sample of
+# the same shape and depth (same generator) that the reference is timed and the parity gate is run on.
 WORKLOADS = {
-    # BASELINE.json configs[1]
-    "hg38_chip_50M_50M": dict(chrom_len=HG38, nt=50_000_000, nc=50_000_000, q=None, p=0.01, atac=False,
-                              spacing=60000, sigma=150.0, enrich=0.25),
-    # configs[2]: ATAC mode, 100 M fragments, -q 0.05
-    "hg38_atac_100M_q": dict(chrom_len=HG38, nt=100_000_000, nc=0, q=0.05, p=None, atac=True,
-                             spacing=60000, sigma=60.0, enrich=0.3),
-    # quick functional run
-    "mini": dict(chrom_len=[60_000_000, 40_000_000, 20_000_000], nt=2_000_000, nc=2_000_000, q=None, p=0.01,
-                 atac=False, spacing=40000, sigma=100.0, enrich=0.3),
+    "hg38_chip_50M_50M": dict(chrom_len=HG38, reps=[(50_000_000, 50_000_000)], q=None, p=0.01, atac=False,
+                              spacing=60000, sigma=150.0, enrich=0.25, multimap=0.0,
+                              sample=dict(chrom_len=[50_000_000] * 8, reps=[(6_500_000, 6_500_000)])),
+    # ATAC without a control: lambda ~ 6.5, and the log-normal tail at mu < 7 is heavy (a 50-fold pileup is only
+    # -log10 p = 5.9 < log10 G: "All q-values are 1") -- few, tall, narrow sites so that the reference calls peaks under -q
+    "hg38_atac_100M_q": dict(chrom_len=HG38, reps=[(100_000_000, 0)], q=0.05, p=None, atac=True,
+                             spacing=1_000_000, sigma=40.0, enrich=0.4, multimap=0.0,
+                             sample=dict(chrom_len=[50_000_000] * 4, reps=[(6_500_000, 0)])),
+    "hg38_fisher3": dict(chrom_len=HG38, reps=[(50_000_000, 50_000_000), (50_000_000, 0), (50_000_000, 0)],
+                         q=None, p=0.01, atac=False, spacing=60000, sigma=150.0, enrich=0.25, multimap=0.0,
+                         sample=dict(chrom_len=[50_000_000] * 4, reps=[(3_250_000, 3_250_000), (3_250_000, 0), (3_250_000, 0)])),
+    "g10_multimap_1B_q": dict(chrom_len=G10, reps=[(1_000_000_000, 0)], q=0.05, p=None, atac=False,
+                              spacing=60000, sigma=150.0, enrich=0.25, multimap=0.3,
+                              sample=dict(chrom_len=[50_000_000], reps=[(5_000_000, 0)])),
+    "g10_shard_125M_q": dict(chrom_len=G10[:5], reps=[(125_000_000, 0)], q=0.05, p=None, atac=False,
+                             spacing=60000, sigma=150.0, enrich=0.25, multimap=0.3,
+                             sample=dict(chrom_len=[50_000_000], reps=[(5_000_000, 0)])),
+    "mini": dict(chrom_len=[60_000_000, 40_000_000, 20_000_000], reps=[(2_000_000, 2_000_000)], q=None, p=0.01,
+                 atac=False, spacing=40000, sigma=100.0, enrich=0.3, multimap=0.0,
+                 sample=dict(chrom_len=[20_000_000] * 2, reps=[(700_000, 700_000)])),
 }
-# bounded CPU sample (same generator, same depth as the workload: 50 M fragments x 400 Mbp / 3.09 Gbp): ~19 s per run
-SAMPLE = dict(chrom_len=[50_000_000] * 8, nt=6_500_000, nc=6_500_000)
-
-
-# Kernel variants that exist behind environment knobs but are not the default because they have not
-# been timed on a B200 yet (written where no GPU was at hand and checked on the CPU by tests/emu).
-# The default run times each of them in a CHILD process (a fault or a hang there cannot take the
-# headline with it), asserts that the peaks are the default path's byte for byte, and reports
-# ms per step under "variants" -- information for the next round, never part of `value` / `e2e`.
-VARIANTS = {           # simplest first: a faulting kernel poisons the child's context for everything after it
-    "rm_per8": {"GR_RM_PER": "8"},
-    "ur_groups2": {"GR_UR_GROUPS": "2"},
-    "ur_groups4": {"GR_UR_GROUPS": "4"},
-    "cl_tiles4": {"GR_CL_TILES": "4"},
-    "ue_warp": {"GR_UE_WARP": "1"},
-    "ue_pair": {"GR_UE_PAIR": "1"},
-    "rank512": {"GR_FUSED_RANK": "1"},
-    "rank1024": {"GR_FUSED_RANK": "1", "GR_FR_CAP": "1024"},
-    "rank512_cps7": {"GR_FUSED_RANK": "1", "GR_FR_CPS": "7"},
-    "rank512_pf4": {"GR_FUSED_RANK": "1", "GR_FR_PF": "4"},
-    "p2": {"GR_FB_P2": "1"},
-    "rank512_slots": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1"},
-    "rank512_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1"},
-    "all": {"GR_FUSED_RANK": "1", "GR_FB_SLOTS": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
-    "all_p2": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1", "GR_UE_WARP": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
-    "all_p2_pair": {"GR_FUSED_RANK": "1", "GR_FB_P2": "1", "GR_UE_PAIR": "1", "GR_UR_GROUPS": "4", "GR_CL_TILES": "4"},
+# what the default run pushes through BOTH the reference and the GPU (the in-run parity gate):
+# the workload's own sample plus one -q and one Fisher + -q sample, so that BH and the combine are reference-checked too
+GATE_EXTRA = {
+    "atac_q": dict(chrom_len=[30_000_000] * 2, reps=[(2_000_000, 0)], q=0.05, p=None, atac=True,
+                   spacing=500_000, sigma=40.0, enrich=0.4, multimap=0.0),
+    "fisher_multimap_q": dict(chrom_len=[12_000_000], reps=[(350_000, 350_000), (350_000, 0), (350_000, 0)],
+                              q=0.05, p=None, atac=False, spacing=60000, sigma=150.0, enrich=0.3, multimap=0.3),
 }
+HOT_FUNCS = ("saveInterval", "addFrac", "subFrac", "savePileupExpt", "savePileupCtrl", "savePileupNoCtrl", "saveLambda",
+             "saveConst", "calcLambda", "calcFactor", "updateVal", "getVal", "savePval", "countIntervals", "calcPval",
+             "plnorm", "pnorm", "do_del", "combinePval", "countIntervals2", "multPval", "pchisq", "pgamma",
+             "pgamma_smallx", "pd_upper_series", "pd_lower_series", "dpois", "stirlerr", "bd0", "computeQval",
+             "hashPval", "recordPval", "jenkins_one_at_a_time_hash", "collectPval", "saveQval", "quickSort",
+             "partition", "lookup", "findPeaks", "callPeaks", "updatePeak", "checkPeak", "resetVars")
 
 
-def run_variant_probe(a, timeout=300):
-    cmd = [sys.executable, os.path.abspath(__file__), "--variant-probe", "--steps", "3", "--workload", a.workload]
-    def last_json(text):
-        for line in reversed((text or "").strip().split("\n")):
-            if line.startswith("{"):
-                try:
-                    return json.loads(line)
-                except ValueError:
-                    continue
-        return None
-    try:
-        p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
-    except subprocess.TimeoutExpired as e:
-        # the child prints the results so far after every variant: a variant that hangs costs only itself
-        out = e.stdout.decode() if isinstance(e.stdout, bytes) else e.stdout
-        got = last_json(out) or {}
-        got["error"] = "variant probe timed out after %d s (results so far kept)" % timeout
-        return got
-    except Exception as e:
-        return {"error": repr(e)[:300]}
-    got = last_json(p.stdout)
-    if got is not None:
-        if p.returncode:
-            got["error"] = "variant probe exit %d: %s" % (p.returncode, (p.stderr or "")[-300:])
-        return got
-    return {"error": "variant probe exit %d: %s" % (p.returncode, (p.stderr or p.stdout)[-300:])}
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum of one k_scan_stream launch (bytes), from the
-# committed ncu capture of exactly this command; null for configurations that were not captured
-NCU_TRAFFIC = {("hg38_chip_50M_50M", 1, "k_scan_stream"): 12.36e9 + 1.10e9,      # built array: nothing to clear behind
-               ("hg38_chip_50M_50M", 1, "k_fb_scan"): 0.225e9 + 1.051e9}
-
-
-def gen_fragments(chrom_len, n, seed, enrich, spacing, sigma, threads=8):
-    from genrich_b200.synth import Workload
-    w = Workload(chrom_len, n, seed, enrich=enrich, spacing=spacing, sigma=sigma)
-    out = np.empty((n, 4), dtype=np.int32)
-    step = (n + threads - 1) // threads
-    ths = []
-    for i in range(threads):
-        a, b = i * step, min(n, (i + 1) * step)
-        if a >= b:
-            break
-        t = threading.Thread(target=w.fragments, args=(a, b - a, out[a:b]))
-        t.start()
-        ths.append(t)
-    for t in ths:
-        t.join()
-    return out
-
-
+# --------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md).
 
@@ -204,38 +163,351 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def peaks_sha256(peaks):
+    """Hash of what the parity bar makes bit-exact: chromosome, start, end, summit of every peak, in order."""
+    h = hashlib.sha256()
+    for f in ("chrom", "start", "end", "summit"):
+        h.update(np.ascontiguousarray(peaks[f]).astype(np.int64).tobytes())
+    return h.hexdigest()
+
+
 # --------------------------------------------------------------------------------------
-def reference_sample_run(steps, warmup):
-    """Time the unmodified reference on the SAM view of the bounded sample."""
+# workload generation: per chromosome (own seed), so that a rank generates only what it owns and
+# every N sees the same genome-wide data; in chunks, so that the host footprint stays small at 1 B fragments
+CHUNK = 4_000_000
+
+
+def chrom_share(chrom_len, n):
+    """fragments per chromosome, proportional to length (largest remainder: sums to n exactly)"""
+    L = np.asarray(chrom_len, dtype=np.float64)
+    raw = L / L.sum() * n
+    base = np.floor(raw).astype(np.int64)
+    rest = int(n - base.sum())
+    if rest:
+        base[np.argsort(-(raw - base), kind="stable")[:rest]] += 1
+    return base
+
+
+def gen_tasks(wl, n, seed, enrich, owned):
+    share = chrom_share(wl["chrom_len"], n)
+    tasks = []
+    for c, nc in enumerate(share):
+        if not owned[c]:
+            continue
+        chunk = CHUNK // 4 if wl["multimap"] else CHUNK       # the generator reserves 10 records per multimapped fragment
+        for first in range(0, int(nc), chunk):
+            tasks.append((c, first, min(chunk, int(nc) - first), seed * 1000 + c, enrich))
+    return tasks
+
+
+def run_tasks(wl, tasks, consume, threads=8):
+    """consume(idx, records int32 (m, 4)) is called from worker threads, once per task"""
     from genrich_b200.synth import Workload
-    ref = os.path.join(ROOT, "oracle", "_ref", "Genrich")
-    wl = WORKLOADS["hg38_chip_50M_50M"]
-    L = SAMPLE["chrom_len"]
-    td_ = tempfile.mkdtemp(prefix="grbench_")
-    tp, cp, op = (os.path.join(td_, x) for x in ("t.sam", "c.sam", "o.np"))
-    Workload(L, SAMPLE["nt"], 3001, enrich=wl["enrich"], spacing=wl["spacing"], sigma=wl["sigma"]).write_sam(tp)
-    Workload(L, SAMPLE["nc"], 3002, enrich=0.0).write_sam(cp)
-    G = sum(L)
-    kind = "reference"
-    cmd = [ref, "-t", tp, "-c", cp, "-o", op, "-p", "0.01"]
-    if not os.path.exists(ref):
-        raise SystemExit("oracle/_ref/Genrich missing: run `make -C oracle ref` where /root/reference exists")
-    times = []
-    for i in range(warmup + steps):
-        t0 = time.perf_counter()
-        subprocess.check_call(cmd, stderr=subprocess.DEVNULL)
-        dt = time.perf_counter() - t0
-        if i >= warmup:
-            times.append(dt)
-    npk = sum(1 for _ in open(op))
-    for f in (tp, cp, op):
-        os.unlink(f)
-    os.rmdir(td_)
-    sec = sum(times) / len(times)
-    return {"value": G / 1e9 / sec, "unit": "Gbp/s", "cores": 1, "kind": kind,
-            "sample": "%d chrom x %d bp, %d + %d fragments (same generator), whole program incl. SAM parse, %.2f s/run, %d peaks"
-                      % (len(L), L[0], SAMPLE["nt"], SAMPLE["nc"], sec, npk),
-            "host_cores_available": os.cpu_count()}, sec
+    lock = threading.Lock()
+    it = iter(enumerate(tasks))
+
+    def work():
+        while True:
+            with lock:
+                nx = next(it, None)
+            if nx is None:
+                return
+            i, (c, first, m, seed, enrich) = nx
+            w = Workload([wl["chrom_len"][c]], first + m, seed, enrich=enrich, spacing=wl["spacing"], sigma=wl["sigma"],
+                         multimap=wl["multimap"])
+            fr = w.fragments(first, m)               # ctypes releases the GIL: the workers run in parallel
+            fr[:, 0] = c
+            consume(i, fr)
+    ths = [threading.Thread(target=work) for _ in range(threads)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+
+
+class Sample:
+    """One input file's worth of interval records: 8-byte words in HBM (device arm), 6- or 8-byte records in
+    pinned host memory (e2e arm)."""
+
+    def __init__(self, torch, host_mod, eng, wl, n, seed, enrich, dev, use6, threads, tag):
+        layout6 = eng.ctx.pack6_layout() if use6 else None
+        L = wl["chrom_len"]
+        # GR_BENCH_CACHE=<dir>: packed records are kept there between runs of one session (the generator is
+        # deterministic; a profiling session runs bench.py many times on the same workload)
+        cache = os.environ.get("GR_BENCH_CACHE")
+        f8 = os.path.join(cache, tag + ".p8.npy") if cache else None
+        f6 = os.path.join(cache, tag + ".p6.npy") if cache else None
+        if cache and os.path.exists(f8) and (layout6 is None or os.path.exists(f6)):
+            p8 = [np.load(f8)]
+            p6 = [np.load(f6)] if layout6 is not None else []
+        else:
+            tasks = gen_tasks(wl, n, seed, enrich, eng.owned)
+            p8 = [None] * len(tasks)
+            p6 = [None] * len(tasks)
+
+            def consume(i, fr):
+                iv = host_mod.fragments_to_intervals(fr, atac=wl["atac"])
+                a, rest = host_mod.pack_records(iv)
+                assert rest.shape[0] == 0, "synthetic workload has records that do not pack"
+                p8[i] = a
+                if layout6 is not None:
+                    b, rest6 = host_mod.pack6_records(iv, layout6, L)
+                    assert rest6.shape[0] == 0, "synthetic workload has records that do not fit 6 bytes"
+                    p6[i] = b.reshape(-1)
+            run_tasks(wl, tasks, consume, threads)
+            if cache:
+                os.makedirs(cache, exist_ok=True)
+                np.save(f8, np.concatenate(p8) if p8 else np.empty(0, np.uint64))
+                if layout6 is not None:
+                    np.save(f6, np.concatenate(p6) if p6 else np.empty(0, np.uint16))
+        self.n = int(sum(len(a) for a in p8))
+        self.fmt = 6 if layout6 is not None else 8
+        self.dev = torch.empty(max(self.n, 1), dtype=torch.int64, device=dev)
+        at = 0
+        for a in p8:                                 # chunk by chunk: no second full-size host copy
+            self.dev[at:at + len(a)].copy_(torch.from_numpy(a.view(np.int64)))
+            at += len(a)
+        if self.fmt == 6:
+            self.host = torch.empty(max(3 * self.n, 1), dtype=torch.int16).pin_memory()
+            at = 0
+            for b in p6:
+                self.host[at:at + len(b)].copy_(torch.from_numpy(b.view(np.int16)))
+                at += len(b)
+        else:
+            self.host = torch.empty(max(self.n, 1), dtype=torch.int64).pin_memory()
+            at = 0
+            for a in p8:
+                self.host[at:at + len(a)].copy_(torch.from_numpy(a.view(np.int64)))
+                at += len(a)
+        self.host_bytes = self.fmt * self.n
+
+    def push_dev(self, c):
+        c.push_packed_ptr(self.dev.data_ptr(), self.n)
+
+    def push_host(self, c):
+        (c.push_packed6_ptr if self.fmt == 6 else c.push_packed_ptr)(self.host.data_ptr(), self.n)
+
+    def prefetch(self, c):
+        (c.prefetch_packed6_ptr if self.fmt == 6 else c.prefetch_packed_ptr)(self.host.data_ptr(), self.n)
+
+
+class Feeder:
+    """e2e arm: the samples of a step in push order, cyclic.  The library has two prefetch slots; a slot
+    is free again once the pileup that read it has been enqueued.  top_up() is called right after pileups
+    were enqueued (no slot in use), so len(ahead) == slots whose copy is under way or done."""
+
+    def __init__(self, order, depth):
+        self.order, self.depth = order, depth
+        self.seq = 0                                 # sequence number of the next push
+        self.ahead = []                              # sequence numbers prefetched and not pushed yet
+
+    def top_up(self, c):
+        while len(self.ahead) < self.depth:
+            k = (self.ahead[-1] if self.ahead else self.seq - 1) + 1
+            s = self.order[k % len(self.order)]
+            if s.n:
+                s.prefetch(c)
+            self.ahead.append(k)
+
+    def push(self, c):
+        self.top_up(c)                               # the previous sample's pileup is enqueued by now
+        if self.ahead and self.ahead[0] == self.seq:
+            self.ahead.pop(0)
+        self.order[self.seq % len(self.order)].push_host(c)
+        self.seq += 1
+
+
+# --------------------------------------------------------------------------------------
+# the unmodified reference on the SAM view of a bounded sample
+def sample_workloads(spec, wl):
+    """one classic multi-chromosome Workload per input file of the sample (SAM view and records agree)"""
+    from genrich_b200.synth import Workload
+    L = spec["chrom_len"]
+    out = []
+    for r, (nt, nc) in enumerate(spec["reps"]):
+        t = Workload(L, nt, 3001 + 10 * r, enrich=wl["enrich"], spacing=wl["spacing"], sigma=wl["sigma"], multimap=wl["multimap"])
+        c = Workload(L, nc, 3002 + 10 * r, enrich=0.0, multimap=wl["multimap"]) if nc else None
+        out.append((t, c))
+    return out
+
+
+def ref_args(wl):
+    a = ["-q", "%g" % wl["q"]] if wl["q"] else ["-p", "%g" % wl["p"]]
+    if wl["atac"]:
+        a += ["-j", "-d", "100"]
+    if wl["multimap"]:
+        a += ["-s", "20"]
+    return a
+
+
+def parse_narrowpeak(path):
+    rows = []
+    for line in open(path):
+        f = line.rstrip("\n").split("\t")
+        rows.append((int(f[0][3:]) - 1, int(f[1]), int(f[2]), int(f[9]), float(f[7]), float(f[8])))
+    return rows
+
+
+class RefSample:
+    """SAM files of a bounded sample on disk + the reference's own runs on them."""
+
+    def __init__(self, spec, wl, name):
+        self.spec, self.wl, self.name = spec, wl, name
+        self.dir = tempfile.mkdtemp(prefix="grbench_")
+        self.wls = sample_workloads(spec, wl)
+        self.tfiles, self.cfiles = [], []
+        for r, (t, c) in enumerate(self.wls):
+            tp = os.path.join(self.dir, "t%d.sam" % r)
+            t.write_sam(tp)
+            self.tfiles.append(tp)
+            if c is not None:
+                cp = os.path.join(self.dir, "c%d.sam" % r)
+                c.write_sam(cp)
+                self.cfiles.append(cp)
+            else:
+                self.cfiles.append("null")
+        self.G = sum(spec["chrom_len"])
+        self.out = os.path.join(self.dir, "ref.narrowPeak")
+
+    def cmd(self, binary, out):
+        c = [binary, "-t", ",".join(self.tfiles), "-o", out] + ref_args(self.wl)
+        if any(x != "null" for x in self.cfiles):
+            c += ["-c", ",".join(self.cfiles)]
+        return c
+
+    def run_reference(self, runs=1):
+        ref = os.path.join(ROOT, "oracle", "_ref", "Genrich")
+        if not os.path.exists(ref):
+            raise SystemExit("oracle/_ref/Genrich missing: run `make -C oracle ref` where /root/reference exists")
+        times = []
+        for _ in range(runs):
+            t0 = time.perf_counter()
+            subprocess.check_call(self.cmd(ref, self.out), stderr=subprocess.DEVNULL)
+            times.append(time.perf_counter() - t0)
+        return times
+
+    def hot_path(self, wall):
+        """share of the reference's time spent in the functions of the path: -pg build, gprof self time of the
+        path's functions, scaled by wall / wall_pg (the instrumented run is slower)"""
+        pg = os.path.join(ROOT, "oracle", "_ref", "Genrich_pg")
+        if not os.path.exists(pg):
+            return None
+        try:
+            t0 = time.perf_counter()
+            subprocess.check_call(self.cmd(pg, os.path.join(self.dir, "pg.narrowPeak")), stderr=subprocess.DEVNULL, cwd=self.dir)
+            wall_pg = time.perf_counter() - t0
+            txt = subprocess.run(["gprof", "-b", "-p", pg, os.path.join(self.dir, "gmon.out")], capture_output=True,
+                                 text=True, timeout=120).stdout
+        except (OSError, subprocess.SubprocessError):
+            return None
+        hot = tot = 0.0
+        for line in txt.split("\n"):
+            f = line.split()
+            if len(f) < 4:
+                continue
+            try:
+                self_s = float(f[2])
+                float(f[0])
+            except ValueError:
+                continue
+            tot += self_s
+            if f[-1] in HOT_FUNCS:
+                hot += self_s
+        if tot <= 0:
+            return None
+        t_hot = hot * wall / wall_pg
+        return {"seconds": round(t_hot, 3), "share_of_wall": round(t_hot / wall, 4), "value": self.G / 1e9 / t_hot if t_hot else None,
+                "unit": "Gbp/s", "method": "gprof self time of the path's functions (saveInterval ... callPeaks) in a -pg build of "
+                "the same source, scaled by wall / wall_pg; libc time (strtok, memset of calloc) is not sampled by gprof",
+                "gprof_self_seconds_hot": round(hot, 3), "gprof_self_seconds_all": round(tot, 3), "wall_pg_s": round(wall_pg, 2)}
+
+    def records(self):
+        """the same fragments as interval records, per replicate (treatment, control or None)"""
+        from genrich_b200 import host
+        out = []
+        for t, c in self.wls:
+            out.append((host.fragments_to_intervals(t.fragments(), atac=self.wl["atac"]),
+                        host.fragments_to_intervals(c.fragments(), atac=self.wl["atac"]) if c is not None else None))
+        return out
+
+    def gpu_check(self, api, capi, host):
+        """push the sample through the CUDA library and compare with the narrowPeak the reference wrote"""
+        par = capi.make_params(p=self.wl["p"], q=self.wl["q"])
+        ctx = capi.Context(api, self.spec["chrom_len"], par)
+        res = host.run_replicates(ctx, self.records(), packed=True)
+        ref = parse_narrowpeak(self.out)
+        pk = res.peaks
+        same = len(ref) == len(pk)
+        worst_p = worst_q = 0.0
+        if same and len(pk):
+            r = np.array([x[:4] for x in ref], dtype=np.int64)
+            g = np.stack([pk["chrom"].astype(np.int64), pk["start"], pk["end"], pk["summit"].astype(np.int64)], axis=1)
+            same = bool(np.array_equal(r, g))
+            if same:
+                worst_p = float(np.max(np.abs(np.array([x[4] for x in ref]) - pk["pval"].astype(np.float64))))
+                if self.wl["q"]:
+                    worst_q = float(np.max(np.abs(np.array([x[5] for x in ref]) - pk["qval"].astype(np.float64))))
+        ctx.close()
+        return {"peaks_reference": len(ref), "peaks_gpu": int(len(pk)), "coords_identical": bool(same),
+                "worst_dp": round(worst_p, 7), "worst_dq": round(worst_q, 7),
+                "ok": bool(same and worst_p <= 1e-4 + 1e-6 and worst_q <= 1e-4 + 1e-6),   # + half a unit of the 6 printed decimals
+                "args": " ".join(ref_args(self.wl)), "genome_bp": self.G,
+                "fragments": [list(x) for x in self.spec["reps"]]}
+
+    def cli_e2e(self, threads):
+        """the drop-in host program on the same SAM files: wall clock of the whole program, decode included"""
+        cli = os.path.join(ROOT, "genrich_b200", "bin", "genrich-b200")
+        if not os.path.exists(cli):
+            return None
+        out = os.path.join(self.dir, "cli.narrowPeak")
+        best = None
+        for _ in range(2):                            # the second run has the library and the files warm
+            t0 = time.perf_counter()
+            r = subprocess.run(self.cmd(cli, out) + ["--threads", str(threads)], stderr=subprocess.PIPE, text=True)
+            dt = time.perf_counter() - t0
+            if r.returncode:
+                return {"error": (r.stderr or "")[-300:]}
+            best = dt if best is None else min(best, dt)
+        ident = [l.split("\t")[:3] + l.rstrip("\n").split("\t")[9:] for l in open(out)] == \
+                [l.split("\t")[:3] + l.rstrip("\n").split("\t")[9:] for l in open(self.out)]
+        return {"seconds": round(best, 3), "value": self.G / 1e9 / best, "unit": "Gbp/s", "threads": threads,
+                "narrowpeak_cols_1_3_10_identical_to_reference": bool(ident),
+                "note": "genrich-b200 (host C program over the CUDA library) on the SAM files the reference was timed on: "
+                        "whole program, SAM decode on the host threads included"}
+
+    def cleanup(self):
+        for f in os.listdir(self.dir):
+            os.unlink(os.path.join(self.dir, f))
+        os.rmdir(self.dir)
+
+
+def describe_sample(spec, sec, npk):
+    return "%d chrom x %d bp, fragments per replicate (treatment, control) %s, same generator and depth as the workload; " \
+           "whole program incl. SAM parse, %.2f s/run, %d peaks" % (
+               len(spec["chrom_len"]), spec["chrom_len"][0], [list(x) for x in spec["reps"]], sec, npk)
+
+
+def reference_arm(a, wl):
+    rs = RefSample(wl["sample"], wl, a.workload)
+    try:
+        times = rs.run_reference(1 + a.steps)[1:]
+        sec = sum(times) / len(times)
+        npk = sum(1 for _ in open(rs.out))
+        cb = {"value": rs.G / 1e9 / sec, "unit": "Gbp/s", "cores": 1, "kind": "reference",
+              "sample": describe_sample(wl["sample"], sec, npk), "host_cores_available": os.cpu_count(),
+              "hot_path": rs.hot_path(sec)}
+    finally:
+        rs.cleanup()
+    return cb, sec
+
+
+# --------------------------------------------------------------------------------------
+def load_dram_table(workload, world):
+    p = os.path.join(ROOT, "profiles", "r02_dram_by_stage.json")
+    if not os.path.exists(p):
+        return None
+    t = json.load(open(p))
+    return t.get("%s@%d" % (workload, world))
 
 
 def main():
@@ -245,13 +517,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--workload", default="hg38_chip_50M_50M")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-dense", action="store_true", help="skip the dense-formulation (GR_FUSED=0) comparison pass")
-    ap.add_argument("--no-variants", action="store_true", help="skip the child process that times the non-default kernel variants")
-    ap.add_argument("--variant-probe", action="store_true", help=argparse.SUPPRESS)
-    ap.add_argument("--no-pack6", action="store_true", help="e2e arm with 8-byte records even where 6-byte records fit")
-    ap.add_argument("--prefetch-depth", type=int, default=2,
-                    help="e2e arm: samples sent ahead of their push (2: both samples of the next step, 1: the next sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the reference run, the parity gate and the host-program timing")
+    ap.add_argument("--no-dense", action="store_true", help="skip the dense-formulation (GR_FUSED=0) and CTA-scan comparison passes")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="warm-up + ONE step and nothing else (for ncu); writes gpurun_out/profile_meta.json")
+    ap.add_argument("--prefetch-depth", type=int, default=2, help="e2e arm: samples sent ahead of their push (<= 2)")
+    ap.add_argument("--gen-threads", type=int, default=0)
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3
@@ -266,7 +538,7 @@ def main():
     if a.impl == "reference":
         if rank != 0:
             return
-        cb, sec = reference_sample_run(a.steps, 1)
+        cb, sec = reference_arm(a, wl)
         line = {"impl": "reference", "metric": "Gbp p-value-scanned/sec", "value": cb["value"], "unit": "Gbp/s",
                 "n_gpus": a.gpus, "steps": a.steps, "warmup": 1, "ms_per_step": sec * 1e3,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32+f32/f64",
@@ -284,109 +556,72 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     sampler = ClockSampler(local)
-    if rank == 0 and not a.variant_probe:
+    if rank == 0:
         sampler.start()                                # comes up while the workload is generated
     host_group = None
     if world > 1:
         td.init_process_group("nccl", device_id=dev)
-        host_group = td.new_group(backend="gloo")      # host-resident scalars and peak records
+        host_group = td.new_group(backend="gloo")      # host-resident scalars
     api = capi.load_cuda()
     par = capi.make_params(p=wl["p"], q=wl["q"])
+    threads = a.gen_threads or max(2, min(16, (os.cpu_count() or 8) // max(world, 1)))
+
+    # N > 1 first proves the sharded path on a small -q workload: every rank computes the whole `mini` genome
+    # alone, then the ranks do it together (chromosomes sharded, sums all-reduced, BH histogram all-gathered,
+    # peaks gathered) -- same records, so rank 0 must see the same peaks, bit for bit.
+    shard_parity = None
+    if world > 1 and not a.profile:
+        mw = dict(WORKLOADS["mini"], q=0.05, p=None)
+        mpar = capi.make_params(p=None, q=0.05)
+        from genrich_b200.synth import Workload
+        mt = Workload(mw["chrom_len"], mw["reps"][0][0], 4001, enrich=mw["enrich"], spacing=mw["spacing"], sigma=mw["sigma"]).fragments()
+        mc = Workload(mw["chrom_len"], mw["reps"][0][1], 4002, enrich=0.0).fragments()
+        single_ctx = capi.Context(api, mw["chrom_len"], mpar, device=local)       # a world-1 context inside a world-N job
+        want = host.run_replicates(single_ctx, [(mt, mc)], packed=True).peaks.copy()
+        single_ctx.close()
+        meng = ShardedEngine(api, mw["chrom_len"], mpar, dev, host_group=host_group)
+        mt_r, mc_r = meng.route(mt), meng.route(mc)
+        pt, _ = host.pack_records(mt_r)
+        pc, _ = host.pack_records(mc_r)
+        meng.replicate(lambda c: c.push_packed(pt), lambda c: c.push_packed(pc), want_stats=False)
+        got, mrs = meng.call_peaks()
+        if rank == 0:
+            shard_parity = {"workload": "mini, -q 0.05 (BH histogram all-gather on the path)", "peaks": int(len(got)),
+                            "identical_to_single_context": bool(got.tobytes() == want.tobytes()),
+                            "distinct_p": int(mrs.n_distinct_p), "hist_allgather_bytes": int(meng.hist_bytes)}
+            assert shard_parity["identical_to_single_context"], "sharded run differs from the single-context run"
+        meng.ctx.close()
+        del meng
+
     eng = ShardedEngine(api, L, par, dev, host_group=host_group)
     ctx = eng.ctx
+    use6 = ctx.pack6_layout() is not None
 
-    # synthetic interval records of this rank's chromosomes, on the host (pinned) and in HBM
-    def make(n, seed, enrich):
-        if n == 0:
-            return None, None, None
-        fr = gen_fragments(L, n, seed, enrich, wl["spacing"], wl["sigma"])
-        iv = eng.route(host.fragments_to_intervals(fr, atac=wl["atac"]))
-        # the producer side of the C-ABI hands over 8-byte GR_PACK records (gr_push_packed) ...
-        packed, rest = host.pack_records(iv)
-        assert rest.shape[0] == 0, "synthetic workload has records that do not pack"
-        pinned = torch.from_numpy(packed.view(np.int64)).pin_memory()
-        # ... or, where the context's layout fits 32 bits, 6-byte GR_PACK6 records (gr_push_packed6):
-        # the e2e arm is bound by the host -> device copy, 25 % fewer bytes
-        p6 = None
-        if layout6 is not None and not a.no_pack6:
-            r6, rest6 = host.pack6_records(iv, layout6, L)
-            if rest6.shape[0] == 0:
-                p6 = torch.from_numpy(r6.view(np.int16).reshape(-1)).pin_memory()
-        return pinned, pinned.to(dev), p6
-    # N > 1 keeps the record format the multi-GPU runs of this round were validated with (8-byte words,
-    # one sample ahead) unless asked otherwise; the 6-byte path itself is rank-agnostic
-    layout6 = ctx.pack6_layout() if (world == 1 or os.environ.get("GR_BENCH_PACK6_MULTI")) else None
-    t_host, t_dev, t_h6 = make(wl["nt"], 2001, wl["enrich"])
-    c_host, c_dev, c_h6 = make(wl["nc"], 2002, 0.0)
-    use6 = t_h6 is not None and (c_host is None or c_h6 is not None)
-    n_t = t_host.shape[0]
-    n_c = c_host.shape[0] if c_host is not None else 0
+    # synthetic interval records of this rank's chromosomes: 8-byte words in HBM, 6-byte records in pinned host memory
+    t_gen0 = time.perf_counter()
+    reps = []
+    for r, (nt, nc) in enumerate(wl["reps"]):
+        tag = "%s_w%d_r%d_rep%d" % (a.workload, world, rank, r)
+        t = Sample(torch, host, eng, wl, nt, 2001 + 10 * r, wl["enrich"], dev, use6, threads, tag + "_t")
+        c = Sample(torch, host, eng, wl, nc, 2002 + 10 * r, 0.0, dev, use6, threads, tag + "_c") if nc else None
+        reps.append((t, c))
+    order = [s for rp in reps for s in rp if s is not None]
     torch.cuda.synchronize()
+    gen_s = time.perf_counter() - t_gen0
+    feeder = Feeder(order, max(0, min(2, a.prefetch_depth)))
 
     def step(from_host, eng=eng):
-        ctx = eng.ctx
-        ctx.reset()
+        eng.ctx.reset()
         eng.saved_any[:] = False
         eng.sample_stats.clear()
-        ahead = None
-        if from_host and use6:
-            # Both samples of the NEXT step are sent while this step computes (the library's two
-            # prefetch slots; a slot is refilled as soon as the pileup that read it is done), so
-            # in steady state every step's 0.6 GB of input travels under the previous step's kernels.
-            def pe(c):
-                c.push_packed6_ptr(t_h6.data_ptr(), n_t)
-                if n_c and a.prefetch_depth < 2:
-                    c.prefetch_packed6_ptr(c_h6.data_ptr(), n_c)
-
-            def pc_(c):
-                c.push_packed6_ptr(c_h6.data_ptr(), n_c)
-                if a.prefetch_depth < 2:
-                    c.prefetch_packed6_ptr(t_h6.data_ptr(), n_t)
-            pc = pc_ if n_c else None
-            if a.prefetch_depth >= 2 or not n_c:
-                def ahead(c):
-                    c.prefetch_packed6_ptr(t_h6.data_ptr(), n_t)
-                    if n_c:
-                        c.prefetch_packed6_ptr(c_h6.data_ptr(), n_c)
-        elif from_host:
-            # host (pinned) -> device copies are inside the timed region; the control sample is
-            # sent while the treatment sample is being integrated, and the next step's treatment
-            # sample while this step's peaks are called (gr_prefetch_intervals)
-            def pe(c):
-                c.push_packed_ptr(t_host.data_ptr(), n_t)
-                if n_c:
-                    c.prefetch_packed_ptr(c_host.data_ptr(), n_c)
-
-            def pc_(c):
-                c.push_packed_ptr(c_host.data_ptr(), n_c)
-                c.prefetch_packed_ptr(t_host.data_ptr(), n_t)
-            pc = pc_ if n_c else None
-        else:
-            pe = lambda c: c.push_packed_ptr(t_dev.data_ptr(), n_t)
-            pc = (lambda c: c.push_packed_ptr(c_dev.data_ptr(), n_c)) if n_c else None
-        eng.replicate(pe, pc, want_stats=False)
-        if ahead is not None:
-            ahead(eng.ctx)
+        for t, c in reps:
+            if from_host:
+                eng.replicate(feeder.push, feeder.push if c is not None else None, want_stats=False)
+            else:
+                eng.replicate(t.push_dev, c.push_dev if c is not None else None, want_stats=False)
+        if from_host:
+            feeder.top_up(eng.ctx)                     # the next step's first samples travel under the peak calling
         return eng.call_peaks()
-
-    trace = {}
-    if os.environ.get("GR_BENCH_TRACE"):
-        # host time of every library call of a step (debugging aid: where the host keeps the GPU waiting)
-        def wrap(obj, name, key=None):
-            f = getattr(obj, name)
-            name = key or name
-
-            def g(*a_, **k_):
-                t0 = time.perf_counter()
-                r = f(*a_, **k_)
-                trace[name] = trace.get(name, 0.0) + time.perf_counter() - t0
-                return r
-            setattr(obj, f.__name__, g)
-        for nm in ("reset", "sample_begin", "push_packed_ptr", "prefetch_packed_ptr", "sample_pileup_async",
-                   "replicate_finish_device", "pvalues_finalize", "call_peaks", "timer_start", "timer_stop"):
-            wrap(eng.ctx, nm)
-        wrap(eng, "replicate", "eng.replicate (incl. the calls above)")
-        wrap(eng, "call_peaks", "eng.call_peaks (incl. call_peaks)")
 
     def timed(from_host, steps, warmup, with_stages=False, eng=eng):
         ctx = eng.ctx
@@ -419,135 +654,191 @@ def main():
             ctx.timing(False)
         return float(t[0]), float(t[1]), ctx.kernel_launches() - l0, peaks, rs, stages
 
-    if a.variant_probe:
-        # child of the default run: every variant against the default path, same records, fresh context each
-        _, _, _, base_peaks, _, _ = timed(False, 2, 3)
-        out = {}
-        for name, env in VARIANTS.items():
-            eng_v = None
-            try:
-                os.environ.update(env)
-                eng_v = ShardedEngine(api, L, par, dev, host_group=None)
-                ms_v, _, launches_v, peaks_v, _, st_v = timed(False, a.steps, 3, with_stages=True, eng=eng_v)
-                out[name] = {"env": env, "ms_per_step_with_stage_events": round(ms_v, 4), "launches": int(launches_v),
-                             "peaks_identical": bool(peaks_v.tobytes() == base_peaks.tobytes()), "peaks": int(len(peaks_v)),
-                             "stage_ms_per_step": {k: round(v[0] / a.steps, 4) for k, v in
-                                                   sorted(st_v.items(), key=lambda kv: -kv[1][0])[:6]}}
-            except Exception as e:                     # a variant that fails says so; the others still run
-                out[name] = {"env": env, "error": repr(e)[:300]}
-            finally:
-                for k in env:
-                    os.environ.pop(k, None)
-                if eng_v is not None:
-                    try:
-                        eng_v.ctx.close()              # its device buffers go back before the next variant allocates
-                    except Exception:
-                        pass
-            print(json.dumps(out), flush=True)         # cumulative: the parent keeps the last complete line
+    if a.profile:
+        # for ncu: the launches of the LAST step are what tools/ncu_dram_by_stage.py keeps
+        _, _, launches, peaks, rs, _ = timed(False, 1, 3)
+        if rank == 0:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump({"workload": a.workload, "world": world, "launches_per_step": int(launches), "peaks": int(len(peaks))},
+                      open(os.path.join(ROOT, "gpurun_out", "profile_meta.json"), "w"))
+        sampler.stop()
+        if world > 1:
+            td.destroy_process_group()
         return
 
     t_w0 = time.time()
     # headline: K steps, nothing but the step itself in the stream; the per-stage CUDA events (two
     # per stage, ~20 stages per step) are recorded in a separate short pass of the same step
     ms_dev, wall_dev, launches, peaks, rs, _ = timed(False, a.steps, a.warmup)
-    if trace:
-        print("host ms per step by call (device arm, %d steps incl. warm-up): %s" % (
-            a.steps + a.warmup, {k: round(v * 1e3 / (a.steps + a.warmup), 3) for k, v in trace.items()}),
-            file=sys.stderr, flush=True)
-        trace.clear()
-    ms_e2e, wall_e2e, _, peaks2, _, _ = timed(True, a.steps, 1)
-    # rank 0's host time by phase of the e2e arm (where the host waits for the device it is device time too)
-    host_phase = {k: round(v * 1e3 / a.steps, 4) for k, v in eng.t_acc.items()}
+    host_phase_dev = {k: round(v * 1e3 / a.steps, 4) for k, v in eng.t_acc.items()}
+    ms_e2e = wall_e2e = None
+    peaks2 = peaks
+    host_phase = {}
+    if not a.no_e2e:
+        ms_e2e, wall_e2e, _, peaks2, _, _ = timed(True, a.steps, 2)
+        # rank 0's host time by phase of the e2e arm (where the host waits for the device it is device time too)
+        host_phase = {k: round(v * 1e3 / a.steps, 4) for k, v in eng.t_acc.items()}
     st_steps = max(2, a.steps // 2)
     ms_staged, _, _, peaks3, _, stages = timed(False, st_steps, 1, with_stages=True)
     assert peaks3.tobytes() == peaks.tobytes()
     clocks = sampler.stop(t_w0, time.time()) if rank == 0 else None
-    # the same per-base pass in its dense formulation (delta array in HBM: bucketed build, then
-    # k_scan_stream reads 4 B per cell): the kernel the HBM-read roofline is literally about
-    dense = None
-    if world == 1 and not a.no_dense:
-        os.environ["GR_FUSED"] = "0"
-        eng_d = ShardedEngine(api, L, par, dev, host_group=None)
-        del os.environ["GR_FUSED"]
-        ms_d, _, _, peaks_d, _, st_d = timed(False, st_steps, 3, with_stages=True, eng=eng_d)
-        assert peaks_d.tobytes() == peaks.tobytes(), "dense and fused formulations disagree"
-        dense = (ms_d, st_d)
-        del eng_d
+    n_breaks = int(sum(ctx.replicate_stats(r).n_pval for r in range(len(reps)))) if rank == 0 else 0
+    hist_bytes = eng.hist_bytes
 
-    variants = None
-    if world == 1 and not a.no_variants and a.workload != "mini":
-        variants = run_variant_probe(a)                # a child process; this one is idle meanwhile
+    # the same per-base pass in its two other formulations, same records, peaks asserted identical:
+    #   dense  (GR_FUSED=0): the delta array is written to HBM by k_sb_build and read back by k_scan_stream -- the
+    #          kernel the HBM-read roofline is literally about
+    #   cta    (GR_FUSED_CTA=1): k_fb_scan, the CTA-owned shared-memory cell array that was the default in round 1
+    dense = cta = None
+    if world == 1 and not a.no_dense and G < (1 << 32):
+        for key, env in (("dense", {"GR_FUSED": "0"}), ("cta", {"GR_FUSED_CTA": "1"})):
+            os.environ.update(env)
+            eng_d = ShardedEngine(api, L, par, dev, host_group=None)
+            ms_d, _, _, peaks_d, _, st_d = timed(False, st_steps, 3, with_stages=True, eng=eng_d)
+            for k in env:
+                del os.environ[k]
+            assert peaks_d.tobytes() == peaks.tobytes(), "%s and default formulations disagree" % key
+            if key == "dense":
+                dense = (ms_d, st_d)
+            else:
+                cta = (ms_d, st_d)
+            eng_d.ctx.close()
+            del eng_d
 
     if eng.debug:
-        print("rank %d host-side ms per step (e2e arm): %s" % (rank, {k: round(v * 1e3 / a.steps, 3) for k, v in eng.t_acc.items()}),
-              file=sys.stderr, flush=True)
+        print("rank %d host-side ms per step (e2e arm): %s" % (rank, host_phase), file=sys.stderr, flush=True)
     if rank != 0:
         if world > 1:
             td.destroy_process_group()
         return
-    n_samples = 2 if n_c else 1
+    n_samples = len(order)
+    n_records = int(sum(s.n for s in order))
     peak_gbs, peak_src = measured_peak_gbs()
     fused = "fused_scan" in stages
-    scan_kernel = "k_fb_scan" if fused else "k_scan_stream"
+    scan_kernel = "k_fr_scan" if fused else "k_scan_stream"
     scan_ms, scan_launches, _ = stages.get("fused_scan" if fused else "dense_scan", (0.0, 0, 0))
     per_launch_ms = scan_ms / max(scan_launches, 1)          # mean over every launch of the staged pass
     place_ms, place_launches, _ = stages.get("scan_place", (0.0, 0, 0))
-    cells = ctx_cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
+    cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
     achieved = 4.0 * cells / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
-    dense_obj = None
-    if dense is not None:
-        d_ms, d_n, _ = dense[1].get("dense_scan", (0.0, 0, 0))
-        b_ms, b_n, _ = dense[1].get("build", (0.0, 0, 0))
+
+    def formulation(kernel, res, stage, note):
+        if res is None:
+            return None
+        d_ms, d_n, _ = res[1].get(stage, (0.0, 0, 0))
+        b_ms, b_n, _ = res[1].get("build", (0.0, 0, 0))
         d_per = d_ms / max(d_n, 1)
         d_ach = 4.0 * cells / (d_per * 1e-3) / 1e9 if d_per else 0.0
-        dense_obj = {"kernel": "k_scan_stream", "achieved": d_ach, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": d_ach / peak_gbs if peak_gbs else None, "ms_per_launch": d_per,
-                     "build_ms_per_launch": b_ms / max(b_n, 1), "ms_per_step": dense[0],
-                     "traffic": NCU_TRAFFIC.get((a.workload, world, "k_scan_stream")),
-                     "note": "GR_FUSED=0: the delta array is written to HBM by k_sb_build and read back by "
-                             "k_scan_stream (4 B per cell each way); same peaks, bit for bit"}
+        return {"kernel": kernel, "achieved": d_ach, "peak": peak_gbs, "unit": "GB/s", "frac": d_ach / peak_gbs if peak_gbs else None,
+                "ms_per_launch": d_per, "build_ms_per_launch": b_ms / max(b_n, 1) if b_n else None, "ms_per_step": res[0], "note": note}
+    dense_obj = formulation("k_scan_stream", dense, "dense_scan",
+                            "GR_FUSED=0: the delta array is written to HBM by k_sb_build and read back by k_scan_stream "
+                            "(4 B per cell each way: here `achieved` IS the HBM read rate); same peaks, bit for bit")
+    cta_obj = formulation("k_fb_scan", cta, "fused_scan", "GR_FUSED_CTA=1: round 1's default scan; same peaks, bit for bit")
+
+    # what really moves through DRAM: per kernel, from the committed ncu pass of `bench.py --profile` on this workload
+    table = load_dram_table(a.workload, world)
+    traffic = frac_dram = None
+    # what the per-base pass cannot avoid moving: the records in, its breaks and one bit per cell out
+    info = 8 * n_records + 8 * n_breaks + (cells // 8) * n_samples
+    step_obj = {"info_lower_bound_bytes": int(info),
+                "info_note": "8 B per record in + 8 B per break out (breaks ~ the p intervals of every replicate) + 1 bit per cell and sample",
+                "frac_info": info / (ms_dev * 1e-3) / 1e9 / peak_gbs if peak_gbs else None}
+    if table is not None:
+        ks = table["kernels"]
+        if scan_kernel not in ks:
+            raise SystemExit("profiles/r02_dram_by_stage.json has no entry for %s on %s: re-run tools/ncu_dram_by_stage.py" %
+                             (scan_kernel, a.workload))
+        k = ks[scan_kernel]
+        traffic = (k["dram_read"] + k["dram_write"]) / max(k["launches"], 1)
+        frac_dram = traffic / (per_launch_ms * 1e-3) / 1e9 / peak_gbs if per_launch_ms else None
+        tot = sum(v["dram_read"] + v["dram_write"] for v in ks.values())
+        step_obj.update({"dram_bytes": int(tot), "frac_dram": tot / (ms_dev * 1e-3) / 1e9 / peak_gbs,
+                         "dram_bytes_by_kernel": {n: int(v["dram_read"] + v["dram_write"]) for n, v in
+                                                  sorted(ks.items(), key=lambda kv: -(kv[1]["dram_read"] + kv[1]["dram_write"]))[:12]},
+                         "source": "profiles/r02_dram_by_stage.json (%s): dram__bytes_read.sum + dram__bytes_write.sum of every "
+                                   "kernel of one step under ncu; memsets and copies are not kernels and are not in it" % table.get("command", "")})
     stage_ms = {k: round(v[0] / st_steps, 4) for k, v in sorted(stages.items(), key=lambda kv: -kv[1][0])}
     stage_ms["_step_with_stage_events"] = round(ms_staged, 4)
+    thr = "-q %g" % wl["q"] if wl["q"] else "-p %g" % wl["p"]
     line = {
         "metric": "Gbp p-value-scanned/sec", "value": G / 1e9 / (ms_dev * 1e-3), "unit": "Gbp/s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_dev,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int32 deltas, f32 pileups, f64 -> f32 -log10 p", "data": "synthetic",
-        "config": {"workload": a.workload, "genome_bp": G, "chromosomes": len(L), "treatment_fragments": wl["nt"],
-                   "control_fragments": wl["nc"], "threshold": "-q %g" % wl["q"] if wl["q"] else "-p %g" % wl["p"],
-                   "atac": wl["atac"], "sharding": "chromosomes over %d rank(s), LPT" % world,
-                   "l2": "inputs (%.1f GB dense delta array per sample) far exceed the 126 MB L2" % (4e-9 * cells),
-                   "peaks": int(len(peaks)), "intervals_rank0": int(rs.n_intervals)},
-        "e2e": {"value": G / 1e9 / (ms_e2e * 1e-3), "unit": "Gbp/s", "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int((6 if use6 else 8) * (n_t + n_c)), "d2h_bytes_per_step": int(peaks2.nbytes + 512),
-                "record_format": "GR_PACK6 (6 B per record, expanded on the device)" if use6 else "GR_PACK (8 B per record)",
-                "wall_ms_per_step": wall_e2e,
-                "peaks_identical_to_device_arm": bool(peaks2.tobytes() == peaks.tobytes())},
+        "config": {"workload": a.workload, "genome_bp": G, "chromosomes": len(L),
+                   "fragments_per_replicate": [list(x) for x in wl["reps"]], "records_rank0": n_records,
+                   "threshold": thr, "atac": wl["atac"], "multimap_fraction": wl["multimap"],
+                   "sharding": "chromosomes over %d rank(s), LPT" % world,
+                   "l2": "inputs (%.1f GB dense delta array per sample, %.2f GB of records) far exceed the 126 MB L2" % (
+                       4e-9 * cells, 8e-9 * n_records),
+                   "peaks": int(len(peaks)), "peaks_sha256": peaks_sha256(peaks), "intervals_rank0": int(rs.n_intervals),
+                   "distinct_p": int(rs.n_distinct_p), "generation_s": round(gen_s, 1)},
         "gpu_launches": int(launches),
         "wall_ms_per_step": wall_dev,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": scan_kernel, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs if peak_gbs else None,
-                     # ncu --set full, hg38 workload, 1 GPU (profiles/r01_scan_stream_ncu.txt): dram read + write per launch
-                     "traffic": NCU_TRAFFIC.get((a.workload, world, scan_kernel)), "peak_source": peak_src,
-                     "bytes_per_launch": 4 * cells, "ms_per_launch": per_launch_ms,
+                     "frac": achieved / peak_gbs if peak_gbs else None, "traffic": traffic, "frac_dram": frac_dram,
+                     "peak_source": peak_src, "bytes_per_launch": 4 * cells, "ms_per_launch": per_launch_ms,
                      "companion_scan_place_ms_per_launch": place_ms / max(place_launches, 1),
                      "launches_per_step": scan_launches / st_steps, "samples_scanned_per_step": n_samples,
-                     "note": ("the delta cells of k_fb_scan live in shared memory only: `achieved` divides the ALGORITHMIC "
-                              "bytes of the per-base pass (SURVEY 8d: 4 B per base per sample array) by the launch time, "
-                              "`traffic` is what the kernel really moves through DRAM (bucket entries in, breaks and "
-                              "bitmap out); frac > 1 = faster than any kernel that reads the array from HBM could be"
-                              if fused else "4 B per delta cell read from HBM"),
-                     "dense_formulation": dense_obj},
+                     "note": "`achieved` / `frac` divide the ALGORITHMIC bytes of the per-base pass (SURVEY 8d: 4 B per base per "
+                             "sample array) by the launch time.  The delta cells of k_fr_scan never exist in HBM (bucketed events "
+                             "in, breaks and a bitmap out), so frac > 1 is not a bandwidth claim: `traffic` / `frac_dram` say what "
+                             "the kernel really moves, `step` what the whole step moves, `dense_formulation` what the kernel that "
+                             "does read 4 B per cell achieves",
+                     "step": step_obj, "dense_formulation": dense_obj, "cta_formulation": cta_obj},
+        "dense_formulation": dense_obj,
         "stage_ms_per_step": stage_ms,
-        "variants": variants,
+        "host_phase_ms_per_step_device_arm": host_phase_dev,
         "host_phase_ms_per_step_e2e": host_phase,
+        "shard_parity": shard_parity,
     }
+    if not a.no_e2e:
+        h2d = int(sum(s.host_bytes for s in order))
+        line["e2e"] = {"value": G / 1e9 / (ms_e2e * 1e-3), "unit": "Gbp/s", "ms_per_step": ms_e2e,
+                       "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(peaks2.nbytes + 512),
+                       "record_format": "GR_PACK6 (6 B per record, expanded on the device)" if order[0].fmt == 6 else "GR_PACK (8 B per record)",
+                       "wall_ms_per_step": wall_e2e, "prefetch_depth": feeder.depth,
+                       "peaks_identical_to_device_arm": bool(peaks2.tobytes() == peaks.tobytes())}
+    if wl["q"]:
+        line["bh"] = {"distinct_p": int(rs.n_distinct_p), "hist_allgather_bytes_per_step": int(hist_bytes),
+                      "stage_ms": {k: stage_ms.get(k) for k in ("bh_hist", "bh")},
+                      "host_phase_ms": {k: host_phase_dev.get(k) for k in ("bh_sizes", "bh_allgather", "bh_exchange_and_q")}}
     if world > 1:
         td.destroy_process_group()                 # nothing below involves the other ranks
-    if world == 1 and not a.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Genrich")):
-        cb, _ = reference_sample_run(1, 0)         # the contract: on rank 0 at N = 1 only
-        line["cpu_baseline"] = cb
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Genrich"))
+    if world == 1 and not a.no_cpu_baseline and have_ref:
+        # the contract: on rank 0 at N = 1 only.  One reference run per sample; the workload's own sample is the
+        # CPU baseline, and every sample goes through the GPU for the parity gate.
+        rsm = RefSample(wl["sample"], wl, a.workload)
+        try:
+            sec = rsm.run_reference(1)[0]
+            npk = sum(1 for _ in open(rsm.out))
+            line["cpu_baseline"] = {"value": rsm.G / 1e9 / sec, "unit": "Gbp/s", "cores": 1, "kind": "reference",
+                                    "sample": describe_sample(wl["sample"], sec, npk),
+                                    "host_cores_available": os.cpu_count(), "hot_path": rsm.hot_path(sec)}
+            gate = {a.workload + " sample": rsm.gpu_check(api, capi, host)}
+            line["cli_e2e"] = rsm.cli_e2e(min(16, os.cpu_count() or 8))
+            if line["cli_e2e"] and "seconds" in line["cli_e2e"]:
+                line["cli_e2e"]["reference_seconds"] = round(sec, 3)
+                line["cli_e2e"]["speedup_vs_reference"] = round(sec / line["cli_e2e"]["seconds"], 2)
+        finally:
+            rsm.cleanup()
+        for name, spec in (GATE_EXTRA.items() if a.workload == "hg38_chip_50M_50M" else ()):
+            g = RefSample(dict(chrom_len=spec["chrom_len"], reps=spec["reps"]), spec, name)
+            try:
+                g.run_reference(1)
+                gate[name] = g.gpu_check(api, capi, host)
+            finally:
+                g.cleanup()
+        line["parity"] = {"identical": all(v["ok"] for v in gate.values()),
+                          "peaks": sum(v["peaks_gpu"] for v in gate.values()),
+                          "worst_dp": max(v["worst_dp"] for v in gate.values()),
+                          "worst_dq": max(v["worst_dq"] for v in gate.values()),
+                          "rule": "narrowPeak of the unmodified reference, written in this run on the SAM view of each sample, vs the "
+                                  "CUDA path on the same fragments: line count, columns 1-3 and 10 identical, columns 8-9 within 1e-4",
+                          "samples": gate}
     else:
         line["cpu_baseline"] = {"value": None, "unit": "Gbp/s", "cores": 1, "kind": "reference",
                                 "sample": "skipped (N > 1, --no-cpu-baseline or oracle/_ref missing)"}

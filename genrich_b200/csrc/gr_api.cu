@@ -110,9 +110,6 @@ struct gr_ctx {
   // bucketed build (large samples)
   DevBuf sbCnt, sbStart, sbCursor, sbBucket, sbSpill, sbSpillCtr;
   u64 sb_min = 1ull << 20;             // samples with fewer records use the plain scatter (GR_SB_MIN)
-  DevBuf p1Cnt, p1Base, p1Cur, p1Pairs;   // two-level partition (GR_FB_P2=1)
-  DevBuf sbSlotCnt, dGate;             // slot path (GR_FB_SLOTS=1): entries per fixed-capacity bucket, overflow flag
-  u32 slot_cap = 0;                    // entries per bucket of the current sample (0: exact buckets)
   int fused = 1;                       // buckets -> breaks in shared memory, no delta array in HBM (GR_FUSED=0: dense array)
   u64 fused_min = 1ull << 16;          // ... for samples of at least this many records (GR_FUSED_MIN)
   // -E regions (saveXBed 1144): per chromosome the merged, clamped boundary list start0,end0,start1,...
@@ -122,7 +119,6 @@ struct gr_ctx {
   DevBuf bedMarks, blkBed;             // boundary cell slots (u64); per 8192-cell block: bit 0 starts inside a region, bit 1 holds boundaries
   u32 n_marks = 0;
   DevBuf ccSlots, ccSkip;              // no-control pileup: break slots and SKIP flags of its intervals
-  int fb_shift = 13;                   // bucket shift of the sample whose events are bucketed right now
 
   // Host mirrors of device-side results lag behind while `lag` is set: nothing on the hot path
   // waits for the device between gr_sample_begin and the peak records; whoever needs a mirror
@@ -426,9 +422,6 @@ extern "C" void gr_destroy(gr_ctx* x) {
   x->dpar.release();
   x->dsums.release();
   x->unpack6.release();
-  x->p1Cnt.release(); x->p1Base.release(); x->p1Cur.release(); x->p1Pairs.release();
-  x->sbSlotCnt.release();
-  x->dGate.release();
   x->ghk.release();
   x->ghl.release();
   if (x->h_acc) cudaFreeHost(x->h_acc);
@@ -689,85 +682,27 @@ static int consume_segments(gr_ctx* x, int* built) {
   u64 bytes = 0;
   for (auto& g : x->segs) bytes += g.n * g.rb;
   if (fb) {
-    const int sh = x->has_bed ? GR_BLOCK_SHIFT : fb_bucket_shift();
-    x->fb_shift = sh;
-    const u64 nbk = x->T >> sh;
+    const u64 nbk = x->nblocks;
     CK(x->sbCnt.ensure(nbk * 4));
     CK(x->sbStart.ensure((nbk + 1) * 4));
     CK(x->sbCursor.ensure(nbk * 4));
     CK(x->sbBucket.ensure(x->n_pushed * 8 + (u64)x->n_marks * 4 + 16));   // at most two event entries per record
     CK(x->sbSpillCtr.ensure(4 + (nbk / 4096 + 2) * 4));  // (unused word), then the scan's chunk sums
     HT("consume: bucket buffers ensured");
-    x->slot_cap = 0;
-    if (!x->has_bed && sh == GR_BLOCK_SHIFT && fb_slots()) {
-      // Fixed-capacity buckets: 4 x the mean number of entries per block, a power of two >= 256.
-      // One pass over the records; the exact chain below runs behind it, gated on the overflow flag.
-      u64 cap = 256;
-      while (cap < 4 * (x->n_pushed / (nbk ? nbk : 1) + 1)) cap <<= 1;
-      if (const char* e = getenv("GR_FB_SLOT_CAP")) cap = strtoull(e, nullptr, 10) ? strtoull(e, nullptr, 10) : cap;   // tests: force the overflow path
-      if (nbk * cap < (1ull << 32)) {
-        x->slot_cap = (u32)cap;
-        CK(x->sbBucket.ensure(nbk * cap * 4));
-        CK(x->sbSlotCnt.ensure(nbk * 4));
-        CK(x->dGate.ensure(4));
-      }
-    }
-    int fsh = -1;
-    if (!x->has_bed && sh == GR_BLOCK_SHIFT && !x->slot_cap && fb_p2()) fsh = fb_p2_shift(nbk);
-    if (fsh >= 0) {
-      // two-level partition: coarse bins of 2^fsh blocks, then one CTA per bin (same outputs as the chain below)
-      const u32 nb1 = (u32)((nbk + (1ull << fsh) - 1) >> fsh);
-      CK(x->p1Cnt.ensure(1024 * 4));
-      CK(x->p1Base.ensure(1025 * 4));
-      CK(x->p1Cur.ensure(1024 * 4));
-      CK(x->p1Pairs.ensure(x->n_pushed * 16 + 16));
-      stage_begin(x, "bucket", bytes);
-      CK(cudaMemsetAsync(x->p1Cnt.p, 0, 1024 * 4, x->stream));
-      for (auto& g : x->segs)
-        launch_p1_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->p1Cnt.as<u32>(), fsh, x->d_err, x->d_clamped);
-      launch_p1_scan(x->stream, x->p1Cnt.as<u32>(), nb1, x->p1Base.as<u32>(), x->p1Cur.as<u32>());
-      for (auto& g : x->segs)
-        launch_p1_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->p1Cur.as<u32>(), x->p1Pairs.as<u64>(), fsh, nb1);
-      launch_p2(x->stream, x->p1Pairs.as<u64>(), x->p1Base.as<u32>(), nb1, fsh, nbk, x->sbStart.as<u32>(),
-                x->sbBucket.as<u32>());
-      CKL();
-      stage_end(x);
-    } else {
     stage_begin(x, "bucket", bytes);
-    const int* gate = nullptr;
-    if (x->slot_cap) {
-      gate = x->dGate.as<int>();
-      CK(cudaMemsetAsync(x->sbSlotCnt.p, 0, nbk * 4, x->stream));
-      CK(cudaMemsetAsync(x->dGate.p, 0, 4, x->stream));
-      for (auto& g : x->segs)
-        launch_fb_move_slot(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbSlotCnt.as<u32>(), x->sbBucket.as<u32>(),
-                            x->slot_cap, x->dGate.as<int>(), x->d_err, x->d_clamped);
-      // the slot scan has to read the slots before the (gated) exact move may overwrite them: it is
-      // launched by pileup_enqueue, i.e. behind the chain below -- which is gated and touches
-      // sbBucket only if the slot scan is going to return at once
-    }
     CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4, x->stream));
-    if (gate) {
-      for (auto& g : x->segs)
-        launch_fb_count_gated(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, gate);
-    } else
     for (auto& g : x->segs)
-      launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped, sh);
+      launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
     HT("consume: memset + count launched");
-    launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, x->sbCnt.as<u32>(), nullptr, nullptr, sh);
+    launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, x->sbCnt.as<u32>(), nullptr, nullptr);
     launch_sb_scan(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
                    x->sbSpillCtr.as<u32>() + 1);
-    if (gate) {
-      for (auto& g : x->segs)
-        launch_fb_move_gated(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), gate);
-    } else
     for (auto& g : x->segs)
-      launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
-    launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, nullptr, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(), sh);
+      launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>());
+    launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, nullptr, x->sbCursor.as<u32>(), x->sbBucket.as<u32>());
     HT("consume: scans + move launched");
     CKL();
     stage_end(x);
-    }
   } else if (sb) {
     CK(x->sbCnt.ensure(x->nblocks * 4));
     CK(x->sbStart.ensure((x->nblocks + 1) * 4));
@@ -932,13 +867,8 @@ static int pileup_enqueue(gr_ctx* x) {
   u32 owners = 0;
   if (built == 2) {
     stage_begin(x, "fused_scan", x->T * 4);
-    if (x->slot_cap)
-      owners = launch_fr_scan_slot(x->stream, x->L, x->sbBucket.as<u32>(), x->sbSlotCnt.as<u32>(), x->slot_cap,
-                                   x->sbStart.as<u32>(), sc, (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err,
-                                   x->dGate.as<int>());
-    else
     owners = launch_fb_scan(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), sc,
-                            (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err, x->fb_shift,
+                            (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err,
                             x->has_bed ? x->blkBed.as<uint8_t>() : nullptr);
     CKL();
     stage_end(x);
@@ -1043,14 +973,12 @@ static int table_build(gr_ctx* x, u64 n, u32& cap_io, F insert) {
 // K5 for one replicate: -log10 p through the table of distinct (expt, ctrl) pairs.  The table
 // capacity is a remembered guess; an overflow shows up as GR_DE_TABLE at the next materialize()
 // and the stage is simply run again with a larger table (its inputs are still in place).
-// inserted: the table was filled by the union emit (GR_UE_PAIR=1); only the evaluation and the gather are left
-static int rep_stage_pvals(gr_ctx* x, Replicate* rep, bool inserted = false) {
+static int rep_stage_pvals(gr_ctx* x, Replicate* rep) {
   CK(x->slot.ensure((rep->n_upper + 1) * sizeof(u32)));
   const u64* n_dev = rep->cnt.as<u64>();
   stage_begin(x, "pval", rep->n_upper * 16);
-  if (!inserted) { int r = table_alloc(x, x->pair_cap); if (r) return r; }
+  { int r = table_alloc(x, x->pair_cap); if (r) return r; }
   PairTable t = table_view(x, x->pair_cap);
-  if (!inserted)
   launch_pair_insert(x->stream, rep->pExpt.as<float>(), rep->pCtrl.as<float>(), rep->n_upper, n_dev, t,
                      x->slot.as<u32>(), x->d_err);
   launch_pair_eval(x->stream, t);
@@ -1146,20 +1074,7 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
   CK(rep->pVal.ensure((np_upper + 1) * sizeof(float)));
   CK(rep->pExpt.ensure((np_upper + 1) * sizeof(float)));
   CK(rep->pCtrl.ensure((np_upper + 1) * sizeof(float)));
-  const bool fuse_pair = ue_pair_fused();
-  if (fuse_pair) {                                             // the table the emit inserts into
-    CK(x->slot.ensure((np_upper + 1) * sizeof(u32)));
-    int r = table_alloc(x, x->pair_cap);
-    if (r) return r;
-  }
   stage_begin(x, "union_emit", x->T / 4 + np_upper * 12);
-  if (fuse_pair)
-    launch_union_emit_pair(x->stream, x->L, x->bmE.as<u32>(), x->bmC.as<u32>(), x->rankE.as<u64>(),
-                           x->rankC.as<u64>(), rep->rankU.as<u64>(), x->exptVal.as<float>(),
-                           x->ctrlVal.as<float>(), rep->pEnd.as<u32>(), rep->pExpt.as<float>(),
-                           rep->pCtrl.as<float>(), rep->bmU.as<u32>(), rep->chrom_start.as<u64>(),
-                           x->d_totals + 2, table_view(x, x->pair_cap), x->slot.as<u32>(), x->d_err);
-  else
   launch_union_emit(x->stream, x->L, x->bmE.as<u32>(), x->bmC.as<u32>(), x->rankE.as<u64>(),
                     x->rankC.as<u64>(), rep->rankU.as<u64>(), x->exptVal.as<float>(),
                     x->ctrlVal.as<float>(), rep->pEnd.as<u32>(), rep->pExpt.as<float>(),
@@ -1168,7 +1083,7 @@ static int replicate_tail(gr_ctx* x, bool has_ctrl) {
   CKL();
   HT("replicate_tail: union_emit launched");
   stage_end(x);
-  { int r = rep_stage_pvals(x, rep, fuse_pair); if (r) return r; }
+  { int r = rep_stage_pvals(x, rep); if (r) return r; }
   HT("replicate_tail: pvals launched");
 
   rep->present_h.resize(nc);
@@ -1410,6 +1325,9 @@ extern "C" int gr_bh_local_hist(gr_ctx* x, const uint32_t** d_keys, const uint64
   launch_table_compact(x->stream, t, cs, x->hk.as<u32>(), x->hl.as<u64>(), x->hcount.as<u64>());
   CKL();
   stage_end(x);
+  // The caller reads hk / hl on a stream of its own (an NCCL all-gather, a copy): the list must be
+  // complete when the pointers are handed out, not merely enqueued on x->stream.
+  CK(cudaStreamSynchronize(x->stream));
   x->hn = occ;
   // remember the table capacity for the q lookup
   x->n_distinct = 0;

@@ -781,8 +781,7 @@ __device__ __forceinline__ u32 fb_entry(u32 so, u32 span, int cnt, u32 kind) {
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
 k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ blk_cnt,
-           int* __restrict__ err, u64* __restrict__ clamped, int shift, const int* __restrict__ gate = nullptr) {
-  if (gate && !*gate) return;                // fallback of the slot path: runs only if a slot overflowed
+           int* __restrict__ err, u64* __restrict__ clamped) {
   const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
   int e_local = 0;
   u32 c_local = 0;
@@ -796,7 +795,7 @@ k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ 
       if (i0 + k * 256 >= n) break;
       u64 s_slot; u32 span; int w;
       if (!decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local)) continue;
-      const u64 bs = s_slot >> shift, be = (s_slot + span) >> shift;
+      const u64 bs = s_slot >> GR_BLOCK_SHIFT, be = (s_slot + span) >> GR_BLOCK_SHIFT;
       atomicAdd(blk_cnt + bs, 1u);
       if (be != bs) atomicAdd(blk_cnt + be, 1u);
     }
@@ -807,10 +806,8 @@ k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ 
 
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
-k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed,
-          int shift, const int* __restrict__ gate = nullptr) {
-  if (gate && !*gate) return;
-  const u32 omask = (1u << shift) - 1;
+k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed) {
+  const u32 omask = GR_BLOCK_SLOTS - 1;
   const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
   int e_local = 0;
   u32 c_local = 0;
@@ -826,8 +823,8 @@ k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
       u64 s_slot = 0; u32 span = 0; int w = 120;
       ok[k] = i0 + k * 256 < n && decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local);
       const u64 e_slot = s_slot + span;
-      bs[k] = (u32)(s_slot >> shift);
-      be[k] = (u32)(e_slot >> shift);
+      bs[k] = (u32)(s_slot >> GR_BLOCK_SHIFT);
+      be[k] = (u32)(e_slot >> GR_BLOCK_SHIFT);
       two[k] = ok[k] && be[k] != bs[k];
       const u32 so = (u32)s_slot & omask;
       const int cnt = 120 / w;
@@ -847,247 +844,20 @@ k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
   }
 }
 
-// Fixed-capacity buckets (GR_FB_SLOTS=1, with the rank-form scan): block b owns the entries
-// bucketed[b * cap .. b * cap + cap) and cnt[b] counts them, so the count pass and the scan of the
-// block counts are not needed -- one pass over the records instead of two (the count pass is
-// 0.30 ms of the 1.0 ms the bucket stage takes per hg38 sample).  An entry that finds its slot
-// full raises *gate: the slot scan then returns at once and the exact count -> scan -> move
-// chain, launched behind it with the same gate, does the sample instead (decided on the device,
-// while the records are still there; nothing is lost but the time of this pass).
-// Errors and the clamp count are reported by this pass (the gated count pass reports errors
-// again -- the same bits -- and leaves the clamp count alone).
-template <bool PACKED>
-__global__ void __launch_bounds__(256)
-k_fb_move_slot(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cnt, u32* __restrict__ bucketed,
-               u32 cap, int* __restrict__ gate, int* __restrict__ err, u64* __restrict__ clamped) {
-  const u32 omask = GR_BLOCK_SLOTS - 1;
-  const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
-  int e_local = 0;
-  u32 c_local = 0;
-  bool over = false;
-  for (u64 i0 = (u64)blockIdx.x * (256 * FB_UNROLL) + threadIdx.x; i0 < n; i0 += stride) {
-    int4 r[FB_UNROLL];
-#pragma unroll
-    for (int k = 0; k < FB_UNROLL; k++)
-      if (i0 + k * 256 < n) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
-    bool ok[FB_UNROLL], two[FB_UNROLL];
-    u32 e0[FB_UNROLL], e1[FB_UNROLL], bs[FB_UNROLL], be[FB_UNROLL], p0[FB_UNROLL], p1[FB_UNROLL];
-#pragma unroll
-    for (int k = 0; k < FB_UNROLL; k++) {
-      u64 s_slot = 0; u32 span = 0; int w = 120;
-      ok[k] = i0 + k * 256 < n && decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local);
-      const u64 e_slot = s_slot + span;
-      bs[k] = (u32)(s_slot >> GR_BLOCK_SHIFT);
-      be[k] = (u32)(e_slot >> GR_BLOCK_SHIFT);
-      two[k] = ok[k] && be[k] != bs[k];
-      const u32 so = (u32)s_slot & omask;
-      const int c = 120 / w;
-      e0[k] = two[k] ? fb_entry(so, 0, c, FB_KIND_START) : fb_entry(so, span, c, FB_KIND_BOTH);
-      e1[k] = fb_entry((u32)e_slot & omask, 0, c, FB_KIND_END);
-    }
-#pragma unroll
-    for (int k = 0; k < FB_UNROLL; k++) {              // the counter atomics of all records, back to back
-      p0[k] = ok[k] ? atomicAdd(cnt + bs[k], 1u) : 0u;
-      p1[k] = two[k] ? atomicAdd(cnt + be[k], 1u) : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < FB_UNROLL; k++) {
-      if (ok[k]) { if (p0[k] < cap) bucketed[(u64)bs[k] * cap + p0[k]] = e0[k]; else over = true; }
-      if (two[k]) { if (p1[k] < cap) bucketed[(u64)be[k] * cap + p1[k]] = e1[k]; else over = true; }
-    }
-  }
-  if (over) atomicOr(gate, 1);
-  if (e_local) atomicOr(err, e_local);
-  if (c_local) atomicAdd(clamped, (u64)c_local);
-}
-
-// Two-level partition (GR_FB_P2=1; not the default until it has been measured).  k_fb_move is bound
-// by RETURNING L2 atomics (one per entry: 52 M ATOM in 0.69 ms, and the count pass pays the same
-// number of REDs), because consecutive records fall into unrelated buckets.  Here the entries are
-// first partitioned into <= 1024 COARSE bins of F = 2^fsh blocks each: a CTA histograms a tile of
-// 16384 records in shared memory and reserves room with one global atomic per bin and tile (~20 x
-// fewer); then one CTA per coarse bin sorts its ~70 k (block, entry) pairs -- L2 resident -- into
-// the exact per-block buckets with shared-memory counters only, and writes blk_start on the way.
-// Output = what count -> scan -> move produce (entries of a bucket in another order, which no
-// consumer depends on).
-//   k_p1_count  records -> pairs per coarse bin (shared-memory histogram; errors, clamp count)
-//   k_p1_scan   exclusive scan of the <= 1024 bin counts
-//   k_p1_move   records -> (block << 32 | entry) pairs, grouped by coarse bin
-//   k_p2        one CTA per bin: pairs -> buckets + blk_start
-#define P1_MAXB 1024
-#define P1_TILE 16384
-#define P2_MAXF 4096
-template <bool PACKED>
-__global__ void __launch_bounds__(256)
-k_p1_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cnt1, int fsh,
-           int* __restrict__ err, u64* __restrict__ clamped) {
-  __shared__ u32 sm_h[P1_MAXB];
-  for (int i = threadIdx.x; i < P1_MAXB; i += 256) sm_h[i] = 0;
-  __syncthreads();
-  const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
-  int e_local = 0;
-  u32 c_local = 0;
-  for (u64 i0 = (u64)blockIdx.x * (256 * FB_UNROLL) + threadIdx.x; i0 < n; i0 += stride) {
-    int4 r[FB_UNROLL];
-#pragma unroll
-    for (int k = 0; k < FB_UNROLL; k++)
-      if (i0 + k * 256 < n) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
-#pragma unroll
-    for (int k = 0; k < FB_UNROLL; k++) {
-      if (i0 + k * 256 >= n) break;
-      u64 s_slot; u32 span; int w;
-      if (!decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local)) continue;
-      const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)((s_slot + span) >> GR_BLOCK_SHIFT);
-      atomicAdd(sm_h + (bs >> fsh), 1u);
-      if (be != bs) atomicAdd(sm_h + (be >> fsh), 1u);
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < P1_MAXB; i += 256)
-    if (sm_h[i]) atomicAdd(cnt1 + i, sm_h[i]);
-  if (e_local) atomicOr(err, e_local);       // errors and clamp counts are reported by this pass only
-  if (c_local) atomicAdd(clamped, (u64)c_local);
-}
-
-__global__ void __launch_bounds__(1024)
-k_p1_scan(const u32* __restrict__ cnt1, u32 nb1, u32* __restrict__ base1, u32* __restrict__ cursor1) {
-  __shared__ u32 sh[32];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const u32 v = (u32)t < nb1 ? cnt1[t] : 0u;
-  const u32 wi = warp_incl_scan_u32(v, lane);
-  if (lane == 31) sh[w] = wi;
-  __syncthreads();
-  if (w == 0) {
-    const u32 x = sh[lane];
-    const u32 xi = warp_incl_scan_u32(x, lane);
-    sh[lane] = xi - x;
-  }
-  __syncthreads();
-  const u32 ex = sh[w] + wi - v;
-  if ((u32)t < nb1) { base1[t] = ex; cursor1[t] = ex; }
-  if ((u32)t == nb1 - 1) base1[nb1] = ex + v;
-}
-
-template <bool PACKED>
-__global__ void __launch_bounds__(256)
-k_p1_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor1, u64* __restrict__ pairs,
-          int fsh, u32 nb1) {
-  __shared__ u32 sm_h[P1_MAXB];
-  const u32 omask = GR_BLOCK_SLOTS - 1;
-  const u64 ntiles = (n + P1_TILE - 1) / P1_TILE;
-  for (u32 i = threadIdx.x; i < nb1; i += 256) sm_h[i] = 0;
-  __syncthreads();
-  int e_local = 0;
-  u32 c_local = 0;
-  for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const u64 t0 = tile * P1_TILE, t1 = min(t0 + (u64)P1_TILE, n);
-    // pass A: pairs of this tile per coarse bin
-    for (u64 i0 = t0 + threadIdx.x; i0 < t1; i0 += 256 * FB_UNROLL) {
-      int4 r[FB_UNROLL];
-#pragma unroll
-      for (int k = 0; k < FB_UNROLL; k++)
-        if (i0 + k * 256 < t1) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
-#pragma unroll
-      for (int k = 0; k < FB_UNROLL; k++) {
-        if (i0 + k * 256 >= t1) break;
-        u64 s_slot; u32 span; int w;
-        if (!decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local)) continue;
-        const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)((s_slot + span) >> GR_BLOCK_SHIFT);
-        atomicAdd(sm_h + (bs >> fsh), 1u);
-        if (be != bs) atomicAdd(sm_h + (be >> fsh), 1u);
-      }
-    }
-    __syncthreads();
-    // room for them: one global atomic per non-empty bin
-    for (u32 i = threadIdx.x; i < nb1; i += 256) {
-      const u32 h = sm_h[i];
-      sm_h[i] = h ? atomicAdd(cursor1 + i, h) : 0u;
-    }
-    __syncthreads();
-    // pass B: the records again (they are in L1 / L2), every pair to its place
-    for (u64 i0 = t0 + threadIdx.x; i0 < t1; i0 += 256 * FB_UNROLL) {
-      int4 r[FB_UNROLL];
-#pragma unroll
-      for (int k = 0; k < FB_UNROLL; k++)
-        if (i0 + k * 256 < t1) r[k] = load_raw<PACKED>(recs, i0 + k * 256);
-#pragma unroll
-      for (int k = 0; k < FB_UNROLL; k++) {
-        if (i0 + k * 256 >= t1) break;
-        u64 s_slot; u32 span; int w;
-        if (!decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local)) continue;
-        const u64 e_slot = s_slot + span;
-        const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)(e_slot >> GR_BLOCK_SHIFT);
-        const u32 so = (u32)s_slot & omask;
-        const int cnt = 120 / w;
-        if (be != bs) {
-          pairs[atomicAdd(sm_h + (bs >> fsh), 1u)] = ((u64)bs << 32) | fb_entry(so, 0, cnt, FB_KIND_START);
-          pairs[atomicAdd(sm_h + (be >> fsh), 1u)] = ((u64)be << 32) | fb_entry((u32)e_slot & omask, 0, cnt, FB_KIND_END);
-        } else {
-          pairs[atomicAdd(sm_h + (bs >> fsh), 1u)] = ((u64)bs << 32) | fb_entry(so, span, cnt, FB_KIND_BOTH);
-        }
-      }
-    }
-    __syncthreads();
-    for (u32 i = threadIdx.x; i < nb1; i += 256) sm_h[i] = 0;
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(512)
-k_p2(const u64* __restrict__ pairs, const u32* __restrict__ base1, u32 nb1, int fsh, u32 nblocks,
-     u32* __restrict__ blk_start, u32* __restrict__ bucketed) {
-  __shared__ u32 sm_c[P2_MAXF];
-  __shared__ u32 sm_w[16];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const u32 bin = blockIdx.x, F = 1u << fsh, blk0 = bin << fsh;
-  const u32 a = base1[bin], b = base1[bin + 1];
-  for (u32 i = t; i < F; i += 512) sm_c[i] = 0;
-  __syncthreads();
-  for (u32 i = a + t; i < b; i += 512) atomicAdd(sm_c + ((u32)(pairs[i] >> 32) - blk0), 1u);
-  __syncthreads();
-  // exclusive scan of the F block counts: every thread owns K = F / 512 consecutive counters
-  const u32 K = F >> 9;
-  u32 s = 0;
-  for (u32 k = 0; k < K; k++) s += sm_c[t * K + k];
-  const u32 wi = warp_incl_scan_u32(s, lane);
-  if (lane == 31) sm_w[w] = wi;
-  __syncthreads();
-  if (w == 0) {
-    const u32 x = lane < 16 ? sm_w[lane] : 0u;
-    const u32 xi = warp_incl_scan_u32(x, lane);
-    if (lane < 16) sm_w[lane] = xi - x;
-  }
-  __syncthreads();
-  u32 run = a + sm_w[w] + wi - s;
-  for (u32 k = 0; k < K; k++) {
-    const u32 c = sm_c[t * K + k];
-    const u32 blk = blk0 + t * K + k;
-    if (blk < nblocks) blk_start[blk] = run;
-    sm_c[t * K + k] = run;                               // becomes the bucket's cursor
-    run += c;
-  }
-  if (bin == nb1 - 1 && t == 0) blk_start[nblocks] = b;
-  __syncthreads();
-  for (u32 i = a + t; i < b; i += 512) {
-    const u64 p = pairs[i];
-    bucketed[atomicAdd(sm_c + ((u32)(p >> 32) - blk0), 1u)] = (u32)p;
-  }
-}
-
 // -E region boundaries (a few thousand at most): one pseudo entry each, so that the scan finds
 // them in the occupancy bitmap like any other event.  cursor == NULL: count pass.
 __global__ void k_fb_marks(const u64* __restrict__ marks, u32 n, u32* __restrict__ blk_cnt,
-                           u32* __restrict__ cursor, u32* __restrict__ bucketed, int shift) {
+                           u32* __restrict__ cursor, u32* __restrict__ bucketed) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const u64 slot = marks[i];
-  const u32 b = (u32)(slot >> shift);
+  const u32 b = (u32)(slot >> GR_BLOCK_SHIFT);
   if (!cursor) atomicAdd(blk_cnt + b, 1u);
-  else bucketed[atomicAdd(cursor + b, 1u)] = fb_entry((u32)slot & ((1u << shift) - 1), 0, 1, FB_KIND_MARK);
+  else bucketed[atomicAdd(cursor + b, 1u)] = fb_entry((u32)slot & (GR_BLOCK_SLOTS - 1), 0, 1, FB_KIND_MARK);
 }
-void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed, int shift) {
+void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed) {
   if (!n) return;
-  k_fb_marks<<<(n + 127) / 128, 128, 0, s>>>(marks, n, blk_cnt, cursor, bucketed, shift); GR_NOTE_LAUNCH();
+  k_fb_marks<<<(n + 127) / 128, 128, 0, s>>>(marks, n, blk_cnt, cursor, bucketed); GR_NOTE_LAUNCH();
 }
 
 #define FB_WORDS (GR_BLOCK_SLOTS / 32)                 // occupancy / break bitmap words per block
@@ -1292,177 +1062,11 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   }
 }
 
-// Warp-owned form: the buckets are 2^SHIFT cells (2048 or 4096), every WARP owns a contiguous
-// run of them and a private cell array -- no __syncthreads anywhere, 24 (12) independent warps
-// per SM instead of 6 CTAs that meet at three barriers per block (ncu on the CTA form: 6 barrier
-// stall cycles per issued instruction, issue slots half empty).
-#define FW_RING 64                                     // page ring per warp: <= 2 * 17 + 2 sequence numbers in flight
-template <int SHIFT>
-__global__ void __launch_bounds__(128)
-k_fw_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
-          u32* __restrict__ bitmap, int* __restrict__ err, u32 nbk, u32 R) {
-  constexpr int CELLS = 1 << SHIFT, WORDS = CELLS / 32, WPT = WORDS / 32, PF = 2;
-  extern __shared__ int sm_cell_all[];                  // 4 * CELLS
-  __shared__ u32 sm_occ_all[4 * WORDS];
-  __shared__ u32 sm_pg_all[4 * FW_RING];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int* const sm_cell = sm_cell_all + wid * CELLS;
-  u32* const sm_occ = sm_occ_all + wid * WORDS;
-  u32* const sm_pg = sm_pg_all + wid * FW_RING;
-  const u32 owner = blockIdx.x * 4 + wid;
-  const u32 b0 = owner * R, b1 = min(b0 + R, nbk);
-  if (b0 >= b1) {
-    if (lane == 0 && owner < SS_MAX_WARPS) W.warp_tot[owner] = make_uint2(0, 0);
-    return;
-  }
-  for (int i = lane; i < CELLS; i += 32) sm_cell[i] = 0;
-  for (int i = lane; i < WORDS; i += 32) sm_occ[i] = 0;
-
-  auto ld_start = [&](u32 i) { return blk_start[min(i, nbk)]; };
-  u32 sA = ld_start(b0), sB = ld_start(b0 + 1), sC = ld_start(b0 + 2);
-  auto ub_of = [&](u32 a, u32 b) { return min(2u * (b - a) + 1u, (u32)CELLS + 1u); };
-
-  const u32 last_page = W.max_pages - 1;
-  int have_seq = -1;
-  u32 pend_p0 = 0;
-  int pend_k = 0;
-  auto page_take = [&]() {
-    for (int i = 0; i < pend_k; i++) {
-      u32 pg = pend_p0 + (u32)i;
-      if (pg > last_page) { atomicOr(err, GR_DE_TABLE); pg = last_page; }
-      have_seq++;
-      W.page_meta[pg] = make_uint2(owner, (u32)have_seq);
-      sm_pg[have_seq & (FW_RING - 1)] = pg;
-    }
-    pend_k = 0;
-  };
-  auto page_ask = [&](u32 upto_idx) {
-    const int target = (int)(upto_idx >> SS_PAGE_SHIFT);
-    if (target > have_seq) {
-      pend_k = target - have_seq;
-      pend_p0 = atomicAdd(W.page_ctr, (u32)pend_k);
-    }
-  };
-  if (lane == 0) page_ask(ub_of(sA, sB));
-
-  u32 v[PF];
-#pragma unroll
-  for (int k = 0; k < PF; k++) {
-    v[k] = 0;
-    if (sA + k * 32 + lane < sB) v[k] = __ldcs(bucketed + sA + k * 32 + lane);
-  }
-  auto apply = [&](u32 e) {
-    const u32 so = e & (CELLS - 1), kind = e >> 30;
-    const int w = 120 / (int)((e >> 26) & 15u);
-    atomicAdd(sm_cell + so, kind == FB_KIND_END ? -w : w);
-    atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
-    if (kind == FB_KIND_BOTH) {
-      const u32 eo = so + ((e >> 13) & (GR_BLOCK_SLOTS - 1));
-      atomicAdd(sm_cell + eo, -w);
-      atomicOr(sm_occ + (eo >> 5), 1u << (eo & 31));
-    }
-  };
-
-  u32 run_s = 0, run_c = 0;
-  bool sat = false;
-  int c = -1;
-  u32 c_last_bk = 0;
-  u64 off = 0;
-  u32 len = 0;
-  bool act = false;
-  __syncwarp();
-  for (u32 b = b0; b < b1; b++) {
-    if (c < 0 || b > c_last_bk) {                      // ~25 times per genome
-      c = L.blk2chrom[b >> (GR_BLOCK_SHIFT - SHIFT)];
-      off = L.off[c];
-      len = L.len[c];
-      c_last_bk = (u32)((off + len) >> SHIFT);
-      act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
-    }
-    const u32 sD = ld_start(b + 3);
-    const u32 jb = (u32)(((u64)b << SHIFT) - off);     // chromosome position of the bucket's first cell
-    if (lane == 0) {
-      if (jb == 0) W.marks[c] = make_uint4(owner, run_s, run_c, 1u);
-      page_take();
-      page_ask(run_c + ub_of(sA, sB) + (b + 1 < b1 ? ub_of(sB, sC) : 0u));
-    }
-    const bool has_end = act && b == c_last_bk;        // cell `len` lies in this bucket
-    u32* const bm_out = bitmap + (u64)b * WORDS + lane * WPT;
-    if (sA == sB && !has_end) {                        // nothing in this bucket
-      if (WPT == 2) *reinterpret_cast<uint2*>(bm_out) = make_uint2(0, 0);
-      else *reinterpret_cast<uint4*>(bm_out) = make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int k = 0; k < PF; k++)
-        if (sB + k * 32 + lane < sC) v[k] = __ldcs(bucketed + sB + k * 32 + lane);
-      sA = sB; sB = sC; sC = sD;
-      continue;
-    }
-#pragma unroll
-    for (int k = 0; k < PF; k++)
-      if (sA + k * 32 + lane < sB) apply(v[k]);
-    for (u32 i = sA + PF * 32 + lane; i < sB; i += 32) apply(__ldcs(bucketed + i));
-#pragma unroll
-    for (int k = 0; k < PF; k++)
-      if (sB + k * 32 + lane < sC) v[k] = __ldcs(bucketed + sB + k * 32 + lane);
-    __syncwarp();
-    const u32 end_cell = len - jb;                     // meaningful if has_end
-    u32 mo[WPT], m[WPT];
-    u32 s = 0, cnt = 0;
-    const int cbase = lane * (32 * WPT);
-    const u32 jt = jb + (u32)cbase;
-#pragma unroll
-    for (int q = 0; q < WPT; q++) {
-      mo[q] = sm_occ[lane * WPT + q];
-      sm_occ[lane * WPT + q] = 0;
-      if (has_end && (int)(end_cell >> 5) == lane * WPT + q) mo[q] |= 1u << (end_cell & 31);
-      m[q] = 0;
-      for (u32 mm = mo[q]; mm; mm &= mm - 1) {
-        const int bit = __ffs(mm) - 1;
-        const int d = sm_cell[cbase + q * 32 + bit];
-        const u32 j = jt + (u32)(q * 32 + bit);
-        s += (u32)d;
-        sat |= cell_saturated(d);
-        const bool brk = (j == len) || (d != 0 && j >= 1u && j < len);
-        m[q] |= (brk ? 1u : 0u) << bit;
-      }
-      if (!act) m[q] = 0;
-      cnt += __popc(m[q]);
-    }
-    const u32 wi_s = warp_incl_scan_u32(s, lane), wi_c = warp_incl_scan_u32(cnt, lane);
-    u32 h = run_s + wi_s - s, idx = run_c + wi_c - cnt;
-#pragma unroll
-    for (int q = 0; q < WPT; q++) {
-      for (u32 mm = mo[q]; mm; mm &= mm - 1) {
-        const int bit = __ffs(mm) - 1;
-        const int d = sm_cell[cbase + q * 32 + bit];
-        sm_cell[cbase + q * 32 + bit] = 0;
-        if ((m[q] >> bit) & 1u) {
-          const u32 pg = sm_pg[(idx >> SS_PAGE_SHIFT) & (FW_RING - 1)];
-          W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(jt + (u32)(q * 32 + bit), h);
-          idx++;
-        }
-        h += (u32)d;
-      }
-    }
-    if (WPT == 2) *reinterpret_cast<uint2*>(bm_out) = make_uint2(m[0], m[1]);
-    else *reinterpret_cast<uint4*>(bm_out) = make_uint4(m[0], m[1], m[WPT > 2 ? 2 : 0], m[WPT > 3 ? 3 : 0]);
-    run_s += __shfl_sync(GR_FULL, wi_s, 31);
-    run_c += __shfl_sync(GR_FULL, wi_c, 31);
-    sA = sB; sB = sC; sC = sD;
-    __syncwarp();                                      // cells and occupancy words are free again
-  }
-  if (sat) atomicOr(err, GR_DE_SAT);
-  if (lane == 0) {
-    page_take();
-    W.warp_tot[owner] = make_uint2(run_s, run_c);
-  }
-}
-
-// Rank form (GR_FUSED_RANK=1; not the default until it has been measured): warp-owned 8192-cell
-// blocks WITHOUT a cell array.  A block of the hg38 workload holds ~265 entries = ~400 distinct
-// event cells out of 8192; k_fb_scan spends its time in three CTA barriers per block and in a
-// walk whose length is the fullest thread's (ncu: issue slots half empty), and the warp-owned
-// k_fw_scan needs small buckets (its cell array is per warp), which the move pass pays for.
+// Rank form -- the default scan: warp-owned 8192-cell blocks WITHOUT a cell array.  A block of the
+// hg38 workload holds ~265 entries = ~400 distinct event cells out of 8192; k_fb_scan spends its
+// time in three CTA barriers per block and in a walk whose length is the fullest thread's (ncu:
+// issue slots half empty).  Measured on the B200 (hg38, 50 M records): 0.67 ms per launch against
+// 1.69 ms, same bits.
 // Here a warp keeps only the block's 256-word occupancy bitmap and, per DISTINCT event cell, a
 // sum and a position:
 //   P1  entries -> occupancy bits
@@ -1473,10 +1077,8 @@ k_fw_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
 //   P5  the occupancy words ARE the break bitmap: written out, cleared
 // Every lane has work in every round, nothing is walked, no __syncthreads.  A block with more
 // than CAP distinct cells takes several rounds of P3/P4, cut at word boundaries (so that the bits
-// P4 clears never sit below a cell that still has to be ranked).  Output contract = k_fw_scan's
-// (owner = warp: pages, warp_tot, marks), so k_scan_fix / k_scan_place follow unchanged.
-// SLOT: the entries of block b lie at bucketed[b * slot_cap ...] and blk_start[b] is their count
-// (fixed-capacity buckets, filled by k_fb_move_slot without a count pass).
+// P4 clears never sit below a cell that still has to be ranked).  Output contract = k_fb_scan's
+// with owner = warp (pages, warp_tot, marks), so k_scan_fix / k_scan_place follow unchanged.
 // 120 / count without the division subroutine (one per entry otherwise): byte `count` of a 16-entry table
 __device__ __forceinline__ int fr_weight(u32 count) {
   const u64 t = (count & 8u) ? 0x0808090A0A0C0D0Full : 0x1114181E283C7800ull;   // 120 / 8..15 | 120 / 0..7 (0 -> 0)
@@ -1484,19 +1086,15 @@ __device__ __forceinline__ int fr_weight(u32 count) {
 }
 #define FR_RING 128                                    // page ring per warp: <= 2 * 33 + 2 sequence numbers in flight
 // PF: entry registers per lane (32 * PF entries of a block are prefetched while the previous block is worked on)
-template <int CAP, int CPS, int PF, bool SLOT>
+template <int CAP, int CPS, int PF>
 __global__ void __launch_bounds__(128, CPS)
 k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
-          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R, u32 slot_cap,
-          const int* __restrict__ gate, int gate_on) {
+          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R) {
   __shared__ __align__(16) u32 sm_occ_all[4 * FB_WORDS];
   __shared__ __align__(16) u32 sm_pre_all[4 * FB_WORDS];
   __shared__ int sm_sum_all[4 * CAP];
   __shared__ unsigned short sm_pos_all[4 * CAP];
   __shared__ u32 sm_pg_all[4 * FR_RING];
-  // slot path: the scan over the slots runs unless one overflowed (gate_on 0), the scan behind the
-  // exact two-pass chain only if one did (gate_on 1)
-  if (gate && (*gate != 0) != (gate_on != 0)) return;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   u32* const sm_occ = sm_occ_all + wid * FB_WORDS;
   u32* const sm_pre = sm_pre_all + wid * FB_WORDS;
@@ -1515,11 +1113,9 @@ k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   // entries of block i: n_of(i) of them, starting at lo_of(i)
   auto n_of = [&](u32 i) -> u32 {
     if (i >= nblocks) return 0u;
-    if (SLOT) return min(blk_start[i], slot_cap);
     return blk_start[i + 1] - blk_start[i];
   };
   auto lo_of = [&](u32 i) -> u64 {
-    if (SLOT) return (u64)i * slot_cap;
     return (u64)blk_start[min(i, nblocks)];
   };
   auto ub_of = [&](u32 n) { return min(2u * n + 1u, (u32)GR_BLOCK_SLOTS + 1u); };   // breaks of a block, upper bound
@@ -1713,99 +1309,33 @@ k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
 }
 
 void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
-                     u32* blk_cnt, int* err, u64* clamped, int shift) {
+                     u32* blk_cnt, int* err, u64* clamped) {
   if (!n) return;
   u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_fb_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped, shift);
-  else k_fb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped, shift);
+  if (packed) k_fb_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
+  else k_fb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
   GR_NOTE_LAUNCH();
 }
-void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
-                    int shift) {
+void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed) {
   if (!n) return;
   u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, shift);
-  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, shift);
+  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
+  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
   GR_NOTE_LAUNCH();
-}
-
-void launch_fb_move_slot(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cnt, u32* bucketed,
-                         u32 cap, int* gate, int* err, u64* clamped) {
-  if (!n) return;
-  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_fb_move_slot<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cnt, bucketed, cap, gate, err, clamped);
-  else k_fb_move_slot<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cnt, bucketed, cap, gate, err, clamped);
-  GR_NOTE_LAUNCH();
-}
-// the exact chain behind the slot pass: runs on the device only if *gate was raised
-void launch_fb_count_gated(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
-                           u32* blk_cnt, int* err, const int* gate) {
-  if (!n) return;
-  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_fb_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, nullptr, GR_BLOCK_SHIFT, gate);
-  else k_fb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, nullptr, GR_BLOCK_SHIFT, gate);
-  GR_NOTE_LAUNCH();
-}
-void launch_fb_move_gated(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor,
-                          u32* bucketed, const int* gate) {
-  if (!n) return;
-  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, GR_BLOCK_SHIFT, gate);
-  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, GR_BLOCK_SHIFT, gate);
-  GR_NOTE_LAUNCH();
-}
-
-// fsh: log2 of the blocks per coarse bin -- at least 512 blocks, at most 1024 bins
-int fb_p2_shift(u64 nblocks) {
-  int fsh = 9;
-  while (((nblocks + (1ull << fsh) - 1) >> fsh) > P1_MAXB) fsh++;
-  return fsh <= 12 ? fsh : -1;                 // more than 4 M blocks (34 Gbp on one device): not this way
-}
-void launch_p1_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cnt1, int fsh,
-                     int* err, u64* clamped) {
-  if (!n) return;
-  u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  if (packed) k_p1_count<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cnt1, fsh, err, clamped);
-  else k_p1_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cnt1, fsh, err, clamped);
-  GR_NOTE_LAUNCH();
-}
-void launch_p1_scan(cudaStream_t s, const u32* cnt1, u32 nb1, u32* base1, u32* cursor1) {
-  k_p1_scan<<<1, 1024, 0, s>>>(cnt1, nb1, base1, cursor1); GR_NOTE_LAUNCH();
-}
-void launch_p1_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor1, u64* pairs,
-                    int fsh, u32 nb1) {
-  if (!n) return;
-  u64 blocks = (n + P1_TILE - 1) / P1_TILE;
-  if (blocks > 148 * 6) blocks = 148 * 6;
-  if (packed) k_p1_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor1, pairs, fsh, nb1);
-  else k_p1_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor1, pairs, fsh, nb1);
-  GR_NOTE_LAUNCH();
-}
-void launch_p2(cudaStream_t s, const u64* pairs, const u32* base1, u32 nb1, int fsh, u64 nblocks, u32* blk_start,
-               u32* bucketed) {
-  k_p2<<<nb1, 512, 0, s>>>(pairs, base1, nb1, fsh, (u32)nblocks, blk_start, bucketed); GR_NOTE_LAUNCH();
 }
 
 static int fb_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
-// GR_FUSED_SHIFT: log2 of the bucket size -- 13 (default): CTA-owned 8192-cell blocks (k_fb_scan,
-// with GR_FUSED_CPS / GR_FUSED_NT); 11 or 12: warp-owned buckets (k_fw_scan).  Measured on the
-// hg38 workload, ms per sample (bucket passes + scan): 13: 1.02 + 1.55; 12: 1.31 + 1.80;
-// 11: 1.84 + 1.25 -- the scan likes small buckets (more independent owners per SM), the move
-// pass does not (4x the open write sectors in L2).
-int fb_bucket_shift() {                                // read per call: the tests switch it inside one process
-  const int sh = fb_env("GR_FUSED_SHIFT", 13);
-  return sh < 11 || sh > 13 ? 13 : sh;
-}
 
-// bucketed events -> breaks (pages) + break bitmap; launch_scan_place(..., owners) follows
+// bucketed events -> breaks (pages) + break bitmap; launch_scan_place(..., owners) follows.
+// Default: k_fr_scan (warp-owned blocks, rank form; 9 CTAs x 4 warps per SM, 512 distinct cells per
+// round) -- measured on the B200 at 0.67 ms per hg38 sample against 1.69 ms for the CTA-owned
+// k_fb_scan, same bits.  k_fb_scan stays for contexts with -E regions (the region boundaries are
+// weightless mark entries only it understands) and, behind GR_FUSED_CTA=1, as the comparison the
+// bench quotes.
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
-                   const ScanScratch& sc, u32* bitmap, int* err, int sh, const uint8_t* blk_bed) {
+                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   cudaMemsetAsync(W.page_ctr, 0, 4, s);
   static int sms = 0;
@@ -1814,88 +1344,20 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int cps = fb_env("GR_FUSED_CPS", 6) == 4 ? 4 : 6, nt = fb_env("GR_FUSED_NT", 128);
+  const u32 nb = (u32)L.nblocks;
   u32 owners;
-  const int rank_form = blk_bed ? 0 : fb_env("GR_FUSED_RANK", 0);   // -E marks exist in k_fb_scan only
-  if (sh == 13 && rank_form) {
-    // warp-owned 8192-cell blocks, rank form (k_fr_scan): 9 CTAs x 4 warps per SM with 512 distinct
-    // cells per round, 6 with 1024 (GR_FR_CAP)
-    // knobs: GR_FR_CAP 512 | 1024 distinct cells per round, GR_FR_CPS 9 | 7 CTAs per SM (56 / 72 registers),
-    // GR_FR_PF 8 | 4 entry registers per lane
-    const int cap = fb_env("GR_FR_CAP", 512) == 1024 ? 1024 : 512;
-    const int cps = cap == 1024 ? 6 : (fb_env("GR_FR_CPS", 9) == 7 ? 7 : 9);
-    const int pf = fb_env("GR_FR_PF", 8) == 4 ? 4 : 8;
-    const int ctas = sms * cps;
-    owners = (u32)ctas * 4;
-    if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
-    const u32 nb = (u32)L.nblocks;
+  if (blk_bed || fb_env("GR_FUSED_CTA", 0)) {            // read per call: the tests switch it inside one process
+    owners = (u32)(sms * 6);
     const u32 R = (nb + owners - 1) / owners;
-#define FR_GO(C, P, F) k_fr_scan<C, P, F, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, nullptr, 0)
-    if (cap == 1024) { if (pf == 4) FR_GO(1024, 6, 4); else FR_GO(1024, 6, 8); }
-    else if (cps == 7) { if (pf == 4) FR_GO(512, 7, 4); else FR_GO(512, 7, 8); }
-    else { if (pf == 4) FR_GO(512, 9, 4); else FR_GO(512, 9, 8); }
-#undef FR_GO
-  } else if (sh == 13) {
-    owners = (u32)(sms * cps);
-    const u32 nb = (u32)L.nblocks;
-    const u32 R = (nb + owners - 1) / owners;
-#define FB_LAUNCH(C, N) k_fb_scan<C, N, false><<<owners, N, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr)
-    if (blk_bed) k_fb_scan<6, 128, true><<<owners = (u32)(sms * 6), 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb,
-                                                                              (nb + sms * 6 - 1) / (sms * 6), blk_bed);
-    else if (cps == 4) { if (nt == 256) FB_LAUNCH(4, 256); else if (nt == 64) FB_LAUNCH(4, 64); else FB_LAUNCH(4, 128); }
-    else { if (nt == 256) FB_LAUNCH(6, 256); else if (nt == 64) FB_LAUNCH(6, 64); else FB_LAUNCH(6, 128); }
-#undef FB_LAUNCH
+    if (blk_bed) k_fb_scan<6, 128, true><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed);
+    else k_fb_scan<6, 128, false><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr);
   } else {
-    const int ctas = sms * (sh == 11 ? 6 : 3);         // 4 warps each: 35 KB (68 KB) of shared memory per CTA
-    owners = (u32)ctas * 4;
+    owners = (u32)(sms * 9) * 4;
     if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
-    const u32 nbk = (u32)(L.T >> sh);
-    const u32 R = (nbk + owners - 1) / owners;
-    const size_t smem = (size_t)16 << sh;              // 4 warps x 2^sh cells x 4 bytes
-    static bool init = false;
-    if (!init) {
-      cudaFuncSetAttribute(k_fw_scan<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 11);
-      cudaFuncSetAttribute(k_fw_scan<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 << 12);
-      init = true;
-    }
-    if (sh == 11) k_fw_scan<11><<<owners / 4, 128, smem, s>>>(bucketed, blk_start, L, W, bitmap, err, nbk, R);
-    else k_fw_scan<12><<<owners / 4, 128, smem, s>>>(bucketed, blk_start, L, W, bitmap, err, nbk, R);
+    const u32 R = (nb + owners - 1) / owners;
+    k_fr_scan<512, 9, 8><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
   }
   GR_NOTE_LAUNCH();
-  return owners;
-}
-
-// Slot path: the rank-form scan over the fixed-capacity buckets, and behind it the same scan over
-// the exact buckets; *gate (raised by k_fb_move_slot on overflow) decides on the device which of
-// the two does anything.  Both fill the same pages / totals, so what follows does not care.
-bool fb_p2() { return fb_env("GR_FB_P2", 0) != 0 && fb_bucket_shift() == 13; }
-bool fb_rank_form() { return fb_env("GR_FUSED_RANK", 0) != 0; }
-bool fb_slots() { return fb_env("GR_FB_SLOTS", 0) != 0 && fb_rank_form() && fb_bucket_shift() == 13; }
-u32 launch_fr_scan_slot(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* slot_cnt, u32 slot_cap,
-                        const u32* blk_start, const ScanScratch& sc, u32* bitmap, int* err, const int* gate) {
-  const StreamWs W = stream_ws(sc, L.nchrom);
-  cudaMemsetAsync(W.page_ctr, 0, 4, s);
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  const int cap = fb_env("GR_FR_CAP", 512) == 1024 ? 1024 : 512;
-  const int cps = cap == 1024 ? 6 : (fb_env("GR_FR_CPS", 9) == 7 ? 7 : 9);
-  const int ctas = sms * cps;
-  u32 owners = (u32)ctas * 4;
-  if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
-  const u32 nb = (u32)L.nblocks;
-  const u32 R = (nb + owners - 1) / owners;
-#define FR_GO2(C, P) do { \
-    k_fr_scan<C, P, 8, true><<<owners / 4, 128, 0, s>>>(bucketed, slot_cnt, L, W, bitmap, err, nb, R, slot_cap, gate, 0); \
-    k_fr_scan<C, P, 8, false><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, 0u, gate, 1); } while (0)
-  if (cap == 1024) FR_GO2(1024, 6);
-  else if (cps == 7) FR_GO2(512, 7);
-  else FR_GO2(512, 9);
-#undef FR_GO2
-  GR_NOTE_LAUNCH(); GR_NOTE_LAUNCH();
   return owners;
 }
 
@@ -1983,94 +1445,11 @@ k_rle_moment(DevRle r, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ 
   flush();
 }
 
-// J intervals per thread and round instead of 4 (GR_RM_PER=8; not the default until it has been measured):
-// the pass moves 0.6 GB per hg38 sample in 0.23 ms (2.6 TB/s) with 12 loads per thread in flight; 24 here.
-template <int J>
-__global__ void __launch_bounds__(256)
-k_rle_moment_j(DevRle r, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ acc_frac) {
-  __shared__ u64 sm_i[8], sm_f[8];
-  const u64 n = *r.total;
-  // each CTA owns one contiguous slice of the interval array, so its running
-  // chromosome changes at most a handful of times: sums stay in registers and
-  // reach the per-chromosome counters with O(#CTAs) atomics instead of O(n/256).
-  // The chromosome of the slice and the index where it ends are block-uniform REGISTERS:
-  // a round that stays below that index needs no search, no shared memory and no barrier
-  // (the first version looked the round's chromosomes up through thread 0 and two barriers
-  // per 1024 intervals: ~3 us of dependent L2 loads per round, 0.28 ms per hg38 sample).
-  const u64 per = ((n + gridDim.x - 1) / gridDim.x + (256 * J - 1)) / (256 * J) * (256 * J);
-  const u64 lo = (u64)blockIdx.x * per;
-  const u64 hi = min(lo + per, n);
-  if (lo >= hi) return;
-  u64 pi = 0, pf = 0;
-  int cur = chrom_of_index(r.chrom_start, nchrom, lo);  // chromosome the register sums belong to
-  u64 cs = r.chrom_start[cur], nb = r.chrom_start[cur + 1];
-  auto flush = [&]() {
-    // block-wide: add (pi, pf) of all threads into chromosome `cur`
-    u64 a = warp_sum_u64(pi), b = warp_sum_u64(pf);
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    __syncthreads();
-    if (lane == 0) { sm_i[w] = a; sm_f[w] = b; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      u64 ti = 0, tf = 0;
-      for (int k = 0; k < 8; k++) { ti += sm_i[k]; tf += sm_f[k]; }
-      ti += tf >> 40;
-      tf &= (1ull << 40) - 1;
-      if (ti) atomicAdd(acc_int + cur, ti);
-      if (tf) atomicAdd(acc_frac + cur, tf);
-    }
-    pi = 0; pf = 0;
-  };
-  for (u64 base = lo; base < hi; base += 256 * J) {    // J intervals per thread per round
-    const u64 last = min(base + 256 * J, hi) - 1;
-    if (last < nb) {
-#pragma unroll
-      for (int j = 0; j < J; j++) {
-        const u64 i = base + j * 256 + threadIdx.x;
-        if (i < hi) {
-          const u32 e = r.end[i];
-          const u32 st = (i == cs) ? 0u : r.end[i - 1];
-          const float v = r.val[i];
-          const float p = v < 0.0f ? 0.0f : __fmul_rn(__uint2float_rn(e - st), v);     // SKIP (-E region): not counted (2016)
-          const u64 ip = (u64)p;                       // p >= 0
-          pi += ip;
-          pf += (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);   // exact: fraction * 2^40
-        }
-      }
-      if (pf >> 62) { pi += pf >> 40; pf &= (1ull << 40) - 1; }
-    } else {
-      // a chromosome boundary inside the round (rare): per-interval atomics
-      flush();
-      for (int j = 0; j < J; j++) {
-        const u64 i = base + j * 256 + threadIdx.x;
-        if (i < hi) {
-          const int c = chrom_of_index(r.chrom_start, nchrom, i);
-          const u32 e = r.end[i];
-          const u32 st = (i == r.chrom_start[c]) ? 0u : r.end[i - 1];
-          const float v = r.val[i];
-          const float p = v < 0.0f ? 0.0f : __fmul_rn(__uint2float_rn(e - st), v);
-          const u64 ip = (u64)p;
-          const u64 fp = (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);
-          if (ip) atomicAdd(acc_int + c, ip);
-          if (fp) atomicAdd(acc_frac + c, fp);
-        }
-      }
-      if (base + 256 * J < hi) {                          // the chromosome the next round starts in
-        cur = chrom_of_index(r.chrom_start, nchrom, base + 256 * J);
-        cs = r.chrom_start[cur]; nb = r.chrom_start[cur + 1];
-      }
-    }
-  }
-  flush();
-}
-
 void launch_rle_moment(cudaStream_t s, const DevRle& r, u64 n_upper, int nchrom,
                        u64* acc_int, u64* acc_frac) {
   if (!n_upper) return;
   u64 blocks = (n_upper + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  const char* pe = getenv("GR_RM_PER");          // read per call: the tests switch it inside one process
-  if (pe && atoi(pe) == 8) { k_rle_moment_j<8><<<(unsigned)blocks, 256, 0, s>>>(r, nchrom, acc_int, acc_frac); GR_NOTE_LAUNCH(); return; }
   k_rle_moment<<<(unsigned)blocks, 256, 0, s>>>(r, nchrom, acc_int, acc_frac); GR_NOTE_LAUNCH();
 }
 

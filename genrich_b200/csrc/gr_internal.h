@@ -58,41 +58,17 @@ void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc
                        float excl_val);
 
 // ---- K1+K2 fused: event buckets -> breaks, the delta cells live in shared memory only ----
-// buckets of 2^shift cells, shift = fb_bucket_shift()
-int fb_bucket_shift();
+// buckets = the 8192-cell blocks of the layout
 void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
-                     u32* blk_cnt, int* err, u64* clamped, int shift);
-void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
-                    int shift);
-// returns the number of run owners (CTAs), to be handed to launch_scan_place
-// sh: bucket shift the entries were made with; blk_bed: per 8192-cell block, bit 0 = the block
-// starts inside a -E region, bit 1 = it holds region boundaries (NULL: no regions; needs sh == 13)
+                     u32* blk_cnt, int* err, u64* clamped);
+void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed);
+// returns the number of run owners (warps or CTAs), to be handed to launch_scan_place
+// blk_bed: per 8192-cell block, bit 0 = the block starts inside a -E region, bit 1 = it holds
+// region boundaries (NULL: no regions)
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
-                   const ScanScratch& sc, u32* bitmap, int* err, int sh, const uint8_t* blk_bed);
-// rank-form scan (GR_FUSED_RANK=1) over fixed-capacity buckets (GR_FB_SLOTS=1): one pass over the
-// records (launch_fb_move_slot), the exact chain behind it gated on the overflow flag
-bool fb_rank_form();
-bool fb_slots();
-void launch_fb_move_slot(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cnt, u32* bucketed,
-                         u32 cap, int* gate, int* err, u64* clamped);
-void launch_fb_count_gated(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
-                           u32* blk_cnt, int* err, const int* gate);
-void launch_fb_move_gated(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor,
-                          u32* bucketed, const int* gate);
-u32 launch_fr_scan_slot(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* slot_cnt, u32 slot_cap,
-                        const u32* blk_start, const ScanScratch& sc, u32* bitmap, int* err, const int* gate);
-// two-level partition (GR_FB_P2=1): coarse bins of 2^fsh blocks, then one CTA per bin
-bool fb_p2();
-int fb_p2_shift(u64 nblocks);
-void launch_p1_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cnt1, int fsh,
-                     int* err, u64* clamped);
-void launch_p1_scan(cudaStream_t s, const u32* cnt1, u32 nb1, u32* base1, u32* cursor1);
-void launch_p1_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor1, u64* pairs,
-                    int fsh, u32 nb1);
-void launch_p2(cudaStream_t s, const u64* pairs, const u32* base1, u32 nb1, int fsh, u64 nblocks, u32* blk_start,
-               u32* bucketed);
+                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed);
 // -E region boundaries as pseudo entries (cursor == NULL: count pass)
-void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed, int shift);
+void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed);
 
 // ---- K2b: per-chromosome sum of (float)(end-start)*val, exact fixed point ------
 // acc_int / acc_frac: [nchrom] u64, zeroed by the caller.  sum = int + frac*2^-40.
@@ -140,13 +116,6 @@ struct PairTable {
 void launch_pair_insert(cudaStream_t s, const float* pExpt, const float* pCtrl, u64 n_upper, const u64* n_dev,
                         const PairTable& t, u32* slot, int* err);
 void launch_pair_eval(cudaStream_t s, const PairTable& t);
-// union emit (warp form) with the pair insert folded in (GR_UE_PAIR=1)
-bool ue_pair_fused();
-void launch_union_emit_pair(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
-                            const u64* rankE, const u64* rankC, const u64* rankU,
-                            const float* exptVal, const float* ctrlVal,
-                            u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
-                            const u64* total, const PairTable& t, u32* slot, int* err);
 void launch_gather_f32(cudaStream_t s, const float* table, const u32* slot, u64 n_upper, const u64* n_dev, float* out);
 
 // ---- K6: Fisher combine over replicates (combinePval 612, multPval 567) ----------

@@ -83,102 +83,6 @@ k_ctrl_clamp(DevLayout L, DevRle raw, const float* __restrict__ fl, Lookback<1> 
   }
 }
 
-// Long-tile form (GR_CL_TILES=4; not the default until it has been measured): M x 8192 raw intervals
-// per look-back tile and a 128-wide look-back window.  With ~1200 tiles resident and a 32-wide
-// window a tile's look-back walks some 30 windows (one L2 round trip each) before it meets a
-// published inclusive prefix; 12 k tiles per hg38 replicate pay that.  Same two passes, same outputs.
-template <int PER>
-__device__ __forceinline__ u64 tile_exclusive_rank_p(const Lookback<1>& lb, u32 tile, u32 cnt, u32& tile_total) {
-  __shared__ u32 sm_w[32];
-  __shared__ u64 sm_ex;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  const u32 wi = warp_incl_scan_u32(cnt, lane);
-  if (lane == 31) sm_w[w] = wi;
-  __syncthreads();
-  u32 wx = 0, tot = 0;
-  for (int k = 0; k < nw; k++) {
-    const u32 a = sm_w[k];
-    if (k < w) wx += a;
-    tot += a;
-  }
-  if (w == 0) {
-    i64 agg[1] = { (i64)tot }, ex[1];
-    lookback_exclusive<1, PER>(lb, tile, agg, ex);
-    if (lane == 0) sm_ex = (u64)ex[0];
-  }
-  __syncthreads();
-  tile_total = tot;
-  return sm_ex + wx + (wi - cnt);
-}
-
-template <int M>
-__global__ void __launch_bounds__(256)
-k_ctrl_clamp_m(DevLayout L, DevRle raw, const float* __restrict__ fl, Lookback<1> lb,
-               DevRle out, u32* __restrict__ bitmap) {
-  constexpr u64 TILE = (u64)CL_TILE * M;
-  const u64 n = *raw.total;
-  if ((u64)blockIdx.x * TILE >= n) return;               // tickets stay dense
-  const float factor = fl[0], lambda = fl[1];
-  const u32 tile = take_ticket(lb.ticket);
-  const u64 t0 = (u64)tile * TILE;
-  const u64 tl = min(t0 + TILE, n) - 1;
-  const TileChrom tc = tile_chrom_range(raw.chrom_start, L.nchrom, t0, tl);
-  const bool uni = tc.c0 == tc.c1;
-  const u64 uni_end = uni ? raw.chrom_start[tc.c0 + 1] : 0;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const u64 wbase = t0 + (u64)w * (1024 * M);             // a warp owns 1024 * M consecutive intervals
-
-  u32 mine[M], cnt = 0;
-#pragma unroll
-  for (int m = 0; m < M; m++) {
-    mine[m] = 0;
-#pragma unroll 4
-    for (int k = 0; k < 32; k++) {
-      const u64 i = wbase + (u64)(m * 32 + k) * 32 + lane;
-      bool keep = false;
-      if (i < n) {
-        const float net = clamp_net(factor, raw.val[i], lambda);
-        int c = tc.c0;
-        bool last;
-        if (uni) last = i + 1 == uni_end;
-        else { c = chrom_of_index(raw.chrom_start, L.nchrom, i); last = i + 1 == raw.chrom_start[c + 1]; }
-        keep = last || net != clamp_net(factor, raw.val[i + 1], lambda);
-        if (!keep) {
-          const u64 g = L.off[c] + raw.end[i];
-          atomicAnd(bitmap + (g >> 5), ~(1u << (g & 31)));
-        }
-      }
-      const u32 bal = __ballot_sync(GR_FULL, keep);
-      if (lane == k) mine[m] = bal;
-      cnt += __popc(bal);
-    }
-  }
-  u32 tot;
-  u64 r = tile_exclusive_rank_p<4>(lb, tile, lane == 31 ? cnt : 0u, tot);
-  r = __shfl_sync(GR_FULL, r, 31);
-  if (tile == 0 && threadIdx.x == 0) out.chrom_start[0] = 0;
-
-#pragma unroll
-  for (int m = 0; m < M; m++) {
-    for (int k = 0; k < 32; k++) {
-      const u32 bal = __shfl_sync(GR_FULL, mine[m], k);
-      if (bal & (1u << lane)) {
-        const u64 i = wbase + (u64)(m * 32 + k) * 32 + lane;
-        const u64 rank = r + __popc(bal & ((1u << lane) - 1));
-        out.end[rank] = raw.end[i];
-        out.val[rank] = clamp_net(factor, raw.val[i], lambda);
-        int c = tc.c0;
-        bool last;
-        if (uni) last = i + 1 == uni_end;
-        else { c = chrom_of_index(raw.chrom_start, L.nchrom, i); last = i + 1 == raw.chrom_start[c + 1]; }
-        if (last) out.chrom_start[c + 1] = rank + 1;
-        if (i == n - 1) *out.total = rank + 1;
-      }
-      r += __popc(bal);
-    }
-  }
-}
-
 // chromosomes without intervals take the running count (forward fill)
 __global__ void k_fill_forward(int nchrom, const u64* raw_start, u64* out_start) {
   if (threadIdx.x || blockIdx.x) return;
@@ -191,18 +95,11 @@ void launch_ctrl_clamp(cudaStream_t s, const DevLayout& L, const DevRle& raw, u6
                        DevRle out, u32* bitmap) {
   cudaMemsetAsync(out.total, 0, sizeof(u64), s);
   if (!n_upper) return;
-  const char* te = getenv("GR_CL_TILES");        // read per call: the tests switch it inside one process
-  const int m = te && atoi(te) == 4 ? 4 : 1;
-  const u64 ntiles = (n_upper + (u64)CL_TILE * m - 1) / ((u64)CL_TILE * m);
+  const u64 ntiles = (n_upper + CL_TILE - 1) / CL_TILE;
   cudaMemsetAsync(sc.st, 0, ntiles * sizeof(u64), s);
   cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
   Lookback<1> lb;
   lb.st[0] = sc.st; lb.ticket = sc.ticket;
-  if (m == 4) {
-    k_ctrl_clamp_m<4><<<(unsigned)ntiles, 256, 0, s>>>(L, raw, factor_lambda, lb, out, bitmap); GR_NOTE_LAUNCH();
-    k_fill_forward<<<1, 32, 0, s>>>(L.nchrom, raw.chrom_start, out.chrom_start); GR_NOTE_LAUNCH();
-    return;
-  }
   k_ctrl_clamp<<<(unsigned)ntiles, 256, 0, s>>>(L, raw, factor_lambda, lb, out, bitmap); GR_NOTE_LAUNCH();
   k_fill_forward<<<1, 32, 0, s>>>(L.nchrom, raw.chrom_start, out.chrom_start); GR_NOTE_LAUNCH();
 }
@@ -315,91 +212,14 @@ k_union_rank(const u32* __restrict__ bmE, const u32* __restrict__ bmC, Lookback<
   }
 }
 
-// Grouped form (GR_UR_GROUPS=2|4; not the default until it has been measured): G x 16 blocks per
-// look-back tile.  The pass reads 0.77 GB per hg38 replicate (0.13 ms at the HBM rate) but takes
-// 0.5 ms: with ~1200 tiles resident, a tile's look-back walks ~20 windows of 64 predecessors, one L2
-// round trip each, before it meets a published inclusive prefix -- 23.5 k tiles pay that.  A tile of
-// G x 16 blocks pays it once for G times the data.
-template <int G>
-__global__ void __launch_bounds__(256)
-k_union_rank_g(const u32* __restrict__ bmE, const u32* __restrict__ bmC, Lookback<3> lb,
-               u64* __restrict__ rankE, u64* __restrict__ rankC, u64* __restrict__ rankU,
-               u64* __restrict__ totals, u32 nblocks, u32 ntiles) {
-  constexpr int NB = UR_BLOCKS * G;
-  __shared__ u32 sm[UR_BLOCKS][3][8];
-  __shared__ u32 sm_blk[NB][3];
-  __shared__ i64 sm_ex[3];
-  const u32 tile = take_ticket(lb.ticket);
-  const u32 b0 = tile * NB;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int g = 0; g < G; g++) {
-    u32 E[UR_BLOCKS], C[UR_BLOCKS];
-#pragma unroll
-    for (int b = 0; b < UR_BLOCKS; b++) {
-      const u32 blk = b0 + g * UR_BLOCKS + b;
-      const u64 widx = (u64)blk * 256 + threadIdx.x;
-      const bool on = blk < nblocks;
-      E[b] = on ? bmE[widx] : 0u;
-      C[b] = (on && bmC) ? bmC[widx] : 0u;
-    }
-#pragma unroll
-    for (int b = 0; b < UR_BLOCKS; b++) {
-      const u32 a = __reduce_add_sync(GR_FULL, __popc(E[b]));
-      const u32 c = __reduce_add_sync(GR_FULL, __popc(C[b]));
-      const u32 u = __reduce_add_sync(GR_FULL, __popc(E[b] | C[b]));
-      if (lane == 0) { sm[b][0][w] = a; sm[b][1][w] = c; sm[b][2][w] = u; }
-    }
-    __syncthreads();
-    if (threadIdx.x < UR_BLOCKS * 3) {
-      const int b = threadIdx.x / 3, k = threadIdx.x % 3;
-      u32 t = 0;
-      for (int q = 0; q < 8; q++) t += sm[b][k][q];
-      sm_blk[g * UR_BLOCKS + b][k] = t;
-    }
-    __syncthreads();                             // sm is rewritten by the next group
-  }
-  if (w == 0) {
-    i64 agg[3] = { 0, 0, 0 }, ex[3];
-    for (int b = 0; b < NB; b++) { agg[0] += sm_blk[b][0]; agg[1] += sm_blk[b][1]; agg[2] += sm_blk[b][2]; }
-    lookback_exclusive<3, 2>(lb, tile, agg, ex);
-    if (lane == 0) {
-      sm_ex[0] = ex[0]; sm_ex[1] = ex[1]; sm_ex[2] = ex[2];
-      if (tile == ntiles - 1) {
-        totals[0] = (u64)(ex[0] + agg[0]);
-        totals[1] = (u64)(ex[1] + agg[1]);
-        totals[2] = (u64)(ex[2] + agg[2]);
-      }
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < NB && b0 + threadIdx.x < nblocks) {
-    u64 e = (u64)sm_ex[0], c = (u64)sm_ex[1], u = (u64)sm_ex[2];
-    for (u32 b = 0; b < threadIdx.x; b++) { e += sm_blk[b][0]; c += sm_blk[b][1]; u += sm_blk[b][2]; }
-    rankE[b0 + threadIdx.x] = e;
-    if (rankC) rankC[b0 + threadIdx.x] = c;
-    rankU[b0 + threadIdx.x] = u;
-  }
-}
-
 void launch_union_rank(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
                        const RankScratch& sc, u64* rankE, u64* rankC, u64* rankU, u64* totals) {
-  const char* ge = getenv("GR_UR_GROUPS");       // read per call: the tests switch it inside one process
-  const int groups = ge ? atoi(ge) : 1;
-  const u32 per = UR_BLOCKS * (groups == 4 ? 4 : groups == 2 ? 2 : 1);
-  const u32 ntiles = (u32)((L.nblocks + per - 1) / per);
+  const u32 ntiles = (u32)((L.nblocks + UR_BLOCKS - 1) / UR_BLOCKS);
   for (int k = 0; k < 3; k++) cudaMemsetAsync(sc.st[k], 0, (size_t)ntiles * sizeof(u64), s);
   cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
   Lookback<3> lb;
   for (int k = 0; k < 3; k++) lb.st[k] = sc.st[k];
   lb.ticket = sc.ticket;
-  if (per == UR_BLOCKS * 4) {
-    k_union_rank_g<4><<<ntiles, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks, ntiles); GR_NOTE_LAUNCH();
-    return;
-  }
-  if (per == UR_BLOCKS * 2) {
-    k_union_rank_g<2><<<ntiles, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks, ntiles); GR_NOTE_LAUNCH();
-    return;
-  }
   k_union_rank<<<ntiles, 256, 0, s>>>(bmE, bmC, lb, rankE, rankC, rankU, totals, (u32)L.nblocks, ntiles); GR_NOTE_LAUNCH();
 }
 
@@ -514,122 +334,14 @@ k_union_emit(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ b
   }
 }
 
-// Warp form (GR_UE_WARP=1; not the default until it has been measured): one WARP per bitmap block,
-// every lane owning 8 consecutive words (256 cells) of it.  ncu on k_union_emit: instruction bound
-// (sm throughput 67 %, DRAM 34 %) -- a thread there owns one word of each of four blocks, so
-// every block costs its warp two 5-step scans plus a cross-warp exchange, and the list loop runs as
-// long as the fullest of 32 single words.  Here the per-word counts add up inside the lane: two warp
-// scans per BLOCK (one packed E|C, one U), no __syncthreads, and the list loop runs over 8 words per
-// lane (the lanes' bit counts are far more even than single words').  Same outputs, bit for bit.
-#define UW_CAP 512             // list entries per round and warp
-__global__ void __launch_bounds__(256)
-k_union_emit_w(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ bmC,
-               const u64* __restrict__ rankE, const u64* __restrict__ rankC,
-               const u64* __restrict__ rankU, const float* __restrict__ exptVal,
-               const float* __restrict__ ctrlVal, u32* __restrict__ pEnd,
-               float* __restrict__ pExpt, float* __restrict__ pCtrl, u32* __restrict__ bmU,
-               u64* __restrict__ chrom_start, u32 nblocks) {
-  __shared__ u32 sm_ent_all[8 * UW_CAP];          // bits 0-12: cell offset inside the block, 13-31: experimental interval number
-  __shared__ unsigned short sm_ctl_all[8 * UW_CAP];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  u32* const sm_ent = sm_ent_all + w * UW_CAP;
-  unsigned short* const sm_ctl = sm_ctl_all + w * UW_CAP;
-  const u32 blk = blockIdx.x * 8 + w;
-  if (blk >= nblocks) return;                    // warp-uniform
-  u32 E[8], C[8];
-  {
-    const uint4* pe = reinterpret_cast<const uint4*>(bmE + (u64)blk * 256 + lane * 8);
-    const uint4* pc = reinterpret_cast<const uint4*>(bmC + (u64)blk * 256 + lane * 8);
-    const uint4 e0 = pe[0], e1 = pe[1], c0 = pc[0], c1 = pc[1];
-    E[0] = e0.x; E[1] = e0.y; E[2] = e0.z; E[3] = e0.w; E[4] = e1.x; E[5] = e1.y; E[6] = e1.z; E[7] = e1.w;
-    C[0] = c0.x; C[1] = c0.y; C[2] = c0.z; C[3] = c0.w; C[4] = c1.x; C[5] = c1.y; C[6] = c1.z; C[7] = c1.w;
-  }
-  const u64 RE0 = rankE[blk], RC0 = rankC[blk], RU0 = rankU[blk];
-  const int c = L.blk2chrom[blk];
-  const u64 off = L.off[c];
-  const u32 jb = (u32)((u64)blk * GR_BLOCK_SLOTS - off);
-  if (lane == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = RU0;
-  {
-    uint4* pu = reinterpret_cast<uint4*>(bmU + (u64)blk * 256 + lane * 8);
-    pu[0] = make_uint4(E[0] | C[0], E[1] | C[1], E[2] | C[2], E[3] | C[3]);
-    pu[1] = make_uint4(E[4] | C[4], E[5] | C[5], E[6] | C[6], E[7] | C[7]);
-  }
-  u32 pa = 0, pu_ = 0;
-#pragma unroll
-  for (int q = 0; q < 8; q++) { pa += __popc(E[q]) | (__popc(C[q]) << 16); pu_ += __popc(E[q] | C[q]); }
-  const u32 ia = warp_incl_scan_u32(pa, lane), iu = warp_incl_scan_u32(pu_, lane);
-  const u32 xa = ia - pa, xu = iu - pu_;          // E and C counts travel packed (<= 8192 each)
-  const u32 tot = __shfl_sync(GR_FULL, iu, 31);
-  for (u32 lo = 0; lo < tot; lo += UW_CAP) {
-    if (lo) __syncwarp();                        // the previous round's list has been streamed
-    u32 e = xa & 0xffffu, cc = xa >> 16, u = xu;
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      u32 U = E[q] | C[q];
-      const u32 nu = __popc(U);
-      if (u < lo + UW_CAP && u + nu > lo) {
-        const u32 cell0 = (u32)(lane * 256 + q * 32);
-        u32 uu = u;
-        while (U) {
-          const int b = __ffs(U) - 1;
-          const u32 low = (1u << b) - 1;
-          if (uu >= lo && uu < lo + UW_CAP) {
-            sm_ent[uu - lo] = (cell0 + b) | ((e + __popc(E[q] & low)) << 13);
-            sm_ctl[uu - lo] = (unsigned short)(cc + __popc(C[q] & low));
-          }
-          uu++;
-          U &= U - 1;
-        }
-      }
-      u += nu; e += __popc(E[q]); cc += __popc(C[q]);
-    }
-    __syncwarp();
-    const u32 cnt = min(tot - lo, (u32)UW_CAP);
-    for (u32 i0 = lane; i0 < cnt; i0 += 32 * UE_UNROLL) {
-      u32 en[UE_UNROLL];
-      float ve[UE_UNROLL], vc[UE_UNROLL];
-#pragma unroll
-      for (int q = 0; q < UE_UNROLL; q++) {
-        const u32 i = i0 + q * 32;
-        if (i < cnt) {
-          en[q] = sm_ent[i];
-          ve[q] = exptVal[RE0 + (en[q] >> 13)];
-          vc[q] = ctrlVal[RC0 + sm_ctl[i]];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < UE_UNROLL; q++) {
-        const u32 i = i0 + q * 32;
-        if (i < cnt) {
-          const u64 uo = RU0 + lo + i;
-          pEnd[uo] = jb + (en[q] & (GR_BLOCK_SLOTS - 1));
-          pExpt[uo] = ve[q];
-          pCtrl[uo] = vc[q];
-        }
-      }
-    }
-  }
-}
-
 void launch_union_emit(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
                        const u64* rankE, const u64* rankC, const u64* rankU,
                        const float* exptVal, const float* ctrlVal,
                        u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
                        const u64* total) {
-  // bitmap blocks per CTA: 4 (default) or 2 (GR_UE_BLOCKS=2: fewer registers, more CTAs per SM)
-  static int ub = 0;
-  if (!ub) { const char* e = getenv("GR_UE_BLOCKS"); ub = e && atoi(e) == 2 ? 2 : 4; }
-  const unsigned grid = (unsigned)((L.nblocks + ub - 1) / ub);
-  const char* uw = getenv("GR_UE_WARP");         // read per call: the tests switch it inside one process
-  if (uw && atoi(uw))
-    k_union_emit_w<<<(unsigned)((L.nblocks + 7) / 8), 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
-                                                                    pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks);
-  else if (ub == 2)
-    k_union_emit<2><<<grid, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
-                                         pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks);
-  else
-    k_union_emit<4><<<grid, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
-                                         pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks);
+  const unsigned grid = (unsigned)((L.nblocks + 3) / 4);       // four bitmap blocks per CTA
+  k_union_emit<4><<<grid, 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
+                                       pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks);
   GR_NOTE_LAUNCH();
   launch_fill_chrom_start(s, L, chrom_start, total);
 }
@@ -721,134 +433,6 @@ void launch_pair_insert(cudaStream_t s, const float* pExpt, const float* pCtrl, 
   if (!n_upper) return;
   k_pair_insert<<<capped_grid(n_upper), 256, 0, s>>>(pExpt, pCtrl, n_dev, t, slot, err); GR_NOTE_LAUNCH();
 }
-
-#define WP_UNROLL 2             // entries per lane in flight (4 spills registers next to the 16 bitmap words)
-// k_union_emit_w with K5's table insert folded in (GR_UE_PAIR=1; not the default until it has been measured):
-// the (expt, ctrl) pair of every union interval is in registers here, so the find-or-insert of
-// k_pair_insert happens in place and only the slot is written -- k_pair_insert's pass over pExpt / pCtrl
-// (8 B per interval read again) disappears.  pExpt / pCtrl are still written (the overflow redo and -f / -k read them).
-__global__ void __launch_bounds__(256)
-k_union_emit_wp(DevLayout L, const u32* __restrict__ bmE, const u32* __restrict__ bmC,
-               const u64* __restrict__ rankE, const u64* __restrict__ rankC,
-               const u64* __restrict__ rankU, const float* __restrict__ exptVal,
-               const float* __restrict__ ctrlVal, u32* __restrict__ pEnd,
-               float* __restrict__ pExpt, float* __restrict__ pCtrl, u32* __restrict__ bmU,
-               u64* __restrict__ chrom_start, u32 nblocks, PairTable t, u32* __restrict__ slot, int* __restrict__ err) {
-  __shared__ u32 sm_ent_all[8 * UW_CAP];          // bits 0-12: cell offset inside the block, 13-31: experimental interval number
-  __shared__ unsigned short sm_ctl_all[8 * UW_CAP];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  u32* const sm_ent = sm_ent_all + w * UW_CAP;
-  unsigned short* const sm_ctl = sm_ctl_all + w * UW_CAP;
-  const u32 blk = blockIdx.x * 8 + w;
-  if (blk >= nblocks) return;                    // warp-uniform
-  u32 E[8], C[8];
-  {
-    const uint4* pe = reinterpret_cast<const uint4*>(bmE + (u64)blk * 256 + lane * 8);
-    const uint4* pc = reinterpret_cast<const uint4*>(bmC + (u64)blk * 256 + lane * 8);
-    const uint4 e0 = pe[0], e1 = pe[1], c0 = pc[0], c1 = pc[1];
-    E[0] = e0.x; E[1] = e0.y; E[2] = e0.z; E[3] = e0.w; E[4] = e1.x; E[5] = e1.y; E[6] = e1.z; E[7] = e1.w;
-    C[0] = c0.x; C[1] = c0.y; C[2] = c0.z; C[3] = c0.w; C[4] = c1.x; C[5] = c1.y; C[6] = c1.z; C[7] = c1.w;
-  }
-  const u64 RE0 = rankE[blk], RC0 = rankC[blk], RU0 = rankU[blk];
-  const int c = L.blk2chrom[blk];
-  const u64 off = L.off[c];
-  const u32 jb = (u32)((u64)blk * GR_BLOCK_SLOTS - off);
-  if (lane == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = RU0;
-  {
-    uint4* pu = reinterpret_cast<uint4*>(bmU + (u64)blk * 256 + lane * 8);
-    pu[0] = make_uint4(E[0] | C[0], E[1] | C[1], E[2] | C[2], E[3] | C[3]);
-    pu[1] = make_uint4(E[4] | C[4], E[5] | C[5], E[6] | C[6], E[7] | C[7]);
-  }
-  u32 pa = 0, pu_ = 0;
-#pragma unroll
-  for (int q = 0; q < 8; q++) { pa += __popc(E[q]) | (__popc(C[q]) << 16); pu_ += __popc(E[q] | C[q]); }
-  const u32 ia = warp_incl_scan_u32(pa, lane), iu = warp_incl_scan_u32(pu_, lane);
-  const u32 xa = ia - pa, xu = iu - pu_;          // E and C counts travel packed (<= 8192 each)
-  const u32 tot = __shfl_sync(GR_FULL, iu, 31);
-  const u32 tmask = t.cap - 1;
-  bool bad = false;
-  for (u32 lo = 0; lo < tot; lo += UW_CAP) {
-    if (lo) __syncwarp();                        // the previous round's list has been streamed
-    u32 e = xa & 0xffffu, cc = xa >> 16, u = xu;
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-      u32 U = E[q] | C[q];
-      const u32 nu = __popc(U);
-      if (u < lo + UW_CAP && u + nu > lo) {
-        const u32 cell0 = (u32)(lane * 256 + q * 32);
-        u32 uu = u;
-        while (U) {
-          const int b = __ffs(U) - 1;
-          const u32 low = (1u << b) - 1;
-          if (uu >= lo && uu < lo + UW_CAP) {
-            sm_ent[uu - lo] = (cell0 + b) | ((e + __popc(E[q] & low)) << 13);
-            sm_ctl[uu - lo] = (unsigned short)(cc + __popc(C[q] & low));
-          }
-          uu++;
-          U &= U - 1;
-        }
-      }
-      u += nu; e += __popc(E[q]); cc += __popc(C[q]);
-    }
-    __syncwarp();
-    const u32 cnt = min(tot - lo, (u32)UW_CAP);
-    for (u32 base = 0; base < cnt; base += 32 * WP_UNROLL) {        // warp-uniform trip count (ballots inside)
-      u32 en[WP_UNROLL], h[WP_UNROLL];
-      float ve[WP_UNROLL], vc[WP_UNROLL];
-      u64 key[WP_UNROLL], k0[WP_UNROLL];
-#pragma unroll
-      for (int q = 0; q < WP_UNROLL; q++) {
-        const u32 i = base + q * 32 + lane;
-        en[q] = 0; ve[q] = 0.0f; vc[q] = 0.0f;
-        if (i < cnt) {
-          en[q] = sm_ent[i];
-          ve[q] = exptVal[RE0 + (en[q] >> 13)];
-          vc[q] = ctrlVal[RC0 + sm_ctl[i]];
-        }
-      }
-#pragma unroll
-      for (int q = 0; q < WP_UNROLL; q++) {                         // the first probe of every key is in flight together
-        key[q] = ((u64)__float_as_uint(ve[q]) << 32) | __float_as_uint(vc[q]);
-        h[q] = mix64(key[q]) & tmask;
-        k0[q] = t.keys[h[q]];
-      }
-      u32 nf = 0;
-#pragma unroll
-      for (int q = 0; q < WP_UNROLL; q++) {
-        const u32 i = base + q * 32 + lane;
-        bool fresh = false;
-        if (i < cnt) {
-          const u32 hs = k0[q] == key[q] ? h[q] : table_upsert(t, key[q], fresh);
-          if (hs == ~0u) bad = true;
-          const u64 uo = RU0 + lo + i;
-          pEnd[uo] = jb + (en[q] & (GR_BLOCK_SLOTS - 1));
-          pExpt[uo] = ve[q];
-          pCtrl[uo] = vc[q];
-          slot[uo] = hs == ~0u ? 0u : hs;
-        }
-        nf += __popc(__ballot_sync(GR_FULL, fresh));
-      }
-      if (lane == 0 && nf) {
-        const u32 tot2 = atomicAdd(t.count, nf) + nf;
-        if (tot2 > (t.cap >> 1)) bad = true;
-      }
-    }
-  }
-  if (bad) atomicOr(err, GR_DE_TABLE);
-}
-
-
-void launch_union_emit_pair(cudaStream_t s, const DevLayout& L, const u32* bmE, const u32* bmC,
-                            const u64* rankE, const u64* rankC, const u64* rankU,
-                            const float* exptVal, const float* ctrlVal,
-                            u32* pEnd, float* pExpt, float* pCtrl, u32* bmU, u64* chrom_start,
-                            const u64* total, const PairTable& t, u32* slot, int* err) {
-  k_union_emit_wp<<<(unsigned)((L.nblocks + 7) / 8), 256, 0, s>>>(L, bmE, bmC, rankE, rankC, rankU, exptVal, ctrlVal,
-                                                                   pEnd, pExpt, pCtrl, bmU, chrom_start, (u32)L.nblocks, t, slot, err);
-  GR_NOTE_LAUNCH();
-  launch_fill_chrom_start(s, L, chrom_start, total);
-}
-bool ue_pair_fused() { const char* e = getenv("GR_UE_PAIR"); return e && atoi(e) != 0; }
 
 __global__ void __launch_bounds__(128)
 k_pair_eval(PairTable t) {

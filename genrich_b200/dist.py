@@ -81,6 +81,8 @@ class ShardedEngine:
         self._send = self._recv = self._host = None
         self.debug = bool(os.environ.get("GR_DIST_DEBUG"))
         self.t_acc = {}
+        self.hist_bytes = 0                 # bytes the last BH histogram all-gather moved (all ranks)
+        self._keep = self._hist_keep = None
 
     def _tick(self, name, t0):
         # host time by phase, always collected (two clock reads per phase); bench.py reports it
@@ -165,25 +167,64 @@ class ShardedEngine:
         return st
 
     def _exchange_histogram(self):
+        """The one data-path collective: all-gather of every rank's (key, bp) histogram of distinct
+        -log10 p (computeQval 352 sees one genome-wide table).
+
+        gr_bh_local_hist returns with the list complete (it waits for its stream), and the host
+        knows its length.  CUDA: the lengths travel through the host group (or one small device
+        all-gather), then ONE NCCL all-gather of fixed-size slots [keys | lens] issued on the
+        library's own stream, so that gr_bh_set_global, which runs on that stream, is ordered
+        behind it without any host synchronisation."""
         kp, lp, n = self.ctx.bh_local_hist_ptrs()
         keys = _tensor_from_ptr(kp, n, np.uint32, self.device).view(torch.int32)
         lens = _tensor_from_ptr(lp, n, np.uint64, self.device).view(torch.int64)
-        if self.world > 1:
-            cnt = torch.tensor([n], dtype=torch.int64, device=self.device)
+        if self.world == 1:
+            return keys, lens
+        cuda = self.device.type == "cuda"
+        t0 = time.perf_counter()
+        if self.host_group is not None or not cuda:
+            cnt = torch.tensor([n], dtype=torch.int64)
             cnts = [torch.zeros_like(cnt) for _ in range(self.world)]
-            td.all_gather(cnts, cnt)
-            sizes = [int(c.item()) for c in cnts]
+            td.all_gather(cnts, cnt, group=self.host_group)
+            sizes = [int(c[0]) for c in cnts]
+        else:
+            cnt = torch.tensor([n], dtype=torch.int64, device=self.device)
+            cnts = torch.empty(self.world, dtype=torch.int64, device=self.device)
+            td.all_gather_into_tensor(cnts, cnt)
+            sizes = [int(v) for v in cnts.tolist()]
+        self._tick("bh_sizes", t0)
+        t0 = time.perf_counter()
+        if not cuda:
             m = max(max(sizes), 1)
-            kpad = torch.zeros(m, dtype=torch.int32, device=self.device)
-            lpad = torch.zeros(m, dtype=torch.int64, device=self.device)
+            kpad = torch.zeros(m, dtype=torch.int32)
+            lpad = torch.zeros(m, dtype=torch.int64)
             kpad[:n] = keys
             lpad[:n] = lens
             kall = [torch.empty_like(kpad) for _ in range(self.world)]
             lall = [torch.empty_like(lpad) for _ in range(self.world)]
-            td.all_gather(kall, kpad)        # the one data-path collective (NCCL over NVLink)
-            td.all_gather(lall, lpad)
+            td.all_gather(kall, kpad, group=self.host_group)
+            td.all_gather(lall, lpad, group=self.host_group)
             keys = torch.cat([k[:s] for k, s in zip(kall, sizes)]).contiguous()
             lens = torch.cat([l[:s] for l, s in zip(lall, sizes)]).contiguous()
+            self._tick("bh_allgather", t0)
+            return keys, lens
+        m = (max(max(sizes), 1) + 1) & ~1                   # even: the lens part of a slot stays 8-byte aligned
+        slot = 12 * m
+        if self._ext_stream is None:
+            self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=self.device)
+        with torch.cuda.stream(self._ext_stream):
+            send = torch.zeros(slot, dtype=torch.uint8, device=self.device)
+            recv = torch.empty(self.world * slot, dtype=torch.uint8, device=self.device)
+            if n:
+                send[:4 * n].view(torch.int32).copy_(keys)
+                send[4 * m:4 * m + 8 * n].view(torch.int64).copy_(lens)
+            td.all_gather_into_tensor(recv, send)            # NCCL over NVLink, on the library's stream
+            rv = recv.view(self.world, slot)
+            keys = torch.cat([rv[r, :4 * s].view(torch.int32) for r, s in enumerate(sizes)]).contiguous()
+            lens = torch.cat([rv[r, 4 * m:4 * m + 8 * s].view(torch.int64) for r, s in enumerate(sizes)]).contiguous()
+        self._hist_keep = (send, recv)                       # stay alive until the next exchange
+        self.hist_bytes = self.world * slot
+        self._tick("bh_allgather", t0)
         return keys, lens
 
     def call_peaks(self):
@@ -193,11 +234,13 @@ class ShardedEngine:
         if self.params.qval_opt:
             G = int(self.params.genome_len) or int((self.chrom_len[self.saved_any].astype(np.int64)
                                                     - self.excluded[self.saved_any]).sum())     # findPeaks 1091-1101
+            t0 = time.perf_counter()
             keys, lens = self._exchange_histogram()
-            if self.device.type == "cuda":
-                torch.cuda.current_stream(self.device).synchronize()
             self._keep = (keys, lens)
+            # CUDA: the gathered lists were produced on the library's own stream (or, at one rank, by
+            # gr_bh_local_hist, which returns with its stream idle): gr_bh_set_global is ordered behind them
             self.ctx.bh_set_global_ptrs(keys.data_ptr(), lens.data_ptr(), keys.numel(), G)
+            self._tick("bh_exchange_and_q", t0)
         t0 = time.perf_counter()
         cuda_gather = self.world > 1 and self.device.type == "cuda"
         peaks, rs = self.ctx.call_peaks(to_host=not cuda_gather) if self.ctx.api.has_device else self.ctx.call_peaks()

@@ -233,6 +233,10 @@ int gr_replicate_end(gr_ctx* ctx, gr_sample_stats* stats);
  * gr_pvalues_finalize: Fisher combine when > 1 replicate (combinePval 612).
  * gr_bh_local_hist / gr_bh_set_global: the exchange step of computeQval 352;
  * pointers are DEVICE pointers (keys = float bits of -log10 p, lens = bp).
+ * gr_bh_local_hist returns with the list COMPLETE in device memory (it waits for the
+ * context's stream), so the caller may read it on any stream; gr_bh_set_global reads its
+ * arguments on gr_stream(ctx) -- a caller that produced them on another stream orders the
+ * two itself (an event, or by issuing its collective on gr_stream(ctx)).
  * gr_call_peaks runs whatever of these has not been run (single context),
  * then callPeaks 977.  The returned array is owned by the context (pinned host memory the
  * records were copied into; no second copy) and stays valid until the next gr_call_peaks,

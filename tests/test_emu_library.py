@@ -8,8 +8,7 @@ and compared with the pinned oracle: peaks, interval partitions, pileup floats b
 
 TEST INFRASTRUCTURE: nothing in the product loads this library (the product path needs a GPU and
 fails without one, tests/test_abi.py).  What it buys: kernels and host plumbing written where no GPU
-is at hand -- the knob-gated variants of DESIGN.md section 7 -- are exercised end to end before they
-ever reach a device; what it cannot see: stream ordering, memory-model races, performance."""
+is at hand are exercised end to end before they ever reach a device; what it cannot see: stream ordering, memory-model races, performance."""
 import os
 import subprocess
 
@@ -27,15 +26,8 @@ LIB = os.path.join(EMU, "_build", "libgenrich_emu.so")
 FUSED = {"GR_FUSED": "1", "GR_FUSED_MIN": "1"}
 MODES = {
     "default_small": {},                                     # plain scatter + streaming scan (small samples)
-    "default_fused": FUSED,                                  # the path the bench takes
-    "rank512": dict(FUSED, GR_FUSED_RANK="1"),
-    "rank1024_slots": dict(FUSED, GR_FUSED_RANK="1", GR_FR_CAP="1024", GR_FB_SLOTS="1"),
-    "p2": dict(FUSED, GR_FB_P2="1"),
-    # slots of 4 entries overflow in every sample: the device-side gate hands the sample to the exact chain
-    "slots_overflow": dict(FUSED, GR_FUSED_RANK="1", GR_FB_SLOTS="1", GR_FB_SLOT_CAP="4"),
-    "all": dict(FUSED, GR_FUSED_RANK="1", GR_FB_SLOTS="1", GR_UE_WARP="1", GR_UR_GROUPS="4", GR_CL_TILES="4"),
-    "all_p2": dict(FUSED, GR_FUSED_RANK="1", GR_FB_P2="1", GR_UE_WARP="1", GR_UR_GROUPS="2", GR_CL_TILES="4"),
-    "all_p2_pair": dict(FUSED, GR_FUSED_RANK="1", GR_FR_CPS="7", GR_FR_PF="4", GR_FB_P2="1", GR_UE_PAIR="1", GR_UR_GROUPS="4", GR_CL_TILES="4"),
+    "default_fused": FUSED,                                  # the path the bench takes: k_fr_scan
+    "fused_cta": dict(FUSED, GR_FUSED_CTA="1"),              # k_fb_scan without -E regions
 }
 
 
@@ -88,30 +80,18 @@ def _compare(case, api, env, monkeypatch, packed=False):
 
 @pytest.mark.parametrize("mode", sorted(MODES))
 def test_emulated_library_matches_oracle(emu_api, mode, monkeypatch):
-    """Treatment + control, -q (every stage incl. BH), through each scan / bucket / union / control-sweep variant."""
+    """Treatment + control, -q (every stage incl. BH), through each formulation of the per-base pass."""
     _compare(BY_NAME["c2_ctrl_q"], emu_api, MODES[mode], monkeypatch)
 
 
 @pytest.mark.parametrize("name,mode,packed", [
-    ("c4_fisher_q", "all", False),               # three replicates, Fisher combine
-    ("c5_multimap_ctrl_p", "all_p2", True),      # fractional weights, 8-byte packed records
-    ("c3_atac_q", "rank1024_slots", 6),          # ATAC intervals, 6-byte packed records
-    ("bed_ctrl_q", "all", False),                # -E regions: marks exist in k_fb_scan only, the other variants still apply
+    ("c4_fisher_q", "default_fused", False),     # three replicates, Fisher combine
+    ("c5_multimap_ctrl_p", "default_fused", True),   # fractional weights, 8-byte packed records
+    ("c3_atac_q", "default_fused", 6),           # ATAC intervals, 6-byte packed records
+    ("bed_ctrl_q", "default_fused", False),      # -E regions: marks exist in k_fb_scan only
 ])
 def test_emulated_library_other_shapes(emu_api, name, mode, packed, monkeypatch):
     _compare(BY_NAME[name], emu_api, MODES[mode], monkeypatch, packed=packed)
-
-
-def test_variant_parity_script_under_emulation(emu_api):
-    """tests/variants_check.py -- what tests/test_gpu_zz_variants.py runs on a device -- with every knob on,
-    against the emulated library: six of the seeded cases with block-spanning records (all twelve: run the script by hand), the edge inputs and a
-    8 Mbp hot-spot sample (1/25 of the device-sized one) identical to the default path."""
-    import sys
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "variants_check.py"), "GR_FUSED_RANK=1", "GR_FB_SLOTS=1",
-                        "GR_UE_WARP=1", "GR_UR_GROUPS=4", "GR_CL_TILES=4"], capture_output=True, text=True, timeout=1200,
-                       env=dict(os.environ, GR_EMU_AS_CUDA="1", GR_EMU_SCALE="25",
-                                GR_VARIANT_CASES="c2_ctrl_q,c4_fisher_q,c5_multimap_ctrl_p,c3_atac_q,sparse_ctrl,null_q"))
-    assert p.returncode == 0 and "identical to the default path" in p.stdout, p.stdout[-2000:] + p.stderr[-3000:]
 
 
 def test_host_program_over_emulated_devices(emu_api, tmp_path):

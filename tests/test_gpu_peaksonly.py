@@ -1,8 +1,4 @@
-"""Kernel variants behind environment knobs that were written where no GPU was at hand (checked on the
-CPU by tests/emu, see tests/test_emu_kernels.py).  They are NOT the default path.  Each runs in a child
-process with a time limit and is marked xfail(strict=False): until a variant has been seen on a device
-its outcome is information (XPASS: same bits as the default path on the device; xfail: not yet), not a
-gate -- the gates are the tests of the default path in the other files."""
+"""-P on the device (gr_load_pvalues + K8) through the host program."""
 import os
 import subprocess
 import sys
@@ -12,43 +8,11 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-VARIANTS = {           # simplest first
-    "rm_per8": ["GR_RM_PER=8"],
-    "ur_groups4": ["GR_UR_GROUPS=4"],
-    "cl_tiles4": ["GR_CL_TILES=4"],
-    "ue_warp": ["GR_UE_WARP=1"],
-    "ue_pair": ["GR_UE_PAIR=1"],
-    "rank512": ["GR_FUSED_RANK=1"],
-    "rank1024": ["GR_FUSED_RANK=1", "GR_FR_CAP=1024"],
-    "p2": ["GR_FB_P2=1"],
-    "rank512_slots": ["GR_FUSED_RANK=1", "GR_FB_SLOTS=1"],
-    "all": ["GR_FUSED_RANK=1", "GR_FB_SLOTS=1", "GR_UE_WARP=1", "GR_UR_GROUPS=4", "GR_CL_TILES=4", "GR_RM_PER=8"],
-    "all_p2": ["GR_FUSED_RANK=1", "GR_FB_P2=1", "GR_UE_PAIR=1", "GR_UR_GROUPS=4", "GR_CL_TILES=4", "GR_RM_PER=8"],
-}
-
-
-_HUNG = []          # a variant that ran into its time limit: the ones after it are skipped (the GPU run has a budget)
-
-
-@pytest.mark.xfail(reason="variant not yet run on a device (CPU-emulated only)", strict=False)
-@pytest.mark.parametrize("name", list(VARIANTS))          # simplest first
-def test_variant_same_bits_as_default(name):
-    if _HUNG:
-        pytest.skip("variant %s ran into its time limit; the remaining variants are not started" % _HUNG[0])
-    try:
-        p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "variants_check.py")] + VARIANTS[name],
-                           capture_output=True, text=True, timeout=150)
-    except subprocess.TimeoutExpired:
-        _HUNG.append(name)
-        raise
-    print(p.stdout[-2000:], p.stderr[-4000:])
-    assert p.returncode == 0
-
 
 def test_cli_peaks_only_on_device(tmp_path):
     """-P on the device: the host program parses a -f log it wrote itself and K8 runs on the loaded
     -log(p) / -log(q) values (gr_load_pvalues); narrowPeak files equal the unmodified reference's
-    (tests/golden/ponly_*).  Checked under CPU emulation before it ever ran on a GPU, hence in this file."""
+    (tests/golden/ponly_*)."""
     import json
     import util
     from cases import BY_NAME
