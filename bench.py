@@ -268,13 +268,13 @@ class Sample:
             self.dev[at:at + len(a)].copy_(torch.from_numpy(a.view(np.int64)))
             at += len(a)
         if self.fmt == 6:
-            self.host = torch.empty(max(3 * self.n, 1), dtype=torch.int16).pin_memory()
+            self.host = torch.empty(max(3 * self.n, 1), dtype=torch.int16, pin_memory=True)
             at = 0
             for b in p6:
                 self.host[at:at + len(b)].copy_(torch.from_numpy(b.view(np.int16)))
                 at += len(b)
         else:
-            self.host = torch.empty(max(self.n, 1), dtype=torch.int64).pin_memory()
+            self.host = torch.empty(max(self.n, 1), dtype=torch.int64, pin_memory=True)
             at = 0
             for a in p8:
                 self.host[at:at + len(a)].copy_(torch.from_numpy(a.view(np.int64)))
