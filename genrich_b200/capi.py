@@ -68,7 +68,7 @@ ABI_SYMBOLS = [
     "gr_last_error_detail", "gr_sample_begin", "gr_push_intervals",
     "gr_push_intervals_device", "gr_prefetch_intervals", "gr_push_packed", "gr_prefetch_packed",
     "gr_pack6_layout", "gr_push_packed6", "gr_prefetch_packed6",
-    "gr_sample_pileup", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
+    "gr_sample_pileup", "gr_sample_skipped", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
     "gr_sums_device", "gr_stream", "gr_replicate_stats",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
     "gr_bh_set_global", "gr_bh_local_hist_host", "gr_bh_set_global_host", "gr_load_pvalues", "gr_call_peaks", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
@@ -160,6 +160,7 @@ class Api:
         self.sample_begin = fn("sample_begin", C.c_int, [vp, i32, vp])
         self.push_intervals = fn("push_intervals", C.c_int, [vp, vp, u64])
         self.sample_pileup = fn("sample_pileup", C.c_int, [vp, C.POINTER(dbl)])
+        self.sample_skipped = fn("sample_skipped", C.c_int, [vp, i32, C.POINTER(u64), C.POINTER(u64), C.POINTER(vp), C.POINTER(u64)])
         self.replicate_finish = fn("replicate_finish", C.c_int, [vp, dbl, dbl, i32, u64, C.POINTER(GrSampleStats)])
         self.replicate_end = fn("replicate_end", C.c_int, [vp, C.POINTER(GrSampleStats)])
         self.pvalues_finalize = fn("pvalues_finalize", C.c_int, [vp])
@@ -313,6 +314,13 @@ class Context:
         sums = np.zeros(self.nchrom, dtype=np.float64)
         self._check(self.api.sample_pileup(self._h, sums.ctypes.data_as(C.POINTER(C.c_double))), "sample_pileup")
         return sums
+
+    def sample_skipped(self, is_ctrl=False):
+        """saveInterval 2558-2573: (dropped for overflow, dropped for underflow, array of (arrival index << 1 | underflow))
+        of the last experimental / control sample."""
+        a, b, n, p = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_void_p()
+        self._check(self.api.sample_skipped(self._h, int(is_ctrl), C.byref(a), C.byref(b), C.byref(p), C.byref(n)), "sample_skipped")
+        return a.value, b.value, _np_from(p.value, n.value, np.uint64)
 
     def replicate_finish(self, frag_len, ctrl_frag, has_ctrl, genome_len=0) -> GrSampleStats:
         st = GrSampleStats()

@@ -65,6 +65,42 @@ static void usage(void) {
 }
 
 /* logCounts 5295-5374 */
+static void chk(gr_ctx* ctx, int rc, const char* what);
+/* saveInterval 2558-2573: the engine drops what the reference's int16 counters would have made it drop
+ * (gr_sample_skipped).  Under -v the reference names every such alignment as it meets it; here a second,
+ * sequential pass over the file, which pushes nothing, finds the names of the listed records. */
+static void report_skipped(HDecode* d, gr_ctx** ctxs, int nctx, int is_ctrl, const char* path) {
+  uint64_t total = 0;
+  HLookup lk;
+  lk.list = (const uint64_t**)gb_alloc((size_t)nctx * sizeof(uint64_t*));
+  lk.n = (uint64_t*)calloc((size_t)nctx, sizeof(uint64_t));
+  lk.pos = (uint64_t*)calloc((size_t)nctx, sizeof(uint64_t));
+  lk.arrival = (uint64_t*)calloc((size_t)nctx, sizeof(uint64_t));
+  uint64_t** copy = (uint64_t**)calloc((size_t)nctx, sizeof(uint64_t*));
+  for (int k = 0; k < nctx; k++) {
+    uint64_t a = 0, b = 0, nl = 0;
+    const uint64_t* l = NULL;
+    chk(ctxs[k], gr_sample_skipped(ctxs[k], is_ctrl, &a, &b, &l, &nl), "gr_sample_skipped");
+    total += a + b;
+    copy[k] = (uint64_t*)gb_alloc((nl ? nl : 1) * sizeof(uint64_t));      /* the library's array lives until its next call */
+    if (nl) memcpy(copy[k], l, nl * sizeof(uint64_t));
+    lk.list[k] = copy[k]; lk.n[k] = nl;
+  }
+  if (total && d->opt->verbose) {
+    HDecode* d2 = (HDecode*)calloc(1, sizeof(HDecode));
+    HIvBuf* bufs = (HIvBuf*)calloc((size_t)nctx, sizeof(HIvBuf));
+    if (!d2 || !bufs) gb_die("", "Cannot allocate memory");
+    d2->opt = d->opt; d2->tab = d->tab; d2->nctx = nctx; d2->ctxs = ctxs; d2->owner = d->owner; d2->bufs = bufs;
+    d2->ctrl = d->ctrl; d2->sample = d->sample; d2->lookup = &lk;
+    gb_decode_file(d2, path);
+    d->cnt.total_len = d2->cnt.total_len;                 /* without the dropped fragments, like the reference's (3174) */
+    free(d2->unp); free(d2->rd_pr.r); free(d2->rd_dc.r); free(d2->rd_sn.r);
+    free(bufs); free(d2);
+  }
+  for (int k = 0; k < nctx; k++) free(copy[k]);
+  free(copy); free(lk.list); free(lk.n); free(lk.pos); free(lk.arrival);
+}
+
 static void log_counts(const HDecode* d, bool bam) {
   const HCounts* c = &d->cnt;
   const HOpts* o = d->opt;
@@ -516,17 +552,16 @@ int main(int argc, char** argv) {
       memset(&d.cnt, 0, sizeof d.cnt);
       d.ctrl = s; d.sample = r;
       gb_decode_file(&d, real_path(fname));
+      /* every device integrates its chromosomes (all enqueued before the first is waited for);
+       * a chromosome has one owner, so the per-chromosome sums simply add up */
+      for (int k = 0; k < nctx; k++) chk(ctxs[k], gr_sample_pileup(ctxs[k], NULL), "gr_sample_pileup");
+      report_skipped(&d, ctxs, nctx, s, real_path(fname));            /* saveInterval 2558-2573 */
       if (o.verbose) log_counts(&d, bam);
-      if (nctx == 1) {
-        if (!s && has_ctrl) chk(ctx, gr_sample_pileup(ctx, NULL), "gr_sample_pileup");
-      } else {
-        /* every device integrates its chromosomes (all enqueued before the first is waited for);
-         * a chromosome has one owner, so the per-chromosome sums simply add up */
+      if (nctx > 1)
         for (int k = 0; k < nctx; k++) {
-          chk(ctxs[k], gr_sample_pileup(ctxs[k], sums), "gr_sample_pileup");
+          chk(ctxs[k], gr_sample_sums(ctxs[k], s ? NULL : sums, s ? sums : NULL), "gr_sample_sums");
           for (int i = 0; i < tab.n; i++) (s ? csum : esum)[i] += sums[i];
         }
-      }
     }
     gr_sample_stats st;
     if (nctx == 1)

@@ -448,9 +448,10 @@ static void decode_sam(HDecode* d, HIn* in) {
  * counters, interval buffers and lists; full interval buffers go to the engine one at a time
  * (gb_flush_intervals).  What depends on file order is put back in file order afterwards: the
  * -x and -r lists are concatenated piece by piece and the -v warnings replayed with the
- * reference's cap (saveInterval 2524: the first MAX_ALNS of them).  The pileups do not depend on
- * the order of the interval records at all (integer adds on the device), so the peaks are those
- * of the sequential decode, bit for bit.  Not order-free in the last bits: the double sum of
+ * reference's cap (saveInterval 2524: the first MAX_ALNS of them).  The interval records reach the
+ * engine in file order as well (HOrder: the pieces push one after the other) -- the pileups are
+ * integer adds and would not care, but the reference's int16 saturation rule (saveInterval 2558-2573),
+ * which the engine replays, is an arrival-order rule.  Not order-free in the last bits: the double sum of
  * fragment lengths behind the printed average length (and the -x extension derived from it) is
  * added per piece and then over the pieces. */
 typedef struct {
@@ -477,7 +478,7 @@ static void* sam_worker(void* arg) {
   }
   if (d->read_name[0] != '\0') gb_process_alns(d, d->read_name);
   d->naln = 0;
-  gb_flush_intervals(d);
+  gb_finish_piece(d);                                    /* its records follow those of the pieces before it */
   free(line);
   return NULL;
 }
@@ -547,8 +548,14 @@ static bool decode_sam_threads(HDecode* d, const char* path, int nthreads) {
   SamWorker* ws = (SamWorker*)calloc((size_t)nthreads, sizeof(SamWorker));
   pthread_t* th = (pthread_t*)gb_alloc((size_t)nthreads * sizeof(pthread_t));
   if (!ws) gb_die("", "Cannot allocate memory");
+  gb_flush_intervals(d);                                 /* nothing of the caller's may arrive after the pieces' records */
+  HOrder order;
+  pthread_mutex_init(&order.mu, NULL);
+  pthread_cond_init(&order.cv, NULL);
+  order.turn = 0;
   for (int k = 0; k < nthreads; k++) {
     SamWorker* w = &ws[k];
+    w->d.order = &order; w->d.piece = k;
     w->d.opt = d->opt; w->d.tab = d->tab; w->d.bed = NULL; w->d.dups = NULL;
     w->d.nctx = d->nctx; w->d.ctxs = d->ctxs; w->d.owner = d->owner;
     w->d.ctrl = d->ctrl; w->d.sample = d->sample;
@@ -605,6 +612,8 @@ static bool decode_sam_threads(HDecode* d, const char* path, int nthreads) {
     free(w->bufs);
   }
   free(ws); free(th); free(cut);
+  pthread_mutex_destroy(&order.mu);
+  pthread_cond_destroy(&order.cv);
   munmap((void*)base, size);
   d->read_name[0] = '\0';
   return true;
@@ -712,7 +721,7 @@ void gb_decode_file(HDecode* d, const char* path) {
   d->last_chrom = -1;
   d->read_name[0] = '\0';
   /* plain SAM files are decoded by several threads; -b wants its lines in file order */
-  const bool threaded = !in.is_gz && !in.is_bam && !d->bed && d->opt->threads > 1 && strcmp(path, "-")
+  const bool threaded = !in.is_gz && !in.is_bam && !d->bed && !d->lookup && d->opt->threads > 1 && strcmp(path, "-")
       && decode_sam_threads(d, path, d->opt->threads);
   if (!threaded) {
     if (in.is_bam) {

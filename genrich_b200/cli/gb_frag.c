@@ -17,24 +17,72 @@ static pthread_mutex_t push_mu = PTHREAD_MUTEX_INITIALIZER;
 #define ATAC_ADJ_F 5      /* ATACADJF, Genrich.h:35 */
 #define ATAC_ADJ_R (-5)   /* ATACADJR, Genrich.h:36 */
 
+static void push_buf(HDecode* d, int k, int kind, const void* data, size_t n) {
+  const int rc = kind ? gr_push_intervals(d->ctxs[k], (const int32_t*)data, n) : gr_push_packed(d->ctxs[k], (const uint64_t*)data, n);
+  if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
+}
+static void push_parked(HDecode* d) {
+  for (size_t i = 0; i < d->n_parked; i++) {
+    push_buf(d, d->parked[i].ctx, d->parked[i].kind, d->parked[i].data, d->parked[i].n);
+    free(d->parked[i].data);
+  }
+  d->n_parked = 0;
+}
+static void park(HDecode* d, int k, int kind, const void* data, size_t n) {
+  if (d->n_parked == d->cap_parked) {
+    d->cap_parked = d->cap_parked ? 2 * d->cap_parked : 16;
+    d->parked = (HParked*)gb_realloc(d->parked, d->cap_parked * sizeof(HParked));
+  }
+  const size_t bytes = n * (kind ? 16 : 8);
+  HParked* q = &d->parked[d->n_parked++];
+  q->ctx = k; q->kind = kind; q->n = n;
+  q->data = gb_alloc(bytes);
+  memcpy(q->data, data, bytes);
+}
+
+/* gb_emit_interval never lets both buffers of a context fill at once (it flushes on a change of record
+ * form), so whatever is flushed here leaves in the order it was emitted */
 static void flush_one(HDecode* d, int k) {
   HIvBuf* b = &d->bufs[k];
   if (!b->npk && !b->n) return;
   static int drop = -1;                        /* GB_DECODE_ONLY: measurement aid, the records are discarded */
   if (drop < 0) drop = getenv("GB_DECODE_ONLY") != NULL;
-  if (drop) { b->npk = 0; b->n = 0; return; }
+  if (drop || d->lookup) { b->npk = 0; b->n = 0; return; }
+  bool mine = true;
+  if (d->order) {
+    pthread_mutex_lock(&d->order->mu);
+    mine = d->order->turn == d->piece;
+    pthread_mutex_unlock(&d->order->mu);
+  }
+  if (!mine) {                                 /* an earlier piece of the file is still being pushed: park */
+    if (b->npk) park(d, k, 0, b->pk, b->npk);
+    if (b->n) park(d, k, 1, b->recs, b->n);
+    b->npk = 0; b->n = 0;
+    return;
+  }
   pthread_mutex_lock(&push_mu);
-  if (b->npk) {
-    int rc = gr_push_packed(d->ctxs[k], b->pk, b->npk);
-    if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
-    b->npk = 0;
-  }
-  if (b->n) {
-    int rc = gr_push_intervals(d->ctxs[k], b->recs, b->n);
-    if (rc) gb_die("pushing intervals: ", gr_strerror(rc));
-    b->n = 0;
-  }
+  push_parked(d);
+  if (b->npk) { push_buf(d, k, 0, b->pk, b->npk); b->npk = 0; }
+  if (b->n) { push_buf(d, k, 1, b->recs, b->n); b->n = 0; }
   pthread_mutex_unlock(&push_mu);
+}
+
+/* end of a worker's piece: wait for its turn, send what is parked and what is left, pass the turn on */
+void gb_finish_piece(HDecode* d) {
+  if (!d->order) { gb_flush_intervals(d); return; }
+  pthread_mutex_lock(&d->order->mu);
+  while (d->order->turn != d->piece) pthread_cond_wait(&d->order->cv, &d->order->mu);
+  pthread_mutex_unlock(&d->order->mu);
+  pthread_mutex_lock(&push_mu);
+  push_parked(d);
+  pthread_mutex_unlock(&push_mu);
+  gb_flush_intervals(d);
+  free(d->parked);
+  d->parked = NULL; d->cap_parked = 0;
+  pthread_mutex_lock(&d->order->mu);
+  d->order->turn++;
+  pthread_cond_broadcast(&d->order->cv);
+  pthread_mutex_unlock(&d->order->mu);
 }
 
 void gb_flush_intervals(HDecode* d) {
@@ -43,6 +91,7 @@ void gb_flush_intervals(HDecode* d) {
 
 /* "counted" warnings are the ones saveInterval stops printing after MAX_ALNS of them (2524, 2538) */
 void gb_warn(HDecode* d, bool counted, const char* msg) {
+  if (d->lookup) return;
   if (counted && d->cnt.err_count++ >= GB_MAX_ALNS) return;
   if (!d->wlog) { fputs(msg, stderr); return; }
   HWarnLog* w = d->wlog;
@@ -57,7 +106,7 @@ void gb_warn(HDecode* d, bool counted, const char* msg) {
 }
 
 /* saveInterval 2516-2591, host half: clamp, messages, BED line, enqueue */
-void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const char* qname, uint8_t count) {
+bool gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const char* qname, uint8_t count) {
   const HChrom* c = &d->tab->c[chrom];
   if (start < 0) {
     if (d->opt->verbose) {
@@ -86,19 +135,31 @@ void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const c
     }
     end = c->len;
   }
+  const int k = d->nctx > 1 ? d->owner[chrom] : 0;         /* the device that holds this chromosome */
+  if (d->lookup) {                                         /* naming pass: saveInterval 2558-2573's warnings */
+    HLookup* lk = d->lookup;
+    const uint64_t idx = lk->arrival[k]++;
+    if (lk->pos[k] < lk->n[k] && (lk->list[k][lk->pos[k]] >> 1) == idx) {
+      fprintf(stderr, "Warning! Read %s, alignment at (%s, %ld-%ld) skipped due to %s\n", qname, c->name, (long)start,
+              (long)end, (lk->list[k][lk->pos[k]] & 1) ? "underflow" : "overflow");
+      lk->pos[k]++;
+      return false;                                         /* saveInterval returned 0 for it (2564, 2572) */
+    }
+    return true;
+  }
   if (d->bed)
     gb_out_printf(d->bed, "%s\t%ld\t%ld\t%s_%d_%c_%d\n", c->name, (long)start, (long)end, qname, count,
                   d->ctrl ? 'C' : 'E', d->sample);
-  const int k = d->nctx > 1 ? d->owner[chrom] : 0;         /* the device that holds this chromosome */
   HIvBuf* b = &d->bufs[k];
   if (end - start >= 0 && end - start < (int64_t)GR_PACK_MAX_LEN && (uint32_t)chrom < GR_PACK_MAX_CHROM) {
-    if (b->npk == b->cap_pk) flush_one(d, k);
+    if (b->npk == b->cap_pk || b->n) flush_one(d, k);      /* full, or records of the other form wait: keep the order */
     b->pk[b->npk++] = GR_PACK(chrom, start, end, count);
-    return;
+    return true;
   }
-  if (b->n == b->cap) flush_one(d, k);
+  if (b->n == b->cap || b->npk) flush_one(d, k);
   int32_t* r = b->recs + 4 * b->n++;
   r[0] = chrom; r[1] = (int32_t)start; r[2] = (int32_t)end; r[3] = count;
+  return true;
 }
 
 static bool usable(const HDecode* d, const HAln* a) {
@@ -181,8 +242,10 @@ static void emit_fragment(HDecode* d, const char* qname, const HAln* a, uint8_t 
   uint32_t s = a->pos[0], e = a->pos[1];
   if (s > e) { uint32_t t = s; s = e; e = t; }          /* saveFragment 2759-2766 */
   if (!o->atac_opt) {
-    gb_emit_interval(d, a->chrom, s, e, qname, count);
-    *frag_len += (e > (uint32_t)d->tab->c[a->chrom].len ? d->tab->c[a->chrom].len : e) - s;
+    /* false only in the naming pass of report_skipped, for a record the engine dropped: the reference's
+     * saveInterval returned 0 for it, so it is not in its average fragment length either */
+    if (gb_emit_interval(d, a->chrom, s, e, qname, count))
+      *frag_len += (e > (uint32_t)d->tab->c[a->chrom].len ? d->tab->c[a->chrom].len : e) - s;
     return;
   }
   if (o->atac_adj) { s += ATAC_ADJ_F; e += ATAC_ADJ_R; }   /* saveFragAtac 2733-2748, uint32 arithmetic */

@@ -11,6 +11,7 @@
 #define GB_HOST_H
 #include <stdbool.h>
 #include <stdint.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <zlib.h>
 #include "../../include/genrich_cuda.h"
@@ -117,6 +118,25 @@ typedef struct {
   size_t n, cap;
 } HWarnLog;
 
+/* Arrival order.  The engine applies the reference's int16 saturation rule (saveInterval 2558-2573) in
+ * the order the records reach it, so they reach it in FILE order: decode workers push one after the
+ * other (the worker whose turn it is streams its full buffers, the later ones park theirs). */
+typedef struct {
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int turn;             /* piece whose records may go to the engine now */
+} HOrder;
+typedef struct { int ctx; int kind; void* data; size_t n; } HParked;   /* kind 0: GR_PACK words, 1: int32 x 4 */
+
+/* -v lines for the records the engine dropped (gr_sample_skipped): a second, sequential decode of the
+ * file that pushes nothing and names the records whose arrival index is listed */
+typedef struct {
+  const uint64_t** list;   /* per context: (arrival index << 1) | underflow, ascending */
+  uint64_t* n;             /* per context: entries */
+  uint64_t* pos;           /* per context: next entry */
+  uint64_t* arrival;       /* per context: records emitted so far */
+} HLookup;
+
 /* state of one input file being decoded (or of one worker's share of it) */
 typedef struct {
   const HOpts* opt;
@@ -141,6 +161,10 @@ typedef struct {
   HReadList rd_pr, rd_dc, rd_sn;
   HOut* dups;
   HWarnLog* wlog;       /* NULL: warnings go to stderr as they arise */
+  HOrder* order;        /* NULL: the only submitter (sequential decode) */
+  int piece;            /* this worker's place in the file */
+  HParked* parked; size_t n_parked, cap_parked;
+  HLookup* lookup;      /* not NULL: the naming pass for dropped records, nothing is pushed or printed but its lines */
   int last_chrom;       /* one-entry cache of the reference-name lookup */
 } HDecode;
 
@@ -164,13 +188,14 @@ int gb_peaks_only(const HOpts* o, char* xfile, float thr);  /* -P: findPeaksOnly
 void gb_scan_header(const char* path, HChromTab* tab, bool ctrl, const HOpts* opt);  /* header-only pass */
 void gb_decode_file(HDecode* d, const char* path);          /* readSAM 4468 / readBAM 4983 */
 void gb_flush_intervals(HDecode* d);
+void gb_finish_piece(HDecode* d);                             /* a decode worker is done: its parked records go out in turn */
 
 /* gb_frag.c */
 bool gb_parse_align(HDecode* d, uint16_t flag, int chrom, uint32_t pos, int length, uint32_t pnext, float score,
                     const char* qual, int qual_len, int qual_offset);
 void gb_process_alns(HDecode* d, const char* qname);
 void gb_process_avg_ext(HDecode* d);
-void gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const char* qname, uint8_t count);
+bool gb_emit_interval(HDecode* d, int chrom, int64_t start, int64_t end, const char* qname, uint8_t count);
 void gb_warn(HDecode* d, bool counted, const char* msg);   /* -v warning: now, or logged for the file-order replay */
 int gb_do_pairs(HDecode* d, const char* qname, const HAln* aln, int naln, float best);      /* processPair 3122 */
 int gb_do_singles(HDecode* d, const char* qname, HAln* aln, int naln, float best, bool first,

@@ -100,6 +100,12 @@ struct gr_ctx {
   struct Segment { const void* d; u64 n; int rb; SegBuf* own; Prefetch* pf; };
   std::vector<Segment> segs;
   DevBuf unpack6;                      // GR_PACK6 segments expanded to GR_PACK words (gr_sample_pileup)
+  // int16 saturation rule (k_sat_resolve): per-cell sums of the suspect blocks, one bit per record, segment table,
+  // and per sample the list of dropped records (arrival index << 1 | underflow) the host fetches for its warnings
+  DevBuf satCells, satBits, satSegs, satList[2];
+  static const u32 SAT_LIST_CAP = 1u << 18;
+  u64 n_sat[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };   // host mirror: dropped for overflow / underflow, list entries
+  std::vector<u64> sat_list_h;
   std::vector<SegBuf*> seg_free, seg_used;
   Prefetch pf[2];                      // buffers on their way ahead of their push (gr_prefetch_*)
   cudaEvent_t h_ready[2] = { nullptr, nullptr };   // pinned bounce buffers for pageable sources
@@ -111,7 +117,7 @@ struct gr_ctx {
   DevBuf sbCnt, sbStart, sbCursor, sbBucket, sbSpill, sbSpillCtr;
   u64 sb_min = 1ull << 20;             // samples with fewer records use the plain scatter (GR_SB_MIN)
   int fused = 1;                       // buckets -> breaks in shared memory, no delta array in HBM (GR_FUSED=0: dense array)
-  u64 fused_min = 1ull << 16;          // ... for samples of at least this many records (GR_FUSED_MIN)
+  u64 fused_min = 32767;               // ... for samples of at least this many records (GR_FUSED_MIN): fewer cannot saturate a cell (k_sat_resolve)
   // -E regions (saveXBed 1144): per chromosome the merged, clamped boundary list start0,end0,start1,...
   std::vector<std::vector<u32>> bed;
   std::vector<u64> bed_bp;             // excluded bp per chromosome
@@ -190,7 +196,7 @@ static const char* kStatusText[] = {
   "Disallowed number of alignments", "interval on an unknown or unowned chromosome",
   "Invalid df in pchisq()", "Genome length does not match p-value length",
   "no CUDA device available",
-  "More than 32767 fragments start or end at one position (the reference's counters saturate there)"
+  "int16 saturation of the delta counters beyond what the path reproduces"
 };
 
 extern "C" const char* gr_strerror(int status) {
@@ -422,6 +428,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   x->dpar.release();
   x->dsums.release();
   x->unpack6.release();
+  x->satCells.release(); x->satBits.release(); x->satSegs.release(); x->satList[0].release(); x->satList[1].release();
   x->ghk.release();
   x->ghl.release();
   if (x->h_acc) cudaFreeHost(x->h_acc);
@@ -683,27 +690,56 @@ static int consume_segments(gr_ctx* x, int* built) {
   for (auto& g : x->segs) bytes += g.n * g.rb;
   if (fb) {
     const u64 nbk = x->nblocks;
-    CK(x->sbCnt.ensure(nbk * 4));
+    const int ctrl = x->filling == FILL_CTRL;
+    CK(x->sbCnt.ensure(nbk * 4 + 64));                   // the counters, then the saturation flag word
     CK(x->sbStart.ensure((nbk + 1) * 4));
     CK(x->sbCursor.ensure(nbk * 4));
     CK(x->sbBucket.ensure(x->n_pushed * 8 + (u64)x->n_marks * 4 + 16));   // at most two event entries per record
     CK(x->sbSpillCtr.ensure(4 + (nbk / 4096 + 2) * 4));  // (unused word), then the scan's chunk sums
+    CK(x->satCells.ensure((size_t)SAT_MAX_BLOCKS * GR_BLOCK_SLOTS * 16));
+    CK(x->satBits.ensure((x->n_pushed + 31) / 32 * 4 + 4));
+    CK(x->satList[ctrl].ensure((size_t)gr_ctx::SAT_LIST_CAP * 8));
+    CK(x->satSegs.ensure(x->segs.size() * sizeof(SatSeg) + 16));
     HT("consume: bucket buffers ensured");
     stage_begin(x, "bucket", bytes);
-    CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4, x->stream));
+    CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4 + 64, x->stream));
     for (auto& g : x->segs)
       launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
     HT("consume: memset + count launched");
     launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, x->sbCnt.as<u32>(), nullptr, nullptr);
-    launch_sb_scan(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
-                   x->sbSpillCtr.as<u32>() + 1);
-    for (auto& g : x->segs)
-      launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>());
+    u32* sat_flag = x->sbCnt.as<u32>() + nbk;
+    u32* sat_res = (u32*)((char*)x->small.p + 40) + 3 * ctrl;
+    launch_sb_scan_a(x->stream, nbk, x->sbCnt.as<u32>(), x->sbSpillCtr.as<u32>() + 1, sat_flag);
+    {
+      // saveInterval's int16 saturation rule (2558-2573): one CTA that returns at once unless a block is
+      // full enough to hold a saturating cell; it needs the records in arrival order
+      std::vector<SatSeg> sg(x->segs.size());
+      u64 base = 0;
+      for (size_t i = 0; i < sg.size(); i++) {
+        sg[i].d = x->segs[i].d; sg[i].n = x->segs[i].n; sg[i].base = base; sg[i].packed = x->segs[i].rb == 8; sg[i].pad_ = 0;
+        base += x->segs[i].n;
+      }
+      { int r = upload(x, x->satSegs.p, sg.data(), sg.size() * sizeof(SatSeg)); if (r) return r; }
+      launch_sat_resolve(x->stream, sat_flag, x->satSegs.p, (int)sg.size(), x->L, x->sbCnt.as<u32>(),
+                         x->sbSpillCtr.as<u32>() + 1, x->satCells.p, x->satBits.as<u32>(), x->n_pushed,
+                         x->satList[ctrl].as<u64>(), gr_ctx::SAT_LIST_CAP, sat_res, x->d_err);
+    }
+    launch_sb_scan_b(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
+                     x->sbSpillCtr.as<u32>() + 1);
+    {
+      u64 base = 0;
+      for (auto& g : x->segs) {
+        launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(),
+                       sat_res, x->satBits.as<u32>(), base);
+        base += g.n;
+      }
+    }
     launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, nullptr, x->sbCursor.as<u32>(), x->sbBucket.as<u32>());
     HT("consume: scans + move launched");
     CKL();
     stage_end(x);
   } else if (sb) {
+    CK(cudaMemsetAsync((char*)x->small.p + 40 + 12 * (x->filling == FILL_CTRL), 0, 12, x->stream));   // no record is dropped on this path
     CK(x->sbCnt.ensure(x->nblocks * 4));
     CK(x->sbStart.ensure((x->nblocks + 1) * 4));
     CK(x->sbCursor.ensure(x->nblocks * 4));
@@ -729,6 +765,7 @@ static int consume_segments(gr_ctx* x, int* built) {
     stage_end(x);
     x->delta_clean = false;
   } else {
+    CK(cudaMemsetAsync((char*)x->small.p + 40 + 12 * (x->filling == FILL_CTRL), 0, 12, x->stream));
     if (!x->delta_clean) {
       stage_begin(x, "memset_delta", x->T * 4);
       CK(cudaMemsetAsync(delta, 0, x->T * sizeof(int32_t), x->stream));   // runProgram 5503-5510
@@ -815,6 +852,7 @@ static int materialize(gr_ctx* x) {
   x->n_clamped = *(u64*)((char*)x->h_small + 8);
   for (int k = 0; k < 2; k++) {
     if (!x->pend_pile[k]) continue;
+    for (int j = 0; j < 3; j++) x->n_sat[k][j] = ((const u32*)((char*)x->h_small + 40))[3 * k + j];
     std::vector<double>& sums = k ? x->ctrl_sums : x->expt_sums;
     for (int c = 0; c < nc; c++)
       sums[c] = (double)hI[2 * k * nc + c] + (double)hI[(2 * k + 1) * nc + c] * (1.0 / 1099511627776.0);
@@ -925,6 +963,28 @@ extern "C" int gr_sample_sums(gr_ctx* x, double* expt_sums, double* ctrl_sums) {
     if (x->have_ctrl) memcpy(ctrl_sums, x->ctrl_sums.data(), x->nchrom * sizeof(double));
     else memset(ctrl_sums, 0, x->nchrom * sizeof(double));
   }
+  return GR_OK;
+}
+
+// saveInterval 2558-2573: what the reference's int16 counters made it drop from the sample, in arrival order
+extern "C" int gr_sample_skipped(gr_ctx* x, int32_t is_ctrl, uint64_t* n_overflow, uint64_t* n_underflow,
+                                 const uint64_t** list, uint64_t* n_list) {
+  if (!x) return GR_ERR_ARG;
+  CK(cudaSetDevice(x->device));
+  { int r = materialize(x); if (r) return r; }
+  const int k = is_ctrl ? 1 : 0;
+  if (n_overflow) *n_overflow = x->n_sat[k][0];
+  if (n_underflow) *n_underflow = x->n_sat[k][1];
+  const u64 nl = x->n_sat[k][2];
+  if (list) {
+    x->sat_list_h.resize(nl ? nl : 1);
+    if (nl) {
+      CK(cudaMemcpyAsync(x->sat_list_h.data(), x->satList[k].p, nl * 8, cudaMemcpyDeviceToHost, x->stream));
+      CK(cudaStreamSynchronize(x->stream));
+    }
+    *list = (const uint64_t*)x->sat_list_h.data();
+  }
+  if (n_list) *n_list = nl;
   return GR_OK;
 }
 

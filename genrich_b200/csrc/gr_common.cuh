@@ -39,11 +39,14 @@ typedef unsigned int u32;
 #define GR_DE_EXPT   128            // no analyzable fragments in the experimental sample (2292)
 #define GR_DE_SAT    256            // a delta cell beyond the reference's int16 range (saveInterval 2558-2573)
 
-// A delta cell, in 1/120 units, that the reference's (int16 cov, uint8 frac) cell cannot hold: it
-// would have skipped intervals there (cov == INT16_MAX before a start, INT16_MIN before an end).
-#define GR_SAT_HI (32767 * 120)
+// A delta cell, in 1/120 units, that the reference's (int16 cov, uint8 frac) cell cannot hold.  The reference never
+// gets there: it drops intervals once cov sits at INT16_MAX / INT16_MIN (saveInterval 2558-2573), and so does the
+// fused path (k_sat_resolve, gr_dense.cu) -- there the test is an assertion.  The dense formulation (GR_FUSED=0)
+// does not replay that arrival-order rule: it reports a cell that needed it (net deltas only: a conservative test).
+#define GR_SAT_HI (32767 * 120 + 193)      /* cov 32767 plus the largest fraction (7/8 + 2/6 + 4/10) */
 #define GR_SAT_LO (-32768 * 120)
 __device__ __forceinline__ bool cell_saturated(int d) { return d > GR_SAT_HI || d < GR_SAT_LO; }
+__device__ __forceinline__ bool cell_saturated_dense(int d) { return d >= 32768 * 120 || d < GR_SAT_LO; }
 
 // ---------------------------------------------------------------------------
 // memory helpers

@@ -155,13 +155,18 @@ k_sb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ 
 // exclusive scan of the per-block counts (~4e5 for a human genome) in three small steps:
 // sums of 4096-counter chunks, scan of the <= 1024 chunk sums (one CTA), rescan with the base
 #define SB_CHUNK 4096
+// sat_flag (may be NULL): raised when a block holds SAT_MIN_EVENTS entries or more -- only such a block can
+// hold a cell the reference's int16 counters saturate on (k_sat_resolve below)
+#define SAT_MIN_EVENTS 32767u
 __global__ void __launch_bounds__(256)
-k_sb_scan1(const u32* __restrict__ blk_cnt, u32* __restrict__ chunk_sum, u64 nblocks) {
+k_sb_scan1(const u32* __restrict__ blk_cnt, u32* __restrict__ chunk_sum, u64 nblocks, u32* __restrict__ sat_flag) {
   __shared__ u32 sh[8];
   const u64 base = (u64)blockIdx.x * SB_CHUNK;
   u32 s = 0;
+  bool big = false;
   for (int i = threadIdx.x; i < SB_CHUNK; i += 256)
-    if (base + i < nblocks) s += blk_cnt[base + i];
+    if (base + i < nblocks) { const u32 v = blk_cnt[base + i]; s += v; big |= v >= SAT_MIN_EVENTS; }
+  if (big && sat_flag) atomicOr(sat_flag, 1u);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(GR_FULL, s, o);
   if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
@@ -280,8 +285,16 @@ void launch_sb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n
 }
 // chunk_sum: scratch of ceil(nblocks / 4096) words
 void launch_sb_scan(cudaStream_t s, u64 nbuckets, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum) {
+  launch_sb_scan_a(s, nbuckets, blk_cnt, chunk_sum, nullptr);
+  launch_sb_scan_b(s, nbuckets, blk_cnt, blk_start, cursor, chunk_sum);
+}
+// the scan in two halves, so that k_sat_resolve can run in between (it may take entries out of blocks)
+void launch_sb_scan_a(cudaStream_t s, u64 nbuckets, const u32* blk_cnt, u32* chunk_sum, u32* sat_flag) {
   const u32 nchunks = (u32)((nbuckets + SB_CHUNK - 1) / SB_CHUNK);
-  k_sb_scan1<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, nbuckets); GR_NOTE_LAUNCH();
+  k_sb_scan1<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, nbuckets, sat_flag); GR_NOTE_LAUNCH();
+}
+void launch_sb_scan_b(cudaStream_t s, u64 nbuckets, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum) {
+  const u32 nchunks = (u32)((nbuckets + SB_CHUNK - 1) / SB_CHUNK);
   k_sb_scan2<<<1, 1024, 0, s>>>(chunk_sum, nchunks, blk_start, nbuckets); GR_NOTE_LAUNCH();
   k_sb_scan3<<<nchunks, 256, 0, s>>>(blk_cnt, chunk_sum, blk_start, cursor, nbuckets); GR_NOTE_LAUNCH();
 }
@@ -489,7 +502,7 @@ k_scan_stream(int32_t* __restrict__ delta, DevLayout L, StreamWs W, u32* __restr
           u32 q = 0;
           if (on) { q = wlist[n]; x = wst[q]; }
           const u32 m4 = (x.x != 0 ? 1u : 0u) | (x.y != 0 ? 2u : 0u) | (x.z != 0 ? 4u : 0u) | (x.w != 0 ? 8u : 0u);
-          sat |= cell_saturated(x.x) | cell_saturated(x.y) | cell_saturated(x.z) | cell_saturated(x.w);
+          sat |= cell_saturated_dense(x.x) | cell_saturated_dense(x.y) | cell_saturated_dense(x.z) | cell_saturated_dense(x.w);
           const u32 c4 = __popc(m4);
           const u32 s1_ = (u32)x.x, s2_ = s1_ + (u32)x.y, s3_ = s2_ + (u32)x.z, s4_ = s3_ + (u32)x.w;
           const u32 inc_s = warp_incl_scan_u32(s4_, lane), inc_c = warp_incl_scan_u32(c4, lane);
@@ -521,7 +534,7 @@ k_scan_stream(int32_t* __restrict__ delta, DevLayout L, StreamWs W, u32* __restr
 #pragma unroll
         for (int i = 0; i < SC_ITEMS; i++) {
           run += (u32)d[i];
-          sat |= cell_saturated(d[i]);
+          sat |= cell_saturated_dense(d[i]);
           const u32 jj = j0 + i;
           const bool brk = (jj == len) || (d[i] != 0 && jj >= 1 && jj < len);
           m |= (brk ? 1u : 0u) << i;
@@ -806,7 +819,10 @@ k_fb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ 
 
 template <bool PACKED>
 __global__ void __launch_bounds__(256)
-k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed) {
+k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ cursor, u32* __restrict__ bucketed,
+          const u32* __restrict__ sat_res, const u32* __restrict__ skip_bits, u64 seg_base) {
+  // records the reference would have skipped (int16 saturation, k_sat_resolve): none in any ordinary sample
+  const bool any_skip = sat_res && (sat_res[0] | sat_res[1]);
   const u32 omask = GR_BLOCK_SLOTS - 1;
   const u64 stride = (u64)gridDim.x * (256 * FB_UNROLL);
   int e_local = 0;
@@ -822,6 +838,10 @@ k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
     for (int k = 0; k < FB_UNROLL; k++) {
       u64 s_slot = 0; u32 span = 0; int w = 120;
       ok[k] = i0 + k * 256 < n && decode_raw<PACKED>(r[k], L, s_slot, span, w, e_local, c_local);
+      if (any_skip && ok[k]) {
+        const u64 gi = seg_base + i0 + k * 256;
+        ok[k] = !((skip_bits[gi >> 5] >> (gi & 31)) & 1u);
+      }
       const u64 e_slot = s_slot + span;
       bs[k] = (u32)(s_slot >> GR_BLOCK_SHIFT);
       be[k] = (u32)(e_slot >> GR_BLOCK_SHIFT);
@@ -842,6 +862,149 @@ k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
       if (two[k]) bucketed[p1[k]] = e1[k];
     }
   }
+}
+
+// ---- the reference's int16 saturation rule (saveInterval, Genrich.c:2558-2573) -------------------
+// The reference keeps (int16 cov, 8-bit frac) per delta cell and, IN ARRIVAL ORDER, drops an interval
+// whole when the cell of its start already holds cov == INT16_MAX, else when the cell of its end holds
+// cov == INT16_MIN.  A cell can get there only if 32767 or more interval starts (ends) land on it, so
+// only a block with SAT_MIN_EVENTS entries can hold one: k_sb_scan1 raises a flag for such blocks, and
+// this kernel -- one CTA, launched for every sample, returning at once unless the flag is up (no
+// ordinary sample raises it: a hot spot of > 32 k identical fragment ends, e.g. chrM or an amplicon) --
+//   1. lists the suspect blocks and sums, per cell of them, the weights of the starts and of the ends;
+//   2. marks the HOT cells: those whose starts (ends) alone could take cov to the limit;
+//   3. replays, in arrival order, the records that touch a hot cell, with the exact cell state (an
+//      integer count of 1/120ths; cov is a function of it, sat_cov) of the hot cells only -- the decision
+//      for a record depends on nothing else, and a cell that is not hot can never sit at a limit;
+//   4. takes the dropped records out: a bit per record (k_fb_move leaves them out), the block counts
+//      and their chunk sums corrected, a list of (arrival index, overflow | underflow) for the host's
+//      warnings (gr_sample_skipped).
+// sat_res (3 words, written in every launch): dropped for overflow, for underflow, list entries.
+// integer part of the reference's cell for a count N of 1/120ths (canonical mixed-radix form, also for N < 0)
+__device__ __forceinline__ int sat_cov(i64 N) {
+  int r = (int)(N % 120);
+  if (r < 0) r += 120;
+  const int s = (2 * (r % 3)) % 3, t = (3 * (r % 5)) % 5, e = (4 * s + 4 * t - r) & 7;
+  return (int)((N - (15 * e + 20 * s + 12 * t)) / 120);
+}
+#define SAT_HOT_STARTS (32767ll * 120)             /* cov == INT16_MAX needs N >= 32767 * 120 */
+#define SAT_HOT_ENDS (32768ll * 120 - 193)         /* cov == INT16_MIN needs N <= -32768 * 120 + 193 (the fraction's maximum) */
+__global__ void __launch_bounds__(1024)
+k_sat_resolve(const u32* __restrict__ flag, const SatSeg* __restrict__ segs, int nseg, DevLayout L,
+              u32* __restrict__ blk_cnt, u32* __restrict__ chunk_sum, u32 nblocks, ulonglong2* __restrict__ cells,
+              u32* __restrict__ skip_bits, u64 nbits, u64* __restrict__ list, u32 list_cap, u32* __restrict__ sat_res,
+              int* __restrict__ err) {
+  __shared__ u32 sm_sb[SAT_MAX_BLOCKS];
+  __shared__ u32 sm_nsb, sm_nhot, sm_pend_n;
+  __shared__ u32 sm_wcnt[32];
+  __shared__ struct { u64 gi; u32 s_id, e_id, bs, be; int w; } sm_pend[1024];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  if (t < 3) sat_res[t] = 0;
+  if (*flag == 0) return;
+  if (t == 0) { sm_nsb = 0; sm_nhot = 0; }
+  __syncthreads();
+  for (u32 b = t; b < nblocks; b += 1024)
+    if (blk_cnt[b] >= SAT_MIN_EVENTS) { const u32 k = atomicAdd(&sm_nsb, 1u); if (k < SAT_MAX_BLOCKS) sm_sb[k] = b; }
+  __syncthreads();
+  const u32 nsb = sm_nsb;
+  if (nsb > SAT_MAX_BLOCKS) {                          // more hot spots than this path is sized for: reported, not guessed
+    if (t == 0) atomicOr(err, GR_DE_SAT);
+    return;
+  }
+  auto find = [&](u32 b) -> int {                      // index of block b among the suspect ones, -1 if it is none
+    for (u32 k = 0; k < nsb; k++) if (sm_sb[k] == b) return (int)k;
+    return -1;
+  };
+  for (u64 i = t; i < (u64)nsb * GR_BLOCK_SLOTS; i += 1024) cells[i] = make_ulonglong2(0, 0);
+  for (u64 i = t; i < (nbits + 31) / 32; i += 1024) skip_bits[i] = 0;
+  __syncthreads();
+  // ---- 1: weights of the starts (.x) and of the ends (.y) per cell of the suspect blocks
+  for (int g = 0; g < nseg; g++) {
+    const SatSeg sg = segs[g];
+    for (u64 i = t; i < sg.n; i += 1024) {
+      u64 s_slot; u32 span; int w, e_local = 0; u32 c_local = 0;
+      const bool ok = sg.packed ? decode_record<true>(sg.d, i, L, s_slot, span, w, e_local, c_local)
+                                : decode_record<false>(sg.d, i, L, s_slot, span, w, e_local, c_local);
+      if (!ok) continue;
+      const u64 e_slot = s_slot + span;
+      const int ks = find((u32)(s_slot >> GR_BLOCK_SHIFT)), ke = find((u32)(e_slot >> GR_BLOCK_SHIFT));
+      if (ks >= 0) atomicAdd(&cells[(u64)ks * GR_BLOCK_SLOTS + (s_slot & (GR_BLOCK_SLOTS - 1))].x, (u64)w);
+      if (ke >= 0) atomicAdd(&cells[(u64)ke * GR_BLOCK_SLOTS + (e_slot & (GR_BLOCK_SLOTS - 1))].y, (u64)w);
+    }
+  }
+  __syncthreads();
+  // ---- 2: hot cells.  .x becomes the flag, .y the running state (starts at 0: the array was zero)
+  for (u64 i = t; i < (u64)nsb * GR_BLOCK_SLOTS; i += 1024) {
+    const ulonglong2 v = cells[i];
+    const bool hot = (i64)v.x >= SAT_HOT_STARTS || (i64)v.y >= SAT_HOT_ENDS;
+    if (hot) atomicAdd(&sm_nhot, 1u);
+    cells[i] = make_ulonglong2(hot ? 1ull : 0ull, 0ull);
+  }
+  __syncthreads();
+  if (sm_nhot == 0) return;                            // a full block, but no cell of it can saturate
+  // ---- 3 + 4: the records that touch a hot cell, 1024 at a time in arrival order; thread 0 decides
+  u32 n_over = 0, n_under = 0, n_list = 0;             // thread 0's
+  for (int g = 0; g < nseg; g++) {
+    const SatSeg sg = segs[g];
+    for (u64 i0 = 0; i0 < sg.n; i0 += 1024) {
+      const u64 i = i0 + t;
+      bool touch = false;
+      u32 s_id = ~0u, e_id = ~0u, bs = 0, be = 0;
+      int w = 0;
+      if (i < sg.n) {
+        u64 s_slot; u32 span; int e_local = 0; u32 c_local = 0;
+        const bool ok = sg.packed ? decode_record<true>(sg.d, i, L, s_slot, span, w, e_local, c_local)
+                                  : decode_record<false>(sg.d, i, L, s_slot, span, w, e_local, c_local);
+        if (ok) {
+          const u64 e_slot = s_slot + span;
+          bs = (u32)(s_slot >> GR_BLOCK_SHIFT); be = (u32)(e_slot >> GR_BLOCK_SHIFT);
+          const int ks = find(bs), ke = find(be);
+          if (ks >= 0) { const u32 id = (u32)ks * GR_BLOCK_SLOTS + (u32)(s_slot & (GR_BLOCK_SLOTS - 1)); if (cells[id].x) s_id = id; }
+          if (ke >= 0) { const u32 id = (u32)ke * GR_BLOCK_SLOTS + (u32)(e_slot & (GR_BLOCK_SLOTS - 1)); if (cells[id].x) e_id = id; }
+          touch = s_id != ~0u || e_id != ~0u;
+        }
+      }
+      const u32 bal = __ballot_sync(GR_FULL, touch);
+      if (lane == 0) sm_wcnt[wid] = __popc(bal);
+      __syncthreads();
+      u32 pos = __popc(bal & ((1u << lane) - 1));
+      for (int k = 0; k < wid; k++) pos += sm_wcnt[k];
+      if (touch) { sm_pend[pos].gi = sg.base + i; sm_pend[pos].s_id = s_id; sm_pend[pos].e_id = e_id;
+                   sm_pend[pos].bs = bs; sm_pend[pos].be = be; sm_pend[pos].w = w; }
+      if (t == 1023) sm_pend_n = pos + (touch ? 1u : 0u);
+      __syncthreads();
+      if (t == 0) {
+        const u32 np = sm_pend_n;
+        for (u32 k = 0; k < np; k++) {
+          const u32 a = sm_pend[k].s_id, b = sm_pend[k].e_id;
+          const int ww = sm_pend[k].w;
+          int kind = -1;
+          if (a != ~0u && sat_cov((i64)cells[a].y) == 32767) kind = 0;            // 2558: overflow
+          else if (b != ~0u && sat_cov((i64)cells[b].y) == -32768) kind = 1;      // 2566: underflow
+          if (kind < 0) {
+            if (a != ~0u) cells[a].y = (u64)((i64)cells[a].y + ww);              // 2576-2583
+            if (b != ~0u) cells[b].y = (u64)((i64)cells[b].y - ww);
+            continue;
+          }
+          const u64 gi = sm_pend[k].gi;
+          skip_bits[gi >> 5] |= 1u << (gi & 31);
+          if (kind) n_under++; else n_over++;
+          if (n_list < list_cap) list[n_list++] = (gi << 1) | (u64)kind;
+          const u32 xs = sm_pend[k].bs, xe = sm_pend[k].be;
+          blk_cnt[xs] -= 1u; chunk_sum[xs / SB_CHUNK] -= 1u;
+          if (xe != xs) { blk_cnt[xe] -= 1u; chunk_sum[xe / SB_CHUNK] -= 1u; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  if (t == 0) { sat_res[0] = n_over; sat_res[1] = n_under; sat_res[2] = n_list; }
+}
+void launch_sat_resolve(cudaStream_t s, const u32* flag, const void* segs, int nseg, const DevLayout& L, u32* blk_cnt,
+                        u32* chunk_sum, void* cells, u32* skip_bits, u64 nbits, u64* list, u32 list_cap, u32* sat_res, int* err) {
+  k_sat_resolve<<<1, 1024, 0, s>>>(flag, (const SatSeg*)segs, nseg, L, blk_cnt, chunk_sum, (u32)L.nblocks, (ulonglong2*)cells,
+                                   skip_bits, nbits, list, list_cap, sat_res, err);
+  GR_NOTE_LAUNCH();
 }
 
 // -E region boundaries (a few thousand at most): one pseudo entry each, so that the scan finds
@@ -1317,12 +1480,13 @@ void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n
   else k_fb_count<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, blk_cnt, err, clamped);
   GR_NOTE_LAUNCH();
 }
-void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed) {
+void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
+                    const u32* sat_res, const u32* skip_bits, u64 seg_base) {
   if (!n) return;
   u64 blocks = (n + 256 * FB_UNROLL - 1) / (256 * FB_UNROLL);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
-  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed);
+  if (packed) k_fb_move<true><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, sat_res, skip_bits, seg_base);
+  else k_fb_move<false><<<(unsigned)blocks, 256, 0, s>>>(recs, n, L, cursor, bucketed, sat_res, skip_bits, seg_base);
   GR_NOTE_LAUNCH();
 }
 

@@ -61,7 +61,19 @@ void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc
 // buckets = the 8192-cell blocks of the layout
 void launch_fb_count(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed,
                      u32* blk_cnt, int* err, u64* clamped);
-void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed);
+// sat_res / skip_bits / seg_base: records k_sat_resolve took out (sat_res: its 3 result words; seg_base:
+// arrival index of the segment's first record)
+void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n, int packed, u32* cursor, u32* bucketed,
+                    const u32* sat_res, const u32* skip_bits, u64 seg_base);
+// the block-count scan in two halves with the reference's int16 saturation rule (saveInterval
+// 2558-2573) resolved in between: see k_sat_resolve (gr_dense.cu)
+void launch_sb_scan_a(cudaStream_t s, u64 nbuckets, const u32* blk_cnt, u32* chunk_sum, u32* sat_flag);
+void launch_sb_scan_b(cudaStream_t s, u64 nbuckets, const u32* blk_cnt, u32* blk_start, u32* cursor, u32* chunk_sum);
+#define SAT_MAX_BLOCKS 32                 // blocks with a saturating cell that one sample may hold
+struct SatSeg { const void* d; u64 n; u64 base; int packed; int pad_; };   // one pushed segment: records, count, arrival index of the first
+void launch_sat_resolve(cudaStream_t s, const u32* flag, const void* segs, int nseg, const DevLayout& L, u32* blk_cnt,
+                        u32* chunk_sum, void* cells /* SAT_MAX_BLOCKS * 8192 * 16 bytes */, u32* skip_bits, u64 nbits,
+                        u64* list, u32 list_cap, u32* sat_res, int* err);
 // returns the number of run owners (warps or CTAs), to be handed to launch_scan_place
 // blk_bed: per 8192-cell block, bit 0 = the block starts inside a -E region, bit 1 = it holds
 // region boundaries (NULL: no regions)

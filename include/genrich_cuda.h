@@ -54,11 +54,11 @@ typedef enum gr_status {
   GR_ERR_DF = 10,        /* ERRDF       Genrich.c:556: > 200 replicates */
   GR_ERR_GENLEN = 11,    /* Genrich.c:377-382: histogram length != genome length */
   GR_ERR_NODEVICE = 12,  /* no CUDA device / library built without one */
-  GR_ERR_SATURATED = 13  /* more than 32767 interval starts (32768 ends) on one base: the reference's int16
-                            delta counters saturate there and it silently SKIPS further intervals, in arrival
-                            order (saveInterval, Genrich.c:2558-2573).  That order-dependent rule is not
-                            reproduced; the condition is detected and reported instead of returning different
-                            pileups.  Reported by gr_sample_pileup / the next call that waits for the device. */
+  GR_ERR_SATURATED = 13  /* the reference's int16 delta counters saturate at 32767 interval starts (32768 ends) on
+                            one base and it then SKIPS further intervals, in arrival order (saveInterval,
+                            Genrich.c:2558-2573).  The default path reproduces that rule (gr_sample_skipped); this
+                            status is left for what it cannot hold: more than 32 such 8192-bp blocks in one sample,
+                            or the dense formulation (GR_FUSED=0, a measurement aid), which only detects it. */
 } gr_status;
 
 /* One reference sequence (Chrom, Genrich.h:183-201, the fields the path reads). */
@@ -201,6 +201,17 @@ int gr_prefetch_packed6(gr_ctx* ctx, const uint16_t* recs, uint64_t n);
  * double sum of (float)(end-start)*val (0 elsewhere); the caller adds them in
  * chromosome order across contexts to get fragLen / ctrlFrag. */
 int gr_sample_pileup(gr_ctx* ctx, double* chrom_sums);
+/* The reference's int16 saturation rule (saveInterval, Genrich.c:2558-2573): an interval is dropped, whole,
+ * when the delta counter of its start already holds INT16_MAX whole fragments, else when that of its end
+ * holds INT16_MIN -- in ARRIVAL order, i.e. the order of the pushes and of the records inside a push (a
+ * caller that wants the reference's decisions pushes in file order).  The library applies the same rule
+ * while it integrates the sample.  This call reports what was dropped from the last experimental
+ * (is_ctrl = 0) or control sample: counts by cause, and for the "Warning! ... skipped due to overflow /
+ * underflow" lines (2560-2571) the dropped records as (arrival index << 1) | (1 if underflow), the first
+ * 262144 of them, in arrival order.  The array is owned by the context (valid until its next call).
+ * Waits for the device. */
+int gr_sample_skipped(gr_ctx* ctx, int32_t is_ctrl, uint64_t* n_overflow, uint64_t* n_underflow,
+                      const uint64_t** list, uint64_t* n_list);
 /* Nothing on this path makes the host wait for the device unless it asks for a result.
  * chrom_sums == NULL above only enqueues the work; the sums of the experimental and the
  * control sample (NULL: not wanted) are then fetched together, one device round trip: */

@@ -51,6 +51,10 @@ int gr_push_packed(gr_ctx* x, const uint64_t* recs, uint64_t n) {        /* GR_P
   return GR_OK;
 }
 int gr_sample_pileup(gr_ctx* x, double* sums) { return orc_sample_pileup(x->o, sums); }
+int gr_sample_sums(gr_ctx* x, double* e, double* c) { return orc_sample_sums(x->o, e, c); }
+int gr_sample_skipped(gr_ctx* x, int32_t is_ctrl, uint64_t* a, uint64_t* b, const uint64_t** list, uint64_t* n) {
+  return orc_sample_skipped(x->o, is_ctrl, a, b, list, n);
+}
 int gr_replicate_end(gr_ctx* x, gr_sample_stats* st) { return orc_replicate_end(x->o, st); }
 int gr_load_pvalues(gr_ctx* x, const uint64_t* cs, const uint32_t* end, const float* pval, const float* qval, uint64_t n) {
   return orc_load_pvalues(x->o, cs, end, pval, qval, n);
@@ -99,7 +103,7 @@ const char* gr_strerror(int status) {
     "Disallowed number of alignments", "interval on an unknown or unowned chromosome",
     "Invalid df in pchisq()", "Genome length does not match p-value length",
     "no CUDA device available",
-    "More than 32767 fragments start or end at one position (the reference's counters saturate there)"
+    "int16 saturation of the delta counters beyond what the path reproduces"
   };
   return status < 0 || status > GR_ERR_SATURATED ? "Unknown error" : text[status];
 }

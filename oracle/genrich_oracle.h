@@ -26,6 +26,9 @@ int  orc_excluded_bp(orc_ctx* ctx, uint64_t* per_chrom);
 int  orc_sample_begin(orc_ctx* ctx, int32_t is_ctrl, const uint8_t* save);
 int  orc_push_intervals(orc_ctx* ctx, const int32_t* recs, uint64_t n);
 int  orc_sample_pileup(orc_ctx* ctx, double* chrom_sums);
+int  orc_sample_sums(orc_ctx* ctx, double* expt_sums, double* ctrl_sums);
+int  orc_sample_skipped(orc_ctx* ctx, int32_t is_ctrl, uint64_t* n_overflow, uint64_t* n_underflow,
+                        const uint64_t** list, uint64_t* n_list);   /* saveInterval 2558-2573 */
 int  orc_replicate_finish(orc_ctx* ctx, double frag_len, double ctrl_frag,
                           int32_t has_ctrl, uint64_t genome_len,
                           gr_sample_stats* stats);
@@ -45,6 +48,7 @@ int  orc_fetch_intervals(orc_ctx* ctx, int32_t which, int32_t replicate,
 
 /* function-level restatements (pinned against oracle/_ref/libref_funcs.so) */
 float  orc_units_to_val(int32_t units);          /* getVal o updateVal state */
+int32_t orc_cell_cov(int64_t units);             /* Diff.cov of a cell holding that many 1/120ths (addFrac 2311 / subFrac 2412) */
 float  orc_calc_pval(float expt, float ctrl);    /* calcPval 1628 */
 double orc_pchisq(double x, int df);             /* pchisq 555 */
 float  orc_mult_pval(const float* vals, int n);  /* multPval 567 */

@@ -309,3 +309,25 @@ def test_peaks_only(twin, tmp_path):
     assert r.returncode == 1 and "Error! -log(p): cannot find field in header" in r.stderr
     r = subprocess.run([twin, "-P", "-o", out], stderr=subprocess.PIPE, text=True)
     assert r.returncode == 1 and "Need input/output files" in r.stderr
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_host_saturation_rule(twin, threads, tmp_path, monkeypatch):
+    """saveInterval 2558-2573 through the host program: 48 466 alignments of tests/satcase.py are dropped by the
+    reference once its int16 counters saturate, in file order.  narrowPeak, -f and -k equal the reference's, and
+    under -v the WHOLE stderr text does, the 48 466 "skipped due to overflow / underflow" lines with their read
+    names included -- also when three decode workers share the file (their records reach the engine in file order)."""
+    import satcase
+    monkeypatch.setenv("GB_THREAD_MIN_BYTES", "1")
+    td = str(tmp_path)
+    sam = os.path.join(td, "t.sam")
+    satcase.write_sam(sam)
+    meta = json.load(open(os.path.join(util.GOLDEN, "sat_hot.json")))
+    out, logf, pile = (os.path.join(td, x) for x in ("o.np", "o.f", "o.k"))
+    r = subprocess.run([twin, "-t", sam, "-o", out, "-f", logf, "-k", pile, "-v", "--threads", str(threads)] + satcase.ARGS,
+                       stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out).read() == open(os.path.join(util.GOLDEN, "sat_hot.narrowPeak")).read()
+    assert _sha(logf) == (meta["log_sha256"], meta["log_lines"])
+    assert _sha(pile, True) == (meta["pile_sha256"], meta["pile_lines"])
+    assert hashlib.sha256(r.stderr.replace(sam, "T.sam").encode()).hexdigest() == meta["verbose_sha256"]

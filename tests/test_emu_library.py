@@ -94,6 +94,14 @@ def test_emulated_library_other_shapes(emu_api, name, mode, packed, monkeypatch)
     _compare(BY_NAME[name], emu_api, MODES[mode], monkeypatch, packed=packed)
 
 
+def test_saturation_rule_under_emulation(emu_api, monkeypatch):
+    """k_sat_resolve (the reference's int16 saturation skips, saveInterval 2558-2573) through the C-ABI: the same
+    records dropped as by the oracle -- which is pinned to the unmodified reference on this very case
+    (tests/test_oracle_pin.py) -- in one push and in many, 16-byte and packed records."""
+    assert util.check_saturation(emu_api) > 0
+    assert util.check_saturation(emu_api, packed=True, chunk=50021) > 0
+
+
 def test_host_program_over_emulated_devices(emu_api, tmp_path):
     """The host program linked against the emulated CUDA library, --gpus 3 over three emulated devices
     (every device allocation remembers its device; a copy or memset issued while another device is

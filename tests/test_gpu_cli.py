@@ -191,3 +191,35 @@ def test_cli_threaded_decode(tmp_path, monkeypatch):
     subprocess.check_call([CLI, "-t", bam_t, "-c", cfiles[0], "-o", o, "--threads", "6"] + args)
     outs.append(open(o).read())
     assert outs[0] == outs[1] == outs[2] and len(outs[0]) > 0
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+def test_cli_saturation_rule(threads, tmp_path, monkeypatch):
+    """saveInterval 2558-2573 through the drop-in program over the CUDA library: the alignments the reference
+    drops once its int16 counters saturate (tests/satcase.py: 48 466 of them, file order) are dropped on the
+    device (k_sat_resolve).  narrowPeak coordinates equal the reference's file; under -v the very same
+    "skipped due to overflow / underflow" lines, in the same order."""
+    import hashlib
+    import json
+    import re
+    import satcase
+    monkeypatch.setenv("GB_THREAD_MIN_BYTES", "1")
+    td = str(tmp_path)
+    sam = os.path.join(td, "t.sam")
+    satcase.write_sam(sam)
+    meta = json.load(open(os.path.join(util.GOLDEN, "sat_hot.json")))
+    out = os.path.join(td, "o.np")
+    r = subprocess.run([CLI, "-t", sam, "-o", out, "-v", "--threads", str(threads)] + satcase.ARGS, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = open(out).read().split("\n")[:-1]
+    want = open(os.path.join(util.GOLDEN, "sat_hot.narrowPeak")).read().split("\n")[:-1]
+    assert len(got) == len(want) == meta["peaks"]
+    _close_lines(got, want, float_cols=(6, 7, 8))
+    over = re.findall(r"Warning! Read (\S+), alignment at \((\S+), (\d+)-(\d+)\) skipped due to overflow", r.stderr)
+    under = re.findall(r"Warning! Read (\S+), alignment at \((\S+), (\d+)-(\d+)\) skipped due to underflow", r.stderr)
+    assert (len(over), len(under)) == (meta["n_overflow"], meta["n_underflow"])
+    h = hashlib.sha256()
+    for a in over + under:
+        h.update(("%s %s %s %s\n" % a).encode())
+    assert h.hexdigest() == meta["skipped_sha256"]
+    assert "Background pileup value: %f" % meta["lambda"][0] in r.stderr

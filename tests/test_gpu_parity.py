@@ -335,6 +335,15 @@ def test_fused_scan_large(monkeypatch):
     assert len(outs[1][0].peaks) > 100
 
 
+def test_saturation_rule():
+    """saveInterval 2558-2573: more than 32767 starts (32768 ends) on one base -- the reference drops
+    intervals in arrival order; the device replays exactly that (k_sat_resolve).  Same dropped records,
+    pileups and peaks as the oracle, which reproduces the unmodified reference's files for this case."""
+    api = capi.load_cuda()
+    assert util.check_saturation(api) > 0
+    assert util.check_saturation(api, packed=True, chunk=50021) > 0
+
+
 def test_async_path_and_retries(monkeypatch):
     """The no-round-trip path (counts, lambda and the scale factor stay on the device; tables and
     candidate buffers sized optimistically) gives the same bits as the synchronous one, also when
@@ -468,26 +477,31 @@ def test_error_codes(monkeypatch):
     with pytest.raises(capi.GenrichError) as e:
         ctx.replicate_end()
     assert e.value.status == 5
-    # more starts on one base than the reference's int16 counter holds (saveInterval 2558-2573 would
-    # skip the rest, in arrival order): reported, on every scan path; one start fewer is fine
+    # more starts on one base than the reference's int16 counter holds: the reference drops the 32768th
+    # (saveInterval 2558-2573), and so do the oracle and the fused paths (k_sat_resolve; the full case is
+    # test_saturation_rule).  The dense formulation -- a measurement aid behind GR_FUSED=0 -- only detects it.
     for env in (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1")):
         for k in ("GR_FUSED", "GR_FUSED_MIN", "GR_SB_MIN", "GR_FUSED_CTA"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
-        for n, want in ((32767, 0), (32768, 13)):
+        for n in (32767, 32768, 32790):
             recs = np.tile(np.array([[0, 5000, 5100, 1]], dtype=np.int32), (n, 1))
             recs[:, 2] += np.arange(n, dtype=np.int32) % 3000          # ends spread out: only the start cell is hot
+            sums = []
             for a in (util.oracle_api(), api):
                 ctx = capi.Context(a, [20000, 9000], par)
                 ctx.sample_begin(False)
                 ctx.push_intervals(recs)
-                if want:
+                if a is api and env is PLAIN and n > 32767:
                     with pytest.raises(capi.GenrichError) as e:
                         ctx.sample_pileup()
-                    assert e.value.status == want, (env, n)
-                else:
-                    ctx.sample_pileup()
+                    assert e.value.status == 13, (env, n)
+                    continue
+                sums.append(ctx.sample_pileup())
+                assert ctx.sample_skipped(False)[:2] == (n - 32767, 0), (env, n)
+            if len(sums) == 2:
+                assert np.array_equal(sums[0], sums[1])
 
 
 def test_large_properties():

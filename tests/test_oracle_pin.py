@@ -172,3 +172,65 @@ def test_qvalues_bitexact(libs):
             q[i] = max(v, np.float32(0.0))
             k += int(hl[i])
         assert np.array_equal(q[:-1][idx].view(np.uint32), q_ref.view(np.uint32))
+
+
+@needs_ref
+def test_cell_cov_matches_reference_cells(libs):
+    """orc_cell_cov(N) == Diff.cov of the reference's own cell after any sequence of addFrac / subFrac /
+    ++ / -- that sums to N 1/120ths -- also for negative cells (the end positions of intervals)."""
+    ref, orc = libs
+    orc.orc_cell_cov.restype = C.c_int32
+    orc.orc_cell_cov.argtypes = [C.c_int64]
+    rng = np.random.RandomState(11)
+    counts = [1, 2, 3, 4, 5, 6, 8, 10]
+    for trial in range(300):
+        cov, frac, N = C.c_int16(0), C.c_uint8(0), 0
+        bias = rng.uniform(0.2, 0.8)
+        for step in range(400):
+            cnt = counts[rng.randint(8)]
+            sign = 1 if rng.uniform() < bias else -1
+            ref.ref_diff_add(C.byref(cov), C.byref(frac), cnt, sign)
+            N += sign * (120 // cnt)
+            assert orc.orc_cell_cov(N) == cov.value, (trial, step, N, cov.value, frac.value)
+    # around the limits the rule tests for
+    for N in (32767 * 120 - 1, 32767 * 120, 32767 * 120 + 193, -32768 * 120, -32768 * 120 + 193, -32768 * 120 + 194):
+        c = orc.orc_cell_cov(N)
+        assert (c == 32767) == (32767 * 120 <= N) if N > 0 else True
+    assert orc.orc_cell_cov(-32768 * 120 + 193) == -32768 and orc.orc_cell_cov(-32768 * 120 + 75) in (-32768, -32767)
+
+
+def test_saturation_rule_matches_reference():
+    """saveInterval 2558-2573 (intervals skipped once a delta counter sits at INT16_MAX / INT16_MIN, in arrival
+    order): the oracle on tests/satcase.py == what the unmodified reference wrote for its SAM view -- narrowPeak
+    byte for byte, the -f / -k text by hash, and the very alignments it reported as skipped."""
+    import hashlib
+    import json
+    import satcase
+    from genrich_b200 import capi, host
+    meta = json.load(open(os.path.join(util.GOLDEN, "sat_hot.json")))
+    recs = satcase.records()
+    par = capi.make_params(p=0.01, keep_pileups=True)
+    ctx = capi.Context(util.oracle_api(), satcase.CHROM_LEN, par)
+    ctx.sample_begin(False, None)
+    ctx.push_intervals(recs)
+    ctx.sample_pileup()
+    n_over, n_under, lst = ctx.sample_skipped(False)
+    assert (n_over, n_under) == (meta["n_overflow"], meta["n_underflow"])
+    # the skipped alignments themselves: record index -> template number (the SAM's read name) and coordinates
+    tmpl = []
+    for n, pl in enumerate(satcase.templates()):
+        tmpl += [n] * len(pl)
+    h = hashlib.sha256()
+    for kind in (0, 1):
+        for v in lst[(lst & np.uint64(1)) == kind]:
+            i = int(v >> np.uint64(1))
+            h.update(("f%d chr1 %d %d\n" % (tmpl[i], recs[i, 1], recs[i, 2])).encode())
+    assert h.hexdigest() == meta["skipped_sha256"]
+    st = ctx.replicate_end()
+    assert abs(st.lambda_ - meta["lambda"][0]) < 1e-5
+    peaks, rs = ctx.call_peaks()
+    got = host.format_narrowpeak(peaks, ["chr1"])
+    want = open(os.path.join(util.GOLDEN, "sat_hot.narrowPeak")).read().split("\n")[:-1]
+    assert got == want and len(got) == meta["peaks"]
+    assert util.sha_lines(host.format_log(ctx, ["chr1"], False, thr=par.min_pqval)) == meta["log_sha256"]
+    assert util.sha_lines(host.format_pile(ctx, ["chr1"], 0)) == meta["pile_sha256"]

@@ -189,3 +189,40 @@ def sam_to_bam(sam_path, bam_path):
             g.write(b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", len(comp) + 25) + comp +
                     struct.pack("<II", zlib.crc32(chunk), len(chunk)))
         g.write(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+
+
+def check_saturation(api, packed=False, chunk=None):
+    """The int16 saturation case (tests/satcase.py) through `api` against the pinned oracle: the very same
+    records dropped (saveInterval 2558-2573, arrival order), pileups bit for bit, the same peaks."""
+    import satcase
+    recs = satcase.records()
+    par = capi.make_params(p=0.01, keep_pileups=True)
+    outs = []
+    for a in (oracle_api(), api):
+        ctx = capi.Context(a, satcase.CHROM_LEN, par)
+        ctx.sample_begin(False, None)
+        step = chunk or len(recs)
+        for i in range(0, len(recs), step):
+            part = recs[i:i + step]
+            if packed and a is api:
+                pk, rest = host.pack_records(part)
+                assert not len(rest)
+                ctx.push_packed(pk)
+            else:
+                ctx.push_intervals(part)
+        ctx.sample_pileup()
+        n_over, n_under, lst = ctx.sample_skipped(False)
+        st = ctx.replicate_end()
+        peaks, rs = ctx.call_peaks()
+        outs.append((n_over, n_under, lst.copy(), st, peaks.copy(), ctx.fetch(0, 0, 0), ctx.fetch(2, 0, 0)))
+    o, g = outs
+    assert (g[0], g[1]) == (o[0], o[1]) and o[0] > 30000 and o[1] > 5000
+    assert np.array_equal(g[2], o[2])
+    assert g[3].frag_len == o[3].frag_len and np.float32(g[3].lambda_).view(np.uint32) == np.float32(o[3].lambda_).view(np.uint32)
+    assert (g[3].n_expt, g[3].n_pval) == (o[3].n_expt, o[3].n_pval)
+    for f in ("chrom", "start", "end", "summit"):
+        assert np.array_equal(g[4][f], o[4][f]), f
+    assert np.max(np.abs(g[4]["pval"].astype(np.float64) - o[4]["pval"])) <= 1e-4
+    assert np.array_equal(g[5].end, o[5].end) and np.array_equal(g[5].val.view(np.uint32), o[5].val.view(np.uint32))
+    assert np.array_equal(g[6].end, o[6].end)
+    return len(g[4])
