@@ -125,7 +125,6 @@ class Api:
 
         if self.has_device:
             self.create = fn("create", C.c_int, [C.POINTER(vp), C.POINTER(GrChrom), i32, C.POINTER(GrParams), i32])
-            self.set_params = fn("set_params", C.c_int, [vp, C.POINTER(GrParams)])
             self.reset = fn("reset", C.c_int, [vp])
             self.strerror = fn("strerror", C.c_char_p, [C.c_int])
             self.last_error_detail = fn("last_error_detail", C.c_char_p, [vp])
@@ -155,6 +154,8 @@ class Api:
         else:
             self.create = fn("create", C.c_int, [C.POINTER(vp), C.POINTER(GrChrom), i32, C.POINTER(GrParams)])
         self.destroy = fn("destroy", None, [vp])
+        self.set_params = fn("set_params", C.c_int, [vp, C.POINTER(GrParams)])
+        self.load_pvalues = fn("load_pvalues", C.c_int, [vp, vp, vp, vp, vp, u64])
         self.set_exclusions = fn("set_exclusions", C.c_int, [vp, vp, vp, vp, u64])
         self.excluded_bp = fn("excluded_bp", C.c_int, [vp, vp])
         self.sample_begin = fn("sample_begin", C.c_int, [vp, i32, vp])
@@ -362,6 +363,18 @@ class Context:
         return st
 
     # -- peaks -----------------------------------------------------------------
+    def set_params(self, params: GrParams):
+        self._check(self.api.set_params(self._h, C.byref(params)), "set_params")
+
+    def load_pvalues(self, chrom_start, end, pval, qval=None):
+        """-P (callPeaksLog 1277): the final -log10 p (and q) intervals come from the caller."""
+        cs = np.ascontiguousarray(chrom_start, dtype=np.uint64)
+        e = np.ascontiguousarray(end, dtype=np.uint32)
+        p = np.ascontiguousarray(pval, dtype=np.float32)
+        q = np.ascontiguousarray(qval, dtype=np.float32) if qval is not None else None
+        self._check(self.api.load_pvalues(self._h, _as_ptr(cs), _as_ptr(e), _as_ptr(p), _as_ptr(q) if q is not None else None,
+                                          len(e)), "load_pvalues")
+
     def pvalues_finalize(self):
         self._check(self.api.pvalues_finalize(self._h), "pvalues_finalize")
 

@@ -123,6 +123,7 @@ struct gr_ctx {
   std::vector<u64> bed_bp;             // excluded bp per chromosome
   bool has_bed = false;
   DevBuf bedMarks, blkBed;             // boundary cell slots (u64); per 8192-cell block: bit 0 starts inside a region, bit 1 holds boundaries
+  DevBuf bedChromMarks;                // boundaries per chromosome (u32)
   u32 n_marks = 0;
   DevBuf ccSlots, ccSkip;              // no-control pileup: break slots and SKIP flags of its intervals
 
@@ -415,7 +416,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   DevBuf* all[] = { &x->d_off, &x->d_len, &x->d_flags, &x->d_blk2chrom, &x->delta, &x->bmE, &x->bmC,
     &x->rankE, &x->rankC, &x->rankTmp, &x->lb0, &x->lb1, &x->lb2, &x->ticket, &x->scanWs, &x->small, &x->accI,
     &x->accF, &x->exptEnd, &x->exptVal, &x->exptCS, &x->exptTot, &x->rawEnd, &x->rawVal, &x->rawCS,
-    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->sbCnt, &x->sbStart, &x->sbCursor, &x->sbBucket, &x->sbSpill, &x->sbSpillCtr, &x->bedMarks, &x->blkBed, &x->ccSlots, &x->ccSkip,
+    &x->rawTot, &x->ctrlEnd, &x->ctrlVal, &x->ctrlCS, &x->ctrlTot, &x->sbCnt, &x->sbStart, &x->sbCursor, &x->sbBucket, &x->sbSpill, &x->sbSpillCtr, &x->bedMarks, &x->blkBed, &x->bedChromMarks, &x->ccSlots, &x->ccSkip,
     &x->qVal, &x->tKeys, &x->tLens, &x->tPval, &x->tQval, &x->tCount, &x->slot, &x->hk, &x->hl,
     &x->hcount, &x->bk0, &x->bk1, &x->bl0, &x->bl1, &x->bhist, &x->bksum, &x->bx, &x->bdk, &x->bdq,
     &x->bdl, &x->bdcount, &x->fsum, &x->fdf, &x->repviews, &x->evIdx, &x->evCount, &x->headIdx,
@@ -469,6 +470,7 @@ extern "C" int gr_set_exclusions(gr_ctx* x, const int32_t* chrom, const uint32_t
   x->bed_bp.assign(nc, 0);
   x->has_bed = false;
   std::vector<u64> marks;
+  std::vector<u32> cmarks(nc, 0);
   std::vector<uint8_t> blk(x->nblocks, 0);
   for (int c = 0; c < nc; c++) {
     std::vector<u32>& b = x->bed[c];
@@ -504,12 +506,14 @@ extern "C" int gr_set_exclusions(gr_ctx* x, const int32_t* chrom, const uint32_t
       blk[blk0 + q] = v;
     }
     for (u32 pos : b)
-      if (pos >= 1 && pos < len) marks.push_back(x->off[c] + pos);
+      if (pos >= 1 && pos < len) { marks.push_back(x->off[c] + pos); cmarks[c]++; }
   }
   x->n_marks = (u32)marks.size();
   if (x->has_bed) {
     CK(x->blkBed.ensure(x->nblocks));
     CK(cudaMemcpy(x->blkBed.p, blk.data(), x->nblocks, cudaMemcpyHostToDevice));
+    CK(x->bedChromMarks.ensure(nc * sizeof(u32)));
+    CK(cudaMemcpy(x->bedChromMarks.p, cmarks.data(), nc * sizeof(u32), cudaMemcpyHostToDevice));
     if (x->n_marks) {
       CK(x->bedMarks.ensure(marks.size() * sizeof(u64)));
       CK(cudaMemcpy(x->bedMarks.p, marks.data(), marks.size() * sizeof(u64), cudaMemcpyHostToDevice));
@@ -907,7 +911,8 @@ static int pileup_enqueue(gr_ctx* x) {
     stage_begin(x, "fused_scan", x->T * 4);
     owners = launch_fb_scan(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), sc,
                             (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err,
-                            x->has_bed ? x->blkBed.as<uint8_t>() : nullptr);
+                            x->has_bed ? x->blkBed.as<uint8_t>() : nullptr,
+                            x->has_bed && !ctrl ? x->bedChromMarks.as<u32>() : nullptr);
     CKL();
     stage_end(x);
   } else {

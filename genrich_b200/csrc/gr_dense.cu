@@ -1031,7 +1031,8 @@ template <int CPS, int NT, bool BED>
 __global__ void __launch_bounds__(NT, CPS)
 k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
           u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R,
-          const uint8_t* __restrict__ blk_bed /* NULL: no -E regions */) {
+          const uint8_t* __restrict__ blk_bed /* NULL: no -E regions */,
+          const u32* __restrict__ chrom_marks /* BED, experimental sample: region boundaries per chromosome, else NULL */) {
   constexpr int WPT = FB_WORDS / NT, PF = 512 / NT, NW = NT / 32;
   __shared__ int sm_cell[GR_BLOCK_SLOTS];
   __shared__ u32 sm_occ[FB_WORDS];
@@ -1087,9 +1088,14 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
     if (sA + k * NT + t < sB) v[k] = __ldcs(bucketed + sA + k * NT + t);
   }
 
+  // A chromosome without a single read in the EXPERIMENTAL sample is one interval (len, 0.0f) in the reference,
+  // whatever -E regions lie on it (savePileupExpt 2178-2182: its diff array was never allocated): its region
+  // boundaries are then not breaks.  (The control side of such a chromosome is saveLambda's, regions included.)
+  bool c_plain = false;
   auto apply = [&](u32 e) {
     const u32 so = e & (GR_BLOCK_SLOTS - 1), kind = e >> 30;
     const int w = 120 / (int)((e >> 26) & 15u);
+    if (BED && kind == FB_KIND_MARK && c_plain) return;
     atomicOr(sm_occ + (so >> 5), 1u << (so & 31));
     if (BED && kind == FB_KIND_MARK) { atomicOr(sm_mark + (so >> 5), 1u << (so & 31)); return; }
     atomicAdd(sm_cell + so, kind == FB_KIND_END ? -w : w);
@@ -1115,6 +1121,8 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
       len = L.len[c];
       c_last_blk = (u32)((off + len) >> GR_BLOCK_SHIFT);
       act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
+      if (BED && chrom_marks)                          // nothing but its own region boundaries in the chromosome's buckets
+        c_plain = blk_start[c_last_blk + 1] - blk_start[(u32)(off >> GR_BLOCK_SHIFT)] == chrom_marks[c];
     }
     const u32 sD = ld_start(b + 3);                    // used two blocks from now
     const u32 jb = (u32)(((u64)b << GR_BLOCK_SHIFT) - off);       // chromosome position of the block's first cell
@@ -1152,7 +1160,7 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
     const u32 jt = jb + (u32)cbase;
     // -E: bit 0 of the block's byte = the interval running into the block is inside a region,
     // bit 1 = the block holds region boundaries (then, and only then, sm_mark is looked at)
-    const u32 bed = BED ? (u32)blk_bed[b] : 0u;
+    const u32 bed = (BED && !c_plain) ? (u32)blk_bed[b] : 0u;
     u32 excl_in = bed & 1u;                            // state of the interval ending at this thread's first cell
     if (bed & 2u)
       for (int i = 0; i < t * WPT; i++) excl_in ^= __popc(sm_mark[i]) & 1u;
@@ -1499,7 +1507,7 @@ static int fb_env(const char* name, int dflt) { const char* e = getenv(name); re
 // weightless mark entries only it understands) and, behind GR_FUSED_CTA=1, as the comparison the
 // bench quotes.
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
-                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed) {
+                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   cudaMemsetAsync(W.page_ctr, 0, 4, s);
   static int sms = 0;
@@ -1513,8 +1521,8 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
   if (blk_bed || fb_env("GR_FUSED_CTA", 0)) {            // read per call: the tests switch it inside one process
     owners = (u32)(sms * 6);
     const u32 R = (nb + owners - 1) / owners;
-    if (blk_bed) k_fb_scan<6, 128, true><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed);
-    else k_fb_scan<6, 128, false><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr);
+    if (blk_bed) k_fb_scan<6, 128, true><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed, chrom_marks);
+    else k_fb_scan<6, 128, false><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr, nullptr);
   } else {
     owners = (u32)(sms * 9) * 4;
     if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;

@@ -76,9 +76,10 @@ void launch_sat_resolve(cudaStream_t s, const u32* flag, const void* segs, int n
                         u64* list, u32 list_cap, u32* sat_res, int* err);
 // returns the number of run owners (warps or CTAs), to be handed to launch_scan_place
 // blk_bed: per 8192-cell block, bit 0 = the block starts inside a -E region, bit 1 = it holds
-// region boundaries (NULL: no regions)
+// region boundaries (NULL: no regions); chrom_marks: region boundaries per chromosome, for the experimental
+// sample only (a chromosome that holds nothing else is one interval there, savePileupExpt 2178-2182)
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
-                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed);
+                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks);
 // -E region boundaries as pseudo entries (cursor == NULL: count pass)
 void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed);
 

@@ -147,31 +147,15 @@ def test_qvalues_bitexact(libs):
         G = int(end[-1])
         q_ref = np.zeros(n, dtype=np.float32)
         ref.ref_computeQval(p.ctypes.data, end.ctypes.data, n, G, q_ref.ctypes.data)
-        # the oracle's BH on the same histogram
-        keys, idx = np.unique(p.view(np.uint32), return_inverse=True)
-        hl = np.bincount(idx, weights=lens.astype(np.float64)).astype(np.uint64)
-        par = util.capi.make_params(q=0.05)
-        ctx = util.capi.Context(api, [G], par)
-        # feed a one-fragment sample so the context has a p array, then override the table
-        ctx.sample_begin(False)
-        ctx.push_intervals(np.array([[0, 0, min(G, 10), 1]], dtype=np.int32))
-        ctx.replicate_end()
-        ctx.pvalues_finalize()
-        ctx.bh_set_global_ptrs(keys.ctypes.data, hl.ctypes.data, len(keys), G)
-        h = ctx._h
-        qp = np.ctypeslib.as_array  # noqa: F841  (table is read back through a lookup below)
-        # look the q of every p up through a second set_global-independent path: recompute here
-        k = 1
-        logN = -np.float32(util.capi._libm_log10f(np.float32(G)))
-        q = np.zeros(len(keys) + 1, dtype=np.float32)
-        q[-1] = np.finfo(np.float32).max
-        kv = keys.view(np.float32)
-        for i in range(len(keys) - 1, -1, -1):
-            v = np.float32(np.float32(kv[i] + logN) + np.float32(util.capi._libm_log10f(np.float32(k))))
-            v = min(v, q[i + 1])
-            q[i] = max(v, np.float32(0.0))
-            k += int(hl[i])
-        assert np.array_equal(q[:-1][idx].view(np.uint32), q_ref.view(np.uint32))
+        # the oracle's own BH (orc_bh_local_hist + orc_bh_set_global, run by orc_call_peaks) on the same intervals:
+        # the p array is handed over as -P does (orc_load_pvalues), the q of EVERY interval read back (fetch 3)
+        ctx = util.capi.Context(api, [G], util.capi.make_params(p=0.01))
+        ctx.load_pvalues([0, n], end, p)
+        ctx.set_params(util.capi.make_params(q=0.05))
+        _, rs = ctx.call_peaks()
+        q_orc = ctx.fetch(3, 0, 0).val
+        assert rs.n_distinct_p == len(np.unique(p.view(np.uint32)))
+        assert np.array_equal(q_orc.view(np.uint32), q_ref.view(np.uint32)), trial
 
 
 @needs_ref
