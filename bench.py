@@ -247,6 +247,11 @@ class Sample:
 
             def consume(i, fr):
                 iv = host_mod.fragments_to_intervals(fr, atac=wl["atac"])
+                if wl["atac"]:
+                    # cut-site intervals reach past the chromosome ends: clamped here as saveInterval does
+                    # (2522-2544) -- the packed record forms hold no negative start
+                    np.clip(iv[:, 1], 0, None, out=iv[:, 1])
+                    np.minimum(iv[:, 2], np.asarray(L, dtype=np.int32)[iv[:, 0]], out=iv[:, 2])
                 a, rest = host_mod.pack_records(iv)
                 assert rest.shape[0] == 0, "synthetic workload has records that do not pack"
                 p8[i] = a

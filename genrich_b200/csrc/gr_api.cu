@@ -136,6 +136,8 @@ struct gr_ctx {
   int retry_flags = 0;              // GR_DE_TABLE / GR_DE_CAP seen by the last materialize()
   u64 cap_expt = 0, cap_raw = 0;    // capacities (upper bounds of the interval counts) of the current sample arrays
   u32 pair_cap = 1u << 20;          // pair-table capacity, grown on overflow and remembered
+  bool pair_valid = false;          // the tables hold the last replicate's (expt, ctrl) pairs and x->slot its intervals' slots
+  bool hist_by_pairs = false;       // the BH histogram was read off the pair table (gr_bh_local_hist)
   u64 head_cap = 0;                 // candidate-peak capacity of the last peak call
   DevBuf dpar;                      // device: float factor, lambda (+ pad)
   DevBuf dsums;                     // device: double[2][nchrom], per-chromosome sum(len*val) of expt / ctrl
@@ -536,7 +538,7 @@ extern "C" int gr_reset(gr_ctx* x) {
   x->pend_reps.clear();
   x->pend_pile[0] = x->pend_pile[1] = false;
   x->finalized = false; x->have_q = false; x->have_expt = x->have_ctrl = false;
-  x->filling = FILL_NONE; x->hist_cap = 0; x->peaks_h.clear();
+  x->filling = FILL_NONE; x->hist_cap = 0; x->peaks_h.clear(); x->pair_valid = false;
   return GR_OK;
 }
 
@@ -912,7 +914,7 @@ static int pileup_enqueue(gr_ctx* x) {
     owners = launch_fb_scan(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), sc,
                             (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err,
                             x->has_bed ? x->blkBed.as<uint8_t>() : nullptr,
-                            x->has_bed && !ctrl ? x->bedChromMarks.as<u32>() : nullptr);
+                            x->has_bed && !ctrl ? x->bedChromMarks.as<u32>() : nullptr, x->n_pushed);
     CKL();
     stage_end(x);
   } else {
@@ -1051,6 +1053,7 @@ static int rep_stage_pvals(gr_ctx* x, Replicate* rep) {
   CKL();
   stage_end(x);
   x->lag = true;
+  x->pair_valid = true;
   return GR_OK;
 }
 
@@ -1367,14 +1370,27 @@ extern "C" int gr_bh_local_hist(gr_ctx* x, const uint32_t** d_keys, const uint64
   { int r = redo_pvals(x); if (r) return r; }
   Replicate* f = x->fin;
   const u64 np = f->n;
-  CK(x->slot.ensure((f->n_upper + 1) * sizeof(u32)));
   u32 cap = 1u << 20;
+  // One replicate, p-values computed here (not loaded, -P): the intervals already know the pair-table slot of
+  // their (expt, ctrl) pair (k_pair_insert), so the bp are summed per slot and the list is read off that table.
+  const bool by_pairs = x->reps.size() == 1 && f == x->reps[0] && x->pair_valid;
+  x->hist_by_pairs = by_pairs;
   stage_begin(x, "bh_hist", np * 12);
-  int r = table_build(x, np, cap, [&](const PairTable& t) {
-    launch_key_insert(x->stream, f->pEnd.as<u32>(), f->pVal.as<float>(), np, f->chrom_start.as<u64>(),
-                      x->nchrom, t, x->slot.as<u32>(), x->d_err);
-  });
-  if (r) return r;
+  if (by_pairs) {
+    cap = x->pair_cap;
+    PairTable pt = table_view(x, cap);
+    CK(cudaMemsetAsync(pt.lens, 0, (size_t)cap * 8, x->stream));
+    launch_slot_hist(x->stream, f->pEnd.as<u32>(), x->slot.as<u32>(), f->n_upper, f->cnt.as<u64>(),
+                     f->chrom_start.as<u64>(), x->nchrom, pt.lens);
+    CKL();
+  } else {
+    CK(x->slot.ensure((f->n_upper + 1) * sizeof(u32)));
+    int r = table_build(x, np, cap, [&](const PairTable& t) {
+      launch_key_insert(x->stream, f->pEnd.as<u32>(), f->pVal.as<float>(), np, f->chrom_start.as<u64>(),
+                        x->nchrom, t, x->slot.as<u32>(), x->d_err);
+    });
+    if (r) return r;
+  }
   PairTable t = table_view(x, cap);
   // occupied count -> list
   CK(cudaMemcpyAsync(x->h_small, x->tCount.p, 4, cudaMemcpyDeviceToHost, x->stream));
@@ -1387,19 +1403,22 @@ extern "C" int gr_bh_local_hist(gr_ctx* x, const uint32_t** d_keys, const uint64
   CK(x->lb0.ensure(ntile * sizeof(u64) > x->lb0.cap ? ntile * sizeof(u64) : x->lb0.cap));
   CompactScratch cs;
   cs.st = x->lb0.as<u64>(); cs.ticket = x->ticket.as<u32>();
-  launch_table_compact(x->stream, t, cs, x->hk.as<u32>(), x->hl.as<u64>(), x->hcount.as<u64>());
+  launch_table_compact(x->stream, t, cs, x->hk.as<u32>(), x->hl.as<u64>(), x->hcount.as<u64>(), by_pairs ? 1 : 0);
   CKL();
   stage_end(x);
   // The caller reads hk / hl on a stream of its own (an NCCL all-gather, a copy): the list must be
   // complete when the pointers are handed out, not merely enqueued on x->stream.
+  CK(cudaMemcpyAsync(x->h_small, x->hcount.p, 8, cudaMemcpyDeviceToHost, x->stream));
   CK(cudaStreamSynchronize(x->stream));
-  x->hn = occ;
+  const u64 listed = *(u64*)x->h_small;                  // <= occ: pairs that evaluate to SKIP are not listed
+  if (!by_pairs) x->pair_valid = false;                  // the key table took the pair table's place
+  x->hn = listed;
   // remember the table capacity for the q lookup
   x->n_distinct = 0;
   x->hist_cap = cap;
   if (d_keys) *d_keys = x->hk.as<u32>();
   if (d_lens) *d_lens = (const uint64_t*)x->hl.as<u64>();
-  if (n) *n = occ;
+  if (n) *n = listed;
   return GR_OK;
 }
 
@@ -1430,7 +1449,7 @@ extern "C" int gr_bh_set_global(gr_ctx* x, const uint32_t* d_keys, const uint64_
   stage_begin(x, "bh", n * 12 * 8);
   launch_bh(x->stream, d_keys, (const u64*)d_lens, n, logN, w);
   PairTable t = table_view(x, cap);
-  launch_table_q(x->stream, t, w.dk, w.dq, w.dcount);
+  launch_table_q(x->stream, t, w.dk, w.dq, w.dcount, x->hist_by_pairs ? 1 : 0);
   CK(x->qVal.ensure((f->n + 1) * sizeof(float)));
   launch_gather_f32(x->stream, t.qval, x->slot.as<u32>(), f->n, f->cnt.as<u64>(), x->qVal.as<float>());
   CKL();
@@ -1492,6 +1511,7 @@ extern "C" int gr_load_pvalues(gr_ctx* x, const uint64_t* chrom_start, const uin
   x->reps.push_back(rep);
   rep->has_ctrl = false;
   rep->has_cols = false;
+  x->pair_valid = false;
   rep->n = rep->n_upper = n;
   rep->n_ctrl = 0;
   CK(rep->cnt.ensure(16));

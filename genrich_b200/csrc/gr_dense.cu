@@ -7,6 +7,7 @@
 #include "gr_common.cuh"
 #include "gr_internal.h"
 #include <stdlib.h>
+#include <math.h>
 #include <stdio.h>
 
 // ============================================================================
@@ -1507,7 +1508,8 @@ static int fb_env(const char* name, int dflt) { const char* e = getenv(name); re
 // weightless mark entries only it understands) and, behind GR_FUSED_CTA=1, as the comparison the
 // bench quotes.
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
-                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks) {
+                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks,
+                   u64 n_records) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   cudaMemsetAsync(W.page_ctr, 0, 4, s);
   static int sms = 0;
@@ -1518,7 +1520,13 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
   }
   const u32 nb = (u32)L.nblocks;
   u32 owners;
-  if (blk_bed || fb_env("GR_FUSED_CTA", 0)) {            // read per call: the tests switch it inside one process
+  // The rank form walks a block's entries once per 512 DISTINCT event cells; a block of a deep sample (the 10 Gbp
+  // / 1 B fragment configuration: ~2200 entries, ~3400 distinct cells per block) takes seven such rounds and the
+  // CTA form's cell array wins (measured on the B200, 333 M records over 1.25 G cells: 9.5 ms against 4.1 ms).
+  // Expected distinct cells per block from the sample size: 8192 (1 - exp(-2 n / cells)).
+  const double per_blk = 2.0 * (double)n_records / (double)(nb ? nb : 1);
+  const bool dense_blocks = 8192.0 * (1.0 - exp(-per_blk / 8192.0)) > (double)fb_env("GR_FUSED_CTA_CELLS", 1536);
+  if (blk_bed || dense_blocks || fb_env("GR_FUSED_CTA", 0)) {   // read per call: the tests switch it inside one process
     owners = (u32)(sms * 6);
     const u32 R = (nb + owners - 1) / owners;
     if (blk_bed) k_fb_scan<6, 128, true><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed, chrom_marks);

@@ -78,8 +78,10 @@ void launch_sat_resolve(cudaStream_t s, const u32* flag, const void* segs, int n
 // blk_bed: per 8192-cell block, bit 0 = the block starts inside a -E region, bit 1 = it holds
 // region boundaries (NULL: no regions); chrom_marks: region boundaries per chromosome, for the experimental
 // sample only (a chromosome that holds nothing else is one interval there, savePileupExpt 2178-2182)
+// n_records: records of the sample (chooses the scan: the rank form for sparse blocks, the cell array for dense ones)
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
-                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks);
+                   const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks,
+                   u64 n_records);
 // -E region boundaries as pseudo entries (cursor == NULL: count pass)
 void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed);
 
@@ -148,8 +150,11 @@ void launch_fisher_eval(cudaStream_t s, const double* sum, const int* df, u64 n,
 // generic single-key table used when the final p array is the Fisher-combined one
 void launch_key_insert(cudaStream_t s, const u32* pEnd, const float* pval, u64 n,
                        const u64* chrom_start, int nchrom, const PairTable& t, u32* slot, int* err);
+// single-replicate runs: bp per pair-table slot (the intervals know their slot), then by_pval = 1 below
+void launch_slot_hist(cudaStream_t s, const u32* pEnd, const u32* slot, u64 n_upper, const u64* n_dev,
+                      const u64* chrom_start, int nchrom, u64* lens);
 void launch_table_compact(cudaStream_t s, const PairTable& t, const CompactScratch& sc,
-                          u32* keys_out, u64* lens_out, u64* count_out);
+                          u32* keys_out, u64* lens_out, u64* count_out, int by_pval);
 // sort (keys,lens) ascending by key, merge equal keys, compute q per distinct key.
 // Work arrays must hold n entries each.  Results: dk (distinct keys), dq (their q),
 // *dcount.  logN = -log10f(genomeLen) is evaluated by the caller (host libm), like
@@ -164,7 +169,7 @@ struct BhWork {
   u64 cap;
 };
 void launch_bh(cudaStream_t s, const u32* keys, const u64* lens, u64 n, float logN, const BhWork& w);
-void launch_table_q(cudaStream_t s, const PairTable& t, const u32* dk, const float* dq, const u64* dcount);
+void launch_table_q(cudaStream_t s, const PairTable& t, const u32* dk, const float* dq, const u64* dcount, int by_pval);
 
 // ---- K8: peak scan (callPeaks 977) ---------------------------------------------
 struct PeakRec {           // mirrors gr_peak

@@ -521,13 +521,55 @@ void launch_key_insert(cudaStream_t s, const u32* pEnd, const float* pval, u64 n
   k_key_insert<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(pEnd, pval, n, chrom_start, nchrom, t, slot, err); GR_NOTE_LAUNCH();
 }
 
+// The same histogram when the final p array is ONE replicate's (no Fisher combine): every interval already knows
+// the slot of its (expt, ctrl) pair in the pair table (k_pair_insert) and the pair's -log10 p sits in t.pval, so
+// the bp are added per SLOT -- no hashing, no probing, no second table.  Distinct pairs with the same p simply
+// show up as repeated keys in the list; the BH pass merges equal keys anyway (it has to, for the all-gather).
+// 8 intervals per thread; equal slots inside a warp are added up first (hot pairs such as (0, lambda)).
+__global__ void __launch_bounds__(256)
+k_slot_hist(const u32* __restrict__ pEnd, const u32* __restrict__ slot, const u64* __restrict__ n_dev,
+            const u64* __restrict__ chrom_start, int nchrom, u64* __restrict__ lens) {
+  const u64 n = *n_dev;
+  const int lane = threadIdx.x & 31;
+  const u64 stride = (u64)gridDim.x * 256;
+  for (u64 i0 = (u64)blockIdx.x * 256; i0 < n; i0 += stride) {         // block-uniform trip count
+    const u64 i = i0 + threadIdx.x;
+    u32 h = 0xfffffffeu, len = 0;
+    if (i < n) {
+      h = slot[i];
+      const u32 e = pEnd[i];
+      u32 st = i ? pEnd[i - 1] : 0u;
+      if (st >= e) st = 0u;                        // first interval of a chromosome: the previous end belongs to another one
+      len = e - st;                                // (ends increase strictly inside a chromosome)
+    }
+    const u32 peers = __match_any_sync(GR_FULL, h);
+    u64 tot = 0;
+    if (peers == (1u << lane)) tot = len;
+    else
+      for (u32 rem = peers; rem; rem &= rem - 1) tot += __shfl_sync(peers, len, __ffs(rem) - 1);   // the group walks its member list
+    if (h < 0xfffffffeu && lane == __ffs(peers) - 1 && tot) atomicAdd(lens + h, tot);
+  }
+  (void)chrom_start; (void)nchrom;
+}
+void launch_slot_hist(cudaStream_t s, const u32* pEnd, const u32* slot, u64 n_upper, const u64* n_dev,
+                      const u64* chrom_start, int nchrom, u64* lens) {
+  if (!n_upper) return;
+  k_slot_hist<<<capped_grid(n_upper), 256, 0, s>>>(pEnd, slot, n_dev, chrom_start, nchrom, lens); GR_NOTE_LAUNCH();
+}
+
 // table -> dense (key, len) list
+// by_pval: the table is the PAIR table -- the list's key is the pair's -log10 p (t.pval), pairs that evaluate to
+// SKIP (-E regions) or that no interval with bp refers to are left out
 __global__ void __launch_bounds__(256)
 k_table_compact(PairTable t, Lookback<1> lb, u32* __restrict__ keys_out,
-                u64* __restrict__ lens_out, u64* __restrict__ count_out, u32 ntiles) {
+                u64* __restrict__ lens_out, u64* __restrict__ count_out, u32 ntiles, int by_pval) {
   const u32 tile = take_ticket(lb.ticket);
   const u32 i = tile * 256 + threadIdx.x;
-  const u64 k = i < t.cap ? t.keys[i] : TBL_EMPTY;
+  u64 k = i < t.cap ? t.keys[i] : TBL_EMPTY;
+  if (by_pval && k != TBL_EMPTY) {
+    const float p = t.pval[i];
+    k = p == -1.0f ? TBL_EMPTY : (u64)__float_as_uint(p);
+  }
   const u32 f = k != TBL_EMPTY;
   u32 tot;
   const u64 r = tile_exclusive_rank(lb, tile, f, tot);
@@ -536,24 +578,29 @@ k_table_compact(PairTable t, Lookback<1> lb, u32* __restrict__ keys_out,
 }
 
 void launch_table_compact(cudaStream_t s, const PairTable& t, const CompactScratch& sc,
-                          u32* keys_out, u64* lens_out, u64* count_out) {
+                          u32* keys_out, u64* lens_out, u64* count_out, int by_pval) {
   const u32 ntiles = (t.cap + 255) / 256;
   cudaMemsetAsync(sc.st, 0, (size_t)ntiles * sizeof(u64), s);
   cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s);
   Lookback<1> lb;
   lb.st[0] = sc.st; lb.ticket = sc.ticket;
-  k_table_compact<<<ntiles, 256, 0, s>>>(t, lb, keys_out, lens_out, count_out, ntiles); GR_NOTE_LAUNCH();
+  k_table_compact<<<ntiles, 256, 0, s>>>(t, lb, keys_out, lens_out, count_out, ntiles, by_pval); GR_NOTE_LAUNCH();
 }
 
 // q of every occupied slot: binary search of its key among the distinct keys
 __global__ void __launch_bounds__(256)
 k_table_q(PairTable t, const u32* __restrict__ dk, const float* __restrict__ dq,
-          const u64* __restrict__ dcount) {
+          const u64* __restrict__ dcount, int by_pval) {
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.cap) return;
   const u64 k = t.keys[i];
   if (k == TBL_EMPTY) return;
-  const u32 key = (u32)k;
+  u32 key = (u32)k;
+  if (by_pval) {                                   // pair table: look the pair's p up; a SKIP pair stays SKIP
+    const float p = t.pval[i];
+    if (p == -1.0f) { t.qval[i] = -1.0f; return; }
+    key = __float_as_uint(p);
+  }
   u64 lo = 0, hi = *dcount;
   while (lo < hi) {
     const u64 mid = (lo + hi) >> 1;
@@ -561,8 +608,8 @@ k_table_q(PairTable t, const u32* __restrict__ dk, const float* __restrict__ dq,
   }
   t.qval[i] = dq[lo];
 }
-void launch_table_q(cudaStream_t s, const PairTable& t, const u32* dk, const float* dq, const u64* dcount) {
-  k_table_q<<<(t.cap + 255) / 256, 256, 0, s>>>(t, dk, dq, dcount); GR_NOTE_LAUNCH();
+void launch_table_q(cudaStream_t s, const PairTable& t, const u32* dk, const float* dq, const u64* dcount, int by_pval) {
+  k_table_q<<<(t.cap + 255) / 256, 256, 0, s>>>(t, dk, dq, dcount, by_pval); GR_NOTE_LAUNCH();
 }
 
 // ============================================================================

@@ -175,9 +175,12 @@ static inline unsigned long long warp_arrive(unsigned long long operand, Group*&
   Warp& w = g->w[t >> 5];
   mask &= w.live_mask;
   Group* gr = nullptr;
-  if (mask == w.live_mask) { gr = &w.full; gr->mask = mask; }
+  // a rendezvous of this very mask that is under way comes first: lanes outside the mask may have returned
+  // since its first member arrived, and the mask now EQUALS the live mask without being another rendezvous
+  for (Group& c : w.part) if (c.mask == mask && (c.arrived || c.pending)) { gr = &c; break; }
+  if (gr) {}
+  else if (mask == w.live_mask && !(w.full.arrived && w.full.mask != mask)) { gr = &w.full; gr->mask = mask; }
   else {
-    for (Group& c : w.part) if (c.mask == mask && (c.arrived || c.pending)) { gr = &c; break; }
     if (!gr) for (Group& c : w.part) if (c.mask == mask) { gr = &c; break; }
     if (!gr) for (Group& c : w.part) if (!c.arrived && !c.pending) { gr = &c; c.mask = mask; c.gen = 0; c.amask[0] = c.amask[1] = 0; break; }
     if (!gr) { fprintf(stderr, "emu: out of rendezvous groups\n"); abort(); }
@@ -265,7 +268,18 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
           if (!any) break;
         }
       }
-      if (!progressed) { fprintf(stderr, "emu: deadlock in CTA %u\n", b); abort(); }
+      if (!progressed) {
+        fprintf(stderr, "emu: deadlock in CTA %u\n", b);
+        if (getenv("EMU_TRACE"))
+          for (unsigned t = 0; t < nt; t++) {
+            const Fiber& f = cta.f[t];
+            if (!f.done) fprintf(stderr, "  thread %u: wait %d%s mask %08x arrived %d pending %d gen %llu (mine %llu)\n", t, f.wait,
+                                 f.wait == 1 && f.grp == &cta.w[t >> 5].full ? " (full)" : "", f.wait == 1 ? f.grp->mask : 0u,
+                                 f.wait == 1 ? f.grp->arrived : 0, f.wait == 1 ? f.grp->pending : 0,
+                                 f.wait == 1 ? f.grp->gen : 0ull, f.wgen);
+          }
+        abort();
+      }
     }
   }
   g = nullptr;

@@ -26,6 +26,8 @@ static std::map<char*, std::pair<size_t, int>> regions;          // start -> (by
 static char dyn_smem_buf[256 * 1024] __attribute__((aligned(128)));
 static char* dyn_smem = dyn_smem_buf;
 static inline int sm_count() { const char* e = getenv("EMU_SMS"); return e ? atoi(e) : 2; }
+// EMU_TRACE=1: the name of every kernel as it is launched (which one deadlocked / aborted?)
+static inline void trace(const char* kernel) { static const bool on = getenv("EMU_TRACE") != nullptr; if (on) fprintf(stderr, "emu: launch %s\n", kernel); }
 template <typename F> static void launch_k(dim3 grid, dim3 block, size_t smem, F body) {
   if (smem > sizeof dyn_smem_buf || grid.y != 1 || grid.z != 1 || block.y != 1 || block.z != 1) {
     fprintf(stderr, "emu: unsupported launch configuration\n"); abort();
