@@ -136,6 +136,7 @@ struct gr_ctx {
   int retry_flags = 0;              // GR_DE_TABLE / GR_DE_CAP seen by the last materialize()
   u64 cap_expt = 0, cap_raw = 0;    // capacities (upper bounds of the interval counts) of the current sample arrays
   u32 pair_cap = 1u << 20;          // pair-table capacity, grown on overflow and remembered
+  u32 fisher_cap = 1u << 22;        // table of distinct Fisher sums (gr_pvalues_finalize), grown on overflow and remembered
   bool pair_valid = false;          // the tables hold the last replicate's (expt, ctrl) pairs and x->slot its intervals' slots
   bool hist_by_pairs = false;       // the BH histogram was read off the pair table (gr_bh_local_hist)
   u64 head_cap = 0;                 // candidate-peak capacity of the last peak call
@@ -369,6 +370,7 @@ extern "C" int gr_create(gr_ctx** out, const gr_chrom* chroms, int32_t nchrom,
     // test knobs: start the optimistic capacities small enough to exercise the retry paths
     { const char* e = getenv("GR_PAIR_CAP"); if (e) { u32 v = (u32)strtoul(e, nullptr, 10); u32 c = 64; while (c < v) c <<= 1; x->pair_cap = c; } }
     { const char* e = getenv("GR_HEAD_CAP"); if (e) x->head_cap = strtoull(e, nullptr, 10); }
+    { const char* e = getenv("GR_FISHER_CAP"); if (e) { u32 v = (u32)strtoul(e, nullptr, 10); u32 c = 64; while (c < v) c <<= 1; x->fisher_cap = c; } }
     CK(cudaEventCreateWithFlags(&x->ev_copy, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(x->stream));
     return GR_OK;
@@ -1338,8 +1340,26 @@ extern "C" int gr_pvalues_finalize(gr_ctx* x) {
   launch_fisher_emit(x->stream, x->L, cb->bmU.as<u32>(), cb->rankU.as<u64>(), x->repviews.as<RepView>(),
                      nrep, cb->pEnd.as<u32>(), x->fsum.as<double>(), x->fdf.as<int>(),
                      cb->chrom_start.as<u64>(), x->d_totals + 2);
-  launch_fisher_eval(x->stream, x->fsum.as<double>(), x->fdf.as<int>(), np, cb->pVal.as<float>());
   CKL();
+  stage_end(x);
+  // chi-square tails through a table of distinct sums (grown until it stays under half full)
+  stage_begin(x, "fisher_eval", np * 16);
+  CK(x->slot.ensure((np + 1) * sizeof(u32)));
+  x->pair_valid = false;                       // the tables are reused
+  for (;;) {
+    int r = table_alloc(x, x->fisher_cap);
+    if (r) return r;
+    launch_fisher_table(x->stream, x->fsum.as<double>(), x->fdf.as<int>(), np, table_view(x, x->fisher_cap),
+                        x->slot.as<u32>(), cb->pVal.as<float>(), x->d_err);
+    CKL();
+    x->lag = true;
+    r = materialize(x);
+    if (r) return r;
+    if (!(x->retry_flags & GR_DE_TABLE)) break;
+    x->retry_flags &= ~GR_DE_TABLE;
+    if (x->fisher_cap >= (1u << 30)) { x->detail = "distinct-sum table overflow"; return GR_ERR_MEM; }
+    x->fisher_cap <<= 2;
+  }
   stage_end(x);
   cb->chrom_start_h.resize(nc + 1);
   CK(cudaMemcpyAsync(cb->chrom_start_h.data(), cb->chrom_start.p, (nc + 1) * sizeof(u64),

@@ -144,7 +144,10 @@ void launch_block_rank(cudaStream_t s, const DevLayout& L, const u32* bm, const 
 void launch_fisher_emit(cudaStream_t s, const DevLayout& L, const u32* bmAll, const u64* rankAll,
                         const RepView* reps_dev, int nrep, u32* end_out, double* sum_out,
                         int* df_out, u64* chrom_start, const u64* total);
-void launch_fisher_eval(cudaStream_t s, const double* sum, const int* df, u64 n, float* pcomb);
+void launch_fisher_eval(cudaStream_t s, const double* sum, const int* df, u64 n, float* pcomb);   // every interval (small inputs)
+// the same through a table of distinct sums: t empty on entry (table_alloc); GR_DE_TABLE in *err: it was too small
+void launch_fisher_table(cudaStream_t s, const double* sum, const int* df, u64 n, const PairTable& t, u32* slot,
+                         float* pcomb, int* err);
 
 // ---- K7: Benjamini-Hochberg over the histogram of distinct p (computeQval 352) ----
 // generic single-key table used when the final p array is the Fisher-combined one

@@ -369,6 +369,22 @@ def test_async_path_and_retries(monkeypatch):
                 assert np.array_equal(a.end, b.end) and np.array_equal(_bits(a.val), _bits(b.val))
 
 
+def test_fisher_table_growth(monkeypatch):
+    """The chi-square tails of the Fisher combine go through a table of distinct sums (k_fsum_*); a table that
+    turns out too small is grown and the stage run again: same combined p, q and peaks."""
+    api = capi.load_cuda()
+    case = BY_NAME["c4_fisher_q"]
+    inputs = util.case_inputs(case)
+    ctx0, ref, par = util.run_case(api, case, inputs=inputs)
+    monkeypatch.setenv("GR_FISHER_CAP", "64")
+    ctx1, got, _ = util.run_case(api, case, inputs=inputs)
+    assert got.peaks.tobytes() == ref.peaks.tobytes() and len(got.peaks) > 0
+    for c in range(len(case.chrom_len)):
+        for which in (2, 3):
+            a, b = ctx1.fetch(which, len(case.reps), c), ctx0.fetch(which, len(case.reps), c)
+            assert np.array_equal(a.end, b.end) and np.array_equal(_bits(a.val), _bits(b.val))
+
+
 def test_edge_inputs():
     api = capi.load_cuda()
     orc = util.oracle_api()
