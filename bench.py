@@ -163,6 +163,31 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_node(local):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned staging buffers are
+    allocated (first touch then puts them on that node): eight ranks pulling records from host memory through the
+    wrong socket is what held the round-1 e2e arm at 21 GB/s per GPU.  Best effort: any failure leaves things as they are."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                                # sysfs uses a 4-digit domain
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"node": node, "cpus": len(allowed)}
+    except (OSError, ValueError, subprocess.SubprocessError):
+        pass
+    return None
+
+
 def peaks_sha256(peaks):
     """Hash of what the parity bar makes bit-exact: chromosome, start, end, summit of every peak, in order."""
     h = hashlib.sha256()
@@ -558,6 +583,7 @@ def main():
     from genrich_b200 import capi, host
     from genrich_b200.dist import ShardedEngine
 
+    numa = bind_to_gpu_node(local) if world > 1 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     sampler = ClockSampler(local)
@@ -657,7 +683,8 @@ def main():
         stages = ctx.timing_get() if with_stages else None
         if with_stages:
             ctx.timing(False)
-        return float(t[0]), float(t[1]), ctx.kernel_launches() - l0, peaks, rs, stages
+        # the engine hands out buffers it reuses (valid until its next call): keep a copy, outside the timed region
+        return float(t[0]), float(t[1]), ctx.kernel_launches() - l0, peaks.copy(), rs, stages
 
     if a.profile:
         # for ncu: the launches of the LAST step are what tools/ncu_dram_by_stage.py keeps
@@ -774,7 +801,7 @@ def main():
         "config": {"workload": a.workload, "genome_bp": G, "chromosomes": len(L),
                    "fragments_per_replicate": [list(x) for x in wl["reps"]], "records_rank0": n_records,
                    "threshold": thr, "atac": wl["atac"], "multimap_fraction": wl["multimap"],
-                   "sharding": "chromosomes over %d rank(s), LPT" % world,
+                   "sharding": "chromosomes over %d rank(s), LPT" % world, "numa_binding_rank0": numa,
                    "l2": "inputs (%.1f GB dense delta array per sample, %.2f GB of records) far exceed the 126 MB L2" % (
                        4e-9 * cells, 8e-9 * n_records),
                    "peaks": int(len(peaks)), "peaks_sha256": peaks_sha256(peaks), "intervals_rank0": int(rs.n_intervals),

@@ -71,7 +71,7 @@ ABI_SYMBOLS = [
     "gr_sample_pileup", "gr_sample_skipped", "gr_sample_sums", "gr_replicate_finish", "gr_replicate_finish_device",
     "gr_sums_device", "gr_stream", "gr_replicate_stats",
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
-    "gr_bh_set_global", "gr_bh_local_hist_host", "gr_bh_set_global_host", "gr_load_pvalues", "gr_call_peaks", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
+    "gr_bh_set_global", "gr_bh_local_hist_host", "gr_bh_set_global_host", "gr_load_pvalues", "gr_call_peaks", "gr_call_peaks_enqueue", "gr_call_peaks_done", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
     "gr_kernel_launches", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
     "gr_pinned_alloc", "gr_pinned_free",
@@ -141,6 +141,8 @@ class Api:
             self.push_packed6 = fn("push_packed6", C.c_int, [vp, vp, u64])
             self.prefetch_packed6 = fn("prefetch_packed6", C.c_int, [vp, vp, u64])
             self.peaks_device = fn("peaks_device", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)])
+            self.call_peaks_enqueue = fn("call_peaks_enqueue", C.c_int, [vp, C.POINTER(vp), C.POINTER(u64)])
+            self.call_peaks_done = fn("call_peaks_done", C.c_int, [vp, vp, C.POINTER(i32), C.POINTER(GrRunStats)])
             self.bh_local_hist_host = fn("bh_local_hist_host", C.c_int, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u64)])
             self.bh_set_global_host = fn("bh_set_global_host", C.c_int, [vp, vp, vp, u64, u64])
             self.merge_peaks = fn("merge_peaks", C.c_int, [C.POINTER(vp), C.POINTER(u64), i32, vp])
@@ -394,6 +396,18 @@ class Context:
         if not to_host:
             return np.empty(0, PEAK_DTYPE), st
         return _np_from(p.value, n.value, PEAK_DTYPE), st
+
+    def call_peaks_enqueue(self):
+        """First half of gr_call_peaks for launchers that gather: (device address of the slot, record capacity)."""
+        p, cap = C.c_void_p(), C.c_uint64()
+        self._check(self.api.call_peaks_enqueue(self._h, C.byref(p), C.byref(cap)), "call_peaks_enqueue")
+        return p.value, cap.value
+
+    def call_peaks_done(self, header_ptr: int):
+        """Second half: this context's 64-byte slot header as the host sees it -> (redo, run stats)."""
+        redo, st = C.c_int32(), GrRunStats()
+        self._check(self.api.call_peaks_done(self._h, C.c_void_p(header_ptr), C.byref(redo), C.byref(st)), "call_peaks_done")
+        return redo.value, st
 
     def peaks_device_ptr(self):
         p, n = C.c_void_p(), C.c_uint64()

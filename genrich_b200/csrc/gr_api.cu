@@ -178,7 +178,7 @@ struct gr_ctx {
   u64 n_distinct = 0;
   int all_q_one = 0;
   DevBuf fsum, fdf, repviews;
-  DevBuf evIdx, evCount, headIdx, headCount, cand, candOk, peakOut, peakCount, peakBp;
+  DevBuf evIdx, evCount, headIdx, headCount, cand, candOk, peakOut;     // peakOut: gr_peak_slot header + records
   std::vector<gr_peak> peaks_h;
   u64 n_peaks = 0;
 
@@ -424,7 +424,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
     &x->qVal, &x->tKeys, &x->tLens, &x->tPval, &x->tQval, &x->tCount, &x->slot, &x->hk, &x->hl,
     &x->hcount, &x->bk0, &x->bk1, &x->bl0, &x->bl1, &x->bhist, &x->bksum, &x->bx, &x->bdk, &x->bdq,
     &x->bdl, &x->bdcount, &x->fsum, &x->fdf, &x->repviews, &x->evIdx, &x->evCount, &x->headIdx,
-    &x->headCount, &x->cand, &x->candOk, &x->peakOut, &x->peakCount, &x->peakBp };
+    &x->headCount, &x->cand, &x->candOk, &x->peakOut };
   for (DevBuf* b : all) b->release();
   if (x->h_small) cudaFreeHost(x->h_small);
   if (x->h_peaks) cudaFreeHost(x->h_peaks);
@@ -879,7 +879,7 @@ static int materialize(gr_ctx* x) {
   }
   x->pend_reps.clear();
   x->lag = false;
-  x->retry_flags = derr & (GR_DE_TABLE | GR_DE_CAP);
+  x->retry_flags = (x->retry_flags & GR_DE_TABLE) | (derr & (GR_DE_TABLE | GR_DE_CAP));   // a pending p-value redo stays pending
   const int hard = derr & ~(GR_DE_TABLE | GR_DE_CAP);
   if (hard) { x->filling = FILL_NONE; return map_dev_err(hard); }
   return GR_OK;
@@ -1031,6 +1031,7 @@ static int table_build(gr_ctx* x, u64 n, u32& cap_io, F insert) {
     r = materialize(x);
     if (r) return r;
     if (!(x->retry_flags & GR_DE_TABLE)) break;
+    x->retry_flags &= ~GR_DE_TABLE;                      // this table's, and dealt with here
     if (cap >= (1u << 30)) { x->detail = "distinct-value table overflow"; return GR_ERR_MEM; }
     cap <<= 2;
   }
@@ -1565,24 +1566,26 @@ extern "C" int gr_load_pvalues(gr_ctx* x, const uint64_t* chrom_start, const uin
 
 // ---- peaks ---------------------------------------------------------------------------
 // events -> heads -> walk -> compaction, all sized by upper bounds with the counts on the device
-static int peaks_enqueue(gr_ctx* x, Replicate* f, int qopt, bool want_host) {
+// want_host: 0 the records stay on the device, 1 the first PEAK_SPEC come back with the counts, 2 nothing is copied
+// to the host at all (the caller gathers the slot: gr_call_peaks_enqueue)
+static int peaks_enqueue(gr_ctx* x, Replicate* f, int qopt, int want_host) {
   const u64 nu = f->n_upper;
   CK(x->evIdx.ensure((nu + 1) * sizeof(u32)));
   CK(x->headIdx.ensure((nu + 1) * sizeof(u32)));
-  CK(x->evCount.ensure(8)); CK(x->headCount.ensure(8)); CK(x->peakCount.ensure(8)); CK(x->peakBp.ensure(8));
+  CK(x->evCount.ensure(8)); CK(x->headCount.ensure(8));
   if (!x->head_cap) x->head_cap = nu / 16 > (1u << 20) ? nu / 16 : (1u << 20);
   if (x->head_cap > nu + 1) x->head_cap = nu + 1;
   const u64 hc = x->head_cap;
   CK(x->cand.ensure(hc * sizeof(PeakRec)));
   CK(x->candOk.ensure(hc));
-  CK(x->peakOut.ensure(hc * sizeof(PeakRec)));
+  CK(x->peakOut.ensure(64 + hc * sizeof(PeakRec)));             // gr_peak_slot header, then the records
   const u64 nt = (nu + 2047) / 2048 + (hc + 255) / 256 + 2;     // status words of the largest tiling
   CK(x->lb0.ensure(nt * sizeof(u64) > x->lb0.cap ? nt * sizeof(u64) : x->lb0.cap));
   PeakWork w;
   w.ev_idx = x->evIdx.as<u32>(); w.ev_count = x->evCount.as<u64>();
   w.head_idx = x->headIdx.as<u32>(); w.head_count = x->headCount.as<u64>();
   w.cand = x->cand.as<PeakRec>(); w.cand_ok = x->candOk.as<uint8_t>();
-  w.out = x->peakOut.as<PeakRec>(); w.out_count = x->peakCount.as<u64>(); w.peak_bp = x->peakBp.as<u64>();
+  w.out = (PeakRec*)((char*)x->peakOut.p + 64); w.out_count = x->peakOut.as<u64>(); w.peak_bp = x->peakOut.as<u64>() + 1;
   w.sc.st = x->lb0.as<u64>(); w.sc.ticket = x->ticket.as<u32>();
   const float* v = qopt ? x->qVal.as<float>() : f->pVal.as<float>();
   stage_begin(x, "peak_events", nu * 4);
@@ -1596,11 +1599,18 @@ static int peaks_enqueue(gr_ctx* x, Replicate* f, int qopt, bool want_host) {
   CKL();
   stage_end(x);
   // the counts and the first PEAK_SPEC records come back together
-  CK(cudaMemcpyAsync((char*)x->h_small + 192, x->peakCount.p, 8, cudaMemcpyDeviceToHost, x->stream));
-  CK(cudaMemcpyAsync((char*)x->h_small + 200, x->peakBp.p, 8, cudaMemcpyDeviceToHost, x->stream));
+  if (want_host == 2) {
+    // gr_call_peaks_enqueue: the rest of the slot header, filled in stream order -- the device error bits as they
+    // stand behind the peak scan (then cleared: they are the caller's now) and the interval count
+    CK(cudaMemcpyAsync((char*)x->peakOut.p + 16, x->d_err, 4, cudaMemcpyDeviceToDevice, x->stream));
+    CK(cudaMemcpyAsync((char*)x->peakOut.p + 24, f->cnt.p, 8, cudaMemcpyDeviceToDevice, x->stream));
+    CK(cudaMemsetAsync(x->d_err, 0, sizeof(int), x->stream));
+    return GR_OK;
+  }
+  CK(cudaMemcpyAsync((char*)x->h_small + 192, x->peakOut.p, 16, cudaMemcpyDeviceToHost, x->stream));
   const u64 spec = hc < gr_ctx::PEAK_SPEC ? hc : gr_ctx::PEAK_SPEC;
   if (want_host)
-    CK(cudaMemcpyAsync(x->h_peaks, x->peakOut.p, spec * sizeof(gr_peak), cudaMemcpyDeviceToHost, x->stream));
+    CK(cudaMemcpyAsync(x->h_peaks, (char*)x->peakOut.p + 64, spec * sizeof(gr_peak), cudaMemcpyDeviceToHost, x->stream));
   x->lag = true;
   return GR_OK;
 }
@@ -1625,7 +1635,7 @@ extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_r
   u64 npk = 0, peak_bp = 0;
   for (;;) {
     const auto t_a = std::chrono::steady_clock::now();
-    { int r = peaks_enqueue(x, f, qopt, peaks != nullptr); if (r) return r; }
+    { int r = peaks_enqueue(x, f, qopt, peaks != nullptr ? 1 : 0); if (r) return r; }
     const auto t_b = std::chrono::steady_clock::now();
     { int r = materialize(x); if (r) return r; }               // the one round trip of a peak call
     HT("call_peaks: device waited for");
@@ -1660,7 +1670,7 @@ extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_r
     } else {
       x->peaks_h.resize(npk);
       memcpy(x->peaks_h.data(), x->h_peaks, spec * sizeof(gr_peak));
-      CK(cudaMemcpy(x->peaks_h.data() + spec, x->peakOut.as<gr_peak>() + spec, (npk - spec) * sizeof(gr_peak),
+      CK(cudaMemcpy(x->peaks_h.data() + spec, (const gr_peak*)((char*)x->peakOut.p + 64) + spec, (npk - spec) * sizeof(gr_peak),
                     cudaMemcpyDeviceToHost));
       *peaks = x->peaks_h.data();
     }
@@ -1682,6 +1692,52 @@ extern "C" int gr_call_peaks(gr_ctx* x, const gr_peak** peaks, uint64_t* n, gr_r
     st->n_intervals = f->n;
     st->n_distinct_p = qopt ? x->n_distinct : 0;
     st->all_q_one = qopt ? x->all_q_one : 0;
+    st->n_replicates = (int)x->reps.size();
+  }
+  return GR_OK;
+}
+
+// gr_call_peaks in two halves for launchers that gather several contexts' peaks with ONE wait: the first half
+// enqueues, the caller moves the slot (an all-gather, a copy) on gr_stream and waits once, the second half takes
+// this context's header as the host now sees it.
+extern "C" int gr_call_peaks_enqueue(gr_ctx* x, const void** d_slot, uint64_t* record_cap) {
+  if (!x || x->reps.empty() || !d_slot) return GR_ERR_ARG;
+  if (!x->finalized) { int r = gr_pvalues_finalize(x); if (r) return r; }
+  CK(cudaSetDevice(x->device));
+  const int qopt = x->par.qval_opt != 0;
+  if (x->retry_flags & GR_DE_TABLE) {                          // left by gr_call_peaks_done: -log10 p came from an overflowed table
+    { int r = materialize(x); if (r) return r; }
+    { int r = redo_pvals(x); if (r) return r; }
+    if (qopt) x->have_q = false;
+  }
+  if (qopt && !x->have_q) return GR_ERR_ARG;                   // the launcher runs the histogram exchange first
+  { int r = peaks_enqueue(x, x->fin, qopt, 2); if (r) return r; }
+  *d_slot = x->peakOut.p;
+  if (record_cap) *record_cap = x->head_cap;
+  return GR_OK;
+}
+extern "C" int gr_call_peaks_done(gr_ctx* x, const gr_peak_slot* hdr, int32_t* redo, gr_run_stats* st) {
+  if (!x || !hdr || !redo) return GR_ERR_ARG;
+  *redo = 0;
+  const int derr = hdr->flags;
+  const int hard = derr & ~(GR_DE_TABLE | GR_DE_CAP);
+  if (hard) return map_dev_err(hard);
+  if (derr & GR_DE_TABLE) { x->retry_flags |= GR_DE_TABLE; *redo = 2; return GR_OK; }   // p-values have to be redone: gr_call_peaks does that
+  if (derr & GR_DE_CAP) {                                      // more candidate peaks than room: once more, with room
+    const u64 lim = x->fin->n_upper + 1;
+    x->head_cap = x->head_cap * 8 < lim ? x->head_cap * 8 : lim;
+    *redo = 1;
+    return GR_OK;
+  }
+  x->n_peaks = hdr->n_peaks;
+  if (st) {
+    memset(st, 0, sizeof *st);
+    st->genome_len = x->par.genome_len;                        // the launcher computed it for the exchange (0: not given)
+    st->n_peaks = hdr->n_peaks;
+    st->peak_bp = hdr->peak_bp;
+    st->n_intervals = hdr->n_intervals;
+    st->n_distinct_p = x->par.qval_opt ? x->n_distinct : 0;
+    st->all_q_one = x->par.qval_opt ? x->all_q_one : 0;
     st->n_replicates = (int)x->reps.size();
   }
   return GR_OK;
@@ -1855,7 +1911,7 @@ extern "C" int gr_merge_peaks(const gr_peak* const* lists, const uint64_t* count
 
 extern "C" int gr_peaks_device(gr_ctx* x, const gr_peak** d_peaks, uint64_t* n) {
   if (!x || !d_peaks || !n) return GR_ERR_ARG;
-  *d_peaks = x->n_peaks ? (const gr_peak*)x->peakOut.p : nullptr;
+  *d_peaks = x->n_peaks ? (const gr_peak*)((char*)x->peakOut.p + 64) : nullptr;
   *n = x->n_peaks;
   return GR_OK;
 }

@@ -122,7 +122,12 @@ k_peak_heads(const u32* __restrict__ pEnd, const float* __restrict__ v,
   }
 }
 
-// ---- walk: one thread per candidate ------------------------------------------------
+// ---- walk: one WARP per candidate ---------------------------------------------------
+// The arithmetic of a candidate is a chain (float AUC in interval order, summit rules), its loads are not: the
+// lanes fetch 32 events at a time (coalesced index loads, then the gathers, all in flight together) and the chain
+// is then run over the 32 register sets by shuffles -- every lane computes the same state.  One thread per
+// candidate (the first version) paid a dependent DRAM round trip per four events: a candidate of a few hundred
+// intervals was ~0.15 ms of latency, the whole kernel's time on a small shard whatever its size.
 __global__ void __launch_bounds__(128)
 k_peak_walk(const u32* __restrict__ pEnd, const float* __restrict__ pval,
             const float* __restrict__ qval, const u64* __restrict__ chrom_start, int nchrom,
@@ -136,58 +141,57 @@ k_peak_walk(const u32* __restrict__ pEnd, const float* __restrict__ pval,
     return;
   }
   const u64 nev = *ev_count;
-  for (u64 h = (u64)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (u64)gridDim.x * blockDim.x) {
-  const u64 t0 = head_idx[h];
-  const u64 t1 = h + 1 < nh ? head_idx[h + 1] : nev;
+  const int lane = threadIdx.x & 31;
+  const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
   const float* __restrict__ v = qopt ? qval : pval;
-  const u32 first = ev_idx[t0];
-  const int c = chrom_of_index(chrom_start, nchrom, first);
-  const u64 cs = chrom_start[c];
+  for (u64 h = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); h < nh; h += nwarps) {
+    const u64 t0 = head_idx[h];
+    const u64 t1 = h + 1 < nh ? head_idx[h + 1] : nev;
+    const u32 first = ev_idx[t0];
+    const int c = chrom_of_index(chrom_start, nchrom, first);
+    const u64 cs = chrom_start[c];
 
-  float auc = 0.0f, sVal = -1.0f, sP = -1.0f, sQ = -1.0f;     // 1001-1006
-  i64 pStart = -1, pEndv = -1;
-  u32 sPos = 0, sLen = 0;
-  // The arithmetic is a chain (float AUC in interval order), the loads are not: four events
-  // are fetched at a time so that their latencies overlap (a long candidate is one thread's
-  // critical path, and on a small shard the whole kernel's).
-  bool open = true;
-  for (u64 t = t0; t < t1 && open; t += 4) {
-    u32 idx[4], end[4], start[4];
-    float xv[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) idx[k] = t + k < t1 ? ev_idx[t + k] : first;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      xv[k] = v[idx[k]];
-      end[k] = pEnd[idx[k]];
-      start[k] = (u64)idx[k] == cs ? 0u : pEnd[idx[k] - 1];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (t + k >= t1) break;
-      const float x = xv[k];
-      if (x == PK_SKIP) { open = false; break; }                 // 1031: SKIP closes the candidate
-      const u32 len = end[k] - start[k];
-      auc = __fadd_rn(auc, __fmul_rn(__uint2float_rn(len), __fsub_rn(x, thr)));   // 950, no FMA
-      if (pStart == -1) pStart = start[k];
-      pEndv = end[k];
-      if (x > sVal) {                                             // 956-961
-        sVal = x;
-        sP = pval[idx[k]];
-        sQ = qopt ? qval[idx[k]] : PK_SKIP;
-        sPos = (u32)((end[k] + start[k]) / 2 - (u32)pStart);      // uint32 arithmetic, 960
-        sLen = len;
-      } else if (x == sVal && len > sLen) {                       // 962-968
-        sPos = (u32)((end[k] + start[k]) / 2 - (u32)pStart);
-        sLen = len;
+    float auc = 0.0f, sVal = -1.0f, sP = -1.0f, sQ = -1.0f;     // 1001-1006
+    i64 pStart = -1, pEndv = -1;
+    u32 sPos = 0, sLen = 0;
+    bool open = true;
+    for (u64 t = t0; t < t1 && open; t += 32) {
+      const u64 mine = t + lane;
+      const bool on = mine < t1;
+      const u32 idx = on ? ev_idx[mine] : first;
+      const float x_ = v[idx];
+      const u32 end_ = pEnd[idx];
+      const u32 start_ = (u64)idx == cs ? 0u : pEnd[idx - 1];
+      const float p_ = pval[idx];
+      const float q_ = qopt ? qval[idx] : PK_SKIP;
+      const int cnt = (int)min((u64)32, t1 - t);
+      for (int k = 0; k < cnt; k++) {                             // the chain, in interval order
+        const float x = __shfl_sync(GR_FULL, x_, k);
+        if (x == PK_SKIP) { open = false; break; }                 // 1031: SKIP closes the candidate
+        const u32 end = __shfl_sync(GR_FULL, end_, k), start = __shfl_sync(GR_FULL, start_, k);
+        const u32 len = end - start;
+        auc = __fadd_rn(auc, __fmul_rn(__uint2float_rn(len), __fsub_rn(x, thr)));   // 950, no FMA
+        if (pStart == -1) pStart = start;
+        pEndv = end;
+        if (x > sVal) {                                             // 956-961
+          sVal = x;
+          sP = __shfl_sync(GR_FULL, p_, k);
+          sQ = __shfl_sync(GR_FULL, q_, k);
+          sPos = (u32)((end + start) / 2 - (u32)pStart);            // uint32 arithmetic, 960
+          sLen = len;
+        } else if (x == sVal && len > sLen) {                       // 962-968
+          sPos = (u32)((end + start) / 2 - (u32)pStart);
+          sLen = len;
+        }
       }
     }
-  }
-  PeakRec r;
-  r.chrom = c; r.summit = sPos; r.start = pStart; r.end = pEndv;
-  r.auc = auc; r.pval = sP; r.qval = sQ; r.reserved = 0.0f;
-  cand[h] = r;
-  cand_ok[h] = (pStart != -1 && auc >= min_auc && pEndv - pStart >= (i64)min_len) ? 1 : 0;   // 920
+    if (lane == 0) {
+      PeakRec r;
+      r.chrom = c; r.summit = sPos; r.start = pStart; r.end = pEndv;
+      r.auc = auc; r.pval = sP; r.qval = sQ; r.reserved = 0.0f;
+      cand[h] = r;
+      cand_ok[h] = (pStart != -1 && auc >= min_auc && pEndv - pStart >= (i64)min_len) ? 1 : 0;   // 920
+    }
   }
 }
 

@@ -78,7 +78,8 @@ class ShardedEngine:
         self._ext_stream = None
         self._dsums = None
         self._gather_cap = 1 << 13          # peak records per rank in the gather slot (grown on demand)
-        self._send = self._recv = self._host = None
+        self._send = self._recv = self._host = self._merged = None
+        self._slot_bytes = 0
         self.debug = bool(os.environ.get("GR_DIST_DEBUG"))
         self.t_acc = {}
         self.hist_bytes = 0                 # bytes the last BH histogram all-gather moved (all ranks)
@@ -227,6 +228,61 @@ class ShardedEngine:
         self._tick("bh_allgather", t0)
         return keys, lens
 
+    def _gather_peaks_one_wait(self):
+        """CUDA, several ranks: the peak scan is enqueued (gr_call_peaks_enqueue), every rank's slot -- a 64-byte
+        header the device fills in (count, bp, condition bits) followed by its records -- is all-gathered over
+        NVLink on the LIBRARY's stream straight out of the library's buffer, rank 0 copies the lot to pinned host
+        memory (the others only the headers), and then the host waits: once per step.  Every rank reads every
+        header, so "a buffer was too small somewhere, again" is decided identically everywhere.  Returns None when
+        a p-value table overflowed on some rank of a -q run (the caller starts over: p, exchange, q)."""
+        t0 = time.perf_counter()
+        isz = PEAK_DTYPE.itemsize
+        if self._ext_stream is None:
+            self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=self.device)
+        while True:
+            dslot, cap = self.ctx.call_peaks_enqueue()
+            g = min(self._gather_cap, cap) if cap else self._gather_cap
+            nb = 64 + g * isz
+            if self._slot_bytes != nb:
+                self._slot_bytes = nb
+                self._recv = torch.empty(self.world * nb, dtype=torch.uint8, device=self.device)
+                self._host = torch.empty(self.world * nb, dtype=torch.uint8, pin_memory=True)
+                self._merged = np.empty(self.world * g, PEAK_DTYPE)
+            with torch.cuda.stream(self._ext_stream):
+                src = _tensor_from_ptr(dslot, nb, np.uint8, self.device)
+                td.all_gather_into_tensor(self._recv, src)               # NCCL over NVLink, on the library's stream
+                if self.rank == 0:
+                    self._host.copy_(self._recv, non_blocking=True)
+                else:
+                    self._host.view(self.world, nb)[:, :64].copy_(self._recv.view(self.world, nb)[:, :64], non_blocking=True)
+                self._ext_stream.synchronize()                            # the one wait of the step
+            host = self._host.numpy().reshape(self.world, nb)
+            hdr = host[:, :64].copy().view(np.int64)                      # n_peaks, peak_bp, flags | reserved, n_intervals, pad
+            flags = (hdr[:, 2] & 0xffffffff).astype(np.int64)
+            redo, rs = self.ctx.call_peaks_done(host[self.rank, :64].ctypes.data)
+            if np.any(flags & 32):                                        # GR_DE_TABLE on some rank: its p-values are redone ...
+                if self.params.qval_opt:
+                    return None                                           # ... and with them the histogram exchange (every rank)
+                continue                                                  # ... by its next gr_call_peaks_enqueue
+            counts = [int(c) for c in hdr[:, 0]]
+            if np.any(flags & 64) or max(counts) > g:                     # GR_DE_CAP somewhere, or more peaks than the gather slot
+                if max(counts) > g:
+                    self._gather_cap = 2 * max(counts)
+                continue
+            break
+        self._tick("call_peaks_gather", t0)
+        t0 = time.perf_counter()
+        peaks = np.empty(0, PEAK_DTYPE)
+        if self.rank == 0:
+            lists = (C.c_void_p * self.world)(*[host[r, 64:].ctypes.data for r in range(self.world)])
+            cnts = (C.c_uint64 * self.world)(*counts)
+            rc = self.ctx.api.merge_peaks(lists, cnts, self.world, self._merged.ctypes.data_as(C.c_void_p))
+            if rc:
+                raise RuntimeError("gr_merge_peaks failed: %d" % rc)
+            peaks = self._merged[:sum(counts)]
+        self._tick("merge_peaks", t0)
+        return peaks, rs
+
     def call_peaks(self):
         """Returns (peaks, run_stats) -- peaks of ALL chromosomes on rank 0; elsewhere the rank's own peaks
         (host engines) or none (CUDA: they stay on the device)."""
@@ -243,50 +299,18 @@ class ShardedEngine:
             self._tick("bh_exchange_and_q", t0)
         t0 = time.perf_counter()
         cuda_gather = self.world > 1 and self.device.type == "cuda"
-        peaks, rs = self.ctx.call_peaks(to_host=not cuda_gather) if self.ctx.api.has_device else self.ctx.call_peaks()
+        if cuda_gather:
+            got = self._gather_peaks_one_wait()
+            if got is None:                      # -q and a p-value table overflowed somewhere: p, the exchange and q once more
+                return self.call_peaks()
+            return got
+        peaks, rs = self.ctx.call_peaks() if self.ctx.api.has_device else self.ctx.call_peaks()
         self._tick("call_peaks", t0)
         t0 = time.perf_counter()
         if self.world > 1:
             isz = PEAK_DTYPE.itemsize
             if cuda_gather:
-                # One collective: every rank contributes a fixed-size slot [count | records] straight
-                # from device memory (NCCL all-gather over NVLink); rank 0 brings the lot to pinned
-                # host memory in one copy, the others only the counts.  A slot that turns out too
-                # small is seen by every rank in the gathered counts, and the exchange is simply
-                # repeated with a larger one.
-                dptr, n = self.ctx.peaks_device_ptr()
-                while True:
-                    capb = self._gather_cap * isz
-                    slot = capb + 16
-                    if self._send is None or self._send.numel() != slot:
-                        self._send = torch.zeros(slot, dtype=torch.uint8, device=self.device)
-                        self._recv = torch.empty(self.world * slot, dtype=torch.uint8, device=self.device)
-                        self._host = torch.empty(self.world * slot, dtype=torch.uint8).pin_memory()
-                    self._send[:8].view(torch.int64)[0] = n
-                    m = min(n, self._gather_cap) * isz
-                    if m:
-                        self._send[16:16 + m] = _tensor_from_ptr(dptr, m, np.uint8, self.device)
-                    td.all_gather_into_tensor(self._recv, self._send)
-                    hv = self._host.view(self.world, slot)
-                    if self.rank == 0:
-                        self._host.copy_(self._recv, non_blocking=True)
-                    else:
-                        hv[:, :16].copy_(self._recv.view(self.world, slot)[:, :16], non_blocking=True)
-                    torch.cuda.current_stream(self.device).synchronize()
-                    host = self._host.numpy().reshape(self.world, slot)
-                    counts = [int(host[r, :8].view(np.int64)[0]) for r in range(self.world)]
-                    if max(counts) <= self._gather_cap:
-                        break
-                    self._gather_cap = 2 * max(counts)
-                self._tick("gather_exchange", t0)
-                if self.rank == 0:
-                    total = sum(counts)
-                    peaks = np.empty(total, PEAK_DTYPE)
-                    lists = (C.c_void_p * self.world)(*[host[r, 16:].ctypes.data for r in range(self.world)])
-                    cnts = (C.c_uint64 * self.world)(*counts)
-                    rc = self.ctx.api.merge_peaks(lists, cnts, self.world, peaks.ctypes.data_as(C.c_void_p))
-                    if rc:
-                        raise RuntimeError("gr_merge_peaks failed: %d" % rc)
+                raise AssertionError("unreachable: the CUDA ranks gather in _gather_peaks_one_wait")
             else:
                 buf = torch.from_numpy(peaks.view(np.uint8).copy())
                 cnt = torch.tensor([buf.numel()], dtype=torch.int64)

@@ -276,6 +276,23 @@ int gr_call_peaks(gr_ctx* ctx, const gr_peak** peaks, uint64_t* n,
 /* The same records where gr_call_peaks left them in DEVICE memory (valid until the next
  * call on the context): lets a multi-GPU launcher all-gather them without a host bounce. */
 int gr_peaks_device(gr_ctx* ctx, const gr_peak** d_peaks, uint64_t* n);
+/* gr_call_peaks in two halves, for launchers that gather several contexts' peaks with ONE wait for the device
+ * (one process per GPU: an NCCL all-gather of every rank's slot).  gr_call_peaks_enqueue runs the peak scan
+ * without waiting and hands out the device address of a SLOT: a 64-byte gr_peak_slot header, which the device
+ * fills in stream order, followed by record_cap gr_peak records.  The caller moves the first 64 + 32 k bytes
+ * wherever it wants them on gr_stream(ctx), waits once, and passes the header as it reads on the host to
+ * gr_call_peaks_done.  redo = 1: a buffer was too small, enqueue again; redo = 2: call gr_call_peaks instead
+ * (rare: a table overflowed).  With -q the histogram exchange (gr_bh_local_hist / gr_bh_set_global) comes first. */
+typedef struct gr_peak_slot {
+  uint64_t n_peaks;      /* records that follow the header (may exceed what the caller chose to move) */
+  uint64_t peak_bp;      /* Genrich.c:924 */
+  int32_t  flags;        /* device-side condition bits, interpreted by gr_call_peaks_done */
+  int32_t  reserved;
+  uint64_t n_intervals;  /* final p/q interval count (owned chromosomes) */
+  uint64_t pad[4];
+} gr_peak_slot;
+int gr_call_peaks_enqueue(gr_ctx* ctx, const void** d_slot, uint64_t* record_cap);
+int gr_call_peaks_done(gr_ctx* ctx, const gr_peak_slot* header, int32_t* redo, gr_run_stats* stats);
 /* gr_call_peaks with peaks == NULL leaves the records on the device (n and stats are still
  * filled).  Host utility for launchers that gathered several contexts' lists (each in chromosome
  * order, every chromosome in exactly one of them): one list in chromosome order, the order in

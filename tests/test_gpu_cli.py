@@ -223,3 +223,28 @@ def test_cli_saturation_rule(threads, tmp_path, monkeypatch):
         h.update(("%s %s %s %s\n" % a).encode())
     assert h.hexdigest() == meta["skipped_sha256"]
     assert "Background pileup value: %f" % meta["lambda"][0] in r.stderr
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_n_gpus() < 2 and not os.environ.get("GR_EMU_AS_CUDA"), reason="needs two GPUs")
+@pytest.mark.parametrize("name", ["c2_ctrl_q", "c4_fisher_q", "bed_ctrl_q"])
+def test_cli_sharded_over_devices(name, tmp_path):
+    """genrich-b200 --gpus N on real devices (runProgram's per-chromosome loop as the multi-GPU dispatcher of the
+    host program: N contexts in one process, per-chromosome sums added on the host, one p-value histogram through
+    gr_bh_*_host, peaks merged in chromosome order): same narrowPeak / -f text as on one device."""
+    case = BY_NAME[name]
+    os.makedirs(str(tmp_path / "one"))
+    os.makedirs(str(tmp_path / "many"))
+    one = _run_cli(case, str(tmp_path / "one"))
+    n = max(2, min(_n_gpus(), 4)) if not os.environ.get("GR_EMU_AS_CUDA") else 3
+    many = _run_cli(case, str(tmp_path / "many"), extra=["--gpus", str(n)])
+    assert many[0] == one[0] and len(one[0]) > 0          # narrowPeak
+    assert many[1] == one[1]                              # -f
+    assert [l for l in many[2] if not l.startswith("#")] == [l for l in one[2] if not l.startswith("#")]   # -k (minus the path lines)
