@@ -1234,6 +1234,225 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   }
 }
 
+__device__ __forceinline__ int fr_weight(u32 count);
+// Dense form: the scan for DEEP samples, whose blocks are mostly occupied (the 10 Gbp / 1 B fragment configuration:
+// ~2200 entries and ~3400 distinct event cells per 8192-cell block).  There the occupancy-driven walks of the two
+// other forms (k_fb_scan: per set bit; k_fr_scan: per 512 distinct cells, every round over all entries) cost more
+// than simply reading every cell: measured on the B200, 333 M records over 1.25 G cells, 4.1 ms and 9.5 ms.
+//   * the CTA's run of bucket entries is ONE contiguous stream (blk_start is cumulative): it is staged through a
+//     two-deep ring of 8 KB tiles by 1-D bulk copies (cp.async.bulk -> mbarrier, the TMA unit; no registers, no
+//     L1) that run ahead of the block being worked on;
+//   * entries -> shared-memory cells by atomicAdd (cell c lives at c + c / 32: a thread's 32 consecutive cells
+//     then fall into 32 different banks);
+//   * every thread reads ITS 32 cells unconditionally (no bit walks, no divergence), clears them, builds the
+//     break mask -- which is the thread's word of the break bitmap -- and after one block-wide scan emits its
+//     breaks from registers.
+// Output contract = k_fb_scan's (owner = CTA: pages, warp_tot, marks).  No -E marks here (k_fb_scan keeps those).
+#define FD_NT 256
+#define FD_STAGE 2048                                  // entries per staging tile
+#define FD_PAD(c) ((c) + ((c) >> 5))
+struct FdSmem {
+  u32 ent[2][FD_STAGE];                                // first: 16-byte aligned with the dynamic shared memory itself
+  int cell[GR_BLOCK_SLOTS + GR_BLOCK_SLOTS / 32];
+  u64 bar[2];
+  u32 pg[FB_RING];
+  u32 ws[FD_NT / 32], wc[FD_NT / 32];
+};
+#ifdef GR_EMU                       // tests/emu: the copy is a memcpy; the barrier word counts completed copies, and a waiter yields
+__device__ __forceinline__ void fd_bar_init(u64* bar) { *bar = 0; }
+__device__ __forceinline__ void fd_bulk_load(void* dst, const void* src, u32 bytes, u64* bar) { memcpy(dst, src, bytes); ++*bar; }
+__device__ __forceinline__ void fd_bar_wait(u64* bar, u32 parity) { while ((u32)(*(volatile u64*)bar & 1u) == parity) emu::spin_yield(); }
+__device__ __forceinline__ void fd_fence_async() {}
+#else
+__device__ __forceinline__ void fd_bar_init(u64* bar) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(a) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// one thread: arm the barrier with the byte count, start the bulk copy that will complete it
+__device__ __forceinline__ void fd_bulk_load(void* dst, const void* src, u32 bytes, u64* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               :: "r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
+}
+__device__ __forceinline__ void fd_bar_wait(u64* bar, u32 parity) {
+  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "FD_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra FD_DONE_%=;\n\t"
+      "bra FD_WAIT_%=;\n\t"
+      "FD_DONE_%=:\n\t}" :: "r"(b), "r"(parity) : "memory");
+}
+// the tile was read through the generic proxy; the next bulk copy writes it through the async proxy
+__device__ __forceinline__ void fd_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+#endif
+
+__global__ void __launch_bounds__(FD_NT, 3)
+k_fd_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
+          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R) {
+  extern __shared__ int4 fd_raw[];                      // 16-byte aligned: the bulk copies' destination tiles
+  FdSmem& S = *reinterpret_cast<FdSmem*>(fd_raw);
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const u32 owner = blockIdx.x;
+  const u32 b0 = owner * R, b1 = min(b0 + R, nblocks);
+  if (b0 >= b1) {
+    if (t == 0) W.warp_tot[owner] = make_uint2(0, 0);
+    return;
+  }
+  for (int i = t; i < GR_BLOCK_SLOTS + GR_BLOCK_SLOTS / 32; i += FD_NT) S.cell[i] = 0;
+  // the run's entries as one stream of FD_STAGE-entry tiles, 16-byte aligned at both ends (the buffer has the room)
+  const u32 run_lo = blk_start[b0] & ~3u, run_hi = blk_start[b1];
+  const u32 nchunk = (run_hi - run_lo + FD_STAGE - 1) / FD_STAGE;
+  if (t == 0) { fd_bar_init(&S.bar[0]); fd_bar_init(&S.bar[1]); }
+  __syncthreads();
+  auto issue = [&](u32 c) {                             // thread 0
+    if (c >= nchunk) return;
+    const u32 e0 = run_lo + c * FD_STAGE;
+    const u32 n = (min((u32)FD_STAGE, run_hi - e0) + 3u) & ~3u;
+    fd_bulk_load(S.ent[c & 1], bucketed + e0, n * 4u, &S.bar[c & 1]);
+  };
+  if (t == 0) { issue(0); issue(1); }
+  u32 waited = 0;                                       // tiles whose arrival this thread has seen
+
+  const u32 last_page = W.max_pages - 1;
+  int have_seq = -1;
+  u32 pend_p0 = 0;
+  int pend_k = 0;
+  auto page_take = [&]() {
+    for (int i = 0; i < pend_k; i++) {
+      u32 pg = pend_p0 + (u32)i;
+      if (pg > last_page) { atomicOr(err, GR_DE_TABLE); pg = last_page; }
+      have_seq++;
+      W.page_meta[pg] = make_uint2(owner, (u32)have_seq);
+      S.pg[have_seq & (FB_RING - 1)] = pg;
+    }
+    pend_k = 0;
+  };
+  auto page_ask = [&](u32 upto_idx) {
+    const int target = (int)(upto_idx >> SS_PAGE_SHIFT);
+    if (target > have_seq) {
+      pend_k = target - have_seq;
+      pend_p0 = atomicAdd(W.page_ctr, (u32)pend_k);
+    }
+  };
+  auto ub_of = [&](u32 a, u32 b) { return min(2u * (b - a) + 1u, (u32)GR_BLOCK_SLOTS + 1u); };
+  auto ld_start = [&](u32 i) { return blk_start[min(i, nblocks)]; };
+  u32 sA = ld_start(b0), sB = ld_start(b0 + 1), sC = ld_start(b0 + 2);
+  if (t == 0) page_ask(ub_of(sA, sB));
+
+  auto apply = [&](u32 e) {
+    const u32 so = e & (GR_BLOCK_SLOTS - 1), kind = e >> 30;
+    const int w = fr_weight((e >> 26) & 15u);
+    atomicAdd(&S.cell[FD_PAD(so)], kind == FB_KIND_END ? -w : w);
+    if (kind == FB_KIND_BOTH) {
+      const u32 eo = so + ((e >> 13) & (GR_BLOCK_SLOTS - 1));
+      atomicAdd(&S.cell[FD_PAD(eo)], -w);
+    }
+  };
+
+  u32 run_s = 0, run_c = 0;
+  bool sat = false;
+  int c = -1;
+  u32 c_last_blk = 0;
+  u64 off = 0;
+  u32 len = 0;
+  bool act = false;
+  for (u32 b = b0; b < b1; b++) {
+    if (c < 0 || b > c_last_blk) {                     // ~25 times per genome
+      c = L.blk2chrom[b];
+      off = L.off[c];
+      len = L.len[c];
+      c_last_blk = (u32)((off + len) >> GR_BLOCK_SHIFT);
+      act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
+    }
+    const u32 sD = ld_start(b + 3);
+    const u32 jb = (u32)(((u64)b << GR_BLOCK_SHIFT) - off);       // chromosome position of the block's first cell
+    if (t == 0) {
+      if (jb == 0) W.marks[c] = make_uint4(owner, run_s, run_c, 1u);
+      page_take();
+      page_ask(run_c + ub_of(sA, sB) + (b + 1 < b1 ? ub_of(sB, sC) : 0u));
+    }
+    const bool has_end = act && b == c_last_blk;       // cell `len` lies in this block
+    if (sA == sB && !has_end) {                        // nothing in this block
+      bitmap[(u64)b * FB_WORDS + t] = 0;
+      sA = sB; sB = sC; sC = sD;
+      continue;
+    }
+    // ---- entries -> cells, tile by tile
+    for (u32 pos = sA; pos < sB;) {
+      const u32 ch = (pos - run_lo) / FD_STAGE;
+      if (ch >= waited) { fd_bar_wait(&S.bar[ch & 1], (ch >> 1) & 1u); waited = ch + 1; }
+      const u32 tile_end = run_lo + (ch + 1) * FD_STAGE;
+      const u32 upto = min(sB, tile_end);
+      const u32* buf = S.ent[ch & 1];
+      for (u32 i = pos + t; i < upto; i += FD_NT) apply(buf[i - (tile_end - FD_STAGE)]);
+      pos = upto;
+      if (pos == tile_end) {                           // the tile is used up: its buffer takes the tile after the next
+        __syncthreads();
+        if (t == 0) { fd_fence_async(); issue(ch + 2); }
+      }
+    }
+    __syncthreads();
+    // ---- this thread's 32 cells: deltas into registers, cleared behind; break mask = its bitmap word
+    int d[32];
+    u32 s = 0, m = 0;
+    const u32 jt = jb + (u32)t * 32u;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      d[k] = S.cell[t * 33 + k];
+      S.cell[t * 33 + k] = 0;
+      s += (u32)d[k];
+      sat |= cell_saturated(d[k]);
+    }
+    if (act) {
+      if (jb >= 1 && (u64)jb + GR_BLOCK_SLOTS < (u64)len) {       // interior block: a break wherever the delta is not zero
+#pragma unroll
+        for (int k = 0; k < 32; k++) m |= (d[k] != 0 ? 1u : 0u) << k;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+          const u32 j = jt + (u32)k;
+          m |= ((j == len) || (d[k] != 0 && j >= 1u && j < len) ? 1u : 0u) << k;
+        }
+      }
+    }
+    const u32 cnt = __popc(m);
+    const u32 wi_s = warp_incl_scan_u32(s, lane), wi_c = warp_incl_scan_u32(cnt, lane);
+    if (lane == 31) { S.ws[wid] = wi_s; S.wc[wid] = wi_c; }
+    __syncthreads();
+    u32 h = run_s + wi_s - s, idx = run_c + wi_c - cnt, tot_s = 0, tot_c = 0;
+#pragma unroll
+    for (int k = 0; k < FD_NT / 32; k++) {
+      const u32 a = S.ws[k], q = S.wc[k];
+      if (k < wid) { h += a; idx += q; }
+      tot_s += a; tot_c += q;
+    }
+    // ---- emit from registers
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+      if ((m >> k) & 1u) {
+        const u32 pg = S.pg[(idx >> SS_PAGE_SHIFT) & (FB_RING - 1)];
+        W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(jt + (u32)k, h);
+        idx++;
+      }
+      h += (u32)d[k];
+    }
+    bitmap[(u64)b * FB_WORDS + t] = m;
+    run_s += tot_s;
+    run_c += tot_c;
+    sA = sB; sB = sC; sC = sD;
+    __syncthreads();                                   // the scan scratch and the page ring are free again
+  }
+  if (sat) atomicOr(err, GR_DE_SAT);
+  if (t == 0) {
+    page_take();
+    W.warp_tot[owner] = make_uint2(run_s, run_c);
+  }
+}
+
 // Rank form -- the default scan: warp-owned 8192-cell blocks WITHOUT a cell array.  A block of the
 // hg38 workload holds ~265 entries = ~400 distinct event cells out of 8192; k_fb_scan spends its
 // time in three CTA barriers per block and in a walk whose length is the fullest thread's (ncu:
@@ -1521,12 +1740,18 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
   const u32 nb = (u32)L.nblocks;
   u32 owners;
   // The rank form walks a block's entries once per 512 DISTINCT event cells; a block of a deep sample (the 10 Gbp
-  // / 1 B fragment configuration: ~2200 entries, ~3400 distinct cells per block) takes seven such rounds and the
-  // CTA form's cell array wins (measured on the B200, 333 M records over 1.25 G cells: 9.5 ms against 4.1 ms).
+  // / 1 B fragment configuration: ~2200 entries, ~3400 distinct cells per block) takes seven such rounds: 9.5 ms
+  // on the B200 for 333 M records over 1.25 G cells.  Such samples go to the dense form (k_fd_scan).
   // Expected distinct cells per block from the sample size: 8192 (1 - exp(-2 n / cells)).
   const double per_blk = 2.0 * (double)n_records / (double)(nb ? nb : 1);
   const bool dense_blocks = 8192.0 * (1.0 - exp(-per_blk / 8192.0)) > (double)fb_env("GR_FUSED_CTA_CELLS", 1536);
-  if (blk_bed || dense_blocks || fb_env("GR_FUSED_CTA", 0)) {   // read per call: the tests switch it inside one process
+  if (!blk_bed && !fb_env("GR_FUSED_CTA", 0) && (dense_blocks || fb_env("GR_FUSED_DENSE", 0))) {
+    static bool init = false;
+    if (!init) { cudaFuncSetAttribute(k_fd_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FdSmem)); init = true; }
+    owners = (u32)(sms * 3);
+    const u32 R = (nb + owners - 1) / owners;
+    k_fd_scan<<<owners, FD_NT, sizeof(FdSmem), s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
+  } else if (blk_bed || fb_env("GR_FUSED_CTA", 0)) {   // read per call: the tests switch it inside one process
     owners = (u32)(sms * 6);
     const u32 R = (nb + owners - 1) / owners;
     if (blk_bed) k_fb_scan<6, 128, true><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed, chrom_marks);

@@ -165,6 +165,16 @@ static void entry() {
   emu_switch(&me.sp, g->sched_sp);
   abort();                                 // a finished fiber is never resumed
 }
+static bool g_spun = false;                // the fiber that just came back was only polling (spin_yield)
+static unsigned long long n_spins = 0;
+static inline void yield_();
+// a polling loop's yield (an mbarrier wait, a flag): the scheduler moves on to the other warps instead of
+// resuming this one at once, and a program in which everybody only polls is reported, not looped forever
+static inline void spin_yield() {
+  if (++n_spins > 200000000ull) { fprintf(stderr, "emu: every fiber polls -- deadlock\n"); abort(); }
+  g_spun = true;
+  yield_();
+}
 static inline void yield_() {
   Fiber& me = g->f[g->cur];
   n_switches++;
@@ -263,8 +273,10 @@ template <typename F> static void launch(unsigned grid, unsigned nt, F body) {
             if (f.wait == 1 && f.grp->gen == f.wgen) continue;        // waits for its siblings
             cta.cur = t;
             threadIdx = uint3{(unsigned)t, 0, 0};
+            g_spun = false;
             emu_switch(&cta.sched_sp, f.sp);
-            any = true; progressed = true;
+            progressed = true;
+            if (!g_spun) { any = true; n_spins = 0; }    // a lane that only polled does not keep the scheduler on this warp
           }
           if (order_mode == 2) order_salt = order_salt * 1103515245u + 12345u;
           if (!any) break;

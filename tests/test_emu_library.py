@@ -28,6 +28,7 @@ MODES = {
     "default_small": {},                                     # plain scatter + streaming scan (small samples)
     "default_fused": FUSED,                                  # the path the bench takes: k_fr_scan
     "fused_cta": dict(FUSED, GR_FUSED_CTA="1"),              # k_fb_scan without -E regions
+    "fused_dense": dict(FUSED, GR_FUSED_DENSE="1"),          # k_fd_scan (deep samples)
 }
 
 

@@ -280,9 +280,11 @@ def test_fused_scan_same_bits(monkeypatch):
         extra = extra[extra[:, 2] <= case.chrom_len[0]]
         inputs[0][0] = np.concatenate([inputs[0][0], extra])
         par = util.case_params(case)
-        outs = _run_modes(monkeypatch, case.chrom_len, par, inputs, (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1")))
+        outs = _run_modes(monkeypatch, case.chrom_len, par, inputs,
+                          (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_DENSE="1")))
         _same_outs(outs[0], outs[1], case.name)            # k_fr_scan (the default fused scan) == scatter + k_scan_stream
         _same_outs(outs[0], outs[2], case.name + " cta")   # k_fb_scan (the form -E contexts use)
+        _same_outs(outs[0], outs[3], case.name + " dense") # k_fd_scan (the form deep samples get)
         assert len(outs[0][0].peaks) > 0 or case.name == "null_q"
     # packed records through the fused path
     case = BY_NAME["c2_ctrl_q"]
@@ -305,7 +307,7 @@ def test_fused_scan_same_bits(monkeypatch):
         [6, 0, 16383, 1], [6, 8100, 16383, 2], [6, 16382, 16383, 3],
     ], dtype=np.int32)
     par = capi.make_params(p=0.2, min_auc=0.5, keep_pileups=True)
-    modes = (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"))
+    modes = (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_DENSE="1"))
     outs = _run_modes(monkeypatch, L, par, [(recs, None)], modes)
     for o in outs[1:]:
         _same_outs(outs[0], o, "edge")
@@ -319,7 +321,7 @@ def test_fused_scan_large(monkeypatch):
     t = Workload(L, 4_000_000, 101, enrich=0.5, spacing=400000, sigma=60.0).fragments()
     c = Workload(L, 4_000_000, 102, enrich=0.0).fragments()
     par = capi.make_params(p=0.01, min_auc=20.0)
-    modes = ({"GR_FUSED": "0"}, {"GR_FUSED": "1"}, {"GR_FUSED": "1", "GR_FUSED_CTA": "1"})
+    modes = ({"GR_FUSED": "0"}, {"GR_FUSED": "1"}, {"GR_FUSED": "1", "GR_FUSED_CTA": "1"}, {"GR_FUSED": "1", "GR_FUSED_DENSE": "1"})
     outs = _run_modes(monkeypatch, L, par, [(t, c)], modes, chunk=1 << 22)
     for o, md in zip(outs[1:], modes[1:]):
         _same_outs(outs[0], o, "large %s" % md)
@@ -489,8 +491,8 @@ def test_error_codes(monkeypatch):
     # more starts on one base than the reference's int16 counter holds: the reference drops the 32768th
     # (saveInterval 2558-2573), and so do the oracle and the fused paths (k_sat_resolve; the full case is
     # test_saturation_rule).  The dense formulation -- a measurement aid behind GR_FUSED=0 -- only detects it.
-    for env in (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1")):
-        for k in ("GR_FUSED", "GR_FUSED_MIN", "GR_SB_MIN", "GR_FUSED_CTA"):
+    for env in (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_DENSE="1")):
+        for k in ("GR_FUSED", "GR_FUSED_MIN", "GR_SB_MIN", "GR_FUSED_CTA", "GR_FUSED_DENSE"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
