@@ -721,21 +721,20 @@ def main():
     #   dense  (GR_FUSED=0): the delta array is written to HBM by k_sb_build and read back by k_scan_stream -- the
     #          kernel the HBM-read roofline is literally about
     #   cta    (GR_FUSED_CTA=1): k_fb_scan, the CTA-owned shared-memory cell array that was the default in round 1
-    dense = cta = None
+    forms = {}
     if world == 1 and not a.no_dense and G < (1 << 32):
-        for key, env in (("dense", {"GR_FUSED": "0"}), ("cta", {"GR_FUSED_CTA": "1"})):
+        for key, env in (("dense_array", {"GR_FUSED": "0"}), ("cta", {"GR_FUSED_CTA": "1"}),
+                         ("rank", {"GR_FUSED_CTA_CELLS": "1000000"}), ("dense_cells", {"GR_FUSED_DENSE": "1"})):
             os.environ.update(env)
             eng_d = ShardedEngine(api, L, par, dev, host_group=None)
             ms_d, _, _, peaks_d, _, st_d = timed(False, st_steps, 3, with_stages=True, eng=eng_d)
             for k in env:
                 del os.environ[k]
             assert peaks_d.tobytes() == peaks.tobytes(), "%s and default formulations disagree" % key
-            if key == "dense":
-                dense = (ms_d, st_d)
-            else:
-                cta = (ms_d, st_d)
+            forms[key] = (ms_d, st_d)
             eng_d.ctx.close()
             del eng_d
+    dense, cta = forms.get("dense_array"), forms.get("cta")
 
     if eng.debug:
         print("rank %d host-side ms per step (e2e arm): %s" % (rank, host_phase), file=sys.stderr, flush=True)
@@ -747,7 +746,9 @@ def main():
     n_records = int(sum(s.n for s in order))
     peak_gbs, peak_src = measured_peak_gbs()
     fused = "fused_scan" in stages
-    scan_kernel = "k_fr_scan" if fused else "k_scan_stream"
+    per_blk = 2.0 * (n_records / max(n_samples, 1)) / max(cells / 8192, 1)
+    deep = 8192.0 * (1.0 - np.exp(-per_blk / 8192.0)) > float(os.environ.get("GR_FUSED_CTA_CELLS", "768"))
+    scan_kernel = ("k_fd_scan" if deep else "k_fr_scan") if fused else "k_scan_stream"
     scan_ms, scan_launches, _ = stages.get("fused_scan" if fused else "dense_scan", (0.0, 0, 0))
     per_launch_ms = scan_ms / max(scan_launches, 1)          # mean over every launch of the staged pass
     place_ms, place_launches, _ = stages.get("scan_place", (0.0, 0, 0))
@@ -767,6 +768,8 @@ def main():
                             "GR_FUSED=0: the delta array is written to HBM by k_sb_build and read back by k_scan_stream "
                             "(4 B per cell each way: here `achieved` IS the HBM read rate); same peaks, bit for bit")
     cta_obj = formulation("k_fb_scan", cta, "fused_scan", "GR_FUSED_CTA=1: round 1's default scan; same peaks, bit for bit")
+    rank_obj = formulation("k_fr_scan", forms.get("rank"), "fused_scan", "rank form forced (GR_FUSED_CTA_CELLS huge): the default for sparse blocks")
+    cells_obj = formulation("k_fd_scan", forms.get("dense_cells"), "fused_scan", "GR_FUSED_DENSE=1: the dense form, the default for deep samples")
 
     # what really moves through DRAM: per kernel, from the committed ncu pass of `bench.py --profile` on this workload
     table = load_dram_table(a.workload, world)
@@ -819,7 +822,8 @@ def main():
                              "in, breaks and a bitmap out), so frac > 1 is not a bandwidth claim: `traffic` / `frac_dram` say what "
                              "the kernel really moves, `step` what the whole step moves, `dense_formulation` what the kernel that "
                              "does read 4 B per cell achieves",
-                     "step": step_obj, "dense_formulation": dense_obj, "cta_formulation": cta_obj},
+                     "step": step_obj, "dense_formulation": dense_obj, "cta_formulation": cta_obj,
+                     "rank_formulation": rank_obj, "dense_cells_formulation": cells_obj},
         "dense_formulation": dense_obj,
         "stage_ms_per_step": stage_ms,
         "host_phase_ms_per_step_device_arm": host_phase_dev,

@@ -1335,10 +1335,8 @@ extern "C" int gr_pvalues_finalize(gr_ctx* x) {
     views[r].pval = x->reps[r]->pVal.as<float>();
     views[r].present = x->reps[r]->present.as<uint8_t>();
   }
-  CK(x->repviews.ensure(nrep * sizeof(RepView)));
-  { int r = upload(x, x->repviews.p, views.data(), nrep * sizeof(RepView)); if (r) return r; }
   stage_begin(x, "fisher_emit", np * 16 * nrep);
-  launch_fisher_emit(x->stream, x->L, cb->bmU.as<u32>(), cb->rankU.as<u64>(), x->repviews.as<RepView>(),
+  launch_fisher_emit(x->stream, x->L, cb->bmU.as<u32>(), cb->rankU.as<u64>(), views.data(),
                      nrep, cb->pEnd.as<u32>(), x->fsum.as<double>(), x->fdf.as<int>(),
                      cb->chrom_start.as<u64>(), x->d_totals + 2);
   CKL();

@@ -1744,7 +1744,7 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
   // on the B200 for 333 M records over 1.25 G cells.  Such samples go to the dense form (k_fd_scan).
   // Expected distinct cells per block from the sample size: 8192 (1 - exp(-2 n / cells)).
   const double per_blk = 2.0 * (double)n_records / (double)(nb ? nb : 1);
-  const bool dense_blocks = 8192.0 * (1.0 - exp(-per_blk / 8192.0)) > (double)fb_env("GR_FUSED_CTA_CELLS", 1536);
+  const bool dense_blocks = 8192.0 * (1.0 - exp(-per_blk / 8192.0)) > (double)fb_env("GR_FUSED_CTA_CELLS", 768);
   if (!blk_bed && !fb_env("GR_FUSED_CTA", 0) && (dense_blocks || fb_env("GR_FUSED_DENSE", 0))) {
     static bool init = false;
     if (!init) { cudaFuncSetAttribute(k_fd_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FdSmem)); init = true; }

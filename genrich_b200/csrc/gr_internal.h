@@ -141,8 +141,9 @@ void launch_or_bitmaps(cudaStream_t s, const u32* a, const u32* b, u32* out, u64
 void launch_block_rank(cudaStream_t s, const DevLayout& L, const u32* bm, const CompactScratch& sc,
                        u64* rank, u64* total);
 // for each combined break: sum of replicate p (double) and df -> sum_out/df_out; end_out
+// reps: HOST array (the views travel to the kernel as parameters, 8 replicates per launch)
 void launch_fisher_emit(cudaStream_t s, const DevLayout& L, const u32* bmAll, const u64* rankAll,
-                        const RepView* reps_dev, int nrep, u32* end_out, double* sum_out,
+                        const RepView* reps, int nrep, u32* end_out, double* sum_out,
                         int* df_out, u64* chrom_start, const u64* total);
 void launch_fisher_eval(cudaStream_t s, const double* sum, const int* df, u64 n, float* pcomb);   // every interval (small inputs)
 // the same through a table of distinct sums: t empty on entry (table_alloc); GR_DE_TABLE in *err: it was too small

@@ -2,6 +2,7 @@
 // scan: K3 control sweep, K4 breakpoint union, K5 -log10 p through a table of
 // distinct (expt, ctrl) pairs, K6 Fisher combine.
 #include <stdlib.h>
+#include <string.h>
 #include "gr_tile.cuh"
 #include "gr_math.cuh"
 #include "gr_internal.h"
@@ -526,9 +527,18 @@ void launch_key_insert(cudaStream_t s, const u32* pEnd, const float* pval, u64 n
 // the bp are added per SLOT -- no hashing, no probing, no second table.  Distinct pairs with the same p simply
 // show up as repeated keys in the list; the BH pass merges equal keys anyway (it has to, for the all-gather).
 // 8 intervals per thread; equal slots inside a warp are added up first (hot pairs such as (0, lambda)).
+// Hot pairs -- (0, lambda) alone covers most of a genome -- would serialise in L2 even after the warp-level
+// merge (224 M intervals of the ATAC configuration: 6.3 ms): every CTA first collects its sums in a direct-mapped
+// shared-memory cache of SH_CACHE slots (tag = table slot; a slot that finds its cache line taken goes straight to
+// global memory) and flushes the cache once at the end.
+#define SH_CACHE 2048
 __global__ void __launch_bounds__(256)
 k_slot_hist(const u32* __restrict__ pEnd, const u32* __restrict__ slot, const u64* __restrict__ n_dev,
-            const u64* __restrict__ chrom_start, int nchrom, u64* __restrict__ lens) {
+            u64* __restrict__ lens) {
+  __shared__ u32 sm_tag[SH_CACHE];                   // table slot + 1; 0: free
+  __shared__ u64 sm_val[SH_CACHE];
+  for (int i = threadIdx.x; i < SH_CACHE; i += 256) { sm_tag[i] = 0; sm_val[i] = 0; }
+  __syncthreads();
   const u64 n = *n_dev;
   const int lane = threadIdx.x & 31;
   const u64 stride = (u64)gridDim.x * 256;
@@ -547,14 +557,23 @@ k_slot_hist(const u32* __restrict__ pEnd, const u32* __restrict__ slot, const u6
     if (peers == (1u << lane)) tot = len;
     else
       for (u32 rem = peers; rem; rem &= rem - 1) tot += __shfl_sync(peers, len, __ffs(rem) - 1);   // the group walks its member list
-    if (h < 0xfffffffeu && lane == __ffs(peers) - 1 && tot) atomicAdd(lens + h, tot);
+    if (h < 0xfffffffeu && lane == __ffs(peers) - 1 && tot) {
+      const u32 ci = (h * 2654435761u) >> (32 - 11);             // SH_CACHE = 2^11 lines
+      const u32 old = atomicCAS(&sm_tag[ci], 0u, h + 1u);
+      if (old == 0u || old == h + 1u) atomicAdd(&sm_val[ci], tot);
+      else atomicAdd(lens + h, tot);
+    }
   }
-  (void)chrom_start; (void)nchrom;
+  __syncthreads();
+  for (int i = threadIdx.x; i < SH_CACHE; i += 256)
+    if (sm_tag[i] && sm_val[i]) atomicAdd(lens + (sm_tag[i] - 1u), sm_val[i]);
 }
 void launch_slot_hist(cudaStream_t s, const u32* pEnd, const u32* slot, u64 n_upper, const u64* n_dev,
                       const u64* chrom_start, int nchrom, u64* lens) {
   if (!n_upper) return;
-  k_slot_hist<<<capped_grid(n_upper), 256, 0, s>>>(pEnd, slot, n_dev, chrom_start, nchrom, lens); GR_NOTE_LAUNCH();
+  const u64 tiles = (n_upper + 255) / 256;
+  k_slot_hist<<<(unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), 256, 0, s>>>(pEnd, slot, n_dev, lens); GR_NOTE_LAUNCH();
+  (void)chrom_start; (void)nchrom;
 }
 
 // table -> dense (key, len) list
@@ -634,84 +653,100 @@ void launch_block_rank(cudaStream_t s, const DevLayout& L, const u32* bm, const 
   launch_union_rank(s, L, bm, nullptr, rs, rank, nullptr, rank, total);
 }
 
-// One CTA per 8192-cell block, one thread per bitmap word.  The replicates are taken FE_CHUNK at a time: their
-// bitmap words and rank bases sit in registers while the thread walks the set bits of its combined word, so an
-// interval's sum and df are built in registers and written once (the first version made one pass per replicate
-// with a read-modify-write of sum / df each: 7.6 GB of DRAM traffic and 9.1 ms per hg38 run of three replicates).
+// One CTA per 8192-cell block, one thread per bitmap word, FE_CHUNK replicates per launch.  The replicates' array
+// pointers arrive as kernel PARAMETERS and everything that depends only on the block (the combined word, every
+// replicate's word and rank base) is requested at once; the p-values of an interval are then gathered together
+// and its sum and df built in registers and written once.  (The first version walked the replicates one by one
+// through a view table in global memory, with a read-modify-write of sum / df per replicate: five dependent
+// round trips per CTA and 7.6 GB of DRAM traffic -- 9-10 ms per hg38 run of three replicates.)
 // Summation order = replicate order (multPval 570-574), in double.
 #define FE_CHUNK 8
+struct FisherChunk {                                 // by value: the pointers are read from the parameter bank, not through memory
+  const u32* bmU[FE_CHUNK]; const u64* rankU[FE_CHUNK]; const float* pval[FE_CHUNK]; const uint8_t* present[FE_CHUNK];
+  int n;                                             // replicates in this chunk
+  int first;                                         // 1: the chunk starts the sums (else they are continued)
+};
 __global__ void __launch_bounds__(256)
-k_fisher_emit(DevLayout L, const u32* __restrict__ bmAll, const u64* __restrict__ rankAll,
-              const RepView* __restrict__ reps, int nrep, u32* __restrict__ end_out,
-              double* __restrict__ sum_out, int* __restrict__ df_out, u64* __restrict__ chrom_start) {
+k_fisher_emit(DevLayout L, const u32* __restrict__ bmAll, const u64* __restrict__ rankAll, FisherChunk R,
+              u32* __restrict__ end_out, double* __restrict__ sum_out, int* __restrict__ df_out,
+              u64* __restrict__ chrom_start) {
   __shared__ u32 sm_w[FE_CHUNK + 1][8];
   const u32 blk = blockIdx.x;
   const u64 widx = (u64)blk * 256 + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // everything that depends on nothing but the block: one round trip
   const u32 A = bmAll[widx];
   const int c = L.blk2chrom[blk];
+  const u64 rA = rankAll[blk];
+  u32 Rw[FE_CHUNK];
+  u64 rb[FE_CHUNK];
+#pragma unroll
+  for (int k = 0; k < FE_CHUNK; k++) {
+    Rw[k] = k < R.n ? R.bmU[k][widx] : 0u;
+    rb[k] = k < R.n ? R.rankU[k][blk] : 0ull;
+  }
+  // second hop: what hangs off the chromosome
   const u64 off = L.off[c];
-  // rank of this word's first bit in the combined array
+  bool on[FE_CHUNK];
+#pragma unroll
+  for (int k = 0; k < FE_CHUNK; k++) on[k] = k < R.n && R.present[k][c];   // pval[j] == NULL (571): no such chromosome in the replicate
   const u32 pa = __popc(A);
   const u32 ia = warp_incl_scan_u32(pa, lane);
   if (lane == 31) sm_w[FE_CHUNK][w] = ia;
-  if (threadIdx.x == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = rankAll[blk];
+  u32 xr[FE_CHUNK];
+#pragma unroll
+  for (int k = 0; k < FE_CHUNK; k++) {
+    if (!on[k]) Rw[k] = 0u;
+    const u32 pr = __popc(Rw[k]);
+    const u32 ir = warp_incl_scan_u32(pr, lane);
+    if (lane == 31) sm_w[k][w] = ir;
+    xr[k] = ir - pr;
+  }
+  __syncthreads();
+  u32 xa = ia - pa;
+  for (int j = 0; j < w; j++) xa += sm_w[FE_CHUNK][j];
+#pragma unroll
+  for (int k = 0; k < FE_CHUNK; k++) {
+    u32 x = xr[k];
+    for (int j = 0; j < w; j++) x += sm_w[k][j];
+    rb[k] += x;
+  }
+  if (R.first && threadIdx.x == 0 && (u64)blk * GR_BLOCK_SLOTS == off) chrom_start[c] = rA;
   const u32 jw = (u32)((u64)blk * GR_BLOCK_SLOTS + (u64)threadIdx.x * 32 - off);
-  u64 u0 = 0;
-  for (int r_lo = 0; r_lo < nrep; r_lo += FE_CHUNK) {
-    u32 Rw[FE_CHUNK], xr[FE_CHUNK];
-    bool on[FE_CHUNK];
+  u64 u = rA + xa;
+  for (u32 m = A; m; m &= m - 1, u++) {
+    const int b = __ffs(m) - 1;
+    const u32 low = (1u << b) - 1;
+    float p[FE_CHUNK];
 #pragma unroll
-    for (int k = 0; k < FE_CHUNK; k++) {
-      const int r = r_lo + k;
-      on[k] = r < nrep && reps[r].present[c];        // pval[j] == NULL (571): the replicate has no such chromosome
-      Rw[k] = on[k] ? reps[r].bmU[widx] : 0u;
-      const u32 pr = __popc(Rw[k]);
-      const u32 ir = warp_incl_scan_u32(pr, lane);
-      if (lane == 31) sm_w[k][w] = ir;
-      xr[k] = ir - pr;
-    }
-    __syncthreads();
-    if (r_lo == 0) {
-      u32 xa = ia - pa;
-      for (int k = 0; k < w; k++) xa += sm_w[FE_CHUNK][k];
-      u0 = rankAll[blk] + xa;
-    }
-    const float* pv[FE_CHUNK];
-    u64 rb[FE_CHUNK];
+    for (int k = 0; k < FE_CHUNK; k++) p[k] = on[k] ? R.pval[k][rb[k] + __popc(Rw[k] & low)] : -1.0f;   // the gathers, together
+    double sum = 0.0;
+    int df = 0;
+    if (!R.first) { sum = sum_out[u]; df = df_out[u]; }
 #pragma unroll
-    for (int k = 0; k < FE_CHUNK; k++) {
-      u32 x = xr[k];
-      for (int j = 0; j < w; j++) x += sm_w[k][j];
-      pv[k] = on[k] ? reps[r_lo + k].pval : nullptr;
-      rb[k] = on[k] ? reps[r_lo + k].rankU[blk] + x : 0;
-    }
-    u64 u = u0;
-    for (u32 m = A; m; m &= m - 1, u++) {
-      const int b = __ffs(m) - 1;
-      const u32 low = (1u << b) - 1;
-      double sum = 0.0;
-      int df = 0;
-      if (r_lo) { sum = sum_out[u]; df = df_out[u]; }
-#pragma unroll
-      for (int k = 0; k < FE_CHUNK; k++) {
-        if (!on[k]) continue;
-        const float p = pv[k][rb[k] + __popc(Rw[k] & low)];
-        if (p != -1.0f) { sum += (double)p; df += 2; }          // SKIP is not counted (572)
-      }
-      if (!r_lo) end_out[u] = jw + b;
-      sum_out[u] = sum;
-      df_out[u] = df;
-    }
-    __syncthreads();                                            // sm_w is rewritten by the next chunk
+    for (int k = 0; k < FE_CHUNK; k++)
+      if (p[k] != -1.0f) { sum += (double)p[k]; df += 2; }      // replicate order (570-574); SKIP is not counted (572)
+    if (R.first) end_out[u] = jw + b;
+    sum_out[u] = sum;
+    df_out[u] = df;
   }
 }
 
 void launch_fisher_emit(cudaStream_t s, const DevLayout& L, const u32* bmAll, const u64* rankAll,
-                        const RepView* reps_dev, int nrep, u32* end_out, double* sum_out,
+                        const RepView* reps_host, int nrep, u32* end_out, double* sum_out,
                         int* df_out, u64* chrom_start, const u64* total) {
-  k_fisher_emit<<<(unsigned)L.nblocks, 256, 0, s>>>(L, bmAll, rankAll, reps_dev, nrep, end_out,
-                                                    sum_out, df_out, chrom_start); GR_NOTE_LAUNCH();
+  for (int r0 = 0; r0 < nrep; r0 += FE_CHUNK) {
+    FisherChunk R;
+    memset(&R, 0, sizeof R);
+    R.n = nrep - r0 < FE_CHUNK ? nrep - r0 : FE_CHUNK;
+    R.first = r0 == 0;
+    for (int k = 0; k < R.n; k++) {
+      R.bmU[k] = reps_host[r0 + k].bmU; R.rankU[k] = reps_host[r0 + k].rankU;
+      R.pval[k] = reps_host[r0 + k].pval; R.present[k] = reps_host[r0 + k].present;
+    }
+    k_fisher_emit<<<(unsigned)L.nblocks, 256, 0, s>>>(L, bmAll, rankAll, R, end_out, sum_out, df_out, chrom_start);
+    GR_NOTE_LAUNCH();
+  }
   launch_fill_chrom_start(s, L, chrom_start, total);
 }
 

@@ -387,6 +387,24 @@ def test_fisher_table_growth(monkeypatch):
             assert np.array_equal(a.end, b.end) and np.array_equal(_bits(a.val), _bits(b.val))
 
 
+def test_fisher_many_replicates():
+    """Ten replicates (the Fisher emit kernel takes eight per launch and continues the sums in the next), one of
+    them without the last chromosome: combined p, q and peaks as the oracle's."""
+    reps = [(Sample(12000, 300 + r, drop_chroms=((1,) if r == 4 else ())), Sample(12000, 400, enrich=0.0) if r == 0 else None)
+            for r in range(10)]
+    case = Case("fisher10", [120000, 60000], reps, q=0.05)
+    inputs = util.case_inputs(case)
+    ctx_o, res_o, par = util.run_case(util.oracle_api(), case, inputs=inputs)
+    ctx_g, res_g, _ = util.run_case(capi.load_cuda(), case, inputs=inputs)
+    a, b = res_g.peaks, res_o.peaks
+    assert len(a) == len(b) and len(a) > 0
+    for f in ("chrom", "start", "end", "summit"):
+        assert np.array_equal(a[f], b[f]), f
+    for ci in range(2):
+        for which in (2, 3):
+            _cmp_intervals(ctx_g.fetch(which, 10, ci), ctx_o.fetch(which, 10, ci), False, "combined %d chr%d" % (which, ci))
+
+
 def test_edge_inputs():
     api = capi.load_cuda()
     orc = util.oracle_api()
