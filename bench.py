@@ -541,6 +541,8 @@ def load_dram_table(workload, world):
 
 
 def main():
+    import faulthandler
+    faulthandler.enable()                            # a crash inside a library says where it was called from
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -746,13 +748,13 @@ def main():
     n_records = int(sum(s.n for s in order))
     peak_gbs, peak_src = measured_peak_gbs()
     fused = "fused_scan" in stages
+    cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
     per_blk = 2.0 * (n_records / max(n_samples, 1)) / max(cells / 8192, 1)
     deep = 8192.0 * (1.0 - np.exp(-per_blk / 8192.0)) > float(os.environ.get("GR_FUSED_CTA_CELLS", "768"))
     scan_kernel = ("k_fd_scan" if deep else "k_fr_scan") if fused else "k_scan_stream"
     scan_ms, scan_launches, _ = stages.get("fused_scan" if fused else "dense_scan", (0.0, 0, 0))
     per_launch_ms = scan_ms / max(scan_launches, 1)          # mean over every launch of the staged pass
     place_ms, place_launches, _ = stages.get("scan_place", (0.0, 0, 0))
-    cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
     achieved = 4.0 * cells / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms else 0.0
 
     def formulation(kernel, res, stage, note):

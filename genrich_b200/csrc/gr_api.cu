@@ -103,6 +103,7 @@ struct gr_ctx {
   // int16 saturation rule (k_sat_resolve): per-cell sums of the suspect blocks, one bit per record, segment table,
   // and per sample the list of dropped records (arrival index << 1 | underflow) the host fetches for its warnings
   DevBuf satCells, satBits, satSegs, satList[2];
+  DevBuf b1Cnt, b1Base, b1Items;       // two-level bucketing: coarse-bin counters + cursors, their scan, the items grouped by coarse bin
   static const u32 SAT_LIST_CAP = 1u << 18;
   u64 n_sat[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };   // host mirror: dropped for overflow / underflow, list entries
   std::vector<u64> sat_list_h;
@@ -433,6 +434,7 @@ extern "C" void gr_destroy(gr_ctx* x) {
   x->dpar.release();
   x->dsums.release();
   x->unpack6.release();
+  x->b1Cnt.release(); x->b1Base.release(); x->b1Items.release();
   x->satCells.release(); x->satBits.release(); x->satSegs.release(); x->satList[0].release(); x->satList[1].release();
   x->ghk.release();
   x->ghl.release();
@@ -709,42 +711,65 @@ static int consume_segments(gr_ctx* x, int* built) {
     CK(x->satList[ctrl].ensure((size_t)gr_ctx::SAT_LIST_CAP * 8));
     CK(x->satSegs.ensure(x->segs.size() * sizeof(SatSeg) + 16));
     HT("consume: bucket buffers ensured");
-    stage_begin(x, "bucket", bytes);
-    CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4 + 64, x->stream));
-    for (auto& g : x->segs)
-      launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
-    HT("consume: memset + count launched");
-    launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, x->sbCnt.as<u32>(), nullptr, nullptr);
     u32* sat_flag = x->sbCnt.as<u32>() + nbk;
     u32* sat_res = (u32*)((char*)x->small.p + 40) + 3 * ctrl;
-    launch_sb_scan_a(x->stream, nbk, x->sbCnt.as<u32>(), x->sbSpillCtr.as<u32>() + 1, sat_flag);
+    // the segments in arrival order: the two-level bucketing walks them in one launch, the saturation rule needs the order
     {
-      // saveInterval's int16 saturation rule (2558-2573): one CTA that returns at once unless a block is
-      // full enough to hold a saturating cell; it needs the records in arrival order
       std::vector<SatSeg> sg(x->segs.size());
       u64 base = 0;
       for (size_t i = 0; i < sg.size(); i++) {
         sg[i].d = x->segs[i].d; sg[i].n = x->segs[i].n; sg[i].base = base; sg[i].packed = x->segs[i].rb == 8; sg[i].pad_ = 0;
         base += x->segs[i].n;
       }
-      { int r = upload(x, x->satSegs.p, sg.data(), sg.size() * sizeof(SatSeg)); if (r) return r; }
-      launch_sat_resolve(x->stream, sat_flag, x->satSegs.p, (int)sg.size(), x->L, x->sbCnt.as<u32>(),
-                         x->sbSpillCtr.as<u32>() + 1, x->satCells.p, x->satBits.as<u32>(), x->n_pushed,
-                         x->satList[ctrl].as<u64>(), gr_ctx::SAT_LIST_CAP, sat_res, x->d_err);
+      int r = upload(x, x->satSegs.p, sg.data(), sg.size() * sizeof(SatSeg));
+      if (r) return r;
     }
-    launch_sb_scan_b(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
-                     x->sbSpillCtr.as<u32>() + 1);
-    {
-      u64 base = 0;
-      for (auto& g : x->segs) {
-        launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(),
-                       sat_res, x->satBits.as<u32>(), base);
-        base += g.n;
+    const int nseg = (int)x->segs.size();
+    static const bool atomic_buckets = getenv("GR_BUCKET_ATOMIC") != nullptr;      // the one-level form (measurement / tests)
+    const int bsh = (x->has_bed || atomic_buckets) ? -1 : b1_bin_shift(nbk);
+    stage_begin(x, "bucket", bytes);
+    if (bsh >= 0) {
+      // two-level: shared-memory histograms and cursors only (-E contexts keep the one-level chain, which knows marks)
+      CK(x->b1Cnt.ensure(2 * 2048 * 4));
+      CK(x->b1Base.ensure(2049 * 4));
+      CK(x->b1Items.ensure(x->n_pushed * 16 + 16));
+      CK(cudaMemsetAsync(x->b1Cnt.p, 0, 2 * 2048 * 4, x->stream));
+      CK(cudaMemsetAsync(sat_flag, 0, 64, x->stream));
+      launch_bucket2(x->stream, x->L, x->satSegs.p, nseg, x->n_pushed, bsh, x->b1Cnt.as<u32>(), x->b1Cnt.as<u32>() + 2048,
+                     x->b1Base.as<u32>(), x->b1Items.as<u64>(), x->sbStart.as<u32>(), x->sbCnt.as<u32>(),
+                     x->sbBucket.as<u32>(), sat_flag, x->d_err, x->d_clamped);
+      // saveInterval's int16 saturation rule (2558-2573): one CTA that returns at once unless a block is full enough to
+      // hold a saturating cell; if it drops records (never in an ordinary sample) the buckets are made again without them
+      launch_sat_resolve(x->stream, sat_flag, x->satSegs.p, nseg, x->L, x->sbCnt.as<u32>(), x->sbSpillCtr.as<u32>() + 1,
+                         x->satCells.p, x->satBits.as<u32>(), x->n_pushed, x->satList[ctrl].as<u64>(),
+                         gr_ctx::SAT_LIST_CAP, sat_res, x->d_err, 0);
+      launch_fb_rebuild(x->stream, sat_res, x->satSegs.p, nseg, x->L, x->sbCnt.as<u32>(), x->sbStart.as<u32>(),
+                        x->sbBucket.as<u32>(), x->satBits.as<u32>());
+      CKL();
+    } else {
+      CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4 + 64, x->stream));
+      for (auto& g : x->segs)
+        launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
+      HT("consume: memset + count launched");
+      launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, x->sbCnt.as<u32>(), nullptr, nullptr);
+      launch_sb_scan_a(x->stream, nbk, x->sbCnt.as<u32>(), x->sbSpillCtr.as<u32>() + 1, sat_flag);
+      launch_sat_resolve(x->stream, sat_flag, x->satSegs.p, nseg, x->L, x->sbCnt.as<u32>(), x->sbSpillCtr.as<u32>() + 1,
+                         x->satCells.p, x->satBits.as<u32>(), x->n_pushed, x->satList[ctrl].as<u64>(),
+                         gr_ctx::SAT_LIST_CAP, sat_res, x->d_err, 1);
+      launch_sb_scan_b(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
+                       x->sbSpillCtr.as<u32>() + 1);
+      {
+        u64 base = 0;
+        for (auto& g : x->segs) {
+          launch_fb_move(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCursor.as<u32>(), x->sbBucket.as<u32>(),
+                         sat_res, x->satBits.as<u32>(), base);
+          base += g.n;
+        }
       }
+      launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, nullptr, x->sbCursor.as<u32>(), x->sbBucket.as<u32>());
+      HT("consume: scans + move launched");
+      CKL();
     }
-    launch_fb_marks(x->stream, x->bedMarks.as<u64>(), x->n_marks, nullptr, x->sbCursor.as<u32>(), x->sbBucket.as<u32>());
-    HT("consume: scans + move launched");
-    CKL();
     stage_end(x);
   } else if (sb) {
     CK(cudaMemsetAsync((char*)x->small.p + 40 + 12 * (x->filling == FILL_CTRL), 0, 12, x->stream));   // no record is dropped on this path

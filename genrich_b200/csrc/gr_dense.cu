@@ -10,6 +10,18 @@
 #include <math.h>
 #include <stdio.h>
 
+// Function attributes (the dynamic shared memory limit) are per DEVICE: a process that drives several contexts
+// (genrich-b200 --gpus N) sets them on each device it launches the kernel on.  which: one small number per kernel.
+static bool first_use_on_device(int which) {
+  static unsigned long long seen[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if (seen[which & 7] >> dev & 1ull) return false;
+  seen[which & 7] |= 1ull << dev;
+  return true;
+}
+
 // ============================================================================
 // K1: two int32 reductions (RED.ADD) per interval record into the dense delta
 // array, in units of 1/120 (weights 120/count, count in {1,2,3,4,5,6,8,10}:
@@ -725,9 +737,8 @@ static StreamWs stream_ws(const ScanScratch& sc, int nchrom) {
 template <int NSTAGE, int CPS>
 static void launch_scan_stream_t(cudaStream_t s, const DevLayout& L, int32_t* delta, const StreamWs& W,
                                  u32* bitmap, int* err, int zero_after, int sms) {
-  static bool init = false;
   const size_t smem = (size_t)16 * NSTAGE * 2048;
-  if (!init) { cudaFuncSetAttribute(k_scan_stream<NSTAGE, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); init = true; }
+  if (first_use_on_device(0 + NSTAGE)) cudaFuncSetAttribute(k_scan_stream<NSTAGE, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const u32 nwarps = (u32)scan_stream_warps();
   const u32 nspans = (u32)(L.T / 512);
   const u32 R = (nspans + nwarps - 1) / nwarps;
@@ -865,6 +876,293 @@ k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
   }
 }
 
+// ---- two-level bucketing ------------------------------------------------------------------------
+// k_fb_count / k_fb_move above pay one L2 atomic per entry and pass -- a RETURNING one in the move pass, and those
+// run at ~75 G/s on the B200 whatever the unroll (0.69 ms per 50 M records; the count pass's 0.33 ms on top).  Here
+// no per-entry atomic leaves the SM:
+//   k_b1_count    records -> entries per COARSE bin (2^bsh blocks each, <= 2048 bins): shared-memory histogram,
+//                 one global add per bin and CTA.  Reports errors and the clamp count.
+//   k_b1_scan     exclusive scan of the bin counts.
+//   k_b1_scatter  a tile of 4096 records (held in registers) is sorted by coarse bin in shared memory -- histogram,
+//                 scan, one global add per non-empty bin to reserve room, cursor scatter -- and written out in runs:
+//                 8-byte items (block << 32 | entry), grouped by coarse bin.
+//   k_b2          one CTA per coarse bin: items -> the exact per-block buckets with shared-memory counters only;
+//                 writes blk_start and blk_cnt on the way (the entries of a bin fill the index range of its items).
+// Output = what count -> scan -> move produce (entries of a bucket in another order, which no consumer depends on).
+#define B1_MAXB 2048
+#define B1_TILE 4096
+#define B1_NT 512
+#define B1_PER (B1_TILE / B1_NT)
+struct B1Tiles {                                     // the records of all segments as one sequence of tiles
+  const SatSeg* segs; int nseg;
+  __device__ __forceinline__ bool find(u64 flat_tile, int& g, u64& tile0, u64& lo) const {
+    // g / tile0: segment cursor kept by the caller (flat tiles are visited in increasing order)
+    while (g < nseg) {
+      const u64 nt = (segs[g].n + B1_TILE - 1) / B1_TILE;
+      if (flat_tile < tile0 + nt) { lo = (flat_tile - tile0) * B1_TILE; return true; }
+      tile0 += nt; g++;
+    }
+    return false;
+  }
+};
+// the (up to two) entries of a record: f(block, entry)
+template <class F>
+__device__ __forceinline__ void b1_entries(const SatSeg& sg, u64 i, const DevLayout& L, int& e_local, u32& c_local, F f) {
+  u64 s_slot; u32 span; int w;
+  const bool ok = sg.packed ? decode_record<true>(sg.d, i, L, s_slot, span, w, e_local, c_local)
+                            : decode_record<false>(sg.d, i, L, s_slot, span, w, e_local, c_local);
+  if (!ok) return;
+  const u64 e_slot = s_slot + span;
+  const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)(e_slot >> GR_BLOCK_SHIFT);
+  const u32 so = (u32)s_slot & (GR_BLOCK_SLOTS - 1);
+  const int cnt = 120 / w;
+  if (be != bs) {
+    f(bs, fb_entry(so, 0, cnt, FB_KIND_START));
+    f(be, fb_entry((u32)e_slot & (GR_BLOCK_SLOTS - 1), 0, cnt, FB_KIND_END));
+  } else
+    f(bs, fb_entry(so, span, cnt, FB_KIND_BOTH));
+}
+
+__global__ void __launch_bounds__(256)
+k_b1_count(B1Tiles T, DevLayout L, int bsh, u32 nbins, u32* __restrict__ cnt1, int* __restrict__ err,
+           u64* __restrict__ clamped) {
+  __shared__ u32 sm_h[B1_MAXB];
+  for (u32 i = threadIdx.x; i < nbins; i += 256) sm_h[i] = 0;
+  __syncthreads();
+  int e_local = 0;
+  u32 c_local = 0;
+  int g = 0;
+  u64 tile0 = 0, lo = 0;
+  for (u64 ft = blockIdx.x; T.find(ft, g, tile0, lo); ft += gridDim.x) {
+    const SatSeg sg = T.segs[g];
+    const u64 hi = min(lo + (u64)B1_TILE, sg.n);
+    for (u64 i = lo + threadIdx.x; i < hi; i += 256)
+      b1_entries(sg, i, L, e_local, c_local, [&](u32 blk, u32) { atomicAdd(&sm_h[blk >> bsh], 1u); });
+  }
+  __syncthreads();
+  for (u32 i = threadIdx.x; i < nbins; i += 256)
+    if (sm_h[i]) atomicAdd(cnt1 + i, sm_h[i]);
+  if (e_local) atomicOr(err, e_local);                 // errors and clamp counts are reported by this pass only
+  if (c_local) atomicAdd(clamped, (u64)c_local);
+}
+
+// base1[0 .. nbins]: exclusive scan of cnt1 (<= 2048 counters)
+__global__ void __launch_bounds__(1024)
+k_b1_scan(const u32* __restrict__ cnt1, u32 nbins, u32* __restrict__ base1) {
+  __shared__ u32 sh[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const u32 a = (u32)(2 * t) < nbins ? cnt1[2 * t] : 0u, b = (u32)(2 * t + 1) < nbins ? cnt1[2 * t + 1] : 0u;
+  const u32 v = a + b;
+  const u32 wi = warp_incl_scan_u32(v, lane);
+  if (lane == 31) sh[w] = wi;
+  __syncthreads();
+  if (w == 0) {
+    const u32 x = sh[lane];
+    const u32 xi = warp_incl_scan_u32(x, lane);
+    sh[lane] = xi - x;
+  }
+  __syncthreads();
+  const u32 ex = sh[w] + wi - v;
+  if ((u32)(2 * t) < nbins) base1[2 * t] = ex;
+  if ((u32)(2 * t + 1) < nbins) base1[2 * t + 1] = ex + a;
+  if ((u32)(2 * t) < nbins && (u32)(2 * t + 2) >= nbins) base1[nbins] = ex + v;
+}
+
+struct B1Smem { u64 item[2 * B1_TILE]; u32 cur[B1_MAXB], lstart[B1_MAXB], gbase[B1_MAXB]; u32 wsum[B1_NT / 32]; };
+__global__ void __launch_bounds__(B1_NT, 2)
+k_b1_scatter(B1Tiles T, DevLayout L, int bsh, u32 nbins, const u32* __restrict__ base1, u32* __restrict__ gcur,
+             u64* __restrict__ items) {
+  extern __shared__ int4 b1_raw[];
+  B1Smem& S = *reinterpret_cast<B1Smem*>(b1_raw);
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  int e_local = 0;
+  u32 c_local = 0;
+  int g = 0;
+  u64 tile0 = 0, lo = 0;
+  for (u64 ft = blockIdx.x; T.find(ft, g, tile0, lo); ft += gridDim.x) {
+    const SatSeg sg = T.segs[g];
+    const u64 hi = min(lo + (u64)B1_TILE, sg.n);
+    for (u32 i = t; i < nbins; i += B1_NT) S.cur[i] = 0;
+    // the tile's records stay in registers between the two passes over them
+    int4 r[B1_PER];
+    bool on[B1_PER];
+#pragma unroll
+    for (int k = 0; k < B1_PER; k++) {
+      const u64 i = lo + (u64)k * B1_NT + t;
+      on[k] = i < hi;
+      if (on[k]) r[k] = sg.packed ? load_raw<true>(sg.d, i) : load_raw<false>(sg.d, i);
+    }
+    auto each = [&](int k, auto f) {
+      if (!on[k]) return;
+      u64 s_slot; u32 span; int w;
+      const bool ok = sg.packed ? decode_raw<true>(r[k], L, s_slot, span, w, e_local, c_local)
+                                : decode_raw<false>(r[k], L, s_slot, span, w, e_local, c_local);
+      if (!ok) return;
+      const u64 e_slot = s_slot + span;
+      const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)(e_slot >> GR_BLOCK_SHIFT);
+      const u32 so = (u32)s_slot & (GR_BLOCK_SLOTS - 1);
+      const int cnt = 120 / w;
+      if (be != bs) {
+        f(bs, fb_entry(so, 0, cnt, FB_KIND_START));
+        f(be, fb_entry((u32)e_slot & (GR_BLOCK_SLOTS - 1), 0, cnt, FB_KIND_END));
+      } else
+        f(bs, fb_entry(so, span, cnt, FB_KIND_BOTH));
+    };
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < B1_PER; k++) each(k, [&](u32 blk, u32) { atomicAdd(&S.cur[blk >> bsh], 1u); });
+    __syncthreads();
+    // exclusive scan of the tile's bin counts (4 per thread), room reserved in the bins' global ranges
+    {
+      u32 c[4], sum = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) { const u32 b = (u32)t * 4 + q; c[q] = b < nbins ? S.cur[b] : 0u; sum += c[q]; }
+      const u32 wi = warp_incl_scan_u32(sum, lane);
+      if (lane == 31) S.wsum[wid] = wi;
+      __syncthreads();
+      u32 ex = wi - sum;
+      for (int q = 0; q < wid; q++) ex += S.wsum[q];
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const u32 b = (u32)t * 4 + q;
+        if (b < nbins) {
+          S.lstart[b] = ex;
+          S.cur[b] = ex;
+          if (c[q]) S.gbase[b] = base1[b] + atomicAdd(gcur + b, c[q]);
+        }
+        ex += c[q];
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < B1_PER; k++)
+      each(k, [&](u32 blk, u32 e) { S.item[atomicAdd(&S.cur[blk >> bsh], 1u)] = ((u64)blk << 32) | e; });
+    __syncthreads();
+    const u32 nitems = S.cur[nbins - 1];               // the last bin's cursor ends at the tile's item count
+    for (u32 j = t; j < nitems; j += B1_NT) {
+      const u64 it = S.item[j];
+      const u32 b = (u32)(it >> 32) >> bsh;
+      items[(u64)S.gbase[b] + (j - S.lstart[b])] = it;
+    }
+    __syncthreads();                                   // the tile's buffers are free again
+  }
+  (void)e_local; (void)c_local;                        // reported by the count pass
+}
+
+// one CTA per coarse bin
+__global__ void __launch_bounds__(512)
+k_b2(const u64* __restrict__ items, const u32* __restrict__ base1, int bsh, u32 nbins, u32 nblocks,
+     u32* __restrict__ blk_start, u32* __restrict__ blk_cnt, u32* __restrict__ bucketed, u32* __restrict__ sat_flag) {
+  __shared__ u32 sm_c[1024];
+  __shared__ u32 sm_w[16];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const u32 bin = blockIdx.x, F = 1u << bsh, blk0 = bin << bsh;
+  const u32 a = base1[bin], b = base1[bin + 1];
+  for (u32 i = t; i < F; i += 512) sm_c[i] = 0;
+  __syncthreads();
+  for (u32 i = a + t; i < b; i += 512) atomicAdd(&sm_c[(u32)(items[i] >> 32) - blk0], 1u);
+  __syncthreads();
+  // exclusive scan of the F block counts: two consecutive counters per thread (F <= 1024)
+  const u32 c0 = (u32)(2 * t) < F ? sm_c[2 * t] : 0u, c1 = (u32)(2 * t + 1) < F ? sm_c[2 * t + 1] : 0u;
+  const u32 s = c0 + c1;
+  const u32 wi = warp_incl_scan_u32(s, lane);
+  if (lane == 31) sm_w[w] = wi;
+  __syncthreads();
+  if (w == 0) {
+    const u32 x = lane < 16 ? sm_w[lane] : 0u;
+    const u32 xi = warp_incl_scan_u32(x, lane);
+    if (lane < 16) sm_w[lane] = xi - x;
+  }
+  __syncthreads();
+  const u32 run = a + sm_w[w] + wi - s;
+  if ((u32)(2 * t) < F) {
+    const u32 blk = blk0 + 2 * t;
+    if (blk < nblocks) { blk_start[blk] = run; blk_cnt[blk] = c0; }
+    sm_c[2 * t] = run;                                 // becomes the bucket's cursor
+  }
+  if ((u32)(2 * t + 1) < F) {
+    const u32 blk = blk0 + 2 * t + 1;
+    if (blk < nblocks) { blk_start[blk] = run + c0; blk_cnt[blk] = c1; }
+    sm_c[2 * t + 1] = run + c0;
+  }
+  if ((c0 >= SAT_MIN_EVENTS || c1 >= SAT_MIN_EVENTS) && sat_flag) atomicOr(sat_flag, 1u);   // k_sat_resolve has work
+  if (bin == nbins - 1 && t == 0) blk_start[nblocks] = b;
+  __syncthreads();
+  for (u32 i = a + t; i < b; i += 512) {
+    const u64 it = items[i];
+    bucketed[atomicAdd(&sm_c[(u32)(it >> 32) - blk0], 1u)] = (u32)it;
+  }
+}
+
+// Records were dropped by k_sat_resolve (sat_res says so; never in an ordinary sample): the buckets are made
+// again without them -- one CTA, global counters, in no hurry.
+__global__ void __launch_bounds__(1024)
+k_fb_rebuild(const u32* __restrict__ sat_res, const SatSeg* __restrict__ segs, int nseg, DevLayout L,
+             u32* __restrict__ blk_cnt, u32* __restrict__ blk_start, u32* __restrict__ bucketed,
+             const u32* __restrict__ skip_bits, u32 nblocks) {
+  if (!(sat_res[0] | sat_res[1])) return;
+  __shared__ u32 sm_run;
+  const int t = threadIdx.x;
+  for (u32 b = t; b < nblocks; b += 1024) blk_cnt[b] = 0;
+  __threadfence();
+  __syncthreads();
+  int e_local = 0;
+  u32 c_local = 0;
+  for (int g = 0; g < nseg; g++) {
+    const SatSeg sg = segs[g];
+    for (u64 i = t; i < sg.n; i += 1024) {
+      const u64 gi = sg.base + i;
+      if ((skip_bits[gi >> 5] >> (gi & 31)) & 1u) continue;
+      b1_entries(sg, i, L, e_local, c_local, [&](u32 blk, u32) { atomicAdd(blk_cnt + blk, 1u); });
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (t == 0) {                                        // exclusive scan; blk_cnt becomes the cursor
+    u32 run = 0;
+    for (u32 b = 0; b < nblocks; b++) { const u32 c = blk_cnt[b]; blk_start[b] = run; blk_cnt[b] = run; run += c; }
+    blk_start[nblocks] = run;
+    sm_run = run;
+  }
+  __threadfence();
+  __syncthreads();
+  for (int g = 0; g < nseg; g++) {
+    const SatSeg sg = segs[g];
+    for (u64 i = t; i < sg.n; i += 1024) {
+      const u64 gi = sg.base + i;
+      if ((skip_bits[gi >> 5] >> (gi & 31)) & 1u) continue;
+      b1_entries(sg, i, L, e_local, c_local, [&](u32 blk, u32 e) { bucketed[atomicAdd(blk_cnt + blk, 1u)] = e; });
+    }
+  }
+  (void)sm_run;
+}
+
+int b1_bin_shift(u64 nblocks) {                        // coarse bins of 2^bsh blocks: at most 1024 of them (2048 at 2^10 blocks per bin)
+  int bsh = 0;
+  while (((nblocks + (1ull << bsh) - 1) >> bsh) > 1024 && bsh < 10) bsh++;
+  return ((nblocks + (1ull << bsh) - 1) >> bsh) <= B1_MAXB ? bsh : -1;
+}
+// cnt1 / gcur: nbins words each, zeroed by the caller; base1: nbins + 1 words; items: one 8-byte word per entry
+void launch_bucket2(cudaStream_t s, const DevLayout& L, const void* segs, int nseg, u64 n_records, int bsh,
+                    u32* cnt1, u32* gcur, u32* base1, u64* items, u32* blk_start, u32* blk_cnt, u32* bucketed,
+                    u32* sat_flag, int* err, u64* clamped) {
+  if (first_use_on_device(5)) cudaFuncSetAttribute(k_b1_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(B1Smem));
+  const u32 nbins = (u32)((L.nblocks + (1ull << bsh) - 1) >> bsh);
+  B1Tiles T;
+  T.segs = (const SatSeg*)segs; T.nseg = nseg;
+  const u64 tiles = (n_records + B1_TILE - 1) / B1_TILE + (u64)nseg;
+  k_b1_count<<<(unsigned)(tiles < 148 * 8 ? tiles : 148 * 8), 256, 0, s>>>(T, L, bsh, nbins, cnt1, err, clamped); GR_NOTE_LAUNCH();
+  k_b1_scan<<<1, 1024, 0, s>>>(cnt1, nbins, base1); GR_NOTE_LAUNCH();
+  k_b1_scatter<<<(unsigned)(tiles < 148 * 2 ? tiles : 148 * 2), B1_NT, sizeof(B1Smem), s>>>(T, L, bsh, nbins, base1, gcur, items);
+  GR_NOTE_LAUNCH();
+  k_b2<<<nbins, 512, 0, s>>>(items, base1, bsh, nbins, (u32)L.nblocks, blk_start, blk_cnt, bucketed, sat_flag); GR_NOTE_LAUNCH();
+}
+void launch_fb_rebuild(cudaStream_t s, const u32* sat_res, const void* segs, int nseg, const DevLayout& L, u32* blk_cnt,
+                       u32* blk_start, u32* bucketed, const u32* skip_bits) {
+  k_fb_rebuild<<<1, 1024, 0, s>>>(sat_res, (const SatSeg*)segs, nseg, L, blk_cnt, blk_start, bucketed, skip_bits, (u32)L.nblocks);
+  GR_NOTE_LAUNCH();
+}
+
 // ---- the reference's int16 saturation rule (saveInterval, Genrich.c:2558-2573) -------------------
 // The reference keeps (int16 cov, 8-bit frac) per delta cell and, IN ARRIVAL ORDER, drops an interval
 // whole when the cell of its start already holds cov == INT16_MAX, else when the cell of its end holds
@@ -894,7 +1192,7 @@ __global__ void __launch_bounds__(1024)
 k_sat_resolve(const u32* __restrict__ flag, const SatSeg* __restrict__ segs, int nseg, DevLayout L,
               u32* __restrict__ blk_cnt, u32* __restrict__ chunk_sum, u32 nblocks, ulonglong2* __restrict__ cells,
               u32* __restrict__ skip_bits, u64 nbits, u64* __restrict__ list, u32 list_cap, u32* __restrict__ sat_res,
-              int* __restrict__ err) {
+              int* __restrict__ err, int patch /* 1: take the dropped records out of blk_cnt / chunk_sum (the scan follows) */) {
   __shared__ u32 sm_sb[SAT_MAX_BLOCKS];
   __shared__ u32 sm_nsb, sm_nhot, sm_pend_n;
   __shared__ u32 sm_wcnt[32];
@@ -992,8 +1290,10 @@ k_sat_resolve(const u32* __restrict__ flag, const SatSeg* __restrict__ segs, int
           if (kind) n_under++; else n_over++;
           if (n_list < list_cap) list[n_list++] = (gi << 1) | (u64)kind;
           const u32 xs = sm_pend[k].bs, xe = sm_pend[k].be;
-          blk_cnt[xs] -= 1u; chunk_sum[xs / SB_CHUNK] -= 1u;
-          if (xe != xs) { blk_cnt[xe] -= 1u; chunk_sum[xe / SB_CHUNK] -= 1u; }
+          if (patch) {
+            blk_cnt[xs] -= 1u; chunk_sum[xs / SB_CHUNK] -= 1u;
+            if (xe != xs) { blk_cnt[xe] -= 1u; chunk_sum[xe / SB_CHUNK] -= 1u; }
+          }
         }
       }
       __syncthreads();
@@ -1002,9 +1302,10 @@ k_sat_resolve(const u32* __restrict__ flag, const SatSeg* __restrict__ segs, int
   if (t == 0) { sat_res[0] = n_over; sat_res[1] = n_under; sat_res[2] = n_list; }
 }
 void launch_sat_resolve(cudaStream_t s, const u32* flag, const void* segs, int nseg, const DevLayout& L, u32* blk_cnt,
-                        u32* chunk_sum, void* cells, u32* skip_bits, u64 nbits, u64* list, u32 list_cap, u32* sat_res, int* err) {
+                        u32* chunk_sum, void* cells, u32* skip_bits, u64 nbits, u64* list, u32 list_cap, u32* sat_res, int* err,
+                        int patch) {
   k_sat_resolve<<<1, 1024, 0, s>>>(flag, (const SatSeg*)segs, nseg, L, blk_cnt, chunk_sum, (u32)L.nblocks, (ulonglong2*)cells,
-                                   skip_bits, nbits, list, list_cap, sat_res, err);
+                                   skip_bits, nbits, list, list_cap, sat_res, err, patch);
   GR_NOTE_LAUNCH();
 }
 
@@ -1746,8 +2047,7 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
   const double per_blk = 2.0 * (double)n_records / (double)(nb ? nb : 1);
   const bool dense_blocks = 8192.0 * (1.0 - exp(-per_blk / 8192.0)) > (double)fb_env("GR_FUSED_CTA_CELLS", 768);
   if (!blk_bed && !fb_env("GR_FUSED_CTA", 0) && (dense_blocks || fb_env("GR_FUSED_DENSE", 0))) {
-    static bool init = false;
-    if (!init) { cudaFuncSetAttribute(k_fd_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FdSmem)); init = true; }
+    if (first_use_on_device(4)) cudaFuncSetAttribute(k_fd_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FdSmem));
     owners = (u32)(sms * 3);
     const u32 R = (nb + owners - 1) / owners;
     k_fd_scan<<<owners, FD_NT, sizeof(FdSmem), s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);

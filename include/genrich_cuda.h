@@ -279,7 +279,7 @@ int gr_peaks_device(gr_ctx* ctx, const gr_peak** d_peaks, uint64_t* n);
 /* gr_call_peaks in two halves, for launchers that gather several contexts' peaks with ONE wait for the device
  * (one process per GPU: an NCCL all-gather of every rank's slot).  gr_call_peaks_enqueue runs the peak scan
  * without waiting and hands out the device address of a SLOT: a 64-byte gr_peak_slot header, which the device
- * fills in stream order, followed by record_cap gr_peak records.  The caller moves the first 64 + 32 k bytes
+ * fills in stream order, followed by record_cap gr_peak records.  The caller moves the first 64 + k * sizeof(gr_peak) bytes
  * wherever it wants them on gr_stream(ctx), waits once, and passes the header as it reads on the host to
  * gr_call_peaks_done.  redo = 1: a buffer was too small, enqueue again; redo = 2: call gr_call_peaks instead
  * (rare: a table overflowed).  With -q the histogram exchange (gr_bh_local_hist / gr_bh_set_global) comes first. */

@@ -30,6 +30,8 @@ def _free_port():
 
 
 def _worker(rank, world, port, case_name, out_dir, want_stats):
+    import faulthandler
+    faulthandler.enable()
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)
     td.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
