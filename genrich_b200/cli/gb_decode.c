@@ -488,6 +488,21 @@ static size_t qname_len(const char* p, const char* end) {
   return t ? (size_t)(t - p) : (size_t)(end - p);
 }
 
+/* would sam_record keep this line for an alignment set?  (flag 0x4 / 0xE00 and MAPQ as in loadFields' callers, 4541-4557) */
+static bool line_kept(const char* p, const char* end, int min_mapq) {
+  const char* f = p;
+  long v[5] = { 0, 0, 0, 0, 0 };                         /* fields 2 (flag) and 5 (MAPQ) are numbers */
+  for (int i = 0; i < 5; i++) {
+    const char* t = (const char*)memchr(f, '\t', (size_t)(end - f));
+    if (!t) return false;
+    if (i == 1 || i == 4) v[i] = strtol(f, NULL, 10);
+    f = t + 1;
+  }
+  if (v[1] & 0x4) return false;
+  if (v[1] & 0xE00) return false;
+  return v[4] >= min_mapq;
+}
+
 static void list_append(HReadList* dst, HReadList* src) {
   if (!src->n) { free(src->r); return; }
   if (dst->n + src->n > dst->cap) {
@@ -526,22 +541,36 @@ static bool decode_sam_threads(HDecode* d, const char* path, int nthreads) {
     sam_header_line(line, d->tab, d->ctrl, d->opt);
   }
   free(line);
-  /* cuts: at a line start whose read name differs from the line before */
+  /* cuts: between two alignment sets.  readSAM starts a new set only at a KEPT record whose name differs from the
+   * previous kept record's (4559-4566: unmapped, supplementary and low-MAPQ lines are dropped before the name is
+   * looked at), so a cut is moved forward until the nearest kept lines on its two sides carry different names --
+   * also in a file whose lines are only loosely grouped (-S). */
   const char** cut = (const char**)gb_alloc((size_t)(nthreads + 1) * sizeof(char*));
   cut[0] = p;
   cut[nthreads] = end;
   for (int k = 1; k < nthreads; k++) {
     const char* q = p + (size_t)(end - p) / (size_t)nthreads * (size_t)k;
     if (q < cut[k - 1]) q = cut[k - 1];
-    /* back to the start of the line that holds q, then forward while the name repeats */
-    while (q > p && q[-1] != '\n') q--;
+    while (q > p && q[-1] != '\n') q--;                  /* the start of the line that holds q */
     while (q < end && q > p) {
-      const char* prev = q - 1;                         /* the newline that ends the previous line */
-      while (prev > p && prev[-1] != '\n') prev--;
-      const size_t a = qname_len(prev, end), b = qname_len(q, end);
-      if (a != b || memcmp(prev, q, a)) break;
-      const char* nl = (const char*)memchr(q, '\n', (size_t)(end - q));
-      q = nl ? nl + 1 : end;
+      const char* prev = q;                              /* nearest kept line before the cut */
+      bool have_prev = false;
+      while (prev > p) {
+        const char* s0 = prev - 1;
+        while (s0 > p && s0[-1] != '\n') s0--;
+        prev = s0;
+        if (line_kept(prev, end, d->opt->min_mapq)) { have_prev = true; break; }
+      }
+      const char* next = q;                              /* nearest kept line at or after the cut */
+      while (next < end && !line_kept(next, end, d->opt->min_mapq)) {
+        const char* nl = (const char*)memchr(next, '\n', (size_t)(end - next));
+        next = nl ? nl + 1 : end;
+      }
+      if (!have_prev || next >= end) break;
+      const size_t a = qname_len(prev, end), b = qname_len(next, end);
+      if (a != b || memcmp(prev, next, a)) break;        /* different sets on the two sides: cut here */
+      const char* nl = (const char*)memchr(next, '\n', (size_t)(end - next));
+      q = nl ? nl + 1 : end;                             /* same set: the cut moves behind that line */
     }
     cut[k] = q;
   }

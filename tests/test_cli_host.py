@@ -331,3 +331,33 @@ def test_host_saturation_rule(twin, threads, tmp_path, monkeypatch):
     assert _sha(logf) == (meta["log_sha256"], meta["log_lines"])
     assert _sha(pile, True) == (meta["pile_sha256"], meta["pile_lines"])
     assert hashlib.sha256(r.stderr.replace(sam, "T.sam").encode()).hexdigest() == meta["verbose_sha256"]
+
+
+def test_threaded_decode_loosely_grouped(twin, tmp_path, monkeypatch):
+    """A file whose alignment sets are interleaved with unmapped lines of OTHER names (A, x unmapped, A): readSAM
+    never looks at the name of a dropped line, so both A lines are one set.  The threaded decoder cuts the file
+    between kept-record sets -- same output with 1 and with 5 workers (and as the reference, where it is built)."""
+    monkeypatch.setenv("GB_THREAD_MIN_BYTES", "1")
+    case = BY_NAME["c2_ctrl_p"]
+    td = str(tmp_path)
+    tfiles, cfiles = util.write_case_sams(case, td)
+    loose = os.path.join(td, "loose.sam")
+    with open(tfiles[0]) as f, open(loose, "w") as g:
+        n = 0
+        for line in f:
+            g.write(line)
+            if not line.startswith("@"):
+                n += 1
+                if n % 2 == 1:                 # between the two mates of every pair
+                    g.write("u%d\t4\t*\t0\t0\t*\t*\t0\t0\t*\t*\n" % n)
+    outs = []
+    for th in (1, 5):
+        o = os.path.join(td, "o%d.np" % th)
+        subprocess.check_call([twin, "-t", loose, "-c", cfiles[0], "-o", o, "-S", "--threads", str(th)] + case.ref_args())
+        outs.append(open(o).read())
+    assert outs[0] == outs[1] and len(outs[0]) > 0
+    ref = os.path.join(util.ORACLE_DIR, "_ref", "Genrich")
+    if os.path.exists(ref):
+        o = os.path.join(td, "ref.np")
+        subprocess.check_call([ref, "-t", loose, "-c", cfiles[0], "-o", o, "-S"] + case.ref_args(), stderr=subprocess.DEVNULL)
+        assert open(o).read() == outs[0]
