@@ -623,7 +623,7 @@ def main():
                             "identical_to_single_context": bool(got.tobytes() == want.tobytes()),
                             "distinct_p": int(mrs.n_distinct_p), "hist_allgather_bytes": int(meng.hist_bytes)}
             assert shard_parity["identical_to_single_context"], "sharded run differs from the single-context run"
-        meng.ctx.close()
+        meng.close()
         del meng
 
     eng = ShardedEngine(api, L, par, dev, host_group=host_group)
@@ -734,13 +734,14 @@ def main():
                 del os.environ[k]
             assert peaks_d.tobytes() == peaks.tobytes(), "%s and default formulations disagree" % key
             forms[key] = (ms_d, st_d)
-            eng_d.ctx.close()
+            eng_d.close()
             del eng_d
     dense, cta = forms.get("dense_array"), forms.get("cta")
 
     if eng.debug:
         print("rank %d host-side ms per step (e2e arm): %s" % (rank, host_phase), file=sys.stderr, flush=True)
     if rank != 0:
+        eng.close()
         if world > 1:
             td.destroy_process_group()
         return
@@ -843,6 +844,7 @@ def main():
         line["bh"] = {"distinct_p": int(rs.n_distinct_p), "hist_allgather_bytes_per_step": int(hist_bytes),
                       "stage_ms": {k: stage_ms.get(k) for k in ("bh_hist", "bh")},
                       "host_phase_ms": {k: host_phase_dev.get(k) for k in ("bh_sizes", "bh_allgather", "bh_exchange_and_q")}}
+    eng.close()                                    # torch objects first, then the context and its stream
     if world > 1:
         td.destroy_process_group()                 # nothing below involves the other ranks
     have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "Genrich"))

@@ -211,22 +211,41 @@ class ShardedEngine:
             return keys, lens
         m = (max(max(sizes), 1) + 1) & ~1                   # even: the lens part of a slot stays 8-byte aligned
         slot = 12 * m
+        tot = sum(sizes)
         if self._ext_stream is None:
             self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=self.device)
+        # The buffers are allocated HERE, on torch's current stream, and kept until the next exchange: memory that
+        # the caching allocator ties to the library's stream would outlive that stream when the context is closed.
+        send = torch.zeros(slot, dtype=torch.uint8, device=self.device)
+        recv = torch.empty(self.world * slot, dtype=torch.uint8, device=self.device)
+        keys_all = torch.empty(max(tot, 1), dtype=torch.int32, device=self.device)
+        lens_all = torch.empty(max(tot, 1), dtype=torch.int64, device=self.device)
+        torch.cuda.current_stream(self.device).synchronize()   # the zero fill is done before the other stream writes
         with torch.cuda.stream(self._ext_stream):
-            send = torch.zeros(slot, dtype=torch.uint8, device=self.device)
-            recv = torch.empty(self.world * slot, dtype=torch.uint8, device=self.device)
             if n:
                 send[:4 * n].view(torch.int32).copy_(keys)
                 send[4 * m:4 * m + 8 * n].view(torch.int64).copy_(lens)
             td.all_gather_into_tensor(recv, send)            # NCCL over NVLink, on the library's stream
             rv = recv.view(self.world, slot)
-            keys = torch.cat([rv[r, :4 * s].view(torch.int32) for r, s in enumerate(sizes)]).contiguous()
-            lens = torch.cat([rv[r, 4 * m:4 * m + 8 * s].view(torch.int64) for r, s in enumerate(sizes)]).contiguous()
+            at = 0
+            for r, sz in enumerate(sizes):
+                if sz:
+                    keys_all[at:at + sz].copy_(rv[r, :4 * sz].view(torch.int32))
+                    lens_all[at:at + sz].copy_(rv[r, 4 * m:4 * m + 8 * sz].view(torch.int64))
+                at += sz
         self._hist_keep = (send, recv)                       # stay alive until the next exchange
         self.hist_bytes = self.world * slot
         self._tick("bh_allgather", t0)
-        return keys, lens
+        return keys_all[:tot], lens_all[:tot]
+
+    def close(self):
+        """Release what refers to the library's stream and buffers, THEN the context (its stream goes with it)."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)
+        self._keep = self._hist_keep = self._send = self._recv = self._host = self._dsums = None
+        self._ext_stream = None
+        self._slot_bytes = 0
+        self.ctx.close()
 
     def _gather_peaks_one_wait(self):
         """CUDA, several ranks: the peak scan is enqueued (gr_call_peaks_enqueue), every rank's slot -- a 64-byte

@@ -47,6 +47,7 @@ def _worker(rank, world, port, case_name, out_dir, want_stats):
     peaks, rs = eng.call_peaks()
     if rank == 0:
         np.save(os.path.join(out_dir, "peaks.npy"), peaks)
+    eng.close()                              # torch's views of the library's stream and buffers go before the context
     td.destroy_process_group()
 
 
