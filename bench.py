@@ -725,8 +725,8 @@ def main():
     #   cta    (GR_FUSED_CTA=1): k_fb_scan, the CTA-owned shared-memory cell array that was the default in round 1
     forms = {}
     if world == 1 and not a.no_dense and G < (1 << 32):
-        for key, env in (("dense_array", {"GR_FUSED": "0"}), ("cta", {"GR_FUSED_CTA": "1"}),
-                         ("rank", {"GR_FUSED_CTA_CELLS": "1000000"}), ("dense_cells", {"GR_FUSED_DENSE": "1"})):
+        for key, env in (("dense_array", {"GR_FUSED": "0"}), ("cta", {"GR_FUSED_CTA": "1"}), ("rank", {"GR_FUSED_RANK": "1"})) + \
+                ((("dense_cells", {"GR_FUSED_DENSE": "1"}),) if os.environ.get("GR_BENCH_FD") else ()):
             os.environ.update(env)
             eng_d = ShardedEngine(api, L, par, dev, host_group=None)
             ms_d, _, _, peaks_d, _, st_d = timed(False, st_steps, 3, with_stages=True, eng=eng_d)
@@ -750,9 +750,9 @@ def main():
     peak_gbs, peak_src = measured_peak_gbs()
     fused = "fused_scan" in stages
     cells = sum((int(l) + 1 + 8191) // 8192 * 8192 for l, o in zip(L, eng.owned) if o)
-    per_blk = 2.0 * (n_records / max(n_samples, 1)) / max(cells / 8192, 1)
-    deep = 8192.0 * (1.0 - np.exp(-per_blk / 8192.0)) > float(os.environ.get("GR_FUSED_CTA_CELLS", "768"))
-    scan_kernel = ("k_fd_scan" if deep else "k_fr_scan") if fused else "k_scan_stream"
+    # the scan form the LAST sample of the step chose on the device (both kernels are launched, one returns at once)
+    form, hot_entries, all_entries = ctx.scan_form()
+    scan_kernel = ("k_fb_scan" if form == 1 else "k_fr_scan") if fused else "k_scan_stream"
     scan_ms, scan_launches, _ = stages.get("fused_scan" if fused else "dense_scan", (0.0, 0, 0))
     per_launch_ms = scan_ms / max(scan_launches, 1)          # mean over every launch of the staged pass
     place_ms, place_launches, _ = stages.get("scan_place", (0.0, 0, 0))
@@ -771,8 +771,8 @@ def main():
                             "GR_FUSED=0: the delta array is written to HBM by k_sb_build and read back by k_scan_stream "
                             "(4 B per cell each way: here `achieved` IS the HBM read rate); same peaks, bit for bit")
     cta_obj = formulation("k_fb_scan", cta, "fused_scan", "GR_FUSED_CTA=1: round 1's default scan; same peaks, bit for bit")
-    rank_obj = formulation("k_fr_scan", forms.get("rank"), "fused_scan", "rank form forced (GR_FUSED_CTA_CELLS huge): the default for sparse blocks")
-    cells_obj = formulation("k_fd_scan", forms.get("dense_cells"), "fused_scan", "GR_FUSED_DENSE=1: the dense form, the default for deep samples")
+    rank_obj = formulation("k_fr_scan", forms.get("rank"), "fused_scan", "GR_FUSED_RANK=1: the rank form whatever the blocks hold")
+    cells_obj = formulation("k_fd_scan", forms.get("dense_cells"), "fused_scan", "GR_FUSED_DENSE=1: bulk-copy staged cell array (measurement only)")
 
     # what really moves through DRAM: per kernel, from the committed ncu pass of `bench.py --profile` on this workload
     table = load_dram_table(a.workload, world)
@@ -784,12 +784,12 @@ def main():
                 "frac_info": info / (ms_dev * 1e-3) / 1e9 / peak_gbs if peak_gbs else None}
     if table is not None:
         ks = table["kernels"]
-        if scan_kernel not in ks:
-            raise SystemExit("profiles/r02_dram_by_stage.json has no entry for %s on %s: re-run tools/ncu_dram_by_stage.py" %
-                             (scan_kernel, a.workload))
-        k = ks[scan_kernel]
-        traffic = (k["dram_read"] + k["dram_write"]) / max(k["launches"], 1)
-        frac_dram = traffic / (per_launch_ms * 1e-3) / 1e9 / peak_gbs if per_launch_ms else None
+        # the kernel that did not run is in the table too (it returns at once: a few KB); a table taken before a
+        # change of the chosen form has no useful entry: traffic stays null rather than quote another kernel's bytes
+        k = ks.get(scan_kernel)
+        if k is not None and k["launches"]:
+            traffic = (k["dram_read"] + k["dram_write"]) / max(k["launches"], 1)
+            frac_dram = traffic / (per_launch_ms * 1e-3) / 1e9 / peak_gbs if per_launch_ms else None
         tot = sum(v["dram_read"] + v["dram_write"] for v in ks.values())
         step_obj.update({"dram_bytes": int(tot), "frac_dram": tot / (ms_dev * 1e-3) / 1e9 / peak_gbs,
                          "dram_bytes_by_kernel": {n: int(v["dram_read"] + v["dram_write"]) for n, v in
@@ -820,8 +820,12 @@ def main():
                      "peak_source": peak_src, "bytes_per_launch": 4 * cells, "ms_per_launch": per_launch_ms,
                      "companion_scan_place_ms_per_launch": place_ms / max(place_launches, 1),
                      "launches_per_step": scan_launches / st_steps, "samples_scanned_per_step": n_samples,
+                     "scan_form": {"chosen": scan_kernel, "entries_in_full_blocks": int(hot_entries), "entries": int(all_entries),
+                                   "rule": "chosen on the device per sample: CTA form when a quarter of the entries lie in blocks of "
+                                           ">= 1024 entries, else rank form; both kernels are launched, the other returns at once "
+                                           "(its launch is inside ms_per_launch)"},
                      "note": "`achieved` / `frac` divide the ALGORITHMIC bytes of the per-base pass (SURVEY 8d: 4 B per base per "
-                             "sample array) by the launch time.  The delta cells of k_fr_scan never exist in HBM (bucketed events "
+                             "sample array) by the launch time.  The delta cells of the fused scan never exist in HBM (bucketed events "
                              "in, breaks and a bitmap out), so frac > 1 is not a bandwidth claim: `traffic` / `frac_dram` say what "
                              "the kernel really moves, `step` what the whole step moves, `dense_formulation` what the kernel that "
                              "does read 4 B per cell achieves",

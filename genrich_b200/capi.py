@@ -73,7 +73,7 @@ ABI_SYMBOLS = [
     "gr_replicate_end", "gr_pvalues_finalize", "gr_bh_local_hist",
     "gr_bh_set_global", "gr_bh_local_hist_host", "gr_bh_set_global_host", "gr_load_pvalues", "gr_call_peaks", "gr_call_peaks_enqueue", "gr_call_peaks_done", "gr_peaks_device", "gr_merge_peaks", "gr_fetch_intervals",
     "gr_timing_enable", "gr_timing_get", "gr_timing_reset",
-    "gr_kernel_launches", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
+    "gr_kernel_launches", "gr_scan_form", "gr_synchronize", "gr_timer_start", "gr_timer_stop",
     "gr_pinned_alloc", "gr_pinned_free",
 ]
 
@@ -150,6 +150,7 @@ class Api:
             self.timing_get = fn("timing_get", C.c_int, [vp, C.POINTER(GrStageTime), i32, C.POINTER(i32)])
             self.timing_reset = fn("timing_reset", C.c_int, [vp])
             self.kernel_launches = fn("kernel_launches", u64, [vp])
+            self.scan_form = fn("scan_form", C.c_int, [vp, C.POINTER(i32), C.POINTER(u64), C.POINTER(u64)])
             self.synchronize = fn("synchronize", C.c_int, [vp])
             self.timer_start = fn("timer_start", C.c_int, [vp])
             self.timer_stop = fn("timer_stop", C.c_int, [vp, C.POINTER(dbl)])
@@ -439,6 +440,12 @@ class Context:
 
     def kernel_launches(self) -> int:
         return int(self.api.kernel_launches(self._h))
+
+    def scan_form(self):
+        """(form, hot_entries, entries) of the last sample: 0 rank form, 1 CTA form, -1 not bucketed"""
+        f, h, e = C.c_int32(), C.c_uint64(), C.c_uint64()
+        self._check(self.api.scan_form(self._h, C.byref(f), C.byref(h), C.byref(e)), "scan_form")
+        return f.value, h.value, e.value
 
     def synchronize(self):
         self._check(self.api.synchronize(self._h), "synchronize")

@@ -103,7 +103,6 @@ struct gr_ctx {
   // int16 saturation rule (k_sat_resolve): per-cell sums of the suspect blocks, one bit per record, segment table,
   // and per sample the list of dropped records (arrival index << 1 | underflow) the host fetches for its warnings
   DevBuf satCells, satBits, satSegs, satList[2];
-  DevBuf b1Cnt, b1Base, b1Items;       // two-level bucketing: coarse-bin counters + cursors, their scan, the items grouped by coarse bin
   static const u32 SAT_LIST_CAP = 1u << 18;
   u64 n_sat[2][3] = { { 0, 0, 0 }, { 0, 0, 0 } };   // host mirror: dropped for overflow / underflow, list entries
   std::vector<u64> sat_list_h;
@@ -156,6 +155,7 @@ struct gr_ctx {
   bool delta_clean = false;         // the delta array is known to be all zero
   int zero_after = 1;               // dense scan clears behind itself (GR_SCAN_ZERO=0: memset per sample)
   u64 n_pushed = 0, n_clamped = 0;
+  int last_built = 0;                  // how the last sample was laid out (2: bucketed for the fused scan)
   std::vector<double> expt_sums, ctrl_sums;
 
   // replicates and final arrays
@@ -434,7 +434,6 @@ extern "C" void gr_destroy(gr_ctx* x) {
   x->dpar.release();
   x->dsums.release();
   x->unpack6.release();
-  x->b1Cnt.release(); x->b1Base.release(); x->b1Items.release();
   x->satCells.release(); x->satBits.release(); x->satSegs.release(); x->satList[0].release(); x->satList[1].release();
   x->ghk.release();
   x->ghl.release();
@@ -701,7 +700,7 @@ static int consume_segments(gr_ctx* x, int* built) {
   if (fb) {
     const u64 nbk = x->nblocks;
     const int ctrl = x->filling == FILL_CTRL;
-    CK(x->sbCnt.ensure(nbk * 4 + 64));                   // the counters, then the saturation flag word
+    CK(x->sbCnt.ensure(nbk * 4 + 64));                   // the counters, then k_sb_scan1's words (saturation flag, entries in full blocks)
     CK(x->sbStart.ensure((nbk + 1) * 4));
     CK(x->sbCursor.ensure(nbk * 4));
     CK(x->sbBucket.ensure(x->n_pushed * 8 + (u64)x->n_marks * 4 + 16));   // at most two event entries per record
@@ -713,7 +712,7 @@ static int consume_segments(gr_ctx* x, int* built) {
     HT("consume: bucket buffers ensured");
     u32* sat_flag = x->sbCnt.as<u32>() + nbk;
     u32* sat_res = (u32*)((char*)x->small.p + 40) + 3 * ctrl;
-    // the segments in arrival order: the two-level bucketing walks them in one launch, the saturation rule needs the order
+    // the segments in arrival order (the saturation rule replays it)
     {
       std::vector<SatSeg> sg(x->segs.size());
       u64 base = 0;
@@ -725,28 +724,8 @@ static int consume_segments(gr_ctx* x, int* built) {
       if (r) return r;
     }
     const int nseg = (int)x->segs.size();
-    static const bool atomic_buckets = getenv("GR_BUCKET_ATOMIC") != nullptr;      // the one-level form (measurement / tests)
-    const int bsh = (x->has_bed || atomic_buckets) ? -1 : b1_bin_shift(nbk);
     stage_begin(x, "bucket", bytes);
-    if (bsh >= 0) {
-      // two-level: shared-memory histograms and cursors only (-E contexts keep the one-level chain, which knows marks)
-      CK(x->b1Cnt.ensure(2 * 2048 * 4));
-      CK(x->b1Base.ensure(2049 * 4));
-      CK(x->b1Items.ensure(x->n_pushed * 16 + 16));
-      CK(cudaMemsetAsync(x->b1Cnt.p, 0, 2 * 2048 * 4, x->stream));
-      CK(cudaMemsetAsync(sat_flag, 0, 64, x->stream));
-      launch_bucket2(x->stream, x->L, x->satSegs.p, nseg, x->n_pushed, bsh, x->b1Cnt.as<u32>(), x->b1Cnt.as<u32>() + 2048,
-                     x->b1Base.as<u32>(), x->b1Items.as<u64>(), x->sbStart.as<u32>(), x->sbCnt.as<u32>(),
-                     x->sbBucket.as<u32>(), sat_flag, x->d_err, x->d_clamped);
-      // saveInterval's int16 saturation rule (2558-2573): one CTA that returns at once unless a block is full enough to
-      // hold a saturating cell; if it drops records (never in an ordinary sample) the buckets are made again without them
-      launch_sat_resolve(x->stream, sat_flag, x->satSegs.p, nseg, x->L, x->sbCnt.as<u32>(), x->sbSpillCtr.as<u32>() + 1,
-                         x->satCells.p, x->satBits.as<u32>(), x->n_pushed, x->satList[ctrl].as<u64>(),
-                         gr_ctx::SAT_LIST_CAP, sat_res, x->d_err, 0);
-      launch_fb_rebuild(x->stream, sat_res, x->satSegs.p, nseg, x->L, x->sbCnt.as<u32>(), x->sbStart.as<u32>(),
-                        x->sbBucket.as<u32>(), x->satBits.as<u32>());
-      CKL();
-    } else {
+    {
       CK(cudaMemsetAsync(x->sbCnt.p, 0, nbk * 4 + 64, x->stream));
       for (auto& g : x->segs)
         launch_fb_count(x->stream, x->L, g.d, g.n, g.rb == 8, x->sbCnt.as<u32>(), x->d_err, x->d_clamped);
@@ -755,7 +734,7 @@ static int consume_segments(gr_ctx* x, int* built) {
       launch_sb_scan_a(x->stream, nbk, x->sbCnt.as<u32>(), x->sbSpillCtr.as<u32>() + 1, sat_flag);
       launch_sat_resolve(x->stream, sat_flag, x->satSegs.p, nseg, x->L, x->sbCnt.as<u32>(), x->sbSpillCtr.as<u32>() + 1,
                          x->satCells.p, x->satBits.as<u32>(), x->n_pushed, x->satList[ctrl].as<u64>(),
-                         gr_ctx::SAT_LIST_CAP, sat_res, x->d_err, 1);
+                         gr_ctx::SAT_LIST_CAP, sat_res, x->d_err);
       launch_sb_scan_b(x->stream, nbk, x->sbCnt.as<u32>(), x->sbStart.as<u32>(), x->sbCursor.as<u32>(),
                        x->sbSpillCtr.as<u32>() + 1);
       {
@@ -929,6 +908,7 @@ static int pileup_enqueue(gr_ctx* x) {
   HT("pileup_enqueue: buffers ensured");
   int built = 0;
   { int r = consume_segments(x, &built); if (r) return r; }
+  x->last_built = built;
   HT("pileup_enqueue: segments consumed");
   // after the plain scatter the scan clears the cells behind itself (the next small sample
   // finds the array zero); a built array is overwritten as a whole by the next build anyway
@@ -941,7 +921,7 @@ static int pileup_enqueue(gr_ctx* x) {
     owners = launch_fb_scan(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), sc,
                             (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err,
                             x->has_bed ? x->blkBed.as<uint8_t>() : nullptr,
-                            x->has_bed && !ctrl ? x->bedChromMarks.as<u32>() : nullptr, x->n_pushed);
+                            x->has_bed && !ctrl ? x->bedChromMarks.as<u32>() : nullptr, x->sbCnt.as<u32>() + x->nblocks);
     CKL();
     stage_end(x);
   } else {
@@ -1876,6 +1856,24 @@ extern "C" int gr_timing_get(gr_ctx* x, gr_stage_time* out, int32_t cap, int32_t
   return GR_OK;
 }
 extern "C" uint64_t gr_kernel_launches(const gr_ctx* x) { (void)x; return g_gr_launches; }
+extern "C" int gr_scan_form(gr_ctx* x, int32_t* form, uint64_t* hot_entries, uint64_t* entries) {
+  if (!x || !form) return GR_ERR_ARG;
+  *form = -1;
+  if (hot_entries) *hot_entries = 0;
+  if (entries) *entries = 0;
+  if (x->last_built != 2) return GR_OK;
+  CK(cudaSetDevice(x->device));
+  u32 stat[2] = {0, 0}, total = 0;
+  CK(cudaMemcpyAsync(stat, x->sbCnt.as<u32>() + x->nblocks, 8, cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaMemcpyAsync(&total, x->sbStart.as<u32>() + x->nblocks, 4, cudaMemcpyDeviceToHost, x->stream));
+  CK(cudaStreamSynchronize(x->stream));
+  if (hot_entries) *hot_entries = stat[1];
+  if (entries) *entries = total;
+  const bool forced_cta = x->has_bed || (getenv("GR_FUSED_CTA") && atoi(getenv("GR_FUSED_CTA")));
+  const bool forced_rank = !forced_cta && getenv("GR_FUSED_RANK") && atoi(getenv("GR_FUSED_RANK"));
+  *form = forced_cta ? 1 : forced_rank ? 0 : ((u64)stat[1] * 4 > (u64)total ? 1 : 0);
+  return GR_OK;
+}
 extern "C" int gr_synchronize(gr_ctx* x) {
   if (!x) return GR_ERR_ARG;
   CK(cudaSetDevice(x->device));

@@ -168,23 +168,35 @@ k_sb_count(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ 
 // exclusive scan of the per-block counts (~4e5 for a human genome) in three small steps:
 // sums of 4096-counter chunks, scan of the <= 1024 chunk sums (one CTA), rescan with the base
 #define SB_CHUNK 4096
-// sat_flag (may be NULL): raised when a block holds SAT_MIN_EVENTS entries or more -- only such a block can
-// hold a cell the reference's int16 counters saturate on (k_sat_resolve below)
+// sat_flag (may be NULL): word 0 is raised when a block holds SAT_MIN_EVENTS entries or more -- only such a block
+// can hold a cell the reference's int16 counters saturate on (k_sat_resolve below); word 1 collects the entries
+// that lie in blocks of FORM_HOT_MIN entries or more (the scan form is chosen by it on the device: form_skip)
 #define SAT_MIN_EVENTS 32767u
+#define FORM_HOT_MIN 1024u
 __global__ void __launch_bounds__(256)
 k_sb_scan1(const u32* __restrict__ blk_cnt, u32* __restrict__ chunk_sum, u64 nblocks, u32* __restrict__ sat_flag) {
   __shared__ u32 sh[8];
   const u64 base = (u64)blockIdx.x * SB_CHUNK;
-  u32 s = 0;
+  __shared__ u32 sh_hot[8];
+  u32 s = 0, hot = 0;
   bool big = false;
   for (int i = threadIdx.x; i < SB_CHUNK; i += 256)
-    if (base + i < nblocks) { const u32 v = blk_cnt[base + i]; s += v; big |= v >= SAT_MIN_EVENTS; }
+    if (base + i < nblocks) {
+      const u32 v = blk_cnt[base + i];
+      s += v; big |= v >= SAT_MIN_EVENTS;
+      if (v >= FORM_HOT_MIN) hot += v;
+    }
   if (big && sat_flag) atomicOr(sat_flag, 1u);
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(GR_FULL, s, o);
-  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(GR_FULL, s, o); hot += __shfl_xor_sync(GR_FULL, hot, o); }
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5] = s; sh_hot[threadIdx.x >> 5] = hot; }
   __syncthreads();
-  if (threadIdx.x == 0) { u32 t = 0; for (int k = 0; k < 8; k++) t += sh[k]; chunk_sum[blockIdx.x] = t; }
+  if (threadIdx.x == 0) {
+    u32 t = 0, h = 0;
+    for (int k = 0; k < 8; k++) { t += sh[k]; h += sh_hot[k]; }
+    chunk_sum[blockIdx.x] = t;
+    if (h && sat_flag) atomicAdd(sat_flag + 1, h);
+  }
 }
 __global__ void __launch_bounds__(1024)
 k_sb_scan2(u32* __restrict__ chunk_sum, u32 nchunks, u32* __restrict__ blk_start, u64 nblocks) {
@@ -876,292 +888,9 @@ k_fb_move(const void* __restrict__ recs, u64 n, DevLayout L, u32* __restrict__ c
   }
 }
 
-// ---- two-level bucketing ------------------------------------------------------------------------
-// k_fb_count / k_fb_move above pay one L2 atomic per entry and pass -- a RETURNING one in the move pass, and those
-// run at ~75 G/s on the B200 whatever the unroll (0.69 ms per 50 M records; the count pass's 0.33 ms on top).  Here
-// no per-entry atomic leaves the SM:
-//   k_b1_count    records -> entries per COARSE bin (2^bsh blocks each, <= 2048 bins): shared-memory histogram,
-//                 one global add per bin and CTA.  Reports errors and the clamp count.
-//   k_b1_scan     exclusive scan of the bin counts.
-//   k_b1_scatter  a tile of 4096 records (held in registers) is sorted by coarse bin in shared memory -- histogram,
-//                 scan, one global add per non-empty bin to reserve room, cursor scatter -- and written out in runs:
-//                 8-byte items (block << 32 | entry), grouped by coarse bin.
-//   k_b2          one CTA per coarse bin: items -> the exact per-block buckets with shared-memory counters only;
-//                 writes blk_start and blk_cnt on the way (the entries of a bin fill the index range of its items).
-// Output = what count -> scan -> move produce (entries of a bucket in another order, which no consumer depends on).
-#define B1_MAXB 2048
-#define B1_TILE 4096
-#define B1_NT 512
-#define B1_PER (B1_TILE / B1_NT)
-struct B1Tiles {                                     // the records of all segments as one sequence of tiles
-  const SatSeg* segs; int nseg;
-  __device__ __forceinline__ bool find(u64 flat_tile, int& g, u64& tile0, u64& lo) const {
-    // g / tile0: segment cursor kept by the caller (flat tiles are visited in increasing order)
-    while (g < nseg) {
-      const u64 nt = (segs[g].n + B1_TILE - 1) / B1_TILE;
-      if (flat_tile < tile0 + nt) { lo = (flat_tile - tile0) * B1_TILE; return true; }
-      tile0 += nt; g++;
-    }
-    return false;
-  }
-};
-// the (up to two) entries of a record: f(block, entry)
-template <class F>
-__device__ __forceinline__ void b1_entries(const SatSeg& sg, u64 i, const DevLayout& L, int& e_local, u32& c_local, F f) {
-  u64 s_slot; u32 span; int w;
-  const bool ok = sg.packed ? decode_record<true>(sg.d, i, L, s_slot, span, w, e_local, c_local)
-                            : decode_record<false>(sg.d, i, L, s_slot, span, w, e_local, c_local);
-  if (!ok) return;
-  const u64 e_slot = s_slot + span;
-  const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)(e_slot >> GR_BLOCK_SHIFT);
-  const u32 so = (u32)s_slot & (GR_BLOCK_SLOTS - 1);
-  const int cnt = 120 / w;
-  if (be != bs) {
-    f(bs, fb_entry(so, 0, cnt, FB_KIND_START));
-    f(be, fb_entry((u32)e_slot & (GR_BLOCK_SLOTS - 1), 0, cnt, FB_KIND_END));
-  } else
-    f(bs, fb_entry(so, span, cnt, FB_KIND_BOTH));
-}
-
-__global__ void __launch_bounds__(256)
-k_b1_count(B1Tiles T, DevLayout L, int bsh, u32 nbins, u32* __restrict__ cnt1, int* __restrict__ err,
-           u64* __restrict__ clamped) {
-  __shared__ u32 sm_h[B1_MAXB];
-  for (u32 i = threadIdx.x; i < nbins; i += 256) sm_h[i] = 0;
-  __syncthreads();
-  int e_local = 0;
-  u32 c_local = 0;
-  int g = 0;
-  u64 tile0 = 0, lo = 0;
-  for (u64 ft = blockIdx.x; T.find(ft, g, tile0, lo); ft += gridDim.x) {
-    const SatSeg sg = T.segs[g];
-    const u64 hi = min(lo + (u64)B1_TILE, sg.n);
-    for (u64 i = lo + threadIdx.x; i < hi; i += 256)
-      b1_entries(sg, i, L, e_local, c_local, [&](u32 blk, u32) { atomicAdd(&sm_h[blk >> bsh], 1u); });
-  }
-  __syncthreads();
-  for (u32 i = threadIdx.x; i < nbins; i += 256)
-    if (sm_h[i]) atomicAdd(cnt1 + i, sm_h[i]);
-  if (e_local) atomicOr(err, e_local);                 // errors and clamp counts are reported by this pass only
-  if (c_local) atomicAdd(clamped, (u64)c_local);
-}
-
-// base1[0 .. nbins]: exclusive scan of cnt1 (<= 2048 counters)
-__global__ void __launch_bounds__(1024)
-k_b1_scan(const u32* __restrict__ cnt1, u32 nbins, u32* __restrict__ base1) {
-  __shared__ u32 sh[32];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const u32 a = (u32)(2 * t) < nbins ? cnt1[2 * t] : 0u, b = (u32)(2 * t + 1) < nbins ? cnt1[2 * t + 1] : 0u;
-  const u32 v = a + b;
-  const u32 wi = warp_incl_scan_u32(v, lane);
-  if (lane == 31) sh[w] = wi;
-  __syncthreads();
-  if (w == 0) {
-    const u32 x = sh[lane];
-    const u32 xi = warp_incl_scan_u32(x, lane);
-    sh[lane] = xi - x;
-  }
-  __syncthreads();
-  const u32 ex = sh[w] + wi - v;
-  if ((u32)(2 * t) < nbins) base1[2 * t] = ex;
-  if ((u32)(2 * t + 1) < nbins) base1[2 * t + 1] = ex + a;
-  if ((u32)(2 * t) < nbins && (u32)(2 * t + 2) >= nbins) base1[nbins] = ex + v;
-}
-
-struct B1Smem { u64 item[2 * B1_TILE]; u32 cur[B1_MAXB], lstart[B1_MAXB], gbase[B1_MAXB]; u32 wsum[B1_NT / 32]; };
-__global__ void __launch_bounds__(B1_NT, 2)
-k_b1_scatter(B1Tiles T, DevLayout L, int bsh, u32 nbins, const u32* __restrict__ base1, u32* __restrict__ gcur,
-             u64* __restrict__ items) {
-  extern __shared__ int4 b1_raw[];
-  B1Smem& S = *reinterpret_cast<B1Smem*>(b1_raw);
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  int e_local = 0;
-  u32 c_local = 0;
-  int g = 0;
-  u64 tile0 = 0, lo = 0;
-  for (u64 ft = blockIdx.x; T.find(ft, g, tile0, lo); ft += gridDim.x) {
-    const SatSeg sg = T.segs[g];
-    const u64 hi = min(lo + (u64)B1_TILE, sg.n);
-    for (u32 i = t; i < nbins; i += B1_NT) S.cur[i] = 0;
-    // the tile's records stay in registers between the two passes over them
-    int4 r[B1_PER];
-    bool on[B1_PER];
-#pragma unroll
-    for (int k = 0; k < B1_PER; k++) {
-      const u64 i = lo + (u64)k * B1_NT + t;
-      on[k] = i < hi;
-      if (on[k]) r[k] = sg.packed ? load_raw<true>(sg.d, i) : load_raw<false>(sg.d, i);
-    }
-    auto each = [&](int k, auto f) {
-      if (!on[k]) return;
-      u64 s_slot; u32 span; int w;
-      const bool ok = sg.packed ? decode_raw<true>(r[k], L, s_slot, span, w, e_local, c_local)
-                                : decode_raw<false>(r[k], L, s_slot, span, w, e_local, c_local);
-      if (!ok) return;
-      const u64 e_slot = s_slot + span;
-      const u32 bs = (u32)(s_slot >> GR_BLOCK_SHIFT), be = (u32)(e_slot >> GR_BLOCK_SHIFT);
-      const u32 so = (u32)s_slot & (GR_BLOCK_SLOTS - 1);
-      const int cnt = 120 / w;
-      if (be != bs) {
-        f(bs, fb_entry(so, 0, cnt, FB_KIND_START));
-        f(be, fb_entry((u32)e_slot & (GR_BLOCK_SLOTS - 1), 0, cnt, FB_KIND_END));
-      } else
-        f(bs, fb_entry(so, span, cnt, FB_KIND_BOTH));
-    };
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < B1_PER; k++) each(k, [&](u32 blk, u32) { atomicAdd(&S.cur[blk >> bsh], 1u); });
-    __syncthreads();
-    // exclusive scan of the tile's bin counts (4 per thread), room reserved in the bins' global ranges
-    {
-      u32 c[4], sum = 0;
-#pragma unroll
-      for (int q = 0; q < 4; q++) { const u32 b = (u32)t * 4 + q; c[q] = b < nbins ? S.cur[b] : 0u; sum += c[q]; }
-      const u32 wi = warp_incl_scan_u32(sum, lane);
-      if (lane == 31) S.wsum[wid] = wi;
-      __syncthreads();
-      u32 ex = wi - sum;
-      for (int q = 0; q < wid; q++) ex += S.wsum[q];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const u32 b = (u32)t * 4 + q;
-        if (b < nbins) {
-          S.lstart[b] = ex;
-          S.cur[b] = ex;
-          if (c[q]) S.gbase[b] = base1[b] + atomicAdd(gcur + b, c[q]);
-        }
-        ex += c[q];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < B1_PER; k++)
-      each(k, [&](u32 blk, u32 e) { S.item[atomicAdd(&S.cur[blk >> bsh], 1u)] = ((u64)blk << 32) | e; });
-    __syncthreads();
-    const u32 nitems = S.cur[nbins - 1];               // the last bin's cursor ends at the tile's item count
-    for (u32 j = t; j < nitems; j += B1_NT) {
-      const u64 it = S.item[j];
-      const u32 b = (u32)(it >> 32) >> bsh;
-      items[(u64)S.gbase[b] + (j - S.lstart[b])] = it;
-    }
-    __syncthreads();                                   // the tile's buffers are free again
-  }
-  (void)e_local; (void)c_local;                        // reported by the count pass
-}
-
-// one CTA per coarse bin
-__global__ void __launch_bounds__(512)
-k_b2(const u64* __restrict__ items, const u32* __restrict__ base1, int bsh, u32 nbins, u32 nblocks,
-     u32* __restrict__ blk_start, u32* __restrict__ blk_cnt, u32* __restrict__ bucketed, u32* __restrict__ sat_flag) {
-  __shared__ u32 sm_c[1024];
-  __shared__ u32 sm_w[16];
-  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const u32 bin = blockIdx.x, F = 1u << bsh, blk0 = bin << bsh;
-  const u32 a = base1[bin], b = base1[bin + 1];
-  for (u32 i = t; i < F; i += 512) sm_c[i] = 0;
-  __syncthreads();
-  for (u32 i = a + t; i < b; i += 512) atomicAdd(&sm_c[(u32)(items[i] >> 32) - blk0], 1u);
-  __syncthreads();
-  // exclusive scan of the F block counts: two consecutive counters per thread (F <= 1024)
-  const u32 c0 = (u32)(2 * t) < F ? sm_c[2 * t] : 0u, c1 = (u32)(2 * t + 1) < F ? sm_c[2 * t + 1] : 0u;
-  const u32 s = c0 + c1;
-  const u32 wi = warp_incl_scan_u32(s, lane);
-  if (lane == 31) sm_w[w] = wi;
-  __syncthreads();
-  if (w == 0) {
-    const u32 x = lane < 16 ? sm_w[lane] : 0u;
-    const u32 xi = warp_incl_scan_u32(x, lane);
-    if (lane < 16) sm_w[lane] = xi - x;
-  }
-  __syncthreads();
-  const u32 run = a + sm_w[w] + wi - s;
-  if ((u32)(2 * t) < F) {
-    const u32 blk = blk0 + 2 * t;
-    if (blk < nblocks) { blk_start[blk] = run; blk_cnt[blk] = c0; }
-    sm_c[2 * t] = run;                                 // becomes the bucket's cursor
-  }
-  if ((u32)(2 * t + 1) < F) {
-    const u32 blk = blk0 + 2 * t + 1;
-    if (blk < nblocks) { blk_start[blk] = run + c0; blk_cnt[blk] = c1; }
-    sm_c[2 * t + 1] = run + c0;
-  }
-  if ((c0 >= SAT_MIN_EVENTS || c1 >= SAT_MIN_EVENTS) && sat_flag) atomicOr(sat_flag, 1u);   // k_sat_resolve has work
-  if (bin == nbins - 1 && t == 0) blk_start[nblocks] = b;
-  __syncthreads();
-  for (u32 i = a + t; i < b; i += 512) {
-    const u64 it = items[i];
-    bucketed[atomicAdd(&sm_c[(u32)(it >> 32) - blk0], 1u)] = (u32)it;
-  }
-}
-
-// Records were dropped by k_sat_resolve (sat_res says so; never in an ordinary sample): the buckets are made
-// again without them -- one CTA, global counters, in no hurry.
-__global__ void __launch_bounds__(1024)
-k_fb_rebuild(const u32* __restrict__ sat_res, const SatSeg* __restrict__ segs, int nseg, DevLayout L,
-             u32* __restrict__ blk_cnt, u32* __restrict__ blk_start, u32* __restrict__ bucketed,
-             const u32* __restrict__ skip_bits, u32 nblocks) {
-  if (!(sat_res[0] | sat_res[1])) return;
-  __shared__ u32 sm_run;
-  const int t = threadIdx.x;
-  for (u32 b = t; b < nblocks; b += 1024) blk_cnt[b] = 0;
-  __threadfence();
-  __syncthreads();
-  int e_local = 0;
-  u32 c_local = 0;
-  for (int g = 0; g < nseg; g++) {
-    const SatSeg sg = segs[g];
-    for (u64 i = t; i < sg.n; i += 1024) {
-      const u64 gi = sg.base + i;
-      if ((skip_bits[gi >> 5] >> (gi & 31)) & 1u) continue;
-      b1_entries(sg, i, L, e_local, c_local, [&](u32 blk, u32) { atomicAdd(blk_cnt + blk, 1u); });
-    }
-  }
-  __threadfence();
-  __syncthreads();
-  if (t == 0) {                                        // exclusive scan; blk_cnt becomes the cursor
-    u32 run = 0;
-    for (u32 b = 0; b < nblocks; b++) { const u32 c = blk_cnt[b]; blk_start[b] = run; blk_cnt[b] = run; run += c; }
-    blk_start[nblocks] = run;
-    sm_run = run;
-  }
-  __threadfence();
-  __syncthreads();
-  for (int g = 0; g < nseg; g++) {
-    const SatSeg sg = segs[g];
-    for (u64 i = t; i < sg.n; i += 1024) {
-      const u64 gi = sg.base + i;
-      if ((skip_bits[gi >> 5] >> (gi & 31)) & 1u) continue;
-      b1_entries(sg, i, L, e_local, c_local, [&](u32 blk, u32 e) { bucketed[atomicAdd(blk_cnt + blk, 1u)] = e; });
-    }
-  }
-  (void)sm_run;
-}
-
-int b1_bin_shift(u64 nblocks) {                        // coarse bins of 2^bsh blocks: at most 1024 of them (2048 at 2^10 blocks per bin)
-  int bsh = 0;
-  while (((nblocks + (1ull << bsh) - 1) >> bsh) > 1024 && bsh < 10) bsh++;
-  return ((nblocks + (1ull << bsh) - 1) >> bsh) <= B1_MAXB ? bsh : -1;
-}
-// cnt1 / gcur: nbins words each, zeroed by the caller; base1: nbins + 1 words; items: one 8-byte word per entry
-void launch_bucket2(cudaStream_t s, const DevLayout& L, const void* segs, int nseg, u64 n_records, int bsh,
-                    u32* cnt1, u32* gcur, u32* base1, u64* items, u32* blk_start, u32* blk_cnt, u32* bucketed,
-                    u32* sat_flag, int* err, u64* clamped) {
-  if (first_use_on_device(5)) cudaFuncSetAttribute(k_b1_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(B1Smem));
-  const u32 nbins = (u32)((L.nblocks + (1ull << bsh) - 1) >> bsh);
-  B1Tiles T;
-  T.segs = (const SatSeg*)segs; T.nseg = nseg;
-  const u64 tiles = (n_records + B1_TILE - 1) / B1_TILE + (u64)nseg;
-  k_b1_count<<<(unsigned)(tiles < 148 * 8 ? tiles : 148 * 8), 256, 0, s>>>(T, L, bsh, nbins, cnt1, err, clamped); GR_NOTE_LAUNCH();
-  k_b1_scan<<<1, 1024, 0, s>>>(cnt1, nbins, base1); GR_NOTE_LAUNCH();
-  k_b1_scatter<<<(unsigned)(tiles < 148 * 2 ? tiles : 148 * 2), B1_NT, sizeof(B1Smem), s>>>(T, L, bsh, nbins, base1, gcur, items);
-  GR_NOTE_LAUNCH();
-  k_b2<<<nbins, 512, 0, s>>>(items, base1, bsh, nbins, (u32)L.nblocks, blk_start, blk_cnt, bucketed, sat_flag); GR_NOTE_LAUNCH();
-}
-void launch_fb_rebuild(cudaStream_t s, const u32* sat_res, const void* segs, int nseg, const DevLayout& L, u32* blk_cnt,
-                       u32* blk_start, u32* bucketed, const u32* skip_bits) {
-  k_fb_rebuild<<<1, 1024, 0, s>>>(sat_res, (const SatSeg*)segs, nseg, L, blk_cnt, blk_start, bucketed, skip_bits, (u32)L.nblocks);
-  GR_NOTE_LAUNCH();
-}
+// Tried and removed: a two-level form (coarse bins sorted in shared memory, then one CTA per coarse bin: no
+// per-entry global atomic).  Measured on the B200 at 2.64 ms per hg38 ChIP step against 2.11 ms for the count /
+// move pair above -- the 8-byte intermediate items cost more HBM traffic than the atomics cost time.
 
 // ---- the reference's int16 saturation rule (saveInterval, Genrich.c:2558-2573) -------------------
 // The reference keeps (int16 cov, 8-bit frac) per delta cell and, IN ARRIVAL ORDER, drops an interval
@@ -1192,7 +921,7 @@ __global__ void __launch_bounds__(1024)
 k_sat_resolve(const u32* __restrict__ flag, const SatSeg* __restrict__ segs, int nseg, DevLayout L,
               u32* __restrict__ blk_cnt, u32* __restrict__ chunk_sum, u32 nblocks, ulonglong2* __restrict__ cells,
               u32* __restrict__ skip_bits, u64 nbits, u64* __restrict__ list, u32 list_cap, u32* __restrict__ sat_res,
-              int* __restrict__ err, int patch /* 1: take the dropped records out of blk_cnt / chunk_sum (the scan follows) */) {
+              int* __restrict__ err) {
   __shared__ u32 sm_sb[SAT_MAX_BLOCKS];
   __shared__ u32 sm_nsb, sm_nhot, sm_pend_n;
   __shared__ u32 sm_wcnt[32];
@@ -1290,10 +1019,8 @@ k_sat_resolve(const u32* __restrict__ flag, const SatSeg* __restrict__ segs, int
           if (kind) n_under++; else n_over++;
           if (n_list < list_cap) list[n_list++] = (gi << 1) | (u64)kind;
           const u32 xs = sm_pend[k].bs, xe = sm_pend[k].be;
-          if (patch) {
-            blk_cnt[xs] -= 1u; chunk_sum[xs / SB_CHUNK] -= 1u;
-            if (xe != xs) { blk_cnt[xe] -= 1u; chunk_sum[xe / SB_CHUNK] -= 1u; }
-          }
+          blk_cnt[xs] -= 1u; chunk_sum[xs / SB_CHUNK] -= 1u;           // the scan's second half follows
+          if (xe != xs) { blk_cnt[xe] -= 1u; chunk_sum[xe / SB_CHUNK] -= 1u; }
         }
       }
       __syncthreads();
@@ -1302,10 +1029,9 @@ k_sat_resolve(const u32* __restrict__ flag, const SatSeg* __restrict__ segs, int
   if (t == 0) { sat_res[0] = n_over; sat_res[1] = n_under; sat_res[2] = n_list; }
 }
 void launch_sat_resolve(cudaStream_t s, const u32* flag, const void* segs, int nseg, const DevLayout& L, u32* blk_cnt,
-                        u32* chunk_sum, void* cells, u32* skip_bits, u64 nbits, u64* list, u32 list_cap, u32* sat_res, int* err,
-                        int patch) {
+                        u32* chunk_sum, void* cells, u32* skip_bits, u64 nbits, u64* list, u32 list_cap, u32* sat_res, int* err) {
   k_sat_resolve<<<1, 1024, 0, s>>>(flag, (const SatSeg*)segs, nseg, L, blk_cnt, chunk_sum, (u32)L.nblocks, (ulonglong2*)cells,
-                                   skip_bits, nbits, list, list_cap, sat_res, err, patch);
+                                   skip_bits, nbits, list, list_cap, sat_res, err);
   GR_NOTE_LAUNCH();
 }
 
@@ -1326,6 +1052,16 @@ void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32*
 }
 
 #define FB_WORDS (GR_BLOCK_SLOTS / 32)                 // occupancy / break bitmap words per block
+// Which scan form runs is decided ON THE DEVICE, from the sample as it was bucketed: the rank form (a warp per
+// block) is the fast one for ordinary blocks, but a block of thousands of entries -- a deep sample, or the
+// pile-ups of an ATAC-seq peak -- is one warp's serial work there, and the CTA form takes it with 128 threads.
+// Both kernels are launched; the one whose turn it is not returns at once (`when`: 0 run, 1 run if a quarter of
+// the entries lie in blocks of >= FORM_HOT_MIN entries, 2 run if not).  stat: k_sb_scan1's words.
+__device__ __forceinline__ bool form_skip(const u32* __restrict__ stat, const u32* __restrict__ blk_start, u32 nblocks, int when) {
+  if (!when) return false;
+  const bool hot = (u64)stat[1] * 4 > (u64)blk_start[nblocks];
+  return when == 1 ? !hot : hot;
+}
 #define FB_RING 128                                    // page ring: sequence numbers in flight <= 2 * 33 + 2
 // NT threads per CTA, each owning WPT = 256 / NT consecutive bitmap words (32 * WPT cells);
 // PF entry registers per thread are fetched one block ahead (PF * NT = 512 entries).
@@ -1334,8 +1070,10 @@ __global__ void __launch_bounds__(NT, CPS)
 k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
           u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R,
           const uint8_t* __restrict__ blk_bed /* NULL: no -E regions */,
-          const u32* __restrict__ chrom_marks /* BED, experimental sample: region boundaries per chromosome, else NULL */) {
+          const u32* __restrict__ chrom_marks /* BED, experimental sample: region boundaries per chromosome, else NULL */,
+          const u32* __restrict__ stat, int when) {
   constexpr int WPT = FB_WORDS / NT, PF = 512 / NT, NW = NT / 32;
+  if (form_skip(stat, blk_start, nblocks, when)) return;
   __shared__ int sm_cell[GR_BLOCK_SLOTS];
   __shared__ u32 sm_occ[FB_WORDS];
   __shared__ u32 sm_mark[BED ? FB_WORDS : 1];          // -E region boundaries of the block (rare)
@@ -1781,7 +1519,8 @@ __device__ __forceinline__ int fr_weight(u32 count) {
 template <int CAP, int CPS, int PF>
 __global__ void __launch_bounds__(128, CPS)
 k_fr_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
-          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R) {
+          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R, const u32* __restrict__ stat, int when) {
+  if (form_skip(stat, blk_start, nblocks, when)) return;
   __shared__ __align__(16) u32 sm_occ_all[4 * FB_WORDS];
   __shared__ __align__(16) u32 sm_pre_all[4 * FB_WORDS];
   __shared__ int sm_sum_all[4 * CAP];
@@ -2022,16 +1761,19 @@ void launch_fb_move(cudaStream_t s, const DevLayout& L, const void* recs, u64 n,
 static int fb_env(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
 
 // bucketed events -> breaks (pages) + break bitmap; launch_scan_place(..., owners) follows.
-// Default: k_fr_scan (warp-owned blocks, rank form; 9 CTAs x 4 warps per SM, 512 distinct cells per
-// round) -- measured on the B200 at 0.67 ms per hg38 sample against 1.69 ms for the CTA-owned
-// k_fb_scan, same bits.  k_fb_scan stays for contexts with -E regions (the region boundaries are
-// weightless mark entries only it understands) and, behind GR_FUSED_CTA=1, as the comparison the
-// bench quotes.
+// k_fr_scan (warp-owned blocks, rank form; 9 CTAs x 4 warps per SM, 512 distinct cells per round) and k_fb_scan
+// (CTA-owned blocks, cell array in shared memory) are both launched and the sample picks one (form_skip):
+// measured on the B200, an hg38 ChIP sample (200 entries per block) takes 0.71 ms in the rank form and 1.69 ms in
+// the CTA form; the 10 Gbp / 1 B fragment shard (2200 entries per block) 9.5 ms against 4.1 ms, an ATAC sample
+// with 13 k cut sites on a block 3.75 against 2.75.  Contexts with -E regions take the CTA form (the region
+// boundaries are weightless mark entries only it understands).  GR_FUSED_CTA=1 / GR_FUSED_RANK=1 force a form
+// (tests, and the comparison the bench quotes); stat: k_sb_scan1's statistic words.
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
                    const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks,
-                   u64 n_records) {
+                   const u32* stat) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   cudaMemsetAsync(W.page_ctr, 0, 4, s);
+  cudaMemsetAsync(W.warp_tot, 0, (size_t)SS_MAX_WARPS * sizeof(uint2), s);   // owners of the form that does not run: empty
   static int sms = 0;
   if (!sms) {
     int dev = 0;
@@ -2039,30 +1781,33 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const u32 nb = (u32)L.nblocks;
-  u32 owners;
-  // The rank form walks a block's entries once per 512 DISTINCT event cells; a block of a deep sample (the 10 Gbp
-  // / 1 B fragment configuration: ~2200 entries, ~3400 distinct cells per block) takes seven such rounds: 9.5 ms
-  // on the B200 for 333 M records over 1.25 G cells.  Such samples go to the dense form (k_fd_scan).
-  // Expected distinct cells per block from the sample size: 8192 (1 - exp(-2 n / cells)).
-  const double per_blk = 2.0 * (double)n_records / (double)(nb ? nb : 1);
-  const bool dense_blocks = 8192.0 * (1.0 - exp(-per_blk / 8192.0)) > (double)fb_env("GR_FUSED_CTA_CELLS", 768);
-  if (!blk_bed && !fb_env("GR_FUSED_CTA", 0) && (dense_blocks || fb_env("GR_FUSED_DENSE", 0))) {
+  const int force_cta = blk_bed || fb_env("GR_FUSED_CTA", 0), force_rank = !force_cta && fb_env("GR_FUSED_RANK", 0);   // read per call: the tests switch it inside one process
+  u32 owners = 0;
+  if (!blk_bed && fb_env("GR_FUSED_DENSE", 0)) {       // measurement only: the bulk-copy staged cell-array form
     if (first_use_on_device(4)) cudaFuncSetAttribute(k_fd_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FdSmem));
     owners = (u32)(sms * 3);
     const u32 R = (nb + owners - 1) / owners;
     k_fd_scan<<<owners, FD_NT, sizeof(FdSmem), s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
-  } else if (blk_bed || fb_env("GR_FUSED_CTA", 0)) {   // read per call: the tests switch it inside one process
-    owners = (u32)(sms * 6);
-    const u32 R = (nb + owners - 1) / owners;
-    if (blk_bed) k_fb_scan<6, 128, true><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed, chrom_marks);
-    else k_fb_scan<6, 128, false><<<owners, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr, nullptr);
-  } else {
-    owners = (u32)(sms * 9) * 4;
-    if (owners > SS_MAX_WARPS) owners = SS_MAX_WARPS & ~3u;
-    const u32 R = (nb + owners - 1) / owners;
-    k_fr_scan<512, 9, 8><<<owners / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
+    GR_NOTE_LAUNCH();
+    return owners;
   }
-  GR_NOTE_LAUNCH();
+  if (!force_rank) {
+    const u32 o = (u32)(sms * 6);
+    const u32 R = (nb + o - 1) / o;
+    const int when = force_cta ? 0 : 1;
+    if (blk_bed) k_fb_scan<6, 128, true><<<o, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed, chrom_marks, stat, 0);
+    else k_fb_scan<6, 128, false><<<o, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr, nullptr, stat, when);
+    GR_NOTE_LAUNCH();
+    owners = o;
+  }
+  if (!force_cta) {
+    u32 o = (u32)(sms * 9) * 4;
+    if (o > SS_MAX_WARPS) o = SS_MAX_WARPS & ~3u;
+    const u32 R = (nb + o - 1) / o;
+    k_fr_scan<512, 9, 8><<<o / 4, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, stat, force_rank ? 0 : 2);
+    GR_NOTE_LAUNCH();
+    if (o > owners) owners = o;
+  }
   return owners;
 }
 

@@ -73,23 +73,16 @@ void launch_sb_scan_b(cudaStream_t s, u64 nbuckets, const u32* blk_cnt, u32* blk
 struct SatSeg { const void* d; u64 n; u64 base; int packed; int pad_; };   // one pushed segment: records, count, arrival index of the first
 void launch_sat_resolve(cudaStream_t s, const u32* flag, const void* segs, int nseg, const DevLayout& L, u32* blk_cnt,
                         u32* chunk_sum, void* cells /* SAT_MAX_BLOCKS * 8192 * 16 bytes */, u32* skip_bits, u64 nbits,
-                        u64* list, u32 list_cap, u32* sat_res, int* err, int patch);
-// two-level bucketing (no per-entry global atomics): see k_b1_* / k_b2 in gr_dense.cu
-int b1_bin_shift(u64 nblocks);                 // -1: the layout has too many blocks for it
-void launch_bucket2(cudaStream_t s, const DevLayout& L, const void* segs, int nseg, u64 n_records, int bsh,
-                    u32* cnt1, u32* gcur, u32* base1, u64* items, u32* blk_start, u32* blk_cnt, u32* bucketed,
-                    u32* sat_flag, int* err, u64* clamped);
-// the buckets once more without the records k_sat_resolve dropped (gated on sat_res on the device)
-void launch_fb_rebuild(cudaStream_t s, const u32* sat_res, const void* segs, int nseg, const DevLayout& L, u32* blk_cnt,
-                       u32* blk_start, u32* bucketed, const u32* skip_bits);
+                        u64* list, u32 list_cap, u32* sat_res, int* err);
 // returns the number of run owners (warps or CTAs), to be handed to launch_scan_place
 // blk_bed: per 8192-cell block, bit 0 = the block starts inside a -E region, bit 1 = it holds
 // region boundaries (NULL: no regions); chrom_marks: region boundaries per chromosome, for the experimental
 // sample only (a chromosome that holds nothing else is one interval there, savePileupExpt 2178-2182)
-// n_records: records of the sample (chooses the scan: the rank form for sparse blocks, the cell array for dense ones)
+// stat: the words k_sb_scan1 leaves behind the block counters (launch_sb_scan_a's sat_flag); the scan form is
+// chosen from them on the device
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
                    const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks,
-                   u64 n_records);
+                   const u32* stat);
 // -E region boundaries as pseudo entries (cursor == NULL: count pass)
 void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed);
 

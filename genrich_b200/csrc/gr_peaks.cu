@@ -122,49 +122,12 @@ k_peak_heads(const u32* __restrict__ pEnd, const float* __restrict__ v,
   }
 }
 
-// ---- walk: candidates 32 at a time per warp ---------------------------------------------
-// The arithmetic of a candidate is a chain (float AUC in interval order, summit rules), its loads are not.
-// Most candidates are a handful of intervals: each lane walks its own, four events in flight at a time.  The
-// LONG ones (hundreds of intervals: on a small shard one of them was the whole kernel's time, ~0.15 ms of
-// dependent DRAM round trips) are then taken one after the other by the whole warp: the lanes fetch 32 events
-// at once and the chain runs over the 32 register sets by shuffles, every lane computing the same state.
-#define PK_LONG 16                 // events from which a candidate is walked by the warp
-struct WalkState {
-  float auc, sVal, sP, sQ;
-  i64 pStart, pEndv;
-  u32 sPos, sLen;
-};
-__device__ __forceinline__ void walk_init(WalkState& w) {
-  w.auc = 0.0f; w.sVal = -1.0f; w.sP = -1.0f; w.sQ = -1.0f;     // 1001-1006
-  w.pStart = -1; w.pEndv = -1; w.sPos = 0; w.sLen = 0;
-}
-// one interval of the candidate; px / qx: its -log10 p and q (read only when it becomes the summit)
-template <class FP, class FQ>
-__device__ __forceinline__ void walk_step(WalkState& w, float x, u32 start, u32 end, float thr, FP px, FQ qx) {
-  const u32 len = end - start;
-  w.auc = __fadd_rn(w.auc, __fmul_rn(__uint2float_rn(len), __fsub_rn(x, thr)));   // 950, no FMA
-  if (w.pStart == -1) w.pStart = start;
-  w.pEndv = end;
-  if (x > w.sVal) {                                             // 956-961
-    w.sVal = x;
-    w.sP = px();
-    w.sQ = qx();
-    w.sPos = (u32)((end + start) / 2 - (u32)w.pStart);          // uint32 arithmetic, 960
-    w.sLen = len;
-  } else if (x == w.sVal && len > w.sLen) {                     // 962-968
-    w.sPos = (u32)((end + start) / 2 - (u32)w.pStart);
-    w.sLen = len;
-  }
-}
-__device__ __forceinline__ void walk_store(const WalkState& w, int c, float min_auc, int min_len, u64 h,
-                                           PeakRec* __restrict__ cand, uint8_t* __restrict__ cand_ok) {
-  PeakRec r;
-  r.chrom = c; r.summit = w.sPos; r.start = w.pStart; r.end = w.pEndv;
-  r.auc = w.auc; r.pval = w.sP; r.qval = w.sQ; r.reserved = 0.0f;
-  cand[h] = r;
-  cand_ok[h] = (w.pStart != -1 && w.auc >= min_auc && w.pEndv - w.pStart >= (i64)min_len) ? 1 : 0;   // 920
-}
-
+// ---- walk: one thread per candidate ------------------------------------------------
+// The arithmetic of a candidate is a chain (float AUC in interval order, summit rules), its loads are not: PK_FETCH
+// events are fetched at a time so that their latencies overlap (a long candidate is one thread's critical path,
+// and on a small shard the whole kernel's).  Candidates of one warp run side by side -- peaks come in runs of long
+// candidates, so handing the long ones of a warp to the whole warp one after the other (tried: 4x slower) loses.
+#define PK_FETCH 8
 __global__ void __launch_bounds__(128)
 k_peak_walk(const u32* __restrict__ pEnd, const float* __restrict__ pval,
             const float* __restrict__ qval, const u64* __restrict__ chrom_start, int nchrom,
@@ -178,71 +141,55 @@ k_peak_walk(const u32* __restrict__ pEnd, const float* __restrict__ pval,
     return;
   }
   const u64 nev = *ev_count;
-  const int lane = threadIdx.x & 31;
-  const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
   const float* __restrict__ v = qopt ? qval : pval;
-  for (u64 h0 = ((u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; h0 < nh; h0 += nwarps * 32) {   // warp-uniform
-    const u64 h = h0 + lane;
-    u64 t0 = 0, t1 = 0;
-    if (h < nh) { t0 = head_idx[h]; t1 = h + 1 < nh ? head_idx[h + 1] : nev; }
-    const bool is_long = t1 - t0 >= PK_LONG;
-    if (h < nh && !is_long) {
-      // ---- a short candidate: this lane alone
-      const u32 first = ev_idx[t0];
-      const int c = chrom_of_index(chrom_start, nchrom, first);
-      const u64 cs = chrom_start[c];
-      WalkState w;
-      walk_init(w);
-      bool open = true;
-      for (u64 t = t0; t < t1 && open; t += 4) {
-        u32 idx[4], end[4], start[4];
-        float xv[4];
+  for (u64 h = (u64)blockIdx.x * blockDim.x + threadIdx.x; h < nh; h += (u64)gridDim.x * blockDim.x) {
+    const u64 t0 = head_idx[h];
+    const u64 t1 = h + 1 < nh ? head_idx[h + 1] : nev;
+    const u32 first = ev_idx[t0];
+    const int c = chrom_of_index(chrom_start, nchrom, first);
+    const u64 cs = chrom_start[c];
+
+    float auc = 0.0f, sVal = -1.0f, sP = -1.0f, sQ = -1.0f;     // 1001-1006
+    i64 pStart = -1, pEndv = -1;
+    u32 sPos = 0, sLen = 0;
+    bool open = true;
+    for (u64 t = t0; t < t1 && open; t += PK_FETCH) {
+      u32 idx[PK_FETCH], end[PK_FETCH], start[PK_FETCH];
+      float xv[PK_FETCH];
 #pragma unroll
-        for (int k = 0; k < 4; k++) idx[k] = t + k < t1 ? ev_idx[t + k] : first;
+      for (int k = 0; k < PK_FETCH; k++) idx[k] = t + k < t1 ? ev_idx[t + k] : first;
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          xv[k] = v[idx[k]];
-          end[k] = pEnd[idx[k]];
-          start[k] = (u64)idx[k] == cs ? 0u : pEnd[idx[k] - 1];
-        }
+      for (int k = 0; k < PK_FETCH; k++) {
+        xv[k] = v[idx[k]];
+        end[k] = pEnd[idx[k]];
+        start[k] = (u64)idx[k] == cs ? 0u : pEnd[idx[k] - 1];
+      }
 #pragma unroll
-        for (int k = 0; k < 4; k++) {
-          if (t + k >= t1) break;
-          if (xv[k] == PK_SKIP) { open = false; break; }            // 1031: SKIP closes the candidate
-          const u32 id = idx[k];
-          walk_step(w, xv[k], start[k], end[k], thr, [&]() { return pval[id]; }, [&]() { return qopt ? qval[id] : PK_SKIP; });
+      for (int k = 0; k < PK_FETCH; k++) {
+        if (t + k >= t1) break;
+        const float x = xv[k];
+        if (x == PK_SKIP) { open = false; break; }                 // 1031: SKIP closes the candidate
+        const u32 len = end[k] - start[k];
+        auc = __fadd_rn(auc, __fmul_rn(__uint2float_rn(len), __fsub_rn(x, thr)));   // 950, no FMA
+        if (pStart == -1) pStart = start[k];
+        pEndv = end[k];
+        if (x > sVal) {                                             // 956-961
+          sVal = x;
+          sP = pval[idx[k]];
+          sQ = qopt ? qval[idx[k]] : PK_SKIP;
+          sPos = (u32)((end[k] + start[k]) / 2 - (u32)pStart);      // uint32 arithmetic, 960
+          sLen = len;
+        } else if (x == sVal && len > sLen) {                       // 962-968
+          sPos = (u32)((end[k] + start[k]) / 2 - (u32)pStart);
+          sLen = len;
         }
       }
-      walk_store(w, c, min_auc, min_len, h, cand, cand_ok);
     }
-    // ---- the long ones of these 32, one after the other, by the whole warp
-    for (u32 todo = __ballot_sync(GR_FULL, h < nh && is_long); todo; todo &= todo - 1) {
-      const int src = __ffs(todo) - 1;
-      const u64 a0 = __shfl_sync(GR_FULL, t0, src), a1 = __shfl_sync(GR_FULL, t1, src);
-      const u32 first = ev_idx[a0];
-      const int c = chrom_of_index(chrom_start, nchrom, first);
-      const u64 cs = chrom_start[c];
-      WalkState w;
-      walk_init(w);
-      bool open = true;
-      for (u64 t = a0; t < a1 && open; t += 32) {
-        const u64 mine = t + lane;
-        const u32 idx = mine < a1 ? ev_idx[mine] : first;
-        const float x_ = v[idx];
-        const u32 end_ = pEnd[idx];
-        const u32 start_ = (u64)idx == cs ? 0u : pEnd[idx - 1];
-        const float p_ = pval[idx];
-        const float q_ = qopt ? qval[idx] : PK_SKIP;
-        const int cnt = (int)min((u64)32, a1 - t);
-        for (int k = 0; k < cnt; k++) {                             // the chain, in interval order, identical in every lane
-          const float x = __shfl_sync(GR_FULL, x_, k);
-          if (x == PK_SKIP) { open = false; break; }
-          const u32 end = __shfl_sync(GR_FULL, end_, k), start = __shfl_sync(GR_FULL, start_, k);
-          walk_step(w, x, start, end, thr, [&]() { return __shfl_sync(GR_FULL, p_, k); }, [&]() { return __shfl_sync(GR_FULL, q_, k); });
-        }
-      }
-      if (lane == 0) walk_store(w, c, min_auc, min_len, h0 + src, cand, cand_ok);
-    }
+    PeakRec r;
+    r.chrom = c; r.summit = sPos; r.start = pStart; r.end = pEndv;
+    r.auc = auc; r.pval = sP; r.qval = sQ; r.reserved = 0.0f;
+    cand[h] = r;
+    cand_ok[h] = (pStart != -1 && auc >= min_auc && pEndv - pStart >= (i64)min_len) ? 1 : 0;   // 920
   }
 }
 

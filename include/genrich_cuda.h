@@ -316,6 +316,12 @@ int gr_timing_enable(gr_ctx* ctx, int32_t on);
 int gr_timing_get(gr_ctx* ctx, gr_stage_time* out, int32_t cap, int32_t* n);
 int gr_timing_reset(gr_ctx* ctx);
 uint64_t gr_kernel_launches(const gr_ctx* ctx);
+/* Which per-base scan the last sample of the context chose on the device (the choice needs no host round trip:
+ * both kernels are launched and the one whose turn it is not returns at once): form 0 = rank form (k_fr_scan),
+ * 1 = CTA form (k_fb_scan), -1 = the sample did not go through the bucketed path.  hot_entries / entries: the
+ * statistic the choice is made from (entries in 8192-cell blocks that hold 1024 or more, all entries).  Waits for
+ * the stream. */
+int gr_scan_form(gr_ctx* ctx, int32_t* form, uint64_t* hot_entries, uint64_t* entries);
 /* CUDA events on the library's own stream: ms between start and stop as the device saw it */
 int gr_timer_start(gr_ctx* ctx);
 int gr_timer_stop(gr_ctx* ctx, double* ms);

@@ -26,9 +26,9 @@ LIB = os.path.join(EMU, "_build", "libgenrich_emu.so")
 FUSED = {"GR_FUSED": "1", "GR_FUSED_MIN": "1"}
 MODES = {
     "default_small": {},                                     # plain scatter + streaming scan (small samples)
-    "default_fused": FUSED,                                  # the path the bench takes: k_fr_scan
+    "default_fused": FUSED,                                  # the path the bench takes: the sample picks the scan form
     "fused_cta": dict(FUSED, GR_FUSED_CTA="1"),              # k_fb_scan without -E regions
-    "fused_dense": dict(FUSED, GR_FUSED_DENSE="1"),          # k_fd_scan (deep samples)
+    "fused_rank": dict(FUSED, GR_FUSED_RANK="1"),            # k_fr_scan whatever the blocks hold
 }
 
 

@@ -281,10 +281,10 @@ def test_fused_scan_same_bits(monkeypatch):
         inputs[0][0] = np.concatenate([inputs[0][0], extra])
         par = util.case_params(case)
         outs = _run_modes(monkeypatch, case.chrom_len, par, inputs,
-                          (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_DENSE="1")))
-        _same_outs(outs[0], outs[1], case.name)            # k_fr_scan (the default fused scan) == scatter + k_scan_stream
-        _same_outs(outs[0], outs[2], case.name + " cta")   # k_fb_scan (the form -E contexts use)
-        _same_outs(outs[0], outs[3], case.name + " dense") # k_fd_scan (the form deep samples get)
+                          (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_RANK="1")))
+        _same_outs(outs[0], outs[1], case.name)            # the fused scan, form chosen on the device == scatter + k_scan_stream
+        _same_outs(outs[0], outs[2], case.name + " cta")   # k_fb_scan forced (the form -E contexts and full blocks get)
+        _same_outs(outs[0], outs[3], case.name + " rank")  # k_fr_scan forced
         assert len(outs[0][0].peaks) > 0 or case.name == "null_q"
     # packed records through the fused path
     case = BY_NAME["c2_ctrl_q"]
@@ -307,7 +307,7 @@ def test_fused_scan_same_bits(monkeypatch):
         [6, 0, 16383, 1], [6, 8100, 16383, 2], [6, 16382, 16383, 3],
     ], dtype=np.int32)
     par = capi.make_params(p=0.2, min_auc=0.5, keep_pileups=True)
-    modes = (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_DENSE="1"))
+    modes = (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_RANK="1"))
     outs = _run_modes(monkeypatch, L, par, [(recs, None)], modes)
     for o in outs[1:]:
         _same_outs(outs[0], o, "edge")
@@ -321,13 +321,43 @@ def test_fused_scan_large(monkeypatch):
     t = Workload(L, 4_000_000, 101, enrich=0.5, spacing=400000, sigma=60.0).fragments()
     c = Workload(L, 4_000_000, 102, enrich=0.0).fragments()
     par = capi.make_params(p=0.01, min_auc=20.0)
-    modes = ({"GR_FUSED": "0"}, {"GR_FUSED": "1"}, {"GR_FUSED": "1", "GR_FUSED_CTA": "1"}, {"GR_FUSED": "1", "GR_FUSED_DENSE": "1"})
+    modes = ({"GR_FUSED": "0"}, {"GR_FUSED": "1"}, {"GR_FUSED": "1", "GR_FUSED_CTA": "1"}, {"GR_FUSED": "1", "GR_FUSED_RANK": "1"})
     outs = _run_modes(monkeypatch, L, par, [(t, c)], modes, chunk=1 << 22)
     for o, md in zip(outs[1:], modes[1:]):
         _same_outs(outs[0], o, "large %s" % md)
     st = outs[1][0].sample_stats[0]
     assert st.frag_len == float(np.sum((t[:, 2] - t[:, 1]).astype(np.int64)))
     assert len(outs[1][0].peaks) > 100
+
+
+def test_scan_form_chosen_on_the_device(monkeypatch):
+    """Both scan kernels are launched and the sample picks one (form_skip): a flat sample takes the rank form, one
+    whose entries sit in full blocks (>= 1024 entries per 8192 cells: a deep sample, ATAC pile-ups) the CTA form;
+    the statistic is exact, and either choice gives the bits of the plain path."""
+    api = capi.load_cuda()
+    L = [3_000_000, 1_000_000]
+    par = capi.make_params(p=0.01)
+    flat = Workload(L, 60_000, 5, enrich=0.2, spacing=100000, sigma=80.0).fragments()
+    deep = Workload(L, 900_000, 6, enrich=0.3, spacing=100000, sigma=80.0).fragments()
+    for k, v in FUSED.items():
+        monkeypatch.setenv(k, v)
+    for recs, want in ((flat, 0), (deep, 1)):
+        ctx = capi.Context(api, L, par)
+        res = host.run_replicates(ctx, [(recs, None)], chunk=1 << 20)
+        form, hot, ent = ctx.scan_form()
+        # the statistic, recomputed: entries per block (an interval that crosses a block border has two)
+        off = np.concatenate([[0], np.cumsum([(l + 1 + 8191) // 8192 for l in L])])[:-1]
+        s = np.clip(recs[:, 1], 0, None); e = np.minimum(recs[:, 2], np.asarray(L)[recs[:, 0]])
+        bs, be = off[recs[:, 0]] + s // 8192, off[recs[:, 0]] + e // 8192
+        cnt = np.bincount(np.concatenate([bs, be[be != bs]]))
+        assert ent == int(cnt.sum()) and hot == int(cnt[cnt >= 1024].sum())
+        assert form == want == int(hot * 4 > ent)
+        for k in FUSED:
+            monkeypatch.delenv(k)
+        ref = _run_modes(monkeypatch, L, par, [(recs, None)], (PLAIN,), chunk=1 << 20)[0][0]
+        assert ref.peaks.tobytes() == res.peaks.tobytes() and len(res.peaks) > 0
+        for k, v in FUSED.items():
+            monkeypatch.setenv(k, v)
 
 
 def test_saturation_rule():
@@ -509,8 +539,8 @@ def test_error_codes(monkeypatch):
     # more starts on one base than the reference's int16 counter holds: the reference drops the 32768th
     # (saveInterval 2558-2573), and so do the oracle and the fused paths (k_sat_resolve; the full case is
     # test_saturation_rule).  The dense formulation -- a measurement aid behind GR_FUSED=0 -- only detects it.
-    for env in (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_DENSE="1")):
-        for k in ("GR_FUSED", "GR_FUSED_MIN", "GR_SB_MIN", "GR_FUSED_CTA", "GR_FUSED_DENSE"):
+    for env in (PLAIN, FUSED, dict(FUSED, GR_FUSED_CTA="1"), dict(FUSED, GR_FUSED_RANK="1")):
+        for k in ("GR_FUSED", "GR_FUSED_MIN", "GR_SB_MIN", "GR_FUSED_CTA", "GR_FUSED_RANK"):
             monkeypatch.delenv(k, raising=False)
         for k, v in env.items():
             monkeypatch.setenv(k, v)
