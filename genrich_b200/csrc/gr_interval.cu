@@ -161,33 +161,38 @@ __global__ void __launch_bounds__(256)
 k_union_rank(const u32* __restrict__ bmE, const u32* __restrict__ bmC, Lookback<3> lb,
              u64* __restrict__ rankE, u64* __restrict__ rankC, u64* __restrict__ rankU,
              u64* __restrict__ totals, u32 nblocks, u32 ntiles) {
-  __shared__ u32 sm[UR_BLOCKS][3][8];
   __shared__ u32 sm_blk[UR_BLOCKS][3];
   __shared__ i64 sm_ex[3];
   const u32 tile = take_ticket(lb.ticket);
   const u32 b0 = tile * UR_BLOCKS;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  u32 E[UR_BLOCKS], C[UR_BLOCKS];
+  // a warp takes UR_BLOCKS / 8 whole blocks (8 words per lane and bitmap of each): the popcounts add up in
+  // registers and one packed warp reduction per block is left (a reduction per word and counter -- 48 per
+  // thread -- was what this kernel spent its time on: 0.5 ms for 0.77 GB)
+  constexpr int PER = UR_BLOCKS / 8;
+  u32 E[PER][8], C[PER][8];
 #pragma unroll
-  for (int b = 0; b < UR_BLOCKS; b++) {
-    const u64 widx = (u64)(b0 + b) * 256 + threadIdx.x;
-    const bool on = b0 + b < nblocks;
-    E[b] = on ? bmE[widx] : 0u;
-    C[b] = (on && bmC) ? bmC[widx] : 0u;
+  for (int q = 0; q < PER; q++) {
+    const u32 b = b0 + w * PER + q;
+    const bool on = b < nblocks;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const u64 widx = (u64)b * 256 + i * 32 + lane;
+      E[q][i] = on ? bmE[widx] : 0u;
+      C[q][i] = (on && bmC) ? bmC[widx] : 0u;
+    }
   }
 #pragma unroll
-  for (int b = 0; b < UR_BLOCKS; b++) {
-    const u32 a = __reduce_add_sync(GR_FULL, __popc(E[b]));
-    const u32 c = __reduce_add_sync(GR_FULL, __popc(C[b]));
-    const u32 u = __reduce_add_sync(GR_FULL, __popc(E[b] | C[b]));
-    if (lane == 0) { sm[b][0][w] = a; sm[b][1][w] = c; sm[b][2][w] = u; }
-  }
-  __syncthreads();
-  if (threadIdx.x < UR_BLOCKS * 3) {
-    const int b = threadIdx.x / 3, k = threadIdx.x % 3;
-    u32 t = 0;
-    for (int q = 0; q < 8; q++) t += sm[b][k][q];
-    sm_blk[b][k] = t;
+  for (int q = 0; q < PER; q++) {
+    u32 ac = 0, u = 0;                                 // <= 8192 per block: E and C counts travel packed
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      ac += __popc(E[q][i]) | (__popc(C[q][i]) << 16);
+      u += __popc(E[q][i] | C[q][i]);
+    }
+    ac = __reduce_add_sync(GR_FULL, ac);
+    u = __reduce_add_sync(GR_FULL, u);
+    if (lane == 0) { sm_blk[w * PER + q][0] = ac & 0xffffu; sm_blk[w * PER + q][1] = ac >> 16; sm_blk[w * PER + q][2] = u; }
   }
   __syncthreads();
   if (w == 0) {
