@@ -490,7 +490,7 @@ class RefSample:
         if not os.path.exists(cli):
             return None
         out = os.path.join(self.dir, "cli.narrowPeak")
-        best = None
+        best, runs = None, []
         for _ in range(2):                            # the second run has the library and the files warm
             t0 = time.perf_counter()
             r = subprocess.run(self.cmd(cli, out) + ["--threads", str(threads)], stderr=subprocess.PIPE, text=True)
@@ -498,9 +498,10 @@ class RefSample:
             if r.returncode:
                 return {"error": (r.stderr or "")[-300:]}
             best = dt if best is None else min(best, dt)
+            runs.append(round(dt, 3))
         ident = [l.split("\t")[:3] + l.rstrip("\n").split("\t")[9:] for l in open(out)] == \
                 [l.split("\t")[:3] + l.rstrip("\n").split("\t")[9:] for l in open(self.out)]
-        return {"seconds": round(best, 3), "value": self.G / 1e9 / best, "unit": "Gbp/s", "threads": threads,
+        return {"seconds": round(best, 3), "runs_s": runs, "value": self.G / 1e9 / best, "unit": "Gbp/s", "threads": threads,
                 "narrowpeak_cols_1_3_10_identical_to_reference": bool(ident),
                 "note": "genrich-b200 (host C program over the CUDA library) on the SAM files the reference was timed on: "
                         "whole program, SAM decode on the host threads included"}
@@ -725,8 +726,7 @@ def main():
     #   cta    (GR_FUSED_CTA=1): k_fb_scan, the CTA-owned shared-memory cell array that was the default in round 1
     forms = {}
     if world == 1 and not a.no_dense and G < (1 << 32):
-        for key, env in (("dense_array", {"GR_FUSED": "0"}), ("cta", {"GR_FUSED_CTA": "1"}), ("rank", {"GR_FUSED_RANK": "1"})) + \
-                ((("dense_cells", {"GR_FUSED_DENSE": "1"}),) if os.environ.get("GR_BENCH_FD") else ()):
+        for key, env in (("dense_array", {"GR_FUSED": "0"}), ("cta", {"GR_FUSED_CTA": "1"}), ("rank", {"GR_FUSED_RANK": "1"})):
             os.environ.update(env)
             eng_d = ShardedEngine(api, L, par, dev, host_group=None)
             ms_d, _, _, peaks_d, _, st_d = timed(False, st_steps, 3, with_stages=True, eng=eng_d)
@@ -772,7 +772,6 @@ def main():
                             "(4 B per cell each way: here `achieved` IS the HBM read rate); same peaks, bit for bit")
     cta_obj = formulation("k_fb_scan", cta, "fused_scan", "GR_FUSED_CTA=1: round 1's default scan; same peaks, bit for bit")
     rank_obj = formulation("k_fr_scan", forms.get("rank"), "fused_scan", "GR_FUSED_RANK=1: the rank form whatever the blocks hold")
-    cells_obj = formulation("k_fd_scan", forms.get("dense_cells"), "fused_scan", "GR_FUSED_DENSE=1: bulk-copy staged cell array (measurement only)")
 
     # what really moves through DRAM: per kernel, from the committed ncu pass of `bench.py --profile` on this workload
     table = load_dram_table(a.workload, world)
@@ -830,7 +829,7 @@ def main():
                              "the kernel really moves, `step` what the whole step moves, `dense_formulation` what the kernel that "
                              "does read 4 B per cell achieves",
                      "step": step_obj, "dense_formulation": dense_obj, "cta_formulation": cta_obj,
-                     "rank_formulation": rank_obj, "dense_cells_formulation": cells_obj},
+                     "rank_formulation": rank_obj},
         "dense_formulation": dense_obj,
         "stage_ms_per_step": stage_ms,
         "host_phase_ms_per_step_device_arm": host_phase_dev,

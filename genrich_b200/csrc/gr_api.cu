@@ -931,17 +931,17 @@ static int pileup_enqueue(gr_ctx* x) {
     CKL();
     stage_end(x);
   }
-  stage_begin(x, "scan_place", cap * 16);
-  launch_scan_place(x->stream, x->L, sc, out, x->d_err, owners, ctrl ? GR_SKIP : 0.0f);
-  HT("pileup_enqueue: scan + place launched");
-  CKL();
-  stage_end(x);
   u64* aI = x->accI.as<u64>() + (ctrl ? x->nchrom : 0);
   u64* aF = x->accF.as<u64>() + (ctrl ? x->nchrom : 0);
   CK(cudaMemsetAsync(aI, 0, x->nchrom * sizeof(u64), x->stream));
   CK(cudaMemsetAsync(aF, 0, x->nchrom * sizeof(u64), x->stream));
+  stage_begin(x, "scan_place", cap * 16);
+  const bool summed = launch_scan_place(x->stream, x->L, sc, out, x->d_err, owners, ctrl ? GR_SKIP : 0.0f, aI, aF);
+  HT("pileup_enqueue: scan + place launched");
+  CKL();
+  stage_end(x);
   stage_begin(x, "rle_moment", 0);
-  launch_rle_moment(x->stream, out, cap, x->nchrom, aI, aF);
+  if (!summed) launch_rle_moment(x->stream, out, cap, x->nchrom, aI, aF);
   launch_sums_double(x->stream, aI, aF, x->nchrom, x->dsums.as<double>() + (ctrl ? x->nchrom : 0));
   HT("pileup_enqueue: moments launched");
   CKL();

@@ -661,24 +661,74 @@ k_scan_fix(DevLayout L, StreamWs W, DevRle out, int* __restrict__ err, u32 nwarp
 // step; keeping four pages in flight (SP_UNROLL 4) was measured slower (0.41 ms), so the
 // three-deep lookup chain (page -> owner -> base) is not what bounds it.
 #define SP_UNROLL 1
+// The per-chromosome sums of (float)(end - start) * val (fragLen / ctrlFrag, Genrich.c:2246 / 2018) are taken
+// here, where every interval passes through registers anyway (a separate pass over the placed arrays read 8 B
+// per interval again: 0.22 ms per hg38 sample).  Every float product is added EXACTLY in fixed point (integer
+// part and 2^-40 fraction in separate u64 counters), so the result does not depend on the order of the adds; a
+// CTA collects in shared memory (SP_MAXC chromosomes) and adds to the global counters once.  The first entry of
+// a page has its predecessor in another page: k_moment_heads takes those, one per page, from the placed arrays.
+#define SP_MAXC 1024
+struct MomentAcc {
+  u64* sm;                                             // [2 * nchrom]: integer parts, fractions
+  __device__ __forceinline__ void add(int c, u64 ip, u64 pf) {
+    atomicAdd((unsigned long long*)sm + 2 * c, (unsigned long long)ip);
+    atomicAdd((unsigned long long*)sm + 2 * c + 1, (unsigned long long)pf);
+  }
+};
+__device__ __forceinline__ void moment_product(u32 end, u32 st, float v, u64& ip, u64& pf) {
+  const float p = v < 0.0f ? 0.0f : __fmul_rn(__uint2float_rn(end - st), v);     // SKIP (-E region): not counted (2016)
+  ip = (u64)p;                                         // p >= 0
+  pf = (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);   // exact: fraction * 2^40
+}
+// warp-wide: the lanes with on == true add their product to chromosome c (uniform over the warp in all but the
+// few warps that hold a chromosome boundary)
+__device__ __forceinline__ void moment_warp_add(MomentAcc A, bool on, int c, u64 ip, u64 pf, int lane) {
+  const u32 act = __ballot_sync(GR_FULL, on);
+  if (!act) return;
+  const int c0 = __shfl_sync(GR_FULL, c, __ffs(act) - 1);
+  if (__all_sync(GR_FULL, !on || c == c0)) {
+    const u64 a = warp_sum_u64(on ? ip : 0ull), b = warp_sum_u64(on ? pf : 0ull);
+    if (lane == 0) A.add(c0, a, b);
+  } else if (on) A.add(c, ip, pf);
+}
+__device__ __forceinline__ void moment_flush(const u64* sm, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ acc_frac,
+                                             int tid, int nt) {
+  for (int c = tid; c < nchrom; c += nt) {
+    u64 ti = sm[2 * c], tf = sm[2 * c + 1];
+    ti += tf >> 40;
+    tf &= (1ull << 40) - 1;
+    if (ti) atomicAdd((unsigned long long*)acc_int + c, (unsigned long long)ti);
+    if (tf) atomicAdd((unsigned long long*)acc_frac + c, (unsigned long long)tf);
+  }
+}
+
+template <bool MOMENT>
 __global__ void __launch_bounds__(2 * SS_PAGE)
-k_scan_place(StreamWs W, DevRle out, int* __restrict__ err, float excl_val) {
+k_scan_place(StreamWs W, DevRle out, int* __restrict__ err, float excl_val, int nchrom,
+             u64* __restrict__ acc_int, u64* __restrict__ acc_frac) {
   __shared__ float4 sm_lut[120];
+  __shared__ u64 sm_acc[MOMENT ? 2 * SP_MAXC : 2];
   units_lut_fill(sm_lut, threadIdx.x, 2 * SS_PAGE);
+  if (MOMENT)
+    for (int i = threadIdx.x; i < 2 * nchrom; i += 2 * SS_PAGE) sm_acc[i] = 0;
   __syncthreads();
+  MomentAcc A;
+  A.sm = sm_acc;
   const u32 npages = min(*W.page_ctr, W.max_pages);
   const u32 t = threadIdx.x & (SS_PAGE - 1), half = threadIdx.x >> SS_PAGE_SHIFT;
+  const int lane = threadIdx.x & 31;
   const u32 pstep = gridDim.x * 2;
   bool neg = false;
-  for (u32 p0 = blockIdx.x * 2 + half; p0 < npages; p0 += pstep * SP_UNROLL) {
+  for (u32 p0 = blockIdx.x * 2 + half; p0 < npages; p0 += pstep * SP_UNROLL) {   // p0 is uniform over the 8 warps of a half
     uint2 meta[SP_UNROLL], e[SP_UNROLL];
-    u32 tot[SP_UNROLL];
+    u32 tot[SP_UNROLL], pe[SP_UNROLL];
     ulonglong2 wb[SP_UNROLL];
 #pragma unroll
     for (int k = 0; k < SP_UNROLL; k++) {
       const u32 p = min(p0 + k * pstep, npages - 1);
       meta[k] = W.page_meta[p];
       e[k] = W.pent[((u64)p << SS_PAGE_SHIFT) + t];    // may be stale past the page's fill: not used then
+      pe[k] = (MOMENT && t) ? W.pent[((u64)p << SS_PAGE_SHIFT) + t - 1].x : 0u;   // the entry before: same line, mostly
     }
 #pragma unroll
     for (int k = 0; k < SP_UNROLL; k++) {
@@ -688,16 +738,68 @@ k_scan_place(StreamWs W, DevRle out, int* __restrict__ err, float excl_val) {
 #pragma unroll
     for (int k = 0; k < SP_UNROLL; k++) {
       const u32 first = meta[k].y << SS_PAGE_SHIFT;
-      if (p0 + k * pstep >= npages || first + t >= tot[k]) continue;   // beyond the owner's last entry / a page held in reserve
-      const int N = (int)((u32)wb[k].x + e[k].y);
-      neg |= N < 0;
+      const bool on = !(p0 + k * pstep >= npages || first + t >= tot[k]);   // else: beyond the owner's last entry / a page held in reserve
       const u64 rank = wb[k].y + first + t;
-      out.end[rank] = e[k].x & 0x7fffffffu;
-      // bit 31: the interval lies in a -E region -- 0.0f in the experimental pileup (2248), SKIP in the control's (2124)
-      out.val[rank] = (e[k].x >> 31) ? excl_val : units_to_val_lut(sm_lut, N < 0 ? 0 : N);
+      float val = 0.0f;
+      if (on) {
+        const int N = (int)((u32)wb[k].x + e[k].y);
+        neg |= N < 0;
+        out.end[rank] = e[k].x & 0x7fffffffu;
+        // bit 31: the interval lies in a -E region -- 0.0f in the experimental pileup (2248), SKIP in the control's (2124)
+        val = (e[k].x >> 31) ? excl_val : units_to_val_lut(sm_lut, N < 0 ? 0 : N);
+        out.val[rank] = val;
+      }
+      if (MOMENT) {
+        // the warp's 32 ranks are consecutive: one chromosome unless a boundary lies among them
+        const u64 r_lo = __shfl_sync(GR_FULL, rank, 0);
+        int c = 0;
+        const u32 on_m = __ballot_sync(GR_FULL, on);       // the lanes that are on are the first popc(on_m) of the warp
+        if (on_m) {
+          const int hi_lane = 31 - __clz(on_m);
+          int cq = (lane == 0 || lane == hi_lane) ? chrom_of_index(out.chrom_start, nchrom, lane == 0 ? r_lo : rank) : 0;
+          const int ca = __shfl_sync(GR_FULL, cq, 0), cb = __shfl_sync(GR_FULL, cq, hi_lane);
+          c = ca;
+          if (ca != cb && on) c = chrom_of_index(out.chrom_start, nchrom, rank);
+        }
+        const bool mine = on && t;                         // t == 0: k_moment_heads
+        u64 ip = 0, pf = 0;
+        if (mine) {
+          const u32 st = rank == out.chrom_start[c] ? 0u : (pe[k] & 0x7fffffffu);
+          moment_product(e[k].x & 0x7fffffffu, st, val, ip, pf);
+        }
+        moment_warp_add(A, mine, c, ip, pf, lane);
+      }
     }
   }
   if (neg) atomicOr(err, GR_DE_PILE);                  // ERRPILE 1921, 1969
+  if (MOMENT) {
+    __syncthreads();
+    moment_flush(sm_acc, nchrom, acc_int, acc_frac, threadIdx.x, 2 * SS_PAGE);
+  }
+}
+
+// the first entry of every page: its predecessor is the last entry of another page (or of another owner's run)
+__global__ void __launch_bounds__(256)
+k_moment_heads(StreamWs W, DevRle out, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ acc_frac) {
+  __shared__ u64 sm_acc[2 * SP_MAXC];
+  for (int i = threadIdx.x; i < 2 * nchrom; i += 256) sm_acc[i] = 0;
+  __syncthreads();
+  MomentAcc A;
+  A.sm = sm_acc;
+  const u32 npages = min(*W.page_ctr, W.max_pages);
+  for (u32 p = blockIdx.x * 256 + threadIdx.x; p < npages; p += gridDim.x * 256) {
+    const uint2 meta = W.page_meta[p];
+    const u32 first = meta.y << SS_PAGE_SHIFT;
+    if (first >= W.warp_tot[meta.x].y) continue;       // a page held in reserve
+    const u64 rank = W.warp_base[meta.x].y + first;
+    const int c = chrom_of_index(out.chrom_start, nchrom, rank);
+    const u32 st = rank == out.chrom_start[c] ? 0u : out.end[rank - 1];
+    u64 ip, pf;
+    moment_product(out.end[rank], st, out.val[rank], ip, pf);
+    A.add(c, ip, pf);
+  }
+  __syncthreads();
+  moment_flush(sm_acc, nchrom, acc_int, acc_frac, threadIdx.x, 256);
 }
 
 // chromosomes without slots start where the next one does
@@ -776,11 +878,17 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
 }
 
 // ... and K2b + K2c, which put the breaks where the rest of the pipeline expects them
-void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners,
-                       float excl_val) {
+bool launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners,
+                       float excl_val, u64* acc_int, u64* acc_frac) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   k_scan_fix<<<1, 1024, 0, s>>>(L, W, out, err, owners ? owners : (u32)scan_stream_warps()); GR_NOTE_LAUNCH();
-  k_scan_place<<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err, excl_val); GR_NOTE_LAUNCH();
+  if (acc_int && L.nchrom <= SP_MAXC) {                // the sums of len * val are taken on the way (else: launch_rle_moment)
+    k_scan_place<true><<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err, excl_val, L.nchrom, acc_int, acc_frac); GR_NOTE_LAUNCH();
+    k_moment_heads<<<148 * 2, 256, 0, s>>>(W, out, L.nchrom, acc_int, acc_frac); GR_NOTE_LAUNCH();
+    return true;
+  }
+  k_scan_place<false><<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err, excl_val, L.nchrom, nullptr, nullptr); GR_NOTE_LAUNCH();
+  return false;
 }
 
 // ============================================================================
@@ -1273,224 +1381,9 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
   }
 }
 
-__device__ __forceinline__ int fr_weight(u32 count);
-// Dense form: the scan for DEEP samples, whose blocks are mostly occupied (the 10 Gbp / 1 B fragment configuration:
-// ~2200 entries and ~3400 distinct event cells per 8192-cell block).  There the occupancy-driven walks of the two
-// other forms (k_fb_scan: per set bit; k_fr_scan: per 512 distinct cells, every round over all entries) cost more
-// than simply reading every cell: measured on the B200, 333 M records over 1.25 G cells, 4.1 ms and 9.5 ms.
-//   * the CTA's run of bucket entries is ONE contiguous stream (blk_start is cumulative): it is staged through a
-//     two-deep ring of 8 KB tiles by 1-D bulk copies (cp.async.bulk -> mbarrier, the TMA unit; no registers, no
-//     L1) that run ahead of the block being worked on;
-//   * entries -> shared-memory cells by atomicAdd (cell c lives at c + c / 32: a thread's 32 consecutive cells
-//     then fall into 32 different banks);
-//   * every thread reads ITS 32 cells unconditionally (no bit walks, no divergence), clears them, builds the
-//     break mask -- which is the thread's word of the break bitmap -- and after one block-wide scan emits its
-//     breaks from registers.
-// Output contract = k_fb_scan's (owner = CTA: pages, warp_tot, marks).  No -E marks here (k_fb_scan keeps those).
-#define FD_NT 256
-#define FD_STAGE 2048                                  // entries per staging tile
-#define FD_PAD(c) ((c) + ((c) >> 5))
-struct FdSmem {
-  u32 ent[2][FD_STAGE];                                // first: 16-byte aligned with the dynamic shared memory itself
-  int cell[GR_BLOCK_SLOTS + GR_BLOCK_SLOTS / 32];
-  u64 bar[2];
-  u32 pg[FB_RING];
-  u32 ws[FD_NT / 32], wc[FD_NT / 32];
-};
-#ifdef GR_EMU                       // tests/emu: the copy is a memcpy; the barrier word counts completed copies, and a waiter yields
-__device__ __forceinline__ void fd_bar_init(u64* bar) { *bar = 0; }
-__device__ __forceinline__ void fd_bulk_load(void* dst, const void* src, u32 bytes, u64* bar) { memcpy(dst, src, bytes); ++*bar; }
-__device__ __forceinline__ void fd_bar_wait(u64* bar, u32 parity) { while ((u32)(*(volatile u64*)bar & 1u) == parity) emu::spin_yield(); }
-__device__ __forceinline__ void fd_fence_async() {}
-#else
-__device__ __forceinline__ void fd_bar_init(u64* bar) {
-  const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(a) : "memory");
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-// one thread: arm the barrier with the byte count, start the bulk copy that will complete it
-__device__ __forceinline__ void fd_bulk_load(void* dst, const void* src, u32 bytes, u64* bar) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               :: "r"(d), "l"(src), "r"(bytes), "r"(b) : "memory");
-}
-__device__ __forceinline__ void fd_bar_wait(u64* bar, u32 parity) {
-  const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "FD_WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra FD_DONE_%=;\n\t"
-      "bra FD_WAIT_%=;\n\t"
-      "FD_DONE_%=:\n\t}" :: "r"(b), "r"(parity) : "memory");
-}
-// the tile was read through the generic proxy; the next bulk copy writes it through the async proxy
-__device__ __forceinline__ void fd_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-#endif
-
-__global__ void __launch_bounds__(FD_NT, 3)
-k_fd_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
-          u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R) {
-  extern __shared__ int4 fd_raw[];                      // 16-byte aligned: the bulk copies' destination tiles
-  FdSmem& S = *reinterpret_cast<FdSmem*>(fd_raw);
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const u32 owner = blockIdx.x;
-  const u32 b0 = owner * R, b1 = min(b0 + R, nblocks);
-  if (b0 >= b1) {
-    if (t == 0) W.warp_tot[owner] = make_uint2(0, 0);
-    return;
-  }
-  for (int i = t; i < GR_BLOCK_SLOTS + GR_BLOCK_SLOTS / 32; i += FD_NT) S.cell[i] = 0;
-  // the run's entries as one stream of FD_STAGE-entry tiles, 16-byte aligned at both ends (the buffer has the room)
-  const u32 run_lo = blk_start[b0] & ~3u, run_hi = blk_start[b1];
-  const u32 nchunk = (run_hi - run_lo + FD_STAGE - 1) / FD_STAGE;
-  if (t == 0) { fd_bar_init(&S.bar[0]); fd_bar_init(&S.bar[1]); }
-  __syncthreads();
-  auto issue = [&](u32 c) {                             // thread 0
-    if (c >= nchunk) return;
-    const u32 e0 = run_lo + c * FD_STAGE;
-    const u32 n = (min((u32)FD_STAGE, run_hi - e0) + 3u) & ~3u;
-    fd_bulk_load(S.ent[c & 1], bucketed + e0, n * 4u, &S.bar[c & 1]);
-  };
-  if (t == 0) { issue(0); issue(1); }
-  u32 waited = 0;                                       // tiles whose arrival this thread has seen
-
-  const u32 last_page = W.max_pages - 1;
-  int have_seq = -1;
-  u32 pend_p0 = 0;
-  int pend_k = 0;
-  auto page_take = [&]() {
-    for (int i = 0; i < pend_k; i++) {
-      u32 pg = pend_p0 + (u32)i;
-      if (pg > last_page) { atomicOr(err, GR_DE_TABLE); pg = last_page; }
-      have_seq++;
-      W.page_meta[pg] = make_uint2(owner, (u32)have_seq);
-      S.pg[have_seq & (FB_RING - 1)] = pg;
-    }
-    pend_k = 0;
-  };
-  auto page_ask = [&](u32 upto_idx) {
-    const int target = (int)(upto_idx >> SS_PAGE_SHIFT);
-    if (target > have_seq) {
-      pend_k = target - have_seq;
-      pend_p0 = atomicAdd(W.page_ctr, (u32)pend_k);
-    }
-  };
-  auto ub_of = [&](u32 a, u32 b) { return min(2u * (b - a) + 1u, (u32)GR_BLOCK_SLOTS + 1u); };
-  auto ld_start = [&](u32 i) { return blk_start[min(i, nblocks)]; };
-  u32 sA = ld_start(b0), sB = ld_start(b0 + 1), sC = ld_start(b0 + 2);
-  if (t == 0) page_ask(ub_of(sA, sB));
-
-  auto apply = [&](u32 e) {
-    const u32 so = e & (GR_BLOCK_SLOTS - 1), kind = e >> 30;
-    const int w = fr_weight((e >> 26) & 15u);
-    atomicAdd(&S.cell[FD_PAD(so)], kind == FB_KIND_END ? -w : w);
-    if (kind == FB_KIND_BOTH) {
-      const u32 eo = so + ((e >> 13) & (GR_BLOCK_SLOTS - 1));
-      atomicAdd(&S.cell[FD_PAD(eo)], -w);
-    }
-  };
-
-  u32 run_s = 0, run_c = 0;
-  bool sat = false;
-  int c = -1;
-  u32 c_last_blk = 0;
-  u64 off = 0;
-  u32 len = 0;
-  bool act = false;
-  for (u32 b = b0; b < b1; b++) {
-    if (c < 0 || b > c_last_blk) {                     // ~25 times per genome
-      c = L.blk2chrom[b];
-      off = L.off[c];
-      len = L.len[c];
-      c_last_blk = (u32)((off + len) >> GR_BLOCK_SHIFT);
-      act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
-    }
-    const u32 sD = ld_start(b + 3);
-    const u32 jb = (u32)(((u64)b << GR_BLOCK_SHIFT) - off);       // chromosome position of the block's first cell
-    if (t == 0) {
-      if (jb == 0) W.marks[c] = make_uint4(owner, run_s, run_c, 1u);
-      page_take();
-      page_ask(run_c + ub_of(sA, sB) + (b + 1 < b1 ? ub_of(sB, sC) : 0u));
-    }
-    const bool has_end = act && b == c_last_blk;       // cell `len` lies in this block
-    if (sA == sB && !has_end) {                        // nothing in this block
-      bitmap[(u64)b * FB_WORDS + t] = 0;
-      sA = sB; sB = sC; sC = sD;
-      continue;
-    }
-    // ---- entries -> cells, tile by tile
-    for (u32 pos = sA; pos < sB;) {
-      const u32 ch = (pos - run_lo) / FD_STAGE;
-      if (ch >= waited) { fd_bar_wait(&S.bar[ch & 1], (ch >> 1) & 1u); waited = ch + 1; }
-      const u32 tile_end = run_lo + (ch + 1) * FD_STAGE;
-      const u32 upto = min(sB, tile_end);
-      const u32* buf = S.ent[ch & 1];
-      for (u32 i = pos + t; i < upto; i += FD_NT) apply(buf[i - (tile_end - FD_STAGE)]);
-      pos = upto;
-      if (pos == tile_end) {                           // the tile is used up: its buffer takes the tile after the next
-        __syncthreads();
-        if (t == 0) { fd_fence_async(); issue(ch + 2); }
-      }
-    }
-    __syncthreads();
-    // ---- this thread's 32 cells: deltas into registers, cleared behind; break mask = its bitmap word
-    int d[32];
-    u32 s = 0, m = 0;
-    const u32 jt = jb + (u32)t * 32u;
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-      d[k] = S.cell[t * 33 + k];
-      S.cell[t * 33 + k] = 0;
-      s += (u32)d[k];
-      sat |= cell_saturated(d[k]);
-    }
-    if (act) {
-      if (jb >= 1 && (u64)jb + GR_BLOCK_SLOTS < (u64)len) {       // interior block: a break wherever the delta is not zero
-#pragma unroll
-        for (int k = 0; k < 32; k++) m |= (d[k] != 0 ? 1u : 0u) << k;
-      } else {
-#pragma unroll
-        for (int k = 0; k < 32; k++) {
-          const u32 j = jt + (u32)k;
-          m |= ((j == len) || (d[k] != 0 && j >= 1u && j < len) ? 1u : 0u) << k;
-        }
-      }
-    }
-    const u32 cnt = __popc(m);
-    const u32 wi_s = warp_incl_scan_u32(s, lane), wi_c = warp_incl_scan_u32(cnt, lane);
-    if (lane == 31) { S.ws[wid] = wi_s; S.wc[wid] = wi_c; }
-    __syncthreads();
-    u32 h = run_s + wi_s - s, idx = run_c + wi_c - cnt, tot_s = 0, tot_c = 0;
-#pragma unroll
-    for (int k = 0; k < FD_NT / 32; k++) {
-      const u32 a = S.ws[k], q = S.wc[k];
-      if (k < wid) { h += a; idx += q; }
-      tot_s += a; tot_c += q;
-    }
-    // ---- emit from registers
-#pragma unroll
-    for (int k = 0; k < 32; k++) {
-      if ((m >> k) & 1u) {
-        const u32 pg = S.pg[(idx >> SS_PAGE_SHIFT) & (FB_RING - 1)];
-        W.pent[((u64)pg << SS_PAGE_SHIFT) | (idx & (SS_PAGE - 1))] = make_uint2(jt + (u32)k, h);
-        idx++;
-      }
-      h += (u32)d[k];
-    }
-    bitmap[(u64)b * FB_WORDS + t] = m;
-    run_s += tot_s;
-    run_c += tot_c;
-    sA = sB; sB = sC; sC = sD;
-    __syncthreads();                                   // the scan scratch and the page ring are free again
-  }
-  if (sat) atomicOr(err, GR_DE_SAT);
-  if (t == 0) {
-    page_take();
-    W.warp_tot[owner] = make_uint2(run_s, run_c);
-  }
-}
+// Tried and removed: k_fd_scan, a cell-array form with the entry stream staged by bulk copies (cp.async.bulk +
+// mbarrier, two 8 KB tiles) and 32 cells per thread.  Measured on the B200 per launch: hg38 ChIP 3.6 ms (rank form
+// 0.71), ATAC 4.3 ms (CTA form 2.8), 10 Gbp shard 3.2 ms (CTA form 4.1) -- a 2 % shorter step on one workload.
 
 // Rank form -- the default scan: warp-owned 8192-cell blocks WITHOUT a cell array.  A block of the
 // hg38 workload holds ~265 entries = ~400 distinct event cells out of 8192; k_fb_scan spends its
@@ -1783,14 +1676,6 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
   const u32 nb = (u32)L.nblocks;
   const int force_cta = blk_bed || fb_env("GR_FUSED_CTA", 0), force_rank = !force_cta && fb_env("GR_FUSED_RANK", 0);   // read per call: the tests switch it inside one process
   u32 owners = 0;
-  if (!blk_bed && fb_env("GR_FUSED_DENSE", 0)) {       // measurement only: the bulk-copy staged cell-array form
-    if (first_use_on_device(4)) cudaFuncSetAttribute(k_fd_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FdSmem));
-    owners = (u32)(sms * 3);
-    const u32 R = (nb + owners - 1) / owners;
-    k_fd_scan<<<owners, FD_NT, sizeof(FdSmem), s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R);
-    GR_NOTE_LAUNCH();
-    return owners;
-  }
   if (!force_rank) {
     const u32 o = (u32)(sms * 6);
     const u32 R = (nb + o - 1) / o;

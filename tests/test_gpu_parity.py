@@ -360,6 +360,37 @@ def test_scan_form_chosen_on_the_device(monkeypatch):
             monkeypatch.setenv(k, v)
 
 
+def test_many_chromosomes():
+    """1100 contigs: more than the placement kernel's shared table of per-chromosome sums holds (SP_MAXC 1024), so the
+    sums come from the separate pass (k_rle_moment); 900: from the placement kernel.  Same lambda / factor bits and
+    peaks as the oracle either way."""
+    api = capi.load_cuda()
+    rng = np.random.RandomState(3)
+    for nchrom in (900, 1100):
+        L = [int(x) for x in rng.randint(2000, 9000, nchrom)]
+        def sample(n, seed, enrich):
+            r = np.random.RandomState(seed)
+            c = r.randint(0, nchrom, n)
+            s = (r.uniform(size=n) * (np.asarray(L)[c] - 300)).astype(np.int64)
+            hot = r.uniform(size=n) < enrich
+            s[hot] = (np.asarray(L)[c[hot]] // 2 + r.randint(-40, 40, hot.sum()))
+            return np.stack([c, s, s + r.randint(80, 300, n), np.ones(n, np.int64)], 1).astype(np.int32)
+        t, c = sample(40000, 1, 0.3), sample(40000, 2, 0.0)
+        par = capi.make_params(p=0.01)
+        outs = []
+        for a in (util.oracle_api(), api):
+            ctx = capi.Context(a, L, par)
+            res = host.run_replicates(ctx, [(t, c)], chunk=1 << 20)
+            outs.append(res)
+        o, g = outs
+        assert _bits(o.sample_stats[0].lambda_) == _bits(g.sample_stats[0].lambda_)
+        assert _bits(o.sample_stats[0].factor) == _bits(g.sample_stats[0].factor)
+        assert o.sample_stats[0].frag_len == g.sample_stats[0].frag_len and o.sample_stats[0].ctrl_frag == g.sample_stats[0].ctrl_frag
+        for f in ("chrom", "start", "end", "summit"):
+            assert np.array_equal(o.peaks[f], g.peaks[f])
+        assert len(g.peaks) > 5
+
+
 def test_saturation_rule():
     """saveInterval 2558-2573: more than 32767 starts (32768 ends) on one base -- the reference drops
     intervals in arrival order; the device replays exactly that (k_sat_resolve).  Same dropped records,
