@@ -600,12 +600,13 @@ def main():
     par = capi.make_params(p=wl["p"], q=wl["q"])
     threads = a.gen_threads or max(2, min(16, (os.cpu_count() or 8) // max(world, 1)))
 
-    # N > 1 first proves the sharded path on a small -q workload: every rank computes the whole `mini` genome
+    # N > 1 first proves the sharded path on a small -q workload with peaks: every rank computes the whole genome
     # alone, then the ranks do it together (chromosomes sharded, sums all-reduced, BH histogram all-gathered,
-    # peaks gathered) -- same records, so rank 0 must see the same peaks, bit for bit.
+    # peaks gathered) -- same records, so rank 0 must see the same peaks, bit for bit.  16 chromosomes: every rank
+    # of an 8-rank job owns some (a context that owns nothing is refused by gr_create).
     shard_parity = None
     if world > 1 and not a.profile:
-        mw = dict(WORKLOADS["mini"], q=0.05, p=None)
+        mw = dict(chrom_len=[6_000_000] * 16, reps=[(1_500_000, 1_500_000)], enrich=0.4, spacing=200000, sigma=60.0)
         mpar = capi.make_params(p=None, q=0.05)
         from genrich_b200.synth import Workload
         mt = Workload(mw["chrom_len"], mw["reps"][0][0], 4001, enrich=mw["enrich"], spacing=mw["spacing"], sigma=mw["sigma"]).fragments()
@@ -620,10 +621,10 @@ def main():
         meng.replicate(lambda c: c.push_packed(pt), lambda c: c.push_packed(pc), want_stats=False)
         got, mrs = meng.call_peaks()
         if rank == 0:
-            shard_parity = {"workload": "mini, -q 0.05 (BH histogram all-gather on the path)", "peaks": int(len(got)),
+            shard_parity = {"workload": "16 x 6 Mbp, 1.5 M + 1.5 M fragments, -q 0.05 (BH histogram all-gather on the path)", "peaks": int(len(got)),
                             "identical_to_single_context": bool(got.tobytes() == want.tobytes()),
                             "distinct_p": int(mrs.n_distinct_p), "hist_allgather_bytes": int(meng.hist_bytes)}
-            assert shard_parity["identical_to_single_context"], "sharded run differs from the single-context run"
+            assert shard_parity["identical_to_single_context"] and len(got) > 0, "sharded run differs from the single-context run"
         meng.close()
         del meng
 

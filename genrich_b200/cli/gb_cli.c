@@ -86,6 +86,13 @@ static void report_skipped(HDecode* d, gr_ctx** ctxs, int nctx, int is_ctrl, con
     if (nl) memcpy(copy[k], l, nl * sizeof(uint64_t));
     lk.list[k] = copy[k]; lk.n[k] = nl;
   }
+  /* Two corners are refused rather than computed differently from the reference: with -x the reference's average
+   * fragment length leaves out the fragments it had dropped by then (3174), which is known here only after the
+   * unpaired alignments were extended by that average; and -b lists the fragments as they were decoded, the
+   * dropped ones included. */
+  if (total && (d->opt->avg_ext_opt || d->opt->bed_file))
+    gb_die("", "More than 32767 fragments start or end on one base (the reference drops fragments there): "
+               "not supported together with -x or -b");
   if (total && d->opt->verbose) {
     HDecode* d2 = (HDecode*)calloc(1, sizeof(HDecode));
     HIvBuf* bufs = (HIvBuf*)calloc((size_t)nctx, sizeof(HIvBuf));

@@ -936,12 +936,12 @@ static int pileup_enqueue(gr_ctx* x) {
   CK(cudaMemsetAsync(aI, 0, x->nchrom * sizeof(u64), x->stream));
   CK(cudaMemsetAsync(aF, 0, x->nchrom * sizeof(u64), x->stream));
   stage_begin(x, "scan_place", cap * 16);
-  const bool summed = launch_scan_place(x->stream, x->L, sc, out, x->d_err, owners, ctrl ? GR_SKIP : 0.0f, aI, aF);
+  launch_scan_place(x->stream, x->L, sc, out, x->d_err, owners, ctrl ? GR_SKIP : 0.0f);
   HT("pileup_enqueue: scan + place launched");
   CKL();
   stage_end(x);
   stage_begin(x, "rle_moment", 0);
-  if (!summed) launch_rle_moment(x->stream, out, cap, x->nchrom, aI, aF);
+  launch_rle_moment(x->stream, out, cap, x->nchrom, aI, aF);
   launch_sums_double(x->stream, aI, aF, x->nchrom, x->dsums.as<double>() + (ctrl ? x->nchrom : 0));
   HT("pileup_enqueue: moments launched");
   CKL();

@@ -661,74 +661,27 @@ k_scan_fix(DevLayout L, StreamWs W, DevRle out, int* __restrict__ err, u32 nwarp
 // step; keeping four pages in flight (SP_UNROLL 4) was measured slower (0.41 ms), so the
 // three-deep lookup chain (page -> owner -> base) is not what bounds it.
 #define SP_UNROLL 1
-// The per-chromosome sums of (float)(end - start) * val (fragLen / ctrlFrag, Genrich.c:2246 / 2018) are taken
-// here, where every interval passes through registers anyway (a separate pass over the placed arrays read 8 B
-// per interval again: 0.22 ms per hg38 sample).  Every float product is added EXACTLY in fixed point (integer
-// part and 2^-40 fraction in separate u64 counters), so the result does not depend on the order of the adds; a
-// CTA collects in shared memory (SP_MAXC chromosomes) and adds to the global counters once.  The first entry of
-// a page has its predecessor in another page: k_moment_heads takes those, one per page, from the placed arrays.
-#define SP_MAXC 1024
-struct MomentAcc {
-  u64* sm;                                             // [2 * nchrom]: integer parts, fractions
-  __device__ __forceinline__ void add(int c, u64 ip, u64 pf) {
-    atomicAdd((unsigned long long*)sm + 2 * c, (unsigned long long)ip);
-    atomicAdd((unsigned long long*)sm + 2 * c + 1, (unsigned long long)pf);
-  }
-};
-__device__ __forceinline__ void moment_product(u32 end, u32 st, float v, u64& ip, u64& pf) {
-  const float p = v < 0.0f ? 0.0f : __fmul_rn(__uint2float_rn(end - st), v);     // SKIP (-E region): not counted (2016)
-  ip = (u64)p;                                         // p >= 0
-  pf = (u64)(__fsub_rn(p, (float)ip) * 1099511627776.0f);   // exact: fraction * 2^40
-}
-// warp-wide: the lanes with on == true add their product to chromosome c (uniform over the warp in all but the
-// few warps that hold a chromosome boundary)
-__device__ __forceinline__ void moment_warp_add(MomentAcc A, bool on, int c, u64 ip, u64 pf, int lane) {
-  const u32 act = __ballot_sync(GR_FULL, on);
-  if (!act) return;
-  const int c0 = __shfl_sync(GR_FULL, c, __ffs(act) - 1);
-  if (__all_sync(GR_FULL, !on || c == c0)) {
-    const u64 a = warp_sum_u64(on ? ip : 0ull), b = warp_sum_u64(on ? pf : 0ull);
-    if (lane == 0) A.add(c0, a, b);
-  } else if (on) A.add(c, ip, pf);
-}
-__device__ __forceinline__ void moment_flush(const u64* sm, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ acc_frac,
-                                             int tid, int nt) {
-  for (int c = tid; c < nchrom; c += nt) {
-    u64 ti = sm[2 * c], tf = sm[2 * c + 1];
-    ti += tf >> 40;
-    tf &= (1ull << 40) - 1;
-    if (ti) atomicAdd((unsigned long long*)acc_int + c, (unsigned long long)ti);
-    if (tf) atomicAdd((unsigned long long*)acc_frac + c, (unsigned long long)tf);
-  }
-}
-
-template <bool MOMENT>
+// Tried and removed: taking the per-chromosome sums of len * val here (shared-memory u64 accumulators per CTA, the
+// page-first entries by a second small kernel) instead of in k_rle_moment -- measured slower on the B200 (this
+// kernel 0.42 -> 1.04 ms per step at two ranks for the 0.25 ms k_rle_moment took).
 __global__ void __launch_bounds__(2 * SS_PAGE)
-k_scan_place(StreamWs W, DevRle out, int* __restrict__ err, float excl_val, int nchrom,
-             u64* __restrict__ acc_int, u64* __restrict__ acc_frac) {
+k_scan_place(StreamWs W, DevRle out, int* __restrict__ err, float excl_val) {
   __shared__ float4 sm_lut[120];
-  __shared__ u64 sm_acc[MOMENT ? 2 * SP_MAXC : 2];
   units_lut_fill(sm_lut, threadIdx.x, 2 * SS_PAGE);
-  if (MOMENT)
-    for (int i = threadIdx.x; i < 2 * nchrom; i += 2 * SS_PAGE) sm_acc[i] = 0;
   __syncthreads();
-  MomentAcc A;
-  A.sm = sm_acc;
   const u32 npages = min(*W.page_ctr, W.max_pages);
   const u32 t = threadIdx.x & (SS_PAGE - 1), half = threadIdx.x >> SS_PAGE_SHIFT;
-  const int lane = threadIdx.x & 31;
   const u32 pstep = gridDim.x * 2;
   bool neg = false;
-  for (u32 p0 = blockIdx.x * 2 + half; p0 < npages; p0 += pstep * SP_UNROLL) {   // p0 is uniform over the 8 warps of a half
+  for (u32 p0 = blockIdx.x * 2 + half; p0 < npages; p0 += pstep * SP_UNROLL) {
     uint2 meta[SP_UNROLL], e[SP_UNROLL];
-    u32 tot[SP_UNROLL], pe[SP_UNROLL];
+    u32 tot[SP_UNROLL];
     ulonglong2 wb[SP_UNROLL];
 #pragma unroll
     for (int k = 0; k < SP_UNROLL; k++) {
       const u32 p = min(p0 + k * pstep, npages - 1);
       meta[k] = W.page_meta[p];
       e[k] = W.pent[((u64)p << SS_PAGE_SHIFT) + t];    // may be stale past the page's fill: not used then
-      pe[k] = (MOMENT && t) ? W.pent[((u64)p << SS_PAGE_SHIFT) + t - 1].x : 0u;   // the entry before: same line, mostly
     }
 #pragma unroll
     for (int k = 0; k < SP_UNROLL; k++) {
@@ -738,68 +691,16 @@ k_scan_place(StreamWs W, DevRle out, int* __restrict__ err, float excl_val, int 
 #pragma unroll
     for (int k = 0; k < SP_UNROLL; k++) {
       const u32 first = meta[k].y << SS_PAGE_SHIFT;
-      const bool on = !(p0 + k * pstep >= npages || first + t >= tot[k]);   // else: beyond the owner's last entry / a page held in reserve
+      if (p0 + k * pstep >= npages || first + t >= tot[k]) continue;   // beyond the owner's last entry / a page held in reserve
+      const int N = (int)((u32)wb[k].x + e[k].y);
+      neg |= N < 0;
       const u64 rank = wb[k].y + first + t;
-      float val = 0.0f;
-      if (on) {
-        const int N = (int)((u32)wb[k].x + e[k].y);
-        neg |= N < 0;
-        out.end[rank] = e[k].x & 0x7fffffffu;
-        // bit 31: the interval lies in a -E region -- 0.0f in the experimental pileup (2248), SKIP in the control's (2124)
-        val = (e[k].x >> 31) ? excl_val : units_to_val_lut(sm_lut, N < 0 ? 0 : N);
-        out.val[rank] = val;
-      }
-      if (MOMENT) {
-        // the warp's 32 ranks are consecutive: one chromosome unless a boundary lies among them
-        const u64 r_lo = __shfl_sync(GR_FULL, rank, 0);
-        int c = 0;
-        const u32 on_m = __ballot_sync(GR_FULL, on);       // the lanes that are on are the first popc(on_m) of the warp
-        if (on_m) {
-          const int hi_lane = 31 - __clz(on_m);
-          int cq = (lane == 0 || lane == hi_lane) ? chrom_of_index(out.chrom_start, nchrom, lane == 0 ? r_lo : rank) : 0;
-          const int ca = __shfl_sync(GR_FULL, cq, 0), cb = __shfl_sync(GR_FULL, cq, hi_lane);
-          c = ca;
-          if (ca != cb && on) c = chrom_of_index(out.chrom_start, nchrom, rank);
-        }
-        const bool mine = on && t;                         // t == 0: k_moment_heads
-        u64 ip = 0, pf = 0;
-        if (mine) {
-          const u32 st = rank == out.chrom_start[c] ? 0u : (pe[k] & 0x7fffffffu);
-          moment_product(e[k].x & 0x7fffffffu, st, val, ip, pf);
-        }
-        moment_warp_add(A, mine, c, ip, pf, lane);
-      }
+      out.end[rank] = e[k].x & 0x7fffffffu;
+      // bit 31: the interval lies in a -E region -- 0.0f in the experimental pileup (2248), SKIP in the control's (2124)
+      out.val[rank] = (e[k].x >> 31) ? excl_val : units_to_val_lut(sm_lut, N < 0 ? 0 : N);
     }
   }
   if (neg) atomicOr(err, GR_DE_PILE);                  // ERRPILE 1921, 1969
-  if (MOMENT) {
-    __syncthreads();
-    moment_flush(sm_acc, nchrom, acc_int, acc_frac, threadIdx.x, 2 * SS_PAGE);
-  }
-}
-
-// the first entry of every page: its predecessor is the last entry of another page (or of another owner's run)
-__global__ void __launch_bounds__(256)
-k_moment_heads(StreamWs W, DevRle out, int nchrom, u64* __restrict__ acc_int, u64* __restrict__ acc_frac) {
-  __shared__ u64 sm_acc[2 * SP_MAXC];
-  for (int i = threadIdx.x; i < 2 * nchrom; i += 256) sm_acc[i] = 0;
-  __syncthreads();
-  MomentAcc A;
-  A.sm = sm_acc;
-  const u32 npages = min(*W.page_ctr, W.max_pages);
-  for (u32 p = blockIdx.x * 256 + threadIdx.x; p < npages; p += gridDim.x * 256) {
-    const uint2 meta = W.page_meta[p];
-    const u32 first = meta.y << SS_PAGE_SHIFT;
-    if (first >= W.warp_tot[meta.x].y) continue;       // a page held in reserve
-    const u64 rank = W.warp_base[meta.x].y + first;
-    const int c = chrom_of_index(out.chrom_start, nchrom, rank);
-    const u32 st = rank == out.chrom_start[c] ? 0u : out.end[rank - 1];
-    u64 ip, pf;
-    moment_product(out.end[rank], st, out.val[rank], ip, pf);
-    A.add(c, ip, pf);
-  }
-  __syncthreads();
-  moment_flush(sm_acc, nchrom, acc_int, acc_frac, threadIdx.x, 256);
 }
 
 // chromosomes without slots start where the next one does
@@ -878,17 +779,11 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
 }
 
 // ... and K2b + K2c, which put the breaks where the rest of the pipeline expects them
-bool launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners,
-                       float excl_val, u64* acc_int, u64* acc_frac) {
+void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners,
+                       float excl_val) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   k_scan_fix<<<1, 1024, 0, s>>>(L, W, out, err, owners ? owners : (u32)scan_stream_warps()); GR_NOTE_LAUNCH();
-  if (acc_int && L.nchrom <= SP_MAXC) {                // the sums of len * val are taken on the way (else: launch_rle_moment)
-    k_scan_place<true><<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err, excl_val, L.nchrom, acc_int, acc_frac); GR_NOTE_LAUNCH();
-    k_moment_heads<<<148 * 2, 256, 0, s>>>(W, out, L.nchrom, acc_int, acc_frac); GR_NOTE_LAUNCH();
-    return true;
-  }
-  k_scan_place<false><<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err, excl_val, L.nchrom, nullptr, nullptr); GR_NOTE_LAUNCH();
-  return false;
+  k_scan_place<<<148 * 4, 2 * SS_PAGE, 0, s>>>(W, out, err, excl_val); GR_NOTE_LAUNCH();
 }
 
 // ============================================================================

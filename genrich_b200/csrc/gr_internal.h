@@ -54,10 +54,8 @@ void launch_dense_scan(cudaStream_t s, const DevLayout& L, int32_t* delta,
                        const ScanScratch& sc, u32* bitmap, int* err, int zero_after);
 // owners: run owners of the scan that filled the pages (0: the warps of launch_dense_scan)
 // excl_val: value of the intervals the scan flagged as lying in a -E region (0.0f expt, SKIP ctrl)
-// acc_int / acc_frac (may be NULL): per-chromosome fixed-point sums of len * val, ADDED to (zero them first); returns
-// whether they were taken (false: more chromosomes than the kernel's shared table holds -- launch_rle_moment)
-bool launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners,
-                       float excl_val, u64* acc_int, u64* acc_frac);
+void launch_scan_place(cudaStream_t s, const DevLayout& L, const ScanScratch& sc, DevRle out, int* err, u32 owners,
+                       float excl_val);
 
 // ---- K1+K2 fused: event buckets -> breaks, the delta cells live in shared memory only ----
 // buckets = the 8192-cell blocks of the layout

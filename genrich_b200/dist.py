@@ -80,6 +80,7 @@ class ShardedEngine:
         self._gather_cap = 1 << 13          # peak records per rank in the gather slot (grown on demand)
         self._send = self._recv = self._host = self._merged = None
         self._slot_bytes = 0
+        self._stage = None
         self.debug = bool(os.environ.get("GR_DIST_DEBUG"))
         self.t_acc = {}
         self.hist_bytes = 0                 # bytes the last BH histogram all-gather moved (all ranks)
@@ -242,7 +243,7 @@ class ShardedEngine:
         """Release what refers to the library's stream and buffers, THEN the context (its stream goes with it)."""
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
-        self._keep = self._hist_keep = self._send = self._recv = self._host = self._dsums = None
+        self._keep = self._hist_keep = self._send = self._recv = self._host = self._dsums = self._stage = None
         self._ext_stream = None
         self._slot_bytes = 0
         self.ctx.close()
@@ -260,15 +261,23 @@ class ShardedEngine:
             self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=self.device)
         while True:
             dslot, cap = self.ctx.call_peaks_enqueue()
-            g = min(self._gather_cap, cap) if cap else self._gather_cap
+            g = self._gather_cap                                          # the same on every rank (it only grows with the global counts)
             nb = 64 + g * isz
             if self._slot_bytes != nb:
                 self._slot_bytes = nb
                 self._recv = torch.empty(self.world * nb, dtype=torch.uint8, device=self.device)
                 self._host = torch.empty(self.world * nb, dtype=torch.uint8, pin_memory=True)
                 self._merged = np.empty(self.world * g, PEAK_DTYPE)
+                self._stage = None
             with torch.cuda.stream(self._ext_stream):
-                src = _tensor_from_ptr(dslot, nb, np.uint8, self.device)
+                if cap >= g:
+                    src = _tensor_from_ptr(dslot, nb, np.uint8, self.device)
+                else:                                                     # a tiny shard: the library's buffer is shorter than the slot
+                    if self._stage is None:
+                        self._stage = torch.zeros(nb, dtype=torch.uint8, device=self.device)
+                    have = 64 + cap * isz
+                    self._stage[:have].copy_(_tensor_from_ptr(dslot, have, np.uint8, self.device), non_blocking=True)
+                    src = self._stage
                 td.all_gather_into_tensor(self._recv, src)               # NCCL over NVLink, on the library's stream
                 if self.rank == 0:
                     self._host.copy_(self._recv, non_blocking=True)

@@ -361,9 +361,8 @@ def test_scan_form_chosen_on_the_device(monkeypatch):
 
 
 def test_many_chromosomes():
-    """1100 contigs: more than the placement kernel's shared table of per-chromosome sums holds (SP_MAXC 1024), so the
-    sums come from the separate pass (k_rle_moment); 900: from the placement kernel.  Same lambda / factor bits and
-    peaks as the oracle either way."""
+    """Around a thousand contigs of a few kb: look-back tiles, bitmap blocks and the per-chromosome sums with a
+    chromosome boundary every few thousand cells.  Same lambda / factor bits and peaks as the oracle."""
     api = capi.load_cuda()
     rng = np.random.RandomState(3)
     for nchrom in (900, 1100):
