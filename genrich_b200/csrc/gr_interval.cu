@@ -534,56 +534,42 @@ void launch_key_insert(cudaStream_t s, const u32* pEnd, const float* pval, u64 n
 // 8 intervals per thread; equal slots inside a warp are added up first (hot pairs such as (0, lambda)).
 // Hot pairs -- (0, lambda) alone covers most of a genome -- would serialise in L2 even after the warp-level
 // merge (224 M intervals of the ATAC configuration: 6.3 ms): every CTA first collects its sums in a direct-mapped
+// (Tried and removed: four intervals per thread in flight and one warp round per distinct slot instead of
+// __match_any_sync -- 1.5x slower on the ATAC sample and 5x slower on the multimapped 10 Gbp shard, whose warps
+// hold many distinct slots.)
 // shared-memory cache of SH_CACHE slots (tag = table slot; a slot that finds its cache line taken goes straight to
 // global memory) and flushes the cache once at the end.
 #define SH_CACHE 2048
 __global__ void __launch_bounds__(256)
 k_slot_hist(const u32* __restrict__ pEnd, const u32* __restrict__ slot, const u64* __restrict__ n_dev,
             u64* __restrict__ lens) {
-  constexpr int SH_UNROLL = 4;
   __shared__ u32 sm_tag[SH_CACHE];                   // table slot + 1; 0: free
   __shared__ u64 sm_val[SH_CACHE];
   for (int i = threadIdx.x; i < SH_CACHE; i += 256) { sm_tag[i] = 0; sm_val[i] = 0; }
   __syncthreads();
   const u64 n = *n_dev;
   const int lane = threadIdx.x & 31;
-  const u64 stride = (u64)gridDim.x * 256 * SH_UNROLL;
-  for (u64 i0 = (u64)blockIdx.x * 256 * SH_UNROLL; i0 < n; i0 += stride) {         // block-uniform trip count
-    // SH_UNROLL intervals per thread: their loads are in flight together (one interval per round left every warp
-    // waiting on one DRAM round trip per 32 intervals: 3.0 ms for the 225 M intervals of the ATAC sample)
-    u32 h[SH_UNROLL], len[SH_UNROLL];
-#pragma unroll
-    for (int k = 0; k < SH_UNROLL; k++) {
-      const u64 i = i0 + (u64)k * 256 + threadIdx.x;
-      h[k] = 0xfffffffeu; len[k] = 0;
-      if (i < n) {
-        h[k] = slot[i];
-        const u32 e = pEnd[i];
-        u32 st = i ? pEnd[i - 1] : 0u;
-        if (st >= e) st = 0u;                        // first interval of a chromosome: the previous end belongs to another one
-        len[k] = e - st;                             // (ends increase strictly inside a chromosome)
-      }
+  const u64 stride = (u64)gridDim.x * 256;
+  for (u64 i0 = (u64)blockIdx.x * 256; i0 < n; i0 += stride) {         // block-uniform trip count
+    const u64 i = i0 + threadIdx.x;
+    u32 h = 0xfffffffeu, len = 0;
+    if (i < n) {
+      h = slot[i];
+      const u32 e = pEnd[i];
+      u32 st = i ? pEnd[i - 1] : 0u;
+      if (st >= e) st = 0u;                        // first interval of a chromosome: the previous end belongs to another one
+      len = e - st;                                // (ends increase strictly inside a chromosome)
     }
-#pragma unroll
-    for (int k = 0; k < SH_UNROLL; k++) {
-      // the lanes that hold the same slot add up first: one round per distinct slot of the warp (a handful --
-      // neighbouring intervals share few (expt, ctrl) pairs), two 16-bit halves per round (a length has 31 bits)
-      u32 todo = __ballot_sync(GR_FULL, h[k] < 0xfffffffeu && len[k]);
-      while (todo) {
-        const int lead = __ffs(todo) - 1;
-        const u32 h0 = __shfl_sync(GR_FULL, h[k], lead);
-        const bool mine = ((todo >> lane) & 1u) && h[k] == h0;
-        const u32 lo = __reduce_add_sync(GR_FULL, mine ? (len[k] & 0xffffu) : 0u);
-        const u32 hi = __reduce_add_sync(GR_FULL, mine ? (len[k] >> 16) : 0u);
-        if (lane == lead) {
-          const u64 tot = (u64)lo + ((u64)hi << 16);
-          const u32 ci = (h0 * 2654435761u) >> (32 - 11);             // SH_CACHE = 2^11 lines
-          const u32 old = atomicCAS(&sm_tag[ci], 0u, h0 + 1u);
-          if (old == 0u || old == h0 + 1u) atomicAdd(&sm_val[ci], tot);
-          else atomicAdd(lens + h0, tot);
-        }
-        todo &= ~__ballot_sync(GR_FULL, mine);
-      }
+    const u32 peers = __match_any_sync(GR_FULL, h);
+    u64 tot = 0;
+    if (peers == (1u << lane)) tot = len;
+    else
+      for (u32 rem = peers; rem; rem &= rem - 1) tot += __shfl_sync(peers, len, __ffs(rem) - 1);   // the group walks its member list
+    if (h < 0xfffffffeu && lane == __ffs(peers) - 1 && tot) {
+      const u32 ci = (h * 2654435761u) >> (32 - 11);             // SH_CACHE = 2^11 lines
+      const u32 old = atomicCAS(&sm_tag[ci], 0u, h + 1u);
+      if (old == 0u || old == h + 1u) atomicAdd(&sm_val[ci], tot);
+      else atomicAdd(lens + h, tot);
     }
   }
   __syncthreads();
@@ -593,7 +579,7 @@ k_slot_hist(const u32* __restrict__ pEnd, const u32* __restrict__ slot, const u6
 void launch_slot_hist(cudaStream_t s, const u32* pEnd, const u32* slot, u64 n_upper, const u64* n_dev,
                       const u64* chrom_start, int nchrom, u64* lens) {
   if (!n_upper) return;
-  const u64 tiles = (n_upper + 1023) / 1024;
+  const u64 tiles = (n_upper + 255) / 256;
   k_slot_hist<<<(unsigned)(tiles < 148 * 4 ? tiles : 148 * 4), 256, 0, s>>>(pEnd, slot, n_dev, lens); GR_NOTE_LAUNCH();
   (void)chrom_start; (void)nchrom;
 }
