@@ -516,6 +516,10 @@ static void list_append(HReadList* dst, HReadList* src) {
 
 /* returns false if the file is not worth / not fit for the threaded path */
 static bool decode_sam_threads(HDecode* d, const char* path, int nthreads) {
+  /* -x: the average fragment length is the reference's RUNNING double sum of fragLen / count (processPair 3174);
+   * sums per piece, added up afterwards, could round differently in the last bit (and the average, rounded to an
+   * integer, extends every unpaired alignment): such files are decoded in file order by one thread */
+  if (d->opt->avg_ext_opt) return false;
   const int fd = open(path, O_RDONLY);
   if (fd < 0) return false;
   struct stat st;
