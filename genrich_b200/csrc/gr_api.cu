@@ -1921,8 +1921,16 @@ extern "C" int gr_merge_peaks(const gr_peak* const* lists, const uint64_t* count
     if (best < 0) break;
     const gr_peak* l = lists[best];
     const int32_t c = l[pos[best]].chrom;
-    u64 e = pos[best];
-    while (e < counts[best] && l[e].chrom == c) e++;
+    // end of the chromosome's run: gallop, then bisect (the lists lie in pinned host memory: every record looked
+    // at is a cache line fetched, and the copy below fetches them all once more)
+    u64 lo = pos[best], step = 1, hi = counts[best];
+    while (lo + step < counts[best] && l[lo + step].chrom == c) { lo += step; step <<= 1; }
+    if (lo + step < hi) hi = lo + step;                  // l[lo].chrom == c, l[hi] (if any) is past the run
+    while (lo + 1 < hi) {
+      const u64 mid = lo + (hi - lo) / 2;
+      if (l[mid].chrom == c) lo = mid; else hi = mid;
+    }
+    const u64 e = lo + 1;
     memcpy(out + w, l + pos[best], (e - pos[best]) * sizeof(gr_peak));
     w += e - pos[best];
     pos[best] = e;
