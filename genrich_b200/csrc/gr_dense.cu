@@ -1280,11 +1280,11 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
 // mbarrier, two 8 KB tiles) and 32 cells per thread.  Measured on the B200 per launch: hg38 ChIP 3.6 ms (rank form
 // 0.71), ATAC 4.3 ms (CTA form 2.8), 10 Gbp shard 3.2 ms (CTA form 4.1) -- a 2 % shorter step on one workload.
 
-// Rank form -- the default scan: warp-owned 8192-cell blocks WITHOUT a cell array.  A block of the
-// hg38 workload holds ~265 entries = ~400 distinct event cells out of 8192; k_fb_scan spends its
-// time in three CTA barriers per block and in a walk whose length is the fullest thread's (ncu:
-// issue slots half empty).  Measured on the B200 (hg38, 50 M records): 0.67 ms per launch against
-// 1.69 ms, same bits.
+// Rank form -- the scan of samples with ordinary blocks (form_skip): warp-owned 8192-cell blocks WITHOUT a
+// cell array.  A block of the hg38 workload holds ~200 entries = ~400 distinct event cells out of 8192;
+// k_fb_scan spends its time in three CTA barriers per block and in a walk whose length is the fullest
+// thread's (ncu: issue slots half empty).  Measured on the B200 (hg38, 50 M records): 0.71 ms per launch
+// against 1.69 ms, same bits.
 // Here a warp keeps only the block's 256-word occupancy bitmap and, per DISTINCT event cell, a
 // sum and a position:
 //   P1  entries -> occupancy bits
