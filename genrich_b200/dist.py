@@ -67,6 +67,10 @@ class ShardedEngine:
         self.owner = lpt_shard(np.where(self.skip != 0, 0, self.chrom_len), self.world)
         self.owned = (self.owner == self.rank).astype(np.uint8)
         dev_index = device.index if device.type == "cuda" and device.index is not None else 0
+        if api.has_device and not np.any((self.owned != 0) & (self.skip == 0) & (self.chrom_len > 0)):
+            raise ValueError("rank %d of %d would own no chromosome (%d in the table): use at most as many ranks as "
+                             "chromosomes -- gr_create refuses a context without analyzable genome" %
+                             (self.rank, self.world, self.nchrom))
         self.ctx = Context(api, chrom_len, params, device=dev_index, skip=self.skip, owned=self.owned)
         self.params = params
         self.excluded = np.zeros(self.nchrom, dtype=np.int64)      # bp per chromosome (saveXBed-merged)
