@@ -88,7 +88,9 @@ class ShardedEngine:
         self.debug = bool(os.environ.get("GR_DIST_DEBUG"))
         self.t_acc = {}
         self.hist_bytes = 0                 # bytes the last BH histogram all-gather moved (all ranks)
-        self._keep = self._hist_keep = None
+        self._keep = None
+        self._hist_cap = 0
+        self._hist_buf = None
 
     def _tick(self, name, t0):
         # host time by phase, always collected (two clock reads per phase); bench.py reports it
@@ -215,18 +217,25 @@ class ShardedEngine:
             lens = torch.cat([l[:s] for l, s in zip(lall, sizes)]).contiguous()
             self._tick("bh_allgather", t0)
             return keys, lens
-        m = (max(max(sizes), 1) + 1) & ~1                   # even: the lens part of a slot stays 8-byte aligned
-        slot = 12 * m
+        need = (max(max(sizes), 1) + 1) & ~1                # even: the lens part of a slot stays 8-byte aligned
         tot = sum(sizes)
         if self._ext_stream is None:
             self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream_handle(), device=self.device)
-        # The buffers are allocated HERE, on torch's current stream, and kept until the next exchange: memory that
-        # the caching allocator ties to the library's stream would outlive that stream when the context is closed.
-        send = torch.zeros(slot, dtype=torch.uint8, device=self.device)
-        recv = torch.empty(self.world * slot, dtype=torch.uint8, device=self.device)
-        keys_all = torch.empty(max(tot, 1), dtype=torch.int32, device=self.device)
-        lens_all = torch.empty(max(tot, 1), dtype=torch.int64, device=self.device)
-        torch.cuda.current_stream(self.device).synchronize()   # the zero fill is done before the other stream writes
+        # The buffers are allocated on torch's current stream (memory that the caching allocator ties to the library's
+        # stream would outlive that stream when the context is closed), sized with room to spare and kept from step to
+        # step: they are only ever written and read on the library's stream, so reuse needs no synchronisation, and
+        # what lies behind a rank's own n entries in its slot is never looked at.
+        if self._hist_cap < need:
+            self._hist_cap = max(need, 2 * self._hist_cap)
+            m = self._hist_cap
+            self._hist_buf = (torch.zeros(12 * m, dtype=torch.uint8, device=self.device),
+                              torch.empty(self.world * 12 * m, dtype=torch.uint8, device=self.device),
+                              torch.empty(self.world * m, dtype=torch.int32, device=self.device),
+                              torch.empty(self.world * m, dtype=torch.int64, device=self.device))
+            torch.cuda.current_stream(self.device).synchronize()   # the fill is done before the other stream writes
+        m = self._hist_cap
+        slot = 12 * m
+        send, recv, keys_all, lens_all = self._hist_buf
         with torch.cuda.stream(self._ext_stream):
             if n:
                 send[:4 * n].view(torch.int32).copy_(keys)
@@ -239,7 +248,6 @@ class ShardedEngine:
                     keys_all[at:at + sz].copy_(rv[r, :4 * sz].view(torch.int32))
                     lens_all[at:at + sz].copy_(rv[r, 4 * m:4 * m + 8 * sz].view(torch.int64))
                 at += sz
-        self._hist_keep = (send, recv)                       # stay alive until the next exchange
         self.hist_bytes = self.world * slot
         self._tick("bh_allgather", t0)
         return keys_all[:tot], lens_all[:tot]
@@ -248,9 +256,10 @@ class ShardedEngine:
         """Release what refers to the library's stream and buffers, THEN the context (its stream goes with it)."""
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
-        self._keep = self._hist_keep = self._send = self._recv = self._host = self._dsums = self._stage = None
+        self._keep = self._hist_buf = self._send = self._recv = self._host = self._dsums = self._stage = None
         self._ext_stream = None
         self._slot_bytes = 0
+        self._hist_cap = 0
         self.ctx.close()
 
     def _gather_peaks_one_wait(self):
