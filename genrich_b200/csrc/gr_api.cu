@@ -517,8 +517,9 @@ extern "C" int gr_set_exclusions(gr_ctx* x, const int32_t* chrom, const uint32_t
   if (x->has_bed) {
     CK(x->blkBed.ensure(x->nblocks));
     CK(cudaMemcpy(x->blkBed.p, blk.data(), x->nblocks, cudaMemcpyHostToDevice));
-    CK(x->bedChromMarks.ensure(nc * sizeof(u32)));
+    CK(x->bedChromMarks.ensure(2 * nc * sizeof(u32)));           // boundaries per chromosome, then the "has had reads" words
     CK(cudaMemcpy(x->bedChromMarks.p, cmarks.data(), nc * sizeof(u32), cudaMemcpyHostToDevice));
+    CK(cudaMemset((char*)x->bedChromMarks.p + nc * sizeof(u32), 0, nc * sizeof(u32)));
     if (x->n_marks) {
       CK(x->bedMarks.ensure(marks.size() * sizeof(u64)));
       CK(cudaMemcpy(x->bedMarks.p, marks.data(), marks.size() * sizeof(u64), cudaMemcpyHostToDevice));
@@ -542,6 +543,8 @@ extern "C" int gr_reset(gr_ctx* x) {
   x->pend_pile[0] = x->pend_pile[1] = false;
   x->finalized = false; x->have_q = false; x->have_expt = x->have_ctrl = false;
   x->filling = FILL_NONE; x->hist_cap = 0; x->peaks_h.clear(); x->pair_valid = false;
+  if (x->has_bed)                                        // a new run: no chromosome has had reads yet (k_fb_scan)
+    CK(cudaMemsetAsync((char*)x->bedChromMarks.p + (size_t)x->nchrom * sizeof(u32), 0, (size_t)x->nchrom * sizeof(u32), x->stream));
   return GR_OK;
 }
 
@@ -921,7 +924,9 @@ static int pileup_enqueue(gr_ctx* x) {
     owners = launch_fb_scan(x->stream, x->L, x->sbBucket.as<u32>(), x->sbStart.as<u32>(), sc,
                             (ctrl ? x->bmC : x->bmE).as<u32>(), x->d_err,
                             x->has_bed ? x->blkBed.as<uint8_t>() : nullptr,
-                            x->has_bed && !ctrl ? x->bedChromMarks.as<u32>() : nullptr, x->sbCnt.as<u32>() + x->nblocks);
+                            x->has_bed ? x->bedChromMarks.as<u32>() : nullptr,
+                            x->has_bed ? x->bedChromMarks.as<u32>() + x->nchrom : nullptr, ctrl ? 0 : 1,
+                            x->sbCnt.as<u32>() + x->nblocks);
     CKL();
     stage_end(x);
   } else {

@@ -1073,7 +1073,8 @@ __global__ void __launch_bounds__(NT, CPS)
 k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, DevLayout L, StreamWs W,
           u32* __restrict__ bitmap, int* __restrict__ err, u32 nblocks, u32 R,
           const uint8_t* __restrict__ blk_bed /* NULL: no -E regions */,
-          const u32* __restrict__ chrom_marks /* BED, experimental sample: region boundaries per chromosome, else NULL */,
+          const u32* __restrict__ chrom_marks /* BED: region boundaries per chromosome, else NULL */,
+          u32* __restrict__ chrom_ever /* BED: 1 once a sample of the context had reads on the chromosome */, int is_expt,
           const u32* __restrict__ stat, int when) {
   constexpr int WPT = FB_WORDS / NT, PF = 512 / NT, NW = NT / 32;
   if (form_skip(stat, blk_start, nblocks, when)) return;
@@ -1131,9 +1132,12 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
     if (sA + k * NT + t < sB) v[k] = __ldcs(bucketed + sA + k * NT + t);
   }
 
-  // A chromosome without a single read in the EXPERIMENTAL sample is one interval (len, 0.0f) in the reference,
-  // whatever -E regions lie on it (savePileupExpt 2178-2182: its diff array was never allocated): its region
-  // boundaries are then not breaks.  (The control side of such a chromosome is saveLambda's, regions included.)
+  // A chromosome that has not had a single read so far -- in this EXPERIMENTAL sample or in any sample before it,
+  // control samples included -- is one interval (len, 0.0f) in the reference, whatever -E regions lie on it
+  // (savePileupExpt 2178-2182: its diff array, which all samples share, was never allocated): its region boundaries
+  // are then not breaks.  Once a sample had reads there the array exists, and a later sample without reads on the
+  // chromosome is cut at the region boundaries like any other.  (The control side of a read-less chromosome is
+  // saveLambda's, regions included: the same intervals either way.)
   bool c_plain = false;
   auto apply = [&](u32 e) {
     const u32 so = e & (GR_BLOCK_SLOTS - 1), kind = e >> 30;
@@ -1164,8 +1168,14 @@ k_fb_scan(const u32* __restrict__ bucketed, const u32* __restrict__ blk_start, D
       len = L.len[c];
       c_last_blk = (u32)((off + len) >> GR_BLOCK_SHIFT);
       act = (L.flags[c] & (GR_CF_OWNED | GR_CF_SAVE)) == (GR_CF_OWNED | GR_CF_SAVE);
-      if (BED && chrom_marks)                          // nothing but its own region boundaries in the chromosome's buckets
-        c_plain = blk_start[c_last_blk + 1] - blk_start[(u32)(off >> GR_BLOCK_SHIFT)] == chrom_marks[c];
+      if (BED && chrom_marks) {
+        // nothing but its own region boundaries in the chromosome's buckets?
+        const bool none = blk_start[c_last_blk + 1] - blk_start[(u32)(off >> GR_BLOCK_SHIFT)] == chrom_marks[c];
+        c_plain = is_expt && none && !chrom_ever[c];
+        // (another CTA may read the word for the same chromosome later in this launch: it is only written when
+        // `none` is false, and then c_plain is false whatever it holds)
+        if (!none && t == 0) chrom_ever[c] = 1u;
+      }
     }
     const u32 sD = ld_start(b + 3);                    // used two blocks from now
     const u32 jb = (u32)(((u64)b << GR_BLOCK_SHIFT) - off);       // chromosome position of the block's first cell
@@ -1558,7 +1568,7 @@ static int fb_env(const char* name, int dflt) { const char* e = getenv(name); re
 // (tests, and the comparison the bench quotes); stat: k_sb_scan1's statistic words.
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
                    const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks,
-                   const u32* stat) {
+                   u32* chrom_ever, int is_expt, const u32* stat) {
   const StreamWs W = stream_ws(sc, L.nchrom);
   cudaMemsetAsync(W.page_ctr, 0, 4, s);
   cudaMemsetAsync(W.warp_tot, 0, (size_t)SS_MAX_WARPS * sizeof(uint2), s);   // owners of the form that does not run: empty
@@ -1575,8 +1585,8 @@ u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, cons
     const u32 o = (u32)(sms * 6);
     const u32 R = (nb + o - 1) / o;
     const int when = force_cta ? 0 : 1;
-    if (blk_bed) k_fb_scan<6, 128, true><<<o, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed, chrom_marks, stat, 0);
-    else k_fb_scan<6, 128, false><<<o, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr, nullptr, stat, when);
+    if (blk_bed) k_fb_scan<6, 128, true><<<o, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, blk_bed, chrom_marks, chrom_ever, is_expt, stat, 0);
+    else k_fb_scan<6, 128, false><<<o, 128, 0, s>>>(bucketed, blk_start, L, W, bitmap, err, nb, R, nullptr, nullptr, nullptr, 0, stat, when);
     GR_NOTE_LAUNCH();
     owners = o;
   }

@@ -76,13 +76,15 @@ void launch_sat_resolve(cudaStream_t s, const u32* flag, const void* segs, int n
                         u64* list, u32 list_cap, u32* sat_res, int* err);
 // returns the number of run owners (warps or CTAs), to be handed to launch_scan_place
 // blk_bed: per 8192-cell block, bit 0 = the block starts inside a -E region, bit 1 = it holds
-// region boundaries (NULL: no regions); chrom_marks: region boundaries per chromosome, for the experimental
-// sample only (a chromosome that holds nothing else is one interval there, savePileupExpt 2178-2182)
+// region boundaries (NULL: no regions); chrom_marks: region boundaries per chromosome; chrom_ever: one word per
+// chromosome, set once a sample of the context had reads there (the reference's shared diff array exists from then
+// on); is_expt: an experimental sample -- a chromosome that has never held a read is one interval there
+// (savePileupExpt 2178-2182)
 // stat: the words k_sb_scan1 leaves behind the block counters (launch_sb_scan_a's sat_flag); the scan form is
 // chosen from them on the device
 u32 launch_fb_scan(cudaStream_t s, const DevLayout& L, const u32* bucketed, const u32* blk_start,
                    const ScanScratch& sc, u32* bitmap, int* err, const uint8_t* blk_bed, const u32* chrom_marks,
-                   const u32* stat);
+                   u32* chrom_ever, int is_expt, const u32* stat);
 // -E region boundaries as pseudo entries (cursor == NULL: count pass)
 void launch_fb_marks(cudaStream_t s, const u64* marks, u32 n, u32* blk_cnt, u32* cursor, u32* bucketed);
 

@@ -94,6 +94,12 @@ CASES = [
     # a chromosome that never receives a read, with regions on it (saveLambda 1847-1877 / saveConst 2178)
     Case("bed_empty_chrom", [300000, 50000], [(Sample(30000, 61, empty_chroms=(1,)), Sample(30000, 62, enrich=0.0, empty_chroms=(1,)))],
          p=0.01, bed=[(1, 0, 1000), (1, 20000, 60000), (0, 100, 200)]),
+    # ... and one that is read-less in both experimental samples but not in the first control: the reference's diff
+    # array (shared by all samples) exists from then on, so the SECOND experimental pileup is cut at the region
+    # boundaries (the normal loop of savePileupExpt) while the first is one interval (saveConst 2178)
+    Case("bed_later_empty", [300000, 50000], [(Sample(30000, 71, empty_chroms=(1,)), Sample(30000, 72, enrich=0.0)),
+                                              (Sample(30000, 73, empty_chroms=(1,)), None)],
+         p=0.01, bed=[(1, 0, 1000), (1, 20000, 60000), (0, 100, 200)]),
 ]
 
 BY_NAME = {c.name: c for c in CASES}

@@ -50,6 +50,8 @@ def _compare(case, api, env, monkeypatch, packed=False):
     if packed:
         from genrich_b200 import host
         ctx_g = capi.Context(api, case.chrom_len, util.case_params(case))
+        if case.bed:
+            ctx_g.set_exclusions(case.bed)
         res_g = host.run_replicates(ctx_g, inputs, chunk=20011, packed=packed)
     else:
         ctx_g, res_g, _ = util.run_case(api, case, inputs=inputs)
@@ -216,3 +218,55 @@ def test_bench_e2e_call_pattern(emu_api, monkeypatch):
             assert peaks.tobytes() == ref.tobytes(), (six, step)
     for p in bufs:
         lib.gr_pinned_free(p)
+
+
+def _random_case(seed):
+    """a small random case: chromosome table, 1-3 replicates with or without control, -p / -q, gap / length / AUC
+    thresholds, multimapped weights, ATAC intervals, -E regions, dropped and empty chromosomes"""
+    from cases import Case, Sample
+    r = np.random.RandomState(seed)
+    nchrom = int(r.randint(1, 5))
+    L = [int(x) for x in r.choice([1, 300, 8191, 8192, 8193, 20000, 70000, 150000], nchrom)]
+    if max(L) < 20000:
+        L[int(r.randint(nchrom))] = 90000
+    nrep = int(r.choice([1, 1, 2, 3]))
+    reps = []
+    for k in range(nrep):
+        e = Sample(int(r.randint(2000, 9000)), 100 * seed + k, enrich=float(r.choice([0.2, 0.4])),
+                   spacing=int(r.choice([5000, 20000])), sigma=float(r.choice([30.0, 100.0])),
+                   multimap=float(r.choice([0.0, 0.3])),
+                   empty_chroms=(int(r.randint(nchrom)),) if nchrom > 1 and r.uniform() < 0.3 else ())
+        c = Sample(int(r.randint(2000, 9000)), 100 * seed + 50 + k, enrich=0.0,
+                   multimap=float(r.choice([0.0, 0.3]))) if r.uniform() < 0.6 else None
+        reps.append((e, c))
+    use_q = r.uniform() < 0.5
+    bed = []
+    if r.uniform() < 0.4:
+        for _ in range(int(r.randint(1, 6))):
+            c = int(r.randint(nchrom))
+            s = int(r.randint(0, max(L[c], 2)))
+            bed.append((c, s, s + int(r.choice([1, 50, 5000, 200000]))))
+    return Case("fuzz%d" % seed, L, reps, p=None if use_q else float(r.choice([0.01, 0.05, 0.2])),
+                q=float(r.choice([0.05, 0.5])) if use_q else None, min_auc=float(r.choice([0.0, 20.0, 200.0])),
+                min_len=int(r.choice([0, 0, 150])), max_gap=int(r.choice([0, 100, 1000])),
+                atac=bool(r.uniform() < 0.25), atac_len=int(r.choice([30, 100])), bed=bed)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_emulated_library_random_cases(emu_api, seed, monkeypatch):
+    """Seeded random cases through the whole library (every kernel, the host logic of gr_api.cu) against the oracle:
+    interval ends, pileup floats, lambda, scale factor, peak coordinates bit for bit; -log10 p / q within 1e-4.
+    The per-base pass alternates between the plain scatter path, the fused scan with the form chosen on the device,
+    and each form forced; every third case travels as packed records."""
+    case = _random_case(seed)
+    mode = sorted(MODES)[seed % len(MODES)]
+    if case.bed and mode == "default_small":
+        mode = "default_fused"                       # -E regions exist in the fused scan only (the library routes them there anyway)
+    try:
+        util.run_case(util.oracle_api(), case)
+    except capi.GenrichError as want:                # e.g. a replicate left without fragments: the same refusal is expected
+        with pytest.raises(capi.GenrichError) as got:
+            _compare(case, emu_api, MODES[mode], monkeypatch, packed=(seed % 3 == 0))
+        assert got.value.status == want.status
+        return
+    _compare(case, emu_api, MODES[mode], monkeypatch, packed=(seed % 3 == 0))
