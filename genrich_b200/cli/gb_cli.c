@@ -325,6 +325,49 @@ static void write_log(gr_ctx** ctxs, const int* owner, HOut* out, const HChromTa
  * the -v warnings of saveXBed 1151-1192.  Records of unknown references are ignored, as in the
  * reference (saveXBed only looks for the names of the chromosomes it knows); sorting, clamping
  * and merging happen in the library (gr_set_exclusions), exactly as saveXBed does them. */
+/* The reference prints them from saveXBed, i.e. when a chromosome is first met in a file header (saveChrom 4265):
+ * behind the "Processing ... file" line of the file that introduces the chromosome, chromosomes in header order,
+ * records in BED order.  The table is complete before the first file is processed here, so the texts are kept
+ * (bed_warnings_flush prints those of the chromosomes a file introduced). */
+typedef struct { int chrom, kind; uint32_t start; size_t seq; char* text; } BedWarn;   /* kind 0: ignored, 1: edited */
+static BedWarn* g_bed_warn = NULL;
+static size_t g_bed_warn_n = 0, g_bed_warn_cap = 0;
+static void bed_warn_keep(int chrom, int kind, uint32_t start, const char* text) {
+  if (g_bed_warn_n == g_bed_warn_cap) {
+    g_bed_warn_cap = g_bed_warn_cap ? 2 * g_bed_warn_cap : 64;
+    g_bed_warn = (BedWarn*)gb_realloc(g_bed_warn, g_bed_warn_cap * sizeof *g_bed_warn);
+  }
+  BedWarn* w = &g_bed_warn[g_bed_warn_n];
+  w->chrom = chrom; w->kind = kind; w->start = start; w->seq = g_bed_warn_n; w->text = strdup(text);
+  g_bed_warn_n++;
+}
+/* saveXBed's order within a chromosome: the "ignored" records as the BED file lists them (first loop, 1153-1161);
+ * then the "edited" ones while the list -- kept sorted by start, a record going IN FRONT of one with the same start
+ * (1164-1167) -- is merged (1181-1189) */
+static int bed_warn_cmp(const void* pa, const void* pb) {
+  const BedWarn* a = (const BedWarn*)pa;
+  const BedWarn* b = (const BedWarn*)pb;
+  if (a->kind != b->kind) return a->kind - b->kind;
+  if (a->kind == 0) return a->seq < b->seq ? -1 : 1;
+  if (a->start != b->start) return a->start < b->start ? -1 : 1;
+  return a->seq > b->seq ? -1 : 1;
+}
+static void bed_warnings_flush(const int* first_file, int nchrom, int file_ordinal) {
+  for (int c = 0; c < nchrom; c++) {
+    if (first_file[c] != file_ordinal) continue;
+    size_t n = 0;
+    for (size_t i = 0; i < g_bed_warn_n; i++) n += g_bed_warn[i].chrom == c && g_bed_warn[i].text;
+    if (!n) continue;
+    BedWarn* sel = (BedWarn*)gb_alloc(n * sizeof *sel);
+    n = 0;
+    for (size_t i = 0; i < g_bed_warn_n; i++)
+      if (g_bed_warn[i].chrom == c && g_bed_warn[i].text) { sel[n++] = g_bed_warn[i]; g_bed_warn[i].text = NULL; }
+    qsort(sel, n, sizeof *sel, bed_warn_cmp);
+    for (size_t i = 0; i < n; i++) { fputs(sel[i].text, stderr); free(sel[i].text); }
+    free(sel);
+  }
+}
+
 static void load_exclusions(gr_ctx** ctxs, int nctx, char* xfile, const HChromTab* tab, bool verbose) {
   int32_t* chrom = NULL;
   uint32_t *start = NULL, *end = NULL;
@@ -354,12 +397,17 @@ static void load_exclusions(gr_ctx** ctxs, int nctx, char* xfile, const HChromTa
       const int c = gb_chrom_find(tab, name);
       if (c < 0) continue;
       const uint32_t len = tab->c[c].len;
-      if (verbose && (uint32_t)pos[0] >= len) {
-        fprintf(stderr, "Warning! BED interval (%s, %d - %d) ignored\n", name, pos[0], pos[1]);
-        fprintf(stderr, "  - located off end of reference %s (length %d)\n", name, (int)len);
-      } else if (verbose && (uint32_t)pos[1] > len) {
-        fprintf(stderr, "Warning! BED interval (%s, %d - %d) extends ", name, pos[0], pos[1]);
-        fprintf(stderr, "past end of ref.\n  - edited to (%s, %d - %d)\n", name, pos[0], (int)len);
+      /* (saveChrom 4264: a chromosome excluded with -e has no region list, hence no warnings) */
+      if (verbose && !tab->c[c].skip && (uint32_t)pos[0] >= len) {
+        char w[1024];
+        snprintf(w, sizeof w, "Warning! BED interval (%s, %d - %d) ignored\n  - located off end of reference %s (length %d)\n",
+                 name, pos[0], pos[1], name, (int)len);
+        bed_warn_keep(c, 0, (uint32_t)pos[0], w);
+      } else if (verbose && !tab->c[c].skip && (uint32_t)pos[1] > len) {
+        char w[1024];
+        snprintf(w, sizeof w, "Warning! BED interval (%s, %d - %d) extends past end of ref.\n  - edited to (%s, %d - %d)\n",
+                 name, pos[0], pos[1], name, pos[0], (int)len);
+        bed_warn_keep(c, 1, (uint32_t)pos[0], w);
       }
       if (n == cap) {
         cap = cap ? 2 * cap : 1024;
@@ -456,10 +504,15 @@ int main(int argc, char** argv) {
   /* the engine needs the whole chromosome table first: header-only pass, in the
    * order the reference meets the files (t0, c0, t1, c1, ...) */
   HChromTab tab = { NULL, 0 };
-  for (int r = 0; r < nt; r++) {
-    gb_scan_header(real_path(tf[r]), &tab, false, &o);
-    if (r < ncf && strcmp(cf[r], "null")) gb_scan_header(real_path(cf[r]), &tab, true, &o);
-  }
+  int* first_file = NULL;                                  /* per chromosome: the file (2 r + is_ctrl) that introduced it */
+  for (int r = 0; r < nt; r++)
+    for (int s = 0; s < 2; s++) {
+      if (s && !(r < ncf && strcmp(cf[r], "null"))) continue;
+      const int before = tab.n;
+      gb_scan_header(real_path(s ? cf[r] : tf[r]), &tab, s != 0, &o);
+      first_file = (int*)gb_realloc(first_file, (size_t)(tab.n ? tab.n : 1) * sizeof(int));
+      for (int i = before; i < tab.n; i++) first_file[i] = 2 * r + s;
+    }
   if (!tab.n) gb_die("", "No analyzable genome (length=0)");
   /* Chromosomes are sharded over the devices (runProgram's per-chromosome loop, 5460-5607, becomes
    * the dispatcher): greedy longest-first assignment to the least loaded device.  Every context
@@ -552,8 +605,10 @@ int main(int argc, char** argv) {
       gb_in_open(&probe, real_path(fname));
       const bool bam = probe.is_bam;
       gb_in_close(&probe, real_path(fname));
-      if (o.verbose)
+      if (o.verbose) {
         fprintf(stderr, "Processing %s file #%d: %s\n", s ? "control" : "experimental", r, fname);
+        bed_warnings_flush(first_file, tab.n, 2 * r + s);      /* saveXBed's warnings for the chromosomes this file introduces */
+      }
       if (dups_verb) gb_out_printf(&dupf, "# %s file #%d: %s\n", s ? "control" : "experimental", r, fname);   /* 5493-5499 */
       for (int k = 0; k < nctx; k++) chk(ctxs[k], gr_sample_begin(ctxs[k], s, s ? NULL : save), "gr_sample_begin");
       memset(&d.cnt, 0, sizeof d.cnt);
@@ -569,6 +624,17 @@ int main(int argc, char** argv) {
           chk(ctxs[k], gr_sample_sums(ctxs[k], s ? NULL : sums, s ? sums : NULL), "gr_sample_sums");
           for (int i = 0; i < tab.n; i++) (s ? csum : esum)[i] += sums[i];
         }
+      if (!s) {
+        /* savePileupExpt 2292-2293: an experimental sample without any weight ends the run HERE, before its
+         * control file is opened (the library would report the same condition at the end of the replicate) */
+        double tot = 0.0;
+        if (nctx == 1) {
+          chk(ctx, gr_sample_sums(ctx, sums, NULL), "gr_sample_sums");
+          for (int i = 0; i < tab.n; i++) tot += sums[i];
+        } else
+          for (int i = 0; i < tab.n; i++) tot += esum[i];
+        if (tot == 0.0) gb_die("", "Experimental sample has no analyzable fragments");
+      }
     }
     gr_sample_stats st;
     if (nctx == 1)

@@ -43,7 +43,10 @@ def fragments_to_intervals(frags: np.ndarray, atac: bool = False, atac_len: int 
     if atac_adj:
         s = s + ATACADJF
         e = e + ATACADJR
-    one = (s + len3) >= (e - len3)
+    # saveFragAtac 2737: `start + atacLen3 >= (signed) (end - atacLen3)` compares a uint32 with an int, i.e. both
+    # as uint32 -- a fragment that ends within atacLen3 of the chromosome start wraps around and is saved as TWO
+    # intervals although they overlap
+    one = ((s + len3) & 0xffffffff) >= ((e - len3) & 0xffffffff)
     n1 = int(one.sum())
     n2 = len(frags) - n1
     out = np.empty((n1 + 2 * n2, 4), dtype=np.int64)

@@ -362,3 +362,48 @@ def test_threaded_decode_loosely_grouped(twin, tmp_path, monkeypatch):
         o = os.path.join(td, "ref.np")
         subprocess.check_call([ref, "-t", loose, "-c", cfiles[0], "-o", o, "-S"] + case.ref_args(), stderr=subprocess.DEVNULL)
         assert open(o).read() == outs[0]
+
+
+REF_BIN = os.path.join(util.ORACLE_DIR, "_ref", "Genrich")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/Genrich not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(5000, 5012))
+def test_random_cases_against_the_reference_binary(twin, seed, tmp_path, monkeypatch):
+    """Seeded random cases (tests/fuzzcases.py) with random host options on mutated SAM files (singletons, discordant
+    pairs, duplicates, low MAPQ): the unmodified reference binary and the host program run on the same files, here,
+    and every output is compared byte for byte -- narrowPeak, -f, -k, -b, -R and the whole -v text.  Odd seeds decode
+    with three threads."""
+    import hostcases
+    from fuzzcases import random_case, random_host_options
+    monkeypatch.setenv("GB_THREAD_MIN_BYTES", "1")
+    case = random_case(seed)
+    extra = random_host_options(seed, case)
+    td = str(tmp_path)
+    tf, cf = util.write_case_sams(case, td)
+
+    def mutated(p, k):
+        q = p.replace(".sam", ".m.sam")
+        hostcases.mutate_sam(p, q, seed + k)
+        return q
+    tf = [mutated(p, i) for i, p in enumerate(tf)]
+    cf = [c if c == "null" else mutated(c, 100 + i) for i, c in enumerate(cf)]
+    res = []
+    for exe, tag in ((REF_BIN, "A"), (twin, "B")):
+        f = {k: os.path.join(td, tag + "." + k) for k in ("np", "f", "k", "R", "b")}
+        cmd = [exe, "-t", ",".join(tf), "-o", f["np"], "-f", f["f"], "-k", f["k"], "-b", f["b"], "-v"] + case.ref_args() + extra
+        if "-r" in extra:
+            cmd += ["-R", f["R"]]
+        if any(c != "null" for c in cf):
+            cmd += ["-c", ",".join(cf)]
+        if case.bed:
+            bedf = os.path.join(td, "x.bed")
+            util.write_case_bed(case, bedf)
+            cmd += ["-E", bedf]
+        if tag == "B" and seed % 2:
+            cmd += ["--threads", "3"]
+        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True)
+        res.append([r.returncode] + [open(p, "rb").read() if os.path.exists(p) else None for p in f.values()] +
+                   [r.stderr.replace(tag + ".", "X.")])
+    for name, a, b in zip(("exit code", "narrowPeak", "-f", "-k", "-R", "-b", "-v text"), res[0], res[1]):
+        assert a == b, (name, case, extra)

@@ -220,45 +220,14 @@ def test_bench_e2e_call_pattern(emu_api, monkeypatch):
         lib.gr_pinned_free(p)
 
 
-def _random_case(seed):
-    """a small random case: chromosome table, 1-3 replicates with or without control, -p / -q, gap / length / AUC
-    thresholds, multimapped weights, ATAC intervals, -E regions, dropped and empty chromosomes"""
-    from cases import Case, Sample
-    r = np.random.RandomState(seed)
-    nchrom = int(r.randint(1, 5))
-    L = [int(x) for x in r.choice([1, 300, 8191, 8192, 8193, 20000, 70000, 150000], nchrom)]
-    if max(L) < 20000:
-        L[int(r.randint(nchrom))] = 90000
-    nrep = int(r.choice([1, 1, 2, 3]))
-    reps = []
-    for k in range(nrep):
-        e = Sample(int(r.randint(2000, 9000)), 100 * seed + k, enrich=float(r.choice([0.2, 0.4])),
-                   spacing=int(r.choice([5000, 20000])), sigma=float(r.choice([30.0, 100.0])),
-                   multimap=float(r.choice([0.0, 0.3])),
-                   empty_chroms=(int(r.randint(nchrom)),) if nchrom > 1 and r.uniform() < 0.3 else ())
-        c = Sample(int(r.randint(2000, 9000)), 100 * seed + 50 + k, enrich=0.0,
-                   multimap=float(r.choice([0.0, 0.3]))) if r.uniform() < 0.6 else None
-        reps.append((e, c))
-    use_q = r.uniform() < 0.5
-    bed = []
-    if r.uniform() < 0.4:
-        for _ in range(int(r.randint(1, 6))):
-            c = int(r.randint(nchrom))
-            s = int(r.randint(0, max(L[c], 2)))
-            bed.append((c, s, s + int(r.choice([1, 50, 5000, 200000]))))
-    return Case("fuzz%d" % seed, L, reps, p=None if use_q else float(r.choice([0.01, 0.05, 0.2])),
-                q=float(r.choice([0.05, 0.5])) if use_q else None, min_auc=float(r.choice([0.0, 20.0, 200.0])),
-                min_len=int(r.choice([0, 0, 150])), max_gap=int(r.choice([0, 100, 1000])),
-                atac=bool(r.uniform() < 0.25), atac_len=int(r.choice([30, 100])), bed=bed)
-
-
 @pytest.mark.parametrize("seed", range(24))
 def test_emulated_library_random_cases(emu_api, seed, monkeypatch):
     """Seeded random cases through the whole library (every kernel, the host logic of gr_api.cu) against the oracle:
     interval ends, pileup floats, lambda, scale factor, peak coordinates bit for bit; -log10 p / q within 1e-4.
     The per-base pass alternates between the plain scatter path, the fused scan with the form chosen on the device,
     and each form forced; every third case travels as packed records."""
-    case = _random_case(seed)
+    from fuzzcases import random_case
+    case = random_case(seed, holes_with_multimap=False)
     mode = sorted(MODES)[seed % len(MODES)]
     if case.bed and mode == "default_small":
         mode = "default_fused"                       # -E regions exist in the fused scan only (the library routes them there anyway)
@@ -270,3 +239,50 @@ def test_emulated_library_random_cases(emu_api, seed, monkeypatch):
         assert got.value.status == want.status
         return
     _compare(case, emu_api, MODES[mode], monkeypatch, packed=(seed % 3 == 0))
+
+
+REF_BIN = os.path.join(util.ORACLE_DIR, "_ref", "Genrich")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref/Genrich not built (needs /root/reference)")
+@pytest.mark.parametrize("seed,gpus", [(6000, 0), (6002, 0), (6007, 0), (6013, 0), (6020, 0), (6044, 0), (6101, 3), (6105, 3)])
+def test_emulated_cli_random_cases_against_the_reference_binary(emu_api, seed, gpus, tmp_path):
+    """The host program over the CUDA library (compiled for the CPU) and the unmodified reference binary on the same
+    mutated SAM files of a seeded random case with random host options: narrowPeak, -f, -k, -b, -R and the whole -v
+    text byte for byte; two of the cases sharded over three emulated devices.  (Offline this ran over 90 seeds.)"""
+    import hostcases
+    from fuzzcases import random_case, random_host_options
+    subprocess.check_call(["make", "-s", "-C", EMU, "_build/genrich-b200-emu"])
+    cli = os.path.join(EMU, "_build", "genrich-b200-emu")
+    case = random_case(seed)
+    extra = random_host_options(seed, case)
+    td = str(tmp_path)
+    tf, cf = util.write_case_sams(case, td)
+
+    def mutated(p, k):
+        q = p.replace(".sam", ".m.sam")
+        hostcases.mutate_sam(p, q, seed + k)
+        return q
+    tf = [mutated(p, i) for i, p in enumerate(tf)]
+    cf = [c if c == "null" else mutated(c, 100 + i) for i, c in enumerate(cf)]
+    res = []
+    for exe, tag in ((REF_BIN, "A"), (cli, "B")):
+        f = {k: os.path.join(td, tag + "." + k) for k in ("np", "f", "k", "R", "b")}
+        cmd = [exe, "-t", ",".join(tf), "-o", f["np"], "-f", f["f"], "-k", f["k"], "-b", f["b"], "-v"] + case.ref_args() + extra
+        if "-r" in extra:
+            cmd += ["-R", f["R"]]
+        if any(c != "null" for c in cf):
+            cmd += ["-c", ",".join(cf)]
+        if case.bed:
+            bedf = os.path.join(td, "x.bed")
+            util.write_case_bed(case, bedf)
+            cmd += ["-E", bedf]
+        env = dict(os.environ, GB_THREAD_MIN_BYTES="1", GR_FUSED="1", GR_FUSED_MIN="1")
+        if tag == "B" and gpus:
+            cmd += ["--gpus", str(gpus)]
+            env["EMU_DEVICES"] = str(gpus)
+        r = subprocess.run(cmd, stderr=subprocess.PIPE, text=True, env=env, timeout=300)
+        res.append([r.returncode] + [open(p, "rb").read() if os.path.exists(p) else None for p in f.values()] +
+                   [r.stderr.replace(tag + ".", "X.")])
+    for name, a, b in zip(("exit code", "narrowPeak", "-f", "-k", "-R", "-b", "-v text"), res[0], res[1]):
+        assert a == b, (name, case, extra)
