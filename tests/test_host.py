@@ -28,7 +28,7 @@ def _atac_loop(frags, len5, len3, adj=True):
         if adj:
             s = _u32(s + 5)
             e = _u32(e - 5)
-        if s + len3 >= _i32(e - len3):
+        if _u32(s + len3) >= _u32(e - len3):          # 2737: a uint32 against an int -> both as uint32 (checked against the reference binary with -d 501)
             out.append((c, _i32(s - len5), e + len5, k))
         else:
             out.append((c, _i32(s - len5), s + len3, k))
