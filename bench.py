@@ -22,7 +22,8 @@ For N > 1 the same genome is sharded by chromosome over the ranks (strong scalin
 `value`  = genome bp / device time per step, interval records already in HBM.
 `e2e`    = same through gr_push_packed6 / gr_push_packed from PINNED HOST buffers (H2D copies inside
            the timed region) with the peak records read back to the host.
-`roofline` is for the per-base pass (k_fr_scan): ALGORITHMIC bytes (4 B per delta cell per sample
+`roofline` is for the per-base pass (k_fr_scan or k_fb_scan, whichever the sample chose on the device --
+           `roofline.scan_form`): ALGORITHMIC bytes (4 B per delta cell per sample
            array) / mean launch time, next to what the kernel and the whole step really
            move through DRAM (`traffic`, `frac_dram`, `step`), from the committed ncu pass
            profiles/r02_dram_by_stage.json, and to the dense formulation (k_scan_stream).
