@@ -14,18 +14,48 @@
 #define RS_CHUNK 4096          // elements per block per pass
 #define RS_THREADS 256
 
-// log10f as glibc 2.39 computes it (e_log10f.c: exponent and mantissa apart, y * log10_2lo + ivln10 * logf(m), then
-// + y * log10_2hi, plain float operations) -- saveQval 226 adds its result to p in float, so a last-bit difference
-// shows in q.  CUDA's log10f differs from it for ~2 % of the counts; this form for 0.014 % (measured on the host
-// over 9e7 counts: the cases in which glibc's logf is not the correctly rounded logarithm of the mantissa).
+// log10f and logf as glibc 2.39 computes them -- saveQval 226 adds log10f(k) to p in float, so a last-bit difference
+// shows in q (and in the sixth decimal of a -f line).  The reference's arithmetic lives in a third-party dependency
+// that is not part of its sources (glibc 2.39 libm, x86-64); its published algorithms are restated here:
+//   logf   (sysdeps/ieee754/flt-32/e_logf.c, the ARM optimized-routines logf): 16-entry table of (1/c, log c),
+//          r = z/c - 1, degree-3 polynomial, all in double, rounded to float once.  Checked on the host against the
+//          installed libm for ALL 2^23 floats in [1, 2) -- the only arguments log10f hands it -- with and without
+//          fused multiply-adds: identical.
+//   log10f (sysdeps/ieee754/flt-32/e_log10f.c): exponent and mantissa apart, y * log10_2lo + ivln10 * logf(m), then
+//          + y * log10_2hi, plain float operations.  Checked against the installed libm over 9e7 counts: identical.
 // x: a count of bp as a float, >= 1.
+__device__ __forceinline__ float logf_glibc_1_2(float x) {      // x in [1, 2)
+  const double T[16][2] = {
+    {0x1.661ec79f8f3bep+0, -0x1.57bf7808caadep-2}, {0x1.571ed4aaf883dp+0, -0x1.2bef0a7c06ddbp-2},
+    {0x1.49539f0f010bp+0, -0x1.01eae7f513a67p-2}, {0x1.3c995b0b80385p+0, -0x1.b31d8a68224e9p-3},
+    {0x1.30d190c8864a5p+0, -0x1.6574f0ac07758p-3}, {0x1.25e227b0b8eap+0, -0x1.1aa2bc79c81p-3},
+    {0x1.1bb4a4a1a343fp+0, -0x1.a4e76ce8c0e5ep-4}, {0x1.12358f08ae5bap+0, -0x1.1973c5a611cccp-4},
+    {0x1.0953f419900a7p+0, -0x1.252f438e10c1ep-5}, {0x1p+0, 0x0p+0},
+    {0x1.e608cfd9a47acp-1, 0x1.aa5aa5df25984p-5}, {0x1.ca4b31f026aap-1, 0x1.c5e53aa362eb4p-4},
+    {0x1.b2036576afce6p-1, 0x1.526e57720db08p-3}, {0x1.9c2d163a1aa2dp-1, 0x1.bc2860d22477p-3},
+    {0x1.886e6037841edp-1, 0x1.1058bc8a07ee1p-2}, {0x1.767dcf5534862p-1, 0x1.4043057b6ee09p-2}};
+  const double Ln2 = 0x1.62e42fefa39efp-1, A0 = -0x1.00ea348b88334p-2, A1 = 0x1.5575b0be00b6ap-2, A2 = -0x1.ffffef20a4123p-2;
+  const u32 ix = __float_as_uint(x);
+  if (ix == 0x3f800000u) return 0.0f;
+  const u32 tmp = ix - 0x3f330000u;
+  const int i = (int)((tmp >> 19) & 15u);
+  const int k = (int)tmp >> 23;
+  const double z = (double)__uint_as_float(ix - (tmp & 0xff800000u));
+  const double r = __dadd_rn(__dmul_rn(z, T[i][0]), -1.0);
+  const double y0 = __dadd_rn(T[i][1], __dmul_rn((double)k, Ln2));
+  const double r2 = __dmul_rn(r, r);
+  double y = __dadd_rn(__dmul_rn(A1, r), A2);
+  y = __dadd_rn(__dmul_rn(A0, r2), y);
+  y = __dadd_rn(__dmul_rn(y, r2), __dadd_rn(y0, r));
+  return (float)y;
+}
 __device__ __forceinline__ float log10f_glibc(float x) {
   const float ivln10 = 4.3429449201e-01f, log10_2hi = 3.0102920532e-01f, log10_2lo = 7.9034151668e-07f;
   const int hx = __float_as_int(x);
   const int k = (hx >> 23) - 127;                      // >= 0 here
   const float y = (float)k;
   const float m = __int_as_float((hx & 0x007fffff) | (0x7f << 23));
-  const float lg = (float)log((double)m);
+  const float lg = logf_glibc_1_2(m);
   const float z = __fadd_rn(__fmul_rn(y, log10_2lo), __fmul_rn(ivln10, lg));
   return __fadd_rn(z, __fmul_rn(y, log10_2hi));
 }

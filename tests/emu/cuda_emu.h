@@ -73,6 +73,8 @@ static inline float __fadd_rn(float a, float b) { volatile float r = a + b; retu
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fdiv_rn(float a, float b) { volatile float r = a / b; return r; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
 static inline float __uint2float_rn(unsigned v) { return (float)v; }
 static inline float __ull2float_rn(unsigned long long v) { return (float)v; }
 static inline float __int2float_rn(int v) { return (float)v; }
